@@ -1,0 +1,242 @@
+"""CPU oracle for the Karras/EDM numerics of DiffSci (TEST INFRASTRUCTURE ONLY).
+
+This file is a plain-PyTorch (CPU, fp32 or fp64) restatement of the reference algorithm
+for the sampler / loss / EMA part of the hot path.  It is *not* product code: only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it, and only as the checker / the CPU arm.
+
+The arithmetic of this path lives in PyTorch ATen (third-party; torch 2.11.0+cu128 in this
+image, the reference pins no version in requirements.txt:10).  The oracle therefore calls
+the same ATen CPU primitives in the same order as the reference call sites quoted on each
+function.  Parity is PINNED: ``tests/golden/*.pt`` were produced by running the live
+reference (``oracle/make_goldens.py``, importing /root/reference) and
+``tests/test_oracle_vs_golden.py`` checks every function here against them.
+
+All functions take/return CPU tensors; ``net`` arguments are callables
+``net(x_scaled, c_noise) -> F`` (see ``oracle/nets_oracle.py``).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+
+Net = Callable[[torch.Tensor, torch.Tensor], torch.Tensor]
+
+
+def bcast(v: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """diffsci/torchutils.py:4-40 -- append singleton dims so v[B] broadcasts against x[B,...]."""
+    return v.reshape(v.shape + (1,) * (x.ndim - v.ndim)).to(x)
+
+
+# ----------------------------------------------------------------------------- schedule
+def edm_steps(n: int, sigma_min=0.002, sigma_max=80.0, rho=7.0, dtype=torch.float32) -> torch.Tensor:
+    """EDMScheduler.create_steps (karras/schedulers.py:377-385): n-1 rho-spaced sigmas then 0.
+
+    The reference evaluates this with 0-dim fp32 buffers; the op order below is the same.
+    """
+    rho_t = torch.tensor(rho, dtype=dtype)
+    smax = torch.tensor(sigma_max, dtype=dtype)
+    smin = torch.tensor(sigma_min, dtype=dtype)
+    s = torch.arange(n - 1).to(rho_t) / (n - 2)
+    start = smax ** (1 / rho_t)
+    end = smin ** (1 / rho_t)
+    steps = (start + s * (end - start)) ** rho_t
+    return torch.cat([steps, torch.zeros([1]).to(steps)])
+
+
+# ----------------------------------------------------------------------------- preconditioner
+def edm_precond(sigma: torch.Tensor, sigma_data: float = 0.5):
+    """EDMPreconditioner (karras/preconditioners.py:30-53) -> (c_in, c_out, c_skip, c_noise)."""
+    sd = torch.tensor(sigma_data, dtype=sigma.dtype)
+    c_skip = sd ** 2 / (sigma ** 2 + sd ** 2)
+    c_out = sigma * sd / torch.sqrt(sigma ** 2 + sd ** 2)
+    c_in = 1 / torch.sqrt(sigma ** 2 + sd ** 2)
+    c_noise = 0.5 * torch.log(sigma)
+    return c_in, c_out, c_skip, c_noise
+
+
+def denoiser(net: Net, x: torch.Tensor, sigma: torch.Tensor, sigma_data: float = 0.5) -> torch.Tensor:
+    """KarrasModule.get_denoiser (karras/karrasmodule.py:690-719), unconditional branch."""
+    c_in, c_out, c_skip, c_noise = edm_precond(sigma, sigma_data)
+    F = net(bcast(c_in, x) * x, c_noise)
+    return bcast(c_out, x) * F + bcast(c_skip, x) * x
+
+
+def score(net: Net, x, sigma, sigma_data=0.5):
+    """KarrasModule.get_score (karrasmodule.py:721-733)."""
+    return (denoiser(net, x, sigma, sigma_data) - x) / (bcast(sigma, x) ** 2)
+
+
+def edm_rhs(net: Net, x, ti, sigma_data=0.5, stochastic=False, langevin_const=1.0,
+            langevin_interval=None):
+    """Scheduler.rhs, EDM branch (karras/schedulers.py:247-274; s=1, sigma=t, sigma'=1)."""
+    t = ti * torch.ones(x.shape[0]).to(x)
+    t_ = bcast(t, x)
+    sc = score(net, x, t, sigma_data)
+    res = -(t_ * (1 + 0 * t_)) * sc
+    if stochastic:
+        res = res + (-(langevin_factor(t_, langevin_const, langevin_interval) * sc))
+    return res
+
+
+def langevin_factor(t, langevin_const=1.0, langevin_interval=None):
+    """Scheduler.langevin_factor (schedulers.py:219-240) for the EDM functions."""
+    std = (1 + 0 * t) ** 2 * (1 + 0 * t) * (1 * t)
+    if langevin_interval is not None:
+        t0 = t.reshape(-1)[0]
+        if not (t0 > langevin_interval[0] and t0 < langevin_interval[1]):
+            return 0 * t
+    return langevin_const * std + 0 * t
+
+
+def noise_injection(t, langevin_const=1.0, langevin_interval=None):
+    """Scheduler.noise_injection (schedulers.py:242-245)."""
+    return torch.sqrt(2 * langevin_factor(t, langevin_const, langevin_interval))
+
+
+# ----------------------------------------------------------------------------- integrators
+def step_euler(net, x, t, dt, **kw):
+    """EulerIntegrator.step (karras/integrators.py:29-35)."""
+    return x + dt * edm_rhs(net, x, t, **kw)
+
+
+def step_heun(net, x, t, dt, **kw):
+    """HeunIntegrator.step (integrators.py:38-54)."""
+    r1 = edm_rhs(net, x, t, **kw)
+    if (t + dt) > 0:
+        r2 = edm_rhs(net, x + dt * r1, t + dt, **kw)
+    elif (t + dt) == 0:
+        r2 = r1
+    else:
+        raise ValueError("t+dt < 0 is not supported")
+    return x + 0.5 * (r1 + r2) * dt
+
+
+def step_euler_maruyama(net, x, t, dt, noise, sigma_data=0.5, langevin_const=1.0,
+                        langevin_interval=None):
+    """EulerMaruyamaIntegrator.step (integrators.py:57-69) with the N(0,1) draw injected."""
+    r = edm_rhs(net, x, t, sigma_data=sigma_data, stochastic=True,
+                langevin_const=langevin_const, langevin_interval=langevin_interval)
+    return x + r * dt + noise_injection(t, langevin_const, langevin_interval) * noise * torch.sqrt(torch.abs(dt))
+
+
+def step_karras(net, x, t, dt, noise, nsteps, s_churn=40.0, s_tmin=0.05, s_tmax=50.0,
+                s_noise=1.003, sigma_data=0.5):
+    """KarrasIntegrator.step (integrators.py:72-113), EDM functions, N(0,1) draw injected."""
+    back = min(s_churn / nsteps, np.sqrt(2) - 1)
+    if s_tmin is not None and not (s_tmin <= t <= s_tmax):
+        back = 0
+    sigma = 1 * t
+    sigma_n = sigma + back * sigma
+    t_n = 1 * sigma_n
+    scale, scale_n = 1 + 0 * t, 1 + 0 * t_n
+    std = scale_n * torch.sqrt(sigma_n ** 2 - sigma ** 2)
+    x_n = (scale_n / scale) * x + std * s_noise * noise
+    r1 = edm_rhs(net, x_n, t_n, sigma_data=sigma_data)
+    dt_n = (t + dt) - t_n
+    x = x_n + dt_n * r1
+    if (t + dt) > 0:
+        r2 = edm_rhs(net, x, t + dt, sigma_data=sigma_data)
+        x = x_n + 0.5 * (r1 + r2) * dt_n
+    return x
+
+
+def propagate_backward(net: Net, x: torch.Tensor, nsteps: int, integrator: str = "heun",
+                       record_history: bool = False, noises: Optional[Sequence[torch.Tensor]] = None,
+                       sigma_data: float = 0.5, langevin_const: float = 1.0,
+                       langevin_interval=None, **integrator_kw):
+    """Scheduler.propagate(backward=True) (schedulers.py:48-89) for an EDMScheduler."""
+    t = edm_steps(nsteps + 1).to(x)
+    dt = torch.diff(t)
+    hist = [x] if record_history else None
+    for i in range(nsteps):
+        if integrator == "euler":
+            x = step_euler(net, x, t[i], dt[i], sigma_data=sigma_data)
+        elif integrator == "heun":
+            x = step_heun(net, x, t[i], dt[i], sigma_data=sigma_data)
+        elif integrator == "euler-maruyama":
+            x = step_euler_maruyama(net, x, t[i], dt[i], noises[i], sigma_data=sigma_data,
+                                    langevin_const=langevin_const, langevin_interval=langevin_interval)
+        elif integrator == "karras":
+            x = step_karras(net, x, t[i], dt[i], noises[i], nsteps, sigma_data=sigma_data, **integrator_kw)
+        else:
+            raise ValueError(f"Unknown integrator: {integrator}")
+        if record_history:
+            hist.append(x)
+    return torch.stack(hist, 0) if record_history else x
+
+
+def sample_from_white_noise(net, white_noise, nsteps, integrator="heun", sigma_max=80.0, **kw):
+    """KarrasModule.propagate_white_noise (karrasmodule.py:867-905) without latent decode."""
+    return propagate_backward(net, white_noise * sigma_max, nsteps, integrator, **kw)
+
+
+# ----------------------------------------------------------------------------- training
+def edm_sigma_from_normal(xi: torch.Tensor, prior_mean=-1.2, prior_std=1.2):
+    """EDMNoiseSampler.sample (karras/noisesamplers.py:35-41) given the N(0,1) draw."""
+    return torch.exp(xi * torch.tensor(prior_std, dtype=xi.dtype) + torch.tensor(prior_mean, dtype=xi.dtype))
+
+
+def edm_loss_weight(sigma, sigma_data=0.5):
+    """EDMNoiseSampler.loss_weighting (noisesamplers.py:30-33)."""
+    sd = torch.tensor(sigma_data, dtype=sigma.dtype)
+    return (sigma ** 2 + sd ** 2) / ((sigma * sd) ** 2)
+
+
+def edm_loss(net, x, sigma, noise, loss_metric="huber", mask=None, sigma_data=0.5):
+    """KarrasModule.loss_fn (karrasmodule.py:569-650), single-loss branch, noise injected."""
+    bs = bcast(sigma, x)
+    x_noised = x + bs * noise
+    D = denoiser(net, x_noised, sigma, sigma_data)
+    w = edm_loss_weight(bs, sigma_data)
+    if loss_metric == "huber":
+        l = torch.nn.functional.huber_loss(D, x, reduction="none", delta=1.0)
+    elif loss_metric == "mse":
+        l = torch.nn.functional.mse_loss(D, x, reduction="none")
+    else:
+        raise ValueError(loss_metric)
+    if mask is not None:
+        l = l * (1 - mask.expand_as(l))
+    return (w * l + torch.zeros_like(w)).mean()
+
+
+# ----------------------------------------------------------------------------- EMA
+def power_function_exp_from_std(std: float) -> float:
+    """karras/ema.py:9-15."""
+    target = float(std) ** -2
+    roots = np.roots([1.0, 7.0, 16.0 - target, 12.0 - target])
+    return float(np.max(roots.real))
+
+
+def ema_beta(kind: str, next_update: int, decay=0.999, halflife_steps=None, rampup_ratio=None, std=0.05) -> float:
+    """ModelEMA._traditional_beta / _power_function_beta (ema.py:18-23, 111-121)."""
+    if kind == "power":
+        if next_update <= 1:
+            return 0.0
+        return float((1.0 - 1.0 / next_update) ** (power_function_exp_from_std(std) + 1.0))
+    if halflife_steps is None:
+        return decay
+    hl = float(halflife_steps)
+    if rampup_ratio is not None:
+        hl = min(hl, max(float(next_update), 1.0) * float(rampup_ratio))
+    return float(0.5 ** (1.0 / max(hl, 1e-8)))
+
+
+def ema_update(shadow: torch.Tensor, param: torch.Tensor, beta: float) -> torch.Tensor:
+    """ModelEMA.update inner op (ema.py:147): shadow.lerp_(param, 1-beta)."""
+    return torch.lerp(shadow, param, 1.0 - beta)
+
+
+def adamw_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, wd=1e-4):
+    """torch.optim.AdamW single-tensor update (reference default optimizer, karrasmodule.py:497-500)."""
+    p = p * (1 - lr * wd)
+    m = torch.lerp(m, g, 1 - b1)
+    v = v * b2 + (1 - b2) * g * g
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    denom = (v.sqrt() / math.sqrt(bc2)) + eps
+    p = p - (lr / bc1) * (m / denom)
+    return p, m, v

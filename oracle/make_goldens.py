@@ -1,0 +1,218 @@
+"""Generate tests/golden/*.pt by running the LIVE reference (/root/reference) on CPU.
+
+Build-container only (the reference cannot travel to the GPU box).  Run:
+
+    python oracle/make_goldens.py
+
+Every fixture stores: the config kwargs, the (key, shape) manifest of the reference
+module's state_dict, the synthetic-weight seed (weights are regenerated with
+``nets_oracle.synth_state_dict`` -- they are NOT stored), the seeded inputs and the
+reference outputs in fp32 plus an fp64 run (``module.double()``) for tolerance budgeting.
+"""
+from __future__ import annotations
+
+import os
+import re
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refload  # noqa: E402
+from nets_oracle import synth_state_dict  # noqa: E402
+
+GRAD_KEYS = re.compile(r"^(net\.|convin|convout|downward_blocks\.0\.0\.|before_block\.0\.conv1|"
+                       r"attn_block\.0\.|upsamplers\.1\.|downsamplers\.0\.)")
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def manifest_of(module):
+    return [(k, list(v.shape)) for k, v in module.state_dict().items()]
+
+
+def load_synth(module, seed):
+    man = manifest_of(module)
+    module.load_state_dict(synth_state_dict(man, seed))
+    return man
+
+
+class _Noise:
+    """Replace torch.randn_like with a replay of pre-drawn tensors (integrators.py:68,105;
+    karrasmodule.py:591 draw on the device generator -- injected for parity)."""
+
+    def __init__(self, tensors):
+        self.tensors = list(tensors)
+        self.i = 0
+
+    def __enter__(self):
+        self.orig = torch.randn_like
+
+        def fake(x, *a, **k):
+            t = self.tensors[self.i].to(x)
+            self.i += 1
+            assert t.shape == x.shape
+            return t
+        torch.randn_like = fake
+        return self
+
+    def __exit__(self, *a):
+        torch.randn_like = self.orig
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    refload.load_reference()
+    import diffsci.models as M
+    from diffsci.models.nets.punetg import PUNetG
+    from diffsci.models.nets.punetg_config import PUNetGConfig
+    from diffsci.models.nets.adm import ADM, ADMConfig
+    from diffsci.models.nets.mlp import MLPUncond
+    from diffsci.models.karras.ema import ModelEMA, _power_function_beta, _power_function_exp_from_std
+    from diffsci.models.karras import integrators as I
+
+    torch.set_num_threads(8)
+
+    # ------------------------------------------------------------------ numerics
+    sch = M.EDMScheduler()
+    pre = M.EDMPreconditioner()
+    ns = M.EDMNoiseSampler()
+    sig = torch.tensor([0.002, 0.0137, 0.25, 0.5, 1.0, 3.7, 21.0, 80.0])
+    g = {
+        "steps": {n: sch.create_steps(n) for n in (3, 4, 11, 19, 41, 65, 257)},
+        "sigma": sig,
+        "c_in": pre.input_scaling(sig), "c_out": pre.output_scaling(sig),
+        "c_skip": pre.skip_scaling(sig), "c_noise": pre.noise_conditioner(sig),
+        "loss_weight": ns.loss_weighting(sig),
+    }
+    torch.manual_seed(7)
+    xi = torch.randn(16)
+    g["sigma_xi"] = xi
+    g["sigma_from_xi"] = torch.exp(xi * ns.prior_std + ns.prior_mean)
+    g["ema_power_exp"] = {s: _power_function_exp_from_std(s) for s in (0.05, 0.1)}
+    g["ema_power_beta"] = {(s, n): _power_function_beta(s, n) for s in (0.05, 0.1) for n in (1, 2, 10, 1000)}
+    lin = torch.nn.Linear(2, 1, bias=False)
+    ema = ModelEMA(lin, ema_type="traditional", halflife_steps=100.0, rampup_ratio=0.5)
+    g["ema_trad_beta"] = {n: ema._traditional_beta(n) for n in (1, 2, 50, 1000)}
+    torch.save(g, os.path.join(OUT, "numerics.pt"))
+
+    # ------------------------------------------------------------------ nets
+    def net_case(name, module, cfg_kwargs, x, t, seed, kind):
+        man = load_synth(module, seed)
+        module.eval()
+        with torch.no_grad():
+            y32 = module(x, t)
+            y64 = module.double()(x.double(), t.double())
+            module.float()
+        torch.save({"kind": kind, "cfg": cfg_kwargs, "manifest": man, "seed": seed,
+                    "x": x, "t": t, "y": y32, "y64": y64}, os.path.join(OUT, name + ".pt"))
+        print(name, tuple(y32.shape), float(y32.abs().max()),
+              "fp32-vs-fp64 maxrel", float((y32 - y64).abs().max() / y64.abs().max()))
+        return module
+
+    torch.manual_seed(11)
+    kw = dict(dimension=2, model_channels=8)
+    p2d = net_case("punetg2d_mc8", PUNetG(PUNetGConfig(**kw)), kw,
+                   torch.randn(2, 1, 28, 28), torch.tensor([-1.3, 0.9]), 101, "punetg")
+    kw = dict(dimension=3, model_channels=8)
+    net_case("punetg3d_mc8", PUNetG(PUNetGConfig(**kw)), kw,
+             torch.randn(2, 1, 8, 8, 8), torch.tensor([0.4, -2.0]), 102, "punetg")
+    kw = dict(dimension=2, model_channels=8, input_channels=2, output_channels=3, channel_expansion=[2],
+              number_resnet_attn_block=3, attn_residual=True)
+    net_case("punetg2d_multi", PUNetG(PUNetGConfig(**kw)), kw,
+             torch.randn(1, 2, 16, 24), torch.tensor([0.1]), 103, "punetg")
+    kw = dict(input_channels=3, output_channels=3, model_channels=8, time_embed_dim=16, output_embed_dim=32)
+    net_case("adm2d_mc8", ADM(ADMConfig(**kw)), kw,
+             torch.randn(2, 3, 16, 16), torch.tensor([-0.7, 1.1]), 104, "adm")
+    kw = dict(input_channels=1, output_channels=1, model_channels=8, time_embed_dim=16, output_embed_dim=32,
+              skip_integration_type="add", channel_expansion=[2])
+    net_case("adm2d_add", ADM(ADMConfig(**kw)), kw,
+             torch.randn(1, 1, 12, 20), torch.tensor([0.3]), 105, "adm")
+    mlp = MLPUncond(2, [16, 16], nonlinearity=torch.nn.SiLU())
+    kw = dict(dim=2, hidden_dims=[16, 16], act="silu")
+    mlp = net_case("mlp_silu", mlp, kw, torch.randn(32, 2), torch.randn(32), 106, "mlp")
+
+    # ------------------------------------------------------------------ denoiser / samplers / loss
+    def sampler_case(name, model, shape, nsteps, seed):
+        cfg = M.KarrasModuleConfig.from_edm()
+        mod = M.KarrasModule(model, cfg)
+        mod.eval()
+        torch.manual_seed(seed)
+        B = shape[0]
+        wn = torch.randn(*shape)
+        out = {"nsteps": nsteps, "white_noise": wn}
+        with torch.no_grad():
+            sg = torch.exp(torch.randn(B) * 1.2 - 1.2)
+            xin = torch.randn(*shape) * (1 + sg.view(-1, *([1] * (len(shape) - 1))))
+            D, cn = mod.get_denoiser(xin, sg)
+            out.update(den_x=xin, den_sigma=sg, den_D=D, den_cnoise=cn, den_score=mod.get_score(xin, sg))
+            out["heun_hist"] = mod.propagate_white_noise(wn, nsteps=nsteps, record_history=True)
+            out["euler"] = mod.propagate_white_noise(wn, nsteps=nsteps, integrator="euler")
+            noises = [torch.randn(*shape) for _ in range(nsteps)]
+            out["noises"] = noises
+            with _Noise(noises):
+                out["em"] = mod.propagate_white_noise(wn, nsteps=nsteps, integrator="euler-maruyama")
+            cfg.noisescheduler.langevin_const = 0.5
+            cfg.noisescheduler.langevin_interval = (0.1, 10.0)
+            with _Noise(noises):
+                out["em_interval"] = mod.propagate_white_noise(wn, nsteps=nsteps, integrator="euler-maruyama")
+            cfg.noisescheduler.langevin_const = 1.0
+            cfg.noisescheduler.langevin_interval = None
+            with _Noise(noises):
+                out["karras"] = mod.propagate_white_noise(wn, nsteps=nsteps, integrator="karras")
+            with _Noise(noises):
+                out["karras_custom"] = mod.propagate_white_noise(
+                    wn, nsteps=nsteps, integrator=I.KarrasIntegrator(s_schurn=10, s_tmin=0.01, s_tmax=1.0, s_noise=1.0))
+        # loss + grads (training path)
+        x0 = torch.randn(*shape) * 0.5
+        ln = torch.randn(*shape)
+        mask = (torch.rand(*shape) > 0.7).float()
+        out.update(loss_x=x0, loss_noise=ln, loss_sigma=sg, loss_mask=mask)
+        for metric in ("huber", "mse"):
+            cfg2 = M.KarrasModuleConfig.from_edm(loss_metric=metric)
+            mod2 = M.KarrasModule(model, cfg2)
+            for use_mask in (False, True):
+                model.zero_grad()
+                with _Noise([ln]):
+                    L = mod2.loss_fn(x0, sg, None, mask if use_mask else None)
+                L.backward()
+                key = f"loss_{metric}{'_mask' if use_mask else ''}"
+                out[key] = L.detach()
+                # a representative subset keeps the fixture small: first/last layers, one deep
+                # conv, norm affine, time MLP, attention projections
+                out[key + "_grads"] = {k: p.grad.clone() for k, p in model.named_parameters()
+                                       if GRAD_KEYS.search(k)}
+        torch.save(out, os.path.join(OUT, name + ".pt"))
+        print(name, "heun final absmax", float(out["heun_hist"][-1].abs().max()))
+
+    sampler_case("sampler_mlp", mlp, (32, 2), 6, 201)
+    sampler_case("sampler_punetg2d", p2d, (2, 1, 28, 28), 4, 202)
+
+    # nsteps edge: nsteps=2 is the smallest valid schedule
+    cfg = M.KarrasModuleConfig.from_edm()
+    mod = M.KarrasModule(mlp, cfg)
+    torch.manual_seed(5)
+    wn = torch.randn(8, 2)
+    with torch.no_grad():
+        torch.save({"white_noise": wn, "heun2": mod.propagate_white_noise(wn, nsteps=2)},
+                   os.path.join(OUT, "sampler_edge.pt"))
+
+    # ------------------------------------------------------------------ EMA known answers (tests/test_karras_ema.py:23-52)
+    lin = torch.nn.Linear(3, 2)
+    torch.manual_seed(3)
+    ema = ModelEMA(lin, ema_type="traditional", decay=0.9)
+    traj = []
+    for i in range(3):
+        with torch.no_grad():
+            for p in lin.parameters():
+                p.add_(torch.randn_like(p))
+        ema.update(lin)
+        traj.append({"params": {k: v.detach().clone() for k, v in lin.named_parameters()},
+                     "shadow": {k: v.clone() for k, v in ema.selected_profile()["params"].items()},
+                     "beta": ema.last_beta})
+    torch.save({"init": None, "traj": traj}, os.path.join(OUT, "ema.pt"))
+    print("done ->", OUT)
+
+
+if __name__ == "__main__":
+    main()

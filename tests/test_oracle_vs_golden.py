@@ -1,0 +1,142 @@
+"""Pin the CPU oracle (oracle/*.py) against golden vectors produced by the LIVE reference
+(oracle/make_goldens.py).  Runs without a GPU."""
+import types
+
+import pytest
+import torch
+
+from oracle import karras_oracle as K
+from oracle import nets_oracle as N
+
+TOL32 = 2e-5   # oracle fp32 vs reference fp32: same ATen ops, op-order rounding only
+
+
+def relmax(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def cfg_for(kind, kw):
+    if kind == "punetg":
+        d = dict(input_channels=1, output_channels=1, dimension=2, model_channels=64, channel_expansion=[2, 4],
+                 number_resnet_downward_block=2, number_resnet_upward_block=2, number_resnet_attn_block=2,
+                 number_resnet_before_attn_block=2, number_resnet_after_attn_block=2, transition_scale_factor=2,
+                 first_resblock_norm="GroupLN", second_resblock_norm="GroupRMS", affine_norm=True,
+                 attn_residual=False, bias=True)
+    else:
+        d = dict(input_channels=1, output_channels=1, dimension=2, model_channels=64, time_embed_dim=64,
+                 output_embed_dim=256, channel_expansion=[2, 4], number_resnet_downward_block=2,
+                 number_resnet_upward_block=2, number_resnet_attn_block=2, number_resnet_before_attn_block=2,
+                 number_resnet_after_attn_block=2, kernel_size=3, transition_scale_factor=2,
+                 first_resblock_norm="GroupLN", second_resblock_norm="GroupRMS", num_groups=1,
+                 skip_integration_type="concat", attn_residual=True, decoder_type=1)
+    d.update(kw)
+    c = types.SimpleNamespace(**d)
+    if kind == "adm":
+        c.middle_block_attn_config = ([False] * c.number_resnet_before_attn_block +
+                                      [True] * (c.number_resnet_attn_block - 1) + [False] +
+                                      [False] * c.number_resnet_after_attn_block)
+    return c
+
+
+def oracle_net(g, dtype=torch.float32):
+    sd = N.synth_state_dict(g["manifest"], g["seed"], dtype)
+    if g["kind"] == "punetg":
+        cfg = cfg_for("punetg", g["cfg"])
+        return lambda x, t: N.punetg_forward(sd, cfg, x, t)
+    if g["kind"] == "adm":
+        cfg = cfg_for("adm", g["cfg"])
+        return lambda x, t: N.adm_forward(sd, cfg, x, t)
+    return lambda x, t: N.mlp_uncond_forward(sd, x, t, g["cfg"]["act"])
+
+
+def test_schedule_and_scalars(golden):
+    g = golden("numerics")
+    for n, ref in g["steps"].items():
+        assert torch.equal(K.edm_steps(n), ref), n
+    c_in, c_out, c_skip, c_noise = K.edm_precond(g["sigma"])
+    for a, b in ((c_in, "c_in"), (c_out, "c_out"), (c_skip, "c_skip"), (c_noise, "c_noise")):
+        assert torch.equal(a, g[b]), b
+    assert torch.equal(K.edm_loss_weight(g["sigma"]), g["loss_weight"])
+    assert torch.equal(K.edm_sigma_from_normal(g["sigma_xi"]), g["sigma_from_xi"])
+
+
+def test_ema_betas(golden):
+    g = golden("numerics")
+    for s, v in g["ema_power_exp"].items():
+        assert K.power_function_exp_from_std(s) == v
+    for (s, n), v in g["ema_power_beta"].items():
+        assert K.ema_beta("power", n, std=s) == v
+    for n, v in g["ema_trad_beta"].items():
+        assert K.ema_beta("traditional", n, halflife_steps=100.0, rampup_ratio=0.5) == v
+    # known answers of reference tests/test_karras_ema.py:23-52
+    assert torch.allclose(K.ema_update(torch.zeros(2), torch.full((2,), 2.0), 0.5), torch.ones(2))
+    assert K.ema_beta("power", 1) == 0.0
+    e = golden("ema")
+    shadow = None
+    for step in e["traj"]:
+        if shadow is None:
+            # ModelEMA.reset clones the params at construction; first shadow = lerp(init, p1, 1-beta)
+            # => recover init from the recorded first update.
+            shadow = {k: (step["shadow"][k] - (1 - step["beta"]) * step["params"][k]) / step["beta"]
+                      for k in step["shadow"]}
+        for k in shadow:
+            shadow[k] = K.ema_update(shadow[k], step["params"][k], step["beta"])
+            assert torch.allclose(shadow[k], step["shadow"][k], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8", "punetg2d_multi", "adm2d_mc8", "adm2d_add",
+                                  "mlp_silu"])
+def test_net_forward(golden, name):
+    g = golden(name)
+    y = oracle_net(g)(g["x"], g["t"])
+    assert y.shape == g["y"].shape
+    assert relmax(y, g["y"]) < TOL32, relmax(y, g["y"])
+    y64 = oracle_net(g, torch.float64)(g["x"].double(), g["t"].double())
+    assert relmax(y64, g["y64"]) < 1e-12
+
+
+@pytest.mark.parametrize("name,netname", [("sampler_mlp", "mlp_silu"), ("sampler_punetg2d", "punetg2d_mc8")])
+def test_denoiser_samplers_loss(golden, name, netname):
+    g = golden(name)
+    net = oracle_net(golden(netname))
+    n = g["nsteps"]
+    assert relmax(K.denoiser(net, g["den_x"], g["den_sigma"]), g["den_D"]) < TOL32
+    assert relmax(K.score(net, g["den_x"], g["den_sigma"]), g["den_score"]) < TOL32
+    wn = g["white_noise"]
+    # N chained evaluations of a random-weight network amplify fp32 rounding chaotically (the reference's own
+    # fp32 run sits ~1e-3..1e-2 from an fp64 run of the same chain).  Budget against fp64 truth: the oracle may
+    # differ from the reference by at most what the reference itself differs from fp64, plus 2e-5.
+    net64 = oracle_net(golden(netname), torch.float64)
+    nz64 = [z.double() for z in g["noises"]]
+
+    def check(ref, integrator, **kw):
+        o32 = K.sample_from_white_noise(net, wn, n, integrator, **kw)
+        kw64 = dict(kw)
+        if "noises" in kw64:
+            kw64["noises"] = nz64
+        o64 = K.sample_from_white_noise(net64, wn.double(), n, integrator, **kw64)
+        budget = 2.0 * relmax(ref.double(), o64) + 2e-5
+        assert relmax(o32, ref) <= budget, (integrator, relmax(o32, ref), budget)
+        return o32
+
+    h = check(g["heun_hist"], "heun", record_history=True)
+    assert torch.equal(h[0], wn * 80.0)
+    check(g["euler"], "euler")
+    check(g["em"], "euler-maruyama", noises=g["noises"])
+    check(g["em_interval"], "euler-maruyama", noises=g["noises"], langevin_const=0.5, langevin_interval=(0.1, 10.0))
+    check(g["karras"], "karras", noises=g["noises"])
+    check(g["karras_custom"], "karras", noises=g["noises"], s_churn=10, s_tmin=0.01, s_tmax=1.0, s_noise=1.0)
+    for metric in ("huber", "mse"):
+        for use_mask in (False, True):
+            L = K.edm_loss(net, g["loss_x"], g["loss_sigma"], g["loss_noise"], metric,
+                           g["loss_mask"] if use_mask else None)
+            ref = g[f"loss_{metric}{'_mask' if use_mask else ''}"]
+            assert abs(float(L) - float(ref)) <= 2e-5 * abs(float(ref)), (metric, use_mask)
+
+
+def test_sampler_edge_nsteps2(golden):
+    g = golden("sampler_edge")
+    net = oracle_net(golden("mlp_silu"))
+    assert relmax(K.sample_from_white_noise(net, g["white_noise"], 2, "heun"), g["heun2"]) < 2e-5
+    # nsteps=1 is outside the reference's domain: create_steps(2) divides by n-2 = 0
+    assert not torch.isfinite(K.edm_steps(2)).all()
