@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Karras/EDM hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c4|c2|c5|c1]
+
+A "step" is ONE full sampling pass of the hot path over one batch of synthetic white noise
+(workload c4: PUNetG-3D, 1x64^3 volumes, EDM Heun 64 steps = 127 denoiser evaluations per sample).
+`value` = samples/s over all ranks with x_T already resident in HBM; `e2e` = the same metric through
+the public API (KarrasModule.propagate_white_noise) with pinned HOST buffers, H2D and D2H inside the
+timed region.  Inputs per step (B x 1 MiB fp32 volumes) are tiny next to the >100 GB of activation
+traffic of one step, so L2 (126 MB) holds no useful state between steps ("inputs larger than L2").
+One rank per GPU; no data-path collective (samples are independent): scaling = weak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (net kind, config kwargs, sample shape, nsteps, integrator, default per-GPU batch)
+    "c4": ("punetg", dict(dimension=3), (1, 64, 64, 64), 64, "heun", 2),
+    "c2": ("punetg", dict(dimension=2, model_channels=128), (1, 28, 28), 40, "heun", 256),
+    "c5": ("punetg", dict(dimension=2), (1, 256, 256), 256, "euler-maruyama", 8),
+    "c1": ("mlp", dict(dim=2, hidden_dims=[128, 128, 128]), (2,), 18, "heun", 65536),
+}
+NAMES = {"c4": "PUNetG-3D(mc=64,[2,4]) 1x64^3 EDM Heun-64 sampling (BASELINE configs[3])",
+         "c2": "PUNetG-2D(mc=128) 1x28x28 EDM Heun-40 sampling (BASELINE configs[1])",
+         "c5": "PUNetG-2D(mc=64) 1x256x256 Euler-Maruyama-256 sampling (BASELINE configs[4])",
+         "c1": "MLPUncond(2,[128]*3,SiLU) toy Heun-18 sampling (BASELINE configs[0])"}
+
+
+def nfe_per_sample(nsteps, integrator):
+    return 2 * nsteps - 1 if integrator in ("heun", "karras") else nsteps
+
+
+def punetg_conv_flops(cfg, spatial):
+    """Algorithmic forward FLOPs of one network evaluation per sample (conv + attention), SURVEY 8d."""
+    nd = cfg.dimension
+    M = cfg.model_channels
+    mult = cfg.extended_channel_expansion
+    k = cfg.kernel_size ** nd
+    S = [1]
+    for s in spatial:
+        S[0] *= s
+    for _ in cfg.channel_expansion:
+        S.append(S[-1] // (2 ** nd))
+    fl = 2 * S[0] * k * (cfg.input_channels * M + M * cfg.output_channels)
+    nl = len(cfg.channel_expansion)
+    for l in range(nl):
+        c, cn = mult[l] * M, mult[l + 1] * M
+        fl += (cfg.number_resnet_downward_block + cfg.number_resnet_upward_block) * 2 * (2 * S[l] * k * c * c)
+        fl += 2 * S[l + 1] * k * c * cn + 2 * S[l] * k * cn * c          # down conv, up conv
+    cb = mult[-1] * M
+    nb = cfg.number_resnet_before_attn_block + cfg.number_resnet_attn_block + cfg.number_resnet_after_attn_block
+    fl += nb * 2 * (2 * S[nl] * k * cb * cb)
+    na = cfg.number_resnet_attn_block - 1
+    fl += na * (8 * S[nl] * cb * cb + 4 * S[nl] * S[nl] * cb)
+    return fl
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def summary(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = [n for i, n in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"),
+                                  (6, "sw_power_cap")) if any(r[i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+
+
+def build_workload(name, device, precision):
+    import torch
+    import diffsci_b200 as d
+    kind, kw, shape, nsteps, integ, batch = WORKLOADS[name]
+    torch.manual_seed(0)
+    if kind == "punetg":
+        cfg = d.PUNetGConfig(**kw)
+        net = d.PUNetG(cfg, precision=precision)
+        flops = punetg_conv_flops(cfg, shape[1:])
+    else:
+        cfg = None
+        net = d.MLPUncond(kw["dim"], kw["hidden_dims"], torch.nn.SiLU())
+        flops = 2 * sum(p.numel() for n, p in net.named_parameters() if n.endswith("weight"))
+    net = net.to(device).eval() if device is not None else net.eval()
+    module = d.KarrasModule(net, d.KarrasModuleConfig.from_edm())
+    return module, net, cfg, shape, nsteps, integ, batch, flops
+
+
+def cpu_reference_arm(name, steps, warmup, max_seconds=25.0):
+    """The oracle port (torch-CPU restatement of the reference, oracle/*.py) timed on the host cores on a
+    BOUNDED sample of the workload: B=1, a few integrator steps, extrapolated linearly in NFE."""
+    import torch
+    from oracle import karras_oracle as K, nets_oracle as N
+    kind, kw, shape, nsteps, integ, _ = WORKLOADS[name]
+    module, net, cfg, *_ = build_workload(name, None, "fp32")
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if kind == "punetg":
+        fn = lambda x, t: N.punetg_forward(sd, cfg, x, t)  # noqa: E731
+        B, sub = 1, 2
+    else:
+        fn = lambda x, t: N.mlp_uncond_forward(sd, x, t, "silu")  # noqa: E731
+        B, sub = 4096, nsteps
+    if name == "c2":
+        B = 8
+    torch.manual_seed(1234)
+    wn = torch.randn(B, *shape)
+    noises = [torch.randn(B, *shape) for _ in range(sub)]
+    nfe_sub = nfe_per_sample(sub, integ)
+    vals = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            K.sample_from_white_noise(fn, wn, sub, integ, noises=noises)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                vals.append(dt)
+            if sum(vals) > max_seconds and len(vals) >= 1:
+                break
+    per_nfe = (sum(vals) / len(vals)) / (nfe_sub * B)                # seconds per sample-NFE
+    value = 1.0 / (per_nfe * nfe_per_sample(nsteps, integ))          # samples/s, extrapolated linearly in NFE
+    sample = (f"oracle port of the reference (torch {torch.__version__} CPU fp32), B={B}, {sub} {integ} steps = {nfe_sub} NFE "
+              f"timed {len(vals)}x, extrapolated linearly to {nfe_per_sample(nsteps, integ)} NFE")
+    return value, cores, sample, sum(vals) / len(vals)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("DSK_BENCH_WORKLOAD", "c4"), choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = workload default)")
+    ap.add_argument("--nsteps", type=int, default=0, help="integrator steps (0 = workload default)")
+    ap.add_argument("--precision", default=os.environ.get("DSK_BENCH_PRECISION", "auto"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    kind, kw, shape, nsteps, integ, batch = WORKLOADS[args.workload]
+    nsteps = args.nsteps or nsteps
+    B = args.batch or batch
+    nfe = nfe_per_sample(nsteps, integ)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        value, cores, sample, secs = cpu_reference_arm(args.workload, max(1, args.steps), min(1, args.warmup))
+        line = {"impl": "reference", "metric": "EDM Heun samples/sec", "value": value, "unit": "samples/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": NAMES[args.workload], "nsteps": nsteps, "nfe_per_sample": nfe},
+                "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "nfe_per_s": value * nfe}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import diffsci_b200 as d
+    from diffsci_b200 import _lib, ops
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    precision = args.precision
+    if precision == "auto":
+        precision = "bf16" if d.TC_CONV_ENABLED else "fp32"
+    module, net, cfg, shape, _, integ, _, flops_per_nfe = build_workload(args.workload, dev, precision)
+    table_integrator = d.name_to_integrator(integ)
+    N_el = B
+    for s in shape:
+        N_el *= s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------------------------------------------------------- resident-input arm (`value`)
+    torch.manual_seed(1234 + rank)
+    wn_host = torch.randn(B, *shape).pin_memory()
+    wn_dev = wn_host.to(dev)
+    for _ in range(args.warmup):
+        module.propagate_white_noise(wn_dev, nsteps=nsteps, integrator=table_integrator)
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    n0 = _lib.launch_count()
+    eng_before = next(iter(module._engines.values()))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        module.propagate_white_noise(wn_dev, nsteps=nsteps, integrator=table_integrator)
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms)
+    clk = clocks.summary() if clocks else None
+    eager_launches = _lib.launch_count() - n0
+    graph_launches = eng_before.graph_launches_per_run() * args.steps if eng_before.use_graphs else 0
+    value = world * B * args.steps / (total_ms / 1e3)
+
+    # ---------------------------------------------------------------- end-to-end arm (`e2e`)
+    out_host = torch.empty(B, *shape).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = module.propagate_white_noise(wn_host, nsteps=nsteps, integrator=table_integrator)   # H2D inside
+        out_host.copy_(res, non_blocking=True)                                                     # D2H inside
+        torch.cuda.synchronize(dev)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(e2e_s)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roofline = None
+    if kind == "punetg":
+        roofline = dominant_conv_roofline(cfg, shape, B, precision, dev, peaks)
+
+    line = {"metric": "EDM Heun samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": NAMES[args.workload], "per_gpu_batch": B, "global_batch": world * B,
+                       "integrator": integ, "nsteps": nsteps, "nfe_per_sample": nfe, "precision": precision,
+                       "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "l2_policy": "inputs larger than L2: >100 GB of activation traffic per step vs 126 MB L2"},
+            "nfe_per_s": value * nfe,
+            "model_tflops": value * nfe * flops_per_nfe / 1e12,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": N_el * 4,
+                    "d2h_bytes_per_step": N_el * 4},
+            "gpu_launches": int(eager_launches + graph_launches),
+            "clocks": clk, "roofline": roofline}
+    if not args.no_cpu_baseline and world == 1:
+        v, cores, sample, _ = cpu_reference_arm(args.workload, 1, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_conv_roofline(cfg, shape, B, precision, dev, peaks, reps=20):
+    """Time the dominant kernel (the full-resolution C->C 3^d convolution: 53% of C4's FLOPs) live with CUDA
+    events on the launching stream: `reps` back-to-back launches on buffers larger than L2."""
+    import torch
+    import diffsci_b200 as d
+    from diffsci_b200 import ops
+    nd, M = cfg.dimension, cfg.model_channels
+    sp = (1,) + tuple(shape[1:]) if nd == 2 else tuple(shape[1:])
+    adt = torch.bfloat16 if precision == "bf16" else torch.float32
+    wd = torch.bfloat16 if (precision == "bf16" and d.TC_CONV_ENABLED) else torch.float32
+    w = torch.randn((M, M) + (cfg.kernel_size,) * nd, device=dev) * 0.02
+    pc = ops.PackedConv(w, torch.zeros(M, device=dev), nd, wd)
+    nbuf = 4                                      # rotate inputs so consecutive launches do not hit in L2
+    xs = [torch.randn((B,) + sp + (M,), device=dev).to(adt) for _ in range(nbuf)]
+    out = torch.empty_like(xs[0])
+    for i in range(3):
+        ops.conv(xs[i % nbuf], pc, out=out)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        ops.conv(xs[i % nbuf], pc, out=out)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    S = 1
+    for s in sp:
+        S *= s
+    flops = 2.0 * B * S * M * M * cfg.kernel_size ** nd
+    achieved = flops / (ms * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops")
+    src = "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    if peak is None:
+        peak, src = 1590.0, "fallback (B200_PROFILING.md)"
+    return {"bound": "tensor", "kernel": f"conv{nd}d {M}->{M} k{cfg.kernel_size} @ {'x'.join(map(str, sp[-nd:]))} "
+            f"({'tcgen05 implicit GEMM' if wd == torch.bfloat16 else 'CUDA-core FFMA implicit GEMM, fp32 parity mode'})",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": src, "ms_per_launch": ms, "flops_per_launch": flops}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,293 @@
+// elementwise.cu -- K5/K6 bandwidth kernels: 2x pooling, skip add, layout conversion, channel
+// concat, Fourier features, grouped small-batch linear (time MLPs), row softmax.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace dsk {
+
+// ---- 2x pooling on channels-last [B, D, H, W, C] (commonlayers.py:60-63,81; adm.py:361-371) ----
+template <typename T, bool IS_MAX>
+__global__ void __launch_bounds__(256) pool2x_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int D, int H, int W,
+                                                      int C, int ndim) {
+  const int Do = ndim == 3 ? D / 2 : 1, Ho = H / 2, Wo = W / 2;
+  const int kd = ndim == 3 ? 2 : 1;
+  const int64_t total = (int64_t)B * Do * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int wo = (int)(p % Wo); p /= Wo;
+    int ho = (int)(p % Ho); p /= Ho;
+    int dz = (int)(p % Do);
+    int b = (int)(p / Do);
+    float acc = IS_MAX ? -INFINITY : 0.0f;
+    for (int a = 0; a < kd; ++a)
+      for (int bb = 0; bb < 2; ++bb)
+        for (int cc = 0; cc < 2; ++cc) {
+          int64_t src = ((((int64_t)b * D + (dz * kd + a)) * H + (ho * 2 + bb)) * W + (wo * 2 + cc)) * C + c;
+          float v = to_f32<T>(x[src]);
+          acc = IS_MAX ? fmaxf(acc, v) : acc + v;
+        }
+    if (!IS_MAX) acc *= (ndim == 3 ? 0.125f : 0.25f);
+    y[i] = from_f32<T>(acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = from_f32<T>(to_f32<T>(a[i]) + to_f32<T>(b[i]));
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = from_f32<TO>(to_f32<TI>(x[i]));
+}
+
+// y[b, s, c] = x[b, c, s]  (C is small at the module boundary: 1..4 channels)
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_cl_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int C, int64_t S) {
+  const int64_t total = (int64_t)B * C * S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int64_t s = p % S;
+    int64_t b = p / S;
+    y[i] = from_f32<T>(x[(b * C + c) * S + s]);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) cl_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int B, int C, int64_t S) {
+  const int64_t total = (int64_t)B * C * S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s = i % S;
+    int64_t p = i / S;
+    int c = (int)(p % C);
+    int64_t b = p / C;
+    y[i] = to_f32<T>(x[(b * S + s) * C + c]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) concat_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y,
+                                                      int64_t rows, int Ca, int Cb) {
+  const int Ct = Ca + Cb;
+  const int64_t total = rows * Ct;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % Ct);
+    int64_t r = i / Ct;
+    y[i] = c < Ca ? a[r * Ca + c] : b[r * Cb + (c - Ca)];
+  }
+}
+
+// ---- Fourier features (commonlayers.py:185-190) ---------------------------------------------
+// x_proj = 2*pi*t*W in the reference's operation order ((2*pi*t)*W in fp32), then accurate
+// sinf/cosf: |arg| reaches ~1e3 rad, fast-math intrinsics would destroy parity.
+__global__ void fourier_kernel(const float* __restrict__ t, const float* __restrict__ W, float* __restrict__ out, int B, int half) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  int b = i / half, j = i - b * half;
+  float p = (6.283185307179586f * t[b]) * W[j];
+  out[(int64_t)b * 2 * half + j] = sinf(p);
+  out[(int64_t)b * 2 * half + half + j] = cosf(p);
+}
+
+// ---- grouped small-batch linear ----------------------------------------------------------------
+// One warp per output feature: the weight row is read once (coalesced) and reused for every batch
+// row; B is small (1..256) on this path, the weights dominate the traffic.
+constexpr int GL_MAXB = 8;
+__global__ void __launch_bounds__(256) grouped_linear_kernel(const float* const* __restrict__ X, const float* const* __restrict__ Wt,
+                                                              const float* const* __restrict__ bias, float* const* __restrict__ Y,
+                                                              const int* __restrict__ in_dim, const int* __restrict__ out_dim,
+                                                              int B, int act) {
+  const int g = blockIdx.y;
+  const int K = in_dim[g], N = out_dim[g];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float* w = Wt[g] + (int64_t)warp * K;
+  const float* x = X[g];
+  float* y = Y[g];
+  const float bv = bias[g] != nullptr ? bias[g][warp] : 0.0f;
+  for (int b0 = 0; b0 < B; b0 += GL_MAXB) {
+    float acc[GL_MAXB];
+#pragma unroll
+    for (int r = 0; r < GL_MAXB; ++r) acc[r] = 0.0f;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = w[k];
+#pragma unroll
+      for (int r = 0; r < GL_MAXB; ++r)
+        if (b0 + r < B) acc[r] += wv * x[(int64_t)(b0 + r) * K + k];
+    }
+#pragma unroll
+    for (int r = 0; r < GL_MAXB; ++r) {
+      float v = warp_sum(acc[r]);
+      if (lane == 0 && b0 + r < B) {
+        v += bv;
+        if (act == 1) v = silu_f(v);
+        else if (act == 2) v = fmaxf(v, 0.0f);
+        y[(int64_t)(b0 + r) * N + warp] = v;
+      }
+    }
+  }
+}
+
+// ---- row softmax (in place, fp32) ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ S, int64_t rows, int cols) {
+  __shared__ float red[8];
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    float* p = S + r * cols;
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, p[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float sum = 0.0f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      float e = expf(p[c] - m);
+      p[c] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
+    __syncthreads();
+    const float inv = 1.0f / sum;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) p[c] *= inv;
+  }
+}
+
+// out = a0*x + a1*r1 + a2*r2 + a3*z  (null pointers are skipped): the arithmetic of the
+// Integrator.step seam (integrators.py:29-113) and Scheduler.rhs scaling for foreign score functions.
+__global__ void __launch_bounds__(256) lincomb_kernel(float* __restrict__ out, int64_t n, const float* __restrict__ x, float a0,
+                                                       const float* __restrict__ r1, float a1, const float* __restrict__ r2,
+                                                       float a2, const float* __restrict__ z, float a3) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = 0.0f;
+    if (x != nullptr) v = a0 * x[i];
+    if (r1 != nullptr) v += a1 * r1[i];
+    if (r2 != nullptr) v += a2 * r2[i];
+    if (z != nullptr) v += a3 * z[i];
+    out[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint32_t stream_id) {
+  const int64_t quads = (n + 3) / 4;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
+    float v[4];
+    philox_normal4(seed, stream_id, (uint64_t)q, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (q * 4 + k < n) out[q * 4 + k] = v[k];
+  }
+}
+
+}  // namespace dsk
+
+using namespace dsk;
+
+extern "C" int dsk_lincomb(float* out, int64_t n, const float* x, float a0, const float* r1, float a1, const float* r2,
+                           float a2, const float* z, float a3, void* stream) {
+  DSK_REQUIRE(out && n > 0, "dsk_lincomb: bad arguments");
+  DSK_LAUNCH(lincomb_kernel, grid_for(n, 256, 16), 256, 0, as_stream(stream), out, n, x, a0, r1, a1, r2, a2, z, a3);
+  return DSK_OK;
+}
+
+extern "C" int dsk_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t stream_id, void* stream) {
+  DSK_REQUIRE(out && n > 0, "dsk_philox_normal: bad arguments");
+  DSK_LAUNCH(philox_normal_kernel, grid_for((n + 3) / 4, 256, 16), 256, 0, as_stream(stream), out, n, seed, stream_id);
+  return DSK_OK;
+}
+
+extern "C" int dsk_pool2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int is_max, int dtype,
+                          void* stream) {
+  DSK_REQUIRE(x && y, "dsk_pool2x: null pointer");
+  DSK_REQUIRE(B > 0 && D > 0 && H > 1 && W > 1 && C > 0 && (ndim == 2 || ndim == 3), "dsk_pool2x: bad shape");
+  DSK_REQUIRE(ndim == 2 ? D == 1 : D > 1, "dsk_pool2x: D=%d inconsistent with ndim=%d", D, ndim);
+  const int64_t total = (int64_t)B * (ndim == 3 ? D / 2 : 1) * (H / 2) * (W / 2) * C;
+  const int grid = grid_for(total, 256, 16);
+  cudaStream_t st = as_stream(stream);
+#define POOL(T, M) DSK_LAUNCH((pool2x_kernel<T, M>), grid, 256, 0, st, (const T*)x, (T*)y, B, D, H, W, C, ndim)
+  if (dtype == DSK_F32) { if (is_max) POOL(float, true); else POOL(float, false); }
+  else if (dtype == DSK_BF16) { if (is_max) POOL(__nv_bfloat16, true); else POOL(__nv_bfloat16, false); }
+  else DSK_REQUIRE(false, "dsk_pool2x: bad dtype %d", dtype);
+#undef POOL
+  return DSK_OK;
+}
+
+extern "C" int dsk_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* stream) {
+  DSK_REQUIRE(a && b && y && n > 0, "dsk_add: bad arguments");
+  const int grid = grid_for(n, 256, 16);
+  if (dtype == DSK_F32) DSK_LAUNCH(add_kernel<float>, grid, 256, 0, as_stream(stream), (const float*)a, (const float*)b, (float*)y, n);
+  else if (dtype == DSK_BF16) DSK_LAUNCH(add_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, n);
+  else DSK_REQUIRE(false, "dsk_add: bad dtype %d", dtype);
+  return DSK_OK;
+}
+
+extern "C" int dsk_cast(const void* x, void* y, int64_t n, int in_dtype, int out_dtype, void* stream) {
+  DSK_REQUIRE(x && y && n > 0, "dsk_cast: bad arguments");
+  const int grid = grid_for(n, 256, 16);
+  cudaStream_t st = as_stream(stream);
+  if (in_dtype == DSK_F32 && out_dtype == DSK_BF16) DSK_LAUNCH((cast_kernel<float, __nv_bfloat16>), grid, 256, 0, st, (const float*)x, (__nv_bfloat16*)y, n);
+  else if (in_dtype == DSK_BF16 && out_dtype == DSK_F32) DSK_LAUNCH((cast_kernel<__nv_bfloat16, float>), grid, 256, 0, st, (const __nv_bfloat16*)x, (float*)y, n);
+  else if (in_dtype == DSK_F32 && out_dtype == DSK_F32) DSK_LAUNCH((cast_kernel<float, float>), grid, 256, 0, st, (const float*)x, (float*)y, n);
+  else DSK_REQUIRE(false, "dsk_cast: bad dtypes %d -> %d", in_dtype, out_dtype);
+  return DSK_OK;
+}
+
+extern "C" int dsk_nchw_to_cl(const float* x, void* y, int B, int C, int64_t S, int dtype, void* stream) {
+  DSK_REQUIRE(x && y && B > 0 && C > 0 && S > 0, "dsk_nchw_to_cl: bad arguments");
+  const int grid = grid_for((int64_t)B * C * S, 256, 16);
+  if (dtype == DSK_F32) DSK_LAUNCH(nchw_to_cl_kernel<float>, grid, 256, 0, as_stream(stream), x, (float*)y, B, C, S);
+  else if (dtype == DSK_BF16) DSK_LAUNCH(nchw_to_cl_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), x, (__nv_bfloat16*)y, B, C, S);
+  else DSK_REQUIRE(false, "dsk_nchw_to_cl: bad dtype %d", dtype);
+  return DSK_OK;
+}
+
+extern "C" int dsk_cl_to_nchw(const void* x, float* y, int B, int C, int64_t S, int dtype, void* stream) {
+  DSK_REQUIRE(x && y && B > 0 && C > 0 && S > 0, "dsk_cl_to_nchw: bad arguments");
+  const int grid = grid_for((int64_t)B * C * S, 256, 16);
+  if (dtype == DSK_F32) DSK_LAUNCH(cl_to_nchw_kernel<float>, grid, 256, 0, as_stream(stream), (const float*)x, y, B, C, S);
+  else if (dtype == DSK_BF16) DSK_LAUNCH(cl_to_nchw_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), (const __nv_bfloat16*)x, y, B, C, S);
+  else DSK_REQUIRE(false, "dsk_cl_to_nchw: bad dtype %d", dtype);
+  return DSK_OK;
+}
+
+extern "C" int dsk_concat_channels(const void* a, const void* b, void* y, int64_t rows, int Ca, int Cb, int dtype,
+                                   void* stream) {
+  DSK_REQUIRE(a && b && y && rows > 0 && Ca > 0 && Cb > 0, "dsk_concat_channels: bad arguments");
+  const int grid = grid_for(rows * (Ca + Cb), 256, 16);
+  if (dtype == DSK_F32) DSK_LAUNCH(concat_kernel<float>, grid, 256, 0, as_stream(stream), (const float*)a, (const float*)b, (float*)y, rows, Ca, Cb);
+  else if (dtype == DSK_BF16) DSK_LAUNCH(concat_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, rows, Ca, Cb);
+  else DSK_REQUIRE(false, "dsk_concat_channels: bad dtype %d", dtype);
+  return DSK_OK;
+}
+
+extern "C" int dsk_fourier(const float* t, const float* W, float* out, int B, int half, void* stream) {
+  DSK_REQUIRE(t && W && out && B > 0 && half > 0, "dsk_fourier: bad arguments");
+  DSK_LAUNCH(fourier_kernel, (B * half + 127) / 128, 128, 0, as_stream(stream), t, W, out, B, half);
+  return DSK_OK;
+}
+
+extern "C" int dsk_grouped_linear(const float* const* X, const float* const* W, const float* const* bias, float* const* Y,
+                                  const int* in_dim, const int* out_dim, int ngroups, int max_out, int B, int act,
+                                  void* stream) {
+  DSK_REQUIRE(X && W && bias && Y && in_dim && out_dim, "dsk_grouped_linear: null pointer");
+  DSK_REQUIRE(ngroups > 0 && max_out > 0 && B > 0 && act >= 0 && act <= 2, "dsk_grouped_linear: bad arguments");
+  dim3 grid((max_out + 7) / 8, ngroups);
+  DSK_LAUNCH(grouped_linear_kernel, grid, 256, 0, as_stream(stream), X, W, bias, Y, in_dim, out_dim, B, act);
+  return DSK_OK;
+}
+
+extern "C" int dsk_softmax_rows(float* S, int64_t rows, int cols, void* stream) {
+  DSK_REQUIRE(S && rows > 0 && cols > 0, "dsk_softmax_rows: bad arguments");
+  int64_t grid = rows < (int64_t)DSK_NUM_SMS * 16 ? rows : (int64_t)DSK_NUM_SMS * 16;
+  DSK_LAUNCH(softmax_rows_kernel, (int)grid, 256, 0, as_stream(stream), S, rows, cols);
+  return DSK_OK;
+}

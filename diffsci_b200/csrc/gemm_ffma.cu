@@ -1,0 +1,338 @@
+// gemm_ffma.cu -- K1 (fp32-parity mode): implicit-GEMM convolution and batched GEMM on the
+// CUDA cores (FFMA, fp32 accumulate).  This is the path that meets the 1e-5 fp32 parity bar
+// of the north star; the bf16 throughput path is the tcgen05 kernel in conv_tc.cu.
+//
+// Reference call sites: torch.nn.Conv2d/Conv3d(padding='same') (nets/commonlayers.py:777-833,
+// 53-58, 123-128; nets/punetg.py:203-214; nets/adm.py:268-284), torch.nn.Linear and the
+// projections / QK^T / PV products inside nn.MultiheadAttention (nets/attention.py:42-44).
+//
+// Tiling: 128 (rows = output pixels) x 64 (cols = output channels) x 16 (k) per CTA of 256
+// threads, 8x4 accumulators per thread, register prefetch of the next k-slab.  The im2col gather
+// (zero padding, optional nearest x2 upsample of the input) happens in the A loader.
+#include "common.cuh"
+
+namespace dsk {
+
+constexpr int BM = 128, BN = 64, BK = 16, GT = 256;
+
+// ------------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+struct ConvProb {
+  static constexpr bool kTransB = false;
+  const TI* in;
+  const float* w;         // [taps*Cin][Cout]
+  const float* bias;      // [Cout] or null
+  const float* chan_bias; // [B][Cout] or null
+  const TO* residual;     // channels-last like out, or null
+  TO* out;
+  float* out_nchw;        // fp32 NC(D)HW output (if set, `out` is unused)
+  int B, D, H, W, Cin, Cout, ks, ndim, up2;
+  int Di, Hi, Wi;         // input spatial size
+  int M, N, K;
+  float alpha;
+  int act;
+
+  struct RowCtx {
+    int b, d, h, w;
+    bool valid;
+  };
+  __device__ __forceinline__ RowCtx row_ctx(int m) const {
+    RowCtx c;
+    c.valid = m < M;
+    int p = c.valid ? m : 0;
+    c.w = p % W; p /= W;
+    c.h = p % H; p /= H;
+    c.d = p % D;
+    c.b = p / D;
+    return c;
+  }
+  // 8 consecutive k (k % 8 == 0) of im2col row `c`
+  __device__ __forceinline__ void load_a(const RowCtx& c, int k, float* o) const {
+    if ((Cin & 7) == 0) {
+      const int tap = k / Cin, ci = k - tap * Cin;
+      const TI* p = tap_ptr(c, tap);
+      if (p == nullptr || k >= K) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.0f;
+      } else {
+        ld8(p + ci, o);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kk = k + j;
+        float v = 0.0f;
+        if (kk < K) {
+          const int tap = kk / Cin, ci = kk - tap * Cin;
+          const TI* p = tap_ptr(c, tap);
+          if (p != nullptr) v = to_f32<TI>(p[ci]);
+        }
+        o[j] = v;
+      }
+    }
+  }
+  __device__ __forceinline__ const TI* tap_ptr(const RowCtx& c, int tap) const {
+    if (!c.valid) return nullptr;
+    const int r = ks >> 1;
+    int kw = tap % ks, t2 = tap / ks;
+    int kh = t2 % ks, kd = t2 / ks;
+    int zw = c.w + kw - r, zh = c.h + kh - r, zd = ndim == 3 ? c.d + kd - r : 0;
+    if ((unsigned)zw >= (unsigned)W || (unsigned)zh >= (unsigned)H || (unsigned)zd >= (unsigned)D) return nullptr;
+    if (up2) {  // conv over F.interpolate(x, 2, 'nearest'): source voxel = floor(coord / 2)
+      zw >>= 1; zh >>= 1;
+      if (ndim == 3) zd >>= 1;
+    }
+    return in + ((((int64_t)c.b * Di + zd) * Hi + zh) * Wi + zw) * Cin;
+  }
+  static __device__ __forceinline__ void ld8(const float* p, float* o) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+  static __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* o) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[2 * j] = __low2float(h[j]); o[2 * j + 1] = __high2float(h[j]); }
+  }
+  // 4 consecutive n of weight row k
+  __device__ __forceinline__ void load_b(int k, int n, float* o) const {
+    if (k < K && (Cout & 3) == 0 && n + 3 < N) {
+      float4 v = *reinterpret_cast<const float4*>(w + (int64_t)k * Cout + n);
+      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = (k < K && n + j < N) ? w[(int64_t)k * Cout + n + j] : 0.0f;
+    }
+  }
+  __device__ __forceinline__ void store(int m, int n, const float* acc) const {
+    if (m >= M) return;
+    RowCtx c = row_ctx(m);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n + j;
+      if (nn >= N) break;
+      float v = acc[j];
+      if (bias != nullptr) v += bias[nn];
+      if (chan_bias != nullptr) v += chan_bias[(int64_t)c.b * Cout + nn];
+      if (residual != nullptr) v += to_f32<TO>(residual[(int64_t)m * Cout + nn]);
+      if (out_nchw != nullptr) {
+        const int64_t S = (int64_t)D * H * W;
+        out_nchw[((int64_t)c.b * Cout + nn) * S + (m - (int64_t)c.b * S)] = v;
+      } else {
+        out[(int64_t)m * Cout + nn] = from_f32<TO>(v);
+      }
+    }
+  }
+  __device__ __forceinline__ void select_batch(int) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+template <bool TRANSB>
+struct GemmProb {
+  static constexpr bool kTransB = TRANSB;
+  const float* A;
+  const float* Bm;
+  float* C;
+  const float* bias;
+  int M, N, K, lda, ldb, ldc;
+  int64_t sA, sB, sC;
+  float alpha;
+  int act;
+  struct RowCtx { int m; bool valid; };
+  __device__ __forceinline__ RowCtx row_ctx(int m) const { return RowCtx{m, m < M}; }
+  __device__ __forceinline__ void load_a(const RowCtx& c, int k, float* o) const {
+    const float* p = A + (int64_t)c.m * lda + k;
+    if (c.valid && k + 7 < K && ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+      float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (c.valid && k + j < K) ? p[j] : 0.0f;
+    }
+  }
+  // TRANSB: B is [N][K]; returns 4 consecutive k of row n.  else: B is [K][N]; 4 consecutive n of row k.
+  __device__ __forceinline__ void load_b(int k, int n, float* o) const {
+    if (TRANSB) {
+      const float* p = Bm + (int64_t)n * ldb + k;
+      if (n < N && k + 3 < K && ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = (n < N && k + j < K) ? p[j] : 0.0f;
+      }
+    } else {
+      const float* p = Bm + (int64_t)k * ldb + n;
+      if (k < K && n + 3 < N && ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = (k < K && n + j < N) ? p[j] : 0.0f;
+      }
+    }
+  }
+  __device__ __forceinline__ void store(int m, int n, const float* acc) const {
+    if (m >= M) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n + j >= N) break;
+      float v = alpha * acc[j];
+      if (bias != nullptr) v += bias[n + j];
+      if (act == 1) v = silu_f(v);
+      else if (act == 2) v = fmaxf(v, 0.0f);
+      C[(int64_t)m * ldc + n + j] = v;
+    }
+  }
+  __device__ __forceinline__ void select_batch(int z) {
+    A += z * sA; Bm += z * sB; C += z * sC;
+  }
+};
+
+// For transB GEMMs (B stored [N][K]) the B tile is loaded k-contiguous (4 consecutive k of one n)
+// so that global reads stay coalesced; the transposing smem store is bank-conflict free.
+template <class Prob>
+__global__ void __launch_bounds__(GT) ffma_gemm_kernel(Prob p) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  p.select_batch(blockIdx.z);
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // A loader: thread -> (row, 8 consecutive k)
+  const int a_row = tid & (BM - 1), a_k = (tid >> 7) * 8;
+  const typename Prob::RowCtx actx = p.row_ctx(m0 + a_row);
+  // B loader: thread -> (k, 4 consecutive n), or for kTransB (n, 4 consecutive k)
+  const int b_k = Prob::kTransB ? (tid & 3) * 4 : tid >> 4;
+  const int b_n = Prob::kTransB ? tid >> 2 : (tid & 15) * 4;
+  const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 thread grid, 8 rows x 4 cols each
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  float ra[8], rb[4];
+  p.load_a(actx, a_k, ra);
+  p.load_b(b_k, n0 + b_n, rb);
+  const int nk = (p.K + BK - 1) / BK;
+  for (int kt = 0; kt < nk; ++kt) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) As[a_k + j][a_row] = ra[j];
+    if (Prob::kTransB) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Bs[b_k + j][b_n] = rb[j];
+    } else {
+      *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    }
+    __syncthreads();
+    if (kt + 1 < nk) {
+      p.load_a(actx, (kt + 1) * BK + a_k, ra);
+      p.load_b((kt + 1) * BK + b_k, n0 + b_n, rb);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p.store(m0 + ty * 8 + i, n0 + tx * 4, acc[i]);
+}
+
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, float* __restrict__ o32,
+                                                           __nv_bfloat16* __restrict__ o16, int Cout, int Cin, int taps) {
+  const int64_t total = (int64_t)Cout * Cin * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // reference layout: w[co][ci][tap]
+    int tap = (int)(i % taps);
+    int64_t r = i / taps;
+    int ci = (int)(r % Cin);
+    int co = (int)(r / Cin);
+    float v = w[i];
+    if (o32 != nullptr) o32[((int64_t)tap * Cin + ci) * Cout + co] = v;          // [tap][ci][co]
+    if (o16 != nullptr) o16[((int64_t)tap * Cout + co) * Cin + ci] = __float2bfloat16_rn(v);  // [tap][co][ci]
+  }
+}
+
+template <typename TI, typename TO>
+static int launch_conv(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
+                       const void* residual, void* out, cudaStream_t st) {
+  ConvProb<TI, TO> p;
+  p.in = (const TI*)in; p.w = (const float*)w; p.bias = bias; p.chan_bias = chan_bias;
+  p.residual = (const TO*)residual;
+  p.out = d->out_nchw_f32 ? nullptr : (TO*)out;
+  p.out_nchw = d->out_nchw_f32 ? (float*)out : nullptr;
+  p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.ks = d->ksize; p.ndim = d->ndim; p.up2 = d->up2;
+  p.Di = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D;
+  p.Hi = d->up2 ? d->H / 2 : d->H;
+  p.Wi = d->up2 ? d->W / 2 : d->W;
+  const int taps = d->ndim == 3 ? d->ksize * d->ksize * d->ksize : d->ksize * d->ksize;
+  const int64_t M = (int64_t)d->B * d->D * d->H * d->W;
+  if (M > 0x7fffffff) { set_error("dsk_conv_fwd: too many output pixels"); return DSK_ERR_ARG; }
+  p.M = (int)M; p.N = d->Cout; p.K = taps * d->Cin; p.alpha = 1.0f; p.act = 0;
+  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, 1);
+  DSK_LAUNCH((ffma_gemm_kernel<ConvProb<TI, TO>>), grid, GT, 0, st, p);
+  return DSK_OK;
+}
+
+}  // namespace dsk
+
+using namespace dsk;
+
+// implemented in conv_tc.cu (tcgen05 path); returns DSK_ERR_UNSUPPORTED for shapes it does not take
+extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const void* w, const float* bias,
+                               const float* chan_bias, const void* residual, void* out, void* stream);
+
+extern "C" int dsk_conv_fwd_ffma(const dsk_conv_desc* d, const void* in, const void* w, const float* bias,
+                                 const float* chan_bias, const void* residual, void* out, void* stream) {
+  DSK_REQUIRE(d && in && w && out, "dsk_conv_fwd: null pointer");
+  DSK_REQUIRE(d->B > 0 && d->D > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "dsk_conv_fwd: bad shape");
+  DSK_REQUIRE((d->ksize == 1 || d->ksize == 3) && (d->ndim == 2 || d->ndim == 3), "dsk_conv_fwd: ksize=%d ndim=%d unsupported", d->ksize, d->ndim);
+  DSK_REQUIRE(d->ndim == 3 || d->D == 1, "dsk_conv_fwd: ndim=2 needs D=1");
+  DSK_REQUIRE(!d->up2 || (d->H % 2 == 0 && d->W % 2 == 0 && (d->ndim == 2 || d->D % 2 == 0)), "dsk_conv_fwd: up2 needs even output size");
+  cudaStream_t st = as_stream(stream);
+  const int ti = d->in_dtype, to = d->out_nchw_f32 ? (residual ? d->out_dtype : DSK_F32) : d->out_dtype;
+  if (ti == DSK_F32 && to == DSK_F32) return launch_conv<float, float>(d, in, w, bias, chan_bias, residual, out, st);
+  if (ti == DSK_BF16 && to == DSK_BF16) return launch_conv<__nv_bfloat16, __nv_bfloat16>(d, in, w, bias, chan_bias, residual, out, st);
+  if (ti == DSK_BF16 && to == DSK_F32) return launch_conv<__nv_bfloat16, float>(d, in, w, bias, chan_bias, residual, out, st);
+  if (ti == DSK_F32 && to == DSK_BF16) return launch_conv<float, __nv_bfloat16>(d, in, w, bias, chan_bias, residual, out, st);
+  DSK_REQUIRE(false, "dsk_conv_fwd: bad dtypes %d -> %d", ti, to);
+  return DSK_OK;
+}
+
+extern "C" int dsk_pack_conv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int taps, int dtype, void* stream) {
+  DSK_REQUIRE(w_ref && w_packed && Cout > 0 && Cin > 0 && taps > 0, "dsk_pack_conv_weight: bad arguments");
+  DSK_REQUIRE(dtype == DSK_F32 || dtype == DSK_BF16, "dsk_pack_conv_weight: bad dtype %d", dtype);
+  const int grid = grid_for((int64_t)Cout * Cin * taps, 256, 8);
+  DSK_LAUNCH(pack_weight_kernel, grid, 256, 0, as_stream(stream), w_ref, dtype == DSK_F32 ? (float*)w_packed : nullptr,
+             dtype == DSK_BF16 ? (__nv_bfloat16*)w_packed : nullptr, Cout, Cin, taps);
+  return DSK_OK;
+}
+
+extern "C" int dsk_gemm_f32(const float* A, const float* Bm, float* Cm, const float* bias, int M, int N, int K, int lda,
+                            int ldb, int ldc, int64_t strideA, int64_t strideB, int64_t strideC, int batch, int transB,
+                            float alpha, int act, void* stream) {
+  DSK_REQUIRE(A && Bm && Cm, "dsk_gemm_f32: null pointer");
+  DSK_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0 && batch <= 65535, "dsk_gemm_f32: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
+  DSK_REQUIRE(lda >= K && ldc >= N && ldb >= (transB ? K : N), "dsk_gemm_f32: bad leading dimensions");
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, batch);
+  DSK_REQUIRE(grid.y <= 65535, "dsk_gemm_f32: N too large");
+  if (transB) {
+    GemmProb<true> p{A, Bm, Cm, bias, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, act};
+    DSK_LAUNCH(ffma_gemm_kernel<GemmProb<true>>, grid, GT, 0, as_stream(stream), p);
+  } else {
+    GemmProb<false> p{A, Bm, Cm, bias, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, act};
+    DSK_LAUNCH(ffma_gemm_kernel<GemmProb<false>>, grid, GT, 0, as_stream(stream), p);
+  }
+  return DSK_OK;
+}

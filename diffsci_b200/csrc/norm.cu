@@ -1,0 +1,213 @@
+// norm.cu -- K4: group LayerNorm / RMS norm + affine (+FiLM) + SiLU on channels-last tensors.
+//
+// Reference: torch.nn.GroupNorm(G, C) and GroupRMSNorm(G, C) followed by SiLU in ResnetBlockC
+// (nets/commonlayers.py:362-384, 824-831); ADM GroupNorm(1, C) + FiLM (nets/adm.py:305-329).
+// GroupRMSNorm alone costs the reference 7 full HBM passes; here a norm is one read for the
+// statistics and one read + one write for the fused normalise/affine/FiLM/SiLU.
+//
+// Three launches: (1) per-(sample, spatial chunk) partial sums in fp32 per thread, combined in
+// fp64 across the block, written to the workspace (deterministic, no atomics);
+// (2) per-(sample, group) finalisation -> (mean, rstd); (3) the apply pass.
+#include "common.cuh"
+
+namespace dsk {
+
+constexpr int NORM_THREADS = 256;
+constexpr int NORM_V = 4;
+
+static inline int norm_chunks(int B, int64_t S, int C) {
+  int cv = C / NORM_V;
+  int pl = NORM_THREADS / cv;
+  if (pl < 1) pl = 1;
+  int64_t by_work = (S + (int64_t)pl * 8 - 1) / ((int64_t)pl * 8);  // >= 8 pixels per thread per chunk
+  int64_t by_grid = (2 * DSK_NUM_SMS + B - 1) / B;
+  int64_t n = by_work < by_grid ? by_work : by_grid;
+  if (n < 1) n = 1;
+  if (n > 512) n = 512;
+  return (int)n;
+}
+
+template <typename T> __device__ __forceinline__ void load4(const T* p, float* o);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float* o) {
+  float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float* o) {
+  uint2 raw = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x), b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+  o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, const float* v);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 raw;
+  raw.x = *reinterpret_cast<uint32_t*>(&a);
+  raw.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = raw;
+}
+
+// partial[b][chunk][c] = (sum, sumsq) in fp64
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS) norm_partial_kernel(const T* __restrict__ x, double2* __restrict__ partial,
+                                                                     int64_t S, int C, int nchunks) {
+  extern __shared__ double2 sm[];  // [pl][C]
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int cv = C / NORM_V;
+  const int pl = max(1, NORM_THREADS / cv);
+  const int64_t per = (S + nchunks - 1) / nchunks;
+  const int64_t s0 = (int64_t)chunk * per;
+  const int64_t s1 = min(S, s0 + per);
+  const T* xb = x + (int64_t)b * S * C;
+  for (int v = threadIdx.x; v < pl * cv; v += NORM_THREADS) {
+    const int lane = v / cv, c0 = (v - lane * cv) * NORM_V;
+    float sum[NORM_V] = {0, 0, 0, 0}, sq[NORM_V] = {0, 0, 0, 0};
+    double dsum[NORM_V] = {0, 0, 0, 0}, dsq[NORM_V] = {0, 0, 0, 0};
+    int cnt = 0;
+    for (int64_t s = s0 + lane; s < s1; s += pl) {
+      float e[NORM_V];
+      load4<T>(xb + s * C + c0, e);
+#pragma unroll
+      for (int k = 0; k < NORM_V; ++k) {
+        sum[k] += e[k];
+        sq[k] += e[k] * e[k];
+      }
+      if (++cnt == 64) {  // flush fp32 partials to fp64 every 64 elements
+#pragma unroll
+        for (int k = 0; k < NORM_V; ++k) {
+          dsum[k] += sum[k]; dsq[k] += sq[k];
+          sum[k] = 0; sq[k] = 0;
+        }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NORM_V; ++k) sm[lane * C + c0 + k] = make_double2(dsum[k] + sum[k], dsq[k] + sq[k]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += NORM_THREADS) {
+    double a = 0, q = 0;
+    for (int l = 0; l < pl; ++l) {
+      double2 v = sm[l * C + c];
+      a += v.x;
+      q += v.y;
+    }
+    partial[((int64_t)b * nchunks + chunk) * C + c] = make_double2(a, q);
+  }
+}
+
+// stats[b][g] = (mean, rstd)
+__global__ void __launch_bounds__(128) norm_finalize_kernel(const double2* __restrict__ partial, float2* __restrict__ stats,
+                                                             int64_t S, int C, int G, int nchunks, int mode, float eps) {
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
+  const int cg = C / G;
+  double a = 0, q = 0;
+  for (int i = threadIdx.x; i < nchunks * cg; i += blockDim.x) {
+    const int chunk = i / cg, c = g * cg + (i - chunk * cg);
+    double2 v = partial[((int64_t)b * nchunks + chunk) * C + c];
+    a += v.x;
+    q += v.y;
+  }
+  __shared__ double sa[128], sq[128];
+  sa[threadIdx.x] = a;
+  sq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sa[threadIdx.x] += sa[threadIdx.x + o];
+      sq[threadIdx.x] += sq[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = (double)S * cg;
+    double mean = sa[0] / n, ex2 = sq[0] / n;
+    float m, r;
+    if (mode == 0) {
+      double var = ex2 - mean * mean;
+      if (var < 0) var = 0;
+      m = (float)mean;
+      r = 1.0f / sqrtf((float)var + eps);
+    } else {
+      m = 0.0f;
+      r = 1.0f / sqrtf((float)ex2 + eps);  // x / sqrt(mean(x^2) + eps), commonlayers.py:377-378
+    }
+    stats[blockIdx.x] = make_float2(m, r);
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) norm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ y,
+                                                          const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ fsc,
+                                                          const float* __restrict__ fsh, int64_t S, int C, int G, int B,
+                                                          int silu) {
+  const int cv = C / NORM_V, cg = C / G;
+  const int64_t per_b = S * cv, total = per_b * B;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_b);
+    const int c0 = (int)(i % cv) * NORM_V;
+    float e[NORM_V], o[NORM_V];
+    load4<TI>(x + i * NORM_V, e);
+#pragma unroll
+    for (int k = 0; k < NORM_V; ++k) {
+      const int c = c0 + k;
+      const float2 st = stats[b * G + c / cg];
+      float v = (e[k] - st.x) * st.y;
+      if (gamma != nullptr) v = v * gamma[c] + beta[c];
+      if (fsc != nullptr) v = v * fsc[(int64_t)b * C + c] + fsh[(int64_t)b * C + c];
+      o[k] = silu ? silu_f(v) : v;
+    }
+    store4<TO>(y + i * NORM_V, o);
+  }
+}
+
+}  // namespace dsk
+
+using namespace dsk;
+
+extern "C" int64_t dsk_norm_ws_bytes(int B, int64_t S, int C) {
+  if (B <= 0 || S <= 0 || C <= 0 || C % NORM_V) return 0;
+  int nchunks = norm_chunks(B, S, C);
+  return (int64_t)B * nchunks * C * (int64_t)sizeof(double2) + (int64_t)B * C * (int64_t)sizeof(float2);
+}
+
+extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const float* beta, const float* film_scale,
+                            const float* film_shift, void* ws, int B, int64_t S, int C, int G, int mode, int silu,
+                            int in_dtype, int out_dtype, void* stream) {
+  DSK_REQUIRE(x && y && ws, "dsk_norm_act: null pointer");
+  DSK_REQUIRE(B > 0 && S > 0 && C > 0 && G > 0 && C % G == 0, "dsk_norm_act: bad shape B=%d S=%lld C=%d G=%d", B, (long long)S, C, G);
+  DSK_REQUIRE(C % NORM_V == 0, "dsk_norm_act: C=%d must be a multiple of %d", C, NORM_V);
+  DSK_REQUIRE(mode == 0 || mode == 1, "dsk_norm_act: bad mode %d", mode);
+  DSK_REQUIRE((gamma == nullptr) == (beta == nullptr), "dsk_norm_act: gamma/beta must both be set or both null");
+  DSK_REQUIRE((film_scale == nullptr) == (film_shift == nullptr), "dsk_norm_act: FiLM scale/shift mismatch");
+  cudaStream_t st = as_stream(stream);
+  const int nchunks = norm_chunks(B, S, C);
+  double2* partial = reinterpret_cast<double2*>(ws);
+  float2* stats = reinterpret_cast<float2*>(partial + (int64_t)B * nchunks * C);
+  const int cv = C / NORM_V;
+  const int pl = NORM_THREADS / cv > 0 ? NORM_THREADS / cv : 1;
+  const size_t smem = (size_t)pl * C * sizeof(double2);
+  DSK_REQUIRE(smem <= 48 * 1024, "dsk_norm_act: C=%d too large for the stats kernel", C);
+  dim3 pg(nchunks, B);
+  if (in_dtype == DSK_F32)
+    DSK_LAUNCH(norm_partial_kernel<float>, pg, NORM_THREADS, smem, st, (const float*)x, partial, S, C, nchunks);
+  else if (in_dtype == DSK_BF16)
+    DSK_LAUNCH(norm_partial_kernel<__nv_bfloat16>, pg, NORM_THREADS, smem, st, (const __nv_bfloat16*)x, partial, S, C, nchunks);
+  else
+    DSK_REQUIRE(false, "dsk_norm_act: bad in_dtype %d", in_dtype);
+  DSK_LAUNCH(norm_finalize_kernel, B * G, 128, 0, st, partial, stats, S, C, G, nchunks, mode, 1e-5f);
+  const int grid = grid_for((int64_t)B * S * cv, 256, 16);
+#define APPLY(TI, TO)                                                                                         \
+  DSK_LAUNCH((norm_apply_kernel<TI, TO>), grid, 256, 0, st, (const TI*)x, (TO*)y, stats, gamma, beta, film_scale, \
+             film_shift, S, C, G, B, silu)
+  if (in_dtype == DSK_F32 && out_dtype == DSK_F32) APPLY(float, float);
+  else if (in_dtype == DSK_F32 && out_dtype == DSK_BF16) APPLY(float, __nv_bfloat16);
+  else if (in_dtype == DSK_BF16 && out_dtype == DSK_BF16) APPLY(__nv_bfloat16, __nv_bfloat16);
+  else if (in_dtype == DSK_BF16 && out_dtype == DSK_F32) APPLY(__nv_bfloat16, float);
+  else DSK_REQUIRE(false, "dsk_norm_act: bad dtype combination %d -> %d", in_dtype, out_dtype);
+#undef APPLY
+  return DSK_OK;
+}

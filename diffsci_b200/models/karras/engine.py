@@ -1,0 +1,186 @@
+"""CUDA-graph sampler engine: the hot loop of ``KarrasModule.sample`` (reference call stack
+karrasmodule.py:801-931 -> schedulers.py:48-89 -> integrators.py:29-113 -> karrasmodule.py:673-733).
+
+One integrator step = {network evaluation(s)} + {one fused elementwise stage per evaluation}
+(csrc/sampler.cu).  Step scalars live in a device table indexed by a device-side step counter, so
+ONE captured graph is replayed for every step (plus a second graph for the final step, whose
+``t + dt == 0`` branch the reference resolves with a host sync, integrators.py:45-50).
+
+Works with
+  * native networks (``PUNetG`` / ``ADM`` / ``MLPUncond`` of this package): their ``plan(...)`` exposes
+    static buffers, the step is captured into a CUDA graph;
+  * any other ``torch.nn.Module`` honouring ``model(x_scaled, c_noise) -> F`` (the reference's
+    denoiser-net seam): the same fused stages run eagerly around the foreign forward.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from ... import ops
+from ..._lib import (lib, check, ptr, stream, dt_code, require_cuda, launch_count, STAGE_INIT, STAGE_EULER, STAGE_HEUN_MID,
+                     STAGE_HEUN_FIN, STAGE_HEUN_LAST, STAGE_EM, STAGE_KARRAS_MID, STAGE_KARRAS_FIN,
+                     STAGE_KARRAS_LAST)
+from . import preconditioners
+
+# program -> (stages of a regular step, stages of the final step); one network evaluation precedes each stage
+PROGRAMS = {
+    "euler": ((STAGE_EULER,), (STAGE_EULER,)),
+    "heun": ((STAGE_HEUN_MID, STAGE_HEUN_FIN), (STAGE_HEUN_LAST,)),
+    "euler-maruyama": ((STAGE_EM,), (STAGE_EM,)),
+    "karras": ((STAGE_KARRAS_MID, STAGE_KARRAS_FIN), (STAGE_KARRAS_LAST,)),
+}
+
+
+def precond_kind(precond) -> Optional[int]:
+    if type(precond) is preconditioners.EDMPreconditioner:
+        return 0
+    if type(precond) is preconditioners.NullPreconditioner:
+        return 1
+    return None
+
+
+class SamplerEngine:
+    def __init__(self, model: torch.nn.Module, B: int, shape: Sequence[int], device, sigma_data: float,
+                 sigma_max: float, kind: int, use_graphs: bool = True):
+        self.model, self.B, self.shape = model, int(B), tuple(int(s) for s in shape)
+        self.device = torch.device(device)
+        self.sigma_data, self.sigma_max, self.kind = float(sigma_data), float(sigma_max), int(kind)
+        self.Cc = self.shape[0]
+        self.S = 1
+        for s in self.shape[1:]:
+            self.S *= s
+        f32 = dict(dtype=torch.float32, device=self.device)
+        full = (self.B,) + self.shape
+        self.x = torch.empty(full, **f32)
+        self.x_aux = torch.empty(full, **f32)
+        self.r1 = torch.empty(full, **f32)
+        self.cnoise = torch.empty((self.B,), **f32)
+        self.row = torch.zeros((4,), dtype=torch.int32, device=self.device)   # [step, seed_lo, seed_hi, -]
+        self.native = hasattr(model, "plan")
+        if self.native:
+            self.plan = model.plan(self.B, self.shape[1:], self.device)
+            self.act_dtype = self.plan.act_dtype
+            self.xin = self.plan.xin
+        else:
+            self.plan = None
+            self.act_dtype = torch.float32
+            self.xin = torch.empty((self.B, self.S, self.Cc), **f32)
+        self.use_graphs = bool(use_graphs and self.native)
+        self._graphs = {}
+        self._graph_launches = {}
+        self._last_graph_launches = 0
+        self._tab = None
+        self._noise = None
+        self._hist = None
+        self._F = None
+        self.seed = 0
+        self.nfe = 0
+
+    # ------------------------------------------------------------------ pieces
+    def _net(self):
+        self.nfe += 1
+        if self.native:
+            self._F = self.plan.forward(self.xin, self.cnoise)
+            return
+        xin = self.xin
+        if self.Cc > 1 and self.S > 1:
+            xin = ops.cl_to_nchw(xin.view(self.B, 1, 1, self.S, self.Cc), 3).view((self.B,) + self.shape)
+        else:
+            xin = xin.view((self.B,) + self.shape)
+        F = self.model(xin, self.cnoise).float().contiguous()
+        if self.Cc > 1 and self.S > 1:
+            F = ops.nchw_to_cl(F.view(self.B, self.Cc, 1, 1, self.S), torch.float32, 3)
+        self._F = F
+
+    def _stage(self, stage: int):
+        check(lib.dsk_sampler_stage(stage, ptr(self.x), ptr(self.x_aux), ptr(self.r1), ptr(self._F), ptr(self.xin),
+                                    ptr(self.cnoise), ptr(self._tab), ptr(self.row), ptr(self._noise),
+                                    C.c_uint64(0), ptr(self._hist), self.B, self.Cc,
+                                    self.S, self.sigma_data, self.sigma_max, self.kind, dt_code(self.act_dtype),
+                                    stream()))
+
+    def _step(self, stages):
+        for st in stages:
+            self._net()
+            self._stage(st)
+        check(lib.dsk_sampler_advance(ptr(self.row), stream()))
+
+    def _graph_for(self, stages, key):
+        """Capture one step; buffers, table pointer, noise/history pointers are all static."""
+        g = self._graphs.get(key)
+        if g is None:
+            self.plan.prepare()
+            self._stage(STAGE_INIT)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):      # warm-up outside capture (lazy module loads, packed weights)
+                self._step(stages)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            c0 = launch_count()
+            with torch.cuda.graph(g):
+                self._step(stages)
+            self._graph_launches[key] = launch_count() - c0     # kernels recorded into this graph
+            self.row.zero_()
+            self._graphs[key] = g
+        return g
+
+    def graph_launches_per_run(self) -> int:
+        """Kernel launches replayed by the graphs of the most recent run()."""
+        return self._last_graph_launches
+
+    # ------------------------------------------------------------------ run
+    def run(self, white_noise: torch.Tensor, table: torch.Tensor, program: str, record_history: bool = False,
+            noises: Optional[torch.Tensor] = None, seed: int = 0) -> torch.Tensor:
+        """white_noise: fp32 [B, *shape] on the device; table: CPU fp32 [nsteps+1, 8] (Scheduler.step_table)."""
+        require_cuda(white_noise, "white noise")
+        if program not in PROGRAMS:
+            raise ValueError(f"Unknown integrator program: {program}")
+        nsteps = table.shape[0] - 1
+        regular, final = PROGRAMS[program]
+        N = self.B * self.Cc * self.S
+        # static-address inputs of the captured graphs: refill in place, re-capture only on shape change
+        if self._tab is None or self._tab.shape != table.shape:
+            self._tab = torch.empty_like(table, device=self.device)
+            self._graphs.clear()
+        self._tab.copy_(table, non_blocking=True)
+        want_hist = (nsteps + 1, N) if record_history else None
+        if (self._hist is None) != (want_hist is None) or (want_hist and tuple(self._hist.shape) != want_hist):
+            self._hist = torch.empty(want_hist, dtype=torch.float32, device=self.device) if want_hist else None
+            self._graphs.clear()
+        want_noise = None if noises is None else (nsteps + 1, N)
+        if (self._noise is None) != (want_noise is None) or (want_noise and tuple(self._noise.shape) != want_noise):
+            self._noise = torch.zeros(want_noise, dtype=torch.float32, device=self.device) if want_noise else None
+            self._graphs.clear()
+        if noises is not None:
+            self._noise[:nsteps].copy_(noises.reshape(nsteps, N))
+        self.seed = int(seed)
+        if self.use_graphs:   # capture (with a throw-away warm-up step on zero state) before the real run starts
+            self.x.zero_()
+            self.row.zero_()
+            g_reg = self._graph_for(regular, (program, "regular"))
+            g_fin = self._graph_for(final, (program, "final"))
+        self.x.copy_(white_noise.reshape(self.x.shape))
+        sd = self.seed & 0xFFFFFFFFFFFFFFFF
+        as_i32 = lambda v: v - (1 << 32) if v >= (1 << 31) else v  # noqa: E731
+        self.row.copy_(torch.tensor([0, as_i32(sd & 0xFFFFFFFF), as_i32(sd >> 32), 0], dtype=torch.int32))
+        self.nfe = 0
+        self._stage(STAGE_INIT)
+        if self.use_graphs:
+            for _ in range(nsteps - 1):
+                g_reg.replay()
+            g_fin.replay()
+            self.nfe = (nsteps - 1) * len(regular) + len(final)
+            self._last_graph_launches = ((nsteps - 1) * self._graph_launches[(program, "regular")] +
+                                         self._graph_launches[(program, "final")])
+        else:
+            for _ in range(nsteps - 1):
+                self._step(regular)
+            self._step(final)
+        if record_history:
+            return self._hist.view((nsteps + 1, self.B) + self.shape).clone()
+        return self.x.clone()

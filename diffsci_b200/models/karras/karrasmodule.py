@@ -1,0 +1,427 @@
+"""KarrasModule / KarrasModuleConfig -- drop-in for diffsci.models.karras.karrasmodule
+(reference karras/karrasmodule.py:30-1253), restricted to the EDM hot path of SURVEY.md section 8:
+``get_denoiser``, ``get_score``, ``loss_fn``, ``training_step``, ``sample``,
+``propagate_white_noise``, ``propagate_toward_sample`` keep their signatures and semantics.
+
+Where the reference launches ~30 elementwise ATen kernels per network evaluation plus host syncs,
+this module drives the fused CUDA stages (csrc/sampler.cu, csrc/train.cu) and, for native networks,
+replays one captured CUDA graph per integrator step (engine.SamplerEngine).
+Latent-diffusion (autoencoder), inpaint/repaint, autoregressive and multi-space-loss recipes are out
+of scope and raise NotImplementedError instead of silently doing something else.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional, Union
+
+import torch
+from torch import Tensor
+
+from ... import ops
+from ..._lib import lib, check, ptr, stream, dt_code, require_cuda
+from ...torchutils import broadcast_from_below, dict_to, dict_unsqueeze
+from ...utils import get_minibatch_sizes
+from . import engine as _engine
+from . import integrators, noisesamplers, preconditioners, schedulers
+
+try:  # Lightning is optional: the hot path never needs it, Trainer users get a real LightningModule
+    import lightning as _lightning
+    _Base = _lightning.LightningModule
+except Exception:  # pragma: no cover - lightning is absent in the build image
+    class _Base(torch.nn.Module):
+        def log(self, *a, **k):
+            return None
+
+        @property
+        def device(self):
+            for t in list(self.parameters()) + list(self.buffers()):
+                return t.device
+            return torch.device("cpu")
+
+
+class KarrasModuleConfig:
+    def __init__(self, preconditioner: preconditioners.KarrasPreconditioner, noisesampler: noisesamplers.NoiseSampler,
+                 noisescheduler: schedulers.Scheduler, loss_metric: Union[str, Dict[str, Any]] = "huber",
+                 tag: str = "custom", has_edm_batch_norm: bool = False, dynamic_loss_weight: Optional[int] = None,
+                 extra_args: Optional[dict] = None, autoregressive_loss_steps: int = 1,
+                 autoregressive_loss_diffusion_steps: int = 100, autoregressive_loss_guidance: float = 1.0,
+                 autoregressive_loss_weights=None, autoregressive_loss_maximum_batch_size=None,
+                 autoregressive_loss_integrator=None, spatial_shape: tuple = None, focus_radius: float = None):
+        self.preconditioner, self.noisesampler, self.noisescheduler = preconditioner, noisesampler, noisescheduler
+        self.loss_metric, self.tag = loss_metric, tag
+        self.has_edm_batch_norm = has_edm_batch_norm
+        self.dynamic_loss_weight = dynamic_loss_weight
+        self.autoregressive_loss_steps = autoregressive_loss_steps
+        self.autoregressive_loss_diffusion_steps = autoregressive_loss_diffusion_steps
+        self.autoregressive_loss_guidance = autoregressive_loss_guidance
+        self.autoregressive_loss_weights = autoregressive_loss_weights
+        self.autoregressive_loss_maximum_batch_size = autoregressive_loss_maximum_batch_size
+        self.autoregressive_loss_integrator = autoregressive_loss_integrator
+        self.spatial_shape, self.focus_radius = spatial_shape, focus_radius
+        self.extra_args = dict() if extra_args is None else extra_args
+
+    @classmethod
+    def _build(cls, tag, pre, smp, sch, loss_metric, own_args, common):
+        extra = dict(own_args, loss_metric=loss_metric, **common)
+        return cls(preconditioner=pre, noisesampler=smp, noisescheduler=sch, loss_metric=loss_metric, tag=tag,
+                   extra_args=extra, **common)
+
+    @classmethod
+    def from_edm(cls, sigma_data: float = 0.5, prior_mean: float = -1.2, prior_std: float = 1.2,
+                 has_edm_batch_norm: bool = False, dynamic_loss_weight: Optional[int] = None,
+                 loss_metric: Union[str, Dict[str, Any]] = "huber", autoregressive_loss_steps: int = 1,
+                 autoregressive_loss_diffusion_steps: int = 100, autoregressive_loss_guidance: float = 1.0,
+                 autoregressive_loss_weights=None, autoregressive_loss_maximum_batch_size=None,
+                 autoregressive_loss_integrator=None, spatial_shape: tuple = None, focus_radius: float = None):
+        common = dict(autoregressive_loss_steps=autoregressive_loss_steps,
+                      autoregressive_loss_diffusion_steps=autoregressive_loss_diffusion_steps,
+                      autoregressive_loss_guidance=autoregressive_loss_guidance,
+                      autoregressive_loss_weights=autoregressive_loss_weights,
+                      autoregressive_loss_maximum_batch_size=autoregressive_loss_maximum_batch_size,
+                      autoregressive_loss_integrator=autoregressive_loss_integrator,
+                      spatial_shape=spatial_shape, focus_radius=focus_radius)
+        cfg = cls._build("edm", preconditioners.EDMPreconditioner(sigma_data=sigma_data),
+                         noisesamplers.EDMNoiseSampler(sigma_data=sigma_data, prior_mean=prior_mean, prior_std=prior_std),
+                         schedulers.EDMScheduler(), loss_metric,
+                         dict(sigma_data=sigma_data, prior_mean=prior_mean, prior_std=prior_std,
+                              has_edm_batch_norm=has_edm_batch_norm, dynamic_loss_weight=dynamic_loss_weight), common)
+        cfg.has_edm_batch_norm, cfg.dynamic_loss_weight = has_edm_batch_norm, dynamic_loss_weight
+        return cfg
+
+    @classmethod
+    def from_vp(cls, beta_data: float = 19.9, beta_min: float = 0.1, epsilon_min: float = 1e-3,
+                epsilon_sampler: float = 1e-5, M: int = 1000, loss_metric="huber", **common):
+        sch = schedulers.VPScheduler(epsilon_min=epsilon_min, beta_data=beta_data, beta_min=beta_min)
+        return cls._build("vp", preconditioners.VPPreconditioner(scheduler=sch, M=M),
+                          noisesamplers.VPNoiseSampler(noise_scheduler=sch, epsilon=epsilon_sampler), sch, loss_metric,
+                          dict(beta_data=beta_data, beta_min=beta_min, epsilon_min=epsilon_min,
+                               epsilon_sampler=epsilon_sampler, M=M), common)
+
+    @classmethod
+    def from_ve(cls, sigma_min: float = 0.02, sigma_max: float = 100, loss_metric="huber", **common):
+        return cls._build("ve", preconditioners.VEPreconditioner(),
+                          noisesamplers.VENoiseSampler(sigma_min=sigma_min, sigma_max=sigma_max),
+                          schedulers.VEScheduler(sigma_min=sigma_min, sigma_max=sigma_max), loss_metric,
+                          dict(sigma_min=sigma_min, sigma_max=sigma_max), common)
+
+    def export_description(self) -> dict[str, Any]:
+        return dict(tag=self.tag, extra_args=self.extra_args)
+
+    @classmethod
+    def load_from_description_with_tag(cls, description: dict[str, Any]):
+        tag, extra = description["tag"], description["extra_args"]
+        if tag == "custom":
+            raise ValueError("Cannot load from a custom tag")
+        ctor = {"edm": cls.from_edm, "vp": cls.from_vp, "ve": cls.from_ve}.get(tag)
+        if ctor is None:
+            raise ValueError(f"Unknown tag: {tag}")
+        return ctor(**extra)
+
+    @property
+    def has_dynamic_loss_weight(self) -> bool:
+        return self.dynamic_loss_weight is not None
+
+    def update_loss_metric(self, loss_config):
+        self.loss_metric = loss_config
+        if "loss_metric" in self.extra_args:
+            self.extra_args["loss_metric"] = loss_config
+
+
+class _EDMLossFn(torch.autograd.Function):
+    """loss = mean(lambda(sigma) * l(c_out F + c_skip (x + sigma n), x) * (1 - mask)); backward = dL/dF from
+    the same fused launch (csrc/train.cu: edm_loss_kernel)."""
+
+    @staticmethod
+    def forward(ctx, F, x, noise, sigma, mask, sigma_data, kind):
+        B = x.shape[0]
+        Cc = x.shape[1] if x.ndim > 1 else 1
+        S = x.numel() // (B * Cc)
+        loss = torch.zeros((), dtype=torch.float32, device=x.device)
+        dF = torch.empty_like(x, dtype=torch.float32)
+        check(lib.dsk_edm_loss_fwd_bwd(ptr(F), ptr(x), ptr(noise), ptr(sigma), ptr(mask), ptr(loss), ptr(dF), B, Cc, S,
+                                       float(sigma_data), int(kind), stream()))
+        ctx.save_for_backward(dF)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dF,) = ctx.saved_tensors
+        return dF * g, None, None, None, None, None, None
+
+
+def _rowwise_axpy(a_vec: Tensor, z: Tensor, b_vec: Tensor, x: Tensor) -> Tensor:
+    """out[b, ...] = a[b]*z[b, ...] + b_vec[b]*x[b, ...] in one launch (dsk_precond_denoise on flat rows)."""
+    B = x.shape[0]
+    n = x.numel() // B
+    out = torch.empty_like(x)
+    check(lib.dsk_precond_denoise(ptr(z), ptr(x), ptr(a_vec), ptr(b_vec), None, ptr(out), None, B, 1, n, 0, stream()))
+    return out
+
+
+class KarrasModule(_Base):
+    def __init__(self, model: torch.nn.Module, config: KarrasModuleConfig, conditional: bool = False,
+                 masked: bool = False, autoencoder: Optional[torch.nn.Module] = None,
+                 autoencoder_conditional: bool = False, encode_y: bool = False, decode_original_y: bool = False):
+        super().__init__()
+        if autoencoder is not None or encode_y or decode_original_y or autoencoder_conditional:
+            raise NotImplementedError("diffsci_b200.KarrasModule: latent-diffusion wrappers are out of scope "
+                                      "(SURVEY.md 8f item 4)")
+        if config.has_edm_batch_norm:
+            raise NotImplementedError("has_edm_batch_norm=True: karras/edmbatchnorm.py is empty in the reference "
+                                      "(karrasmodule.py:1241 crashes there too)")
+        self.model, self.config = model, config
+        self.conditional, self.masked = conditional, masked
+        self.autoencoder = None
+        self.autoencoder_conditional = self.encode_y = self.decode_original_y = False
+        self.norm = 1.0
+        self.set_optimizer_and_scheduler()
+        self.set_loss_metric()
+        self.edm_batch_norm = None
+        self.dynamic_loss_weight = None
+        if config.has_dynamic_loss_weight:
+            raise NotImplementedError("diffsci_b200.KarrasModule: dynamic_loss_weight is not built yet")
+        self._engines: dict[Any, _engine.SamplerEngine] = {}
+        self.use_cuda_graphs = True
+        self.last_nfe = 0
+
+    # ------------------------------------------------------------------ optimiser / loss config
+    def set_optimizer_and_scheduler(self, optimizer=None, scheduler=None, scheduler_interval="step"):
+        """Defaults as the reference (karrasmodule.py:476-508): AdamW(1e-3, (0.9, 0.999), wd 1e-4), identity LR."""
+        params = [p for p in self.parameters()]
+        if optimizer is not None:
+            self.optimizer = optimizer
+        elif params:
+            self.optimizer = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-4)
+        else:
+            self.optimizer = None
+        if scheduler is not None:
+            self.lr_scheduler = scheduler
+        elif self.optimizer is not None:
+            self.lr_scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizer, lr_lambda=lambda step: 1.0 + 0 * step)
+        else:
+            self.lr_scheduler = None
+        self.lr_scheduler_interval = scheduler_interval
+
+    def configure_optimizers(self):
+        if self.lr_scheduler is not None:
+            return [self.optimizer], [{"scheduler": self.lr_scheduler, "interval": self.lr_scheduler_interval}]
+        return self.optimizer
+
+    def set_loss_metric(self):
+        lm = self.config.loss_metric
+        if isinstance(lm, dict) and len(lm) == 1 and "losses" not in lm:
+            name, params = next(iter(lm.items()))
+            if name == "huber" and (params or {}).get("delta", 1.0) != 1.0:
+                raise NotImplementedError("diffsci_b200: Huber delta != 1 is not fused yet")
+            lm = name
+        if lm not in ("huber", "mse"):
+            raise NotImplementedError(f"diffsci_b200.KarrasModule: loss_metric={self.config.loss_metric!r} is out of "
+                                      "scope (SURVEY.md section 2 #10); 'huber' (default) and 'mse' are fused")
+        self.loss_kind = 0 if lm == "huber" else 1
+        self.loss_metric = lm
+
+    # ------------------------------------------------------------------ denoiser
+    @property
+    def latent_model(self) -> bool:
+        return False
+
+    def encode(self, x, y=None, record_history=False):
+        return x / self.norm
+
+    def decode(self, x, y=None, record_history=False):
+        return x * self.norm
+
+    def _sigma_data(self) -> float:
+        sd = getattr(self.config.preconditioner, "sigma_data", None)
+        return float(sd) if sd is not None else 0.5
+
+    def _network(self, x: Tensor, c_in: Tensor, cond_noise: Tensor):
+        """F = model(c_in * x, c_noise): returns (F, act dtype, channels-last?)."""
+        B = x.shape[0]
+        Cc = x.shape[1] if x.ndim > 1 else 1
+        S = x.numel() // (B * Cc)
+        if hasattr(self.model, "plan") and not (torch.is_grad_enabled() and self.training):
+            plan = self.model.plan(B, tuple(x.shape[2:]) if x.ndim > 2 else tuple(x.shape[1:]), x.device)
+            check(lib.dsk_precond_scale(ptr(x), ptr(c_in), ptr(plan.xin), B, Cc, S, dt_code(plan.act_dtype), stream()))
+            F = plan.forward(plan.xin, cond_noise)
+            return F, plan.act_dtype
+        xin = torch.empty((B, S, Cc), dtype=torch.float32, device=x.device)
+        check(lib.dsk_precond_scale(ptr(x), ptr(c_in), ptr(xin), B, Cc, S, 0, stream()))
+        if Cc > 1 and S > 1:
+            xin = ops.cl_to_nchw(xin.view(B, 1, 1, S, Cc), 3)
+        F = self.model(xin.view(x.shape), cond_noise)
+        return F, None
+
+    def _denoise(self, x: Tensor, sigma: Tensor, y, guidance: float, want_score: bool):
+        if y is not None or (self.conditional and guidance != 0.0):
+            raise NotImplementedError("diffsci_b200.KarrasModule: conditional / guided denoising not built yet (8f)")
+        require_cuda(x, "x")
+        x = x.float().contiguous()
+        sigma = sigma.to(x).contiguous()
+        pre = self.config.preconditioner
+        c_in = pre.input_scaling(sigma).float().contiguous()
+        c_out = pre.output_scaling(sigma).float().contiguous()
+        c_skip = pre.skip_scaling(sigma).float().contiguous()
+        cond_noise = pre.noise_conditioner(sigma).float().contiguous()
+        B = x.shape[0]
+        Cc = x.shape[1] if x.ndim > 1 else 1
+        S = x.numel() // (B * Cc)
+        F, adt = self._network(x, c_in, cond_noise)
+        if adt is None:                 # foreign model: F is fp32 in the user's NC(D)HW layout
+            F = F.detach().float().contiguous()
+            if Cc > 1 and S > 1:
+                F = ops.nchw_to_cl(F.view(B, Cc, 1, 1, S), torch.float32, 3)
+            adt = torch.float32
+        D = torch.empty_like(x)
+        score = torch.empty_like(x) if want_score else None
+        check(lib.dsk_precond_denoise(ptr(F), ptr(x), ptr(c_out), ptr(c_skip), ptr(sigma), ptr(D), ptr(score), B, Cc, S,
+                                      dt_code(adt), stream()))
+        return D, score, cond_noise
+
+    def get_denoiser(self, x: Tensor, sigma: Tensor, y=None, guidance: float = 1.0):
+        """D(x; sigma) = c_skip x + c_out F(c_in x, c_noise)  ->  (D, c_noise)  (karrasmodule.py:673-719)."""
+        D, _, cond_noise = self._denoise(x, sigma, y, guidance, False)
+        return D, cond_noise
+
+    def get_score(self, x: Tensor, sigma: Tensor, y=None, guidance: float = 1.0) -> Tensor:
+        """(D - x) / sigma^2  (karrasmodule.py:721-733), fused with the denoiser epilogue."""
+        return self._denoise(x, sigma, y, guidance, True)[1]
+
+    # ------------------------------------------------------------------ training
+    def loss_fn(self, x: Tensor, sigma: Tensor, y=None, mask: Optional[Tensor] = None) -> Tensor:
+        """EDM denoising loss (karrasmodule.py:569-650).  Needs an EDMPreconditioner (the weighting
+        lambda(sigma) and D are evaluated inside one fused kernel together with dL/dF)."""
+        if y is not None:
+            raise NotImplementedError("diffsci_b200.KarrasModule.loss_fn: conditional training not built yet (8f)")
+        if type(self.config.preconditioner) is not preconditioners.EDMPreconditioner:
+            raise NotImplementedError("diffsci_b200.KarrasModule.loss_fn: only the EDM preconditioner is fused")
+        require_cuda(x, "x")
+        x = x.float().contiguous()
+        sigma = sigma.to(x).contiguous()
+        if self._injected_loss_noise is not None:
+            noise = self._injected_loss_noise.to(x).contiguous()
+        else:   # device-side N(0,1) (the reference uses torch.randn_like on the device generator, :591)
+            noise = ops.philox_normal(x.shape, int(torch.randint(0, 2 ** 62, (1,)).item()), 0, x.device)
+        x_noised = _rowwise_axpy(sigma.float(), noise, torch.ones_like(sigma, dtype=torch.float32), x)
+        pre = self.config.preconditioner
+        c_in = pre.input_scaling(sigma).float().contiguous()
+        cond_noise = pre.noise_conditioner(sigma).float().contiguous()
+        F, adt = self._network(x_noised, c_in, cond_noise)
+        B = x.shape[0]
+        Cc = x.shape[1] if x.ndim > 1 else 1
+        S = x.numel() // (B * Cc)
+        if adt is not None:            # native plan output: channels-last act dtype -> fp32 NC(D)HW
+            F = ops.cl_to_nchw(F.view(B, 1, 1, S, Cc), 3).view(x.shape)
+        m = None if mask is None else mask.to(x).expand_as(x).contiguous()
+        return _EDMLossFn.apply(F.float().contiguous().view(x.shape), x, noise.contiguous(), sigma, m,
+                                self._sigma_data(), self.loss_kind)
+
+    _injected_loss_noise: Optional[Tensor] = None
+
+    def select_batch(self, batch):
+        if self.conditional and self.masked:
+            x, y, mask = batch
+        elif self.masked:
+            (x, mask), y = batch, None
+        elif self.conditional:
+            (x, y), mask = batch, None
+        else:
+            x, y, mask = batch, None, None
+        return x, y, mask
+
+    def training_step(self, batch, batch_idx):
+        x, y, mask = self.select_batch(batch)
+        sigma = self.config.noisesampler.sample(x.shape[0]).to(x)
+        loss = self.loss_fn(x, sigma, y, mask)
+        self.log("train_loss", loss, prog_bar=True, sync_dist=True)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        x, y, mask = self.select_batch(batch)
+        sigma = self.config.noisesampler.sample(x.shape[0]).to(x)
+        loss = self.loss_fn(x, sigma, y, mask)
+        self.log("valid_loss", loss, prog_bar=True, sync_dist=True)
+        self.log("val_loss", loss, prog_bar=True, sync_dist=True)
+        return loss
+
+    # ------------------------------------------------------------------ sampling
+    def sample(self, nsamples: int, shape, y=None, guidance: float = 1.0, nsteps: int = 100,
+               record_history: bool = False, maximum_batch_size: Optional[int] = None, integrator=None,
+               move_to_cpu: bool = False, is_latent_shape: bool = False, squeeze_memory_efficiency: bool = False,
+               return_in_latent_space: bool = False) -> Tensor:
+        """Draw x_T ~ N(0, I) on the CPU generator (as the reference, karrasmodule.py:838: reproducible across
+        devices), scale by sigma_max and integrate the probability-flow ODE / reverse SDE to sigma = 0."""
+        with torch.inference_mode():
+            if maximum_batch_size is not None:
+                parts = [self.sample(b, shape, y, guidance, nsteps, record_history, None, integrator, move_to_cpu)
+                         for b in get_minibatch_sizes(nsamples, maximum_batch_size)]
+                return torch.cat(parts, dim=1 if record_history else 0)
+            white_noise = torch.randn(*([nsamples] + list(shape))).to(self.device)
+            if y is not None:
+                y = dict_to(y, self.device)
+            return self.propagate_white_noise(white_noise, y, guidance, nsteps, record_history,
+                                              integrator=integrator, move_to_cpu=move_to_cpu)
+
+    def propagate_white_noise(self, x: Tensor, y=None, guidance: float = 1.0, nsteps: int = 100,
+                              record_history: bool = False, integrator=None, original_y=None,
+                              move_to_cpu: bool = False, latent_shape: bool = False,
+                              squeeze_memory_efficiency: bool = False, return_in_latent_space: bool = False):
+        """x: white noise [B, *shape] (host or device).  The sigma_max scaling (karrasmodule.py:881) is fused
+        into the first sampler stage."""
+        with torch.inference_mode():
+            if not x.is_cuda:
+                x = x.to(self.device, non_blocking=True)
+            result = self.propagate_toward_sample(x, y, guidance, nsteps, record_history, integrator=integrator,
+                                                  _prescaled=False)
+            result = self.decode(result, y, record_history) if self.norm != 1.0 else result
+        return result.detach().cpu() if move_to_cpu else result
+
+    def _resolve_integrator(self, integrator):
+        sch = self.config.noisescheduler
+        if integrator is None:
+            return sch.integrator
+        if type(integrator) is str:
+            return integrators.name_to_integrator(integrator)
+        return integrator
+
+    def propagate_toward_sample(self, x: Tensor, y=None, guidance: float = 1.0, nsteps: int = 100,
+                                record_history: bool = False, integrator=None, _prescaled: bool = True):
+        """Integrate from x (already scaled by sigma_max unless called through propagate_white_noise)."""
+        if y is not None:
+            raise NotImplementedError("diffsci_b200.KarrasModule: conditional sampling not built yet (8f)")
+        require_cuda(x, "x")
+        sch = self.config.noisescheduler
+        integ = self._resolve_integrator(integrator)
+        kind = _engine.precond_kind(self.config.preconditioner)
+        fused = sch.fused_supported and kind is not None and integ.fused_program in _engine.PROGRAMS
+        x = x.float().contiguous()
+        if not fused:      # foreign preconditioner / scheduler / integrator: the duck-typed seam
+            if not _prescaled:
+                x = ops.lincomb(x, float(sch.maximum_scale))
+            if integrator is not None:
+                sch.set_temporary_integrator(integ)
+            try:
+                return sch.propagate_backward(x, lambda xx, sg: self.get_score(xx, sg, y, guidance), nsteps,
+                                              record_history=record_history)
+            finally:
+                if integrator is not None:
+                    sch.unset_temporary_integrator()
+        B, shape = x.shape[0], tuple(x.shape[1:])
+        key = (B, shape, str(x.device), id(self.model), getattr(self.model, "precision", None), kind,
+               self._sigma_data(), self.use_cuda_graphs)
+        eng = self._engines.get(key)
+        if eng is None:
+            if len(self._engines) >= 2:
+                self._engines.clear()
+            eng = self._engines[key] = _engine.SamplerEngine(self.model, B, shape, x.device, self._sigma_data(),
+                                                             1.0, kind, use_graphs=self.use_cuda_graphs)
+        eng.sigma_max = 1.0 if _prescaled else float(sch.maximum_scale)
+        table = sch.step_table(nsteps, integ)
+        noises = None
+        if integ.injected_noise is not None:
+            noises = torch.stack([n.to(x) for n in integ.injected_noise[:nsteps]], 0)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if integ.fused_program in ("euler-maruyama", "karras") else 0
+        if getattr(integ, "_fixed_seed", None) is not None:
+            seed = integ._fixed_seed
+        out = eng.run(x, table, integ.fused_program, record_history=record_history, noises=noises, seed=seed)
+        self.last_nfe = eng.nfe
+        return out

@@ -1,0 +1,82 @@
+"""MLPUncond -- drop-in for diffsci.models.nets.mlp.MLPUncond (reference nets/mlp.py:4-58).
+
+cat[x, t] -> (Linear, act)* -> Linear, each layer one fused GEMM+bias+activation launch
+(dsk_gemm_f32).  State-dict keys ``net.{i}.weight/bias`` match the reference's nn.Sequential.
+"""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import torch
+from torch import nn
+
+from ... import ops
+from ..._lib import require_cuda
+from .layers import LinearParams, _Act
+
+_ACT_CODE = {nn.ReLU: 2, nn.SiLU: 1}
+
+
+class MLPUncond(nn.Module):
+    def __init__(self, dim: int, hidden_dims=[10], nonlinearity: nn.Module = nn.ReLU(), dropout: float = 0.0):
+        super().__init__()
+        if type(nonlinearity) not in _ACT_CODE:
+            raise NotImplementedError(f"diffsci_b200.MLPUncond: activation {type(nonlinearity).__name__} not built "
+                                      "(ReLU and SiLU are fused into the GEMM epilogue)")
+        self.dim, self.act = dim, _ACT_CODE[type(nonlinearity)]
+        self.dropout = dropout
+        layers, d = [], dim + 1
+        for h in hidden_dims:
+            layers += [LinearParams(d, h), _Act()]
+            if dropout > 0:
+                layers.append(_Act())      # Dropout slot keeps the reference's Sequential indices
+            d = h
+        layers.append(LinearParams(d, dim))
+        self.net = nn.Sequential(*layers)
+        self._plans: dict[Any, "_MLPPlan"] = {}
+        self.precision = "fp32"
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        require_cuda(x, "MLPUncond input")
+        if self.training and self.dropout > 0:
+            raise NotImplementedError("diffsci_b200.MLPUncond: training-mode dropout not built")
+        plan = self.plan(x.shape[0], tuple(x.shape[1:]), x.device)
+        plan.xin.copy_(x.reshape(plan.xin.shape))
+        return plan.forward(plan.xin, t.float().contiguous()).reshape(x.shape).clone()
+
+    def plan(self, B: int, spatial: tuple, device, precision: Optional[str] = None) -> "_MLPPlan":
+        key = (B, str(device))
+        sig = tuple(p.data_ptr() for p in self.parameters())
+        plan = self._plans.get(key)
+        if plan is None or plan.sig != sig:
+            if len(self._plans) >= 4:
+                self._plans.clear()
+            plan = self._plans[key] = _MLPPlan(self, B, device, sig)
+        return plan
+
+    def _apply(self, fn, *a, **k):
+        self._plans = {}
+        return super()._apply(fn, *a, **k)
+
+
+class _MLPPlan:
+    act_dtype = torch.float32
+
+    def __init__(self, net: MLPUncond, B: int, device, sig):
+        self.net, self.B, self.sig = net, B, sig
+        f32 = dict(dtype=torch.float32, device=device)
+        self.xin = torch.empty((B, net.dim), **f32)
+        self.cat = torch.empty((B, net.dim + 1), **f32)
+        self.layers = [m for m in net.net if isinstance(m, LinearParams)]
+        self.h = [torch.empty((B, m.weight.shape[0]), **f32) for m in self.layers]
+        self.F = self.h[-1]
+
+    def prepare(self):
+        pass
+
+    def forward(self, xin: torch.Tensor, cnoise: torch.Tensor, **_) -> torch.Tensor:
+        h = ops.concat_channels(xin.view(self.B, -1), cnoise.view(self.B, 1), out=self.cat)
+        for i, m in enumerate(self.layers):
+            last = i == len(self.layers) - 1
+            h = ops.linear(h, m.weight, m.bias, act=0 if last else self.net.act, out=self.h[i])
+        return h

@@ -1,0 +1,296 @@
+"""PUNetG -- drop-in for diffsci.models.nets.punetg.PUNetG (reference nets/punetg.py:10-416).
+
+Same constructor signature, same ``forward(x, t, y=None)`` contract (fp32 NC(D)HW in/out) and the
+same ``state_dict()`` keys/shapes, so reference checkpoints load unchanged.  The forward pass is a
+sequence of hand-written sm_100a kernels (diffsci_b200.ops -> libdiffsci_b200.so) on channels-last
+activations held in a per-(batch, shape, precision) plan of preallocated buffers, which makes the
+whole evaluation CUDA-graph capturable (no allocation, no host sync, no pointer-table upload).
+
+Fusions relative to the reference graph:
+  * conv epilogue adds bias, the time-embedding vector y + timeblock(te)[:, :, None...] and the
+    ResNet identity residual (commonlayers.py:824-833) -- no separate elementwise passes;
+  * UpSampler's F.interpolate(x2, nearest) is folded into the conv's input gather and the additive
+    U-Net skip (punetg.py:373) into its epilogue -- the 8x upsampled tensor never exists;
+  * ``skips.append(x.clone())`` (punetg.py:363) is a buffer hand-off, not a copy;
+  * the 3-layer time MLPs of all ResNet blocks run as 3 grouped launches.
+"""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import torch
+from torch import nn
+
+from ... import ops
+from ..._lib import require_cuda
+from .layers import (AttentionParams, ConvParams, FourierParams, NormParams, TimeBlockParams, _Holder)
+from .punetg_config import PUNetGConfig
+
+_NORM_MODE = {"GroupLN": 0, "GroupRMS": 1}
+DEFAULT_PRECISION = "fp32"
+
+
+def _tc_eligible(cin: int, cout: int) -> bool:
+    """Shapes the tcgen05 implicit-GEMM kernel takes (see csrc/conv_tc.cu)."""
+    from ... import TC_CONV_ENABLED
+    return TC_CONV_ENABLED and cin % 64 == 0 and cout % 64 == 0 and cout <= 256
+
+
+class ResnetBlockParams(_Holder):
+    """ResnetBlockC as PUNetG builds it (punetg.py:238-261): C_in == C_out, own time MLP."""
+
+    def __init__(self, channels: int, embed: int, ndim: int, ksize: int, affine: bool, bias: bool):
+        super().__init__()
+        self.channels = channels
+        self.gnorm1 = NormParams(channels, affine)
+        self.gnorm2 = NormParams(channels, affine)
+        self.conv1 = ConvParams(channels, channels, ksize, ndim, bias)
+        self.conv2 = ConvParams(channels, channels, ksize, ndim, bias)
+        self.timeblock = TimeBlockParams(embed, channels)
+
+
+class SamplerParams(_Holder):
+    """DownSampler / UpSampler (commonlayers.py:25-158): one conv; pooling / upsampling is weight-free."""
+
+    def __init__(self, cin: int, cout: int, ndim: int, ksize: int, bias: bool):
+        super().__init__()
+        self.conv = ConvParams(cin, cout, ksize, ndim, bias)
+
+
+class PUNetG(nn.Module):
+    def __init__(self, config: PUNetGConfig, conditional_embedding: Optional[nn.Module] = None,
+                 extra_residual: Optional[nn.Module] = None, *, precision: Optional[str] = None):
+        super().__init__()
+        c = self.config = config
+        unsupported = []
+        if c.convolution_type != "default":
+            unsupported.append(f"convolution_type={c.convolution_type!r}")
+        if c.in_embedding:
+            unsupported.append("in_embedding=True")
+        if c.first_resblock_norm not in _NORM_MODE or c.second_resblock_norm not in _NORM_MODE:
+            unsupported.append("norms other than GroupLN/GroupRMS")
+        if c.attn_type != "default":
+            unsupported.append(f"attn_type={c.attn_type!r}")
+        if conditional_embedding is not None or extra_residual is not None:
+            unsupported.append("conditional_embedding / extra_residual")
+        if not c.bias:
+            unsupported.append("bias=False")
+        if c.dimension not in (2, 3) or c.transition_scale_factor != 2:
+            unsupported.append("dimension not in {2,3} or transition_scale_factor != 2")
+        if c.kernel_size not in (1, 3) or c.in_out_kernel_size not in (1, 3) or c.transition_kernel_size not in (1, 3):
+            unsupported.append("kernel sizes other than 1/3")
+        if unsupported:
+            raise NotImplementedError("diffsci_b200.PUNetG: not built yet (SURVEY.md 8f): " + ", ".join(unsupported))
+        self.precision = precision or DEFAULT_PRECISION
+        self.conditional_embedding = None
+        self.extra_residual = None
+        nd, M = c.dimension, c.model_channels
+        mult = c.extended_channel_expansion
+
+        def blocks(m, n):
+            return nn.ModuleList([ResnetBlockParams(m * M, M, nd, c.kernel_size, c.affine_norm, c.bias) for _ in range(n)])
+
+        self.time_projection = FourierParams(M, c.time_projection_scale)
+        self.convin = ConvParams(c.input_channels, M, c.in_out_kernel_size, nd, c.bias)
+        self.convout = ConvParams(M, c.output_channels, c.in_out_kernel_size, nd, c.bias)
+        self.downward_blocks = nn.ModuleList([blocks(m, c.number_resnet_downward_block) for m in mult[:-1]])
+        self.downsamplers = nn.ModuleList([SamplerParams(a * M, b * M, nd, c.transition_kernel_size, c.bias)
+                                           for a, b in zip(mult[:-1], mult[1:])])
+        rev = mult[::-1]
+        self.upward_blocks = nn.ModuleList([blocks(m, c.number_resnet_upward_block) for m in rev[1:]])
+        self.upsamplers = nn.ModuleList([SamplerParams(a * M, b * M, nd, c.transition_kernel_size, c.bias)
+                                         for a, b in zip(rev[:-1], rev[1:])])
+        self.before_block = blocks(mult[-1], c.number_resnet_before_attn_block)
+        self.after_block = blocks(mult[-1], c.number_resnet_after_attn_block)
+        self.attn_resnet_block = blocks(mult[-1], c.number_resnet_attn_block)
+        self.attn_block = nn.ModuleList([AttentionParams(mult[-1] * M) for _ in range(c.number_resnet_attn_block - 1)])
+        self.cond_dropout = nn.Dropout(c.cond_dropout)
+        self.cond_drop = None
+        self._plans: dict[Any, "_Plan"] = {}
+
+    # ------------------------------------------------------------------ reference API
+    def export_description(self) -> dict[str, Any]:
+        return dict(config=self.config.export_description(), conditional_embedding_args=None,
+                    has_conditional_embedding=False)
+
+    def forward(self, x: torch.Tensor, t: Optional[torch.Tensor] = None, y=None) -> torch.Tensor:
+        """x: fp32 [B, Cin, *S]; t: [B] (= c_noise); returns fp32 [B, Cout, *S] (punetg.py:389-416)."""
+        if y is not None:
+            raise NotImplementedError("diffsci_b200.PUNetG: conditional path (y) not built yet (SURVEY.md 8f)")
+        require_cuda(x, "PUNetG input")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("diffsci_b200.PUNetG: backward kernels (K2) not built yet; call under "
+                                      "torch.no_grad()/inference_mode() or .eval()")
+        B = x.shape[0]
+        plan = self.plan(B, tuple(x.shape[2:]), x.device)
+        xin = ops.nchw_to_cl(x.float(), plan.act_dtype, self.config.dimension, out=plan.xin)
+        tt = torch.zeros(B, device=x.device) if t is None else t.float().contiguous()
+        out = torch.empty((B, self.config.output_channels) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+        plan.forward(xin, tt, out_nchw=out, zero_time=t is None)
+        return out
+
+    # ------------------------------------------------------------------ plans
+    def plan(self, B: int, spatial: tuple, device, precision: Optional[str] = None) -> "_Plan":
+        precision = precision or self.precision
+        key = (B, tuple(spatial), str(device), precision)
+        sig = tuple(p.data_ptr() for p in self.parameters())
+        plan = self._plans.get(key)
+        if plan is None or plan.sig != sig:
+            if len(self._plans) >= 4:   # bound the HBM held by cached plans
+                self._plans.clear()
+            plan = self._plans[key] = _Plan(self, B, tuple(spatial), device, precision, sig)
+        return plan
+
+    def _apply(self, fn, *a, **k):
+        self._plans = {}
+        return super()._apply(fn, *a, **k)
+
+
+class _Plan:
+    """Preallocated buffers + packed weights + pointer tables for one (B, shape, precision)."""
+
+    def __init__(self, net: PUNetG, B: int, spatial: tuple, device, precision: str, sig):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        c = net.config
+        self.net, self.B, self.sig, self.precision = net, B, sig, precision
+        self.ndim = nd = c.dimension
+        self.act_dtype = adt = torch.float32 if precision == "fp32" else torch.bfloat16
+        dev = self.device = torch.device(device)
+        if len(spatial) != nd:
+            raise ValueError(f"PUNetG(dimension={nd}) got spatial shape {spatial}")
+        M, mult = c.model_channels, c.extended_channel_expansion
+        self.nlev = nlev = len(c.channel_expansion)
+        sp = [(1,) + tuple(spatial) if nd == 2 else tuple(spatial)]
+        for _ in range(nlev):
+            d, h, w = sp[-1]
+            if h % 2 or w % 2 or (nd == 3 and d % 2):
+                raise ValueError(f"PUNetG: spatial size {sp[-1]} is not divisible by 2 at a down-sampling level "
+                                 "(the reference fails at `x + skip` for such shapes)")
+            sp.append((d // 2 if nd == 3 else 1, h // 2, w // 2))
+        self.sp = sp
+        ch = [m * M for m in mult]
+
+        def buf(l, cc, dtype=adt):
+            return torch.empty((B,) + sp[l] + (cc,), dtype=dtype, device=dev)
+
+        def pack(cp):
+            wd = torch.bfloat16 if (precision == "bf16" and _tc_eligible(cp.cin, cp.cout)) else torch.float32
+            return ops.PackedConv(cp.weight, cp.bias, nd, wd)
+
+        self.xin = buf(0, c.input_channels)
+        self.X = [buf(l, ch[l]) for l in range(nlev + 1)]          # encoder / bottom state (doubles as skip)
+        self.XU = [buf(l, ch[l]) for l in range(nlev)]             # decoder state
+        self.N = [buf(l, ch[l]) for l in range(nlev + 1)]          # norm+SiLU output == conv input
+        self.Y = [buf(l, ch[l]) for l in range(nlev + 1)]          # conv1 output
+        self.P = [buf(l + 1, ch[l]) for l in range(nlev)]          # pooled
+        self.XA = buf(nlev, ch[nlev])
+        self.XA2 = buf(nlev, ch[nlev])
+        self.F = buf(0, c.output_channels)
+        self.WS = [ops.norm_ws(B, sp[l][0] * sp[l][1] * sp[l][2], ch[l], dev) for l in range(nlev + 1)]
+        self.pc_in, self.pc_out = pack(net.convin), pack(net.convout)
+        self.pc_down = [pack(s.conv) for s in net.downsamplers]
+        self.pc_up = [pack(s.conv) for s in net.upsamplers]
+
+        # every ResNet block in execution order, with its level
+        self.blocks = []
+        for l in range(nlev):
+            self.blocks += [(b, l) for b in net.downward_blocks[l]]
+        for grp in (net.before_block, net.attn_resnet_block, net.after_block):
+            self.blocks += [(b, nlev) for b in grp]
+        for i in range(nlev):
+            self.blocks += [(b, nlev - 1 - i) for b in net.upward_blocks[i]]
+        self.pc = {id(b): (pack(b.conv1), pack(b.conv2)) for b, _ in self.blocks}
+
+        # time embedding: Fourier features + 3 grouped launches for all blocks' MLPs
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.te = torch.empty((B, M), **f32)
+        self.tvec = {id(b): torch.empty((B, b.channels), **f32) for b, _ in self.blocks}
+        h1 = [torch.empty((B, 4 * M), **f32) for _ in self.blocks]
+        h2 = [torch.empty((B, 4 * M), **f32) for _ in self.blocks]
+        net_ = [b.timeblock.net for b, _ in self.blocks]
+        self.tmlp = [
+            ops.GroupedLinear([self.te] * len(net_), [n[0].weight for n in net_], [n[0].bias for n in net_], h1, 1),
+            ops.GroupedLinear(h1, [n[2].weight for n in net_], [n[2].bias for n in net_], h2, 1),
+            ops.GroupedLinear(h2, [n[4].weight for n in net_], [n[4].bias for n in net_],
+                              [self.tvec[id(b)] for b, _ in self.blocks], 0),
+        ]
+        # attention scratch (fp32 tokens)
+        Lq = sp[nlev][0] * sp[nlev][1] * sp[nlev][2]
+        Cb = ch[nlev]
+        self.attn = None
+        if len(net.attn_block) > 0:
+            self.attn = dict(qkv=torch.empty((B * Lq, 3 * Cb), **f32), scores=torch.empty((B, Lq, Lq), **f32),
+                             ao=torch.empty((B * Lq, Cb), **f32), out=torch.empty((B, Lq, Cb), **f32))
+            if adt != torch.float32:
+                self.attn["tok"] = torch.empty((B, Lq, Cb), **f32)
+        self.Lq, self.Cb = Lq, Cb
+        self.prepare()
+
+    def prepare(self):
+        """Materialise packed weights (must happen outside CUDA-graph capture)."""
+        for pc in [self.pc_in, self.pc_out, *self.pc_down, *self.pc_up, *[p for pair in self.pc.values() for p in pair]]:
+            pc.packed()
+
+    # ------------------------------------------------------------------ forward
+    def _resblock(self, x, blk, l, out):
+        c = self.net.config
+        C = blk.channels
+        pc1, pc2 = self.pc[id(blk)]
+        n = ops.norm_act(x, blk.gnorm1.weight, blk.gnorm1.bias, C, _NORM_MODE[c.first_resblock_norm], True,
+                         out=self.N[l], ws=self.WS[l])
+        y = ops.conv(n, pc1, out=self.Y[l], chan_bias=self.tvec[id(blk)])
+        n = ops.norm_act(y, blk.gnorm2.weight, blk.gnorm2.bias, C, _NORM_MODE[c.second_resblock_norm], True,
+                         out=self.N[l], ws=self.WS[l])
+        return ops.conv(n, pc2, out=out, residual=x)
+
+    def _attention(self, x, attn, out):
+        a = self.attn
+        m = attn.mhattn
+        B, Lq, Cb = self.B, self.Lq, self.Cb
+        if x.dtype == torch.float32:
+            tok = x.view(B, Lq, Cb)
+        else:
+            tok = ops.cast(x.view(B, Lq, Cb), torch.float32, out=a["tok"])
+        o = ops.self_attention_f32(tok, m.in_proj_weight, m.in_proj_bias, m.out_proj.weight, m.out_proj.bias, a,
+                                   self.net.config.attn_residual)
+        ops.cast(o, out.dtype, out=out.view(B, Lq, Cb))
+        return out
+
+    def forward(self, xin: torch.Tensor, cnoise: torch.Tensor, out_nchw: Optional[torch.Tensor] = None,
+                zero_time: bool = False) -> torch.Tensor:
+        """xin: channels-last [B, D, H, W, Cin] (act dtype); cnoise: fp32 [B].
+        Returns F channels-last (self.F), or writes fp32 NC(D)HW into `out_nchw`."""
+        net, c, nlev = self.net, self.net.config, self.nlev
+        if zero_time:
+            self.te.zero_()       # te = zeros when t is None (punetg.py:398-399)
+        else:
+            ops.fourier(cnoise, net.time_projection.W, out=self.te)
+        for g in self.tmlp:
+            g.run()
+        x = ops.conv(xin, self.pc_in, out=self.X[0])
+        for l in range(nlev):
+            for blk in net.downward_blocks[l]:
+                x = self._resblock(x, blk, l, x)
+            p = ops.pool2x(x, self.ndim, True, out=self.P[l])            # MaxPool (commonlayers.py:60-63)
+            x = ops.conv(p, self.pc_down[l], out=self.X[l + 1])
+        for blk in net.before_block:
+            x = self._resblock(x, blk, nlev, x)
+        xa = x
+        for r, blk in enumerate(net.attn_resnet_block):
+            xa = self._resblock(xa, blk, nlev, self.XA)
+            if r < len(net.attn_block):
+                xa = self._attention(xa, net.attn_block[r], self.XA2)
+                # next block reads XA2 and writes XA (its residual input is XA2)
+        x = ops.add(x, xa, out=x)
+        for blk in net.after_block:
+            x = self._resblock(x, blk, nlev, x)
+        for i in range(nlev):
+            l = nlev - 1 - i
+            # conv(F.interpolate(x, 2)) + skip, fused (commonlayers.py:145; punetg.py:372-373)
+            x = ops.conv(x, self.pc_up[i], out=self.XU[l], residual=self.X[l], up2=True)
+            for blk in net.upward_blocks[i]:
+                x = self._resblock(x, blk, l, x)
+        if out_nchw is not None:
+            return ops.conv(x, self.pc_out, out=out_nchw, out_nchw=True)
+        return ops.conv(x, self.pc_out, out=self.F)

@@ -1,0 +1,252 @@
+"""Thin tensor-level wrappers over the C ABI (include/diffsci_b200.h).
+
+PyTorch is used here only for device memory (torch.empty), streams and dtype bookkeeping; all
+arithmetic is done by the hand-written kernels in libdiffsci_b200.so.  Activations are
+CHANNELS-LAST tensors of shape [B, D, H, W, C] (D == 1 for 2-D nets), fp32 or bf16.
+Every function raises RuntimeError for CPU tensors: there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from ._lib import lib, check, ptr, stream, dt_code, require_cuda
+
+
+class PackedConv:
+    """Device-side packed copy of a reference-layout conv weight [Cout, Cin, k(,k)(,k)].
+
+    fp32 mode  : fp32 [taps][Cin][Cout]  (CUDA-core FFMA implicit GEMM, 1e-5 parity path)
+    bf16 mode  : bf16 [taps][Cout][Cin]  (tcgen05 implicit GEMM, K-major B operand)
+    Rebuilt whenever the source parameter's version counter changes (optimizer step / load).
+    """
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], ndim: int, w_dtype: torch.dtype):
+        self.weight, self.bias, self.ndim = weight, bias, ndim
+        self.cout, self.cin = int(weight.shape[0]), int(weight.shape[1])
+        self.ksize = int(weight.shape[-1])
+        self.taps = self.ksize ** ndim
+        self.w_dtype = w_dtype
+        self._packed = None
+        self._version = None
+
+    def packed(self) -> torch.Tensor:
+        w = self.weight
+        key = (w._version, w.data_ptr())
+        if self._packed is None or self._version != key or self._packed.device != w.device:
+            require_cuda(w, "conv weight")
+            src = w.detach().float().contiguous()
+            if self._packed is None or self._packed.device != w.device:
+                self._packed = torch.empty(self.taps * self.cin * self.cout, dtype=self.w_dtype, device=w.device)
+            check(lib.dsk_pack_conv_weight(ptr(src), ptr(self._packed), self.cout, self.cin, self.taps,
+                                           dt_code(self.w_dtype), stream()))
+            self._version = key
+        return self._packed
+
+
+def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, chan_bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, up2: bool = False, out_dtype: Optional[torch.dtype] = None,
+         out_nchw: bool = False) -> torch.Tensor:
+    """y = conv_same(x) + bias + chan_bias[b, :] + residual  (dsk_conv_fwd)."""
+    require_cuda(x, "conv input")
+    B, D, H, W, Cin = x.shape
+    assert Cin == pc.cin, (Cin, pc.cin)
+    if up2:
+        D, H, W = (D * 2 if pc.ndim == 3 else D), H * 2, W * 2
+    out_dtype = out_dtype or x.dtype
+    if out is None:
+        shape = (B, pc.cout, D, H, W) if out_nchw else (B, D, H, W, pc.cout)
+        if out_nchw and pc.ndim == 2:
+            shape = (B, pc.cout, H, W)
+        out = torch.empty(shape, dtype=torch.float32 if out_nchw else out_dtype, device=x.device)
+    d = L.ConvDesc(B, D, H, W, Cin, pc.cout, pc.ksize, pc.ndim, int(up2), dt_code(pc.w_dtype), dt_code(x.dtype),
+                   dt_code(residual.dtype if (out_nchw and residual is not None) else
+                           (torch.float32 if out_nchw else out.dtype)), int(out_nchw))
+    bias = pc.bias.detach() if pc.bias is not None else None
+    check(lib.dsk_conv_fwd(C.byref(d), ptr(x), ptr(pc.packed()), ptr(bias), ptr(chan_bias), ptr(residual), ptr(out),
+                           stream()))
+    return out
+
+
+def gemm(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, lda: int, ldb: int, ldc: int,
+         bias: Optional[torch.Tensor] = None, transB: bool = True, alpha: float = 1.0, act: int = 0, batch: int = 1,
+         strideA: int = 0, strideB: int = 0, strideC: int = 0, a_off: int = 0, b_off: int = 0) -> torch.Tensor:
+    """Batched fp32 GEMM on raw buffers with element offsets (dsk_gemm_f32)."""
+    require_cuda(A, "gemm A")
+    es = 4
+    a = C.c_void_p(A.data_ptr() + a_off * es)
+    b = C.c_void_p(Bm.data_ptr() + b_off * es)
+    check(lib.dsk_gemm_f32(a, b, ptr(out), ptr(bias), M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch,
+                           int(transB), alpha, act, stream()))
+    return out
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int = 0,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = act(x W^T + b) for fp32 x [M, K], W [N, K]."""
+    M, K = x.shape
+    N = weight.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    return gemm(x, weight.detach(), out, M=M, N=N, K=K, lda=K, ldb=K, ldc=N,
+                bias=bias.detach() if bias is not None else None, transB=True, act=act)
+
+
+def norm_act(x: torch.Tensor, gamma, beta, G: int, mode: int, silu: bool, out: Optional[torch.Tensor] = None,
+             film_scale=None, film_shift=None, out_dtype: Optional[torch.dtype] = None, ws=None) -> torch.Tensor:
+    """Group LayerNorm (mode 0) / RMS norm (mode 1) + affine (+FiLM) + SiLU  (dsk_norm_act)."""
+    require_cuda(x, "norm input")
+    B, Cc = x.shape[0], x.shape[-1]
+    S = x.numel() // (B * Cc)
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    if ws is None:
+        ws = torch.empty(int(lib.dsk_norm_ws_bytes(B, S, Cc)), dtype=torch.uint8, device=x.device)
+    g = gamma.detach() if gamma is not None else None
+    b = beta.detach() if beta is not None else None
+    check(lib.dsk_norm_act(ptr(x), ptr(out), ptr(g), ptr(b), ptr(film_scale), ptr(film_shift), ptr(ws), B, S, Cc, G,
+                           mode, int(silu), dt_code(x.dtype), dt_code(out.dtype), stream()))
+    return out
+
+
+def norm_ws(B: int, S: int, Cc: int, device) -> torch.Tensor:
+    return torch.empty(int(lib.dsk_norm_ws_bytes(B, S, Cc)), dtype=torch.uint8, device=device)
+
+
+def pool2x(x: torch.Tensor, ndim: int, is_max: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    require_cuda(x, "pool input")
+    B, D, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, D // 2 if ndim == 3 else 1, H // 2, W // 2, Cc), dtype=x.dtype, device=x.device)
+    check(lib.dsk_pool2x(ptr(x), ptr(out), B, D, H, W, Cc, ndim, int(is_max), dt_code(x.dtype), stream()))
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    require_cuda(a, "add input")
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib.dsk_add(ptr(a), ptr(b), ptr(out), a.numel(), dt_code(a.dtype), stream()))
+    return out
+
+
+def cast(x: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    require_cuda(x, "cast input")
+    if out is None:
+        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    check(lib.dsk_cast(ptr(x), ptr(out), x.numel(), dt_code(x.dtype), dt_code(out.dtype), stream()))
+    return out
+
+
+def concat_channels(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    require_cuda(a, "concat input")
+    Ca, Cb = a.shape[-1], b.shape[-1]
+    rows = a.numel() // Ca
+    if out is None:
+        out = torch.empty(a.shape[:-1] + (Ca + Cb,), dtype=a.dtype, device=a.device)
+    check(lib.dsk_concat_channels(ptr(a), ptr(b), ptr(out), rows, Ca, Cb, dt_code(a.dtype), stream()))
+    return out
+
+
+def nchw_to_cl(x: torch.Tensor, dtype: torch.dtype, ndim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [B, C, *S] -> channels-last [B, D, H, W, C]."""
+    require_cuda(x, "input")
+    x = x.contiguous()
+    B, Cc = x.shape[0], x.shape[1]
+    sp = tuple(x.shape[2:])
+    if ndim == 2:
+        sp = (1,) + sp
+    S = sp[0] * sp[1] * sp[2]
+    if out is None:
+        out = torch.empty((B,) + sp + (Cc,), dtype=dtype, device=x.device)
+    check(lib.dsk_nchw_to_cl(ptr(x), ptr(out), B, Cc, S, dt_code(dtype), stream()))
+    return out
+
+
+def cl_to_nchw(x: torch.Tensor, ndim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    require_cuda(x, "input")
+    B, D, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, Cc, H, W) if ndim == 2 else (B, Cc, D, H, W), dtype=torch.float32, device=x.device)
+    check(lib.dsk_cl_to_nchw(ptr(x), ptr(out), B, Cc, D * H * W, dt_code(x.dtype), stream()))
+    return out
+
+
+def fourier(t: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    require_cuda(t, "time input")
+    B, half = t.shape[0], W.shape[0]
+    if out is None:
+        out = torch.empty((B, 2 * half), dtype=torch.float32, device=t.device)
+    check(lib.dsk_fourier(ptr(t), ptr(W), ptr(out), B, half, stream()))
+    return out
+
+
+class GroupedLinear:
+    """Pointer tables for one dsk_grouped_linear launch (built once; graph-capturable)."""
+
+    def __init__(self, xs, ws, bs, ys, act: int):
+        dev = ws[0].device
+        self.keep = (xs, ws, bs, ys)
+        self.B = int(xs[0].shape[0])
+        mk = lambda ts: torch.tensor([0 if t is None else t.data_ptr() for t in ts], dtype=torch.int64, device=dev)  # noqa: E731
+        self.X, self.W, self.Bi, self.Y = mk(xs), mk(ws), mk(bs), mk(ys)
+        self.in_dim = torch.tensor([w.shape[1] for w in ws], dtype=torch.int32, device=dev)
+        self.out_dim = torch.tensor([w.shape[0] for w in ws], dtype=torch.int32, device=dev)
+        self.max_out = max(int(w.shape[0]) for w in ws)
+        self.n = len(ws)
+        self.act = act
+        self.sig = tuple(int(w.data_ptr()) for w in ws)
+
+    def run(self):
+        check(lib.dsk_grouped_linear(ptr(self.X), ptr(self.W), ptr(self.Bi), ptr(self.Y), ptr(self.in_dim),
+                                     ptr(self.out_dim), self.n, self.max_out, self.B, self.act, stream()))
+
+
+def softmax_rows(S: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    require_cuda(S, "scores")
+    check(lib.dsk_softmax_rows(ptr(S), rows, cols, stream()))
+    return S
+
+
+def self_attention_f32(tok: torch.Tensor, in_w, in_b, out_w, out_b, bufs: dict, residual: bool) -> torch.Tensor:
+    """nn.MultiheadAttention(C, 1 head) self-attention on fp32 tokens [B, L, C] (nets/attention.py:54-72).
+
+    fp32-parity path: packed QKV projection GEMM, batched QK^T, row softmax, batched PV, output
+    projection -- all through dsk_gemm_f32 / dsk_softmax_rows.  `bufs` holds preallocated scratch.
+    """
+    B, Lq, Cc = tok.shape
+    qkv, sc, ao, out = bufs["qkv"], bufs["scores"], bufs["ao"], bufs["out"]
+    gemm(tok, in_w.detach(), qkv, M=B * Lq, N=3 * Cc, K=Cc, lda=Cc, ldb=Cc, ldc=3 * Cc, bias=in_b.detach(), transB=True)
+    gemm(qkv, qkv, sc, M=Lq, N=Lq, K=Cc, lda=3 * Cc, ldb=3 * Cc, ldc=Lq, transB=True, alpha=Cc ** -0.5, batch=B,
+         strideA=Lq * 3 * Cc, strideB=Lq * 3 * Cc, strideC=Lq * Lq, a_off=0, b_off=Cc)
+    softmax_rows(sc, B * Lq, Lq)
+    gemm(sc, qkv, ao, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=3 * Cc, ldc=Cc, transB=False, batch=B, strideA=Lq * Lq,
+         strideB=Lq * 3 * Cc, strideC=Lq * Cc, b_off=2 * Cc)
+    gemm(ao, out_w.detach(), out, M=B * Lq, N=Cc, K=Cc, lda=Cc, ldb=Cc, ldc=Cc, bias=out_b.detach(), transB=True)
+    if residual:
+        add(out, tok, out)
+    return out
+
+
+def lincomb(x=None, a0: float = 0.0, r1=None, a1: float = 0.0, r2=None, a2: float = 0.0, z=None, a3: float = 0.0,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = a0*x + a1*r1 + a2*r2 + a3*z on fp32 tensors (dsk_lincomb); None operands are skipped."""
+    ref = next(t for t in (x, r1, r2, z) if t is not None)
+    require_cuda(ref, "integrator state")
+    ts = [None if t is None else t.float().contiguous() for t in (x, r1, r2, z)]
+    if out is None:
+        out = torch.empty(ref.shape, dtype=torch.float32, device=ref.device)
+    check(lib.dsk_lincomb(ptr(out), out.numel(), ptr(ts[0]), a0, ptr(ts[1]), a1, ptr(ts[2]), a2, ptr(ts[3]), a3,
+                          stream()))
+    return out
+
+
+def philox_normal(shape, seed: int, stream_id: int, device) -> torch.Tensor:
+    """N(0,1) tensor from the library's counter-based Philox4x32-10 (dsk_philox_normal)."""
+    out = torch.empty(tuple(shape), dtype=torch.float32, device=device)
+    require_cuda(out, "noise")
+    check(lib.dsk_philox_normal(ptr(out), out.numel(), seed & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, stream()))
+    return out

@@ -1,0 +1,208 @@
+/*
+ * diffsci_b200.h -- C ABI of libdiffsci_b200.so (hand-written sm_100a CUDA for the
+ * Karras/EDM hot path of Lacadame/DiffSci).
+ *
+ * The reference is pure Python/PyTorch and defines no FFI of its own; every
+ * entry point below names the reference call site (file:line under /root/reference) whose
+ * arithmetic it replaces.  The reference-side binding is a ctypes stub.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative code on error; the message is in
+ *    dsk_last_error() (thread-local).  There is NO CPU fallback: a non-sm_100 device, a
+ *    null pointer or an unsupported shape is an error, never a silent slow path.
+ *  - all pointers are DEVICE pointers unless named host_*; the caller owns every buffer
+ *    (inputs, outputs, workspaces).  No hidden allocations, no internal threads.
+ *  - every launch is asynchronous on the cudaStream_t passed as `stream` (void* here so
+ *    that the header needs no CUDA include); functions are CUDA-graph capturable.
+ *  - activations inside the networks are CHANNELS-LAST [B, D, H, W, C] (D = 1 for 2-D),
+ *    dtype DSK_F32 or DSK_BF16; user-facing tensors x / D(x) / noise are fp32 NC(D)HW as in
+ *    the reference.
+ */
+#ifndef DIFFSCI_B200_H
+#define DIFFSCI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSK_OK 0
+#define DSK_ERR_ARG -1
+#define DSK_ERR_CUDA -2
+#define DSK_ERR_UNSUPPORTED -3
+
+enum { DSK_F32 = 0, DSK_BF16 = 1 };
+
+/* ---- library ---------------------------------------------------------------------- */
+int dsk_version(void);
+const char* dsk_last_error(void);
+/* number of kernels this library has launched (or recorded into a graph) in this process */
+uint64_t dsk_launch_count(void);
+/* fails unless `device` is compute capability 10.x (B200) */
+int dsk_check_device(int device);
+
+/* ---- K7: EDM preconditioning + sampler stages ---------------------------------------
+ * Replaces KarrasModule.get_denoiser / get_score (karras/karrasmodule.py:673-733),
+ * EDMPreconditioner (karras/preconditioners.py:30-53), Scheduler.rhs EDM branch
+ * (karras/schedulers.py:247-274) and the integrator steps (karras/integrators.py:29-113).
+ *
+ * x, x_aux, r1, noise, hist_row: fp32 [B, C, S] (reference NC(D)HW layout, S = prod(spatial)).
+ * F / xin: network output / input, channels-last [B, S, C], dtype `act_dtype`.
+ * cnoise: fp32 [B] = c_noise(sigma), the network's second argument.
+ */
+
+/* xin[b,s,c] = c_in[b] * x[b,c,s] for ANY preconditioner: the [B] coefficient vectors come from the
+ * host-side preconditioner object (preconditioners.py:30-161). */
+int dsk_precond_scale(const float* x, const float* c_in, void* xin, int B, int C, int64_t S, int act_dtype,
+                      void* stream);
+/* D = c_out[b]*F + c_skip[b]*x (D may be NULL); score = (D - x)/sigma[b]^2 (score may be NULL). */
+int dsk_precond_denoise(const void* F, const float* x, const float* c_out, const float* c_skip, const float* sigma,
+                        float* D, float* score, int B, int C, int64_t S, int act_dtype, void* stream);
+
+/* Step table: fp32 [nrows][DSK_TAB_COLS], one row per integrator step, built on the host
+ * (diffsci_b200.models.karras.schedulers) exactly as EDMScheduler.create_steps does
+ * (schedulers.py:377-385).  `row` is a DEVICE int32[4]: row[0] = current step (so that one captured
+ * CUDA graph serves every step; dsk_sampler_advance increments it), row[1], row[2] = low / high word of
+ * a run-time Philox seed that is XOR-ed into the by-value `seed` (replayable graphs, new noise). */
+#define DSK_TAB_COLS 8
+enum {
+  DSK_TAB_T = 0,      /* t_i                                             */
+  DSK_TAB_DT = 1,     /* dt_i = t_{i+1} - t_i                            */
+  DSK_TAB_THAT = 2,   /* Karras: t_i + gamma_i*t_i ; otherwise t_i       */
+  DSK_TAB_LANG = 3,   /* EM: langevin_factor(t_i) (0 outside interval)   */
+  DSK_TAB_NOISE = 4,  /* EM: noise_injection(t_i) = sqrt(2*lang)         */
+  DSK_TAB_SQDT = 5,   /* EM: sqrt(|dt_i|)                                */
+  DSK_TAB_TNEXT = 6,  /* sigma of the first network evaluation of step i+1 (t_{i+1}, or its t_hat) */
+  DSK_TAB_CHURN = 7   /* Karras: sqrt(that^2-t^2)*S_noise of THIS step (0 otherwise).  The table has
+                         nsteps+1 rows (last row zero) because KARRAS_FIN reads the next row's churn. */
+};
+enum {
+  DSK_STAGE_INIT = 0,       /* x *= sigma_max ; (Karras churn) ; prep first evaluation       */
+  DSK_STAGE_EULER = 1,      /* x += dt*rhs ; prep next step                                  */
+  DSK_STAGE_HEUN_MID = 2,   /* r1 = rhs ; x_aux = x + dt*r1 ; prep evaluation at t+dt        */
+  DSK_STAGE_HEUN_FIN = 3,   /* r2 = rhs(x_aux) ; x += 0.5*(r1+r2)*dt ; prep next step        */
+  DSK_STAGE_HEUN_LAST = 4,  /* t+dt == 0: x += 0.5*(r1+r1)*dt (integrators.py:49-53)         */
+  DSK_STAGE_EM = 5,         /* x += rhs_stoch*dt + noise_strength*xi*sqrt|dt| ; prep next     */
+  DSK_STAGE_KARRAS_MID = 6, /* r1 at (x_hat,t_hat); x_aux = x_hat + dt_hat*r1 ; prep at t+dt  */
+  DSK_STAGE_KARRAS_FIN = 7, /* x = x_hat + 0.5*(r1+r2)*dt_hat ; churn + prep next step       */
+  DSK_STAGE_KARRAS_LAST = 8 /* t+dt == 0: x = x_aux (Euler from t_hat, integrators.py:108-112) */
+};
+/* One fused elementwise pass of an integrator stage.  `noise` is an injected N(0,1) tensor
+ * array (fp32 [nrows][B,C,S], indexed by the step that consumes it) or NULL, in which case a
+ * counter-based Philox4x32-10 stream keyed by (seed, row, element) supplies it.  hist (may be NULL)
+ * is fp32 [nrows+1][B,C,S]; slot row+1 receives the new x when the stage completes a step
+ * (history[i+1], schedulers.py:86-87), slot 0 the scaled initial noise.
+ * precond_kind: 0 = EDMPreconditioner(sigma_data), 1 = NullPreconditioner. */
+int dsk_sampler_stage(int stage, float* x, float* x_aux, float* r1, const void* F, void* xin, float* cnoise,
+                      const float* tab, const int* row, const float* noise, uint64_t seed, float* hist,
+                      int B, int C, int64_t S, float sigma_data, float sigma_max, int precond_kind, int act_dtype,
+                      void* stream);
+int dsk_sampler_advance(int* row, void* stream);
+
+/* Integrator.step seam for foreign score functions (integrators.py:29-113; schedulers.py:266-274):
+ * out = a0*x + a1*r1 + a2*r2 + a3*z, fp32, null inputs skipped; out may alias any input. */
+int dsk_lincomb(float* out, int64_t n, const float* x, float a0, const float* r1, float a1, const float* r2, float a2,
+                const float* z, float a3, void* stream);
+/* N(0,1) draws from the same Philox4x32-10 stream the fused stages use: element i of stream
+ * `stream_id` (= step row) under `seed`.  Replaces torch.randn_like (integrators.py:68,105). */
+int dsk_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t stream_id, void* stream);
+
+/* ---- K1: convolution / GEMM ----------------------------------------------------------
+ * Replaces torch.nn.Conv2d/Conv3d(padding='same') in ResnetBlockC (nets/commonlayers.py:777-833),
+ * DownSampler/UpSampler (commonlayers.py:53-58,123-128), convin/convout (nets/punetg.py:203-214),
+ * ADM convs (nets/adm.py:268-284) and torch.nn.Linear / in/out projections of MultiheadAttention.
+ *
+ * in  : [B, Di, Hi, Wi, Cin]  (if up2: the conv sees nearest-upsampled x2 input, i.e. F.interpolate
+ *        fused into the gather: commonlayers.py:129,145)
+ * w   : packed weights. DSK_F32 path: fp32 [taps][Cin][Cout];  DSK_BF16 path: bf16 [taps][Cout][Cin]
+ * out : [B, D, H, W, Cout] ; y = conv(in) + bias[co] + chan_bias[b,co] + residual[b,..,co]
+ * ksize in {1,3}; ndim in {2,3} (ndim 2 => D = 1, taps = k*k).
+ */
+typedef struct {
+  int B, D, H, W;      /* OUTPUT spatial size (input is half of it when up2)            */
+  int Cin, Cout;
+  int ksize, ndim;
+  int up2;             /* 1: nearest x2 upsample fused into the input gather             */
+  int w_dtype;         /* DSK_F32: w is fp32 [taps][Cin][Cout] -> CUDA-core FFMA kernel (fp32 parity mode);
+                          DSK_BF16: w is bf16 [taps][Cout][Cin] -> tcgen05 implicit-GEMM kernel          */
+  int in_dtype;        /* dtype of `in`                                                   */
+  int out_dtype;       /* dtype of `out` and `residual`                                   */
+  int out_nchw_f32;    /* 1: write fp32 NC(D)HW (user layout) instead of channels-last    */
+} dsk_conv_desc;
+int dsk_conv_fwd(const dsk_conv_desc* d, const void* in, const void* w, const float* bias,
+                 const float* chan_bias, const void* residual, void* out, void* stream);
+/* repack a reference-layout weight [Cout, Cin, k(,k)(,k)] fp32 into the two packed layouts */
+int dsk_pack_conv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int taps, int dtype, void* stream);
+
+/* Batched C[b] = act(alpha * A[b] (MxK, row-major, lda) * B[b] + bias[n]) (act: 0 none, 1 SiLU, 2 ReLU);
+ * transB = 1: B is [N][K] row-major (C = A*B^T) ; transB = 0: B is [K][N].  fp32 CUDA-core path. */
+int dsk_gemm_f32(const float* A, const float* Bm, float* Cm, const float* bias, int M, int N, int K, int lda,
+                 int ldb, int ldc, int64_t strideA, int64_t strideB, int64_t strideC, int batch, int transB,
+                 float alpha, int act, void* stream);
+
+/* ---- K4: per-group norm + affine (+FiLM) + SiLU ---------------------------------------
+ * Replaces torch.nn.GroupNorm(G,C) / GroupRMSNorm(G,C) (+ SiLU) in ResnetBlockC
+ * (commonlayers.py:362-384, 824-831) and ADMBaseBlock (nets/adm.py:305-329).
+ * mode 0 = LayerNorm-style (mean/var, biased), 1 = RMS.  eps = 1e-5.
+ * x,y: [B, S, C]; G groups of C/G channels (G == C for PUNetG, G == 1 default for ADM).
+ * film_scale/film_shift: optional fp32 [B, C] (y = norm*film_scale + film_shift, adm.py:305-308).
+ * ws: workspace of dsk_norm_ws_bytes(B, S, C) bytes.
+ */
+int64_t dsk_norm_ws_bytes(int B, int64_t S, int C);
+int dsk_norm_act(const void* x, void* y, const float* gamma, const float* beta, const float* film_scale,
+                 const float* film_shift, void* ws, int B, int64_t S, int C, int G, int mode, int silu,
+                 int in_dtype, int out_dtype, void* stream);
+
+/* ---- K5: 2x pooling -------------------------------------------------------------------
+ * Replaces torch.nn.MaxPool{2,3}d(2) (commonlayers.py:60-63,81) / AvgPool (adm.py:361-371).
+ * x: [B, D, H, W, C] -> y: [B, D/2 (or 1), H/2, W/2, C] (floor, like torch). */
+int dsk_pool2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int is_max, int dtype,
+               void* stream);
+/* y = a + b (elementwise, same dtype); used for the additive U-Net skips (punetg.py:373,384) */
+int dsk_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* stream);
+/* NCHW fp32 <-> channels-last conversions at the module boundary */
+int dsk_nchw_to_cl(const float* x, void* y, int B, int C, int64_t S, int dtype, void* stream);
+int dsk_cl_to_nchw(const void* x, float* y, int B, int C, int64_t S, int dtype, void* stream);
+int dsk_cast(const void* x, void* y, int64_t n, int in_dtype, int out_dtype, void* stream);
+/* channel concat of two channels-last tensors (ADM 'concat' skips, adm.py:296-297) */
+int dsk_concat_channels(const void* a, const void* b, void* y, int64_t rows, int Ca, int Cb, int dtype,
+                        void* stream);
+
+/* ---- K6: time embedding ----------------------------------------------------------------
+ * Fourier features (commonlayers.py:175-190): out[b] = cat(sin(2*pi*t_b*W), cos(2*pi*t_b*W)), fp32. */
+int dsk_fourier(const float* t, const float* W, float* out, int B, int half, void* stream);
+/* Grouped small-batch linear: for g in [0,ngroups): Y_g[B,out_g] = act(X_g[B,in_g] W_g^T + b_g).
+ * Device arrays of pointers / sizes (one launch for the time MLP layer of every ResNet block;
+ * commonlayers.py:516-550, adm.py:331-343, nets/mlp.py:38-58).  act: 0 none, 1 SiLU, 2 ReLU. */
+int dsk_grouped_linear(const float* const* X, const float* const* W, const float* const* bias, float* const* Y,
+                       const int* in_dim, const int* out_dim, int ngroups, int max_out, int B, int act,
+                       void* stream);
+
+/* ---- K3: attention ----------------------------------------------------------------------
+ * softmax over the last dim of S[batch*rows, cols] in place (fp32), the middle of
+ * nn.MultiheadAttention (nets/attention.py:42-44,68): softmax(QK^T/sqrt(d)). */
+int dsk_softmax_rows(float* S, int64_t rows, int cols, void* stream);
+
+/* ---- K8/K9: training ---------------------------------------------------------------------
+ * EDM loss forward + dL/dF (karrasmodule.py:590-650; noisesamplers.py:30-33):
+ *   D = c_out*F + c_skip*(x+sigma*n);  L = mean(lambda(sigma) * l(D,x) * (1-mask)),
+ *   l = Huber(delta=1) (loss_kind 0) | MSE (loss_kind 1);  dF = dL/dF (same layout/dtype as F, fp32).
+ * loss_out: fp32 [1], must be zeroed by the caller.  mask may be NULL. */
+int dsk_edm_loss_fwd_bwd(const float* F, const float* x, const float* noise, const float* sigma,
+                         const float* mask, float* loss_out, float* dF, int B, int C, int64_t S,
+                         float sigma_data, int loss_kind, void* stream);
+/* Multi-tensor EMA: shadow_i <- lerp(shadow_i, p_i, 1-beta) (karras/ema.py:139-147) in one launch. */
+int dsk_ema_update(float* const* shadow, const float* const* param, const int64_t* numel, int ntensors,
+                   int64_t max_numel, float beta, void* stream);
+/* Multi-tensor AdamW (reference default optimizer, karrasmodule.py:497-500) fused with the EMA lerp
+ * (shadow may be NULL to skip EMA). */
+int dsk_adamw_ema_step(float* const* p, const float* const* g, float* const* m, float* const* v,
+                       float* const* shadow, const int64_t* numel, int ntensors, int64_t max_numel, float lr,
+                       float beta1, float beta2, float eps, float wd, int step, float ema_beta, float grad_scale,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFSCI_B200_H */

@@ -1,0 +1,231 @@
+"""GPU parity tests, kernel level: every C-ABI compute entry point against the CPU oracle / ATen fp32
+reference on seeded inputs.  Tolerances are stated per test (fp32 accumulation-order noise unless noted)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def relmax(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def to_cl(x):
+    """NC(D)HW cpu -> channels-last [B, D, H, W, C] on the GPU."""
+    if x.ndim == 4:
+        x = x.unsqueeze(2)
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+
+
+def from_cl(y, ndim):
+    y = y.float().cpu().permute(0, 4, 1, 2, 3)
+    return y.squeeze(2) if ndim == 2 else y
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from diffsci_b200 import ops as o
+    return o
+
+
+CONV_CASES = [
+    # ndim, B, Cin, Cout, spatial, k, up2
+    (2, 2, 8, 8, (12, 20), 3, False),
+    (2, 1, 1, 16, (28, 28), 3, False),      # convin-like (Cin = 1)
+    (2, 2, 16, 1, (7, 7), 3, False),        # convout-like (Cout = 1), odd spatial size
+    (2, 1, 3, 5, (9, 11), 3, False),        # ragged channels
+    (3, 2, 8, 16, (6, 8, 10), 3, False),
+    (3, 1, 16, 8, (4, 6, 8), 3, True),      # fused nearest x2 upsample
+    (2, 2, 8, 12, (8, 8), 3, True),
+    (2, 2, 24, 8, (5, 6), 1, False),        # 1x1 conv (ADM residual path)
+    (3, 1, 64, 64, (8, 8, 8), 3, False),    # C4-like channel count
+]
+
+
+@pytest.mark.parametrize("ndim,B,Cin,Cout,sp,k,up2", CONV_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_fwd(ops, ndim, B, Cin, Cout, sp, k, up2, dtype):
+    torch.manual_seed(1)
+    x = torch.randn(B, Cin, *sp)
+    w = torch.randn(Cout, Cin, *([k] * ndim)) / math.sqrt(Cin * k ** ndim)
+    b = torch.randn(Cout) * 0.1
+    xs = x.to(dtype).float()
+    xr = F.interpolate(xs, scale_factor=2, mode="nearest") if up2 else xs
+    ref = (F.conv2d if ndim == 2 else F.conv3d)(xr, w, b, padding=k // 2)
+    cb = torch.randn(B, Cout) * 0.3
+    res = torch.randn_like(ref).to(dtype).float()
+    ref = ref + cb.view(B, Cout, *([1] * ndim)) + res
+    pc = ops.PackedConv(w.to(DEV), b.to(DEV), ndim, torch.float32)
+    y = ops.conv(to_cl(x).to(dtype), pc, chan_bias=cb.to(DEV), residual=to_cl(res).to(dtype), up2=up2)
+    tol = 2e-5 if dtype == torch.float32 else 8e-3   # bf16: one rounding of the stored output
+    assert relmax(from_cl(y, ndim), ref) < tol
+    # NC(D)HW fp32 output variant (convout)
+    y2 = ops.conv(to_cl(x).to(dtype), pc, up2=up2, out_nchw=True)
+    ref2 = (F.conv2d if ndim == 2 else F.conv3d)(xr, w, b, padding=k // 2)
+    assert relmax(y2.cpu(), ref2) < 2e-5
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("B,C,G,sp", [(2, 8, 8, (5, 7)), (2, 16, 1, (6, 6)), (1, 64, 64, (4, 8, 8)), (3, 32, 4, (9,)),
+                                       (2, 256, 256, (16, 16))])
+def test_norm_act(ops, mode, B, C, G, sp):
+    from oracle import nets_oracle as N
+    torch.manual_seed(2)
+    x = torch.randn(B, C, *sp) * 2 + 3.0          # non-zero mean: exercises the variance cancellation
+    g, b = 1 + 0.1 * torch.randn(C), 0.1 * torch.randn(C)
+    fs, fh = torch.randn(B, C), torch.randn(B, C)
+    ref = F.group_norm(x, G, g, b, 1e-5) if mode == 0 else N.group_rms_norm(x, G, g, b)
+    xcl = x.reshape(B, C, -1).permute(0, 2, 1).contiguous().to(DEV)
+    y = ops.norm_act(xcl, g.to(DEV), b.to(DEV), G, mode, True)
+    assert relmax(y.cpu().permute(0, 2, 1).reshape(x.shape), F.silu(ref)) < 1e-5
+    y = ops.norm_act(xcl, g.to(DEV), b.to(DEV), G, mode, True, film_scale=fs.to(DEV), film_shift=fh.to(DEV))
+    shp = (B, C) + (1,) * len(sp)
+    assert relmax(y.cpu().permute(0, 2, 1).reshape(x.shape), F.silu(ref * fs.view(shp) + fh.view(shp))) < 1e-5
+    yb = ops.norm_act(xcl.bfloat16(), g.to(DEV), b.to(DEV), G, mode, False)
+    xb = x.bfloat16().float()
+    refb = F.group_norm(xb, G, g, b, 1e-5) if mode == 0 else N.group_rms_norm(xb, G, g, b)
+    assert relmax(yb.float().cpu().permute(0, 2, 1).reshape(x.shape), refb) < 8e-3
+
+
+@pytest.mark.parametrize("ndim,sp", [(2, (8, 10)), (2, (7, 9)), (3, (4, 6, 8))])
+@pytest.mark.parametrize("is_max", [True, False])
+def test_pool_add_layout(ops, ndim, sp, is_max):
+    torch.manual_seed(3)
+    x = torch.randn(2, 8, *sp)
+    fn = {(2, True): F.max_pool2d, (2, False): F.avg_pool2d, (3, True): F.max_pool3d, (3, False): F.avg_pool3d}[ndim, is_max]
+    y = ops.pool2x(to_cl(x), ndim, is_max)
+    assert relmax(from_cl(y, ndim), fn(x, 2)) < 1e-6
+    a = ops.add(to_cl(x), to_cl(2 * x))
+    assert relmax(from_cl(a, ndim), 3 * x) < 1e-6
+    cl = ops.nchw_to_cl(x.to(DEV), torch.float32, ndim)
+    assert torch.equal(cl.cpu(), to_cl(x).cpu())
+    assert torch.equal(ops.cl_to_nchw(cl, ndim).cpu(), x)
+    cc = ops.concat_channels(to_cl(x), to_cl(x[:, :3]))
+    assert torch.equal(from_cl(cc, ndim), torch.cat([x, x[:, :3]], 1))
+
+
+def test_fourier_and_grouped_linear(ops):
+    from oracle import nets_oracle as N
+    torch.manual_seed(4)
+    t = torch.tensor([-3.4, 0.0, 0.35, 2.19])        # c_noise range of EDM: 0.5*log(0.002..80)
+    W = torch.randn(32) * 30.0
+    out = ops.fourier(t.to(DEV), W.to(DEV))
+    assert float((out.cpu() - N.fourier(t, W)).abs().max()) < 2e-4   # |arg| ~ 1e3 rad: fp32 argument rounding
+    B = 5
+    xs = [torch.randn(B, k) for k in (16, 16, 64)]
+    ws = [torch.randn(n, k) / math.sqrt(k) for n, k in ((64, 16), (24, 16), (8, 64))]
+    bs = [torch.randn(w.shape[0]) for w in ws]
+    ys = [torch.empty(B, w.shape[0], device=DEV) for w in ws]
+    for act, fn in ((0, lambda v: v), (1, F.silu), (2, F.relu)):
+        g = ops.GroupedLinear([x.to(DEV) for x in xs], [w.to(DEV) for w in ws], [b.to(DEV) for b in bs], ys, act)
+        g.run()
+        for x, w, b, y in zip(xs, ws, bs, ys):
+            assert relmax(y.cpu(), fn(F.linear(x, w, b))) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,batch,transB", [(200, 70, 33, 1, True), (128, 64, 256, 3, True), (50, 130, 75, 2, False),
+                                                 (1000, 128, 3, 1, True)])
+def test_gemm_and_softmax(ops, M, N, K, batch, transB):
+    torch.manual_seed(5)
+    A = torch.randn(batch, M, K)
+    Bm = torch.randn(batch, N, K) if transB else torch.randn(batch, K, N)
+    bias = torch.randn(N)
+    ref = 0.7 * (A @ (Bm.transpose(1, 2) if transB else Bm)) + bias
+    out = torch.empty(batch, M, N, device=DEV)
+    ops.gemm(A.to(DEV), Bm.to(DEV), out, M=M, N=N, K=K, lda=K, ldb=K if transB else N, ldc=N, bias=bias.to(DEV),
+             transB=transB, alpha=0.7, batch=batch, strideA=M * K, strideB=N * K, strideC=M * N)
+    assert relmax(out.cpu(), ref) < 1e-5
+    sm = ops.softmax_rows(out.clone(), batch * M, N)
+    assert relmax(sm.cpu(), torch.softmax(ref, -1)) < 1e-5
+
+
+def test_attention(ops):
+    from oracle import nets_oracle as N
+    torch.manual_seed(6)
+    B, C, sp = 2, 32, (6, 7)
+    x = torch.randn(B, C, *sp)
+    sd = {"a.mhattn.in_proj_weight": torch.randn(3 * C, C) / math.sqrt(C), "a.mhattn.in_proj_bias": torch.randn(3 * C) * 0.1,
+          "a.mhattn.out_proj.weight": torch.randn(C, C) / math.sqrt(C), "a.mhattn.out_proj.bias": torch.randn(C) * 0.1}
+    Lq = sp[0] * sp[1]
+    for residual in (False, True):
+        ref = N.mha_self_attention(x, sd, "a.", residual)
+        f32 = dict(dtype=torch.float32, device=DEV)
+        bufs = dict(qkv=torch.empty(B * Lq, 3 * C, **f32), scores=torch.empty(B, Lq, Lq, **f32),
+                    ao=torch.empty(B * Lq, C, **f32), out=torch.empty(B, Lq, C, **f32))
+        tok = x.reshape(B, C, Lq).permute(0, 2, 1).contiguous().to(DEV)
+        o = ops.self_attention_f32(tok, *[sd[k].to(DEV) for k in sd], bufs, residual)
+        assert relmax(o.cpu().permute(0, 2, 1).reshape(x.shape), ref) < 1e-5
+
+
+def test_lincomb_and_philox(ops):
+    torch.manual_seed(7)
+    x, r1, r2, z = (torch.randn(1000) for _ in range(4))
+    o = ops.lincomb(x.to(DEV), 1.0, r1.to(DEV), -0.3, r2.to(DEV), 0.7, z.to(DEV), 2.0)
+    assert relmax(o.cpu(), x - 0.3 * r1 + 0.7 * r2 + 2.0 * z) < 1e-6
+    n = ops.philox_normal((1 << 20,), 1234, 3, DEV).cpu()
+    assert abs(float(n.mean())) < 5e-3 and abs(float(n.std()) - 1) < 5e-3
+    assert abs(float((n ** 3).mean())) < 2e-2 and abs(float((n ** 4).mean()) - 3) < 5e-2
+    assert torch.equal(n, ops.philox_normal((1 << 20,), 1234, 3, DEV).cpu())          # counter-based: reproducible
+    assert not torch.equal(n, ops.philox_normal((1 << 20,), 1234, 4, DEV).cpu())      # new stream id -> new draws
+    # Kolmogorov-Smirnov distance against the normal CDF
+    s, _ = torch.sort(n.double())
+    cdf = 0.5 * (1 + torch.erf(s / math.sqrt(2)))
+    ks = float((cdf - torch.arange(1, len(s) + 1).double() / len(s)).abs().max())
+    assert ks < 2e-3
+
+
+def test_loss_ema_adamw():
+    from diffsci_b200._lib import lib, check, ptr, stream
+    from oracle import karras_oracle as K
+    torch.manual_seed(8)
+    B, shape = 3, (2, 5, 6)
+    x, noise = torch.randn(B, *shape) * 0.5, torch.randn(B, *shape)
+    Fv = torch.randn(B, *shape, requires_grad=True)
+    sigma = torch.exp(torch.randn(B) * 1.2 - 1.2)
+    mask = (torch.rand(B, *shape) > 0.6).float()
+    for kind, name in ((0, "huber"), (1, "mse")):
+        for m in (None, mask):
+            ref = K.edm_loss(lambda xs, cn: Fv, x, sigma, noise, name, m)
+            (gref,) = torch.autograd.grad(ref, Fv)
+            loss = torch.zeros((), device=DEV)
+            dF = torch.empty(B, *shape, device=DEV)
+            check(lib.dsk_edm_loss_fwd_bwd(ptr(Fv.detach().to(DEV)), ptr(x.to(DEV)), ptr(noise.to(DEV)), ptr(sigma.to(DEV)),
+                                           ptr(None if m is None else m.to(DEV)), ptr(loss), ptr(dF), B, shape[0],
+                                           shape[1] * shape[2], 0.5, kind, stream()))
+            assert abs(float(loss) - float(ref)) < 2e-5 * abs(float(ref))
+            assert relmax(dF.cpu(), gref) < 2e-5
+    # EMA + AdamW multi-tensor kernels
+    ps = [torch.randn(n) for n in (7, 1000, 33)]
+    gs = [torch.randn_like(p) for p in ps]
+    sh = [torch.randn_like(p) for p in ps]
+    dps, dgs, dsh = [[t.to(DEV) for t in ts] for ts in (ps, gs, sh)]
+    mk = lambda ts: torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64, device=DEV)  # noqa: E731
+    numel = torch.tensor([p.numel() for p in ps], dtype=torch.int64, device=DEV)
+    check(lib.dsk_ema_update(ptr(mk(dsh)), ptr(mk(dps)), ptr(numel), 3, 1000, 0.9, stream()))
+    for s_, p_, d_ in zip(sh, ps, dsh):
+        assert relmax(d_.cpu(), K.ema_update(s_, p_, 0.9)) < 1e-6
+    ms, vs = [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps]
+    dms, dvs = [t.to(DEV) for t in ms], [t.to(DEV) for t in vs]
+    shadow = [t.clone() for t in dsh]
+    for step in (1, 2, 3):
+        check(lib.dsk_adamw_ema_step(ptr(mk(dps)), ptr(mk(dgs)), ptr(mk(dms)), ptr(mk(dvs)), ptr(mk(shadow)), ptr(numel), 3,
+                                     1000, 1e-3, 0.9, 0.999, 1e-8, 1e-4, step, 0.99, 1.0, stream()))
+        for i in range(3):
+            ps[i], ms[i], vs[i] = K.adamw_step(ps[i], gs[i], ms[i], vs[i], step)
+    for i in range(3):
+        assert relmax(dps[i].cpu(), ps[i]) < 1e-5
+        assert relmax(dms[i].cpu(), ms[i]) < 1e-5 and relmax(dvs[i].cpu(), vs[i]) < 1e-5
+    ref = [torch.optim.AdamW([torch.nn.Parameter(p.clone())], lr=1e-3, weight_decay=1e-4) for p in
+           (torch.randn(5),)]  # sanity: oracle adamw == torch.optim.AdamW
+    p0 = ref[0].param_groups[0]["params"][0]
+    g0 = torch.randn(5)
+    start = p0.detach().clone()
+    p0.grad = g0.clone()
+    ref[0].step()
+    pe, _, _ = K.adamw_step(start, g0, torch.zeros(5), torch.zeros(5), 1)
+    assert relmax(pe, p0.detach()) < 1e-6

@@ -1,0 +1,134 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol of include/diffsci_b200.h; host-side
+logic (step tables, configs, state-dict layout, chunking, EMA schedules, batch sharding) matches the
+reference's golden vectors.  No compute call is made (no GPU here)."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    from diffsci_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "diffsci_b200.h")).read()
+    declared = set(re.findall(r"\b(dsk_[a-z0-9_]+)\s*\(", header))
+    declared -= {"dsk_conv_desc"}
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(_lib.lib, name), f"{name} declared in the header but not exported by the .so"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_lib.SIGNATURES) <= declared
+    assert _lib.lib.dsk_version() >= 100
+    # no GPU in this container: the device check must fail loudly, not fall back
+    if not torch.cuda.is_available():
+        assert _lib.lib.dsk_check_device(0) != 0 and len(_lib.last_error()) > 0
+
+
+def test_no_cpu_fallback():
+    import diffsci_b200 as d
+    net = d.PUNetG(d.PUNetGConfig(model_channels=8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.randn(1, 1, 8, 8), torch.zeros(1))
+    mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm())
+    with pytest.raises(RuntimeError):
+        mod.get_denoiser(torch.randn(1, 1, 8, 8), torch.ones(1))
+
+
+def test_step_table_matches_reference_schedule(golden):
+    import diffsci_b200 as d
+    from diffsci_b200._lib import TAB_T, TAB_DT, TAB_THAT, TAB_LANG, TAB_NOISE, TAB_SQDT, TAB_TNEXT, TAB_CHURN
+    g = golden("numerics")
+    sch = d.EDMScheduler()
+    for n, ref in g["steps"].items():
+        assert torch.equal(sch.create_steps(n), ref), n            # bit-identical to EDMScheduler.create_steps
+    n = 18
+    t = g["steps"][n + 1]
+    tab = sch.step_table(n, d.HeunIntegrator())
+    assert tab.shape == (n + 1, 8)
+    assert torch.equal(tab[:n, TAB_T], t[:n]) and torch.equal(tab[:n, TAB_DT], torch.diff(t))
+    assert torch.equal(tab[:n - 1, TAB_TNEXT], t[1:n]) and float(tab[n - 1, TAB_TNEXT]) == 0.0
+    assert float((tab[n - 1, TAB_T] + tab[n - 1, TAB_DT])) == 0.0   # last step lands exactly on sigma = 0
+    assert float(tab[n].abs().sum()) == 0.0
+    # Euler-Maruyama columns: langevin_factor = const * t inside the interval, noise = sqrt(2 lang)
+    sch.langevin_const, sch.langevin_interval = 0.5, (0.1, 10.0)
+    tab = sch.step_table(n, d.EulerMaruyamaIntegrator())
+    inside = (t[:n] > 0.1) & (t[:n] < 10.0)
+    assert torch.equal(tab[:n, TAB_LANG], torch.where(inside, 0.5 * t[:n], torch.zeros(n)))
+    assert torch.allclose(tab[:n, TAB_NOISE], torch.sqrt(2 * tab[:n, TAB_LANG]))
+    assert torch.equal(tab[:n, TAB_SQDT], torch.sqrt(torch.abs(torch.diff(t))))
+    # Karras churn: gamma = min(S_churn/N, sqrt(2)-1) inside [S_tmin, S_tmax]
+    tab = sch.step_table(n, d.KarrasIntegrator())
+    gamma = min(40 / n, 2 ** 0.5 - 1)
+    for i in range(n):
+        gi = gamma if 0.05 <= float(t[i]) <= 50 else 0.0
+        assert abs(float(tab[i, TAB_THAT]) - float(t[i]) * (1 + gi)) <= 1e-6 * float(t[i])
+        want = ((float(t[i]) * (1 + gi)) ** 2 - float(t[i]) ** 2) ** 0.5 * 1.003
+        assert abs(float(tab[i, TAB_CHURN]) - want) <= 2e-5 * max(want, 1e-3)
+    assert torch.equal(tab[:n - 1, TAB_TNEXT], tab[1:n, TAB_THAT])
+    with pytest.raises(ValueError):
+        sch.step_table(1)
+
+
+def test_scalar_api_matches_reference(golden):
+    import diffsci_b200 as d
+    g = golden("numerics")
+    pre, ns = d.EDMPreconditioner(), d.EDMNoiseSampler()
+    s = g["sigma"]
+    assert torch.equal(pre.input_scaling(s), g["c_in"]) and torch.equal(pre.output_scaling(s), g["c_out"])
+    assert torch.equal(pre.skip_scaling(s), g["c_skip"]) and torch.equal(pre.noise_conditioner(s), g["c_noise"])
+    assert torch.equal(ns.loss_weighting(s), g["loss_weight"])
+    torch.manual_seed(7)
+    assert torch.equal(ns.sample(16), g["sigma_from_xi"])          # same CPU-generator draw as the reference
+    from diffsci_b200.models.karras import ema
+    for sd_, v in g["ema_power_exp"].items():
+        assert ema._power_function_exp_from_std(sd_) == v
+    for (sd_, n), v in g["ema_power_beta"].items():
+        assert ema._power_function_beta(sd_, n) == v
+
+
+@pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8", "punetg2d_multi", "mlp_silu"])
+def test_state_dict_layout_is_the_reference_layout(golden, name):
+    import diffsci_b200 as d
+    g = golden(name)
+    if g["kind"] == "punetg":
+        net = d.PUNetG(d.PUNetGConfig(**g["cfg"]))
+    else:
+        net = d.MLPUncond(g["cfg"]["dim"], g["cfg"]["hidden_dims"], torch.nn.SiLU())
+    got = [(k, list(v.shape)) for k, v in net.state_dict().items()]
+    assert got == [(k, list(s)) for k, s in g["manifest"]]
+
+
+def test_default_punetg_has_213_tensors():
+    import diffsci_b200 as d
+    sd = d.PUNetG(d.PUNetGConfig(dimension=3)).state_dict()          # 213 tensors, 29.9 M params
+    assert len(sd) == 213
+    assert abs(sum(v.numel() for v in sd.values()) / 1e6 - 29.9) < 0.1
+
+
+def test_config_and_utils():
+    import diffsci_b200 as d
+    from diffsci_b200.utils import get_minibatch_sizes
+    from diffsci_b200.torchutils import broadcast_from_below
+    assert get_minibatch_sizes(10, 4) == [4, 4, 2] and get_minibatch_sizes(8, 4) == [4, 4]
+    assert broadcast_from_below(torch.ones(3), torch.ones(3, 4, 5)).shape == (3, 1, 1)
+    with pytest.raises(ValueError):
+        broadcast_from_below(torch.ones(3, 4), torch.ones(3))
+    c = d.PUNetGConfig(dimension=3, model_channels=32)
+    assert d.PUNetGConfig.from_description(c.export_description()).export_description() == c.export_description()
+    assert c.extended_channel_expansion == [1, 2, 4]
+    k = d.KarrasModuleConfig.from_edm(sigma_data=0.4, loss_metric="mse")
+    k2 = d.KarrasModuleConfig.load_from_description_with_tag(k.export_description())
+    assert k2.tag == "edm" and float(k2.preconditioner.sigma_data) == pytest.approx(0.4) and k2.loss_metric == "mse"
+    assert isinstance(d.name_to_integrator("heun"), d.HeunIntegrator)
+    assert d.name_to_integrator("euler-maruyama").stochastic and d.name_to_integrator("karras").need_fns
+    with pytest.raises(ValueError):
+        d.name_to_integrator("rk4")
+    with pytest.raises(NotImplementedError):
+        d.PUNetG(d.PUNetGConfig(convolution_type="circular"))
+    sch = d.EDMScheduler()
+    sch.set_temporary_integrator("euler")
+    assert isinstance(sch.integrator, d.EulerIntegrator)
+    sch.unset_temporary_integrator()
+    assert isinstance(sch.integrator, d.HeunIntegrator) and sch.maximum_scale == 80.0
