@@ -5,7 +5,7 @@ Importing the package loads ``libdiffsci_b200.so`` (hand-written CUDA behind a C
 PyTorch-eager fallback on the product path.
 """
 # tcgen05 implicit-GEMM convolution path for bf16 precision (csrc/conv_tc.cu)
-TC_CONV_ENABLED = False
+TC_CONV_ENABLED = True
 
 from . import _lib  # noqa: E402,F401  (raises ImportError when the shared library is missing)
 from . import ops, models  # noqa: E402,F401

@@ -1,10 +1,420 @@
-// conv_tc.cu -- K1 (bf16 throughput mode): tcgen05/TMEM implicit-GEMM convolution fed by TMA.
-// (placeholder until the tcgen05 kernel lands: reports UNSUPPORTED, never falls back silently)
+// conv_tc.cu -- K1 (bf16 throughput mode): implicit-GEMM 3x3(x3) convolution on the 5th-gen tensor
+// cores (tcgen05.mma, accumulators in TMEM) fed by TMA.  sm_100a only.
+//
+// Reference call sites: torch.nn.Conv2d/Conv3d(k=3, padding='same') in ResnetBlockC
+// (nets/commonlayers.py:777-833), DownSampler/UpSampler (commonlayers.py:53-58,123-128).
+//
+// Formulation.  Activations are channels-last bf16 [B, D, H, W, C]; a pixel is one 128-byte row per
+// 64-channel chunk.  A CTA tile is 16 (h) x 8 (w) output pixels (= the 128 rows of one UMMA, M = 128)
+// on P consecutive d-planes, all N_TILE output channels; accumulators: P x N_TILE fp32 TMEM columns.
+// For every input plane the tile touches, ONE TMA box load brings the (16+2) x (8+2) halo'd patch of a
+// 64-channel chunk into shared memory (zero padding = TMA out-of-bounds fill, signed coordinates).
+// The 9 in-plane taps are then just 9 shifted *views* of that patch: the UMMA shared-memory descriptor
+// (K-major, SWIZZLE_128B) takes start = patch + (kh*10 + kw)*128 B and SBO = 10*128 B -- the hardware
+// swizzle is a function of the absolute smem address (verified by tests/cuda/umma_probe.cu), so views
+// that are not 1024-B aligned read exactly "pixel rows r .. r+7" of each 8-row group.  No im2col matrix
+// is ever materialised, in HBM or in shared memory: each activation byte crosses L2->SM about 1.4x
+// (halo) x (P+2)/P (depth halo) instead of 27x.
+// Weights are bf16 [tap][Cout][Cin] (K-major B operand), streamed per tap through a TMA ring and shared
+// by the P planes of the tile.
+//
+// Pipeline (persistent CTAs, 1 per SM, static tile schedule):
+//   warp 0   TMA producer, activations (patch ring, per-patch full/empty mbarriers)
+//   warp 1   TMA producer, weights     (tap ring)
+//   warp 2   MMA issuer (one elected thread), owns the TMEM allocation
+//   warps 4-7 epilogue: tcgen05.ld -> +bias +time-embedding vector +residual -> bf16 -> global
+// TMEM accumulators are double buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+
 #include "common.cuh"
+
+namespace dsk {
+
+constexpr int TC_BW = 8, TC_BH = 16;                 // output tile (w, h) = 128 rows
+constexpr int TC_PW = TC_BW + 2, TC_PH = TC_BH + 2;  // halo'd patch
+constexpr int TC_PATCH_BYTES = TC_PW * TC_PH * 128;  // 23040
+constexpr int TC_PATCH_STRIDE = 23552;               // rounded up to 1024
+constexpr int TC_THREADS = 256;
+
+struct TcParams {
+  int B, D, H, W, Cin, Cout;
+  int KD;                 // 3 for 3-D convs, 1 for 2-D (then D is the batch-of-planes axis)
+  int tiles_w, tiles_h, groups_d, n_tiles, total_tiles;
+  const float* bias;      // [Cout] or null
+  const float* chan_bias; // [B][Cout] or null
+  const __nv_bfloat16* residual;  // like out, or null
+  __nv_bfloat16* out;     // [B, D, H, W, Cout]
+  int planes_per_sample;  // D for 3-D; 1 for 2-D  (chan_bias row = plane / planes_per_sample)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+#ifdef DSK_DEBUG_TIMEOUT
+  for (long spin = 0; spin < (1L << 28) && !ok; ++spin)
+#else
+  while (!ok)
+#endif
+  {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  }
+#ifdef DSK_DEBUG_TIMEOUT
+  if (!ok) { printf("conv_tc: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x); __trap(); }
+#endif
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp bit layout)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct TileCoord {
+  int w0, h0, d0, b, n0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t, int n_tile_size, int P) {
+  TileCoord c;
+  c.w0 = (t % p.tiles_w) * TC_BW; t /= p.tiles_w;
+  c.h0 = (t % p.tiles_h) * TC_BH; t /= p.tiles_h;
+  c.d0 = (t % p.groups_d) * P;    t /= p.groups_d;
+  c.b = t % p.B;                  t /= p.B;
+  c.n0 = t * n_tile_size;
+  return c;
+}
+
+// N_TILE: output channels per CTA tile (64 | 128); P: planes per tile; NA: patch ring depth; NB: weight ring depth
+template <int N_TILE, int P, int NA, int NB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                   // NA patches
+  uint8_t* sB = smem + (size_t)NA * TC_PATCH_STRIDE;    // NB weight tiles of N_TILE x 128 B
+  constexpr int B_BYTES = N_TILE * 128;
+  __shared__ uint64_t full_a[NA], empty_a[NA], full_b[NB], empty_b[NB], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  constexpr uint32_t TMEM_COLS = 2 * P * N_TILE;        // double-buffered accumulators
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KD = p.KD, NJ = P + KD - 1;                 // patches per (tile, chunk)
+  const int nchunks = p.Cin / 64;
+  const int dpad = KD >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapW)) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer: activation patches =====================
+    if (lane == 0) {
+      uint32_t seq = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(p, t, N_TILE, P);
+        for (int c = 0; c < nchunks; ++c)
+          for (int j = 0; j < NJ; ++j, ++seq) {
+            const uint32_t slot = seq % NA, ph = (seq / NA) & 1;
+            mbar_wait(&empty_a[slot], ph ^ 1);
+            mbar_expect_tx(&full_a[slot], TC_PATCH_BYTES);
+            asm volatile(
+                "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+                    smem_u32(sA + (size_t)slot * TC_PATCH_STRIDE)),
+                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(c * 64), "r"(tc.w0 - 1), "r"(tc.h0 - 1), "r"(tc.d0 + j - dpad), "r"(tc.b),
+                "r"(smem_u32(&full_a[slot]))
+                : "memory");
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== TMA producer: weight taps =====================
+    if (lane == 0) {
+      uint32_t seq = 0;
+      const int ntaps = KD * 9;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(p, t, N_TILE, P);
+        for (int c = 0; c < nchunks; ++c)
+          for (int tap = 0; tap < ntaps; ++tap, ++seq) {
+            const uint32_t slot = seq % NB, ph = (seq / NB) & 1;
+            mbar_wait(&empty_b[slot], ph ^ 1);
+            mbar_expect_tx(&full_b[slot], B_BYTES);
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                    smem_u32(sB + (size_t)slot * B_BYTES)),
+                "l"(reinterpret_cast<uint64_t>(&tmapW)), "r"(c * 64), "r"(tap * p.Cout + tc.n0), "r"(smem_u32(&full_b[slot]))
+                : "memory");
+          }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t seq_a = 0, seq_b = 0, it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);               // epilogue has drained this accumulator set
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_acc = tmem_base + as * (P * N_TILE);
+        for (int c = 0; c < nchunks; ++c) {
+          const uint32_t seq_c = seq_a;                    // first patch of this (tile, chunk)
+          for (int kd = 0; kd < KD; ++kd) {
+            // patches first needed at this kd: j = 0..P-1 at kd == 0, else j = P-1+kd
+            const int jlo = kd == 0 ? 0 : P - 1 + kd, jhi = P - 1 + kd;
+            for (int j = jlo; j <= jhi; ++j) {
+              const uint32_t s = seq_c + j;
+              mbar_wait(&full_a[s % NA], (s / NA) & 1);
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kh = 0; kh < 3; ++kh)
+              for (int kw = 0; kw < 3; ++kw, ++seq_b) {
+                const uint32_t bs = seq_b % NB;
+                mbar_wait(&full_b[bs], (seq_b / NB) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t b_addr = smem_u32(sB + (size_t)bs * B_BYTES);
+#pragma unroll
+                for (int pp = 0; pp < P; ++pp) {
+                  const uint32_t s = seq_c + pp + kd;
+                  const uint32_t a_addr = smem_u32(sA + (size_t)(s % NA) * TC_PATCH_STRIDE) + (kh * TC_PW + kw) * 128;
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4) {
+                    const uint32_t acc = (c | kd | kh | kw | k4) != 0;
+                    umma_bf16(tmem_acc + pp * N_TILE, umma_desc(a_addr + k4 * 32, TC_PW * 128), umma_desc(b_addr + k4 * 32, 1024),
+                              idesc, acc);
+                  }
+                }
+                umma_commit(&empty_b[bs]);                 // weight slot free once these MMAs retire
+              }
+            // patches whose last use was this kd
+            const int rlo = kd, rhi = (kd == KD - 1) ? NJ - 1 : kd;
+            for (int j = rlo; j <= rhi; ++j) umma_commit(&empty_a[(seq_c + j) % NA]);
+          }
+          seq_a += NJ;
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                               // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;                        // accumulator row = pixel of the 16x8 tile
+    const int line = row >> 3, wp = row & 7;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const TileCoord tc = tile_coord(p, t, N_TILE, P);
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(&acc_full[as], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int h = tc.h0 + line, w = tc.w0 + wp;
+      const bool in_hw = h < p.H && w < p.W;
+#pragma unroll
+      for (int pp = 0; pp < P; ++pp) {
+        const int d = tc.d0 + pp;
+        const bool valid = in_hw && d < p.D;
+        const int64_t pix = (((int64_t)tc.b * p.D + d) * p.H + h) * p.W + w;
+        const int brow = (tc.b * p.D + d) / p.planes_per_sample;
+        const uint32_t taddr = tmem_base + as * (P * N_TILE) + pp * N_TILE + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+          uint32_t v[32];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(taddr + c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (valid) {
+            const int n = tc.n0 + c0;
+            __nv_bfloat16* optr = p.out + pix * p.Cout + n;
+            const __nv_bfloat16* rptr = p.residual != nullptr ? p.residual + pix * p.Cout + n : nullptr;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {                  // 4 x (8 channels = 16 B)
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float x = __uint_as_float(v[g * 8 + e]);
+                if (p.bias != nullptr) x += __ldg(p.bias + n + g * 8 + e);
+                if (p.chan_bias != nullptr) x += __ldg(p.chan_bias + (int64_t)brow * p.Cout + n + g * 8 + e);
+                f[e] = x;
+              }
+              if (rptr != nullptr) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(rptr + g * 8);
+                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { f[2 * e] += __low2float(rh[e]); f[2 * e + 1] += __high2float(rh[e]); }
+              }
+              uint4 o;
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              *reinterpret_cast<uint4*>(optr + g * 8) = o;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);          // 4 epilogue warps -> count 4
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+}
+
+// nearest x2 upsample of a channels-last bf16 tensor (input of the UpSampler conv on the tcgen05 path)
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int D, int H, int W,
+                                                          int C8, int ndim) {
+  const int Do = ndim == 3 ? D * 2 : D, Ho = H * 2, Wo = W * 2;
+  const int64_t total = (int64_t)B * Do * Ho * Wo * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C8);
+    int64_t r = i / C8;
+    int w = (int)(r % Wo); r /= Wo;
+    int h = (int)(r % Ho); r /= Ho;
+    int d = (int)(r % Do);
+    int b = (int)(r / Do);
+    const int ds = ndim == 3 ? d >> 1 : d;
+    y[i] = x[((((int64_t)b * D + ds) * H + (h >> 1)) * W + (w >> 1)) * C8 + c];
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    cudaDriverEntryPointQueryResult q;
+    void* ptr = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+template <int N_TILE, int P, int NA, int NB>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const TcParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)NA * TC_PATCH_STRIDE + (size_t)NB * N_TILE * 128 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<N_TILE, P, NA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e)); return DSK_ERR_CUDA; }
+    configured = true;
+  }
+  const int grid = p.total_tiles < DSK_NUM_SMS ? p.total_tiles : DSK_NUM_SMS;
+  DSK_LAUNCH((conv_tc_kernel<N_TILE, P, NA, NB>), grid, TC_THREADS, smem, st, ta, tw, p);
+  return DSK_OK;
+}
+
+}  // namespace dsk
+
 using namespace dsk;
+
+extern "C" int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, void* stream) {
+  DSK_REQUIRE(x && y && B > 0 && D > 0 && H > 0 && W > 0 && C > 0, "dsk_upsample2x: bad arguments");
+  DSK_REQUIRE(dtype == DSK_BF16 && C % 8 == 0, "dsk_upsample2x: bf16 with C %% 8 == 0 only (got dtype %d, C %d)", dtype, C);
+  const int64_t total = (int64_t)B * (ndim == 3 ? 2 * D : D) * 2 * H * 2 * W * (C / 8);
+  DSK_LAUNCH(upsample2x_kernel, grid_for(total, 256, 16), 256, 0, as_stream(stream), (const uint4*)x, (uint4*)y, B, D, H, W, C / 8, ndim);
+  return DSK_OK;
+}
+
 extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const void* w, const float* bias,
                                const float* chan_bias, const void* residual, void* out, void* stream) {
-  (void)d; (void)in; (void)w; (void)bias; (void)chan_bias; (void)residual; (void)out; (void)stream;
-  set_error("dsk_conv_fwd: the tcgen05 (bf16-weight) path does not support this shape yet");
-  return DSK_ERR_UNSUPPORTED;
+  DSK_REQUIRE(d && in && w && out, "dsk_conv_fwd(tc): null pointer");
+  if (d->ksize != 3 || d->up2 || d->out_nchw_f32 || d->in_dtype != DSK_BF16 || d->out_dtype != DSK_BF16 || d->Cin % 64 != 0 ||
+      d->Cout % 64 != 0) {
+    set_error("dsk_conv_fwd: the tcgen05 path takes k=3, bf16 in/out, Cin %% 64 == 0, Cout %% 64 == 0, no fused upsample "
+              "(got k=%d Cin=%d Cout=%d up2=%d in=%d out=%d nchw=%d)", d->ksize, d->Cin, d->Cout, d->up2, d->in_dtype, d->out_dtype,
+              d->out_nchw_f32);
+    return DSK_ERR_UNSUPPORTED;
+  }
+  DSK_REQUIRE((d->ndim == 2 && d->D == 1) || d->ndim == 3, "dsk_conv_fwd(tc): bad ndim/D");
+  EncodeTiledFn encode = get_encode();
+  DSK_REQUIRE(encode != nullptr, "dsk_conv_fwd(tc): cuTensorMapEncodeTiled is unavailable");
+  // 2-D: the batch is the plane axis (no depth taps); 3-D: planes = D with zero padding per sample
+  const int KD = d->ndim == 3 ? 3 : 1;
+  const int planes = d->ndim == 3 ? d->D : d->B;
+  const int batch = d->ndim == 3 ? d->B : 1;
+  CUtensorMap ta, tw;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)planes, (cuuint64_t)batch};
+    cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->W * d->Cin * 2, (cuuint64_t)d->H * d->W * d->Cin * 2,
+                             (cuuint64_t)planes * d->H * d->W * d->Cin * 2};
+    cuuint32_t box[5] = {64, TC_PW, TC_PH, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DSK_REQUIRE(r == CUDA_SUCCESS, "dsk_conv_fwd(tc): activation tensor map failed (CUresult %d)", (int)r);
+  }
+  const int ntaps = KD * 9;
+  const int n_tile = d->Cout % 128 == 0 ? 128 : 64;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)ntaps * d->Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)d->Cin * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)n_tile};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DSK_REQUIRE(r == CUDA_SUCCESS, "dsk_conv_fwd(tc): weight tensor map failed (CUresult %d)", (int)r);
+  }
+  TcParams p;
+  p.B = batch; p.D = planes; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.KD = KD;
+  constexpr int P = 2;
+  p.tiles_w = (d->W + TC_BW - 1) / TC_BW;
+  p.tiles_h = (d->H + TC_BH - 1) / TC_BH;
+  p.groups_d = (planes + P - 1) / P;
+  p.n_tiles = d->Cout / n_tile;
+  p.total_tiles = p.tiles_w * p.tiles_h * p.groups_d * batch * p.n_tiles;
+  p.bias = bias; p.chan_bias = chan_bias;
+  p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
+  p.planes_per_sample = d->ndim == 3 ? d->D : 1;
+  cudaStream_t st = as_stream(stream);
+  // smem: N_TILE=64: 6 patches (138 KB) + 8 taps x 8 KB (64 KB) = 202 KB; N_TILE=128: 6 patches + 5 x 16 KB = 218 KB
+  if (n_tile == 64) return launch_tc<64, P, 6, 8>(ta, tw, p, st);
+  return launch_tc<128, P, 6, 5>(ta, tw, p, st);
 }

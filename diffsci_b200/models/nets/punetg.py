@@ -30,10 +30,10 @@ _NORM_MODE = {"GroupLN": 0, "GroupRMS": 1}
 DEFAULT_PRECISION = "fp32"
 
 
-def _tc_eligible(cin: int, cout: int) -> bool:
+def _tc_eligible(cin: int, cout: int, ksize: int = 3) -> bool:
     """Shapes the tcgen05 implicit-GEMM kernel takes (see csrc/conv_tc.cu)."""
-    from ... import TC_CONV_ENABLED
-    return TC_CONV_ENABLED and cin % 64 == 0 and cout % 64 == 0 and cout <= 256
+    import diffsci_b200
+    return diffsci_b200.TC_CONV_ENABLED and ksize == 3 and cin % 64 == 0 and cout % 64 == 0
 
 
 class ResnetBlockParams(_Holder):
@@ -175,7 +175,7 @@ class _Plan:
             return torch.empty((B,) + sp[l] + (cc,), dtype=dtype, device=dev)
 
         def pack(cp):
-            wd = torch.bfloat16 if (precision == "bf16" and _tc_eligible(cp.cin, cp.cout)) else torch.float32
+            wd = torch.bfloat16 if (precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize)) else torch.float32
             return ops.PackedConv(cp.weight, cp.bias, nd, wd)
 
         self.xin = buf(0, c.input_channels)
@@ -184,6 +184,9 @@ class _Plan:
         self.N = [buf(l, ch[l]) for l in range(nlev + 1)]          # norm+SiLU output == conv input
         self.Y = [buf(l, ch[l]) for l in range(nlev + 1)]          # conv1 output
         self.P = [buf(l + 1, ch[l]) for l in range(nlev)]          # pooled
+        # the tcgen05 conv has no fused upsample: materialise F.interpolate(x, 2) for those layers
+        self.U = [buf(l, ch[l + 1]) if (precision == "bf16" and _tc_eligible(ch[l + 1], ch[l], c.transition_kernel_size))
+                  else None for l in range(nlev)]
         self.XA = buf(nlev, ch[nlev])
         self.XA2 = buf(nlev, ch[nlev])
         self.F = buf(0, c.output_channels)
@@ -288,7 +291,11 @@ class _Plan:
         for i in range(nlev):
             l = nlev - 1 - i
             # conv(F.interpolate(x, 2)) + skip, fused (commonlayers.py:145; punetg.py:372-373)
-            x = ops.conv(x, self.pc_up[i], out=self.XU[l], residual=self.X[l], up2=True)
+            if self.U[l] is not None:
+                u = ops.upsample2x(x, self.ndim, out=self.U[l])
+                x = ops.conv(u, self.pc_up[i], out=self.XU[l], residual=self.X[l])
+            else:
+                x = ops.conv(x, self.pc_up[i], out=self.XU[l], residual=self.X[l], up2=True)
             for blk in net.upward_blocks[i]:
                 x = self._resblock(x, blk, l, x)
         if out_nchw is not None:

@@ -71,6 +71,16 @@ def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, ch
     return out
 
 
+def upsample2x(x: torch.Tensor, ndim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Nearest x2 upsample (bf16 channels-last), input of the tcgen05 UpSampler conv (dsk_upsample2x)."""
+    require_cuda(x, "upsample input")
+    B, D, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, D * 2 if ndim == 3 else D, H * 2, W * 2, Cc), dtype=x.dtype, device=x.device)
+    check(lib.dsk_upsample2x(ptr(x), ptr(out), B, D, H, W, Cc, ndim, dt_code(x.dtype), stream()))
+    return out
+
+
 def gemm(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, lda: int, ldb: int, ldc: int,
          bias: Optional[torch.Tensor] = None, transB: bool = True, alpha: float = 1.0, act: int = 0, batch: int = 1,
          strideA: int = 0, strideB: int = 0, strideC: int = 0, a_off: int = 0, b_off: int = 0) -> torch.Tensor:

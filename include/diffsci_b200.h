@@ -132,6 +132,9 @@ typedef struct {
 } dsk_conv_desc;
 int dsk_conv_fwd(const dsk_conv_desc* d, const void* in, const void* w, const float* bias,
                  const float* chan_bias, const void* residual, void* out, void* stream);
+/* nearest x2 upsample of a channels-last tensor (torch.nn.Upsample(scale_factor=2), commonlayers.py:129):
+ * only needed in front of the tcgen05 conv; the FFMA conv fuses it into its gather (up2). bf16, C % 8 == 0. */
+int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, void* stream);
 /* repack a reference-layout weight [Cout, Cin, k(,k)(,k)] fp32 into the two packed layouts */
 int dsk_pack_conv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int taps, int dtype, void* stream);
 

@@ -194,10 +194,10 @@ def test_loss_ema_adamw():
             (gref,) = torch.autograd.grad(ref, Fv)
             loss = torch.zeros((), device=DEV)
             dF = torch.empty(B, *shape, device=DEV)
-            check(lib.dsk_edm_loss_fwd_bwd(ptr(Fv.detach().to(DEV)), ptr(x.to(DEV)), ptr(noise.to(DEV)), ptr(sigma.to(DEV)),
-                                           ptr(None if m is None else m.to(DEV)), ptr(loss), ptr(dF), B, shape[0],
+            keep = [Fv.detach().to(DEV), x.to(DEV), noise.to(DEV), sigma.to(DEV), None if m is None else m.to(DEV)]
+            check(lib.dsk_edm_loss_fwd_bwd(*[ptr(t) for t in keep], ptr(loss), ptr(dF), B, shape[0],
                                            shape[1] * shape[2], 0.5, kind, stream()))
-            assert abs(float(loss) - float(ref)) < 2e-5 * abs(float(ref))
+            assert abs(float(loss) - float(ref.detach())) < 2e-5 * abs(float(ref.detach()))
             assert relmax(dF.cpu(), gref) < 2e-5
     # EMA + AdamW multi-tensor kernels
     ps = [torch.randn(n) for n in (7, 1000, 33)]
