@@ -206,14 +206,16 @@ def test_loss_ema_adamw():
     dps, dgs, dsh = [[t.to(DEV) for t in ts] for ts in (ps, gs, sh)]
     mk = lambda ts: torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64, device=DEV)  # noqa: E731
     numel = torch.tensor([p.numel() for p in ps], dtype=torch.int64, device=DEV)
-    check(lib.dsk_ema_update(ptr(mk(dsh)), ptr(mk(dps)), ptr(numel), 3, 1000, 0.9, stream()))
+    t_sh, t_p = mk(dsh), mk(dps)        # keep the pointer tables alive until the launch is enqueued
+    check(lib.dsk_ema_update(ptr(t_sh), ptr(t_p), ptr(numel), 3, 1000, 0.9, stream()))
     for s_, p_, d_ in zip(sh, ps, dsh):
         assert relmax(d_.cpu(), K.ema_update(s_, p_, 0.9)) < 1e-6
     ms, vs = [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps]
     dms, dvs = [t.to(DEV) for t in ms], [t.to(DEV) for t in vs]
     shadow = [t.clone() for t in dsh]
+    tabs = [mk(ts) for ts in (dps, dgs, dms, dvs, shadow)]
     for step in (1, 2, 3):
-        check(lib.dsk_adamw_ema_step(ptr(mk(dps)), ptr(mk(dgs)), ptr(mk(dms)), ptr(mk(dvs)), ptr(mk(shadow)), ptr(numel), 3,
+        check(lib.dsk_adamw_ema_step(*[ptr(t) for t in tabs], ptr(numel), 3,
                                      1000, 1e-3, 0.9, 0.999, 1e-8, 1e-4, step, 0.99, 1.0, stream()))
         for i in range(3):
             ps[i], ms[i], vs[i] = K.adamw_step(ps[i], gs[i], ms[i], vs[i], step)
@@ -229,3 +231,51 @@ def test_loss_ema_adamw():
     ref[0].step()
     pe, _, _ = K.adamw_step(start, g0, torch.zeros(5), torch.zeros(5), 1)
     assert relmax(pe, p0.detach()) < 1e-6
+
+
+TC_CASES = [
+    # ndim, B, Cin, Cout, spatial
+    (3, 1, 64, 64, (4, 16, 8)),          # exactly one tile pair
+    (3, 2, 64, 64, (5, 20, 12)),         # ragged tiles in d, h and w (TMA zero fill + masked stores)
+    (3, 1, 128, 64, (4, 16, 16)),        # two K chunks
+    (3, 1, 64, 128, (2, 16, 8)),         # N_TILE = 128
+    (3, 1, 128, 256, (4, 8, 8)),         # two N tiles of 128
+    (3, 1, 64, 192, (2, 16, 8)),         # N_TILE = 64 x 3
+    (2, 3, 64, 64, (16, 8)),             # 2-D: the batch is the plane axis
+    (2, 5, 128, 128, (28, 28)),          # MNIST-like, odd number of planes
+    (3, 1, 64, 64, (16, 32, 32)),        # 64 tiles
+    (3, 2, 64, 64, (32, 32, 32)),        # > 148 tiles: persistent loop, accumulator double buffering
+]
+
+
+@pytest.mark.parametrize("ndim,B,Cin,Cout,sp", TC_CASES)
+def test_conv_tcgen05(ops, ndim, B, Cin, Cout, sp):
+    """tcgen05 implicit-GEMM conv (bf16 operands, fp32 TMEM accumulation) vs ATen fp32 conv on the same
+    bf16-rounded operands.  Tolerance: one bf16 rounding of the stored output (2^-8 relative to the value,
+    checked as 6e-3 of the output range) -- accumulation itself is fp32."""
+    torch.manual_seed(11)
+    x = torch.randn(B, Cin, *sp).bfloat16().float()
+    w = (torch.randn(Cout, Cin, *([3] * ndim)) / math.sqrt(Cin * 3 ** ndim)).bfloat16().float()
+    b = torch.randn(Cout) * 0.1
+    cb = torch.randn(B, Cout) * 0.3
+    ref0 = (F.conv2d if ndim == 2 else F.conv3d)(x, w, b, padding=1)
+    res = torch.randn_like(ref0).bfloat16().float()
+    ref = ref0 + cb.view(B, Cout, *([1] * ndim)) + res
+    pc = ops.PackedConv(w.to(DEV), b.to(DEV), ndim, torch.bfloat16)
+    y = ops.conv(to_cl(x).bfloat16(), pc, chan_bias=cb.to(DEV), residual=to_cl(res).bfloat16())
+    err = relmax(from_cl(y, ndim), ref)
+    assert err < 6e-3, err
+    y0 = ops.conv(to_cl(x).bfloat16(), pc)          # no epilogue operands
+    assert relmax(from_cl(y0, ndim), ref0) < 6e-3
+    # against the FFMA kernel on the same operands the only difference is summation order (+ output rounding)
+    pc32 = ops.PackedConv(w.to(DEV), b.to(DEV), ndim, torch.float32)
+    y32 = ops.conv(to_cl(x).bfloat16(), pc32)
+    assert relmax(y0.float(), y32.float()) < 6e-3
+
+
+def test_upsample2x(ops):
+    torch.manual_seed(12)
+    for ndim, sp in ((2, (5, 6)), (3, (3, 4, 5))):
+        x = torch.randn(2, 16, *sp).bfloat16()
+        y = ops.upsample2x(to_cl(x.float()).bfloat16(), ndim)
+        assert torch.equal(from_cl(y, ndim), F.interpolate(x.float(), scale_factor=2, mode="nearest"))
