@@ -1,0 +1,200 @@
+// conv_small.cu -- the first and last convolutions of the U-Nets (convin: Cin <= 4 -> C; convout: C -> Cout <= 4;
+// reference nets/punetg.py:203-214, nets/adm.py:189-196).  They carry < 0.2% of the FLOPs but touch a full-resolution
+// activation tensor, so they are HBM-bandwidth kernels, not GEMMs: one coalesced read (convout) or write (convin) of the
+// C-channel tensor, fp32 accumulation on the CUDA cores, neighbouring taps served by L1.
+#include "common.cuh"
+
+namespace dsk {
+
+struct SmallConvArgs {
+  const void* in;
+  const float* w;        // packed fp32 [taps][Cin][Cout]
+  const float* bias;
+  void* out;
+  float* out_nchw;
+  int B, D, H, W, Cin, Cout, ks, ndim;
+};
+
+template <typename T> __device__ __forceinline__ void ld8f(const T* p, float* o);
+template <> __device__ __forceinline__ void ld8f<float>(const float* p, float* o) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+template <> __device__ __forceinline__ void ld8f<__nv_bfloat16>(const __nv_bfloat16* p, float* o) {
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { o[2 * j] = __low2float(h[j]); o[2 * j + 1] = __high2float(h[j]); }
+}
+template <typename T> __device__ __forceinline__ void st8f(T* p, const float* v);
+template <> __device__ __forceinline__ void st8f<float>(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void st8f<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+  uint4 o;
+  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+// ---- convout: C (multiple of 8) -> COUT <= 4.  Thread = (pixel, 8-channel chunk); the C/8 chunk-threads of a
+// pixel are adjacent lanes, so each warp load is a contiguous run of pixels; partial sums meet by shuffle.
+template <typename TI, typename TO, int COUT>
+__global__ void __launch_bounds__(256) conv_few_out_kernel(SmallConvArgs a) {
+  extern __shared__ float wsm[];                      // [taps][Cin][COUT]
+  const int taps = a.ndim == 3 ? a.ks * a.ks * a.ks : a.ks * a.ks;
+  for (int i = threadIdx.x; i < taps * a.Cin * COUT; i += blockDim.x) wsm[i] = a.w[i];
+  __syncthreads();
+  const int chunks = a.Cin >> 3;                      // power of two <= 32 (checked on the host)
+  const int64_t npix = (int64_t)a.B * a.D * a.H * a.W;
+  const int64_t S = (int64_t)a.D * a.H * a.W;
+  const TI* in = reinterpret_cast<const TI*>(a.in);
+  const int r = a.ks >> 1;
+  const int64_t total = npix * chunks;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // every lane of a warp runs the same number of iterations (total is padded to a warp multiple by the loop bound)
+  const int64_t padded = (total + 31) & ~(int64_t)31;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += stride) {
+    const bool live = i < total;
+    const int64_t pix = live ? i / chunks : 0;
+    const int ch = (int)(i % chunks) * 8;
+    int64_t t = pix;
+    const int w0 = (int)(t % a.W); t /= a.W;
+    const int h0 = (int)(t % a.H); t /= a.H;
+    const int d0 = (int)(t % a.D);
+    const int b = (int)(t / a.D);
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = 0.0f;
+    if (live) {
+      int tap = 0;
+      for (int kd = 0; kd < (a.ndim == 3 ? a.ks : 1); ++kd)
+        for (int kh = 0; kh < a.ks; ++kh)
+          for (int kw = 0; kw < a.ks; ++kw, ++tap) {
+            const int zd = a.ndim == 3 ? d0 + kd - r : 0, zh = h0 + kh - r, zw = w0 + kw - r;
+            if ((unsigned)zd >= (unsigned)a.D || (unsigned)zh >= (unsigned)a.H || (unsigned)zw >= (unsigned)a.W) continue;
+            float x[8];
+            ld8f<TI>(in + ((((int64_t)b * a.D + zd) * a.H + zh) * a.W + zw) * a.Cin + ch, x);
+            const float* wp = wsm + ((int64_t)tap * a.Cin + ch) * COUT;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+#pragma unroll
+              for (int co = 0; co < COUT; ++co) acc[co] = fmaf(x[e], wp[e * COUT + co], acc[co]);
+          }
+    }
+    for (int o = chunks >> 1; o > 0; o >>= 1)
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+    if (live && ch == 0) {
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) {
+        if (co >= a.Cout) break;
+        float v = acc[co] + (a.bias != nullptr ? a.bias[co] : 0.0f);
+        if (a.out_nchw != nullptr) a.out_nchw[((int64_t)b * a.Cout + co) * S + (pix - (int64_t)b * S)] = v;
+        else reinterpret_cast<TO*>(a.out)[pix * a.Cout + co] = from_f32<TO>(v);
+      }
+    }
+  }
+}
+
+// ---- convin: CIN <= 4 -> Cout (multiple of 8).  Thread = (pixel, 8 output channels): the taps of a pixel are a
+// handful of scalars (L1 broadcast across the chunk-threads), the store is a coalesced 16/32-byte vector.
+template <typename TI, typename TO, int CIN>
+__global__ void __launch_bounds__(256) conv_few_in_kernel(SmallConvArgs a) {
+  extern __shared__ float wsm[];                      // [taps][CIN][Cout]
+  const int taps = a.ndim == 3 ? a.ks * a.ks * a.ks : a.ks * a.ks;
+  for (int i = threadIdx.x; i < taps * CIN * a.Cout; i += blockDim.x) wsm[i] = a.w[i];
+  __syncthreads();
+  const int chunks = a.Cout >> 3;
+  const int64_t npix = (int64_t)a.B * a.D * a.H * a.W;
+  const TI* in = reinterpret_cast<const TI*>(a.in);
+  TO* out = reinterpret_cast<TO*>(a.out);
+  const int r = a.ks >> 1;
+  const int64_t total = npix * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / chunks;
+    const int ch = (int)(i % chunks) * 8;
+    int64_t t = pix;
+    const int w0 = (int)(t % a.W); t /= a.W;
+    const int h0 = (int)(t % a.H); t /= a.H;
+    const int d0 = (int)(t % a.D);
+    const int b = (int)(t / a.D);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = a.bias != nullptr ? a.bias[ch + e] : 0.0f;
+    int tap = 0;
+    for (int kd = 0; kd < (a.ndim == 3 ? a.ks : 1); ++kd)
+      for (int kh = 0; kh < a.ks; ++kh)
+        for (int kw = 0; kw < a.ks; ++kw, ++tap) {
+          const int zd = a.ndim == 3 ? d0 + kd - r : 0, zh = h0 + kh - r, zw = w0 + kw - r;
+          if ((unsigned)zd >= (unsigned)a.D || (unsigned)zh >= (unsigned)a.H || (unsigned)zw >= (unsigned)a.W) continue;
+          const TI* ip = in + ((((int64_t)b * a.D + zd) * a.H + zh) * a.W + zw) * CIN;
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) {
+            const float x = to_f32<TI>(ip[ci]);
+            const float* wp = wsm + ((int64_t)tap * CIN + ci) * a.Cout + ch;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(x, wp[e], acc[e]);
+          }
+        }
+    st8f<TO>(out + pix * a.Cout + ch, acc);
+  }
+}
+
+template <typename TI, typename TO>
+static int launch_few_out(const SmallConvArgs& a, cudaStream_t st) {
+  const int taps = a.ndim == 3 ? a.ks * a.ks * a.ks : a.ks * a.ks;
+  const size_t smem = (size_t)taps * a.Cin * 4 * sizeof(float);
+  const int64_t total = (int64_t)a.B * a.D * a.H * a.W * (a.Cin / 8);
+  const int grid = grid_for(total, 256, 16);
+  switch (a.Cout) {
+    case 1: DSK_LAUNCH((conv_few_out_kernel<TI, TO, 1>), grid, 256, smem, st, a); break;
+    case 2: DSK_LAUNCH((conv_few_out_kernel<TI, TO, 2>), grid, 256, smem, st, a); break;
+    case 3: DSK_LAUNCH((conv_few_out_kernel<TI, TO, 3>), grid, 256, smem, st, a); break;
+    default: DSK_LAUNCH((conv_few_out_kernel<TI, TO, 4>), grid, 256, smem, st, a); break;
+  }
+  return DSK_OK;
+}
+
+template <typename TI, typename TO>
+static int launch_few_in(const SmallConvArgs& a, cudaStream_t st) {
+  const int taps = a.ndim == 3 ? a.ks * a.ks * a.ks : a.ks * a.ks;
+  const size_t smem = (size_t)taps * a.Cin * a.Cout * sizeof(float);
+  const int64_t total = (int64_t)a.B * a.D * a.H * a.W * (a.Cout / 8);
+  const int grid = grid_for(total, 256, 16);
+  switch (a.Cin) {
+    case 1: DSK_LAUNCH((conv_few_in_kernel<TI, TO, 1>), grid, 256, smem, st, a); break;
+    case 2: DSK_LAUNCH((conv_few_in_kernel<TI, TO, 2>), grid, 256, smem, st, a); break;
+    case 3: DSK_LAUNCH((conv_few_in_kernel<TI, TO, 3>), grid, 256, smem, st, a); break;
+    default: DSK_LAUNCH((conv_few_in_kernel<TI, TO, 4>), grid, 256, smem, st, a); break;
+  }
+  return DSK_OK;
+}
+
+// returns 1 if handled, 0 if the shape is not a few-channel conv, negative on error
+int conv_small_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
+                        const void* residual, void* out, cudaStream_t st) {
+  if (chan_bias != nullptr || residual != nullptr || d->up2) return 0;
+  const int taps = d->ndim == 3 ? d->ksize * d->ksize * d->ksize : d->ksize * d->ksize;
+  SmallConvArgs a{in, (const float*)w, bias, d->out_nchw_f32 ? nullptr : out, d->out_nchw_f32 ? (float*)out : nullptr,
+                  d->B, d->D, d->H, d->W, d->Cin, d->Cout, d->ksize, d->ndim};
+  const int chunks = d->Cin / 8;
+  const bool few_out = d->Cout <= 4 && d->Cin % 8 == 0 && chunks <= 32 && (chunks & (chunks - 1)) == 0 &&
+                       (size_t)taps * d->Cin * 4 * 4 <= 48 * 1024;
+  const bool few_in = d->Cin <= 4 && d->Cout % 8 == 0 && !d->out_nchw_f32 && (size_t)taps * d->Cin * d->Cout * 4 <= 48 * 1024;
+  if (!few_out && !few_in) return 0;
+  const int ti = d->in_dtype, to = d->out_nchw_f32 ? DSK_F32 : d->out_dtype;
+  int rc;
+#define GO(FN)                                                                                        \
+  if (ti == DSK_F32 && to == DSK_F32) rc = FN<float, float>(a, st);                                   \
+  else if (ti == DSK_BF16 && to == DSK_BF16) rc = FN<__nv_bfloat16, __nv_bfloat16>(a, st);            \
+  else if (ti == DSK_BF16 && to == DSK_F32) rc = FN<__nv_bfloat16, float>(a, st);                     \
+  else rc = FN<float, __nv_bfloat16>(a, st);
+  if (few_out) { GO(launch_few_out) } else { GO(launch_few_in) }
+#undef GO
+  return rc == DSK_OK ? 1 : rc;
+}
+
+}  // namespace dsk

@@ -287,6 +287,10 @@ static int launch_conv(const dsk_conv_desc* d, const void* in, const void* w, co
 
 }  // namespace dsk
 
+namespace dsk {
+int conv_small_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
+                        const void* residual, void* out, cudaStream_t st);
+}
 using namespace dsk;
 
 // implemented in conv_tc.cu (tcgen05 path); returns DSK_ERR_UNSUPPORTED for shapes it does not take
@@ -301,6 +305,10 @@ extern "C" int dsk_conv_fwd_ffma(const dsk_conv_desc* d, const void* in, const v
   DSK_REQUIRE(d->ndim == 3 || d->D == 1, "dsk_conv_fwd: ndim=2 needs D=1");
   DSK_REQUIRE(!d->up2 || (d->H % 2 == 0 && d->W % 2 == 0 && (d->ndim == 2 || d->D % 2 == 0)), "dsk_conv_fwd: up2 needs even output size");
   cudaStream_t st = as_stream(stream);
+  {  // few-channel first/last convs are bandwidth kernels (conv_small.cu), not GEMM tiles
+    const int handled = conv_small_dispatch(d, in, w, bias, chan_bias, residual, out, st);
+    if (handled != 0) return handled < 0 ? handled : DSK_OK;
+  }
   const int ti = d->in_dtype, to = d->out_nchw_f32 ? (residual ? d->out_dtype : DSK_F32) : d->out_dtype;
   if (ti == DSK_F32 && to == DSK_F32) return launch_conv<float, float>(d, in, w, bias, chan_bias, residual, out, st);
   if (ti == DSK_BF16 && to == DSK_BF16) return launch_conv<__nv_bfloat16, __nv_bfloat16>(d, in, w, bias, chan_bias, residual, out, st);

@@ -13,70 +13,90 @@
 namespace dsk {
 
 constexpr int NORM_THREADS = 256;
-constexpr int NORM_V = 4;
 
-static inline int norm_chunks(int B, int64_t S, int C) {
-  int cv = C / NORM_V;
-  int pl = NORM_THREADS / cv;
-  if (pl < 1) pl = 1;
-  int64_t by_work = (S + (int64_t)pl * 8 - 1) / ((int64_t)pl * 8);  // >= 8 pixels per thread per chunk
-  int64_t by_grid = (2 * DSK_NUM_SMS + B - 1) / B;
-  int64_t n = by_work < by_grid ? by_work : by_grid;
-  if (n < 1) n = 1;
-  if (n > 512) n = 512;
-  return (int)n;
-}
-
-template <typename T> __device__ __forceinline__ void load4(const T* p, float* o);
-template <> __device__ __forceinline__ void load4<float>(const float* p, float* o) {
-  float4 v = *reinterpret_cast<const float4*>(p);
-  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-}
-template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float* o) {
-  uint2 raw = *reinterpret_cast<const uint2*>(p);
-  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x), b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
-  o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
-}
-template <typename T> __device__ __forceinline__ void store4(T* p, const float* v);
-template <> __device__ __forceinline__ void store4<float>(float* p, const float* v) {
+template <typename T> struct NormVec;                 // 16-byte vectors: 4 fp32 or 8 bf16
+template <> struct NormVec<float> {
+  static constexpr int V = 4;
+  static __device__ __forceinline__ void ld(const float* p, float* o) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+};
+template <> struct NormVec<__nv_bfloat16> {
+  static constexpr int V = 8;
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* o) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[2 * j] = __low2float(h[j]); o[2 * j + 1] = __high2float(h[j]); }
+  }
+};
+template <typename T, int V> __device__ __forceinline__ void st_vec(T* p, const float* v);
+template <> __device__ __forceinline__ void st_vec<float, 4>(float* p, const float* v) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
-template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+template <> __device__ __forceinline__ void st_vec<float, 8>(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void st_vec<__nv_bfloat16, 4>(__nv_bfloat16* p, const float* v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
   uint2 raw;
   raw.x = *reinterpret_cast<uint32_t*>(&a);
   raw.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p) = raw;
 }
+template <> __device__ __forceinline__ void st_vec<__nv_bfloat16, 8>(__nv_bfloat16* p, const float* v) {
+  uint4 o;
+  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
 
-// partial[b][chunk][c] = (sum, sumsq) in fp64
+static inline int norm_chunks(int B, int64_t S, int C, int V) {
+  int cv = C / V;
+  int pl = NORM_THREADS / cv;
+  if (pl < 1) pl = 1;
+  int64_t by_work = (S + (int64_t)pl * 8 - 1) / ((int64_t)pl * 8);  // >= 8 pixels per thread per chunk
+  int64_t by_grid = (4 * DSK_NUM_SMS + B - 1) / B;
+  int64_t n = by_work < by_grid ? by_work : by_grid;
+  if (n < 1) n = 1;
+  if (n > 1024) n = 1024;
+  return (int)n;
+}
+
+// partial[b][chunk][c] = (sum, sumsq) in fp64.  Thread = fixed V-channel vector, strided over the chunk's pixels.
 template <typename T>
 __global__ void __launch_bounds__(NORM_THREADS) norm_partial_kernel(const T* __restrict__ x, double2* __restrict__ partial,
                                                                      int64_t S, int C, int nchunks) {
+  constexpr int V = NormVec<T>::V;
   extern __shared__ double2 sm[];  // [pl][C]
   const int b = blockIdx.y, chunk = blockIdx.x;
-  const int cv = C / NORM_V;
+  const int cv = C / V;
   const int pl = max(1, NORM_THREADS / cv);
   const int64_t per = (S + nchunks - 1) / nchunks;
   const int64_t s0 = (int64_t)chunk * per;
   const int64_t s1 = min(S, s0 + per);
   const T* xb = x + (int64_t)b * S * C;
   for (int v = threadIdx.x; v < pl * cv; v += NORM_THREADS) {
-    const int lane = v / cv, c0 = (v - lane * cv) * NORM_V;
-    float sum[NORM_V] = {0, 0, 0, 0}, sq[NORM_V] = {0, 0, 0, 0};
-    double dsum[NORM_V] = {0, 0, 0, 0}, dsq[NORM_V] = {0, 0, 0, 0};
+    const int lane = v / cv, c0 = (v - lane * cv) * V;
+    float sum[V], sq[V];
+    double dsum[V], dsq[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { sum[k] = 0; sq[k] = 0; dsum[k] = 0; dsq[k] = 0; }
     int cnt = 0;
     for (int64_t s = s0 + lane; s < s1; s += pl) {
-      float e[NORM_V];
-      load4<T>(xb + s * C + c0, e);
+      float e[V];
+      NormVec<T>::ld(xb + s * C + c0, e);
 #pragma unroll
-      for (int k = 0; k < NORM_V; ++k) {
+      for (int k = 0; k < V; ++k) {
         sum[k] += e[k];
         sq[k] += e[k] * e[k];
       }
       if (++cnt == 64) {  // flush fp32 partials to fp64 every 64 elements
 #pragma unroll
-        for (int k = 0; k < NORM_V; ++k) {
+        for (int k = 0; k < V; ++k) {
           dsum[k] += sum[k]; dsq[k] += sq[k];
           sum[k] = 0; sq[k] = 0;
         }
@@ -84,7 +104,7 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_partial_kernel(const T* __r
       }
     }
 #pragma unroll
-    for (int k = 0; k < NORM_V; ++k) sm[lane * C + c0 + k] = make_double2(dsum[k] + sum[k], dsq[k] + sq[k]);
+    for (int k = 0; k < V; ++k) sm[lane * C + c0 + k] = make_double2(dsum[k] + sum[k], dsq[k] + sq[k]);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += NORM_THREADS) {
@@ -98,8 +118,11 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_partial_kernel(const T* __r
   }
 }
 
-// stats[b][g] = (mean, rstd)
-__global__ void __launch_bounds__(128) norm_finalize_kernel(const double2* __restrict__ partial, float2* __restrict__ stats,
+// One block per (sample, group): combine the chunk partials, then fold mean / rstd / gamma / beta / FiLM into a
+// per-(b, c) scale-shift pair:  y = act(x * a + s).
+__global__ void __launch_bounds__(128) norm_finalize_kernel(const double2* __restrict__ partial, float2* __restrict__ table,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ fsc, const float* __restrict__ fsh,
                                                              int64_t S, int C, int G, int nchunks, int mode, float eps) {
   const int b = blockIdx.x / G, g = blockIdx.x % G;
   const int cg = C / G;
@@ -111,6 +134,7 @@ __global__ void __launch_bounds__(128) norm_finalize_kernel(const double2* __res
     q += v.y;
   }
   __shared__ double sa[128], sq[128];
+  __shared__ float2 mr;
   sa[threadIdx.x] = a;
   sq[threadIdx.x] = q;
   __syncthreads();
@@ -124,43 +148,52 @@ __global__ void __launch_bounds__(128) norm_finalize_kernel(const double2* __res
   if (threadIdx.x == 0) {
     const double n = (double)S * cg;
     double mean = sa[0] / n, ex2 = sq[0] / n;
-    float m, r;
     if (mode == 0) {
       double var = ex2 - mean * mean;
       if (var < 0) var = 0;
-      m = (float)mean;
-      r = 1.0f / sqrtf((float)var + eps);
+      mr = make_float2((float)mean, 1.0f / sqrtf((float)var + eps));
     } else {
-      m = 0.0f;
-      r = 1.0f / sqrtf((float)ex2 + eps);  // x / sqrt(mean(x^2) + eps), commonlayers.py:377-378
+      mr = make_float2(0.0f, 1.0f / sqrtf((float)ex2 + eps));  // x / sqrt(mean(x^2) + eps), commonlayers.py:377-378
     }
-    stats[blockIdx.x] = make_float2(m, r);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cg; i += blockDim.x) {
+    const int c = g * cg + i;
+    float sc = mr.y, sh = -mr.x * mr.y;
+    if (gamma != nullptr) { sc *= gamma[c]; sh = sh * gamma[c] + beta[c]; }
+    if (fsc != nullptr) { const float f = fsc[(int64_t)b * C + c]; sc *= f; sh = sh * f + fsh[(int64_t)b * C + c]; }
+    table[(int64_t)b * C + c] = make_float2(sc, sh);
   }
 }
 
+// Thread = fixed V-channel vector (scale/shift held in registers), strided over the pixels of one sample.
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(256) norm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ y,
-                                                          const float2* __restrict__ stats, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, const float* __restrict__ fsc,
-                                                          const float* __restrict__ fsh, int64_t S, int C, int G, int B,
-                                                          int silu) {
-  const int cv = C / NORM_V, cg = C / G;
-  const int64_t per_b = S * cv, total = per_b * B;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int b = (int)(i / per_b);
-    const int c0 = (int)(i % cv) * NORM_V;
-    float e[NORM_V], o[NORM_V];
-    load4<TI>(x + i * NORM_V, e);
+__global__ void __launch_bounds__(NORM_THREADS) norm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ y,
+                                                                   const float2* __restrict__ table, int64_t S, int C, int silu) {
+  constexpr int V = NormVec<TI>::V;
+  const int b = blockIdx.y;
+  const int cv = C / V;
+  const int pl = max(1, NORM_THREADS / cv);
+  const TI* xb = x + (int64_t)b * S * C;
+  TO* yb = y + (int64_t)b * S * C;
+  for (int v = threadIdx.x; v < pl * cv; v += NORM_THREADS) {
+    const int lane = v / cv, c0 = (v - lane * cv) * V;
+    float sc[V], sh[V];
 #pragma unroll
-    for (int k = 0; k < NORM_V; ++k) {
-      const int c = c0 + k;
-      const float2 st = stats[b * G + c / cg];
-      float v = (e[k] - st.x) * st.y;
-      if (gamma != nullptr) v = v * gamma[c] + beta[c];
-      if (fsc != nullptr) v = v * fsc[(int64_t)b * C + c] + fsh[(int64_t)b * C + c];
-      o[k] = silu ? silu_f(v) : v;
+    for (int k = 0; k < V; ++k) {
+      const float2 t = table[(int64_t)b * C + c0 + k];
+      sc[k] = t.x; sh[k] = t.y;
     }
-    store4<TO>(y + i * NORM_V, o);
+    for (int64_t s = (int64_t)blockIdx.x * pl + lane; s < S; s += (int64_t)gridDim.x * pl) {
+      float e[V], o[V];
+      NormVec<TI>::ld(xb + s * C + c0, e);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float t = fmaf(e[k], sc[k], sh[k]);
+        o[k] = silu ? silu_f(t) : t;
+      }
+      st_vec<TO, V>(yb + s * C + c0, o);
+    }
   }
 }
 
@@ -168,9 +201,13 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const TI* __restrict__ 
 
 using namespace dsk;
 
+static inline int norm_v(int in_dtype) { return in_dtype == DSK_BF16 ? 8 : 4; }
+
 extern "C" int64_t dsk_norm_ws_bytes(int B, int64_t S, int C) {
-  if (B <= 0 || S <= 0 || C <= 0 || C % NORM_V) return 0;
-  int nchunks = norm_chunks(B, S, C);
+  if (B <= 0 || S <= 0 || C <= 0 || C % 4) return 0;
+  int nchunks = norm_chunks(B, S, C, 4);   // upper bound over both vector widths
+  int n8 = (C % 8 == 0) ? norm_chunks(B, S, C, 8) : 0;
+  if (n8 > nchunks) nchunks = n8;
   return (int64_t)B * nchunks * C * (int64_t)sizeof(double2) + (int64_t)B * C * (int64_t)sizeof(float2);
 }
 
@@ -178,31 +215,34 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
                             const float* film_shift, void* ws, int B, int64_t S, int C, int G, int mode, int silu,
                             int in_dtype, int out_dtype, void* stream) {
   DSK_REQUIRE(x && y && ws, "dsk_norm_act: null pointer");
-  DSK_REQUIRE(B > 0 && S > 0 && C > 0 && G > 0 && C % G == 0, "dsk_norm_act: bad shape B=%d S=%lld C=%d G=%d", B, (long long)S, C, G);
-  DSK_REQUIRE(C % NORM_V == 0, "dsk_norm_act: C=%d must be a multiple of %d", C, NORM_V);
+  DSK_REQUIRE(B > 0 && B <= 65535 && S > 0 && C > 0 && G > 0 && C % G == 0, "dsk_norm_act: bad shape B=%d S=%lld C=%d G=%d", B, (long long)S, C, G);
+  DSK_REQUIRE(in_dtype == DSK_F32 || in_dtype == DSK_BF16, "dsk_norm_act: bad in_dtype %d", in_dtype);
+  const int V = norm_v(in_dtype);
+  DSK_REQUIRE(C % V == 0, "dsk_norm_act: C=%d must be a multiple of %d for this dtype", C, V);
   DSK_REQUIRE(mode == 0 || mode == 1, "dsk_norm_act: bad mode %d", mode);
   DSK_REQUIRE((gamma == nullptr) == (beta == nullptr), "dsk_norm_act: gamma/beta must both be set or both null");
   DSK_REQUIRE((film_scale == nullptr) == (film_shift == nullptr), "dsk_norm_act: FiLM scale/shift mismatch");
   cudaStream_t st = as_stream(stream);
-  const int nchunks = norm_chunks(B, S, C);
+  const int nchunks = norm_chunks(B, S, C, V);
   double2* partial = reinterpret_cast<double2*>(ws);
-  float2* stats = reinterpret_cast<float2*>(partial + (int64_t)B * nchunks * C);
-  const int cv = C / NORM_V;
+  float2* table = reinterpret_cast<float2*>(partial + (int64_t)B * nchunks * C);
+  const int cv = C / V;
   const int pl = NORM_THREADS / cv > 0 ? NORM_THREADS / cv : 1;
   const size_t smem = (size_t)pl * C * sizeof(double2);
   DSK_REQUIRE(smem <= 48 * 1024, "dsk_norm_act: C=%d too large for the stats kernel", C);
   dim3 pg(nchunks, B);
   if (in_dtype == DSK_F32)
     DSK_LAUNCH(norm_partial_kernel<float>, pg, NORM_THREADS, smem, st, (const float*)x, partial, S, C, nchunks);
-  else if (in_dtype == DSK_BF16)
-    DSK_LAUNCH(norm_partial_kernel<__nv_bfloat16>, pg, NORM_THREADS, smem, st, (const __nv_bfloat16*)x, partial, S, C, nchunks);
   else
-    DSK_REQUIRE(false, "dsk_norm_act: bad in_dtype %d", in_dtype);
-  DSK_LAUNCH(norm_finalize_kernel, B * G, 128, 0, st, partial, stats, S, C, G, nchunks, mode, 1e-5f);
-  const int grid = grid_for((int64_t)B * S * cv, 256, 16);
-#define APPLY(TI, TO)                                                                                         \
-  DSK_LAUNCH((norm_apply_kernel<TI, TO>), grid, 256, 0, st, (const TI*)x, (TO*)y, stats, gamma, beta, film_scale, \
-             film_shift, S, C, G, B, silu)
+    DSK_LAUNCH(norm_partial_kernel<__nv_bfloat16>, pg, NORM_THREADS, smem, st, (const __nv_bfloat16*)x, partial, S, C, nchunks);
+  DSK_LAUNCH(norm_finalize_kernel, B * G, 128, 0, st, partial, table, gamma, beta, film_scale, film_shift, S, C, G, nchunks, mode,
+             1e-5f);
+  int64_t gx = (S + (int64_t)pl * 4 - 1) / ((int64_t)pl * 4);          // >= 4 pixels per thread
+  const int64_t cap = (8LL * DSK_NUM_SMS + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 ag((unsigned)gx, B);
+#define APPLY(TI, TO) DSK_LAUNCH((norm_apply_kernel<TI, TO>), ag, NORM_THREADS, 0, st, (const TI*)x, (TO*)y, table, S, C, silu)
   if (in_dtype == DSK_F32 && out_dtype == DSK_F32) APPLY(float, float);
   else if (in_dtype == DSK_F32 && out_dtype == DSK_BF16) APPLY(float, __nv_bfloat16);
   else if (in_dtype == DSK_BF16 && out_dtype == DSK_BF16) APPLY(__nv_bfloat16, __nv_bfloat16);

@@ -140,6 +140,10 @@ class SamplerEngine:
         require_cuda(white_noise, "white noise")
         if program not in PROGRAMS:
             raise ValueError(f"Unknown integrator program: {program}")
+        with torch.inference_mode(False), torch.no_grad():
+            return self._run(white_noise, table, program, record_history, noises, seed)
+
+    def _run(self, white_noise, table, program, record_history, noises, seed):
         nsteps = table.shape[0] - 1
         regular, final = PROGRAMS[program]
         N = self.B * self.Cc * self.S

@@ -412,8 +412,9 @@ class KarrasModule(_Base):
         if eng is None:
             if len(self._engines) >= 2:
                 self._engines.clear()
-            eng = self._engines[key] = _engine.SamplerEngine(self.model, B, shape, x.device, self._sigma_data(),
-                                                             1.0, kind, use_graphs=self.use_cuda_graphs)
+            with torch.inference_mode(False), torch.no_grad():
+                eng = self._engines[key] = _engine.SamplerEngine(self.model, B, shape, x.device, self._sigma_data(),
+                                                                 1.0, kind, use_graphs=self.use_cuda_graphs)
         eng.sigma_max = 1.0 if _prescaled else float(sch.maximum_scale)
         table = sch.step_table(nsteps, integ)
         noises = None

@@ -51,7 +51,8 @@ class MLPUncond(nn.Module):
         if plan is None or plan.sig != sig:
             if len(self._plans) >= 4:
                 self._plans.clear()
-            plan = self._plans[key] = _MLPPlan(self, B, device, sig)
+            with torch.inference_mode(False), torch.no_grad():   # persistent buffers must be normal tensors
+                plan = self._plans[key] = _MLPPlan(self, B, device, sig)
         return plan
 
     def _apply(self, fn, *a, **k):

@@ -138,7 +138,8 @@ class PUNetG(nn.Module):
         if plan is None or plan.sig != sig:
             if len(self._plans) >= 4:   # bound the HBM held by cached plans
                 self._plans.clear()
-            plan = self._plans[key] = _Plan(self, B, tuple(spatial), device, precision, sig)
+            with torch.inference_mode(False), torch.no_grad():   # persistent buffers must be normal tensors
+                plan = self._plans[key] = _Plan(self, B, tuple(spatial), device, precision, sig)
         return plan
 
     def _apply(self, fn, *a, **k):

@@ -38,6 +38,12 @@ class PackedConv:
         key = (w._version, w.data_ptr())
         if self._packed is None or self._version != key or self._packed.device != w.device:
             require_cuda(w, "conv weight")
+            with torch.inference_mode(False), torch.no_grad():
+                return self._repack(w, key)
+        return self._packed
+
+    def _repack(self, w, key):
+        if True:
             src = w.detach().float().contiguous()
             if self._packed is None or self._packed.device != w.device:
                 self._packed = torch.empty(self.taps * self.cin * self.cout, dtype=self.w_dtype, device=w.device)
