@@ -24,9 +24,7 @@
 //   warp 2   MMA issuer (one elected thread), owns the TMEM allocation
 //   warps 4-7 epilogue: tcgen05.ld -> +bias +time-embedding vector +residual -> bf16 -> global
 // TMEM accumulators are double buffered so the epilogue of tile i overlaps the main loop of tile i+1.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dsk {
 
@@ -46,54 +44,6 @@ struct TcParams {
   __nv_bfloat16* out;     // [B, D, H, W, Cout]
   int planes_per_sample;  // D for 3-D; 1 for 2-D  (chan_bias row = plane / planes_per_sample)
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-#ifdef DSK_DEBUG_TIMEOUT
-  for (long spin = 0; spin < (1L << 28) && !ok; ++spin)
-#else
-  while (!ok)
-#endif
-  {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-  }
-#ifdef DSK_DEBUG_TIMEOUT
-  if (!ok) { printf("conv_tc: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x); __trap(); }
-#endif
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp bit layout)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 
 struct TileCoord {
   int w0, h0, d0, b, n0;
@@ -320,19 +270,6 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
     const int ds = ndim == 3 ? d >> 1 : d;
     y[i] = x[((((int64_t)b * D + ds) * H + (h >> 1)) * W + (w >> 1)) * C8 + c];
   }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    cudaDriverEntryPointQueryResult q;
-    void* ptr = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
 }
 
 template <int N_TILE, int P, int NA, int NB>

@@ -1,0 +1,287 @@
+// gemm_tc.cu -- batched bf16 GEMM on tcgen05/TMEM fed by TMA:  C[b] = alpha * A[b] * B[b]^T (+ bias) (+ residual)
+// A: [M, K] row-major (K contiguous, leading dimension lda), B: [N, K] row-major (ldb): both K-major operands.
+//
+// Used for everything GEMM-shaped around the attention block (nn.MultiheadAttention(C, 1 head), reference
+// nets/attention.py:42-44,68): packed Q|K projection, V^T projection (row bias), Q K^T, P V and the output
+// projection; and for 1x1 convolutions.  Same skeleton as conv_tc.cu: persistent CTAs, warp-specialised
+// TMA producer / MMA issuer / 4 epilogue warps, SWIZZLE_128B K-major tiles, double-buffered TMEM accumulators.
+#include "tc_common.cuh"
+
+namespace dsk {
+
+constexpr int GT_THREADS = 192;   // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: epilogue
+constexpr int GT_STAGES = 4;
+
+struct GemmTcParams {
+  int M, N, K, batch;
+  int a_bmul, b_bmul;       // 0: operand shared by every batch (stride 0), 1: per-batch
+  int tiles_m, tiles_n, total_tiles;
+  float alpha;
+  const float* bias;        // [N] (bias_rows == 0) or [M] (bias_rows == 1), or null
+  int bias_rows;
+  const __nv_bfloat16* residual;  // [batch][M][ldc] bf16 or null
+  void* out;                // bf16 or fp32 [batch][M][ldc]
+  int out_f32;
+  int64_t ldc, strideC;
+};
+
+template <int N_TILE>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const GemmTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = 128 * 128, B_BYTES = N_TILE * 128, STAGE = A_BYTES + B_BYTES;
+  __shared__ uint64_t full[GT_STAGES], empty[GT_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  constexpr uint32_t TMEM_COLS = 2 * N_TILE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = (p.K + 63) / 64;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t seq = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int tn = t % p.tiles_n, tm = (t / p.tiles_n) % p.tiles_m, b = t / (p.tiles_n * p.tiles_m);
+        for (int kc = 0; kc < kchunks; ++kc, ++seq) {
+          const uint32_t slot = seq % GT_STAGES, ph = (seq / GT_STAGES) & 1;
+          mbar_wait(&empty[slot], ph ^ 1);
+          mbar_expect_tx(&full[slot], STAGE);
+          uint8_t* sa = smem + (size_t)slot * STAGE;
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                  smem_u32(sa)),
+              "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(kc * 64), "r"(tm * 128), "r"(b * p.a_bmul), "r"(smem_u32(&full[slot]))
+              : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                  smem_u32(sa + A_BYTES)),
+              "l"(reinterpret_cast<uint64_t>(&tmapB)), "r"(kc * 64), "r"(tn * N_TILE), "r"(b * p.b_bmul), "r"(smem_u32(&full[slot]))
+              : "memory");
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(N_TILE);
+      uint32_t seq = 0, it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_acc = tmem_base + as * N_TILE;
+        for (int kc = 0; kc < kchunks; ++kc, ++seq) {
+          const uint32_t slot = seq % GT_STAGES;
+          mbar_wait(&full[slot], (seq / GT_STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = smem_u32(smem + (size_t)slot * STAGE), b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_bf16(tmem_acc, umma_desc(a_addr + k4 * 32, 1024), umma_desc(b_addr + k4 * 32, 1024), idesc, (kc | k4) != 0);
+          umma_commit(&empty[slot]);
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int tn = t % p.tiles_n, tm = (t / p.tiles_n) % p.tiles_m, b = t / (p.tiles_n * p.tiles_m);
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(&acc_full[as], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = tm * 128 + row;
+      const bool mvalid = m < p.M;
+      const float rb = (p.bias != nullptr && p.bias_rows && mvalid) ? p.bias[m] : 0.0f;
+      const int64_t obase = (int64_t)b * p.strideC + (int64_t)m * p.ldc;
+      const uint32_t taddr = tmem_base + as * N_TILE + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t v[32];
+        DSK_TMEM_LD_X32(v, taddr + c0);
+        const int n = tn * N_TILE + c0;
+        if (mvalid && n < p.N) {
+          const bool full32 = n + 32 <= p.N;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = p.alpha * __uint_as_float(v[g * 8 + e]) + rb;
+              if (p.bias != nullptr && !p.bias_rows && (full32 || n + g * 8 + e < p.N)) x += __ldg(p.bias + n + g * 8 + e);
+              f[e] = x;
+            }
+            if (full32 || n + g * 8 + 8 <= p.N) {
+              if (p.residual != nullptr) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + obase + n + g * 8);
+                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { f[2 * e] += __low2float(rh[e]); f[2 * e + 1] += __high2float(rh[e]); }
+              }
+              if (p.out_f32) {
+                float* o = reinterpret_cast<float*>(p.out) + obase + n + g * 8;
+                *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                uint4 o;
+                __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n + g * 8) = o;
+              }
+            } else {
+              for (int e = 0; e < 8 && n + g * 8 + e < p.N; ++e) {   // ragged N tail
+                float x = f[e];
+                if (p.residual != nullptr) x += __bfloat162float(p.residual[obase + n + g * 8 + e]);
+                if (p.out_f32) reinterpret_cast<float*>(p.out)[obase + n + g * 8 + e] = x;
+                else reinterpret_cast<__nv_bfloat16*>(p.out)[obase + n + g * 8 + e] = __float2bfloat16_rn(x);
+              }
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+}
+
+// fp32 scores -> bf16 probabilities, one block per row (row cached in registers: cols <= 256 * 32)
+__global__ void __launch_bounds__(256) softmax_rows_bf16_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P,
+                                                                 int64_t rows, int cols) {
+  __shared__ float red[8];
+  constexpr int MAXV = 8;   // float4 vectors per thread (cols <= 8192)
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float4* src = reinterpret_cast<const float4*>(S + r * cols);
+    const int nv = cols >> 2;
+    float4 v[MAXV];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      if (idx < nv) {
+        v[i] = src[idx];
+        m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      if (idx < nv) {
+        v[i].x = expf(v[i].x - m); v[i].y = expf(v[i].y - m); v[i].z = expf(v[i].z - m); v[i].w = expf(v[i].w - m);
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w];
+    __syncthreads();
+    const float inv = 1.0f / sum;
+    uint2* dst = reinterpret_cast<uint2*>(P + r * cols);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      if (idx < nv) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[i].x * inv, v[i].y * inv), b = __floats2bfloat162_rn(v[i].z * inv, v[i].w * inv);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&a);
+        o.y = *reinterpret_cast<uint32_t*>(&b);
+        dst[idx] = o;
+      }
+    }
+  }
+}
+
+template <int N_TILE>
+static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)GT_STAGES * (128 * 128 + N_TILE * 128) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSK_ERR_CUDA; }
+    configured = true;
+  }
+  const int grid = p.total_tiles < DSK_NUM_SMS ? p.total_tiles : DSK_NUM_SMS;
+  DSK_LAUNCH((gemm_tc_kernel<N_TILE>), grid, GT_THREADS, smem, st, ta, tb, p);
+  return DSK_OK;
+}
+
+}  // namespace dsk
+
+using namespace dsk;
+
+extern "C" int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const float* bias, int bias_rows, const void* residual,
+                                int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
+                                int64_t strideC, int batch, float alpha, int out_f32, void* stream) {
+  DSK_REQUIRE(A && Bm && C, "dsk_gemm_bf16_tc: null pointer");
+  DSK_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "dsk_gemm_bf16_tc: bad shape");
+  DSK_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && strideA % 8 == 0 && strideB % 8 == 0,
+              "dsk_gemm_bf16_tc: K, lda, ldb, ldc and batch strides must be multiples of 8 elements (16-byte TMA alignment)");
+  DSK_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Bm & 15) == 0 && ((uintptr_t)C & 15) == 0, "dsk_gemm_bf16_tc: 16-byte alignment");
+  EncodeTiledFn encode = get_encode();
+  DSK_REQUIRE(encode != nullptr, "dsk_gemm_bf16_tc: cuTensorMapEncodeTiled is unavailable");
+  const int n_tile = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  CUtensorMap ta, tb;
+  auto make = [&](CUtensorMap* tm, const void* base, int rows, int64_t ld, int64_t stride, int box_rows) -> bool {
+    const bool shared = batch == 1 || stride == 0;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(shared ? 1 : batch)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(shared ? (int64_t)rows * ld : stride) * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  DSK_REQUIRE(make(&ta, A, M, lda, strideA, 128), "dsk_gemm_bf16_tc: tensor map for A failed");
+  DSK_REQUIRE(make(&tb, Bm, N, ldb, strideB, n_tile), "dsk_gemm_bf16_tc: tensor map for B failed");
+  GemmTcParams p;
+  p.M = M; p.N = N; p.K = K; p.batch = batch;
+  p.a_bmul = (batch > 1 && strideA != 0) ? 1 : 0;
+  p.b_bmul = (batch > 1 && strideB != 0) ? 1 : 0;
+  p.tiles_m = (M + 127) / 128; p.tiles_n = (N + n_tile - 1) / n_tile;
+  p.total_tiles = p.tiles_m * p.tiles_n * batch;
+  p.alpha = alpha; p.bias = bias; p.bias_rows = bias_rows;
+  p.residual = (const __nv_bfloat16*)residual; p.out = C; p.out_f32 = out_f32; p.ldc = ldc; p.strideC = strideC;
+  cudaStream_t st = as_stream(stream);
+  if (n_tile == 64) return launch_gemm_tc<64>(ta, tb, p, st);
+  if (n_tile == 128) return launch_gemm_tc<128>(ta, tb, p, st);
+  return launch_gemm_tc<256>(ta, tb, p, st);
+}
+
+extern "C" int dsk_softmax_rows_bf16(const float* S, void* P, int64_t rows, int cols, void* stream) {
+  DSK_REQUIRE(S && P && rows > 0 && cols > 0, "dsk_softmax_rows_bf16: bad arguments");
+  DSK_REQUIRE(cols % 4 == 0 && cols <= 8192, "dsk_softmax_rows_bf16: cols=%d must be a multiple of 4 and <= 8192", cols);
+  int64_t grid = rows < (int64_t)DSK_NUM_SMS * 16 ? rows : (int64_t)DSK_NUM_SMS * 16;
+  DSK_LAUNCH(softmax_rows_bf16_kernel, (int)grid, 256, 0, as_stream(stream), S, (__nv_bfloat16*)P, rows, cols);
+  return DSK_OK;
+}

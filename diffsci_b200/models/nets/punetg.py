@@ -223,7 +223,15 @@ class _Plan:
         Lq = sp[nlev][0] * sp[nlev][1] * sp[nlev][2]
         Cb = ch[nlev]
         self.attn = None
-        if len(net.attn_block) > 0:
+        self.attn_tc = (precision == "bf16" and _tc_eligible(Cb, Cb) and Lq % 8 == 0 and Lq <= 8192)
+        if len(net.attn_block) > 0 and self.attn_tc:
+            bf = dict(dtype=torch.bfloat16, device=dev)
+            self.attn = dict(qk=torch.empty((B * Lq, 2 * Cb), **bf), vt=torch.empty((B, Cb, Lq), **bf),
+                             scores=torch.empty((B, Lq, Lq), **f32), probs=torch.empty((B, Lq, Lq), **bf),
+                             ao=torch.empty((B * Lq, Cb), **bf))
+            self.attn_w = [(ops.PackedLinear(a.mhattn.in_proj_weight), ops.PackedLinear(a.mhattn.out_proj.weight))
+                           for a in net.attn_block]
+        elif len(net.attn_block) > 0:
             self.attn = dict(qkv=torch.empty((B * Lq, 3 * Cb), **f32), scores=torch.empty((B, Lq, Lq), **f32),
                              ao=torch.empty((B * Lq, Cb), **f32), out=torch.empty((B, Lq, Cb), **f32))
             if adt != torch.float32:
@@ -235,6 +243,10 @@ class _Plan:
         """Materialise packed weights (must happen outside CUDA-graph capture)."""
         for pc in [self.pc_in, self.pc_out, *self.pc_down, *self.pc_up, *[p for pair in self.pc.values() for p in pair]]:
             pc.packed()
+        if self.attn_tc and len(self.net.attn_block) > 0:
+            for wi, wo in self.attn_w:
+                wi.packed()
+                wo.packed()
 
     # ------------------------------------------------------------------ forward
     def _resblock(self, x, blk, l, out):
@@ -248,10 +260,15 @@ class _Plan:
                          out=self.N[l], ws=self.WS[l])
         return ops.conv(n, pc2, out=out, residual=x)
 
-    def _attention(self, x, attn, out):
+    def _attention(self, x, attn, out, index=0):
         a = self.attn
         m = attn.mhattn
         B, Lq, Cb = self.B, self.Lq, self.Cb
+        if self.attn_tc:
+            wi, wo = self.attn_w[index]
+            ops.self_attention_tc(x.view(B, Lq, Cb), wi, m.in_proj_bias, wo, m.out_proj.bias, a, out.view(B, Lq, Cb),
+                                  self.net.config.attn_residual)
+            return out
         if x.dtype == torch.float32:
             tok = x.view(B, Lq, Cb)
         else:
@@ -284,7 +301,7 @@ class _Plan:
         for r, blk in enumerate(net.attn_resnet_block):
             xa = self._resblock(xa, blk, nlev, self.XA)
             if r < len(net.attn_block):
-                xa = self._attention(xa, net.attn_block[r], self.XA2)
+                xa = self._attention(xa, net.attn_block[r], self.XA2, r)
                 # next block reads XA2 and writes XA (its residual input is XA2)
         x = ops.add(x, xa, out=x)
         for blk in net.after_block:

@@ -266,3 +266,60 @@ def philox_normal(shape, seed: int, stream_id: int, device) -> torch.Tensor:
     require_cuda(out, "noise")
     check(lib.dsk_philox_normal(ptr(out), out.numel(), seed & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, stream()))
     return out
+
+
+class PackedLinear:
+    """bf16 device copy of an fp32 [N, K] weight (K-major B/A operand of dsk_gemm_bf16_tc), version tracked."""
+
+    def __init__(self, weight: torch.Tensor):
+        self.weight = weight
+        self._packed = None
+        self._version = None
+
+    def packed(self) -> torch.Tensor:
+        w = self.weight
+        key = (w._version, w.data_ptr())
+        if self._packed is None or self._version != key or self._packed.device != w.device:
+            require_cuda(w, "linear weight")
+            with torch.inference_mode(False), torch.no_grad():
+                if self._packed is None or self._packed.device != w.device:
+                    self._packed = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+                cast(w.detach().float().contiguous(), torch.bfloat16, out=self._packed)
+                self._version = key
+        return self._packed
+
+
+def gemm_bf16_tc(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, lda: int, ldb: int,
+                 ldc: int, bias: Optional[torch.Tensor] = None, bias_rows: bool = False,
+                 residual: Optional[torch.Tensor] = None, alpha: float = 1.0, batch: int = 1, strideA: int = 0,
+                 strideB: int = 0, strideC: int = 0, a_off: int = 0, b_off: int = 0) -> torch.Tensor:
+    """Batched bf16 tensor-core GEMM C = alpha A B^T + bias (+ residual) on raw buffers (dsk_gemm_bf16_tc)."""
+    require_cuda(A, "gemm A")
+    assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16
+    a = C.c_void_p(A.data_ptr() + a_off * 2)
+    b = C.c_void_p(Bm.data_ptr() + b_off * 2)
+    check(lib.dsk_gemm_bf16_tc(a, b, ptr(out), ptr(bias), int(bias_rows), ptr(residual), M, N, K, lda, ldb, ldc, strideA,
+                               strideB, strideC, batch, alpha, int(out.dtype == torch.float32), stream()))
+    return out
+
+
+def self_attention_tc(tok: torch.Tensor, w_in: PackedLinear, in_b: torch.Tensor, w_out: PackedLinear, out_b: torch.Tensor,
+                      bufs: dict, out: torch.Tensor, residual: bool) -> torch.Tensor:
+    """nn.MultiheadAttention(C, 1 head) on bf16 tokens [B, L, C] with every product on the tensor cores
+    (reference nets/attention.py:54-72):  Q|K projection, V^T projection, S = QK^T/sqrt(C) (fp32), softmax -> bf16 P,
+    O = P V, output projection (+ residual) written straight into `out` ([B, L, C] bf16)."""
+    B, Lq, Cc = tok.shape
+    qk, vt, sc, pr, ao = bufs["qk"], bufs["vt"], bufs["scores"], bufs["probs"], bufs["ao"]
+    wi, wo, ib = w_in.packed(), w_out.packed(), in_b.detach()
+    gemm_bf16_tc(tok, wi, qk, M=B * Lq, N=2 * Cc, K=Cc, lda=Cc, ldb=Cc, ldc=2 * Cc, bias=ib)
+    # V^T[b] = W_v tok[b]^T + b_v : [C, L] so that it is the K-major B operand of P V
+    gemm_bf16_tc(wi, tok, vt, M=Cc, N=Lq, K=Cc, lda=Cc, ldb=Cc, ldc=Lq, bias=ib[2 * Cc:], bias_rows=True, batch=B,
+                 strideA=0, strideB=Lq * Cc, strideC=Cc * Lq, a_off=2 * Cc * Cc)
+    gemm_bf16_tc(qk, qk, sc, M=Lq, N=Lq, K=Cc, lda=2 * Cc, ldb=2 * Cc, ldc=Lq, alpha=Cc ** -0.5, batch=B,
+                 strideA=Lq * 2 * Cc, strideB=Lq * 2 * Cc, strideC=Lq * Lq, b_off=Cc)
+    check(lib.dsk_softmax_rows_bf16(ptr(sc), ptr(pr), B * Lq, Lq, stream()))
+    gemm_bf16_tc(pr, vt, ao, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=Lq, ldc=Cc, batch=B, strideA=Lq * Lq, strideB=Cc * Lq,
+                 strideC=Lq * Cc)
+    gemm_bf16_tc(ao, wo, out, M=B * Lq, N=Cc, K=Cc, lda=Cc, ldb=Cc, ldc=Cc, bias=out_b.detach(),
+                 residual=tok if residual else None)
+    return out

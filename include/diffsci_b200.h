@@ -144,6 +144,17 @@ int dsk_gemm_f32(const float* A, const float* Bm, float* Cm, const float* bias, 
                  int ldb, int ldc, int64_t strideA, int64_t strideB, int64_t strideC, int batch, int transB,
                  float alpha, int act, void* stream);
 
+/* Batched bf16 GEMM on tcgen05/TMEM (csrc/gemm_tc.cu): C[b] = alpha * A[b] B[b]^T + bias (+ residual).
+ * A [M,K] (lda), B [N,K] (ldb): bf16, K contiguous; C bf16 or fp32 (out_f32) with leading dimension ldc;
+ * bias fp32 per column (bias_rows = 0) or per row (bias_rows = 1); residual bf16 laid out like C.
+ * A batch stride of 0 shares the operand across the batch.  K, ld*, strides: multiples of 8 elements.
+ * The tensor-core form of the projections / QK^T / PV inside nn.MultiheadAttention (nets/attention.py:42-44). */
+int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const float* bias, int bias_rows, const void* residual, int M,
+                     int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
+                     int64_t strideC, int batch, float alpha, int out_f32, void* stream);
+/* softmax over the last dim: fp32 scores [rows, cols] -> bf16 probabilities (cols % 4 == 0, cols <= 8192) */
+int dsk_softmax_rows_bf16(const float* S, void* P, int64_t rows, int cols, void* stream);
+
 /* ---- K4: per-group norm + affine (+FiLM) + SiLU ---------------------------------------
  * Replaces torch.nn.GroupNorm(G,C) / GroupRMSNorm(G,C) (+ SiLU) in ResnetBlockC
  * (commonlayers.py:362-384, 824-831) and ADMBaseBlock (nets/adm.py:305-329).

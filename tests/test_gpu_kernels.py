@@ -279,3 +279,54 @@ def test_upsample2x(ops):
         x = torch.randn(2, 16, *sp).bfloat16()
         y = ops.upsample2x(to_cl(x.float()).bfloat16(), ndim)
         assert torch.equal(from_cl(y, ndim), F.interpolate(x.float(), scale_factor=2, mode="nearest"))
+
+
+@pytest.mark.parametrize("M,N,K,batch", [(128, 64, 64, 1), (300, 200, 136, 2), (64, 512, 256, 1), (1000, 96, 64, 3)])
+def test_gemm_bf16_tcgen05(ops, M, N, K, batch):
+    """tcgen05 batched GEMM vs fp32 matmul on the same bf16-rounded operands (fp32 accumulation both sides)."""
+    torch.manual_seed(13)
+    A = torch.randn(batch, M, K).bfloat16()
+    Bm = torch.randn(batch, N, K).bfloat16()
+    bias = torch.randn(N)
+    res = torch.randn(batch, M, N).bfloat16()
+    ref = 0.5 * (A.float() @ Bm.float().transpose(1, 2)) + bias + res.float()
+    ldc = (N + 7) // 8 * 8
+    out = torch.zeros(batch, M, ldc, device=DEV)
+    resp = torch.zeros(batch, M, ldc, dtype=torch.bfloat16)
+    resp[..., :N] = res
+    ops.gemm_bf16_tc(A.to(DEV), Bm.to(DEV), out, M=M, N=N, K=K, lda=K, ldb=K, ldc=ldc, bias=bias.to(DEV),
+                     residual=resp.to(DEV), alpha=0.5, batch=batch, strideA=M * K, strideB=N * K, strideC=M * ldc)
+    assert relmax(out.cpu()[..., :N], ref) < 1e-5
+    # shared A (stride 0), per-row bias, bf16 output: the V^T projection pattern
+    rb = torch.randn(M)
+    ref2 = A[0].float() @ Bm.float().transpose(1, 2) + rb.view(1, M, 1)
+    out2 = torch.zeros(batch, M, ldc, dtype=torch.bfloat16, device=DEV)
+    ops.gemm_bf16_tc(A[0].contiguous().to(DEV), Bm.to(DEV), out2, M=M, N=N, K=K, lda=K, ldb=K, ldc=ldc, bias=rb.to(DEV),
+                     bias_rows=True, batch=batch, strideA=0, strideB=N * K, strideC=M * ldc)
+    assert relmax(out2.float().cpu()[..., :N], ref2) < 6e-3
+
+
+def test_attention_tcgen05(ops):
+    from oracle import nets_oracle as N
+    torch.manual_seed(14)
+    B, C, sp = 2, 64, (8, 16)
+    Lq = sp[0] * sp[1]
+    x = torch.randn(B, C, *sp).bfloat16().float()
+    sd = {"a.mhattn.in_proj_weight": (torch.randn(3 * C, C) / math.sqrt(C)).bfloat16().float(),
+          "a.mhattn.in_proj_bias": torch.randn(3 * C) * 0.1,
+          "a.mhattn.out_proj.weight": (torch.randn(C, C) / math.sqrt(C)).bfloat16().float(),
+          "a.mhattn.out_proj.bias": torch.randn(C) * 0.1}
+    bf, f32 = dict(dtype=torch.bfloat16, device=DEV), dict(dtype=torch.float32, device=DEV)
+    bufs = dict(qk=torch.empty(B * Lq, 2 * C, **bf), vt=torch.empty(B, C, Lq, **bf), scores=torch.empty(B, Lq, Lq, **f32),
+                probs=torch.empty(B, Lq, Lq, **bf), ao=torch.empty(B * Lq, C, **bf))
+    tok = x.reshape(B, C, Lq).permute(0, 2, 1).contiguous().bfloat16().to(DEV)
+    wi = ops.PackedLinear(sd["a.mhattn.in_proj_weight"].to(DEV))
+    wo = ops.PackedLinear(sd["a.mhattn.out_proj.weight"].to(DEV))
+    for residual in (False, True):
+        ref = N.mha_self_attention(x, sd, "a.", residual)
+        out = torch.empty(B, Lq, C, **bf)
+        ops.self_attention_tc(tok, wi, sd["a.mhattn.in_proj_bias"].to(DEV), wo, sd["a.mhattn.out_proj.bias"].to(DEV), bufs, out,
+                              residual)
+        got = out.float().cpu().permute(0, 2, 1).reshape(x.shape)
+        # bf16 storage of Q|K, V^T, P and the attention output: stated tolerance 2e-2 of the output range
+        assert relmax(got, ref) < 2e-2, relmax(got, ref)

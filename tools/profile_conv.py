@@ -1,0 +1,37 @@
+"""The dominant kernel alone (tcgen05 conv C->C k3 at full resolution) for `ncu --set full`:
+  ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 3 -c 2 -o gpurun_out/prof python tools/profile_conv.py
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from diffsci_b200 import ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=2)
+ap.add_argument("--size", type=int, default=64)
+ap.add_argument("--cin", type=int, default=64)
+ap.add_argument("--cout", type=int, default=64)
+ap.add_argument("--reps", type=int, default=6)
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+w = torch.randn(a.cout, a.cin, 3, 3, 3, device=dev) * 0.02
+pc = ops.PackedConv(w, torch.zeros(a.cout, device=dev), 3, torch.bfloat16)
+xs = [torch.randn(a.batch, a.size, a.size, a.size, a.cin, device=dev).bfloat16() for _ in range(3)]
+out = torch.empty(a.batch, a.size, a.size, a.size, a.cout, device=dev, dtype=torch.bfloat16)
+for i in range(3):
+    ops.conv(xs[i % 3], pc, out=out)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(a.reps):
+    ops.conv(xs[i % 3], pc, out=out)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.reps
+fl = 2.0 * a.batch * a.size ** 3 * a.cin * a.cout * 27
+print(f"conv3d {a.cin}->{a.cout} @ {a.size}^3 B={a.batch}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s")
