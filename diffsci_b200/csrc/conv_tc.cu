@@ -98,7 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer: activation patches =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t seq = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = tile_coord(p, t, N_TILE, P);
@@ -118,7 +118,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== TMA producer: weight taps =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t seq = 0;
       const int ntaps = KD * 9;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -138,51 +138,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     }
   } else if (warp == 2) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      uint32_t seq_a = 0, seq_b = 0, it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        const uint32_t as = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(&acc_empty[as], aph ^ 1);               // epilogue has drained this accumulator set
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_acc = tmem_base + as * (P * N_TILE);
-        for (int c = 0; c < nchunks; ++c) {
-          const uint32_t seq_c = seq_a;                    // first patch of this (tile, chunk)
-          for (int kd = 0; kd < KD; ++kd) {
-            // patches first needed at this kd: j = 0..P-1 at kd == 0, else j = P-1+kd
-            const int jlo = kd == 0 ? 0 : P - 1 + kd, jhi = P - 1 + kd;
-            for (int j = jlo; j <= jhi; ++j) {
-              const uint32_t s = seq_c + j;
-              mbar_wait(&full_a[s % NA], (s / NA) & 1);
-            }
+    // The whole warp walks the control flow (barrier waits are warp-uniform); one elected lane issues.
+    const uint32_t idesc = umma_idesc_bf16(N_TILE);
+    constexpr uint32_t A_HI = umma_desc_hi(TC_PW * 128), B_HI = umma_desc_hi(1024);
+    uint32_t seq_a = 0, seq_b = 0, it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(&acc_empty[as], aph ^ 1);               // epilogue has drained this accumulator set
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_acc = tmem_base + as * (P * N_TILE);
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t seq_c = seq_a;                    // first patch of this (tile, chunk)
+        for (int kd = 0; kd < KD; ++kd) {
+          // patches first needed at this kd: j = 0..P-1 at kd == 0, else j = P-1+kd
+          const int jlo = kd == 0 ? 0 : P - 1 + kd, jhi = P - 1 + kd;
+          for (int j = jlo; j <= jhi; ++j) {
+            const uint32_t s = seq_c + j;
+            mbar_wait(&full_a[s % NA], (s / NA) & 1);
+          }
+          uint32_t a_lo[P];
+#pragma unroll
+          for (int pp = 0; pp < P; ++pp)
+            a_lo[pp] = umma_desc_lo(smem_u32(sA + (size_t)((seq_c + pp + kd) % NA) * TC_PATCH_STRIDE));
+#pragma unroll
+          for (int khw = 0; khw < 9; ++khw, ++seq_b) {
+            const uint32_t bs = seq_b % NB;
+            mbar_wait(&full_b[bs], (seq_b / NB) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int kh = 0; kh < 3; ++kh)
-              for (int kw = 0; kw < 3; ++kw, ++seq_b) {
-                const uint32_t bs = seq_b % NB;
-                mbar_wait(&full_b[bs], (seq_b / NB) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t b_addr = smem_u32(sB + (size_t)bs * B_BYTES);
+            const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_BYTES));
+            const uint32_t tap_off = ((khw / 3) * TC_PW + (khw % 3)) * 8;      // (kh*10 + kw) * 128 B >> 4
+            const uint32_t first = (c | kd | khw) == 0 ? 0u : 1u;
+            if (elect_one_sync()) {
 #pragma unroll
-                for (int pp = 0; pp < P; ++pp) {
-                  const uint32_t s = seq_c + pp + kd;
-                  const uint32_t a_addr = smem_u32(sA + (size_t)(s % NA) * TC_PATCH_STRIDE) + (kh * TC_PW + kw) * 128;
+              for (int pp = 0; pp < P; ++pp) {
 #pragma unroll
-                  for (int k4 = 0; k4 < 4; ++k4) {
-                    const uint32_t acc = (c | kd | kh | kw | k4) != 0;
-                    umma_bf16(tmem_acc + pp * N_TILE, umma_desc(a_addr + k4 * 32, TC_PW * 128), umma_desc(b_addr + k4 * 32, 1024),
-                              idesc, acc);
-                  }
-                }
-                umma_commit(&empty_b[bs]);                 // weight slot free once these MMAs retire
+                for (int k4 = 0; k4 < 4; ++k4)
+                  umma_bf16(tmem_acc + pp * N_TILE, umma_desc64(a_lo[pp] + tap_off + k4 * 2, A_HI),
+                            umma_desc64(b_lo + k4 * 2, B_HI), idesc, k4 == 0 ? first : 1u);
               }
-            // patches whose last use was this kd
-            const int rlo = kd, rhi = (kd == KD - 1) ? NJ - 1 : kd;
+              umma_commit(&empty_b[bs]);                 // weight slot free once these MMAs retire
+            }
+            __syncwarp();
+          }
+          // patches whose last use was this kd
+          const int rlo = kd, rhi = (kd == KD - 1) ? NJ - 1 : kd;
+          if (elect_one_sync()) {
             for (int j = rlo; j <= rhi; ++j) umma_commit(&empty_a[(seq_c + j) % NA]);
           }
-          seq_a += NJ;
+          __syncwarp();
         }
-        umma_commit(&acc_full[as]);
+        seq_a += NJ;
       }
+      if (elect_one_sync()) umma_commit(&acc_full[as]);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================

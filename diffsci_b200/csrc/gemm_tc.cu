@@ -52,7 +52,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t seq = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int tn = t % p.tiles_n, tm = (t / p.tiles_n) % p.tiles_m, b = t / (p.tiles_n * p.tiles_m);
@@ -75,26 +75,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(N_TILE);
-      uint32_t seq = 0, it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        const uint32_t as = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(&acc_empty[as], aph ^ 1);
+    const uint32_t idesc = umma_idesc_bf16(N_TILE);
+    constexpr uint32_t HI = umma_desc_hi(1024);
+    uint32_t seq = 0, it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(&acc_empty[as], aph ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_acc = tmem_base + as * N_TILE;
+      for (int kc = 0; kc < kchunks; ++kc, ++seq) {
+        const uint32_t slot = seq % GT_STAGES;
+        mbar_wait(&full[slot], (seq / GT_STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_acc = tmem_base + as * N_TILE;
-        for (int kc = 0; kc < kchunks; ++kc, ++seq) {
-          const uint32_t slot = seq % GT_STAGES;
-          mbar_wait(&full[slot], (seq / GT_STAGES) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_addr = smem_u32(smem + (size_t)slot * STAGE), b_addr = a_addr + A_BYTES;
+        const uint32_t a_lo = umma_desc_lo(smem_u32(smem + (size_t)slot * STAGE)), b_lo = a_lo + (A_BYTES >> 4);
+        if (elect_one_sync()) {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
-            umma_bf16(tmem_acc, umma_desc(a_addr + k4 * 32, 1024), umma_desc(b_addr + k4 * 32, 1024), idesc, (kc | k4) != 0);
+            umma_bf16(tmem_acc, umma_desc64(a_lo + k4 * 2, HI), umma_desc64(b_lo + k4 * 2, HI), idesc, (kc | k4) != 0);
           umma_commit(&empty[slot]);
         }
-        umma_commit(&acc_full[as]);
+        __syncwarp();
       }
+      if (elect_one_sync()) umma_commit(&acc_full[as]);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

@@ -67,6 +67,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
       : "r"(taddr));                                                                                                       \
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 
+// One lane of a fully-active warp, chosen by the hardware: the form the compiler turns into a plain predicated
+// UTCHMMA / UTMALDG (an `if (lane == 0)` region makes it wrap every uniform-datapath op in a waterfall loop).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+// Descriptor words for K-major SWIZZLE_128B operands.  lo = start address >> 4 | LBO(=1) << 16 ; hi = SBO >> 4 |
+// version(1) << 14 | SWIZZLE_128B(2) << 29.  Shared memory is < 256 KB so (addr >> 4) never carries into the LBO field
+// and a view is advanced by adding (bytes >> 4) to the low word.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return (saddr >> 4) | 0x10000u; }
+__device__ __forceinline__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint64_t umma_desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 // bf16 x bf16 -> fp32, both operands K-major, M = 128
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
