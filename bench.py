@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (net kind, config kwargs, sample shape, nsteps, integrator, default per-GPU batch)
-    "c4": ("punetg", dict(dimension=3), (1, 64, 64, 64), 64, "heun", 2),
+    "c4": ("punetg", dict(dimension=3), (1, 64, 64, 64), 64, "heun", 8),
     "c2": ("punetg", dict(dimension=2, model_channels=128), (1, 28, 28), 40, "heun", 256),
     "c5": ("punetg", dict(dimension=2), (1, 256, 256), 256, "euler-maruyama", 8),
     "c1": ("mlp", dict(dim=2, hidden_dims=[128, 128, 128]), (2,), 18, "heun", 65536),

@@ -39,8 +39,10 @@ template <> __device__ __forceinline__ void st8f<__nv_bfloat16>(__nv_bfloat16* p
   *reinterpret_cast<uint4*>(p) = o;
 }
 
-// ---- convout: C (multiple of 8) -> COUT <= 4.  Thread = (pixel, 8-channel chunk); the C/8 chunk-threads of a
-// pixel are adjacent lanes, so each warp load is a contiguous run of pixels; partial sums meet by shuffle.
+// ---- convout: C (multiple of 8) -> COUT <= 4.  Thread = (run of FO_PW pixels along w, 8-channel chunk): the kw
+// taps of neighbouring outputs share their input vectors in registers (FO_PW + 2 loads feed 3 * FO_PW tap products),
+// the C/8 chunk-threads of a pixel run are adjacent lanes and meet by shuffle.
+constexpr int FO_PW = 4;
 template <typename TI, typename TO, int COUT>
 __global__ void __launch_bounds__(256) conv_few_out_kernel(SmallConvArgs a) {
   extern __shared__ float wsm[];                      // [taps][Cin][COUT]
@@ -48,82 +50,105 @@ __global__ void __launch_bounds__(256) conv_few_out_kernel(SmallConvArgs a) {
   for (int i = threadIdx.x; i < taps * a.Cin * COUT; i += blockDim.x) wsm[i] = a.w[i];
   __syncthreads();
   const int chunks = a.Cin >> 3;                      // power of two <= 32 (checked on the host)
-  const int64_t npix = (int64_t)a.B * a.D * a.H * a.W;
+  const int wruns = (a.W + FO_PW - 1) / FO_PW;
+  const int64_t nruns = (int64_t)a.B * a.D * a.H * wruns;
   const int64_t S = (int64_t)a.D * a.H * a.W;
   const TI* in = reinterpret_cast<const TI*>(a.in);
   const int r = a.ks >> 1;
-  const int64_t total = npix * chunks;
+  const int64_t total = nruns * chunks;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  // every lane of a warp runs the same number of iterations (total is padded to a warp multiple by the loop bound)
-  const int64_t padded = (total + 31) & ~(int64_t)31;
+  const int64_t padded = (total + 31) & ~(int64_t)31;  // whole warps iterate together (shuffles below)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += stride) {
     const bool live = i < total;
-    const int64_t pix = live ? i / chunks : 0;
+    int64_t t = live ? i / chunks : 0;
     const int ch = (int)(i % chunks) * 8;
-    int64_t t = pix;
-    const int w0 = (int)(t % a.W); t /= a.W;
+    const int w0 = (int)(t % wruns) * FO_PW; t /= wruns;
     const int h0 = (int)(t % a.H); t /= a.H;
     const int d0 = (int)(t % a.D);
     const int b = (int)(t / a.D);
-    float acc[COUT];
+    float acc[FO_PW][COUT];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = 0.0f;
+    for (int px = 0; px < FO_PW; ++px)
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) acc[px][co] = 0.0f;
     if (live) {
-      int tap = 0;
       for (int kd = 0; kd < (a.ndim == 3 ? a.ks : 1); ++kd)
-        for (int kh = 0; kh < a.ks; ++kh)
-          for (int kw = 0; kw < a.ks; ++kw, ++tap) {
-            const int zd = a.ndim == 3 ? d0 + kd - r : 0, zh = h0 + kh - r, zw = w0 + kw - r;
-            if ((unsigned)zd >= (unsigned)a.D || (unsigned)zh >= (unsigned)a.H || (unsigned)zw >= (unsigned)a.W) continue;
+        for (int kh = 0; kh < a.ks; ++kh) {
+          const int zd = a.ndim == 3 ? d0 + kd - r : 0, zh = h0 + kh - r;
+          if ((unsigned)zd >= (unsigned)a.D || (unsigned)zh >= (unsigned)a.H) continue;
+          const TI* rowp = in + (((int64_t)b * a.D + zd) * a.H + zh) * a.W * a.Cin + ch;
+          const int tap0 = (kd * a.ks + kh) * a.ks;
+          // input columns w0 - r .. w0 + FO_PW - 1 + r
+#pragma unroll
+          for (int xi = 0; xi < FO_PW + 2; ++xi) {
+            const int zw = w0 + xi - 1;                // ks == 3: r == 1; ks == 1 uses only xi = 1..FO_PW
+            if (a.ks == 1 && (xi == 0 || xi == FO_PW + 1)) continue;
+            if ((unsigned)zw >= (unsigned)a.W) continue;
             float x[8];
-            ld8f<TI>(in + ((((int64_t)b * a.D + zd) * a.H + zh) * a.W + zw) * a.Cin + ch, x);
-            const float* wp = wsm + ((int64_t)tap * a.Cin + ch) * COUT;
+            ld8f<TI>(rowp + (int64_t)zw * a.Cin, x);
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
+            for (int kw = 0; kw < 3; ++kw) {
+              const int px = xi - kw;                  // output pixel (relative) that sees this column through tap kw
+              if (px < 0 || px >= FO_PW) continue;
+              if (a.ks == 1 && kw != 1) continue;
+              const float* wp = wsm + ((int64_t)(tap0 + (a.ks == 1 ? 0 : kw)) * a.Cin + ch) * COUT;
 #pragma unroll
-              for (int co = 0; co < COUT; ++co) acc[co] = fmaf(x[e], wp[e * COUT + co], acc[co]);
+              for (int e = 0; e < 8; ++e)
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) acc[px][co] = fmaf(x[e], wp[e * COUT + co], acc[px][co]);
+            }
           }
+        }
     }
     for (int o = chunks >> 1; o > 0; o >>= 1)
 #pragma unroll
-      for (int co = 0; co < COUT; ++co) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+      for (int px = 0; px < FO_PW; ++px)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[px][co] += __shfl_xor_sync(0xffffffffu, acc[px][co], o);
     if (live && ch == 0) {
 #pragma unroll
-      for (int co = 0; co < COUT; ++co) {
-        if (co >= a.Cout) break;
-        float v = acc[co] + (a.bias != nullptr ? a.bias[co] : 0.0f);
-        if (a.out_nchw != nullptr) a.out_nchw[((int64_t)b * a.Cout + co) * S + (pix - (int64_t)b * S)] = v;
-        else reinterpret_cast<TO*>(a.out)[pix * a.Cout + co] = from_f32<TO>(v);
+      for (int px = 0; px < FO_PW; ++px) {
+        if (w0 + px >= a.W) break;
+        const int64_t pix = (((int64_t)b * a.D + d0) * a.H + h0) * a.W + w0 + px;
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+          if (co >= a.Cout) break;
+          float v = acc[px][co] + (a.bias != nullptr ? a.bias[co] : 0.0f);
+          if (a.out_nchw != nullptr) a.out_nchw[((int64_t)b * a.Cout + co) * S + (pix - (int64_t)b * S)] = v;
+          else reinterpret_cast<TO*>(a.out)[pix * a.Cout + co] = from_f32<TO>(v);
+        }
       }
     }
   }
 }
 
-// ---- convin: CIN <= 4 -> Cout (multiple of 8).  Thread = (pixel, 8 output channels): the taps of a pixel are a
-// handful of scalars (L1 broadcast across the chunk-threads), the store is a coalesced 16/32-byte vector.
+// ---- convin: CIN <= 4 -> Cout (multiple of 32).  Thread = (pixel, 32 output channels): the taps of a pixel are a
+// handful of scalars, amortised over 32 accumulators; weights are smem broadcasts; the store is 4 x 16 B.
+constexpr int FI_CO = 32;
 template <typename TI, typename TO, int CIN>
 __global__ void __launch_bounds__(256) conv_few_in_kernel(SmallConvArgs a) {
   extern __shared__ float wsm[];                      // [taps][CIN][Cout]
   const int taps = a.ndim == 3 ? a.ks * a.ks * a.ks : a.ks * a.ks;
   for (int i = threadIdx.x; i < taps * CIN * a.Cout; i += blockDim.x) wsm[i] = a.w[i];
   __syncthreads();
-  const int chunks = a.Cout >> 3;
+  const int chunks = a.Cout / FI_CO;
   const int64_t npix = (int64_t)a.B * a.D * a.H * a.W;
   const TI* in = reinterpret_cast<const TI*>(a.in);
   TO* out = reinterpret_cast<TO*>(a.out);
   const int r = a.ks >> 1;
   const int64_t total = npix * chunks;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t pix = i / chunks;
-    const int ch = (int)(i % chunks) * 8;
+    // pixel-major within a warp: consecutive lanes = consecutive pixels (coalesced tap loads), chunk outermost per block row
+    const int64_t pix = i % npix;
+    const int ch = (int)(i / npix) * FI_CO;
     int64_t t = pix;
     const int w0 = (int)(t % a.W); t /= a.W;
     const int h0 = (int)(t % a.H); t /= a.H;
     const int d0 = (int)(t % a.D);
     const int b = (int)(t / a.D);
-    float acc[8];
+    float acc[FI_CO];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = a.bias != nullptr ? a.bias[ch + e] : 0.0f;
+    for (int e = 0; e < FI_CO; ++e) acc[e] = a.bias != nullptr ? a.bias[ch + e] : 0.0f;
     int tap = 0;
     for (int kd = 0; kd < (a.ndim == 3 ? a.ks : 1); ++kd)
       for (int kh = 0; kh < a.ks; ++kh)
@@ -134,12 +159,19 @@ __global__ void __launch_bounds__(256) conv_few_in_kernel(SmallConvArgs a) {
 #pragma unroll
           for (int ci = 0; ci < CIN; ++ci) {
             const float x = to_f32<TI>(ip[ci]);
-            const float* wp = wsm + ((int64_t)tap * CIN + ci) * a.Cout + ch;
+            const float4* wp = reinterpret_cast<const float4*>(wsm + ((int64_t)tap * CIN + ci) * a.Cout + ch);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = fmaf(x, wp[e], acc[e]);
+            for (int e4 = 0; e4 < FI_CO / 4; ++e4) {
+              const float4 w4 = wp[e4];
+              acc[4 * e4] = fmaf(x, w4.x, acc[4 * e4]);
+              acc[4 * e4 + 1] = fmaf(x, w4.y, acc[4 * e4 + 1]);
+              acc[4 * e4 + 2] = fmaf(x, w4.z, acc[4 * e4 + 2]);
+              acc[4 * e4 + 3] = fmaf(x, w4.w, acc[4 * e4 + 3]);
+            }
           }
         }
-    st8f<TO>(out + pix * a.Cout + ch, acc);
+#pragma unroll
+    for (int e8 = 0; e8 < FI_CO / 8; ++e8) st8f<TO>(out + pix * a.Cout + ch + e8 * 8, acc + e8 * 8);
   }
 }
 
@@ -147,7 +179,7 @@ template <typename TI, typename TO>
 static int launch_few_out(const SmallConvArgs& a, cudaStream_t st) {
   const int taps = a.ndim == 3 ? a.ks * a.ks * a.ks : a.ks * a.ks;
   const size_t smem = (size_t)taps * a.Cin * 4 * sizeof(float);
-  const int64_t total = (int64_t)a.B * a.D * a.H * a.W * (a.Cin / 8);
+  const int64_t total = (int64_t)a.B * a.D * a.H * ((a.W + FO_PW - 1) / FO_PW) * (a.Cin / 8);
   const int grid = grid_for(total, 256, 16);
   switch (a.Cout) {
     case 1: DSK_LAUNCH((conv_few_out_kernel<TI, TO, 1>), grid, 256, smem, st, a); break;
@@ -162,7 +194,7 @@ template <typename TI, typename TO>
 static int launch_few_in(const SmallConvArgs& a, cudaStream_t st) {
   const int taps = a.ndim == 3 ? a.ks * a.ks * a.ks : a.ks * a.ks;
   const size_t smem = (size_t)taps * a.Cin * a.Cout * sizeof(float);
-  const int64_t total = (int64_t)a.B * a.D * a.H * a.W * (a.Cout / 8);
+  const int64_t total = (int64_t)a.B * a.D * a.H * a.W * (a.Cout / FI_CO);
   const int grid = grid_for(total, 256, 16);
   switch (a.Cin) {
     case 1: DSK_LAUNCH((conv_few_in_kernel<TI, TO, 1>), grid, 256, smem, st, a); break;
@@ -182,8 +214,8 @@ int conv_small_dispatch(const dsk_conv_desc* d, const void* in, const void* w, c
                   d->B, d->D, d->H, d->W, d->Cin, d->Cout, d->ksize, d->ndim};
   const int chunks = d->Cin / 8;
   const bool few_out = d->Cout <= 4 && d->Cin % 8 == 0 && chunks <= 32 && (chunks & (chunks - 1)) == 0 &&
-                       (size_t)taps * d->Cin * 4 * 4 <= 48 * 1024;
-  const bool few_in = d->Cin <= 4 && d->Cout % 8 == 0 && !d->out_nchw_f32 && (size_t)taps * d->Cin * d->Cout * 4 <= 48 * 1024;
+                       (size_t)taps * d->Cin * 4 * 4 <= 48 * 1024 && (d->ksize == 3 || d->ksize == 1);
+  const bool few_in = d->Cin <= 4 && d->Cout % FI_CO == 0 && !d->out_nchw_f32 && (size_t)taps * d->Cin * d->Cout * 4 <= 48 * 1024;
   if (!few_out && !few_in) return 0;
   const int ti = d->in_dtype, to = d->out_nchw_f32 ? DSK_F32 : d->out_dtype;
   int rc;

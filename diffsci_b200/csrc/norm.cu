@@ -58,11 +58,13 @@ static inline int norm_chunks(int B, int64_t S, int C, int V) {
   int cv = C / V;
   int pl = NORM_THREADS / cv;
   if (pl < 1) pl = 1;
-  int64_t by_work = (S + (int64_t)pl * 8 - 1) / ((int64_t)pl * 8);  // >= 8 pixels per thread per chunk
-  int64_t by_grid = (4 * DSK_NUM_SMS + B - 1) / B;
-  int64_t n = by_work < by_grid ? by_work : by_grid;
+  // each thread accumulates at most 64 pixels in fp32 (then everything is combined in fp64)
+  int64_t need = (S + (int64_t)pl * 64 - 1) / ((int64_t)pl * 64);
+  int64_t fill = (2 * DSK_NUM_SMS + B - 1) / B;                       // enough blocks to occupy the chip
+  int64_t by_work = (S + (int64_t)pl * 8 - 1) / ((int64_t)pl * 8);    // but >= 8 pixels per thread
+  if (fill > by_work) fill = by_work;
+  int64_t n = need > fill ? need : fill;
   if (n < 1) n = 1;
-  if (n > 1024) n = 1024;
   return (int)n;
 }
 
@@ -71,7 +73,7 @@ template <typename T>
 __global__ void __launch_bounds__(NORM_THREADS) norm_partial_kernel(const T* __restrict__ x, double2* __restrict__ partial,
                                                                      int64_t S, int C, int nchunks) {
   constexpr int V = NormVec<T>::V;
-  extern __shared__ double2 sm[];  // [pl][C]
+  extern __shared__ float2 sm[];   // [pl][C] per-thread fp32 partials (<= 64 pixels each)
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int cv = C / V;
   const int pl = max(1, NORM_THREADS / cv);
@@ -82,37 +84,41 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_partial_kernel(const T* __r
   for (int v = threadIdx.x; v < pl * cv; v += NORM_THREADS) {
     const int lane = v / cv, c0 = (v - lane * cv) * V;
     float sum[V], sq[V];
-    double dsum[V], dsq[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) { sum[k] = 0; sq[k] = 0; dsum[k] = 0; dsq[k] = 0; }
-    int cnt = 0;
-    for (int64_t s = s0 + lane; s < s1; s += pl) {
+    for (int k = 0; k < V; ++k) { sum[k] = 0; sq[k] = 0; }
+    int64_t s = s0 + lane;
+    // 8 independent 16-byte loads in flight per thread before any dependent arithmetic
+    for (; s + 7 * (int64_t)pl < s1; s += 8 * (int64_t)pl) {
+      float e[8][V];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) NormVec<T>::ld(xb + (s + u * (int64_t)pl) * C + c0, e[u]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          sum[k] += e[u][k];
+          sq[k] = fmaf(e[u][k], e[u][k], sq[k]);
+        }
+    }
+    for (; s < s1; s += pl) {
       float e[V];
       NormVec<T>::ld(xb + s * C + c0, e);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         sum[k] += e[k];
-        sq[k] += e[k] * e[k];
-      }
-      if (++cnt == 64) {  // flush fp32 partials to fp64 every 64 elements
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          dsum[k] += sum[k]; dsq[k] += sq[k];
-          sum[k] = 0; sq[k] = 0;
-        }
-        cnt = 0;
+        sq[k] = fmaf(e[k], e[k], sq[k]);
       }
     }
 #pragma unroll
-    for (int k = 0; k < V; ++k) sm[lane * C + c0 + k] = make_double2(dsum[k] + sum[k], dsq[k] + sq[k]);
+    for (int k = 0; k < V; ++k) sm[lane * C + c0 + k] = make_float2(sum[k], sq[k]);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += NORM_THREADS) {
     double a = 0, q = 0;
     for (int l = 0; l < pl; ++l) {
-      double2 v = sm[l * C + c];
-      a += v.x;
-      q += v.y;
+      float2 v = sm[l * C + c];
+      a += (double)v.x;
+      q += (double)v.y;
     }
     partial[((int64_t)b * nchunks + chunk) * C + c] = make_double2(a, q);
   }
@@ -166,6 +172,11 @@ __global__ void __launch_bounds__(128) norm_finalize_kernel(const double2* __res
   }
 }
 
+template <typename TO> __device__ __forceinline__ float silu_out(float v) { return silu_f(v); }
+// bf16 output keeps 8 mantissa bits: the approximate exp / divide (rel. error ~1e-6) is invisible after rounding and
+// takes the kernel from instruction-bound back to HBM-bound
+template <> __device__ __forceinline__ float silu_out<__nv_bfloat16>(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
 // Thread = fixed V-channel vector (scale/shift held in registers), strided over the pixels of one sample.
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(NORM_THREADS) norm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ y,
@@ -184,13 +195,28 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_apply_kernel(const TI* __re
       const float2 t = table[(int64_t)b * C + c0 + k];
       sc[k] = t.x; sh[k] = t.y;
     }
-    for (int64_t s = (int64_t)blockIdx.x * pl + lane; s < S; s += (int64_t)gridDim.x * pl) {
+    const int64_t step = (int64_t)gridDim.x * pl;
+    int64_t s = (int64_t)blockIdx.x * pl + lane;
+    for (; s + step < S; s += 2 * step) {     // two independent load->store chains per iteration
+      float e0[V], e1[V], o0[V], o1[V];
+      NormVec<TI>::ld(xb + s * C + c0, e0);
+      NormVec<TI>::ld(xb + (s + step) * C + c0, e1);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float t0 = fmaf(e0[k], sc[k], sh[k]), t1 = fmaf(e1[k], sc[k], sh[k]);
+        o0[k] = silu ? silu_out<TO>(t0) : t0;
+        o1[k] = silu ? silu_out<TO>(t1) : t1;
+      }
+      st_vec<TO, V>(yb + s * C + c0, o0);
+      st_vec<TO, V>(yb + (s + step) * C + c0, o1);
+    }
+    for (; s < S; s += step) {
       float e[V], o[V];
       NormVec<TI>::ld(xb + s * C + c0, e);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         const float t = fmaf(e[k], sc[k], sh[k]);
-        o[k] = silu ? silu_f(t) : t;
+        o[k] = silu ? silu_out<TO>(t) : t;
       }
       st_vec<TO, V>(yb + s * C + c0, o);
     }
@@ -228,7 +254,7 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
   float2* table = reinterpret_cast<float2*>(partial + (int64_t)B * nchunks * C);
   const int cv = C / V;
   const int pl = NORM_THREADS / cv > 0 ? NORM_THREADS / cv : 1;
-  const size_t smem = (size_t)pl * C * sizeof(double2);
+  const size_t smem = (size_t)pl * C * sizeof(float2);
   DSK_REQUIRE(smem <= 48 * 1024, "dsk_norm_act: C=%d too large for the stats kernel", C);
   dim3 pg(nchunks, B);
   if (in_dtype == DSK_F32)
