@@ -24,6 +24,8 @@ def build_net(g, precision="fp32"):
     from oracle.nets_oracle import synth_state_dict
     if g["kind"] == "punetg":
         net = d.PUNetG(d.PUNetGConfig(**g["cfg"]), precision=precision)
+    elif g["kind"] == "adm":
+        net = d.ADM(d.ADMConfig(**g["cfg"]), precision=precision)
     elif g["kind"] == "mlp":
         net = d.MLPUncond(g["cfg"]["dim"], g["cfg"]["hidden_dims"], torch.nn.SiLU())
     else:
@@ -35,7 +37,7 @@ def build_net(g, precision="fp32"):
     return net.to(DEV).eval()
 
 
-@pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8", "punetg2d_multi", "mlp_silu"])
+@pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8", "punetg2d_multi", "mlp_silu", "adm2d_mc8", "adm2d_add"])
 def test_net_forward_fp32(golden, name):
     g = golden(name)
     net = build_net(g)
@@ -49,7 +51,7 @@ def test_net_forward_fp32(golden, name):
     assert relmax(y, g["y"]) < max(4 * e_ref, FP32_TOL)
 
 
-@pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8"])
+@pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8", "adm2d_mc8"])
 def test_net_forward_bf16(golden, name):
     g = golden(name)
     net = build_net(g, "bf16")

@@ -88,16 +88,25 @@ def test_scalar_api_matches_reference(golden):
         assert ema._power_function_beta(sd_, n) == v
 
 
-@pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8", "punetg2d_multi", "mlp_silu"])
+@pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8", "punetg2d_multi", "mlp_silu", "adm2d_mc8", "adm2d_add"])
 def test_state_dict_layout_is_the_reference_layout(golden, name):
     import diffsci_b200 as d
     g = golden(name)
     if g["kind"] == "punetg":
         net = d.PUNetG(d.PUNetGConfig(**g["cfg"]))
+    elif g["kind"] == "adm":
+        net = d.ADM(d.ADMConfig(**g["cfg"]))
     else:
         net = d.MLPUncond(g["cfg"]["dim"], g["cfg"]["hidden_dims"], torch.nn.SiLU())
     got = [(k, list(v.shape)) for k, v in net.state_dict().items()]
     assert got == [(k, list(s)) for k, s in g["manifest"]]
+
+
+def test_default_adm_has_181_tensors():
+    import diffsci_b200 as d
+    sd = d.ADM(d.ADMConfig(input_channels=3, output_channels=3)).state_dict()    # 181 tensors, 18.19 M params
+    assert len(sd) == 181
+    assert abs(sum(v.numel() for v in sd.values()) / 1e6 - 18.19) < 0.05
 
 
 def test_default_punetg_has_213_tensors():
