@@ -43,13 +43,18 @@ struct TcParams {
   const __nv_bfloat16* residual;  // like out, or null
   __nv_bfloat16* out;     // [B, D, H, W, Cout]
   int planes_per_sample;  // D for 3-D; 1 for 2-D  (chan_bias row = plane / planes_per_sample)
+  int nphase;             // sub-pixel UpSampler conv: 8 (3-D) / 4 (2-D) output parities per input-resolution tile, else 1
 };
 
 struct TileCoord {
   int w0, h0, d0, b, n0;
+  int pa, pb, pc;   // output parity (depth, height, width) of a sub-pixel phase; 0 otherwise
+  int phase;
 };
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t, int n_tile_size, int P) {
   TileCoord c;
+  c.phase = t % p.nphase; t /= p.nphase;            // phases of one tile run back to back (same patches: L2 hits)
+  c.pc = c.phase & 1; c.pb = (c.phase >> 1) & 1; c.pa = (c.phase >> 2) & 1;
   c.w0 = (t % p.tiles_w) * TC_BW; t /= p.tiles_w;
   c.h0 = (t % p.tiles_h) * TC_BH; t /= p.tiles_h;
   c.d0 = (t % p.groups_d) * P;    t /= p.groups_d;
@@ -59,7 +64,10 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t, int n_
 }
 
 // N_TILE: output channels per CTA tile (64 | 128); P: planes per tile; NA: patch ring depth; NB: weight ring depth
-template <int N_TILE, int P, int NA, int NB>
+// UPS: conv(nearest_upsample_x2(x)) evaluated at INPUT resolution: for each output parity (a,b,c) the 3 taps of an axis
+// collapse onto 2 input offsets {a-1, a} (weights pre-summed by pack_upconv_weight_kernel), i.e. 8 phase-specific
+// 2x2x2 convolutions -- 64 tap-GEMMs per 8 outputs instead of 27 per output (3.4x fewer MACs), no 8x tensor in HBM.
+template <int N_TILE, int P, int NA, int NB, bool UPS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -120,11 +128,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     // ===================== TMA producer: weight taps =====================
     if (elect_one_sync()) {
       uint32_t seq = 0;
-      const int ntaps = KD * 9;
+      const int ntaps = UPS ? (KD == 3 ? 8 : 4) : KD * 9;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = tile_coord(p, t, N_TILE, P);
+        const int tap_base = UPS ? tc.phase * ntaps : 0;
         for (int c = 0; c < nchunks; ++c)
-          for (int tap = 0; tap < ntaps; ++tap, ++seq) {
+          for (int tap = tap_base; tap < tap_base + ntaps; ++tap, ++seq) {
             const uint32_t slot = seq % NB, ph = (seq / NB) & 1;
             mbar_wait(&empty_b[slot], ph ^ 1);
             mbar_expect_tx(&full_b[slot], B_BYTES);
@@ -147,8 +156,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       mbar_wait(&acc_empty[as], aph ^ 1);               // epilogue has drained this accumulator set
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_acc = tmem_base + as * (P * N_TILE);
+      const TileCoord tc = tile_coord(p, t, N_TILE, P);
       for (int c = 0; c < nchunks; ++c) {
         const uint32_t seq_c = seq_a;                    // first patch of this (tile, chunk)
+        if constexpr (UPS) {
+          // all patches of the chunk up front; taps kd in {a, a+1}, kh in {b, b+1}, kw in {c, c+1}
+          for (int j = 0; j < NJ; ++j) mbar_wait(&full_a[(seq_c + j) % NA], ((seq_c + j) / NA) & 1);
+          const int ntd = KD == 3 ? 2 : 1;
+          for (int td = 0; td < ntd; ++td) {
+            const int kd = KD == 3 ? tc.pa + td : 0;
+            uint32_t a_lo[P];
+#pragma unroll
+            for (int pp = 0; pp < P; ++pp)
+              a_lo[pp] = umma_desc_lo(smem_u32(sA + (size_t)((seq_c + pp + kd) % NA) * TC_PATCH_STRIDE));
+            for (int thw = 0; thw < 4; ++thw, ++seq_b) {
+              const int kh = tc.pb + (thw >> 1), kw = tc.pc + (thw & 1);
+              const uint32_t bs = seq_b % NB;
+              mbar_wait(&full_b[bs], (seq_b / NB) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_BYTES));
+              const uint32_t tap_off = (kh * TC_PW + kw) * 8;
+              const uint32_t first = (c | td | thw) == 0 ? 0u : 1u;
+              if (elect_one_sync()) {
+#pragma unroll
+                for (int pp = 0; pp < P; ++pp) {
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    umma_bf16(tmem_acc + pp * N_TILE, umma_desc64(a_lo[pp] + tap_off + k4 * 2, A_HI),
+                              umma_desc64(b_lo + k4 * 2, B_HI), idesc, k4 == 0 ? first : 1u);
+                }
+                umma_commit(&empty_b[bs]);
+              }
+              __syncwarp();
+            }
+          }
+          if (elect_one_sync()) {
+            for (int j = 0; j < NJ; ++j) umma_commit(&empty_a[(seq_c + j) % NA]);
+          }
+          __syncwarp();
+        } else {
         for (int kd = 0; kd < KD; ++kd) {
           // patches first needed at this kd: j = 0..P-1 at kd == 0, else j = P-1+kd
           const int jlo = kd == 0 ? 0 : P - 1 + kd, jhi = P - 1 + kd;
@@ -187,6 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
           }
           __syncwarp();
         }
+        }
         seq_a += NJ;
       }
       if (elect_one_sync()) umma_commit(&acc_full[as]);
@@ -209,7 +256,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       for (int pp = 0; pp < P; ++pp) {
         const int d = tc.d0 + pp;
         const bool valid = in_hw && d < p.D;
-        const int64_t pix = (((int64_t)tc.b * p.D + d) * p.H + h) * p.W + w;
+        int64_t pix;
+        if constexpr (UPS) {   // output lives on the 2x grid: (2d+a, 2h+b, 2w+c); 2-D convs do not upsample the plane axis
+          const int od = p.KD == 3 ? 2 * d + tc.pa : d, OD = p.KD == 3 ? 2 * p.D : p.D;
+          pix = (((int64_t)tc.b * OD + od) * (2 * p.H) + (2 * h + tc.pb)) * (2 * p.W) + (2 * w + tc.pc);
+        } else {
+          pix = (((int64_t)tc.b * p.D + d) * p.H + h) * p.W + w;
+        }
         const int brow = (tc.b * p.D + d) / p.planes_per_sample;
         const uint32_t taddr = tmem_base + as * (P * N_TILE) + pp * N_TILE + ((uint32_t)(q * 32) << 16);
 #pragma unroll
@@ -280,23 +333,65 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
   }
 }
 
-template <int N_TILE, int P, int NA, int NB>
+template <int N_TILE, int P, int NA, int NB, bool UPS>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const TcParams& p, cudaStream_t st) {
   const size_t smem = (size_t)NA * TC_PATCH_STRIDE + (size_t)NB * N_TILE * 128 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<N_TILE, P, NA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<N_TILE, P, NA, NB, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e)); return DSK_ERR_CUDA; }
     configured = true;
   }
   const int grid = p.total_tiles < DSK_NUM_SMS ? p.total_tiles : DSK_NUM_SMS;
-  DSK_LAUNCH((conv_tc_kernel<N_TILE, P, NA, NB>), grid, TC_THREADS, smem, st, ta, tw, p);
+  DSK_LAUNCH((conv_tc_kernel<N_TILE, P, NA, NB, UPS>), grid, TC_THREADS, smem, st, ta, tw, p);
   return DSK_OK;
+}
+
+// Sub-pixel weights of conv3(nearest_up2(x)):  out[2i+a] = sum_k w[k] x[i + floor((a+k-1)/2)].  Per axis the three taps
+// collapse onto two input offsets: a = 0: offset -1 <- {k0}, 0 <- {k1,k2};  a = 1: 0 <- {k0,k1}, +1 <- {k2}.
+// Layout: bf16 [phase = (a*2+b)*2+c][tap = (td*2+th)*2+tw][Cout][Cin] (2-D: phase = b*2+c, tap = th*2+tw), summed in fp32.
+__global__ void __launch_bounds__(256) pack_upconv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout,
+                                                                  int Cin, int ndim) {
+  const int nax = ndim, nph = 1 << nax, ntap = 1 << nax, k3 = ndim == 3 ? 27 : 9;
+  const int64_t total = (int64_t)nph * ntap * Cout * Cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    int64_t r = i / Cin;
+    const int co = (int)(r % Cout); r /= Cout;
+    const int tap = (int)(r % ntap);
+    const int ph = (int)(r / ntap);
+    // per-axis parity and 2-tap index, innermost axis = w
+    int par[3], tt[3];
+    for (int ax = 0; ax < nax; ++ax) { par[nax - 1 - ax] = (ph >> ax) & 1; tt[nax - 1 - ax] = (tap >> ax) & 1; }
+    float acc = 0.0f;
+    const float* wp = w + ((int64_t)co * Cin + ci) * k3;
+    for (int k = 0; k < k3; ++k) {
+      int kk[3];
+      int q = k;
+      for (int ax = nax - 1; ax >= 0; --ax) { kk[ax] = q % 3; q /= 3; }
+      bool match = true;
+      for (int ax = 0; ax < nax; ++ax) {
+        // low-res offset of tap kk for parity par: floor((par + kk - 1) / 2) in {-1, 0, 1}; 2-tap index = offset - (par - 1)
+        const int off = (par[ax] + kk[ax] - 1 + 2) / 2 - 1;
+        if (off - (par[ax] - 1) != tt[ax]) match = false;
+      }
+      if (match) acc += wp[k];
+    }
+    o[i] = __float2bfloat16_rn(acc);
+  }
 }
 
 }  // namespace dsk
 
 using namespace dsk;
+
+extern "C" int dsk_pack_upconv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int ndim, void* stream) {
+  DSK_REQUIRE(w_ref && w_packed && Cout > 0 && Cin > 0 && (ndim == 2 || ndim == 3), "dsk_pack_upconv_weight: bad arguments");
+  const int64_t total = (int64_t)(1 << ndim) * (1 << ndim) * Cout * Cin;
+  DSK_LAUNCH(pack_upconv_weight_kernel, grid_for(total, 256, 8), 256, 0, as_stream(stream), w_ref, (__nv_bfloat16*)w_packed, Cout, Cin,
+             ndim);
+  return DSK_OK;
+}
 
 extern "C" int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, void* stream) {
   DSK_REQUIRE(x && y && B > 0 && D > 0 && H > 0 && W > 0 && C > 0, "dsk_upsample2x: bad arguments");
@@ -309,9 +404,9 @@ extern "C" int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W
 extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const void* w, const float* bias,
                                const float* chan_bias, const void* residual, void* out, void* stream) {
   DSK_REQUIRE(d && in && w && out, "dsk_conv_fwd(tc): null pointer");
-  if (d->ksize != 3 || d->up2 || d->out_nchw_f32 || d->in_dtype != DSK_BF16 || d->out_dtype != DSK_BF16 || d->Cin % 64 != 0 ||
+  if (d->ksize != 3 || d->out_nchw_f32 || d->in_dtype != DSK_BF16 || d->out_dtype != DSK_BF16 || d->Cin % 64 != 0 ||
       d->Cout % 64 != 0) {
-    set_error("dsk_conv_fwd: the tcgen05 path takes k=3, bf16 in/out, Cin %% 64 == 0, Cout %% 64 == 0, no fused upsample "
+    set_error("dsk_conv_fwd: the tcgen05 path takes k=3, bf16 in/out, Cin %% 64 == 0, Cout %% 64 == 0 "
               "(got k=%d Cin=%d Cout=%d up2=%d in=%d out=%d nchw=%d)", d->ksize, d->Cin, d->Cout, d->up2, d->in_dtype, d->out_dtype,
               d->out_nchw_f32);
     return DSK_ERR_UNSUPPORTED;
@@ -321,13 +416,15 @@ extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const voi
   DSK_REQUIRE(encode != nullptr, "dsk_conv_fwd(tc): cuTensorMapEncodeTiled is unavailable");
   // 2-D: the batch is the plane axis (no depth taps); 3-D: planes = D with zero padding per sample
   const int KD = d->ndim == 3 ? 3 : 1;
-  const int planes = d->ndim == 3 ? d->D : d->B;
+  // up2: D/H/W in the descriptor are the OUTPUT size; the kernel tiles the INPUT (half-size) grid
+  const int iD = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D, iH = d->up2 ? d->H / 2 : d->H, iW = d->up2 ? d->W / 2 : d->W;
+  const int planes = d->ndim == 3 ? iD : d->B;
   const int batch = d->ndim == 3 ? d->B : 1;
   CUtensorMap ta, tw;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)planes, (cuuint64_t)batch};
-    cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->W * d->Cin * 2, (cuuint64_t)d->H * d->W * d->Cin * 2,
-                             (cuuint64_t)planes * d->H * d->W * d->Cin * 2};
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)iW, (cuuint64_t)iH, (cuuint64_t)planes, (cuuint64_t)batch};
+    cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)iW * d->Cin * 2, (cuuint64_t)iH * iW * d->Cin * 2,
+                             (cuuint64_t)planes * iH * iW * d->Cin * 2};
     cuuint32_t box[5] = {64, TC_PW, TC_PH, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, es,
@@ -335,7 +432,8 @@ extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const voi
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DSK_REQUIRE(r == CUDA_SUCCESS, "dsk_conv_fwd(tc): activation tensor map failed (CUresult %d)", (int)r);
   }
-  const int ntaps = KD * 9;
+  const int nphase = d->up2 ? (KD == 3 ? 8 : 4) : 1;
+  const int ntaps = d->up2 ? nphase * (KD == 3 ? 8 : 4) : KD * 9;     // weight rows: [phase][tap][Cout] or [tap][Cout]
   const int n_tile = d->Cout % 128 == 0 ? 128 : 64;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)ntaps * d->Cout};
@@ -348,18 +446,23 @@ extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const voi
     DSK_REQUIRE(r == CUDA_SUCCESS, "dsk_conv_fwd(tc): weight tensor map failed (CUresult %d)", (int)r);
   }
   TcParams p;
-  p.B = batch; p.D = planes; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.KD = KD;
+  p.B = batch; p.D = planes; p.H = iH; p.W = iW; p.Cin = d->Cin; p.Cout = d->Cout; p.KD = KD;
   constexpr int P = 2;
-  p.tiles_w = (d->W + TC_BW - 1) / TC_BW;
-  p.tiles_h = (d->H + TC_BH - 1) / TC_BH;
+  p.nphase = nphase;
+  p.tiles_w = (iW + TC_BW - 1) / TC_BW;
+  p.tiles_h = (iH + TC_BH - 1) / TC_BH;
   p.groups_d = (planes + P - 1) / P;
   p.n_tiles = d->Cout / n_tile;
-  p.total_tiles = p.tiles_w * p.tiles_h * p.groups_d * batch * p.n_tiles;
+  p.total_tiles = p.tiles_w * p.tiles_h * p.groups_d * batch * p.n_tiles * nphase;
   p.bias = bias; p.chan_bias = chan_bias;
   p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
-  p.planes_per_sample = d->ndim == 3 ? d->D : 1;
+  p.planes_per_sample = d->ndim == 3 ? iD : 1;
   cudaStream_t st = as_stream(stream);
   // smem: N_TILE=64: 6 patches (138 KB) + 8 taps x 8 KB (64 KB) = 202 KB; N_TILE=128: 6 patches + 5 x 16 KB = 218 KB
-  if (n_tile == 64) return launch_tc<64, P, 6, 8>(ta, tw, p, st);
-  return launch_tc<128, P, 6, 5>(ta, tw, p, st);
+  if (d->up2) {
+    if (n_tile == 64) return launch_tc<64, P, 6, 8, true>(ta, tw, p, st);
+    return launch_tc<128, P, 6, 5, true>(ta, tw, p, st);
+  }
+  if (n_tile == 64) return launch_tc<64, P, 6, 8, false>(ta, tw, p, st);
+  return launch_tc<128, P, 6, 5, false>(ta, tw, p, st);
 }

@@ -190,12 +190,12 @@ class _ADMPlan:
         self.xin = torch.empty((B, 1, H, W, c.input_channels), dtype=adt, device=dev)
         self.F = torch.empty((B, 1, H, W, c.output_channels), dtype=adt, device=dev)
 
-        def pack(cp):
-            wd = torch.bfloat16 if (precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize)) else torch.float32
-            return ops.PackedConv(cp.weight, cp.bias, 2, wd)
+        def pack(cp, subpixel=False):
+            tc = precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize)
+            return ops.PackedConv(cp.weight, cp.bias, 2, torch.bfloat16 if tc else torch.float32, subpixel and tc)
 
         self.pc_in, self.pc_out = pack(net.input_layer), pack(net.output_layer)
-        self.pc = {id(b): (pack(b.conv1), pack(b.conv2), pack(b.convresidual)) for b in self.blocks}
+        self.pc = {id(b): (pack(b.conv1, b.sample == "up"), pack(b.conv2), pack(b.convresidual)) for b in self.blocks}
         # time embedding + one grouped launch for every block's embed_linear (two groups per block: te1 | te2)
         f32 = dict(dtype=torch.float32, device=dev)
         E = c.output_embed_dim
@@ -235,10 +235,7 @@ class _ADMPlan:
         return x
 
     def _conv(self, x, pc, out, up: bool, **kw):
-        if up and pc.w_dtype == torch.bfloat16:      # tcgen05 conv has no fused upsample: materialise it
-            B, _, H, W, C = x.shape
-            x = ops.upsample2x(x, 2, out=self.buf(("up", C), (B, 1, 2 * H, 2 * W, C)))
-            up = False
+        # nearest x2 upsample is never materialised: FFMA folds it into the gather, tcgen05 runs the sub-pixel form
         return ops.conv(x, pc, out=out, up2=up, **kw)
 
     def _attention(self, x, blk, idx):

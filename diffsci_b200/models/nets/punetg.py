@@ -175,9 +175,9 @@ class _Plan:
         def buf(l, cc, dtype=adt):
             return torch.empty((B,) + sp[l] + (cc,), dtype=dtype, device=dev)
 
-        def pack(cp):
-            wd = torch.bfloat16 if (precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize)) else torch.float32
-            return ops.PackedConv(cp.weight, cp.bias, nd, wd)
+        def pack(cp, subpixel=False):
+            tc = precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize)
+            return ops.PackedConv(cp.weight, cp.bias, nd, torch.bfloat16 if tc else torch.float32, subpixel and tc)
 
         self.xin = buf(0, c.input_channels)
         self.X = [buf(l, ch[l]) for l in range(nlev + 1)]          # encoder / bottom state (doubles as skip)
@@ -185,16 +185,13 @@ class _Plan:
         self.N = [buf(l, ch[l]) for l in range(nlev + 1)]          # norm+SiLU output == conv input
         self.Y = [buf(l, ch[l]) for l in range(nlev + 1)]          # conv1 output
         self.P = [buf(l + 1, ch[l]) for l in range(nlev)]          # pooled
-        # the tcgen05 conv has no fused upsample: materialise F.interpolate(x, 2) for those layers
-        self.U = [buf(l, ch[l + 1]) if (precision == "bf16" and _tc_eligible(ch[l + 1], ch[l], c.transition_kernel_size))
-                  else None for l in range(nlev)]
         self.XA = buf(nlev, ch[nlev])
         self.XA2 = buf(nlev, ch[nlev])
         self.F = buf(0, c.output_channels)
         self.WS = [ops.norm_ws(B, sp[l][0] * sp[l][1] * sp[l][2], ch[l], dev) for l in range(nlev + 1)]
         self.pc_in, self.pc_out = pack(net.convin), pack(net.convout)
         self.pc_down = [pack(s.conv) for s in net.downsamplers]
-        self.pc_up = [pack(s.conv) for s in net.upsamplers]
+        self.pc_up = [pack(s.conv, subpixel=True) for s in net.upsamplers]   # conv(up2(x)) in sub-pixel form on tcgen05
 
         # every ResNet block in execution order, with its level
         self.blocks = []
@@ -309,11 +306,7 @@ class _Plan:
         for i in range(nlev):
             l = nlev - 1 - i
             # conv(F.interpolate(x, 2)) + skip, fused (commonlayers.py:145; punetg.py:372-373)
-            if self.U[l] is not None:
-                u = ops.upsample2x(x, self.ndim, out=self.U[l])
-                x = ops.conv(u, self.pc_up[i], out=self.XU[l], residual=self.X[l])
-            else:
-                x = ops.conv(x, self.pc_up[i], out=self.XU[l], residual=self.X[l], up2=True)
+            x = ops.conv(x, self.pc_up[i], out=self.XU[l], residual=self.X[l], up2=True)
             for blk in net.upward_blocks[i]:
                 x = self._resblock(x, blk, l, x)
         if out_nchw is not None:

@@ -24,7 +24,11 @@ class PackedConv:
     Rebuilt whenever the source parameter's version counter changes (optimizer step / load).
     """
 
-    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], ndim: int, w_dtype: torch.dtype):
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], ndim: int, w_dtype: torch.dtype,
+                 subpixel: bool = False):
+        """subpixel=True (bf16 only): pack for the phase-decomposed conv(nearest_up2(x)) of the tcgen05 UpSampler path."""
+        assert not subpixel or (w_dtype == torch.bfloat16 and int(weight.shape[-1]) == 3)
+        self.subpixel = subpixel
         self.weight, self.bias, self.ndim = weight, bias, ndim
         self.cout, self.cin = int(weight.shape[0]), int(weight.shape[1])
         self.ksize = int(weight.shape[-1])
@@ -45,10 +49,14 @@ class PackedConv:
     def _repack(self, w, key):
         if True:
             src = w.detach().float().contiguous()
+            ntap = (4 ** self.ndim) if self.subpixel else self.taps
             if self._packed is None or self._packed.device != w.device:
-                self._packed = torch.empty(self.taps * self.cin * self.cout, dtype=self.w_dtype, device=w.device)
-            check(lib.dsk_pack_conv_weight(ptr(src), ptr(self._packed), self.cout, self.cin, self.taps,
-                                           dt_code(self.w_dtype), stream()))
+                self._packed = torch.empty(ntap * self.cin * self.cout, dtype=self.w_dtype, device=w.device)
+            if self.subpixel:
+                check(lib.dsk_pack_upconv_weight(ptr(src), ptr(self._packed), self.cout, self.cin, self.ndim, stream()))
+            else:
+                check(lib.dsk_pack_conv_weight(ptr(src), ptr(self._packed), self.cout, self.cin, self.taps,
+                                               dt_code(self.w_dtype), stream()))
             self._version = key
         return self._packed
 
@@ -60,6 +68,7 @@ def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, ch
     require_cuda(x, "conv input")
     B, D, H, W, Cin = x.shape
     assert Cin == pc.cin, (Cin, pc.cin)
+    assert up2 == pc.subpixel or pc.w_dtype == torch.float32, "bf16 weights of an up2 conv must be sub-pixel packed"
     if up2:
         D, H, W = (D * 2 if pc.ndim == 3 else D), H * 2, W * 2
     out_dtype = out_dtype or x.dtype

@@ -116,6 +116,7 @@ int dsk_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t stream_id, 
  * in  : [B, Di, Hi, Wi, Cin]  (if up2: the conv sees nearest-upsampled x2 input, i.e. F.interpolate
  *        fused into the gather: commonlayers.py:129,145)
  * w   : packed weights. DSK_F32 path: fp32 [taps][Cin][Cout];  DSK_BF16 path: bf16 [taps][Cout][Cin]
+ *       (bf16 + up2: the sub-pixel layout of dsk_pack_upconv_weight)
  * out : [B, D, H, W, Cout] ; y = conv(in) + bias[co] + chan_bias[b,co] + residual[b,..,co]
  * ksize in {1,3}; ndim in {2,3} (ndim 2 => D = 1, taps = k*k).
  */
@@ -135,6 +136,9 @@ int dsk_conv_fwd(const dsk_conv_desc* d, const void* in, const void* w, const fl
 /* nearest x2 upsample of a channels-last tensor (torch.nn.Upsample(scale_factor=2), commonlayers.py:129):
  * only needed in front of the tcgen05 conv; the FFMA conv fuses it into its gather (up2). bf16, C % 8 == 0. */
 int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, void* stream);
+/* Sub-pixel weights for the tcgen05 UpSampler conv (up2 = 1 with bf16 weights): bf16 [2^ndim phases][2^ndim taps][Cout][Cin],
+ * the three taps of each axis pre-summed onto the two input offsets an output parity sees (csrc/conv_tc.cu). */
+int dsk_pack_upconv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int ndim, void* stream);
 /* repack a reference-layout weight [Cout, Cin, k(,k)(,k)] fp32 into the two packed layouts */
 int dsk_pack_conv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int taps, int dtype, void* stream);
 

@@ -330,3 +330,20 @@ def test_attention_tcgen05(ops):
         got = out.float().cpu().permute(0, 2, 1).reshape(x.shape)
         # bf16 storage of Q|K, V^T, P and the attention output: stated tolerance 2e-2 of the output range
         assert relmax(got, ref) < 2e-2, relmax(got, ref)
+
+
+@pytest.mark.parametrize("ndim,B,Cin,Cout,sp", [(3, 1, 64, 64, (2, 16, 8)), (3, 2, 128, 64, (3, 10, 12)), (2, 3, 64, 128, (16, 8)),
+                                                 (2, 2, 128, 64, (7, 9)), (3, 1, 256, 128, (4, 8, 8))])
+def test_upconv_subpixel_tcgen05(ops, ndim, B, Cin, Cout, sp):
+    """conv3(nearest_up2(x)) in sub-pixel (phase-decomposed, pre-summed taps) form on tcgen05 vs ATen on the same bf16 inputs.
+    The pre-summed weights are rounded to bf16 after summation, so the tolerance is 2 bf16 roundings of the range."""
+    torch.manual_seed(21)
+    x = torch.randn(B, Cin, *sp).bfloat16().float()
+    w = (torch.randn(Cout, Cin, *([3] * ndim)) / math.sqrt(Cin * 3 ** ndim)).bfloat16().float()
+    b = torch.randn(Cout) * 0.1
+    ref = (F.conv2d if ndim == 2 else F.conv3d)(F.interpolate(x, scale_factor=2, mode="nearest"), w, b, padding=1)
+    res = torch.randn_like(ref).bfloat16().float()
+    pc = ops.PackedConv(w.to(DEV), b.to(DEV), ndim, torch.bfloat16, subpixel=True)
+    y = ops.conv(to_cl(x).bfloat16(), pc, residual=to_cl(res).bfloat16(), up2=True)
+    assert y.shape[1:4] == tuple((1,) + tuple(2 * s for s in sp)) if ndim == 2 else tuple(2 * s for s in sp)
+    assert relmax(from_cl(y, ndim), ref + res) < 1e-2
