@@ -43,6 +43,8 @@ struct TcParams {
   const __nv_bfloat16* residual;  // like out, or null
   __nv_bfloat16* out;     // [B, D, H, W, Cout]
   int planes_per_sample;  // D for 3-D; 1 for 2-D  (chan_bias row = plane / planes_per_sample)
+  int cout_real;          // N_TILE = 16 path (convout): the first cout_real (<= 16) channels are real, the rest zero padding
+  float* out_nchw;        // N_TILE = 16 path: fp32 NC(D)HW output (user layout) instead of channels-last bf16
   int nphase;             // sub-pixel UpSampler conv: 8 (3-D) / 4 (2-D) output parities per input-resolution tile, else 1
 };
 
@@ -265,6 +267,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         }
         const int brow = (tc.b * p.D + d) / p.planes_per_sample;
         const uint32_t taddr = tmem_base + as * (P * N_TILE) + pp * N_TILE + ((uint32_t)(q * 32) << 16);
+        if constexpr (N_TILE == 16) {
+          // few-output-channel conv (convout, reference punetg.py:209-214): only cout_real columns are stored
+          uint32_t v[16];
+          DSK_TMEM_LD_X16(v, taddr);
+          if (valid) {
+            const int64_t S = (int64_t)p.planes_per_sample * p.H * p.W;
+#pragma unroll
+            for (int co = 0; co < 16; ++co) {
+              if (co < p.cout_real) {
+                float x = __uint_as_float(v[co]);
+                if (p.bias != nullptr) x += __ldg(p.bias + co);
+                if (p.out_nchw != nullptr) p.out_nchw[((int64_t)brow * p.cout_real + co) * S + (pix - (int64_t)brow * S)] = x;
+                else p.out[pix * p.cout_real + co] = __float2bfloat16_rn(x);
+              }
+            }
+          }
+        } else
 #pragma unroll
         for (int c0 = 0; c0 < N_TILE; c0 += 32) {
           uint32_t v[32];
@@ -404,8 +423,9 @@ extern "C" int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W
 extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const void* w, const float* bias,
                                const float* chan_bias, const void* residual, void* out, void* stream) {
   DSK_REQUIRE(d && in && w && out, "dsk_conv_fwd(tc): null pointer");
-  if (d->ksize != 3 || d->out_nchw_f32 || d->in_dtype != DSK_BF16 || d->out_dtype != DSK_BF16 || d->Cin % 64 != 0 ||
-      d->Cout % 64 != 0) {
+  const bool few_out = d->Cout <= 16 && !d->up2 && chan_bias == nullptr && residual == nullptr;
+  if (d->ksize != 3 || (d->out_nchw_f32 && !few_out) || d->in_dtype != DSK_BF16 || (!d->out_nchw_f32 && d->out_dtype != DSK_BF16) ||
+      d->Cin % 64 != 0 || (d->Cout % 64 != 0 && !few_out)) {
     set_error("dsk_conv_fwd: the tcgen05 path takes k=3, bf16 in/out, Cin %% 64 == 0, Cout %% 64 == 0 "
               "(got k=%d Cin=%d Cout=%d up2=%d in=%d out=%d nchw=%d)", d->ksize, d->Cin, d->Cout, d->up2, d->in_dtype, d->out_dtype,
               d->out_nchw_f32);
@@ -434,9 +454,10 @@ extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const voi
   }
   const int nphase = d->up2 ? (KD == 3 ? 8 : 4) : 1;
   const int ntaps = d->up2 ? nphase * (KD == 3 ? 8 : 4) : KD * 9;     // weight rows: [phase][tap][Cout] or [tap][Cout]
-  const int n_tile = d->Cout % 128 == 0 ? 128 : 64;
+  const int n_tile = few_out ? 16 : (d->Cout % 128 == 0 ? 128 : 64);
+  const int w_rows = few_out ? 16 : d->Cout;                          // few_out weights are zero-padded to 16 output channels
   {
-    cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)ntaps * d->Cout};
+    cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)ntaps * w_rows};
     cuuint64_t strides[1] = {(cuuint64_t)d->Cin * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)n_tile};
     cuuint32_t es[2] = {1, 1};
@@ -446,19 +467,22 @@ extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const voi
     DSK_REQUIRE(r == CUDA_SUCCESS, "dsk_conv_fwd(tc): weight tensor map failed (CUresult %d)", (int)r);
   }
   TcParams p;
-  p.B = batch; p.D = planes; p.H = iH; p.W = iW; p.Cin = d->Cin; p.Cout = d->Cout; p.KD = KD;
+  p.B = batch; p.D = planes; p.H = iH; p.W = iW; p.Cin = d->Cin; p.Cout = w_rows; p.KD = KD;
+  p.cout_real = d->Cout;
+  p.out_nchw = d->out_nchw_f32 ? (float*)out : nullptr;
   constexpr int P = 2;
   p.nphase = nphase;
   p.tiles_w = (iW + TC_BW - 1) / TC_BW;
   p.tiles_h = (iH + TC_BH - 1) / TC_BH;
   p.groups_d = (planes + P - 1) / P;
-  p.n_tiles = d->Cout / n_tile;
+  p.n_tiles = w_rows / n_tile;
   p.total_tiles = p.tiles_w * p.tiles_h * p.groups_d * batch * p.n_tiles * nphase;
   p.bias = bias; p.chan_bias = chan_bias;
   p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
   p.planes_per_sample = d->ndim == 3 ? iD : 1;
   cudaStream_t st = as_stream(stream);
   // smem: N_TILE=64: 6 patches (138 KB) + 8 taps x 8 KB (64 KB) = 202 KB; N_TILE=128: 6 patches + 5 x 16 KB = 218 KB
+  if (few_out) return launch_tc<16, P, 6, 8, false>(ta, tw, p, st);
   if (d->up2) {
     if (n_tile == 64) return launch_tc<64, P, 6, 8, true>(ta, tw, p, st);
     return launch_tc<128, P, 6, 5, true>(ta, tw, p, st);

@@ -248,9 +248,15 @@ __global__ void __launch_bounds__(GT) ffma_gemm_kernel(Prob p) {
   for (int i = 0; i < 8; ++i) p.store(m0 + ty * 8 + i, n0 + tx * 4, acc[i]);
 }
 
+// bf16 layout: [tap][rows][Cin] with rows = max(Cout, pad_rows) (zero rows beyond Cout: the N_TILE = 16 convout path)
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, float* __restrict__ o32,
-                                                           __nv_bfloat16* __restrict__ o16, int Cout, int Cin, int taps) {
+                                                           __nv_bfloat16* __restrict__ o16, int Cout, int Cin, int taps, int rows) {
   const int64_t total = (int64_t)Cout * Cin * taps;
+  if (o16 != nullptr && rows > Cout) {
+    const int64_t padded = (int64_t)taps * rows * Cin;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += (int64_t)gridDim.x * blockDim.x)
+      if ((i / Cin) % rows >= Cout) o16[i] = __float2bfloat16_rn(0.0f);
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     // reference layout: w[co][ci][tap]
     int tap = (int)(i % taps);
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
     int co = (int)(r / Cin);
     float v = w[i];
     if (o32 != nullptr) o32[((int64_t)tap * Cin + ci) * Cout + co] = v;          // [tap][ci][co]
-    if (o16 != nullptr) o16[((int64_t)tap * Cout + co) * Cin + ci] = __float2bfloat16_rn(v);  // [tap][co][ci]
+    if (o16 != nullptr) o16[((int64_t)tap * rows + co) * Cin + ci] = __float2bfloat16_rn(v);  // [tap][co][ci]
   }
 }
 
@@ -321,9 +327,10 @@ extern "C" int dsk_conv_fwd_ffma(const dsk_conv_desc* d, const void* in, const v
 extern "C" int dsk_pack_conv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int taps, int dtype, void* stream) {
   DSK_REQUIRE(w_ref && w_packed && Cout > 0 && Cin > 0 && taps > 0, "dsk_pack_conv_weight: bad arguments");
   DSK_REQUIRE(dtype == DSK_F32 || dtype == DSK_BF16, "dsk_pack_conv_weight: bad dtype %d", dtype);
-  const int grid = grid_for((int64_t)Cout * Cin * taps, 256, 8);
+  const int rows = (dtype == DSK_BF16 && Cout <= 16) ? 16 : Cout;
+  const int grid = grid_for((int64_t)rows * Cin * taps, 256, 8);
   DSK_LAUNCH(pack_weight_kernel, grid, 256, 0, as_stream(stream), w_ref, dtype == DSK_F32 ? (float*)w_packed : nullptr,
-             dtype == DSK_BF16 ? (__nv_bfloat16*)w_packed : nullptr, Cout, Cin, taps);
+             dtype == DSK_BF16 ? (__nv_bfloat16*)w_packed : nullptr, Cout, Cin, taps, rows);
   return DSK_OK;
 }
 

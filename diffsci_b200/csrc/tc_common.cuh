@@ -81,6 +81,14 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return (saddr
 __device__ __forceinline__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
 __device__ __forceinline__ uint64_t umma_desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
+#define DSK_TMEM_LD_X16(v, taddr)                                                                                          \
+  asm volatile(                                                                                                            \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"              \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),      \
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                                                 \
+      : "r"(taddr));                                                                                                       \
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+
 // bf16 x bf16 -> fp32, both operands K-major, M = 128
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);

@@ -190,11 +190,11 @@ class _ADMPlan:
         self.xin = torch.empty((B, 1, H, W, c.input_channels), dtype=adt, device=dev)
         self.F = torch.empty((B, 1, H, W, c.output_channels), dtype=adt, device=dev)
 
-        def pack(cp, subpixel=False):
-            tc = precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize)
+        def pack(cp, subpixel=False, few_out_ok=False):
+            tc = precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize, few_out_ok)
             return ops.PackedConv(cp.weight, cp.bias, 2, torch.bfloat16 if tc else torch.float32, subpixel and tc)
 
-        self.pc_in, self.pc_out = pack(net.input_layer), pack(net.output_layer)
+        self.pc_in, self.pc_out = pack(net.input_layer), pack(net.output_layer, few_out_ok=True)
         self.pc = {id(b): (pack(b.conv1, b.sample == "up"), pack(b.conv2), pack(b.convresidual)) for b in self.blocks}
         # time embedding + one grouped launch for every block's embed_linear (two groups per block: te1 | te2)
         f32 = dict(dtype=torch.float32, device=dev)

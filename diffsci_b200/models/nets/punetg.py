@@ -30,10 +30,12 @@ _NORM_MODE = {"GroupLN": 0, "GroupRMS": 1}
 DEFAULT_PRECISION = "fp32"
 
 
-def _tc_eligible(cin: int, cout: int, ksize: int = 3) -> bool:
-    """Shapes the tcgen05 implicit-GEMM kernel takes (see csrc/conv_tc.cu)."""
+def _tc_eligible(cin: int, cout: int, ksize: int = 3, few_out_ok: bool = False) -> bool:
+    """Shapes the tcgen05 implicit-GEMM kernel takes (see csrc/conv_tc.cu): Cin % 64 == 0 and Cout % 64 == 0, or -- for a
+    plain conv without epilogue operands (convout) -- the few-output-channel tile Cout <= 16."""
     import diffsci_b200
-    return diffsci_b200.TC_CONV_ENABLED and ksize == 3 and cin % 64 == 0 and cout % 64 == 0
+    return (diffsci_b200.TC_CONV_ENABLED and ksize == 3 and cin % 64 == 0 and
+            (cout % 64 == 0 or (few_out_ok and cout <= 16)))
 
 
 class ResnetBlockParams(_Holder):
@@ -175,8 +177,8 @@ class _Plan:
         def buf(l, cc, dtype=adt):
             return torch.empty((B,) + sp[l] + (cc,), dtype=dtype, device=dev)
 
-        def pack(cp, subpixel=False):
-            tc = precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize)
+        def pack(cp, subpixel=False, few_out_ok=False):
+            tc = precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize, few_out_ok)
             return ops.PackedConv(cp.weight, cp.bias, nd, torch.bfloat16 if tc else torch.float32, subpixel and tc)
 
         self.xin = buf(0, c.input_channels)
@@ -189,7 +191,7 @@ class _Plan:
         self.XA2 = buf(nlev, ch[nlev])
         self.F = buf(0, c.output_channels)
         self.WS = [ops.norm_ws(B, sp[l][0] * sp[l][1] * sp[l][2], ch[l], dev) for l in range(nlev + 1)]
-        self.pc_in, self.pc_out = pack(net.convin), pack(net.convout)
+        self.pc_in, self.pc_out = pack(net.convin), pack(net.convout, few_out_ok=True)
         self.pc_down = [pack(s.conv) for s in net.downsamplers]
         self.pc_up = [pack(s.conv, subpixel=True) for s in net.upsamplers]   # conv(up2(x)) in sub-pixel form on tcgen05
 

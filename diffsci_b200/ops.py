@@ -50,8 +50,9 @@ class PackedConv:
         if True:
             src = w.detach().float().contiguous()
             ntap = (4 ** self.ndim) if self.subpixel else self.taps
+            rows = 16 if (self.w_dtype == torch.bfloat16 and self.cout <= 16) else self.cout   # convout: zero-padded to N = 16
             if self._packed is None or self._packed.device != w.device:
-                self._packed = torch.empty(ntap * self.cin * self.cout, dtype=self.w_dtype, device=w.device)
+                self._packed = torch.empty(ntap * self.cin * rows, dtype=self.w_dtype, device=w.device)
             if self.subpixel:
                 check(lib.dsk_pack_upconv_weight(ptr(src), ptr(self._packed), self.cout, self.cin, self.ndim, stream()))
             else:

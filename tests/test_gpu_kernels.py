@@ -347,3 +347,18 @@ def test_upconv_subpixel_tcgen05(ops, ndim, B, Cin, Cout, sp):
     y = ops.conv(to_cl(x).bfloat16(), pc, residual=to_cl(res).bfloat16(), up2=True)
     assert y.shape[1:4] == tuple((1,) + tuple(2 * s for s in sp)) if ndim == 2 else tuple(2 * s for s in sp)
     assert relmax(from_cl(y, ndim), ref + res) < 1e-2
+
+
+@pytest.mark.parametrize("ndim,B,Cin,Cout,sp", [(3, 2, 64, 1, (4, 16, 8)), (3, 1, 64, 3, (3, 10, 12)), (2, 3, 128, 2, (20, 12))])
+def test_convout_tcgen05(ops, ndim, B, Cin, Cout, sp):
+    """convout (few output channels) on the N = 16 tcgen05 tile, fp32 NC(D)HW and bf16 channels-last outputs."""
+    torch.manual_seed(22)
+    x = torch.randn(B, Cin, *sp).bfloat16().float()
+    w = (torch.randn(Cout, Cin, *([3] * ndim)) / math.sqrt(Cin * 3 ** ndim)).bfloat16().float()
+    b = torch.randn(Cout) * 0.1
+    ref = (F.conv2d if ndim == 2 else F.conv3d)(x, w, b, padding=1)
+    pc = ops.PackedConv(w.to(DEV), b.to(DEV), ndim, torch.bfloat16)
+    y = ops.conv(to_cl(x).bfloat16(), pc, out_nchw=True)
+    assert y.dtype == torch.float32 and relmax(y.cpu(), ref) < 2e-5       # fp32 accumulation, fp32 store
+    y2 = ops.conv(to_cl(x).bfloat16(), pc)
+    assert relmax(from_cl(y2, ndim), ref) < 6e-3
