@@ -68,8 +68,24 @@ SIGNATURES = {
     "dsk_edm_loss_fwd_bwd": [p, p, p, p, p, p, p, i32, i32, i64, f32, i32, p],
     "dsk_ema_update": [p, p, p, i32, i64, f32, p],
     "dsk_adamw_ema_step": [p, p, p, p, p, p, i32, i64, f32, f32, f32, f32, f32, i32, f32, f32, p],
+    "dsk_gemm_f32_ex": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i32, i32, i32, f32, f32, i32, p],
+    "dsk_pack_conv_weight_dgrad": [p, p, i32, i32, i32, i32, p],
+    "dsk_conv_wgrad_ws_bytes": [C.POINTER(ConvDesc)],
+    "dsk_conv_wgrad": [C.POINTER(ConvDesc), p, p, p, p, i32, p],
+    "dsk_bwd_ws_bytes": [i32, i64, i32],
+    "dsk_channel_sum": [p, p, p, i32, i64, i32, i32, i32, p],
+    "dsk_colsum_f32": [p, p, i64, i32, i32, p],
+    "dsk_norm_act_bwd": [p, p, p, p, p, p, p, p, p, p, p, p, p, i32, i64, i32, i32, i32, i32, i32, p],
+    "dsk_pool2x_bwd": [p, p, p, p, i32, i32, i32, i32, i32, i32, i32, i32, p],
+    "dsk_upsample2x_bwd": [p, p, p, i32, i32, i32, i32, i32, i32, i32, p],
+    "dsk_softmax_bwd_rows": [p, p, i64, i32, p],
+    "dsk_silu_fwd": [p, p, i64, p],
+    "dsk_silu_bwd": [p, p, p, i64, p],
+    "dsk_add_ex": [p, i32, p, i32, p, i32, i64, p],
+    "dsk_split_channels": [p, p, p, p, p, i64, i32, i32, i32, p],
 }
-_RESTYPE = {"dsk_last_error": C.c_char_p, "dsk_launch_count": u64, "dsk_norm_ws_bytes": i64}
+_RESTYPE = {"dsk_last_error": C.c_char_p, "dsk_launch_count": u64, "dsk_norm_ws_bytes": i64,
+            "dsk_conv_wgrad_ws_bytes": i64, "dsk_bwd_ws_bytes": i64}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)          # AttributeError here == header/library mismatch: fail loudly

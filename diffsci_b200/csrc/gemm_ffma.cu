@@ -18,7 +18,10 @@ constexpr int BM = 128, BN = 64, BK = 16, GT = 256;
 // ------------------------------------------------------------------------------------------------
 template <typename TI, typename TO>
 struct ConvProb {
+  static constexpr bool kTransA = false;
   static constexpr bool kTransB = false;
+  __device__ __forceinline__ int k_begin() const { return 0; }
+  __device__ __forceinline__ int k_end() const { return K; }
   const TI* in;
   const float* w;         // [taps*Cin][Cout]
   const float* bias;      // [Cout] or null
@@ -127,8 +130,9 @@ struct ConvProb {
 };
 
 // ------------------------------------------------------------------------------------------------
-template <bool TRANSB>
+template <bool TRANSA, bool TRANSB>
 struct GemmProb {
+  static constexpr bool kTransA = TRANSA;
   static constexpr bool kTransB = TRANSB;
   const float* A;
   const float* Bm;
@@ -138,6 +142,20 @@ struct GemmProb {
   int64_t sA, sB, sC;
   float alpha;
   int act;
+  float beta;   // C = act(alpha * op(A) op(B) + bias) + beta * C
+  __device__ __forceinline__ int k_begin() const { return 0; }
+  __device__ __forceinline__ int k_end() const { return K; }
+  // TRANSA: A is stored [K][M] (lda >= M); 8 consecutive m of row k
+  __device__ __forceinline__ void load_a_t(int k, int m, float* o) const {
+    const float* p = A + (int64_t)k * lda + m;
+    if (k < K && m + 7 < M && ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+      float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (k < K && m + j < M) ? p[j] : 0.0f;
+    }
+  }
   struct RowCtx { int m; bool valid; };
   __device__ __forceinline__ RowCtx row_ctx(int m) const { return RowCtx{m, m < M}; }
   __device__ __forceinline__ void load_a(const RowCtx& c, int k, float* o) const {
@@ -181,6 +199,7 @@ struct GemmProb {
       if (bias != nullptr) v += bias[n + j];
       if (act == 1) v = silu_f(v);
       else if (act == 2) v = fmaxf(v, 0.0f);
+      if (beta != 0.0f) v += beta * C[(int64_t)m * ldc + n + j];
       C[(int64_t)m * ldc + n + j] = v;
     }
   }
@@ -191,6 +210,8 @@ struct GemmProb {
 
 // For transB GEMMs (B stored [N][K]) the B tile is loaded k-contiguous (4 consecutive k of one n)
 // so that global reads stay coalesced; the transposing smem store is bank-conflict free.
+// kTransA problems (A stored [K][M]: weight-gradient and A^T B products) load 8 consecutive m of one k.
+// blockIdx.z selects a batch entry or, for the split-K weight gradient, a slice [k_begin, k_end) of the reduction.
 template <class Prob>
 __global__ void __launch_bounds__(GT) ffma_gemm_kernel(Prob p) {
   __shared__ __align__(16) float As[BK][BM + 4];
@@ -198,8 +219,9 @@ __global__ void __launch_bounds__(GT) ffma_gemm_kernel(Prob p) {
   p.select_batch(blockIdx.z);
   const int tid = threadIdx.x;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  // A loader: thread -> (row, 8 consecutive k)
-  const int a_row = tid & (BM - 1), a_k = (tid >> 7) * 8;
+  // A loader: thread -> (row, 8 consecutive k); kTransA: thread -> (k, 8 consecutive rows)
+  const int a_row = Prob::kTransA ? (tid & 15) * 8 : tid & (BM - 1);
+  const int a_k = Prob::kTransA ? tid >> 4 : (tid >> 7) * 8;
   const typename Prob::RowCtx actx = p.row_ctx(m0 + a_row);
   // B loader: thread -> (k, 4 consecutive n), or for kTransB (n, 4 consecutive k)
   const int b_k = Prob::kTransB ? (tid & 3) * 4 : tid >> 4;
@@ -213,12 +235,19 @@ __global__ void __launch_bounds__(GT) ffma_gemm_kernel(Prob p) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
   float ra[8], rb[4];
-  p.load_a(actx, a_k, ra);
-  p.load_b(b_k, n0 + b_n, rb);
-  const int nk = (p.K + BK - 1) / BK;
+  const int kbeg = p.k_begin(), kend = p.k_end();
+  if constexpr (Prob::kTransA) p.load_a_t(kbeg + a_k, m0 + a_row, ra);
+  else p.load_a(actx, kbeg + a_k, ra);
+  p.load_b(kbeg + b_k, n0 + b_n, rb);
+  const int nk = (kend - kbeg + BK - 1) / BK;
   for (int kt = 0; kt < nk; ++kt) {
+    if constexpr (Prob::kTransA) {
+      *reinterpret_cast<float4*>(&As[a_k][a_row]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+      *reinterpret_cast<float4*>(&As[a_k][a_row + 4]) = make_float4(ra[4], ra[5], ra[6], ra[7]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) As[a_k + j][a_row] = ra[j];
+      for (int j = 0; j < 8; ++j) As[a_k + j][a_row] = ra[j];
+    }
     if (Prob::kTransB) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) Bs[b_k + j][b_n] = rb[j];
@@ -227,8 +256,10 @@ __global__ void __launch_bounds__(GT) ffma_gemm_kernel(Prob p) {
     }
     __syncthreads();
     if (kt + 1 < nk) {
-      p.load_a(actx, (kt + 1) * BK + a_k, ra);
-      p.load_b((kt + 1) * BK + b_k, n0 + b_n, rb);
+      const int kn = kbeg + (kt + 1) * BK;
+      if constexpr (Prob::kTransA) p.load_a_t(kn + a_k, m0 + a_row, ra);
+      else p.load_a(actx, kn + a_k, ra);
+      p.load_b(kn + b_k, n0 + b_n, rb);
     }
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
@@ -248,9 +279,107 @@ __global__ void __launch_bounds__(GT) ffma_gemm_kernel(Prob p) {
   for (int i = 0; i < 8; ++i) p.store(m0 + ty * 8 + i, n0 + tx * 4, acc[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient of conv_same as a split-K "A^T B" product (backward of torch.nn.Conv2d/3d, reached by
+// loss.backward() in KarrasModule.training_step, karrasmodule.py:1146-1155):
+//   dW[tap*Cin + ci][co] = sum_pix Xcol[pix][tap*Cin + ci] * dY[pix][co]
+// rows m = (tap, ci), columns n = co, reduction k = output pixel.  Both operands are read k-major exactly as they lie in
+// HBM (channels-last), the im2col gather (zero padding, optional nearest x2 upsample of x) happens in the A loader.
+// Each blockIdx.z reduces one slice of the pixels into ws[z][m][n]; wgrad_reduce_kernel sums the slices in a fixed
+// order (deterministic, no atomics) and writes the reference layout [Cout][Cin][taps].
+template <typename TI, typename TG>
+struct WgradProb {
+  static constexpr bool kTransA = true;
+  static constexpr bool kTransB = false;
+  const TI* x;
+  const TG* dy;
+  float* ws;
+  int B, D, H, W, Cin, Cout, ks, ndim, up2;
+  int Di, Hi, Wi;
+  int M, N, K;           // taps*Cin, Cout, pixels
+  int kper;              // pixels per split (multiple of BK)
+  int kb, ke;
+  struct RowCtx { int dummy; };
+  __device__ __forceinline__ RowCtx row_ctx(int) const { return RowCtx{0}; }
+  __device__ __forceinline__ int k_begin() const { return kb; }
+  __device__ __forceinline__ int k_end() const { return ke; }
+  __device__ __forceinline__ void select_batch(int z) {
+    kb = z * kper;
+    ke = min(K, kb + kper);
+    ws += (int64_t)z * M * N;
+  }
+  __device__ __forceinline__ const TI* tap_ptr(int pb, int pd, int ph, int pw, int tap) const {
+    const int r = ks >> 1;
+    int kw = tap % ks, t2 = tap / ks;
+    int kh = t2 % ks, kd = t2 / ks;
+    int zw = pw + kw - r, zh = ph + kh - r, zd = ndim == 3 ? pd + kd - r : 0;
+    if ((unsigned)zw >= (unsigned)W || (unsigned)zh >= (unsigned)H || (unsigned)zd >= (unsigned)D) return nullptr;
+    if (up2) {
+      zw >>= 1; zh >>= 1;
+      if (ndim == 3) zd >>= 1;
+    }
+    return x + ((((int64_t)pb * Di + zd) * Hi + zh) * Wi + zw) * Cin;
+  }
+  // 8 consecutive rows m (m % 8 == 0) of im2col column `k` (= output pixel)
+  __device__ __forceinline__ void load_a_t(int k, int m, float* o) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.0f;
+    if (k >= ke || m >= M) return;
+    int p = k;
+    const int pw = p % W; p /= W;
+    const int ph = p % H; p /= H;
+    const int pd = p % D;
+    const int pb = p / D;
+    if ((Cin & 7) == 0) {
+      const int tap = m / Cin, ci = m - tap * Cin;
+      const TI* q = tap_ptr(pb, pd, ph, pw, tap);
+      if (q != nullptr) ConvProb<TI, float>::ld8(q + ci, o);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int mm = m + j;
+        if (mm < M) {
+          const int tap = mm / Cin, ci = mm - tap * Cin;
+          const TI* q = tap_ptr(pb, pd, ph, pw, tap);
+          if (q != nullptr) o[j] = to_f32<TI>(q[ci]);
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void load_b(int k, int n, float* o) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = (k < ke && n + j < N) ? to_f32<TG>(dy[(int64_t)k * Cout + n + j]) : 0.0f;
+  }
+  __device__ __forceinline__ void store(int m, int n, const float* acc) const {
+    if (m >= M) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n + j < N) ws[(int64_t)m * N + n + j] = acc[j];
+  }
+};
+
+// dw[co][ci][tap] (reference layout) (+)= sum_z ws[z][tap*Cin + ci][co]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin,
+                                                            int taps, int nsplit, int accumulate) {
+  const int64_t MN = (int64_t)taps * Cin * Cout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < MN; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes ws row-major [m][co] so that the reads are coalesced
+    const int co = (int)(i % Cout);
+    const int m = (int)(i / Cout);
+    const int tap = m / Cin, ci = m - tap * Cin;
+    float s = 0.0f;
+    for (int z = 0; z < nsplit; ++z) s += ws[(int64_t)z * MN + i];
+    float* o = dw + ((int64_t)co * Cin + ci) * taps + tap;
+    *o = accumulate ? *o + s : s;
+  }
+}
+
 // bf16 layout: [tap][rows][Cin] with rows = max(Cout, pad_rows) (zero rows beyond Cout: the N_TILE = 16 convout path)
+// dgrad = 1: the packed weights of the DATA-GRADIENT convolution dX = conv_same(dY, W') with W'[tap'][co -> in][ci -> out],
+// tap' = taps-1-tap (all axes flipped): the same two layouts with the roles of Cin and Cout exchanged.
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, float* __restrict__ o32,
-                                                           __nv_bfloat16* __restrict__ o16, int Cout, int Cin, int taps, int rows) {
+                                                           __nv_bfloat16* __restrict__ o16, int Cout, int Cin, int taps, int rows,
+                                                           int dgrad) {
   const int64_t total = (int64_t)Cout * Cin * taps;
   if (o16 != nullptr && rows > Cout) {
     const int64_t padded = (int64_t)taps * rows * Cin;
@@ -264,6 +393,12 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
     int ci = (int)(r % Cin);
     int co = (int)(r / Cin);
     float v = w[i];
+    if (dgrad) {
+      const int tf = taps - 1 - tap;
+      if (o32 != nullptr) o32[((int64_t)tf * Cout + co) * Cin + ci] = v;                      // [tap'][in = co][out = ci]
+      if (o16 != nullptr) o16[((int64_t)tf * Cin + ci) * Cout + co] = __float2bfloat16_rn(v);   // [tap'][out = ci][in = co]
+      continue;
+    }
     if (o32 != nullptr) o32[((int64_t)tap * Cin + ci) * Cout + co] = v;          // [tap][ci][co]
     if (o16 != nullptr) o16[((int64_t)tap * rows + co) * Cin + ci] = __float2bfloat16_rn(v);  // [tap][co][ci]
   }
@@ -330,24 +465,109 @@ extern "C" int dsk_pack_conv_weight(const float* w_ref, void* w_packed, int Cout
   const int rows = (dtype == DSK_BF16 && Cout <= 16) ? 16 : Cout;
   const int grid = grid_for((int64_t)rows * Cin * taps, 256, 8);
   DSK_LAUNCH(pack_weight_kernel, grid, 256, 0, as_stream(stream), w_ref, dtype == DSK_F32 ? (float*)w_packed : nullptr,
-             dtype == DSK_BF16 ? (__nv_bfloat16*)w_packed : nullptr, Cout, Cin, taps, rows);
+             dtype == DSK_BF16 ? (__nv_bfloat16*)w_packed : nullptr, Cout, Cin, taps, rows, 0);
+  return DSK_OK;
+}
+
+extern "C" int dsk_pack_conv_weight_dgrad(const float* w_ref, void* w_packed, int Cout, int Cin, int taps, int dtype, void* stream) {
+  DSK_REQUIRE(w_ref && w_packed && Cout > 0 && Cin > 0 && taps > 0, "dsk_pack_conv_weight_dgrad: bad arguments");
+  DSK_REQUIRE(dtype == DSK_F32 || dtype == DSK_BF16, "dsk_pack_conv_weight_dgrad: bad dtype %d", dtype);
+  const int grid = grid_for((int64_t)Cout * Cin * taps, 256, 8);
+  DSK_LAUNCH(pack_weight_kernel, grid, 256, 0, as_stream(stream), w_ref, dtype == DSK_F32 ? (float*)w_packed : nullptr,
+             dtype == DSK_BF16 ? (__nv_bfloat16*)w_packed : nullptr, Cout, Cin, taps, Cout, 1);
+  return DSK_OK;
+}
+
+// ---- weight gradient (CUDA-core path) ---------------------------------------------------------------------------
+static int wgrad_splits(int M, int N, int K) {
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int want = (4 * DSK_NUM_SMS + tiles - 1) / tiles;          // ~4 waves of CTAs
+  int maxs = (K + 4 * BK - 1) / (4 * BK);                    // at least 64 pixels per slice
+  if (want > maxs) want = maxs;
+  if (want > 512) want = 512;
+  if (want < 1) want = 1;
+  return want;
+}
+
+extern "C" int64_t dsk_conv_wgrad_ws_bytes(const dsk_conv_desc* d) {
+  if (!d || d->B <= 0 || d->Cin <= 0 || d->Cout <= 0) return 0;
+  const int taps = d->ndim == 3 ? d->ksize * d->ksize * d->ksize : d->ksize * d->ksize;
+  const int64_t K = (int64_t)d->B * d->D * d->H * d->W;
+  if (K > 0x7fffffff) return 0;
+  const int M = taps * d->Cin, N = d->Cout;
+  return (int64_t)wgrad_splits(M, N, (int)K) * M * N * (int64_t)sizeof(float);
+}
+
+template <typename TI, typename TG>
+static int launch_wgrad(const dsk_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, int accumulate, cudaStream_t st) {
+  const int taps = d->ndim == 3 ? d->ksize * d->ksize * d->ksize : d->ksize * d->ksize;
+  WgradProb<TI, TG> p;
+  p.x = (const TI*)x; p.dy = (const TG*)dy; p.ws = (float*)ws;
+  p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.ks = d->ksize; p.ndim = d->ndim; p.up2 = d->up2;
+  p.Di = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D;
+  p.Hi = d->up2 ? d->H / 2 : d->H;
+  p.Wi = d->up2 ? d->W / 2 : d->W;
+  p.M = taps * d->Cin; p.N = d->Cout; p.K = (int)((int64_t)d->B * d->D * d->H * d->W);
+  const int nsplit = wgrad_splits(p.M, p.N, p.K);
+  int kper = (p.K + nsplit - 1) / nsplit;
+  kper = (kper + BK - 1) / BK * BK;
+  p.kper = kper; p.kb = 0; p.ke = 0;
+  const int used = (p.K + kper - 1) / kper;                  // slices that own at least one pixel
+  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, used);
+  DSK_LAUNCH((ffma_gemm_kernel<WgradProb<TI, TG>>), grid, GT, 0, st, p);
+  DSK_LAUNCH(wgrad_reduce_kernel, grid_for((int64_t)p.M * p.N, 256, 8), 256, 0, st, (const float*)ws, dw, d->Cout, d->Cin, taps, used,
+             accumulate);
+  return DSK_OK;
+}
+
+// implemented in wgrad_tc.cu (tcgen05 path); returns DSK_ERR_UNSUPPORTED for shapes it does not take
+extern "C" int dsk_conv_wgrad_tc(const dsk_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, int accumulate,
+                                 void* stream);
+
+extern "C" int dsk_conv_wgrad(const dsk_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, int accumulate,
+                              void* stream) {
+  DSK_REQUIRE(d && x && dy && dw && ws, "dsk_conv_wgrad: null pointer");
+  DSK_REQUIRE(d->B > 0 && d->D > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "dsk_conv_wgrad: bad shape");
+  DSK_REQUIRE((d->ksize == 1 || d->ksize == 3) && (d->ndim == 2 || d->ndim == 3), "dsk_conv_wgrad: ksize=%d ndim=%d unsupported", d->ksize, d->ndim);
+  DSK_REQUIRE(d->ndim == 3 || d->D == 1, "dsk_conv_wgrad: ndim=2 needs D=1");
+  DSK_REQUIRE((int64_t)d->B * d->D * d->H * d->W <= 0x7fffffff, "dsk_conv_wgrad: too many pixels");
+  if (d->w_dtype == DSK_BF16) {
+    const int rc = dsk_conv_wgrad_tc(d, x, dy, dw, ws, accumulate, stream);
+    if (rc != DSK_ERR_UNSUPPORTED) return rc;
+  }
+  cudaStream_t st = as_stream(stream);
+  if (d->in_dtype == DSK_F32 && d->out_dtype == DSK_F32) return launch_wgrad<float, float>(d, x, dy, dw, ws, accumulate, st);
+  if (d->in_dtype == DSK_BF16 && d->out_dtype == DSK_BF16) return launch_wgrad<__nv_bfloat16, __nv_bfloat16>(d, x, dy, dw, ws, accumulate, st);
+  if (d->in_dtype == DSK_F32 && d->out_dtype == DSK_BF16) return launch_wgrad<float, __nv_bfloat16>(d, x, dy, dw, ws, accumulate, st);
+  if (d->in_dtype == DSK_BF16 && d->out_dtype == DSK_F32) return launch_wgrad<__nv_bfloat16, float>(d, x, dy, dw, ws, accumulate, st);
+  DSK_REQUIRE(false, "dsk_conv_wgrad: bad dtypes %d / %d", d->in_dtype, d->out_dtype);
+  return DSK_OK;
+}
+
+extern "C" int dsk_gemm_f32_ex(const float* A, const float* Bm, float* Cm, const float* bias, int M, int N, int K, int lda,
+                               int ldb, int ldc, int64_t strideA, int64_t strideB, int64_t strideC, int batch, int transA,
+                               int transB, float alpha, float beta, int act, void* stream) {
+  DSK_REQUIRE(A && Bm && Cm, "dsk_gemm_f32: null pointer");
+  DSK_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0 && batch <= 65535, "dsk_gemm_f32: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
+  DSK_REQUIRE(lda >= (transA ? M : K) && ldc >= N && ldb >= (transB ? K : N), "dsk_gemm_f32: bad leading dimensions");
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, batch);
+  DSK_REQUIRE(grid.y <= 65535, "dsk_gemm_f32: N too large");
+#define GO(TA, TB)                                                                                                    \
+  {                                                                                                                   \
+    GemmProb<TA, TB> p{A, Bm, Cm, bias, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, act, beta};         \
+    DSK_LAUNCH((ffma_gemm_kernel<GemmProb<TA, TB>>), grid, GT, 0, as_stream(stream), p);                              \
+  }
+  if (transA && transB) GO(true, true)
+  else if (transA) GO(true, false)
+  else if (transB) GO(false, true)
+  else GO(false, false)
+#undef GO
   return DSK_OK;
 }
 
 extern "C" int dsk_gemm_f32(const float* A, const float* Bm, float* Cm, const float* bias, int M, int N, int K, int lda,
                             int ldb, int ldc, int64_t strideA, int64_t strideB, int64_t strideC, int batch, int transB,
                             float alpha, int act, void* stream) {
-  DSK_REQUIRE(A && Bm && Cm, "dsk_gemm_f32: null pointer");
-  DSK_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0 && batch <= 65535, "dsk_gemm_f32: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
-  DSK_REQUIRE(lda >= K && ldc >= N && ldb >= (transB ? K : N), "dsk_gemm_f32: bad leading dimensions");
-  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, batch);
-  DSK_REQUIRE(grid.y <= 65535, "dsk_gemm_f32: N too large");
-  if (transB) {
-    GemmProb<true> p{A, Bm, Cm, bias, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, act};
-    DSK_LAUNCH(ffma_gemm_kernel<GemmProb<true>>, grid, GT, 0, as_stream(stream), p);
-  } else {
-    GemmProb<false> p{A, Bm, Cm, bias, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, act};
-    DSK_LAUNCH(ffma_gemm_kernel<GemmProb<false>>, grid, GT, 0, as_stream(stream), p);
-  }
-  return DSK_OK;
+  return dsk_gemm_f32_ex(A, Bm, Cm, bias, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch, 0, transB, alpha, 0.0f, act,
+                         stream);
 }

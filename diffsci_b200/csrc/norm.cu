@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_partial_kernel(const T* __r
 // One block per (sample, group): combine the chunk partials, then fold mean / rstd / gamma / beta / FiLM into a
 // per-(b, c) scale-shift pair:  y = act(x * a + s).
 __global__ void __launch_bounds__(128) norm_finalize_kernel(const double2* __restrict__ partial, float2* __restrict__ table,
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float2* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              const float* __restrict__ fsc, const float* __restrict__ fsh,
                                                              int64_t S, int C, int G, int nchunks, int mode, float eps) {
   const int b = blockIdx.x / G, g = blockIdx.x % G;
@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(128) norm_finalize_kernel(const double2* __res
     } else {
       mr = make_float2(0.0f, 1.0f / sqrtf((float)ex2 + eps));  // x / sqrt(mean(x^2) + eps), commonlayers.py:377-378
     }
+    stats[blockIdx.x] = mr;                                      // (mean, rstd) per (b, g): kept for dsk_norm_act_bwd
   }
   __syncthreads();
   for (int i = threadIdx.x; i < cg; i += blockDim.x) {
@@ -234,7 +235,8 @@ extern "C" int64_t dsk_norm_ws_bytes(int B, int64_t S, int C) {
   int nchunks = norm_chunks(B, S, C, 4);   // upper bound over both vector widths
   int n8 = (C % 8 == 0) ? norm_chunks(B, S, C, 8) : 0;
   if (n8 > nchunks) nchunks = n8;
-  return (int64_t)B * nchunks * C * (int64_t)sizeof(double2) + (int64_t)B * C * (int64_t)sizeof(float2);
+  // [table: B*C float2 (folded scale, shift)] [stats: B*C float2 slots, B*G used (mean, rstd)] [partials]
+  return (int64_t)B * nchunks * C * (int64_t)sizeof(double2) + 2 * (int64_t)B * C * (int64_t)sizeof(float2);
 }
 
 extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const float* beta, const float* film_scale,
@@ -250,8 +252,9 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
   DSK_REQUIRE((film_scale == nullptr) == (film_shift == nullptr), "dsk_norm_act: FiLM scale/shift mismatch");
   cudaStream_t st = as_stream(stream);
   const int nchunks = norm_chunks(B, S, C, V);
-  double2* partial = reinterpret_cast<double2*>(ws);
-  float2* table = reinterpret_cast<float2*>(partial + (int64_t)B * nchunks * C);
+  float2* table = reinterpret_cast<float2*>(ws);
+  float2* stats = table + (int64_t)B * C;
+  double2* partial = reinterpret_cast<double2*>(stats + (int64_t)B * C);
   const int cv = C / V;
   const int pl = NORM_THREADS / cv > 0 ? NORM_THREADS / cv : 1;
   const size_t smem = (size_t)pl * C * sizeof(float2);
@@ -261,7 +264,7 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
     DSK_LAUNCH(norm_partial_kernel<float>, pg, NORM_THREADS, smem, st, (const float*)x, partial, S, C, nchunks);
   else
     DSK_LAUNCH(norm_partial_kernel<__nv_bfloat16>, pg, NORM_THREADS, smem, st, (const __nv_bfloat16*)x, partial, S, C, nchunks);
-  DSK_LAUNCH(norm_finalize_kernel, B * G, 128, 0, st, partial, table, gamma, beta, film_scale, film_shift, S, C, G, nchunks, mode,
+  DSK_LAUNCH(norm_finalize_kernel, B * G, 128, 0, st, partial, table, stats, gamma, beta, film_scale, film_shift, S, C, G, nchunks, mode,
              1e-5f);
   int64_t gx = (S + (int64_t)pl * 4 - 1) / ((int64_t)pl * 4);          // >= 4 pixels per thread
   const int64_t cap = (8LL * DSK_NUM_SMS + B - 1) / B;

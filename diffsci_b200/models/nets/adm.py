@@ -148,7 +148,8 @@ class ADM(nn.Module):
             raise NotImplementedError("diffsci_b200.ADM: conditional path (y) not built yet (SURVEY.md 8f)")
         require_cuda(x, "ADM input")
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("diffsci_b200.ADM: backward kernels (K2) not built yet")
+            from .graph import NetFunction
+            return NetFunction.apply(self.train_graph(x.shape[0], tuple(x.shape[2:]), x.device), x, t, *self.parameters())
         plan = self.plan(x.shape[0], tuple(x.shape[2:]), x.device)
         xin = ops.nchw_to_cl(x.float(), plan.act_dtype, 2, out=plan.xin)
         out = torch.empty((x.shape[0], self.config.output_channels) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
@@ -166,6 +167,19 @@ class ADM(nn.Module):
             with torch.inference_mode(False), torch.no_grad():
                 plan = self._plans[key] = _ADMPlan(self, B, tuple(spatial), device, precision, sig)
         return plan
+
+    def train_graph(self, B: int, spatial: tuple, device, precision: Optional[str] = None):
+        from .graph import build_adm
+        precision = precision or self.precision
+        key = ("train", B, tuple(spatial), str(device), precision)
+        sig = tuple(p.data_ptr() for p in self.parameters())
+        g = self._plans.get(key)
+        if g is None or g.sig != sig:
+            for k in [k for k in self._plans if k[0] == "train"]:
+                del self._plans[k]
+            with torch.inference_mode(False), torch.no_grad():
+                g = self._plans[key] = build_adm(self, B, tuple(spatial), device, precision)
+        return g
 
     def _apply(self, fn, *a, **k):
         self._plans = {}

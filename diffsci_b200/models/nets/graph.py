@@ -1,0 +1,562 @@
+"""Static training graph for the native score networks: forward + hand-written backward (K2).
+
+The reference trains with ATen autograd: ``KarrasModule.training_step`` -> ``loss_fn`` -> ``loss.backward()``
+(karras/karrasmodule.py:569-662, 1146-1155) through PUNetG / ADM (nets/punetg.py:389-416, nets/adm.py:199-216).
+Here a network instance is unrolled ONCE per (batch, shape, precision) into a list of forward launches and a list of
+backward launches over preallocated buffers -- no autograd tape, no allocation and no host synchronisation per step,
+so a whole training step is a fixed launch sequence (CUDA-graph capturable).  Every launch is a libdiffsci_b200
+kernel (diffsci_b200.ops); PyTorch only owns the memory.
+
+Gradient bookkeeping is resolved at build time.  A ``Var`` is a forward buffer plus a gradient slot that is
+  NONE  -> nothing has contributed yet,
+  ALIAS -> exactly one consumer contributed a pure copy (ResNet identity, U-Net skip, `+`): the slot just points at
+           that consumer's own gradient buffer, no pass over memory,
+  OWN   -> a buffer of its own; later contributions are accumulated through the kernels' ``dres`` operand
+           (out = f(...) + dres, dres may alias out) instead of a separate add pass.
+Backward ops are generated in reverse forward order, so when an op asks for the gradient of its output every consumer
+has already contributed.  Parameter gradients are fp32 views (reference layout) of ONE flat buffer in
+``net.parameters()`` order -- the unit of the data-parallel all-reduce and of the fused AdamW/EMA step.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional
+
+import torch
+
+from ... import ops
+
+_NORM_MODE = {"GroupLN": 0, "GroupRMS": 1}
+NONE, ALIAS, OWN = 0, 1, 2
+
+
+class Var:
+    __slots__ = ("t", "needs_grad", "state", "g", "name")
+
+    def __init__(self, t: torch.Tensor, needs_grad: bool = True, name: str = ""):
+        self.t, self.needs_grad, self.state, self.g, self.name = t, needs_grad, NONE, None, name
+
+
+class TrainGraph:
+    """Forward/backward launch lists of one network for one (batch, spatial shape, precision)."""
+
+    def __init__(self, net: torch.nn.Module, B: int, device, precision: str, ndim: int):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        self.net, self.B, self.device, self.precision, self.ndim = net, B, torch.device(device), precision, ndim
+        self.act_dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.fwd: list[Callable[[], None]] = []
+        self._bwd_builders: list[Callable[[], list]] = []
+        self.bwd: list[Callable[[], None]] = []
+        self.params = [p for p in net.parameters()]
+        self.sig = tuple(p.data_ptr() for p in self.params)
+        total = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(max(total, 1), dtype=torch.float32, device=self.device)
+        self._gviews, off = {}, 0
+        for p in self.params:
+            self._gviews[id(p)] = self.flat_grad[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self._written: set[int] = set()
+        self._scratch: dict = {}
+        self._packs: list = []
+        self.nbytes = 0
+
+    # ------------------------------------------------------------------ memory
+    def empty(self, shape, dtype=None) -> torch.Tensor:
+        t = torch.empty(tuple(shape), dtype=dtype or self.act_dtype, device=self.device)
+        self.nbytes += t.numel() * t.element_size()
+        return t
+
+    def scratch(self, tag, nbytes_or_shape, dtype=torch.uint8) -> torch.Tensor:
+        """Buffers that live only inside one op's launches are shared across ops (execution is sequential)."""
+        shape = (int(nbytes_or_shape),) if isinstance(nbytes_or_shape, int) else tuple(nbytes_or_shape)
+        n = 1
+        for s in shape:
+            n *= s
+        key = (tag, dtype)
+        t = self._scratch.get(key)
+        if t is None or t.numel() < n:
+            t = self._scratch[key] = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+        return t[:n].view(shape)
+
+    def lazy_scratch(self, tag, shape, dtype=torch.uint8):
+        """Scratch resolved at call time (the backing buffer may grow while the graph is being built)."""
+        self.scratch(tag, shape, dtype)
+        return lambda: self.scratch(tag, shape, dtype)
+
+    def grad_view(self, p: torch.Tensor, rows: Optional[slice] = None) -> torch.Tensor:
+        g = self._gviews[id(p)]
+        key = (id(p), None if rows is None else (rows.start, rows.stop))
+        if key in self._written or (id(p), None) in self._written:
+            raise RuntimeError("TrainGraph: a parameter is used by more than one op (gradient accumulation across ops "
+                               "is not built)")
+        self._written.add(key)
+        return g if rows is None else g[rows]
+
+    # ------------------------------------------------------------------ gradient slots (build time)
+    def contribute_compute(self, v: Var):
+        """-> (dres, out) for a kernel that writes out = f(...) (+ dres)."""
+        if v.state == NONE:
+            v.g, v.state = self.empty(v.t.shape, v.t.dtype), OWN
+            return None, v.g
+        if v.state == ALIAS:
+            src = v.g
+            v.g, v.state = self.empty(v.t.shape, v.t.dtype), OWN
+            return src, v.g
+        return v.g, v.g
+
+    def contribute_copy(self, v: Var, src: torch.Tensor) -> list:
+        """The contribution IS `src` (same shape/dtype as v)."""
+        assert src.shape == v.t.shape and src.dtype == v.t.dtype, (src.shape, v.t.shape, src.dtype, v.t.dtype)
+        if v.state == NONE:
+            v.g, v.state = src, ALIAS
+            return []
+        if v.state == ALIAS:
+            a = v.g
+            v.g, v.state = self.empty(v.t.shape, v.t.dtype), OWN
+            out = v.g
+            return [lambda: ops.add_ex(a, src, out)]
+        out = v.g
+        return [lambda: ops.add_ex(out, src, out)]
+
+    @staticmethod
+    def grad_of(v: Var) -> Optional[torch.Tensor]:
+        return v.g if v.state != NONE else None
+
+    # ------------------------------------------------------------------ ops
+    def conv(self, x: Var, cp, chan_bias: Optional[Var] = None, residual: Optional[Var] = None, up2: bool = False,
+             few_out_ok: bool = False) -> Var:
+        """y = conv_same([up2](x)) + bias + chan_bias[b, :] + residual  (forward: dsk_conv_fwd; backward: dsk_conv_wgrad,
+        dsk_channel_sum, dsk_conv_fwd with dgrad-packed weights [+ dsk_upsample2x_bwd])."""
+        from .punetg import _tc_eligible
+        nd = self.ndim
+        tc = self.precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize, few_out_ok)
+        wdt = torch.bfloat16 if tc else torch.float32
+        pc = ops.PackedConv(cp.weight, cp.bias, nd, wdt, subpixel=bool(up2 and tc))
+        self._packs.append(pc)
+        B, D, H, W, _ = x.t.shape
+        if up2:
+            D, H, W = (D * 2 if nd == 3 else D), H * 2, W * 2
+        y = Var(self.empty((B, D, H, W, cp.cout)))
+        xt, yt = x.t, y.t
+        cb = chan_bias.t if chan_bias is not None else None
+        rs = residual.t if residual is not None else None
+        self.fwd.append(lambda: ops.conv(xt, pc, out=yt, chan_bias=cb, residual=rs, up2=up2))
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return []
+            out = []
+            gb = self.grad_view(cp.bias) if cp.bias is not None else None
+            S = D * H * W
+            csws = self.lazy_scratch("bwd_ws", ops.bwd_ws_bytes(B, S, cp.cout))
+            if chan_bias is not None:
+                dres, dcb = self.contribute_compute(chan_bias)
+                assert dres is None, "chan_bias with several consumers is not supported"
+                out.append(lambda: ops.channel_sum(dy, dcb, csws(), True))
+                if gb is not None:
+                    out.append(lambda: ops.colsum(dcb, gb))
+            elif gb is not None:
+                out.append(lambda: ops.channel_sum(dy, gb, csws(), False))
+            gw = self.grad_view(cp.weight)
+            # the tcgen05 weight-gradient kernel reads a materialised operand; the CUDA-core one gathers (up2 folded in)
+            desc = ops.conv_desc(B, D, H, W, cp.cin, cp.cout, cp.ksize, nd, up2, wdt, xt.dtype, dy.dtype)
+            wws = self.lazy_scratch("wgrad_ws", ops.conv_wgrad_ws_bytes(desc))
+            out.append(lambda: ops.conv_wgrad(desc, xt, dy, gw, wws()))
+            if residual is not None and residual.needs_grad:
+                out.extend(self.contribute_copy(residual, dy))
+            if x.needs_grad:
+                dg_tc = self.precision == "bf16" and _tc_eligible(cp.cout, cp.cin, cp.ksize)
+                pd = ops.PackedConv(cp.weight, None, nd, torch.bfloat16 if dg_tc else torch.float32, dgrad=True)
+                self._packs.append(pd)
+                if not up2:
+                    dres, dx = self.contribute_compute(x)
+                    out.append(lambda: ops.conv(dy, pd, out=dx, residual=dres))
+                else:
+                    du = self.lazy_scratch("du", (B, D, H, W, cp.cin), xt.dtype)
+                    dres, dx = self.contribute_compute(x)
+                    out.append(lambda: ops.conv(dy, pd, out=du()))
+                    out.append(lambda: ops.upsample2x_bwd(du(), dx, nd, dres=dres))
+            return out
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
+    def norm(self, x: Var, np_, G: int, kind: str, silu: bool, film: Optional[tuple] = None) -> Var:
+        mode = _NORM_MODE[kind]
+        B, Cc = x.t.shape[0], x.t.shape[-1]
+        S = x.t.numel() // (B * Cc)
+        y = Var(self.empty(x.t.shape))
+        fws = self.empty((int(ops.lib.dsk_norm_ws_bytes(B, S, Cc)),), torch.uint8)    # kept: table + stats feed the backward
+        xt, yt = x.t, y.t
+        fsc = film[0].t if film is not None else None
+        fsh = film[1].t if film is not None else None
+        self.fwd.append(lambda: ops.norm_act(xt, np_.weight, np_.bias, G, mode, silu, out=yt, film_scale=fsc, film_shift=fsh,
+                                             ws=fws))
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return []
+            affine = np_.weight is not None
+            dg = self.grad_view(np_.weight) if affine else None
+            db = self.grad_view(np_.bias) if affine else None
+            dfs = dfh = None
+            if film is not None:
+                r1, dfs = self.contribute_compute(film[0])
+                r2, dfh = self.contribute_compute(film[1])
+                assert r1 is None and r2 is None, "FiLM vectors with several consumers are not supported"
+            ws = self.lazy_scratch("bwd_ws", ops.bwd_ws_bytes(B, S, Cc))
+            if not x.needs_grad:
+                raise RuntimeError("norm of a tensor that needs no gradient")
+            dres, dx = self.contribute_compute(x)
+            return [lambda: ops.norm_act_bwd(xt, dy, dx, np_.weight, np_.bias, G, mode, silu, fws, ws(), dgamma=dg, dbeta=db,
+                                             dres=dres, film_scale=fsc, dfilm_scale=dfs, dfilm_shift=dfh)]
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
+    def pool(self, x: Var, is_max: bool) -> Var:
+        nd = self.ndim
+        B, D, H, W, Cc = x.t.shape
+        y = Var(self.empty((B, D // 2 if nd == 3 else 1, H // 2, W // 2, Cc)))
+        xt, yt = x.t, y.t
+        self.fwd.append(lambda: ops.pool2x(xt, nd, is_max, out=yt))
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None or not x.needs_grad:
+                return []
+            dres, dx = self.contribute_compute(x)
+            return [lambda: ops.pool2x_bwd(xt, dy, dx, nd, is_max, dres=dres)]
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
+    def add(self, a: Var, b: Var) -> Var:
+        y = Var(self.empty(a.t.shape))
+        at, bt, yt = a.t, b.t, y.t
+        self.fwd.append(lambda: ops.add(at, bt, out=yt))
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return []
+            return self.contribute_copy(a, dy) + self.contribute_copy(b, dy)
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
+    def concat(self, a: Var, b: Var) -> Var:
+        y = Var(self.empty(a.t.shape[:-1] + (a.t.shape[-1] + b.t.shape[-1],)))
+        at, bt, yt = a.t, b.t, y.t
+        self.fwd.append(lambda: ops.concat_channels(at, bt, out=yt))
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return []
+            ra, da = self.contribute_compute(a)
+            rb, db = self.contribute_compute(b)
+            return [lambda: ops.split_channels(dy, da, db, ra, rb)]
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
+    def fourier(self, t_buf: torch.Tensor, W: torch.Tensor) -> Var:
+        y = Var(self.empty((self.B, 2 * W.shape[0]), torch.float32), needs_grad=False)
+        yt = y.t
+        self.fwd.append(lambda: ops.fourier(t_buf, W, out=yt))
+        return y
+
+    def linear(self, x: Var, weight: torch.Tensor, bias: Optional[torch.Tensor], silu: bool, param_w: torch.Tensor,
+               param_b: Optional[torch.Tensor], rows: Optional[slice] = None) -> Var:
+        """y = [silu](x W^T + b) on fp32 [B, K] vectors (time MLPs).  `weight`/`bias` may be row slices of the parameters
+        `param_w`/`param_b` (ADM's packed FiLM projection, adm.py:331-343); `rows` names that slice for the gradient."""
+        Bn, K = x.t.shape
+        N = weight.shape[0]
+        f32 = torch.float32
+        z = self.empty((Bn, N), f32)
+        y = Var(self.empty((Bn, N), f32) if silu else z)
+        xt, yt = x.t, y.t
+        wd = weight.detach()
+        bd = bias.detach() if bias is not None else None
+        self.fwd.append(lambda: ops.gemm_ex(xt, wd, z, M=Bn, N=N, K=K, lda=K, ldb=K, ldc=N, bias=bd, transB=True))
+        if silu:
+            self.fwd.append(lambda: ops.silu_fwd(z, yt))
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return []
+            out = []
+            if silu:
+                dz = self.empty((Bn, N), f32)
+                out.append(lambda: ops.silu_bwd(z, dy, dz))
+            else:
+                dz = dy
+            gw = self.grad_view(param_w, rows)
+            # dW[n][k] = sum_b dz[b][n] x[b][k]  (A = dz stored [K'=B][M'=N])
+            out.append(lambda: ops.gemm_ex(dz, xt, gw, M=N, N=K, K=Bn, lda=N, ldb=K, ldc=K, transA=True, transB=False))
+            if param_b is not None:
+                gbv = self.grad_view(param_b, rows)
+                out.append(lambda: ops.colsum(dz, gbv))
+            if x.needs_grad:
+                dres, dx = self.contribute_compute(x)
+                if dres is not None and dres is not dx:
+                    out.append(lambda: ops.add_ex(dres, None, dx))
+                beta = 0.0 if dres is None else 1.0
+                out.append(lambda: ops.gemm_ex(dz, wd, dx, M=Bn, N=K, K=N, lda=N, ldb=K, ldc=K, transB=False, beta=beta))
+            return out
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
+    def attention(self, x: Var, mha, residual: bool) -> Var:
+        """nn.MultiheadAttention(C, 1 head) self-attention over the spatial positions (nets/attention.py:54-102), fp32
+        CUDA-core GEMMs in both directions (the training path keeps Q, K, V and the probabilities for the backward)."""
+        B = self.B
+        Cc = x.t.shape[-1]
+        Lq = x.t.numel() // (B * Cc)
+        f32 = torch.float32
+        y = Var(self.empty(x.t.shape))
+        xt, yt = x.t, y.t
+        tok = xt.view(B, Lq, Cc) if xt.dtype == f32 else self.empty((B, Lq, Cc), f32)
+        bufs = dict(qkv=self.empty((B * Lq, 3 * Cc), f32), scores=self.empty((B, Lq, Lq), f32),
+                    ao=self.empty((B * Lq, Cc), f32), out=self.empty((B, Lq, Cc), f32))
+
+        def fwd():
+            if tok.data_ptr() != xt.data_ptr():
+                ops.cast(xt.view(B, Lq, Cc), f32, out=tok)
+            o = ops.self_attention_f32(tok, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, bufs,
+                                       residual)
+            ops.cast(o, yt.dtype, out=yt.view(B, Lq, Cc))
+
+        self.fwd.append(fwd)
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return []
+            gwi, gbi = self.grad_view(mha.in_proj_weight), self.grad_view(mha.in_proj_bias)
+            gwo, gbo = self.grad_view(mha.out_proj.weight), self.grad_view(mha.out_proj.bias)
+            wi, wo = mha.in_proj_weight.detach(), mha.out_proj.weight.detach()
+            qkv, P, ao = bufs["qkv"], bufs["scores"], bufs["ao"]
+            M = B * Lq
+            dout = dy.view(M, Cc) if dy.dtype == f32 else self.empty((M, Cc), f32)
+            dO = self.empty((M, Cc), f32)
+            dP = self.lazy_scratch("attn_dP", (B, Lq, Lq), f32)
+            dqkv = self.empty((M, 3 * Cc), f32)
+            dtok = self.empty((M, Cc), f32)
+            alpha = Cc ** -0.5
+            out = []
+            if dout.data_ptr() != dy.data_ptr():
+                out.append(lambda: ops.cast(dy.view(M, Cc), f32, out=dout))
+            # out = ao Wo^T + bo :  dWo = dout^T ao ; dbo = colsum(dout) ; dO = dout Wo
+            out.append(lambda: ops.gemm_ex(dout, ao, gwo, M=Cc, N=Cc, K=M, lda=Cc, ldb=Cc, ldc=Cc, transA=True, transB=False))
+            out.append(lambda: ops.colsum(dout, gbo))
+            out.append(lambda: ops.gemm_ex(dout, wo, dO, M=M, N=Cc, K=Cc, lda=Cc, ldb=Cc, ldc=Cc, transB=False))
+            s3 = Lq * 3 * Cc
+            # O = P V :  dP = dO V^T ; dV = P^T dO
+            out.append(lambda: ops.gemm_ex(dO, qkv, dP(), M=Lq, N=Lq, K=Cc, lda=Cc, ldb=3 * Cc, ldc=Lq, transB=True, batch=B,
+                                           strideA=Lq * Cc, strideB=s3, strideC=Lq * Lq, b_off=2 * Cc))
+            out.append(lambda: ops.gemm_ex(P, dO, dqkv, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=Cc, ldc=3 * Cc, transA=True, transB=False,
+                                           batch=B, strideA=Lq * Lq, strideB=Lq * Cc, strideC=s3, c_off=2 * Cc))
+            # P = softmax(alpha Q K^T) :  dS = P (dP - rowsum(dP P)) ; dQ = alpha dS K ; dK = alpha dS^T Q
+            out.append(lambda: ops.softmax_bwd_rows(P, dP(), B * Lq, Lq))
+            out.append(lambda: ops.gemm_ex(dP(), qkv, dqkv, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=3 * Cc, ldc=3 * Cc, transB=False,
+                                           alpha=alpha, batch=B, strideA=Lq * Lq, strideB=s3, strideC=s3, b_off=Cc, c_off=0))
+            out.append(lambda: ops.gemm_ex(dP(), qkv, dqkv, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=3 * Cc, ldc=3 * Cc, transA=True,
+                                           transB=False, alpha=alpha, batch=B, strideA=Lq * Lq, strideB=s3, strideC=s3, b_off=0,
+                                           c_off=Cc))
+            # qkv = tok Wi^T + bi :  dWi = dqkv^T tok ; dbi = colsum(dqkv) ; dtok = dqkv Wi
+            out.append(lambda: ops.gemm_ex(dqkv, tok.view(M, Cc), gwi, M=3 * Cc, N=Cc, K=M, lda=3 * Cc, ldb=Cc, ldc=Cc, transA=True,
+                                           transB=False))
+            out.append(lambda: ops.colsum(dqkv, gbi))
+            if x.needs_grad:
+                out.append(lambda: ops.gemm_ex(dqkv, wi, dtok, M=M, N=Cc, K=3 * Cc, lda=3 * Cc, ldb=Cc, ldc=Cc, transB=False))
+                if residual:
+                    out.append(lambda: ops.add_ex(dtok, dout, dtok))
+                dres, dx = self.contribute_compute(x)
+                out.append(lambda: ops.add_ex(dtok, dres.view(M, Cc) if dres is not None else None, dx.view(M, Cc)))
+            return out
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
+    # ------------------------------------------------------------------ finalisation / execution
+    def finalize(self, output: Var):
+        """Set the gradient slot of the network output and generate the backward launch list."""
+        output.g, output.state = self.empty(output.t.shape, output.t.dtype), OWN
+        self.output = output
+        self.bwd = []
+        for build in reversed(self._bwd_builders):
+            self.bwd.extend(build())
+        self._bwd_builders = []
+        missing = [n for n, p in self.net.named_parameters() if p.requires_grad and not any(k[0] == id(p) for k in self._written)]
+        if missing:
+            raise RuntimeError(f"TrainGraph: no backward op writes the gradient of {missing[:4]}...")
+        self.prepare()
+
+    def prepare(self):
+        """(Re)pack derived weight layouts; called before every forward so optimizer steps are picked up."""
+        for pc in self._packs:
+            pc.packed()
+
+    def run_forward(self):
+        self.prepare()
+        for f in self.fwd:
+            f()
+
+    def run_backward(self):
+        for f in self.bwd:
+            f()
+
+    def grads(self) -> list:
+        return [self._gviews[id(p)] for p in self.params]
+
+
+def time_block(g: TrainGraph, te: Var, tb) -> Var:
+    """ResnetTimeBlock (commonlayers.py:516-550): Linear-SiLU-Linear-SiLU-Linear on the shared Fourier embedding."""
+    n = tb.net
+    h = g.linear(te, n[0].weight, n[0].bias, True, n[0].weight, n[0].bias)
+    h = g.linear(h, n[2].weight, n[2].bias, True, n[2].weight, n[2].bias)
+    return g.linear(h, n[4].weight, n[4].bias, False, n[4].weight, n[4].bias)
+
+
+def build_punetg(net, B: int, spatial: tuple, device, precision: str) -> TrainGraph:
+    """PUNetG.forward (nets/punetg.py:389-416) unrolled into a TrainGraph."""
+    c = net.config
+    nd = c.dimension
+    if c.dropout != 0.0:
+        raise NotImplementedError("diffsci_b200.PUNetG: dropout > 0 in training is not built yet")
+    g = TrainGraph(net, B, device, precision, nd)
+    sp = (1,) + tuple(spatial) if nd == 2 else tuple(spatial)
+    nlev = len(c.channel_expansion)
+    for l in range(nlev):
+        if any(s % (2 ** (l + 1)) for s in spatial):
+            raise ValueError(f"PUNetG: spatial size {spatial} is not divisible by 2 at a down-sampling level")
+    g.t_in = torch.empty(B, dtype=torch.float32, device=g.device)
+    g.x_in = Var(g.empty((B,) + sp + (c.input_channels,)), needs_grad=False)
+    te = g.fourier(g.t_in, net.time_projection.W)
+
+    def resblock(x: Var, blk) -> Var:
+        C = blk.channels
+        tv = time_block(g, te, blk.timeblock)
+        n1 = g.norm(x, blk.gnorm1, C, c.first_resblock_norm, True)
+        y = g.conv(n1, blk.conv1, chan_bias=tv)
+        n2 = g.norm(y, blk.gnorm2, C, c.second_resblock_norm, True)
+        return g.conv(n2, blk.conv2, residual=x)
+
+    x = g.conv(g.x_in, net.convin)
+    skips = []
+    for l in range(nlev):
+        for blk in net.downward_blocks[l]:
+            x = resblock(x, blk)
+        skips.append(x)
+        x = g.conv(g.pool(x, True), net.downsamplers[l].conv)
+    for blk in net.before_block:
+        x = resblock(x, blk)
+    xa = x
+    for r, blk in enumerate(net.attn_resnet_block):
+        xa = resblock(xa, blk)
+        if r < len(net.attn_block):
+            xa = g.attention(xa, net.attn_block[r].mhattn, c.attn_residual)
+    x = g.add(x, xa)
+    for blk in net.after_block:
+        x = resblock(x, blk)
+    for i in range(nlev):
+        x = g.conv(x, net.upsamplers[i].conv, residual=skips.pop(), up2=True)
+        for blk in net.upward_blocks[i]:
+            x = resblock(x, blk)
+    g.finalize(g.conv(x, net.convout, few_out_ok=True))
+    return g
+
+
+def build_adm(net, B: int, spatial: tuple, device, precision: str) -> TrainGraph:
+    """ADM.forward (nets/adm.py:199-216; block :292-343) unrolled into a TrainGraph."""
+    c = net.config
+    if getattr(c, "dropout", 0.0) != 0.0:
+        raise NotImplementedError("diffsci_b200.ADM: dropout > 0 in training is not built yet")
+    g = TrainGraph(net, B, device, precision, 2)
+    H, W = spatial
+    nlev = len(c.channel_expansion)
+    if H % (2 ** nlev) or W % (2 ** nlev):
+        raise ValueError(f"ADM: spatial size {spatial} must be divisible by {2 ** nlev}")
+    G = c.num_groups
+    g.t_in = torch.empty(B, dtype=torch.float32, device=g.device)
+    g.x_in = Var(g.empty((B, 1, H, W, c.input_channels)), needs_grad=False)
+    four = g.fourier(g.t_in, net.time_embedding.projection.W)
+    mlp = net.time_embedding.mlp
+    h1 = g.linear(four, mlp[0].weight, mlp[0].bias, True, mlp[0].weight, mlp[0].bias)
+    te = g.linear(h1, mlp[2].weight, mlp[2].bias, True, mlp[2].weight, mlp[2].bias)      # + act_final SiLU (adm.py:1047-1053)
+
+    def block(x: Var, blk) -> Var:
+        down, up = blk.sample == "down", blk.sample == "up"
+        n = g.norm(x, blk.norm1, G, c.first_resblock_norm, True)
+        xr = x
+        if down:
+            n, xr = g.pool(n, False), g.pool(x, False)
+        y = g.conv(n, blk.conv1, up2=up)
+        w, b = blk.embed_linear.weight, blk.embed_linear.bias
+        Cc = blk.cout
+        te1 = g.linear(te, w[:Cc], b[:Cc], False, w, b, slice(0, Cc))
+        te2 = g.linear(te, w[Cc:], b[Cc:], False, w, b, slice(Cc, 2 * Cc))
+        h = g.norm(y, blk.norm2, G, c.second_resblock_norm, True, film=(te1, te2))
+        r = g.conv(xr, blk.convresidual, up2=up)
+        o = g.conv(h, blk.conv2, residual=r)
+        if blk.has_attn:
+            o = g.attention(o, blk.attn.mhattn, c.attn_residual)
+        return o
+
+    x = g.conv(g.x_in, net.input_layer)
+    skips = [x]
+    for layer in net.encoder.layers:
+        for blk in layer.input_blocks:
+            x = block(x, blk)
+        skips.append(x)
+    for blk in net.middle_block.middle_blocks:
+        x = block(x, blk)
+    for layer in net.decoder.layers:
+        hskip = skips.pop()
+        x = g.concat(x, hskip) if c.skip_integration_type == "concat" else g.add(x, hskip)
+        for blk in layer.input_blocks:
+            x = block(x, blk)
+    g.finalize(g.conv(x, net.output_layer, few_out_ok=True))
+    return g
+
+
+class NetFunction(torch.autograd.Function):
+    """Autograd seam: F = net(x, t) with the hand-written backward; gradients flow to the nn.Parameters (and not to x)."""
+
+    @staticmethod
+    def forward(ctx, graph: TrainGraph, x: torch.Tensor, t: torch.Tensor, *params):
+        ctx.graph = graph
+        return graph.forward_nchw(x, t)
+
+    @staticmethod
+    def backward(ctx, dF):
+        g = ctx.graph
+        g.backward_nchw(dF)
+        # clones: AccumulateGrad may keep the tensors it is handed, and flat_grad is rewritten by the next step
+        return (None, None, None) + tuple(v.clone() for v in g.grads())
+
+
+def _forward_nchw(self: TrainGraph, x: torch.Tensor, t: Optional[torch.Tensor]) -> torch.Tensor:
+    """x fp32 [B, C, *S] -> F fp32 [B, Cout, *S] (user layout in/out, channels-last inside)."""
+    if t is None:
+        raise NotImplementedError("diffsci_b200: training with t=None (zero time embedding) is not built")
+    ops.nchw_to_cl(x.float(), self.act_dtype, self.ndim, out=self.x_in.t)
+    self.t_in.copy_(t.float().reshape(-1))
+    self.run_forward()
+    return ops.cl_to_nchw(self.output.t, self.ndim)
+
+
+def _backward_nchw(self: TrainGraph, dF: torch.Tensor) -> None:
+    ops.nchw_to_cl(dF.float().contiguous(), self.output.t.dtype, self.ndim, out=self.output.g)
+    self.run_backward()
+
+
+TrainGraph.forward_nchw = _forward_nchw
+TrainGraph.backward_nchw = _backward_nchw

@@ -121,8 +121,9 @@ class PUNetG(nn.Module):
             raise NotImplementedError("diffsci_b200.PUNetG: conditional path (y) not built yet (SURVEY.md 8f)")
         require_cuda(x, "PUNetG input")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("diffsci_b200.PUNetG: backward kernels (K2) not built yet; call under "
-                                      "torch.no_grad()/inference_mode() or .eval()")
+            # training: static forward/backward launch lists with hand-written backward kernels (graph.py)
+            from .graph import NetFunction
+            return NetFunction.apply(self.train_graph(x.shape[0], tuple(x.shape[2:]), x.device), x, t, *self.parameters())
         B = x.shape[0]
         plan = self.plan(B, tuple(x.shape[2:]), x.device)
         xin = ops.nchw_to_cl(x.float(), plan.act_dtype, self.config.dimension, out=plan.xin)
@@ -143,6 +144,20 @@ class PUNetG(nn.Module):
             with torch.inference_mode(False), torch.no_grad():   # persistent buffers must be normal tensors
                 plan = self._plans[key] = _Plan(self, B, tuple(spatial), device, precision, sig)
         return plan
+
+    def train_graph(self, B: int, spatial: tuple, device, precision: Optional[str] = None):
+        """The TrainGraph (forward + backward launch lists, saved activations, flat gradient buffer) of this shape."""
+        from .graph import build_punetg
+        precision = precision or self.precision
+        key = ("train", B, tuple(spatial), str(device), precision)
+        sig = tuple(p.data_ptr() for p in self.parameters())
+        g = self._plans.get(key)
+        if g is None or g.sig != sig:
+            for k in [k for k in self._plans if k[0] == "train"]:
+                del self._plans[k]                                  # one training shape resident at a time
+            with torch.inference_mode(False), torch.no_grad():
+                g = self._plans[key] = build_punetg(self, B, tuple(spatial), device, precision)
+        return g
 
     def _apply(self, fn, *a, **k):
         self._plans = {}

@@ -25,12 +25,16 @@ class PackedConv:
     """
 
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], ndim: int, w_dtype: torch.dtype,
-                 subpixel: bool = False):
-        """subpixel=True (bf16 only): pack for the phase-decomposed conv(nearest_up2(x)) of the tcgen05 UpSampler path."""
+                 subpixel: bool = False, dgrad: bool = False):
+        """subpixel=True (bf16 only): pack for the phase-decomposed conv(nearest_up2(x)) of the tcgen05 UpSampler path.
+        dgrad=True: the weights of the data-gradient convolution dX = conv_same(dY, flip(W)^T) (Cin and Cout exchanged)."""
         assert not subpixel or (w_dtype == torch.bfloat16 and int(weight.shape[-1]) == 3)
-        self.subpixel = subpixel
+        assert not (dgrad and (subpixel or bias is not None))
+        self.subpixel, self.dgrad = subpixel, dgrad
         self.weight, self.bias, self.ndim = weight, bias, ndim
         self.cout, self.cin = int(weight.shape[0]), int(weight.shape[1])
+        if dgrad:
+            self.cout, self.cin = self.cin, self.cout
         self.ksize = int(weight.shape[-1])
         self.taps = self.ksize ** ndim
         self.w_dtype = w_dtype
@@ -50,11 +54,14 @@ class PackedConv:
         if True:
             src = w.detach().float().contiguous()
             ntap = (4 ** self.ndim) if self.subpixel else self.taps
-            rows = 16 if (self.w_dtype == torch.bfloat16 and self.cout <= 16) else self.cout   # convout: zero-padded to N = 16
+            rows = 16 if (self.w_dtype == torch.bfloat16 and self.cout <= 16 and not self.dgrad) else self.cout   # convout: zero-padded to N = 16
             if self._packed is None or self._packed.device != w.device:
                 self._packed = torch.empty(ntap * self.cin * rows, dtype=self.w_dtype, device=w.device)
             if self.subpixel:
                 check(lib.dsk_pack_upconv_weight(ptr(src), ptr(self._packed), self.cout, self.cin, self.ndim, stream()))
+            elif self.dgrad:   # reference weight is [Cout_w = self.cin, Cin_w = self.cout, taps]
+                check(lib.dsk_pack_conv_weight_dgrad(ptr(src), ptr(self._packed), self.cin, self.cout, self.taps,
+                                                     dt_code(self.w_dtype), stream()))
             else:
                 check(lib.dsk_pack_conv_weight(ptr(src), ptr(self._packed), self.cout, self.cin, self.taps,
                                                dt_code(self.w_dtype), stream()))
@@ -333,3 +340,120 @@ def self_attention_tc(tok: torch.Tensor, w_in: PackedLinear, in_b: torch.Tensor,
     gemm_bf16_tc(ao, wo, out, M=B * Lq, N=Cc, K=Cc, lda=Cc, ldb=Cc, ldc=Cc, bias=out_b.detach(),
                  residual=tok if residual else None)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ backward (K2)
+def conv_desc(B, D, H, W, cin, cout, ksize, ndim, up2, w_dtype, in_dtype, out_dtype) -> "L.ConvDesc":
+    return L.ConvDesc(B, D, H, W, cin, cout, ksize, ndim, int(up2), dt_code(w_dtype), dt_code(in_dtype), dt_code(out_dtype), 0)
+
+
+def conv_wgrad_ws_bytes(desc) -> int:
+    return int(lib.dsk_conv_wgrad_ws_bytes(C.byref(desc)))
+
+
+def conv_wgrad(desc, x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, ws: torch.Tensor, accumulate: bool = False):
+    """dw[Cout, Cin, k..] (fp32, reference layout) (+)= sum_pixels dy * shifted x  (dsk_conv_wgrad)."""
+    require_cuda(x, "wgrad input")
+    assert dw.dtype == torch.float32 and dw.is_contiguous()
+    assert ws.numel() * ws.element_size() >= conv_wgrad_ws_bytes(desc)
+    check(lib.dsk_conv_wgrad(C.byref(desc), ptr(x), ptr(dy), ptr(dw), ptr(ws), int(accumulate), stream()))
+    return dw
+
+
+def bwd_ws_bytes(B: int, S: int, Cc: int) -> int:
+    return int(lib.dsk_bwd_ws_bytes(B, S, Cc))
+
+
+def channel_sum(dy: torch.Tensor, out: torch.Tensor, ws: Optional[torch.Tensor], per_sample: bool):
+    """out[b, c] (per_sample) or out[c] = sum over the spatial (and batch) positions of channels-last dy."""
+    require_cuda(dy, "channel_sum input")
+    B, Cc = dy.shape[0], dy.shape[-1]
+    S = dy.numel() // (B * Cc)
+    check(lib.dsk_channel_sum(ptr(dy), ptr(out), ptr(ws), B, S, Cc, dt_code(dy.dtype), int(per_sample), stream()))
+    return out
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor):
+    """out[c] = sum_r x[r, c] for a contiguous fp32 matrix."""
+    require_cuda(x, "colsum input")
+    rows, cols = x.shape
+    check(lib.dsk_colsum_f32(ptr(x), ptr(out), rows, cols, cols, stream()))
+    return out
+
+
+def norm_act_bwd(x, dy, dx, gamma, beta, G: int, mode: int, silu: bool, fwd_ws, ws, dgamma=None, dbeta=None, dres=None,
+                 film_scale=None, dfilm_scale=None, dfilm_shift=None):
+    require_cuda(x, "norm input")
+    B, Cc = x.shape[0], x.shape[-1]
+    S = x.numel() // (B * Cc)
+    assert x.dtype == dy.dtype == dx.dtype and (dres is None or dres.dtype == x.dtype)
+    g = gamma.detach() if gamma is not None else None
+    b = beta.detach() if beta is not None else None
+    check(lib.dsk_norm_act_bwd(ptr(x), ptr(dy), ptr(dres), ptr(dx), ptr(g), ptr(b), ptr(film_scale), ptr(fwd_ws), ptr(dgamma),
+                               ptr(dbeta), ptr(dfilm_scale), ptr(dfilm_shift), ptr(ws), B, S, Cc, G, mode, int(silu),
+                               dt_code(x.dtype), stream()))
+    return dx
+
+
+def pool2x_bwd(x, dy, dx, ndim: int, is_max: bool, dres=None):
+    require_cuda(dy, "pool grad")
+    B, D, H, W, Cc = dx.shape
+    check(lib.dsk_pool2x_bwd(ptr(x), ptr(dy), ptr(dres), ptr(dx), B, D, H, W, Cc, ndim, int(is_max), dt_code(dx.dtype), stream()))
+    return dx
+
+
+def upsample2x_bwd(dy, dx, ndim: int, dres=None):
+    require_cuda(dy, "upsample grad")
+    B, D, H, W, Cc = dx.shape
+    check(lib.dsk_upsample2x_bwd(ptr(dy), ptr(dres), ptr(dx), B, D, H, W, Cc, ndim, dt_code(dx.dtype), stream()))
+    return dx
+
+
+def add_ex(a: torch.Tensor, b: Optional[torch.Tensor], out: torch.Tensor):
+    """out = a (+ b), any mix of fp32 / bf16 operands (dsk_add_ex); out may alias a or b."""
+    require_cuda(a, "add input")
+    assert b is None or b.numel() == a.numel()
+    check(lib.dsk_add_ex(ptr(a), dt_code(a.dtype), ptr(b), dt_code(b.dtype) if b is not None else 0, ptr(out), dt_code(out.dtype),
+                         a.numel(), stream()))
+    return out
+
+
+def split_channels(dy, da, db, ra=None, rb=None):
+    require_cuda(dy, "concat grad")
+    ref = da if da is not None else db
+    Ct = dy.shape[-1]
+    Ca = da.shape[-1] if da is not None else Ct - db.shape[-1]
+    rows = dy.numel() // Ct
+    check(lib.dsk_split_channels(ptr(dy), ptr(ra), ptr(rb), ptr(da), ptr(db), rows, Ca, Ct - Ca, dt_code(ref.dtype), stream()))
+
+
+def gemm_ex(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, lda: int, ldb: int, ldc: int,
+            bias: Optional[torch.Tensor] = None, transA: bool = False, transB: bool = True, alpha: float = 1.0,
+            beta: float = 0.0, act: int = 0, batch: int = 1, strideA: int = 0, strideB: int = 0, strideC: int = 0,
+            a_off: int = 0, b_off: int = 0, c_off: int = 0) -> torch.Tensor:
+    """Batched fp32 GEMM C = act(alpha op(A) op(B) + bias) + beta C on raw buffers with element offsets (dsk_gemm_f32_ex)."""
+    require_cuda(A, "gemm A")
+    a = C.c_void_p(A.data_ptr() + a_off * 4)
+    b = C.c_void_p(Bm.data_ptr() + b_off * 4)
+    c = C.c_void_p(out.data_ptr() + c_off * 4)
+    check(lib.dsk_gemm_f32_ex(a, b, c, ptr(bias), M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch, int(transA),
+                              int(transB), alpha, beta, act, stream()))
+    return out
+
+
+def silu_fwd(z: torch.Tensor, out: torch.Tensor):
+    require_cuda(z, "silu input")
+    check(lib.dsk_silu_fwd(ptr(z), ptr(out), z.numel(), stream()))
+    return out
+
+
+def silu_bwd(z: torch.Tensor, da: torch.Tensor, out: torch.Tensor):
+    require_cuda(z, "silu input")
+    check(lib.dsk_silu_bwd(ptr(z), ptr(da), ptr(out), z.numel(), stream()))
+    return out
+
+
+def softmax_bwd_rows(P: torch.Tensor, dP: torch.Tensor, rows: int, cols: int):
+    require_cuda(P, "softmax probabilities")
+    check(lib.dsk_softmax_bwd_rows(ptr(P), ptr(dP), rows, cols, stream()))
+    return dP

@@ -148,6 +148,12 @@ int dsk_gemm_f32(const float* A, const float* Bm, float* Cm, const float* bias, 
                  int ldb, int ldc, int64_t strideA, int64_t strideB, int64_t strideC, int batch, int transB,
                  float alpha, int act, void* stream);
 
+/* General form: C[b] = act(alpha * op(A[b]) op(B[b]) + bias[n]) + beta * C[b];  transA = 1: A is stored [K][M] (lda >= M).
+ * The A^T B and A B products of the attention / linear backward passes. */
+int dsk_gemm_f32_ex(const float* A, const float* Bm, float* Cm, const float* bias, int M, int N, int K, int lda, int ldb,
+                    int ldc, int64_t strideA, int64_t strideB, int64_t strideC, int batch, int transA, int transB,
+                    float alpha, float beta, int act, void* stream);
+
 /* Batched bf16 GEMM on tcgen05/TMEM (csrc/gemm_tc.cu): C[b] = alpha * A[b] B[b]^T + bias (+ residual).
  * A [M,K] (lda), B [N,K] (ldb): bf16, K contiguous; C bf16 or fp32 (out_f32) with leading dimension ldc;
  * bias fp32 per column (bias_rows = 0) or per row (bias_rows = 1); residual bf16 laid out like C.
@@ -219,6 +225,54 @@ int dsk_adamw_ema_step(float* const* p, const float* const* g, float* const* m, 
                        float* const* shadow, const int64_t* numel, int ntensors, int64_t max_numel, float lr,
                        float beta1, float beta2, float eps, float wd, int step, float ema_beta, float grad_scale,
                        void* stream);
+
+/* ---- K2: backward kernels ----------------------------------------------------------------------
+ * What loss.backward() runs below KarrasModule.loss_fn in training_step (karras/karrasmodule.py:1146-1155;
+ * the reference relies on ATen autograd of the layers cited per function).  Gradients of activations use the
+ * activation dtype (channels-last), parameter gradients are fp32 in the REFERENCE parameter layout.
+ * `dres` (optional, same layout/dtype as the output, may alias it) is added to the result: gradient accumulation
+ * for tensors with several consumers (ResNet identity, U-Net skips) without a separate pass. */
+
+/* Data gradient of conv_same = conv_same(dY) with the taps flipped and Cin/Cout exchanged: pack the weights with this
+ * function and call dsk_conv_fwd with Cin' = Cout, Cout' = Cin (residual = dres).  Backward of torch.nn.Conv2d/3d
+ * (commonlayers.py:777-833, 53-58, 123-128; punetg.py:203-214; adm.py:268-284). */
+int dsk_pack_conv_weight_dgrad(const float* w_ref, void* w_packed, int Cout, int Cin, int taps, int dtype, void* stream);
+/* Weight gradient: dw[co][ci][tap] (+)= sum_pixels dy[p][co] * x[p + tap][ci]  (fp32, reference layout [Cout,Cin,k..]).
+ * `d` describes the FORWARD conv: B,D,H,W = output size, in_dtype = dtype of x, out_dtype = dtype of dy, up2 = x is the
+ * low-resolution input of conv(nearest_up2(x)); w_dtype selects the path (DSK_BF16: tcgen05 where the shape allows,
+ * otherwise / DSK_F32: CUDA-core split-K, fp32 accumulate, deterministic).  ws: dsk_conv_wgrad_ws_bytes(d) bytes. */
+int64_t dsk_conv_wgrad_ws_bytes(const dsk_conv_desc* d);
+int dsk_conv_wgrad(const dsk_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, int accumulate, void* stream);
+/* Channel sums of a channels-last tensor dy [B, S, C]: out[b][c] (per_sample = 1: gradient of the time-embedding vector
+ * added per sample and channel, commonlayers.py:826-829) or out[c] (bias gradient).  ws: dsk_bwd_ws_bytes(B,S,C). */
+int64_t dsk_bwd_ws_bytes(int B, int64_t S, int C);
+int dsk_channel_sum(const void* dy, float* out, void* ws, int B, int64_t S, int C, int dtype, int per_sample, void* stream);
+/* out[c] = sum_r in[r][c] for fp32 matrices (bias gradients of Linear layers) */
+int dsk_colsum_f32(const float* in, float* out, int64_t rows, int cols, int ld, void* stream);
+/* Backward of dsk_norm_act.  x: the forward input; dy: gradient of the forward output; fwd_ws: the workspace the forward
+ * call filled for this x (folded scale/shift table + (mean, rstd)); dx = d/dx (+ dres).  dgamma/dbeta [C], dfilm_* [B, C]
+ * (null iff the corresponding forward operand was null).  ws: dsk_bwd_ws_bytes(B,S,C).  Autograd of GroupNorm /
+ * GroupRMSNorm (+FiLM) + SiLU (commonlayers.py:362-384, 824-831; adm.py:305-329). */
+int dsk_norm_act_bwd(const void* x, const void* dy, const void* dres, void* dx, const float* gamma, const float* beta,
+                     const float* film_scale, const void* fwd_ws, float* dgamma, float* dbeta, float* dfilm_scale,
+                     float* dfilm_shift, void* ws, int B, int64_t S, int C, int G, int mode, int silu, int dtype,
+                     void* stream);
+/* Backward of dsk_pool2x (x: forward input, needed for max; D,H,W: INPUT size) and of nearest x2 upsampling
+ * (D,H,W: low-resolution size; dx = sum of the 2^ndim children of dy). */
+int dsk_pool2x_bwd(const void* x, const void* dy, const void* dres, void* dx, int B, int D, int H, int W, int C, int ndim,
+                   int is_max, int dtype, void* stream);
+int dsk_upsample2x_bwd(const void* dy, const void* dres, void* dx, int B, int D, int H, int W, int C, int ndim, int dtype,
+                       void* stream);
+/* Softmax backward on rows, in place on dP: dS = P * (dP - sum_j dP_j P_j)  (attention.py:42-44,68). */
+int dsk_softmax_bwd_rows(const float* P, float* dP, int64_t rows, int cols, void* stream);
+/* SiLU forward / backward on fp32 vectors (time MLPs, commonlayers.py:516-550; adm.py:1047-1053). */
+int dsk_silu_fwd(const float* z, float* a, int64_t n, void* stream);
+int dsk_silu_bwd(const float* z, const float* da, float* dz, int64_t n, void* stream);
+/* y = a (+ b) with per-operand dtypes (b may be NULL: cast/copy).  Gradient accumulation across fp32 / bf16 buffers. */
+int dsk_add_ex(const void* a, int a_dtype, const void* b, int b_dtype, void* y, int y_dtype, int64_t n, void* stream);
+/* Backward of dsk_concat_channels: da = dy[:, :Ca] (+ ra), db = dy[:, Ca:] (+ rb); da or db may be NULL. */
+int dsk_split_channels(const void* dy, const void* ra, const void* rb, void* da, void* db, int64_t rows, int Ca, int Cb,
+                       int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -141,3 +141,23 @@ def test_config_and_utils():
     assert isinstance(sch.integrator, d.EulerIntegrator)
     sch.unset_temporary_integrator()
     assert isinstance(sch.integrator, d.HeunIntegrator) and sch.maximum_scale == 80.0
+
+
+def test_training_graph_builds_and_covers_every_parameter(monkeypatch):
+    """Host logic of the training path (no GPU): the static forward/backward launch lists build for PUNetG and ADM, and
+    every parameter has exactly one gradient writer (TrainGraph.finalize raises otherwise)."""
+    import diffsci_b200 as d
+    from diffsci_b200.models.nets import graph as G
+    monkeypatch.setattr(G.TrainGraph, "prepare", lambda self: None)      # weight packing needs the device
+    for prec in ("fp32", "bf16"):
+        net = d.PUNetG(d.PUNetGConfig(dimension=3, model_channels=8))
+        g = G.build_punetg(net, 2, (8, 8, 8), "cpu", prec)
+        assert len(g.fwd) > 100 and len(g.bwd) > 2 * len(g.fwd)
+        assert sum(v.numel() for v in g.grads()) == sum(p.numel() for p in net.parameters())
+        for cfg in (d.ADMConfig(input_channels=3, output_channels=3), d.ADMConfig(skip_integration_type="add")):
+            net = d.ADM(cfg)
+            g = G.build_adm(net, 1, (16, 16), "cpu", prec)
+            assert len(g.bwd) > 2 * len(g.fwd)
+    import pytest
+    with pytest.raises(ValueError):
+        G.build_punetg(d.PUNetG(d.PUNetGConfig(dimension=2, model_channels=8)), 1, (6, 6), "cpu", "fp32")
