@@ -478,6 +478,14 @@ extern "C" int dsk_pack_conv_weight_dgrad(const float* w_ref, void* w_packed, in
   return DSK_OK;
 }
 
+namespace dsk {
+int wgrad_reduce_launch(const float* ws, float* dw, int Cout, int Cin, int taps, int nsplit, int accumulate, cudaStream_t st) {
+  DSK_LAUNCH(wgrad_reduce_kernel, grid_for((int64_t)taps * Cin * Cout, 256, 8), 256, 0, st, ws, dw, Cout, Cin, taps, nsplit, accumulate);
+  return DSK_OK;
+}
+}  // namespace dsk
+extern "C" int64_t dsk_conv_wgrad_tc_ws_bytes(const dsk_conv_desc* d);
+
 // ---- weight gradient (CUDA-core path) ---------------------------------------------------------------------------
 static int wgrad_splits(int M, int N, int K) {
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
@@ -495,7 +503,9 @@ extern "C" int64_t dsk_conv_wgrad_ws_bytes(const dsk_conv_desc* d) {
   const int64_t K = (int64_t)d->B * d->D * d->H * d->W;
   if (K > 0x7fffffff) return 0;
   const int M = taps * d->Cin, N = d->Cout;
-  return (int64_t)wgrad_splits(M, N, (int)K) * M * N * (int64_t)sizeof(float);
+  const int64_t ffma = (int64_t)wgrad_splits(M, N, (int)K) * M * N * (int64_t)sizeof(float);
+  const int64_t tc = dsk_conv_wgrad_tc_ws_bytes(d);
+  return ffma > tc ? ffma : tc;
 }
 
 template <typename TI, typename TG>
@@ -515,9 +525,7 @@ static int launch_wgrad(const dsk_conv_desc* d, const void* x, const void* dy, f
   const int used = (p.K + kper - 1) / kper;                  // slices that own at least one pixel
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, used);
   DSK_LAUNCH((ffma_gemm_kernel<WgradProb<TI, TG>>), grid, GT, 0, st, p);
-  DSK_LAUNCH(wgrad_reduce_kernel, grid_for((int64_t)p.M * p.N, 256, 8), 256, 0, st, (const float*)ws, dw, d->Cout, d->Cin, taps, used,
-             accumulate);
-  return DSK_OK;
+  return wgrad_reduce_launch((const float*)ws, dw, d->Cout, d->Cin, taps, used, accumulate, st);
 }
 
 // implemented in wgrad_tc.cu (tcgen05 path); returns DSK_ERR_UNSUPPORTED for shapes it does not take

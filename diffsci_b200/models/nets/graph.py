@@ -161,9 +161,16 @@ class TrainGraph:
                 out.append(lambda: ops.channel_sum(dy, gb, csws(), False))
             gw = self.grad_view(cp.weight)
             # the tcgen05 weight-gradient kernel reads a materialised operand; the CUDA-core one gathers (up2 folded in)
-            desc = ops.conv_desc(B, D, H, W, cp.cin, cp.cout, cp.ksize, nd, up2, wdt, xt.dtype, dy.dtype)
-            wws = self.lazy_scratch("wgrad_ws", ops.conv_wgrad_ws_bytes(desc))
-            out.append(lambda: ops.conv_wgrad(desc, xt, dy, gw, wws()))
+            if up2 and self.precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize):
+                desc = ops.conv_desc(B, D, H, W, cp.cin, cp.cout, cp.ksize, nd, False, wdt, xt.dtype, dy.dtype)
+                wws = self.lazy_scratch("wgrad_ws", ops.conv_wgrad_ws_bytes(desc))
+                u = self.lazy_scratch("u_up", (B, D, H, W, cp.cin), xt.dtype)
+                out.append(lambda: ops.upsample2x(xt, nd, out=u()))
+                out.append(lambda: ops.conv_wgrad(desc, u(), dy, gw, wws()))
+            else:
+                desc = ops.conv_desc(B, D, H, W, cp.cin, cp.cout, cp.ksize, nd, up2, wdt, xt.dtype, dy.dtype)
+                wws = self.lazy_scratch("wgrad_ws", ops.conv_wgrad_ws_bytes(desc))
+                out.append(lambda: ops.conv_wgrad(desc, xt, dy, gw, wws()))
             if residual is not None and residual.needs_grad:
                 out.extend(self.contribute_copy(residual, dy))
             if x.needs_grad:

@@ -70,6 +70,9 @@ CONV_CASES = [
     (2, 2, 24, 8, (5, 6), 1, True),
     (3, 1, 64, 64, (8, 8, 8), 3, False),
     (2, 3, 64, 128, (16, 24), 3, False),
+    (2, 5, 128, 64, (7, 7), 3, False),      # tiles mostly out of bounds (MNIST bottom level)
+    (3, 2, 64, 128, (6, 10, 12), 3, False),
+    (3, 1, 128, 128, (16, 16, 16), 3, False),
 ]
 
 
@@ -98,7 +101,7 @@ def test_conv_backward(ops, ndim, B, Cin, Cout, sp, k, up2, dtype):
     ws = torch.empty(max(ops.conv_wgrad_ws_bytes(desc), 1), dtype=torch.uint8, device=DEV)
     gw = torch.full_like(wd, 7.0)
     ops.conv_wgrad(desc, xc, dyc, gw, ws)
-    tol_w = 2e-5 if dtype == torch.float32 else (2e-2 if tc else 2e-5)   # bf16 inputs are exact in fp32; tc rounds nothing extra either
+    tol_w = 2e-4 if tc else 2e-5     # bf16 products are exact in fp32; only the summation order differs (fp32 in TMEM / registers)
     assert relmax(gw, w.grad) < tol_w, ("wgrad", relmax(gw, w.grad))
     gw2 = gw.clone()
     ops.conv_wgrad(desc, xc, dyc, gw2, ws, accumulate=True)
