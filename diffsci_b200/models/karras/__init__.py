@@ -11,3 +11,4 @@ from .integrators import (Integrator, EulerIntegrator, HeunIntegrator, EulerMaru
                           name_to_integrator)
 from .ema import ModelEMA
 from .engine import SamplerEngine
+from .trainer import EDMTrainer

@@ -57,6 +57,8 @@ class TrainGraph:
             self._gviews[id(p)] = self.flat_grad[off:off + p.numel()].view(p.shape)
             off += p.numel()
         self._written: set[int] = set()
+        self._written_log: list = []          # parameter ids in the order their gradient writers were generated
+        self.grad_ready_pos: dict = {}        # id(param) -> number of backward launches after which its gradient is final
         self._scratch: dict = {}
         self._packs: list = []
         self.nbytes = 0
@@ -91,6 +93,7 @@ class TrainGraph:
             raise RuntimeError("TrainGraph: a parameter is used by more than one op (gradient accumulation across ops "
                                "is not built)")
         self._written.add(key)
+        self._written_log.append(id(p))
         return g if rows is None else g[rows]
 
     # ------------------------------------------------------------------ gradient slots (build time)
@@ -399,7 +402,10 @@ class TrainGraph:
         self.output = output
         self.bwd = []
         for build in reversed(self._bwd_builders):
+            n0 = len(self._written_log)
             self.bwd.extend(build())
+            for pid in self._written_log[n0:]:
+                self.grad_ready_pos[pid] = len(self.bwd)
         self._bwd_builders = []
         missing = [n for n, p in self.net.named_parameters() if p.requires_grad and not any(k[0] == id(p) for k in self._written)]
         if missing:
@@ -416,9 +422,18 @@ class TrainGraph:
         for f in self.fwd:
             f()
 
-    def run_backward(self):
-        for f in self.bwd:
+    def run_backward(self, hooks: Optional[dict] = None):
+        """hooks: {number of completed backward launches: callable} -- e.g. the per-bucket gradient all-reduce of the
+        data-parallel trainer, issued as soon as the bucket's last writer has been enqueued."""
+        if not hooks:
+            for f in self.bwd:
+                f()
+            return
+        for i, f in enumerate(self.bwd):
             f()
+            h = hooks.get(i + 1)
+            if h is not None:
+                h()
 
     def grads(self) -> list:
         return [self._gviews[id(p)] for p in self.params]
@@ -560,9 +575,9 @@ def _forward_nchw(self: TrainGraph, x: torch.Tensor, t: Optional[torch.Tensor]) 
     return ops.cl_to_nchw(self.output.t, self.ndim)
 
 
-def _backward_nchw(self: TrainGraph, dF: torch.Tensor) -> None:
+def _backward_nchw(self: TrainGraph, dF: torch.Tensor, hooks: Optional[dict] = None) -> None:
     ops.nchw_to_cl(dF.float().contiguous(), self.output.t.dtype, self.ndim, out=self.output.g)
-    self.run_backward()
+    self.run_backward(hooks)
 
 
 TrainGraph.forward_nchw = _forward_nchw

@@ -16,6 +16,15 @@ from . import _lib as L
 from ._lib import lib, check, ptr, stream, dt_code, require_cuda
 
 
+_weight_epoch = [0]
+
+
+def bump_weight_epoch() -> None:
+    """Invalidate every packed weight copy: called by code that updates parameters with a library kernel (fused AdamW),
+    which PyTorch's per-tensor version counters cannot see."""
+    _weight_epoch[0] += 1
+
+
 class PackedConv:
     """Device-side packed copy of a reference-layout conv weight [Cout, Cin, k(,k)(,k)].
 
@@ -43,7 +52,7 @@ class PackedConv:
 
     def packed(self) -> torch.Tensor:
         w = self.weight
-        key = (w._version, w.data_ptr())
+        key = (w._version, w.data_ptr(), _weight_epoch[0])
         if self._packed is None or self._version != key or self._packed.device != w.device:
             require_cuda(w, "conv weight")
             with torch.inference_mode(False), torch.no_grad():
@@ -295,7 +304,7 @@ class PackedLinear:
 
     def packed(self) -> torch.Tensor:
         w = self.weight
-        key = (w._version, w.data_ptr())
+        key = (w._version, w.data_ptr(), _weight_epoch[0])
         if self._packed is None or self._version != key or self._packed.device != w.device:
             require_cuda(w, "linear weight")
             with torch.inference_mode(False), torch.no_grad():

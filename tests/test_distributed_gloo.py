@@ -54,3 +54,51 @@ def test_two_rank_gather_matches_single_process():
         assert p.exitcode == 0
     single = D.white_noise_shard(nsamples, (1, 4, 4), 123, 1, 0) * 2.0 + 1.0
     assert torch.equal(out, single) and tmax == 2.0
+
+
+# ------------------------------------------------------------------------------------------------ training exchange
+def test_grad_bucket_plan():
+    from diffsci_b200.distributed import GradBucketer
+    numels = [10, 20, 30, 40, 50]
+    ready = [50, 40, 30, 20, 10]                       # the backward pass finishes the LAST parameter first
+    b = GradBucketer.plan(numels, ready, bucket_elems=60)
+    assert b == [(60, 150, 20), (0, 60, 50)]                                          # contiguous cover, cut from the end
+    assert GradBucketer.plan(numels, ready, bucket_elems=45) == [(100, 150, 10), (30, 100, 30), (0, 30, 50)]
+    assert GradBucketer.plan(numels, ready, bucket_elems=10 ** 9) == [(0, 150, 50)]
+
+
+def _ddp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from diffsci_b200.distributed import GradBucketer
+    numels = [7, 5, 9, 3]
+    flat = torch.arange(24, dtype=torch.float32) * (rank + 1)          # this rank's "gradients"
+    bk = GradBucketer(flat, numels, ready_pos=[4, 3, 2, 1], bucket_bytes=8 * 4)
+    hooks = bk.hooks()
+    fired = []
+    for pos in range(1, 5):                                           # stand-in for TrainGraph.run_backward
+        if pos in hooks:
+            hooks[pos]()
+            fired.append(pos)
+    scale = bk.finish()
+    if rank == 0:
+        q.put((flat * scale, fired, bk.buckets))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_bucketed_gradient_allreduce():
+    """world_size 2 over gloo: every bucket is all-reduced exactly once, as soon as it is ready, and sum * 1/world is the
+    mean of the ranks' gradients (the host logic of EDMTrainer's data-parallel step)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    mean, fired, buckets = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert torch.equal(mean, torch.arange(24, dtype=torch.float32) * 1.5)
+    assert fired == sorted({r for _, _, r in buckets})

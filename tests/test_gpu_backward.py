@@ -343,3 +343,94 @@ def test_training_loss_grads_vs_live_reference(golden):
             for k, ref in g[key + "_grads"].items():
                 e = relmax(grads[k].grad, ref)
                 assert e < 3e-4, (key, k, e)
+
+
+# ------------------------------------------------------------------------------------------------ fused training step
+@pytest.mark.parametrize("name,metric", [("punetg2d_mc8", "huber"), ("adm2d_mc8", "mse")])
+def test_trainer_steps_match_oracle(golden, name, metric):
+    """EDMTrainer.step (noising, forward, fused loss, hand-written backward, fused AdamW + EMA) against the CPU oracle:
+    autograd through the oracle network + the oracle's AdamW / EMA restatements, 3 iterations on identical sigma / noise."""
+    import diffsci_b200 as d
+    from oracle import karras_oracle as K, nets_oracle as N
+    from tests.test_gpu_nets import build_net
+    g = golden(name)
+    net = build_net(g).train()
+    mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm(loss_metric=metric)).train()
+    ema = d.ModelEMA(net, ema_type="traditional", decay=0.9)
+    tr = d.EDMTrainer(mod, lr=2e-3, ema=ema)
+    cfg = (d.PUNetGConfig if g["kind"] == "punetg" else d.ADMConfig)(**g["cfg"])
+    fwd = N.punetg_forward if g["kind"] == "punetg" else N.adm_forward
+    dt = torch.float64
+    sd = {k: v.to(dt) for k, v in N.synth_state_dict(g["manifest"], g["seed"]).items()}
+    names = [k for k, _ in net.named_parameters()]
+    P = {k: sd[k].clone() for k in names}
+    Mo = {k: torch.zeros_like(v) for k, v in P.items()}
+    Vo = {k: torch.zeros_like(v) for k, v in P.items()}
+    Sh = {k: v.clone() for k, v in P.items()}
+    torch.manual_seed(21)
+    shape = g["x"].shape
+    for it in range(1, 4):
+        x = torch.randn(shape) * 0.5
+        sigma = torch.exp(torch.randn(shape[0]) * 1.2 - 1.2)
+        noise = torch.randn(shape)
+        loss = tr.step(x.to(DEV), sigma=sigma.to(DEV), noise=noise.to(DEV))
+        graph = net.train_graph(shape[0], tuple(shape[2:]), torch.device(DEV))
+        g_gpu = {k: gv.detach().double().cpu() for k, gv in zip(names, graph.grads())}
+        # (1) loss and gradients at the parameters the step started from
+        leaves = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+        full = dict(sd, **leaves)
+        L = K.edm_loss(lambda xx, tt: fwd(full, cfg, xx, tt), x.to(dt), sigma.to(dt), noise.to(dt), loss_metric=metric)
+        L.backward()
+        assert abs(float(loss) - float(L)) < 1e-4 * abs(float(L)), (it, float(loss), float(L))
+        worst_g = max(relmax(g_gpu[k], leaves[k].grad) for k in names)
+        assert worst_g < 5e-4, (it, worst_g)
+        # (2) the fused AdamW + EMA arithmetic.  Adam divides by sqrt(v): for elements whose gradient is within rounding
+        # of zero the update is +-lr whatever the sign noise says, so the optimizer restatement is fed the gradients the
+        # device produced (checked above) -- what is compared here is the update rule, bit-close.
+        for k in names:
+            P[k], Mo[k], Vo[k] = K.adamw_step(P[k], g_gpu[k], Mo[k], Vo[k], it, lr=2e-3)
+            Sh[k] = K.ema_update(Sh[k], P[k], 0.9)
+        worst = max(relmax(p.detach(), P[k]) for k, p in net.named_parameters())
+        worst_s = max(relmax(ema.selected_profile()["params"][k], Sh[k]) for k in names)
+        assert worst < 2e-6 and worst_s < 2e-6, (it, worst, worst_s)
+    assert ema.num_updates == 3 and tr.nstep == 3
+    # inference after training sees the updated weights (packed copies were invalidated)
+    net.eval()
+    with torch.no_grad():
+        y = net(g["x"].to(DEV), g["t"].to(DEV)).cpu()
+    yo = fwd(dict(sd, **P), cfg, g["x"].to(dt), g["t"].to(dt))
+    assert relmax(y, yo) < 2e-3
+
+
+def test_trainer_equals_autograd_seam(golden):
+    """The fused trainer and KarrasModule.loss_fn + backward (autograd seam) produce the same gradients (bf16 mode,
+    tcgen05 kernels where the shapes allow: PUNetG-2D mc=64)."""
+    import diffsci_b200 as d
+    torch.manual_seed(5)
+    cfgk = dict(dimension=2, model_channels=64)
+    net = d.PUNetG(d.PUNetGConfig(**cfgk), precision="bf16").to(DEV).train()
+    mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm()).train()
+    x = (torch.randn(4, 1, 32, 32) * 0.5).to(DEV)
+    sigma = torch.exp(torch.randn(4) * 1.2 - 1.2).to(DEV)
+    noise = torch.randn(4, 1, 32, 32).to(DEV)
+    mod._injected_loss_noise = noise
+    L = mod.loss_fn(x, sigma)
+    L.backward()
+    ref = [p.grad.clone() for p in net.parameters()]
+    tr = d.EDMTrainer(mod, lr=0.0, weight_decay=0.0)
+    L2 = tr.step(x, sigma=sigma, noise=noise)
+    graph = net.train_graph(4, (32, 32), x.device)
+    assert abs(float(L2) - float(L)) < 1e-6 * abs(float(L))
+    for a, b in zip(graph.grads(), ref):
+        assert torch.equal(a, b)
+    # and against fp32 mode: the bf16 step is a faithful (bf16-accurate) gradient
+    net32 = d.PUNetG(d.PUNetGConfig(**cfgk), precision="fp32").to(DEV).train()
+    net32.load_state_dict(net.state_dict())
+    mod32 = d.KarrasModule(net32, d.KarrasModuleConfig.from_edm()).train()
+    mod32._injected_loss_noise = noise
+    mod32.loss_fn(x, sigma).backward()
+    num = sum(float((a - p.grad).double().pow(2).sum()) for a, p in zip(ref, net32.parameters()))
+    den = sum(float(p.grad.double().pow(2).sum()) for p in net32.parameters())
+    err = math.sqrt(num / den)
+    print(f"PUNetG-2D mc=64 bf16-vs-fp32 global gradient L2 error: {err:.2e}")
+    assert err < 6e-2
