@@ -31,6 +31,15 @@ WORKLOADS = {
     "c5": ("punetg", dict(dimension=2), (1, 256, 256), 256, "euler-maruyama", 8),
     "c1": ("mlp", dict(dim=2, hidden_dims=[128, 128, 128]), (2,), 18, "heun", 65536),
 }
+# training workloads: (net kind, config kwargs, sample shape, loss metric, per-GPU batch, forward GFLOP/sample or None)
+TRAIN_WORKLOADS = {
+    "c2train": ("punetg", dict(dimension=2, model_channels=128), (1, 28, 28), "huber", 256, None),
+    "c3train": ("adm", dict(input_channels=3, output_channels=3), (3, 128, 128), "huber", 32, 59.44),   # SURVEY 8a row a9 probe
+    "c4train": ("punetg", dict(dimension=3), (1, 64, 64, 64), "huber", 2, None),
+}
+TRAIN_NAMES = {"c2train": "PUNetG-2D(mc=128) 1x28x28 EDM training iteration, batch 256/GPU (BASELINE configs[1])",
+               "c3train": "ADM-2D(mc=64,[2,4]) 3x128x128 EDM training iteration + EMA(0.999), batch 32/GPU, data-parallel (BASELINE configs[2])",
+               "c4train": "PUNetG-3D(mc=64,[2,4]) 1x64^3 EDM training iteration, batch 2/GPU"}
 NAMES = {"c4": "PUNetG-3D(mc=64,[2,4]) 1x64^3 EDM Heun-64 sampling (BASELINE configs[3])",
          "c2": "PUNetG-2D(mc=128) 1x28x28 EDM Heun-40 sampling (BASELINE configs[1])",
          "c5": "PUNetG-2D(mc=64) 1x256x256 Euler-Maruyama-256 sampling (BASELINE configs[4])",
@@ -156,13 +165,190 @@ def cpu_reference_arm(name, steps, warmup, max_seconds=25.0):
     return value, cores, sample, sum(vals) / len(vals)
 
 
+def build_train_workload(name, device, precision):
+    import torch
+    import diffsci_b200 as d
+    kind, kw, shape, metric, batch, gf = TRAIN_WORKLOADS[name]
+    torch.manual_seed(0)
+    if kind == "punetg":
+        cfg = d.PUNetGConfig(**kw)
+        net = d.PUNetG(cfg, precision=precision)
+        flops = punetg_conv_flops(cfg, shape[1:])
+    else:
+        cfg = d.ADMConfig(**kw)
+        net = d.ADM(cfg, precision=precision)
+        flops = gf * 1e9
+    if device is not None:
+        net = net.to(device)
+    net.train()
+    module = d.KarrasModule(net, d.KarrasModuleConfig.from_edm(loss_metric=metric)).train()
+    return module, net, cfg, shape, metric, batch, flops
+
+
+def cpu_train_arm(name, steps, warmup, max_seconds=25.0):
+    """Oracle port of one training iteration (forward, EDM loss, autograd backward, AdamW, EMA lerp) on the host
+    cores, on a reduced batch; it/s scaled linearly to the workload's per-GPU batch."""
+    import torch
+    from oracle import karras_oracle as K, nets_oracle as N
+    kind, kw, shape, metric, batch, _ = TRAIN_WORKLOADS[name]
+    module, net, cfg, *_ = build_train_workload(name, None, "fp32")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    names = [k for k, _ in net.named_parameters()]
+    fwd = N.punetg_forward if kind == "punetg" else N.adm_forward
+    Bs = {"c2train": 16, "c3train": 2, "c4train": 1}[name]
+    m = {k: torch.zeros_like(sd[k]) for k in names}
+    v = {k: torch.zeros_like(sd[k]) for k in names}
+    sh = {k: sd[k].clone() for k in names}
+    torch.manual_seed(7)
+    vals = []
+    for i in range(warmup + steps):
+        x = torch.randn(Bs, *shape) * 0.5
+        sigma = torch.exp(torch.randn(Bs) * 1.2 - 1.2)
+        noise = torch.randn(Bs, *shape)
+        t0 = time.perf_counter()
+        leaves = {k: sd[k].clone().requires_grad_(True) for k in names}
+        full = dict(sd, **leaves)
+        L = K.edm_loss(lambda xx, tt: fwd(full, cfg, xx, tt), x, sigma, noise, loss_metric=metric)
+        L.backward()
+        with torch.no_grad():
+            for k in names:
+                sd[k], m[k], v[k] = K.adamw_step(sd[k], leaves[k].grad, m[k], v[k], i + 1)
+                sh[k] = K.ema_update(sh[k], sd[k], 0.999)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            vals.append(dt)
+        if sum(vals) > max_seconds and vals:
+            break
+    per_sample = (sum(vals) / len(vals)) / Bs
+    value = 1.0 / (per_sample * batch)
+    sample = (f"oracle port (torch {torch.__version__} CPU fp32 autograd + AdamW + EMA), batch {Bs} timed {len(vals)}x, scaled "
+              f"linearly to batch {batch}")
+    return value, cores, sample, sum(vals) / len(vals)
+
+
+def train_arm(args, rank, world, local_rank):
+    """`--workload c2train|c3train|c4train`: one step = one EDM training iteration through EDMTrainer.step (noising,
+    forward, fused loss, backward, bucketed gradient all-reduce over NCCL for N>1, fused AdamW + EMA)."""
+    kind, kw, shape, metric, batch, _ = TRAIN_WORKLOADS[args.workload]
+    B = args.batch or batch
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        value, cores, sample, secs = cpu_train_arm(args.workload, max(1, args.steps), min(1, args.warmup))
+        line = {"impl": "reference", "metric": "EDM train it/s", "value": value, "unit": "it/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": TRAIN_NAMES[args.workload], "per_gpu_batch": batch},
+                "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+    import diffsci_b200 as d
+    from diffsci_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    precision = args.precision
+    if precision == "auto":
+        precision = "bf16" if d.TC_CONV_ENABLED else "fp32"
+    module, net, cfg, shape, metric, _, flops = build_train_workload(args.workload, dev, precision)
+    ema = d.ModelEMA(net, ema_type="traditional", decay=0.999)
+    tr = d.EDMTrainer(module, ema=ema)
+    nparams = sum(p.numel() for p in net.parameters())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    torch.manual_seed(2 + rank)
+    nb = 4                                                   # distinct synthetic batches, rotated
+    x_host = [(torch.randn(B, *shape) * 0.5).pin_memory() for _ in range(nb)]
+    x_dev = [x.to(dev) for x in x_host]
+    losses = []
+    for i in range(args.warmup):
+        losses.append(tr.step(x_dev[i % nb]))
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    n0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        loss = tr.step(x_dev[i % nb])
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms)
+    clk = clocks.summary() if clocks else None
+    launches = _lib.launch_count() - n0
+    value = args.steps / (total_ms / 1e3)                    # iterations/s of the whole data-parallel job
+    # e2e: pinned host batch -> device, step, loss read back on the host, every iteration
+    barrier()
+    t0 = time.perf_counter()
+    last = 0.0
+    for i in range(args.steps):
+        xb = x_host[i % nb].to(dev, non_blocking=True)
+        last = float(tr.step(xb))
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    import math
+    assert math.isfinite(last), "training loss is not finite"
+    N_el = B
+    for s_ in shape:
+        N_el *= s_
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
+    tfl = 3.0 * flops * B * world * value / 1e12
+    line = {"metric": "EDM train it/s", "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": TRAIN_NAMES[args.workload], "per_gpu_batch": B, "global_batch": world * B,
+                       "loss": metric, "optimizer": "AdamW(1e-3,(0.9,0.999),wd=1e-4) fused with EMA(0.999)",
+                       "parameters": nparams, "precision": precision,
+                       "parallelism": f"data-parallel x{world}, bucketed NCCL all-reduce of the flat fp32 gradient",
+                       "l2_policy": "4 rotating input batches; activations per iteration exceed L2"},
+            "samples_per_s": value * B * world, "model_tflops": tfl,
+            "e2e": {"value": args.steps / float(e2e_s), "unit": "it/s", "h2d_bytes_per_step": N_el * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clk, "final_loss": last,
+            "roofline": {"bound": "tensor", "kernel": "whole iteration (fwd + dgrad + wgrad = 3x forward FLOPs)", "achieved": tfl / world,
+                         "peak": peak, "unit": "TFLOP/s", "frac": tfl / world / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json (sustained)" if peaks else "fallback (B200_PROFILING.md)"}}
+    if not args.no_cpu_baseline and world == 1:
+        v, cores, sample, _ = cpu_train_arm(args.workload, 1, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("DSK_BENCH_WORKLOAD", "c4"), choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("DSK_BENCH_WORKLOAD", "c4"), choices=list(WORKLOADS) + list(TRAIN_WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = workload default)")
     ap.add_argument("--nsteps", type=int, default=0, help="integrator steps (0 = workload default)")
     ap.add_argument("--precision", default=os.environ.get("DSK_BENCH_PRECISION", "auto"))
@@ -171,6 +357,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload in TRAIN_WORKLOADS:
+        return train_arm(args, rank, world, local_rank)
     kind, kw, shape, nsteps, integ, batch = WORKLOADS[args.workload]
     nsteps = args.nsteps or nsteps
     B = args.batch or batch

@@ -78,9 +78,9 @@ class GradBucketer:
     """
 
     def __init__(self, flat_grad: torch.Tensor, numels: Sequence[int], ready_pos: Sequence[int], bucket_bytes: int = 32 << 20,
-                 group=None):
+                 group=None, enabled: bool = True):
         self.flat, self.group = flat_grad, group
-        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.on = enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.world = dist.get_world_size(group) if self.on else 1
         self.buckets = self.plan(numels, ready_pos, bucket_bytes // flat_grad.element_size())
         self._works: list = []

@@ -32,7 +32,8 @@ from .ema import ModelEMA
 
 class EDMTrainer:
     def __init__(self, module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-4,
-                 ema: Optional[ModelEMA] = None, process_group=None, bucket_mb: float = 32.0, seed: int = 0xD1FF5C1):
+                 ema: Optional[ModelEMA] = None, process_group=None, bucket_mb: float = 32.0, seed: int = 0xD1FF5C1,
+                 data_parallel: bool = True):
         """Defaults = the reference's default optimizer (karrasmodule.py:497-500).  `ema`: a ModelEMA over
         ``module.model`` (its first profile is updated inside the AdamW kernel, further profiles by dsk_ema_update)."""
         net = module.model
@@ -44,7 +45,7 @@ class EDMTrainer:
         self.module, self.net, self.ema, self.group = module, net, ema, process_group
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         self.bucket_bytes = int(bucket_mb * (1 << 20))
-        self.seed, self.nstep = int(seed), 0
+        self.seed, self.nstep, self.data_parallel = int(seed), 0, bool(data_parallel)
         self._state = None        # (graph id, tables...)
         self.params = [p for p in net.parameters()]
         self.exp_avg = [torch.zeros_like(p) for p in self.params]
@@ -58,7 +59,7 @@ class EDMTrainer:
             mk = lambda ts: torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64, device=dev)  # noqa: E731
             numels = [p.numel() for p in self.params]
             ready = [g.grad_ready_pos[id(p)] for p in self.params]
-            bucketer = GradBucketer(g.flat_grad, numels, ready, self.bucket_bytes, self.group)
+            bucketer = GradBucketer(g.flat_grad, numels, ready, self.bucket_bytes, self.group, self.data_parallel)
             self._state = (key, mk(self.params), mk(g.grads()), mk(self.exp_avg), mk(self.exp_avg_sq),
                            torch.tensor(numels, dtype=torch.int64, device=dev), max(numels), bucketer)
         return self._state
