@@ -63,7 +63,8 @@ SIGNATURES = {
     "dsk_cast": [p, p, i64, i32, i32, p],
     "dsk_concat_channels": [p, p, p, i64, i32, i32, i32, p],
     "dsk_fourier": [p, p, p, i32, i32, p],
-    "dsk_grouped_linear": [p, p, p, p, p, p, i32, i32, i32, i32, p],
+    "dsk_grouped_linear": [p, p, p, p, p, p, p, i32, i32, i32, i32, p],
+    "dsk_grouped_linear_bwd": [p, p, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, p],
     "dsk_softmax_rows": [p, i64, i32, p],
     "dsk_edm_loss_fwd_bwd": [p, p, p, p, p, p, p, i32, i32, i64, f32, i32, p],
     "dsk_ema_update": [p, p, p, i32, i64, f32, p],

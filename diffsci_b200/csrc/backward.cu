@@ -166,20 +166,60 @@ __global__ void __launch_bounds__(128) norm_bwd_finalize_kernel(const double2* _
   for (int i = threadIdx.x; i < cg; i += blockDim.x) coef[(int64_t)b * C + g * cg + i] = make_float2(cb, cc);
 }
 
-// dgamma[c] = sum_b film[b,c]*S2[b,c] ; dbeta[c] = sum_b film[b,c]*S1[b,c]
-__global__ void __launch_bounds__(128) norm_bwd_param_kernel(const float2* __restrict__ sums, const float* __restrict__ fsc,
-                                                              float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double g = 0, bt = 0;
-  for (int b = 0; b < B; ++b) {
-    const float2 v = sums[(int64_t)b * C + c];
-    const double f = fsc != nullptr ? (double)fsc[(int64_t)b * C + c] : 1.0;
-    g += f * v.y;
-    bt += f * v.x;
+// G == C: one thread per (b, c) (the group reductions are over a single channel).
+__global__ void __launch_bounds__(128) norm_bwd_finalize_pc_kernel(const double2* __restrict__ partial, const float2* __restrict__ stats,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    const float* __restrict__ fsc, float2* __restrict__ coef,
+                                                                    float2* __restrict__ sums, float* __restrict__ dfsc,
+                                                                    float* __restrict__ dfsh, int64_t S, int B, int C, int nchunks, int mode) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const float2 mr = stats[i];
+  const double mean = mr.x, rstd = mr.y;
+  double s1 = 0, sx = 0;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const double2 v = partial[((int64_t)b * nchunks + ch) * C + c];
+    s1 += v.x;
+    sx += v.y;
   }
-  dgamma[c] = (float)g;
-  dbeta[c] = (float)bt;
+  const double s2 = rstd * (sx - mean * s1);
+  sums[i] = make_float2((float)s1, (float)s2);
+  const double gm = gamma != nullptr ? (double)gamma[c] : 1.0;
+  const double f = fsc != nullptr ? (double)fsc[i] : 1.0;
+  if (dfsc != nullptr) {
+    const double bt = beta != nullptr ? (double)beta[c] : 0.0;
+    dfsc[i] = (float)(gm * s2 + bt * s1);
+    dfsh[i] = (float)s1;
+  }
+  const double n = (double)S;
+  const double m1 = mode == 0 ? gm * f * s1 / n : 0.0, m2 = gm * f * s2 / n;
+  coef[i] = make_float2((float)(-rstd * rstd * m2), (float)(-rstd * m1 + mean * rstd * rstd * m2));
+}
+
+// dgamma[c] = sum_b film[b,c]*S2[b,c] ; dbeta[c] = sum_b film[b,c]*S1[b,c]
+__global__ void __launch_bounds__(256) norm_bwd_param_kernel(const float2* __restrict__ sums, const float* __restrict__ fsc,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int C) {
+  // block = 32 channels x 8 sample lanes
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  double g = 0, bt = 0;
+  if (c < C)
+    for (int b = rl; b < B; b += 8) {
+      const float2 v = sums[(int64_t)b * C + c];
+      const double f = fsc != nullptr ? (double)fsc[(int64_t)b * C + c] : 1.0;
+      g += f * v.y;
+      bt += f * v.x;
+    }
+  __shared__ double rg[8][33], rb[8][33];
+  rg[rl][threadIdx.x & 31] = g;
+  rb[rl][threadIdx.x & 31] = bt;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    double sg = 0, sb = 0;
+    for (int k = 0; k < 8; ++k) { sg += rg[k][threadIdx.x & 31]; sb += rb[k][threadIdx.x & 31]; }
+    dgamma[c] = (float)sg;
+    dbeta[c] = (float)sb;
+  }
 }
 
 // dx = dz*a + x*cb + cc (+ dres);  dres may alias dx.
@@ -222,20 +262,22 @@ __global__ void __launch_bounds__(BW_THREADS) norm_bwd_apply_kernel(const T* __r
 }
 
 // channel sums: out[b][c] (per_sample) or out[c] = sum over chunk partials (and samples)
-__global__ void __launch_bounds__(128) chansum_finalize_kernel(const double2* __restrict__ partial, float* __restrict__ out, int B,
+__global__ void __launch_bounds__(256) chansum_finalize_kernel(const double2* __restrict__ partial, float* __restrict__ out, int B,
                                                                 int C, int nchunks, int per_sample) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (per_sample) {
-    const int b = blockIdx.y;
-    double s = 0;
-    for (int ch = 0; ch < nchunks; ++ch) s += partial[((int64_t)b * nchunks + ch) * C + c].x;
-    out[(int64_t)b * C + c] = (float)s;
-  } else {
-    double s = 0;
-    for (int b = 0; b < B; ++b)
-      for (int ch = 0; ch < nchunks; ++ch) s += partial[((int64_t)b * nchunks + ch) * C + c].x;
-    out[c] = (float)s;
+  // block = 32 channels x 8 row lanes over the (sample, chunk) partial rows
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  const int64_t r0 = per_sample ? (int64_t)blockIdx.y * nchunks : 0;
+  const int64_t rows = per_sample ? nchunks : (int64_t)B * nchunks;
+  double s = 0;
+  if (c < C)
+    for (int64_t r = rl; r < rows; r += 8) s += partial[(r0 + r) * C + c].x;
+  __shared__ double red[8][33];
+  red[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    double t = 0;
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+    out[per_sample ? (int64_t)blockIdx.y * C + c : c] = (float)t;
   }
 }
 
@@ -468,9 +510,13 @@ extern "C" int dsk_norm_act_bwd(const void* x, const void* dy, const void* dres,
   else
     DSK_LAUNCH((bwd_partial_kernel<__nv_bfloat16, true>), pg, BW_THREADS, smem, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, table,
                partial, S, C, nchunks, silu);
-  DSK_LAUNCH(norm_bwd_finalize_kernel, B * G, 128, 0, st, partial, stats, gamma, beta, film_scale, coef, sums, dfilm_scale, dfilm_shift, S, C,
-             G, nchunks, mode);
-  if (dgamma != nullptr) DSK_LAUNCH(norm_bwd_param_kernel, (C + 127) / 128, 128, 0, st, sums, film_scale, dgamma, dbeta, B, C);
+  if (G == C)
+    DSK_LAUNCH(norm_bwd_finalize_pc_kernel, (B * C + 127) / 128, 128, 0, st, partial, stats, gamma, beta, film_scale, coef, sums, dfilm_scale,
+               dfilm_shift, S, B, C, nchunks, mode);
+  else
+    DSK_LAUNCH(norm_bwd_finalize_kernel, B * G, 128, 0, st, partial, stats, gamma, beta, film_scale, coef, sums, dfilm_scale, dfilm_shift, S,
+               C, G, nchunks, mode);
+  if (dgamma != nullptr) DSK_LAUNCH(norm_bwd_param_kernel, (C + 31) / 32, 256, 0, st, sums, film_scale, dgamma, dbeta, B, C);
   int64_t gx = (S + (int64_t)pl * 4 - 1) / ((int64_t)pl * 4);
   const int64_t cap = (8LL * DSK_NUM_SMS + B - 1) / B;
   if (gx > cap) gx = cap;
@@ -510,8 +556,8 @@ extern "C" int dsk_channel_sum(const void* dy, float* out, void* ws, int B, int6
   else
     DSK_LAUNCH((bwd_partial_kernel<__nv_bfloat16, false>), pg, BW_THREADS, smem, st, nullptr, (const __nv_bfloat16*)dy, nullptr, partial, S, C,
                nchunks, 0);
-  dim3 fg((C + 127) / 128, per_sample ? B : 1);
-  DSK_LAUNCH(chansum_finalize_kernel, fg, 128, 0, st, partial, out, B, C, nchunks, per_sample);
+  dim3 fg((C + 31) / 32, per_sample ? B : 1);
+  DSK_LAUNCH(chansum_finalize_kernel, fg, 256, 0, st, partial, out, B, C, nchunks, per_sample);
   return DSK_OK;
 }
 

@@ -98,8 +98,8 @@ __global__ void fourier_kernel(const float* __restrict__ t, const float* __restr
 constexpr int GL_MAXB = 8;
 __global__ void __launch_bounds__(256) grouped_linear_kernel(const float* const* __restrict__ X, const float* const* __restrict__ Wt,
                                                               const float* const* __restrict__ bias, float* const* __restrict__ Y,
-                                                              const int* __restrict__ in_dim, const int* __restrict__ out_dim,
-                                                              int B, int act) {
+                                                              float* const* __restrict__ Z, const int* __restrict__ in_dim,
+                                                              const int* __restrict__ out_dim, int B, int act) {
   const int g = blockIdx.y;
   const int K = in_dim[g], N = out_dim[g];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(256) grouped_linear_kernel(const float* const*
   const float* w = Wt[g] + (int64_t)warp * K;
   const float* x = X[g];
   float* y = Y[g];
+  float* z = Z != nullptr ? Z[g] : nullptr;           // pre-activation, kept for the backward pass
   const float bv = bias[g] != nullptr ? bias[g][warp] : 0.0f;
   for (int b0 = 0; b0 < B; b0 += GL_MAXB) {
     float acc[GL_MAXB];
@@ -123,11 +124,95 @@ __global__ void __launch_bounds__(256) grouped_linear_kernel(const float* const*
       float v = warp_sum(acc[r]);
       if (lane == 0 && b0 + r < B) {
         v += bv;
+        if (z != nullptr) z[(int64_t)(b0 + r) * N + warp] = v;
         if (act == 1) v = silu_f(v);
         else if (act == 2) v = fmaxf(v, 0.0f);
         y[(int64_t)(b0 + r) * N + warp] = v;
       }
     }
+  }
+}
+
+// ---- grouped small-batch linear, backward ------------------------------------------------------------------------
+// (a) one warp per (group, output feature n):  dz[b] = dy[b,n] * act'(z[b,n]) (written to dZ for pass (b)),
+//     db[n] = sum_b dz[b],  dW[n,:] = sum_b dz[b] * x[b,:]   (lanes stride k; 16 accumulators = 512 k per sweep).
+__global__ void __launch_bounds__(256) grouped_linear_wgrad_kernel(const float* const* __restrict__ dY, const float* const* __restrict__ Z,
+                                                                    const float* const* __restrict__ X, float* const* __restrict__ dZ,
+                                                                    float* const* __restrict__ dW, float* const* __restrict__ db,
+                                                                    const int* __restrict__ in_dim, const int* __restrict__ out_dim,
+                                                                    int B, int act) {
+  const int g = blockIdx.y;
+  const int K = in_dim[g], N = out_dim[g];
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* dy = dY[g];
+  const float* z = (act != 0 && Z != nullptr) ? Z[g] : nullptr;
+  const float* x = X[g];
+  float* dz = dZ[g];
+  float* dw = dW[g] + (int64_t)n * K;
+  float bsum = 0.0f;
+  for (int kc = 0; kc < K; kc += 512) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+    for (int b = 0; b < B; ++b) {
+      float d = dy[(int64_t)b * N + n];
+      if (z != nullptr) {
+        const float zz = z[(int64_t)b * N + n];
+        if (act == 1) { const float sg = 1.0f / (1.0f + expf(-zz)); d *= sg * (1.0f + zz * (1.0f - sg)); }
+        else d = zz > 0.0f ? d : 0.0f;
+      }
+      if (kc == 0) {
+        bsum += d;
+        if (lane == 0 && dz != dy) dz[(int64_t)b * N + n] = d;
+      }
+      const float* xr = x + (int64_t)b * K + kc + lane;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (kc + lane + 32 * j < K) acc[j] = fmaf(d, xr[32 * j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (kc + lane + 32 * j < K) dw[kc + lane + 32 * j] = acc[j];
+  }
+  if (lane == 0 && db != nullptr && db[g] != nullptr) db[g][n] = bsum;
+}
+
+// (b) dX[b,k] = sum_n dZ[b,n] W[n,k]; `shared`: every group consumed the same X, so ONE dX = sum over groups too
+//     (ADM's per-block FiLM projections of the shared embedding).  Block = 128 k-columns x GLB_ROWS batch rows.
+constexpr int GLB_ROWS = 8;
+__global__ void __launch_bounds__(128) grouped_linear_dgrad_kernel(const float* const* __restrict__ dZ, const float* const* __restrict__ Wt,
+                                                                    float* const* __restrict__ dX, const int* __restrict__ in_dim,
+                                                                    const int* __restrict__ out_dim, int ngroups, int B, int shared,
+                                                                    int accumulate) {
+  const int g0 = shared ? 0 : blockIdx.z, g1 = shared ? ngroups : blockIdx.z + 1;
+  const int K = in_dim[g0];
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  const int b0 = blockIdx.y * GLB_ROWS;
+  if (dX[g0] == nullptr) return;
+  float acc[GLB_ROWS];
+#pragma unroll
+  for (int r = 0; r < GLB_ROWS; ++r) acc[r] = 0.0f;
+  for (int g = g0; g < g1; ++g) {
+    const int N = out_dim[g];
+    const float* w = Wt[g];
+    const float* dz = dZ[g];
+    if (k < K)
+      for (int n = 0; n < N; ++n) {
+        const float wv = w[(int64_t)n * K + k];
+#pragma unroll
+        for (int r = 0; r < GLB_ROWS; ++r)
+          if (b0 + r < B) acc[r] = fmaf(dz[(int64_t)(b0 + r) * N + n], wv, acc[r]);
+      }
+  }
+  if (k < K) {
+    float* o = dX[g0];
+#pragma unroll
+    for (int r = 0; r < GLB_ROWS; ++r)
+      if (b0 + r < B) {
+        const int64_t i = (int64_t)(b0 + r) * K + k;
+        o[i] = accumulate ? o[i] + acc[r] : acc[r];
+      }
   }
 }
 
@@ -276,12 +361,31 @@ extern "C" int dsk_fourier(const float* t, const float* W, float* out, int B, in
 }
 
 extern "C" int dsk_grouped_linear(const float* const* X, const float* const* W, const float* const* bias, float* const* Y,
-                                  const int* in_dim, const int* out_dim, int ngroups, int max_out, int B, int act,
+                                  float* const* Z, const int* in_dim, const int* out_dim, int ngroups, int max_out, int B, int act,
                                   void* stream) {
   DSK_REQUIRE(X && W && bias && Y && in_dim && out_dim, "dsk_grouped_linear: null pointer");
-  DSK_REQUIRE(ngroups > 0 && max_out > 0 && B > 0 && act >= 0 && act <= 2, "dsk_grouped_linear: bad arguments");
+  DSK_REQUIRE(ngroups > 0 && ngroups <= 65535 && max_out > 0 && B > 0 && act >= 0 && act <= 2, "dsk_grouped_linear: bad arguments");
   dim3 grid((max_out + 7) / 8, ngroups);
-  DSK_LAUNCH(grouped_linear_kernel, grid, 256, 0, as_stream(stream), X, W, bias, Y, in_dim, out_dim, B, act);
+  DSK_LAUNCH(grouped_linear_kernel, grid, 256, 0, as_stream(stream), X, W, bias, Y, Z, in_dim, out_dim, B, act);
+  return DSK_OK;
+}
+
+extern "C" int dsk_grouped_linear_bwd(const float* const* dY, const float* const* Z, const float* const* X, const float* const* W,
+                                      float* const* dZ, float* const* dW, float* const* db, float* const* dX, const int* in_dim,
+                                      const int* out_dim, int ngroups, int max_out, int max_in, int B, int act, int shared_dx,
+                                      int accumulate_dx, void* stream) {
+  DSK_REQUIRE(dY && X && W && dZ && dW && in_dim && out_dim, "dsk_grouped_linear_bwd: null pointer");
+  DSK_REQUIRE(ngroups > 0 && ngroups <= 65535 && max_out > 0 && max_in > 0 && B > 0 && act >= 0 && act <= 2 && (act == 0 || Z != nullptr),
+              "dsk_grouped_linear_bwd: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  dim3 wg((max_out + 7) / 8, ngroups);
+  DSK_LAUNCH(grouped_linear_wgrad_kernel, wg, 256, 0, st, dY, Z, X, dZ, dW, db, in_dim, out_dim, B, act);
+  if (dX != nullptr) {
+    DSK_REQUIRE((B + GLB_ROWS - 1) / GLB_ROWS <= 65535, "dsk_grouped_linear_bwd: B too large");
+    dim3 dg((max_in + 127) / 128, (B + GLB_ROWS - 1) / GLB_ROWS, shared_dx ? 1 : ngroups);
+    DSK_LAUNCH(grouped_linear_dgrad_kernel, dg, 128, 0, st, (const float* const*)dZ, W, dX, in_dim, out_dim, ngroups, B, shared_dx,
+               accumulate_dx);
+  }
   return DSK_OK;
 }
 

@@ -173,6 +173,38 @@ __global__ void __launch_bounds__(128) norm_finalize_kernel(const double2* __res
   }
 }
 
+// G == C (one channel per group: the PUNetG norms): one THREAD per (b, c) instead of one block.
+__global__ void __launch_bounds__(128) norm_finalize_pc_kernel(const double2* __restrict__ partial, float2* __restrict__ table,
+                                                                float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, const float* __restrict__ fsc,
+                                                                const float* __restrict__ fsh, int64_t S, int B, int C, int nchunks, int mode,
+                                                                float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  double a = 0, q = 0;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const double2 v = partial[((int64_t)b * nchunks + ch) * C + c];
+    a += v.x;
+    q += v.y;
+  }
+  const double n = (double)S;
+  const double mean = a / n, ex2 = q / n;
+  float2 mr;
+  if (mode == 0) {
+    double var = ex2 - mean * mean;
+    if (var < 0) var = 0;
+    mr = make_float2((float)mean, 1.0f / sqrtf((float)var + eps));
+  } else {
+    mr = make_float2(0.0f, 1.0f / sqrtf((float)ex2 + eps));
+  }
+  stats[i] = mr;
+  float sc = mr.y, sh = -mr.x * mr.y;
+  if (gamma != nullptr) { sc *= gamma[c]; sh = sh * gamma[c] + beta[c]; }
+  if (fsc != nullptr) { const float f = fsc[i]; sc *= f; sh = sh * f + fsh[i]; }
+  table[i] = make_float2(sc, sh);
+}
+
 template <typename TO> __device__ __forceinline__ float silu_out(float v) { return silu_f(v); }
 // bf16 output keeps 8 mantissa bits: the approximate exp / divide (rel. error ~1e-6) is invisible after rounding and
 // takes the kernel from instruction-bound back to HBM-bound
@@ -264,8 +296,12 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
     DSK_LAUNCH(norm_partial_kernel<float>, pg, NORM_THREADS, smem, st, (const float*)x, partial, S, C, nchunks);
   else
     DSK_LAUNCH(norm_partial_kernel<__nv_bfloat16>, pg, NORM_THREADS, smem, st, (const __nv_bfloat16*)x, partial, S, C, nchunks);
-  DSK_LAUNCH(norm_finalize_kernel, B * G, 128, 0, st, partial, table, stats, gamma, beta, film_scale, film_shift, S, C, G, nchunks, mode,
-             1e-5f);
+  if (G == C)
+    DSK_LAUNCH(norm_finalize_pc_kernel, (B * C + 127) / 128, 128, 0, st, partial, table, stats, gamma, beta, film_scale, film_shift, S, B, C,
+               nchunks, mode, 1e-5f);
+  else
+    DSK_LAUNCH(norm_finalize_kernel, B * G, 128, 0, st, partial, table, stats, gamma, beta, film_scale, film_shift, S, C, G, nchunks, mode,
+               1e-5f);
   int64_t gx = (S + (int64_t)pl * 4 - 1) / ((int64_t)pl * 4);          // >= 4 pixels per thread
   const int64_t cap = (8LL * DSK_NUM_SMS + B - 1) / B;
   if (gx > cap) gx = cap;

@@ -50,43 +50,95 @@ __global__ void __launch_bounds__(256) edm_loss_kernel(const float* __restrict__
   }
 }
 
-// One launch for every parameter tensor: blockIdx.y = tensor, blockIdx.x strides its elements.
-__global__ void __launch_bounds__(256) ema_kernel(float* const* __restrict__ shadow, const float* const* __restrict__ param,
-                                                   const int64_t* __restrict__ numel, float w) {
-  const int t = blockIdx.y;
-  float* s = shadow[t];
-  const float* p = param[t];
-  const int64_t n = numel[t];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    // torch.lerp(s, p, w) = s + w*(p - s) for w < 0.5, else p - (p - s)*(1 - w)
-    const float sv = s[i], pv = p[i];
-    s[i] = w < 0.5f ? sv + w * (pv - sv) : pv - (pv - sv) * (1.0f - w);
+// Multi-tensor kernels.  The tensors differ in size by four orders of magnitude (a bias vs a 512x512x3x3 weight), so
+// the work is cut into fixed chunks of MT_CHUNK elements over ALL tensors: every block builds the prefix of chunk counts in
+// shared memory (a few hundred entries) and grid-strides over the global chunk index, binary-searching its tensor.
+constexpr int MT_CHUNK = 2048, MT_THREADS = 256, MT_MAX_TENSORS = 4096;
+
+struct MtChunk { int t; int64_t off; int n; };
+
+__device__ __forceinline__ int64_t mt_prefix(const int64_t* __restrict__ numel, int nt, int64_t* pre) {
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) pre[i + 1] = (numel[i] + MT_CHUNK - 1) / MT_CHUNK;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    pre[0] = 0;
+    for (int i = 0; i < nt; ++i) pre[i + 1] += pre[i];
+  }
+  __syncthreads();
+  return pre[nt];
+}
+
+__device__ __forceinline__ MtChunk mt_find(const int64_t* __restrict__ numel, int nt, const int64_t* pre, int64_t chunk) {
+  int lo = 0, hi = nt;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (pre[mid] <= chunk) lo = mid; else hi = mid;
+  }
+  MtChunk c;
+  c.t = lo;
+  c.off = (chunk - pre[lo]) * MT_CHUNK;
+  const int64_t left = numel[lo] - c.off;
+  c.n = left < MT_CHUNK ? (int)left : MT_CHUNK;
+  return c;
+}
+
+__global__ void __launch_bounds__(MT_THREADS) ema_kernel(float* const* __restrict__ shadow, const float* const* __restrict__ param,
+                                                          const int64_t* __restrict__ numel, int nt, float w) {
+  extern __shared__ int64_t mt_pre[];
+  const int64_t total = mt_prefix(numel, nt, mt_pre);
+  for (int64_t chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+    const MtChunk c = mt_find(numel, nt, mt_pre, chunk);
+    float* s = shadow[c.t] + c.off;
+    const float* p = param[c.t] + c.off;
+#pragma unroll
+    for (int k = 0; k < MT_CHUNK / MT_THREADS; ++k) {
+      const int i = threadIdx.x + k * MT_THREADS;
+      if (i < c.n) {
+        // torch.lerp(s, p, w) = s + w*(p - s) for w < 0.5, else p - (p - s)*(1 - w)
+        const float sv = s[i], pv = p[i];
+        s[i] = w < 0.5f ? sv + w * (pv - sv) : pv - (pv - sv) * (1.0f - w);
+      }
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) adamw_ema_kernel(float* const* __restrict__ P, const float* const* __restrict__ G,
-                                                         float* const* __restrict__ Mo, float* const* __restrict__ Vo,
-                                                         float* const* __restrict__ Sh, const int64_t* __restrict__ numel,
-                                                         float lr, float b1, float b2, float eps, float wd, float bc1,
-                                                         float bc2_sqrt, float ema_w, float gscale) {
-  const int t = blockIdx.y;
-  float* p = P[t];
-  const float* g = G[t];
-  float* m = Mo[t];
-  float* v = Vo[t];
-  float* s = Sh != nullptr ? Sh[t] : nullptr;
-  const int64_t n = numel[t];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gv = g[i] * gscale;
-    float pv = p[i] * (1.0f - lr * wd);
-    const float mv = m[i] + (gv - m[i]) * (1.0f - b1);
-    const float vv = v[i] * b2 + (1.0f - b2) * gv * gv;
-    const float denom = sqrtf(vv) / bc2_sqrt + eps;
-    pv = pv - (lr / bc1) * (mv / denom);
-    p[i] = pv; m[i] = mv; v[i] = vv;
-    if (s != nullptr) {
-      const float sv = s[i];
-      s[i] = ema_w < 0.5f ? sv + ema_w * (pv - sv) : pv - (pv - sv) * (1.0f - ema_w);
+__global__ void __launch_bounds__(MT_THREADS) adamw_ema_kernel(float* const* __restrict__ P, const float* const* __restrict__ G,
+                                                                float* const* __restrict__ Mo, float* const* __restrict__ Vo,
+                                                                float* const* __restrict__ Sh, const int64_t* __restrict__ numel, int nt,
+                                                                float lr, float b1, float b2, float eps, float wd, float bc1,
+                                                                float bc2_sqrt, float ema_w, float gscale) {
+  extern __shared__ int64_t mt_pre[];
+  const int64_t total = mt_prefix(numel, nt, mt_pre);
+  for (int64_t chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+    const MtChunk c = mt_find(numel, nt, mt_pre, chunk);
+    float* p = P[c.t] + c.off;
+    const float* g = G[c.t] + c.off;
+    float* m = Mo[c.t] + c.off;
+    float* v = Vo[c.t] + c.off;
+    float* s = Sh != nullptr ? Sh[c.t] + c.off : nullptr;
+    constexpr int U = MT_CHUNK / MT_THREADS;
+    float gv[U], pv[U], mv[U], vv[U], sv[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int i = threadIdx.x + k * MT_THREADS;
+      if (i < c.n) {
+        gv[k] = g[i]; pv[k] = p[i]; mv[k] = m[i]; vv[k] = v[i];
+        sv[k] = s != nullptr ? s[i] : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int i = threadIdx.x + k * MT_THREADS;
+      if (i < c.n) {
+        const float gk = gv[k] * gscale;
+        float pk = pv[k] * (1.0f - lr * wd);
+        const float mk = mv[k] + (gk - mv[k]) * (1.0f - b1);
+        const float vk = vv[k] * b2 + (1.0f - b2) * gk * gk;
+        const float denom = sqrtf(vk) / bc2_sqrt + eps;
+        pk = pk - (lr / bc1) * (mk / denom);
+        p[i] = pk; m[i] = mk; v[i] = vk;
+        if (s != nullptr) s[i] = ema_w < 0.5f ? sv[k] + ema_w * (pk - sv[k]) : pk - (pk - sv[k]) * (1.0f - ema_w);
+      }
     }
   }
 }
@@ -106,19 +158,19 @@ extern "C" int dsk_edm_loss_fwd_bwd(const float* F, const float* x, const float*
   return DSK_OK;
 }
 
-static inline dim3 multi_grid(int ntensors, int64_t max_numel) {
-  int64_t bx = (max_numel + 255) / 256;
-  int64_t cap = (4LL * DSK_NUM_SMS + ntensors - 1) / ntensors;
-  if (cap < 1) cap = 1;
-  if (bx > cap) bx = cap;
-  if (bx < 1) bx = 1;
-  return dim3((unsigned)bx, (unsigned)ntensors);
+static inline int multi_grid(int ntensors, int64_t max_numel) {
+  // upper bound of the chunk count, capped at a few waves of the machine
+  int64_t chunks = (int64_t)ntensors * ((max_numel + MT_CHUNK - 1) / MT_CHUNK);
+  const int64_t cap = 8LL * DSK_NUM_SMS;
+  if (chunks > cap) chunks = cap;
+  return chunks < 1 ? 1 : (int)chunks;
 }
 
 extern "C" int dsk_ema_update(float* const* shadow, const float* const* param, const int64_t* numel, int ntensors,
                               int64_t max_numel, float beta, void* stream) {
-  DSK_REQUIRE(shadow && param && numel && ntensors > 0 && ntensors <= 65535 && max_numel > 0, "dsk_ema_update: bad arguments");
-  DSK_LAUNCH(ema_kernel, multi_grid(ntensors, max_numel), 256, 0, as_stream(stream), shadow, param, numel, 1.0f - beta);
+  DSK_REQUIRE(shadow && param && numel && ntensors > 0 && ntensors <= MT_MAX_TENSORS && max_numel > 0, "dsk_ema_update: bad arguments");
+  DSK_LAUNCH(ema_kernel, multi_grid(ntensors, max_numel), MT_THREADS, (size_t)(ntensors + 1) * sizeof(int64_t), as_stream(stream), shadow,
+             param, numel, ntensors, 1.0f - beta);
   return DSK_OK;
 }
 
@@ -126,11 +178,11 @@ extern "C" int dsk_adamw_ema_step(float* const* p, const float* const* g, float*
                                   float* const* shadow, const int64_t* numel, int ntensors, int64_t max_numel, float lr,
                                   float beta1, float beta2, float eps, float wd, int step, float ema_beta,
                                   float grad_scale, void* stream) {
-  DSK_REQUIRE(p && g && m && v && numel && ntensors > 0 && ntensors <= 65535 && max_numel > 0 && step > 0,
+  DSK_REQUIRE(p && g && m && v && numel && ntensors > 0 && ntensors <= MT_MAX_TENSORS && max_numel > 0 && step > 0,
               "dsk_adamw_ema_step: bad arguments");
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
-  DSK_LAUNCH(adamw_ema_kernel, multi_grid(ntensors, max_numel), 256, 0, as_stream(stream), p, g, m, v, shadow, numel, lr,
-             beta1, beta2, eps, wd, bc1, bc2s, 1.0f - ema_beta, grad_scale);
+  DSK_LAUNCH(adamw_ema_kernel, multi_grid(ntensors, max_numel), MT_THREADS, (size_t)(ntensors + 1) * sizeof(int64_t), as_stream(stream),
+             p, g, m, v, shadow, numel, ntensors, lr, beta1, beta2, eps, wd, bc1, bc2s, 1.0f - ema_beta, grad_scale);
   return DSK_OK;
 }

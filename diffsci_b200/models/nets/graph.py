@@ -439,12 +439,58 @@ class TrainGraph:
         return [self._gviews[id(p)] for p in self.params]
 
 
-def time_block(g: TrainGraph, te: Var, tb) -> Var:
-    """ResnetTimeBlock (commonlayers.py:516-550): Linear-SiLU-Linear-SiLU-Linear on the shared Fourier embedding."""
-    n = tb.net
-    h = g.linear(te, n[0].weight, n[0].bias, True, n[0].weight, n[0].bias)
-    h = g.linear(h, n[2].weight, n[2].bias, True, n[2].weight, n[2].bias)
-    return g.linear(h, n[4].weight, n[4].bias, False, n[4].weight, n[4].bias)
+def grouped_linear_layer(g: TrainGraph, xs: list, specs: list, silu: bool, shared_x: bool = False) -> list:
+    """One dsk_grouped_linear launch for many small fp32 linears y_i = [silu](x_i W_i^T + b_i)  (the time MLPs of every
+    ResNet block / ADM's FiLM projections), and ONE dsk_grouped_linear_bwd (two kernels) for all their gradients.
+
+    xs: input Vars (one per group; the same Var for every group if `shared_x`).  specs: (weight, bias, param_w, param_b,
+    rows) per group -- weight/bias may be row slices of the parameters, `rows` names the slice for the gradient view.
+    The builder is registered at the point of the call, so calling this BEFORE the consumers are built makes the backward
+    run after every consumer has contributed."""
+    f32 = torch.float32
+    Bn = xs[0].t.shape[0]
+    ws = [sp[0].detach() for sp in specs]
+    bs = [sp[1].detach() if sp[1] is not None else None for sp in specs]
+    zs = [g.empty((Bn, w.shape[0]), f32) for w in ws] if silu else None
+    ys = [Var(g.empty((Bn, w.shape[0]), f32)) for w in ws]
+    layer = ops.GroupedLinear([x.t for x in xs], ws, bs, [y.t for y in ys], 1 if silu else 0, zs)
+    g.fwd.append(layer.run)
+
+    def build_bwd():
+        dys = []
+        for y in ys:
+            dy = g.grad_of(y)
+            if dy is None:
+                raise RuntimeError("grouped_linear_layer: an output has no consumer")
+            dys.append(dy)
+        dzs = [g.empty(dy.shape, f32) for dy in dys] if silu else dys
+        dws = [g.grad_view(sp[2], sp[4]) for sp in specs]
+        dbs = [g.grad_view(sp[3], sp[4]) if sp[3] is not None else None for sp in specs]
+        dxs = None
+        if xs[0].needs_grad:
+            if shared_x:
+                dres, dx = g.contribute_compute(xs[0])
+                assert dres is None, "shared input with other consumers is not supported"
+                dxs = [dx] + [None] * (len(xs) - 1)
+            else:
+                dxs = []
+                for x in xs:
+                    dres, dx = g.contribute_compute(x)
+                    assert dres is None, "time-MLP activations have exactly one consumer"
+                    dxs.append(dx)
+        return [layer.backward_tables(dys, dzs, dws, dbs, dxs, shared_dx=shared_x)]
+
+    g._bwd_builders.append(build_bwd)
+    return ys
+
+
+def time_blocks(g: TrainGraph, te: Var, tbs: list) -> list:
+    """ResnetTimeBlock (commonlayers.py:516-550) of EVERY ResNet block at once: Linear-SiLU-Linear-SiLU-Linear on the
+    shared Fourier embedding = three grouped launches forward, three grouped backward launches."""
+    spec = lambda i: [(tb.net[i].weight, tb.net[i].bias, tb.net[i].weight, tb.net[i].bias, None) for tb in tbs]  # noqa: E731
+    h = grouped_linear_layer(g, [te] * len(tbs), spec(0), True, shared_x=True)
+    h = grouped_linear_layer(g, h, spec(2), True)
+    return grouped_linear_layer(g, h, spec(4), False)
 
 
 def build_punetg(net, B: int, spatial: tuple, device, precision: str) -> TrainGraph:
@@ -462,10 +508,13 @@ def build_punetg(net, B: int, spatial: tuple, device, precision: str) -> TrainGr
     g.t_in = torch.empty(B, dtype=torch.float32, device=g.device)
     g.x_in = Var(g.empty((B,) + sp + (c.input_channels,)), needs_grad=False)
     te = g.fourier(g.t_in, net.time_projection.W)
+    blocks = [b for l in range(nlev) for b in net.downward_blocks[l]] + list(net.before_block) + list(net.attn_resnet_block) + \
+        list(net.after_block) + [b for i in range(nlev) for b in net.upward_blocks[i]]
+    tvs = dict(zip((id(b) for b in blocks), time_blocks(g, te, [b.timeblock for b in blocks])))
 
     def resblock(x: Var, blk) -> Var:
         C = blk.channels
-        tv = time_block(g, te, blk.timeblock)
+        tv = tvs[id(blk)]
         n1 = g.norm(x, blk.gnorm1, C, c.first_resblock_norm, True)
         y = g.conv(n1, blk.conv1, chan_bias=tv)
         n2 = g.norm(y, blk.gnorm2, C, c.second_resblock_norm, True)
@@ -511,8 +560,16 @@ def build_adm(net, B: int, spatial: tuple, device, precision: str) -> TrainGraph
     g.x_in = Var(g.empty((B, 1, H, W, c.input_channels)), needs_grad=False)
     four = g.fourier(g.t_in, net.time_embedding.projection.W)
     mlp = net.time_embedding.mlp
-    h1 = g.linear(four, mlp[0].weight, mlp[0].bias, True, mlp[0].weight, mlp[0].bias)
-    te = g.linear(h1, mlp[2].weight, mlp[2].bias, True, mlp[2].weight, mlp[2].bias)      # + act_final SiLU (adm.py:1047-1053)
+    h1 = grouped_linear_layer(g, [four], [(mlp[0].weight, mlp[0].bias, mlp[0].weight, mlp[0].bias, None)], True)[0]
+    te = grouped_linear_layer(g, [h1], [(mlp[2].weight, mlp[2].bias, mlp[2].weight, mlp[2].bias, None)], True)[0]  # + act_final SiLU (adm.py:1047-1053)
+    blocks = [b for layer in net.encoder.layers for b in layer.input_blocks] + list(net.middle_block.middle_blocks) + \
+        [b for layer in net.decoder.layers for b in layer.input_blocks]
+    specs = []
+    for b in blocks:                                   # FiLM projection (adm.py:331-343): rows [:C] scale, [C:] shift
+        w, bb, Cc = b.embed_linear.weight, b.embed_linear.bias, b.cout
+        specs += [(w[:Cc], bb[:Cc], w, bb, slice(0, Cc)), (w[Cc:], bb[Cc:], w, bb, slice(Cc, 2 * Cc))]
+    films = grouped_linear_layer(g, [te] * len(specs), specs, False, shared_x=True)
+    film_of = {id(b): (films[2 * i], films[2 * i + 1]) for i, b in enumerate(blocks)}
 
     def block(x: Var, blk) -> Var:
         down, up = blk.sample == "down", blk.sample == "up"
@@ -521,11 +578,7 @@ def build_adm(net, B: int, spatial: tuple, device, precision: str) -> TrainGraph
         if down:
             n, xr = g.pool(n, False), g.pool(x, False)
         y = g.conv(n, blk.conv1, up2=up)
-        w, b = blk.embed_linear.weight, blk.embed_linear.bias
-        Cc = blk.cout
-        te1 = g.linear(te, w[:Cc], b[:Cc], False, w, b, slice(0, Cc))
-        te2 = g.linear(te, w[Cc:], b[Cc:], False, w, b, slice(Cc, 2 * Cc))
-        h = g.norm(y, blk.norm2, G, c.second_resblock_norm, True, film=(te1, te2))
+        h = g.norm(y, blk.norm2, G, c.second_resblock_norm, True, film=film_of[id(blk)])
         r = g.conv(xr, blk.convresidual, up2=up)
         o = g.conv(h, blk.conv2, residual=r)
         if blk.has_attn:

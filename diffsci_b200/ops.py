@@ -226,25 +226,45 @@ def fourier(t: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None
     return out
 
 
-class GroupedLinear:
-    """Pointer tables for one dsk_grouped_linear launch (built once; graph-capturable)."""
+def _ptr_table(ts, dev) -> torch.Tensor:
+    return torch.tensor([0 if t is None else t.data_ptr() for t in ts], dtype=torch.int64, device=dev)
 
-    def __init__(self, xs, ws, bs, ys, act: int):
+
+class GroupedLinear:
+    """Pointer tables for one dsk_grouped_linear launch (built once; graph-capturable).  `zs` (optional): buffers that
+    receive the pre-activations (training)."""
+
+    def __init__(self, xs, ws, bs, ys, act: int, zs=None):
         dev = ws[0].device
-        self.keep = (xs, ws, bs, ys)
+        self.keep = (xs, ws, bs, ys, zs)
         self.B = int(xs[0].shape[0])
-        mk = lambda ts: torch.tensor([0 if t is None else t.data_ptr() for t in ts], dtype=torch.int64, device=dev)  # noqa: E731
-        self.X, self.W, self.Bi, self.Y = mk(xs), mk(ws), mk(bs), mk(ys)
+        self.X, self.W, self.Bi, self.Y = (_ptr_table(t, dev) for t in (xs, ws, bs, ys))
+        self.Z = _ptr_table(zs, dev) if zs is not None else None
         self.in_dim = torch.tensor([w.shape[1] for w in ws], dtype=torch.int32, device=dev)
         self.out_dim = torch.tensor([w.shape[0] for w in ws], dtype=torch.int32, device=dev)
         self.max_out = max(int(w.shape[0]) for w in ws)
+        self.max_in = max(int(w.shape[1]) for w in ws)
         self.n = len(ws)
         self.act = act
         self.sig = tuple(int(w.data_ptr()) for w in ws)
 
     def run(self):
-        check(lib.dsk_grouped_linear(ptr(self.X), ptr(self.W), ptr(self.Bi), ptr(self.Y), ptr(self.in_dim),
+        check(lib.dsk_grouped_linear(ptr(self.X), ptr(self.W), ptr(self.Bi), ptr(self.Y), ptr(self.Z), ptr(self.in_dim),
                                      ptr(self.out_dim), self.n, self.max_out, self.B, self.act, stream()))
+
+    def backward_tables(self, dys, dzs, dws, dbs, dxs, shared_dx: bool = False, accumulate_dx: bool = False):
+        """Bind the gradient buffers of this layer (dsk_grouped_linear_bwd); returns the launch closure."""
+        dev = self.W.device
+        keep = (dys, dzs, dws, dbs, dxs)
+        dY, dZ, dW, dB = (_ptr_table(t, dev) for t in (dys, dzs, dws, dbs))
+        dX = _ptr_table(dxs, dev) if dxs is not None else None
+
+        def run():
+            _ = keep
+            check(lib.dsk_grouped_linear_bwd(ptr(dY), ptr(self.Z), ptr(self.X), ptr(self.W), ptr(dZ), ptr(dW), ptr(dB), ptr(dX),
+                                             ptr(self.in_dim), ptr(self.out_dim), self.n, self.max_out, self.max_in, self.B,
+                                             self.act, int(shared_dx), int(accumulate_dx), stream()))
+        return run
 
 
 def softmax_rows(S: torch.Tensor, rows: int, cols: int) -> torch.Tensor:

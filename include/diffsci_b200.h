@@ -198,10 +198,20 @@ int dsk_concat_channels(const void* a, const void* b, void* y, int64_t rows, int
 int dsk_fourier(const float* t, const float* W, float* out, int B, int half, void* stream);
 /* Grouped small-batch linear: for g in [0,ngroups): Y_g[B,out_g] = act(X_g[B,in_g] W_g^T + b_g).
  * Device arrays of pointers / sizes (one launch for the time MLP layer of every ResNet block;
- * commonlayers.py:516-550, adm.py:331-343, nets/mlp.py:38-58).  act: 0 none, 1 SiLU, 2 ReLU. */
+ * commonlayers.py:516-550, adm.py:331-343, nets/mlp.py:38-58).  act: 0 none, 1 SiLU, 2 ReLU.
+ * Z (optional table): receives the pre-activation X W^T + b, which the backward pass needs. */
 int dsk_grouped_linear(const float* const* X, const float* const* W, const float* const* bias, float* const* Y,
-                       const int* in_dim, const int* out_dim, int ngroups, int max_out, int B, int act,
-                       void* stream);
+                       float* const* Z, const int* in_dim, const int* out_dim, int ngroups, int max_out, int B,
+                       int act, void* stream);
+/* Backward of the same layer for every group in two launches (what autograd runs below loss.backward() for the
+ * nn.Linear + SiLU pairs of ResnetTimeBlock / ADM time embedding):
+ *   dZ_g = dY_g * act'(Z_g)  (dZ_g may alias dY_g when act == 0),  dW_g = dZ_g^T X_g,  db_g = colsum(dZ_g),
+ *   dX_g = dZ_g W_g -- or, with shared_dx, ONE dX (table entry 0) = sum_g dZ_g W_g for groups that read the same X.
+ * dX == NULL (or a NULL entry) skips the input gradient; accumulate_dx adds into dX. */
+int dsk_grouped_linear_bwd(const float* const* dY, const float* const* Z, const float* const* X,
+                           const float* const* W, float* const* dZ, float* const* dW, float* const* db,
+                           float* const* dX, const int* in_dim, const int* out_dim, int ngroups, int max_out,
+                           int max_in, int B, int act, int shared_dx, int accumulate_dx, void* stream);
 
 /* ---- K3: attention ----------------------------------------------------------------------
  * softmax over the last dim of S[batch*rows, cols] in place (fp32), the middle of

@@ -434,3 +434,44 @@ def test_trainer_equals_autograd_seam(golden):
     err = math.sqrt(num / den)
     print(f"PUNetG-2D mc=64 bf16-vs-fp32 global gradient L2 error: {err:.2e}")
     assert err < 6e-2
+
+
+# ------------------------------------------------------------------------------------------------ grouped time-MLP layer
+@pytest.mark.parametrize("act,shared,B", [(1, False, 5), (0, False, 37), (0, True, 6), (1, True, 3)])
+def test_grouped_linear_bwd(ops, act, shared, B):
+    """dsk_grouped_linear (+ pre-activation output) and dsk_grouped_linear_bwd against autograd of F.linear / F.silu."""
+    torch.manual_seed(8)
+    dims = [(64, 24), (40, 24), (600, 24)] if shared else [(64, 16), (24, 48), (8, 700)]     # (N, K); K > 512 sweeps twice
+    x0 = torch.randn(B, dims[0][1], dtype=torch.float64)
+    xs = [x0.clone().requires_grad_(True)] if shared else [torch.randn(B, k, dtype=torch.float64, requires_grad=True) for _, k in dims]
+    ws = [(torch.randn(n, k, dtype=torch.float64) / math.sqrt(k)).requires_grad_(True) for n, k in dims]
+    bs = [torch.randn(n, dtype=torch.float64, requires_grad=True) for n, _ in dims]
+    dys = [torch.randn(B, n, dtype=torch.float64) for n, _ in dims]
+    tot = 0
+    for i, (w, b, dy) in enumerate(zip(ws, bs, dys)):
+        z = F.linear(xs[0] if shared else xs[i], w, b)
+        tot = tot + ((F.silu(z) if act else z) * dy).sum()
+    tot.backward()
+    f = lambda t: t.detach().float().to(DEV).contiguous()  # noqa: E731
+    xd = [f(xs[0])] * len(dims) if shared else [f(x) for x in xs]
+    wd, bd, dyd = [f(w) for w in ws], [f(b) for b in bs], [f(d) for d in dys]
+    yd = [torch.empty(B, n, device=DEV) for n, _ in dims]
+    zd = [torch.empty(B, n, device=DEV) for n, _ in dims] if act else None
+    layer = ops.GroupedLinear(xd, wd, bd, yd, act, zd)
+    layer.run()
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        z = F.linear(xs[0] if shared else xs[i], w, b).detach()
+        assert relmax(yd[i], F.silu(z) if act else z) < 1e-5
+        if act:
+            assert relmax(zd[i], z) < 1e-5
+    dzd = [torch.empty_like(d) for d in dyd] if act else dyd
+    dwd, dbd = [torch.empty_like(w) for w in wd], [torch.empty_like(b) for b in bd]
+    dxd = ([torch.empty_like(xd[0])] + [None] * (len(dims) - 1)) if shared else [torch.empty_like(x) for x in xd]
+    layer.backward_tables(dyd, dzd, dwd, dbd, dxd, shared_dx=shared)()
+    for i in range(len(dims)):
+        assert relmax(dwd[i], ws[i].grad) < 2e-5, i
+        assert relmax(dbd[i], bs[i].grad) < 2e-5, i
+        if not shared:
+            assert relmax(dxd[i], xs[i].grad) < 2e-5, i
+    if shared:
+        assert relmax(dxd[0], xs[0].grad) < 2e-5
