@@ -52,7 +52,8 @@ SIGNATURES = {
     "dsk_pack_upconv_weight": [p, p, i32, i32, i32, p],
     "dsk_pack_conv_weight": [p, p, i32, i32, i32, i32, p],
     "dsk_gemm_f32": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i32, i32, f32, i32, p],
-    "dsk_gemm_bf16_tc": [p, p, p, p, i32, p, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, f32, i32, p],
+    "dsk_gemm_bf16_tc": [p, p, p, p, i32, p, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, f32, i32, i32, i32, p],
+    "dsk_softmax_bwd_rows_bf16": [p, p, p, i64, i32, p],
     "dsk_softmax_rows_bf16": [p, p, i64, i32, p],
     "dsk_norm_ws_bytes": [i32, i64, i32],
     "dsk_norm_act": [p, p, p, p, p, p, p, i32, i64, i32, i32, i32, i32, i32, i32, p],

@@ -1,5 +1,9 @@
 // gemm_tc.cu -- batched bf16 GEMM on tcgen05/TMEM fed by TMA:  C[b] = alpha * A[b] * B[b]^T (+ bias) (+ residual)
 // A: [M, K] row-major (K contiguous, leading dimension lda), B: [N, K] row-major (ldb): both K-major operands.
+// transA / transB: the operand is stored [K, M] / [K, N] (M / N contiguous) and is consumed as it lies, as an MN-MAJOR
+// UMMA operand (64-element x 64-row SWIZZLE_128B boxes, LBO = 8 KB between the 64-wide atoms, SBO = 1 KB between
+// 8-row K groups) -- the A^T B products of the backward passes (weight gradients, dV = P^T dO, dK = dS^T Q) need no
+// transposition pass.
 //
 // Used for everything GEMM-shaped around the attention block (nn.MultiheadAttention(C, 1 head), reference
 // nets/attention.py:42-44,68): packed Q|K projection, V^T projection (row bias), Q K^T, P V and the output
@@ -23,6 +27,7 @@ struct GemmTcParams {
   void* out;                // bf16 or fp32 [batch][M][ldc]
   int out_f32;
   int64_t ldc, strideC;
+  int transA, transB;       // operand stored [K][M] / [K][N] (MN-major)
 };
 
 template <int N_TILE>
@@ -61,22 +66,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
           mbar_wait(&empty[slot], ph ^ 1);
           mbar_expect_tx(&full[slot], STAGE);
           uint8_t* sa = smem + (size_t)slot * STAGE;
-          asm volatile(
-              "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                  smem_u32(sa)),
-              "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(kc * 64), "r"(tm * 128), "r"(b * p.a_bmul), "r"(smem_u32(&full[slot]))
-              : "memory");
-          asm volatile(
-              "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                  smem_u32(sa + A_BYTES)),
-              "l"(reinterpret_cast<uint64_t>(&tmapB)), "r"(kc * 64), "r"(tn * N_TILE), "r"(b * p.b_bmul), "r"(smem_u32(&full[slot]))
-              : "memory");
+          auto tma3 = [&](const CUtensorMap* tm_, uint8_t* dst, int c0, int c1, int c2) {
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                    smem_u32(dst)),
+                "l"(reinterpret_cast<uint64_t>(tm_)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(&full[slot]))
+                : "memory");
+          };
+          if (!p.transA) {
+            tma3(&tmapA, sa, kc * 64, tm * 128, b * p.a_bmul);
+          } else {
+            tma3(&tmapA, sa, tm * 128, kc * 64, b * p.a_bmul);
+            tma3(&tmapA, sa + 8192, tm * 128 + 64, kc * 64, b * p.a_bmul);
+          }
+          if (!p.transB) {
+            tma3(&tmapB, sa + A_BYTES, kc * 64, tn * N_TILE, b * p.b_bmul);
+          } else {
+#pragma unroll
+            for (int h = 0; h < N_TILE / 64; ++h) tma3(&tmapB, sa + A_BYTES + h * 8192, tn * N_TILE + h * 64, kc * 64, b * p.b_bmul);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_bf16(N_TILE);
+    const uint32_t idesc = umma_idesc_bf16(N_TILE) | (p.transA ? 1u << 15 : 0u) | (p.transB ? 1u << 16 : 0u);
     constexpr uint32_t HI = umma_desc_hi(1024);
+    // descriptor low word: K-major: LBO field = 1 (unused), k-step of 16 elements = 32 B; MN-major: LBO = 8 KB, k-step of
+    // 16 rows = 2 KB
+    const uint32_t a_lbo = p.transA ? (8192u >> 4) << 16 : 0x10000u, a_step = p.transA ? 2048u >> 4 : 2u;
+    const uint32_t b_lbo = p.transB ? (8192u >> 4) << 16 : 0x10000u, b_step = p.transB ? 2048u >> 4 : 2u;
     uint32_t seq = 0, it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
@@ -87,11 +105,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         const uint32_t slot = seq % GT_STAGES;
         mbar_wait(&full[slot], (seq / GT_STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_lo = umma_desc_lo(smem_u32(smem + (size_t)slot * STAGE)), b_lo = a_lo + (A_BYTES >> 4);
+        const uint32_t sa16 = smem_u32(smem + (size_t)slot * STAGE) >> 4;
+        const uint32_t a_lo = sa16 | a_lbo, b_lo = (sa16 + (A_BYTES >> 4)) | b_lbo;
         if (elect_one_sync()) {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
-            umma_bf16(tmem_acc, umma_desc64(a_lo + k4 * 2, HI), umma_desc64(b_lo + k4 * 2, HI), idesc, (kc | k4) != 0);
+            umma_bf16(tmem_acc, umma_desc64(a_lo + k4 * a_step, HI), umma_desc64(b_lo + k4 * b_step, HI), idesc, (kc | k4) != 0);
           umma_commit(&empty[slot]);
         }
         __syncwarp();
@@ -226,6 +245,51 @@ __global__ void __launch_bounds__(256) softmax_rows_bf16_kernel(const float* __r
   }
 }
 
+// dS = P * (dP - rowsum(dP * P)) for softmax rows: P bf16 probabilities, dP fp32 (GEMM output), dS bf16 (next GEMM operand)
+__global__ void __launch_bounds__(256) softmax_bwd_rows_bf16_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict__ dP,
+                                                                     __nv_bfloat16* __restrict__ dS, int64_t rows, int cols) {
+  __shared__ float red[8];
+  constexpr int MAXV = 8;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float4* g = reinterpret_cast<const float4*>(dP + r * cols);
+    const uint2* pp = reinterpret_cast<const uint2*>(P + r * cols);
+    const int nv = cols >> 2;
+    float4 pv[MAXV], gv[MAXV];
+    float dot = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      if (idx < nv) {
+        gv[i] = g[idx];
+        const uint2 u = pp[idx];
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        pv[i] = make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+        dot += (gv[i].x * pv[i].x + gv[i].y * pv[i].y) + (gv[i].z * pv[i].z + gv[i].w * pv[i].w);
+      }
+    }
+    dot = warp_sum(dot);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    dot = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) dot += red[w];
+    __syncthreads();
+    uint2* dst = reinterpret_cast<uint2*>(dS + r * cols);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      if (idx < nv) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(pv[i].x * (gv[i].x - dot), pv[i].y * (gv[i].y - dot));
+        __nv_bfloat162 b = __floats2bfloat162_rn(pv[i].z * (gv[i].z - dot), pv[i].w * (gv[i].w - dot));
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&a);
+        o.y = *reinterpret_cast<uint32_t*>(&b);
+        dst[idx] = o;
+      }
+    }
+  }
+}
+
 template <int N_TILE>
 static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, cudaStream_t st) {
   const size_t smem = (size_t)GT_STAGES * (128 * 128 + N_TILE * 128) + 1024;
@@ -246,7 +310,7 @@ using namespace dsk;
 
 extern "C" int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const float* bias, int bias_rows, const void* residual,
                                 int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
-                                int64_t strideC, int batch, float alpha, int out_f32, void* stream) {
+                                int64_t strideC, int batch, float alpha, int out_f32, int transA, int transB, void* stream) {
   DSK_REQUIRE(A && Bm && C, "dsk_gemm_bf16_tc: null pointer");
   DSK_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "dsk_gemm_bf16_tc: bad shape");
   DSK_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && strideA % 8 == 0 && strideB % 8 == 0,
@@ -256,17 +320,19 @@ extern "C" int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const fl
   DSK_REQUIRE(encode != nullptr, "dsk_gemm_bf16_tc: cuTensorMapEncodeTiled is unavailable");
   const int n_tile = N > 128 ? 256 : (N > 64 ? 128 : 64);
   CUtensorMap ta, tb;
-  auto make = [&](CUtensorMap* tm, const void* base, int rows, int64_t ld, int64_t stride, int box_rows) -> bool {
+  // K-major operand [rows][K]: box 64 (k) x box_rows;  MN-major operand [K][rows]: box 64 (rows) x 64 (k)
+  auto make = [&](CUtensorMap* tm, const void* base, int rows, int64_t ld, int64_t stride, int box_rows, int trans) -> bool {
     const bool shared = batch == 1 || stride == 0;
-    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(shared ? 1 : batch)};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(shared ? (int64_t)rows * ld : stride) * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    const int inner = trans ? rows : K, outer = trans ? K : rows;
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(shared ? 1 : batch)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(shared ? (int64_t)outer * ld : stride) * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)(trans ? 64 : box_rows), 1};
     cuuint32_t es[3] = {1, 1, 1};
     return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
-  DSK_REQUIRE(make(&ta, A, M, lda, strideA, 128), "dsk_gemm_bf16_tc: tensor map for A failed");
-  DSK_REQUIRE(make(&tb, Bm, N, ldb, strideB, n_tile), "dsk_gemm_bf16_tc: tensor map for B failed");
+  DSK_REQUIRE(make(&ta, A, M, lda, strideA, 128, transA), "dsk_gemm_bf16_tc: tensor map for A failed");
+  DSK_REQUIRE(make(&tb, Bm, N, ldb, strideB, n_tile, transB), "dsk_gemm_bf16_tc: tensor map for B failed");
   GemmTcParams p;
   p.M = M; p.N = N; p.K = K; p.batch = batch;
   p.a_bmul = (batch > 1 && strideA != 0) ? 1 : 0;
@@ -275,6 +341,7 @@ extern "C" int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const fl
   p.total_tiles = p.tiles_m * p.tiles_n * batch;
   p.alpha = alpha; p.bias = bias; p.bias_rows = bias_rows;
   p.residual = (const __nv_bfloat16*)residual; p.out = C; p.out_f32 = out_f32; p.ldc = ldc; p.strideC = strideC;
+  p.transA = transA ? 1 : 0; p.transB = transB ? 1 : 0;
   cudaStream_t st = as_stream(stream);
   if (n_tile == 64) return launch_gemm_tc<64>(ta, tb, p, st);
   if (n_tile == 128) return launch_gemm_tc<128>(ta, tb, p, st);
@@ -286,5 +353,13 @@ extern "C" int dsk_softmax_rows_bf16(const float* S, void* P, int64_t rows, int 
   DSK_REQUIRE(cols % 4 == 0 && cols <= 8192, "dsk_softmax_rows_bf16: cols=%d must be a multiple of 4 and <= 8192", cols);
   int64_t grid = rows < (int64_t)DSK_NUM_SMS * 16 ? rows : (int64_t)DSK_NUM_SMS * 16;
   DSK_LAUNCH(softmax_rows_bf16_kernel, (int)grid, 256, 0, as_stream(stream), S, (__nv_bfloat16*)P, rows, cols);
+  return DSK_OK;
+}
+
+extern "C" int dsk_softmax_bwd_rows_bf16(const void* P, const float* dP, void* dS, int64_t rows, int cols, void* stream) {
+  DSK_REQUIRE(P && dP && dS && rows > 0 && cols > 0, "dsk_softmax_bwd_rows_bf16: bad arguments");
+  DSK_REQUIRE(cols % 4 == 0 && cols <= 8192, "dsk_softmax_bwd_rows_bf16: cols=%d must be a multiple of 4 and <= 8192", cols);
+  int64_t grid = rows < (int64_t)DSK_NUM_SMS * 16 ? rows : (int64_t)DSK_NUM_SMS * 16;
+  DSK_LAUNCH(softmax_bwd_rows_bf16_kernel, (int)grid, 256, 0, as_stream(stream), (const __nv_bfloat16*)P, dP, (__nv_bfloat16*)dS, rows, cols);
   return DSK_OK;
 }

@@ -330,6 +330,9 @@ class TrainGraph:
         Cc = x.t.shape[-1]
         Lq = x.t.numel() // (B * Cc)
         f32 = torch.float32
+        import diffsci_b200
+        if (self.precision == "bf16" and diffsci_b200.TC_CONV_ENABLED and Cc % 64 == 0 and Lq % 8 == 0 and Lq <= 8192):
+            return self._attention_tc(x, mha, residual)
         y = Var(self.empty(x.t.shape))
         xt, yt = x.t, y.t
         tok = xt.view(B, Lq, Cc) if xt.dtype == f32 else self.empty((B, Lq, Cc), f32)
@@ -390,6 +393,87 @@ class TrainGraph:
                     out.append(lambda: ops.add_ex(dtok, dout, dtok))
                 dres, dx = self.contribute_compute(x)
                 out.append(lambda: ops.add_ex(dtok, dres.view(M, Cc) if dres is not None else None, dx.view(M, Cc)))
+            return out
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
+    def _attention_tc(self, x: Var, mha, residual: bool) -> Var:
+        """The same attention block with every product on the tensor cores (bf16 operands, fp32 accumulation): forward as
+        ops.self_attention_tc but keeping Q|K|V, P and the attention output; backward = 9 dsk_gemm_bf16_tc launches (the
+        A^T B products take their operands MN-major, as they lie) + the bf16 softmax backward."""
+        B = self.B
+        Cc = x.t.shape[-1]
+        Lq = x.t.numel() // (B * Cc)
+        M = B * Lq
+        f32, bf = torch.float32, torch.bfloat16
+        y = Var(self.empty(x.t.shape))
+        tok, yt = x.t.view(M, Cc), y.t.view(M, Cc)
+        qkv = self.empty((M, 3 * Cc), bf)
+        P = self.empty((B, Lq, Lq), bf)
+        ao = self.empty((M, Cc), bf)
+        sc = self.lazy_scratch("attn_scores", (B, Lq, Lq), f32)
+        wi, wo = ops.PackedLinear(mha.in_proj_weight), ops.PackedLinear(mha.out_proj.weight)
+        self._packs += [wi, wo]
+        bi, bo = mha.in_proj_bias.detach(), mha.out_proj.bias.detach()
+        alpha = Cc ** -0.5
+        s3, sLL, sLC = Lq * 3 * Cc, Lq * Lq, Lq * Cc
+        G = ops.gemm_bf16_tc
+
+        def fwd():
+            G(tok, wi.packed(), qkv, M=M, N=3 * Cc, K=Cc, lda=Cc, ldb=Cc, ldc=3 * Cc, bias=bi)
+            G(qkv, qkv, sc(), M=Lq, N=Lq, K=Cc, lda=3 * Cc, ldb=3 * Cc, ldc=Lq, alpha=alpha, batch=B, strideA=s3, strideB=s3,
+              strideC=sLL, b_off=Cc)
+            ops.softmax_rows_bf16(sc(), P, B * Lq, Lq)
+            G(P, qkv, ao, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=3 * Cc, ldc=Cc, batch=B, strideA=sLL, strideB=s3, strideC=sLC,
+              b_off=2 * Cc, transB=True)                                              # O = P V, V as it lies ([L, C] = [K, N])
+            G(ao, wo.packed(), yt, M=M, N=Cc, K=Cc, lda=Cc, ldb=Cc, ldc=Cc, bias=bo, residual=tok if residual else None)
+
+        self.fwd.append(fwd)
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return []
+            gwi, gbi = self.grad_view(mha.in_proj_weight), self.grad_view(mha.in_proj_bias)
+            gwo, gbo = self.grad_view(mha.out_proj.weight), self.grad_view(mha.out_proj.bias)
+            dyt = dy.view(M, Cc)
+            dAO = self.empty((M, Cc), bf)
+            dqkv = self.empty((M, 3 * Cc), bf)
+            dP = self.lazy_scratch("attn_scores", (B, Lq, Lq), f32)
+            dS = self.lazy_scratch("attn_dS", (B, Lq, Lq), bf)
+            wsp = self.lazy_scratch("attn_wsplit", (B, 3 * Cc * Cc), f32)
+            csws = self.lazy_scratch("bwd_ws", ops.bwd_ws_bytes(B, Lq, 3 * Cc))
+            out = []
+            # out = ao Wo^T + bo :  dWo = dy^T ao (split over the batch, summed in a fixed order) ; dbo ; dAO = dy Wo
+            out.append(lambda: G(dyt, ao, wsp()[:, :Cc * Cc], M=Cc, N=Cc, K=Lq, lda=Cc, ldb=Cc, ldc=Cc, batch=B, strideA=sLC,
+                                 strideB=sLC, strideC=3 * Cc * Cc, transA=True, transB=True))
+            out.append(lambda: ops.colsum(wsp()[:, :Cc * Cc], gwo.view(-1), ld=3 * Cc * Cc))
+            out.append(lambda: ops.channel_sum(dy.view(B, Lq, Cc), gbo, csws(), False))
+            out.append(lambda: G(dyt, wo.packed(), dAO, M=M, N=Cc, K=Cc, lda=Cc, ldb=Cc, ldc=Cc, transB=True))
+            # O = P V :  dP = dAO V^T ; dV = P^T dAO
+            out.append(lambda: G(dAO, qkv, dP(), M=Lq, N=Lq, K=Cc, lda=Cc, ldb=3 * Cc, ldc=Lq, batch=B, strideA=sLC, strideB=s3,
+                                 strideC=sLL, b_off=2 * Cc))
+            out.append(lambda: G(P, dAO, dqkv, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=Cc, ldc=3 * Cc, batch=B, strideA=sLL, strideB=sLC,
+                                 strideC=s3, c_off=2 * Cc, transA=True, transB=True))
+            # P = softmax(alpha Q K^T) :  dS = P (dP - rowsum(dP P)) ; dQ = alpha dS K ; dK = alpha dS^T Q
+            out.append(lambda: ops.softmax_bwd_rows_bf16(P, dP(), dS(), B * Lq, Lq))
+            out.append(lambda: G(dS(), qkv, dqkv, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=3 * Cc, ldc=3 * Cc, alpha=alpha, batch=B,
+                                 strideA=sLL, strideB=s3, strideC=s3, b_off=Cc, c_off=0, transB=True))
+            out.append(lambda: G(dS(), qkv, dqkv, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=3 * Cc, ldc=3 * Cc, alpha=alpha, batch=B,
+                                 strideA=sLL, strideB=s3, strideC=s3, b_off=0, c_off=Cc, transA=True, transB=True))
+            # qkv = tok Wi^T + bi :  dWi = dqkv^T tok ; dbi ; dtok = dqkv Wi
+            out.append(lambda: G(dqkv, tok, wsp(), M=3 * Cc, N=Cc, K=Lq, lda=3 * Cc, ldb=Cc, ldc=Cc, batch=B, strideA=s3,
+                                 strideB=sLC, strideC=3 * Cc * Cc, transA=True, transB=True))
+            out.append(lambda: ops.colsum(wsp(), gwi.view(-1)))
+            out.append(lambda: ops.channel_sum(dqkv.view(B, Lq, 3 * Cc), gbi, csws(), False))
+            if x.needs_grad:
+                dres, dx = self.contribute_compute(x)
+                dxt = dx.view(M, Cc)
+                out.append(lambda: G(dqkv, wi.packed(), dxt, M=M, N=Cc, K=3 * Cc, lda=3 * Cc, ldb=Cc, ldc=Cc, transB=True,
+                                     residual=dyt if residual else (dres.view(M, Cc) if dres is not None else None)))
+                if residual and dres is not None:
+                    out.append(lambda: ops.add_ex(dx, dres, dx))
             return out
 
         self._bwd_builders.append(build_bwd)

@@ -338,14 +338,18 @@ class PackedLinear:
 def gemm_bf16_tc(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, lda: int, ldb: int,
                  ldc: int, bias: Optional[torch.Tensor] = None, bias_rows: bool = False,
                  residual: Optional[torch.Tensor] = None, alpha: float = 1.0, batch: int = 1, strideA: int = 0,
-                 strideB: int = 0, strideC: int = 0, a_off: int = 0, b_off: int = 0) -> torch.Tensor:
-    """Batched bf16 tensor-core GEMM C = alpha A B^T + bias (+ residual) on raw buffers (dsk_gemm_bf16_tc)."""
+                 strideB: int = 0, strideC: int = 0, a_off: int = 0, b_off: int = 0, c_off: int = 0, transA: bool = False,
+                 transB: bool = False) -> torch.Tensor:
+    """Batched bf16 tensor-core GEMM C = alpha op(A) op(B)^T + bias (+ residual) on raw buffers (dsk_gemm_bf16_tc).
+    transA / transB: the operand is stored [K, M] / [K, N].  Offsets are in elements."""
     require_cuda(A, "gemm A")
     assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16
     a = C.c_void_p(A.data_ptr() + a_off * 2)
     b = C.c_void_p(Bm.data_ptr() + b_off * 2)
-    check(lib.dsk_gemm_bf16_tc(a, b, ptr(out), ptr(bias), int(bias_rows), ptr(residual), M, N, K, lda, ldb, ldc, strideA,
-                               strideB, strideC, batch, alpha, int(out.dtype == torch.float32), stream()))
+    c = C.c_void_p(out.data_ptr() + c_off * out.element_size())
+    r = None if residual is None else C.c_void_p(residual.data_ptr() + c_off * 2)
+    check(lib.dsk_gemm_bf16_tc(a, b, c, ptr(bias), int(bias_rows), r, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch,
+                               alpha, int(out.dtype == torch.float32), int(transA), int(transB), stream()))
     return out
 
 
@@ -402,12 +406,23 @@ def channel_sum(dy: torch.Tensor, out: torch.Tensor, ws: Optional[torch.Tensor],
     return out
 
 
-def colsum(x: torch.Tensor, out: torch.Tensor):
-    """out[c] = sum_r x[r, c] for a contiguous fp32 matrix."""
+def colsum(x: torch.Tensor, out: torch.Tensor, ld: Optional[int] = None):
+    """out[c] = sum_r x[r, c] for an fp32 matrix with row stride `ld` (default: contiguous)."""
     require_cuda(x, "colsum input")
     rows, cols = x.shape
-    check(lib.dsk_colsum_f32(ptr(x), ptr(out), rows, cols, cols, stream()))
+    check(lib.dsk_colsum_f32(ptr(x), ptr(out), rows, cols, cols if ld is None else ld, stream()))
     return out
+
+
+def softmax_rows_bf16(S: torch.Tensor, P: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    check(lib.dsk_softmax_rows_bf16(ptr(S), ptr(P), rows, cols, stream()))
+    return P
+
+
+def softmax_bwd_rows_bf16(P: torch.Tensor, dP: torch.Tensor, dS: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    """dS = P * (dP - rowsum(dP * P)): P bf16, dP fp32, dS bf16 (dsk_softmax_bwd_rows_bf16)."""
+    check(lib.dsk_softmax_bwd_rows_bf16(ptr(P), ptr(dP), ptr(dS), rows, cols, stream()))
+    return dS
 
 
 def norm_act_bwd(x, dy, dx, gamma, beta, G: int, mode: int, silu: bool, fwd_ws, ws, dgamma=None, dbeta=None, dres=None,

@@ -158,10 +158,14 @@ int dsk_gemm_f32_ex(const float* A, const float* Bm, float* Cm, const float* bia
  * A [M,K] (lda), B [N,K] (ldb): bf16, K contiguous; C bf16 or fp32 (out_f32) with leading dimension ldc;
  * bias fp32 per column (bias_rows = 0) or per row (bias_rows = 1); residual bf16 laid out like C.
  * A batch stride of 0 shares the operand across the batch.  K, ld*, strides: multiples of 8 elements.
+ * transA / transB: the operand is stored [K, M] / [K, N] (lda >= M / ldb >= N) and is fed to the tensor core as an
+ * MN-major operand -- the A^T B products of autograd's backward (weight gradients, dV = P^T dO, dK = dS^T Q).
  * The tensor-core form of the projections / QK^T / PV inside nn.MultiheadAttention (nets/attention.py:42-44). */
 int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const float* bias, int bias_rows, const void* residual, int M,
                      int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
-                     int64_t strideC, int batch, float alpha, int out_f32, void* stream);
+                     int64_t strideC, int batch, float alpha, int out_f32, int transA, int transB, void* stream);
+/* softmax backward on rows: dS = P * (dP - rowsum(dP * P)); P bf16, dP fp32, dS bf16 (cols % 4 == 0, cols <= 8192) */
+int dsk_softmax_bwd_rows_bf16(const void* P, const float* dP, void* dS, int64_t rows, int cols, void* stream);
 /* softmax over the last dim: fp32 scores [rows, cols] -> bf16 probabilities (cols % 4 == 0, cols <= 8192) */
 int dsk_softmax_rows_bf16(const float* S, void* P, int64_t rows, int cols, void* stream);
 

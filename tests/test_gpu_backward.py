@@ -475,3 +475,45 @@ def test_grouped_linear_bwd(ops, act, shared, B):
             assert relmax(dxd[i], xs[i].grad) < 2e-5, i
     if shared:
         assert relmax(dxd[0], xs[0].grad) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core attention
+@pytest.mark.parametrize("residual", [False, True])
+def test_attention_tc_forward_backward(residual):
+    """TrainGraph.attention on the tcgen05 path (bf16 operands, MN-major A^T B products) against fp64 autograd of
+    nn.MultiheadAttention(C, 1 head) on the same bf16-rounded input and weights."""
+    from diffsci_b200.models.nets.graph import TrainGraph, Var
+    torch.manual_seed(31)
+    B, C, H, W = 3, 64, 8, 16
+    L = H * W
+    mha = torch.nn.MultiheadAttention(C, 1, batch_first=True)
+    with torch.no_grad():
+        for p in mha.parameters():
+            p.copy_((torch.randn_like(p) * (0.1 if p.ndim == 1 else C ** -0.5)).bfloat16().float())
+    holder = torch.nn.Module()
+    holder.mhattn = mha
+    holder = holder.to(DEV)
+    g = TrainGraph(holder, B, torch.device(DEV), "bf16", 2)
+    x = Var(g.empty((B, 1, H, W, C)))
+    y = g.attention(x, holder.mhattn, residual)
+    g.finalize(y)
+    xv = torch.randn(B, L, C).bfloat16()
+    dyv = torch.randn(B, L, C).bfloat16()
+    x.t.copy_(xv.view(B, 1, H, W, C))
+    g.run_forward()
+    y.g.copy_(dyv.view(B, 1, H, W, C))
+    g.run_backward()
+    ref = torch.nn.MultiheadAttention(C, 1, batch_first=True).double()
+    ref.load_state_dict({k: v.double().cpu() for k, v in mha.state_dict().items()})
+    xr = xv.double().requires_grad_(True)
+    out = ref(xr, xr, xr, need_weights=False)[0]
+    if residual:
+        out = out + xr
+    out.backward(dyv.double())
+    # bf16 storage of Q|K|V, P, the attention output and every intermediate gradient: stated tolerance 2e-2 of the range
+    assert relmax(y.t.float().view(B, L, C), out.detach()) < 2e-2
+    assert relmax(x.g.float().view(B, L, C), xr.grad) < 2e-2
+    grads = dict(zip((n for n, _ in holder.named_parameters()), g.grads()))
+    for n, p in ref.named_parameters():
+        e = relmax(grads["mhattn." + n], p.grad)
+        assert e < 2e-2, (n, e)

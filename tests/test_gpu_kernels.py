@@ -306,6 +306,35 @@ def test_gemm_bf16_tcgen05(ops, M, N, K, batch):
     assert relmax(out2.float().cpu()[..., :N], ref2) < 6e-3
 
 
+@pytest.mark.parametrize("transA,transB", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K,batch", [(128, 64, 64, 1), (200, 136, 72, 2), (64, 256, 264, 1), (256, 192, 1000, 3)])
+def test_gemm_bf16_tcgen05_mn_major(ops, M, N, K, batch, transA, transB):
+    """MN-major operands: A stored [K, M] and / or B stored [K, N] -- the A^T B products of the backward passes."""
+    torch.manual_seed(15)
+    A = torch.randn(batch, K, M).bfloat16() if transA else torch.randn(batch, M, K).bfloat16()
+    Bm = torch.randn(batch, K, N).bfloat16() if transB else torch.randn(batch, N, K).bfloat16()
+    opA = A.float().transpose(1, 2) if transA else A.float()
+    opB = Bm.float() if transB else Bm.float().transpose(1, 2)
+    ref = 0.25 * (opA @ opB)
+    out = torch.zeros(batch, M, N, device=DEV)
+    ops.gemm_bf16_tc(A.to(DEV), Bm.to(DEV), out, M=M, N=N, K=K, lda=A.shape[2], ldb=Bm.shape[2], ldc=N, alpha=0.25, batch=batch,
+                     strideA=A[0].numel(), strideB=Bm[0].numel(), strideC=M * N, transA=transA, transB=transB)
+    assert relmax(out.cpu(), ref) < 1e-5
+
+
+def test_softmax_bwd_rows_bf16(ops):
+    torch.manual_seed(16)
+    rows, cols = 37, 1024
+    P = torch.softmax(torch.randn(rows, cols) * 2, -1).bfloat16()
+    dP = torch.randn(rows, cols)
+    ref = P.float() * (dP - (dP * P.float()).sum(-1, keepdim=True))
+    dS = torch.empty(rows, cols, dtype=torch.bfloat16, device=DEV)
+    from diffsci_b200._lib import lib, check, ptr, stream
+    Pd, dPd = P.to(DEV), dP.to(DEV)
+    check(lib.dsk_softmax_bwd_rows_bf16(ptr(Pd), ptr(dPd), ptr(dS), rows, cols, stream()))
+    assert relmax(dS.float().cpu(), ref) < 6e-3
+
+
 def test_attention_tcgen05(ops):
     from oracle import nets_oracle as N
     torch.manual_seed(14)
