@@ -229,4 +229,132 @@ int conv_small_dispatch(const dsk_conv_desc* d, const void* in, const void* w, c
   return rc == DSK_OK ? 1 : rc;
 }
 
+// ---- weight gradient of the few-channel convolutions --------------------------------------------------------------
+//   dW[co][ci][tap] = sum_pix dY[pix][co] * X[pix + tap][ci]
+// One side is WIDE (32 / 64 / 128 channels), the other NARROW (<= 4): FEW_IN: narrow = Cin (convin), wide = Cout;
+// otherwise narrow = Cout (convout), wide = Cin.  Thread = (wide channel, group of taps); a block walks a contiguous
+// pixel range keeping its [taps-in-group][narrow] partial sums in registers: the wide tensor is read exactly once
+// (convin: dY once per pixel; convout: X once per tap, the 27 shifted re-reads hit L1), the narrow one is broadcast.
+// Block partials go to ws[block][tap*Cin + ci][co] and are summed in a fixed order by wgrad_reduce_kernel.
+constexpr int WF_NARROW = 4, WF_THREADS = 256;
+template <typename TX, typename TG, bool FEW_IN, int TPG>
+__global__ void __launch_bounds__(WF_THREADS) wgrad_few_kernel(const TX* __restrict__ x, const TG* __restrict__ dy, float* __restrict__ ws,
+                                                                int B, int D, int H, int W, int Cin, int Cout, int ndim,
+                                                                int64_t pix_per_block) {
+  const int taps = ndim == 3 ? 27 : 9;
+  const int Cw = FEW_IN ? Cout : Cin, Cn = FEW_IN ? Cin : Cout;
+  const int wch = threadIdx.x % Cw, grp = threadIdx.x / Cw;
+  const int t_lo = grp * TPG, t_hi = min(taps, t_lo + TPG);
+  float acc[TPG][WF_NARROW];
+#pragma unroll
+  for (int t = 0; t < TPG; ++t)
+#pragma unroll
+    for (int n = 0; n < WF_NARROW; ++n) acc[t][n] = 0.0f;
+  const int64_t total = (int64_t)B * D * H * W;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block, p1 = min(total, p0 + pix_per_block);
+  for (int64_t pix = p0; pix < p1; ++pix) {
+    int64_t r = pix;
+    const int w0 = (int)(r % W); r /= W;
+    const int h0 = (int)(r % H); r /= H;
+    const int d0 = (int)(r % D);
+    float gw = 0.0f, gn[WF_NARROW];
+    if (FEW_IN) {
+      gw = to_f32<TG>(dy[pix * Cout + wch]);
+    } else {
+#pragma unroll
+      for (int n = 0; n < WF_NARROW; ++n) gn[n] = n < Cn ? to_f32<TG>(dy[pix * Cout + n]) : 0.0f;
+    }
+#pragma unroll
+    for (int t = 0; t < TPG; ++t) {
+      const int tap = t_lo + t;
+      if (tap < t_hi) {
+        const int kw = tap % 3, kh = (tap / 3) % 3, kd = tap / 9;
+        const int zd = ndim == 3 ? d0 + kd - 1 : 0, zh = h0 + kh - 1, zw = w0 + kw - 1;
+        if ((unsigned)zd < (unsigned)D && (unsigned)zh < (unsigned)H && (unsigned)zw < (unsigned)W) {
+          const int64_t q = pix + ((int64_t)(zd - d0) * H + (zh - h0)) * W + (zw - w0);
+          if (FEW_IN) {
+#pragma unroll
+            for (int n = 0; n < WF_NARROW; ++n)
+              if (n < Cn) acc[t][n] = fmaf(gw, to_f32<TX>(x[q * Cin + n]), acc[t][n]);
+          } else {
+            const float xv = to_f32<TX>(x[q * Cin + wch]);
+#pragma unroll
+            for (int n = 0; n < WF_NARROW; ++n) acc[t][n] = fmaf(gn[n], xv, acc[t][n]);
+          }
+        }
+      }
+    }
+  }
+  float* o = ws + (int64_t)blockIdx.x * taps * Cin * Cout;
+#pragma unroll
+  for (int t = 0; t < TPG; ++t) {
+    const int tap = t_lo + t;
+    if (tap < t_hi) {
+#pragma unroll
+      for (int n = 0; n < WF_NARROW; ++n)
+        if (n < Cn) {
+          const int ci = FEW_IN ? n : wch, co = FEW_IN ? wch : n;
+          o[((int64_t)tap * Cin + ci) * Cout + co] = acc[t][n];
+        }
+    }
+  }
+}
+
+int wgrad_reduce_launch(const float* ws, float* dw, int Cout, int Cin, int taps, int nsplit, int accumulate, cudaStream_t st);
+
+static bool wgrad_few_shape(const dsk_conv_desc* d, bool* few_in, int* tpg) {
+  if (d->ksize != 3 || d->up2) return false;
+  const int taps = d->ndim == 3 ? 27 : 9;
+  const bool fi = d->Cin <= WF_NARROW, fo = d->Cout <= WF_NARROW;
+  if (fi == fo) return false;                                   // both narrow (tiny) or neither
+  const int Cw = fi ? d->Cout : d->Cin;
+  if (Cw != 32 && Cw != 64 && Cw != 128) return false;
+  const int groups = WF_THREADS / Cw;
+  const int need = (taps + groups - 1) / groups;
+  *few_in = fi;
+  *tpg = need <= 7 ? 7 : 14;
+  return need <= 14;
+}
+
+static int wgrad_few_blocks(const dsk_conv_desc* d) {
+  const int64_t total = (int64_t)d->B * d->D * d->H * d->W;
+  int64_t blocks = (total + 63) / 64;                           // >= 64 pixels per block
+  if (blocks > 4 * DSK_NUM_SMS) blocks = 4 * DSK_NUM_SMS;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+int64_t wgrad_few_ws_bytes(const dsk_conv_desc* d) {
+  bool fi; int tpg;
+  if (!wgrad_few_shape(d, &fi, &tpg)) return 0;
+  return (int64_t)wgrad_few_blocks(d) * (d->ndim == 3 ? 27 : 9) * d->Cin * d->Cout * (int64_t)sizeof(float);
+}
+
+// returns 1 if handled, 0 if the shape is not a few-channel conv, negative on error
+int wgrad_few_dispatch(const dsk_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, int accumulate, cudaStream_t st) {
+  bool fi; int tpg;
+  if (!wgrad_few_shape(d, &fi, &tpg)) return 0;
+  const int blocks = wgrad_few_blocks(d);
+  const int64_t total = (int64_t)d->B * d->D * d->H * d->W;
+  const int64_t ppb = (total + blocks - 1) / blocks;
+  const int used = (int)((total + ppb - 1) / ppb);
+#define WF_GO(TX, TG)                                                                                                              \
+  do {                                                                                                                             \
+    if (fi && tpg == 7) DSK_LAUNCH((wgrad_few_kernel<TX, TG, true, 7>), used, WF_THREADS, 0, st, (const TX*)x, (const TG*)dy, (float*)ws, \
+                                   d->B, d->D, d->H, d->W, d->Cin, d->Cout, d->ndim, ppb);                                          \
+    else if (fi) DSK_LAUNCH((wgrad_few_kernel<TX, TG, true, 14>), used, WF_THREADS, 0, st, (const TX*)x, (const TG*)dy, (float*)ws,   \
+                            d->B, d->D, d->H, d->W, d->Cin, d->Cout, d->ndim, ppb);                                                 \
+    else if (tpg == 7) DSK_LAUNCH((wgrad_few_kernel<TX, TG, false, 7>), used, WF_THREADS, 0, st, (const TX*)x, (const TG*)dy,          \
+                                  (float*)ws, d->B, d->D, d->H, d->W, d->Cin, d->Cout, d->ndim, ppb);                               \
+    else DSK_LAUNCH((wgrad_few_kernel<TX, TG, false, 14>), used, WF_THREADS, 0, st, (const TX*)x, (const TG*)dy, (float*)ws, d->B,    \
+                    d->D, d->H, d->W, d->Cin, d->Cout, d->ndim, ppb);                                                               \
+  } while (0)
+  if (d->in_dtype == DSK_F32 && d->out_dtype == DSK_F32) WF_GO(float, float);
+  else if (d->in_dtype == DSK_BF16 && d->out_dtype == DSK_BF16) WF_GO(__nv_bfloat16, __nv_bfloat16);
+  else if (d->in_dtype == DSK_F32 && d->out_dtype == DSK_BF16) WF_GO(float, __nv_bfloat16);
+  else WF_GO(__nv_bfloat16, float);
+#undef WF_GO
+  const int rc = wgrad_reduce_launch((const float*)ws, dw, d->Cout, d->Cin, d->ndim == 3 ? 27 : 9, used, accumulate, st);
+  return rc == DSK_OK ? 1 : rc;
+}
+
 }  // namespace dsk

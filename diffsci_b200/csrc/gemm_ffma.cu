@@ -485,6 +485,11 @@ int wgrad_reduce_launch(const float* ws, float* dw, int Cout, int Cin, int taps,
 }
 }  // namespace dsk
 extern "C" int64_t dsk_conv_wgrad_tc_ws_bytes(const dsk_conv_desc* d);
+namespace dsk {
+// conv_small.cu: weight gradient of the few-channel first / last convolutions
+int64_t wgrad_few_ws_bytes(const dsk_conv_desc* d);
+int wgrad_few_dispatch(const dsk_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, int accumulate, cudaStream_t st);
+}
 
 // ---- weight gradient (CUDA-core path) ---------------------------------------------------------------------------
 static int wgrad_splits(int M, int N, int K) {
@@ -505,7 +510,9 @@ extern "C" int64_t dsk_conv_wgrad_ws_bytes(const dsk_conv_desc* d) {
   const int M = taps * d->Cin, N = d->Cout;
   const int64_t ffma = (int64_t)wgrad_splits(M, N, (int)K) * M * N * (int64_t)sizeof(float);
   const int64_t tc = dsk_conv_wgrad_tc_ws_bytes(d);
-  return ffma > tc ? ffma : tc;
+  const int64_t few = wgrad_few_ws_bytes(d);
+  const int64_t m = ffma > tc ? ffma : tc;
+  return m > few ? m : few;
 }
 
 template <typename TI, typename TG>
@@ -544,6 +551,10 @@ extern "C" int dsk_conv_wgrad(const dsk_conv_desc* d, const void* x, const void*
     if (rc != DSK_ERR_UNSUPPORTED) return rc;
   }
   cudaStream_t st = as_stream(stream);
+  {
+    const int rc = wgrad_few_dispatch(d, x, dy, dw, ws, accumulate, st);
+    if (rc != 0) return rc < 0 ? rc : DSK_OK;
+  }
   if (d->in_dtype == DSK_F32 && d->out_dtype == DSK_F32) return launch_wgrad<float, float>(d, x, dy, dw, ws, accumulate, st);
   if (d->in_dtype == DSK_BF16 && d->out_dtype == DSK_BF16) return launch_wgrad<__nv_bfloat16, __nv_bfloat16>(d, x, dy, dw, ws, accumulate, st);
   if (d->in_dtype == DSK_F32 && d->out_dtype == DSK_BF16) return launch_wgrad<float, __nv_bfloat16>(d, x, dy, dw, ws, accumulate, st);

@@ -132,7 +132,11 @@ class TrainGraph:
         """y = conv_same([up2](x)) + bias + chan_bias[b, :] + residual  (forward: dsk_conv_fwd; backward: dsk_conv_wgrad,
         dsk_channel_sum, dsk_conv_fwd with dgrad-packed weights [+ dsk_upsample2x_bwd])."""
         from .punetg import _tc_eligible
+        import diffsci_b200
         nd = self.ndim
+        if (cp.ksize == 1 and self.precision == "bf16" and diffsci_b200.TC_CONV_ENABLED and cp.cin % 8 == 0 and cp.cout % 8 == 0
+                and chan_bias is None and not (up2 and residual is not None)):
+            return self._conv1x1_tc(x, cp, residual, up2)
         tc = self.precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize, few_out_ok)
         wdt = torch.bfloat16 if tc else torch.float32
         pc = ops.PackedConv(cp.weight, cp.bias, nd, wdt, subpixel=bool(up2 and tc))
@@ -188,6 +192,72 @@ class TrainGraph:
                     dres, dx = self.contribute_compute(x)
                     out.append(lambda: ops.conv(dy, pd, out=du()))
                     out.append(lambda: ops.upsample2x_bwd(du(), dx, nd, dres=dres))
+            return out
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
+    def _conv1x1_tc(self, x: Var, cp, residual: Optional[Var], up2: bool) -> Var:
+        """1x1 convolution (ADM's residual projection, adm.py:433-441) as plain tensor-core GEMMs over the pixel rows:
+        y = x W^T + b (+ residual);  dX = dY W;  dW = dY^T X with the pixel range split into slices that are summed in a
+        fixed order.  A 1x1 conv commutes with nearest upsampling, so `up2` runs at the input resolution."""
+        nd = self.ndim
+        B, D, H, W, Cin = x.t.shape
+        Cout = cp.cout
+        pix = B * D * H * W
+        oD, oH, oW = (D * 2 if (up2 and nd == 3) else D), (H * 2 if up2 else H), (W * 2 if up2 else W)
+        bf, f32 = torch.bfloat16, torch.float32
+        y = Var(self.empty((B, oD, oH, oW, Cout)))
+        wl = ops.PackedLinear(cp.weight)
+        self._packs.append(wl)
+        bias = cp.bias.detach() if cp.bias is not None else None
+        xt = x.t.view(pix, Cin)
+        G = ops.gemm_bf16_tc
+        if up2:
+            low = self.lazy_scratch("c1_low", (B, D, H, W, Cout), bf)
+            yt = y.t
+            self.fwd.append(lambda: G(xt, wl.packed(), low().view(pix, Cout), M=pix, N=Cout, K=Cin, lda=Cin, ldb=Cin, ldc=Cout,
+                                      bias=bias))
+            self.fwd.append(lambda: ops.upsample2x(low(), nd, out=yt))
+        else:
+            yt = y.t.view(pix, Cout)
+            rs = residual.t.view(pix, Cout) if residual is not None else None
+            self.fwd.append(lambda: G(xt, wl.packed(), yt, M=pix, N=Cout, K=Cin, lda=Cin, ldb=Cin, ldc=Cout, bias=bias,
+                                      residual=rs))
+        # pixel slices of the weight-gradient GEMM: enough CTAs to fill the machine, >= 512 rows each
+        tiles = ((Cout + 127) // 128) * ((Cin + 63) // 64)
+        nsl = 1
+        while tiles * nsl < 148 and pix % (nsl * 2) == 0 and (pix // (nsl * 2)) % 8 == 0 and pix // (nsl * 2) >= 512:
+            nsl *= 2
+        rows = pix // nsl
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return []
+            out = []
+            if up2:
+                dl = self.lazy_scratch("c1_dlow", (B, D, H, W, Cout), bf)
+                out.append(lambda: ops.upsample2x_bwd(dy, dl(), nd))
+                dyl = lambda: dl().view(pix, Cout)  # noqa: E731
+            else:
+                dyl = lambda: dy.view(pix, Cout)  # noqa: E731
+            if cp.bias is not None:
+                gb = self.grad_view(cp.bias)
+                csws = self.lazy_scratch("bwd_ws", ops.bwd_ws_bytes(B, D * H * W, Cout))
+                out.append(lambda: ops.channel_sum(dyl().view(B, D * H * W, Cout), gb, csws(), False))
+            gw = self.grad_view(cp.weight)
+            wsp = self.lazy_scratch("c1_wsplit", (nsl, Cout * Cin), f32)
+            out.append(lambda: G(dyl(), xt, wsp(), M=Cout, N=Cin, K=rows, lda=Cout, ldb=Cin, ldc=Cin, batch=nsl,
+                                 strideA=rows * Cout, strideB=rows * Cin, strideC=Cout * Cin, transA=True, transB=True))
+            out.append(lambda: ops.colsum(wsp(), gw.view(-1)))
+            if residual is not None and residual.needs_grad:
+                out.extend(self.contribute_copy(residual, dy))
+            if x.needs_grad:
+                dres, dx = self.contribute_compute(x)
+                dxt = dx.view(pix, Cin)
+                out.append(lambda: G(dyl(), wl.packed(), dxt, M=pix, N=Cin, K=Cout, lda=Cout, ldb=Cin, ldc=Cin, transB=True,
+                                     residual=dres.view(pix, Cin) if dres is not None else None))
             return out
 
         self._bwd_builders.append(build_bwd)

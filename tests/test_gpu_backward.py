@@ -73,6 +73,12 @@ CONV_CASES = [
     (2, 5, 128, 64, (7, 7), 3, False),      # tiles mostly out of bounds (MNIST bottom level)
     (3, 2, 64, 128, (6, 10, 12), 3, False),
     (3, 1, 128, 128, (16, 16, 16), 3, False),
+    (2, 2, 1, 64, (14, 14), 3, False),      # few-channel weight-gradient kernel (wide side 32 / 64 / 128)
+    (3, 1, 1, 64, (6, 8, 10), 3, False),
+    (2, 2, 64, 1, (7, 9), 3, False),
+    (3, 2, 128, 3, (4, 6, 8), 3, False),
+    (2, 2, 3, 128, (9, 11), 3, False),
+    (3, 1, 32, 2, (5, 6, 7), 3, False),
 ]
 
 
