@@ -66,6 +66,8 @@ SIGNATURES = {
     "dsk_fourier": [p, p, p, i32, i32, p],
     "dsk_grouped_linear": [p, p, p, p, p, p, p, i32, i32, i32, i32, p],
     "dsk_grouped_linear_bwd": [p, p, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, p],
+    "dsk_grouped_gemm_f32": [p, i32, i32, i32, i32, i32, i32, p],
+    "dsk_grouped_dz_bias": [p, p, p, p, p, i32, i32, i32, i32, p],
     "dsk_softmax_rows": [p, i64, i32, p],
     "dsk_edm_loss_fwd_bwd": [p, p, p, p, p, p, p, i32, i32, i64, f32, i32, p],
     "dsk_ema_update": [p, p, p, i32, i64, f32, p],

@@ -250,28 +250,38 @@ __global__ void __launch_bounds__(WF_THREADS) wgrad_few_kernel(const TX* __restr
   for (int t = 0; t < TPG; ++t)
 #pragma unroll
     for (int n = 0; n < WF_NARROW; ++n) acc[t][n] = 0.0f;
-  const int64_t total = (int64_t)B * D * H * W;
-  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block, p1 = min(total, p0 + pix_per_block);
-  for (int64_t pix = p0; pix < p1; ++pix) {
-    int64_t r = pix;
-    const int w0 = (int)(r % W); r /= W;
-    const int h0 = (int)(r % H); r /= H;
-    const int d0 = (int)(r % D);
-    float gw = 0.0f, gn[WF_NARROW];
-    if (FEW_IN) {
-      gw = to_f32<TG>(dy[pix * Cout + wch]);
-    } else {
-#pragma unroll
-      for (int n = 0; n < WF_NARROW; ++n) gn[n] = n < Cn ? to_f32<TG>(dy[pix * Cout + n]) : 0.0f;
-    }
+  // the block owns a contiguous range of (b, d, h) rows; tap validity in d and h and the tap's pixel offset are per row,
+  // only the w bound is checked per pixel
+  const int64_t rows = (int64_t)B * D * H;
+  const int64_t r0 = (int64_t)blockIdx.x * pix_per_block, r1 = min(rows, r0 + pix_per_block);
+  for (int64_t row = r0; row < r1; ++row) {
+    const int h0 = (int)(row % H), d0 = (int)((row / H) % D);
+    const int64_t base = row * W;
+    bool ok[TPG];
+    int off[TPG], kwm[TPG];
 #pragma unroll
     for (int t = 0; t < TPG; ++t) {
       const int tap = t_lo + t;
-      if (tap < t_hi) {
-        const int kw = tap % 3, kh = (tap / 3) % 3, kd = tap / 9;
-        const int zd = ndim == 3 ? d0 + kd - 1 : 0, zh = h0 + kh - 1, zw = w0 + kw - 1;
-        if ((unsigned)zd < (unsigned)D && (unsigned)zh < (unsigned)H && (unsigned)zw < (unsigned)W) {
-          const int64_t q = pix + ((int64_t)(zd - d0) * H + (zh - h0)) * W + (zw - w0);
+      const int kw = tap % 3, kh = (tap / 3) % 3, kd = tap / 9;
+      const int zd = ndim == 3 ? d0 + kd - 1 : 0, zh = h0 + kh - 1;
+      ok[t] = tap < t_hi && (unsigned)zd < (unsigned)D && (unsigned)zh < (unsigned)H;
+      off[t] = ((zd - d0) * H + (zh - h0)) * W + kw - 1;
+      kwm[t] = kw - 1;
+    }
+#pragma unroll 4
+    for (int w0 = 0; w0 < W; ++w0) {
+      const int64_t pix = base + w0;
+      float gw = 0.0f, gn[WF_NARROW];
+      if (FEW_IN) {
+        gw = to_f32<TG>(dy[pix * Cout + wch]);
+      } else {
+#pragma unroll
+        for (int n = 0; n < WF_NARROW; ++n) gn[n] = n < Cn ? to_f32<TG>(dy[pix * Cout + n]) : 0.0f;
+      }
+#pragma unroll
+      for (int t = 0; t < TPG; ++t) {
+        if (ok[t] && (unsigned)(w0 + kwm[t]) < (unsigned)W) {
+          const int64_t q = pix + off[t];
           if (FEW_IN) {
 #pragma unroll
             for (int n = 0; n < WF_NARROW; ++n)
@@ -317,9 +327,9 @@ static bool wgrad_few_shape(const dsk_conv_desc* d, bool* few_in, int* tpg) {
 }
 
 static int wgrad_few_blocks(const dsk_conv_desc* d) {
-  const int64_t total = (int64_t)d->B * d->D * d->H * d->W;
-  int64_t blocks = (total + 63) / 64;                           // >= 64 pixels per block
-  if (blocks > 4 * DSK_NUM_SMS) blocks = 4 * DSK_NUM_SMS;
+  const int64_t rows = (int64_t)d->B * d->D * d->H;             // the unit of work is one (b, d, h) row of W pixels
+  int64_t blocks = rows;
+  if (blocks > 16 * DSK_NUM_SMS) blocks = 16 * DSK_NUM_SMS;
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
@@ -334,7 +344,7 @@ int wgrad_few_dispatch(const dsk_conv_desc* d, const void* x, const void* dy, fl
   bool fi; int tpg;
   if (!wgrad_few_shape(d, &fi, &tpg)) return 0;
   const int blocks = wgrad_few_blocks(d);
-  const int64_t total = (int64_t)d->B * d->D * d->H * d->W;
+  const int64_t total = (int64_t)d->B * d->D * d->H;           // rows
   const int64_t ppb = (total + blocks - 1) / blocks;
   const int used = (int)((total + ppb - 1) / ppb);
 #define WF_GO(TX, TG)                                                                                                              \

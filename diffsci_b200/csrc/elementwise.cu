@@ -216,6 +216,39 @@ __global__ void __launch_bounds__(128) grouped_linear_dgrad_kernel(const float* 
   }
 }
 
+// (c) dZ_g = dY_g * act'(Z_g) and db_g = colsum(dZ_g) for every group: block = 32 columns x 8 row lanes.
+__global__ void __launch_bounds__(256) grouped_dz_bias_kernel(const float* const* __restrict__ dY, const float* const* __restrict__ Z,
+                                                               float* const* __restrict__ dZ, float* const* __restrict__ db,
+                                                               const int* __restrict__ out_dim, int B, int act) {
+  const int g = blockIdx.y;
+  const int N = out_dim[g];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  if (blockIdx.x * 32 >= N) return;
+  const float* dy = dY[g];
+  const float* z = (act != 0 && Z != nullptr) ? Z[g] : nullptr;
+  float* dz = dZ[g];
+  double acc = 0;
+  if (n < N)
+    for (int b = rl; b < B; b += 8) {
+      float d = dy[(int64_t)b * N + n];
+      if (z != nullptr) {
+        const float zz = z[(int64_t)b * N + n];
+        if (act == 1) { const float sg = 1.0f / (1.0f + expf(-zz)); d *= sg * (1.0f + zz * (1.0f - sg)); }
+        else d = zz > 0.0f ? d : 0.0f;
+        dz[(int64_t)b * N + n] = d;
+      }
+      acc += (double)d;
+    }
+  __shared__ double red[8][33];
+  red[rl][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rl == 0 && n < N && db != nullptr && db[g] != nullptr) {
+    double s = 0;
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x & 31];
+    db[g][n] = (float)s;
+  }
+}
+
 // ---- row softmax (in place, fp32) ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ S, int64_t rows, int cols) {
   __shared__ float red[8];
@@ -393,5 +426,14 @@ extern "C" int dsk_softmax_rows(float* S, int64_t rows, int cols, void* stream) 
   DSK_REQUIRE(S && rows > 0 && cols > 0, "dsk_softmax_rows: bad arguments");
   int64_t grid = rows < (int64_t)DSK_NUM_SMS * 16 ? rows : (int64_t)DSK_NUM_SMS * 16;
   DSK_LAUNCH(softmax_rows_kernel, (int)grid, 256, 0, as_stream(stream), S, rows, cols);
+  return DSK_OK;
+}
+
+extern "C" int dsk_grouped_dz_bias(const float* const* dY, const float* const* Z, float* const* dZ, float* const* db, const int* out_dim,
+                                   int ngroups, int max_out, int B, int act, void* stream) {
+  DSK_REQUIRE(dY && dZ && out_dim && ngroups > 0 && ngroups <= 65535 && max_out > 0 && B > 0 && act >= 0 && act <= 2 && (act == 0 || Z),
+              "dsk_grouped_dz_bias: bad arguments");
+  dim3 grid((max_out + 31) / 32, ngroups);
+  DSK_LAUNCH(grouped_dz_bias_kernel, grid, 256, 0, as_stream(stream), dY, Z, dZ, db, out_dim, B, act);
   return DSK_OK;
 }

@@ -22,6 +22,7 @@ struct ConvProb {
   static constexpr bool kTransB = false;
   __device__ __forceinline__ int k_begin() const { return 0; }
   __device__ __forceinline__ int k_end() const { return K; }
+  __device__ __forceinline__ bool tile_is_empty(int, int) const { return false; }
   const TI* in;
   const float* w;         // [taps*Cin][Cout]
   const float* bias;      // [Cout] or null
@@ -145,6 +146,7 @@ struct GemmProb {
   float beta;   // C = act(alpha * op(A) op(B) + bias) + beta * C
   __device__ __forceinline__ int k_begin() const { return 0; }
   __device__ __forceinline__ int k_end() const { return K; }
+  __device__ __forceinline__ bool tile_is_empty(int m0, int n0) const { return m0 >= M || n0 >= N; }
   // TRANSA: A is stored [K][M] (lda >= M); 8 consecutive m of row k
   __device__ __forceinline__ void load_a_t(int k, int m, float* o) const {
     const float* p = A + (int64_t)k * lda + m;
@@ -208,6 +210,41 @@ struct GemmProb {
   }
 };
 
+// Grouped GEMM: blockIdx.z selects one of many small independent problems described by a device table (the per-block
+// time MLPs: one launch per layer for every ResNet block).  `Z` (optional) receives the pre-activation.
+struct GroupedGemmDesc {
+  const float* A;
+  const float* Bm;
+  float* C;
+  const float* bias;
+  float* Z;
+  int M, N, K, lda, ldb, ldc;
+};
+template <bool TRANSA, bool TRANSB>
+struct GroupedGemmProb : GemmProb<TRANSA, TRANSB> {
+  using Base = GemmProb<TRANSA, TRANSB>;
+  const GroupedGemmDesc* table;
+  float* Z;
+  __device__ __forceinline__ void select_batch(int z) {
+    const GroupedGemmDesc d = table[z];
+    this->A = d.A; this->Bm = d.Bm; this->C = d.C; this->bias = d.bias; Z = d.Z;
+    this->M = d.M; this->N = d.N; this->K = d.K; this->lda = d.lda; this->ldb = d.ldb; this->ldc = d.ldc;
+  }
+  __device__ __forceinline__ void store(int m, int n, const float* acc) const {
+    if (m >= this->M) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n + j >= this->N) break;
+      float v = this->alpha * acc[j];
+      if (this->bias != nullptr) v += this->bias[n + j];
+      if (Z != nullptr) Z[(int64_t)m * this->ldc + n + j] = v;
+      if (this->act == 1) v = silu_f(v);
+      else if (this->act == 2) v = fmaxf(v, 0.0f);
+      this->C[(int64_t)m * this->ldc + n + j] = v;
+    }
+  }
+};
+
 // For transB GEMMs (B stored [N][K]) the B tile is loaded k-contiguous (4 consecutive k of one n)
 // so that global reads stay coalesced; the transposing smem store is bank-conflict free.
 // kTransA problems (A stored [K][M]: weight-gradient and A^T B products) load 8 consecutive m of one k.
@@ -219,6 +256,7 @@ __global__ void __launch_bounds__(GT) ffma_gemm_kernel(Prob p) {
   p.select_batch(blockIdx.z);
   const int tid = threadIdx.x;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (p.tile_is_empty(m0, n0)) return;     // grouped launches size the grid for the largest problem (block-uniform exit)
   // A loader: thread -> (row, 8 consecutive k); kTransA: thread -> (k, 8 consecutive rows)
   const int a_row = Prob::kTransA ? (tid & 15) * 8 : tid & (BM - 1);
   const int a_k = Prob::kTransA ? tid >> 4 : (tid >> 7) * 8;
@@ -303,6 +341,7 @@ struct WgradProb {
   __device__ __forceinline__ RowCtx row_ctx(int) const { return RowCtx{0}; }
   __device__ __forceinline__ int k_begin() const { return kb; }
   __device__ __forceinline__ int k_end() const { return ke; }
+  __device__ __forceinline__ bool tile_is_empty(int, int) const { return false; }
   __device__ __forceinline__ void select_batch(int z) {
     kb = z * kper;
     ke = min(K, kb + kper);
@@ -589,4 +628,25 @@ extern "C" int dsk_gemm_f32(const float* A, const float* Bm, float* Cm, const fl
                             float alpha, int act, void* stream) {
   return dsk_gemm_f32_ex(A, Bm, Cm, bias, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch, 0, transB, alpha, 0.0f, act,
                          stream);
+}
+
+// Grouped fp32 GEMM over a device table of problems (see GroupedGemmDesc): C_g = act(op(A_g) op(B_g) + bias_g), Z_g = pre-activation.
+extern "C" int dsk_grouped_gemm_f32(const void* table, int ngroups, int max_m, int max_n, int transA, int transB, int act, void* stream) {
+  DSK_REQUIRE(table && ngroups > 0 && ngroups <= 65535 && max_m > 0 && max_n > 0 && act >= 0 && act <= 2, "dsk_grouped_gemm_f32: bad arguments");
+  dim3 grid((max_m + BM - 1) / BM, (max_n + BN - 1) / BN, ngroups);
+  DSK_REQUIRE(grid.y <= 65535, "dsk_grouped_gemm_f32: N too large");
+#define GO(TA, TB)                                                                                       \
+  {                                                                                                      \
+    GroupedGemmProb<TA, TB> p;                                                                           \
+    p.A = nullptr; p.Bm = nullptr; p.C = nullptr; p.bias = nullptr; p.M = p.N = p.K = 0;                 \
+    p.lda = p.ldb = p.ldc = 0; p.sA = p.sB = p.sC = 0; p.alpha = 1.0f; p.act = act; p.beta = 0.0f;        \
+    p.table = (const GroupedGemmDesc*)table; p.Z = nullptr;                                              \
+    DSK_LAUNCH((ffma_gemm_kernel<GroupedGemmProb<TA, TB>>), grid, GT, 0, as_stream(stream), p);          \
+  }
+  if (transA && transB) GO(true, true)
+  else if (transA) GO(true, false)
+  else if (transB) GO(false, true)
+  else GO(false, false)
+#undef GO
+  return DSK_OK;
 }

@@ -230,13 +230,23 @@ def _ptr_table(ts, dev) -> torch.Tensor:
     return torch.tensor([0 if t is None else t.data_ptr() for t in ts], dtype=torch.int64, device=dev)
 
 
+def _gemm_table(descs, dev) -> torch.Tensor:
+    """Device table of GroupedGemmDesc {A, B, C, bias, Z, M, N, K, lda, ldb, ldc} (csrc/gemm_ffma.cu)."""
+    import struct
+    raw = b"".join(struct.pack("5Q6i", *(0 if t is None else t.data_ptr() for t in d[:5]), *d[5:]) for d in descs)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+
+
 class GroupedLinear:
-    """Pointer tables for one dsk_grouped_linear launch (built once; graph-capturable).  `zs` (optional): buffers that
-    receive the pre-activations (training)."""
+    """One launch for many small fp32 linears y_g = act(x_g W_g^T + b_g) (built once; graph-capturable).  `zs` (optional):
+    buffers that receive the pre-activations (training).  Small batches run one warp per output feature
+    (dsk_grouped_linear); from GEMM_MIN_B rows on, a grouped smem-tiled GEMM (dsk_grouped_gemm_f32)."""
+    GEMM_MIN_B = 32
 
     def __init__(self, xs, ws, bs, ys, act: int, zs=None):
         dev = ws[0].device
         self.keep = (xs, ws, bs, ys, zs)
+        self.xs, self.ws = xs, ws
         self.B = int(xs[0].shape[0])
         self.X, self.W, self.Bi, self.Y = (_ptr_table(t, dev) for t in (xs, ws, bs, ys))
         self.Z = _ptr_table(zs, dev) if zs is not None else None
@@ -247,23 +257,59 @@ class GroupedLinear:
         self.n = len(ws)
         self.act = act
         self.sig = tuple(int(w.data_ptr()) for w in ws)
+        self.gemm = self.B >= self.GEMM_MIN_B
+        if self.gemm:
+            B = self.B
+            self.fwd_table = _gemm_table([(x, w, y, b, None if zs is None else zs[i], B, w.shape[0], w.shape[1], w.shape[1],
+                                           w.shape[1], w.shape[0]) for i, (x, w, b, y) in enumerate(zip(xs, ws, bs, ys))], dev)
 
     def run(self):
+        if self.gemm:
+            check(lib.dsk_grouped_gemm_f32(ptr(self.fwd_table), self.n, self.B, self.max_out, 0, 1, self.act, stream()))
+            return
         check(lib.dsk_grouped_linear(ptr(self.X), ptr(self.W), ptr(self.Bi), ptr(self.Y), ptr(self.Z), ptr(self.in_dim),
                                      ptr(self.out_dim), self.n, self.max_out, self.B, self.act, stream()))
 
     def backward_tables(self, dys, dzs, dws, dbs, dxs, shared_dx: bool = False, accumulate_dx: bool = False):
-        """Bind the gradient buffers of this layer (dsk_grouped_linear_bwd); returns the launch closure."""
+        """Bind the gradient buffers of this layer; returns the launch closure (dsk_grouped_linear_bwd, or for large
+        batches dsk_grouped_dz_bias + two dsk_grouped_gemm_f32 [+ a fixed-order sum over the groups for a shared input])."""
         dev = self.W.device
-        keep = (dys, dzs, dws, dbs, dxs)
+        keep = [dys, dzs, dws, dbs, dxs]
         dY, dZ, dW, dB = (_ptr_table(t, dev) for t in (dys, dzs, dws, dbs))
         dX = _ptr_table(dxs, dev) if dxs is not None else None
+        B = self.B
+        if not self.gemm:
+            def run():
+                _ = keep
+                check(lib.dsk_grouped_linear_bwd(ptr(dY), ptr(self.Z), ptr(self.X), ptr(self.W), ptr(dZ), ptr(dW), ptr(dB), ptr(dX),
+                                                 ptr(self.in_dim), ptr(self.out_dim), self.n, self.max_out, self.max_in, B,
+                                                 self.act, int(shared_dx), int(accumulate_dx), stream()))
+            return run
+        assert not accumulate_dx
+        # dW_g [N, K] = dZ_g^T X_g : A = dZ_g stored [B][N] (transA), B = X_g stored [B][K]
+        wtab = _gemm_table([(dz, x, dw, None, None, w.shape[0], w.shape[1], B, w.shape[0], w.shape[1], w.shape[1])
+                            for dz, x, dw, w in zip(dzs, self.xs, dws, self.ws)], dev)
+        xtab = part = None
+        if dxs is not None:
+            K = self.max_in
+            if shared_dx:                       # per-group partials dZ_g W_g, then a fixed-order sum over the groups
+                part = torch.empty((self.n, B * K), dtype=torch.float32, device=dev)
+                outs = [part[i] for i in range(self.n)]
+            else:
+                outs = dxs
+            xtab = _gemm_table([(dz, w, o, None, None, B, w.shape[1], w.shape[0], w.shape[0], w.shape[1], w.shape[1])
+                                for dz, w, o in zip(dzs, self.ws, outs)], dev)
+        keep += [wtab, xtab, part]
 
         def run():
             _ = keep
-            check(lib.dsk_grouped_linear_bwd(ptr(dY), ptr(self.Z), ptr(self.X), ptr(self.W), ptr(dZ), ptr(dW), ptr(dB), ptr(dX),
-                                             ptr(self.in_dim), ptr(self.out_dim), self.n, self.max_out, self.max_in, self.B,
-                                             self.act, int(shared_dx), int(accumulate_dx), stream()))
+            check(lib.dsk_grouped_dz_bias(ptr(dY), ptr(self.Z), ptr(dZ), ptr(dB), ptr(self.out_dim), self.n, self.max_out, B, self.act,
+                                          stream()))
+            check(lib.dsk_grouped_gemm_f32(ptr(wtab), self.n, self.max_out, self.max_in, 1, 0, 0, stream()))
+            if xtab is not None:
+                check(lib.dsk_grouped_gemm_f32(ptr(xtab), self.n, B, self.max_in, 0, 0, 0, stream()))
+                if part is not None:
+                    colsum(part, dxs[0].view(-1))
         return run
 
 

@@ -217,6 +217,15 @@ int dsk_grouped_linear_bwd(const float* const* dY, const float* const* Z, const 
                            float* const* dX, const int* in_dim, const int* out_dim, int ngroups, int max_out,
                            int max_in, int B, int act, int shared_dx, int accumulate_dx, void* stream);
 
+/* The same layers at large batch (B > 32): a grouped smem-tiled fp32 GEMM over a device table of
+ *   struct { const float* A; const float* B; float* C; const float* bias; float* Z; int M, N, K, lda, ldb, ldc; }
+ * C_g = act(op(A_g) op(B_g) + bias_g), Z_g (optional) = the pre-activation; transA: A stored [K][M]; transB: B stored [N][K].
+ * Forward X W^T, weight gradient dZ^T X and input gradient dZ W are the three transpose combinations. */
+int dsk_grouped_gemm_f32(const void* table, int ngroups, int max_m, int max_n, int transA, int transB, int act, void* stream);
+/* dZ_g = dY_g * act'(Z_g) (skipped for act == 0) and db_g = colsum(dZ_g) for every group in one launch. */
+int dsk_grouped_dz_bias(const float* const* dY, const float* const* Z, float* const* dZ, float* const* db, const int* out_dim,
+                        int ngroups, int max_out, int B, int act, void* stream);
+
 /* ---- K3: attention ----------------------------------------------------------------------
  * softmax over the last dim of S[batch*rows, cols] in place (fp32), the middle of
  * nn.MultiheadAttention (nets/attention.py:42-44,68): softmax(QK^T/sqrt(d)). */

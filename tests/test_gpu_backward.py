@@ -443,7 +443,8 @@ def test_trainer_equals_autograd_seam(golden):
 
 
 # ------------------------------------------------------------------------------------------------ grouped time-MLP layer
-@pytest.mark.parametrize("act,shared,B", [(1, False, 5), (0, False, 37), (0, True, 6), (1, True, 3)])
+@pytest.mark.parametrize("act,shared,B", [(1, False, 5), (0, False, 37), (0, True, 6), (1, True, 3), (1, False, 70), (0, True, 33),
+                                          (1, True, 64)])
 def test_grouped_linear_bwd(ops, act, shared, B):
     """dsk_grouped_linear (+ pre-activation output) and dsk_grouped_linear_bwd against autograd of F.linear / F.silu."""
     torch.manual_seed(8)
