@@ -24,6 +24,8 @@
 //   warp 2   MMA issuer (one elected thread), owns the TMEM allocation
 //   warps 4-7 epilogue: tcgen05.ld -> +bias +time-embedding vector +residual -> bf16 -> global
 // TMEM accumulators are double buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace dsk {
@@ -335,6 +337,333 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
 }
 
+// ====================================================================================================================
+// cta_group::2 variant: a CTA PAIR (cluster of 2 = one TPC) works on two neighbouring pixel tiles (16 x 8 each, side by
+// side in w) of the same output-channel tile.  One tcgen05.mma.cta_group::2 of M = 256 covers both tiles: every CTA feeds
+// its own 128 activation rows from its own shared memory, and only HALF of the weight tile (N_TILE/2 rows) -- the tensor
+// core reads the two halves from the two SMs.  Per SM this halves the weight bytes read per MMA from shared memory (the
+// operand port is what bounds the N = 64 layers: 6 KB per 32 tensor-clocks at cta_group::1, 5 KB here) and halves the
+// L2 -> SM weight stream.  Protocol:
+//   * both CTAs run the two TMA producer warps; the loads are cta_group::2 loads whose mbarrier is the LEADER's (rank 0)
+//     full barrier, which expects the bytes of both CTAs;
+//   * only the leader's warp 2 issues MMAs; its tcgen05.commit multicasts the arrival to the empty / acc_full barriers of
+//     both CTAs;
+//   * each CTA's epilogue warps drain their own TMEM (rows of their own tile) and arrive -- remotely for rank 1 -- on the
+//     leader's acc_empty barrier (count 8).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;    // shared::cluster address of the even (leader) CTA of a pair
+
+__device__ __forceinline__ TileCoord tile_coord2(const TcParams& p, int u, int rank, int n_tile_size, int P) {
+  TileCoord c;
+  c.phase = u % p.nphase; u /= p.nphase;
+  c.pc = c.phase & 1; c.pb = (c.phase >> 1) & 1; c.pa = (c.phase >> 2) & 1;
+  const int pairs_w = p.tiles_w >> 1;
+  c.w0 = ((u % pairs_w) * 2 + rank) * TC_BW; u /= pairs_w;
+  c.h0 = (u % p.tiles_h) * TC_BH; u /= p.tiles_h;
+  c.d0 = (u % p.groups_d) * P;    u /= p.groups_d;
+  c.b = u % p.B;                  u /= p.B;
+  c.n0 = u * n_tile_size;
+  return c;
+}
+
+template <int N_TILE, int P, int NA, int NB, bool UPS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)NA * TC_PATCH_STRIDE;
+  constexpr int B_HALF = (N_TILE / 2) * 128;            // this CTA's half of a weight tap tile
+  __shared__ uint64_t full_a[NA], empty_a[NA], full_b[NB], empty_b[NB], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  constexpr uint32_t TMEM_COLS = 2 * P * N_TILE;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int total_pairs = p.total_tiles >> 1;
+  const int KD = p.KD, NJ = P + KD - 1;
+  const int nchunks = p.Cin / 64;
+  const int dpad = KD >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapW)) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                   // barriers of both CTAs initialised before any remote arrive / TMA
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer: activation patches (both CTAs, own tile) =====================
+    if (elect_one_sync()) {
+      uint32_t seq = 0;
+      for (int u = cluster_id; u < total_pairs; u += nclusters) {
+        const TileCoord tc = tile_coord2(p, u, rank, N_TILE, P);
+        for (int c = 0; c < nchunks; ++c)
+          for (int j = 0; j < NJ; ++j, ++seq) {
+            const uint32_t slot = seq % NA, ph = (seq / NA) & 1;
+            mbar_wait(&empty_a[slot], ph ^ 1);
+            if (leader) mbar_expect_tx(&full_a[slot], 2 * TC_PATCH_BYTES);
+            asm volatile(
+                "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+                    smem_u32(sA + (size_t)slot * TC_PATCH_STRIDE)),
+                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(c * 64), "r"(tc.w0 - 1), "r"(tc.h0 - 1), "r"(tc.d0 + j - dpad), "r"(tc.b),
+                "r"(smem_u32(&full_a[slot]) & kPeerBitMask)
+                : "memory");
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== TMA producer: this CTA's half of every weight tap =====================
+    if (elect_one_sync()) {
+      uint32_t seq = 0;
+      const int ntaps = UPS ? (KD == 3 ? 8 : 4) : KD * 9;
+      for (int u = cluster_id; u < total_pairs; u += nclusters) {
+        const TileCoord tc = tile_coord2(p, u, rank, N_TILE, P);
+        const int tap_base = UPS ? tc.phase * ntaps : 0;
+        for (int c = 0; c < nchunks; ++c)
+          for (int tap = tap_base; tap < tap_base + ntaps; ++tap, ++seq) {
+            const uint32_t slot = seq % NB, ph = (seq / NB) & 1;
+            mbar_wait(&empty_b[slot], ph ^ 1);
+            if (leader) mbar_expect_tx(&full_b[slot], 2 * B_HALF);
+            asm volatile(
+                "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                    smem_u32(sB + (size_t)slot * B_HALF)),
+                "l"(reinterpret_cast<uint64_t>(&tmapW)), "r"(c * 64), "r"(tap * p.Cout + tc.n0 + (int)rank * (N_TILE / 2)),
+                "r"(smem_u32(&full_b[slot]) & kPeerBitMask)
+                : "memory");
+          }
+      }
+    }
+  } else if (warp == 2) {
+    if (leader) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    constexpr uint32_t A_HI = umma_desc_hi(TC_PW * 128), B_HI = umma_desc_hi(1024);
+    uint32_t seq_a = 0, seq_b = 0, it = 0;
+    for (int u = cluster_id; u < total_pairs; u += nclusters, ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(&acc_empty[as], aph ^ 1);               // the epilogues of BOTH CTAs have drained this accumulator set
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_acc = tmem_base + as * (P * N_TILE);
+      const TileCoord tc = tile_coord2(p, u, 0, N_TILE, P);
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t seq_c = seq_a;
+        if constexpr (UPS) {
+          for (int j = 0; j < NJ; ++j) mbar_wait(&full_a[(seq_c + j) % NA], ((seq_c + j) / NA) & 1);
+          const int ntd = KD == 3 ? 2 : 1;
+          for (int td = 0; td < ntd; ++td) {
+            const int kd = KD == 3 ? tc.pa + td : 0;
+            uint32_t a_lo[P];
+#pragma unroll
+            for (int pp = 0; pp < P; ++pp)
+              a_lo[pp] = umma_desc_lo(smem_u32(sA + (size_t)((seq_c + pp + kd) % NA) * TC_PATCH_STRIDE));
+            for (int thw = 0; thw < 4; ++thw, ++seq_b) {
+              const int kh = tc.pb + (thw >> 1), kw = tc.pc + (thw & 1);
+              const uint32_t bs = seq_b % NB;
+              mbar_wait(&full_b[bs], (seq_b / NB) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_HALF));
+              const uint32_t tap_off = (kh * TC_PW + kw) * 8;
+              const uint32_t first = (c | td | thw) == 0 ? 0u : 1u;
+              if (elect_one_sync()) {
+#pragma unroll
+                for (int pp = 0; pp < P; ++pp) {
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    umma_bf16_2cta(tmem_acc + pp * N_TILE, umma_desc64(a_lo[pp] + tap_off + k4 * 2, A_HI),
+                                   umma_desc64(b_lo + k4 * 2, B_HI), idesc, k4 == 0 ? first : 1u);
+                }
+                umma_commit_2cta(&empty_b[bs]);
+              }
+              __syncwarp();
+            }
+          }
+          if (elect_one_sync()) {
+            for (int j = 0; j < NJ; ++j) umma_commit_2cta(&empty_a[(seq_c + j) % NA]);
+          }
+          __syncwarp();
+        } else {
+        for (int kd = 0; kd < KD; ++kd) {
+          const int jlo = kd == 0 ? 0 : P - 1 + kd, jhi = P - 1 + kd;
+          for (int j = jlo; j <= jhi; ++j) {
+            const uint32_t s = seq_c + j;
+            mbar_wait(&full_a[s % NA], (s / NA) & 1);
+          }
+          uint32_t a_lo[P];
+#pragma unroll
+          for (int pp = 0; pp < P; ++pp)
+            a_lo[pp] = umma_desc_lo(smem_u32(sA + (size_t)((seq_c + pp + kd) % NA) * TC_PATCH_STRIDE));
+#pragma unroll
+          for (int khw = 0; khw < 9; ++khw, ++seq_b) {
+            const uint32_t bs = seq_b % NB;
+            mbar_wait(&full_b[bs], (seq_b / NB) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_HALF));
+            const uint32_t tap_off = ((khw / 3) * TC_PW + (khw % 3)) * 8;
+            const uint32_t first = (c | kd | khw) == 0 ? 0u : 1u;
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int pp = 0; pp < P; ++pp) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                  umma_bf16_2cta(tmem_acc + pp * N_TILE, umma_desc64(a_lo[pp] + tap_off + k4 * 2, A_HI),
+                                 umma_desc64(b_lo + k4 * 2, B_HI), idesc, k4 == 0 ? first : 1u);
+              }
+              umma_commit_2cta(&empty_b[bs]);
+            }
+            __syncwarp();
+          }
+          const int rlo = kd, rhi = (kd == KD - 1) ? NJ - 1 : kd;
+          if (elect_one_sync()) {
+            for (int j = rlo; j <= rhi; ++j) umma_commit_2cta(&empty_a[(seq_c + j) % NA]);
+          }
+          __syncwarp();
+        }
+        }
+        seq_a += NJ;
+      }
+      if (elect_one_sync()) umma_commit_2cta(&acc_full[as]);
+      __syncwarp();
+    }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own tile / own TMEM) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int line = row >> 3, wp = row & 7;
+    uint32_t it = 0;
+    for (int u = cluster_id; u < total_pairs; u += nclusters, ++it) {
+      const TileCoord tc = tile_coord2(p, u, rank, N_TILE, P);
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(&acc_full[as], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int h = tc.h0 + line, w = tc.w0 + wp;
+      const bool in_hw = h < p.H && w < p.W;
+#pragma unroll
+      for (int pp = 0; pp < P; ++pp) {
+        const int d = tc.d0 + pp;
+        const bool valid = in_hw && d < p.D;
+        int64_t pix;
+        if constexpr (UPS) {
+          const int od = p.KD == 3 ? 2 * d + tc.pa : d, OD = p.KD == 3 ? 2 * p.D : p.D;
+          pix = (((int64_t)tc.b * OD + od) * (2 * p.H) + (2 * h + tc.pb)) * (2 * p.W) + (2 * w + tc.pc);
+        } else {
+          pix = (((int64_t)tc.b * p.D + d) * p.H + h) * p.W + w;
+        }
+        const int brow = (tc.b * p.D + d) / p.planes_per_sample;
+        const uint32_t taddr = tmem_base + as * (P * N_TILE) + pp * N_TILE + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+          uint32_t v[32];
+          DSK_TMEM_LD_X32(v, taddr + c0);
+          if (valid) {
+            const int n = tc.n0 + c0;
+            __nv_bfloat16* optr = p.out + pix * p.Cout + n;
+            const __nv_bfloat16* rptr = p.residual != nullptr ? p.residual + pix * p.Cout + n : nullptr;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float x = __uint_as_float(v[g * 8 + e]);
+                if (p.bias != nullptr) x += __ldg(p.bias + n + g * 8 + e);
+                if (p.chan_bias != nullptr) x += __ldg(p.chan_bias + (int64_t)brow * p.Cout + n + g * 8 + e);
+                f[e] = x;
+              }
+              if (rptr != nullptr) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(rptr + g * 8);
+                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { f[2 * e] += __low2float(rh[e]); f[2 * e + 1] += __high2float(rh[e]); }
+              }
+              uint4 o;
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              *reinterpret_cast<uint4*>(optr + g * 8) = o;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);   // 2 CTAs x 4 epilogue warps -> count 8 on the leader
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                    // the peer's shared memory / barriers stay alive until both are done
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+}
+
+template <int N_TILE, int P, int NA, int NB, bool UPS>
+static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const TcParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)NA * TC_PATCH_STRIDE + (size_t)NB * (N_TILE / 2) * 128 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<N_TILE, P, NA, NB, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("conv_tc2: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e)); return DSK_ERR_CUDA; }
+    configured = true;
+  }
+  const int pairs = p.total_tiles / 2;
+  const int clusters = pairs < DSK_NUM_SMS / 2 ? pairs : DSK_NUM_SMS / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<N_TILE, P, NA, NB, UPS>, ta, tw, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) { set_error("conv_tc2_kernel launch failed: %s", cudaGetErrorString(e)); return DSK_ERR_CUDA; }
+  return DSK_OK;
+}
+
 // nearest x2 upsample of a channels-last bf16 tensor (input of the UpSampler conv on the tcgen05 path)
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int D, int H, int W,
                                                           int C8, int ndim) {
@@ -481,6 +810,27 @@ extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const voi
   p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
   p.planes_per_sample = d->ndim == 3 ? iD : 1;
   cudaStream_t st = as_stream(stream);
+  // cta_group::2 (CTA pairs): needs an even number of w-tiles (the pair sits side by side in w).  DSK_CONV_CG=1 forces
+  // the single-CTA kernel (A/B measurements).
+  static const int force_cg = [] { const char* e = getenv("DSK_CONV_CG"); return e ? atoi(e) : 0; }();
+  if (!few_out && force_cg != 1 && (p.tiles_w % 2) == 0) {
+    CUtensorMap tw2;
+    cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)ntaps * w_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)d->Cin * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(n_tile / 2)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&tw2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DSK_REQUIRE(r == CUDA_SUCCESS, "dsk_conv_fwd(tc2): weight tensor map failed (CUresult %d)", (int)r);
+    // smem: 7 patches (161 KB) + 8 half-taps (N=64: 32 KB, N=128: 64 KB... 6 patches then)
+    if (d->up2) {
+      if (n_tile == 64) return launch_tc2<64, P, 7, 8, true>(ta, tw2, p, st);
+      return launch_tc2<128, P, 6, 8, true>(ta, tw2, p, st);
+    }
+    if (n_tile == 64) return launch_tc2<64, P, 7, 8, false>(ta, tw2, p, st);
+    return launch_tc2<128, P, 6, 8, false>(ta, tw2, p, st);
+  }
   // smem: N_TILE=64: 6 patches (138 KB) + 8 taps x 8 KB (64 KB) = 202 KB; N_TILE=128: 6 patches + 5 x 16 KB = 218 KB
   if (few_out) return launch_tc<16, P, 6, 8, false>(ta, tw, p, st);
   if (d->up2) {
