@@ -48,6 +48,10 @@ SIGNATURES = {
     "dsk_lincomb": [p, i64, p, f32, p, f32, p, f32, p, f32, p],
     "dsk_philox_normal": [p, i64, u64, C.c_uint32, p],
     "dsk_conv_fwd": [C.POINTER(ConvDesc), p, p, p, p, p, p, p],
+    "dsk_conv_stats_supported": [C.POINTER(ConvDesc)],
+    "dsk_conv_stats_slots": [],
+    "dsk_conv_fwd_stats": [C.POINTER(ConvDesc), p, p, p, p, p, p, p, p],
+    "dsk_norm_act_prestat": [p, p, p, p, p, p, p, i32, p, i32, i64, i32, i32, i32, i32, i32, i32, p],
     "dsk_upsample2x": [p, p, i32, i32, i32, i32, i32, i32, i32, p],
     "dsk_pack_upconv_weight": [p, p, i32, i32, i32, p],
     "dsk_pack_conv_weight": [p, p, i32, i32, i32, i32, p],

@@ -48,7 +48,10 @@ struct TcParams {
   int cout_real;          // N_TILE = 16 path (convout): the first cout_real (<= 16) channels are real, the rest zero padding
   float* out_nchw;        // N_TILE = 16 path: fp32 NC(D)HW output (user layout) instead of channels-last bf16
   int nphase;             // sub-pixel UpSampler conv: 8 (3-D) / 4 (2-D) output parities per input-resolution tile, else 1
+  float2* stats;          // cta_group::2 kernel: per-(sample, slot, channel) partial (sum, sum of squares) of the output, or null
+  int samples;            // number of samples the stats are kept for (3-D: B; 2-D: the planes ARE the samples)
 };
+constexpr int TC_STAT_SLOTS = DSK_NUM_SMS * 8;      // one slot per (CTA, epilogue warp)
 
 struct TileCoord {
   int w0, h0, d0, b, n0;
@@ -392,8 +395,9 @@ __device__ __forceinline__ TileCoord tile_coord2(const TcParams& p, int u, int r
   return c;
 }
 
+constexpr int TC2_THREADS = 384;   // warp 0/1: TMA producers, warp 2: MMA issuer, warp 3: idle, warps 4-11: epilogue
 template <int N_TILE, int P, int NA, int NB, bool UPS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -417,7 +421,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -570,66 +574,136 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own tile / own TMEM) =====================
-    const int q = warp & 3;
+    // 8 warps: warp w serves TMEM lane quadrant q = w & 3 (hardware rule) and plane pp = (w - 4) >> 2 of the tile, so the two
+    // planes drain concurrently.  Everything the epilogue reads from global memory for a tile (residual rows) is requested
+    // BEFORE the wait on the accumulator, so the load latency hides behind the tile's MMAs.
+    static_assert(P == 2, "one epilogue warp set per plane");
+    const int q = warp & 3, pp = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const int line = row >> 3, wp = row & 7;
+    // Fused norm statistics (optional): per output channel, sum and sum of squares of the fp32 results over the pixels
+    // this warp stores, accumulated in registers while the CTA stays inside one (n-tile, sample) range of the tile order
+    // and flushed to stats[sample][slot = cta*8 + warp][channel] when it leaves it -- no atomics, fixed summation order.
+    // Lane l of the warp ends up owning channel c0 + l of every 32-channel group (butterfly transpose-reduce).
+    constexpr int NG = N_TILE / 32;
+    constexpr int DEP = NG < 2 ? NG : 2;                  // residual prefetch depth in 32-channel groups
+    float st_s[NG], st_q[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) { st_s[g] = 0.0f; st_q[g] = 0.0f; }
+    const bool do_stats = p.stats != nullptr;
+    // a "range" = all tiles of one (n-tile, sample).  3-D convolutions only: the planes of a tile belong to one sample
+    // (the host does not enable stats for 2-D convs, whose plane axis is the batch).
+    const int per_range = p.nphase * (p.tiles_w >> 1) * p.tiles_h * p.groups_d;
+    const int nranges = total_pairs / per_range;             // n_tiles * B
+    int cur_range = -1;
+    const int slot = (int)blockIdx.x * 8 + (warp - 4);
+    auto flush = [&](int range, bool zero) {
+      const int nt = range / p.B, sg = range - nt * p.B;        // range -> (n-tile, sample)
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int ch = nt * N_TILE + g * 32 + lane;
+        p.stats[((int64_t)sg * TC_STAT_SLOTS + slot) * p.Cout + ch] = zero ? make_float2(0.0f, 0.0f) : make_float2(st_s[g], st_q[g]);
+        st_s[g] = 0.0f; st_q[g] = 0.0f;
+      }
+    };
     uint32_t it = 0;
     for (int u = cluster_id; u < total_pairs; u += nclusters, ++it) {
       const TileCoord tc = tile_coord2(p, u, rank, N_TILE, P);
+      if (do_stats) {
+        const int r = u / per_range;
+        if (r != cur_range) {
+          if (cur_range >= 0) flush(cur_range, false);
+          for (int z = cur_range + 1; z < r; ++z) flush(z, true);
+          cur_range = r;
+        }
+      }
+      const int h = tc.h0 + line, w = tc.w0 + wp;
+      const int d = tc.d0 + pp;
+      const bool valid = h < p.H && w < p.W && d < p.D;
+      int64_t pix;
+      if constexpr (UPS) {
+        const int od = p.KD == 3 ? 2 * d + tc.pa : d, OD = p.KD == 3 ? 2 * p.D : p.D;
+        pix = (((int64_t)tc.b * OD + od) * (2 * p.H) + (2 * h + tc.pb)) * (2 * p.W) + (2 * w + tc.pc);
+      } else {
+        pix = (((int64_t)tc.b * p.D + d) * p.H + h) * p.W + w;
+      }
+      const int brow = (tc.b * p.D + d) / p.planes_per_sample;
+      __nv_bfloat16* orow = p.out + pix * p.Cout + tc.n0;
+      const __nv_bfloat16* rrow = (p.residual != nullptr && valid) ? p.residual + pix * p.Cout + tc.n0 : nullptr;
+      const float* cbrow = p.chan_bias != nullptr ? p.chan_bias + (int64_t)brow * p.Cout + tc.n0 : nullptr;
+      uint4 rr[DEP][4];
+      if (rrow != nullptr) {
+#pragma unroll
+        for (int gg = 0; gg < DEP; ++gg)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rr[gg][g] = *reinterpret_cast<const uint4*>(rrow + gg * 32 + g * 8);
+      }
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       mbar_wait(&acc_full[as], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int h = tc.h0 + line, w = tc.w0 + wp;
-      const bool in_hw = h < p.H && w < p.W;
+      const uint32_t taddr = tmem_base + as * (P * N_TILE) + pp * N_TILE + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-      for (int pp = 0; pp < P; ++pp) {
-        const int d = tc.d0 + pp;
-        const bool valid = in_hw && d < p.D;
-        int64_t pix;
-        if constexpr (UPS) {
-          const int od = p.KD == 3 ? 2 * d + tc.pa : d, OD = p.KD == 3 ? 2 * p.D : p.D;
-          pix = (((int64_t)tc.b * OD + od) * (2 * p.H) + (2 * h + tc.pb)) * (2 * p.W) + (2 * w + tc.pc);
-        } else {
-          pix = (((int64_t)tc.b * p.D + d) * p.H + h) * p.W + w;
+      for (int gi = 0; gi < NG; ++gi) {
+        const int c0 = gi * 32;
+        uint32_t v[32];
+        DSK_TMEM_LD_X32(v, taddr + c0);
+        float f[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float x = __uint_as_float(v[e]);
+          if (p.bias != nullptr) x += __ldg(p.bias + tc.n0 + c0 + e);
+          if (cbrow != nullptr) x += __ldg(cbrow + c0 + e);
+          f[e] = x;
         }
-        const int brow = (tc.b * p.D + d) / p.planes_per_sample;
-        const uint32_t taddr = tmem_base + as * (P * N_TILE) + pp * N_TILE + ((uint32_t)(q * 32) << 16);
+        if (rrow != nullptr) {
 #pragma unroll
-        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-          uint32_t v[32];
-          DSK_TMEM_LD_X32(v, taddr + c0);
-          if (valid) {
-            const int n = tc.n0 + c0;
-            __nv_bfloat16* optr = p.out + pix * p.Cout + n;
-            const __nv_bfloat16* rptr = p.residual != nullptr ? p.residual + pix * p.Cout + n : nullptr;
+          for (int g = 0; g < 4; ++g) {
+            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr[gi % DEP][g]);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float f[8];
+            for (int e = 0; e < 4; ++e) { f[g * 8 + 2 * e] += __low2float(rh[e]); f[g * 8 + 2 * e + 1] += __high2float(rh[e]); }
+          }
+          if (gi + DEP < NG) {                               // refill the slot just consumed
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float x = __uint_as_float(v[g * 8 + e]);
-                if (p.bias != nullptr) x += __ldg(p.bias + n + g * 8 + e);
-                if (p.chan_bias != nullptr) x += __ldg(p.chan_bias + (int64_t)brow * p.Cout + n + g * 8 + e);
-                f[e] = x;
-              }
-              if (rptr != nullptr) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(rptr + g * 8);
-                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
+            for (int g = 0; g < 4; ++g) rr[gi % DEP][g] = *reinterpret_cast<const uint4*>(rrow + (gi + DEP) * 32 + g * 8);
+          }
+        }
+        if (valid) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { f[2 * e] += __low2float(rh[e]); f[2 * e + 1] += __high2float(rh[e]); }
-              }
-              uint4 o;
-              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-              *reinterpret_cast<uint4*>(optr + g * 8) = o;
+            for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = o;
+          }
+        }
+        if (do_stats) {
+          // butterfly transpose-reduce over the 32 lanes (= 32 pixels): lane l keeps channel c0 + l
+          float sq[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) { f[e] = valid ? f[e] : 0.0f; sq[e] = f[e] * f[e]; }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; ++i) {
+              const float ks = up ? f[i + o] : f[i], gs = up ? f[i] : f[i + o];
+              const float kq = up ? sq[i + o] : sq[i], gq = up ? sq[i] : sq[i + o];
+              f[i] = ks + __shfl_xor_sync(0xffffffffu, gs, o);
+              sq[i] = kq + __shfl_xor_sync(0xffffffffu, gq, o);
             }
           }
+          st_s[gi] += f[0];
+          st_q[gi] += sq[0];
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);   // 2 CTAs x 4 epilogue warps -> count 8 on the leader
+      if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);   // 2 CTAs x 8 epilogue warps -> count 16 on the leader
+    }
+    if (do_stats) {
+      if (cur_range >= 0) flush(cur_range, false);
+      for (int z = cur_range + 1; z < nranges; ++z) flush(z, true);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -651,7 +725,7 @@ static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const TcPara
   const int clusters = pairs < DSK_NUM_SMS / 2 ? pairs : DSK_NUM_SMS / 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(TC2_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -749,8 +823,35 @@ extern "C" int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W
   return DSK_OK;
 }
 
+static bool tc_pair_eligible(const dsk_conv_desc* d) {
+  static const int force_cg = [] { const char* e = getenv("DSK_CONV_CG"); return e ? atoi(e) : 0; }();
+  if (force_cg == 1 || d->ksize != 3 || d->in_dtype != DSK_BF16 || d->out_dtype != DSK_BF16 || d->out_nchw_f32 || d->w_dtype != DSK_BF16 ||
+      d->Cin % 64 != 0 || d->Cout % 64 != 0)
+    return false;
+  const int iW = d->up2 ? d->W / 2 : d->W;
+  return (((iW + TC_BW - 1) / TC_BW) % 2) == 0;
+}
+
+// 1 if dsk_conv_fwd_stats can emit fused norm statistics for this convolution (cta_group::2 kernel, 3-D)
+extern "C" int dsk_conv_stats_supported(const dsk_conv_desc* d) { return d != nullptr && d->ndim == 3 && tc_pair_eligible(d) ? 1 : 0; }
+extern "C" int dsk_conv_stats_slots(void) { return TC_STAT_SLOTS; }
+
+static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
+                            const void* residual, void* out, float2* stats, void* stream);
+
 extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const void* w, const float* bias,
                                const float* chan_bias, const void* residual, void* out, void* stream) {
+  return conv_fwd_tc_impl(d, in, w, bias, chan_bias, residual, out, nullptr, stream);
+}
+
+extern "C" int dsk_conv_fwd_stats(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
+                                  const void* residual, void* out, void* stats, void* stream) {
+  DSK_REQUIRE(stats != nullptr && dsk_conv_stats_supported(d), "dsk_conv_fwd_stats: this convolution cannot emit fused statistics");
+  return conv_fwd_tc_impl(d, in, w, bias, chan_bias, residual, out, (float2*)stats, stream);
+}
+
+static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
+                            const void* residual, void* out, float2* stats, void* stream) {
   DSK_REQUIRE(d && in && w && out, "dsk_conv_fwd(tc): null pointer");
   const bool few_out = d->Cout <= 16 && !d->up2 && chan_bias == nullptr && residual == nullptr;
   if (d->ksize != 3 || (d->out_nchw_f32 && !few_out) || d->in_dtype != DSK_BF16 || (!d->out_nchw_f32 && d->out_dtype != DSK_BF16) ||
@@ -809,11 +910,16 @@ extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const voi
   p.bias = bias; p.chan_bias = chan_bias;
   p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
   p.planes_per_sample = d->ndim == 3 ? iD : 1;
+  p.stats = stats; p.samples = d->B;
   cudaStream_t st = as_stream(stream);
   // cta_group::2 (CTA pairs): needs an even number of w-tiles (the pair sits side by side in w).  DSK_CONV_CG=1 forces
   // the single-CTA kernel (A/B measurements).
-  static const int force_cg = [] { const char* e = getenv("DSK_CONV_CG"); return e ? atoi(e) : 0; }();
-  if (!few_out && force_cg != 1 && (p.tiles_w % 2) == 0) {
+  if (!few_out && tc_pair_eligible(d)) {
+    if (stats != nullptr && p.total_tiles / 2 < DSK_NUM_SMS / 2) {
+      // fewer CTAs than slots: the slots of the CTAs that do not exist read as zero
+      cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)d->B * TC_STAT_SLOTS * d->Cout * sizeof(float2), st);
+      DSK_REQUIRE(e == cudaSuccess, "dsk_conv_fwd_stats: memset failed: %s", cudaGetErrorString(e));
+    }
     CUtensorMap tw2;
     cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)ntaps * w_rows};
     cuuint64_t strides[1] = {(cuuint64_t)d->Cin * 2};

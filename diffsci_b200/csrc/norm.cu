@@ -205,6 +205,57 @@ __global__ void __launch_bounds__(128) norm_finalize_pc_kernel(const double2* __
   table[i] = make_float2(sc, sh);
 }
 
+// Finalize from the statistics a convolution epilogue left behind (conv_tc.cu): stats[b][slot][c] = (sum, sum of squares)
+// over the pixels one epilogue warp stored.  G == C only.  Block = 32 channels x 8 slot lanes of one sample.
+__global__ void __launch_bounds__(1024) norm_finalize_stats_kernel(const float2* __restrict__ st, float2* __restrict__ table,
+                                                                    float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, const float* __restrict__ fsc,
+                                                                    const float* __restrict__ fsh, int64_t S, int C, int nslots, int mode,
+                                                                    float eps) {
+  // block = 32 channels x 32 slot lanes of one sample; 4 loads in flight per thread
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  double a = 0, q = 0;
+  if (c < C) {
+    const float2* base = st + (int64_t)b * nslots * C + c;
+    int s = rl;
+    for (; s + 96 < nslots; s += 128) {
+      const float2 v0 = base[(int64_t)s * C], v1 = base[(int64_t)(s + 32) * C], v2 = base[(int64_t)(s + 64) * C],
+                   v3 = base[(int64_t)(s + 96) * C];
+      a += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
+      q += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
+    }
+    for (; s < nslots; s += 32) {
+      const float2 v = base[(int64_t)s * C];
+      a += (double)v.x;
+      q += (double)v.y;
+    }
+  }
+  __shared__ double ra[32][33], rq[32][33];
+  ra[rl][threadIdx.x & 31] = a;
+  rq[rl][threadIdx.x & 31] = q;
+  __syncthreads();
+  if (rl != 0 || c >= C) return;
+  a = 0; q = 0;
+  for (int k = 0; k < 32; ++k) { a += ra[k][threadIdx.x & 31]; q += rq[k][threadIdx.x & 31]; }
+  const double n = (double)S;
+  const double mean = a / n, ex2 = q / n;
+  float2 mr;
+  if (mode == 0) {
+    double var = ex2 - mean * mean;
+    if (var < 0) var = 0;
+    mr = make_float2((float)mean, 1.0f / sqrtf((float)var + eps));
+  } else {
+    mr = make_float2(0.0f, 1.0f / sqrtf((float)ex2 + eps));
+  }
+  const int64_t i = (int64_t)b * C + c;
+  stats[i] = mr;
+  float sc = mr.y, sh = -mr.x * mr.y;
+  if (gamma != nullptr) { sc *= gamma[c]; sh = sh * gamma[c] + beta[c]; }
+  if (fsc != nullptr) { const float f = fsc[i]; sc *= f; sh = sh * f + fsh[i]; }
+  table[i] = make_float2(sc, sh);
+}
+
 template <typename TO> __device__ __forceinline__ float silu_out(float v) { return silu_f(v); }
 // bf16 output keeps 8 mantissa bits: the approximate exp / divide (rel. error ~1e-6) is invisible after rounding and
 // takes the kernel from instruction-bound back to HBM-bound
@@ -271,6 +322,26 @@ extern "C" int64_t dsk_norm_ws_bytes(int B, int64_t S, int C) {
   return (int64_t)B * nchunks * C * (int64_t)sizeof(double2) + 2 * (int64_t)B * C * (int64_t)sizeof(float2);
 }
 
+static int norm_apply_launch(const void* x, void* y, const float2* table, int B, int64_t S, int C, int silu, int in_dtype,
+                             int out_dtype, cudaStream_t st) {
+  const int V = norm_v(in_dtype);
+  const int cv = C / V;
+  const int pl = NORM_THREADS / cv > 0 ? NORM_THREADS / cv : 1;
+  int64_t gx = (S + (int64_t)pl * 4 - 1) / ((int64_t)pl * 4);          // >= 4 pixels per thread
+  const int64_t cap = (8LL * DSK_NUM_SMS + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 ag((unsigned)gx, B);
+#define APPLY(TI, TO) DSK_LAUNCH((norm_apply_kernel<TI, TO>), ag, NORM_THREADS, 0, st, (const TI*)x, (TO*)y, table, S, C, silu)
+  if (in_dtype == DSK_F32 && out_dtype == DSK_F32) APPLY(float, float);
+  else if (in_dtype == DSK_F32 && out_dtype == DSK_BF16) APPLY(float, __nv_bfloat16);
+  else if (in_dtype == DSK_BF16 && out_dtype == DSK_BF16) APPLY(__nv_bfloat16, __nv_bfloat16);
+  else if (in_dtype == DSK_BF16 && out_dtype == DSK_F32) APPLY(__nv_bfloat16, float);
+  else DSK_REQUIRE(false, "dsk_norm_act: bad dtype combination %d -> %d", in_dtype, out_dtype);
+#undef APPLY
+  return DSK_OK;
+}
+
 extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const float* beta, const float* film_scale,
                             const float* film_shift, void* ws, int B, int64_t S, int C, int G, int mode, int silu,
                             int in_dtype, int out_dtype, void* stream) {
@@ -302,17 +373,23 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
   else
     DSK_LAUNCH(norm_finalize_kernel, B * G, 128, 0, st, partial, table, stats, gamma, beta, film_scale, film_shift, S, C, G, nchunks, mode,
                1e-5f);
-  int64_t gx = (S + (int64_t)pl * 4 - 1) / ((int64_t)pl * 4);          // >= 4 pixels per thread
-  const int64_t cap = (8LL * DSK_NUM_SMS + B - 1) / B;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  dim3 ag((unsigned)gx, B);
-#define APPLY(TI, TO) DSK_LAUNCH((norm_apply_kernel<TI, TO>), ag, NORM_THREADS, 0, st, (const TI*)x, (TO*)y, table, S, C, silu)
-  if (in_dtype == DSK_F32 && out_dtype == DSK_F32) APPLY(float, float);
-  else if (in_dtype == DSK_F32 && out_dtype == DSK_BF16) APPLY(float, __nv_bfloat16);
-  else if (in_dtype == DSK_BF16 && out_dtype == DSK_BF16) APPLY(__nv_bfloat16, __nv_bfloat16);
-  else if (in_dtype == DSK_BF16 && out_dtype == DSK_F32) APPLY(__nv_bfloat16, float);
-  else DSK_REQUIRE(false, "dsk_norm_act: bad dtype combination %d -> %d", in_dtype, out_dtype);
-#undef APPLY
-  return DSK_OK;
+  return norm_apply_launch(x, y, table, B, S, C, silu, in_dtype, out_dtype, st);
+}
+
+
+extern "C" int dsk_norm_act_prestat(const void* x, void* y, const float* gamma, const float* beta, const float* film_scale,
+                                    const float* film_shift, const void* conv_stats, int nslots, void* ws, int B, int64_t S, int C,
+                                    int G, int mode, int silu, int in_dtype, int out_dtype, void* stream) {
+  DSK_REQUIRE(x && y && ws && conv_stats, "dsk_norm_act_prestat: null pointer");
+  DSK_REQUIRE(B > 0 && B <= 65535 && S > 0 && C > 0 && G == C && nslots > 0, "dsk_norm_act_prestat: needs one channel per group (G == C)");
+  DSK_REQUIRE(in_dtype == DSK_F32 || in_dtype == DSK_BF16, "dsk_norm_act_prestat: bad in_dtype %d", in_dtype);
+  DSK_REQUIRE(C % norm_v(in_dtype) == 0 && (mode == 0 || mode == 1), "dsk_norm_act_prestat: bad C / mode");
+  DSK_REQUIRE((gamma == nullptr) == (beta == nullptr) && (film_scale == nullptr) == (film_shift == nullptr), "dsk_norm_act_prestat: affine / FiLM mismatch");
+  cudaStream_t st = as_stream(stream);
+  float2* table = reinterpret_cast<float2*>(ws);
+  float2* stats = table + (int64_t)B * C;
+  dim3 fg((C + 31) / 32, B);
+  DSK_LAUNCH(norm_finalize_stats_kernel, fg, 1024, 0, st, (const float2*)conv_stats, table, stats, gamma, beta, film_scale, film_shift, S, C,
+             nslots, mode, 1e-5f);
+  return norm_apply_launch(x, y, table, B, S, C, silu, in_dtype, out_dtype, st);
 }

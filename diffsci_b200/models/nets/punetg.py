@@ -206,6 +206,9 @@ class _Plan:
         self.XA2 = buf(nlev, ch[nlev])
         self.F = buf(0, c.output_channels)
         self.WS = [ops.norm_ws(B, sp[l][0] * sp[l][1] * sp[l][2], ch[l], dev) for l in range(nlev + 1)]
+        # fused norm statistics (conv epilogue -> following per-channel norm): one buffer per level, consumed by the very
+        # next norm.  Only where the convolution kernel can emit them and the norms are per channel (G == C: the PUNetG norms).
+        self.ST = [None] * (nlev + 1)
         self.pc_in, self.pc_out = pack(net.convin), pack(net.convout, few_out_ok=True)
         self.pc_down = [pack(s.conv) for s in net.downsamplers]
         self.pc_up = [pack(s.conv, subpixel=True) for s in net.upsamplers]   # conv(up2(x)) in sub-pixel form on tcgen05
@@ -219,6 +222,17 @@ class _Plan:
         for i in range(nlev):
             self.blocks += [(b, nlev - 1 - i) for b in net.upward_blocks[i]]
         self.pc = {id(b): (pack(b.conv1), pack(b.conv2)) for b, _ in self.blocks}
+        if adt == torch.bfloat16:
+            sup = ops.conv_stats_supported
+            lvl_pc = {l: self.pc[id(b)][0] for b, l in self.blocks}
+            self.st_ok = [sup(self.X[l].shape, adt, lvl_pc[l]) for l in range(nlev + 1)]
+            self.st_down = [sup(self.P[l].shape, adt, self.pc_down[l]) for l in range(nlev)]
+            self.st_up = [sup(self.X[nlev - i].shape, adt, self.pc_up[i], up2=True) for i in range(nlev)]
+            for l in range(nlev + 1):
+                if self.st_ok[l] or (l > 0 and self.st_down[l - 1]) or (l < nlev and self.st_up[nlev - 1 - l]):
+                    self.ST[l] = ops.conv_stats_buffer(B, ch[l], dev)
+        else:
+            self.st_ok, self.st_down, self.st_up = [False] * (nlev + 1), [False] * nlev, [False] * nlev
 
         # time embedding: Fourier features + 3 grouped launches for all blocks' MLPs
         f32 = dict(dtype=torch.float32, device=dev)
@@ -263,16 +277,18 @@ class _Plan:
                 wo.packed()
 
     # ------------------------------------------------------------------ forward
-    def _resblock(self, x, blk, l, out):
+    def _resblock(self, x, blk, l, out, xs=None):
+        """-> (block output, its fused norm statistics or None).  `xs`: statistics of x left by the conv that produced it."""
         c = self.net.config
         C = blk.channels
         pc1, pc2 = self.pc[id(blk)]
+        st = self.ST[l] if self.st_ok[l] else None
         n = ops.norm_act(x, blk.gnorm1.weight, blk.gnorm1.bias, C, _NORM_MODE[c.first_resblock_norm], True,
-                         out=self.N[l], ws=self.WS[l])
-        y = ops.conv(n, pc1, out=self.Y[l], chan_bias=self.tvec[id(blk)])
+                         out=self.N[l], ws=self.WS[l], conv_stats=xs)
+        y = ops.conv(n, pc1, out=self.Y[l], chan_bias=self.tvec[id(blk)], stats=st)
         n = ops.norm_act(y, blk.gnorm2.weight, blk.gnorm2.bias, C, _NORM_MODE[c.second_resblock_norm], True,
-                         out=self.N[l], ws=self.WS[l])
-        return ops.conv(n, pc2, out=out, residual=x)
+                         out=self.N[l], ws=self.WS[l], conv_stats=st)
+        return ops.conv(n, pc2, out=out, residual=x, stats=st), st
 
     def _attention(self, x, attn, out, index=0):
         a = self.attn
@@ -303,29 +319,31 @@ class _Plan:
             ops.fourier(cnoise, net.time_projection.W, out=self.te)
         for g in self.tmlp:
             g.run()
-        x = ops.conv(xin, self.pc_in, out=self.X[0])
+        x, xs = ops.conv(xin, self.pc_in, out=self.X[0]), None
         for l in range(nlev):
             for blk in net.downward_blocks[l]:
-                x = self._resblock(x, blk, l, x)
+                x, xs = self._resblock(x, blk, l, x, xs)
             p = ops.pool2x(x, self.ndim, True, out=self.P[l])            # MaxPool (commonlayers.py:60-63)
-            x = ops.conv(p, self.pc_down[l], out=self.X[l + 1])
+            xs = self.ST[l + 1] if self.st_down[l] else None
+            x = ops.conv(p, self.pc_down[l], out=self.X[l + 1], stats=xs)
         for blk in net.before_block:
-            x = self._resblock(x, blk, nlev, x)
-        xa = x
+            x, xs = self._resblock(x, blk, nlev, x, xs)
+        xa, xas = x, xs
         for r, blk in enumerate(net.attn_resnet_block):
-            xa = self._resblock(xa, blk, nlev, self.XA)
+            xa, xas = self._resblock(xa, blk, nlev, self.XA, xas)
             if r < len(net.attn_block):
-                xa = self._attention(xa, net.attn_block[r], self.XA2, r)
+                xa, xas = self._attention(xa, net.attn_block[r], self.XA2, r), None
                 # next block reads XA2 and writes XA (its residual input is XA2)
-        x = ops.add(x, xa, out=x)
+        x, xs = ops.add(x, xa, out=x), None
         for blk in net.after_block:
-            x = self._resblock(x, blk, nlev, x)
+            x, xs = self._resblock(x, blk, nlev, x, xs)
         for i in range(nlev):
             l = nlev - 1 - i
             # conv(F.interpolate(x, 2)) + skip, fused (commonlayers.py:145; punetg.py:372-373)
-            x = ops.conv(x, self.pc_up[i], out=self.XU[l], residual=self.X[l], up2=True)
+            xs = self.ST[l] if self.st_up[i] else None
+            x = ops.conv(x, self.pc_up[i], out=self.XU[l], residual=self.X[l], up2=True, stats=xs)
             for blk in net.upward_blocks[i]:
-                x = self._resblock(x, blk, l, x)
+                x, xs = self._resblock(x, blk, l, x, xs)
         if out_nchw is not None:
             return ops.conv(x, self.pc_out, out=out_nchw, out_nchw=True)
         return ops.conv(x, self.pc_out, out=self.F)

@@ -78,10 +78,31 @@ class PackedConv:
         return self._packed
 
 
+def _conv_desc_of(x, pc, out, residual, up2, out_nchw, D, H, W):
+    return L.ConvDesc(x.shape[0], D, H, W, x.shape[-1], pc.cout, pc.ksize, pc.ndim, int(up2), dt_code(pc.w_dtype), dt_code(x.dtype),
+                      dt_code(residual.dtype if (out_nchw and residual is not None) else
+                              (torch.float32 if out_nchw else out.dtype)), int(out_nchw))
+
+
+def conv_stats_supported(x_shape, x_dtype, pc: "PackedConv", up2: bool = False) -> bool:
+    """Can the convolution of an input of this shape emit fused norm statistics (dsk_conv_stats_supported)?"""
+    B, D, H, W, Cin = x_shape
+    if up2:
+        D, H, W = (D * 2 if pc.ndim == 3 else D), H * 2, W * 2
+    d = L.ConvDesc(B, D, H, W, Cin, pc.cout, pc.ksize, pc.ndim, int(up2), dt_code(pc.w_dtype), dt_code(x_dtype), dt_code(x_dtype), 0)
+    return bool(lib.dsk_conv_stats_supported(C.byref(d)))
+
+
+def conv_stats_buffer(B: int, cout: int, device) -> torch.Tensor:
+    """[B, slots, Cout, 2] fp32 buffer for the statistics a convolution epilogue leaves for the following norm."""
+    return torch.empty((B, int(lib.dsk_conv_stats_slots()), cout, 2), dtype=torch.float32, device=device)
+
+
 def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, chan_bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, up2: bool = False, out_dtype: Optional[torch.dtype] = None,
-         out_nchw: bool = False) -> torch.Tensor:
-    """y = conv_same(x) + bias + chan_bias[b, :] + residual  (dsk_conv_fwd)."""
+         out_nchw: bool = False, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = conv_same(x) + bias + chan_bias[b, :] + residual  (dsk_conv_fwd).  `stats` (conv_stats_buffer): also leave the
+    per-(sample, channel) statistics of y for norm_act(..., conv_stats=stats) (dsk_conv_fwd_stats)."""
     require_cuda(x, "conv input")
     B, D, H, W, Cin = x.shape
     assert Cin == pc.cin, (Cin, pc.cin)
@@ -94,12 +115,14 @@ def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, ch
         if out_nchw and pc.ndim == 2:
             shape = (B, pc.cout, H, W)
         out = torch.empty(shape, dtype=torch.float32 if out_nchw else out_dtype, device=x.device)
-    d = L.ConvDesc(B, D, H, W, Cin, pc.cout, pc.ksize, pc.ndim, int(up2), dt_code(pc.w_dtype), dt_code(x.dtype),
-                   dt_code(residual.dtype if (out_nchw and residual is not None) else
-                           (torch.float32 if out_nchw else out.dtype)), int(out_nchw))
+    d = _conv_desc_of(x, pc, out, residual, up2, out_nchw, D, H, W)
     bias = pc.bias.detach() if pc.bias is not None else None
-    check(lib.dsk_conv_fwd(C.byref(d), ptr(x), ptr(pc.packed()), ptr(bias), ptr(chan_bias), ptr(residual), ptr(out),
-                           stream()))
+    if stats is not None:
+        check(lib.dsk_conv_fwd_stats(C.byref(d), ptr(x), ptr(pc.packed()), ptr(bias), ptr(chan_bias), ptr(residual), ptr(out),
+                                     ptr(stats), stream()))
+    else:
+        check(lib.dsk_conv_fwd(C.byref(d), ptr(x), ptr(pc.packed()), ptr(bias), ptr(chan_bias), ptr(residual), ptr(out),
+                               stream()))
     return out
 
 
@@ -138,8 +161,10 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
 
 
 def norm_act(x: torch.Tensor, gamma, beta, G: int, mode: int, silu: bool, out: Optional[torch.Tensor] = None,
-             film_scale=None, film_shift=None, out_dtype: Optional[torch.dtype] = None, ws=None) -> torch.Tensor:
-    """Group LayerNorm (mode 0) / RMS norm (mode 1) + affine (+FiLM) + SiLU  (dsk_norm_act)."""
+             film_scale=None, film_shift=None, out_dtype: Optional[torch.dtype] = None, ws=None,
+             conv_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Group LayerNorm (mode 0) / RMS norm (mode 1) + affine (+FiLM) + SiLU  (dsk_norm_act).  `conv_stats`: statistics the
+    convolution that produced x left behind (ops.conv(..., stats=...)): the statistics pass over x is skipped."""
     require_cuda(x, "norm input")
     B, Cc = x.shape[0], x.shape[-1]
     S = x.numel() // (B * Cc)
@@ -149,6 +174,11 @@ def norm_act(x: torch.Tensor, gamma, beta, G: int, mode: int, silu: bool, out: O
         ws = torch.empty(int(lib.dsk_norm_ws_bytes(B, S, Cc)), dtype=torch.uint8, device=x.device)
     g = gamma.detach() if gamma is not None else None
     b = beta.detach() if beta is not None else None
+    if conv_stats is not None:
+        check(lib.dsk_norm_act_prestat(ptr(x), ptr(out), ptr(g), ptr(b), ptr(film_scale), ptr(film_shift), ptr(conv_stats),
+                                       conv_stats.shape[1], ptr(ws), B, S, Cc, G, mode, int(silu), dt_code(x.dtype),
+                                       dt_code(out.dtype), stream()))
+        return out
     check(lib.dsk_norm_act(ptr(x), ptr(out), ptr(g), ptr(b), ptr(film_scale), ptr(film_shift), ptr(ws), B, S, Cc, G,
                            mode, int(silu), dt_code(x.dtype), dt_code(out.dtype), stream()))
     return out

@@ -133,6 +133,15 @@ typedef struct {
 } dsk_conv_desc;
 int dsk_conv_fwd(const dsk_conv_desc* d, const void* in, const void* w, const float* bias,
                  const float* chan_bias, const void* residual, void* out, void* stream);
+/* The same convolution with the statistics of the FOLLOWING per-channel norm fused into its epilogue (the reference
+ * runs GroupNorm(C, C) / GroupRMSNorm(C, C) as separate passes over the conv output, commonlayers.py:824-831):
+ * stats[b][slot][c] (float2: sum, sum of squares over the pixels one epilogue warp stored; dsk_conv_stats_slots() slots
+ * per sample, fixed summation order) is consumed by dsk_norm_act_prestat.  Only the cta_group::2 tcgen05 kernel emits
+ * them: query dsk_conv_stats_supported(d) first. */
+int dsk_conv_stats_supported(const dsk_conv_desc* d);
+int dsk_conv_stats_slots(void);
+int dsk_conv_fwd_stats(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
+                       const void* residual, void* out, void* stats, void* stream);
 /* nearest x2 upsample of a channels-last tensor (torch.nn.Upsample(scale_factor=2), commonlayers.py:129):
  * only needed in front of the tcgen05 conv; the FFMA conv fuses it into its gather (up2). bf16, C % 8 == 0. */
 int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, void* stream);
@@ -181,6 +190,11 @@ int64_t dsk_norm_ws_bytes(int B, int64_t S, int C);
 int dsk_norm_act(const void* x, void* y, const float* gamma, const float* beta, const float* film_scale,
                  const float* film_shift, void* ws, int B, int64_t S, int C, int G, int mode, int silu,
                  int in_dtype, int out_dtype, void* stream);
+/* dsk_norm_act without the statistics pass: mean / rstd come from the `conv_stats` a preceding dsk_conv_fwd_stats left
+ * (G == C only).  One finalize launch + the apply pass: 2 N s bytes instead of 3 N s. */
+int dsk_norm_act_prestat(const void* x, void* y, const float* gamma, const float* beta, const float* film_scale,
+                         const float* film_shift, const void* conv_stats, int nslots, void* ws, int B, int64_t S, int C,
+                         int G, int mode, int silu, int in_dtype, int out_dtype, void* stream);
 
 /* ---- K5: 2x pooling -------------------------------------------------------------------
  * Replaces torch.nn.MaxPool{2,3}d(2) (commonlayers.py:60-63,81) / AvgPool (adm.py:361-371).

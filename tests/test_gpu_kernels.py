@@ -391,3 +391,34 @@ def test_convout_tcgen05(ops, ndim, B, Cin, Cout, sp):
     assert y.dtype == torch.float32 and relmax(y.cpu(), ref) < 2e-5       # fp32 accumulation, fp32 store
     y2 = ops.conv(to_cl(x).bfloat16(), pc)
     assert relmax(from_cl(y2, ndim), ref) < 6e-3
+
+
+@pytest.mark.parametrize("B,Cin,Cout,sp,up2", [(2, 64, 64, (4, 16, 16), False), (1, 128, 128, (6, 32, 16), False),
+                                               (3, 64, 128, (2, 16, 32), False), (2, 128, 64, (4, 8, 16), True),
+                                               (1, 64, 64, (64, 64, 64), False)])
+def test_conv_fused_norm_statistics(ops, B, Cin, Cout, sp, up2):
+    """dsk_conv_fwd_stats: the per-(sample, channel) sum / sum of squares left by the cta_group::2 conv epilogue equal the
+    statistics of the stored output, and dsk_norm_act_prestat reproduces dsk_norm_act on it."""
+    torch.manual_seed(41)
+    x = torch.randn(B, *sp, Cin, device=DEV).bfloat16()
+    w = torch.randn(Cout, Cin, 3, 3, 3, device=DEV) / math.sqrt(27 * Cin)
+    pc = ops.PackedConv(w, torch.randn(Cout, device=DEV), 3, torch.bfloat16, subpixel=up2)
+    assert ops.conv_stats_supported(tuple(x.shape), x.dtype, pc, up2=up2)
+    cb = torch.randn(B, Cout, device=DEV)
+    osp = tuple(2 * s for s in sp) if up2 else sp
+    res = torch.randn(B, *osp, Cout, device=DEV).bfloat16()
+    st = ops.conv_stats_buffer(B, Cout, DEV)
+    st.fill_(float("nan"))                                   # every slot must be written (or zero-filled) by the launch
+    y = ops.conv(x, pc, chan_bias=None if up2 else cb, residual=res, up2=up2, stats=st)
+    y0 = ops.conv(x, pc, chan_bias=None if up2 else cb, residual=res, up2=up2)
+    assert torch.equal(y, y0)
+    tot = st.double().sum(1)                                 # [B, Cout, 2]
+    yf = y.double().flatten(1, 3)
+    # statistics are taken on the fp32 values before the bf16 rounding of the store
+    assert relmax(tot[..., 0], yf.sum(1)) < 2e-3
+    assert relmax(tot[..., 1], (yf * yf).sum(1)) < 2e-3
+    g, b_ = torch.randn(Cout, device=DEV), torch.randn(Cout, device=DEV)
+    for mode in (0, 1):
+        ref = ops.norm_act(y, g, b_, Cout, mode, True)
+        got = ops.norm_act(y, g, b_, Cout, mode, True, conv_stats=st)
+        assert relmax(got.float(), ref.float()) < 1e-2

@@ -16,6 +16,8 @@ ap.add_argument("--size", type=int, default=64)
 ap.add_argument("--cin", type=int, default=64)
 ap.add_argument("--cout", type=int, default=64)
 ap.add_argument("--reps", type=int, default=6)
+ap.add_argument("--stats", action="store_true")
+ap.add_argument("--residual", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -23,15 +25,17 @@ w = torch.randn(a.cout, a.cin, 3, 3, 3, device=dev) * 0.02
 pc = ops.PackedConv(w, torch.zeros(a.cout, device=dev), 3, torch.bfloat16)
 xs = [torch.randn(a.batch, a.size, a.size, a.size, a.cin, device=dev).bfloat16() for _ in range(3)]
 out = torch.empty(a.batch, a.size, a.size, a.size, a.cout, device=dev, dtype=torch.bfloat16)
+st = ops.conv_stats_buffer(a.batch, a.cout, dev) if a.stats else None
+res = torch.randn_like(out) if a.residual else None
 for i in range(3):
-    ops.conv(xs[i % 3], pc, out=out)
+    ops.conv(xs[i % 3], pc, out=out, stats=st, residual=res)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for i in range(a.reps):
-    ops.conv(xs[i % 3], pc, out=out)
+    ops.conv(xs[i % 3], pc, out=out, stats=st, residual=res)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.reps
 fl = 2.0 * a.batch * a.size ** 3 * a.cin * a.cout * 27
-print(f"conv3d {a.cin}->{a.cout} @ {a.size}^3 B={a.batch}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s")
+print(f"conv3d {a.cin}->{a.cout} @ {a.size}^3 B={a.batch} stats={a.stats} residual={a.residual}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s")
