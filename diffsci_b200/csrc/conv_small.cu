@@ -205,6 +205,8 @@ static int launch_few_in(const SmallConvArgs& a, cudaStream_t st) {
   return DSK_OK;
 }
 
+int convin_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, void* out, cudaStream_t st);
+
 // returns 1 if handled, 0 if the shape is not a few-channel conv, negative on error
 int conv_small_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
                         const void* residual, void* out, cudaStream_t st) {
@@ -217,6 +219,10 @@ int conv_small_dispatch(const dsk_conv_desc* d, const void* in, const void* w, c
                        (size_t)taps * d->Cin * 4 * 4 <= 48 * 1024 && (d->ksize == 3 || d->ksize == 1);
   const bool few_in = d->Cin <= 4 && d->Cout % FI_CO == 0 && !d->out_nchw_f32 && (size_t)taps * d->Cin * d->Cout * 4 <= 48 * 1024;
   if (!few_out && !few_in) return 0;
+  if (few_in && !few_out) {      // tensor-core im2col form (convin_tc.cu) where it applies
+    const int rc = convin_tc_dispatch(d, in, w, bias, out, st);
+    if (rc != DSK_ERR_UNSUPPORTED) return rc == DSK_OK ? 1 : rc;
+  }
   const int ti = d->in_dtype, to = d->out_nchw_f32 ? DSK_F32 : d->out_dtype;
   int rc;
 #define GO(FN)                                                                                        \

@@ -823,6 +823,10 @@ extern "C" int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W
   return DSK_OK;
 }
 
+namespace dsk {
+int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, void* out, cudaStream_t st);
+}
+
 static bool tc_pair_eligible(const dsk_conv_desc* d) {
   static const int force_cg = [] { const char* e = getenv("DSK_CONV_CG"); return e ? atoi(e) : 0; }();
   if (force_cg == 1 || d->ksize != 3 || d->in_dtype != DSK_BF16 || d->out_dtype != DSK_BF16 || d->out_nchw_f32 || d->w_dtype != DSK_BF16 ||
@@ -862,6 +866,13 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
     return DSK_ERR_UNSUPPORTED;
   }
   DSK_REQUIRE((d->ndim == 2 && d->D == 1) || d->ndim == 3, "dsk_conv_fwd(tc): bad ndim/D");
+  if (few_out) {     // in-plane taps as the N dimension (convout_tc.cu); DSK_CONVOUT_OLD=1 keeps the N = 16 tile for A/B runs
+    static const int old_path = [] { const char* e = getenv("DSK_CONVOUT_OLD"); return e ? atoi(e) : 0; }();
+    if (!old_path) {
+      const int rc = convout_tc_dispatch(d, in, w, bias, out, as_stream(stream));
+      if (rc != DSK_ERR_UNSUPPORTED) return rc;
+    }
+  }
   EncodeTiledFn encode = get_encode();
   DSK_REQUIRE(encode != nullptr, "dsk_conv_fwd(tc): cuTensorMapEncodeTiled is unavailable");
   // 2-D: the batch is the plane axis (no depth taps); 3-D: planes = D with zero padding per sample

@@ -1,0 +1,225 @@
+// convin_tc.cu -- the FIRST convolution of the U-Nets (Cin <= 4 -> C, k = 3; reference nets/punetg.py:203-208,
+// nets/adm.py:183-188) on the tensor cores.
+//
+// With Cin = 1..3 the whole receptive field of an output pixel is K = taps * Cin <= 64 numbers: the im2col row of a pixel
+// is ONE 128-byte shared-memory row.  Four builder warps gather those rows (the input tensor is tiny and L1/L2 resident)
+// straight into the K-major SWIZZLE_128B layout, one tcgen05 MMA group (M = 128 pixels, N = Cout, K = 64) turns a tile
+// into accumulators, and four epilogue warps stream the C-channel result out -- the kernel is bound by the write of the
+// output tensor (the CUDA-core version was bound by shared-memory weight reads at 1/10 of that).
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace dsk {
+
+constexpr int CI_BW = 8, CI_BH = 16;               // 128 output pixels per tile
+constexpr int CI_NG = 3;                           // builder groups of 4 warps: CI_NG tiles are gathered concurrently
+constexpr int CI_BUILD = CI_NG * 4;                // warps 0..CI_BUILD-1: im2col builders
+constexpr int CI_THREADS = (CI_BUILD + 1 + 4) * 32;  // + warp CI_BUILD: MMA / TMEM owner, + 4 epilogue warps
+constexpr int CI_STAGES = 6;
+constexpr int CI_A_BYTES = 128 * 128;
+
+struct CiParams {
+  const __nv_bfloat16* x;   // channels-last [B, D, H, W, Cin]
+  const float* w;           // packed fp32 [taps][Cin][Cout]
+  const float* bias;
+  __nv_bfloat16* out;       // channels-last [B, D, H, W, Cout]
+  int B, D, H, W, Cin, Cout, ndim;
+  int tiles_w, tiles_h, total_tiles;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                        // CI_STAGES x [128 rows x 128 B]
+  uint8_t* sB = smem + (size_t)CI_STAGES * CI_A_BYTES;       // [Cout rows x 128 B]
+  __shared__ uint64_t full_a[CI_STAGES], empty_a[CI_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.Cout;
+  const uint32_t tmem_cols = N <= 64 ? 128u : (N <= 128 ? 256u : 512u);   // 2 x N, power of two
+  const int taps = p.ndim == 3 ? 27 : 9;
+  const int K = taps * CIN;                                  // <= 64 (host-checked)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < CI_STAGES; ++i) { mbar_init(&full_a[i], 4); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == CI_BUILD) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // weights -> bf16 K-major SWIZZLE_128B rows: B[co][k = tap*CIN + ci] = w[k][co], zero beyond K
+  for (int i = threadIdx.x; i < N * 8; i += CI_THREADS) {
+    const int j = i & 7, co = i >> 3;
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k0 = j * 8 + 2 * e;
+      const float a = k0 < K ? p.w[(int64_t)k0 * N + co] : 0.0f, b = k0 + 1 < K ? p.w[(int64_t)(k0 + 1) * N + co] : 0.0f;
+      h[e] = __floats2bfloat162_rn(a, b);
+    }
+    *reinterpret_cast<uint4*>(sB + co * 128 + ((j ^ (co & 7)) << 4)) = *reinterpret_cast<const uint4*>(h);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  auto coord = [&](int t, int& w0, int& h0, int& d, int& b) {
+    w0 = (t % p.tiles_w) * CI_BW; t /= p.tiles_w;
+    h0 = (t % p.tiles_h) * CI_BH; t /= p.tiles_h;
+    d = t % p.D;
+    b = t / p.D;
+  };
+
+  if (warp < CI_BUILD) {
+    // ===================== im2col builders: group g gathers tiles seq = g, g + CI_NG, ...; thread = one pixel row ===========
+    const int grp = warp >> 2;
+    const int r = threadIdx.x & 127, line = r >> 3, wp = r & 7;
+    const int kdn = p.ndim == 3 ? 3 : 1;
+    uint32_t seq = grp;
+    for (int t = blockIdx.x + grp * gridDim.x; t < p.total_tiles; t += CI_NG * gridDim.x, seq += CI_NG) {
+      int w0, h0, d, b;
+      coord(t, w0, h0, d, b);
+      const int h = h0 + line, w = w0 + wp;
+      const uint32_t slot = seq % CI_STAGES, ph = (seq / CI_STAGES) & 1;
+      // gather the receptive field first (loads in flight while waiting for the slot); validity factorises per axis
+      bool dv[3], hv[3], wv[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        dv[k] = p.ndim == 3 ? (unsigned)(d + k - 1) < (unsigned)p.D : k == 0;
+        hv[k] = (unsigned)(h + k - 1) < (unsigned)p.H;
+        wv[k] = (unsigned)(w + k - 1) < (unsigned)p.W;
+      }
+      const __nv_bfloat16* ctr = p.x + ((((int64_t)b * p.D + d) * p.H + h) * p.W + w) * CIN;
+      const int sH = p.W * CIN, sD = p.H * sH;
+      __nv_bfloat16 v[64];
+#pragma unroll
+      for (int k = 0; k < 64; ++k) v[k] = __float2bfloat16_rn(0.0f);
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+        if (kd >= kdn) break;
+        const int od = p.ndim == 3 ? (kd - 1) * sD : 0;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const bool ok = dv[kd] && hv[kh] && wv[kw];
+            const __nv_bfloat16* src = ctr + od + (kh - 1) * sH + (kw - 1) * CIN;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci)
+              if (ok) v[((kd * 3 + kh) * 3 + kw) * CIN + ci] = src[ci];
+          }
+      }
+      mbar_wait(&empty_a[slot], ph ^ 1);
+      uint8_t* row = sA + (size_t)slot * CI_A_BYTES + r * 128;
+      constexpr int PIECES = (27 * CIN + 7) / 8;               // 16-byte pieces that can be non-zero
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 piece = make_uint4(0, 0, 0, 0);
+        if (j < PIECES) piece = *reinterpret_cast<const uint4*>(&v[j * 8]);
+        *reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4)) = piece;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_a[slot]);
+    }
+  } else if (warp == CI_BUILD) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16(N);
+    constexpr uint32_t HI = umma_desc_hi(1024);
+    const uint32_t b_lo = umma_desc_lo(smem_u32(sB));
+    uint32_t seq = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++seq) {
+      const uint32_t as = seq & 1, aph = (seq >> 1) & 1;
+      const uint32_t slot = seq % CI_STAGES;
+      mbar_wait(&acc_empty[as], aph ^ 1);
+      mbar_wait(&full_a[slot], (seq / CI_STAGES) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_lo = umma_desc_lo(smem_u32(sA + (size_t)slot * CI_A_BYTES));
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          if (k4 * 16 < K) umma_bf16(tmem_base + as * N, umma_desc64(a_lo + k4 * 2, HI), umma_desc64(b_lo + k4 * 2, HI), idesc, k4 != 0);
+        umma_commit(&empty_a[slot]);
+        umma_commit(&acc_full[as]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane, line = r >> 3, wp = r & 7;
+    uint32_t seq = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++seq) {
+      int w0, h0, d, b;
+      coord(t, w0, h0, d, b);
+      const uint32_t as = seq & 1, aph = (seq >> 1) & 1;
+      mbar_wait(&acc_full[as], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int h = h0 + line, w = w0 + wp;
+      const bool valid = h < p.H && w < p.W;
+      __nv_bfloat16* orow = p.out + ((((int64_t)b * p.D + d) * p.H + h) * p.W + w) * N;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        DSK_TMEM_LD_X32(v, tmem_base + as * N + c0 + ((uint32_t)(q * 32) << 16));
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float f0 = __uint_as_float(v[g * 8 + 2 * e]), f1 = __uint_as_float(v[g * 8 + 2 * e + 1]);
+              if (p.bias != nullptr) { f0 += __ldg(p.bias + c0 + g * 8 + 2 * e); f1 += __ldg(p.bias + c0 + g * 8 + 2 * e + 1); }
+              oh[e] = __floats2bfloat162_rn(f0, f1);
+            }
+            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = o;
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == CI_BUILD) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+}
+
+template <int CIN>
+static int launch_convin(const CiParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)CI_STAGES * CI_A_BYTES + (size_t)p.Cout * 128 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(convin_tc_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("convin_tc: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e)); return DSK_ERR_CUDA; }
+  const int grid = p.total_tiles < DSK_NUM_SMS ? p.total_tiles : DSK_NUM_SMS;
+  DSK_LAUNCH((convin_tc_kernel<CIN>), grid, CI_THREADS, smem, st, p);
+  return DSK_OK;
+}
+
+// returns DSK_ERR_UNSUPPORTED for shapes it does not take (the caller keeps the CUDA-core few-channel kernel)
+int convin_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, void* out, cudaStream_t st) {
+  static const int old_path = [] { const char* e = getenv("DSK_CONVIN_OLD"); return e ? atoi(e) : 0; }();
+  const int taps = d->ndim == 3 ? 27 : 9;
+  if (old_path || d->ksize != 3 || d->up2 || d->out_nchw_f32 || d->in_dtype != DSK_BF16 || d->out_dtype != DSK_BF16 || d->w_dtype != DSK_F32 ||
+      d->Cin > 4 || taps * d->Cin > 64 || (d->Cout != 64 && d->Cout != 128 && d->Cout != 256))
+    return DSK_ERR_UNSUPPORTED;
+  CiParams p;
+  p.x = (const __nv_bfloat16*)in; p.w = (const float*)w; p.bias = bias; p.out = (__nv_bfloat16*)out;
+  p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.ndim = d->ndim;
+  p.tiles_w = (d->W + CI_BW - 1) / CI_BW; p.tiles_h = (d->H + CI_BH - 1) / CI_BH;
+  p.total_tiles = p.tiles_w * p.tiles_h * d->D * d->B;
+  switch (d->Cin) {
+    case 1: return launch_convin<1>(p, st);
+    case 2: return launch_convin<2>(p, st);
+    case 3: return launch_convin<3>(p, st);
+    default: return launch_convin<4>(p, st);
+  }
+}
+
+}  // namespace dsk

@@ -378,9 +378,12 @@ def test_upconv_subpixel_tcgen05(ops, ndim, B, Cin, Cout, sp):
     assert relmax(from_cl(y, ndim), ref + res) < 1e-2
 
 
-@pytest.mark.parametrize("ndim,B,Cin,Cout,sp", [(3, 2, 64, 1, (4, 16, 8)), (3, 1, 64, 3, (3, 10, 12)), (2, 3, 128, 2, (20, 12))])
+@pytest.mark.parametrize("ndim,B,Cin,Cout,sp", [(3, 2, 64, 1, (4, 16, 8)), (3, 1, 64, 3, (3, 10, 12)), (2, 3, 128, 2, (20, 12)),
+                                                (3, 1, 64, 1, (32, 32, 32)), (2, 5, 64, 1, (28, 28)), (3, 2, 128, 1, (5, 7, 9)),
+                                                (2, 2, 64, 4, (16, 16))])
 def test_convout_tcgen05(ops, ndim, B, Cin, Cout, sp):
-    """convout (few output channels) on the N = 16 tcgen05 tile, fp32 NC(D)HW and bf16 channels-last outputs."""
+    """convout (few output channels): the taps-as-N tensor-core kernel (convout_tc.cu; Cout <= 3) and the N = 16 tile it
+    falls back to (Cout = 4); fp32 NC(D)HW and bf16 channels-last outputs."""
     torch.manual_seed(22)
     x = torch.randn(B, Cin, *sp).bfloat16().float()
     w = (torch.randn(Cout, Cin, *([3] * ndim)) / math.sqrt(Cin * 3 ** ndim)).bfloat16().float()
@@ -422,3 +425,17 @@ def test_conv_fused_norm_statistics(ops, B, Cin, Cout, sp, up2):
         ref = ops.norm_act(y, g, b_, Cout, mode, True)
         got = ops.norm_act(y, g, b_, Cout, mode, True, conv_stats=st)
         assert relmax(got.float(), ref.float()) < 1e-2
+
+
+@pytest.mark.parametrize("ndim,B,Cin,Cout,sp", [(3, 2, 1, 64, (5, 16, 8)), (3, 1, 2, 64, (4, 9, 11)), (2, 3, 3, 128, (20, 12)),
+                                                (2, 4, 1, 128, (28, 28)), (3, 1, 1, 64, (32, 32, 32)), (2, 2, 4, 256, (7, 9))])
+def test_convin_tcgen05(ops, ndim, B, Cin, Cout, sp):
+    """convin (Cin <= 4) as an im2col-row tcgen05 GEMM (convin_tc.cu) vs ATen on the same bf16-rounded operands."""
+    torch.manual_seed(23)
+    x = torch.randn(B, Cin, *sp).bfloat16().float()
+    w = (torch.randn(Cout, Cin, *([3] * ndim)) / math.sqrt(Cin * 3 ** ndim))
+    b = torch.randn(Cout) * 0.1
+    ref = (F.conv2d if ndim == 2 else F.conv3d)(x, w.bfloat16().float(), b, padding=1)
+    pc = ops.PackedConv(w.to(DEV), b.to(DEV), ndim, torch.float32)        # the few-channel path keeps fp32 packed weights
+    y = ops.conv(to_cl(x).bfloat16(), pc)
+    assert y.dtype == torch.bfloat16 and relmax(from_cl(y, ndim), ref) < 6e-3
