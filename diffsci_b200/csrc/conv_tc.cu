@@ -591,14 +591,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
     for (int g = 0; g < NG; ++g) { st_s[g] = 0.0f; st_q[g] = 0.0f; }
     const bool do_stats = p.stats != nullptr;
-    // a "range" = all tiles of one (n-tile, sample).  3-D convolutions only: the planes of a tile belong to one sample
-    // (the host does not enable stats for 2-D convs, whose plane axis is the batch).
-    const int per_range = p.nphase * (p.tiles_w >> 1) * p.tiles_h * p.groups_d;
-    const int nranges = total_pairs / per_range;             // n_tiles * B
+    // a "range" = all tiles of one (n-tile, sample).  3-D: sample = batch entry (both planes of a tile belong to it);
+    // 2-D: the plane axis IS the batch, a tile holds P samples and this warp (plane pp) owns sample d0 + pp.
+    const bool is3d = p.KD == 3;
+    const int srange = is3d ? p.B : p.groups_d;              // sample ranges per n-tile
+    const int per_range = p.nphase * (p.tiles_w >> 1) * p.tiles_h * (is3d ? p.groups_d : 1);
+    const int nranges = total_pairs / per_range;             // n_tiles * srange
     int cur_range = -1;
     const int slot = (int)blockIdx.x * 8 + (warp - 4);
     auto flush = [&](int range, bool zero) {
-      const int nt = range / p.B, sg = range - nt * p.B;        // range -> (n-tile, sample)
+      const int nt = range / srange, sr = range - nt * srange;  // range -> (n-tile, sample range)
+      const int sg = is3d ? sr : sr * P + pp;
+      if (sg >= p.samples) return;
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
         const int ch = nt * N_TILE + g * 32 + lane;
@@ -836,8 +840,13 @@ static bool tc_pair_eligible(const dsk_conv_desc* d) {
   return (((iW + TC_BW - 1) / TC_BW) % 2) == 0;
 }
 
-// 1 if dsk_conv_fwd_stats can emit fused norm statistics for this convolution (cta_group::2 kernel, 3-D)
-extern "C" int dsk_conv_stats_supported(const dsk_conv_desc* d) { return d != nullptr && d->ndim == 3 && tc_pair_eligible(d) ? 1 : 0; }
+// 1 if dsk_conv_fwd_stats should emit fused norm statistics for this convolution: the cta_group::2 kernel, 3-D only.
+// (The epilogue can do it for 2-D too -- tests exercise it with DSK_CONV_STATS_2D=1 -- but a 2-D tile has 3x fewer MMAs to
+// hide the reduction behind and one slot set per sample of a large batch: measured on C5 / C2 it does not pay.)
+extern "C" int dsk_conv_stats_supported(const dsk_conv_desc* d) {
+  static const int allow2d = [] { const char* e = getenv("DSK_CONV_STATS_2D"); return e ? atoi(e) : 0; }();
+  return d != nullptr && (d->ndim == 3 || allow2d) && tc_pair_eligible(d) ? 1 : 0;
+}
 extern "C" int dsk_conv_stats_slots(void) { return TC_STAT_SLOTS; }
 
 static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,

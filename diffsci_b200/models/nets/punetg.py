@@ -252,6 +252,7 @@ class _Plan:
         Cb = ch[nlev]
         self.attn = None
         self.attn_tc = (precision == "bf16" and _tc_eligible(Cb, Cb) and Lq % 8 == 0 and Lq <= 8192)
+        self.attn_hybrid = False
         if len(net.attn_block) > 0 and self.attn_tc:
             bf = dict(dtype=torch.bfloat16, device=dev)
             self.attn = dict(qk=torch.empty((B * Lq, 2 * Cb), **bf), vt=torch.empty((B, Cb, Lq), **bf),
@@ -264,6 +265,11 @@ class _Plan:
                              ao=torch.empty((B * Lq, Cb), **f32), out=torch.empty((B, Lq, Cb), **f32))
             if adt != torch.float32:
                 self.attn["tok"] = torch.empty((B, Lq, Cb), **f32)
+                if _tc_eligible(Cb, Cb) and (B * Lq) % 8 == 0:
+                    self.attn_hybrid = True
+                    self.attn["ao16"] = torch.empty((B * Lq, Cb), dtype=torch.bfloat16, device=dev)
+                    self.attn_w = [(ops.PackedLinear(a.mhattn.in_proj_weight), ops.PackedLinear(a.mhattn.out_proj.weight))
+                                   for a in net.attn_block]
         self.Lq, self.Cb = Lq, Cb
         self.prepare()
 
@@ -271,7 +277,7 @@ class _Plan:
         """Materialise packed weights (must happen outside CUDA-graph capture)."""
         for pc in [self.pc_in, self.pc_out, *self.pc_down, *self.pc_up, *[p for pair in self.pc.values() for p in pair]]:
             pc.packed()
-        if self.attn_tc and len(self.net.attn_block) > 0:
+        if (self.attn_tc or self.attn_hybrid) and len(self.net.attn_block) > 0:
             for wi, wo in self.attn_w:
                 wi.packed()
                 wo.packed()
@@ -301,6 +307,18 @@ class _Plan:
             return out
         if x.dtype == torch.float32:
             tok = x.view(B, Lq, Cb)
+        elif self.attn_hybrid:
+            # token counts the tensor-core score path does not take (L % 8 != 0, e.g. the 7x7 bottom level of MNIST): the two
+            # projections -- 99% of the block's FLOPs at small L -- still run on tcgen05, the tiny per-sample L x L part in fp32
+            wi, wo = self.attn_w[index]
+            M = B * Lq
+            ops.gemm_bf16_tc(x.view(M, Cb), wi.packed(), a["qkv"], M=M, N=3 * Cb, K=Cb, lda=Cb, ldb=Cb, ldc=3 * Cb,
+                             bias=m.in_proj_bias.detach())
+            ops.attention_core_f32(a["qkv"], a["scores"], a["ao"], B, Lq, Cb)
+            ao16 = ops.cast(a["ao"], torch.bfloat16, out=a["ao16"])
+            ops.gemm_bf16_tc(ao16, wo.packed(), out.view(M, Cb), M=M, N=Cb, K=Cb, lda=Cb, ldb=Cb, ldc=Cb,
+                             bias=m.out_proj.bias.detach(), residual=x.view(M, Cb) if self.net.config.attn_residual else None)
+            return out
         else:
             tok = ops.cast(x.view(B, Lq, Cb), torch.float32, out=a["tok"])
         o = ops.self_attention_f32(tok, m.in_proj_weight, m.in_proj_bias, m.out_proj.weight, m.out_proj.bias, a,

@@ -369,6 +369,17 @@ def self_attention_f32(tok: torch.Tensor, in_w, in_b, out_w, out_b, bufs: dict, 
     return out
 
 
+def attention_core_f32(qkv: torch.Tensor, sc: torch.Tensor, ao: torch.Tensor, B: int, Lq: int, Cc: int) -> torch.Tensor:
+    """softmax(Q K^T / sqrt(C)) V per sample on fp32 packed projections qkv [B*L, 3C] -> ao [B*L, C] (the middle of
+    self_attention_f32, for callers that run the projections elsewhere)."""
+    gemm(qkv, qkv, sc, M=Lq, N=Lq, K=Cc, lda=3 * Cc, ldb=3 * Cc, ldc=Lq, transB=True, alpha=Cc ** -0.5, batch=B,
+         strideA=Lq * 3 * Cc, strideB=Lq * 3 * Cc, strideC=Lq * Lq, a_off=0, b_off=Cc)
+    softmax_rows(sc, B * Lq, Lq)
+    gemm(sc, qkv, ao, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=3 * Cc, ldc=Cc, transB=False, batch=B, strideA=Lq * Lq,
+         strideB=Lq * 3 * Cc, strideC=Lq * Cc, b_off=2 * Cc)
+    return ao
+
+
 def lincomb(x=None, a0: float = 0.0, r1=None, a1: float = 0.0, r2=None, a2: float = 0.0, z=None, a3: float = 0.0,
             out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = a0*x + a1*r1 + a2*r2 + a3*z on fp32 tensors (dsk_lincomb); None operands are skipped."""

@@ -398,17 +398,23 @@ def test_convout_tcgen05(ops, ndim, B, Cin, Cout, sp):
 
 @pytest.mark.parametrize("B,Cin,Cout,sp,up2", [(2, 64, 64, (4, 16, 16), False), (1, 128, 128, (6, 32, 16), False),
                                                (3, 64, 128, (2, 16, 32), False), (2, 128, 64, (4, 8, 16), True),
-                                               (1, 64, 64, (64, 64, 64), False)])
+                                               (1, 64, 64, (64, 64, 64), False), (5, 64, 64, (32, 48), False),
+                                               (2, 128, 256, (16, 16), False), (3, 128, 64, (8, 16), True)])
 def test_conv_fused_norm_statistics(ops, B, Cin, Cout, sp, up2):
     """dsk_conv_fwd_stats: the per-(sample, channel) sum / sum of squares left by the cta_group::2 conv epilogue equal the
-    statistics of the stored output, and dsk_norm_act_prestat reproduces dsk_norm_act on it."""
+    statistics of the stored output, and dsk_norm_act_prestat reproduces dsk_norm_act on it (3-D and 2-D)."""
     torch.manual_seed(41)
-    x = torch.randn(B, *sp, Cin, device=DEV).bfloat16()
-    w = torch.randn(Cout, Cin, 3, 3, 3, device=DEV) / math.sqrt(27 * Cin)
-    pc = ops.PackedConv(w, torch.randn(Cout, device=DEV), 3, torch.bfloat16, subpixel=up2)
+    nd = len(sp)
+    full = sp if nd == 3 else (1,) + tuple(sp)
+    x = torch.randn(B, *full, Cin, device=DEV).bfloat16()
+    w = torch.randn(Cout, Cin, *([3] * nd), device=DEV) / math.sqrt(3 ** nd * Cin)
+    pc = ops.PackedConv(w, torch.randn(Cout, device=DEV), nd, torch.bfloat16, subpixel=up2)
+    if nd == 2 and not ops.conv_stats_supported(tuple(x.shape), x.dtype, pc, up2=up2):
+        pytest.skip("fused statistics are enabled for 3-D convolutions only (set DSK_CONV_STATS_2D=1 to test the 2-D epilogue)")
     assert ops.conv_stats_supported(tuple(x.shape), x.dtype, pc, up2=up2)
     cb = torch.randn(B, Cout, device=DEV)
-    osp = tuple(2 * s for s in sp) if up2 else sp
+    osp = tuple(2 * s for s in sp) if up2 else tuple(sp)
+    osp = osp if nd == 3 else (1,) + osp
     res = torch.randn(B, *osp, Cout, device=DEV).bfloat16()
     st = ops.conv_stats_buffer(B, Cout, DEV)
     st.fill_(float("nan"))                                   # every slot must be written (or zero-filled) by the launch
