@@ -132,48 +132,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       const float rb = (p.bias != nullptr && p.bias_rows && mvalid) ? p.bias[m] : 0.0f;
       const int64_t obase = (int64_t)b * p.strideC + (int64_t)m * p.ldc;
       const uint32_t taddr = tmem_base + as * N_TILE + ((uint32_t)(q * 32) << 16);
-#pragma unroll
+      // The 32-column groups are NOT unrolled and every data-dependent choice (output dtype, residual, bias kind, ragged
+      // edge) is a warp-uniform branch around a small straight-line body: the first version unrolled everything into
+      // 11.6 K SASS instructions and ran at the speed of the instruction cache (ncu: tensor pipe 4-6 % active).
+      const bool full_n = (tn + 1) * N_TILE <= p.N;
+      const bool col_bias = p.bias != nullptr && !p.bias_rows;
+#pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         uint32_t v[32];
         DSK_TMEM_LD_X32(v, taddr + c0);
         const int n = tn * N_TILE + c0;
-        if (mvalid && n < p.N) {
-          const bool full32 = n + 32 <= p.N;
+        if (!mvalid || n >= p.N) continue;
+        float f[32];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float f[8];
+        for (int e = 0; e < 32; ++e) f[e] = fmaf(p.alpha, __uint_as_float(v[e]), rb);
+        if (full_n || n + 32 <= p.N) {
+          if (col_bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float x = p.alpha * __uint_as_float(v[g * 8 + e]) + rb;
-              if (p.bias != nullptr && !p.bias_rows && (full32 || n + g * 8 + e < p.N)) x += __ldg(p.bias + n + g * 8 + e);
-              f[e] = x;
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 bb = __ldg(bp + e4);
+              f[4 * e4] += bb.x; f[4 * e4 + 1] += bb.y; f[4 * e4 + 2] += bb.z; f[4 * e4 + 3] += bb.w;
             }
-            if (full32 || n + g * 8 + 8 <= p.N) {
-              if (p.residual != nullptr) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + obase + n + g * 8);
-                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
+          }
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + n);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { f[2 * e] += __low2float(rh[e]); f[2 * e + 1] += __high2float(rh[e]); }
-              }
-              if (p.out_f32) {
-                float* o = reinterpret_cast<float*>(p.out) + obase + n + g * 8;
-                *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-                *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
-              } else {
-                uint4 o;
-                __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+            for (int g = 0; g < 4; ++g) {
+              const uint4 rr = rp[g];
+              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n + g * 8) = o;
-              }
-            } else {
-              for (int e = 0; e < 8 && n + g * 8 + e < p.N; ++e) {   // ragged N tail
-                float x = f[e];
-                if (p.residual != nullptr) x += __bfloat162float(p.residual[obase + n + g * 8 + e]);
-                if (p.out_f32) reinterpret_cast<float*>(p.out)[obase + n + g * 8 + e] = x;
-                else reinterpret_cast<__nv_bfloat16*>(p.out)[obase + n + g * 8 + e] = __float2bfloat16_rn(x);
-              }
+              for (int e = 0; e < 4; ++e) { f[g * 8 + 2 * e] += __low2float(rh[e]); f[g * 8 + 2 * e + 1] += __high2float(rh[e]); }
             }
+          }
+          if (p.out_f32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + n);
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) o[e4] = make_float4(f[4 * e4], f[4 * e4 + 1], f[4 * e4 + 2], f[4 * e4 + 3]);
+          } else {
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 pk;
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+              o[g] = pk;
+            }
+          }
+        } else {
+          // ragged N edge: scalar, rolled (f is indexed dynamically -> local memory; rare and tiny)
+#pragma unroll 1
+          for (int e = 0; e < 32 && n + e < p.N; ++e) {
+            float x = f[e];
+            if (col_bias) x += __ldg(p.bias + n + e);
+            if (p.residual != nullptr) x += __bfloat162float(p.residual[obase + n + e]);
+            if (p.out_f32) reinterpret_cast<float*>(p.out)[obase + n + e] = x;
+            else reinterpret_cast<__nv_bfloat16*>(p.out)[obase + n + e] = __float2bfloat16_rn(x);
           }
         }
       }
