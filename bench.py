@@ -509,14 +509,21 @@ def dominant_conv_roofline(cfg, shape, B, precision, dev, peaks, reps=20):
         S *= s
     flops = 2.0 * B * S * M * M * cfg.kernel_size ** nd
     achieved = flops / (ms * 1e-3) / 1e12
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this shape, from the committed
+    # `ncu --set full` capture (profiles/r1q_conv_tc2_64x64_64cube_B8_ncu_full.txt); scaled by batch (the kernel reads its
+    # input once and writes its output once: traffic is linear in the number of samples); null for other shapes
+    traffic, traffic_src = None, None
+    if nd == 3 and M == 64 and tuple(sp) == (64, 64, 64) and wd == torch.bfloat16:
+        traffic = 490.4e6 * B / 8.0
+        traffic_src = "ncu --set full, profiles/r1q_conv_tc2_64x64_64cube_B8_ncu_full.txt (268.8 MB read + 221.6 MB written at B=8)"
     peak = peaks.get("bf16_tflops")
     src = "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
     if peak is None:
         peak, src = 1590.0, "fallback (B200_PROFILING.md)"
     return {"bound": "tensor", "kernel": f"conv{nd}d {M}->{M} k{cfg.kernel_size} @ {'x'.join(map(str, sp[-nd:]))} "
             f"({'tcgen05 implicit GEMM' if wd == torch.bfloat16 else 'CUDA-core FFMA implicit GEMM, fp32 parity mode'})",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": src, "ms_per_launch": ms, "flops_per_launch": flops}
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_src, "peak_source": src, "ms_per_launch": ms, "flops_per_launch": flops}
 
 
 if __name__ == "__main__":

@@ -152,12 +152,12 @@ def test_training_graph_builds_and_covers_every_parameter(monkeypatch):
     for prec in ("fp32", "bf16"):
         net = d.PUNetG(d.PUNetGConfig(dimension=3, model_channels=8))
         g = G.build_punetg(net, 2, (8, 8, 8), "cpu", prec)
-        assert len(g.fwd) > 100 and len(g.bwd) > 2 * len(g.fwd)
+        assert len(g.fwd) > 60 and len(g.bwd) > len(g.fwd)        # time MLPs are grouped: 3 launches forward, 3 backward
         assert sum(v.numel() for v in g.grads()) == sum(p.numel() for p in net.parameters())
         for cfg in (d.ADMConfig(input_channels=3, output_channels=3), d.ADMConfig(skip_integration_type="add")):
             net = d.ADM(cfg)
             g = G.build_adm(net, 1, (16, 16), "cpu", prec)
-            assert len(g.bwd) > 2 * len(g.fwd)
+            assert len(g.bwd) > len(g.fwd)
     import pytest
     with pytest.raises(ValueError):
         G.build_punetg(d.PUNetG(d.PUNetGConfig(dimension=2, model_channels=8)), 1, (6, 6), "cpu", "fp32")
