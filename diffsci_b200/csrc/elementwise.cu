@@ -249,6 +249,16 @@ __global__ void __launch_bounds__(256) grouped_dz_bias_kernel(const float* const
   }
 }
 
+// out = x * (1 - m) + y * m, the known-region blend of Scheduler.inpaint / repaint (schedulers.py:111-116,151,162);
+// the mask is broadcast over the leading dimensions (m index = i mod mask_n).  out may alias x.
+__global__ void __launch_bounds__(256) mask_blend_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ y,
+                                                          const float* __restrict__ m, int64_t n, int64_t mask_n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float mv = m[i % mask_n];
+    out[i] = x[i] * (1.0f - mv) + y[i] * mv;
+  }
+}
+
 // ---- row softmax (in place, fp32) ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ S, int64_t rows, int cols) {
   __shared__ float red[8];
@@ -435,5 +445,11 @@ extern "C" int dsk_grouped_dz_bias(const float* const* dY, const float* const* Z
               "dsk_grouped_dz_bias: bad arguments");
   dim3 grid((max_out + 31) / 32, ngroups);
   DSK_LAUNCH(grouped_dz_bias_kernel, grid, 256, 0, as_stream(stream), dY, Z, dZ, db, out_dim, B, act);
+  return DSK_OK;
+}
+
+extern "C" int dsk_mask_blend(float* out, const float* x, const float* y, const float* mask, int64_t n, int64_t mask_n, void* stream) {
+  DSK_REQUIRE(out && x && y && mask && n > 0 && mask_n > 0 && n % mask_n == 0, "dsk_mask_blend: bad arguments");
+  DSK_LAUNCH(mask_blend_kernel, grid_for(n, 256, 8), 256, 0, as_stream(stream), out, x, y, mask, n, mask_n);
   return DSK_OK;
 }

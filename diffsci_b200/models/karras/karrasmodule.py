@@ -426,3 +426,91 @@ class KarrasModule(_Base):
         out = eng.run(x, table, integ.fused_program, record_history=record_history, noises=noises, seed=seed)
         self.last_nfe = eng.nfe
         return out
+
+    # ------------------------------------------------------------------ partial / forward propagation, inpainting
+    def _score_fn(self, y=None):
+        if y is not None:
+            raise NotImplementedError("diffsci_b200.KarrasModule: conditional sampling not built yet (8f)")
+        return lambda xx, sg: self.get_score(xx, sg)
+
+    def propagate_partial_toward_sample(self, x: Tensor, initial_step: int, final_step: Optional[int] = None, y=None,
+                                        nsteps: int = 100, record_history: bool = False, integrator=None,
+                                        analytical_score=None, interp_fn=None) -> Tensor:
+        """Steps initial_step .. final_step of an nsteps schedule (karrasmodule.py:933-976).  `interp_fn(sigma)` blends the
+        trained score with `analytical_score` (evaluated on the host, as in the reference)."""
+        require_cuda(x, "x")
+        trained = self._score_fn(y)
+
+        def score(xx, sigma):
+            s = trained(xx, sigma)
+            if interp_fn is None:
+                return s
+            assert analytical_score is not None
+            alpha = interp_fn(sigma).unsqueeze(-1).to(s.device)
+            analytic = analytical_score(xx.cpu().detach(), sigma.cpu().detach()).to(s.device)
+            return alpha * s + (1 - alpha) * analytic
+        sch = self.config.noisescheduler
+        final_step = nsteps if final_step is None else final_step
+        with torch.inference_mode():
+            if integrator is not None:
+                sch.set_temporary_integrator(integrator)
+            try:
+                return sch.propagate_partial(x, score, nsteps, initial_step, final_step, record_history=record_history)
+            finally:
+                if integrator is not None:
+                    sch.unset_temporary_integrator()
+
+    def propagate_toward_noise(self, x: Tensor, y=None, nsteps: int = 100, record_history: bool = False,
+                               stochastic_integration: bool = False) -> Tensor:
+        """Forward integration data -> noise (karrasmodule.py:1096-1117)."""
+        require_cuda(x, "x")
+        with torch.inference_mode():
+            return self.config.noisescheduler.propagate_forward(x, self._score_fn(y), nsteps, record_history=record_history,
+                                                                stochastic=stochastic_integration)
+
+    def propagate_inpaint_toward_sample(self, x: Tensor, x_inpaint: Tensor, mask: Tensor, y=None,
+                                        record_history: bool = False) -> Tensor:
+        """karrasmodule.py:1048-1070: x_inpaint is the forward history [nsteps+1, B, *shape] of the known data."""
+        with torch.inference_mode():
+            return self.config.noisescheduler.inpaint(x, x_inpaint, mask, self._score_fn(y), x_inpaint.shape[0] - 1,
+                                                      record_history=record_history)
+
+    def propagate_repaint_toward_sample(self, x: Tensor, x_inpaint: Tensor, mask: Tensor, y=None,
+                                        record_history: bool = False) -> Tensor:
+        """karrasmodule.py:1072-1094 (Scheduler.repaint with its default rsteps / nresamples)."""
+        with torch.inference_mode():
+            return self.config.noisescheduler.repaint(x, x_inpaint, mask, self._score_fn(y), x_inpaint.shape[0] - 1,
+                                                      record_history=record_history)
+
+    def inpaint(self, x_orig: Tensor, mask: Tensor, y=None, nsteps: int = 100, record_history: bool = False,
+                maximum_batch_size: Optional[int] = None, mode: str = "inpaint") -> Tensor:
+        """karrasmodule.py:978-1030: noise the known data forward (stochastic integration, history kept), start from
+        N(0, sigma_max^2) and integrate back re-imposing the known region (mask == 1) after every step."""
+        if maximum_batch_size is not None:
+            sizes = get_minibatch_sizes(x_orig.shape[0], maximum_batch_size)
+            xs, ms = x_orig.chunk(len(sizes)), mask.chunk(len(sizes))
+            parts = [self.inpaint(xs[i], ms[i], y, nsteps, record_history, None, mode) for i in range(len(sizes))]
+            return torch.cat(parts, dim=1 if record_history else 0)
+        require_cuda(x_orig, "x_orig")
+        hist = self.propagate_toward_noise(x_orig, nsteps=nsteps, y=y, record_history=True, stochastic_integration=True)
+        sch = self.config.noisescheduler
+        noise = ops.lincomb(sch.integrator._randn_like(x_orig.float()), float(sch.maximum_scale))
+        fn = self.propagate_inpaint_toward_sample if mode == "inpaint" else self.propagate_repaint_toward_sample
+        return fn(noise, hist, mask, y=y, record_history=record_history)
+
+    def repaint(self, x_orig: Tensor, mask: Tensor, y=None, nsteps: int = 100, record_history: bool = False,
+                maximum_batch_size: Optional[int] = None) -> Tensor:
+        return self.inpaint(x_orig, mask, y, nsteps, record_history, maximum_batch_size, mode="repaint")
+
+    def interpolate_images(self, x1: Tensor, x2: Tensor, ninterp: int, jitter: Optional[float] = 1e-2, y=None,
+                           nsteps: int = 100, record_history: bool = False) -> Tensor:
+        """karrasmodule.py:1119-1144: noise both images with the probability-flow ODE, interpolate linearly in noise
+        space, integrate back."""
+        x = torch.stack([x1, x2], dim=0).float()
+        require_cuda(x, "images")
+        if jitter is not None:
+            x = ops.lincomb(x, 1.0, None, 0.0, None, 0.0, self.config.noisescheduler.integrator._randn_like(x), float(jitter))
+        xn = self.propagate_toward_noise(x, y, nsteps)
+        w = torch.linspace(0, 1, ninterp, device=xn.device).view(-1, *([1] * (xn.ndim - 1)))
+        xi = (1 - w) * xn[0].unsqueeze(0) + w * xn[1].unsqueeze(0)
+        return self.propagate_toward_sample(xi.contiguous(), y=y, nsteps=nsteps, record_history=record_history)

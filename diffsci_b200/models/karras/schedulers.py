@@ -126,6 +126,59 @@ class Scheduler(torch.nn.Module):
                 history[k + 1 + (skip if full else 0)] = x
         return history if record_history else x
 
+    def inpaint(self, x: Tensor, y: Tensor, mask: Tensor, score_fn: ScoreFunction, nsteps: int = 100,
+                record_history: bool = False) -> Tensor:
+        """Reverse integration with the known region re-imposed after every step from the forward history `y`
+        [nsteps+1, B, *shape] (schedulers.py:91-122): x <- step(x); x <- x (1 - mask) + y[-i-2] mask."""
+        t = self.create_steps(nsteps + 1).float().cpu()
+        dt = torch.diff(t)
+        x = x.float().contiguous()
+        if record_history:
+            history = torch.zeros((nsteps + 1,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+            history[0] = x
+        rhs = functools.partial(self.rhs, score_fn=score_fn, backward=True)
+        x = ops.mask_blend(x, y[-1], mask)
+        for i in range(nsteps):
+            x = self.integrator.step(x, t[i], dt[i], rhs, self.noise_injection)
+            x = ops.mask_blend(x, y[-i - 2], mask)
+            if record_history:
+                history[i + 1] = x
+        return history if record_history else x
+
+    def repaint(self, x: Tensor, y: Tensor, mask: Tensor, score_fn: ScoreFunction, nsteps: int = 100, rsteps: int = 10,
+                nresamples: int = 10, record_history: bool = False) -> Tensor:
+        """RePaint resampling (schedulers.py:124-175): every `rsteps` steps, `nresamples` times: re-impose the known
+        region, jump back in noise level (renoise) and integrate the same stretch again."""
+        if not (nsteps % rsteps) == 0:
+            raise ValueError("rsteps should divide nsteps")
+        t = self.create_steps(nsteps + 1).float().cpu()
+        x = x.float().contiguous()
+        if record_history:
+            history = torch.zeros((int(nresamples * (nsteps / rsteps - 1)) + 2,) + tuple(x.shape), dtype=x.dtype,
+                                  device=x.device)
+            history[0] = x
+        x = ops.mask_blend(x, y[-1], mask)
+        step, fstep = 0, rsteps
+        x = self.propagate_partial(x, score_fn, nsteps, step, fstep)
+        step, fstep = fstep, fstep + rsteps
+        level = 0
+        while fstep <= nsteps:
+            x = self.propagate_partial(x, score_fn, nsteps, step, fstep)
+            for i in range(nresamples):
+                x = ops.mask_blend(x, y[-fstep - 1], mask)
+                if record_history:
+                    history[level + i + 1] = x
+                x = self.renoise(x, t[fstep], t[step])
+                x = self.propagate_partial(x, score_fn, nsteps, step, fstep)
+            step, fstep = fstep, fstep + rsteps
+            level = level + nresamples
+        if not step == nsteps:
+            raise ValueError("Wrong counting")
+        if record_history:
+            history[level + 1] = x
+            return history
+        return x
+
     def propagate_backward(self, x, score_fn, nsteps: int = 100, record_history: bool = False,
                            stochastic: bool = False):
         return self.propagate(x, score_fn, nsteps, record_history, backward=True, stochastic=stochastic)

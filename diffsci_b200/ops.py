@@ -393,6 +393,22 @@ def lincomb(x=None, a0: float = 0.0, r1=None, a1: float = 0.0, r2=None, a2: floa
     return out
 
 
+def mask_blend(x: torch.Tensor, y: torch.Tensor, mask: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x * (1 - mask) + y * mask with torch broadcasting of the mask (dsk_mask_blend)."""
+    require_cuda(x, "inpainting state")
+    x = x.float().contiguous()
+    y = y.to(x).contiguous()
+    assert y.shape == x.shape, (y.shape, x.shape)
+    m = mask.to(x)
+    if not (m.ndim <= x.ndim and tuple(x.shape[x.ndim - m.ndim:]) == tuple(m.shape)):
+        m = m.expand_as(x)                   # general broadcasting (e.g. a size-1 batch or channel dimension)
+    m = m.contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.dsk_mask_blend(ptr(out), ptr(x), ptr(y), ptr(m), x.numel(), m.numel(), stream()))
+    return out
+
+
 def philox_normal(shape, seed: int, stream_id: int, device) -> torch.Tensor:
     """N(0,1) tensor from the library's counter-based Philox4x32-10 (dsk_philox_normal)."""
     out = torch.empty(tuple(shape), dtype=torch.float32, device=device)

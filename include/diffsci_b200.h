@@ -211,6 +211,10 @@ int dsk_cast(const void* x, void* y, int64_t n, int in_dtype, int out_dtype, voi
 int dsk_concat_channels(const void* a, const void* b, void* y, int64_t rows, int Ca, int Cb, int dtype,
                         void* stream);
 
+/* out = x * (1 - mask) + y * mask on fp32 tensors: the known-region blend of Scheduler.inpaint / Scheduler.repaint
+ * (karras/schedulers.py:111-116, 151, 162).  mask has mask_n elements and is broadcast over the leading dimensions. */
+int dsk_mask_blend(float* out, const float* x, const float* y, const float* mask, int64_t n, int64_t mask_n, void* stream);
+
 /* ---- K6: time embedding ----------------------------------------------------------------
  * Fourier features (commonlayers.py:175-190): out[b] = cat(sin(2*pi*t_b*W), cos(2*pi*t_b*W)), fp32. */
 int dsk_fourier(const float* t, const float* W, float* out, int B, int half, void* stream);

@@ -60,7 +60,50 @@ class _Noise:
         torch.randn_like = self.orig
 
 
+def inpaint_goldens():
+    """Scheduler.inpaint / repaint / propagate_partial / propagate_forward of the LIVE reference on the
+    punetg2d_mc8 network (step noise injected)  ->  tests/golden/inpaint_punetg2d.pt.   python oracle/make_goldens.py --only inpaint"""
+    os.makedirs(OUT, exist_ok=True)
+    refload.load_reference()
+    import diffsci.models as M
+    from diffsci.models.nets.punetg import PUNetG
+    from diffsci.models.nets.punetg_config import PUNetGConfig
+    torch.set_num_threads(8)
+    kw = dict(dimension=2, model_channels=8)
+    net = PUNetG(PUNetGConfig(**kw))
+    load_synth(net, 101)                                   # the weights of punetg2d_mc8
+    net.eval()
+    cfg = M.KarrasModuleConfig.from_edm()
+    mod = M.KarrasModule(net, cfg)
+    mod.eval()
+    torch.manual_seed(303)
+    shape, nsteps = (2, 1, 28, 28), 4
+    x_orig = torch.randn(*shape) * 0.5
+    mask = (torch.rand(*shape[1:]) > 0.5).float()
+    start = torch.randn(*shape) * 80.0
+    fwd_noise = [torch.randn(*shape) for _ in range(nsteps)]
+    re_noise = [torch.randn(*shape) for _ in range(8)]
+    out = dict(nsteps=nsteps, x_orig=x_orig, mask=mask, start=start, fwd_noise=fwd_noise, re_noise=re_noise)
+    with torch.no_grad():
+        with _Noise(fwd_noise):
+            hist = mod.propagate_toward_noise(x_orig, nsteps=nsteps, record_history=True, stochastic_integration=True)
+        out["fwd_hist"] = hist
+        out["fwd_ode"] = mod.propagate_toward_noise(x_orig, nsteps=nsteps)
+        out["inpaint_hist"] = mod.propagate_inpaint_toward_sample(start, hist, mask, record_history=True)
+        sch = cfg.noisescheduler
+
+        def rhs(x, sigma):
+            return mod.get_score(x, sigma, None)
+        with _Noise(re_noise):
+            out["repaint_hist"] = sch.repaint(start, hist, mask, rhs, nsteps, rsteps=2, nresamples=2, record_history=True)
+        out["partial"] = mod.propagate_partial_toward_sample(start, 1, 3, nsteps=nsteps, record_history=True)
+    torch.save(out, os.path.join(OUT, "inpaint_punetg2d.pt"))
+    print("inpaint_punetg2d", {k: (tuple(v.shape), float(v.abs().max())) for k, v in out.items() if torch.is_tensor(v)})
+
+
 def main():
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "inpaint":
+        return inpaint_goldens()
     os.makedirs(OUT, exist_ok=True)
     refload.load_reference()
     import diffsci.models as M
