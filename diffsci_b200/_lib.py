@@ -59,6 +59,8 @@ SIGNATURES = {
     "dsk_gemm_f32": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i32, i32, f32, i32, p],
     "dsk_gemm_bf16_tc": [p, p, p, p, i32, p, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, f32, i32, i32, i32, p],
     "dsk_softmax_bwd_rows_bf16": [p, p, p, i64, i32, p],
+    "dsk_attn_softmax_ws_bytes": [i32, i32],
+    "dsk_attn_softmax_qk": [p, p, p, p, i32, i32, i64, i64, i64, i64, i32, f32, p],
     "dsk_softmax_rows_bf16": [p, p, i64, i32, p],
     "dsk_norm_ws_bytes": [i32, i64, i32],
     "dsk_norm_act": [p, p, p, p, p, p, p, i32, i64, i32, i32, i32, i32, i32, i32, p],
@@ -94,7 +96,7 @@ SIGNATURES = {
     "dsk_split_channels": [p, p, p, p, p, i64, i32, i32, i32, p],
 }
 _RESTYPE = {"dsk_last_error": C.c_char_p, "dsk_launch_count": u64, "dsk_norm_ws_bytes": i64,
-            "dsk_conv_wgrad_ws_bytes": i64, "dsk_bwd_ws_bytes": i64}
+            "dsk_conv_wgrad_ws_bytes": i64, "dsk_bwd_ws_bytes": i64, "dsk_attn_softmax_ws_bytes": i64}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)          # AttributeError here == header/library mismatch: fail loudly

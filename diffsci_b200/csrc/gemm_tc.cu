@@ -28,7 +28,11 @@ struct GemmTcParams {
   int out_f32;
   int64_t ldc, strideC;
   int transA, transB;       // operand stored [K][M] / [K][N] (MN-major)
+  int epi;                  // 0: C = alpha A B^T (+bias, +residual);  1: row statistics only;  2: softmax probabilities
+  float2* rowstat;          // epi 1: [batch][M][tiles_n] (max, sum exp(s - max)) of s = alpha * acc over this tile's columns
+  const float2* rowfinal;   // epi 2: [batch][M] (row max, 1 / row sum): out = exp(s - max) / sum as bf16
 };
+constexpr int EPI_NORMAL = 0, EPI_ROWSTAT = 1, EPI_SOFTMAX = 2;
 
 template <int N_TILE>
 __global__ void __launch_bounds__(GT_THREADS, 1)
@@ -137,6 +141,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       // 11.6 K SASS instructions and ran at the speed of the instruction cache (ncu: tensor pipe 4-6 % active).
       const bool full_n = (tn + 1) * N_TILE <= p.N;
       const bool col_bias = p.bias != nullptr && !p.bias_rows;
+      if (p.epi == EPI_ROWSTAT) {
+        // online (max, sum of exp) of this row over the tile's columns; nothing else is written: the scores never reach HBM
+        float mx = -INFINITY, sm = 0.0f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+          uint32_t v[32];
+          DSK_TMEM_LD_X32(v, taddr + c0);
+          const int n = tn * N_TILE + c0;
+          if (n >= p.N) continue;
+          const int nv = p.N - n;
+          float sv[32], g = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            sv[e] = (full_n || e < nv) ? p.alpha * __uint_as_float(v[e]) : -INFINITY;
+            g = fmaxf(g, sv[e]);
+          }
+          const float nm = fmaxf(mx, g);
+          float acc = 0.0f;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) acc += __expf(sv[e] - nm);
+          sm = sm * __expf(mx - nm) + acc;
+          mx = nm;
+        }
+        if (mvalid) p.rowstat[((int64_t)b * p.M + m) * p.tiles_n + tn] = make_float2(mx, sm);
+      } else if (p.epi == EPI_SOFTMAX) {
+        const float2 rf = mvalid ? p.rowfinal[(int64_t)b * p.M + m] : make_float2(0.0f, 0.0f);
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+          uint32_t v[32];
+          DSK_TMEM_LD_X32(v, taddr + c0);
+          const int n = tn * N_TILE + c0;
+          if (!mvalid || n >= p.N) continue;
+          float f[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) f[e] = __expf(fmaf(p.alpha, __uint_as_float(v[e]), -rf.x)) * rf.y;
+          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n;
+          if (full_n || n + 32 <= p.N) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 pk;
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+              reinterpret_cast<uint4*>(orow)[g] = pk;
+            }
+          } else {
+#pragma unroll 1
+            for (int e = 0; e < 32 && n + e < p.N; ++e) orow[e] = __float2bfloat16_rn(f[e]);
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         uint32_t v[32];
@@ -305,6 +360,18 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_bf16_kernel(const __nv_b
   }
 }
 
+// (max, sum) partials of the score tiles of a row -> (row max, 1 / row sum)
+__global__ void __launch_bounds__(256) rowstat_combine_kernel(const float2* __restrict__ part, float2* __restrict__ fin, int64_t rows, int tiles) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float2* p = part + r * tiles;
+  float mx = -INFINITY;
+  for (int t = 0; t < tiles; ++t) mx = fmaxf(mx, p[t].x);
+  float sm = 0.0f;
+  for (int t = 0; t < tiles; ++t) sm += p[t].y * __expf(p[t].x - mx);
+  fin[r] = make_float2(mx, 1.0f / sm);
+}
+
 template <int N_TILE>
 static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, cudaStream_t st) {
   const size_t smem = (size_t)GT_STAGES * (128 * 128 + N_TILE * 128) + 1024;
@@ -323,17 +390,18 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
 
 using namespace dsk;
 
-extern "C" int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const float* bias, int bias_rows, const void* residual,
-                                int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
-                                int64_t strideC, int batch, float alpha, int out_f32, int transA, int transB, void* stream) {
-  DSK_REQUIRE(A && Bm && C, "dsk_gemm_bf16_tc: null pointer");
+static int gemm_tc_run(const void* A, const void* Bm, void* C, const float* bias, int bias_rows, const void* residual, int M, int N, int K,
+                       int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC, int batch, float alpha,
+                       int out_f32, int transA, int transB, int epi, float2* rowstat, const float2* rowfinal, int force_tile,
+                       void* stream) {
+  DSK_REQUIRE(A && Bm && (C || epi == EPI_ROWSTAT), "dsk_gemm_bf16_tc: null pointer");
   DSK_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "dsk_gemm_bf16_tc: bad shape");
   DSK_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && strideA % 8 == 0 && strideB % 8 == 0,
               "dsk_gemm_bf16_tc: K, lda, ldb, ldc and batch strides must be multiples of 8 elements (16-byte TMA alignment)");
   DSK_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Bm & 15) == 0 && ((uintptr_t)C & 15) == 0, "dsk_gemm_bf16_tc: 16-byte alignment");
   EncodeTiledFn encode = get_encode();
   DSK_REQUIRE(encode != nullptr, "dsk_gemm_bf16_tc: cuTensorMapEncodeTiled is unavailable");
-  const int n_tile = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  const int n_tile = force_tile ? force_tile : (N > 128 ? 256 : (N > 64 ? 128 : 64));
   CUtensorMap ta, tb;
   // K-major operand [rows][K]: box 64 (k) x box_rows;  MN-major operand [K][rows]: box 64 (rows) x 64 (k)
   auto make = [&](CUtensorMap* tm, const void* base, int rows, int64_t ld, int64_t stride, int box_rows, int trans) -> bool {
@@ -357,10 +425,41 @@ extern "C" int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const fl
   p.alpha = alpha; p.bias = bias; p.bias_rows = bias_rows;
   p.residual = (const __nv_bfloat16*)residual; p.out = C; p.out_f32 = out_f32; p.ldc = ldc; p.strideC = strideC;
   p.transA = transA ? 1 : 0; p.transB = transB ? 1 : 0;
+  p.epi = epi; p.rowstat = rowstat; p.rowfinal = rowfinal;
   cudaStream_t st = as_stream(stream);
   if (n_tile == 64) return launch_gemm_tc<64>(ta, tb, p, st);
   if (n_tile == 128) return launch_gemm_tc<128>(ta, tb, p, st);
   return launch_gemm_tc<256>(ta, tb, p, st);
+}
+
+extern "C" int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const float* bias, int bias_rows, const void* residual,
+                                int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
+                                int64_t strideC, int batch, float alpha, int out_f32, int transA, int transB, void* stream) {
+  return gemm_tc_run(A, Bm, C, bias, bias_rows, residual, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch, alpha, out_f32, transA,
+                     transB, EPI_NORMAL, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int64_t dsk_attn_softmax_ws_bytes(int batch, int L) {
+  if (batch <= 0 || L <= 0) return 0;
+  const int tiles = (L + 255) / 256;
+  return (int64_t)batch * L * (tiles + 1) * (int64_t)sizeof(float2);
+}
+
+// P[b] = softmax(alpha Q[b] K[b]^T) as bf16, without the scores ever reaching HBM: pass 1 = QK^T with a row-statistics
+// epilogue (per 256-column tile), a tiny combine, pass 2 = QK^T again with the exp / normalise / bf16 epilogue.
+extern "C" int dsk_attn_softmax_qk(const void* Q, const void* Kmat, void* P, void* ws, int L, int C, int64_t ldq, int64_t ldk,
+                                   int64_t strideQ, int64_t strideK, int batch, float alpha, void* stream) {
+  DSK_REQUIRE(Q && Kmat && P && ws && L > 0 && C > 0 && batch > 0 && L % 8 == 0, "dsk_attn_softmax_qk: bad arguments (L %% 8 == 0)");
+  const int tiles = (L + 255) / 256;
+  float2* part = reinterpret_cast<float2*>(ws);
+  float2* fin = part + (int64_t)batch * L * tiles;
+  int rc = gemm_tc_run(Q, Kmat, P, nullptr, 0, nullptr, L, L, C, ldq, ldk, L, strideQ, strideK, (int64_t)L * L, batch, alpha, 0, 0, 0,
+                       EPI_ROWSTAT, part, nullptr, 256, stream);
+  if (rc != DSK_OK) return rc;
+  const int64_t rows = (int64_t)batch * L;
+  DSK_LAUNCH(rowstat_combine_kernel, (int)((rows + 255) / 256), 256, 0, as_stream(stream), part, fin, rows, tiles);
+  return gemm_tc_run(Q, Kmat, P, nullptr, 0, nullptr, L, L, C, ldq, ldk, L, strideQ, strideK, (int64_t)L * L, batch, alpha, 0, 0, 0,
+                     EPI_SOFTMAX, nullptr, fin, 256, stream);
 }
 
 extern "C" int dsk_softmax_rows_bf16(const float* S, void* P, int64_t rows, int cols, void* stream) {

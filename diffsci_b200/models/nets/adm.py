@@ -228,6 +228,7 @@ class _ADMPlan:
             ys += list(self.film[id(b)])
         self.film_gl = ops.GroupedLinear([self.te] * len(ws), ws, bs, ys, 0)
         self.attn_state = {}
+        self.attn_bufs = {}
         self.prepare()
 
     def buf(self, tag, shape, dtype=None):
@@ -264,9 +265,9 @@ class _ADMPlan:
             st = self.attn_state.get(idx)
             if st is None:
                 st = self.attn_state[idx] = (ops.PackedLinear(m.in_proj_weight), ops.PackedLinear(m.out_proj.weight))
-            bufs = dict(qk=self.buf("qk", (B * Lq, 2 * C)), vt=self.buf("vt", (B, C, Lq)),
-                        scores=self.buf("scores", (B, Lq, Lq), f32), probs=self.buf("probs", (B, Lq, Lq)),
-                        ao=self.buf("ao", (B * Lq, C)))
+            bufs = self.attn_bufs.get((B, Lq, C))
+            if bufs is None:
+                bufs = self.attn_bufs[(B, Lq, C)] = ops.attention_tc_buffers(B, Lq, C, x.device)
             ops.self_attention_tc(x.view(B, Lq, C), st[0], m.in_proj_bias, st[1], m.out_proj.bias, bufs, out.view(B, Lq, C), res)
             return out
         bufs = dict(qkv=self.buf("qkv", (B * Lq, 3 * C), f32), scores=self.buf("scores", (B, Lq, Lq), f32),

@@ -254,10 +254,7 @@ class _Plan:
         self.attn_tc = (precision == "bf16" and _tc_eligible(Cb, Cb) and Lq % 8 == 0 and Lq <= 8192)
         self.attn_hybrid = False
         if len(net.attn_block) > 0 and self.attn_tc:
-            bf = dict(dtype=torch.bfloat16, device=dev)
-            self.attn = dict(qk=torch.empty((B * Lq, 2 * Cb), **bf), vt=torch.empty((B, Cb, Lq), **bf),
-                             scores=torch.empty((B, Lq, Lq), **f32), probs=torch.empty((B, Lq, Lq), **bf),
-                             ao=torch.empty((B * Lq, Cb), **bf))
+            self.attn = ops.attention_tc_buffers(B, Lq, Cb, dev)
             self.attn_w = [(ops.PackedLinear(a.mhattn.in_proj_weight), ops.PackedLinear(a.mhattn.out_proj.weight))
                            for a in net.attn_block]
         elif len(net.attn_block) > 0:

@@ -456,24 +456,35 @@ def gemm_bf16_tc(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, *, M: int
     return out
 
 
+def attention_tc_buffers(B: int, Lq: int, Cc: int, device) -> dict:
+    """Scratch of self_attention_tc: packed Q|K|V, the bf16 probabilities, the attention output and the row-statistics
+    workspace of dsk_attn_softmax_qk.  (No fp32 score tensor: the scores never leave the SM.)"""
+    bf = dict(dtype=torch.bfloat16, device=device)
+    return dict(qkv=torch.empty((B * Lq, 3 * Cc), **bf), probs=torch.empty((B, Lq, Lq), **bf), ao=torch.empty((B * Lq, Cc), **bf),
+                rowstat=torch.empty(int(lib.dsk_attn_softmax_ws_bytes(B, Lq)), dtype=torch.uint8, device=device))
+
+
+def attn_softmax_qk(qkv: torch.Tensor, probs: torch.Tensor, ws: torch.Tensor, B: int, Lq: int, Cc: int) -> torch.Tensor:
+    """probs[b] = softmax(Q[b] K[b]^T / sqrt(C)) (bf16) from packed projections qkv [B*L, 3C] (dsk_attn_softmax_qk)."""
+    q = C.c_void_p(qkv.data_ptr())
+    k = C.c_void_p(qkv.data_ptr() + Cc * 2)
+    check(lib.dsk_attn_softmax_qk(q, k, ptr(probs), ptr(ws), Lq, Cc, 3 * Cc, 3 * Cc, Lq * 3 * Cc, Lq * 3 * Cc, B, Cc ** -0.5, stream()))
+    return probs
+
+
 def self_attention_tc(tok: torch.Tensor, w_in: PackedLinear, in_b: torch.Tensor, w_out: PackedLinear, out_b: torch.Tensor,
                       bufs: dict, out: torch.Tensor, residual: bool) -> torch.Tensor:
     """nn.MultiheadAttention(C, 1 head) on bf16 tokens [B, L, C] with every product on the tensor cores
-    (reference nets/attention.py:54-72):  Q|K projection, V^T projection, S = QK^T/sqrt(C) (fp32), softmax -> bf16 P,
-    O = P V, output projection (+ residual) written straight into `out` ([B, L, C] bf16)."""
+    (reference nets/attention.py:54-72):  packed Q|K|V projection, P = softmax(QK^T/sqrt(C)) written once as bf16 (two
+    QK^T passes, row statistics in the epilogue of the first), O = P V with V as it lies (MN-major operand), output
+    projection (+ residual) written straight into `out` ([B, L, C] bf16).  `bufs`: attention_tc_buffers."""
     B, Lq, Cc = tok.shape
-    qk, vt, sc, pr, ao = bufs["qk"], bufs["vt"], bufs["scores"], bufs["probs"], bufs["ao"]
-    wi, wo, ib = w_in.packed(), w_out.packed(), in_b.detach()
-    gemm_bf16_tc(tok, wi, qk, M=B * Lq, N=2 * Cc, K=Cc, lda=Cc, ldb=Cc, ldc=2 * Cc, bias=ib)
-    # V^T[b] = W_v tok[b]^T + b_v : [C, L] so that it is the K-major B operand of P V
-    gemm_bf16_tc(wi, tok, vt, M=Cc, N=Lq, K=Cc, lda=Cc, ldb=Cc, ldc=Lq, bias=ib[2 * Cc:], bias_rows=True, batch=B,
-                 strideA=0, strideB=Lq * Cc, strideC=Cc * Lq, a_off=2 * Cc * Cc)
-    gemm_bf16_tc(qk, qk, sc, M=Lq, N=Lq, K=Cc, lda=2 * Cc, ldb=2 * Cc, ldc=Lq, alpha=Cc ** -0.5, batch=B,
-                 strideA=Lq * 2 * Cc, strideB=Lq * 2 * Cc, strideC=Lq * Lq, b_off=Cc)
-    check(lib.dsk_softmax_rows_bf16(ptr(sc), ptr(pr), B * Lq, Lq, stream()))
-    gemm_bf16_tc(pr, vt, ao, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=Lq, ldc=Cc, batch=B, strideA=Lq * Lq, strideB=Cc * Lq,
-                 strideC=Lq * Cc)
-    gemm_bf16_tc(ao, wo, out, M=B * Lq, N=Cc, K=Cc, lda=Cc, ldb=Cc, ldc=Cc, bias=out_b.detach(),
+    qkv, pr, ao = bufs["qkv"], bufs["probs"], bufs["ao"]
+    gemm_bf16_tc(tok, w_in.packed(), qkv, M=B * Lq, N=3 * Cc, K=Cc, lda=Cc, ldb=Cc, ldc=3 * Cc, bias=in_b.detach())
+    attn_softmax_qk(qkv, pr, bufs["rowstat"], B, Lq, Cc)
+    gemm_bf16_tc(pr, qkv, ao, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=3 * Cc, ldc=Cc, batch=B, strideA=Lq * Lq, strideB=Lq * 3 * Cc,
+                 strideC=Lq * Cc, b_off=2 * Cc, transB=True)
+    gemm_bf16_tc(ao, w_out.packed(), out, M=B * Lq, N=Cc, K=Cc, lda=Cc, ldb=Cc, ldc=Cc, bias=out_b.detach(),
                  residual=tok if residual else None)
     return out
 

@@ -175,6 +175,13 @@ int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const float* bias, 
                      int64_t strideC, int batch, float alpha, int out_f32, int transA, int transB, void* stream);
 /* softmax backward on rows: dS = P * (dP - rowsum(dP * P)); P bf16, dP fp32, dS bf16 (cols % 4 == 0, cols <= 8192) */
 int dsk_softmax_bwd_rows_bf16(const void* P, const float* dP, void* dS, int64_t rows, int cols, void* stream);
+/* P[b] = softmax(alpha Q[b] K[b]^T) written once as bf16 [batch, L, L] -- the middle of nn.MultiheadAttention
+ * (nets/attention.py:42-44,68) without the fp32 score tensor: QK^T runs twice on the tensor cores, first with a
+ * row-statistics epilogue, then with the exp / normalise epilogue.  Q, K: bf16 [L, C] per batch (K-major, ldq / ldk, batch
+ * strides); L % 8 == 0; ws: dsk_attn_softmax_ws_bytes(batch, L) bytes. */
+int64_t dsk_attn_softmax_ws_bytes(int batch, int L);
+int dsk_attn_softmax_qk(const void* Q, const void* K, void* P, void* ws, int L, int C, int64_t ldq, int64_t ldk,
+                        int64_t strideQ, int64_t strideK, int batch, float alpha, void* stream);
 /* softmax over the last dim: fp32 scores [rows, cols] -> bf16 probabilities (cols % 4 == 0, cols <= 8192) */
 int dsk_softmax_rows_bf16(const float* S, void* P, int64_t rows, int cols, void* stream);
 

@@ -18,9 +18,8 @@ a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 B, L, C = a.batch, a.tokens, a.channels
-bf, f32 = dict(dtype=torch.bfloat16, device=dev), dict(dtype=torch.float32, device=dev)
-bufs = dict(qk=torch.empty(B * L, 2 * C, **bf), vt=torch.empty(B, C, L, **bf), scores=torch.empty(B, L, L, **f32),
-            probs=torch.empty(B, L, L, **bf), ao=torch.empty(B * L, C, **bf))
+bf = dict(dtype=torch.bfloat16, device=dev)
+bufs = ops.attention_tc_buffers(B, L, C, dev)
 tok = torch.randn(B, L, C, device=dev).bfloat16()
 wi = ops.PackedLinear(torch.randn(3 * C, C, device=dev) / C ** 0.5)
 wo = ops.PackedLinear(torch.randn(C, C, device=dev) / C ** 0.5)
