@@ -42,6 +42,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   constexpr int A_BYTES = 128 * 128, B_BYTES = N_TILE * 128, STAGE = A_BYTES + B_BYTES;
   __shared__ uint64_t full[GT_STAGES], empty[GT_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint4 stage_s[4][32 * 8];                   // per epilogue warp: 32 rows x 128 B (coalescing stage of the stores)
   constexpr uint32_t TMEM_COLS = 2 * N_TILE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = (p.K + 63) / 64;
@@ -166,42 +167,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         }
         if (mvalid) p.rowstat[((int64_t)b * p.M + m) * p.tiles_n + tn] = make_float2(mx, sm);
       } else if (p.epi == EPI_SOFTMAX) {
+        // 64 columns = one 128-byte line per row per iteration.  A thread holds one ROW of the tile; storing it directly
+        // makes every warp-wide st.global.v4 touch 32 different lines.  Instead the warp stages its 32 x 128 B in shared
+        // memory (XOR-swizzled 16-byte slots, conflict-free both ways) and writes it back transposed: 8 lanes per row,
+        // 4 complete lines per store instruction.
         const float2 rf = mvalid ? p.rowfinal[(int64_t)b * p.M + m] : make_float2(0.0f, 0.0f);
+        uint4* stg = stage_s[q];
+        const int m_warp = tm * 128 + q * 32;
 #pragma unroll 1
-        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-          uint32_t v[32];
-          DSK_TMEM_LD_X32(v, taddr + c0);
+        for (int c0 = 0; c0 < N_TILE; c0 += 64) {
           const int n = tn * N_TILE + c0;
-          if (!mvalid || n >= p.N) continue;
-          float f[32];
+          if (n >= p.N) continue;                               // warp-uniform
+          uint4 pk[8];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) f[e] = __expf(fmaf(p.alpha, __uint_as_float(v[e]), -rf.x)) * rf.y;
-          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n;
-          if (full_n || n + 32 <= p.N) {
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            DSK_TMEM_LD_X32(v, taddr + c0 + hh * 32);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              uint4 pk;
-              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&pk);
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&pk[hh * 4 + g]);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
-              reinterpret_cast<uint4*>(orow)[g] = pk;
+              for (int e = 0; e < 4; ++e) {
+                const float f0 = __expf(fmaf(p.alpha, __uint_as_float(v[g * 8 + 2 * e]), -rf.x)) * rf.y;
+                const float f1 = __expf(fmaf(p.alpha, __uint_as_float(v[g * 8 + 2 * e + 1]), -rf.x)) * rf.y;
+                oh[e] = __floats2bfloat162_rn(f0, f1);
+              }
             }
-          } else {
+          }
+          if (n + 64 <= p.N) {                                  // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 8; ++j) stg[lane * 8 + (j ^ (lane & 7))] = pk[j];
+            __syncwarp();
+            const int j = lane & 7;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int r = 4 * k + (lane >> 3);
+              const uint4 val = stg[r * 8 + (j ^ (r & 7))];
+              if (m_warp + r < p.M)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)b * p.strideC + (int64_t)(m_warp + r) * p.ldc + n +
+                                          j * 8) = val;
+            }
+            __syncwarp();
+          } else if (mvalid) {                                  // ragged right edge: per-row scalar stores
+            const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(pk);
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n;
 #pragma unroll 1
-            for (int e = 0; e < 32 && n + e < p.N; ++e) orow[e] = __float2bfloat16_rn(f[e]);
+            for (int e = 0; e < 64 && n + e < p.N; ++e) orow[e] = src[e];
           }
         }
-      } else
+      } else {
+      const int m_warp = tm * 128 + q * 32;
 #pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         uint32_t v[32];
         DSK_TMEM_LD_X32(v, taddr + c0);
         const int n = tn * N_TILE + c0;
-        if (!mvalid || n >= p.N) continue;
+        if (n >= p.N) continue;                                 // warp-uniform
         float f[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) f[e] = fmaf(p.alpha, __uint_as_float(v[e]), rb);
-        if (full_n || n + 32 <= p.N) {
+        if (full_n || n + 32 <= p.N) {                          // warp-uniform
           if (col_bias) {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
@@ -210,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
               f[4 * e4] += bb.x; f[4 * e4 + 1] += bb.y; f[4 * e4 + 2] += bb.z; f[4 * e4 + 3] += bb.w;
             }
           }
-          if (p.residual != nullptr) {
+          if (p.residual != nullptr && mvalid) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + n);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -221,21 +246,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             }
           }
           if (p.out_f32) {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + n);
+            if (mvalid) {
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + n);
 #pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4) o[e4] = make_float4(f[4 * e4], f[4 * e4 + 1], f[4 * e4 + 2], f[4 * e4 + 3]);
+              for (int e4 = 0; e4 < 8; ++e4) o[e4] = make_float4(f[4 * e4], f[4 * e4 + 1], f[4 * e4 + 2], f[4 * e4 + 3]);
+            }
           } else {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + n);
+            // staged, transposed store (see the softmax epilogue): 4 lanes per row write 64 contiguous bytes, 8 rows per
+            // instruction; every lane takes part, row validity is checked where the row is written
+            uint4* stg = stage_s[q];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 pk;
               __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
               for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
-              o[g] = pk;
+              stg[lane * 4 + (g ^ (lane & 3))] = pk;
             }
+            __syncwarp();
+            const int j = lane & 3;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int r = 8 * k + (lane >> 2);
+              const uint4 val = stg[r * 4 + (j ^ (r & 3))];
+              if (m_warp + r < p.M)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)b * p.strideC + (int64_t)(m_warp + r) * p.ldc + n +
+                                          j * 8) = val;
+            }
+            __syncwarp();
           }
-        } else {
+        } else if (mvalid) {
           // ragged N edge: scalar, rolled (f is indexed dynamically -> local memory; rare and tiny)
 #pragma unroll 1
           for (int e = 0; e < 32 && n + e < p.N; ++e) {
@@ -246,6 +286,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             else reinterpret_cast<__nv_bfloat16*>(p.out)[obase + n + e] = __float2bfloat16_rn(x);
           }
         }
+      }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
