@@ -408,6 +408,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   constexpr int B_HALF = (N_TILE / 2) * 128;            // this CTA's half of a weight tap tile
   __shared__ uint64_t full_a[NA], empty_a[NA], full_b[NB], empty_b[NB], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint4 stage_s[8][32 * 4];                  // per epilogue warp: 32 rows x 64 B (coalescing stage of the stores)
   constexpr uint32_t TMEM_COLS = 2 * P * N_TILE;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
 
@@ -601,6 +602,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     const int nranges = total_pairs / per_range;             // n_tiles * srange
     int cur_range = -1;
     const int slot = (int)blockIdx.x * 8 + (warp - 4);
+    uint4* stg = stage_s[warp - 4];
     auto flush = [&](int range, bool zero) {
       const int nt = range / srange, sr = range - nt * srange;  // range -> (n-tile, sample range)
       const int sg = is3d ? sr : sr * P + pp;
@@ -634,7 +636,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         pix = (((int64_t)tc.b * p.D + d) * p.H + h) * p.W + w;
       }
       const int brow = (tc.b * p.D + d) / p.planes_per_sample;
-      __nv_bfloat16* orow = p.out + pix * p.Cout + tc.n0;
+      // store-side mapping (see the staged store below): this lane writes column chunk lane&3 of rows (line q*4+k, w lane>>2)
+      const int w_st = tc.w0 + (lane >> 2);
+      const bool st_ok = w_st < p.W && d < p.D;
+      int64_t st_pix;
+      if constexpr (UPS) {
+        const int od = p.KD == 3 ? 2 * d + tc.pa : d, OD = p.KD == 3 ? 2 * p.D : p.D;
+        st_pix = (((int64_t)tc.b * OD + od) * (2 * p.H) + (2 * (tc.h0 + q * 4) + tc.pb)) * (2 * p.W) + (2 * w_st + tc.pc);
+      } else {
+        st_pix = (((int64_t)tc.b * p.D + d) * p.H + tc.h0 + q * 4) * p.W + w_st;
+      }
       const __nv_bfloat16* rrow = (p.residual != nullptr && valid) ? p.residual + pix * p.Cout + tc.n0 : nullptr;
       const float* cbrow = p.chan_bias != nullptr ? p.chan_bias + (int64_t)brow * p.Cout + tc.n0 : nullptr;
       uint4 rr[DEP][4];
@@ -690,15 +701,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             for (int g = 0; g < 4; ++g) rr[gi % DEP][g] = *reinterpret_cast<const uint4*>(rrow + (gi + DEP) * 32 + g * 8);
           }
         }
-        if (valid) {
+        {
+          // staged, transposed store: a thread holds one pixel ROW, so a direct st.global.v4 touches 32 lines per
+          // instruction; through this warp's 2 KB stage (XOR-swizzled 16-byte slots) 4 lanes write 64 contiguous bytes
+          // of a row and one instruction covers 8 rows.  Row r = 8k + lane/4 of the warp is pixel (line q*4 + k, w lane/4).
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 o;
             __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
             for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
-            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = o;
+            stg[lane * 4 + (g ^ (lane & 3))] = o;
           }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = 8 * k + (lane >> 2);
+            const uint4 val = stg[r * 4 + ((lane & 3) ^ (r & 3))];
+            if (st_ok && tc.h0 + q * 4 + k < p.H) {
+              int64_t px;
+              if constexpr (UPS) px = st_pix + (int64_t)k * 2 * (2 * p.W);
+              else px = st_pix + (int64_t)k * p.W;
+              *reinterpret_cast<uint4*>(p.out + px * p.Cout + tc.n0 + c0 + (lane & 3) * 8) = val;
+            }
+          }
+          __syncwarp();
         }
         if (do_stats) {
           // butterfly transpose-reduce over the 32 lanes (= 32 pixels): lane l keeps channel c0 + l
