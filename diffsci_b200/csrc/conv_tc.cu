@@ -51,7 +51,7 @@ struct TcParams {
   float2* stats;          // cta_group::2 kernel: per-(sample, slot, channel) partial (sum, sum of squares) of the output, or null
   int samples;            // number of samples the stats are kept for (3-D: B; 2-D: the planes ARE the samples)
 };
-constexpr int TC_STAT_SLOTS = DSK_NUM_SMS * 8;      // one slot per (CTA, epilogue warp)
+constexpr int TC_STAT_SLOTS = DSK_NUM_SMS;          // one slot per CTA
 
 struct TileCoord {
   int w0, h0, d0, b, n0;
@@ -586,7 +586,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     const int line = row >> 3, wp = row & 7;
     // Fused norm statistics (optional): per output channel, sum and sum of squares of the fp32 results over the pixels
     // this warp stores, accumulated in registers while the CTA stays inside one (n-tile, sample) range of the tile order
-    // and flushed to stats[sample][slot = cta*8 + warp][channel] when it leaves it -- no atomics, fixed summation order.
+    // and flushed (combined over the CTA's epilogue warps) to stats[sample][slot = cta][channel] when it leaves it -- no
+    // atomics, fixed summation order.
     // Lane l of the warp ends up owning channel c0 + l of every 32-channel group (butterfly transpose-reduce).
     constexpr int NG = N_TILE / 32;
     constexpr int DEP = NG < 2 ? NG : 2;                  // residual prefetch depth in 32-channel groups
@@ -601,18 +602,34 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     const int per_range = p.nphase * (p.tiles_w >> 1) * p.tiles_h * (is3d ? p.groups_d : 1);
     const int nranges = total_pairs / per_range;             // n_tiles * srange
     int cur_range = -1;
-    const int slot = (int)blockIdx.x * 8 + (warp - 4);
     uint4* stg = stage_s[warp - 4];
+    // flush: the 8 epilogue warps of the CTA reach a range change together (same tile sequence); their partials meet in
+    // shared memory (the store stage is idle between tiles) and ONE slot per CTA goes to global memory, summed in a fixed
+    // order.  3-D: all 8 warps belong to one sample; 2-D: the warps of plane pp belong to sample d0 + pp.
     auto flush = [&](int range, bool zero) {
       const int nt = range / srange, sr = range - nt * srange;  // range -> (n-tile, sample range)
-      const int sg = is3d ? sr : sr * P + pp;
-      if (sg >= p.samples) return;
+      float2* mine = reinterpret_cast<float2*>(stage_s[warp - 4]);      // each warp parks its partials in its OWN stage
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
-        const int ch = nt * N_TILE + g * 32 + lane;
-        p.stats[((int64_t)sg * TC_STAT_SLOTS + slot) * p.Cout + ch] = zero ? make_float2(0.0f, 0.0f) : make_float2(st_s[g], st_q[g]);
+        mine[g * 32 + lane] = zero ? make_float2(0.0f, 0.0f) : make_float2(st_s[g], st_q[g]);
         st_s[g] = 0.0f; st_q[g] = 0.0f;
       }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const bool lead = is3d ? warp == 4 : (warp == 4 || warp == 8);
+      const int sg = is3d ? sr : sr * P + pp;
+      if (lead && sg < p.samples) {
+        const int w0 = warp - 4, nw = is3d ? 8 : 4;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          float2 t = make_float2(0.0f, 0.0f);
+          for (int w = w0; w < w0 + nw; ++w) {
+            const float2 v = reinterpret_cast<const float2*>(stage_s[w])[g * 32 + lane];
+            t.x += v.x; t.y += v.y;
+          }
+          p.stats[((int64_t)sg * TC_STAT_SLOTS + blockIdx.x) * p.Cout + nt * N_TILE + g * 32 + lane] = t;
+        }
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
     };
     uint32_t it = 0;
     for (int u = cluster_id; u < total_pairs; u += nclusters, ++it) {
