@@ -54,6 +54,11 @@ struct StageArgs {
   int64_t S;
   float sigma_data, sigma_max;
   int precond;   // 0 EDM, 1 Null
+  // conditional path: the network input rows hold xin_ld >= C channels (PUNetGCond's channel-concatenated
+  // conditioning lives in channels C..xin_ld-1 and is written once per run by the host); cfg != 0: the network runs a
+  // 2B batch (rows [0,B) unconditional, [B,2B) conditional) and F = (1-g) F_u + g F_c (karrasmodule.py:705-713).
+  int xin_ld, cfg;
+  float guidance;
 };
 
 template <int V> struct Vec;
@@ -85,7 +90,7 @@ template <> struct Vec<4> {
   }
 };
 
-// V == 4 requires C == 1 (channels-last == NCHW) and (B*S) % 4 == 0.
+// V == 4 requires C == 1 == xin_ld (channels-last == NCHW) and (B*S) % 4 == 0.
 template <typename T, int V, int STAGE>
 __global__ void __launch_bounds__(256) sampler_stage_kernel(StageArgs a) {
   const int rowi = a.row[0];
@@ -122,19 +127,33 @@ __global__ void __launch_bounds__(256) sampler_stage_kernel(StageArgs a) {
   const float dth = (t + dt) - that;  // Karras: dt_noise = (t+dt) - t_noise (integrators.py:107)
 
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (do_prep && tid < a.B) a.cnoise[tid] = a.precond == 1 ? sig_next : 0.5f * logf(sig_next);
+  if (do_prep && tid < a.B) {
+    const float cn = a.precond == 1 ? sig_next : 0.5f * logf(sig_next);
+    a.cnoise[tid] = cn;
+    if (a.cfg) a.cnoise[a.B + tid] = cn;
+  }
+  const bool strided = (V == 1) && (a.C > 1 || a.xin_ld != a.C);
 
   for (int64_t i = tid * V; i < N; i += (int64_t)gridDim.x * blockDim.x * V) {
     // channels-last index of element i (NCHW order); identical when C == 1
-    int64_t cl = i;
-    if (V == 1 && a.C > 1) {
+    int64_t cl = i, cli = i;   // cl: index into F rows [.., C]; cli: index into network-input rows [.., xin_ld]
+    if (strided) {
       int64_t b = i / CS, rem = i - b * CS;
       int64_t c = rem / a.S, s = rem - c * a.S;
       cl = (b * a.S + s) * a.C + c;
+      cli = (b * a.S + s) * a.xin_ld + c;
     }
     float xv[V], fv[V], av[V], rv[V], zv[V], xo[V], pv[V];
     Vec<V>::ld(a.x, i, xv);
-    if (STAGE != DSK_STAGE_INIT) Vec<V>::ld(Fp, cl, fv);
+    if (STAGE != DSK_STAGE_INIT) {
+      Vec<V>::ld(Fp, cl, fv);
+      if (a.cfg) {
+        float fc[V];
+        Vec<V>::ld(Fp, N + cl, fc);
+#pragma unroll
+        for (int k = 0; k < V; ++k) fv[k] = (1.0f - a.guidance) * fv[k] + a.guidance * fc[k];
+      }
+    }
     if (STAGE == DSK_STAGE_HEUN_FIN || STAGE == DSK_STAGE_KARRAS_FIN) {
       Vec<V>::ld(a.x_aux, i, av);
       Vec<V>::ld(a.r1, i, rv);
@@ -208,7 +227,8 @@ __global__ void __launch_bounds__(256) sampler_stage_kernel(StageArgs a) {
     if (do_prep) {
 #pragma unroll
       for (int k = 0; k < V; ++k) pv[k] = pn.c_in * pv[k];
-      Vec<V>::st(xin, cl, pv);
+      Vec<V>::st(xin, cli, pv);
+      if (a.cfg) Vec<V>::st(xin, (int64_t)a.B * a.S * a.xin_ld + cli, pv);
     }
   }
 }
@@ -216,15 +236,25 @@ __global__ void __launch_bounds__(256) sampler_stage_kernel(StageArgs a) {
 __global__ void advance_kernel(int* row) { *row += 1; }
 
 // xin[b, s, c] = c_in[b] * x[b, c, s]  -- any preconditioner (karrasmodule.py:690-702)
+// ld >= C: channel stride of the network-input rows; dup: also write the second half of a 2B (CFG) batch.
 template <typename T>
 __global__ void __launch_bounds__(256) precond_scale_kernel(const float* __restrict__ x, const float* __restrict__ c_in,
-                                                             T* __restrict__ xin, int B, int C, int64_t S) {
+                                                             T* __restrict__ xin, int B, int C, int64_t S, int ld, int dup) {
   const int64_t N = (int64_t)B * C * S, CS = (int64_t)C * S;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = i / CS, rem = i - b * CS;
     int64_t c = rem / S, s = rem - c * S;
-    xin[(b * S + s) * C + c] = from_f32<T>(c_in[b] * x[i]);
+    const T v = from_f32<T>(c_in[b] * x[i]);
+    xin[(b * S + s) * ld + c] = v;
+    if (dup) xin[((b + B) * S + s) * ld + c] = v;
   }
+}
+
+// F_u <- (1 - g) F_u + g F_c over n elements (classifier-free guidance mix, karrasmodule.py:711-713)
+template <typename T>
+__global__ void __launch_bounds__(256) cfg_mix_kernel(T* __restrict__ Fu, const T* __restrict__ Fc, float g, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    Fu[i] = from_f32<T>((1.0f - g) * to_f32<T>(Fu[i]) + g * to_f32<T>(Fc[i]));
 }
 
 // D = c_out[b]*F + c_skip[b]*x ; score = (D - x)/sigma[b]^2  (karrasmodule.py:717-733)
@@ -281,6 +311,16 @@ extern "C" int dsk_sampler_stage(int stage, float* x, float* x_aux, float* r1, c
                                  float* cnoise, const float* tab, const int* row, const float* noise, uint64_t seed,
                                  float* hist, int B, int C, int64_t S, float sigma_data, float sigma_max,
                                  int precond_kind, int act_dtype, void* stream) {
+  return dsk_sampler_stage_cond(stage, x, x_aux, r1, F, xin, cnoise, tab, row, noise, seed, hist, B, C, S, sigma_data,
+                                sigma_max, precond_kind, act_dtype, C, 0, 1.0f, stream);
+}
+
+extern "C" int dsk_sampler_stage_cond(int stage, float* x, float* x_aux, float* r1, const void* F, void* xin,
+                                      float* cnoise, const float* tab, const int* row, const float* noise, uint64_t seed,
+                                      float* hist, int B, int C, int64_t S, float sigma_data, float sigma_max,
+                                      int precond_kind, int act_dtype, int xin_ld, int cfg, float guidance,
+                                      void* stream) {
+  DSK_REQUIRE(xin_ld >= C, "dsk_sampler_stage_cond: xin_ld=%d < C=%d", xin_ld, C);
   DSK_REQUIRE(x && tab && row && cnoise, "dsk_sampler_stage: null x/tab/row/cnoise");
   DSK_REQUIRE(B > 0 && C > 0 && S > 0, "dsk_sampler_stage: bad shape B=%d C=%d S=%lld", B, C, (long long)S);
   DSK_REQUIRE(stage == DSK_STAGE_INIT || F != nullptr, "dsk_sampler_stage: F is null");
@@ -291,9 +331,10 @@ extern "C" int dsk_sampler_stage(int stage, float* x, float* x_aux, float* r1, c
                          stage == DSK_STAGE_KARRAS_MID || stage == DSK_STAGE_KARRAS_FIN;
   DSK_REQUIRE(!needs_aux || (x_aux && r1), "dsk_sampler_stage: x_aux/r1 are null");
   DSK_REQUIRE(act_dtype == DSK_F32 || act_dtype == DSK_BF16, "dsk_sampler_stage: bad dtype %d", act_dtype);
-  StageArgs a{x, x_aux, r1, F, xin, cnoise, tab, row, noise, hist, seed, B, C, S, sigma_data, sigma_max, precond_kind};
+  StageArgs a{x, x_aux, r1, F, xin, cnoise, tab, row, noise, hist, seed, B, C, S, sigma_data, sigma_max, precond_kind,
+              xin_ld, cfg ? 1 : 0, guidance};
   const int64_t N = (int64_t)B * C * S;
-  const bool vec = (C == 1) && (N % 4 == 0);
+  const bool vec = (C == 1) && (xin_ld == 1) && (N % 4 == 0);
   cudaStream_t st = as_stream(stream);
   if (act_dtype == DSK_F32) return vec ? launch_stage<float, 4>(stage, a, st) : launch_stage<float, 1>(stage, a, st);
   return vec ? launch_stage<__nv_bfloat16, 4>(stage, a, st) : launch_stage<__nv_bfloat16, 1>(stage, a, st);
@@ -307,15 +348,34 @@ extern "C" int dsk_sampler_advance(int* row, void* stream) {
 
 extern "C" int dsk_precond_scale(const float* x, const float* c_in, void* xin, int B, int C, int64_t S, int act_dtype,
                                  void* stream) {
+  return dsk_precond_scale_cond(x, c_in, xin, B, C, S, act_dtype, C, 0, stream);
+}
+
+extern "C" int dsk_precond_scale_cond(const float* x, const float* c_in, void* xin, int B, int C, int64_t S,
+                                      int act_dtype, int xin_ld, int dup, void* stream) {
   DSK_REQUIRE(x && c_in && xin, "dsk_precond_scale: null pointer");
-  DSK_REQUIRE(B > 0 && C > 0 && S > 0, "dsk_precond_scale: bad shape");
+  DSK_REQUIRE(B > 0 && C > 0 && S > 0 && xin_ld >= C, "dsk_precond_scale: bad shape");
   const int grid = grid_for((int64_t)B * C * S, 256, 16);
   if (act_dtype == DSK_F32)
-    DSK_LAUNCH(precond_scale_kernel<float>, grid, 256, 0, as_stream(stream), x, c_in, (float*)xin, B, C, S);
+    DSK_LAUNCH(precond_scale_kernel<float>, grid, 256, 0, as_stream(stream), x, c_in, (float*)xin, B, C, S, xin_ld, dup);
   else if (act_dtype == DSK_BF16)
-    DSK_LAUNCH(precond_scale_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), x, c_in, (__nv_bfloat16*)xin, B, C, S);
+    DSK_LAUNCH(precond_scale_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), x, c_in, (__nv_bfloat16*)xin, B, C, S,
+               xin_ld, dup);
   else
     DSK_REQUIRE(false, "dsk_precond_scale: bad dtype %d", act_dtype);
+  return DSK_OK;
+}
+
+extern "C" int dsk_cfg_mix(void* F_uncond, const void* F_cond, float guidance, int64_t n, int act_dtype, void* stream) {
+  DSK_REQUIRE(F_uncond && F_cond && n > 0, "dsk_cfg_mix: bad arguments");
+  const int grid = grid_for(n, 256, 16);
+  if (act_dtype == DSK_F32)
+    DSK_LAUNCH(cfg_mix_kernel<float>, grid, 256, 0, as_stream(stream), (float*)F_uncond, (const float*)F_cond, guidance, n);
+  else if (act_dtype == DSK_BF16)
+    DSK_LAUNCH(cfg_mix_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), (__nv_bfloat16*)F_uncond,
+               (const __nv_bfloat16*)F_cond, guidance, n);
+  else
+    DSK_REQUIRE(false, "dsk_cfg_mix: bad dtype %d", act_dtype);
   return DSK_OK;
 }
 

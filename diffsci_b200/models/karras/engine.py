@@ -44,8 +44,15 @@ def precond_kind(precond) -> Optional[int]:
 
 class SamplerEngine:
     def __init__(self, model: torch.nn.Module, B: int, shape: Sequence[int], device, sigma_data: float,
-                 sigma_max: float, kind: int, use_graphs: bool = True):
+                 sigma_max: float, kind: int, use_graphs: bool = True, cond_channels: int = 0,
+                 cond_vector: bool = False, guidance: Optional[float] = None):
+        """cond_channels: channel-concatenated conditioning (PUNetGCond) held in the network-input buffer; cond_vector:
+        a [B, M] conditioning vector is added to the time embedding; guidance (not None): classifier-free guidance, the
+        network runs a 2B batch per evaluation (rows [0,B) unconditional, [B,2B) conditional) -- native networks only."""
         self.model, self.B, self.shape = model, int(B), tuple(int(s) for s in shape)
+        self.cond_channels, self.cond_vector, self.guidance = int(cond_channels), bool(cond_vector), guidance
+        self.cfg = guidance is not None
+        self.Bn = 2 * self.B if self.cfg else self.B
         self.device = torch.device(device)
         self.sigma_data, self.sigma_max, self.kind = float(sigma_data), float(sigma_max), int(kind)
         self.Cc = self.shape[0]
@@ -57,13 +64,22 @@ class SamplerEngine:
         self.x = torch.empty(full, **f32)
         self.x_aux = torch.empty(full, **f32)
         self.r1 = torch.empty(full, **f32)
-        self.cnoise = torch.empty((self.B,), **f32)
+        self.cnoise = torch.empty((self.Bn,), **f32)
         self.row = torch.zeros((4,), dtype=torch.int32, device=self.device)   # [step, seed_lo, seed_hi, -]
         self.native = hasattr(model, "plan")
+        self.xin_ld = self.Cc + self.cond_channels
+        self.ye = None
+        if (self.cond_channels or self.cond_vector or self.cfg) and not self.native:
+            raise NotImplementedError("SamplerEngine: the conditional path needs a native network")
         if self.native:
-            self.plan = model.plan(self.B, self.shape[1:], self.device)
+            self.plan = model.plan(self.Bn, self.shape[1:], self.device)
             self.act_dtype = self.plan.act_dtype
             self.xin = self.plan.xin
+            if self.xin.shape[-1] != self.xin_ld:
+                raise ValueError(f"network expects {self.xin.shape[-1]} input channels, got {self.Cc} state + "
+                                 f"{self.cond_channels} conditioning channels")
+            if self.cond_vector:
+                self.ye = torch.zeros((self.Bn, model.config.model_channels), **f32)   # rows [0,B) stay 0 under CFG
         else:
             self.plan = None
             self.act_dtype = torch.float32
@@ -83,7 +99,8 @@ class SamplerEngine:
     def _net(self):
         self.nfe += 1
         if self.native:
-            self._F = self.plan.forward(self.xin, self.cnoise)
+            self._F = self.plan.forward(self.xin, self.cnoise, ye=self.ye) if self.ye is not None else \
+                self.plan.forward(self.xin, self.cnoise)
             return
         xin = self.xin
         if self.Cc > 1 and self.S > 1:
@@ -96,11 +113,25 @@ class SamplerEngine:
         self._F = F
 
     def _stage(self, stage: int):
-        check(lib.dsk_sampler_stage(stage, ptr(self.x), ptr(self.x_aux), ptr(self.r1), ptr(self._F), ptr(self.xin),
-                                    ptr(self.cnoise), ptr(self._tab), ptr(self.row), ptr(self._noise),
-                                    C.c_uint64(0), ptr(self._hist), self.B, self.Cc,
-                                    self.S, self.sigma_data, self.sigma_max, self.kind, dt_code(self.act_dtype),
-                                    stream()))
+        check(lib.dsk_sampler_stage_cond(stage, ptr(self.x), ptr(self.x_aux), ptr(self.r1), ptr(self._F), ptr(self.xin),
+                                         ptr(self.cnoise), ptr(self._tab), ptr(self.row), ptr(self._noise),
+                                         C.c_uint64(0), ptr(self._hist), self.B, self.Cc,
+                                         self.S, self.sigma_data, self.sigma_max, self.kind, dt_code(self.act_dtype),
+                                         self.xin_ld, 1 if self.cfg else 0,
+                                         float(self.guidance) if self.cfg else 1.0, stream()))
+
+    def set_condition(self, ychan: Optional[torch.Tensor], ye: Optional[torch.Tensor]):
+        """Write the run's conditioning into the static buffers the captured graphs read: channel conditioning
+        [B, Cy, *S] into channels [C, C+Cy) of the network-input rows, the vector [B, M] into the (conditional half of
+        the) time-embedding addend.  Once per run -- the reference recomputes both at every network evaluation."""
+        if (ychan is None) != (self.cond_channels == 0) or (ye is None) != (not self.cond_vector):
+            raise ValueError("SamplerEngine.set_condition: conditioning does not match the engine")
+        with torch.inference_mode(False), torch.no_grad():
+            if ychan is not None:
+                src = ychan.detach().reshape(self.B, self.cond_channels, self.S).transpose(1, 2)
+                self.xin.view(self.Bn, self.S, self.xin_ld)[:self.B, :, self.Cc:].copy_(src)
+            if ye is not None:
+                self.ye[self.Bn - self.B:].copy_(ye.detach())
 
     def _step(self, stages):
         for st in stages:

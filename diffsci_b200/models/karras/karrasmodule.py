@@ -234,26 +234,61 @@ class KarrasModule(_Base):
         sd = getattr(self.config.preconditioner, "sigma_data", None)
         return float(sd) if sd is not None else 0.5
 
-    def _network(self, x: Tensor, c_in: Tensor, cond_noise: Tensor):
-        """F = model(c_in * x, c_noise): returns (F, act dtype, channels-last?)."""
+    def _network(self, x: Tensor, c_in: Tensor, cond_noise: Tensor, y=None, guidance: float = 1.0):
+        """F = model(c_in * x, c_noise[, y]) with the reference's conditional dispatch (karrasmodule.py:703-716):
+        conditional call iff ``self.conditional and guidance != 0``; classifier-free mix (1-g) F_u + g F_c iff additionally
+        guidance != 1 -- evaluated as ONE 2B-sample network call on native networks.  Returns (F, act dtype or None)."""
         B = x.shape[0]
         Cc = x.shape[1] if x.ndim > 1 else 1
         S = x.numel() // (B * Cc)
-        if hasattr(self.model, "plan") and not (torch.is_grad_enabled() and self.training):
-            plan = self.model.plan(B, tuple(x.shape[2:]) if x.ndim > 2 else tuple(x.shape[1:]), x.device)
-            check(lib.dsk_precond_scale(ptr(x), ptr(c_in), ptr(plan.xin), B, Cc, S, dt_code(plan.act_dtype), stream()))
-            F = plan.forward(plan.xin, cond_noise)
+        cond = bool(self.conditional and guidance != 0.0)
+        cfg = cond and guidance != 1.0
+        native = hasattr(self.model, "plan") and not (torch.is_grad_enabled() and self.training)
+        if native and cond and not hasattr(self.model, "conditioning_vector"):
+            raise NotImplementedError(f"diffsci_b200: {type(self.model).__name__} has no conditional path")
+        if native:
+            spatial = tuple(x.shape[2:]) if x.ndim > 2 else tuple(x.shape[1:])
+            ychan, ye = None, None
+            if cond:
+                ychan, rest = self.model.split_condition(y, x)
+                if cfg and ychan is not None:      # the reference's unconditional call model(x, t) fails here too (:718)
+                    raise TypeError("classifier-free guidance needs an unconditional evaluation, which a channel-"
+                                    "conditioned network (PUNetGCond) does not have")
+                ye = self.model.conditioning_vector(rest, B)
+            Bn = 2 * B if cfg else B
+            plan = self.model.plan(Bn, spatial, x.device)
+            ld = plan.xin.shape[-1]
+            if ld != Cc + (0 if ychan is None else ychan.shape[1]):
+                raise ValueError(f"network expects {ld} input channels, got {Cc} state + "
+                                 f"{0 if ychan is None else ychan.shape[1]} conditioning channels")
+            check(lib.dsk_precond_scale_cond(ptr(x), ptr(c_in), ptr(plan.xin), B, Cc, S, dt_code(plan.act_dtype), ld,
+                                             1 if cfg else 0, stream()))
+            if ychan is not None:
+                plan.xin.view(B, S, ld)[:, :, Cc:].copy_(ychan.reshape(B, ld - Cc, S).transpose(1, 2))
+            cn = torch.cat([cond_noise, cond_noise]) if cfg else cond_noise
+            if cfg:
+                ye = torch.cat([torch.zeros_like(ye), ye]) if ye is not None else None
+            F = plan.forward(plan.xin, cn, ye=None if ye is None else ye.contiguous())
+            if cfg:
+                half = F.numel() // 2
+                Fv = F.view(-1)
+                check(lib.dsk_cfg_mix(ptr(Fv[:half]), ptr(Fv[half:]), float(guidance), half, dt_code(plan.act_dtype),
+                                      stream()))
+                F = Fv[:half]
             return F, plan.act_dtype
         xin = torch.empty((B, S, Cc), dtype=torch.float32, device=x.device)
         check(lib.dsk_precond_scale(ptr(x), ptr(c_in), ptr(xin), B, Cc, S, 0, stream()))
         if Cc > 1 and S > 1:
             xin = ops.cl_to_nchw(xin.view(B, 1, 1, S, Cc), 3)
-        F = self.model(xin.view(x.shape), cond_noise)
+        xin = xin.view(x.shape)
+        if not cond:
+            return self.model(xin, cond_noise), None
+        F = self.model(xin, cond_noise, y)
+        if cfg:
+            F = (1 - guidance) * self.model(xin, cond_noise) + guidance * F
         return F, None
 
     def _denoise(self, x: Tensor, sigma: Tensor, y, guidance: float, want_score: bool):
-        if y is not None or (self.conditional and guidance != 0.0):
-            raise NotImplementedError("diffsci_b200.KarrasModule: conditional / guided denoising not built yet (8f)")
         require_cuda(x, "x")
         x = x.float().contiguous()
         sigma = sigma.to(x).contiguous()
@@ -265,7 +300,7 @@ class KarrasModule(_Base):
         B = x.shape[0]
         Cc = x.shape[1] if x.ndim > 1 else 1
         S = x.numel() // (B * Cc)
-        F, adt = self._network(x, c_in, cond_noise)
+        F, adt = self._network(x, c_in, cond_noise, y, guidance)
         if adt is None:                 # foreign model: F is fp32 in the user's NC(D)HW layout
             F = F.detach().float().contiguous()
             if Cc > 1 and S > 1:
@@ -290,8 +325,6 @@ class KarrasModule(_Base):
     def loss_fn(self, x: Tensor, sigma: Tensor, y=None, mask: Optional[Tensor] = None) -> Tensor:
         """EDM denoising loss (karrasmodule.py:569-650).  Needs an EDMPreconditioner (the weighting
         lambda(sigma) and D are evaluated inside one fused kernel together with dL/dF)."""
-        if y is not None:
-            raise NotImplementedError("diffsci_b200.KarrasModule.loss_fn: conditional training not built yet (8f)")
         if type(self.config.preconditioner) is not preconditioners.EDMPreconditioner:
             raise NotImplementedError("diffsci_b200.KarrasModule.loss_fn: only the EDM preconditioner is fused")
         require_cuda(x, "x")
@@ -305,7 +338,7 @@ class KarrasModule(_Base):
         pre = self.config.preconditioner
         c_in = pre.input_scaling(sigma).float().contiguous()
         cond_noise = pre.noise_conditioner(sigma).float().contiguous()
-        F, adt = self._network(x_noised, c_in, cond_noise)
+        F, adt = self._network(x_noised, c_in, cond_noise, y, 1.0)
         B = x.shape[0]
         Cc = x.shape[1] if x.ndim > 1 else 1
         S = x.numel() // (B * Cc)
@@ -386,13 +419,16 @@ class KarrasModule(_Base):
     def propagate_toward_sample(self, x: Tensor, y=None, guidance: float = 1.0, nsteps: int = 100,
                                 record_history: bool = False, integrator=None, _prescaled: bool = True):
         """Integrate from x (already scaled by sigma_max unless called through propagate_white_noise)."""
-        if y is not None:
-            raise NotImplementedError("diffsci_b200.KarrasModule: conditional sampling not built yet (8f)")
         require_cuda(x, "x")
+        if y is not None:
+            y = dict_unsqueeze(y, 0)   # one condition, broadcast over the samples (karrasmodule.py:914-915)
         sch = self.config.noisescheduler
         integ = self._resolve_integrator(integrator)
         kind = _engine.precond_kind(self.config.preconditioner)
         fused = sch.fused_supported and kind is not None and integ.fused_program in _engine.PROGRAMS
+        cond = bool(self.conditional and guidance != 0.0)
+        if cond and not hasattr(self.model, "conditioning_vector"):
+            fused = False              # foreign / not-yet-conditional networks: the duck-typed seam
         x = x.float().contiguous()
         if not fused:      # foreign preconditioner / scheduler / integrator: the duck-typed seam
             if not _prescaled:
@@ -406,15 +442,27 @@ class KarrasModule(_Base):
                 if integrator is not None:
                     sch.unset_temporary_integrator()
         B, shape = x.shape[0], tuple(x.shape[1:])
+        ychan = ye = None
+        cfg = cond and guidance != 1.0
+        if cond:                       # evaluated ONCE per run: the conditioning is constant along the trajectory
+            ychan, rest = self.model.split_condition(y, x)
+            if cfg and ychan is not None:
+                raise TypeError("classifier-free guidance needs an unconditional evaluation, which a channel-"
+                                "conditioned network (PUNetGCond) does not have")
+            ye = self.model.conditioning_vector(rest, B)
+        ncond = 0 if ychan is None else int(ychan.shape[1])
         key = (B, shape, str(x.device), id(self.model), getattr(self.model, "precision", None), kind,
-               self._sigma_data(), self.use_cuda_graphs)
+               self._sigma_data(), self.use_cuda_graphs, ncond, ye is not None, float(guidance) if cfg else None)
         eng = self._engines.get(key)
         if eng is None:
             if len(self._engines) >= 2:
                 self._engines.clear()
             with torch.inference_mode(False), torch.no_grad():
                 eng = self._engines[key] = _engine.SamplerEngine(self.model, B, shape, x.device, self._sigma_data(),
-                                                                 1.0, kind, use_graphs=self.use_cuda_graphs)
+                                                                 1.0, kind, use_graphs=self.use_cuda_graphs,
+                                                                 cond_channels=ncond, cond_vector=ye is not None,
+                                                                 guidance=float(guidance) if cfg else None)
+        eng.set_condition(ychan, ye)
         eng.sigma_max = 1.0 if _prescaled else float(sch.maximum_scale)
         table = sch.step_table(nsteps, integ)
         noises = None
@@ -429,9 +477,7 @@ class KarrasModule(_Base):
 
     # ------------------------------------------------------------------ partial / forward propagation, inpainting
     def _score_fn(self, y=None):
-        if y is not None:
-            raise NotImplementedError("diffsci_b200.KarrasModule: conditional sampling not built yet (8f)")
-        return lambda xx, sg: self.get_score(xx, sg)
+        return lambda xx, sg: self.get_score(xx, sg, y)
 
     def propagate_partial_toward_sample(self, x: Tensor, initial_step: int, final_step: Optional[int] = None, y=None,
                                         nsteps: int = 100, record_history: bool = False, integrator=None,

@@ -149,7 +149,7 @@ class ADM(nn.Module):
         require_cuda(x, "ADM input")
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
             from .graph import NetFunction
-            return NetFunction.apply(self.train_graph(x.shape[0], tuple(x.shape[2:]), x.device), x, t, *self.parameters())
+            return NetFunction.apply(self.train_graph(x.shape[0], tuple(x.shape[2:]), x.device), x, t, None, *self.parameters())
         plan = self.plan(x.shape[0], tuple(x.shape[2:]), x.device)
         xin = ops.nchw_to_cl(x.float(), plan.act_dtype, 2, out=plan.xin)
         out = torch.empty((x.shape[0], self.config.output_channels) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)

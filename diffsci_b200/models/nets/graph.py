@@ -48,7 +48,9 @@ class TrainGraph:
         self.fwd: list[Callable[[], None]] = []
         self._bwd_builders: list[Callable[[], list]] = []
         self.bwd: list[Callable[[], None]] = []
-        self.params = [p for p in net.parameters()]
+        # the parameters the CUDA path owns (a conditional net's embedder / ConditionDrop stay with torch autograd)
+        self.params = list(net.native_parameters()) if hasattr(net, "native_parameters") else [p for p in net.parameters()]
+        self.ye_in: Optional[Var] = None          # conditioning vector [B, M], set by the builders
         self.sig = tuple(p.data_ptr() for p in self.params)
         total = sum(p.numel() for p in self.params)
         self.flat_grad = torch.zeros(max(total, 1), dtype=torch.float32, device=self.device)
@@ -328,6 +330,25 @@ class TrainGraph:
         self._bwd_builders.append(build_bwd)
         return y
 
+    def add_vec(self, a: Var, b: Var) -> Var:
+        """fp32 [B, M] vectors: y = a + b (te + ye, punetg.py:410 / adm.py:1050-1051); dy flows to whichever input needs it."""
+        y = Var(self.empty(a.t.shape, torch.float32))
+        at, bt, yt = a.t, b.t, y.t
+        self.fwd.append(lambda: ops.add_ex(at, bt, yt))
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return []
+            out = []
+            for v in (a, b):
+                if v.needs_grad:
+                    out += self.contribute_copy(v, dy)
+            return out
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
     def concat(self, a: Var, b: Var) -> Var:
         y = Var(self.empty(a.t.shape[:-1] + (a.t.shape[-1] + b.t.shape[-1],)))
         at, bt, yt = a.t, b.t, y.t
@@ -561,7 +582,9 @@ class TrainGraph:
             for pid in self._written_log[n0:]:
                 self.grad_ready_pos[pid] = len(self.bwd)
         self._bwd_builders = []
-        missing = [n for n, p in self.net.named_parameters() if p.requires_grad and not any(k[0] == id(p) for k in self._written)]
+        owned = {id(p) for p in self.params}
+        missing = [n for n, p in self.net.named_parameters()
+                   if id(p) in owned and p.requires_grad and not any(k[0] == id(p) for k in self._written)]
         if missing:
             raise RuntimeError(f"TrainGraph: no backward op writes the gradient of {missing[:4]}...")
         self.prepare()
@@ -647,8 +670,9 @@ def time_blocks(g: TrainGraph, te: Var, tbs: list) -> list:
     return grouped_linear_layer(g, h, spec(4), False)
 
 
-def build_punetg(net, B: int, spatial: tuple, device, precision: str) -> TrainGraph:
-    """PUNetG.forward (nets/punetg.py:389-416) unrolled into a TrainGraph."""
+def build_punetg(net, B: int, spatial: tuple, device, precision: str, cond: bool = False) -> TrainGraph:
+    """PUNetG.forward (nets/punetg.py:389-416) unrolled into a TrainGraph.  cond: te + ye with ye an input [B, M] whose
+    gradient is returned (the conditional embedding that produced it is trained by torch autograd around this graph)."""
     c = net.config
     nd = c.dimension
     if c.dropout != 0.0:
@@ -662,6 +686,9 @@ def build_punetg(net, B: int, spatial: tuple, device, precision: str) -> TrainGr
     g.t_in = torch.empty(B, dtype=torch.float32, device=g.device)
     g.x_in = Var(g.empty((B,) + sp + (c.input_channels,)), needs_grad=False)
     te = g.fourier(g.t_in, net.time_projection.W)
+    if cond:
+        g.ye_in = Var(g.empty((B, c.model_channels), torch.float32), needs_grad=True, name="ye")
+        te = g.add_vec(te, g.ye_in)
     blocks = [b for l in range(nlev) for b in net.downward_blocks[l]] + list(net.before_block) + list(net.attn_resnet_block) + \
         list(net.after_block) + [b for i in range(nlev) for b in net.upward_blocks[i]]
     tvs = dict(zip((id(b) for b in blocks), time_blocks(g, te, [b.timeblock for b in blocks])))
@@ -757,19 +784,27 @@ def build_adm(net, B: int, spatial: tuple, device, precision: str) -> TrainGraph
 
 
 class NetFunction(torch.autograd.Function):
-    """Autograd seam: F = net(x, t) with the hand-written backward; gradients flow to the nn.Parameters (and not to x)."""
+    """Autograd seam: F = net(x, t[, ye]) with the hand-written backward; gradients flow to the nn.Parameters and to the
+    conditioning vector ye (so that a torch conditional_embedding trains), not to x."""
 
     @staticmethod
-    def forward(ctx, graph: TrainGraph, x: torch.Tensor, t: torch.Tensor, *params):
+    def forward(ctx, graph: TrainGraph, x: torch.Tensor, t: torch.Tensor, ye: Optional[torch.Tensor], *params):
         ctx.graph = graph
+        if (ye is None) != (graph.ye_in is None):
+            raise RuntimeError("NetFunction: conditioning vector does not match the graph (build with cond=True)")
+        if ye is not None:
+            graph.ye_in.t.copy_(ye.detach().float())
         return graph.forward_nchw(x, t)
 
     @staticmethod
     def backward(ctx, dF):
         g = ctx.graph
         g.backward_nchw(dF)
+        dye = None
+        if g.ye_in is not None and ctx.needs_input_grad[3]:
+            dye = g.grad_of(g.ye_in).clone()
         # clones: AccumulateGrad may keep the tensors it is handed, and flat_grad is rewritten by the next step
-        return (None, None, None) + tuple(v.clone() for v in g.grads())
+        return (None, None, None, dye) + tuple(v.clone() for v in g.grads())
 
 
 def _forward_nchw(self: TrainGraph, x: torch.Tensor, t: Optional[torch.Tensor]) -> torch.Tensor:

@@ -92,3 +92,24 @@ class FourierParams(_Holder):
     def __init__(self, embed_dim: int, scale: float = 30.0):
         super().__init__()
         self.register_buffer("W", torch.randn(embed_dim // 2) * scale)
+
+
+class ConditionDrop(nn.Module):
+    """commonlayers.py:1100-1127: during training, replace a sample's conditioning vector by a (learnable) null embedding
+    with probability p.  Acts on the [B, M] conditioning vectors, i.e. before they enter the fused network path; it is a
+    real (callable) module, unlike the holders above."""
+
+    def __init__(self, p: float, hidden_dim: int, null_is_learnable: bool = True):
+        super().__init__()
+        self.p = p
+        if null_is_learnable:
+            self.null_embedding = nn.Parameter(torch.randn(1, hidden_dim))
+        else:
+            self.register_buffer("null_embedding", torch.zeros(1, hidden_dim))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not self.training or self.p == 0.0:
+            return x
+        mask_shape = (x.shape[0],) + (1,) * (x.ndim - 1)
+        mask = torch.bernoulli(torch.full(mask_shape, 1 - self.p, device=x.device))
+        return torch.where(mask == 1, x, self.null_embedding)

@@ -23,7 +23,7 @@ from torch import nn
 
 from ... import ops
 from ..._lib import require_cuda
-from .layers import (AttentionParams, ConvParams, FourierParams, NormParams, TimeBlockParams, _Holder)
+from .layers import (AttentionParams, ConditionDrop, ConvParams, FourierParams, NormParams, TimeBlockParams, _Holder)
 from .punetg_config import PUNetGConfig
 
 _NORM_MODE = {"GroupLN": 0, "GroupRMS": 1}
@@ -73,8 +73,8 @@ class PUNetG(nn.Module):
             unsupported.append("norms other than GroupLN/GroupRMS")
         if c.attn_type != "default":
             unsupported.append(f"attn_type={c.attn_type!r}")
-        if conditional_embedding is not None or extra_residual is not None:
-            unsupported.append("conditional_embedding / extra_residual")
+        if extra_residual is not None:
+            unsupported.append("extra_residual")
         if not c.bias:
             unsupported.append("bias=False")
         if c.dimension not in (2, 3) or c.transition_scale_factor != 2:
@@ -84,8 +84,6 @@ class PUNetG(nn.Module):
         if unsupported:
             raise NotImplementedError("diffsci_b200.PUNetG: not built yet (SURVEY.md 8f): " + ", ".join(unsupported))
         self.precision = precision or DEFAULT_PRECISION
-        self.conditional_embedding = None
-        self.extra_residual = None
         nd, M = c.dimension, c.model_channels
         mult = c.extended_channel_expansion
 
@@ -93,6 +91,8 @@ class PUNetG(nn.Module):
             return nn.ModuleList([ResnetBlockParams(m * M, M, nd, c.kernel_size, c.affine_norm, c.bias) for _ in range(n)])
 
         self.time_projection = FourierParams(M, c.time_projection_scale)
+        self.extra_residual = None
+        self.conditional_embedding = conditional_embedding      # any torch module: y -> [B, M] (punetg.py:93, 400-404)
         self.convin = ConvParams(c.input_channels, M, c.in_out_kernel_size, nd, c.bias)
         self.convout = ConvParams(M, c.output_channels, c.in_out_kernel_size, nd, c.bias)
         self.downward_blocks = nn.ModuleList([blocks(m, c.number_resnet_downward_block) for m in mult[:-1]])
@@ -107,36 +107,74 @@ class PUNetG(nn.Module):
         self.attn_resnet_block = blocks(mult[-1], c.number_resnet_attn_block)
         self.attn_block = nn.ModuleList([AttentionParams(mult[-1] * M) for _ in range(c.number_resnet_attn_block - 1)])
         self.cond_dropout = nn.Dropout(c.cond_dropout)
-        self.cond_drop = None
+        if c.cond_drop is not None and c.cond_drop > 0:
+            self.cond_drop = ConditionDrop(p=c.cond_drop, hidden_dim=M, null_is_learnable=c.cond_drop_learnable)
+        else:
+            self.cond_drop = None
         self._plans: dict[Any, "_Plan"] = {}
 
     # ------------------------------------------------------------------ reference API
     def export_description(self) -> dict[str, Any]:
-        return dict(config=self.config.export_description(), conditional_embedding_args=None,
-                    has_conditional_embedding=False)
+        emb = self.conditional_embedding
+        cemb_args = emb.export_description() if getattr(emb, "export_description", None) else None
+        return dict(config=self.config.export_description(), conditional_embedding_args=cemb_args,
+                    has_conditional_embedding=emb is not None)
+
+    def set_conditional_embedding(self, conditional_embedding: Optional[nn.Module] = None):
+        self.conditional_embedding = conditional_embedding
+
+    # ------------------------------------------------------------------ conditioning
+    def native_parameters(self) -> list:
+        """The parameters the CUDA path owns (everything except the user's embedder and ConditionDrop's null embedding,
+        which act on the [B, M] conditioning vector before it enters the network)."""
+        return [p for n, p in self.named_parameters()
+                if not (n.startswith("conditional_embedding.") or n.startswith("cond_drop."))]
+
+    def conditioning_vector(self, y, B: int) -> Optional[torch.Tensor]:
+        """ye of punetg.py:400-410: cond_dropout(cond_drop(conditional_embedding(y))) as fp32 [B, M] (None if y is None)."""
+        if y is None:
+            return None
+        ye = y if self.conditional_embedding is None else self.conditional_embedding(y)
+        if not torch.is_tensor(ye):
+            raise TypeError("diffsci_b200.PUNetG: y must be a tensor when the network has no conditional_embedding")
+        if self.cond_drop is not None:
+            ye = self.cond_drop(ye)
+        ye = self.cond_dropout(ye)
+        M = self.config.model_channels
+        if ye.ndim == 1:
+            ye = ye.unsqueeze(0)
+        if ye.ndim != 2 or ye.shape[-1] != M or ye.shape[0] not in (1, B):
+            raise NotImplementedError(f"diffsci_b200.PUNetG: conditioning of shape {tuple(ye.shape)} (only [B or 1, "
+                                      f"model_channels={M}] vectors added to the time embedding are built)")
+        return ye.float().expand(B, M)
+
+    def split_condition(self, y, x: torch.Tensor):
+        """-> (channel conditioning fp32 [B, Cy, *S] or None, remaining y).  PUNetG has none (PUNetGCond overrides)."""
+        return None, y
 
     def forward(self, x: torch.Tensor, t: Optional[torch.Tensor] = None, y=None) -> torch.Tensor:
         """x: fp32 [B, Cin, *S]; t: [B] (= c_noise); returns fp32 [B, Cout, *S] (punetg.py:389-416)."""
-        if y is not None:
-            raise NotImplementedError("diffsci_b200.PUNetG: conditional path (y) not built yet (SURVEY.md 8f)")
         require_cuda(x, "PUNetG input")
+        B = x.shape[0]
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
             # training: static forward/backward launch lists with hand-written backward kernels (graph.py)
             from .graph import NetFunction
-            return NetFunction.apply(self.train_graph(x.shape[0], tuple(x.shape[2:]), x.device), x, t, *self.parameters())
-        B = x.shape[0]
+            ye = self.conditioning_vector(y, B)
+            graph = self.train_graph(B, tuple(x.shape[2:]), x.device, cond=ye is not None)
+            return NetFunction.apply(graph, x, t, None if ye is None else ye.contiguous(), *self.native_parameters())
+        ye = self.conditioning_vector(y, B)
         plan = self.plan(B, tuple(x.shape[2:]), x.device)
         xin = ops.nchw_to_cl(x.float(), plan.act_dtype, self.config.dimension, out=plan.xin)
         tt = torch.zeros(B, device=x.device) if t is None else t.float().contiguous()
         out = torch.empty((B, self.config.output_channels) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
-        plan.forward(xin, tt, out_nchw=out, zero_time=t is None)
+        plan.forward(xin, tt, out_nchw=out, zero_time=t is None, ye=None if ye is None else ye.contiguous())
         return out
 
     # ------------------------------------------------------------------ plans
     def plan(self, B: int, spatial: tuple, device, precision: Optional[str] = None) -> "_Plan":
         precision = precision or self.precision
         key = (B, tuple(spatial), str(device), precision)
-        sig = tuple(p.data_ptr() for p in self.parameters())
+        sig = tuple(p.data_ptr() for p in self.native_parameters())
         plan = self._plans.get(key)
         if plan is None or plan.sig != sig:
             if len(self._plans) >= 4:   # bound the HBM held by cached plans
@@ -145,18 +183,19 @@ class PUNetG(nn.Module):
                 plan = self._plans[key] = _Plan(self, B, tuple(spatial), device, precision, sig)
         return plan
 
-    def train_graph(self, B: int, spatial: tuple, device, precision: Optional[str] = None):
-        """The TrainGraph (forward + backward launch lists, saved activations, flat gradient buffer) of this shape."""
+    def train_graph(self, B: int, spatial: tuple, device, precision: Optional[str] = None, cond: bool = False):
+        """The TrainGraph (forward + backward launch lists, saved activations, flat gradient buffer) of this shape.
+        cond: the graph takes a conditioning vector ye [B, M] (te + ye, punetg.py:410) and returns its gradient."""
         from .graph import build_punetg
         precision = precision or self.precision
-        key = ("train", B, tuple(spatial), str(device), precision)
-        sig = tuple(p.data_ptr() for p in self.parameters())
+        key = ("train", B, tuple(spatial), str(device), precision, bool(cond))
+        sig = tuple(p.data_ptr() for p in self.native_parameters())
         g = self._plans.get(key)
         if g is None or g.sig != sig:
             for k in [k for k in self._plans if k[0] == "train"]:
                 del self._plans[k]                                  # one training shape resident at a time
             with torch.inference_mode(False), torch.no_grad():
-                g = self._plans[key] = build_punetg(self, B, tuple(spatial), device, precision)
+                g = self._plans[key] = build_punetg(self, B, tuple(spatial), device, precision, cond=cond)
         return g
 
     def _apply(self, fn, *a, **k):
@@ -324,14 +363,17 @@ class _Plan:
         return out
 
     def forward(self, xin: torch.Tensor, cnoise: torch.Tensor, out_nchw: Optional[torch.Tensor] = None,
-                zero_time: bool = False) -> torch.Tensor:
-        """xin: channels-last [B, D, H, W, Cin] (act dtype); cnoise: fp32 [B].
+                zero_time: bool = False, ye: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """xin: channels-last [B, D, H, W, Cin] (act dtype); cnoise: fp32 [B]; ye: fp32 [B, M] conditioning vector added to
+        the time embedding (punetg.py:410) or None.
         Returns F channels-last (self.F), or writes fp32 NC(D)HW into `out_nchw`."""
         net, c, nlev = self.net, self.net.config, self.nlev
         if zero_time:
             self.te.zero_()       # te = zeros when t is None (punetg.py:398-399)
         else:
             ops.fourier(cnoise, net.time_projection.W, out=self.te)
+        if ye is not None:
+            ops.add_ex(self.te, ye, self.te)
         for g in self.tmlp:
             g.run()
         x, xs = ops.conv(xin, self.pc_in, out=self.X[0]), None
@@ -362,3 +404,34 @@ class _Plan:
         if out_nchw is not None:
             return ops.conv(x, self.pc_out, out=out_nchw, out_nchw=True)
         return ops.conv(x, self.pc_out, out=self.F)
+
+
+class PUNetGCond(PUNetG):
+    """PUNetGCond (reference nets/punetg.py:633-735): the items of ``y`` named in ``channel_conditional_items`` are
+    concatenated to x along the channel axis (``config.input_channels`` counts them); what is left of ``y`` goes to the
+    conditional embedding.  In the sampler engine the conditioning channels are written into the network-input buffer
+    ONCE per run and the fused stage kernels fill only the state channels (dsk_sampler_stage_cond, xin_ld)."""
+
+    def __init__(self, config: PUNetGConfig, conditional_embedding: Optional[nn.Module] = None,
+                 channel_conditional_items=False, extra_residual: Optional[nn.Module] = None, *,
+                 precision: Optional[str] = None):
+        super().__init__(config, conditional_embedding, extra_residual=extra_residual, precision=precision)
+        self.channel_conditional_items = channel_conditional_items
+
+    def export_description(self) -> dict[str, Any]:
+        args = super().export_description()
+        args["channel_conditional_items"] = self.channel_conditional_items
+        return args
+
+    def split_condition(self, y, x: torch.Tensor):
+        items = self.channel_conditional_items
+        y_channels = [y[item] for item in items]           # y is None -> TypeError, as in the reference (:718-719)
+        rest = {k: v for k, v in y.items() if k not in items}
+        y_cat = torch.cat(y_channels, dim=1)
+        if y_cat.shape[0] == 1 and x.shape[0] > 1:
+            y_cat = y_cat.expand((x.shape[0],) + tuple(y_cat.shape[1:]))
+        return y_cat.to(x), (rest if len(rest) else None)
+
+    def forward(self, x: torch.Tensor, t: Optional[torch.Tensor] = None, y=None) -> torch.Tensor:
+        y_cat, rest = self.split_condition(y, x)
+        return super().forward(torch.cat([x, y_cat], dim=1), t, rest)

@@ -100,6 +100,23 @@ int dsk_sampler_stage(int stage, float* x, float* x_aux, float* r1, const void* 
                       void* stream);
 int dsk_sampler_advance(int* row, void* stream);
 
+/* Conditional sampling (KarrasModule.get_denoiser with y / guidance, karrasmodule.py:703-716;
+ * PUNetGCond's channel concatenation, nets/punetg.py:716-735).  Same stage, with
+ *   xin_ld >= C : the network-input rows hold xin_ld channels, the state x fills channels [0, C); channels [C, xin_ld)
+ *                 carry the channel-concatenated conditioning, written once per run by the caller;
+ *   cfg != 0    : classifier-free guidance evaluated as ONE 2B-sample network call -- xin/cnoise rows [B, 2B) receive
+ *                 copies of rows [0, B), and F is read as (1-guidance)*F[0:B] + guidance*F[B:2B] (rows [0,B) = the
+ *                 unconditional evaluation, rows [B,2B) the conditional one). */
+int dsk_sampler_stage_cond(int stage, float* x, float* x_aux, float* r1, const void* F, void* xin, float* cnoise,
+                           const float* tab, const int* row, const float* noise, uint64_t seed, float* hist,
+                           int B, int C, int64_t S, float sigma_data, float sigma_max, int precond_kind, int act_dtype,
+                           int xin_ld, int cfg, float guidance, void* stream);
+/* dsk_precond_scale into rows of xin_ld channels; dup != 0 also fills rows [B, 2B) (the CFG batch). */
+int dsk_precond_scale_cond(const float* x, const float* c_in, void* xin, int B, int C, int64_t S, int act_dtype,
+                           int xin_ld, int dup, void* stream);
+/* F_uncond <- (1-guidance)*F_uncond + guidance*F_cond over n elements of `act_dtype` (karrasmodule.py:711-713). */
+int dsk_cfg_mix(void* F_uncond, const void* F_cond, float guidance, int64_t n, int act_dtype, void* stream);
+
 /* Integrator.step seam for foreign score functions (integrators.py:29-113; schedulers.py:266-274):
  * out = a0*x + a1*r1 + a2*r2 + a3*z, fp32, null inputs skipped; out may alias any input. */
 int dsk_lincomb(float* out, int64_t n, const float* x, float a0, const float* r1, float a1, const float* r2, float a2,

@@ -65,6 +65,16 @@ def denoiser(net: Net, x: torch.Tensor, sigma: torch.Tensor, sigma_data: float =
     return bcast(c_out, x) * F + bcast(c_skip, x) * x
 
 
+def guided_net(net_cond: Net, net_uncond: Optional[Net], guidance: float = 1.0, conditional: bool = True) -> Net:
+    """The network dispatch of KarrasModule.get_denoiser (karrasmodule.py:703-716): conditional call iff
+    ``conditional and guidance != 0``; classifier-free mix (1-g) F_u + g F_c iff additionally guidance != 1."""
+    if not (conditional and guidance != 0.0):
+        return net_uncond
+    if guidance == 1.0:
+        return net_cond
+    return lambda x, t: (1 - guidance) * net_uncond(x, t) + guidance * net_cond(x, t)
+
+
 def score(net: Net, x, sigma, sigma_data=0.5):
     """KarrasModule.get_score (karrasmodule.py:721-733)."""
     return (denoiser(net, x, sigma, sigma_data) - x) / (bcast(sigma, x) ** 2)

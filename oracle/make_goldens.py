@@ -101,9 +101,82 @@ def inpaint_goldens():
     print("inpaint_punetg2d", {k: (tuple(v.shape), float(v.abs().max())) for k, v in out.items() if torch.is_tensor(v)})
 
 
+def cond_goldens():
+    """conditional path of the LIVE reference -- PUNetG + PorosityEmbedder (vector conditioning, classifier-
+    free guidance) and PUNetGCond (channel conditioning + embedder): network forward, get_denoiser at guidance 0 / 1 /
+    2.5, Heun / Euler-Maruyama sampling with y, conditional loss + gradients (incl. the embedder's)
+    ->  tests/golden/cond_*.pt.   python oracle/make_goldens.py --only cond"""
+    os.makedirs(OUT, exist_ok=True)
+    refload.load_reference()
+    import diffsci.models as M
+    from diffsci.models.nets.punetg import PUNetG, PUNetGCond
+    from diffsci.models.nets.punetg_config import PUNetGConfig
+    from diffsci.models.nets.embedder import PorosityEmbedder
+    torch.set_num_threads(8)
+    gk = re.compile(r"^(conditional_embedding\.|convin|convout|downward_blocks\.0\.0\.|before_block\.0\.conv1|"
+                    r"attn_block\.0\.|upsamplers\.1\.)")
+
+    def case(name, net, kw, shape, seed, chan_shape, cfg_ok):
+        man = load_synth(net, seed)
+        net.eval()
+        mod = M.KarrasModule(net, M.KarrasModuleConfig.from_edm(), conditional=True)
+        mod.eval()
+        torch.manual_seed(seed + 1000)
+        B, nsteps = shape[0], 4
+        x = torch.randn(*shape)
+        t = torch.randn(B) * 0.7
+        yb = {"porosity": torch.rand(B, 1)}
+        y1 = {"porosity": torch.rand(1)}               # one condition for the whole sample() batch (unsqueezed inside)
+        if chan_shape is not None:
+            yb["cond"] = torch.randn(B, *chan_shape)
+            y1["cond"] = torch.randn(*chan_shape)
+        out = dict(cfg=kw, manifest=man, seed=seed, x=x, t=t, y_batch=yb, y_one=y1, nsteps=nsteps)
+        with torch.no_grad():
+            out["net_y"] = net(x, t, dict(yb))
+            out["net_y64"] = net.double()(x.double(), t.double(), {k: v.double() for k, v in yb.items()})
+            net.float()
+            sg = torch.exp(torch.randn(B) * 1.2 - 1.2)
+            xin = torch.randn(*shape) * (1 + sg.view(-1, *([1] * (len(shape) - 1))))
+            out.update(den_x=xin, den_sigma=sg)
+            for g in ((1.0, 0.0, 2.5) if cfg_ok else (1.0,)):
+                out[f"den_D_g{g}"] = mod.get_denoiser(xin, sg, dict(yb), guidance=g)[0]
+            out["den_score_g1.0"] = mod.get_score(xin, sg, dict(yb))
+            wn = torch.randn(*shape)
+            out["white_noise"] = wn
+            out["heun_hist_g1.0"] = mod.propagate_white_noise(wn, dict(y1), 1.0, nsteps, record_history=True)
+            if cfg_ok:
+                out["heun_hist_g2.5"] = mod.propagate_white_noise(wn, dict(y1), 2.5, nsteps, record_history=True)
+            noises = [torch.randn(*shape) for _ in range(nsteps)]
+            out["noises"] = noises
+            with _Noise(noises):
+                out["em_g1.0"] = mod.propagate_white_noise(wn, dict(y1), 1.0, nsteps, integrator="euler-maruyama")
+        x0 = torch.randn(*shape) * 0.5
+        ln = torch.randn(*shape)
+        out.update(loss_x=x0, loss_noise=ln, loss_sigma=sg)
+        net.train()                                     # dropout probabilities are 0: train == eval numerically
+        net.zero_grad()
+        with _Noise([ln]):
+            L = mod.loss_fn(x0, sg, dict(yb), None)
+        L.backward()
+        out["loss_huber"] = L.detach()
+        out["loss_huber_grads"] = {k: p.grad.clone() for k, p in net.named_parameters() if gk.search(k)}
+        torch.save(out, os.path.join(OUT, name + ".pt"))
+        print(name, {k: (tuple(v.shape), float(v.abs().max())) for k, v in out.items() if torch.is_tensor(v)})
+
+    kw = dict(dimension=2, model_channels=8)
+    case("cond_punetg2d_embed", PUNetG(PUNetGConfig(**kw), conditional_embedding=PorosityEmbedder(8)), kw,
+         (2, 1, 16, 16), 111, None, True)
+    kw = dict(dimension=3, model_channels=8, input_channels=2, channel_expansion=[2])
+    case("cond_punetg3d_chan", PUNetGCond(PUNetGConfig(**kw), conditional_embedding=PorosityEmbedder(8),
+                                          channel_conditional_items=["cond"]), kw,
+         (2, 1, 8, 8, 8), 112, (1, 8, 8, 8), False)
+
+
 def main():
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "inpaint":
         return inpaint_goldens()
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "cond":
+        return cond_goldens()
     os.makedirs(OUT, exist_ok=True)
     refload.load_reference()
     import diffsci.models as M

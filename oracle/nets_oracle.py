@@ -94,8 +94,25 @@ def resnet_block_c(x, te, sd, p, cfg):
     return y + x
 
 
-def punetg_forward(sd, cfg, x, t):
-    """PUNetG.forward (nets/punetg.py:389-416), unconditional, default layer types, eval mode."""
+def porosity_embedder(sd, prefix, porosity):
+    """PorosityEmbedder.forward (nets/embedder.py:217-221): y['porosity'] [B, 1] -> squeeze(-1) -> Fourier features ->
+    Linear-SiLU-Linear-SiLU-Linear -> [B, dembed]."""
+    e = fourier(porosity.squeeze(-1), sd[prefix + "gaussian_proj.W"])
+    return _time_block(e, sd, prefix)
+
+
+def punetg_cond_forward(sd, cfg, x, t, y_channels, ye=None):
+    """PUNetGCond.forward (nets/punetg.py:716-735): channel conditioning concatenated to x (a batch-1 condition is
+    repeated over the batch), the rest of y reaches PUNetG.forward as the embedding vector."""
+    y_cat = torch.cat(list(y_channels), dim=1)
+    if y_cat.shape[0] == 1 and x.shape[0] > 1:
+        y_cat = torch.cat([y_cat] * x.shape[0], dim=0)
+    return punetg_forward(sd, cfg, torch.cat([x, y_cat], dim=1), t, ye)
+
+
+def punetg_forward(sd, cfg, x, t, ye=None):
+    """PUNetG.forward (nets/punetg.py:389-416), default layer types, eval mode.  ye: the conditional embedding vector
+    [B or 1, M] added to the time embedding (punetg.py:400-410; cond_drop / cond_dropout are identities in eval)."""
     dim = cfg.dimension
     pool = F.max_pool2d if dim == 2 else F.max_pool3d
     nlev = len(cfg.channel_expansion)
@@ -104,6 +121,8 @@ def punetg_forward(sd, cfg, x, t):
         x = torch.cat([x, ones], dim=1)
     x = _conv(x, sd["convin.weight"], sd.get("convin.bias"), dim)
     te = fourier(t, sd["time_projection.W"])
+    if ye is not None:
+        te = te + ye
     skips = []
     for l in range(nlev):                                   # encode, punetg.py:356-365
         for r in range(cfg.number_resnet_downward_block):

@@ -140,3 +140,45 @@ def test_sampler_edge_nsteps2(golden):
     assert relmax(K.sample_from_white_noise(net, g["white_noise"], 2, "heun"), g["heun2"]) < 2e-5
     # nsteps=1 is outside the reference's domain: create_steps(2) divides by n-2 = 0
     assert not torch.isfinite(K.edm_steps(2)).all()
+
+
+# ----------------------------------------------------------------------------- conditional path
+def cond_oracle_nets(g, dtype=torch.float32, batch=True):
+    """-> (net_cond, net_uncond or None) of a tests/golden/cond_*.pt fixture.  batch: per-sample conditions (y_batch)
+    or the single condition sample() broadcasts (y_one, unsqueezed as karrasmodule.py:914-915 does)."""
+    sd = N.synth_state_dict(g["manifest"], g["seed"], dtype)
+    cfg = cfg_for("punetg", g["cfg"])
+    y = g["y_batch"] if batch else {k: v.unsqueeze(0) for k, v in g["y_one"].items()}
+    y = {k: v.to(dtype) for k, v in y.items()}
+    ye = N.porosity_embedder(sd, "conditional_embedding.", y["porosity"])
+    if "cond" in y:
+        return (lambda x, t: N.punetg_cond_forward(sd, cfg, x, t, [y["cond"]], ye)), None
+    return (lambda x, t: N.punetg_forward(sd, cfg, x, t, ye)), (lambda x, t: N.punetg_forward(sd, cfg, x, t))
+
+
+@pytest.mark.parametrize("name", ["cond_punetg2d_embed", "cond_punetg3d_chan"])
+def test_conditional_path(golden, name):
+    g = golden(name)
+    nc, nu = cond_oracle_nets(g)
+    assert relmax(nc(g["x"], g["t"]), g["net_y"]) < TOL32
+    nc64, _ = cond_oracle_nets(g, torch.float64)
+    assert relmax(nc64(g["x"].double(), g["t"].double()), g["net_y64"]) < 1e-12
+    for key in [k for k in g if k.startswith("den_D_g")]:
+        gd = float(key[len("den_D_g"):])
+        net = K.guided_net(nc, nu, gd)
+        assert relmax(K.denoiser(net, g["den_x"], g["den_sigma"]), g[key]) < TOL32, key
+    assert relmax(K.score(nc, g["den_x"], g["den_sigma"]), g["den_score_g1.0"]) < TOL32
+    # sampling with ONE condition broadcast over the batch; budget against fp64 truth as above
+    n, wn = g["nsteps"], g["white_noise"]
+    oc, ou = cond_oracle_nets(g, batch=False)
+    oc64, ou64 = cond_oracle_nets(g, torch.float64, batch=False)
+    for key in [k for k in g if k.startswith("heun_hist_g")]:
+        gd = float(key[len("heun_hist_g"):])
+        o32 = K.sample_from_white_noise(K.guided_net(oc, ou, gd), wn, n, "heun", record_history=True)
+        o64 = K.sample_from_white_noise(K.guided_net(oc64, ou64, gd), wn.double(), n, "heun", record_history=True)
+        assert relmax(o32, g[key]) <= 2.0 * relmax(g[key].double(), o64) + 2e-5, key
+    o32 = K.sample_from_white_noise(oc, wn, n, "euler-maruyama", noises=g["noises"])
+    o64 = K.sample_from_white_noise(oc64, wn.double(), n, "euler-maruyama", noises=[z.double() for z in g["noises"]])
+    assert relmax(o32, g["em_g1.0"]) <= 2.0 * relmax(g["em_g1.0"].double(), o64) + 2e-5
+    L = K.edm_loss(nc, g["loss_x"], g["loss_sigma"], g["loss_noise"], "huber")
+    assert abs(float(L) - float(g["loss_huber"])) <= 2e-5 * abs(float(g["loss_huber"]))
