@@ -32,7 +32,7 @@ p, i32, i64, u64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("B", "D", "H", "W", "Cin", "Cout", "ksize", "ndim", "up2", "w_dtype", "in_dtype",
-                                   "out_dtype", "out_nchw_f32")]
+                                   "out_dtype", "out_nchw_f32", "circular")]
 
 
 # name -> argtypes (every function returns int unless listed in _RESTYPE)
@@ -54,6 +54,9 @@ SIGNATURES = {
     "dsk_conv_fwd": [C.POINTER(ConvDesc), p, p, p, p, p, p, p],
     "dsk_conv_stats_supported": [C.POINTER(ConvDesc)],
     "dsk_conv_stats_slots": [],
+    "dsk_pad_circular": [p, p, i32, i32, i32, i32, i32, i32, i32, p],
+    "dsk_conv_pad_ws_bytes": [C.POINTER(ConvDesc)],
+    "dsk_conv_fwd_circ": [C.POINTER(ConvDesc), p, p, p, p, p, p, p, p, p],
     "dsk_conv_fwd_stats": [C.POINTER(ConvDesc), p, p, p, p, p, p, p, p],
     "dsk_norm_act_prestat": [p, p, p, p, p, p, p, i32, p, i32, i64, i32, i32, i32, i32, i32, i32, p],
     "dsk_upsample2x": [p, p, i32, i32, i32, i32, i32, i32, i32, p],
@@ -98,7 +101,7 @@ SIGNATURES = {
     "dsk_add_ex": [p, i32, p, i32, p, i32, i64, p],
     "dsk_split_channels": [p, p, p, p, p, i64, i32, i32, i32, p],
 }
-_RESTYPE = {"dsk_last_error": C.c_char_p, "dsk_launch_count": u64, "dsk_norm_ws_bytes": i64,
+_RESTYPE = {"dsk_conv_pad_ws_bytes": i64, "dsk_last_error": C.c_char_p, "dsk_launch_count": u64, "dsk_norm_ws_bytes": i64,
             "dsk_conv_wgrad_ws_bytes": i64, "dsk_bwd_ws_bytes": i64, "dsk_attn_softmax_ws_bytes": i64}
 
 for _name, _args in SIGNATURES.items():

@@ -64,4 +64,6 @@ inline int grid_for(int64_t work_items, int per_block, int max_waves = 8) {
   return (int)blocks;
 }
 
+// y[B, D + 2*(ndim==3), H+2, W+2, C] = x[B, D, H, W, C] wrapped by one pixel per spatial axis (elementwise.cu)
+int pad_circular_launch(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, cudaStream_t st);
 }  // namespace dsk

@@ -210,7 +210,7 @@ int convin_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, co
 // returns 1 if handled, 0 if the shape is not a few-channel conv, negative on error
 int conv_small_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
                         const void* residual, void* out, cudaStream_t st) {
-  if (chan_bias != nullptr || residual != nullptr || d->up2) return 0;
+  if (chan_bias != nullptr || residual != nullptr || d->up2 || d->circular) return 0;   // circular: generic wrapping kernel
   const int taps = d->ndim == 3 ? d->ksize * d->ksize * d->ksize : d->ksize * d->ksize;
   SmallConvArgs a{in, (const float*)w, bias, d->out_nchw_f32 ? nullptr : out, d->out_nchw_f32 ? (float*)out : nullptr,
                   d->B, d->D, d->H, d->W, d->Cin, d->Cout, d->ksize, d->ndim};
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(WF_THREADS) wgrad_few_kernel(const TX* __restr
 int wgrad_reduce_launch(const float* ws, float* dw, int Cout, int Cin, int taps, int nsplit, int accumulate, cudaStream_t st);
 
 static bool wgrad_few_shape(const dsk_conv_desc* d, bool* few_in, int* tpg) {
-  if (d->ksize != 3 || d->up2) return false;
+  if (d->ksize != 3 || d->up2 || d->circular) return false;
   const int taps = d->ndim == 3 ? 27 : 9;
   const bool fi = d->Cin <= WF_NARROW, fo = d->Cout <= WF_NARROW;
   if (fi == fo) return false;                                   // both narrow (tiny) or neither

@@ -50,6 +50,8 @@ struct TcParams {
   int nphase;             // sub-pixel UpSampler conv: 8 (3-D) / 4 (2-D) output parities per input-resolution tile, else 1
   float2* stats;          // cta_group::2 kernel: per-(sample, slot, channel) partial (sum, sum of squares) of the output, or null
   int samples;            // number of samples the stats are kept for (3-D: B; 2-D: the planes ARE the samples)
+  int pad_hw, pad_d;      // circular padding: the activation tensor map covers a halo-padded copy ([.., D+2*pad_d, H+2, W+2, C]);
+                          // these offsets move the patch coordinates into it (0: zero 'same' padding through TMA OOB fill)
 };
 constexpr int TC_STAT_SLOTS = DSK_NUM_SMS;          // one slot per CTA
 
@@ -125,7 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             asm volatile(
                 "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
                     smem_u32(sA + (size_t)slot * TC_PATCH_STRIDE)),
-                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(c * 64), "r"(tc.w0 - 1), "r"(tc.h0 - 1), "r"(tc.d0 + j - dpad), "r"(tc.b),
+                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(c * 64), "r"(tc.w0 - 1 + p.pad_hw), "r"(tc.h0 - 1 + p.pad_hw), "r"(tc.d0 + j - dpad + p.pad_d), "r"(tc.b),
                 "r"(smem_u32(&full_a[slot]))
                 : "memory");
           }
@@ -455,7 +457,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             asm volatile(
                 "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
                     smem_u32(sA + (size_t)slot * TC_PATCH_STRIDE)),
-                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(c * 64), "r"(tc.w0 - 1), "r"(tc.h0 - 1), "r"(tc.d0 + j - dpad), "r"(tc.b),
+                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(c * 64), "r"(tc.w0 - 1 + p.pad_hw), "r"(tc.h0 - 1 + p.pad_hw), "r"(tc.d0 + j - dpad + p.pad_d), "r"(tc.b),
                 "r"(smem_u32(&full_a[slot]) & kPeerBitMask)
                 : "memory");
           }
@@ -913,21 +915,45 @@ extern "C" int dsk_conv_stats_supported(const dsk_conv_desc* d) {
 extern "C" int dsk_conv_stats_slots(void) { return TC_STAT_SLOTS; }
 
 static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
-                            const void* residual, void* out, float2* stats, void* stream);
+                            const void* residual, void* out, float2* stats, void* pad_ws, void* stream);
 
 extern "C" int dsk_conv_fwd_tc(const dsk_conv_desc* d, const void* in, const void* w, const float* bias,
                                const float* chan_bias, const void* residual, void* out, void* stream) {
-  return conv_fwd_tc_impl(d, in, w, bias, chan_bias, residual, out, nullptr, stream);
+  DSK_REQUIRE(d == nullptr || !d->circular, "dsk_conv_fwd: circular padding on the tcgen05 path needs dsk_conv_fwd_circ (padded copy)");
+  return conv_fwd_tc_impl(d, in, w, bias, chan_bias, residual, out, nullptr, nullptr, stream);
+}
+
+extern "C" int dsk_conv_fwd_ffma(const dsk_conv_desc*, const void*, const void*, const float*, const float*, const void*, void*, void*);
+
+// bytes of the halo-padded input copy a circular convolution on the tcgen05 path reads (0: CUDA-core kernel, wraps in place)
+extern "C" int64_t dsk_conv_pad_ws_bytes(const dsk_conv_desc* d) {
+  if (d == nullptr || !d->circular || d->w_dtype != DSK_BF16) return 0;
+  const int iD = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D, iH = d->up2 ? d->H / 2 : d->H, iW = d->up2 ? d->W / 2 : d->W;
+  const int pd = d->ndim == 3 ? 1 : 0;
+  return (int64_t)d->B * (iD + 2 * pd) * (iH + 2) * (iW + 2) * d->Cin * 2;
+}
+
+extern "C" int dsk_conv_fwd_circ(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
+                                 const void* residual, void* out, void* stats, void* pad_ws, void* stream) {
+  DSK_REQUIRE(d != nullptr && d->circular, "dsk_conv_fwd_circ: descriptor is not circular");
+  if (d->w_dtype == DSK_F32) {
+    DSK_REQUIRE(stats == nullptr, "dsk_conv_fwd_circ: fused statistics need the tcgen05 path");
+    return dsk_conv_fwd_ffma(d, in, w, bias, chan_bias, residual, out, stream);
+  }
+  DSK_REQUIRE(pad_ws != nullptr, "dsk_conv_fwd_circ: the tcgen05 path needs pad_ws (dsk_conv_pad_ws_bytes)");
+  DSK_REQUIRE(stats == nullptr || dsk_conv_stats_supported(d), "dsk_conv_fwd_circ: this convolution cannot emit fused statistics");
+  return conv_fwd_tc_impl(d, in, w, bias, chan_bias, residual, out, (float2*)stats, pad_ws, stream);
 }
 
 extern "C" int dsk_conv_fwd_stats(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
                                   const void* residual, void* out, void* stats, void* stream) {
   DSK_REQUIRE(stats != nullptr && dsk_conv_stats_supported(d), "dsk_conv_fwd_stats: this convolution cannot emit fused statistics");
-  return conv_fwd_tc_impl(d, in, w, bias, chan_bias, residual, out, (float2*)stats, stream);
+  DSK_REQUIRE(!d->circular, "dsk_conv_fwd_stats: circular padding needs dsk_conv_fwd_circ");
+  return conv_fwd_tc_impl(d, in, w, bias, chan_bias, residual, out, (float2*)stats, nullptr, stream);
 }
 
 static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
-                            const void* residual, void* out, float2* stats, void* stream) {
+                            const void* residual, void* out, float2* stats, void* pad_ws, void* stream) {
   DSK_REQUIRE(d && in && w && out, "dsk_conv_fwd(tc): null pointer");
   const bool few_out = d->Cout <= 16 && !d->up2 && chan_bias == nullptr && residual == nullptr;
   if (d->ksize != 3 || (d->out_nchw_f32 && !few_out) || d->in_dtype != DSK_BF16 || (!d->out_nchw_f32 && d->out_dtype != DSK_BF16) ||
@@ -940,7 +966,7 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   DSK_REQUIRE((d->ndim == 2 && d->D == 1) || d->ndim == 3, "dsk_conv_fwd(tc): bad ndim/D");
   if (few_out) {     // in-plane taps as the N dimension (convout_tc.cu); DSK_CONVOUT_OLD=1 keeps the N = 16 tile for A/B runs
     static const int old_path = [] { const char* e = getenv("DSK_CONVOUT_OLD"); return e ? atoi(e) : 0; }();
-    if (!old_path) {
+    if (!old_path && !d->circular) {      // circular: the N = 16 tile of the generic kernel below reads the padded copy
       const int rc = convout_tc_dispatch(d, in, w, bias, out, as_stream(stream));
       if (rc != DSK_ERR_UNSUPPORTED) return rc;
     }
@@ -953,11 +979,21 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   const int iD = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D, iH = d->up2 ? d->H / 2 : d->H, iW = d->up2 ? d->W / 2 : d->W;
   const int planes = d->ndim == 3 ? iD : d->B;
   const int batch = d->ndim == 3 ? d->B : 1;
+  // circular padding: TMA boxes cannot wrap, so the kernel reads a halo-padded copy (one extra pass over the input) and the
+  // patch coordinates are shifted into it; nothing else in the kernel changes (no OOB fill is ever hit inside the image).
+  const int pad_hw = d->circular ? 1 : 0, pad_d = (d->circular && d->ndim == 3) ? 1 : 0;
+  if (d->circular) {
+    DSK_REQUIRE(pad_ws != nullptr, "dsk_conv_fwd(tc): circular padding needs pad_ws");
+    const int rc = pad_circular_launch(in, pad_ws, d->B, d->ndim == 3 ? iD : 1, iH, iW, d->Cin, d->ndim, DSK_BF16, as_stream(stream));
+    if (rc != DSK_OK) return rc;
+    in = pad_ws;
+  }
+  const int tW = iW + 2 * pad_hw, tH = iH + 2 * pad_hw, tP = planes + 2 * pad_d;
   CUtensorMap ta, tw;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)iW, (cuuint64_t)iH, (cuuint64_t)planes, (cuuint64_t)batch};
-    cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)iW * d->Cin * 2, (cuuint64_t)iH * iW * d->Cin * 2,
-                             (cuuint64_t)planes * iH * iW * d->Cin * 2};
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)tW, (cuuint64_t)tH, (cuuint64_t)tP, (cuuint64_t)batch};
+    cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)tW * d->Cin * 2, (cuuint64_t)tH * tW * d->Cin * 2,
+                             (cuuint64_t)tP * tH * tW * d->Cin * 2};
     cuuint32_t box[5] = {64, TC_PW, TC_PH, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, es,
@@ -994,6 +1030,7 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
   p.planes_per_sample = d->ndim == 3 ? iD : 1;
   p.stats = stats; p.samples = d->B;
+  p.pad_hw = pad_hw; p.pad_d = pad_d;
   cudaStream_t st = as_stream(stream);
   // cta_group::2 (CTA pairs): needs an even number of w-tiles (the pair sits side by side in w).  DSK_CONV_CG=1 forces
   // the single-CTA kernel (A/B measurements).

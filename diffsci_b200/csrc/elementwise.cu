@@ -370,6 +370,46 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ 
   }
 }
 
+
+// ---- circular padding (CircularConv2d/3d, commonlayers.py:918-1032): y[b, d', h', w', :] = x[b, (d'-pd) mod D, (h'-1) mod H,
+// (w'-1) mod W, :] with pd = 1 for 3-D, 0 for 2-D.  The halo-padded copy is what the tcgen05 convolution kernels read through
+// TMA (a box load cannot wrap).  V = elements moved per thread (16-byte vectors when the channel run allows).
+template <typename VT>
+__global__ void __launch_bounds__(256) pad_circular_kernel(const VT* __restrict__ x, VT* __restrict__ y, int B, int D, int H, int W,
+                                                            int Cv, int pd) {
+  const int Dp = D + 2 * pd, Hp = H + 2, Wp = W + 2;
+  const int64_t total = (int64_t)B * Dp * Hp * Wp * Cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int c = (int)(t % Cv); t /= Cv;
+    int w = (int)(t % Wp) - 1; t /= Wp;
+    int h = (int)(t % Hp) - 1; t /= Hp;
+    int d = (int)(t % Dp) - pd;
+    const int b = (int)(t / Dp);
+    w = w < 0 ? w + W : (w >= W ? w - W : w);
+    h = h < 0 ? h + H : (h >= H ? h - H : h);
+    d = d < 0 ? d + D : (d >= D ? d - D : d);
+    y[i] = x[((((int64_t)b * D + d) * H + h) * W + w) * Cv + c];
+  }
+}
+
+int pad_circular_launch(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, cudaStream_t st) {
+  const int pd = ndim == 3 ? 1 : 0;
+  const int es = dtype == DSK_BF16 ? 2 : 4;
+  const int64_t row = (int64_t)C * es;                      // bytes of one pixel's channel run
+  const int64_t npix = (int64_t)B * (D + 2 * pd) * (H + 2) * (W + 2);
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (row % 16 == 0 && al) {
+    const int Cv = (int)(row / 16);
+    DSK_LAUNCH(pad_circular_kernel<uint4>, grid_for(npix * Cv, 256, 16), 256, 0, st, (const uint4*)x, (uint4*)y, B, D, H, W, Cv, pd);
+  } else if (es == 4) {
+    DSK_LAUNCH(pad_circular_kernel<float>, grid_for(npix * C, 256, 16), 256, 0, st, (const float*)x, (float*)y, B, D, H, W, C, pd);
+  } else {
+    DSK_LAUNCH(pad_circular_kernel<uint16_t>, grid_for(npix * C, 256, 16), 256, 0, st, (const uint16_t*)x, (uint16_t*)y, B, D, H, W, C,
+               pd);
+  }
+  return DSK_OK;
+}
 }  // namespace dsk
 
 using namespace dsk;
@@ -512,4 +552,11 @@ extern "C" int dsk_mask_blend(float* out, const float* x, const float* y, const 
   DSK_REQUIRE(out && x && y && mask && n > 0 && mask_n > 0 && n % mask_n == 0, "dsk_mask_blend: bad arguments");
   DSK_LAUNCH(mask_blend_kernel, grid_for(n, 256, 8), 256, 0, as_stream(stream), out, x, y, mask, n, mask_n);
   return DSK_OK;
+}
+
+extern "C" int dsk_pad_circular(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, void* stream) {
+  DSK_REQUIRE(x && y && B > 0 && D > 0 && H > 0 && W > 0 && C > 0, "dsk_pad_circular: bad arguments");
+  DSK_REQUIRE((ndim == 2 && D == 1) || ndim == 3, "dsk_pad_circular: bad ndim/D");
+  DSK_REQUIRE(dtype == DSK_F32 || dtype == DSK_BF16, "dsk_pad_circular: bad dtype %d", dtype);
+  return pad_circular_launch(x, y, B, D, H, W, C, ndim, dtype, as_stream(stream));
 }

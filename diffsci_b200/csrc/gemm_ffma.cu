@@ -35,6 +35,7 @@ struct ConvProb {
   int M, N, K;
   float alpha;
   int act;
+  int circ;               // circular padding: wrap the gather coordinates (CircularConv, commonlayers.py:918-1032)
 
   struct RowCtx {
     int b, d, h, w;
@@ -81,7 +82,11 @@ struct ConvProb {
     int kw = tap % ks, t2 = tap / ks;
     int kh = t2 % ks, kd = t2 / ks;
     int zw = c.w + kw - r, zh = c.h + kh - r, zd = ndim == 3 ? c.d + kd - r : 0;
-    if ((unsigned)zw >= (unsigned)W || (unsigned)zh >= (unsigned)H || (unsigned)zd >= (unsigned)D) return nullptr;
+    if (circ) {
+      zw = zw < 0 ? zw + W : (zw >= W ? zw - W : zw);
+      zh = zh < 0 ? zh + H : (zh >= H ? zh - H : zh);
+      zd = zd < 0 ? zd + D : (zd >= D ? zd - D : zd);
+    } else if ((unsigned)zw >= (unsigned)W || (unsigned)zh >= (unsigned)H || (unsigned)zd >= (unsigned)D) return nullptr;
     if (up2) {  // conv over F.interpolate(x, 2, 'nearest'): source voxel = floor(coord / 2)
       zw >>= 1; zh >>= 1;
       if (ndim == 3) zd >>= 1;
@@ -337,6 +342,7 @@ struct WgradProb {
   int M, N, K;           // taps*Cin, Cout, pixels
   int kper;              // pixels per split (multiple of BK)
   int kb, ke;
+  int circ;
   struct RowCtx { int dummy; };
   __device__ __forceinline__ RowCtx row_ctx(int) const { return RowCtx{0}; }
   __device__ __forceinline__ int k_begin() const { return kb; }
@@ -352,7 +358,11 @@ struct WgradProb {
     int kw = tap % ks, t2 = tap / ks;
     int kh = t2 % ks, kd = t2 / ks;
     int zw = pw + kw - r, zh = ph + kh - r, zd = ndim == 3 ? pd + kd - r : 0;
-    if ((unsigned)zw >= (unsigned)W || (unsigned)zh >= (unsigned)H || (unsigned)zd >= (unsigned)D) return nullptr;
+    if (circ) {
+      zw = zw < 0 ? zw + W : (zw >= W ? zw - W : zw);
+      zh = zh < 0 ? zh + H : (zh >= H ? zh - H : zh);
+      zd = zd < 0 ? zd + D : (zd >= D ? zd - D : zd);
+    } else if ((unsigned)zw >= (unsigned)W || (unsigned)zh >= (unsigned)H || (unsigned)zd >= (unsigned)D) return nullptr;
     if (up2) {
       zw >>= 1; zh >>= 1;
       if (ndim == 3) zd >>= 1;
@@ -452,7 +462,7 @@ static int launch_conv(const dsk_conv_desc* d, const void* in, const void* w, co
   p.out = d->out_nchw_f32 ? nullptr : (TO*)out;
   p.out_nchw = d->out_nchw_f32 ? (float*)out : nullptr;
   p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
-  p.ks = d->ksize; p.ndim = d->ndim; p.up2 = d->up2;
+  p.ks = d->ksize; p.ndim = d->ndim; p.up2 = d->up2; p.circ = d->circular;
   p.Di = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D;
   p.Hi = d->up2 ? d->H / 2 : d->H;
   p.Wi = d->up2 ? d->W / 2 : d->W;
@@ -560,6 +570,7 @@ static int launch_wgrad(const dsk_conv_desc* d, const void* x, const void* dy, f
   WgradProb<TI, TG> p;
   p.x = (const TI*)x; p.dy = (const TG*)dy; p.ws = (float*)ws;
   p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.ks = d->ksize; p.ndim = d->ndim; p.up2 = d->up2;
+  p.circ = d->circular;
   p.Di = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D;
   p.Hi = d->up2 ? d->H / 2 : d->H;
   p.Wi = d->up2 ? d->W / 2 : d->W;

@@ -42,6 +42,7 @@ struct WgParams {
   int tiles_w, tiles_h, total_tiles, tiles_per_split;
   int n_ci, n_co;
   float* ws;                       // [nsplit][taps*Cin][Cout]
+  int pad_hw, pad_d;               // circular padding: x tensor map covers the halo-padded copy (see conv_tc.cu)
 };
 
 // MN-major SWIZZLE_128B descriptors: lo = start >> 4 | (LBO >> 4) << 16 ; hi = SBO >> 4 | version | swizzle mode
@@ -104,7 +105,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
         asm volatile(
             "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
                 smem_u32(st)),
-            "l"(reinterpret_cast<uint64_t>(&tmapX)), "r"(ci_chunk * 64), "r"(w0 - 1), "r"(h0 - 1), "r"(d + kd - dpad), "r"(b),
+            "l"(reinterpret_cast<uint64_t>(&tmapX)), "r"(ci_chunk * 64), "r"(w0 - 1 + p.pad_hw), "r"(h0 - 1 + p.pad_hw), "r"(d + kd - dpad + p.pad_d), "r"(b),
             "r"(smem_u32(&full[slot]))
             : "memory");
         asm volatile(
@@ -217,6 +218,17 @@ static WgPlan wg_plan(const dsk_conv_desc* d) {
   return w;
 }
 
+static int64_t wg_split_bytes(const dsk_conv_desc* d, const WgPlan& w) {
+  const int64_t b = (int64_t)w.nsplit * (w.KD * 9) * d->Cin * d->Cout * (int64_t)sizeof(float);
+  return (b + 1023) & ~(int64_t)1023;
+}
+// circular padding: the halo-padded copy of x lives behind the split-K slices in the same workspace
+static int64_t wg_pad_bytes(const dsk_conv_desc* d) {
+  if (!d->circular) return 0;
+  const int pd = d->ndim == 3 ? 1 : 0;
+  return (int64_t)d->B * (d->D + 2 * pd) * (d->H + 2) * (d->W + 2) * d->Cin * 2;
+}
+
 }  // namespace dsk
 
 using namespace dsk;
@@ -225,7 +237,7 @@ extern "C" int64_t dsk_conv_wgrad_tc_ws_bytes(const dsk_conv_desc* d) {
   if (!d || d->w_dtype != DSK_BF16) return 0;
   const WgPlan w = wg_plan(d);
   if (!w.ok) return 0;
-  return (int64_t)w.nsplit * (w.KD * 9) * d->Cin * d->Cout * (int64_t)sizeof(float);
+  return wg_split_bytes(d, w) + wg_pad_bytes(d);
 }
 
 extern "C" int dsk_conv_wgrad_tc(const dsk_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, int accumulate,
@@ -235,10 +247,18 @@ extern "C" int dsk_conv_wgrad_tc(const dsk_conv_desc* d, const void* x, const vo
   EncodeTiledFn encode = get_encode();
   DSK_REQUIRE(encode != nullptr, "dsk_conv_wgrad(tc): cuTensorMapEncodeTiled is unavailable");
   CUtensorMap tx, ty;
+  const int pad_hw = d->circular ? 1 : 0, pad_d = (d->circular && d->ndim == 3) ? 1 : 0;
+  if (d->circular) {
+    void* xp = (uint8_t*)ws + wg_split_bytes(d, w);
+    const int rc = pad_circular_launch(x, xp, d->B, d->D, d->H, d->W, d->Cin, d->ndim, DSK_BF16, as_stream(stream));
+    if (rc != DSK_OK) return rc;
+    x = xp;
+  }
   {
-    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)w.planes, (cuuint64_t)w.batch};
-    cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->W * d->Cin * 2, (cuuint64_t)d->H * d->W * d->Cin * 2,
-                             (cuuint64_t)w.planes * d->H * d->W * d->Cin * 2};
+    const int tW = d->W + 2 * pad_hw, tH = d->H + 2 * pad_hw, tP = w.planes + 2 * pad_d;
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)tW, (cuuint64_t)tH, (cuuint64_t)tP, (cuuint64_t)w.batch};
+    cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)tW * d->Cin * 2, (cuuint64_t)tH * tW * d->Cin * 2,
+                             (cuuint64_t)tP * tH * tW * d->Cin * 2};
     cuuint32_t box[5] = {64, WG_PW, WG_PH, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es,
@@ -262,6 +282,7 @@ extern "C" int dsk_conv_wgrad_tc(const dsk_conv_desc* d, const void* x, const vo
   p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.total_tiles = w.total_tiles; p.tiles_per_split = w.tiles_per_split;
   p.n_ci = d->Cin / 64; p.n_co = d->Cout / 64;
   p.ws = (float*)ws;
+  p.pad_hw = pad_hw; p.pad_d = pad_d;
   const size_t smem = (size_t)WG_STAGES * WG_STAGE + 1024;
   static bool configured = false;
   if (!configured) {

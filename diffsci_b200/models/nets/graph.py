@@ -141,8 +141,10 @@ class TrainGraph:
             return self._conv1x1_tc(x, cp, residual, up2)
         tc = self.precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize, few_out_ok)
         wdt = torch.bfloat16 if tc else torch.float32
-        pc = ops.PackedConv(cp.weight, cp.bias, nd, wdt, subpixel=bool(up2 and tc))
+        circ = bool(getattr(cp, "circular", False))       # CircularConv (commonlayers.py:918-1032): forward, dgrad and wgrad wrap
+        pc = ops.PackedConv(cp.weight, cp.bias, nd, wdt, subpixel=bool(up2 and tc), circular=circ)
         self._packs.append(pc)
+        pws = self.lazy_scratch("pad_ws", max(ops.conv_pad_ws_bytes(x.t.shape, x.t.dtype, pc, up2), 1))
         B, D, H, W, _ = x.t.shape
         if up2:
             D, H, W = (D * 2 if nd == 3 else D), H * 2, W * 2
@@ -150,7 +152,7 @@ class TrainGraph:
         xt, yt = x.t, y.t
         cb = chan_bias.t if chan_bias is not None else None
         rs = residual.t if residual is not None else None
-        self.fwd.append(lambda: ops.conv(xt, pc, out=yt, chan_bias=cb, residual=rs, up2=up2))
+        self.fwd.append(lambda: ops.conv(xt, pc, out=yt, chan_bias=cb, residual=rs, up2=up2, pad_ws=pws))
 
         def build_bwd():
             dy = self.grad_of(y)
@@ -171,28 +173,29 @@ class TrainGraph:
             gw = self.grad_view(cp.weight)
             # the tcgen05 weight-gradient kernel reads a materialised operand; the CUDA-core one gathers (up2 folded in)
             if up2 and self.precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize):
-                desc = ops.conv_desc(B, D, H, W, cp.cin, cp.cout, cp.ksize, nd, False, wdt, xt.dtype, dy.dtype)
+                desc = ops.conv_desc(B, D, H, W, cp.cin, cp.cout, cp.ksize, nd, False, wdt, xt.dtype, dy.dtype, circ)
                 wws = self.lazy_scratch("wgrad_ws", ops.conv_wgrad_ws_bytes(desc))
                 u = self.lazy_scratch("u_up", (B, D, H, W, cp.cin), xt.dtype)
                 out.append(lambda: ops.upsample2x(xt, nd, out=u()))
                 out.append(lambda: ops.conv_wgrad(desc, u(), dy, gw, wws()))
             else:
-                desc = ops.conv_desc(B, D, H, W, cp.cin, cp.cout, cp.ksize, nd, up2, wdt, xt.dtype, dy.dtype)
+                desc = ops.conv_desc(B, D, H, W, cp.cin, cp.cout, cp.ksize, nd, up2, wdt, xt.dtype, dy.dtype, circ)
                 wws = self.lazy_scratch("wgrad_ws", ops.conv_wgrad_ws_bytes(desc))
                 out.append(lambda: ops.conv_wgrad(desc, xt, dy, gw, wws()))
             if residual is not None and residual.needs_grad:
                 out.extend(self.contribute_copy(residual, dy))
             if x.needs_grad:
                 dg_tc = self.precision == "bf16" and _tc_eligible(cp.cout, cp.cin, cp.ksize)
-                pd = ops.PackedConv(cp.weight, None, nd, torch.bfloat16 if dg_tc else torch.float32, dgrad=True)
+                pd = ops.PackedConv(cp.weight, None, nd, torch.bfloat16 if dg_tc else torch.float32, dgrad=True, circular=circ)
                 self._packs.append(pd)
+                dpws = self.lazy_scratch("pad_ws", max(ops.conv_pad_ws_bytes(dy.shape, dy.dtype, pd), 1))
                 if not up2:
                     dres, dx = self.contribute_compute(x)
-                    out.append(lambda: ops.conv(dy, pd, out=dx, residual=dres))
+                    out.append(lambda: ops.conv(dy, pd, out=dx, residual=dres, pad_ws=dpws))
                 else:
                     du = self.lazy_scratch("du", (B, D, H, W, cp.cin), xt.dtype)
                     dres, dx = self.contribute_compute(x)
-                    out.append(lambda: ops.conv(dy, pd, out=du()))
+                    out.append(lambda: ops.conv(dy, pd, out=du(), pad_ws=dpws))
                     out.append(lambda: ops.upsample2x_bwd(du(), dx, nd, dres=dres))
             return out
 

@@ -25,6 +25,7 @@ def _uniform_(t: torch.Tensor, bound: float):
 
 class ConvParams(_Holder):
     """weight [Cout, Cin, k(,k)(,k)], bias [Cout] -- torch.nn.Conv{2,3}d keys."""
+    circular = False
 
     def __init__(self, cin: int, cout: int, ksize: int, ndim: int, bias: bool = True):
         super().__init__()
@@ -33,6 +34,31 @@ class ConvParams(_Holder):
         bound = 1.0 / math.sqrt(cin * ksize ** ndim)
         _uniform_(self.weight, bound)
         self.bias = nn.Parameter(_uniform_(torch.empty(cout), bound)) if bias else None
+
+
+class CircularConvParams(_Holder):
+    """CircularConv2d / CircularConv3d (commonlayers.py:918-1032; all spatial axes periodic): the reference wraps a Conv
+    as ``self.conv``, so the state-dict keys are ``<name>.conv.weight`` / ``<name>.conv.bias``."""
+    circular = True
+
+    def __init__(self, cin: int, cout: int, ksize: int, ndim: int, bias: bool = True):
+        super().__init__()
+        self.cin, self.cout, self.ksize, self.ndim = cin, cout, ksize, ndim
+        self.conv = ConvParams(cin, cout, ksize, ndim, bias)
+
+    @property
+    def weight(self):
+        return self.conv.weight
+
+    @property
+    def bias(self):
+        return self.conv.bias
+
+
+def make_conv(cin: int, cout: int, ksize: int, ndim: int, bias: bool = True, convolution_type: str = "default"):
+    if convolution_type == "circular":
+        return CircularConvParams(cin, cout, ksize, ndim, bias)
+    return ConvParams(cin, cout, ksize, ndim, bias)
 
 
 class LinearParams(_Holder):

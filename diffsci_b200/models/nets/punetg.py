@@ -23,7 +23,7 @@ from torch import nn
 
 from ... import ops
 from ..._lib import require_cuda
-from .layers import (AttentionParams, ConditionDrop, ConvParams, FourierParams, NormParams, TimeBlockParams, _Holder)
+from .layers import (AttentionParams, ConditionDrop, FourierParams, NormParams, TimeBlockParams, _Holder, make_conv)
 from .punetg_config import PUNetGConfig
 
 _NORM_MODE = {"GroupLN": 0, "GroupRMS": 1}
@@ -41,22 +41,23 @@ def _tc_eligible(cin: int, cout: int, ksize: int = 3, few_out_ok: bool = False) 
 class ResnetBlockParams(_Holder):
     """ResnetBlockC as PUNetG builds it (punetg.py:238-261): C_in == C_out, own time MLP."""
 
-    def __init__(self, channels: int, embed: int, ndim: int, ksize: int, affine: bool, bias: bool):
+    def __init__(self, channels: int, embed: int, ndim: int, ksize: int, affine: bool, bias: bool,
+                 convolution_type: str = "default"):
         super().__init__()
         self.channels = channels
         self.gnorm1 = NormParams(channels, affine)
         self.gnorm2 = NormParams(channels, affine)
-        self.conv1 = ConvParams(channels, channels, ksize, ndim, bias)
-        self.conv2 = ConvParams(channels, channels, ksize, ndim, bias)
+        self.conv1 = make_conv(channels, channels, ksize, ndim, bias, convolution_type)
+        self.conv2 = make_conv(channels, channels, ksize, ndim, bias, convolution_type)
         self.timeblock = TimeBlockParams(embed, channels)
 
 
 class SamplerParams(_Holder):
     """DownSampler / UpSampler (commonlayers.py:25-158): one conv; pooling / upsampling is weight-free."""
 
-    def __init__(self, cin: int, cout: int, ndim: int, ksize: int, bias: bool):
+    def __init__(self, cin: int, cout: int, ndim: int, ksize: int, bias: bool, convolution_type: str = "default"):
         super().__init__()
-        self.conv = ConvParams(cin, cout, ksize, ndim, bias)
+        self.conv = make_conv(cin, cout, ksize, ndim, bias, convolution_type)
 
 
 class PUNetG(nn.Module):
@@ -65,7 +66,7 @@ class PUNetG(nn.Module):
         super().__init__()
         c = self.config = config
         unsupported = []
-        if c.convolution_type != "default":
+        if c.convolution_type not in ("default", "circular"):
             unsupported.append(f"convolution_type={c.convolution_type!r}")
         if c.in_embedding:
             unsupported.append("in_embedding=True")
@@ -86,21 +87,22 @@ class PUNetG(nn.Module):
         self.precision = precision or DEFAULT_PRECISION
         nd, M = c.dimension, c.model_channels
         mult = c.extended_channel_expansion
+        ct = c.convolution_type          # "circular": every conv pads periodically (punetg.py:221-232, commonlayers.py:84-88)
 
         def blocks(m, n):
-            return nn.ModuleList([ResnetBlockParams(m * M, M, nd, c.kernel_size, c.affine_norm, c.bias) for _ in range(n)])
+            return nn.ModuleList([ResnetBlockParams(m * M, M, nd, c.kernel_size, c.affine_norm, c.bias, ct) for _ in range(n)])
 
         self.time_projection = FourierParams(M, c.time_projection_scale)
         self.extra_residual = None
         self.conditional_embedding = conditional_embedding      # any torch module: y -> [B, M] (punetg.py:93, 400-404)
-        self.convin = ConvParams(c.input_channels, M, c.in_out_kernel_size, nd, c.bias)
-        self.convout = ConvParams(M, c.output_channels, c.in_out_kernel_size, nd, c.bias)
+        self.convin = make_conv(c.input_channels, M, c.in_out_kernel_size, nd, c.bias, ct)
+        self.convout = make_conv(M, c.output_channels, c.in_out_kernel_size, nd, c.bias, ct)
         self.downward_blocks = nn.ModuleList([blocks(m, c.number_resnet_downward_block) for m in mult[:-1]])
-        self.downsamplers = nn.ModuleList([SamplerParams(a * M, b * M, nd, c.transition_kernel_size, c.bias)
+        self.downsamplers = nn.ModuleList([SamplerParams(a * M, b * M, nd, c.transition_kernel_size, c.bias, ct)
                                            for a, b in zip(mult[:-1], mult[1:])])
         rev = mult[::-1]
         self.upward_blocks = nn.ModuleList([blocks(m, c.number_resnet_upward_block) for m in rev[1:]])
-        self.upsamplers = nn.ModuleList([SamplerParams(a * M, b * M, nd, c.transition_kernel_size, c.bias)
+        self.upsamplers = nn.ModuleList([SamplerParams(a * M, b * M, nd, c.transition_kernel_size, c.bias, ct)
                                          for a, b in zip(rev[:-1], rev[1:])])
         self.before_block = blocks(mult[-1], c.number_resnet_before_attn_block)
         self.after_block = blocks(mult[-1], c.number_resnet_after_attn_block)
@@ -233,7 +235,8 @@ class _Plan:
 
         def pack(cp, subpixel=False, few_out_ok=False):
             tc = precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize, few_out_ok)
-            return ops.PackedConv(cp.weight, cp.bias, nd, torch.bfloat16 if tc else torch.float32, subpixel and tc)
+            return ops.PackedConv(cp.weight, cp.bias, nd, torch.bfloat16 if tc else torch.float32, subpixel and tc,
+                                  circular=cp.circular)
 
         self.xin = buf(0, c.input_channels)
         self.X = [buf(l, ch[l]) for l in range(nlev + 1)]          # encoder / bottom state (doubles as skip)
@@ -245,6 +248,11 @@ class _Plan:
         self.XA2 = buf(nlev, ch[nlev])
         self.F = buf(0, c.output_channels)
         self.WS = [ops.norm_ws(B, sp[l][0] * sp[l][1] * sp[l][2], ch[l], dev) for l in range(nlev + 1)]
+        # circular padding: one halo-padded input copy for the tcgen05 convs (TMA boxes cannot wrap), sized for the largest
+        self.pad_ws = None
+        if c.convolution_type == "circular" and precision == "bf16":
+            halo = lambda s: (s[0] + (2 if nd == 3 else 0)) * (s[1] + 2) * (s[2] + 2)  # noqa: E731
+            self.pad_ws = torch.empty(max(B * halo(sp[l]) * ch[l] * 2 for l in range(nlev + 1)), dtype=torch.uint8, device=dev)
         # fused norm statistics (conv epilogue -> following per-channel norm): one buffer per level, consumed by the very
         # next norm.  Only where the convolution kernel can emit them and the norms are per channel (G == C: the PUNetG norms).
         self.ST = [None] * (nlev + 1)
@@ -318,6 +326,9 @@ class _Plan:
                 wi.packed()
                 wo.packed()
 
+    def _conv(self, *a, **k):
+        return ops.conv(*a, pad_ws=self.pad_ws, **k)
+
     # ------------------------------------------------------------------ forward
     def _resblock(self, x, blk, l, out, xs=None):
         """-> (block output, its fused norm statistics or None).  `xs`: statistics of x left by the conv that produced it."""
@@ -327,10 +338,10 @@ class _Plan:
         st = self.ST[l] if self.st_ok[l] else None
         n = ops.norm_act(x, blk.gnorm1.weight, blk.gnorm1.bias, C, _NORM_MODE[c.first_resblock_norm], True,
                          out=self.N[l], ws=self.WS[l], conv_stats=xs)
-        y = ops.conv(n, pc1, out=self.Y[l], chan_bias=self.tvec[id(blk)], stats=st)
+        y = self._conv(n, pc1, out=self.Y[l], chan_bias=self.tvec[id(blk)], stats=st)
         n = ops.norm_act(y, blk.gnorm2.weight, blk.gnorm2.bias, C, _NORM_MODE[c.second_resblock_norm], True,
                          out=self.N[l], ws=self.WS[l], conv_stats=st)
-        return ops.conv(n, pc2, out=out, residual=x, stats=st), st
+        return self._conv(n, pc2, out=out, residual=x, stats=st), st
 
     def _attention(self, x, attn, out, index=0):
         a = self.attn
@@ -376,13 +387,13 @@ class _Plan:
             ops.add_ex(self.te, ye, self.te)
         for g in self.tmlp:
             g.run()
-        x, xs = ops.conv(xin, self.pc_in, out=self.X[0]), None
+        x, xs = self._conv(xin, self.pc_in, out=self.X[0]), None
         for l in range(nlev):
             for blk in net.downward_blocks[l]:
                 x, xs = self._resblock(x, blk, l, x, xs)
             p = ops.pool2x(x, self.ndim, True, out=self.P[l])            # MaxPool (commonlayers.py:60-63)
             xs = self.ST[l + 1] if self.st_down[l] else None
-            x = ops.conv(p, self.pc_down[l], out=self.X[l + 1], stats=xs)
+            x = self._conv(p, self.pc_down[l], out=self.X[l + 1], stats=xs)
         for blk in net.before_block:
             x, xs = self._resblock(x, blk, nlev, x, xs)
         xa, xas = x, xs
@@ -398,12 +409,12 @@ class _Plan:
             l = nlev - 1 - i
             # conv(F.interpolate(x, 2)) + skip, fused (commonlayers.py:145; punetg.py:372-373)
             xs = self.ST[l] if self.st_up[i] else None
-            x = ops.conv(x, self.pc_up[i], out=self.XU[l], residual=self.X[l], up2=True, stats=xs)
+            x = self._conv(x, self.pc_up[i], out=self.XU[l], residual=self.X[l], up2=True, stats=xs)
             for blk in net.upward_blocks[i]:
                 x, xs = self._resblock(x, blk, l, x, xs)
         if out_nchw is not None:
-            return ops.conv(x, self.pc_out, out=out_nchw, out_nchw=True)
-        return ops.conv(x, self.pc_out, out=self.F)
+            return self._conv(x, self.pc_out, out=out_nchw, out_nchw=True)
+        return self._conv(x, self.pc_out, out=self.F)
 
 
 class PUNetGCond(PUNetG):

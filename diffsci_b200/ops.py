@@ -34,12 +34,13 @@ class PackedConv:
     """
 
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], ndim: int, w_dtype: torch.dtype,
-                 subpixel: bool = False, dgrad: bool = False):
+                 subpixel: bool = False, dgrad: bool = False, circular: bool = False):
         """subpixel=True (bf16 only): pack for the phase-decomposed conv(nearest_up2(x)) of the tcgen05 UpSampler path.
         dgrad=True: the weights of the data-gradient convolution dX = conv_same(dY, flip(W)^T) (Cin and Cout exchanged)."""
         assert not subpixel or (w_dtype == torch.bfloat16 and int(weight.shape[-1]) == 3)
         assert not (dgrad and (subpixel or bias is not None))
         self.subpixel, self.dgrad = subpixel, dgrad
+        self.circular = bool(circular)   # circular padding on every spatial axis (CircularConv2d/3d, commonlayers.py:918-1032)
         self.weight, self.bias, self.ndim = weight, bias, ndim
         self.cout, self.cin = int(weight.shape[0]), int(weight.shape[1])
         if dgrad:
@@ -81,7 +82,28 @@ class PackedConv:
 def _conv_desc_of(x, pc, out, residual, up2, out_nchw, D, H, W):
     return L.ConvDesc(x.shape[0], D, H, W, x.shape[-1], pc.cout, pc.ksize, pc.ndim, int(up2), dt_code(pc.w_dtype), dt_code(x.dtype),
                       dt_code(residual.dtype if (out_nchw and residual is not None) else
-                              (torch.float32 if out_nchw else out.dtype)), int(out_nchw))
+                              (torch.float32 if out_nchw else out.dtype)), int(out_nchw), int(pc.circular))
+
+
+def conv_pad_ws_bytes(x_shape, x_dtype, pc: "PackedConv", up2: bool = False) -> int:
+    """Bytes of the halo-padded input copy a circular convolution needs (0: zero padding, or a wrapping CUDA-core kernel)."""
+    if not pc.circular:
+        return 0
+    B, D, H, W, Cin = x_shape
+    if up2:
+        D, H, W = (D * 2 if pc.ndim == 3 else D), H * 2, W * 2
+    d = L.ConvDesc(B, D, H, W, Cin, pc.cout, pc.ksize, pc.ndim, int(up2), dt_code(pc.w_dtype), dt_code(x_dtype), dt_code(x_dtype), 0, 1)
+    return int(lib.dsk_conv_pad_ws_bytes(C.byref(d)))
+
+
+def pad_circular(x: torch.Tensor, ndim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B, D, H, W, C] -> [B, D+2 (3-D only), H+2, W+2, C], wrapped by one pixel per spatial axis (dsk_pad_circular)."""
+    require_cuda(x, "pad input")
+    B, D, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, D + 2 if ndim == 3 else D, H + 2, W + 2, Cc), dtype=x.dtype, device=x.device)
+    check(lib.dsk_pad_circular(ptr(x), ptr(out), B, D, H, W, Cc, ndim, dt_code(x.dtype), stream()))
+    return out
 
 
 def conv_stats_supported(x_shape, x_dtype, pc: "PackedConv", up2: bool = False) -> bool:
@@ -100,9 +122,11 @@ def conv_stats_buffer(B: int, cout: int, device) -> torch.Tensor:
 
 def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, chan_bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, up2: bool = False, out_dtype: Optional[torch.dtype] = None,
-         out_nchw: bool = False, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out_nchw: bool = False, stats: Optional[torch.Tensor] = None, pad_ws=None) -> torch.Tensor:
     """y = conv_same(x) + bias + chan_bias[b, :] + residual  (dsk_conv_fwd).  `stats` (conv_stats_buffer): also leave the
-    per-(sample, channel) statistics of y for norm_act(..., conv_stats=stats) (dsk_conv_fwd_stats)."""
+    per-(sample, channel) statistics of y for norm_act(..., conv_stats=stats) (dsk_conv_fwd_stats).
+    pc.circular: circular instead of zero padding (dsk_conv_fwd_circ); `pad_ws` (tensor, or callable returning one) is the
+    preallocated workspace of the padded copy the tcgen05 path reads -- allocated here if missing (not graph-safe)."""
     require_cuda(x, "conv input")
     B, D, H, W, Cin = x.shape
     assert Cin == pc.cin, (Cin, pc.cin)
@@ -117,6 +141,14 @@ def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, ch
         out = torch.empty(shape, dtype=torch.float32 if out_nchw else out_dtype, device=x.device)
     d = _conv_desc_of(x, pc, out, residual, up2, out_nchw, D, H, W)
     bias = pc.bias.detach() if pc.bias is not None else None
+    if pc.circular:
+        need = int(lib.dsk_conv_pad_ws_bytes(C.byref(d)))
+        ws = pad_ws() if callable(pad_ws) else pad_ws
+        if need > 0 and (ws is None or ws.numel() * ws.element_size() < need):
+            ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        check(lib.dsk_conv_fwd_circ(C.byref(d), ptr(x), ptr(pc.packed()), ptr(bias), ptr(chan_bias), ptr(residual), ptr(out),
+                                    ptr(stats), ptr(ws) if need > 0 else None, stream()))
+        return out
     if stats is not None:
         check(lib.dsk_conv_fwd_stats(C.byref(d), ptr(x), ptr(pc.packed()), ptr(bias), ptr(chan_bias), ptr(residual), ptr(out),
                                      ptr(stats), stream()))
@@ -490,8 +522,9 @@ def self_attention_tc(tok: torch.Tensor, w_in: PackedLinear, in_b: torch.Tensor,
 
 
 # ------------------------------------------------------------------------------------------------ backward (K2)
-def conv_desc(B, D, H, W, cin, cout, ksize, ndim, up2, w_dtype, in_dtype, out_dtype) -> "L.ConvDesc":
-    return L.ConvDesc(B, D, H, W, cin, cout, ksize, ndim, int(up2), dt_code(w_dtype), dt_code(in_dtype), dt_code(out_dtype), 0)
+def conv_desc(B, D, H, W, cin, cout, ksize, ndim, up2, w_dtype, in_dtype, out_dtype, circular: bool = False) -> "L.ConvDesc":
+    return L.ConvDesc(B, D, H, W, cin, cout, ksize, ndim, int(up2), dt_code(w_dtype), dt_code(in_dtype), dt_code(out_dtype), 0,
+                      int(circular))
 
 
 def conv_wgrad_ws_bytes(desc) -> int:

@@ -147,6 +147,10 @@ typedef struct {
   int in_dtype;        /* dtype of `in`                                                   */
   int out_dtype;       /* dtype of `out` and `residual`                                   */
   int out_nchw_f32;    /* 1: write fp32 NC(D)HW (user layout) instead of channels-last    */
+  int circular;        /* 1: circular ('periodic') padding on every spatial axis instead of zeros:
+                          CircularConv2d / CircularConv3d (commonlayers.py:918-1032), PUNetGConfig(convolution_type=
+                          "circular").  CUDA-core kernels wrap their gather; tcgen05 kernels read a halo-padded copy
+                          (dsk_conv_fwd_circ / the workspace of dsk_conv_wgrad).                                       */
 } dsk_conv_desc;
 int dsk_conv_fwd(const dsk_conv_desc* d, const void* in, const void* w, const float* bias,
                  const float* chan_bias, const void* residual, void* out, void* stream);
@@ -159,6 +163,15 @@ int dsk_conv_stats_supported(const dsk_conv_desc* d);
 int dsk_conv_stats_slots(void);
 int dsk_conv_fwd_stats(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
                        const void* residual, void* out, void* stats, void* stream);
+/* Circular padding.  dsk_pad_circular: y[B, D+2, H+2, W+2, C] (ndim 2: [B, 1, H+2, W+2, C]) = x wrapped by one
+ * pixel on every spatial axis (torch.nn.functional.pad(mode='circular'), commonlayers.py:960-967, 1015-1030).
+ * dsk_conv_fwd_circ: dsk_conv_fwd / dsk_conv_fwd_stats (stats may be NULL) for d->circular = 1; `pad_ws` holds the padded
+ * copy the tcgen05 kernels read through TMA (dsk_conv_pad_ws_bytes(d) bytes; 0 = this convolution runs on a CUDA-core
+ * kernel that wraps its indices, pad_ws may be NULL). */
+int dsk_pad_circular(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, void* stream);
+int64_t dsk_conv_pad_ws_bytes(const dsk_conv_desc* d);
+int dsk_conv_fwd_circ(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
+                      const void* residual, void* out, void* stats, void* pad_ws, void* stream);
 /* nearest x2 upsample of a channels-last tensor (torch.nn.Upsample(scale_factor=2), commonlayers.py:129):
  * only needed in front of the tcgen05 conv; the FFMA conv fuses it into its gather (up2). bf16, C % 8 == 0. */
 int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, void* stream);

@@ -172,7 +172,57 @@ def cond_goldens():
          (2, 1, 8, 8, 8), 112, (1, 8, 8, 8), False)
 
 
+def circular_goldens():
+    """PUNetGConfig(convolution_type='circular') of the LIVE reference (periodic porous media): network
+    forward (fp32 + fp64), Heun history, loss + gradients  ->  tests/golden/circ_*.pt.   python oracle/make_goldens.py --only circular"""
+    os.makedirs(OUT, exist_ok=True)
+    refload.load_reference()
+    import diffsci.models as M
+    from diffsci.models.nets.punetg import PUNetG
+    from diffsci.models.nets.punetg_config import PUNetGConfig
+    torch.set_num_threads(8)
+    gk = re.compile(r"^(convin|convout|downward_blocks\.0\.0\.|before_block\.0\.conv1|attn_block\.0\.|upsamplers\.0\.|"
+                    r"downsamplers\.0\.)")
+
+    def case(name, kw, shape, seed):
+        net = PUNetG(PUNetGConfig(**kw))
+        man = load_synth(net, seed)
+        net.eval()
+        mod = M.KarrasModule(net, M.KarrasModuleConfig.from_edm())
+        mod.eval()
+        torch.manual_seed(seed + 1000)
+        B, nsteps = shape[0], 3
+        x, t = torch.randn(*shape), torch.randn(B) * 0.7
+        out = dict(kind="punetg", cfg=kw, manifest=man, seed=seed, x=x, t=t, nsteps=nsteps)
+        with torch.no_grad():
+            out["y"] = net(x, t)
+            out["y64"] = net.double()(x.double(), t.double())
+            net.float()
+            wn = torch.randn(*shape)
+            out["white_noise"] = wn
+            out["heun_hist"] = mod.propagate_white_noise(wn, nsteps=nsteps, record_history=True)
+        sg = torch.exp(torch.randn(B) * 1.2 - 1.2)
+        x0, ln = torch.randn(*shape) * 0.5, torch.randn(*shape)
+        out.update(loss_x=x0, loss_noise=ln, loss_sigma=sg)
+        net.train()
+        net.zero_grad()
+        with _Noise([ln]):
+            L = mod.loss_fn(x0, sg, None, None)
+        L.backward()
+        out["loss_huber"] = L.detach()
+        out["loss_huber_grads"] = {k: p.grad.clone() for k, p in net.named_parameters() if gk.search(k)}
+        torch.save(out, os.path.join(OUT, name + ".pt"))
+        print(name, tuple(out["y"].shape), "fp32-vs-fp64", float((out["y"] - out["y64"]).abs().max() / out["y64"].abs().max()),
+              "loss", float(L))
+
+    case("circ_punetg2d", dict(dimension=2, model_channels=8, convolution_type="circular"), (2, 1, 16, 24), 121)
+    case("circ_punetg3d", dict(dimension=3, model_channels=8, channel_expansion=[2], convolution_type="circular"),
+         (2, 1, 8, 8, 8), 122)
+
+
 def main():
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "circular":
+        return circular_goldens()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "inpaint":
         return inpaint_goldens()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "cond":

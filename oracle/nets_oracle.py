@@ -24,6 +24,28 @@ def _conv(x, w, b, dim):
     return (F.conv2d if dim == 2 else F.conv3d)(x, w, b, padding=pad)
 
 
+def _circular_conv(x, w, b, dim):
+    """CircularConv2d / CircularConv3d.forward (commonlayers.py:955-972, 1010-1032), all axes circular: pad W, then H
+    (then D) with mode='circular', then a padding-free convolution."""
+    p = w.shape[-1] // 2
+    if dim == 2:
+        x = F.pad(x, (p, p, 0, 0), mode="circular")
+        x = F.pad(x, (0, 0, p, p), mode="circular")
+        return F.conv2d(x, w, b)
+    x = F.pad(x, (p, p, 0, 0, 0, 0), mode="circular")
+    x = F.pad(x, (0, 0, p, p, 0, 0), mode="circular")
+    x = F.pad(x, (0, 0, 0, 0, p, p), mode="circular")
+    return F.conv3d(x, w, b)
+
+
+def _pconv(x, sd, name, cfg):
+    """A PUNetG convolution by state-dict name: convolution_type 'default' -> keys <name>.weight/.bias, zero padding;
+    'circular' -> keys <name>.conv.weight/.bias (the wrapped Conv), periodic padding (punetg.py:221-232)."""
+    if getattr(cfg, "convolution_type", "default") == "circular":
+        return _circular_conv(x, sd[name + ".conv.weight"], sd.get(name + ".conv.bias"), cfg.dimension)
+    return _conv(x, sd[name + ".weight"], sd.get(name + ".bias"), cfg.dimension)
+
+
 def _bc(v, x):
     return v.reshape(v.shape + (1,) * (x.ndim - v.ndim))
 
@@ -86,11 +108,9 @@ def resnet_block_c(x, te, sd, p, cfg):
     C = x.shape[1]
     aff = getattr(cfg, "affine_norm", True)
     g = lambda n: (sd[p + n + ".weight"], sd[p + n + ".bias"]) if aff else (None, None)  # noqa: E731
-    y = _conv(F.silu(_norm(cfg.first_resblock_norm, x, C, *g("gnorm1"))),
-              sd[p + "conv1.weight"], sd.get(p + "conv1.bias"), dim)
+    y = _pconv(F.silu(_norm(cfg.first_resblock_norm, x, C, *g("gnorm1"))), sd, p + "conv1", cfg)
     y = y + _bc(_time_block(te, sd, p + "timeblock."), y)
-    y = _conv(F.silu(_norm(cfg.second_resblock_norm, y, C, *g("gnorm2"))),
-              sd[p + "conv2.weight"], sd.get(p + "conv2.bias"), dim)
+    y = _pconv(F.silu(_norm(cfg.second_resblock_norm, y, C, *g("gnorm2"))), sd, p + "conv2", cfg)
     return y + x
 
 
@@ -119,7 +139,7 @@ def punetg_forward(sd, cfg, x, t, ye=None):
     if not getattr(cfg, "bias", True):
         ones = torch.ones_like(x[:, :1])
         x = torch.cat([x, ones], dim=1)
-    x = _conv(x, sd["convin.weight"], sd.get("convin.bias"), dim)
+    x = _pconv(x, sd, "convin", cfg)
     te = fourier(t, sd["time_projection.W"])
     if ye is not None:
         te = te + ye
@@ -128,8 +148,7 @@ def punetg_forward(sd, cfg, x, t, ye=None):
         for r in range(cfg.number_resnet_downward_block):
             x = resnet_block_c(x, te, sd, f"downward_blocks.{l}.{r}.", cfg)
         skips.append(x)
-        x = _conv(pool(x, cfg.transition_scale_factor),
-                  sd[f"downsamplers.{l}.conv.weight"], sd.get(f"downsamplers.{l}.conv.bias"), dim)
+        x = _pconv(pool(x, cfg.transition_scale_factor), sd, f"downsamplers.{l}.conv", cfg)
     for r in range(cfg.number_resnet_before_attn_block):    # bottom, punetg.py:378-387
         x = resnet_block_c(x, te, sd, f"before_block.{r}.", cfg)
     xa = x
@@ -142,11 +161,11 @@ def punetg_forward(sd, cfg, x, t, ye=None):
         x = resnet_block_c(x, te, sd, f"after_block.{r}.", cfg)
     for l in range(nlev):                                   # decode, punetg.py:367-376
         x = F.interpolate(x, scale_factor=cfg.transition_scale_factor, mode="nearest")
-        x = _conv(x, sd[f"upsamplers.{l}.conv.weight"], sd.get(f"upsamplers.{l}.conv.bias"), dim)
+        x = _pconv(x, sd, f"upsamplers.{l}.conv", cfg)
         x = x + skips.pop()
         for r in range(cfg.number_resnet_upward_block):
             x = resnet_block_c(x, te, sd, f"upward_blocks.{l}.{r}.", cfg)
-    return _conv(x, sd["convout.weight"], sd.get("convout.bias"), dim)
+    return _pconv(x, sd, "convout", cfg)
 
 
 # ----------------------------------------------------------------------------- ADM

@@ -135,7 +135,9 @@ def test_config_and_utils():
     with pytest.raises(ValueError):
         d.name_to_integrator("rk4")
     with pytest.raises(NotImplementedError):
-        d.PUNetG(d.PUNetGConfig(convolution_type="circular"))
+        d.PUNetG(d.PUNetGConfig(convolution_type="mp"))
+    circ = d.PUNetG(d.PUNetGConfig(model_channels=8, convolution_type="circular"))     # reference keys: <name>.conv.weight
+    assert "convin.conv.weight" in circ.state_dict() and "downsamplers.0.conv.conv.bias" in circ.state_dict()
     sch = d.EDMScheduler()
     sch.set_temporary_integrator("euler")
     assert isinstance(sch.integrator, d.EulerIntegrator)

@@ -182,3 +182,19 @@ def test_conditional_path(golden, name):
     assert relmax(o32, g["em_g1.0"]) <= 2.0 * relmax(g["em_g1.0"].double(), o64) + 2e-5
     L = K.edm_loss(nc, g["loss_x"], g["loss_sigma"], g["loss_noise"], "huber")
     assert abs(float(L) - float(g["loss_huber"])) <= 2e-5 * abs(float(g["loss_huber"]))
+
+
+# ----------------------------------------------------------------------------- circular convolution
+@pytest.mark.parametrize("name", ["circ_punetg2d", "circ_punetg3d"])
+def test_circular_punetg(golden, name):
+    g = golden(name)
+    net = oracle_net(g)
+    assert relmax(net(g["x"], g["t"]), g["y"]) < TOL32
+    net64 = oracle_net(g, torch.float64)
+    assert relmax(net64(g["x"].double(), g["t"].double()), g["y64"]) < 1e-12
+    n, wn = g["nsteps"], g["white_noise"]
+    o32 = K.sample_from_white_noise(net, wn, n, "heun", record_history=True)
+    o64 = K.sample_from_white_noise(net64, wn.double(), n, "heun", record_history=True)
+    assert relmax(o32, g["heun_hist"]) <= 2.0 * relmax(g["heun_hist"].double(), o64) + 2e-5
+    L = K.edm_loss(net, g["loss_x"], g["loss_sigma"], g["loss_noise"], "huber")
+    assert abs(float(L) - float(g["loss_huber"])) <= 2e-5 * abs(float(g["loss_huber"]))
