@@ -12,16 +12,23 @@ namespace dsk {
 __global__ void __launch_bounds__(256) edm_loss_kernel(const float* __restrict__ F, const float* __restrict__ x,
                                                         const float* __restrict__ noise, const float* __restrict__ sigma,
                                                         const float* __restrict__ mask, float* __restrict__ loss_out,
-                                                        float* __restrict__ dF, int B, int64_t CS, float sd, int kind) {
+                                                        float* __restrict__ dF, int B, int64_t CS, float sd, int kind,
+                                                        const float* __restrict__ c_out_v, const float* __restrict__ c_skip_v,
+                                                        const float* __restrict__ lam_v) {
   const int64_t N = (int64_t)B * CS;
   const float invN = 1.0f / (float)N;
   float local = 0.0f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / CS);
     const float sg = sigma[b];
-    const float sum = sg * sg + sd * sd, rt = sqrtf(sum);
-    const float c_skip = (sd * sd) / sum, c_out = (sg * sd) / rt;
-    const float lam = sum / ((sg * sd) * (sg * sd));
+    float c_skip, c_out, lam;
+    if (c_out_v != nullptr) {   // any preconditioner / noise sampler: per-sample coefficients from the host objects
+      c_out = c_out_v[b]; c_skip = c_skip_v[b]; lam = lam_v[b];
+    } else {
+      const float sum = sg * sg + sd * sd, rt = sqrtf(sum);
+      c_skip = (sd * sd) / sum; c_out = (sg * sd) / rt;
+      lam = sum / ((sg * sd) * (sg * sd));
+    }
     const float xv = x[i];
     const float xn = xv + sg * noise[i];
     const float D = c_out * F[i] + c_skip * xn;
@@ -154,7 +161,18 @@ extern "C" int dsk_edm_loss_fwd_bwd(const float* F, const float* x, const float*
   DSK_REQUIRE(B > 0 && C > 0 && S > 0 && (loss_kind == 0 || loss_kind == 1), "dsk_edm_loss_fwd_bwd: bad arguments");
   const int grid = grid_for((int64_t)B * C * S, 256, 8);
   DSK_LAUNCH(edm_loss_kernel, grid, 256, 0, as_stream(stream), F, x, noise, sigma, mask, loss_out, dF, B, (int64_t)C * S,
-             sigma_data, loss_kind);
+             sigma_data, loss_kind, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr);
+  return DSK_OK;
+}
+
+extern "C" int dsk_precond_loss_fwd_bwd(const float* F, const float* x, const float* noise, const float* sigma,
+                                        const float* c_out, const float* c_skip, const float* weight, const float* mask,
+                                        float* loss_out, float* dF, int B, int C, int64_t S, int loss_kind, void* stream) {
+  DSK_REQUIRE(F && x && noise && sigma && c_out && c_skip && weight && loss_out && dF, "dsk_precond_loss_fwd_bwd: null pointer");
+  DSK_REQUIRE(B > 0 && C > 0 && S > 0 && (loss_kind == 0 || loss_kind == 1), "dsk_precond_loss_fwd_bwd: bad arguments");
+  const int grid = grid_for((int64_t)B * C * S, 256, 8);
+  DSK_LAUNCH(edm_loss_kernel, grid, 256, 0, as_stream(stream), F, x, noise, sigma, mask, loss_out, dF, B, (int64_t)C * S, 0.0f,
+             loss_kind, c_out, c_skip, weight);
   return DSK_OK;
 }
 

@@ -131,21 +131,28 @@ class _EDMLossFn(torch.autograd.Function):
     the same fused launch (csrc/train.cu: edm_loss_kernel)."""
 
     @staticmethod
-    def forward(ctx, F, x, noise, sigma, mask, sigma_data, kind):
+    def forward(ctx, F, x, noise, sigma, mask, sigma_data, kind, coeffs=None):
+        """coeffs: None (EDM preconditioner + EDM weighting evaluated in the kernel) or fp32 [B] vectors (c_out, c_skip,
+        lambda) from any preconditioner / noise sampler (dsk_precond_loss_fwd_bwd)."""
         B = x.shape[0]
         Cc = x.shape[1] if x.ndim > 1 else 1
         S = x.numel() // (B * Cc)
         loss = torch.zeros((), dtype=torch.float32, device=x.device)
         dF = torch.empty_like(x, dtype=torch.float32)
-        check(lib.dsk_edm_loss_fwd_bwd(ptr(F), ptr(x), ptr(noise), ptr(sigma), ptr(mask), ptr(loss), ptr(dF), B, Cc, S,
-                                       float(sigma_data), int(kind), stream()))
+        if coeffs is None:
+            check(lib.dsk_edm_loss_fwd_bwd(ptr(F), ptr(x), ptr(noise), ptr(sigma), ptr(mask), ptr(loss), ptr(dF), B, Cc, S,
+                                           float(sigma_data), int(kind), stream()))
+        else:
+            c_out, c_skip, lam = coeffs
+            check(lib.dsk_precond_loss_fwd_bwd(ptr(F), ptr(x), ptr(noise), ptr(sigma), ptr(c_out), ptr(c_skip), ptr(lam),
+                                               ptr(mask), ptr(loss), ptr(dF), B, Cc, S, int(kind), stream()))
         ctx.save_for_backward(dF)
         return loss
 
     @staticmethod
     def backward(ctx, g):
         (dF,) = ctx.saved_tensors
-        return dF * g, None, None, None, None, None, None
+        return dF * g, None, None, None, None, None, None, None
 
 
 def _rowwise_axpy(a_vec: Tensor, z: Tensor, b_vec: Tensor, x: Tensor) -> Tensor:
@@ -323,10 +330,8 @@ class KarrasModule(_Base):
 
     # ------------------------------------------------------------------ training
     def loss_fn(self, x: Tensor, sigma: Tensor, y=None, mask: Optional[Tensor] = None) -> Tensor:
-        """EDM denoising loss (karrasmodule.py:569-650).  Needs an EDMPreconditioner (the weighting
-        lambda(sigma) and D are evaluated inside one fused kernel together with dL/dF)."""
-        if type(self.config.preconditioner) is not preconditioners.EDMPreconditioner:
-            raise NotImplementedError("diffsci_b200.KarrasModule.loss_fn: only the EDM preconditioner is fused")
+        """Denoising loss (karrasmodule.py:569-650): D, lambda(sigma), the loss and dL/dF in one fused kernel -- scalars
+        evaluated in-kernel for the EDM preconditioner, passed as [B] vectors for VP / VE / SR3 / custom objects."""
         require_cuda(x, "x")
         x = x.float().contiguous()
         sigma = sigma.to(x).contiguous()
@@ -345,8 +350,14 @@ class KarrasModule(_Base):
         if adt is not None:            # native plan output: channels-last act dtype -> fp32 NC(D)HW
             F = ops.cl_to_nchw(F.view(B, 1, 1, S, Cc), 3).view(x.shape)
         m = None if mask is None else mask.to(x).expand_as(x).contiguous()
+        coeffs = None
+        if not (type(pre) is preconditioners.EDMPreconditioner and
+                type(self.config.noisesampler) is noisesamplers.EDMNoiseSampler):
+            # VP / VE / SR3 / custom objects: their per-sample scalars, the same fused loss + dL/dF kernel
+            coeffs = tuple(v.float().contiguous() for v in (pre.output_scaling(sigma), pre.skip_scaling(sigma),
+                                                            self.config.noisesampler.loss_weighting(sigma)))
         return _EDMLossFn.apply(F.float().contiguous().view(x.shape), x, noise.contiguous(), sigma, m,
-                                self._sigma_data(), self.loss_kind)
+                                self._sigma_data(), self.loss_kind, coeffs)
 
     _injected_loss_noise: Optional[Tensor] = None
 

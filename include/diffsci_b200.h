@@ -294,6 +294,12 @@ int dsk_softmax_rows(float* S, int64_t rows, int cols, void* stream);
 int dsk_edm_loss_fwd_bwd(const float* F, const float* x, const float* noise, const float* sigma,
                          const float* mask, float* loss_out, float* dF, int B, int C, int64_t S,
                          float sigma_data, int loss_kind, void* stream);
+/* The same loss for ANY preconditioner / noise sampler (VP, VE, SR3, uniform; preconditioners.py:56-136,
+ * noisesamplers.py:44-110): the per-sample coefficients c_out[b], c_skip[b] and the loss weight lambda[b] are evaluated by
+ * the host-side objects and passed in as fp32 [B] vectors. */
+int dsk_precond_loss_fwd_bwd(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
+                             const float* c_skip, const float* weight, const float* mask, float* loss_out, float* dF,
+                             int B, int C, int64_t S, int loss_kind, void* stream);
 /* Multi-tensor EMA: shadow_i <- lerp(shadow_i, p_i, 1-beta) (karras/ema.py:139-147) in one launch. */
 int dsk_ema_update(float* const* shadow, const float* const* param, const int64_t* numel, int ntensors,
                    int64_t max_numel, float beta, void* stream);

@@ -250,3 +250,142 @@ def adamw_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, wd=1e-4):
     denom = (v.sqrt() / math.sqrt(bc2)) + eps
     p = p - (lr / bc1) * (m / denom)
     return p, m, v
+
+
+# ----------------------------------------------------------------------------- VP / VE / SR3
+class SchedFns:
+    """schedulingfunctions.py:39-170 restated for tag in {"edm", "vp", "ve"}: s(t), s'(t), sigma(t), sigma'(t),
+    sigma^{-1}, and the flags Scheduler.rhs branches on."""
+
+    def __init__(self, tag: str, beta_data: float = 19.9, beta_min: float = 0.1):
+        self.tag, self.bd, self.bm = tag, beta_data, beta_min
+        self.constant_scaling = tag in ("edm", "ve")            # constant_scaling_fn
+        self.has_pf_score_multiplier = tag == "ve"              # VP's flag is False upstream ("TODO: Set to true")
+
+    def _e(self, t):
+        return 0.5 * self.bd * t ** 2 + self.bm * t
+
+    def scaling(self, t):
+        return torch.exp(-self._e(t) / 2) if self.tag == "vp" else 1 + 0 * t
+
+    def scaling_deriv(self, t):
+        if self.tag == "vp":
+            return -(self.bd * t + self.bm) / 2 * torch.exp(-self._e(t) / 2)
+        return 0 * t
+
+    def noise(self, t):
+        if self.tag == "vp":
+            return torch.sqrt(torch.exp(self._e(t)) - 1)
+        return torch.sqrt(t) if self.tag == "ve" else 1 * t
+
+    def noise_deriv(self, t):
+        if self.tag == "vp":
+            ex = torch.exp(self._e(t))
+            return ((self.bd * t + self.bm) * ex) / (2 * torch.sqrt(ex - 1))
+        return 0.5 / torch.sqrt(t) if self.tag == "ve" else 1 + 0 * t
+
+    def inverse_noise(self, s):
+        if self.tag == "vp":
+            y = torch.log(s ** 2 + 1)
+            return (-self.bm + torch.sqrt(self.bm ** 2 + 2 * self.bd * y)) / self.bd
+        return s ** 2 if self.tag == "ve" else 1 * s
+
+    def pf_score_multiplier(self, t):
+        assert self.tag == "ve"
+        return 0.5 + 0 * t
+
+
+def generic_steps(tag: str, n: int, epsilon_min=1e-3, sigma_min=0.02, sigma_max=100.0) -> torch.Tensor:
+    """VPScheduler.create_steps / VEScheduler.create_steps (schedulers.py:411-414, 437-440); EDM: edm_steps."""
+    if tag == "vp":
+        eps = torch.tensor(epsilon_min)
+        return 1 + (torch.arange(n).to(eps) / (n - 1)) * (eps - 1)
+    if tag == "ve":
+        smin, smax = torch.tensor(float(sigma_min)), torch.tensor(float(sigma_max))
+        return smax ** 2 * (smin ** 2 / smax ** 2) ** (torch.arange(n).to(smin) / (n - 1))
+    return edm_steps(n)
+
+
+def generic_precond(kind: str, sigma: torch.Tensor, fns: Optional[SchedFns] = None, M: int = 1000, sigma_data: float = 0.5):
+    """(c_in, c_out, c_skip, c_noise) of VPPreconditioner / VEPreconditioner / SR3Preconditioner / EDMPreconditioner
+    (preconditioners.py:30-136)."""
+    if kind == "vp":
+        return 1 / torch.sqrt(sigma ** 2 + 1.0), -sigma, 1 + 0.0 * sigma, (M - 1) * fns.inverse_noise(sigma)
+    if kind == "ve":
+        return 1 + 0.0 * sigma, sigma, 1 + 0.0 * sigma, torch.log(0.5 * sigma)
+    c_in, c_out, c_skip, c_noise = edm_precond(sigma, sigma_data)
+    if kind == "sr3":
+        sd = torch.as_tensor(sigma_data, dtype=sigma.dtype)
+        c_skip = sd ** 2 / (2 * (sigma ** 2 + sd ** 2))
+        c_out = sigma * sd / (2 * torch.sqrt(sigma ** 2 + sd ** 2))
+    return c_in, c_out, c_skip, c_noise
+
+
+def generic_denoiser(net: Net, x, sigma, kind: str, fns: Optional[SchedFns] = None):
+    """KarrasModule.get_denoiser (karrasmodule.py:690-719) for any preconditioner."""
+    c_in, c_out, c_skip, c_noise = generic_precond(kind, sigma, fns)
+    return bcast(c_out, x) * net(bcast(c_in, x) * x, c_noise) + bcast(c_skip, x) * x
+
+
+def generic_score(net: Net, x, sigma, kind: str, fns: Optional[SchedFns] = None):
+    return (generic_denoiser(net, x, sigma, kind, fns) - x) / (bcast(sigma, x) ** 2)
+
+
+def generic_rhs(net: Net, x, ti, kind: str, fns: SchedFns, stochastic=False, langevin_const=1.0):
+    """Scheduler.rhs (schedulers.py:247-294), both branches (constant and non-constant s(t)), backward direction."""
+    t = ti * torch.ones(x.shape[0]).to(x)
+    t_ = bcast(t, x)
+    sigma = fns.noise(t)
+    lang = langevin_const * (fns.scaling(t_) ** 2 * fns.noise_deriv(t_) * fns.noise(t_)) + 0 * t_     # langevin_factor :219-241
+    if fns.constant_scaling:
+        mult = fns.pf_score_multiplier(t_) if fns.has_pf_score_multiplier else bcast(sigma, x) * bcast(fns.noise_deriv(t), x)
+        sc = generic_score(net, x, sigma, kind, fns)
+        res = -mult * sc
+        if stochastic:
+            res = res + (-(lang * sc))
+        return res
+    s, sd = fns.scaling(t_), fns.scaling_deriv(t_)
+    mult = s * (fns.noise_deriv(t_) * fns.noise(t_))
+    sc = generic_score(net, x / s, sigma, kind, fns)
+    res = (sd / s) * x - mult * sc
+    if stochastic:
+        res = res + (-(lang * 1 / s * sc))
+    return res
+
+
+def generic_propagate(net: Net, x, nsteps: int, tag: str, kind: Optional[str] = None, integrator: str = "heun",
+                      record_history: bool = False, noises=None, langevin_const: float = 1.0):
+    """Scheduler.propagate(backward=True) (schedulers.py:48-89) with the Euler / Heun / Euler-Maruyama steps
+    (integrators.py:29-69) for the VP, VE or EDM scheduler; `kind` names the preconditioner (default: the tag's own)."""
+    kind = kind or tag
+    fns = SchedFns(tag)
+    t = generic_steps(tag, nsteps + 1).to(x)
+    dt = torch.diff(t)
+    hist = [x] if record_history else None
+    for i in range(nsteps):
+        ti, dti = t[i], dt[i]
+        if integrator == "euler":
+            x = x + dti * generic_rhs(net, x, ti, kind, fns)
+        elif integrator == "heun":
+            r1 = generic_rhs(net, x, ti, kind, fns)
+            r2 = generic_rhs(net, x + dti * r1, ti + dti, kind, fns) if (ti + dti) > 0 else r1
+            x = x + 0.5 * (r1 + r2) * dti
+        elif integrator == "euler-maruyama":
+            strength = torch.sqrt(2 * (langevin_const * (fns.scaling(ti) ** 2 * fns.noise_deriv(ti) * fns.noise(ti)) + 0 * ti))
+            x = (x + generic_rhs(net, x, ti, kind, fns, stochastic=True, langevin_const=langevin_const) * dti +
+                 (strength * noises[i] * torch.sqrt(torch.abs(dti))))
+        else:
+            raise ValueError(integrator)
+        if record_history:
+            hist.append(x)
+    return torch.stack(hist, 0) if record_history else x
+
+
+def generic_loss(net: Net, x, sigma, noise, kind: str, fns: Optional[SchedFns] = None, sigma_data=0.5):
+    """KarrasModule.loss_fn (karrasmodule.py:569-650), Huber, for any preconditioner; weights of VPNoiseSampler /
+    VENoiseSampler (1/sigma^2, noisesamplers.py:59-60, 84-85) or EDMNoiseSampler (SR3 fixtures)."""
+    bs = bcast(sigma, x)
+    D = generic_denoiser(net, x + bs * noise, sigma, kind, fns)
+    w = 1 / (bs ** 2) if kind in ("vp", "ve") else edm_loss_weight(bs, sigma_data)
+    l = torch.nn.functional.huber_loss(D, x, reduction="none", delta=1.0)
+    return (w * l + torch.zeros_like(w)).mean()

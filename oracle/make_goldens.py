@@ -220,7 +220,83 @@ def circular_goldens():
          (2, 1, 8, 8, 8), 122)
 
 
+def precond_goldens():
+    """VP / VE / SR3 preconditioners, noise samplers and schedulers of the LIVE reference
+    (preconditioners.py:56-136, noisesamplers.py:44-110, schedulers.py:393-448, rhs with non-constant s(t) :275-293):
+    get_denoiser / get_score, Heun + Euler + Euler-Maruyama sampling, loss + gradients
+    ->  tests/golden/precond_*.pt.   python oracle/make_goldens.py --only precond"""
+    os.makedirs(OUT, exist_ok=True)
+    refload.load_reference()
+    import diffsci.models as M
+    from diffsci.models.nets.punetg import PUNetG
+    from diffsci.models.nets.punetg_config import PUNetGConfig
+    from diffsci.models.nets.mlp import MLPUncond
+    from diffsci.models.karras import preconditioners as P, noisesamplers as NS, schedulers as S
+    torch.set_num_threads(8)
+
+    def config(tag):
+        if tag == "vp":
+            return M.KarrasModuleConfig.from_vp()
+        if tag == "ve":
+            return M.KarrasModuleConfig.from_ve()
+        return M.KarrasModuleConfig(preconditioner=P.SR3Preconditioner(), noisesampler=NS.EDMNoiseSampler(),
+                                    noisescheduler=S.EDMScheduler())
+
+    def case(name, tag, model, man_seed, netname, shape, seed, nsteps=5):
+        cfg = config(tag)
+        mod = M.KarrasModule(model, cfg)
+        mod.eval()
+        torch.manual_seed(seed)
+        B = shape[0]
+        wn = torch.randn(*shape)
+        out = dict(tag=tag, net=netname, out_scale=0.02, nsteps=nsteps, white_noise=wn, steps=cfg.noisescheduler.create_steps(nsteps + 1),
+                   maximum_scale=float(cfg.noisescheduler.maximum_scale))
+        with torch.no_grad():
+            torch.manual_seed(seed + 1)
+            sg = cfg.noisesampler.sample([B])
+            out["sampled_sigma"] = sg
+            xin = torch.randn(*shape) * (1 + sg.view(-1, *([1] * (len(shape) - 1))))
+            D, cn = mod.get_denoiser(xin, sg)
+            out.update(den_x=xin, den_sigma=sg, den_D=D, den_cnoise=cn, den_score=mod.get_score(xin, sg),
+                       loss_weight=cfg.noisesampler.loss_weighting(sg))
+            out["heun_hist"] = mod.propagate_white_noise(wn, nsteps=nsteps, record_history=True)
+            out["euler"] = mod.propagate_white_noise(wn, nsteps=nsteps, integrator="euler")
+            noises = [torch.randn(*shape) for _ in range(nsteps)]
+            out["noises"] = noises
+            with _Noise(noises):
+                out["em"] = mod.propagate_white_noise(wn, nsteps=nsteps, integrator="euler-maruyama")
+        x0, ln = torch.randn(*shape) * 0.5, torch.randn(*shape)
+        out.update(loss_x=x0, loss_noise=ln, loss_sigma=sg)
+        model.zero_grad()
+        with _Noise([ln]):
+            L = mod.loss_fn(x0, sg, None, None)
+        L.backward()
+        out["loss_huber"] = L.detach()
+        out["loss_huber_grads"] = {k: p.grad.clone() for k, p in model.named_parameters() if GRAD_KEYS.search(k)}
+        torch.save(out, os.path.join(OUT, name + ".pt"))
+        print(name, "heun final absmax", float(out["heun_hist"][-1].abs().max()), "loss", float(L.detach()))
+
+    # synthetic-weight networks are not denoisers: with the VP / VE schedules their trajectories blow up (1e4 .. 1e10) and a
+    # comparison would only measure chaos.  The fixtures therefore scale the LAST layer by OUT_SCALE (recorded; the tests
+    # apply the same factor), which keeps F small and the trajectories O(sigma_max).
+    OUT_SCALE = 0.02
+    mlp = MLPUncond(2, [16, 16], nonlinearity=torch.nn.SiLU())
+    load_synth(mlp, 106)                                   # the weights of mlp_silu
+    p2d = PUNetG(PUNetGConfig(dimension=2, model_channels=8))
+    load_synth(p2d, 101)                                   # the weights of punetg2d_mc8
+    with torch.no_grad():
+        last = [m for m in mlp.modules() if isinstance(m, torch.nn.Linear)][-1]
+        for t_ in (last.weight, last.bias, p2d.convout.weight, p2d.convout.bias):
+            t_.mul_(OUT_SCALE)
+    for tag in ("vp", "ve", "sr3"):
+        case(f"precond_{tag}_mlp", tag, mlp, 106, "mlp_silu", (16, 2), 301)
+    for tag in ("vp", "ve"):
+        case(f"precond_{tag}_punetg2d", tag, p2d, 101, "punetg2d_mc8", (2, 1, 16, 16), 302, nsteps=3)
+
+
 def main():
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "precond":
+        return precond_goldens()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "circular":
         return circular_goldens()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "inpaint":

@@ -198,3 +198,43 @@ def test_circular_punetg(golden, name):
     assert relmax(o32, g["heun_hist"]) <= 2.0 * relmax(g["heun_hist"].double(), o64) + 2e-5
     L = K.edm_loss(net, g["loss_x"], g["loss_sigma"], g["loss_noise"], "huber")
     assert abs(float(L) - float(g["loss_huber"])) <= 2e-5 * abs(float(g["loss_huber"]))
+
+
+# ----------------------------------------------------------------------------- VP / VE / SR3
+def precond_case(g, dtype=torch.float32):
+    """-> (net with the fixture's scaled last layer, scheduler tag, preconditioner kind)."""
+    base = torch.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", g["net"] + ".pt"),
+                      weights_only=False)
+    sd = N.synth_state_dict(base["manifest"], base["seed"], dtype)
+    last = "convout." if base["kind"] == "punetg" else [k for k, _ in base["manifest"] if k.endswith(".weight")][-1][:-6]
+    for k in (last + "weight", last + "bias"):
+        sd[k] = sd[k] * g["out_scale"]
+    if base["kind"] == "punetg":
+        cfg = cfg_for("punetg", base["cfg"])
+        net = lambda x, t: N.punetg_forward(sd, cfg, x, t)  # noqa: E731
+    else:
+        net = lambda x, t: N.mlp_uncond_forward(sd, x, t, base["cfg"]["act"])  # noqa: E731
+    tag = "edm" if g["tag"] == "sr3" else g["tag"]
+    return net, tag, g["tag"]
+
+
+@pytest.mark.parametrize("name", ["precond_vp_mlp", "precond_ve_mlp", "precond_sr3_mlp", "precond_vp_punetg2d",
+                                  "precond_ve_punetg2d"])
+def test_vp_ve_sr3(golden, name):
+    g = golden(name)
+    net, tag, kind = precond_case(g)
+    net64, _, _ = precond_case(g, torch.float64)
+    fns = K.SchedFns(tag)
+    n = g["nsteps"]
+    assert torch.allclose(K.generic_steps(tag, n + 1), g["steps"], rtol=1e-6, atol=0)
+    assert relmax(K.generic_precond(kind, g["den_sigma"], fns)[3], g["den_cnoise"]) < 1e-6
+    assert relmax(K.generic_denoiser(net, g["den_x"], g["den_sigma"], kind, fns), g["den_D"]) < TOL32
+    assert relmax(K.generic_score(net, g["den_x"], g["den_sigma"], kind, fns), g["den_score"]) < 5 * TOL32
+    x0 = g["white_noise"] * g["maximum_scale"]
+    for key, integ, nz in (("heun_hist", "heun", None), ("euler", "euler", None), ("em", "euler-maruyama", g["noises"])):
+        o32 = K.generic_propagate(net, x0, n, tag, kind, integ, record_history=key == "heun_hist", noises=nz)
+        o64 = K.generic_propagate(net64, x0.double(), n, tag, kind, integ, record_history=key == "heun_hist",
+                                  noises=None if nz is None else [z.double() for z in nz])
+        assert relmax(o32, g[key]) <= 2.0 * relmax(g[key].double(), o64) + 2e-5, (key, relmax(o32, g[key]))
+    L = K.generic_loss(net, g["loss_x"], g["loss_sigma"], g["loss_noise"], kind, fns)
+    assert abs(float(L) - float(g["loss_huber"])) <= 2e-5 * abs(float(g["loss_huber"]))
