@@ -79,7 +79,8 @@ class SamplerEngine:
                 raise ValueError(f"network expects {self.xin.shape[-1]} input channels, got {self.Cc} state + "
                                  f"{self.cond_channels} conditioning channels")
             if self.cond_vector:
-                self.ye = torch.zeros((self.Bn, model.config.model_channels), **f32)   # rows [0,B) stay 0 under CFG
+                cdim = getattr(model, "cond_dim", None) or model.config.model_channels
+                self.ye = torch.zeros((self.Bn, cdim), **f32)   # rows [0,B) stay 0 under CFG
         else:
             self.plan = None
             self.act_dtype = torch.float32

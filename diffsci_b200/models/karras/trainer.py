@@ -42,6 +42,9 @@ class EDMTrainer:
                             "KarrasModule.training_step + a torch optimizer")
         if type(module.config.preconditioner) is not preconditioners.EDMPreconditioner:
             raise NotImplementedError("EDMTrainer: only the EDM preconditioner is fused")
+        if module.conditional or getattr(net, "conditional_embedding", None) is not None or getattr(net, "cond_drop", None) is not None:
+            raise NotImplementedError("EDMTrainer: conditional models train through KarrasModule.training_step + a torch "
+                                      "optimizer (the native backward returns d loss / d embedding to autograd)")
         self.module, self.net, self.ema, self.group = module, net, ema, process_group
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         self.bucket_bytes = int(bucket_mb * (1 << 20))

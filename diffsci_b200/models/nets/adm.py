@@ -110,14 +110,12 @@ class ADM(nn.Module):
             bad.append("norms other than GroupLN/GroupRMS")
         if c.decoder_type != 1 or c.skip_integration_type not in ("concat", "add"):
             bad.append("decoder_type != 1 / unknown skip_integration_type")
-        if conditional_embedding is not None:
-            bad.append("conditional_embedding")
         if c.transition_scale_factor != 2 or c.kernel_size != 3:
             bad.append("transition_scale_factor != 2 or kernel_size != 3")
         if bad:
             raise NotImplementedError("diffsci_b200.ADM: not built yet (SURVEY.md 8f): " + "; ".join(bad))
         self.precision = precision or DEFAULT_PRECISION
-        self.conditional_embedding = None
+        self.conditional_embedding = conditional_embedding     # any torch module: y -> [B, output_embed_dim] (adm.py:199-203)
         M, E, nd = c.model_channels, c.output_embed_dim, c.dimension
         mult = c.extended_channel_expansion
         self.time_embedding = _TimeEmbedding(c.time_embed_dim, E, c.time_projection_scale)
@@ -143,23 +141,51 @@ class ADM(nn.Module):
         self.cond_dropout = nn.Dropout(c.cond_dropout)
         self._plans: dict[Any, "_ADMPlan"] = {}
 
+    # ------------------------------------------------------------------ conditioning
+    @property
+    def cond_dim(self) -> int:
+        return self.config.output_embed_dim
+
+    def native_parameters(self) -> list:
+        """The parameters the CUDA path owns (everything except the user's conditional embedding)."""
+        return [p for n, p in self.named_parameters() if not n.startswith("conditional_embedding.")]
+
+    def conditioning_vector(self, y, B: int) -> Optional[torch.Tensor]:
+        """ye of adm.py:199-209: cond_dropout(conditional_embedding(y)) as fp32 [B, output_embed_dim]; None when y is None
+        (the reference adds zeros then, which is the same thing)."""
+        if y is None:
+            return None
+        if self.conditional_embedding is None:
+            raise TypeError("'NoneType' object is not callable (ADM got y but has no conditional_embedding, adm.py:201)")
+        ye = self.cond_dropout(self.conditional_embedding(y))
+        E = self.config.output_embed_dim
+        if ye.ndim == 1:
+            ye = ye.unsqueeze(0)
+        if ye.ndim != 2 or ye.shape[-1] != E or ye.shape[0] not in (1, B):
+            raise NotImplementedError(f"diffsci_b200.ADM: conditioning of shape {tuple(ye.shape)} (expected [B or 1, {E}])")
+        return ye.float().expand(B, E)
+
+    def split_condition(self, y, x: torch.Tensor):
+        return None, y
+
     def forward(self, x: torch.Tensor, t: torch.Tensor, y=None) -> torch.Tensor:
-        if y is not None:
-            raise NotImplementedError("diffsci_b200.ADM: conditional path (y) not built yet (SURVEY.md 8f)")
         require_cuda(x, "ADM input")
+        B = x.shape[0]
+        ye = self.conditioning_vector(y, B)
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
             from .graph import NetFunction
-            return NetFunction.apply(self.train_graph(x.shape[0], tuple(x.shape[2:]), x.device), x, t, None, *self.parameters())
-        plan = self.plan(x.shape[0], tuple(x.shape[2:]), x.device)
+            graph = self.train_graph(B, tuple(x.shape[2:]), x.device, cond=ye is not None)
+            return NetFunction.apply(graph, x, t, None if ye is None else ye.contiguous(), *self.native_parameters())
+        plan = self.plan(B, tuple(x.shape[2:]), x.device)
         xin = ops.nchw_to_cl(x.float(), plan.act_dtype, 2, out=plan.xin)
-        out = torch.empty((x.shape[0], self.config.output_channels) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
-        plan.forward(xin, t.float().contiguous(), out_nchw=out)
+        out = torch.empty((B, self.config.output_channels) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+        plan.forward(xin, t.float().contiguous(), out_nchw=out, ye=None if ye is None else ye.contiguous())
         return out
 
     def plan(self, B: int, spatial: tuple, device, precision: Optional[str] = None) -> "_ADMPlan":
         precision = precision or self.precision
         key = (B, tuple(spatial), str(device), precision)
-        sig = tuple(p.data_ptr() for p in self.parameters())
+        sig = tuple(p.data_ptr() for p in self.native_parameters())
         plan = self._plans.get(key)
         if plan is None or plan.sig != sig:
             if len(self._plans) >= 4:
@@ -168,17 +194,17 @@ class ADM(nn.Module):
                 plan = self._plans[key] = _ADMPlan(self, B, tuple(spatial), device, precision, sig)
         return plan
 
-    def train_graph(self, B: int, spatial: tuple, device, precision: Optional[str] = None):
+    def train_graph(self, B: int, spatial: tuple, device, precision: Optional[str] = None, cond: bool = False):
         from .graph import build_adm
         precision = precision or self.precision
-        key = ("train", B, tuple(spatial), str(device), precision)
-        sig = tuple(p.data_ptr() for p in self.parameters())
+        key = ("train", B, tuple(spatial), str(device), precision, bool(cond))
+        sig = tuple(p.data_ptr() for p in self.native_parameters())
         g = self._plans.get(key)
         if g is None or g.sig != sig:
             for k in [k for k in self._plans if k[0] == "train"]:
                 del self._plans[k]
             with torch.inference_mode(False), torch.no_grad():
-                g = self._plans[key] = build_adm(self, B, tuple(spatial), device, precision)
+                g = self._plans[key] = build_adm(self, B, tuple(spatial), device, precision, cond=cond)
         return g
 
     def _apply(self, fn, *a, **k):
@@ -219,6 +245,9 @@ class _ADMPlan:
         mlp = net.time_embedding.mlp
         self.t_mlp = [ops.GroupedLinear([self.four], [mlp[0].weight], [mlp[0].bias], [self.h1], 1),
                       ops.GroupedLinear([self.h1], [mlp[2].weight], [mlp[2].bias], [self.te], 1)]   # + act_final SiLU
+        # conditional: te = SiLU(mlp(fourier(t)) + ye)  (adm.py:1047-1053): second linear without activation, add, SiLU
+        self.tez = torch.empty((B, E), **f32)
+        self.t_mlp2_noact = ops.GroupedLinear([self.h1], [mlp[2].weight], [mlp[2].bias], [self.tez], 0)
         self.film = {id(b): (torch.empty((B, b.cout), **f32), torch.empty((B, b.cout), **f32)) for b in self.blocks}
         ws, bs, ys = [], [], []
         for b in self.blocks:
@@ -301,11 +330,18 @@ class _ADMPlan:
             o = self._attention(o, blk, idx)
         return o
 
-    def forward(self, xin: torch.Tensor, cnoise: torch.Tensor, out_nchw: Optional[torch.Tensor] = None, **_):
+    def forward(self, xin: torch.Tensor, cnoise: torch.Tensor, out_nchw: Optional[torch.Tensor] = None,
+                ye: Optional[torch.Tensor] = None, **_):
         net, c = self.net, self.net.config
         ops.fourier(cnoise, net.time_embedding.projection.W, out=self.four)
-        for g in self.t_mlp:
-            g.run()                                                              # te = SiLU(mlp(fourier(t)))  (adm.py:1047-1053)
+        if ye is None:
+            for g in self.t_mlp:
+                g.run()                                                          # te = SiLU(mlp(fourier(t)))  (adm.py:1047-1053)
+        else:
+            self.t_mlp[0].run()
+            self.t_mlp2_noact.run()
+            ops.add_ex(self.tez, ye, self.tez)                                   # + ye before the final SiLU (adm.py:1050-1052)
+            ops.silu_fwd(self.tez, self.te)
         self.film_gl.run()
         x = ops.conv(xin, self.pc_in, out=self.buf("x0", xin.shape[:-1] + (c.model_channels,)))
         skips, idx = [x], 0

@@ -352,6 +352,23 @@ class TrainGraph:
         self._bwd_builders.append(build_bwd)
         return y
 
+    def silu_vec(self, x: Var) -> Var:
+        """fp32 vectors: y = SiLU(x) (ADM's act_final after the conditioning add, adm.py:1052)."""
+        y = Var(self.empty(x.t.shape, torch.float32))
+        xt, yt = x.t, y.t
+        self.fwd.append(lambda: ops.silu_fwd(xt, yt))
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None or not x.needs_grad:
+                return []
+            dres, dx = self.contribute_compute(x)
+            assert dres is None, "silu_vec input with several consumers is not supported"
+            return [lambda: ops.silu_bwd(xt, dy, dx)]
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
     def concat(self, a: Var, b: Var) -> Var:
         y = Var(self.empty(a.t.shape[:-1] + (a.t.shape[-1] + b.t.shape[-1],)))
         at, bt, yt = a.t, b.t, y.t
@@ -729,8 +746,9 @@ def build_punetg(net, B: int, spatial: tuple, device, precision: str, cond: bool
     return g
 
 
-def build_adm(net, B: int, spatial: tuple, device, precision: str) -> TrainGraph:
-    """ADM.forward (nets/adm.py:199-216; block :292-343) unrolled into a TrainGraph."""
+def build_adm(net, B: int, spatial: tuple, device, precision: str, cond: bool = False) -> TrainGraph:
+    """ADM.forward (nets/adm.py:199-216; block :292-343) unrolled into a TrainGraph.  cond: te = SiLU(mlp(fourier) + ye) with
+    ye an input [B, output_embed_dim] whose gradient is returned (adm.py:1047-1053)."""
     c = net.config
     if getattr(c, "dropout", 0.0) != 0.0:
         raise NotImplementedError("diffsci_b200.ADM: dropout > 0 in training is not built yet")
@@ -745,7 +763,12 @@ def build_adm(net, B: int, spatial: tuple, device, precision: str) -> TrainGraph
     four = g.fourier(g.t_in, net.time_embedding.projection.W)
     mlp = net.time_embedding.mlp
     h1 = grouped_linear_layer(g, [four], [(mlp[0].weight, mlp[0].bias, mlp[0].weight, mlp[0].bias, None)], True)[0]
-    te = grouped_linear_layer(g, [h1], [(mlp[2].weight, mlp[2].bias, mlp[2].weight, mlp[2].bias, None)], True)[0]  # + act_final SiLU (adm.py:1047-1053)
+    if cond:
+        z = grouped_linear_layer(g, [h1], [(mlp[2].weight, mlp[2].bias, mlp[2].weight, mlp[2].bias, None)], False)[0]
+        g.ye_in = Var(g.empty((B, c.output_embed_dim), torch.float32), needs_grad=True, name="ye")
+        te = g.silu_vec(g.add_vec(z, g.ye_in))
+    else:
+        te = grouped_linear_layer(g, [h1], [(mlp[2].weight, mlp[2].bias, mlp[2].weight, mlp[2].bias, None)], True)[0]  # + act_final SiLU (adm.py:1047-1053)
     blocks = [b for layer in net.encoder.layers for b in layer.input_blocks] + list(net.middle_block.middle_blocks) + \
         [b for layer in net.decoder.layers for b in layer.input_blocks]
     specs = []

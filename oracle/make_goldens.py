@@ -114,9 +114,10 @@ def cond_goldens():
     from diffsci.models.nets.embedder import PorosityEmbedder
     torch.set_num_threads(8)
     gk = re.compile(r"^(conditional_embedding\.|convin|convout|downward_blocks\.0\.0\.|before_block\.0\.conv1|"
-                    r"attn_block\.0\.|upsamplers\.1\.)")
+                    r"attn_block\.0\.|upsamplers\.1\.|time_embedding\.|input_layer|output_layer|"
+                    r"encoder\.layers\.0\.input_blocks\.0\.|middle_block\.middle_blocks\.2\.)")
 
-    def case(name, net, kw, shape, seed, chan_shape, cfg_ok):
+    def case(name, net, kw, shape, seed, chan_shape, cfg_ok, kind="punetg"):
         man = load_synth(net, seed)
         net.eval()
         mod = M.KarrasModule(net, M.KarrasModuleConfig.from_edm(), conditional=True)
@@ -130,7 +131,7 @@ def cond_goldens():
         if chan_shape is not None:
             yb["cond"] = torch.randn(B, *chan_shape)
             y1["cond"] = torch.randn(*chan_shape)
-        out = dict(cfg=kw, manifest=man, seed=seed, x=x, t=t, y_batch=yb, y_one=y1, nsteps=nsteps)
+        out = dict(kind=kind, cfg=kw, manifest=man, seed=seed, x=x, t=t, y_batch=yb, y_one=y1, nsteps=nsteps)
         with torch.no_grad():
             out["net_y"] = net(x, t, dict(yb))
             out["net_y64"] = net.double()(x.double(), t.double(), {k: v.double() for k, v in yb.items()})
@@ -163,6 +164,11 @@ def cond_goldens():
         torch.save(out, os.path.join(OUT, name + ".pt"))
         print(name, {k: (tuple(v.shape), float(v.abs().max())) for k, v in out.items() if torch.is_tensor(v)})
 
+    if "--adm" in sys.argv:      # added after the PUNetG fixtures were committed; regenerates only the ADM one
+        from diffsci.models.nets.adm import ADM, ADMConfig
+        kw = dict(input_channels=3, output_channels=3, model_channels=8, time_embed_dim=16, output_embed_dim=32)
+        return case("cond_adm2d_embed", ADM(ADMConfig(**kw), conditional_embedding=PorosityEmbedder(32)), kw,
+                    (2, 3, 16, 16), 113, None, True, kind="adm")
     kw = dict(dimension=2, model_channels=8)
     case("cond_punetg2d_embed", PUNetG(PUNetGConfig(**kw), conditional_embedding=PorosityEmbedder(8)), kw,
          (2, 1, 16, 16), 111, None, True)

@@ -196,11 +196,14 @@ def adm_block(x, te, sd, p, cfg, sample=None, attn=False):
     return y
 
 
-def adm_forward(sd, cfg, x, t):
-    """ADM.forward (nets/adm.py:199-216), unconditional, decoder_type 1."""
+def adm_forward(sd, cfg, x, t, ye=None):
+    """ADM.forward (nets/adm.py:199-216), decoder_type 1.  ye: conditional embedding vector [B or 1, output_embed_dim],
+    added before the final SiLU of the time embedding (adm.py:1047-1053; zeros / None when y is None)."""
     te = fourier(t, sd["time_embedding.projection.W"])
     te = F.linear(F.silu(F.linear(te, sd["time_embedding.mlp.0.weight"], sd["time_embedding.mlp.0.bias"])),
                   sd["time_embedding.mlp.2.weight"], sd["time_embedding.mlp.2.bias"])
+    if ye is not None:
+        te = te + ye
     te = F.silu(te)                                          # adm.py:1047-1053
     x = F.conv2d(x, sd["input_layer.weight"], sd["input_layer.bias"], padding=cfg.kernel_size // 2)
     nlev = len(cfg.channel_expansion)

@@ -16,6 +16,13 @@ def build(g, precision="fp32"):
     import diffsci_b200 as d
     from diffsci_b200.models.nets.embedder import PorosityEmbedder
     from oracle.nets_oracle import synth_state_dict
+    if g.get("kind", "punetg") == "adm":
+        cfg = d.ADMConfig(**g["cfg"])
+        net = d.ADM(cfg, conditional_embedding=PorosityEmbedder(cfg.output_embed_dim), precision=precision)
+        assert list(net.state_dict().keys()) == [k for k, _ in g["manifest"]]
+        net.load_state_dict(synth_state_dict(g["manifest"], g["seed"]))
+        net = net.to(DEV).eval()
+        return net, d.KarrasModule(net, d.KarrasModuleConfig.from_edm(), conditional=True)
     cfg = d.PUNetGConfig(**g["cfg"])
     emb = PorosityEmbedder(cfg.model_channels)
     if "cond" in g["y_batch"]:
@@ -33,7 +40,7 @@ def dev(y):
     return {k: v.to(DEV) for k, v in y.items()}
 
 
-@pytest.mark.parametrize("name", ["cond_punetg2d_embed", "cond_punetg3d_chan"])
+@pytest.mark.parametrize("name", ["cond_punetg2d_embed", "cond_punetg3d_chan", "cond_adm2d_embed"])
 def test_conditional_forward_and_denoiser(golden, name):
     g = golden(name)
     net, mod = build(g)
@@ -62,7 +69,7 @@ def test_conditional_forward_and_denoiser(golden, name):
             mod.get_denoiser(g["den_x"].to(DEV), g["den_sigma"].to(DEV), dev(g["y_batch"]), guidance=2.0)
 
 
-@pytest.mark.parametrize("name", ["cond_punetg2d_embed", "cond_punetg3d_chan"])
+@pytest.mark.parametrize("name", ["cond_punetg2d_embed", "cond_punetg3d_chan", "cond_adm2d_embed"])
 def test_conditional_sampling(golden, name):
     """Heun / Euler-Maruyama with y through the graph engine (conditioning written once per run; CFG = one 2B-sample
     evaluation, mixed inside the fused stage) vs histories of the live reference, budgeted against fp64 truth."""
@@ -99,7 +106,7 @@ def test_conditional_sampling(golden, name):
     assert s.shape == (3,) + tuple(wn.shape[1:]) and torch.isfinite(s).all()
 
 
-@pytest.mark.parametrize("name", ["cond_punetg2d_embed", "cond_punetg3d_chan"])
+@pytest.mark.parametrize("name", ["cond_punetg2d_embed", "cond_punetg3d_chan", "cond_adm2d_embed"])
 def test_conditional_sampling_bf16(golden, name):
     from oracle import karras_oracle as K
     from tests.test_oracle_vs_golden import cond_oracle_nets
@@ -116,7 +123,7 @@ def test_conditional_sampling_bf16(golden, name):
         assert relmax(D.cpu(), truth) < 3e-2, gd
 
 
-@pytest.mark.parametrize("name", ["cond_punetg2d_embed", "cond_punetg3d_chan"])
+@pytest.mark.parametrize("name", ["cond_punetg2d_embed", "cond_punetg3d_chan", "cond_adm2d_embed"])
 def test_conditional_loss_and_gradients(golden, name):
     """loss_fn(x, sigma, y) -> backward: the native backward returns d(loss)/d(ye), torch autograd carries it into the
     user's embedder; every recorded gradient of the live reference (network AND embedder) is matched."""

@@ -147,16 +147,19 @@ def cond_oracle_nets(g, dtype=torch.float32, batch=True):
     """-> (net_cond, net_uncond or None) of a tests/golden/cond_*.pt fixture.  batch: per-sample conditions (y_batch)
     or the single condition sample() broadcasts (y_one, unsqueezed as karrasmodule.py:914-915 does)."""
     sd = N.synth_state_dict(g["manifest"], g["seed"], dtype)
-    cfg = cfg_for("punetg", g["cfg"])
     y = g["y_batch"] if batch else {k: v.unsqueeze(0) for k, v in g["y_one"].items()}
     y = {k: v.to(dtype) for k, v in y.items()}
     ye = N.porosity_embedder(sd, "conditional_embedding.", y["porosity"])
+    if g.get("kind", "punetg") == "adm":
+        acfg = cfg_for("adm", g["cfg"])
+        return (lambda x, t: N.adm_forward(sd, acfg, x, t, ye)), (lambda x, t: N.adm_forward(sd, acfg, x, t))
+    cfg = cfg_for("punetg", g["cfg"])
     if "cond" in y:
         return (lambda x, t: N.punetg_cond_forward(sd, cfg, x, t, [y["cond"]], ye)), None
     return (lambda x, t: N.punetg_forward(sd, cfg, x, t, ye)), (lambda x, t: N.punetg_forward(sd, cfg, x, t))
 
 
-@pytest.mark.parametrize("name", ["cond_punetg2d_embed", "cond_punetg3d_chan"])
+@pytest.mark.parametrize("name", ["cond_punetg2d_embed", "cond_punetg3d_chan", "cond_adm2d_embed"])
 def test_conditional_path(golden, name):
     g = golden(name)
     nc, nu = cond_oracle_nets(g)
