@@ -339,7 +339,139 @@ static int wgrad_few_blocks(const dsk_conv_desc* d) {
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
+// ---- few-channel weight gradient on the tensor cores (bf16) ----------------------------------------------------------
+// The CUDA-core kernel above keeps one pixel in flight per block iteration and is latency-bound (2.3 ms for the convin of
+// a 2 x 64^3 volume -- 100x its HBM roofline).  In bf16 mode the same sum is a GEMM with a tiny MN extent and a huge
+// reduction:   FEW_IN : dW[(tap,ci)][co] = sum_pix  Ncol[pix][(tap,ci)] * dY[pix][co],   Ncol = im2col of the NARROW x
+//              FEW_OUT: dW[ci][(tap,co)] = sum_q    X[q][ci] * Ncol[q][(tap,co)],        Ncol[q][(tap,co)] = dY[q - off(tap)][co]
+// Only the narrow tensor is expanded (pixels x KP bf16, KP = taps*Cn rounded up to 8: 27 -> 32), the wide tensor is read once,
+// in place, as an MN-major operand of the tcgen05 GEMM (dsk_gemm_bf16_tc, transA = transB = 1), split over the pixels into
+// `nsplit` batch entries whose fp32 partials are summed in a fixed order.  Zero or circular padding is decided in the
+// expansion kernel, so periodic convolutions take this path too.
+struct FewTcPlan {
+  bool ok, few_in;
+  int taps, Cn, Cw, KP, nsplit;
+  int64_t pix, kc;
+};
+
+static FewTcPlan few_tc_plan(const dsk_conv_desc* d) {
+  FewTcPlan f{};
+  if (d->ksize != 3 || d->up2 || d->in_dtype != DSK_BF16 || d->out_dtype != DSK_BF16) return f;
+  const bool fi = d->Cin <= WF_NARROW, fo = d->Cout <= WF_NARROW;
+  if (fi == fo) return f;
+  f.few_in = fi;
+  f.taps = d->ndim == 3 ? 27 : 9;
+  f.Cn = fi ? d->Cin : d->Cout;
+  f.Cw = fi ? d->Cout : d->Cin;
+  if (f.Cw % 8 != 0 || f.Cw > 256) return f;
+  f.KP = (f.taps * f.Cn + 7) & ~7;
+  f.pix = (int64_t)d->B * d->D * d->H * d->W;
+  // the GEMM reads the wide tensor in place: the split must tile the pixels exactly, in multiples of 8 (16-byte TMA rows)
+  for (int ns = DSK_NUM_SMS; ns >= 16; --ns)
+    if (f.pix % ns == 0 && (f.pix / ns) % 8 == 0) { f.nsplit = ns; break; }
+  if (f.nsplit == 0) return f;
+  f.kc = f.pix / f.nsplit;
+  f.ok = true;
+  return f;
+}
+
+static int64_t few_tc_part_bytes(const FewTcPlan& f) {
+  const int64_t b = (int64_t)f.nsplit * f.KP * f.Cw * (int64_t)sizeof(float);
+  return (b + 1023) & ~(int64_t)1023;
+}
+
+// Ncol[pix][j], j = tap*Cn + n (zero for j >= taps*Cn): the narrow tensor shifted by +off(tap) (FEW_IN: x under the tap)
+// or by -off(tap) (FEW_OUT: the dY that this x pixel meets through the tap); zero outside the image, or wrapped.
+__global__ void __launch_bounds__(256) few_expand_kernel(const __nv_bfloat16* __restrict__ nar, __nv_bfloat16* __restrict__ col, int B, int D,
+                                                          int H, int W, int Cn, int taps, int KP, int ndim, int sign, int circ) {
+  const int64_t pix = (int64_t)B * D * H * W;
+  const int chunks = KP / 8;
+  const int64_t total = pix * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks);
+    int64_t t = i / chunks;
+    const int w0 = (int)(t % W); t /= W;
+    const int h0 = (int)(t % H); t /= H;
+    const int d0 = (int)(t % D);
+    const int b = (int)(t / D);
+    uint4 o;
+    __nv_bfloat16* ov = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = ch * 8 + e;
+      __nv_bfloat16 v = __float2bfloat16_rn(0.0f);
+      if (j < taps * Cn) {
+        const int tap = j / Cn, n = j - tap * Cn;
+        const int kw = tap % 3, kh = (tap / 3) % 3, kd = tap / 9;
+        int zw = w0 + sign * (kw - 1), zh = h0 + sign * (kh - 1), zd = ndim == 3 ? d0 + sign * (kd - 1) : 0;
+        bool ok = true;
+        if (circ) {
+          zw = zw < 0 ? zw + W : (zw >= W ? zw - W : zw);
+          zh = zh < 0 ? zh + H : (zh >= H ? zh - H : zh);
+          zd = zd < 0 ? zd + D : (zd >= D ? zd - D : zd);
+        } else {
+          ok = (unsigned)zw < (unsigned)W && (unsigned)zh < (unsigned)H && (unsigned)zd < (unsigned)D;
+        }
+        if (ok) v = nar[((((int64_t)b * D + zd) * H + zh) * W + zw) * Cn + n];
+      }
+      ov[e] = v;
+    }
+    reinterpret_cast<uint4*>(col)[i] = o;
+  }
+}
+
+// dw[co][ci][tap] (+)= sum_z part[z][..]:  FEW_IN: part[z][tap*Cin + ci][co] (rows KP, cols Cout);
+//                                          FEW_OUT: part[z][ci][tap*Cout + co] (rows Cin, cols KP)
+__global__ void __launch_bounds__(256) few_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int Cout, int Cin, int taps,
+                                                          int KP, int few_in, int nsplit, int accumulate) {
+  const int total = Cout * Cin * taps;
+  const int64_t zs = (int64_t)KP * (few_in ? Cout : Cin);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int co, ci, tap;
+    int64_t src;
+    if (few_in) {                 // i walks part rows: coalesced over co
+      co = i % Cout; const int m = i / Cout; tap = m / Cin; ci = m - tap * Cin;
+      src = (int64_t)m * Cout + co;
+    } else {                      // i walks part row ci, column (tap, co)
+      const int j = i % (taps * Cout); ci = i / (taps * Cout); tap = j / Cout; co = j - tap * Cout;
+      src = (int64_t)ci * KP + j;
+    }
+    float s = 0.0f;
+    for (int z = 0; z < nsplit; ++z) s += part[z * zs + src];
+    float* o = dw + ((int64_t)co * Cin + ci) * taps + tap;
+    *o = accumulate ? *o + s : s;
+  }
+}
+
+}  // namespace dsk
+extern "C" int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const float* bias, int bias_rows, const void* residual,
+                                int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
+                                int64_t strideC, int batch, float alpha, int out_f32, int transA, int transB, void* stream);
+namespace dsk {
+
+static int few_tc_run(const dsk_conv_desc* d, const FewTcPlan& f, const void* x, const void* dy, float* dw, void* ws, int accumulate,
+                      cudaStream_t st) {
+  float* part = (float*)ws;
+  __nv_bfloat16* col = (__nv_bfloat16*)((uint8_t*)ws + few_tc_part_bytes(f));
+  const void* nar = f.few_in ? x : dy;
+  DSK_LAUNCH(few_expand_kernel, grid_for(f.pix * (f.KP / 8), 256, 16), 256, 0, st, (const __nv_bfloat16*)nar, col, d->B, d->D, d->H, d->W,
+             f.Cn, f.taps, f.KP, d->ndim, f.few_in ? 1 : -1, d->circular);
+  int rc;
+  if (f.few_in)     // C[(tap,ci)][co] = sum_pix col[pix][(tap,ci)] dY[pix][co]
+    rc = dsk_gemm_bf16_tc(col, dy, part, nullptr, 0, nullptr, f.KP, d->Cout, (int)f.kc, f.KP, d->Cout, d->Cout, f.kc * f.KP,
+                          f.kc * d->Cout, (int64_t)f.KP * d->Cout, f.nsplit, 1.0f, 1, 1, 1, st);
+  else              // C[ci][(tap,co)] = sum_q X[q][ci] col[q][(tap,co)]
+    rc = dsk_gemm_bf16_tc(x, col, part, nullptr, 0, nullptr, d->Cin, f.KP, (int)f.kc, d->Cin, f.KP, f.KP, f.kc * d->Cin, f.kc * f.KP,
+                          (int64_t)d->Cin * f.KP, f.nsplit, 1.0f, 1, 1, 1, st);
+  if (rc != DSK_OK) return rc;
+  DSK_LAUNCH(few_reduce_kernel, grid_for((int64_t)d->Cout * d->Cin * f.taps, 256, 8), 256, 0, st, part, dw, d->Cout, d->Cin, f.taps, f.KP,
+             f.few_in ? 1 : 0, f.nsplit, accumulate);
+  return DSK_OK;
+}
+
 int64_t wgrad_few_ws_bytes(const dsk_conv_desc* d) {
+  const FewTcPlan f = few_tc_plan(d);
+  if (f.ok) return few_tc_part_bytes(f) + f.pix * f.KP * 2;
   bool fi; int tpg;
   if (!wgrad_few_shape(d, &fi, &tpg)) return 0;
   return (int64_t)wgrad_few_blocks(d) * (d->ndim == 3 ? 27 : 9) * d->Cin * d->Cout * (int64_t)sizeof(float);
@@ -347,6 +479,12 @@ int64_t wgrad_few_ws_bytes(const dsk_conv_desc* d) {
 
 // returns 1 if handled, 0 if the shape is not a few-channel conv, negative on error
 int wgrad_few_dispatch(const dsk_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, int accumulate, cudaStream_t st) {
+  static const int old_path = [] { const char* e = getenv("DSK_WGRAD_FEW_OLD"); return e ? atoi(e) : 0; }();   // A/B measurements
+  const FewTcPlan f = few_tc_plan(d);
+  if (f.ok && !old_path) {
+    const int rc = few_tc_run(d, f, x, dy, dw, ws, accumulate, st);
+    return rc == DSK_OK ? 1 : rc;
+  }
   bool fi; int tpg;
   if (!wgrad_few_shape(d, &fi, &tpg)) return 0;
   const int blocks = wgrad_few_blocks(d);
