@@ -45,6 +45,13 @@ __device__ __forceinline__ float dsilu_f(float z) {
   const float s = 1.0f / (1.0f + expf(-z));
   return s * (1.0f + z * (1.0f - s));
 }
+// bf16 tensors keep 8 mantissa bits: the approximate exp / divide (rel. error ~1e-6) is invisible after the rounding of the
+// stored gradient and takes the norm-backward passes from instruction-bound back to HBM-bound (as silu_out in norm.cu).
+template <typename T> __device__ __forceinline__ float dsilu_t(float z) { return dsilu_f(z); }
+template <> __device__ __forceinline__ float dsilu_t<__nv_bfloat16>(float z) {
+  const float s = __fdividef(1.0f, 1.0f + __expf(-z));
+  return s * (1.0f + z * (1.0f - s));
+}
 
 static inline int bw_chunks(int B, int64_t S, int C, int V) {
   int cv = C / V;
@@ -86,6 +93,7 @@ __global__ void __launch_bounds__(BW_THREADS) bwd_partial_kernel(const T* __rest
       acc1[k] = 0; accx[k] = 0; a[k] = 1.0f; sh[k] = 0.0f;
       if (NORM) { const float2 t = table[(int64_t)b * C + c0 + k]; a[k] = t.x; sh[k] = t.y; }
     }
+#pragma unroll 4
     for (int64_t s = s0 + lane; s < s1; s += pl) {
       float g[V], e[V];
       Vec<T>::ld(gb + s * C + c0, g);
@@ -93,7 +101,7 @@ __global__ void __launch_bounds__(BW_THREADS) bwd_partial_kernel(const T* __rest
         Vec<T>::ld(xb + s * C + c0, e);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-          const float dz = silu ? g[k] * dsilu_f(fmaf(e[k], a[k], sh[k])) : g[k];
+          const float dz = silu ? g[k] * dsilu_t<T>(fmaf(e[k], a[k], sh[k])) : g[k];
           acc1[k] += dz;
           accx[k] = fmaf(dz, e[k], accx[k]);
         }
@@ -166,8 +174,47 @@ __global__ void __launch_bounds__(128) norm_bwd_finalize_kernel(const double2* _
   for (int i = threadIdx.x; i < cg; i += blockDim.x) coef[(int64_t)b * C + g * cg + i] = make_float2(cb, cc);
 }
 
+// G == C: block = 32 channels x 32 chunk lanes of one sample (see norm_finalize_pc_kernel), fixed-order combine.
+__global__ void __launch_bounds__(1024) norm_bwd_finalize_pc_kernel(const double2* __restrict__ partial, const float2* __restrict__ stats,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     const float* __restrict__ fsc, float2* __restrict__ coef,
+                                                                     float2* __restrict__ sums, float* __restrict__ dfsc,
+                                                                     float* __restrict__ dfsh, int64_t S, int B, int C, int nchunks, int mode) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  double s1 = 0, sx = 0;
+  if (c < C)
+    for (int ch = rl; ch < nchunks; ch += 32) {
+      const double2 v = partial[((int64_t)b * nchunks + ch) * C + c];
+      s1 += v.x;
+      sx += v.y;
+    }
+  __shared__ double r1[32][33], rx[32][33];
+  r1[rl][threadIdx.x & 31] = s1;
+  rx[rl][threadIdx.x & 31] = sx;
+  __syncthreads();
+  if (rl != 0 || c >= C) return;
+  s1 = 0; sx = 0;
+  for (int k = 0; k < 32; ++k) { s1 += r1[k][threadIdx.x & 31]; sx += rx[k][threadIdx.x & 31]; }
+  const int i = b * C + c;
+  const float2 mr = stats[i];
+  const double mean = mr.x, rstd = mr.y;
+  const double s2 = rstd * (sx - mean * s1);
+  sums[i] = make_float2((float)s1, (float)s2);
+  const double gm = gamma != nullptr ? (double)gamma[c] : 1.0;
+  const double f = fsc != nullptr ? (double)fsc[i] : 1.0;
+  if (dfsc != nullptr) {
+    const double bt = beta != nullptr ? (double)beta[c] : 0.0;
+    dfsc[i] = (float)(gm * s2 + bt * s1);
+    dfsh[i] = (float)s1;
+  }
+  const double n = (double)S;
+  const double m1 = mode == 0 ? gm * f * s1 / n : 0.0, m2 = gm * f * s2 / n;
+  coef[i] = make_float2((float)(-rstd * rstd * m2), (float)(-rstd * m1 + mean * rstd * rstd * m2));
+}
+
 // G == C: one thread per (b, c) (the group reductions are over a single channel).
-__global__ void __launch_bounds__(128) norm_bwd_finalize_pc_kernel(const double2* __restrict__ partial, const float2* __restrict__ stats,
+__global__ void __launch_bounds__(128) norm_bwd_finalize_pc_serial_kernel(const double2* __restrict__ partial, const float2* __restrict__ stats,
                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                     const float* __restrict__ fsc, float2* __restrict__ coef,
                                                                     float2* __restrict__ sums, float* __restrict__ dfsc,
@@ -244,6 +291,7 @@ __global__ void __launch_bounds__(BW_THREADS) norm_bwd_apply_kernel(const T* __r
       a[k] = t.x; sh[k] = t.y; cb[k] = q.x; cc[k] = q.y;
     }
     const int64_t step = (int64_t)gridDim.x * pl;
+#pragma unroll 4
     for (int64_t s = (int64_t)blockIdx.x * pl + lane; s < S; s += step) {
       float e[V], g[V], r[V], o[V];
       Vec<T>::ld(xb + s * C + c0, e);
@@ -251,7 +299,7 @@ __global__ void __launch_bounds__(BW_THREADS) norm_bwd_apply_kernel(const T* __r
       if (rb != nullptr) Vec<T>::ld(rb + s * C + c0, r);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const float dz = silu ? g[k] * dsilu_f(fmaf(e[k], a[k], sh[k])) : g[k];
+        const float dz = silu ? g[k] * dsilu_t<T>(fmaf(e[k], a[k], sh[k])) : g[k];
         float t = fmaf(dz, a[k], fmaf(e[k], cb[k], cc[k]));
         if (rb != nullptr) t += r[k];
         o[k] = t;
@@ -511,8 +559,14 @@ extern "C" int dsk_norm_act_bwd(const void* x, const void* dy, const void* dres,
     DSK_LAUNCH((bwd_partial_kernel<__nv_bfloat16, true>), pg, BW_THREADS, smem, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, table,
                partial, S, C, nchunks, silu);
   if (G == C)
-    DSK_LAUNCH(norm_bwd_finalize_pc_kernel, (B * C + 127) / 128, 128, 0, st, partial, stats, gamma, beta, film_scale, coef, sums, dfilm_scale,
-               dfilm_shift, S, B, C, nchunks, mode);
+  {
+    if (nchunks >= 8)
+      DSK_LAUNCH(norm_bwd_finalize_pc_kernel, dim3((C + 31) / 32, B), 1024, 0, st, partial, stats, gamma, beta, film_scale, coef, sums,
+                 dfilm_scale, dfilm_shift, S, B, C, nchunks, mode);
+    else
+      DSK_LAUNCH(norm_bwd_finalize_pc_serial_kernel, (B * C + 127) / 128, 128, 0, st, partial, stats, gamma, beta, film_scale, coef, sums,
+                 dfilm_scale, dfilm_shift, S, B, C, nchunks, mode);
+  }
   else
     DSK_LAUNCH(norm_bwd_finalize_kernel, B * G, 128, 0, st, partial, stats, gamma, beta, film_scale, coef, sums, dfilm_scale, dfilm_shift, S,
                C, G, nchunks, mode);
