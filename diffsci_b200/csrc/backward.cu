@@ -330,15 +330,19 @@ __global__ void __launch_bounds__(256) chansum_finalize_kernel(const double2* __
 }
 
 // generic scalar fallback for channel counts that are not a multiple of the vector width (convout: C = 1..4)
+constexpr int CS_SPLITS = 64;
 template <typename T>
 __global__ void __launch_bounds__(256) chansum_small_kernel(const T* __restrict__ dy, float* __restrict__ out, int B, int64_t S, int C,
-                                                             int per_sample) {
-  // one block per (b or all, c)
+                                                             int per_sample, double* __restrict__ part) {
+  // one block per (b or all, c[, slice of the pixels]): with `part` the pixel range is cut into gridDim.z slices whose sums
+  // chansum_small_finalize_kernel adds in a fixed order (a single block per channel took 267 us on a 2 x 64^3 volume)
   const int c = blockIdx.x, b0 = per_sample ? blockIdx.y : 0, b1 = per_sample ? blockIdx.y + 1 : B;
+  const int64_t per = (S + gridDim.z - 1) / gridDim.z;
+  const int64_t sa = (int64_t)blockIdx.z * per, sb = min(S, sa + per);
   double acc = 0;
   for (int b = b0; b < b1; ++b) {
     float local = 0.0f;
-    for (int64_t s = threadIdx.x; s < S; s += blockDim.x) local += to_f32<T>(dy[((int64_t)b * S + s) * C + c]);
+    for (int64_t s = sa + threadIdx.x; s < sb; s += blockDim.x) local += to_f32<T>(dy[((int64_t)b * S + s) * C + c]);
     acc += (double)local;
   }
   __shared__ double red[256];
@@ -348,7 +352,18 @@ __global__ void __launch_bounds__(256) chansum_small_kernel(const T* __restrict_
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[per_sample ? (int64_t)blockIdx.y * C + c : c] = (float)red[0];
+  if (threadIdx.x != 0) return;
+  const int64_t o = per_sample ? (int64_t)blockIdx.y * C + c : c;
+  if (part != nullptr) part[o * gridDim.z + blockIdx.z] = red[0];
+  else out[o] = (float)red[0];
+}
+
+__global__ void __launch_bounds__(128) chansum_small_finalize_kernel(const double* __restrict__ part, float* __restrict__ out, int n, int splits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0;
+  for (int z = 0; z < splits; ++z) s += part[(int64_t)i * splits + z];
+  out[i] = (float)s;
 }
 
 // out[c] = sum_r in[r][c]  (fp32, small matrices: bias gradients of the time-MLP linears and attention projections)
@@ -524,8 +539,9 @@ extern "C" int64_t dsk_bwd_ws_bytes(int B, int64_t S, int C) {
   int nchunks = 1;
   if (C % 4 == 0) nchunks = bw_chunks(B, S, C, 4);
   if (C % 8 == 0) { const int n8 = bw_chunks(B, S, C, 8); if (n8 > nchunks) nchunks = n8; }
-  // [coef B*C float2][sums B*C float2][partials B*nchunks*C double2]
-  return 2 * (int64_t)B * C * (int64_t)sizeof(float2) + (int64_t)B * nchunks * C * (int64_t)sizeof(double2);
+  // [coef B*C float2][sums B*C float2][partials B*nchunks*C double2]   (few-channel sums: B*C*CS_SPLITS doubles)
+  const int64_t part = (int64_t)B * nchunks * C * (int64_t)sizeof(double2), small = (int64_t)B * C * CS_SPLITS * (int64_t)sizeof(double);
+  return 2 * (int64_t)B * C * (int64_t)sizeof(float2) + (part > small ? part : small);
 }
 
 extern "C" int dsk_norm_act_bwd(const void* x, const void* dy, const void* dres, void* dx, const float* gamma, const float* beta,
@@ -592,9 +608,13 @@ extern "C" int dsk_channel_sum(const void* dy, float* out, void* ws, int B, int6
   const int V = vec_of(dtype);
   if (C % V != 0) {
     DSK_REQUIRE(C <= 65535, "dsk_channel_sum: C too large for the scalar path");
-    dim3 g(C, per_sample ? B : 1);
-    if (dtype == DSK_F32) DSK_LAUNCH(chansum_small_kernel<float>, g, 256, 0, st, (const float*)dy, out, B, S, C, per_sample);
-    else DSK_LAUNCH(chansum_small_kernel<__nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)dy, out, B, S, C, per_sample);
+    const int rows = per_sample ? B : 1;
+    const bool split = ws != nullptr && S >= 65536 && (int64_t)rows * C <= 4096;
+    double* part = split ? reinterpret_cast<double*>(reinterpret_cast<float2*>(ws) + 2 * (int64_t)B * C) : nullptr;
+    dim3 g(C, rows, split ? CS_SPLITS : 1);
+    if (dtype == DSK_F32) DSK_LAUNCH(chansum_small_kernel<float>, g, 256, 0, st, (const float*)dy, out, B, S, C, per_sample, part);
+    else DSK_LAUNCH(chansum_small_kernel<__nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)dy, out, B, S, C, per_sample, part);
+    if (split) DSK_LAUNCH(chansum_small_finalize_kernel, (rows * C + 127) / 128, 128, 0, st, part, out, rows * C, CS_SPLITS);
     return DSK_OK;
   }
   DSK_REQUIRE(ws != nullptr, "dsk_channel_sum: workspace required");
