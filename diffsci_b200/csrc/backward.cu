@@ -465,6 +465,101 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict
   }
 }
 
+// ---- 16-byte (8 x bf16) forms of the pooling / upsampling backward passes: one thread per (pixel, 8-channel chunk) ----
+__device__ __forceinline__ void bf8_unpack(const uint4& r, float* o) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { o[2 * j] = __low2float(h[j]); o[2 * j + 1] = __high2float(h[j]); }
+}
+__device__ __forceinline__ uint4 bf8_pack(const float* v) {
+  uint4 o;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  return o;
+}
+
+__global__ void __launch_bounds__(256) upsample2x_bwd_vec8_kernel(const uint4* __restrict__ dy, const uint4* dres, uint4* dx, int B, int D,
+                                                                   int H, int W, int Cv, int ndim) {
+  const int kd = ndim == 3 ? 2 : 1;
+  const int Do = D * kd, Ho = H * 2, Wo = W * 2;
+  const int64_t total = (int64_t)B * D * H * W * Cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cv);
+    int64_t p = i / Cv;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H); p /= H;
+    const int d = (int)(p % D);
+    const int b = (int)(p / D);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t[8];
+    for (int a = 0; a < kd; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {   // same summation order as the scalar kernel
+          bf8_unpack(dy[((((int64_t)b * Do + (d * kd + a)) * Ho + (h * 2 + bb)) * Wo + (w * 2 + cc)) * Cv + c], t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += t[k];
+        }
+    if (dres != nullptr) {
+      bf8_unpack(dres[i], t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += t[k];
+    }
+    dx[i] = bf8_pack(acc);
+  }
+}
+
+template <bool IS_MAX>
+__global__ void __launch_bounds__(256) pool2x_bwd_vec8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, const uint4* dres,
+                                                               uint4* dx, int B, int D, int H, int W, int Cv, int ndim) {
+  const int Do = ndim == 3 ? D / 2 : 1, Ho = H / 2, Wo = W / 2;
+  const int kd = ndim == 3 ? 2 : 1;
+  const int64_t total = (int64_t)B * Do * Ho * Wo * Cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cv);
+    int64_t p = i / Cv;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho); p /= Ho;
+    const int dz = (int)(p % Do);
+    const int b = (int)(p / Do);
+    float g[8];
+    bf8_unpack(dy[i], g);
+    int best[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (IS_MAX) {
+      float m[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+      int idx = 0;
+      for (int a = 0; a < kd; ++a)
+        for (int bb = 0; bb < 2; ++bb)
+          for (int cc = 0; cc < 2; ++cc, ++idx) {
+            float v[8];
+            bf8_unpack(x[((((int64_t)b * D + (dz * kd + a)) * H + (ho * 2 + bb)) * W + (wo * 2 + cc)) * Cv + c], v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (v[k] > m[k] || (v[k] != v[k] && !(m[k] != m[k]))) { m[k] = v[k]; best[k] = idx; }
+          }
+    }
+    const float share = ndim == 3 ? 0.125f : 0.25f;
+    int idx = 0;
+    for (int a = 0; a < kd; ++a)
+      for (int bb = 0; bb < 2; ++bb)
+        for (int cc = 0; cc < 2; ++cc, ++idx) {
+          const int64_t dst = ((((int64_t)b * D + (dz * kd + a)) * H + (ho * 2 + bb)) * W + (wo * 2 + cc)) * Cv + c;
+          float v[8], r[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = IS_MAX ? (idx == best[k] ? g[k] : 0.0f) : g[k] * share;
+          if (dres != nullptr) {
+            bf8_unpack(dres[dst], r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += r[k];
+          }
+          dx[dst] = bf8_pack(v);
+        }
+  }
+}
+
 // ---- softmax backward (rows): dS = P * (dP - sum_j dP_j P_j), in place on dP ------------------------------------------
 __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dP, int64_t rows,
                                                                 int cols) {
@@ -650,7 +745,14 @@ extern "C" int dsk_pool2x_bwd(const void* x, const void* dy, const void* dres, v
   const int grid = grid_for(total, 256, 16);
   cudaStream_t st = as_stream(stream);
 #define PB(T, M) DSK_LAUNCH((pool2x_bwd_kernel<T, M>), grid, 256, 0, st, (const T*)x, (const T*)dy, (const T*)dres, (T*)dx, B, D, H, W, C, ndim)
-  if (dtype == DSK_F32) { if (is_max) PB(float, true); else PB(float, false); }
+  const bool al16 = (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dres) & 15) == 0;
+  if (dtype == DSK_BF16 && C % 8 == 0 && al16) {
+    const int vg = grid_for((int64_t)B * (ndim == 3 ? D / 2 : 1) * (H / 2) * (W / 2) * (C / 8), 256, 16);
+    if (is_max) DSK_LAUNCH(pool2x_bwd_vec8_kernel<true>, vg, 256, 0, st, (const uint4*)x, (const uint4*)dy, (const uint4*)dres, (uint4*)dx, B, D,
+                           H, W, C / 8, ndim);
+    else DSK_LAUNCH(pool2x_bwd_vec8_kernel<false>, vg, 256, 0, st, (const uint4*)x, (const uint4*)dy, (const uint4*)dres, (uint4*)dx, B, D, H, W,
+                    C / 8, ndim);
+  } else if (dtype == DSK_F32) { if (is_max) PB(float, true); else PB(float, false); }
   else if (dtype == DSK_BF16) { if (is_max) PB(__nv_bfloat16, true); else PB(__nv_bfloat16, false); }
   else DSK_REQUIRE(false, "dsk_pool2x_bwd: bad dtype %d", dtype);
 #undef PB
@@ -667,7 +769,10 @@ extern "C" int dsk_upsample2x_bwd(const void* dy, const void* dres, void* dx, in
   DSK_REQUIRE(dy && dx && B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (ndim == 2 || ndim == 3), "dsk_upsample2x_bwd: bad arguments");
   const int grid = grid_for((int64_t)B * D * H * W * C, 256, 16);
   cudaStream_t st = as_stream(stream);
-  if (dtype == DSK_F32) DSK_LAUNCH(upsample2x_bwd_kernel<float>, grid, 256, 0, st, (const float*)dy, (const float*)dres, (float*)dx, B, D, H, W, C, ndim);
+  if (dtype == DSK_BF16 && C % 8 == 0 && ((((uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dres) & 15) == 0))
+    DSK_LAUNCH(upsample2x_bwd_vec8_kernel, grid_for((int64_t)B * D * H * W * (C / 8), 256, 16), 256, 0, st, (const uint4*)dy, (const uint4*)dres,
+               (uint4*)dx, B, D, H, W, C / 8, ndim);
+  else if (dtype == DSK_F32) DSK_LAUNCH(upsample2x_bwd_kernel<float>, grid, 256, 0, st, (const float*)dy, (const float*)dres, (float*)dx, B, D, H, W, C, ndim);
   else if (dtype == DSK_BF16)
     DSK_LAUNCH(upsample2x_bwd_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, B,
                D, H, W, C, ndim);

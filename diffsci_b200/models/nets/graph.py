@@ -31,10 +31,11 @@ NONE, ALIAS, OWN = 0, 1, 2
 
 
 class Var:
-    __slots__ = ("t", "needs_grad", "state", "g", "name")
+    __slots__ = ("t", "needs_grad", "state", "g", "name", "stats")
 
     def __init__(self, t: torch.Tensor, needs_grad: bool = True, name: str = ""):
         self.t, self.needs_grad, self.state, self.g, self.name = t, needs_grad, NONE, None, name
+        self.stats = None      # per-(sample, channel) statistics the producing conv epilogue left for a following per-channel norm
 
 
 class TrainGraph:
@@ -130,7 +131,7 @@ class TrainGraph:
 
     # ------------------------------------------------------------------ ops
     def conv(self, x: Var, cp, chan_bias: Optional[Var] = None, residual: Optional[Var] = None, up2: bool = False,
-             few_out_ok: bool = False) -> Var:
+             few_out_ok: bool = False, want_stats: bool = False) -> Var:
         """y = conv_same([up2](x)) + bias + chan_bias[b, :] + residual  (forward: dsk_conv_fwd; backward: dsk_conv_wgrad,
         dsk_channel_sum, dsk_conv_fwd with dgrad-packed weights [+ dsk_upsample2x_bwd])."""
         from .punetg import _tc_eligible
@@ -152,7 +153,12 @@ class TrainGraph:
         xt, yt = x.t, y.t
         cb = chan_bias.t if chan_bias is not None else None
         rs = residual.t if residual is not None else None
-        self.fwd.append(lambda: ops.conv(xt, pc, out=yt, chan_bias=cb, residual=rs, up2=up2, pad_ws=pws))
+        st = None
+        if want_stats and tc and ops.conv_stats_supported(tuple(xt.shape), xt.dtype, pc, up2=up2):
+            # norm statistics fused into the conv epilogue (as on the inference plan): the following norm skips its statistics pass
+            st = y.stats = ops.conv_stats_buffer(B, cp.cout, self.device)
+            self.nbytes += st.numel() * 4
+        self.fwd.append(lambda: ops.conv(xt, pc, out=yt, chan_bias=cb, residual=rs, up2=up2, pad_ws=pws, stats=st))
 
         def build_bwd():
             dy = self.grad_of(y)
@@ -277,8 +283,9 @@ class TrainGraph:
         xt, yt = x.t, y.t
         fsc = film[0].t if film is not None else None
         fsh = film[1].t if film is not None else None
+        cs = x.stats if G == Cc else None
         self.fwd.append(lambda: ops.norm_act(xt, np_.weight, np_.bias, G, mode, silu, out=yt, film_scale=fsc, film_shift=fsh,
-                                             ws=fws))
+                                             ws=fws, conv_stats=cs))
 
         def build_bwd():
             dy = self.grad_of(y)
@@ -717,9 +724,9 @@ def build_punetg(net, B: int, spatial: tuple, device, precision: str, cond: bool
         C = blk.channels
         tv = tvs[id(blk)]
         n1 = g.norm(x, blk.gnorm1, C, c.first_resblock_norm, True)
-        y = g.conv(n1, blk.conv1, chan_bias=tv)
+        y = g.conv(n1, blk.conv1, chan_bias=tv, want_stats=True)
         n2 = g.norm(y, blk.gnorm2, C, c.second_resblock_norm, True)
-        return g.conv(n2, blk.conv2, residual=x)
+        return g.conv(n2, blk.conv2, residual=x, want_stats=True)
 
     x = g.conv(g.x_in, net.convin)
     skips = []
@@ -727,7 +734,7 @@ def build_punetg(net, B: int, spatial: tuple, device, precision: str, cond: bool
         for blk in net.downward_blocks[l]:
             x = resblock(x, blk)
         skips.append(x)
-        x = g.conv(g.pool(x, True), net.downsamplers[l].conv)
+        x = g.conv(g.pool(x, True), net.downsamplers[l].conv, want_stats=True)
     for blk in net.before_block:
         x = resblock(x, blk)
     xa = x
@@ -739,7 +746,7 @@ def build_punetg(net, B: int, spatial: tuple, device, precision: str, cond: bool
     for blk in net.after_block:
         x = resblock(x, blk)
     for i in range(nlev):
-        x = g.conv(x, net.upsamplers[i].conv, residual=skips.pop(), up2=True)
+        x = g.conv(x, net.upsamplers[i].conv, residual=skips.pop(), up2=True, want_stats=True)
         for blk in net.upward_blocks[i]:
             x = resblock(x, blk)
     g.finalize(g.conv(x, net.convout, few_out_ok=True))
