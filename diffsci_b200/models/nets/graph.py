@@ -28,6 +28,7 @@ from ... import ops
 
 _NORM_MODE = {"GroupLN": 0, "GroupRMS": 1}
 NONE, ALIAS, OWN = 0, 1, 2
+HYBRID_ATTENTION = True     # bf16 training, token counts off the tensor-core score path: projections on tcgen05 (A/B switch for tests)
 
 
 class Var:
@@ -451,6 +452,8 @@ class TrainGraph:
         import diffsci_b200
         if (self.precision == "bf16" and diffsci_b200.TC_CONV_ENABLED and Cc % 64 == 0 and Lq % 8 == 0 and Lq <= 8192):
             return self._attention_tc(x, mha, residual)
+        if HYBRID_ATTENTION and self.precision == "bf16" and diffsci_b200.TC_CONV_ENABLED and Cc % 64 == 0 and (B * Lq) % 8 == 0:
+            return self._attention_hybrid(x, mha, residual)
         y = Var(self.empty(x.t.shape))
         xt, yt = x.t, y.t
         tok = xt.view(B, Lq, Cc) if xt.dtype == f32 else self.empty((B, Lq, Cc), f32)
@@ -511,6 +514,87 @@ class TrainGraph:
                     out.append(lambda: ops.add_ex(dtok, dout, dtok))
                 dres, dx = self.contribute_compute(x)
                 out.append(lambda: ops.add_ex(dtok, dres.view(M, Cc) if dres is not None else None, dx.view(M, Cc)))
+            return out
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
+    def _attention_hybrid(self, x: Var, mha, residual: bool) -> Var:
+        """Token counts the tensor-core score path does not take (L % 8 != 0: the 7x7 bottom level of MNIST): the two
+        projections and their gradients -- 99% of the block's FLOPs at small L -- run on tcgen05 over the flattened B*L token
+        axis (weight gradients split over `nb` token slices, summed in a fixed order), the per-sample L x L part stays fp32."""
+        B = self.B
+        Cc = x.t.shape[-1]
+        Lq = x.t.numel() // (B * Cc)
+        M = B * Lq
+        f32, bf = torch.float32, torch.bfloat16
+        y = Var(self.empty(x.t.shape))
+        tok, yt = x.t.view(M, Cc), y.t.view(M, Cc)
+        qkv = self.empty((M, 3 * Cc), f32)
+        P = self.empty((B, Lq, Lq), f32)
+        ao = self.empty((M, Cc), f32)
+        ao16 = self.empty((M, Cc), bf)
+        wi, wo = ops.PackedLinear(mha.in_proj_weight), ops.PackedLinear(mha.out_proj.weight)
+        self._packs += [wi, wo]
+        bi, bo = mha.in_proj_bias.detach(), mha.out_proj.bias.detach()
+        alpha = Cc ** -0.5
+        s3, sLL, sLC = Lq * 3 * Cc, Lq * Lq, Lq * Cc
+        G = ops.gemm_bf16_tc
+        nb = max(n for n in range(1, 65) if M % n == 0 and (M // n) % 8 == 0)     # token slices of the weight gradients
+        Kb = M // nb
+
+        def fwd():
+            G(tok, wi.packed(), qkv, M=M, N=3 * Cc, K=Cc, lda=Cc, ldb=Cc, ldc=3 * Cc, bias=bi)
+            ops.attention_core_f32(qkv, P, ao, B, Lq, Cc)
+            ops.cast(ao, bf, out=ao16)
+            G(ao16, wo.packed(), yt, M=M, N=Cc, K=Cc, lda=Cc, ldb=Cc, ldc=Cc, bias=bo, residual=tok if residual else None)
+
+        self.fwd.append(fwd)
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return []
+            gwi, gbi = self.grad_view(mha.in_proj_weight), self.grad_view(mha.in_proj_bias)
+            gwo, gbo = self.grad_view(mha.out_proj.weight), self.grad_view(mha.out_proj.bias)
+            dyt = dy.view(M, Cc)
+            dO = self.empty((M, Cc), f32)
+            dP = self.lazy_scratch("attn_dP", (B, Lq, Lq), f32)
+            dqkv = self.empty((M, 3 * Cc), f32)
+            dqkv16 = self.empty((M, 3 * Cc), bf)
+            wsp = self.lazy_scratch("attn_wsplit", (nb, 3 * Cc * Cc), f32)
+            csws = self.lazy_scratch("bwd_ws", ops.bwd_ws_bytes(B, Lq, 3 * Cc))
+            out = []
+            # out = ao Wo^T + bo :  dWo = dy^T ao ; dbo ; dO = dy Wo
+            out.append(lambda: G(dyt, ao16, wsp()[:, :Cc * Cc], M=Cc, N=Cc, K=Kb, lda=Cc, ldb=Cc, ldc=Cc, batch=nb, strideA=Kb * Cc,
+                                 strideB=Kb * Cc, strideC=3 * Cc * Cc, transA=True, transB=True))
+            out.append(lambda: ops.colsum(wsp()[:, :Cc * Cc], gwo.view(-1), ld=3 * Cc * Cc))
+            out.append(lambda: ops.channel_sum(dy.view(B, Lq, Cc), gbo, csws(), False))
+            out.append(lambda: G(dyt, wo.packed(), dO, M=M, N=Cc, K=Cc, lda=Cc, ldb=Cc, ldc=Cc, transB=True))
+            # the L x L part in fp32 (as TrainGraph.attention):  dP = dO V^T ; dV = P^T dO ; dS ; dQ = alpha dS K ; dK = alpha dS^T Q
+            out.append(lambda: ops.gemm_ex(dO, qkv, dP(), M=Lq, N=Lq, K=Cc, lda=Cc, ldb=3 * Cc, ldc=Lq, transB=True, batch=B,
+                                           strideA=sLC, strideB=s3, strideC=sLL, b_off=2 * Cc))
+            out.append(lambda: ops.gemm_ex(P, dO, dqkv, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=Cc, ldc=3 * Cc, transA=True, transB=False,
+                                           batch=B, strideA=sLL, strideB=sLC, strideC=s3, c_off=2 * Cc))
+            out.append(lambda: ops.softmax_bwd_rows(P, dP(), B * Lq, Lq))
+            out.append(lambda: ops.gemm_ex(dP(), qkv, dqkv, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=3 * Cc, ldc=3 * Cc, transB=False,
+                                           alpha=alpha, batch=B, strideA=sLL, strideB=s3, strideC=s3, b_off=Cc, c_off=0))
+            out.append(lambda: ops.gemm_ex(dP(), qkv, dqkv, M=Lq, N=Cc, K=Lq, lda=Lq, ldb=3 * Cc, ldc=3 * Cc, transA=True,
+                                           transB=False, alpha=alpha, batch=B, strideA=sLL, strideB=s3, strideC=s3, b_off=0,
+                                           c_off=Cc))
+            # qkv = tok Wi^T + bi :  dWi = dqkv^T tok ; dbi ; dtok = dqkv Wi
+            out.append(lambda: ops.cast(dqkv, bf, out=dqkv16))
+            out.append(lambda: G(dqkv16, tok, wsp(), M=3 * Cc, N=Cc, K=Kb, lda=3 * Cc, ldb=Cc, ldc=Cc, batch=nb, strideA=Kb * 3 * Cc,
+                                 strideB=Kb * Cc, strideC=3 * Cc * Cc, transA=True, transB=True))
+            out.append(lambda: ops.colsum(wsp(), gwi.view(-1)))
+            out.append(lambda: ops.colsum(dqkv, gbi))
+            if x.needs_grad:
+                dres, dx = self.contribute_compute(x)
+                dxt = dx.view(M, Cc)
+                out.append(lambda: G(dqkv16, wi.packed(), dxt, M=M, N=Cc, K=3 * Cc, lda=3 * Cc, ldb=Cc, ldc=Cc, transB=True,
+                                     residual=dyt if residual else (dres.view(M, Cc) if dres is not None else None)))
+                if residual and dres is not None:
+                    out.append(lambda: ops.add_ex(dx, dres, dx))
             return out
 
         self._bwd_builders.append(build_bwd)
