@@ -99,6 +99,8 @@ SIGNATURES = {
     "dsk_softmax_bwd_rows": [p, p, i64, i32, p],
     "dsk_silu_fwd": [p, p, i64, p],
     "dsk_silu_bwd": [p, p, p, i64, p],
+    "dsk_relu_fwd": [p, p, i64, p],
+    "dsk_relu_bwd": [p, p, p, i64, p],
     "dsk_add_ex": [p, i32, p, i32, p, i32, i64, p],
     "dsk_split_channels": [p, p, p, p, p, i64, i32, i32, i32, p],
 }

@@ -589,6 +589,15 @@ __global__ void __launch_bounds__(256) silu_bwd_kernel(const float* __restrict__
     dz[i] = da[i] * dsilu_f(z[i]);
 }
 
+__global__ void __launch_bounds__(256) relu_fwd_kernel(const float* __restrict__ z, float* __restrict__ a, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = fmaxf(z[i], 0.0f);
+}
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ da, float* __restrict__ dz,
+                                                        int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dz[i] = z[i] > 0.0f ? da[i] : 0.0f;      // torch.relu: zero gradient at z == 0
+}
+
 // ---- y = a (+ b), each operand with its own dtype (gradient accumulation / casts between fp32 and bf16 buffers) --------
 template <typename TA, typename TB, typename TO>
 __global__ void __launch_bounds__(256) add_ex_kernel(const TA* __restrict__ a, const TB* b, TO* y, int64_t n) {
@@ -796,6 +805,18 @@ extern "C" int dsk_silu_fwd(const float* z, float* a, int64_t n, void* stream) {
 extern "C" int dsk_silu_bwd(const float* z, const float* da, float* dz, int64_t n, void* stream) {
   DSK_REQUIRE(z && da && dz && n > 0, "dsk_silu_bwd: bad arguments");
   DSK_LAUNCH(silu_bwd_kernel, grid_for(n, 256, 8), 256, 0, as_stream(stream), z, da, dz, n);
+  return DSK_OK;
+}
+
+extern "C" int dsk_relu_fwd(const float* z, float* a, int64_t n, void* stream) {
+  DSK_REQUIRE(z && a && n > 0, "dsk_relu_fwd: bad arguments");
+  DSK_LAUNCH(relu_fwd_kernel, grid_for(n, 256, 8), 256, 0, as_stream(stream), z, a, n);
+  return DSK_OK;
+}
+
+extern "C" int dsk_relu_bwd(const float* z, const float* da, float* dz, int64_t n, void* stream) {
+  DSK_REQUIRE(z && da && dz && n > 0, "dsk_relu_bwd: bad arguments");
+  DSK_LAUNCH(relu_bwd_kernel, grid_for(n, 256, 8), 256, 0, as_stream(stream), z, da, dz, n);
   return DSK_OK;
 }
 

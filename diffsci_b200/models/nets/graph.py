@@ -401,7 +401,8 @@ class TrainGraph:
 
     def linear(self, x: Var, weight: torch.Tensor, bias: Optional[torch.Tensor], silu: bool, param_w: torch.Tensor,
                param_b: Optional[torch.Tensor], rows: Optional[slice] = None) -> Var:
-        """y = [silu](x W^T + b) on fp32 [B, K] vectors (time MLPs).  `weight`/`bias` may be row slices of the parameters
+        """y = [act](x W^T + b) on fp32 [B, K] vectors (time MLPs, MLPUncond); silu: False / True (SiLU) / 2 (ReLU).
+        `weight`/`bias` may be row slices of the parameters
         `param_w`/`param_b` (ADM's packed FiLM projection, adm.py:331-343); `rows` names that slice for the gradient."""
         Bn, K = x.t.shape
         N = weight.shape[0]
@@ -412,8 +413,9 @@ class TrainGraph:
         wd = weight.detach()
         bd = bias.detach() if bias is not None else None
         self.fwd.append(lambda: ops.gemm_ex(xt, wd, z, M=Bn, N=N, K=K, lda=K, ldb=K, ldc=N, bias=bd, transB=True))
+        act = int(silu)
         if silu:
-            self.fwd.append(lambda: ops.silu_fwd(z, yt))
+            self.fwd.append(lambda: ops.act_fwd(z, yt, act))
 
         def build_bwd():
             dy = self.grad_of(y)
@@ -422,7 +424,7 @@ class TrainGraph:
             out = []
             if silu:
                 dz = self.empty((Bn, N), f32)
-                out.append(lambda: ops.silu_bwd(z, dy, dz))
+                out.append(lambda: ops.act_bwd(z, dy, dz, act))
             else:
                 dz = dy
             gw = self.grad_view(param_w, rows)
@@ -900,6 +902,28 @@ def build_adm(net, B: int, spatial: tuple, device, precision: str, cond: bool = 
     return g
 
 
+def build_mlp(net, B: int, device) -> TrainGraph:
+    """MLPUncond.forward (nets/mlp.py:38-58) unrolled into a TrainGraph: cat[x, t] -> (Linear, act)* -> Linear, fp32
+    CUDA-core GEMMs (the toy configuration the reference trains in tests/test_karras_on_toy_dataset.py:86-93)."""
+    from .layers import LinearParams
+    if net.dropout > 0:
+        raise NotImplementedError("diffsci_b200.MLPUncond: training-mode dropout not built")
+    g = TrainGraph(net, B, device, "fp32", 2)
+    g.flat_io = True
+    g.t_in = torch.empty(B, dtype=torch.float32, device=g.device)
+    g.x_in = Var(g.empty((B, net.dim), torch.float32), needs_grad=False)
+    cat = Var(g.empty((B, net.dim + 1), torch.float32), needs_grad=False)
+    xt, tt, ct = g.x_in.t, g.t_in, cat.t
+    g.fwd.append(lambda: ops.concat_channels(xt, tt.view(B, 1), out=ct))
+    layers = [m for m in net.net if isinstance(m, LinearParams)]
+    h = cat
+    for i, m in enumerate(layers):
+        last = i == len(layers) - 1
+        h = g.linear(h, m.weight, m.bias, False if last else net.act, m.weight, m.bias)
+    g.finalize(h)
+    return g
+
+
 class NetFunction(torch.autograd.Function):
     """Autograd seam: F = net(x, t[, ye]) with the hand-written backward; gradients flow to the nn.Parameters and to the
     conditioning vector ye (so that a torch conditional_embedding trains), not to x."""
@@ -928,6 +952,11 @@ def _forward_nchw(self: TrainGraph, x: torch.Tensor, t: Optional[torch.Tensor]) 
     """x fp32 [B, C, *S] -> F fp32 [B, Cout, *S] (user layout in/out, channels-last inside)."""
     if t is None:
         raise NotImplementedError("diffsci_b200: training with t=None (zero time embedding) is not built")
+    if getattr(self, "flat_io", False):       # MLPUncond: [B, dim] vectors, no layout change
+        self.x_in.t.copy_(x.float().reshape(self.x_in.t.shape))
+        self.t_in.copy_(t.float().reshape(-1))
+        self.run_forward()
+        return self.output.t.reshape(x.shape).clone()
     ops.nchw_to_cl(x.float(), self.act_dtype, self.ndim, out=self.x_in.t)
     self.t_in.copy_(t.float().reshape(-1))
     self.run_forward()
@@ -935,6 +964,9 @@ def _forward_nchw(self: TrainGraph, x: torch.Tensor, t: Optional[torch.Tensor]) 
 
 
 def _backward_nchw(self: TrainGraph, dF: torch.Tensor, hooks: Optional[dict] = None) -> None:
+    if getattr(self, "flat_io", False):
+        self.output.g.copy_(dF.float().reshape(self.output.g.shape))
+        return self.run_backward(hooks)
     ops.nchw_to_cl(dF.float().contiguous(), self.output.t.dtype, self.ndim, out=self.output.g)
     self.run_backward(hooks)
 

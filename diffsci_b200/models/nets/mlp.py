@@ -40,6 +40,9 @@ class MLPUncond(nn.Module):
         require_cuda(x, "MLPUncond input")
         if self.training and self.dropout > 0:
             raise NotImplementedError("diffsci_b200.MLPUncond: training-mode dropout not built")
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            from .graph import NetFunction        # training: hand-written backward (graph.build_mlp)
+            return NetFunction.apply(self.train_graph(x.shape[0], x.device), x, t, None, *self.parameters())
         plan = self.plan(x.shape[0], tuple(x.shape[1:]), x.device)
         plan.xin.copy_(x.reshape(plan.xin.shape))
         return plan.forward(plan.xin, t.float().contiguous()).reshape(x.shape).clone()
@@ -54,6 +57,18 @@ class MLPUncond(nn.Module):
             with torch.inference_mode(False), torch.no_grad():   # persistent buffers must be normal tensors
                 plan = self._plans[key] = _MLPPlan(self, B, device, sig)
         return plan
+
+    def train_graph(self, B: int, device, *_, **__):
+        from .graph import build_mlp
+        key = ("train", B, str(device))
+        sig = tuple(p.data_ptr() for p in self.parameters())
+        g = self._plans.get(key)
+        if g is None or g.sig != sig:
+            for k in [k for k in self._plans if k[0] == "train"]:
+                del self._plans[k]
+            with torch.inference_mode(False), torch.no_grad():
+                g = self._plans[key] = build_mlp(self, B, device)
+        return g
 
     def _apply(self, fn, *a, **k):
         self._plans = {}

@@ -638,6 +638,19 @@ def silu_fwd(z: torch.Tensor, out: torch.Tensor):
     return out
 
 
+def act_fwd(z: torch.Tensor, out: torch.Tensor, act: int):
+    """out = SiLU(z) (act 1) or ReLU(z) (act 2) on fp32 vectors."""
+    require_cuda(z, "activation input")
+    check((lib.dsk_silu_fwd if act == 1 else lib.dsk_relu_fwd)(ptr(z), ptr(out), z.numel(), stream()))
+    return out
+
+
+def act_bwd(z: torch.Tensor, da: torch.Tensor, out: torch.Tensor, act: int):
+    require_cuda(z, "activation input")
+    check((lib.dsk_silu_bwd if act == 1 else lib.dsk_relu_bwd)(ptr(z), ptr(da), ptr(out), z.numel(), stream()))
+    return out
+
+
 def silu_bwd(z: torch.Tensor, da: torch.Tensor, out: torch.Tensor):
     require_cuda(z, "silu input")
     check(lib.dsk_silu_bwd(ptr(z), ptr(da), ptr(out), z.numel(), stream()))

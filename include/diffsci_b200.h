@@ -352,6 +352,9 @@ int dsk_softmax_bwd_rows(const float* P, float* dP, int64_t rows, int cols, void
 /* SiLU forward / backward on fp32 vectors (time MLPs, commonlayers.py:516-550; adm.py:1047-1053). */
 int dsk_silu_fwd(const float* z, float* a, int64_t n, void* stream);
 int dsk_silu_bwd(const float* z, const float* da, float* dz, int64_t n, void* stream);
+/* ReLU of the default MLPUncond (nets/mlp.py:20-35) in the training graph: a = max(z, 0); dz = da * [z > 0]. */
+int dsk_relu_fwd(const float* z, float* a, int64_t n, void* stream);
+int dsk_relu_bwd(const float* z, const float* da, float* dz, int64_t n, void* stream);
 /* y = a (+ b) with per-operand dtypes (b may be NULL: cast/copy).  Gradient accumulation across fp32 / bf16 buffers. */
 int dsk_add_ex(const void* a, int a_dtype, const void* b, int b_dtype, void* y, int y_dtype, int64_t n, void* stream);
 /* Backward of dsk_concat_channels: da = dy[:, :Ca] (+ ra), db = dy[:, Ca:] (+ rb); da or db may be NULL. */

@@ -195,6 +195,43 @@ def test_loss_and_training_seam(golden):
             assert abs(float(L) - float(ref)) < 5e-5 * abs(float(ref)), (metric, use_mask)
 
 
+def test_mlp_training_gradients(golden):
+    """MLPUncond in training mode (graph.build_mlp: fp32 GEMMs + SiLU / ReLU backward kernels): loss_fn -> backward vs the
+    gradients recorded from the LIVE reference (SiLU MLP of the fixtures), and a default-ReLU MLP vs autograd of the oracle
+    -- the configuration the reference trains in tests/test_karras_on_toy_dataset.py:86-93."""
+    import diffsci_b200 as d
+    from oracle import nets_oracle as N
+    g = golden("sampler_mlp")
+    net = build_net(golden("mlp_silu")).train()
+    for metric in ("huber", "mse"):
+        mod = make_module(net, loss_metric=metric).train()
+        net.zero_grad()
+        mod._injected_loss_noise = g["loss_noise"]
+        L = mod.loss_fn(g["loss_x"].to(DEV), g["loss_sigma"].to(DEV))
+        L.backward()
+        assert abs(float(L.detach()) - float(g[f"loss_{metric}"])) < 5e-5 * abs(float(g[f"loss_{metric}"]))
+        for k, ref in g[f"loss_{metric}_grads"].items():
+            e = relmax(dict(net.named_parameters())[k].grad.cpu(), ref)
+            assert e < 2e-4, (metric, k, e)
+    torch.manual_seed(4)
+    relu = d.MLPUncond(3, [20, 12]).to(DEV).train()              # reference default: ReLU
+    sd = {k: v.detach().cpu().double().requires_grad_(True) for k, v in relu.state_dict().items()}
+    x, t, dF = torch.randn(9, 3), torch.randn(9), torch.randn(9, 3)
+    N.mlp_uncond_forward(sd, x.double(), t.double(), "relu").backward(dF.double())
+    out = relu(x.to(DEV), t.to(DEV))
+    out.backward(dF.to(DEV))
+    for k, p in relu.named_parameters():
+        assert relmax(p.grad.cpu(), sd[k].grad) < 2e-5, k
+    # one optimizer step through the reference's training_step seam
+    mod = make_module(relu).train()
+    opt = torch.optim.AdamW(relu.parameters(), lr=1e-3)
+    before = [p.detach().clone() for p in relu.parameters()]
+    loss = mod.training_step(torch.randn(16, 3, device=DEV), 0)
+    loss.backward()
+    opt.step()
+    assert torch.isfinite(loss) and any(not torch.equal(a, b) for a, b in zip(before, relu.parameters()))
+
+
 def test_model_ema_known_answers():
     """reference tests/test_karras_ema.py:23-52 on the device (fused multi-tensor EMA kernel)."""
     import diffsci_b200 as d
