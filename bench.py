@@ -114,6 +114,8 @@ def build_workload(name, device, precision):
     kind, kw, shape, nsteps, integ, batch = WORKLOADS[name]
     torch.manual_seed(0)
     if kind == "punetg":
+        if os.environ.get("DSK_BENCH_CIRCULAR"):     # periodic variant of the same network, for A/B runs
+            kw = dict(kw, convolution_type="circular")
         cfg = d.PUNetGConfig(**kw)
         net = d.PUNetG(cfg, precision=precision)
         flops = punetg_conv_flops(cfg, shape[1:])
@@ -171,6 +173,8 @@ def build_train_workload(name, device, precision):
     kind, kw, shape, metric, batch, gf = TRAIN_WORKLOADS[name]
     torch.manual_seed(0)
     if kind == "punetg":
+        if os.environ.get("DSK_BENCH_CIRCULAR"):     # periodic variant of the same network, for A/B runs
+            kw = dict(kw, convolution_type="circular")
         cfg = d.PUNetGConfig(**kw)
         net = d.PUNetG(cfg, precision=precision)
         flops = punetg_conv_flops(cfg, shape[1:])

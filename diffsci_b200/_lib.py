@@ -70,6 +70,7 @@ SIGNATURES = {
     "dsk_softmax_rows_bf16": [p, p, i64, i32, p],
     "dsk_norm_ws_bytes": [i32, i64, i32],
     "dsk_norm_act": [p, p, p, p, p, p, p, i32, i64, i32, i32, i32, i32, i32, i32, p],
+    "dsk_norm_apply_padded": [p, p, p, i32, i32, i32, i32, i32, i32, i32, i32, i32, p],
     "dsk_pool2x": [p, p, i32, i32, i32, i32, i32, i32, i32, i32, p],
     "dsk_add": [p, p, p, i64, i32, p],
     "dsk_nchw_to_cl": [p, p, i32, i32, i64, i32, p],

@@ -210,7 +210,7 @@ int convin_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, co
 // returns 1 if handled, 0 if the shape is not a few-channel conv, negative on error
 int conv_small_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
                         const void* residual, void* out, cudaStream_t st) {
-  if (chan_bias != nullptr || residual != nullptr || d->up2 || d->circular) return 0;   // circular: generic wrapping kernel
+  if (chan_bias != nullptr || residual != nullptr || d->up2) return 0;
   const int taps = d->ndim == 3 ? d->ksize * d->ksize * d->ksize : d->ksize * d->ksize;
   SmallConvArgs a{in, (const float*)w, bias, d->out_nchw_f32 ? nullptr : out, d->out_nchw_f32 ? (float*)out : nullptr,
                   d->B, d->D, d->H, d->W, d->Cin, d->Cout, d->ksize, d->ndim};
@@ -219,10 +219,11 @@ int conv_small_dispatch(const dsk_conv_desc* d, const void* in, const void* w, c
                        (size_t)taps * d->Cin * 4 * 4 <= 48 * 1024 && (d->ksize == 3 || d->ksize == 1);
   const bool few_in = d->Cin <= 4 && d->Cout % FI_CO == 0 && !d->out_nchw_f32 && (size_t)taps * d->Cin * d->Cout * 4 <= 48 * 1024;
   if (!few_out && !few_in) return 0;
-  if (few_in && !few_out) {      // tensor-core im2col form (convin_tc.cu) where it applies
+  if (few_in && !few_out) {      // tensor-core im2col form (convin_tc.cu) where it applies (its gather wraps for circular padding)
     const int rc = convin_tc_dispatch(d, in, w, bias, out, st);
     if (rc != DSK_ERR_UNSUPPORTED) return rc == DSK_OK ? 1 : rc;
   }
+  if (d->circular) return 0;     // the CUDA-core few-channel kernels zero-pad: hand over to the generic wrapping kernel
   const int ti = d->in_dtype, to = d->out_nchw_f32 ? DSK_F32 : d->out_dtype;
   int rc;
 #define GO(FN)                                                                                        \

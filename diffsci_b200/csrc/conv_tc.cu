@@ -893,7 +893,7 @@ extern "C" int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W
 }
 
 namespace dsk {
-int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, void* out, cudaStream_t st);
+int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, void* out, cudaStream_t st, int padded);
 }
 
 static bool tc_pair_eligible(const dsk_conv_desc* d) {
@@ -927,7 +927,7 @@ extern "C" int dsk_conv_fwd_ffma(const dsk_conv_desc*, const void*, const void*,
 
 // bytes of the halo-padded input copy a circular convolution on the tcgen05 path reads (0: CUDA-core kernel, wraps in place)
 extern "C" int64_t dsk_conv_pad_ws_bytes(const dsk_conv_desc* d) {
-  if (d == nullptr || !d->circular || d->w_dtype != DSK_BF16) return 0;
+  if (d == nullptr || d->circular != 1 || d->w_dtype != DSK_BF16) return 0;     // circular == 2: the input is already padded
   const int iD = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D, iH = d->up2 ? d->H / 2 : d->H, iW = d->up2 ? d->W / 2 : d->W;
   const int pd = d->ndim == 3 ? 1 : 0;
   return (int64_t)d->B * (iD + 2 * pd) * (iH + 2) * (iW + 2) * d->Cin * 2;
@@ -937,10 +937,11 @@ extern "C" int dsk_conv_fwd_circ(const dsk_conv_desc* d, const void* in, const v
                                  const void* residual, void* out, void* stats, void* pad_ws, void* stream) {
   DSK_REQUIRE(d != nullptr && d->circular, "dsk_conv_fwd_circ: descriptor is not circular");
   if (d->w_dtype == DSK_F32) {
+    DSK_REQUIRE(d->circular == 1, "dsk_conv_fwd_circ: a pre-padded input (circular = 2) needs the tcgen05 path");
     DSK_REQUIRE(stats == nullptr, "dsk_conv_fwd_circ: fused statistics need the tcgen05 path");
     return dsk_conv_fwd_ffma(d, in, w, bias, chan_bias, residual, out, stream);
   }
-  DSK_REQUIRE(pad_ws != nullptr, "dsk_conv_fwd_circ: the tcgen05 path needs pad_ws (dsk_conv_pad_ws_bytes)");
+  DSK_REQUIRE(pad_ws != nullptr || d->circular == 2, "dsk_conv_fwd_circ: the tcgen05 path needs pad_ws (dsk_conv_pad_ws_bytes)");
   DSK_REQUIRE(stats == nullptr || dsk_conv_stats_supported(d), "dsk_conv_fwd_circ: this convolution cannot emit fused statistics");
   return conv_fwd_tc_impl(d, in, w, bias, chan_bias, residual, out, (float2*)stats, pad_ws, stream);
 }
@@ -964,10 +965,20 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
     return DSK_ERR_UNSUPPORTED;
   }
   DSK_REQUIRE((d->ndim == 2 && d->D == 1) || d->ndim == 3, "dsk_conv_fwd(tc): bad ndim/D");
+  // circular padding: TMA boxes cannot wrap, so the kernels read a halo-padded copy (one extra pass over the input) and the
+  // patch coordinates are shifted into it; nothing else in the kernels changes (no OOB fill is ever hit inside the image).
+  const int iD = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D, iH = d->up2 ? d->H / 2 : d->H, iW = d->up2 ? d->W / 2 : d->W;
+  const int pad_hw = d->circular ? 1 : 0, pad_d = (d->circular && d->ndim == 3) ? 1 : 0;
+  if (d->circular == 1) {
+    DSK_REQUIRE(pad_ws != nullptr, "dsk_conv_fwd(tc): circular padding needs pad_ws");
+    const int rc = pad_circular_launch(in, pad_ws, d->B, d->ndim == 3 ? iD : 1, iH, iW, d->Cin, d->ndim, DSK_BF16, as_stream(stream));
+    if (rc != DSK_OK) return rc;
+    in = pad_ws;
+  }
   if (few_out) {     // in-plane taps as the N dimension (convout_tc.cu); DSK_CONVOUT_OLD=1 keeps the N = 16 tile for A/B runs
     static const int old_path = [] { const char* e = getenv("DSK_CONVOUT_OLD"); return e ? atoi(e) : 0; }();
-    if (!old_path && !d->circular) {      // circular: the N = 16 tile of the generic kernel below reads the padded copy
-      const int rc = convout_tc_dispatch(d, in, w, bias, out, as_stream(stream));
+    if (!old_path) {
+      const int rc = convout_tc_dispatch(d, in, w, bias, out, as_stream(stream), d->circular);
       if (rc != DSK_ERR_UNSUPPORTED) return rc;
     }
   }
@@ -976,18 +987,8 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   // 2-D: the batch is the plane axis (no depth taps); 3-D: planes = D with zero padding per sample
   const int KD = d->ndim == 3 ? 3 : 1;
   // up2: D/H/W in the descriptor are the OUTPUT size; the kernel tiles the INPUT (half-size) grid
-  const int iD = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D, iH = d->up2 ? d->H / 2 : d->H, iW = d->up2 ? d->W / 2 : d->W;
   const int planes = d->ndim == 3 ? iD : d->B;
   const int batch = d->ndim == 3 ? d->B : 1;
-  // circular padding: TMA boxes cannot wrap, so the kernel reads a halo-padded copy (one extra pass over the input) and the
-  // patch coordinates are shifted into it; nothing else in the kernel changes (no OOB fill is ever hit inside the image).
-  const int pad_hw = d->circular ? 1 : 0, pad_d = (d->circular && d->ndim == 3) ? 1 : 0;
-  if (d->circular) {
-    DSK_REQUIRE(pad_ws != nullptr, "dsk_conv_fwd(tc): circular padding needs pad_ws");
-    const int rc = pad_circular_launch(in, pad_ws, d->B, d->ndim == 3 ? iD : 1, iH, iW, d->Cin, d->ndim, DSK_BF16, as_stream(stream));
-    if (rc != DSK_OK) return rc;
-    in = pad_ws;
-  }
   const int tW = iW + 2 * pad_hw, tH = iH + 2 * pad_hw, tP = planes + 2 * pad_d;
   CUtensorMap ta, tw;
   {

@@ -26,6 +26,7 @@ struct CiParams {
   __nv_bfloat16* out;       // channels-last [B, D, H, W, Cout]
   int B, D, H, W, Cin, Cout, ndim;
   int tiles_w, tiles_h, total_tiles;
+  int circ;                 // circular padding: the gather wraps instead of zero-filling (CircularConv, commonlayers.py:918-1032)
 };
 
 template <int CIN>
@@ -89,27 +90,41 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
       const uint32_t slot = seq % CI_STAGES, ph = (seq / CI_STAGES) & 1;
       // gather the receptive field first (loads in flight while waiting for the slot); validity factorises per axis
       bool dv[3], hv[3], wv[3];
+      const int sH = p.W * CIN, sD = p.H * sH;
+      int od[3], oh[3], ow[3];                                  // element offsets of the three taps of each axis from the centre
+      const bool pv = h < p.H && w < p.W;                       // ragged tiles: pixels outside the image gather nothing
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        dv[k] = p.ndim == 3 ? (unsigned)(d + k - 1) < (unsigned)p.D : k == 0;
-        hv[k] = (unsigned)(h + k - 1) < (unsigned)p.H;
-        wv[k] = (unsigned)(w + k - 1) < (unsigned)p.W;
+        int zd = d + k - 1, zh = h + k - 1, zw = w + k - 1;
+        if (p.circ) {
+          zd = zd < 0 ? zd + p.D : (zd >= p.D ? zd - p.D : zd);
+          zh = zh < 0 ? zh + p.H : (zh >= p.H ? zh - p.H : zh);
+          zw = zw < 0 ? zw + p.W : (zw >= p.W ? zw - p.W : zw);
+          dv[k] = pv && (p.ndim == 3 || k == 0);
+          hv[k] = pv;
+          wv[k] = pv;
+        } else {
+          dv[k] = p.ndim == 3 ? (unsigned)zd < (unsigned)p.D : k == 0;
+          hv[k] = (unsigned)zh < (unsigned)p.H;
+          wv[k] = (unsigned)zw < (unsigned)p.W;
+        }
+        od[k] = p.ndim == 3 ? (zd - d) * sD : 0;
+        oh[k] = (zh - h) * sH;
+        ow[k] = (zw - w) * CIN;
       }
       const __nv_bfloat16* ctr = p.x + ((((int64_t)b * p.D + d) * p.H + h) * p.W + w) * CIN;
-      const int sH = p.W * CIN, sD = p.H * sH;
       __nv_bfloat16 v[64];
 #pragma unroll
       for (int k = 0; k < 64; ++k) v[k] = __float2bfloat16_rn(0.0f);
 #pragma unroll
       for (int kd = 0; kd < 3; ++kd) {
         if (kd >= kdn) break;
-        const int od = p.ndim == 3 ? (kd - 1) * sD : 0;
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const bool ok = dv[kd] && hv[kh] && wv[kw];
-            const __nv_bfloat16* src = ctr + od + (kh - 1) * sH + (kw - 1) * CIN;
+            const __nv_bfloat16* src = ctr + od[kd] + oh[kh] + ow[kw];
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci)
               if (ok) v[((kd * 3 + kh) * 3 + kw) * CIN + ci] = src[ci];
@@ -212,6 +227,7 @@ int convin_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, co
   CiParams p;
   p.x = (const __nv_bfloat16*)in; p.w = (const float*)w; p.bias = bias; p.out = (__nv_bfloat16*)out;
   p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.ndim = d->ndim;
+  p.circ = d->circular;
   p.tiles_w = (d->W + CI_BW - 1) / CI_BW; p.tiles_h = (d->H + CI_BH - 1) / CI_BH;
   p.total_tiles = p.tiles_w * p.tiles_h * d->D * d->B;
   switch (d->Cin) {

@@ -34,6 +34,7 @@ struct CoParams {
   __nv_bfloat16* out;                 // channels-last [.., Cout] bf16, or
   float* out_nchw;                    // fp32 NC(D)HW
   int planes_per_sample;
+  int pad_hw, pad_d;                  // circular padding: the tensor map covers the halo-padded copy (see conv_tc.cu)
 };
 
 template <int COUT>
@@ -108,7 +109,7 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
             asm volatile(
                 "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
                     smem_u32(sA + (size_t)slot * CO_PATCH_STRIDE)),
-                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(c * 64), "r"(w0 - 1), "r"(h0 - 1), "r"(d0 + j - dpad), "r"(b),
+                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(c * 64), "r"(w0 - 1 + p.pad_hw), "r"(h0 - 1 + p.pad_hw), "r"(d0 + j - dpad + p.pad_d), "r"(b),
                 "r"(smem_u32(&full_a[slot]))
                 : "memory");
           }
@@ -247,7 +248,8 @@ static int launch_convout(const CUtensorMap& ta, const CoParams& p, cudaStream_t
 }
 
 // returns DSK_ERR_UNSUPPORTED for shapes it does not take (the caller falls back to the N = 16 tile of conv_tc.cu)
-int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, void* out, cudaStream_t st) {
+// padded != 0: `in` is the halo-padded copy [B, D+2 (3-D), H+2, W+2, Cin] of a circular convolution
+int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, void* out, cudaStream_t st, int padded) {
   if (d->ksize != 3 || d->up2 || d->in_dtype != DSK_BF16 || d->Cin % 64 != 0 || d->Cout > 3) return DSK_ERR_UNSUPPORTED;
   if (!d->out_nchw_f32 && d->out_dtype != DSK_BF16) return DSK_ERR_UNSUPPORTED;
   EncodeTiledFn encode = get_encode();
@@ -255,9 +257,11 @@ int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, c
   const int KD = d->ndim == 3 ? 3 : 1;
   const int planes = d->ndim == 3 ? d->D : d->B, batch = d->ndim == 3 ? d->B : 1;
   CUtensorMap ta;
-  cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)planes, (cuuint64_t)batch};
-  cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->W * d->Cin * 2, (cuuint64_t)d->H * d->W * d->Cin * 2,
-                           (cuuint64_t)planes * d->H * d->W * d->Cin * 2};
+  const int pad_hw = padded ? 1 : 0, pad_d = (padded && d->ndim == 3) ? 1 : 0;
+  const int tW = d->W + 2 * pad_hw, tH = d->H + 2 * pad_hw, tP = planes + 2 * pad_d;
+  cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)tW, (cuuint64_t)tH, (cuuint64_t)tP, (cuuint64_t)batch};
+  cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)tW * d->Cin * 2, (cuuint64_t)tH * tW * d->Cin * 2,
+                           (cuuint64_t)tP * tH * tW * d->Cin * 2};
   cuuint32_t box[5] = {64, CO_PW, CO_PH, 1, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, es,
@@ -272,6 +276,7 @@ int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, c
   p.out = d->out_nchw_f32 ? nullptr : (__nv_bfloat16*)out;
   p.out_nchw = d->out_nchw_f32 ? (float*)out : nullptr;
   p.planes_per_sample = d->ndim == 3 ? d->D : 1;
+  p.pad_hw = pad_hw; p.pad_d = pad_d;
   if (d->Cout == 1) return launch_convout<1>(ta, p, st);
   if (d->Cout == 2) return launch_convout<2>(ta, p, st);
   return launch_convout<3>(ta, p, st);

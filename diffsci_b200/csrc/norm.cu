@@ -349,6 +349,58 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_apply_kernel(const TI* __re
   }
 }
 
+// The same apply pass writing a HALO-PADDED tensor y[B, D+2*pd, H+2, W+2, C] (pd = 1 for 3-D): every pixel goes to its interior
+// position and, on a face / edge / corner, to the wrapped halo positions as well -- the input layout of a circular convolution on
+// the tcgen05 path (conv_tc.cu), so periodic networks need no separate padding pass over the conv inputs.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(NORM_THREADS) norm_apply_pad_kernel(const TI* __restrict__ x, TO* __restrict__ y,
+                                                                       const float2* __restrict__ table, int D, int H, int W, int C,
+                                                                       int pd, int silu) {
+  constexpr int V = NormVec<TI>::V;
+  const int b = blockIdx.y;
+  const int cv = C / V;
+  const int pl = max(1, NORM_THREADS / cv);
+  const unsigned S = (unsigned)D * H * W;
+  const int Dp = D + 2 * pd, Hp = H + 2, Wp = W + 2;
+  const TI* xb = x + (int64_t)b * S * C;
+  TO* yb = y + (int64_t)b * Dp * Hp * Wp * C;
+  for (int v = threadIdx.x; v < pl * cv; v += NORM_THREADS) {
+    const int lane = v / cv, c0 = (v - lane * cv) * V;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float2 t = table[(int64_t)b * C + c0 + k];
+      sc[k] = t.x; sh[k] = t.y;
+    }
+    const unsigned step = gridDim.x * pl;
+    for (unsigned s = blockIdx.x * pl + lane; s < S; s += step) {
+      float e[V], o[V];
+      NormVec<TI>::ld(xb + (int64_t)s * C + c0, e);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float t = fmaf(e[k], sc[k], sh[k]);
+        o[k] = silu ? silu_out<TO>(t) : t;
+      }
+      const unsigned w = s % W, t2 = s / W, h = t2 % H, d = t2 / H;
+      // target coordinates per axis: the interior position, plus the opposite halo when the pixel lies on a face
+      int tw[3], th[3], td[3], nw = 1, nh = 1, nd = 1;
+      tw[0] = w + 1; th[0] = h + 1; td[0] = d + pd;
+      if (w == 0) tw[nw++] = W + 1;
+      if (w == (unsigned)W - 1) tw[nw++] = 0;
+      if (h == 0) th[nh++] = H + 1;
+      if (h == (unsigned)H - 1) th[nh++] = 0;
+      if (pd) {
+        if (d == 0) td[nd++] = D + 1;
+        if (d == (unsigned)D - 1) td[nd++] = 0;
+      }
+      for (int a = 0; a < nd; ++a)
+        for (int bb = 0; bb < nh; ++bb)
+          for (int cc = 0; cc < nw; ++cc)
+            st_vec<TO, V>(yb + (((int64_t)td[a] * Hp + th[bb]) * Wp + tw[cc]) * C + c0, o);
+    }
+  }
+}
+
 }  // namespace dsk
 
 using namespace dsk;
@@ -387,7 +439,7 @@ static int norm_apply_launch(const void* x, void* y, const float2* table, int B,
 extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const float* beta, const float* film_scale,
                             const float* film_shift, void* ws, int B, int64_t S, int C, int G, int mode, int silu,
                             int in_dtype, int out_dtype, void* stream) {
-  DSK_REQUIRE(x && y && ws, "dsk_norm_act: null pointer");
+  DSK_REQUIRE(x && ws, "dsk_norm_act: null pointer");
   DSK_REQUIRE(B > 0 && B <= 65535 && S > 0 && C > 0 && G > 0 && C % G == 0, "dsk_norm_act: bad shape B=%d S=%lld C=%d G=%d", B, (long long)S, C, G);
   DSK_REQUIRE(in_dtype == DSK_F32 || in_dtype == DSK_BF16, "dsk_norm_act: bad in_dtype %d", in_dtype);
   const int V = norm_v(in_dtype);
@@ -421,6 +473,7 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
   else
     DSK_LAUNCH(norm_finalize_kernel, B * G, 128, 0, st, partial, table, stats, gamma, beta, film_scale, film_shift, S, C, G, nchunks, mode,
                1e-5f);
+  if (y == nullptr) return DSK_OK;      // statistics + folded table only (dsk_norm_apply_padded follows)
   return norm_apply_launch(x, y, table, B, S, C, silu, in_dtype, out_dtype, st);
 }
 
@@ -428,7 +481,7 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
 extern "C" int dsk_norm_act_prestat(const void* x, void* y, const float* gamma, const float* beta, const float* film_scale,
                                     const float* film_shift, const void* conv_stats, int nslots, void* ws, int B, int64_t S, int C,
                                     int G, int mode, int silu, int in_dtype, int out_dtype, void* stream) {
-  DSK_REQUIRE(x && y && ws && conv_stats, "dsk_norm_act_prestat: null pointer");
+  DSK_REQUIRE(x && ws && conv_stats, "dsk_norm_act_prestat: null pointer");
   DSK_REQUIRE(B > 0 && B <= 65535 && S > 0 && C > 0 && G == C && nslots > 0, "dsk_norm_act_prestat: needs one channel per group (G == C)");
   DSK_REQUIRE(in_dtype == DSK_F32 || in_dtype == DSK_BF16, "dsk_norm_act_prestat: bad in_dtype %d", in_dtype);
   DSK_REQUIRE(C % norm_v(in_dtype) == 0 && (mode == 0 || mode == 1), "dsk_norm_act_prestat: bad C / mode");
@@ -439,5 +492,26 @@ extern "C" int dsk_norm_act_prestat(const void* x, void* y, const float* gamma, 
   dim3 fg((C + 31) / 32, B);
   DSK_LAUNCH(norm_finalize_stats_kernel, fg, 1024, 0, st, (const float2*)conv_stats, table, stats, gamma, beta, film_scale, film_shift, S, C,
              nslots, mode, 1e-5f);
+  if (y == nullptr) return DSK_OK;      // table only
   return norm_apply_launch(x, y, table, B, S, C, silu, in_dtype, out_dtype, st);
+}
+
+extern "C" int dsk_norm_apply_padded(const void* x, void* y_padded, const void* ws, int B, int D, int H, int W, int C, int ndim, int silu,
+                                     int in_dtype, int out_dtype, void* stream) {
+  DSK_REQUIRE(x && y_padded && ws, "dsk_norm_apply_padded: null pointer");
+  DSK_REQUIRE(B > 0 && B <= 65535 && D > 0 && H > 0 && W > 0 && C > 0 && ((ndim == 2 && D == 1) || ndim == 3), "dsk_norm_apply_padded: bad shape");
+  DSK_REQUIRE((int64_t)D * H * W < 0x7fffffff, "dsk_norm_apply_padded: sample too large");
+  DSK_REQUIRE(in_dtype == DSK_BF16 && out_dtype == DSK_BF16 && C % 8 == 0, "dsk_norm_apply_padded: bf16 tensors with C %% 8 == 0 only");
+  const float2* table = reinterpret_cast<const float2*>(ws);
+  const int64_t S = (int64_t)D * H * W;
+  const int cv = C / 8;
+  const int pl = NORM_THREADS / cv > 0 ? NORM_THREADS / cv : 1;
+  int64_t gx = (S + (int64_t)pl * 4 - 1) / ((int64_t)pl * 4);
+  const int64_t cap = (8LL * DSK_NUM_SMS + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 ag((unsigned)gx, B);
+  DSK_LAUNCH((norm_apply_pad_kernel<__nv_bfloat16, __nv_bfloat16>), ag, NORM_THREADS, 0, as_stream(stream), (const __nv_bfloat16*)x,
+             (__nv_bfloat16*)y_padded, table, D, H, W, C, ndim == 3 ? 1 : 0, silu);
+  return DSK_OK;
 }

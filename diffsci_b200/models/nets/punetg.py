@@ -250,9 +250,14 @@ class _Plan:
         self.WS = [ops.norm_ws(B, sp[l][0] * sp[l][1] * sp[l][2], ch[l], dev) for l in range(nlev + 1)]
         # circular padding: one halo-padded input copy for the tcgen05 convs (TMA boxes cannot wrap), sized for the largest
         self.pad_ws = None
+        self.NP = [None] * (nlev + 1)      # norm+SiLU outputs in the halo-padded layout (the norm's apply pass writes the halos)
         if c.convolution_type == "circular" and precision == "bf16":
             halo = lambda s: (s[0] + (2 if nd == 3 else 0)) * (s[1] + 2) * (s[2] + 2)  # noqa: E731
             self.pad_ws = torch.empty(max(B * halo(sp[l]) * ch[l] * 2 for l in range(nlev + 1)), dtype=torch.uint8, device=dev)
+            for l in range(nlev + 1):
+                if _tc_eligible(ch[l], ch[l], c.kernel_size):
+                    d_, h_, w_ = sp[l]
+                    self.NP[l] = torch.empty((B, d_ + 2 if nd == 3 else d_, h_ + 2, w_ + 2, ch[l]), dtype=adt, device=dev)
         # fused norm statistics (conv epilogue -> following per-channel norm): one buffer per level, consumed by the very
         # next norm.  Only where the convolution kernel can emit them and the norms are per channel (G == C: the PUNetG norms).
         self.ST = [None] * (nlev + 1)
@@ -336,6 +341,15 @@ class _Plan:
         C = blk.channels
         pc1, pc2 = self.pc[id(blk)]
         st = self.ST[l] if self.st_ok[l] else None
+        if self.NP[l] is not None:      # periodic net on the tcgen05 path: the norm's apply pass writes the padded conv input
+            ops.norm_act(x, blk.gnorm1.weight, blk.gnorm1.bias, C, _NORM_MODE[c.first_resblock_norm], True, ws=self.WS[l],
+                         conv_stats=xs, table_only=True)
+            n = ops.norm_apply_padded(x, self.WS[l], self.NP[l], self.ndim)
+            y = self._conv(n, pc1, out=self.Y[l], chan_bias=self.tvec[id(blk)], stats=st, prepadded=True)
+            ops.norm_act(y, blk.gnorm2.weight, blk.gnorm2.bias, C, _NORM_MODE[c.second_resblock_norm], True, ws=self.WS[l],
+                         conv_stats=st, table_only=True)
+            n = ops.norm_apply_padded(y, self.WS[l], self.NP[l], self.ndim)
+            return self._conv(n, pc2, out=out, residual=x, stats=st, prepadded=True), st
         n = ops.norm_act(x, blk.gnorm1.weight, blk.gnorm1.bias, C, _NORM_MODE[c.first_resblock_norm], True,
                          out=self.N[l], ws=self.WS[l], conv_stats=xs)
         y = self._conv(n, pc1, out=self.Y[l], chan_bias=self.tvec[id(blk)], stats=st)

@@ -122,13 +122,17 @@ def conv_stats_buffer(B: int, cout: int, device) -> torch.Tensor:
 
 def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, chan_bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, up2: bool = False, out_dtype: Optional[torch.dtype] = None,
-         out_nchw: bool = False, stats: Optional[torch.Tensor] = None, pad_ws=None) -> torch.Tensor:
+         out_nchw: bool = False, stats: Optional[torch.Tensor] = None, pad_ws=None, prepadded: bool = False) -> torch.Tensor:
     """y = conv_same(x) + bias + chan_bias[b, :] + residual  (dsk_conv_fwd).  `stats` (conv_stats_buffer): also leave the
     per-(sample, channel) statistics of y for norm_act(..., conv_stats=stats) (dsk_conv_fwd_stats).
     pc.circular: circular instead of zero padding (dsk_conv_fwd_circ); `pad_ws` (tensor, or callable returning one) is the
-    preallocated workspace of the padded copy the tcgen05 path reads -- allocated here if missing (not graph-safe)."""
+    preallocated workspace of the padded copy the tcgen05 path reads -- allocated here if missing (not graph-safe).
+    prepadded: x IS the halo-padded tensor [B, D+2 (3-D), H+2, W+2, Cin] (norm_apply_padded): no padding pass."""
     require_cuda(x, "conv input")
     B, D, H, W, Cin = x.shape
+    if prepadded:
+        assert pc.circular and pc.w_dtype == torch.bfloat16, "a pre-padded input is the layout of circular tcgen05 convolutions"
+        D, H, W = (D - 2 if pc.ndim == 3 else D), H - 2, W - 2
     assert Cin == pc.cin, (Cin, pc.cin)
     assert up2 == pc.subpixel or pc.w_dtype == torch.float32, "bf16 weights of an up2 conv must be sub-pixel packed"
     if up2:
@@ -141,6 +145,8 @@ def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, ch
         out = torch.empty(shape, dtype=torch.float32 if out_nchw else out_dtype, device=x.device)
     d = _conv_desc_of(x, pc, out, residual, up2, out_nchw, D, H, W)
     bias = pc.bias.detach() if pc.bias is not None else None
+    if prepadded:
+        d.circular = 2
     if pc.circular:
         need = int(lib.dsk_conv_pad_ws_bytes(C.byref(d)))
         ws = pad_ws() if callable(pad_ws) else pad_ws
@@ -194,13 +200,16 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
 
 def norm_act(x: torch.Tensor, gamma, beta, G: int, mode: int, silu: bool, out: Optional[torch.Tensor] = None,
              film_scale=None, film_shift=None, out_dtype: Optional[torch.dtype] = None, ws=None,
-             conv_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+             conv_stats: Optional[torch.Tensor] = None, table_only: bool = False) -> torch.Tensor:
     """Group LayerNorm (mode 0) / RMS norm (mode 1) + affine (+FiLM) + SiLU  (dsk_norm_act).  `conv_stats`: statistics the
     convolution that produced x left behind (ops.conv(..., stats=...)): the statistics pass over x is skipped."""
     require_cuda(x, "norm input")
     B, Cc = x.shape[0], x.shape[-1]
     S = x.numel() // (B * Cc)
-    if out is None:
+    if table_only:       # statistics + folded scale/shift table into `ws` only; norm_apply_padded writes the output
+        assert ws is not None
+        out = None
+    elif out is None:
         out = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
     if ws is None:
         ws = torch.empty(int(lib.dsk_norm_ws_bytes(B, S, Cc)), dtype=torch.uint8, device=x.device)
@@ -209,10 +218,21 @@ def norm_act(x: torch.Tensor, gamma, beta, G: int, mode: int, silu: bool, out: O
     if conv_stats is not None:
         check(lib.dsk_norm_act_prestat(ptr(x), ptr(out), ptr(g), ptr(b), ptr(film_scale), ptr(film_shift), ptr(conv_stats),
                                        conv_stats.shape[1], ptr(ws), B, S, Cc, G, mode, int(silu), dt_code(x.dtype),
-                                       dt_code(out.dtype), stream()))
+                                       dt_code(x.dtype if out is None else out.dtype), stream()))
         return out
     check(lib.dsk_norm_act(ptr(x), ptr(out), ptr(g), ptr(b), ptr(film_scale), ptr(film_shift), ptr(ws), B, S, Cc, G,
-                           mode, int(silu), dt_code(x.dtype), dt_code(out.dtype), stream()))
+                           mode, int(silu), dt_code(x.dtype), dt_code(x.dtype if out is None else out.dtype), stream()))
+    return out
+
+
+def norm_apply_padded(x: torch.Tensor, ws: torch.Tensor, out: torch.Tensor, ndim: int, silu: bool = True) -> torch.Tensor:
+    """The apply pass of norm_act(..., table_only=True) writing the halo-padded input layout of a circular tcgen05
+    convolution: out [B, D+2 (3-D), H+2, W+2, C] = wrap(act(x * scale + shift))  (dsk_norm_apply_padded)."""
+    require_cuda(x, "norm input")
+    B, D, H, W, Cc = x.shape
+    assert tuple(out.shape) == (B, D + 2 if ndim == 3 else D, H + 2, W + 2, Cc), (out.shape, x.shape)
+    check(lib.dsk_norm_apply_padded(ptr(x), ptr(out), ptr(ws), B, D, H, W, Cc, ndim, int(silu), dt_code(x.dtype),
+                                    dt_code(out.dtype), stream()))
     return out
 
 

@@ -172,6 +172,12 @@ int dsk_pad_circular(const void* x, void* y, int B, int D, int H, int W, int C, 
 int64_t dsk_conv_pad_ws_bytes(const dsk_conv_desc* d);
 int dsk_conv_fwd_circ(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
                       const void* residual, void* out, void* stats, void* pad_ws, void* stream);
+/* d->circular = 2: `in` is ALREADY the halo-padded tensor [B, D+2, H+2, W+2, C] (written by dsk_norm_apply_padded): tcgen05
+ * kernels only, no padding pass.  dsk_norm_apply_padded: the apply pass of dsk_norm_act / dsk_norm_act_prestat (called with
+ * y = NULL: statistics + folded scale/shift table in `ws` only) writing that padded layout directly -- interior plus wrapped
+ * halos -- so the GroupNorm + SiLU in front of a circular convolution (commonlayers.py:824-831, 918-1032) costs no extra pass. */
+int dsk_norm_apply_padded(const void* x, void* y_padded, const void* ws, int B, int D, int H, int W, int C, int ndim, int silu,
+                          int in_dtype, int out_dtype, void* stream);
 /* nearest x2 upsample of a channels-last tensor (torch.nn.Upsample(scale_factor=2), commonlayers.py:129):
  * only needed in front of the tcgen05 conv; the FFMA conv fuses it into its gather (up2). bf16, C % 8 == 0. */
 int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, void* stream);

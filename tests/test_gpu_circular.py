@@ -74,7 +74,11 @@ CASES = [
     (2, 5, 128, 128, (7, 7), 3, False),      # single-CTA kernel (odd number of w-tiles)
     (3, 2, 128, 64, (4, 8, 16), 3, True),    # sub-pixel up-conv on the padded low-resolution input
     (2, 3, 128, 64, (8, 16), 3, True),
-    (3, 1, 64, 1, (6, 10, 12), 3, False),    # convout on the N = 16 tensor-core tile
+    (3, 1, 64, 1, (6, 10, 12), 3, False),    # convout: in-plane taps as N (convout_tc) on the padded copy
+    (2, 2, 128, 3, (9, 20), 3, False),       # convout, 3 output channels, ragged tiles
+    (3, 2, 1, 64, (5, 16, 8), 3, False),     # convin on the tensor cores: the im2col-row builders wrap their gather
+    (3, 1, 2, 64, (4, 9, 11), 3, False),     # ... ragged tiles
+    (2, 3, 3, 128, (20, 12), 3, False),
 ]
 
 
@@ -257,3 +261,35 @@ def test_circular_network_tensor_core_path():
     print("gradient global-L2 errors:", {k: f"{v:.2e}" for k, v in err.items()})
     assert err["circular", "fp32"] < 2e-4 and err["default", "fp32"] < 1e-4
     assert err["default", "bf16"] < 8e-2 and err["circular", "bf16"] < 3 * err["default", "bf16"]
+
+
+@pytest.mark.parametrize("ndim,shape", [(3, (2, 6, 10, 12, 64)), (2, (3, 1, 9, 16, 128)), (3, (1, 1, 4, 8, 64))])
+def test_norm_apply_padded_and_prepadded_conv(ops, ndim, shape):
+    """The norm's apply pass writing the halo-padded conv input directly (dsk_norm_apply_padded) == apply + dsk_pad_circular,
+    bit for bit; a circular tcgen05 convolution on that pre-padded input (d->circular = 2) == the same convolution padding
+    internally, bit for bit (including the fused statistics)."""
+    torch.manual_seed(8)
+    B, D, H, W, C = shape
+    if ndim == 2:
+        D = 1
+    x = torch.randn(B, D, H, W, C, device=DEV).bfloat16()
+    g, b_ = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    for mode in (0, 1):
+        ws = ops.norm_ws(B, D * H * W, C, DEV)
+        ref = ops.pad_circular(ops.norm_act(x, g, b_, C, mode, True, ws=ws), ndim)
+        ws2 = ops.norm_ws(B, D * H * W, C, DEV)
+        ops.norm_act(x, g, b_, C, mode, True, ws=ws2, table_only=True)
+        out = torch.full_like(ref, float("nan"))
+        ops.norm_apply_padded(x, ws2, out, ndim)
+        assert torch.equal(out, ref)
+    w = torch.randn(C, C, *([3] * ndim), device=DEV) / math.sqrt(C * 3 ** ndim)
+    pc = ops.PackedConv(w, torch.randn(C, device=DEV), ndim, BF, circular=True)
+    res = torch.randn(B, D, H, W, C, device=DEV).bfloat16()
+    y_int = ops.conv(x, pc, residual=res)
+    y_pre = ops.conv(ops.pad_circular(x, ndim), pc, residual=res, prepadded=True)
+    assert torch.equal(y_int, y_pre)
+    if ops.conv_stats_supported(tuple(x.shape), x.dtype, pc):
+        s1, s2 = ops.conv_stats_buffer(B, C, DEV), ops.conv_stats_buffer(B, C, DEV)
+        ops.conv(x, pc, residual=res, stats=s1)
+        ops.conv(ops.pad_circular(x, ndim), pc, residual=res, stats=s2, prepadded=True)
+        assert torch.equal(s1, s2)
