@@ -52,6 +52,8 @@ struct TcParams {
   int samples;            // number of samples the stats are kept for (3-D: B; 2-D: the planes ARE the samples)
   int pad_hw, pad_d;      // circular padding: the activation tensor map covers a halo-padded copy ([.., D+2*pad_d, H+2, W+2, C]);
                           // these offsets move the patch coordinates into it (0: zero 'same' padding through TMA OOB fill)
+  int pair_d;             // cta_group::2 kernel: the two CTAs of a pair take neighbouring plane groups instead of neighbouring
+                          // w-tiles (odd number of w-tiles, e.g. the 7x7 planes of MNIST's bottom level); no fused statistics
 };
 constexpr int TC_STAT_SLOTS = DSK_NUM_SMS;          // one slot per CTA
 
@@ -390,10 +392,17 @@ __device__ __forceinline__ TileCoord tile_coord2(const TcParams& p, int u, int r
   TileCoord c;
   c.phase = u % p.nphase; u /= p.nphase;
   c.pc = c.phase & 1; c.pb = (c.phase >> 1) & 1; c.pa = (c.phase >> 2) & 1;
-  const int pairs_w = p.tiles_w >> 1;
-  c.w0 = ((u % pairs_w) * 2 + rank) * TC_BW; u /= pairs_w;
-  c.h0 = (u % p.tiles_h) * TC_BH; u /= p.tiles_h;
-  c.d0 = (u % p.groups_d) * P;    u /= p.groups_d;
+  if (p.pair_d) {
+    c.w0 = (u % p.tiles_w) * TC_BW; u /= p.tiles_w;
+    c.h0 = (u % p.tiles_h) * TC_BH; u /= p.tiles_h;
+    const int pairs_d = p.groups_d >> 1;
+    c.d0 = ((u % pairs_d) * 2 + rank) * P; u /= pairs_d;
+  } else {
+    const int pairs_w = p.tiles_w >> 1;
+    c.w0 = ((u % pairs_w) * 2 + rank) * TC_BW; u /= pairs_w;
+    c.h0 = (u % p.tiles_h) * TC_BH; u /= p.tiles_h;
+    c.d0 = (u % p.groups_d) * P;    u /= p.groups_d;
+  }
   c.b = u % p.B;                  u /= p.B;
   c.n0 = u * n_tile_size;
   return c;
@@ -601,7 +610,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     // 2-D: the plane axis IS the batch, a tile holds P samples and this warp (plane pp) owns sample d0 + pp.
     const bool is3d = p.KD == 3;
     const int srange = is3d ? p.B : p.groups_d;              // sample ranges per n-tile
-    const int per_range = p.nphase * (p.tiles_w >> 1) * p.tiles_h * (is3d ? p.groups_d : 1);
+    const int per_range = p.pair_d ? 1 : p.nphase * (p.tiles_w >> 1) * p.tiles_h * (is3d ? p.groups_d : 1);   // pair_d: no statistics
     const int nranges = total_pairs / per_range;             // n_tiles * srange
     int cur_range = -1;
     uint4* stg = stage_s[warp - 4];
@@ -956,6 +965,18 @@ static bool tc_pair_eligible(const dsk_conv_desc* d) {
   return (((iW + TC_BW - 1) / TC_BW) % 2) == 0;
 }
 
+// odd number of w-tiles: pair along the plane axis instead (both CTAs still share every weight tap); needs an even number of
+// plane groups per batch entry and no fused statistics (the two CTAs of a pair may work on different samples)
+static bool tc_pair_d_eligible(const dsk_conv_desc* d, bool stats) {
+  static const int force_cg = [] { const char* e = getenv("DSK_CONV_CG"); return e ? atoi(e) : 0; }();
+  if (stats || force_cg == 1 || d->ksize != 3 || d->in_dtype != DSK_BF16 || d->out_dtype != DSK_BF16 || d->out_nchw_f32 ||
+      d->w_dtype != DSK_BF16 || d->Cin % 64 != 0 || d->Cout % 64 != 0 || tc_pair_eligible(d))
+    return false;
+  const int iD = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D;
+  const int planes = d->ndim == 3 ? iD : d->B;
+  return (((planes + 1) / 2) % 2) == 0;      // groups_d with P = 2
+}
+
 // 1 if dsk_conv_fwd_stats should emit fused norm statistics for this convolution: the cta_group::2 kernel, 3-D only.
 // (The epilogue can do it for 2-D too -- tests exercise it with DSK_CONV_STATS_2D=1 -- but a 2-D tile has 3x fewer MMAs to
 // hide the reduction behind and one slot set per sample of a large batch: measured on C5 / C2 it does not pay.)
@@ -1083,10 +1104,11 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   p.planes_per_sample = d->ndim == 3 ? iD : 1;
   p.stats = stats; p.samples = d->B;
   p.pad_hw = pad_hw; p.pad_d = pad_d;
+  p.pair_d = (!few_out && tc_pair_d_eligible(d, stats != nullptr)) ? 1 : 0;
   cudaStream_t st = as_stream(stream);
   // cta_group::2 (CTA pairs): needs an even number of w-tiles (the pair sits side by side in w).  DSK_CONV_CG=1 forces
   // the single-CTA kernel (A/B measurements).
-  if (!few_out && tc_pair_eligible(d)) {
+  if (!few_out && (tc_pair_eligible(d) || p.pair_d)) {
     if (stats != nullptr && p.total_tiles / 2 < DSK_NUM_SMS / 2) {
       // fewer CTAs than slots: the slots of the CTAs that do not exist read as zero
       cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)d->B * TC_STAT_SLOTS * d->Cout * sizeof(float2), st);
