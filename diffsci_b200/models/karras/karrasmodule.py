@@ -1,13 +1,15 @@
 """KarrasModule / KarrasModuleConfig -- drop-in for diffsci.models.karras.karrasmodule
-(reference karras/karrasmodule.py:30-1253), restricted to the EDM hot path of SURVEY.md section 8:
-``get_denoiser``, ``get_score``, ``loss_fn``, ``training_step``, ``sample``,
-``propagate_white_noise``, ``propagate_toward_sample`` keep their signatures and semantics.
+(reference karras/karrasmodule.py:30-1253), restricted to the Karras/EDM hot path of SURVEY.md section 8:
+``get_denoiser``, ``get_score``, ``loss_fn``, ``training_step``, ``sample``, ``propagate_white_noise``,
+``propagate_toward_sample`` and -- section 8(f) -- ``inpaint`` / ``repaint`` / ``propagate_partial_toward_sample`` /
+``propagate_toward_noise`` / ``interpolate_images``, conditional models (``conditional=True``: ``y``, classifier-free
+``guidance``) and the VP / VE configurations keep their signatures and semantics.
 
 Where the reference launches ~30 elementwise ATen kernels per network evaluation plus host syncs,
 this module drives the fused CUDA stages (csrc/sampler.cu, csrc/train.cu) and, for native networks,
 replays one captured CUDA graph per integrator step (engine.SamplerEngine).
-Latent-diffusion (autoencoder), inpaint/repaint, autoregressive and multi-space-loss recipes are out
-of scope (SURVEY.md 8f) and raise NotImplementedError instead of silently doing something else.
+Latent-diffusion (autoencoder), autoregressive, dynamic-loss-weight and multi-space-loss recipes are out
+of scope and raise NotImplementedError instead of silently doing something else.
 """
 from __future__ import annotations
 

@@ -245,6 +245,9 @@ TC_CASES = [
     (2, 5, 128, 128, (28, 28)),          # MNIST-like, odd number of planes
     (3, 1, 64, 64, (16, 32, 32)),        # 64 tiles
     (3, 2, 64, 64, (32, 32, 32)),        # > 148 tiles: persistent loop, accumulator double buffering
+    (2, 4, 128, 128, (7, 7)),            # odd number of w-tiles, even number of plane groups: CTA pairs along the plane axis
+    (2, 8, 64, 64, (14, 7)),
+    (3, 2, 64, 128, (4, 16, 24)),        # 3-D, 3 w-tiles: pairs along depth
 ]
 
 
@@ -376,7 +379,8 @@ def test_attention_tcgen05(ops):
 
 
 @pytest.mark.parametrize("ndim,B,Cin,Cout,sp", [(3, 1, 64, 64, (2, 16, 8)), (3, 2, 128, 64, (3, 10, 12)), (2, 3, 64, 128, (16, 8)),
-                                                 (2, 2, 128, 64, (7, 9)), (3, 1, 256, 128, (4, 8, 8))])
+                                                 (2, 2, 128, 64, (7, 9)), (3, 1, 256, 128, (4, 8, 8)),
+                                                 (2, 4, 128, 64, (7, 7)), (3, 2, 64, 64, (4, 8, 8))])   # last two: pairs along the plane axis
 def test_upconv_subpixel_tcgen05(ops, ndim, B, Cin, Cout, sp):
     """conv3(nearest_up2(x)) in sub-pixel (phase-decomposed, pre-summed taps) form on tcgen05 vs ATen on the same bf16 inputs.
     The pre-summed weights are rounded to bf16 after summation, so the tolerance is 2 bf16 roundings of the range."""
