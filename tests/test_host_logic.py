@@ -163,3 +163,42 @@ def test_training_graph_builds_and_covers_every_parameter(monkeypatch):
     import pytest
     with pytest.raises(ValueError):
         G.build_punetg(d.PUNetG(d.PUNetGConfig(dimension=2, model_channels=8)), 1, (6, 6), "cpu", "fp32")
+
+
+def test_conditional_and_circular_host_logic(golden):
+    """SURVEY 8(f)-2/3 host side (no GPU): state-dict manifests of the conditional / circular modules equal the live
+    reference's (recorded in the golden fixtures), conditioning plumbing, error behaviour."""
+    import torch
+    import diffsci_b200 as d
+    g = golden("cond_punetg2d_embed")
+    net = d.PUNetG(d.PUNetGConfig(**g["cfg"]), conditional_embedding=d.PorosityEmbedder(8))
+    assert [(k, list(v.shape)) for k, v in net.state_dict().items()] == [(k, list(s)) for k, s in g["manifest"]]
+    native = {id(p) for p in net.native_parameters()}
+    assert all((id(p) in native) != n.startswith("conditional_embedding.") for n, p in net.named_parameters())
+    ye = net.conditioning_vector({"porosity": torch.rand(1, 1)}, 3)
+    assert ye.shape == (3, 8)                                       # one condition broadcast over the batch
+    assert net.conditioning_vector(None, 3) is None
+    with pytest.raises(NotImplementedError):                        # spatial embeddings are not built
+        d.PUNetG(d.PUNetGConfig(**g["cfg"])).conditioning_vector(torch.zeros(3, 8, 4, 4), 3)
+    g = golden("cond_punetg3d_chan")
+    cnet = d.PUNetGCond(d.PUNetGConfig(**g["cfg"]), conditional_embedding=d.PorosityEmbedder(8), channel_conditional_items=["cond"])
+    assert [(k, list(v.shape)) for k, v in cnet.state_dict().items()] == [(k, list(s)) for k, s in g["manifest"]]
+    x = torch.zeros(2, 1, 8, 8, 8)
+    ychan, rest = cnet.split_condition({"cond": torch.ones(1, 1, 8, 8, 8), "porosity": torch.rand(1, 1)}, x)
+    assert ychan.shape == (2, 1, 8, 8, 8) and set(rest) == {"porosity"}
+    with pytest.raises(TypeError):
+        cnet.split_condition(None, x)                               # as the reference: y[item] on None (punetg.py:718)
+    g = golden("cond_adm2d_embed")
+    anet = d.ADM(d.ADMConfig(**g["cfg"]), conditional_embedding=d.PorosityEmbedder(32))
+    assert [(k, list(v.shape)) for k, v in anet.state_dict().items()] == [(k, list(s)) for k, s in g["manifest"]]
+    assert anet.cond_dim == 32
+    g = golden("circ_punetg3d")
+    circ = d.PUNetG(d.PUNetGConfig(**g["cfg"]))
+    assert [(k, list(v.shape)) for k, v in circ.state_dict().items()] == [(k, list(s)) for k, s in g["manifest"]]
+    # a conditional model cannot use the fused unconditional trainer; VP / VE configs build with the reference's defaults
+    mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm(), conditional=True)
+    with pytest.raises(NotImplementedError):
+        d.EDMTrainer(mod)
+    vp, ve = d.KarrasModuleConfig.from_vp(), d.KarrasModuleConfig.from_ve()
+    assert vp.tag == "vp" and ve.tag == "ve" and float(ve.noisescheduler.maximum_scale) == 100.0
+    assert abs(float(vp.noisescheduler.maximum_scale) - float(golden("precond_vp_mlp")["maximum_scale"])) < 1e-5
