@@ -675,7 +675,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         st_pix = (((int64_t)tc.b * p.D + d) * p.H + tc.h0 + q * 4) * p.W + w_st;
       }
       const __nv_bfloat16* rrow = (p.residual != nullptr && valid) ? p.residual + pix * p.Cout + tc.n0 : nullptr;
-      const float* cbrow = p.chan_bias != nullptr ? p.chan_bias + (int64_t)brow * p.Cout + tc.n0 : nullptr;
+      // d >= p.D: the second plane of a tile past an odd plane count (e.g. a 2-D batch of 1) -- its row of chan_bias does not exist
+      const float* cbrow = (p.chan_bias != nullptr && d < p.D) ? p.chan_bias + (int64_t)brow * p.Cout + tc.n0 : nullptr;
       uint4 rr[DEP][4];
       if (rrow != nullptr) {
 #pragma unroll

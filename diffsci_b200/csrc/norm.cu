@@ -401,6 +401,96 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_apply_pad_kernel(const TI* 
   }
 }
 
+// ---- small samples, per-channel norms (G == C), bf16: ONE kernel, ONE read.  A CTA owns (sample b, 32 channels): it loads its
+// S x 32-channel slab into shared memory (64 B per pixel), reduces (sum, sum of squares) per channel -- fp32 per thread over at
+// most S/64 pixels, fp64 across threads, fixed order -- folds the affine / FiLM parameters and applies scale/shift + SiLU from
+// shared memory.  Replaces the statistics pass + finalize + apply launches (31 us -> ~12 us per norm on MNIST-size tensors,
+// where each of the three is launch-latency bound); writes the same (scale, shift) / (mean, rstd) tables for the backward.
+constexpr int SLAB_THREADS = 256, SLAB_CH = 32;
+__global__ void __launch_bounds__(SLAB_THREADS) norm_slab_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                                  float2* __restrict__ table, float2* __restrict__ stats,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ fsc, const float* __restrict__ fsh, int S, int C,
+                                                                  int mode, int silu, float eps) {
+  extern __shared__ __align__(16) uint8_t slab_raw[];
+  uint4* slab = reinterpret_cast<uint4*>(slab_raw);                 // [S][4] 16-byte pieces (8 channels each)
+  __shared__ double red_s[SLAB_THREADS / 32][SLAB_CH], red_q[SLAB_THREADS / 32][SLAB_CH];
+  __shared__ float2 coef[SLAB_CH];
+  const int b = blockIdx.y, c0 = blockIdx.x * SLAB_CH;
+  const int j = threadIdx.x & 3, pl = threadIdx.x >> 2;             // piece within the pixel row, pixel lane (64 lanes)
+  const __nv_bfloat16* xb = x + ((int64_t)b * S) * C + c0 + j * 8;
+  float s8[8], q8[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s8[k] = 0.0f; q8[k] = 0.0f; }
+  for (int p = pl; p < S; p += SLAB_THREADS / 4) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
+    slab[p * 4 + j] = raw;
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = __low2float(h[k]), c = __high2float(h[k]);
+      s8[2 * k] += a; q8[2 * k] = fmaf(a, a, q8[2 * k]);
+      s8[2 * k + 1] += c; q8[2 * k + 1] = fmaf(c, c, q8[2 * k + 1]);
+    }
+  }
+  // lanes of a warp that share j (lane bits 2..4) meet by shuffle; the 8 warps meet in shared memory (fp64, fixed order)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    double ds = (double)s8[k], dq = (double)q8[k];
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, o); dq += __shfl_xor_sync(0xffffffffu, dq, o); }
+    if ((threadIdx.x & 31) < 4) { red_s[threadIdx.x >> 5][j * 8 + k] = ds; red_q[threadIdx.x >> 5][j * 8 + k] = dq; }
+  }
+  __syncthreads();
+  if (threadIdx.x < SLAB_CH) {
+    const int c = c0 + threadIdx.x;
+    double a = 0, q = 0;
+    for (int w = 0; w < SLAB_THREADS / 32; ++w) { a += red_s[w][threadIdx.x]; q += red_q[w][threadIdx.x]; }
+    const double n = (double)S, mean = a / n, ex2 = q / n;
+    float2 mr;
+    if (mode == 0) {
+      double var = ex2 - mean * mean;
+      if (var < 0) var = 0;
+      mr = make_float2((float)mean, 1.0f / sqrtf((float)var + eps));
+    } else {
+      mr = make_float2(0.0f, 1.0f / sqrtf((float)ex2 + eps));
+    }
+    const int64_t i = (int64_t)b * C + c;
+    float sc = mr.y, sh = -mr.x * mr.y;
+    if (gamma != nullptr) { sc *= gamma[c]; sh = sh * gamma[c] + beta[c]; }
+    if (fsc != nullptr) { const float f = fsc[i]; sc *= f; sh = sh * f + fsh[i]; }
+    stats[i] = mr;
+    table[i] = make_float2(sc, sh);
+    coef[threadIdx.x] = make_float2(sc, sh);
+  }
+  __syncthreads();
+  if (y == nullptr) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const float2 t = coef[j * 8 + k]; sc[k] = t.x; sh[k] = t.y; }
+  __nv_bfloat16* yb = y + ((int64_t)b * S) * C + c0 + j * 8;
+  for (int p = pl; p < S; p += SLAB_THREADS / 4) {
+    const uint4 raw = slab[p * 4 + j];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float t0 = fmaf(__low2float(h[k]), sc[2 * k], sh[2 * k]), t1 = fmaf(__high2float(h[k]), sc[2 * k + 1], sh[2 * k + 1]);
+      o[2 * k] = silu ? silu_out<__nv_bfloat16>(t0) : t0;
+      o[2 * k + 1] = silu ? silu_out<__nv_bfloat16>(t1) : t1;
+    }
+    st_vec<__nv_bfloat16, 8>(yb + (int64_t)p * C, o);
+  }
+}
+
+// shapes the slab kernel takes: per-channel bf16 norms whose 32-channel slab of one sample fits in shared memory, with
+// enough (sample, channel-group) CTAs to fill the machine
+static bool norm_slab_ok(int B, int64_t S, int C, int G, int in_dtype, int out_dtype) {
+  static const int off = [] { const char* e = getenv("DSK_NORM_SLAB_OFF"); return e ? atoi(e) : 0; }();   // A/B measurements
+  return !off && G == C && in_dtype == DSK_BF16 && out_dtype == DSK_BF16 && C % SLAB_CH == 0 && S * 64 <= 96 * 1024 &&
+         (int64_t)B * (C / SLAB_CH) >= DSK_NUM_SMS;
+}
+
 }  // namespace dsk
 
 using namespace dsk;
@@ -452,6 +542,18 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
   float2* table = reinterpret_cast<float2*>(ws);
   float2* stats = table + (int64_t)B * C;
   double2* partial = reinterpret_cast<double2*>(stats + (int64_t)B * C);
+  if (norm_slab_ok(B, S, C, G, in_dtype, y == nullptr ? DSK_BF16 : out_dtype)) {
+    const size_t smem = (size_t)S * 64;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(norm_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e != cudaSuccess) { set_error("dsk_norm_act: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSK_ERR_CUDA; }
+      configured = true;
+    }
+    DSK_LAUNCH(norm_slab_kernel, dim3(C / SLAB_CH, B), SLAB_THREADS, smem, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, table, stats, gamma,
+               beta, film_scale, film_shift, (int)S, C, mode, silu, 1e-5f);
+    return DSK_OK;
+  }
   const int cv = C / V;
   const int pl = NORM_THREADS / cv > 0 ? NORM_THREADS / cv : 1;
   const size_t smem = (size_t)pl * C * sizeof(float2);

@@ -92,6 +92,40 @@ def test_norm_act(ops, mode, B, C, G, sp):
     assert relmax(yb.float().cpu().permute(0, 2, 1).reshape(x.shape), refb) < 8e-3
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("B,C,sp", [(64, 128, (28, 28)), (160, 32, (7, 7)), (40, 256, (14, 14)), (5, 1024, (3, 5))])
+def test_norm_act_small_samples_one_kernel(ops, mode, B, C, sp):
+    """Per-channel bf16 norms on many small samples (MNIST-size tensors): the single-kernel slab path (norm_slab_kernel: one
+    read, statistics + fold + apply in shared memory) vs ATen on the same bf16 input, with and without FiLM / SiLU, the
+    table-only form, and the (mean, rstd) it leaves for the backward."""
+    from oracle import nets_oracle as N
+    torch.manual_seed(5)
+    x = (torch.randn(B, C, *sp) * 2 + 1.5).bfloat16()
+    g, b = 1 + 0.1 * torch.randn(C), 0.1 * torch.randn(C)
+    fs, fh = torch.randn(B, C), torch.randn(B, C)
+    xf = x.float()
+    ref = F.group_norm(xf, C, g, b, 1e-5) if mode == 0 else N.group_rms_norm(xf, C, g, b)
+    S = sp[0] * sp[1]
+    xcl = xf.reshape(B, C, S).permute(0, 2, 1).contiguous().to(DEV).bfloat16()
+    back = lambda y: y.float().cpu().permute(0, 2, 1).reshape(xf.shape)  # noqa: E731
+    ws = ops.norm_ws(B, S, C, DEV)
+    y = ops.norm_act(xcl, g.to(DEV), b.to(DEV), C, mode, True, ws=ws)
+    assert relmax(back(y), F.silu(ref)) < 8e-3
+    # statistics left for the backward: (mean, rstd) per (b, c) behind the (scale, shift) table
+    st = ws.view(torch.float32)[2 * B * C: 4 * B * C].view(B, C, 2).cpu()
+    mean = xf.flatten(2).mean(-1)
+    var = xf.flatten(2).var(-1, unbiased=False) if mode == 0 else (xf.flatten(2) ** 2).mean(-1)
+    assert relmax(st[..., 1], 1 / torch.sqrt(var + 1e-5)) < 1e-5
+    if mode == 0:
+        assert relmax(st[..., 0], mean) < 1e-5
+    shp = (B, C, 1, 1)
+    y = ops.norm_act(xcl, g.to(DEV), b.to(DEV), C, mode, False, film_scale=fs.to(DEV), film_shift=fh.to(DEV))
+    assert relmax(back(y), ref * fs.view(shp) + fh.view(shp)) < 8e-3
+    y = ops.norm_act(xcl, None, None, C, mode, True)
+    plain = F.group_norm(xf, C, None, None, 1e-5) if mode == 0 else N.group_rms_norm(xf, C, torch.ones(C), torch.zeros(C))
+    assert relmax(back(y), F.silu(plain)) < 8e-3
+
+
 @pytest.mark.parametrize("ndim,sp", [(2, (8, 10)), (2, (7, 9)), (3, (4, 6, 8))])
 @pytest.mark.parametrize("is_max", [True, False])
 def test_pool_add_layout(ops, ndim, sp, is_max):
