@@ -422,15 +422,25 @@ __global__ void __launch_bounds__(SLAB_THREADS) norm_slab_kernel(const __nv_bflo
   float s8[8], q8[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s8[k] = 0.0f; q8[k] = 0.0f; }
-  for (int p = pl; p < S; p += SLAB_THREADS / 4) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
-    slab[p * 4 + j] = raw;
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  constexpr int PSTEP = SLAB_THREADS / 4, UNR = 4;            // 4 independent 16-byte loads in flight per thread
+  for (int p0 = pl; p0 < S; p0 += PSTEP * UNR) {
+    uint4 raw[UNR];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float a = __low2float(h[k]), c = __high2float(h[k]);
-      s8[2 * k] += a; q8[2 * k] = fmaf(a, a, q8[2 * k]);
-      s8[2 * k + 1] += c; q8[2 * k + 1] = fmaf(c, c, q8[2 * k + 1]);
+    for (int u = 0; u < UNR; ++u) {
+      const int p = p0 + u * PSTEP;
+      raw[u] = p < S ? *reinterpret_cast<const uint4*>(xb + (int64_t)p * C) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int p = p0 + u * PSTEP;
+      if (p < S) slab[p * 4 + j] = raw[u];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {                            // zeros past the end add nothing (same order as a rolled loop)
+        const float a = __low2float(h[k]), c = __high2float(h[k]);
+        s8[2 * k] += a; q8[2 * k] = fmaf(a, a, q8[2 * k]);
+        s8[2 * k + 1] += c; q8[2 * k + 1] = fmaf(c, c, q8[2 * k + 1]);
+      }
     }
   }
   // lanes of a warp that share j (lane bits 2..4) meet by shuffle; the 8 warps meet in shared memory (fp64, fixed order)
@@ -469,6 +479,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) norm_slab_kernel(const __nv_bflo
 #pragma unroll
   for (int k = 0; k < 8; ++k) { const float2 t = coef[j * 8 + k]; sc[k] = t.x; sh[k] = t.y; }
   __nv_bfloat16* yb = y + ((int64_t)b * S) * C + c0 + j * 8;
+#pragma unroll 4
   for (int p = pl; p < S; p += SLAB_THREADS / 4) {
     const uint4 raw = slab[p * 4 + j];
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
