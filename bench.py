@@ -128,9 +128,13 @@ def build_workload(name, device, precision):
     return module, net, cfg, shape, nsteps, integ, batch, flops
 
 
-def cpu_reference_arm(name, steps, warmup, max_seconds=25.0):
+def cpu_reference_arm(name, steps, warmup, max_seconds=25.0, ref_device="cpu", ref_mode="fp32", ref_batch=0):
     """The oracle port (torch-CPU restatement of the reference, oracle/*.py) timed on the host cores on a
-    BOUNDED sample of the workload: B=1, a few integrator steps, extrapolated linearly in NFE."""
+    BOUNDED sample of the workload: B=1, a few integrator steps, extrapolated linearly in NFE.
+
+    ref_device="cuda" (never the default, never what the driver runs) times the SAME port on torch's own CUDA path
+    (cuDNN / cuBLAS; ref_mode fp32 = TF32 off, tf32 = TF32 on, bf16 = autocast) -- the "reference on the box's
+    PyTorch-CUDA path" SURVEY 8(d) asks for beside the CPU number."""
     import torch
     from oracle import karras_oracle as K, nets_oracle as N
     kind, kw, shape, nsteps, integ, _ = WORKLOADS[name]
@@ -138,6 +142,8 @@ def cpu_reference_arm(name, steps, warmup, max_seconds=25.0):
     sd = {k: v.detach() for k, v in net.state_dict().items()}
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    if ref_device == "cuda":
+        return cuda_port_arm(name, steps, warmup, sd, cfg, ref_mode, ref_batch, max_seconds)
     if kind == "punetg":
         fn = lambda x, t: N.punetg_forward(sd, cfg, x, t)  # noqa: E731
         B, sub = 1, 2
@@ -165,6 +171,48 @@ def cpu_reference_arm(name, steps, warmup, max_seconds=25.0):
     sample = (f"oracle port of the reference (torch {torch.__version__} CPU fp32), B={B}, {sub} {integ} steps = {nfe_sub} NFE "
               f"timed {len(vals)}x, extrapolated linearly to {nfe_per_sample(nsteps, integ)} NFE")
     return value, cores, sample, sum(vals) / len(vals)
+
+
+def cuda_port_arm(name, steps, warmup, sd, cfg, mode, batch, max_seconds):
+    """Oracle port on torch CUDA (library kernels: cuDNN convolutions, cuBLAS / SDPA attention).  Side measurement only."""
+    import contextlib
+    import torch
+    from oracle import karras_oracle as K, nets_oracle as N
+    kind, kw, shape, nsteps, integ, wl_batch = WORKLOADS[name]
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.allow_tf32 = mode != "fp32"
+    torch.backends.cuda.matmul.allow_tf32 = mode != "fp32"
+    torch.backends.cudnn.benchmark = True
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    B = batch or wl_batch
+    sub = 2 if kind == "punetg" else nsteps
+    if kind == "punetg":
+        fn = lambda x, t: N.punetg_forward(sd, cfg, x, t).float()  # noqa: E731
+    else:
+        fn = lambda x, t: N.mlp_uncond_forward(sd, x, t, "silu")  # noqa: E731
+    ctx = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if mode == "bf16" else contextlib.nullcontext
+    torch.manual_seed(1234)
+    wn = torch.randn(B, *shape).to(dev)
+    noises = [torch.randn(B, *shape).to(dev) for _ in range(sub)]
+    nfe_sub = nfe_per_sample(sub, integ)
+    vals = []
+    with torch.no_grad(), ctx():
+        for i in range(max(3, warmup) + steps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            K.sample_from_white_noise(fn, wn, sub, integ, noises=noises)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if i >= max(3, warmup):
+                vals.append(dt)
+            if sum(vals) > max_seconds and vals:
+                break
+    per_nfe = (sum(vals) / len(vals)) / (nfe_sub * B)
+    value = 1.0 / (per_nfe * nfe_per_sample(nsteps, integ))
+    sample = (f"oracle port of the reference on torch {torch.__version__} CUDA ({mode}: cuDNN {torch.backends.cudnn.version()}, "
+              f"benchmark=True), B={B}, {sub} {integ} steps = {nfe_sub} NFE timed {len(vals)}x, extrapolated linearly to "
+              f"{nfe_per_sample(nsteps, integ)} NFE; {per_nfe * B * 1e3:.2f} ms per batched evaluation")
+    return value, 0, sample, sum(vals) / len(vals)
 
 
 def build_train_workload(name, device, precision):
@@ -357,6 +405,9 @@ def main():
     ap.add_argument("--nsteps", type=int, default=0, help="integrator steps (0 = workload default)")
     ap.add_argument("--precision", default=os.environ.get("DSK_BENCH_PRECISION", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cuda = the oracle port on torch's cuDNN/cuBLAS path (side measurement)")
+    ap.add_argument("--ref-mode", default="fp32", choices=["fp32", "tf32", "bf16"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -371,12 +422,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        value, cores, sample, secs = cpu_reference_arm(args.workload, max(1, args.steps), min(1, args.warmup))
+        value, cores, sample, secs = cpu_reference_arm(args.workload, max(1, args.steps), min(1, args.warmup),
+                                                       ref_device=args.ref_device, ref_mode=args.ref_mode, ref_batch=args.batch)
         line = {"impl": "reference", "metric": "EDM Heun samples/sec", "value": value, "unit": "samples/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": NAMES[args.workload], "nsteps": nsteps, "nfe_per_sample": nfe},
-                "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores,
+                                 "kind": "port" if args.ref_device == "cpu" else "port-on-torch-cuda", "sample": sample},
                 "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "nfe_per_s": value * nfe}
         print(json.dumps(line), flush=True)

@@ -150,6 +150,130 @@ __global__ void __launch_bounds__(MT_THREADS) adamw_ema_kernel(float* const* __r
   }
 }
 
+
+// ---- ensemble losses --------------------------------------------------------------------------------
+// EnsembleKarrasModule.loss_fn (karras/karrasmodule_new.py:963-1149): E noisy copies per sample, ONE network call on
+// B*E rows, then an ensemble-aware loss (custom_losses.py:536-865) reduced to a scalar that is multiplied by
+// mean_b(lambda(sigma_b)).  x_noised[b][e] = x[b] + sigma[b] * noise[b][e]   (karrasmodule_new.py:1014-1040)
+__global__ void __launch_bounds__(256) ens_noise_add_kernel(const float* __restrict__ x, const float* __restrict__ noise,
+                                                             const float* __restrict__ sigma, float* __restrict__ out, int E,
+                                                             int64_t CS, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t be = i / CS, n = i - be * CS;
+    const int b = (int)(be / E);
+    out[i] = x[(int64_t)b * CS + n] + sigma[b] * noise[i];
+  }
+}
+
+__device__ __forceinline__ float sgn_f(float v) { return (float)(v > 0.0f) - (float)(v < 0.0f); }
+
+// One thread owns V consecutive elements n of one sample b and walks its E members: D_e = c_out F[b][e][n] + c_skip x_noised,
+//   kind 0 / 1: sum_e l(D_e - x) * keep * s1[b]            (Huber delta=1 / MSE, EnsembleAwareHuberLoss / ...MSELoss)
+//   kind 2    : s1[b] sum_e |D_e - x|  -  s2[b] sum_{i<j} |D_i - D_j|      (EnsembleAwareCRPSLoss, custom_losses.py:765-865)
+// s1 / s2 carry every constant of the reference's reductions (1/(B E N), valid-pixel counts, mean lambda), computed per
+// sample on the host side from sigma and the mask; dF = c_out * dL/dD in the same pass.
+template <int E, int V>
+__global__ void __launch_bounds__(256) ens_loss_kernel(const float* __restrict__ F, const float* __restrict__ x,
+                                                        const float* __restrict__ noise, const float* __restrict__ sigma,
+                                                        const float* __restrict__ c_out_v, const float* __restrict__ c_skip_v,
+                                                        const float* __restrict__ s1_v, const float* __restrict__ s2_v,
+                                                        const float* __restrict__ mask, float* __restrict__ loss_out,
+                                                        float* __restrict__ dF, int B, int64_t CS, int64_t S, int mask_C, int kind) {
+  const int64_t per_b = CS / V, total = (int64_t)B * per_b;
+  float local = 0.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_b);
+    const int64_t n = (i - (int64_t)b * per_b) * V;
+    const float sg = sigma[b], c_out = c_out_v[b], c_skip = c_skip_v[b], s1 = s1_v[b];
+    float xv[V], keep[V], D[E][V], g[E][V];
+    if (V == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(x + (int64_t)b * CS + n);
+      xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+    } else {
+      xv[0] = x[(int64_t)b * CS + n];
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) keep[v] = 1.0f;
+    if (mask != nullptr) {
+      const int64_t mo = mask_C == 1 ? (int64_t)b * S + (n % S) : (int64_t)b * CS + n;
+#pragma unroll
+      for (int v = 0; v < V; ++v) keep[v] = 1.0f - mask[mo + v];
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int64_t o = ((int64_t)b * E + e) * CS + n;
+      float f[V], z[V];
+      if (V == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(F + o), c = *reinterpret_cast<const float4*>(noise + o);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+        z[0] = c.x; z[1] = c.y; z[2] = c.z; z[3] = c.w;
+      } else {
+        f[0] = F[o]; z[0] = noise[o];
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float d = c_out * f[v] + c_skip * (xv[v] + sg * z[v]);
+        D[e][v] = d;
+        const float r = d - xv[v], a = fabsf(r);
+        float l, gr;
+        if (kind == 0) { l = a <= 1.0f ? 0.5f * r * r : a - 0.5f; gr = fminf(fmaxf(r, -1.0f), 1.0f); }
+        else if (kind == 1) { l = r * r; gr = 2.0f * r; }
+        else { l = a; gr = sgn_f(r); }
+        local += s1 * (l * keep[v]);
+        g[e][v] = s1 * (gr * keep[v]);
+      }
+    }
+    if (kind == 2 && E > 1) {
+      const float s2 = s2_v[b];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float sg_sum = 0.0f, pair = 0.0f;
+#pragma unroll
+          for (int j = 0; j < E; ++j) {
+            const float d = D[e][v] - D[j][v];
+            sg_sum += sgn_f(d);
+            if (j > e) pair += fabsf(d);
+          }
+          local -= s2 * pair;
+          g[e][v] -= s2 * sg_sum;
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int64_t o = ((int64_t)b * E + e) * CS + n;
+      if (V == 4) *reinterpret_cast<float4*>(dF + o) = make_float4(c_out * g[e][0], c_out * g[e][1], c_out * g[e][2], c_out * g[e][3]);
+      else dF[o] = c_out * g[e][0];
+    }
+  }
+  local = warp_sum(local);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(loss_out, s);
+  }
+}
+
+template <int E>
+static int ens_loss_launch(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
+                           const float* c_skip, const float* s1, const float* s2, const float* mask, float* loss_out, float* dF,
+                           int B, int64_t CS, int64_t S, int mask_C, int kind, cudaStream_t st) {
+  const bool vec = E <= 8 && CS % 4 == 0 && S % 4 == 0;   // 16-byte accesses; E > 8 would need > 128 registers per thread
+  if (vec) {
+    DSK_LAUNCH((ens_loss_kernel<E, 4>), grid_for((int64_t)B * CS / 4, 256, 8), 256, 0, st, F, x, noise, sigma, c_out, c_skip, s1, s2,
+               mask, loss_out, dF, B, CS, S, mask_C, kind);
+  } else {
+    DSK_LAUNCH((ens_loss_kernel<E, 1>), grid_for((int64_t)B * CS, 256, 8), 256, 0, st, F, x, noise, sigma, c_out, c_skip, s1, s2,
+               mask, loss_out, dF, B, CS, S, mask_C, kind);
+  }
+  return DSK_OK;
+}
+
 }  // namespace dsk
 
 using namespace dsk;
@@ -174,6 +298,39 @@ extern "C" int dsk_precond_loss_fwd_bwd(const float* F, const float* x, const fl
   DSK_LAUNCH(edm_loss_kernel, grid, 256, 0, as_stream(stream), F, x, noise, sigma, mask, loss_out, dF, B, (int64_t)C * S, 0.0f,
              loss_kind, c_out, c_skip, weight);
   return DSK_OK;
+}
+
+
+extern "C" int dsk_ensemble_noise_add(const float* x, const float* noise, const float* sigma, float* out, int B, int E,
+                                      int64_t CS, void* stream) {
+  DSK_REQUIRE(x && noise && sigma && out, "dsk_ensemble_noise_add: null pointer");
+  DSK_REQUIRE(B > 0 && E > 0 && CS > 0, "dsk_ensemble_noise_add: bad arguments");
+  const int64_t total = (int64_t)B * E * CS;
+  DSK_LAUNCH(ens_noise_add_kernel, grid_for(total, 256, 8), 256, 0, as_stream(stream), x, noise, sigma, out, E, CS, total);
+  return DSK_OK;
+}
+
+extern "C" int dsk_ensemble_loss_fwd_bwd(const float* F, const float* x, const float* noise, const float* sigma,
+                                         const float* c_out, const float* c_skip, const float* s1, const float* s2,
+                                         const float* mask, int mask_C, float* loss_out, float* dF, int B, int E, int C,
+                                         int64_t S, int loss_kind, void* stream) {
+  DSK_REQUIRE(F && x && noise && sigma && c_out && c_skip && s1 && loss_out && dF, "dsk_ensemble_loss_fwd_bwd: null pointer");
+  DSK_REQUIRE(B > 0 && C > 0 && S > 0 && loss_kind >= 0 && loss_kind <= 2, "dsk_ensemble_loss_fwd_bwd: bad arguments");
+  DSK_REQUIRE(E >= 1 && E <= 16, "dsk_ensemble_loss_fwd_bwd: ensemble size %d outside 1..16", E);
+  DSK_REQUIRE(loss_kind != 2 || s2 != nullptr, "dsk_ensemble_loss_fwd_bwd: CRPS needs the pair-term scale s2");
+  DSK_REQUIRE(mask == nullptr || mask_C == 1 || mask_C == C, "dsk_ensemble_loss_fwd_bwd: mask channels must be 1 or C");
+  DSK_REQUIRE(mask == nullptr || loss_kind != 2, "dsk_ensemble_loss_fwd_bwd: the CRPS mask acts through s1 / s2 only");
+  const int64_t CS = (int64_t)C * S;
+  cudaStream_t st = as_stream(stream);
+#define DSK_ENS_CASE(e) \
+  case e: return ens_loss_launch<e>(F, x, noise, sigma, c_out, c_skip, s1, s2, mask, loss_out, dF, B, CS, S, mask_C, loss_kind, st);
+  switch (E) {
+    DSK_ENS_CASE(1) DSK_ENS_CASE(2) DSK_ENS_CASE(3) DSK_ENS_CASE(4) DSK_ENS_CASE(5) DSK_ENS_CASE(6) DSK_ENS_CASE(7) DSK_ENS_CASE(8)
+    DSK_ENS_CASE(9) DSK_ENS_CASE(10) DSK_ENS_CASE(11) DSK_ENS_CASE(12) DSK_ENS_CASE(13) DSK_ENS_CASE(14) DSK_ENS_CASE(15)
+    DSK_ENS_CASE(16)
+  }
+#undef DSK_ENS_CASE
+  return DSK_ERR_ARG;
 }
 
 static inline int multi_grid(int ntensors, int64_t max_numel) {

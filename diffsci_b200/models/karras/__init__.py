@@ -1,6 +1,7 @@
 # flake8: noqa
 """Mirror of diffsci.models.karras (reference karras/__init__.py) for the EDM hot path."""
 from .karrasmodule import KarrasModule, KarrasModuleConfig
+from .karrasmodule_new import EnsembleKarrasModule, EnsembleKarrasModuleConfig
 from .schedulers import Scheduler, EDMScheduler, VPScheduler, VEScheduler
 from .noisesamplers import NoiseSampler, EDMNoiseSampler, VPNoiseSampler, VENoiseSampler, UniformNoiseSampler
 from .schedulingfunctions import (SchedulingFunctions, EDMSchedulingFunctions, VPSchedulingFunctions,

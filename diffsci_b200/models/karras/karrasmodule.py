@@ -8,8 +8,10 @@
 Where the reference launches ~30 elementwise ATen kernels per network evaluation plus host syncs,
 this module drives the fused CUDA stages (csrc/sampler.cu, csrc/train.cu) and, for native networks,
 replays one captured CUDA graph per integrator step (engine.SamplerEngine).
-Latent-diffusion (autoencoder), autoregressive, dynamic-loss-weight and multi-space-loss recipes are out
-of scope and raise NotImplementedError instead of silently doing something else.
+Section 8(f)-4: the latent-diffusion wrapper (``autoencoder=``: a frozen user torch module whose ``encode`` / ``decode``
+bracket the loss and the sampler, karrasmodule.py:1192-1234) and, in ``karrasmodule_new.py``, the ensemble losses.
+Autoregressive, dynamic-loss-weight and multi-space-loss recipes (and ``encode_y`` / ``decode_original_y``) are out of
+scope and raise NotImplementedError instead of silently doing something else.
 """
 from __future__ import annotations
 
@@ -171,16 +173,21 @@ class KarrasModule(_Base):
                  masked: bool = False, autoencoder: Optional[torch.nn.Module] = None,
                  autoencoder_conditional: bool = False, encode_y: bool = False, decode_original_y: bool = False):
         super().__init__()
-        if autoencoder is not None or encode_y or decode_original_y or autoencoder_conditional:
-            raise NotImplementedError("diffsci_b200.KarrasModule: latent-diffusion wrappers are out of scope "
-                                      "(SURVEY.md 8f item 4)")
+        if encode_y or decode_original_y:
+            raise NotImplementedError("diffsci_b200.KarrasModule: encode_y / decode_original_y (autoencoders that also "
+                                      "re-encode the condition) are not built")
+        if autoencoder_conditional and autoencoder is None:
+            raise ValueError("autoencoder_conditional=True needs an autoencoder")
         if config.has_edm_batch_norm:
             raise NotImplementedError("has_edm_batch_norm=True: karras/edmbatchnorm.py is empty in the reference "
                                       "(karrasmodule.py:1241 crashes there too)")
         self.model, self.config = model, config
         self.conditional, self.masked = conditional, masked
-        self.autoencoder = None
-        self.autoencoder_conditional = self.encode_y = self.decode_original_y = False
+        self.autoencoder = autoencoder
+        if self.autoencoder is not None:
+            self.freeze_autoencoder()
+        self.autoencoder_conditional = bool(autoencoder_conditional)
+        self.encode_y = self.decode_original_y = False
         self.norm = 1.0
         self.set_optimizer_and_scheduler()
         self.set_loss_metric()
@@ -191,6 +198,16 @@ class KarrasModule(_Base):
         self._engines: dict[Any, _engine.SamplerEngine] = {}
         self.use_cuda_graphs = True
         self.last_nfe = 0
+
+    def freeze_autoencoder(self):
+        """karrasmodule.py:457-460: the autoencoder is a fixed pre-/post-processor, never trained here."""
+        for param in self.autoencoder.parameters():
+            param.requires_grad = False
+
+    def export_description(self) -> dict[str, Any]:
+        return dict(config_description=self.config.export_description(), conditional=self.conditional, masked=self.masked,
+                    autoencoder=self.autoencoder is not None, autoencoder_conditional=self.autoencoder_conditional,
+                    encode_y=self.encode_y)
 
     # ------------------------------------------------------------------ optimiser / loss config
     def set_optimizer_and_scheduler(self, optimizer=None, scheduler=None, scheduler_interval="step"):
@@ -231,13 +248,26 @@ class KarrasModule(_Base):
     # ------------------------------------------------------------------ denoiser
     @property
     def latent_model(self) -> bool:
-        return False
+        return self.autoencoder is not None
 
     def encode(self, x, y=None, record_history=False):
-        return x / self.norm
+        """Data space -> the space the diffusion runs in (karrasmodule.py:1192-1214).  The autoencoder is the user's torch
+        module (any ``encode(x[, y])`` / ``decode(z[, y])`` pair); it runs on torch, outside the fused path."""
+        if record_history:
+            return torch.stack([self.encode(xx, y, record_history=False) for xx in x], dim=0)
+        if self.latent_model:
+            x = self.autoencoder.encode(x, y) if self.autoencoder_conditional else self.autoencoder.encode(x)
+        return x / self.norm if self.norm != 1.0 else x
 
     def decode(self, x, y=None, record_history=False):
-        return x * self.norm
+        """karrasmodule.py:1216-1234."""
+        if record_history:
+            return torch.stack([self.decode(xx, y, record_history=False) for xx in x], dim=0)
+        if self.norm != 1.0:
+            x = x * self.norm
+        if self.latent_model:
+            x = self.autoencoder.decode(x, y) if self.autoencoder_conditional else self.autoencoder.decode(x)
+        return x
 
     def _sigma_data(self) -> float:
         sd = getattr(self.config.preconditioner, "sigma_data", None)
@@ -335,6 +365,9 @@ class KarrasModule(_Base):
         """Denoising loss (karrasmodule.py:569-650): D, lambda(sigma), the loss and dL/dF in one fused kernel -- scalars
         evaluated in-kernel for the EDM preconditioner, passed as [B] vectors for VP / VE / SR3 / custom objects."""
         require_cuda(x, "x")
+        if self.latent_model or self.norm != 1.0:    # the loss lives in the latent space (karrasmodule.py:583-587)
+            with torch.no_grad():
+                x = self.encode(x, y)
         x = x.float().contiguous()
         sigma = sigma.to(x).contiguous()
         if self._injected_loss_noise is not None:
@@ -398,14 +431,22 @@ class KarrasModule(_Base):
         devices), scale by sigma_max and integrate the probability-flow ODE / reverse SDE to sigma = 0."""
         with torch.inference_mode():
             if maximum_batch_size is not None:
-                parts = [self.sample(b, shape, y, guidance, nsteps, record_history, None, integrator, move_to_cpu)
+                parts = [self.sample(b, shape, y, guidance, nsteps, record_history, None, integrator, move_to_cpu,
+                                     is_latent_shape, squeeze_memory_efficiency, return_in_latent_space)
                          for b in get_minibatch_sizes(nsamples, maximum_batch_size)]
                 return torch.cat(parts, dim=1 if record_history else 0)
-            white_noise = torch.randn(*([nsamples] + list(shape))).to(self.device)
             if y is not None:
                 y = dict_to(y, self.device)
+            if self.latent_model and not is_latent_shape:
+                # `shape` is a data-space shape (karrasmodule.py:842-852): the latent shape is whatever the encoder makes
+                # of it; x_T is then drawn at that shape (here on the CPU generator, like every other x_T).
+                probe = self.encode(torch.zeros(*([nsamples] + list(shape)), device=self.device), y)
+                shape = list(probe.shape[1:])
+            white_noise = torch.randn(*([nsamples] + list(shape))).to(self.device)
             return self.propagate_white_noise(white_noise, y, guidance, nsteps, record_history,
-                                              integrator=integrator, move_to_cpu=move_to_cpu)
+                                              integrator=integrator, move_to_cpu=move_to_cpu, latent_shape=is_latent_shape,
+                                              squeeze_memory_efficiency=squeeze_memory_efficiency,
+                                              return_in_latent_space=return_in_latent_space)
 
     def propagate_white_noise(self, x: Tensor, y=None, guidance: float = 1.0, nsteps: int = 100,
                               record_history: bool = False, integrator=None, original_y=None,
@@ -418,7 +459,8 @@ class KarrasModule(_Base):
                 x = x.to(self.device, non_blocking=True)
             result = self.propagate_toward_sample(x, y, guidance, nsteps, record_history, integrator=integrator,
                                                   _prescaled=False)
-            result = self.decode(result, y, record_history) if self.norm != 1.0 else result
+            if not return_in_latent_space and (self.norm != 1.0 or self.latent_model):
+                result = self.decode(result, original_y if original_y is not None else y, record_history)
         return result.detach().cpu() if move_to_cpu else result
 
     def _resolve_integrator(self, integrator):

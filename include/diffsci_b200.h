@@ -306,6 +306,22 @@ int dsk_edm_loss_fwd_bwd(const float* F, const float* x, const float* noise, con
 int dsk_precond_loss_fwd_bwd(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
                              const float* c_skip, const float* weight, const float* mask, float* loss_out, float* dF,
                              int B, int C, int64_t S, int loss_kind, void* stream);
+/* Ensemble training loss (EnsembleKarrasModule.loss_fn, karras/karrasmodule_new.py:963-1149, with the
+ * ensemble-aware metrics of custom_losses.py:536-690 and :765-865).  Layouts: x fp32 [B][C*S]; noise, F, dF, out fp32
+ * [B][E][C*S] (the B*E rows the network sees).
+ *   dsk_ensemble_noise_add:  out[b][e] = x[b] + sigma[b] * noise[b][e]                  (karrasmodule_new.py:1014-1040)
+ *   dsk_ensemble_loss_fwd_bwd: D[b][e] = c_out[b] F[b][e] + c_skip[b] (x[b] + sigma[b] noise[b][e]);
+ *     loss_kind 0 Huber(delta=1) | 1 MSE:  loss += s1[b] * l(D[b][e] - x[b]) * (1 - mask)
+ *     loss_kind 2 CRPS:                    loss += s1[b] * sum_e |D[b][e] - x[b]| - s2[b] * sum_{i<j} |D[b][i] - D[b][j]|
+ *     dF = c_out[b] * dloss/dD.  s1, s2: fp32 [B], every constant of the reference's reductions folded in by the caller
+ *     (mean lambda, 1/(B E N), valid-pixel counts).  mask: NULL or fp32 [B][mask_C][S], mask_C in {1, C}; not for CRPS
+ *     (the reference's CRPS mask only rescales per sample, custom_losses.py:851-857).  E in 1..16.
+ *     loss_out: fp32 [1], zeroed by the caller. */
+int dsk_ensemble_noise_add(const float* x, const float* noise, const float* sigma, float* out, int B, int E, int64_t CS,
+                           void* stream);
+int dsk_ensemble_loss_fwd_bwd(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
+                              const float* c_skip, const float* s1, const float* s2, const float* mask, int mask_C,
+                              float* loss_out, float* dF, int B, int E, int C, int64_t S, int loss_kind, void* stream);
 /* Multi-tensor EMA: shadow_i <- lerp(shadow_i, p_i, 1-beta) (karras/ema.py:139-147) in one launch. */
 int dsk_ema_update(float* const* shadow, const float* const* param, const int64_t* numel, int ntensors,
                    int64_t max_numel, float beta, void* stream);

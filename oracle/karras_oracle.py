@@ -213,6 +213,63 @@ def edm_loss(net, x, sigma, noise, loss_metric="huber", mask=None, sigma_data=0.
     return (w * l + torch.zeros_like(w)).mean()
 
 
+
+# ----------------------------------------------------------------------------- ensemble losses
+def ensemble_metric(D, x, metric: str, mask=None):
+    """The ensemble-aware metrics (custom_losses.py:536-690 Huber / MSE, :765-865 CRPS) as scalars.
+    D: [B, E, *shape] -- or [B, *shape], the 4-D branch the same objects take when n_ensemble <= 1 --, x: [B, *shape],
+    mask: None | [B, 1 | C, *spatial] (1 = ignore)."""
+    single = D.ndim == x.ndim
+    if metric == "CRPS":
+        D5 = D.unsqueeze(1) if single else D
+        B, E = D5.shape[:2]
+        flat = D5.reshape(B, E, -1)
+        to_target = (flat - x.reshape(B, 1, -1)).abs().mean(2).mean(1)                         # :817-819
+        pair = torch.zeros(B, dtype=D.dtype)
+        if E > 1:                                                                             # :823-849
+            pm = (flat.unsqueeze(2) - flat.unsqueeze(1)).abs().mean(3)                         # [B, E, E]
+            iu = torch.triu(torch.ones(E, E), diagonal=1).bool()
+            pair = pm[:, iu].sum(1) / max(E * (E - 1) / 2, 1)
+        crps = to_target - 0.5 * pair
+        if mask is not None:                                                                  # :851-857: a per-sample rescale only
+            mexp = mask.expand(x.shape) if mask.shape[1] == 1 else mask
+            valid = (~mexp.bool()).reshape(B, -1).sum(1).to(D.dtype).clamp(min=1)
+            crps = crps * (valid / flat.shape[2])
+        return crps.mean()
+    el = (lambda a, b: torch.nn.functional.huber_loss(a, b, reduction="none", delta=1.0)) if metric == "huber" else \
+        (lambda a, b: torch.nn.functional.mse_loss(a, b, reduction="none"))
+
+    def masked_mean_4d(pred):                                                                 # :553-560, :610-621
+        l = el(pred, x)
+        if mask is None:
+            return l.mean()
+        return (l * (1 - mask)).sum() / (1 - mask).sum().clamp(min=1)
+    if single:
+        return masked_mean_4d(D)
+    B, E = D.shape[:2]
+    if metric == "mse":                                                                       # :544-552: member by member
+        return torch.stack([masked_mean_4d(D[:, e]) for e in range(E)]).mean()
+    l = el(D, x.unsqueeze(1).expand_as(D))                                                    # Huber, :623-690
+    dims = tuple(range(1, l.ndim))
+    if mask is None:
+        return l.mean(dim=dims).mean()
+    m5 = mask.unsqueeze(2) if mask.shape[1] == 1 else mask.unsqueeze(1)     # [B,1,1,*sp] | [B,1,C,*sp]
+    per_b = (l * (1 - m5)).sum(dim=dims) / (1 - m5).sum(dim=dims).clamp(min=1)                 # the count is NOT expanded over E / C
+    return per_b.mean()
+
+
+def ensemble_loss(net, x, sigma, noise, metric="huber", mask=None, sigma_data=0.5, single=False):
+    """EnsembleKarrasModule.loss_fn (karrasmodule_new.py:963-1149) for n_ensemble = noise.shape[1] > 1, and -- single=True,
+    noise [B, 1, ...] -- old_loss_fn (:1151-1235) on an ensemble-configured module: one denoiser call on the B*E rows, the
+    scalar metric, times the batch MEAN of lambda(sigma)."""
+    B, E = noise.shape[:2]
+    xn = (x.unsqueeze(1) + bcast(sigma, x).unsqueeze(1) * noise).reshape(B * E, *x.shape[1:])
+    D = denoiser(net, xn, sigma.repeat_interleave(E), sigma_data).reshape(B, E, *x.shape[1:])
+    if single:
+        assert E == 1
+        D = D[:, 0]
+    return edm_loss_weight(bcast(sigma, x), sigma_data).mean() * ensemble_metric(D, x, metric, mask)
+
 # ----------------------------------------------------------------------------- EMA
 def power_function_exp_from_std(std: float) -> float:
     """karras/ema.py:9-15."""

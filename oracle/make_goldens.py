@@ -300,7 +300,130 @@ def precond_goldens():
         case(f"precond_{tag}_punetg2d", tag, p2d, 101, "punetg2d_mc8", (2, 1, 16, 16), 302, nsteps=3)
 
 
+
+class _Randn:
+    """Replace torch.randn for ONE expected shape with a pre-drawn tensor (EnsembleKarrasModule.loss_fn draws its [B, E, ...]
+    noise with torch.randn(shape, device=..., dtype=...), karrasmodule_new.py:1024-1025)."""
+
+    def __init__(self, tensor):
+        self.tensor, self.used = tensor, 0
+
+    def __enter__(self):
+        self.orig = torch.randn
+
+        def fake(*a, **k):
+            shape = tuple(a[0]) if len(a) == 1 and isinstance(a[0], (tuple, list, torch.Size)) else tuple(a)
+            if shape == tuple(self.tensor.shape):
+                self.used += 1
+                return self.tensor.clone()
+            return self.orig(*a, **k)
+        torch.randn = fake
+        return self
+
+    def __exit__(self, *a):
+        torch.randn = self.orig
+
+
+class ToyAutoencoder(torch.nn.Module):
+    """A fixed, parameter-carrying encode / decode pair for the latent-diffusion fixtures (NOT an inverse pair -- the wrapper
+    never assumes one): encode = 2x2 average pooling then a 1x1 conv, decode = a 1x1 conv then nearest 2x upsampling.
+    tests/test_gpu_ensemble_latent.py rebuilds it from the same numbers."""
+
+    def __init__(self):
+        super().__init__()
+        self.enc = torch.nn.Conv2d(1, 1, 1)
+        self.dec = torch.nn.Conv2d(1, 1, 1)
+        with torch.no_grad():
+            self.enc.weight.fill_(0.8)
+            self.enc.bias.fill_(0.05)
+            self.dec.weight.fill_(0.7)
+            self.dec.bias.fill_(0.02)
+
+    def encode(self, x):
+        return self.enc(torch.nn.functional.avg_pool2d(x, 2))
+
+    def decode(self, z):
+        return torch.nn.functional.interpolate(self.dec(z), scale_factor=2, mode="nearest")
+
+
+def ensemble_goldens():
+    """SURVEY 8(f)-4 from the LIVE reference: EnsembleKarrasModule.loss_fn (karrasmodule_new.py:963-1149) with the
+    ensemble-aware Huber / MSE / CRPS metrics (custom_losses.py:536-690, 765-865), with and without a mask, for E = 3 and
+    for the n_ensemble = 1 path of an ensemble-configured module; and the latent-diffusion wrapper of KarrasModule
+    (karrasmodule.py:583-587, 1192-1234): loss in the latent space and decode after sampling.
+    ->  tests/golden/ensemble_punetg2d.pt, latent_punetg2d.pt.   python oracle/make_goldens.py --only ensemble"""
+    os.makedirs(OUT, exist_ok=True)
+    refload.load_reference()
+    import diffsci.models as M
+    from diffsci.models.karras.karrasmodule_new import EnsembleKarrasModule, EnsembleKarrasModuleConfig
+    from diffsci.models.nets.punetg import PUNetG
+    from diffsci.models.nets.punetg_config import PUNetGConfig
+    torch.set_num_threads(8)
+    B, E, shape = 3, 3, (1, 16, 16)
+    net = PUNetG(PUNetGConfig(dimension=2, model_channels=8))
+    load_synth(net, 101)                                   # the weights of punetg2d_mc8
+    torch.manual_seed(401)
+    x = torch.randn(B, *shape) * 0.5
+    sigma = torch.tensor([0.07, 0.6, 2.5])
+    noise = torch.randn(B, E, *shape)
+    noise1 = torch.randn(B, 1, *shape)
+    mask = (torch.rand(B, 1, *shape[1:]) > 0.6).float()
+    mask[2] = 1.0                                           # a fully masked sample: the clamp(min=1) branches
+    out = dict(net="punetg2d_mc8", B=B, E=E, x=x, sigma=sigma, noise=noise, noise1=noise1, mask=mask, cases={})
+    for metric in ("huber", "mse", "CRPS"):
+        cfg = EnsembleKarrasModuleConfig.from_edm(loss_metric=metric)
+        cfg.ensemble_size_train = E
+        mod = EnsembleKarrasModule(net, cfg)
+        mod.train()
+        for tag, nz, n_ens, mk in (("E3", noise, E, None), ("E3_mask", noise, E, mask), ("E1", noise1, 1, None),
+                                   ("E1_mask", noise1, 1, mask)):
+            net.zero_grad()
+            if n_ens > 1:
+                with _Randn(nz) as ctx:
+                    L = mod.loss_fn(x, sigma, None, mk, n_ensemble=n_ens)
+                assert ctx.used == 1
+            else:
+                with _Noise([nz[:, 0]]):
+                    L = mod.loss_fn(x, sigma, None, mk, n_ensemble=1)
+            L.backward()
+            out["cases"][f"{metric}_{tag}"] = dict(loss=L.detach().clone(),
+                                                   grads={k: p.grad.clone() for k, p in net.named_parameters() if GRAD_KEYS.search(k)})
+            print(metric, tag, float(L.detach()))
+    torch.save(out, os.path.join(OUT, "ensemble_punetg2d.pt"))
+
+    # ---- latent-diffusion wrapper (plain KarrasModule with an autoencoder)
+    ae = ToyAutoencoder()
+    mod = M.KarrasModule(net, M.KarrasModuleConfig.from_edm(), autoencoder=ae)
+    mod.train()
+    torch.manual_seed(402)
+    xd = torch.randn(2, 1, 32, 32) * 0.5                    # data space 32 x 32 -> latent 16 x 16
+    lat = dict(net="punetg2d_mc8")
+    sg = torch.tensor([0.2, 1.7])
+    ln = torch.randn(2, 1, 16, 16)
+    net.zero_grad()
+    with _Noise([ln]):
+        L = mod.loss_fn(xd, sg, None, None)
+    L.backward()
+    lat.update(x=xd, sigma=sg, noise=ln, loss=L.detach().clone(), encoded=ae.encode(xd).detach(),
+               grads={k: p.grad.clone() for k, p in net.named_parameters() if GRAD_KEYS.search(k)})
+    assert all(p.grad is None for p in ae.parameters()) and not any(p.requires_grad for p in ae.parameters())
+    mod.eval()
+    wn = torch.randn(2, 1, 16, 16)
+    with torch.no_grad():
+        lat["white_noise"] = wn
+        lat["sample_latent"] = mod.propagate_white_noise(wn, nsteps=4, return_in_latent_space=True)
+        lat["sample_decoded"] = mod.propagate_white_noise(wn, nsteps=4)
+        lat["sample_hist_decoded"] = mod.propagate_white_noise(wn, nsteps=4, record_history=True)
+        torch.manual_seed(77)
+        lat["sample_api"] = mod.sample(2, [1, 16, 16], nsteps=4, is_latent_shape=True)
+    print("latent loss", float(L.detach()), "decoded absmax", float(lat["sample_decoded"].abs().max()),
+          tuple(lat["sample_hist_decoded"].shape))
+    torch.save(lat, os.path.join(OUT, "latent_punetg2d.pt"))
+
+
 def main():
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ensemble":
+        return ensemble_goldens()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "precond":
         return precond_goldens()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "circular":

@@ -202,3 +202,81 @@ def test_conditional_and_circular_host_logic(golden):
     vp, ve = d.KarrasModuleConfig.from_vp(), d.KarrasModuleConfig.from_ve()
     assert vp.tag == "vp" and ve.tag == "ve" and float(ve.noisescheduler.maximum_scale) == 100.0
     assert abs(float(vp.noisescheduler.maximum_scale) - float(golden("precond_vp_mlp")["maximum_scale"])) < 1e-5
+
+
+def test_ensemble_config_and_scale_vectors():
+    """SURVEY 8(f)-4 host logic: the factory error behaviour of EnsembleKarrasModuleConfig (karrasmodule_new.py:204-211),
+    the metric switch of EnsembleKarrasModule.set_loss_metric (:832-961) and the per-sample scale vectors handed to
+    dsk_ensemble_loss_fwd_bwd, checked against the oracle metric by evaluating the kernel's formula in fp64 torch."""
+    import diffsci_b200 as d
+    from diffsci_b200.models.karras.karrasmodule_new import _ensemble_scales
+    from oracle import karras_oracle as K
+    with pytest.raises(TypeError, match="Unexpected EMA config key"):
+        d.EnsembleKarrasModuleConfig.from_edm(ensemble_size_train=3)
+    with pytest.raises(NotImplementedError):
+        d.EnsembleKarrasModuleConfig.from_edm(replay_enabled=True)
+    cfg = d.EnsembleKarrasModuleConfig.from_edm(loss_metric="CRPS", ema_enabled=True, ema_type="power")
+    assert (cfg.ensemble_size_train, cfg.ensemble_size_val, cfg.ensemble_size_test) == (1, 1, 1) and cfg.ema_enabled
+    assert cfg.extra_args["ema_type"] == "power" and cfg.tag == "edm"
+    net = d.MLPUncond(2, [8], torch.nn.SiLU())
+    with pytest.raises(ValueError, match="not recognized"):      # CRPS only exists on the ensemble side of the switch
+        d.EnsembleKarrasModule(net, cfg)
+    cfg.ensemble_size_train = 4
+    mod = d.EnsembleKarrasModule(net, cfg)
+    assert mod.loss_metric == "CRPS" and mod.ensemble_metrics and mod.has_ema and len(mod.ema_tracker.profiles) == 1
+    with pytest.raises(NotImplementedError):
+        d.EnsembleKarrasModule(net, d.EnsembleKarrasModuleConfig.from_edm(loss_metric="smoothed_indicator"))
+    with pytest.raises(NotImplementedError):
+        d.EnsembleKarrasModule(net, d.EnsembleKarrasModuleConfig.from_edm(loss_metric={"losses": []}))
+    y = {"a": torch.arange(6.).view(3, 2), "n": None}
+    ye = d.EnsembleKarrasModule._expand_condition(y, 3, 2)
+    assert list(ye) == ["a"] and torch.equal(ye["a"], y["a"].repeat_interleave(2, 0))
+
+    kinds = {"huber": 0, "mse": 1, "CRPS": 2}
+    for metric, kind in kinds.items():
+        for B, E, C, sp, mc, single in [(3, 1, 1, (8, 8), 1, True), (2, 2, 3, (5, 7), 1, False), (4, 3, 2, (4, 4), 2, False),
+                                        (2, 5, 1, (4, 4), 0, False), (3, 1, 2, (4, 4), 0, True)]:
+            torch.manual_seed(B * 10 + E)
+            x = torch.randn(B, C, *sp, dtype=torch.float64)
+            D = torch.randn(B, E, C, *sp, dtype=torch.float64)
+            mask = None
+            if mc:
+                mask = (torch.rand(B, mc, *sp) > 0.5).double()
+                mask[-1] = 1.0
+            lam = torch.tensor(3.7, dtype=torch.float64)
+            truth = lam * K.ensemble_metric(D[:, 0] if single else D, x, metric, mask)
+            s1, s2, mk = _ensemble_scales(kind, lam, B, E, C, x[0, 0].numel(), mask, single=single)
+            r = D - x.unsqueeze(1)
+            el = [torch.where(r.abs() <= 1, 0.5 * r * r, r.abs() - 0.5), r * r, r.abs()][kind]
+            keep = 1.0 if mk is None else (1 - mk.double()).unsqueeze(1)
+            bc = lambda v: v.double().view(B, 1, 1, 1, 1)  # noqa: E731
+            tot = (bc(s1) * el * keep).sum()
+            if kind == 2 and E > 1:
+                for i in range(E):
+                    for j in range(i + 1, E):
+                        tot = tot - (bc(s2)[:, 0] * (D[:, i] - D[:, j]).abs()).sum()
+            assert abs(float(tot - truth)) <= 1e-6 * abs(float(truth)), (metric, B, E, C, mc, single)
+
+
+def test_latent_wrapper_host_logic():
+    """karrasmodule.py:447-460, 1192-1234: the autoencoder is frozen, encode / decode bracket the diffusion space, the
+    condition-encoding variants stay unbuilt."""
+    import diffsci_b200 as d
+    from tests.test_oracle_vs_golden import toy_autoencoder
+    ae = toy_autoencoder()
+    net = d.MLPUncond(2, [8], torch.nn.SiLU())
+    mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm(), autoencoder=ae)
+    assert mod.latent_model and not any(p.requires_grad for p in ae.parameters())
+    assert mod.export_description()["autoencoder"] is True
+    x = torch.randn(2, 1, 8, 8)
+    assert mod.encode(x).shape == (2, 1, 4, 4) and mod.decode(mod.encode(x)).shape == x.shape
+    h = mod.decode(torch.randn(3, 2, 1, 4, 4), record_history=True)
+    assert h.shape == (3, 2, 1, 8, 8)
+    mod.norm = 2.0
+    assert torch.allclose(mod.encode(x), ae.encode(x) / 2.0)
+    assert not d.KarrasModule(net, d.KarrasModuleConfig.from_edm()).latent_model
+    for kw in (dict(encode_y=True), dict(decode_original_y=True)):
+        with pytest.raises(NotImplementedError):
+            d.KarrasModule(net, d.KarrasModuleConfig.from_edm(), autoencoder=ae, **kw)
+    with pytest.raises(ValueError):
+        d.KarrasModule(net, d.KarrasModuleConfig.from_edm(), autoencoder_conditional=True)

@@ -241,3 +241,69 @@ def test_vp_ve_sr3(golden, name):
         assert relmax(o32, g[key]) <= 2.0 * relmax(g[key].double(), o64) + 2e-5, (key, relmax(o32, g[key]))
     L = K.generic_loss(net, g["loss_x"], g["loss_sigma"], g["loss_noise"], kind, fns)
     assert abs(float(L) - float(g["loss_huber"])) <= 2e-5 * abs(float(g["loss_huber"]))
+
+
+# ----------------------------------------------------------------------------- ensemble losses, latent wrapper
+def _leaf_net(g_net, dtype=torch.float32):
+    sd = N.synth_state_dict(g_net["manifest"], g_net["seed"], dtype)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and k != "time_projection.W"}
+    full = dict(sd, **leaves)
+    cfg = cfg_for("punetg", g_net["cfg"])
+    return (lambda x, t: N.punetg_forward(full, cfg, x, t)), leaves
+
+
+@pytest.mark.parametrize("metric", ["huber", "mse", "CRPS"])
+def test_ensemble_losses(golden, metric):
+    """oracle.ensemble_loss vs EnsembleKarrasModule.loss_fn of the LIVE reference (loss and parameter gradients)."""
+    g = golden("ensemble_punetg2d")
+    for tag in ("E3", "E3_mask", "E1", "E1_mask"):
+        ref = g["cases"][f"{metric}_{tag}"]
+        net, leaves = _leaf_net(golden(g["net"]))
+        single = tag.startswith("E1")
+        L = K.ensemble_loss(net, g["x"], g["sigma"], g["noise1"] if single else g["noise"], metric,
+                            g["mask"] if tag.endswith("mask") else None, single=single)
+        assert abs(float(L.detach()) - float(ref["loss"])) <= 5e-6 * abs(float(ref["loss"])), (metric, tag)
+        L.backward()
+        for k, gr in ref["grads"].items():
+            assert relmax(leaves[k].grad, gr) < 2e-4, (metric, tag, k, relmax(leaves[k].grad, gr))
+
+
+def toy_autoencoder():
+    """The fixed encode / decode pair of oracle/make_goldens.py: ToyAutoencoder (same numbers)."""
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.enc, self.dec = torch.nn.Conv2d(1, 1, 1), torch.nn.Conv2d(1, 1, 1)
+            with torch.no_grad():
+                self.enc.weight.fill_(0.8), self.enc.bias.fill_(0.05), self.dec.weight.fill_(0.7), self.dec.bias.fill_(0.02)
+
+        def encode(self, x):
+            return self.enc(torch.nn.functional.avg_pool2d(x, 2))
+
+        def decode(self, z):
+            return torch.nn.functional.interpolate(self.dec(z), scale_factor=2, mode="nearest")
+    return Toy()
+
+
+def test_latent_wrapper(golden):
+    """karrasmodule.py:583-587, 893-896, 1192-1234: loss on encode(x), decode after sampling."""
+    g = golden("latent_punetg2d")
+    ae = toy_autoencoder()
+    with torch.no_grad():
+        z = ae.encode(g["x"])
+    assert torch.allclose(z, g["encoded"], rtol=1e-6, atol=1e-7)
+    net, leaves = _leaf_net(golden(g["net"]))
+    L = K.edm_loss(net, z, g["sigma"], g["noise"], "huber")
+    assert abs(float(L.detach()) - float(g["loss"])) <= 5e-6 * abs(float(g["loss"]))
+    L.backward()
+    for k, gr in g["grads"].items():
+        assert relmax(leaves[k].grad, gr) < 2e-4, k
+    net32, net64 = oracle_net(golden(g["net"])), oracle_net(golden(g["net"]), torch.float64)
+    with torch.no_grad():
+        lat = K.sample_from_white_noise(net32, g["white_noise"], 4, "heun")
+        lat64 = K.sample_from_white_noise(net64, g["white_noise"].double(), 4, "heun")
+        budget = 2.0 * relmax(g["sample_latent"].double(), lat64) + 2e-5
+        assert relmax(lat, g["sample_latent"]) <= budget
+        assert torch.allclose(ae.decode(g["sample_latent"]), g["sample_decoded"], rtol=1e-6, atol=1e-6)
+        assert torch.allclose(g["sample_hist_decoded"][-1], g["sample_decoded"], rtol=1e-6, atol=1e-6)
+        assert tuple(g["sample_hist_decoded"].shape) == (5, 2, 1, 32, 32)
