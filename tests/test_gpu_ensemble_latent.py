@@ -11,7 +11,8 @@ KINDS = {"huber": 0, "mse": 1, "CRPS": 2}
 
 
 def relmax(a, b):
-    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
 @pytest.mark.parametrize("metric", ["huber", "mse", "CRPS"])
@@ -173,7 +174,11 @@ def test_latent_wrapper_vs_live_reference(golden):
     assert hist.shape == g["sample_hist_decoded"].shape and relmax(hist, g["sample_hist_decoded"]) <= budget
     torch.manual_seed(77)
     api = mod.sample(2, [1, 16, 16], nsteps=4, is_latent_shape=True).cpu()
-    assert relmax(api, g["sample_api"]) <= budget
+    torch.manual_seed(77)                       # its own x_T, hence its own fp64 budget (chained random-weight evaluations)
+    wn2 = torch.randn(2, 1, 16, 16)
+    with torch.no_grad():
+        truth = toy_autoencoder().double().decode(K.sample_from_white_noise(net64, wn2.double(), 4, "heun"))
+    assert relmax(api, g["sample_api"]) <= 2.0 * relmax(g["sample_api"], truth) + 2e-5
     # a data-space shape: the latent shape comes from the encoder
     out = mod.sample(3, [1, 32, 32], nsteps=3)
     assert out.shape == (3, 1, 32, 32) and torch.isfinite(out).all()
