@@ -195,6 +195,8 @@ class SamplerEngine:
         if noises is not None:
             self._noise[:nsteps].copy_(noises.reshape(nsteps, N))
         self.seed = int(seed)
+        if self.native:       # captured graphs read the PACKED weight copies: refresh them (in place, same addresses) when the
+            self.plan.prepare()   # parameters changed since the last run (optimizer steps, EMA apply_to, load_state_dict)
         if self.use_graphs:   # capture (with a throw-away warm-up step on zero state) before the real run starts
             self.x.zero_()
             self.row.zero_()

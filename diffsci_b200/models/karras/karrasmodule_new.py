@@ -17,6 +17,7 @@ raise NotImplementedError.
 """
 from __future__ import annotations
 
+from contextlib import contextmanager
 from typing import Any, Dict, Optional, Union
 
 import torch
@@ -167,6 +168,8 @@ class EnsembleKarrasModule(KarrasModule):
         super().__init__(model, config, conditional, masked, autoencoder, autoencoder_conditional, encode_y,
                          decode_original_y)
         self.start_ema()
+        self._ema_scope_depth = 0
+        self._ema_validation_backup = None
 
     # ------------------------------------------------------------------ loss configuration
     def set_loss_metric(self):
@@ -297,3 +300,51 @@ class EnsembleKarrasModule(KarrasModule):
     def on_before_zero_grad(self, optimizer):
         if self.has_ema:
             self.ema_tracker.update(self.model)
+
+    # EMA weights for validation / eval-time sampling (karrasmodule_new.py:2190-2227).  apply_to / restore copy into the live
+    # parameters in place; the sampler engine refreshes its packed weight copies at the start of every run.
+    def _should_use_ema_for_validation(self) -> bool:
+        return self.has_ema and getattr(self.config, "ema_use_for_validation", True) and self._ema_scope_depth == 0
+
+    def _should_use_ema_for_sampling(self) -> bool:
+        return (self.has_ema and getattr(self.config, "ema_use_for_sampling", True) and not self.training and
+                self._ema_scope_depth == 0)
+
+    @contextmanager
+    def ema_scope(self, enabled: bool = True):
+        if not enabled or not self.has_ema or self._ema_scope_depth > 0:
+            yield
+            return
+        with torch.inference_mode(False), torch.no_grad():
+            backup = self.ema_tracker.apply_to(self.model)
+        self._ema_scope_depth += 1
+        try:
+            yield
+        finally:
+            with torch.inference_mode(False), torch.no_grad():
+                self.ema_tracker.restore(self.model, backup)
+            self._ema_scope_depth = max(self._ema_scope_depth - 1, 0)
+
+    def on_validation_epoch_start(self):
+        if self._should_use_ema_for_validation():
+            with torch.no_grad():
+                self._ema_validation_backup = self.ema_tracker.apply_to(self.model)
+            self._ema_scope_depth += 1
+
+    def on_validation_epoch_end(self):
+        if self._ema_validation_backup is not None:
+            self.ema_tracker.restore(self.model, self._ema_validation_backup)
+            self._ema_validation_backup = None
+            self._ema_scope_depth = max(self._ema_scope_depth - 1, 0)
+
+    def sample(self, nsamples: int, shape, y=None, guidance: float = 1.0, nsteps: int = 100, record_history: bool = False,
+               maximum_batch_size: Optional[int] = None, integrator=None, move_to_cpu: bool = False,
+               is_latent_shape: bool = False, squeeze_memory_efficiency: bool = False,
+               return_in_latent_space: bool = False, use_ema: Optional[bool] = None) -> Tensor:
+        """karrasmodule_new.py:1386-1471: KarrasModule.sample, on the EMA weights when the module is in eval mode and the
+        config says so (or use_ema=True)."""
+        if use_ema is None:
+            use_ema = self._should_use_ema_for_sampling()
+        with self.ema_scope(enabled=bool(use_ema)):
+            return super().sample(nsamples, shape, y, guidance, nsteps, record_history, maximum_batch_size, integrator,
+                                  move_to_cpu, is_latent_shape, squeeze_memory_efficiency, return_in_latent_space)

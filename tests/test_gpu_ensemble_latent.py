@@ -185,3 +185,39 @@ def test_latent_wrapper_vs_live_reference(golden):
     assert mod.sample(3, [1, 32, 32], nsteps=3, return_in_latent_space=True).shape == (3, 1, 16, 16)
     with pytest.raises(NotImplementedError):
         d.KarrasModule(net, d.KarrasModuleConfig.from_edm(), autoencoder=ae, encode_y=True)
+
+
+def test_ema_weights_for_sampling(golden):
+    """karrasmodule_new.py:1400-1405, 2208-2227: in eval mode sample() runs on the EMA weights (apply_to, sample, restore) --
+    with the engine cached from an earlier run on the live weights."""
+    import diffsci_b200 as d
+    from tests.test_gpu_nets import build_net
+    g = golden("punetg2d_mc8")
+    net = build_net(g, "bf16")
+    cfg = d.EnsembleKarrasModuleConfig.from_edm(ema_enabled=True, ema_decay=0.0)
+    mod = d.EnsembleKarrasModule(net, cfg)
+    shape = list(g["x"].shape[1:])
+
+    def draw(use_ema=None):
+        torch.manual_seed(21)
+        return mod.sample(2, shape, nsteps=3, use_ema=use_ema).cpu()
+    mod.eval()
+    live0 = draw(use_ema=False)
+    assert torch.equal(draw(), live0)                         # shadow == live weights right after construction
+    mod.train()
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if k.endswith("weight") and p.ndim >= 4:
+                p.mul_(0.5)
+    mod.on_before_zero_grad(None)                             # decay 0: the shadow becomes the updated weights ...
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if k.endswith("weight") and p.ndim >= 4:
+                p.mul_(2.0)                                   # ... and the live weights go back
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    mod.eval()
+    ema = draw()
+    assert not torch.equal(ema, live0) and torch.equal(draw(use_ema=False), live0)
+    assert all(torch.equal(v, before[k]) for k, v in net.state_dict().items())      # restored
+    mod.train()
+    assert torch.equal(draw(), live0)                         # training mode: live weights

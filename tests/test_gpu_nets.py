@@ -319,3 +319,29 @@ def test_inpaint_repaint_partial_vs_live_reference(golden):
     assert r.shape == g["x_orig"].shape and torch.isfinite(r).all()
     it = mod.interpolate_images(dev(g["x_orig"][0]), dev(g["x_orig"][1]), 3, nsteps=n)
     assert it.shape == (3,) + tuple(g["x_orig"].shape[1:]) and torch.isfinite(it).all()
+
+
+@pytest.mark.parametrize("name,precision", [("punetg2d_mc8", "fp32"), ("punetg2d_mc8", "bf16"), ("adm2d_mc8", "bf16")])
+def test_cached_sampler_engine_sees_weight_updates(golden, name, precision):
+    """sample -> change the weights in place (an optimizer step, EMA apply_to / restore, load_state_dict) -> sample again with
+    the CACHED engine: the captured graphs read packed weight copies, which must be refreshed before they are replayed."""
+    import diffsci_b200 as d
+    g = golden(name)
+    net = build_net(g, precision)
+    mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm()).eval()
+    torch.manual_seed(11)
+    wn = torch.randn(2, *g["x"].shape[1:])
+    a0 = mod.propagate_white_noise(wn.to(DEV), nsteps=3).cpu()
+    engines = dict(mod._engines)
+    backup = {k: v.clone() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if k.endswith("weight") and p.ndim >= 4:
+                p.mul_(0.5)
+    a1 = mod.propagate_white_noise(wn.to(DEV), nsteps=3).cpu()
+    assert dict(mod._engines).keys() == engines.keys() and all(mod._engines[k] is engines[k] for k in engines)
+    fresh = d.KarrasModule(net, d.KarrasModuleConfig.from_edm()).eval()       # same (updated) parameters, new engine
+    b1 = fresh.propagate_white_noise(wn.to(DEV), nsteps=3).cpu()
+    assert torch.equal(a1, b1) and not torch.equal(a1, a0)
+    net.load_state_dict(backup)
+    assert torch.equal(mod.propagate_white_noise(wn.to(DEV), nsteps=3).cpu(), a0)
