@@ -85,6 +85,7 @@ SIGNATURES = {
     "dsk_softmax_rows": [p, i64, i32, p],
     "dsk_edm_loss_fwd_bwd": [p, p, p, p, p, p, p, i32, i32, i64, f32, i32, p],
     "dsk_precond_loss_fwd_bwd": [p, p, p, p, p, p, p, p, p, p, i32, i32, i64, i32, p],
+    "dsk_precond_loss_rows": [p, p, p, p, p, p, p, p, p, p, i32, i32, i64, i32, p],
     "dsk_ensemble_noise_add": [p, p, p, p, i32, i32, i64, p],
     "dsk_ensemble_loss_fwd_bwd": [p, p, p, p, p, p, p, p, p, i32, p, p, i32, i32, i32, i64, i32, p],
     "dsk_ema_update": [p, p, p, i32, i64, f32, p],

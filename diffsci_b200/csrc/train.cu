@@ -57,6 +57,48 @@ __global__ void __launch_bounds__(256) edm_loss_kernel(const float* __restrict__
   }
 }
 
+// The same loss with one partial sum PER SAMPLE (grid.y = b): loss_b[b] = sum_n lam_b l(D, x) keep / (B C S).  Needed when a
+// per-sample factor multiplies the loss on the host side and has its own gradient -- the learned uncertainty weighting
+// exp(-u(c_noise)) of KarrasModule.loss_fn with has_dynamic_loss_weight (karrasmodule.py:594-602, DynamicLossWeight :1256-1278).
+__global__ void __launch_bounds__(256) precond_loss_rows_kernel(const float* __restrict__ F, const float* __restrict__ x,
+                                                                 const float* __restrict__ noise, const float* __restrict__ sigma,
+                                                                 const float* __restrict__ mask, float* __restrict__ loss_b,
+                                                                 float* __restrict__ dF, int B, int64_t CS, int kind,
+                                                                 const float* __restrict__ c_out_v, const float* __restrict__ c_skip_v,
+                                                                 const float* __restrict__ lam_v) {
+  const int b = blockIdx.y;
+  const float invN = 1.0f / (float)((int64_t)B * CS);
+  const float sg = sigma[b], c_out = c_out_v[b], c_skip = c_skip_v[b], lam = lam_v[b];
+  const int64_t base = (int64_t)b * CS;
+  float local = 0.0f;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < CS; n += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = base + n;
+    const float xv = x[i];
+    const float r = c_out * F[i] + c_skip * (xv + sg * noise[i]) - xv;
+    float l, g;
+    if (kind == 0) {
+      const float a = fabsf(r);
+      l = a <= 1.0f ? 0.5f * r * r : a - 0.5f;
+      g = fminf(fmaxf(r, -1.0f), 1.0f);
+    } else {
+      l = r * r;
+      g = 2.0f * r;
+    }
+    const float keep = mask != nullptr ? 1.0f - mask[i] : 1.0f;
+    local += lam * (l * keep);
+    dF[i] = (c_out * lam) * (g * keep) * invN;
+  }
+  local = warp_sum(local);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(loss_b + b, s * invN);
+  }
+}
+
 // Multi-tensor kernels.  The tensors differ in size by four orders of magnitude (a bias vs a 512x512x3x3 weight), so
 // the work is cut into fixed chunks of MT_CHUNK elements over ALL tensors: every block builds the prefix of chunk counts in
 // shared memory (a few hundred entries) and grid-strides over the global chunk index, binary-searching its tensor.
@@ -263,14 +305,15 @@ template <int E>
 static int ens_loss_launch(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
                            const float* c_skip, const float* s1, const float* s2, const float* mask, float* loss_out, float* dF,
                            int B, int64_t CS, int64_t S, int mask_C, int kind, cudaStream_t st) {
-  const bool vec = E <= 8 && CS % 4 == 0 && S % 4 == 0;   // 16-byte accesses; E > 8 would need > 128 registers per thread
-  if (vec) {
-    DSK_LAUNCH((ens_loss_kernel<E, 4>), grid_for((int64_t)B * CS / 4, 256, 8), 256, 0, st, F, x, noise, sigma, c_out, c_skip, s1, s2,
-               mask, loss_out, dF, B, CS, S, mask_C, kind);
-  } else {
-    DSK_LAUNCH((ens_loss_kernel<E, 1>), grid_for((int64_t)B * CS, 256, 8), 256, 0, st, F, x, noise, sigma, c_out, c_skip, s1, s2,
-               mask, loss_out, dF, B, CS, S, mask_C, kind);
+  if constexpr (E <= 8) {   // 16-byte accesses; E > 8 would need > 128 registers per thread
+    if (CS % 4 == 0 && S % 4 == 0) {
+      DSK_LAUNCH((ens_loss_kernel<E, 4>), grid_for((int64_t)B * CS / 4, 256, 8), 256, 0, st, F, x, noise, sigma, c_out, c_skip, s1,
+                 s2, mask, loss_out, dF, B, CS, S, mask_C, kind);
+      return DSK_OK;
+    }
   }
+  DSK_LAUNCH((ens_loss_kernel<E, 1>), grid_for((int64_t)B * CS, 256, 8), 256, 0, st, F, x, noise, sigma, c_out, c_skip, s1, s2,
+             mask, loss_out, dF, B, CS, S, mask_C, kind);
   return DSK_OK;
 }
 
@@ -300,6 +343,21 @@ extern "C" int dsk_precond_loss_fwd_bwd(const float* F, const float* x, const fl
   return DSK_OK;
 }
 
+
+extern "C" int dsk_precond_loss_rows(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
+                                     const float* c_skip, const float* weight, const float* mask, float* loss_b, float* dF,
+                                     int B, int C, int64_t S, int loss_kind, void* stream) {
+  DSK_REQUIRE(F && x && noise && sigma && c_out && c_skip && weight && loss_b && dF, "dsk_precond_loss_rows: null pointer");
+  DSK_REQUIRE(B > 0 && B <= 65535 && C > 0 && S > 0 && (loss_kind == 0 || loss_kind == 1), "dsk_precond_loss_rows: bad arguments");
+  const int64_t CS = (int64_t)C * S;
+  int per_b = (int)((CS + 255) / 256);
+  const int cap = (8 * DSK_NUM_SMS + B - 1) / B;
+  if (per_b > cap) per_b = cap;
+  if (per_b < 1) per_b = 1;
+  DSK_LAUNCH(precond_loss_rows_kernel, dim3(per_b, B), 256, 0, as_stream(stream), F, x, noise, sigma, mask, loss_b, dF, B, CS,
+             loss_kind, c_out, c_skip, weight);
+  return DSK_OK;
+}
 
 extern "C" int dsk_ensemble_noise_add(const float* x, const float* noise, const float* sigma, float* out, int B, int E,
                                       int64_t CS, void* stream) {

@@ -159,6 +159,46 @@ class _EDMLossFn(torch.autograd.Function):
         return dF * g, None, None, None, None, None, None, None
 
 
+class _RowLossFn(torch.autograd.Function):
+    """sum_b m[b] * loss_b[b] with loss_b from dsk_precond_loss_rows (per-sample partial sums of the fused loss): gradients
+    flow to F (m[b] * dF[b], dF from the same launch) and to the per-sample factor m (loss_b)."""
+
+    @staticmethod
+    def forward(ctx, F, m, x, noise, sigma, mask, coeffs, kind):
+        B = x.shape[0]
+        Cc = x.shape[1] if x.ndim > 1 else 1
+        S = x.numel() // (B * Cc)
+        loss_b = torch.zeros((B,), dtype=torch.float32, device=x.device)
+        dF = torch.empty_like(x, dtype=torch.float32)
+        c_out, c_skip, lam = coeffs
+        check(lib.dsk_precond_loss_rows(ptr(F), ptr(x), ptr(noise), ptr(sigma), ptr(c_out), ptr(c_skip), ptr(lam), ptr(mask),
+                                        ptr(loss_b), ptr(dF), B, Cc, S, int(kind), stream()))
+        ctx.save_for_backward(dF, loss_b, m)
+        return (m * loss_b).sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        dF, loss_b, m = ctx.saved_tensors
+        return dF * (g * m).view(-1, *([1] * (dF.ndim - 1))), g * loss_b, None, None, None, None, None, None
+
+
+class DynamicLossWeight(torch.nn.Module):
+    """Learned log-uncertainty u(c_noise) of the loss weighting (karrasmodule.py:1256-1278): a fixed random cosine feature
+    map of the noise conditioner followed by one linear layer; the loss becomes mean(lambda * exp(-u) * l + u).  A [B]-sized
+    torch module, like the preconditioner scalars."""
+
+    def __init__(self, nhidden: int, scale: float = 1.0):
+        super().__init__()
+        self.nhidden = nhidden
+        self.register_buffer("fourier_weights", torch.randn(nhidden) * scale)
+        self.register_buffer("fourier_bias", torch.rand(nhidden) * scale)
+        self.linear = torch.nn.Linear(nhidden, 1)
+
+    def forward(self, x):
+        h = torch.cos(x.unsqueeze(1) * self.fourier_weights + self.fourier_bias)
+        return self.linear(h).squeeze(1)
+
+
 def _rowwise_axpy(a_vec: Tensor, z: Tensor, b_vec: Tensor, x: Tensor) -> Tensor:
     """out[b, ...] = a[b]*z[b, ...] + b_vec[b]*x[b, ...] in one launch (dsk_precond_denoise on flat rows)."""
     B = x.shape[0]
@@ -192,12 +232,16 @@ class KarrasModule(_Base):
         self.set_optimizer_and_scheduler()
         self.set_loss_metric()
         self.edm_batch_norm = None
-        self.dynamic_loss_weight = None
-        if config.has_dynamic_loss_weight:
-            raise NotImplementedError("diffsci_b200.KarrasModule: dynamic_loss_weight is not built yet")
+        self.start_dynamic_loss_weight()
         self._engines: dict[Any, _engine.SamplerEngine] = {}
         self.use_cuda_graphs = True
         self.last_nfe = 0
+
+    def start_dynamic_loss_weight(self):
+        """karrasmodule.py:1243-1249 (created after the default optimizer, as in the reference: pass your own optimizer
+        over module.parameters() to train it)."""
+        self.dynamic_loss_weight = (DynamicLossWeight(self.config.dynamic_loss_weight)
+                                    if self.config.has_dynamic_loss_weight else None)
 
     def freeze_autoencoder(self):
         """karrasmodule.py:457-460: the autoencoder is a fixed pre-/post-processor, never trained here."""
@@ -386,11 +430,16 @@ class KarrasModule(_Base):
             F = ops.cl_to_nchw(F.view(B, 1, 1, S, Cc), 3).view(x.shape)
         m = None if mask is None else mask.to(x).expand_as(x).contiguous()
         coeffs = None
-        if not (type(pre) is preconditioners.EDMPreconditioner and
-                type(self.config.noisesampler) is noisesamplers.EDMNoiseSampler):
+        if self.dynamic_loss_weight is not None or not (type(pre) is preconditioners.EDMPreconditioner and
+                                                        type(self.config.noisesampler) is noisesamplers.EDMNoiseSampler):
             # VP / VE / SR3 / custom objects: their per-sample scalars, the same fused loss + dL/dF kernel
             coeffs = tuple(v.float().contiguous() for v in (pre.output_scaling(sigma), pre.skip_scaling(sigma),
                                                             self.config.noisesampler.loss_weighting(sigma)))
+        if self.dynamic_loss_weight is not None:
+            # weight / exp(u), bias + u  (karrasmodule.py:596-602): u on torch autograd, the per-sample losses from one launch
+            u = self.dynamic_loss_weight(cond_noise).float()
+            return _RowLossFn.apply(F.float().contiguous().view(x.shape), torch.exp(-u), x, noise.contiguous(), sigma, m,
+                                    coeffs, self.loss_kind) + u.mean()
         return _EDMLossFn.apply(F.float().contiguous().view(x.shape), x, noise.contiguous(), sigma, m,
                                 self._sigma_data(), self.loss_kind, coeffs)
 

@@ -213,6 +213,9 @@ class EnsembleKarrasModule(KarrasModule):
         if n_ensemble <= 1 and not _force_ensemble:
             return self.old_loss_fn(x, sigma, y, mask)
         E = max(int(n_ensemble), 1)
+        if self.dynamic_loss_weight is not None:
+            # the reference's own ensemble branch fails here (cond_noise.mean(dim=1) on a 1-D tensor, karrasmodule_new.py:1103)
+            raise NotImplementedError("diffsci_b200: dynamic_loss_weight with the ensemble-aware metrics")
         if E > MAX_ENSEMBLE:
             raise NotImplementedError(f"diffsci_b200: n_ensemble={E} > {MAX_ENSEMBLE}")
         require_cuda(x, "x")

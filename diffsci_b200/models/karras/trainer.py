@@ -45,6 +45,9 @@ class EDMTrainer:
         if module.conditional or getattr(net, "conditional_embedding", None) is not None or getattr(net, "cond_drop", None) is not None:
             raise NotImplementedError("EDMTrainer: conditional models train through KarrasModule.training_step + a torch "
                                       "optimizer (the native backward returns d loss / d embedding to autograd)")
+        if getattr(module, "dynamic_loss_weight", None) is not None or getattr(module, "latent_model", False):
+            raise NotImplementedError("EDMTrainer: dynamic loss weighting and latent-diffusion wrappers train through "
+                                      "KarrasModule.training_step + a torch optimizer")
         self.module, self.net, self.ema, self.group = module, net, ema, process_group
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         self.bucket_bytes = int(bucket_mb * (1 << 20))

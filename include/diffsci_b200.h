@@ -306,6 +306,13 @@ int dsk_edm_loss_fwd_bwd(const float* F, const float* x, const float* noise, con
 int dsk_precond_loss_fwd_bwd(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
                              const float* c_skip, const float* weight, const float* mask, float* loss_out, float* dF,
                              int B, int C, int64_t S, int loss_kind, void* stream);
+/* The same loss reduced PER SAMPLE: loss_b[b] (fp32 [B], zeroed by the caller) = sum over the sample of weight[b] * l * (1-mask)
+ * / (B*C*S), so that sum_b loss_b = the scalar above.  For a per-sample factor applied on the host side that needs its own
+ * gradient: the learned uncertainty weighting of has_dynamic_loss_weight (karrasmodule.py:594-602, DynamicLossWeight
+ * :1256-1278): loss = sum_b exp(-u_b) loss_b + mean(u). */
+int dsk_precond_loss_rows(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
+                          const float* c_skip, const float* weight, const float* mask, float* loss_b, float* dF,
+                          int B, int C, int64_t S, int loss_kind, void* stream);
 /* Ensemble training loss (EnsembleKarrasModule.loss_fn, karras/karrasmodule_new.py:963-1149, with the
  * ensemble-aware metrics of custom_losses.py:536-690 and :765-865).  Layouts: x fp32 [B][C*S]; noise, F, dF, out fp32
  * [B][E][C*S] (the B*E rows the network sees).

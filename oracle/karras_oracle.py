@@ -196,12 +196,24 @@ def edm_loss_weight(sigma, sigma_data=0.5):
     return (sigma ** 2 + sd ** 2) / ((sigma * sd) ** 2)
 
 
-def edm_loss(net, x, sigma, noise, loss_metric="huber", mask=None, sigma_data=0.5):
-    """KarrasModule.loss_fn (karrasmodule.py:569-650), single-loss branch, noise injected."""
+def dynamic_loss_weight(state, c_noise):
+    """DynamicLossWeight.forward (karrasmodule.py:1270-1278): cos features of c_noise, one linear layer -> u [B]."""
+    h = torch.cos(c_noise.unsqueeze(1) * state["fourier_weights"] + state["fourier_bias"])
+    return (h @ state["linear.weight"].t() + state["linear.bias"]).squeeze(1)
+
+
+def edm_loss(net, x, sigma, noise, loss_metric="huber", mask=None, sigma_data=0.5, dynamic_state=None):
+    """KarrasModule.loss_fn (karrasmodule.py:569-650), single-loss branch, noise injected.  dynamic_state: the state dict of
+    a DynamicLossWeight -> weight / exp(u), bias + u with u = u(c_noise) (:594-602)."""
     bs = bcast(sigma, x)
     x_noised = x + bs * noise
     D = denoiser(net, x_noised, sigma, sigma_data)
     w = edm_loss_weight(bs, sigma_data)
+    bias = torch.zeros_like(w)
+    if dynamic_state is not None:
+        u = bcast(dynamic_loss_weight(dynamic_state, edm_precond(sigma, sigma_data)[3]), x)
+        w = w / torch.exp(u)
+        bias = bias + u
     if loss_metric == "huber":
         l = torch.nn.functional.huber_loss(D, x, reduction="none", delta=1.0)
     elif loss_metric == "mse":
@@ -210,7 +222,7 @@ def edm_loss(net, x, sigma, noise, loss_metric="huber", mask=None, sigma_data=0.
         raise ValueError(loss_metric)
     if mask is not None:
         l = l * (1 - mask.expand_as(l))
-    return (w * l + torch.zeros_like(w)).mean()
+    return (w * l + bias).mean()
 
 
 

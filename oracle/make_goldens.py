@@ -420,6 +420,37 @@ def ensemble_goldens():
           tuple(lat["sample_hist_decoded"].shape))
     torch.save(lat, os.path.join(OUT, "latent_punetg2d.pt"))
 
+    # ---- learned uncertainty weighting (has_dynamic_loss_weight; karrasmodule.py:594-602, 1243-1278)
+    dyn = dict(net="punetg2d_mc8", nhidden=8)
+    mod = M.KarrasModule(net, M.KarrasModuleConfig.from_edm(dynamic_loss_weight=8))
+    mod.train()
+    torch.manual_seed(403)
+    dlw = mod.dynamic_loss_weight
+    with torch.no_grad():
+        dlw.fourier_weights.copy_(torch.randn(8))
+        dlw.fourier_bias.copy_(torch.rand(8))
+        dlw.linear.weight.copy_(torch.randn(1, 8) * 0.3)
+        dlw.linear.bias.fill_(0.1)
+    dyn["dlw_state"] = {k: v.clone() for k, v in dlw.state_dict().items()}
+    xq, sq, nq = torch.randn(3, 1, 16, 16) * 0.5, torch.tensor([0.05, 0.7, 3.0]), torch.randn(3, 1, 16, 16)
+    mq = (torch.rand(3, 1, 16, 16) > 0.5).float()
+    dyn.update(x=xq, sigma=sq, noise=nq, mask=mq)
+    for metric in ("huber", "mse"):
+        mod = M.KarrasModule(net, M.KarrasModuleConfig.from_edm(dynamic_loss_weight=8, loss_metric=metric))
+        mod.dynamic_loss_weight.load_state_dict(dyn["dlw_state"])
+        mod.train()
+        for tag, mk in (("", None), ("_mask", mq)):
+            net.zero_grad()
+            mod.dynamic_loss_weight.zero_grad()
+            with _Noise([nq]):
+                L = mod.loss_fn(xq, sq, None, mk)
+            L.backward()
+            dyn[f"{metric}{tag}"] = dict(loss=L.detach().clone(),
+                                         grads={k: p.grad.clone() for k, p in net.named_parameters() if GRAD_KEYS.search(k)},
+                                         dlw_grads={k: p.grad.clone() for k, p in mod.dynamic_loss_weight.named_parameters()})
+            print("dynamic", metric, tag, float(L.detach()))
+    torch.save(dyn, os.path.join(OUT, "dynweight_punetg2d.pt"))
+
 
 def main():
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ensemble":

@@ -221,3 +221,30 @@ def test_ema_weights_for_sampling(golden):
     assert all(torch.equal(v, before[k]) for k, v in net.state_dict().items())      # restored
     mod.train()
     assert torch.equal(draw(), live0)                         # training mode: live weights
+
+
+@pytest.mark.parametrize("metric", ["huber", "mse"])
+def test_dynamic_loss_weight_vs_live_reference(golden, metric):
+    """KarrasModuleConfig.from_edm(dynamic_loss_weight=n): loss = mean(lambda exp(-u) l + u), u = DynamicLossWeight(c_noise);
+    per-sample loss sums from dsk_precond_loss_rows; gradients of the network AND of the uncertainty head vs the live reference."""
+    import diffsci_b200 as d
+    from tests.test_gpu_nets import build_net
+    g = golden("dynweight_punetg2d")
+    net = build_net(golden(g["net"])).train()
+    mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm(dynamic_loss_weight=g["nhidden"], loss_metric=metric)).train()
+    assert list(mod.dynamic_loss_weight.state_dict().keys()) == list(g["dlw_state"].keys())
+    mod.dynamic_loss_weight.load_state_dict(g["dlw_state"])
+    mod.dynamic_loss_weight.to(DEV)
+    for tag in ("", "_mask"):
+        ref = g[metric + tag]
+        net.zero_grad()
+        mod.dynamic_loss_weight.zero_grad()
+        mod._injected_loss_noise = g["noise"]
+        L = mod.loss_fn(g["x"].to(DEV), g["sigma"].to(DEV), None, g["mask"].to(DEV) if tag else None)
+        L.backward()
+        assert abs(float(L) - float(ref["loss"])) < 5e-5 * abs(float(ref["loss"])), (tag, float(L), float(ref["loss"]))
+        grads = dict(net.named_parameters())
+        for k, gr in ref["grads"].items():
+            assert relmax(grads[k].grad, gr) < 3e-4, (tag, k)
+        for k, p in mod.dynamic_loss_weight.named_parameters():
+            assert relmax(p.grad, ref["dlw_grads"][k]) < 5e-5, (tag, k, relmax(p.grad, ref["dlw_grads"][k]))

@@ -280,3 +280,20 @@ def test_latent_wrapper_host_logic():
             d.KarrasModule(net, d.KarrasModuleConfig.from_edm(), autoencoder=ae, **kw)
     with pytest.raises(ValueError):
         d.KarrasModule(net, d.KarrasModuleConfig.from_edm(), autoencoder_conditional=True)
+
+
+def test_dynamic_loss_weight_host_logic(golden):
+    """DynamicLossWeight (karrasmodule.py:1256-1278) vs the oracle restatement; where it is and is not wired."""
+    import diffsci_b200 as d
+    from oracle import karras_oracle as K
+    g = golden("dynweight_punetg2d")
+    net = d.MLPUncond(2, [8], torch.nn.SiLU())
+    mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm(dynamic_loss_weight=g["nhidden"]))
+    assert mod.config.has_dynamic_loss_weight and list(mod.dynamic_loss_weight.state_dict()) == list(g["dlw_state"])
+    mod.dynamic_loss_weight.load_state_dict(g["dlw_state"])
+    cn = 0.5 * torch.log(g["sigma"])
+    assert torch.allclose(mod.dynamic_loss_weight(cn), K.dynamic_loss_weight(g["dlw_state"], cn), rtol=1e-6, atol=1e-7)
+    # created after the default optimizer, as in the reference: its parameters are not in the default AdamW
+    opt_ids = {id(p) for grp in mod.optimizer.param_groups for p in grp["params"]}
+    assert not any(id(p) in opt_ids for p in mod.dynamic_loss_weight.parameters())
+    assert d.KarrasModule(net, d.KarrasModuleConfig.from_edm()).dynamic_loss_weight is None

@@ -307,3 +307,21 @@ def test_latent_wrapper(golden):
         assert torch.allclose(ae.decode(g["sample_latent"]), g["sample_decoded"], rtol=1e-6, atol=1e-6)
         assert torch.allclose(g["sample_hist_decoded"][-1], g["sample_decoded"], rtol=1e-6, atol=1e-6)
         assert tuple(g["sample_hist_decoded"].shape) == (5, 2, 1, 32, 32)
+
+
+@pytest.mark.parametrize("metric", ["huber", "mse"])
+def test_dynamic_loss_weight(golden, metric):
+    """has_dynamic_loss_weight (karrasmodule.py:594-602, 1243-1278): loss, network gradients and the gradients of the
+    uncertainty head vs the LIVE reference."""
+    g = golden("dynweight_punetg2d")
+    for tag in ("", "_mask"):
+        ref = g[metric + tag]
+        net, leaves = _leaf_net(golden(g["net"]))
+        st = {k: v.clone().requires_grad_(k.startswith("linear")) for k, v in g["dlw_state"].items()}
+        L = K.edm_loss(net, g["x"], g["sigma"], g["noise"], metric, g["mask"] if tag else None, dynamic_state=st)
+        assert abs(float(L.detach()) - float(ref["loss"])) <= 5e-6 * abs(float(ref["loss"]))
+        L.backward()
+        for k, gr in ref["grads"].items():
+            assert relmax(leaves[k].grad, gr) < 2e-4, (metric, tag, k)
+        for k, gr in ref["dlw_grads"].items():
+            assert relmax(st[k].grad, gr) < 1e-5, (metric, tag, k)
