@@ -403,6 +403,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("DSK_BENCH_WORKLOAD", "c4"), choices=list(WORKLOADS) + list(TRAIN_WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = workload default)")
     ap.add_argument("--nsteps", type=int, default=0, help="integrator steps (0 = workload default)")
+    ap.add_argument("--integrator", default="", choices=["", "euler", "heun", "euler-maruyama", "karras"],
+                    help="override the workload's integrator (sweeps; e.g. the Karras-churn variant of c5)")
     ap.add_argument("--precision", default=os.environ.get("DSK_BENCH_PRECISION", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
@@ -414,6 +416,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload in TRAIN_WORKLOADS:
         return train_arm(args, rank, world, local_rank)
+    if args.integrator:
+        WORKLOADS[args.workload] = WORKLOADS[args.workload][:4] + (args.integrator,) + WORKLOADS[args.workload][5:]
     kind, kw, shape, nsteps, integ, batch = WORKLOADS[args.workload]
     nsteps = args.nsteps or nsteps
     B = args.batch or batch
