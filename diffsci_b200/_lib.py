@@ -51,6 +51,7 @@ SIGNATURES = {
     "dsk_lincomb": [p, i64, p, f32, p, f32, p, f32, p, f32, p],
     "dsk_mask_blend": [p, p, p, p, i64, i64, p],
     "dsk_philox_normal": [p, i64, u64, C.c_uint32, p],
+    "dsk_dropout": [p, p, p, i64, f32, u64, C.c_uint32, i32, p],
     "dsk_conv_fwd": [C.POINTER(ConvDesc), p, p, p, p, p, p, p],
     "dsk_conv_stats_supported": [C.POINTER(ConvDesc)],
     "dsk_conv_stats_slots": [],

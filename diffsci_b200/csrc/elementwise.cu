@@ -359,6 +359,30 @@ __global__ void __launch_bounds__(256) lincomb_kernel(float* __restrict__ out, i
   }
 }
 
+// ---- dropout (training): y = x * keep / (1 - p) (+ dres), keep(i) = [u_i >= p] with u_i the i-th uniform of Philox stream
+// (seed, stream_id) -- counter-based, so the backward pass regenerates the mask of its forward site instead of storing it.
+// Replaces torch.nn.Dropout in ResnetBlockC / ADMBaseBlock (commonlayers.py:792, 830; adm.py:312-313).
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, const T* dres, T* y, int64_t n, float p, float scale,
+                                                       uint64_t seed, uint32_t stream_id) {
+  const int64_t quads = (n + 3) / 4;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 ctr = make_uint4((uint32_t)q, (uint32_t)(q >> 32), stream_id, 0xD509u);
+    const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i = q * 4 + k;
+      if (i < n) {
+        const float u = (float)(rr[k] >> 8) * 5.9604644775390625e-08f;   // 24-bit uniform in [0, 1)
+        float v = u >= p ? to_f32<T>(x[i]) * scale : 0.0f;
+        if (dres != nullptr) v += to_f32<T>(dres[i]);
+        y[i] = from_f32<T>(v);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint32_t stream_id) {
   const int64_t quads = (n + 3) / 4;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
@@ -418,6 +442,22 @@ extern "C" int dsk_lincomb(float* out, int64_t n, const float* x, float a0, cons
                            float a2, const float* z, float a3, void* stream) {
   DSK_REQUIRE(out && n > 0, "dsk_lincomb: bad arguments");
   DSK_LAUNCH(lincomb_kernel, grid_for(n, 256, 16), 256, 0, as_stream(stream), out, n, x, a0, r1, a1, r2, a2, z, a3);
+  return DSK_OK;
+}
+
+extern "C" int dsk_dropout(const void* x, const void* dres, void* y, int64_t n, float p, uint64_t seed, uint32_t stream_id,
+                           int dtype, void* stream) {
+  DSK_REQUIRE(x && y && n > 0, "dsk_dropout: bad arguments");
+  DSK_REQUIRE(p >= 0.0f && p < 1.0f, "dsk_dropout: p = %f outside [0, 1)", (double)p);
+  const int grid = grid_for((n + 3) / 4, 256, 16);
+  const float scale = 1.0f / (1.0f - p);
+  if (dtype == DSK_F32)
+    DSK_LAUNCH(dropout_kernel<float>, grid, 256, 0, as_stream(stream), (const float*)x, (const float*)dres, (float*)y, n, p, scale, seed,
+               stream_id);
+  else if (dtype == DSK_BF16)
+    DSK_LAUNCH(dropout_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), (const __nv_bfloat16*)x, (const __nv_bfloat16*)dres,
+               (__nv_bfloat16*)y, n, p, scale, seed, stream_id);
+  else DSK_REQUIRE(false, "dsk_dropout: bad dtype %d", dtype);
   return DSK_OK;
 }
 

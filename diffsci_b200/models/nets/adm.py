@@ -176,6 +176,8 @@ class ADM(nn.Module):
             from .graph import NetFunction
             graph = self.train_graph(B, tuple(x.shape[2:]), x.device, cond=ye is not None)
             return NetFunction.apply(graph, x, t, None if ye is None else ye.contiguous(), *self.native_parameters())
+        if self.training and float(getattr(self.config, "dropout", 0.0)) > 0.0:
+            raise NotImplementedError("dropout > 0 acts on the training path (gradients enabled); call .eval() for inference")
         plan = self.plan(B, tuple(x.shape[2:]), x.device)
         xin = ops.nchw_to_cl(x.float(), plan.act_dtype, 2, out=plan.xin)
         out = torch.empty((B, self.config.output_channels) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)

@@ -66,6 +66,9 @@ class TrainGraph:
         self._scratch: dict = {}
         self._packs: list = []
         self.nbytes = 0
+        self.dropout_sites: list = []          # (module name, Philox stream id, shape) of every dropout op, in forward order
+        self.dropout_seed = 0
+        self.fixed_dropout_seed: Optional[int] = None      # tests: pin the masks
 
     # ------------------------------------------------------------------ memory
     def empty(self, shape, dtype=None) -> torch.Tensor:
@@ -306,6 +309,26 @@ class TrainGraph:
             dres, dx = self.contribute_compute(x)
             return [lambda: ops.norm_act_bwd(xt, dy, dx, np_.weight, np_.bias, G, mode, silu, fws, ws(), dgamma=dg, dbeta=db,
                                              dres=dres, film_scale=fsc, dfilm_scale=dfs, dfilm_shift=dfh)]
+
+        self._bwd_builders.append(build_bwd)
+        return y
+
+    def dropout(self, x: Var, p: float, name: str = "") -> Var:
+        """Training-mode torch.nn.Dropout(p) (commonlayers.py:792, 830; adm.py:312-313).  Each site owns a Philox stream; the
+        seed is redrawn (CPU generator) at every run_forward, and the backward launch regenerates the site's mask from the
+        same (seed, stream) instead of reading a stored one."""
+        sid = len(self.dropout_sites)
+        self.dropout_sites.append((name, sid, tuple(x.t.shape)))
+        y = Var(self.empty(x.t.shape))
+        xt, yt = x.t, y.t
+        self.fwd.append(lambda: ops.dropout(xt, p, self.dropout_seed, sid, out=yt))
+
+        def build_bwd():
+            dy = self.grad_of(y)
+            if dy is None or not x.needs_grad:
+                return []
+            dres, dx = self.contribute_compute(x)
+            return [lambda: ops.dropout(dy, p, self.dropout_seed, sid, out=dx, dres=dres)]
 
         self._bwd_builders.append(build_bwd)
         return y
@@ -709,6 +732,9 @@ class TrainGraph:
 
     def run_forward(self):
         self.prepare()
+        if self.dropout_sites:
+            self.dropout_seed = (int(torch.randint(0, 2 ** 62, (1,)).item()) if self.fixed_dropout_seed is None
+                                 else int(self.fixed_dropout_seed))
         for f in self.fwd:
             f()
 
@@ -788,9 +814,10 @@ def build_punetg(net, B: int, spatial: tuple, device, precision: str, cond: bool
     gradient is returned (the conditional embedding that produced it is trained by torch autograd around this graph)."""
     c = net.config
     nd = c.dimension
-    if c.dropout != 0.0:
-        raise NotImplementedError("diffsci_b200.PUNetG: dropout > 0 in training is not built yet")
+    if not 0.0 <= c.dropout < 1.0:
+        raise ValueError(f"dropout probability has to be in [0, 1), got {c.dropout}")
     g = TrainGraph(net, B, device, precision, nd)
+    names = {id(m): n for n, m in net.named_modules()}
     sp = (1,) + tuple(spatial) if nd == 2 else tuple(spatial)
     nlev = len(c.channel_expansion)
     for l in range(nlev):
@@ -812,6 +839,8 @@ def build_punetg(net, B: int, spatial: tuple, device, precision: str, cond: bool
         n1 = g.norm(x, blk.gnorm1, C, c.first_resblock_norm, True)
         y = g.conv(n1, blk.conv1, chan_bias=tv, want_stats=True)
         n2 = g.norm(y, blk.gnorm2, C, c.second_resblock_norm, True)
+        if c.dropout > 0.0:                     # conv2(dropout(act(gnorm2(y)))), commonlayers.py:829-831
+            n2 = g.dropout(n2, c.dropout, names[id(blk)])
         return g.conv(n2, blk.conv2, residual=x, want_stats=True)
 
     x = g.conv(g.x_in, net.convin)
@@ -843,9 +872,11 @@ def build_adm(net, B: int, spatial: tuple, device, precision: str, cond: bool = 
     """ADM.forward (nets/adm.py:199-216; block :292-343) unrolled into a TrainGraph.  cond: te = SiLU(mlp(fourier) + ye) with
     ye an input [B, output_embed_dim] whose gradient is returned (adm.py:1047-1053)."""
     c = net.config
-    if getattr(c, "dropout", 0.0) != 0.0:
-        raise NotImplementedError("diffsci_b200.ADM: dropout > 0 in training is not built yet")
+    pdrop = float(getattr(c, "dropout", 0.0))
+    if not 0.0 <= pdrop < 1.0:
+        raise ValueError(f"dropout probability has to be in [0, 1), got {pdrop}")
     g = TrainGraph(net, B, device, precision, 2)
+    names = {id(m): n for n, m in net.named_modules()}
     H, W = spatial
     nlev = len(c.channel_expansion)
     if H % (2 ** nlev) or W % (2 ** nlev):
@@ -879,6 +910,8 @@ def build_adm(net, B: int, spatial: tuple, device, precision: str, cond: bool = 
             n, xr = g.pool(n, False), g.pool(x, False)
         y = g.conv(n, blk.conv1, up2=up)
         h = g.norm(y, blk.norm2, G, c.second_resblock_norm, True, film=film_of[id(blk)])
+        if pdrop > 0.0:                         # conv2(dropout(SiLU(FiLM(norm2)))), adm.py:305-313
+            h = g.dropout(h, pdrop, names[id(blk)])
         r = g.conv(xr, blk.convresidual, up2=up)
         o = g.conv(h, blk.conv2, residual=r)
         if blk.has_attn:

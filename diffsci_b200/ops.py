@@ -469,6 +469,18 @@ def philox_normal(shape, seed: int, stream_id: int, device) -> torch.Tensor:
     return out
 
 
+def dropout(x: torch.Tensor, p: float, seed: int, stream_id: int, out: Optional[torch.Tensor] = None,
+            dres: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = x * keep / (1 - p) (+ dres); the mask is a function of (seed, stream_id, element index) only (dsk_dropout), so a
+    backward launch with the same pair applies the mask of its forward site."""
+    require_cuda(x, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.dsk_dropout(ptr(x), ptr(dres), ptr(out), x.numel(), float(p), seed & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF,
+                          dt_code(x.dtype), stream()))
+    return out
+
+
 class PackedLinear:
     """bf16 device copy of an fp32 [N, K] weight (K-major B/A operand of dsk_gemm_bf16_tc), version tracked."""
 

@@ -124,6 +124,12 @@ int dsk_lincomb(float* out, int64_t n, const float* x, float a0, const float* r1
 /* N(0,1) draws from the same Philox4x32-10 stream the fused stages use: element i of stream
  * `stream_id` (= step row) under `seed`.  Replaces torch.randn_like (integrators.py:68,105). */
 int dsk_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t stream_id, void* stream);
+/* Training-mode dropout, forward AND backward: y = x * keep / (1-p) (+ dres), keep(i) = [u_i >= p] from Philox stream
+ * (seed, stream_id): the backward launch of a site passes the same (seed, stream_id) and regenerates the mask.
+ * Replaces torch.nn.Dropout in ResnetBlockC / ADMBaseBlock (commonlayers.py:792,830; adm.py:312-313).  dtype: DSK_F32 | DSK_BF16;
+ * y may alias x or dres. */
+int dsk_dropout(const void* x, const void* dres, void* y, int64_t n, float p, uint64_t seed, uint32_t stream_id, int dtype,
+                void* stream);
 
 /* ---- K1: convolution / GEMM ----------------------------------------------------------
  * Replaces torch.nn.Conv2d/Conv3d(padding='same') in ResnetBlockC (nets/commonlayers.py:777-833),

@@ -452,7 +452,57 @@ def ensemble_goldens():
     torch.save(dyn, os.path.join(OUT, "dynweight_punetg2d.pt"))
 
 
+def dropout_goldens():
+    """Training-mode dropout (commonlayers.py:792, 829-831; adm.py:279, 323-329) from the LIVE reference with INJECTED masks:
+    torch.nn.Dropout.forward is replaced by x * keep / (1 - p) with a recorded keep mask per block, so the restatement
+    (nets_oracle: dropout_masks) can be pinned on forward output and parameter gradients.
+    ->  tests/golden/dropout_{punetg2d,adm2d}.pt.   python oracle/make_goldens.py --only dropout"""
+    os.makedirs(OUT, exist_ok=True)
+    refload.load_reference()
+    from diffsci.models.nets.punetg import PUNetG
+    from diffsci.models.nets.punetg_config import PUNetGConfig
+    from diffsci.models.nets.adm import ADM, ADMConfig
+    torch.set_num_threads(8)
+    P = 0.25
+
+    def case(name, net, base_name, seed):
+        base = torch.load(os.path.join(OUT, base_name + ".pt"), weights_only=False)
+        load_synth(net, base["seed"])
+        net.train()
+        x, t = base["x"], base["t"]
+        names = {id(m): n for n, m in net.named_modules()}
+        gen_ = torch.Generator().manual_seed(seed)
+        keep = {}
+        orig = torch.nn.Dropout.forward
+
+        def fake(self, inp):
+            blk = names[id(self)].rsplit(".", 1)[0]
+            if self.p == 0.0 or "cond" in names[id(self)]:
+                return inp
+            keep[blk] = (torch.rand(inp.shape, generator=gen_) >= self.p)
+            return inp * keep[blk].to(inp) / (1.0 - self.p)
+        torch.nn.Dropout.forward = fake
+        try:
+            net.zero_grad()
+            y = net(x, t)
+            torch.manual_seed(seed + 1)
+            dF = torch.randn_like(y)
+            (y * dF).sum().backward()
+        finally:
+            torch.nn.Dropout.forward = orig
+        out = dict(net=base_name, p=P, keep={k: v.to(torch.uint8) for k, v in keep.items()}, dF=dF, y=y.detach().clone(),
+                   grads={k: p.grad.clone() for k, p in net.named_parameters() if GRAD_KEYS.search(k) or "conv2" in k and ".0." in k})
+        torch.save(out, os.path.join(OUT, name + ".pt"))
+        print(name, len(keep), "sites; |y| max", float(y.detach().abs().max()), "grads", len(out["grads"]))
+
+    case("dropout_punetg2d", PUNetG(PUNetGConfig(dimension=2, model_channels=8, dropout=P)), "punetg2d_mc8", 501)
+    base = torch.load(os.path.join(OUT, "adm2d_mc8.pt"), weights_only=False)
+    case("dropout_adm2d", ADM(ADMConfig(**dict(base["cfg"], dropout=P))), "adm2d_mc8", 502)
+
+
 def main():
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "dropout":
+        return dropout_goldens()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ensemble":
         return ensemble_goldens()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "precond":

@@ -101,7 +101,7 @@ def _time_block(te, sd, p):
     return F.linear(h, sd[p + "net.4.weight"], sd[p + "net.4.bias"])
 
 
-def resnet_block_c(x, te, sd, p, cfg):
+def resnet_block_c(x, te, sd, p, cfg, dropout_masks=None):
     """ResnetBlockC.forward (commonlayers.py:809-836) as built by PUNetG.resnet_fn (punetg.py:238-261):
     C_in == C_out, identity residual, num_groups == num_channels for both norms."""
     dim = cfg.dimension
@@ -110,7 +110,10 @@ def resnet_block_c(x, te, sd, p, cfg):
     g = lambda n: (sd[p + n + ".weight"], sd[p + n + ".bias"]) if aff else (None, None)  # noqa: E731
     y = _pconv(F.silu(_norm(cfg.first_resblock_norm, x, C, *g("gnorm1"))), sd, p + "conv1", cfg)
     y = y + _bc(_time_block(te, sd, p + "timeblock."), y)
-    y = _pconv(F.silu(_norm(cfg.second_resblock_norm, y, C, *g("gnorm2"))), sd, p + "conv2", cfg)
+    h = F.silu(_norm(cfg.second_resblock_norm, y, C, *g("gnorm2")))
+    if dropout_masks is not None:          # training-mode Dropout (commonlayers.py:829-831) with an explicit, pre-scaled mask
+        h = h * dropout_masks[p[:-1]].to(h)
+    y = _pconv(h, sd, p + "conv2", cfg)
     return y + x
 
 
@@ -130,7 +133,7 @@ def punetg_cond_forward(sd, cfg, x, t, y_channels, ye=None):
     return punetg_forward(sd, cfg, torch.cat([x, y_cat], dim=1), t, ye)
 
 
-def punetg_forward(sd, cfg, x, t, ye=None):
+def punetg_forward(sd, cfg, x, t, ye=None, dropout_masks=None):
     """PUNetG.forward (nets/punetg.py:389-416), default layer types, eval mode.  ye: the conditional embedding vector
     [B or 1, M] added to the time embedding (punetg.py:400-410; cond_drop / cond_dropout are identities in eval)."""
     dim = cfg.dimension
@@ -146,30 +149,30 @@ def punetg_forward(sd, cfg, x, t, ye=None):
     skips = []
     for l in range(nlev):                                   # encode, punetg.py:356-365
         for r in range(cfg.number_resnet_downward_block):
-            x = resnet_block_c(x, te, sd, f"downward_blocks.{l}.{r}.", cfg)
+            x = resnet_block_c(x, te, sd, f"downward_blocks.{l}.{r}.", cfg, dropout_masks)
         skips.append(x)
         x = _pconv(pool(x, cfg.transition_scale_factor), sd, f"downsamplers.{l}.conv", cfg)
     for r in range(cfg.number_resnet_before_attn_block):    # bottom, punetg.py:378-387
-        x = resnet_block_c(x, te, sd, f"before_block.{r}.", cfg)
+        x = resnet_block_c(x, te, sd, f"before_block.{r}.", cfg, dropout_masks)
     xa = x
     for r in range(cfg.number_resnet_attn_block):
-        xa = resnet_block_c(xa, te, sd, f"attn_resnet_block.{r}.", cfg)
+        xa = resnet_block_c(xa, te, sd, f"attn_resnet_block.{r}.", cfg, dropout_masks)
         if r < cfg.number_resnet_attn_block - 1:
             xa = mha_self_attention(xa, sd, f"attn_block.{r}.", getattr(cfg, "attn_residual", False))
     x = x + xa
     for r in range(cfg.number_resnet_after_attn_block):
-        x = resnet_block_c(x, te, sd, f"after_block.{r}.", cfg)
+        x = resnet_block_c(x, te, sd, f"after_block.{r}.", cfg, dropout_masks)
     for l in range(nlev):                                   # decode, punetg.py:367-376
         x = F.interpolate(x, scale_factor=cfg.transition_scale_factor, mode="nearest")
         x = _pconv(x, sd, f"upsamplers.{l}.conv", cfg)
         x = x + skips.pop()
         for r in range(cfg.number_resnet_upward_block):
-            x = resnet_block_c(x, te, sd, f"upward_blocks.{l}.{r}.", cfg)
+            x = resnet_block_c(x, te, sd, f"upward_blocks.{l}.{r}.", cfg, dropout_masks)
     return _pconv(x, sd, "convout", cfg)
 
 
 # ----------------------------------------------------------------------------- ADM
-def adm_block(x, te, sd, p, cfg, sample=None, attn=False):
+def adm_block(x, te, sd, p, cfg, sample=None, attn=False, dropout_masks=None):
     """ADMBaseBlock.forward (nets/adm.py:292-343): norm1-SiLU-[pool|up]-conv1-norm2, FiLM
     x*te1+te2 (no '1+'), SiLU-conv2, + conv1x1([pool|up](x)), optional attention."""
     dim = cfg.dimension
@@ -189,14 +192,17 @@ def adm_block(x, te, sd, p, cfg, sample=None, attn=False):
     e = F.linear(te, sd[p + "embed_linear.weight"], sd[p + "embed_linear.bias"])
     te1, te2 = torch.chunk(e, 2, dim=-1)
     y = y * _bc(te1, y) + _bc(te2, y)
-    y = _conv(F.silu(y), sd[p + "conv2.weight"], sd[p + "conv2.bias"], dim)
+    y = F.silu(y)
+    if dropout_masks is not None:          # ADMBaseBlock.second_block (adm.py:323-329) with an explicit, pre-scaled mask
+        y = y * dropout_masks[p[:-1]].to(y)
+    y = _conv(y, sd[p + "conv2.weight"], sd[p + "conv2.bias"], dim)
     y = y + _conv(resample(x), sd[p + "convresidual.weight"], sd[p + "convresidual.bias"], dim)
     if attn:
         y = mha_self_attention(y, sd, p + "attn.", cfg.attn_residual)
     return y
 
 
-def adm_forward(sd, cfg, x, t, ye=None):
+def adm_forward(sd, cfg, x, t, ye=None, dropout_masks=None):
     """ADM.forward (nets/adm.py:199-216), decoder_type 1.  ye: conditional embedding vector [B or 1, output_embed_dim],
     added before the final SiLU of the time embedding (adm.py:1047-1053; zeros / None when y is None)."""
     te = fourier(t, sd["time_embedding.projection.W"])
@@ -212,11 +218,11 @@ def adm_forward(sd, cfg, x, t, ye=None):
         nb = cfg.number_resnet_downward_block
         for r in range(nb):
             x = adm_block(x, te, sd, f"encoder.layers.{l}.input_blocks.{r}.", cfg,
-                          sample="down" if r == nb - 1 else None)
+                          sample="down" if r == nb - 1 else None, dropout_masks=dropout_masks)
         skips.append(x)
     flags = cfg.middle_block_attn_config                     # adm.py:73-77
     for r, has_attn in enumerate(flags):
-        x = adm_block(x, te, sd, f"middle_block.middle_blocks.{r}.", cfg, attn=has_attn)
+        x = adm_block(x, te, sd, f"middle_block.middle_blocks.{r}.", cfg, attn=has_attn, dropout_masks=dropout_masks)
     assert getattr(cfg, "decoder_type", 1) == 1
     for l in range(nlev):                                    # ADMDecoderLayer1, adm.py:642-740
         h = skips.pop()
@@ -224,7 +230,7 @@ def adm_forward(sd, cfg, x, t, ye=None):
         nb = cfg.number_resnet_upward_block
         for r in range(nb):
             x = adm_block(x, te, sd, f"decoder.layers.{l}.input_blocks.{r}.", cfg,
-                          sample="up" if r == nb - 1 else None)
+                          sample="up" if r == nb - 1 else None, dropout_masks=dropout_masks)
     return F.conv2d(x, sd["output_layer.weight"], sd["output_layer.bias"], padding=cfg.kernel_size // 2)
 
 

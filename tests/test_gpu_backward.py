@@ -564,3 +564,78 @@ def test_hybrid_attention_training_path():
             G.HYBRID_ATTENTION = True
     print(f"global gradient L2 error vs fp64: hybrid {err[True]:.3e}, fp32-core attention {err[False]:.3e}")
     assert err[True] < max(1.25 * err[False], 6e-2) and err[True] < 1e-1, err
+
+
+# ------------------------------------------------------------------------------------------------ training-mode dropout
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dropout_kernel(dtype):
+    """dsk_dropout: y in {0, x / (1-p)}, keep fraction 1-p, the mask depends on (seed, stream, index) only -- so the backward
+    launch regenerates the forward's mask --, streams and seeds are independent, dres is added after masking."""
+    from diffsci_b200 import ops
+    torch.manual_seed(0)
+    n, p = 1_000_003, 0.3
+    x = (torch.randn(n, device=DEV) + 3.0).to(dtype)
+    y = ops.dropout(x, p, 1234, 5)
+    keep = y != 0
+    assert abs(float(keep.float().mean()) - (1 - p)) < 3e-3
+    assert relmax(y[keep].float(), (x[keep].float() / (1 - p)).to(dtype).float()) < 1e-6
+    assert torch.equal(ops.dropout(x, p, 1234, 5), y)
+    other_stream, other_seed = ops.dropout(x, p, 1234, 6) != 0, ops.dropout(x, p, 1235, 5) != 0
+    for o in (other_stream, other_seed):        # independent masks agree on (1-p)^2 + p^2 of the positions
+        assert abs(float((o == keep).float().mean()) - ((1 - p) ** 2 + p ** 2)) < 5e-3
+    dy, dres = torch.randn(n, device=DEV).to(dtype), torch.randn(n, device=DEV).to(dtype)
+    dx = ops.dropout(dy, p, 1234, 5, dres=dres)
+    ref = torch.where(keep, dy.float() / (1 - p), torch.zeros_like(dy.float())) + dres.float()
+    assert relmax(dx.float(), ref.to(dtype).float()) < (1e-6 if dtype == torch.float32 else 8e-3)
+    assert torch.equal(ops.dropout(x, 0.0, 1, 1), x)
+    with pytest.raises(RuntimeError):
+        ops.dropout(x, 1.0, 1, 1)
+
+
+@pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8", "adm2d_mc8"])
+def test_net_backward_with_dropout(golden, name):
+    """dropout > 0 on the training path: the masks the device drew (regenerated per site from the pinned seed) are fed to the
+    fp64 oracle; forward output and every parameter gradient agree, i.e. the backward applied the same masks."""
+    import diffsci_b200 as d
+    from diffsci_b200 import ops
+    from oracle import nets_oracle as N
+    g = golden(name)
+    p = 0.25
+    cfg_kw = dict(g["cfg"], dropout=p)
+    net = (d.PUNetG(d.PUNetGConfig(**cfg_kw)) if g["kind"] == "punetg" else d.ADM(d.ADMConfig(**cfg_kw)))
+    net.load_state_dict(N.synth_state_dict(g["manifest"], g["seed"]))
+    net = net.to(DEV).train()
+    x, t = g["x"], g["t"]
+    graph = net.train_graph(x.shape[0], tuple(x.shape[2:]), torch.device(DEV))
+    assert len(graph.dropout_sites) == 14
+    graph.fixed_dropout_seed = 987654321
+    out = net(x.to(DEV), t.to(DEV))
+    torch.manual_seed(11)
+    dF = torch.randn_like(g["y"])
+    out.backward(dF.to(DEV))
+    masks = {}
+    for site, sid, shape in graph.dropout_sites:
+        m = ops.dropout(torch.ones(shape, device=DEV), p, graph.fixed_dropout_seed, sid)      # [B, D, H, W, C], pre-scaled
+        m = m.permute(0, 4, 1, 2, 3)
+        masks[site] = (m.squeeze(2) if len(x.shape) == 4 else m).cpu().double()
+    keep_frac = sum(float((m != 0).sum()) for m in masks.values()) / sum(m.numel() for m in masks.values())
+    assert abs(keep_frac - (1 - p)) < 0.02
+    sd = {k: v.double() for k, v in N.synth_state_dict(g["manifest"], g["seed"]).items()}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if not k.endswith(".W")}
+    cfg = (d.PUNetGConfig if g["kind"] == "punetg" else d.ADMConfig)(**cfg_kw)
+    fwd = N.punetg_forward if g["kind"] == "punetg" else N.adm_forward
+    Fo = fwd(dict(sd, **leaves), cfg, x.double(), t.double(), dropout_masks=masks)
+    (Fo * dF.double()).sum().backward()
+    assert relmax(out.detach(), Fo.detach()) < 5e-5
+    worst = max((relmax(pp.grad, leaves[k].grad), k) for k, pp in net.named_parameters())
+    assert worst[0] < 2e-4, worst
+    # a fresh seed per forward when nothing is pinned; evaluation ignores dropout; no-grad training-mode forward fails loudly
+    graph.fixed_dropout_seed = None
+    a, b = net(x.to(DEV), t.to(DEV)).detach(), net(x.to(DEV), t.to(DEV)).detach()
+    assert not torch.equal(a, b)
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        net(x.to(DEV), t.to(DEV))
+    net.eval()
+    with torch.no_grad():
+        e = net(x.to(DEV), t.to(DEV))
+    assert relmax(e, g["y"]) < 5e-5

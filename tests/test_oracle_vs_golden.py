@@ -325,3 +325,23 @@ def test_dynamic_loss_weight(golden, metric):
             assert relmax(leaves[k].grad, gr) < 2e-4, (metric, tag, k)
         for k, gr in ref["dlw_grads"].items():
             assert relmax(st[k].grad, gr) < 1e-5, (metric, tag, k)
+
+
+@pytest.mark.parametrize("name", ["dropout_punetg2d", "dropout_adm2d"])
+def test_training_dropout(golden, name):
+    """Training-mode dropout (commonlayers.py:829-831; adm.py:323-329): the oracle with the recorded keep masks vs the LIVE
+    reference run with the same masks injected -- forward output and parameter gradients."""
+    g = golden(name)
+    base = golden(g["net"])
+    sd = N.synth_state_dict(base["manifest"], base["seed"])
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and not k.endswith(".W")}
+    cfg = cfg_for(base["kind"], dict(base["cfg"], dropout=g["p"]))
+    masks = {k: v.float() / (1.0 - g["p"]) for k, v in g["keep"].items()}
+    fwd = N.punetg_forward if base["kind"] == "punetg" else N.adm_forward
+    y = fwd(dict(sd, **leaves), cfg, base["x"], base["t"], dropout_masks=masks)
+    assert relmax(y.detach(), g["y"]) < TOL32
+    (y * g["dF"]).sum().backward()
+    for k, gr in g["grads"].items():
+        assert relmax(leaves[k].grad, gr) < 2e-4, k
+    frac = sum(float(v.float().sum()) for v in g["keep"].values()) / sum(v.numel() for v in g["keep"].values())
+    assert abs(frac - (1 - g["p"])) < 0.02
