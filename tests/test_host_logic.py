@@ -297,3 +297,42 @@ def test_dynamic_loss_weight_host_logic(golden):
     opt_ids = {id(p) for grp in mod.optimizer.param_groups for p in grp["params"]}
     assert not any(id(p) in opt_ids for p in mod.dynamic_loss_weight.parameters())
     assert d.KarrasModule(net, d.KarrasModuleConfig.from_edm()).dynamic_loss_weight is None
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference (the CPU arm the driver runs next to ours): one JSON line with the contract's keys, rank 0
+    only under a multi-rank launch, and the algorithmic-FLOP model bench.py divides by (C4 = 1 086.6 GFLOP per
+    evaluation, C2 = 7.755, C5 = 178.9 incl. attention)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, env=env, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    other = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1", "--gpus", "2"],
+                           capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=120,
+                           cwd=root)
+    assert other.returncode == 0 and other.stdout.strip() == ""          # the other ranks exit 0 without work
+
+    sys.path.insert(0, root)
+    import bench
+    import diffsci_b200 as dd
+    for name, gf in (("c4", 1086.56), ("c2", 7.755), ("c5", 178.9)):
+        kind, kw, shape, *_ = bench.WORKLOADS[name]
+        flops = bench.punetg_conv_flops(dd.PUNetGConfig(**kw), shape[1:])
+        assert abs(flops / 1e9 - gf) < 2e-3 * gf, (name, flops / 1e9)
+    assert bench.nfe_per_sample(64, "heun") == 127 and bench.nfe_per_sample(256, "euler-maruyama") == 256
+    assert bench.nfe_per_sample(256, "karras") == 511
