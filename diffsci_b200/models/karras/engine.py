@@ -67,7 +67,7 @@ class SamplerEngine:
         self.cnoise = torch.empty((self.Bn,), **f32)
         self.row = torch.zeros((4,), dtype=torch.int32, device=self.device)   # [step, seed_lo, seed_hi, -]
         self.native = hasattr(model, "plan")
-        self.xin_ld = self.Cc + self.cond_channels
+        self.xin_ld = self.Cc + self.cond_channels + int(getattr(model, "ones_channel", 0))   # + the bias=False ones channel
         self.ye = None
         if (self.cond_channels or self.cond_vector or self.cfg) and not self.native:
             raise NotImplementedError("SamplerEngine: the conditional path needs a native network")
@@ -130,7 +130,7 @@ class SamplerEngine:
         with torch.inference_mode(False), torch.no_grad():
             if ychan is not None:
                 src = ychan.detach().reshape(self.B, self.cond_channels, self.S).transpose(1, 2)
-                self.xin.view(self.Bn, self.S, self.xin_ld)[:self.B, :, self.Cc:].copy_(src)
+                self.xin.view(self.Bn, self.S, self.xin_ld)[:self.B, :, self.Cc:self.Cc + self.cond_channels].copy_(src)
             if ye is not None:
                 self.ye[self.Bn - self.B:].copy_(ye.detach())
 

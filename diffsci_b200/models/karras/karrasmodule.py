@@ -341,13 +341,13 @@ class KarrasModule(_Base):
             Bn = 2 * B if cfg else B
             plan = self.model.plan(Bn, spatial, x.device)
             ld = plan.xin.shape[-1]
-            if ld != Cc + (0 if ychan is None else ychan.shape[1]):
-                raise ValueError(f"network expects {ld} input channels, got {Cc} state + "
-                                 f"{0 if ychan is None else ychan.shape[1]} conditioning channels")
+            ncond = 0 if ychan is None else int(ychan.shape[1])
+            if ld != Cc + ncond + int(getattr(self.model, "ones_channel", 0)):
+                raise ValueError(f"network expects {ld} input channels, got {Cc} state + {ncond} conditioning channels")
             check(lib.dsk_precond_scale_cond(ptr(x), ptr(c_in), ptr(plan.xin), B, Cc, S, dt_code(plan.act_dtype), ld,
                                              1 if cfg else 0, stream()))
             if ychan is not None:
-                plan.xin.view(B, S, ld)[:, :, Cc:].copy_(ychan.reshape(B, ld - Cc, S).transpose(1, 2))
+                plan.xin.view(B, S, ld)[:, :, Cc:Cc + ncond].copy_(ychan.reshape(B, ncond, S).transpose(1, 2))
             cn = torch.cat([cond_noise, cond_noise]) if cfg else cond_noise
             if cfg:
                 ye = torch.cat([torch.zeros_like(ye), ye]) if ye is not None else None
@@ -496,6 +496,30 @@ class KarrasModule(_Base):
                                               integrator=integrator, move_to_cpu=move_to_cpu, latent_shape=is_latent_shape,
                                               squeeze_memory_efficiency=squeeze_memory_efficiency,
                                               return_in_latent_space=return_in_latent_space)
+
+    def sample_and_filter(self, nsamples: int, shape, filter_fn, y=None, guidance: float = 1.0, nsteps: int = 100,
+                          record_history: bool = False, maximum_batch_size: Optional[int] = None, integrator=None,
+                          move_to_cpu: bool = False, return_only_positives: bool = False) -> dict:
+        """Rejection sampling around sample() (karrasmodule.py:735-799): `filter_fn(encode(samples)) -> bool [nsamples]`;
+        returns the samples, the filter and the hit rate."""
+        if record_history:
+            raise ValueError("record_history is not supported for filtering at the moment")
+        if maximum_batch_size is not None:
+            parts = [self.sample_and_filter(b, shape, filter_fn, y, guidance, nsteps, record_history, None, integrator,
+                                            move_to_cpu, return_only_positives)
+                     for b in get_minibatch_sizes(nsamples, maximum_batch_size)]
+            hits = sum(p["filter"].sum().item() for p in parts)
+            return dict(samples=torch.cat([p["samples"] for p in parts], dim=0),
+                        filter=torch.cat([p["filter"] for p in parts], dim=0), hit_rate=hits / nsamples)
+        samples = self.sample(nsamples, shape, y=y, guidance=guidance, nsteps=nsteps, record_history=record_history,
+                              maximum_batch_size=maximum_batch_size, integrator=integrator, move_to_cpu=False)
+        with torch.inference_mode():
+            keep = filter_fn(self.encode(samples, y, record_history))
+        if return_only_positives:
+            samples, keep = samples[keep], keep[keep]
+        if move_to_cpu:
+            samples = samples.detach().cpu()
+        return dict(samples=samples, filter=keep, hit_rate=keep.sum() / nsamples)
 
     def propagate_white_noise(self, x: Tensor, y=None, guidance: float = 1.0, nsteps: int = 100,
                               record_history: bool = False, integrator=None, original_y=None,

@@ -824,7 +824,7 @@ def build_punetg(net, B: int, spatial: tuple, device, precision: str, cond: bool
         if any(s % (2 ** (l + 1)) for s in spatial):
             raise ValueError(f"PUNetG: spatial size {spatial} is not divisible by 2 at a down-sampling level")
     g.t_in = torch.empty(B, dtype=torch.float32, device=g.device)
-    g.x_in = Var(g.empty((B,) + sp + (c.input_channels,)), needs_grad=False)
+    g.x_in = Var(g.empty((B,) + sp + (net.convin.cin,)), needs_grad=False)
     te = g.fourier(g.t_in, net.time_projection.W)
     if cond:
         g.ye_in = Var(g.empty((B, c.model_channels), torch.float32), needs_grad=True, name="ye")

@@ -76,8 +76,6 @@ class PUNetG(nn.Module):
             unsupported.append(f"attn_type={c.attn_type!r}")
         if extra_residual is not None:
             unsupported.append("extra_residual")
-        if not c.bias:
-            unsupported.append("bias=False")
         if c.dimension not in (2, 3) or c.transition_scale_factor != 2:
             unsupported.append("dimension not in {2,3} or transition_scale_factor != 2")
         if c.kernel_size not in (1, 3) or c.in_out_kernel_size not in (1, 3) or c.transition_kernel_size not in (1, 3):
@@ -95,7 +93,9 @@ class PUNetG(nn.Module):
         self.time_projection = FourierParams(M, c.time_projection_scale)
         self.extra_residual = None
         self.conditional_embedding = conditional_embedding      # any torch module: y -> [B, M] (punetg.py:93, 400-404)
-        self.convin = make_conv(c.input_channels, M, c.in_out_kernel_size, nd, c.bias, ct)
+        # bias=False: no conv carries a bias; the network input gets a constant ones channel instead (punetg.py:190-193, 390-394)
+        self.ones_channel = 0 if c.bias else 1
+        self.convin = make_conv(c.input_channels + self.ones_channel, M, c.in_out_kernel_size, nd, c.bias, ct)
         self.convout = make_conv(M, c.output_channels, c.in_out_kernel_size, nd, c.bias, ct)
         self.downward_blocks = nn.ModuleList([blocks(m, c.number_resnet_downward_block) for m in mult[:-1]])
         self.downsamplers = nn.ModuleList([SamplerParams(a * M, b * M, nd, c.transition_kernel_size, c.bias, ct)
@@ -158,6 +158,8 @@ class PUNetG(nn.Module):
         """x: fp32 [B, Cin, *S]; t: [B] (= c_noise); returns fp32 [B, Cout, *S] (punetg.py:389-416)."""
         require_cuda(x, "PUNetG input")
         B = x.shape[0]
+        if self.ones_channel:
+            x = torch.cat([x, torch.ones_like(x[:, :1])], dim=1)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
             # training: static forward/backward launch lists with hand-written backward kernels (graph.py)
             from .graph import NetFunction
@@ -240,7 +242,9 @@ class _Plan:
             return ops.PackedConv(cp.weight, cp.bias, nd, torch.bfloat16 if tc else torch.float32, subpixel and tc,
                                   circular=cp.circular)
 
-        self.xin = buf(0, c.input_channels)
+        self.xin = buf(0, net.convin.cin)
+        if net.ones_channel:          # constant last channel; the fused stages / scale kernels only write the state channels
+            self.xin[..., -1] = 1.0
         self.X = [buf(l, ch[l]) for l in range(nlev + 1)]          # encoder / bottom state (doubles as skip)
         self.XU = [buf(l, ch[l]) for l in range(nlev)]             # decoder state
         self.N = [buf(l, ch[l]) for l in range(nlev + 1)]          # norm+SiLU output == conv input

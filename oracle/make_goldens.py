@@ -500,7 +500,59 @@ def dropout_goldens():
     case("dropout_adm2d", ADM(ADMConfig(**dict(base["cfg"], dropout=P))), "adm2d_mc8", 502)
 
 
+def nobias_goldens():
+    """PUNetGConfig(bias=False) (punetg.py:188-216, 389-394): no conv bias, a constant ones channel appended to the network
+    input.  Forward (fp32 + fp64), denoiser, Heun / Euler-Maruyama sampling, loss + gradients from the LIVE reference, 2-D
+    and 3-D  ->  tests/golden/nobias_punetg{2,3}d.pt.   python oracle/make_goldens.py --only nobias"""
+    os.makedirs(OUT, exist_ok=True)
+    refload.load_reference()
+    import diffsci.models as M
+    from diffsci.models.nets.punetg import PUNetG
+    from diffsci.models.nets.punetg_config import PUNetGConfig
+    torch.set_num_threads(8)
+    for name, kw, shape, seed in (("nobias_punetg2d", dict(dimension=2, model_channels=8, bias=False), (2, 1, 16, 16), 111),
+                                  ("nobias_punetg3d", dict(dimension=3, model_channels=8, bias=False, input_channels=2,
+                                                           output_channels=2), (2, 2, 8, 8, 8), 112)):
+        net = PUNetG(PUNetGConfig(**kw))
+        man = load_synth(net, seed)
+        assert not any(k.endswith("conv1.bias") or k.startswith("convin.bias") for k, _ in man)
+        net.eval()
+        torch.manual_seed(seed)
+        x, t = torch.randn(*shape), torch.tensor([-1.1, 0.7])
+        with torch.no_grad():
+            y32 = net(x, t)
+            y64 = net.double()(x.double(), t.double())
+            net.float()
+        out = {"kind": "punetg", "cfg": kw, "manifest": man, "seed": seed, "x": x, "t": t, "y": y32, "y64": y64, "nsteps": 4}
+        mod = M.KarrasModule(net, M.KarrasModuleConfig.from_edm())
+        mod.eval()
+        wn = torch.randn(*shape)
+        sg = torch.tensor([0.3, 4.0])
+        xin = torch.randn(*shape) * (1 + sg.view(-1, *([1] * (len(shape) - 1))))
+        with torch.no_grad():
+            D, _ = mod.get_denoiser(xin, sg)
+            out.update(white_noise=wn, den_x=xin, den_sigma=sg, den_D=D,
+                       heun_hist=mod.propagate_white_noise(wn, nsteps=4, record_history=True))
+            noises = [torch.randn(*shape) for _ in range(4)]
+            out["noises"] = noises
+            with _Noise(noises):
+                out["em"] = mod.propagate_white_noise(wn, nsteps=4, integrator="euler-maruyama")
+        mod.train()
+        x0, ln = torch.randn(*shape) * 0.5, torch.randn(*shape)
+        net.zero_grad()
+        with _Noise([ln]):
+            L = mod.loss_fn(x0, sg, None, None)
+        L.backward()
+        out.update(loss_x=x0, loss_noise=ln, loss_sigma=sg, loss_huber=L.detach().clone(),
+                   loss_huber_grads={k: p.grad.clone() for k, p in net.named_parameters() if GRAD_KEYS.search(k)})
+        torch.save(out, os.path.join(OUT, name + ".pt"))
+        print(name, "fp32-vs-fp64", float((y32 - y64).abs().max() / y64.abs().max()), "loss", float(L.detach()),
+              "convin", [s_ for k, s_ in man if k == "convin.weight"])
+
+
 def main():
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "nobias":
+        return nobias_goldens()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "dropout":
         return dropout_goldens()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ensemble":

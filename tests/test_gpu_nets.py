@@ -345,3 +345,71 @@ def test_cached_sampler_engine_sees_weight_updates(golden, name, precision):
     assert torch.equal(a1, b1) and not torch.equal(a1, a0)
     net.load_state_dict(backup)
     assert torch.equal(mod.propagate_white_noise(wn.to(DEV), nsteps=3).cpu(), a0)
+
+
+def test_sample_and_filter(golden):
+    """karrasmodule.py:735-799: rejection sampling around sample(); chunked and unchunked runs see the same samples."""
+    import diffsci_b200 as d
+    net = build_net(golden("mlp_silu"))
+    mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm()).eval()
+    flt = lambda s: s[:, 0] > 0  # noqa: E731
+    torch.manual_seed(5)
+    ref = mod.sample(64, [2], nsteps=6)
+    torch.manual_seed(5)
+    r = mod.sample_and_filter(64, [2], flt, nsteps=6)
+    assert torch.equal(r["samples"], ref) and torch.equal(r["filter"], ref[:, 0] > 0)
+    assert abs(float(r["hit_rate"]) - float((ref[:, 0] > 0).float().mean())) < 1e-6
+    torch.manual_seed(5)
+    pos = mod.sample_and_filter(64, [2], flt, nsteps=6, return_only_positives=True, move_to_cpu=True)
+    assert torch.equal(pos["samples"], ref[ref[:, 0] > 0].cpu()) and bool(pos["filter"].all()) and not pos["samples"].is_cuda
+    ch = mod.sample_and_filter(64, [2], flt, nsteps=6, maximum_batch_size=24)
+    assert ch["samples"].shape == (64, 2) and ch["filter"].shape == (64,) and 0.0 <= ch["hit_rate"] <= 1.0
+    with pytest.raises(ValueError):
+        mod.sample_and_filter(8, [2], flt, record_history=True)
+
+
+@pytest.mark.parametrize("name", ["nobias_punetg2d", "nobias_punetg3d"])
+def test_bias_false_punetg(golden, name):
+    """PUNetGConfig(bias=False) (punetg.py:188-216, 389-394): bias-free convolutions + a constant ones channel that lives in
+    the network-input buffer (written once; the fused stages fill the state channels only).  Forward (fp32 and bf16),
+    denoiser, graph-engine and eager sampling, loss + gradients vs the LIVE reference."""
+    import diffsci_b200 as d
+    from oracle import karras_oracle as K
+    from tests.test_oracle_vs_golden import oracle_net
+    g = golden(name)
+    net = build_net(g)
+    assert net.ones_channel == 1 and net.convin.bias is None and net.convin.cin == g["x"].shape[1] + 1
+    with torch.no_grad():
+        y = net(g["x"].to(DEV), g["t"].to(DEV)).cpu()
+    e_ref = relmax(g["y"], g["y64"])
+    assert relmax(y, g["y64"]) < max(3 * e_ref, 2e-5) and relmax(y, g["y"]) < max(4 * e_ref, 2e-5)
+    net16 = build_net(g, "bf16")
+    with torch.no_grad():
+        y16 = net16(g["x"].to(DEV), g["t"].to(DEV)).cpu()
+    assert relmax(y16, g["y64"]) < 3e-2
+    mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm()).eval()
+    D, _ = mod.get_denoiser(g["den_x"].to(DEV), g["den_sigma"].to(DEV))
+    assert relmax(D.cpu(), g["den_D"]) < 5e-5
+    net64 = oracle_net(g, torch.float64)
+    wn, n = g["white_noise"], g["nsteps"]
+    h64 = K.sample_from_white_noise(net64, wn.double(), n, "heun", record_history=True)
+    budget = 2.0 * relmax(g["heun_hist"].double(), h64) + 2e-5
+    for graphs in (True, False):
+        mod.use_cuda_graphs = graphs
+        mod._engines.clear()
+        h = mod.propagate_white_noise(wn.to(DEV), nsteps=n, record_history=True).cpu()
+        assert relmax(h, g["heun_hist"]) <= budget, (graphs, relmax(h, g["heun_hist"]), budget)
+    em64 = K.sample_from_white_noise(net64, wn.double(), n, "euler-maruyama", noises=[z.double() for z in g["noises"]])
+    integ = d.name_to_integrator("euler-maruyama")
+    integ.reset_noise(injected=g["noises"])
+    em = mod.propagate_white_noise(wn.to(DEV), nsteps=n, integrator=integ).cpu()
+    assert relmax(em, g["em"]) <= 2.0 * relmax(g["em"].double(), em64) + 2e-5
+    net.train(), mod.train()
+    net.zero_grad()
+    mod._injected_loss_noise = g["loss_noise"]
+    L = mod.loss_fn(g["loss_x"].to(DEV), g["loss_sigma"].to(DEV))
+    L.backward()
+    assert abs(float(L) - float(g["loss_huber"])) < 5e-5 * abs(float(g["loss_huber"]))
+    grads = dict(net.named_parameters())
+    for k, ref in g["loss_huber_grads"].items():
+        assert relmax(grads[k].grad.cpu(), ref) < 3e-4, (k, relmax(grads[k].grad.cpu(), ref))

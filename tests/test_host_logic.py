@@ -88,7 +88,8 @@ def test_scalar_api_matches_reference(golden):
         assert ema._power_function_beta(sd_, n) == v
 
 
-@pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8", "punetg2d_multi", "mlp_silu", "adm2d_mc8", "adm2d_add"])
+@pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8", "punetg2d_multi", "mlp_silu", "adm2d_mc8", "adm2d_add",
+                                  "nobias_punetg2d", "nobias_punetg3d"])
 def test_state_dict_layout_is_the_reference_layout(golden, name):
     import diffsci_b200 as d
     g = golden(name)

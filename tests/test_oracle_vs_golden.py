@@ -85,7 +85,7 @@ def test_ema_betas(golden):
 
 
 @pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8", "punetg2d_multi", "adm2d_mc8", "adm2d_add",
-                                  "mlp_silu"])
+                                  "mlp_silu", "nobias_punetg2d", "nobias_punetg3d"])
 def test_net_forward(golden, name):
     g = golden(name)
     y = oracle_net(g)(g["x"], g["t"])
@@ -345,3 +345,25 @@ def test_training_dropout(golden, name):
         assert relmax(leaves[k].grad, gr) < 2e-4, k
     frac = sum(float(v.float().sum()) for v in g["keep"].values()) / sum(v.numel() for v in g["keep"].values())
     assert abs(frac - (1 - g["p"])) < 0.02
+
+
+@pytest.mark.parametrize("name", ["nobias_punetg2d", "nobias_punetg3d"])
+def test_bias_false_punetg(golden, name):
+    """PUNetGConfig(bias=False) (punetg.py:188-216, 389-394): denoiser, Heun / Euler-Maruyama sampling and loss + gradients of
+    the LIVE reference with bias-free convolutions and the appended ones channel."""
+    g = golden(name)
+    net = oracle_net(g)
+    assert relmax(K.denoiser(net, g["den_x"], g["den_sigma"]), g["den_D"]) < TOL32
+    net64 = oracle_net(g, torch.float64)
+    wn, n = g["white_noise"], g["nsteps"]
+    for key, integ, kw in (("heun_hist", "heun", dict(record_history=True)), ("em", "euler-maruyama", dict(noises=g["noises"]))):
+        o32 = K.sample_from_white_noise(net, wn, n, integ, **kw)
+        kw64 = {k: ([z.double() for z in v] if k == "noises" else v) for k, v in kw.items()}
+        o64 = K.sample_from_white_noise(net64, wn.double(), n, integ, **kw64)
+        assert relmax(o32, g[key]) <= 2.0 * relmax(g[key].double(), o64) + 2e-5, key
+    netg, leaves = _leaf_net(g)
+    L = K.edm_loss(netg, g["loss_x"], g["loss_sigma"], g["loss_noise"], "huber")
+    assert abs(float(L.detach()) - float(g["loss_huber"])) <= 5e-6 * abs(float(g["loss_huber"]))
+    L.backward()
+    for k, gr in g["loss_huber_grads"].items():
+        assert relmax(leaves[k].grad, gr) < 2e-4, k
