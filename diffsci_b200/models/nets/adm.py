@@ -20,7 +20,7 @@ from torch import nn
 
 from ... import ops
 from ..._lib import require_cuda
-from .layers import AttentionParams, ConvParams, FourierParams, LinearParams, NormParams, _Act, _Holder
+from .layers import AttentionParams, ConvParams, FourierParams, LinearParams, NormParams, _Act, _Holder, make_conv
 from .punetg import _NORM_MODE, _tc_eligible, DEFAULT_PRECISION
 
 
@@ -64,15 +64,18 @@ class ADMConfig:
 class ADMBlockParams(_Holder):
     """Parameters of one ADMBaseBlock in the reference's registration order."""
 
-    def __init__(self, cin: int, cout: int, cembed: int, ndim: int, attn: bool, sample: Optional[str]):
+    def __init__(self, cin: int, cout: int, cembed: int, ndim: int, attn: bool, sample: Optional[str],
+                 convolution_type: str = "default"):
         super().__init__()
         self.cin, self.cout, self.sample, self.has_attn = cin, cout, sample, attn
         self.norm1 = NormParams(cin)
         self.norm2 = NormParams(cout)
-        self.conv1 = ConvParams(cin, cout, 3, ndim)
-        self.conv2 = ConvParams(cout, cout, 3, ndim)
+        # convolution_type="circular": the three block convolutions are CircularConv2d (adm.py:427-441; keys <name>.conv.*);
+        # the 1x1 residual projection has no halo, so periodic and zero padding coincide for it
+        self.conv1 = make_conv(cin, cout, 3, ndim, True, convolution_type)
+        self.conv2 = make_conv(cout, cout, 3, ndim, True, convolution_type)
         self.embed_linear = LinearParams(cembed, 2 * cout)
-        self.convresidual = ConvParams(cin, cout, 1, ndim)
+        self.convresidual = make_conv(cin, cout, 1, ndim, True, convolution_type)
         if attn:
             self.attn = AttentionParams(cout)
 
@@ -104,7 +107,7 @@ class ADM(nn.Module):
         bad = []
         if c.dimension != 2:
             bad.append("dimension != 2 (the reference hard-codes Conv2d input/output layers, adm.py:189-196)")
-        if c.convolution_type != "default":
+        if c.convolution_type not in ("default", "circular"):
             bad.append(f"convolution_type={c.convolution_type!r}")
         if c.first_resblock_norm not in _NORM_MODE or c.second_resblock_norm not in _NORM_MODE:
             bad.append("norms other than GroupLN/GroupRMS")
@@ -117,16 +120,17 @@ class ADM(nn.Module):
         self.precision = precision or DEFAULT_PRECISION
         self.conditional_embedding = conditional_embedding     # any torch module: y -> [B, output_embed_dim] (adm.py:199-203)
         M, E, nd = c.model_channels, c.output_embed_dim, c.dimension
+        ct = c.convolution_type          # the input / output layers stay zero-padded torch.nn.Conv2d in the reference (adm.py:189-196)
         mult = c.extended_channel_expansion
         self.time_embedding = _TimeEmbedding(c.time_embed_dim, E, c.time_projection_scale)
         enc = []
         for i in range(len(mult) - 1):
             cin, cout, nb = M * mult[i], M * mult[i + 1], c.number_resnet_downward_block
             enc.append(_BlockList("input_blocks", [ADMBlockParams(cin, cout if r == nb - 1 else cin, E, nd, False,
-                                                                  "down" if r == nb - 1 else None) for r in range(nb)]))
+                                                                  "down" if r == nb - 1 else None, ct) for r in range(nb)]))
         self.encoder = _Layers(enc)
         mc = c.middle_channel
-        self.middle_block = _BlockList("middle_blocks", [ADMBlockParams(mc, mc, E, nd, a, None)
+        self.middle_block = _BlockList("middle_blocks", [ADMBlockParams(mc, mc, E, nd, a, None, ct)
                                                          for a in c.middle_block_attn_config])
         rev = mult[::-1]
         dec = []
@@ -134,7 +138,7 @@ class ADM(nn.Module):
             cin, cout, nb = M * rev[i], M * rev[i + 1], c.number_resnet_upward_block
             cc = 2 * cin if c.skip_integration_type == "concat" else cin
             dec.append(_BlockList("input_blocks", [ADMBlockParams(cc, cout if r == nb - 1 else cc, E, nd, False,
-                                                                  "up" if r == nb - 1 else None) for r in range(nb)]))
+                                                                  "up" if r == nb - 1 else None, ct) for r in range(nb)]))
         self.decoder = _Layers(dec)
         self.input_layer = ConvParams(c.input_channels, M, c.kernel_size, 2)
         self.output_layer = ConvParams(M, c.output_channels, c.kernel_size, 2)
@@ -229,12 +233,14 @@ class _ADMPlan:
         self.blocks = ([b for layer in net.encoder.layers for b in layer.input_blocks] + list(net.middle_block.middle_blocks) +
                        [b for layer in net.decoder.layers for b in layer.input_blocks])
         self._bufs: dict[Any, torch.Tensor] = {}
+        self._pad_ws = None
         self.xin = torch.empty((B, 1, H, W, c.input_channels), dtype=adt, device=dev)
         self.F = torch.empty((B, 1, H, W, c.output_channels), dtype=adt, device=dev)
 
         def pack(cp, subpixel=False, few_out_ok=False):
             tc = precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize, few_out_ok)
-            return ops.PackedConv(cp.weight, cp.bias, 2, torch.bfloat16 if tc else torch.float32, subpixel and tc)
+            return ops.PackedConv(cp.weight, cp.bias, 2, torch.bfloat16 if tc else torch.float32, subpixel and tc,
+                                  circular=bool(getattr(cp, "circular", False)) and cp.ksize > 1)
 
         self.pc_in, self.pc_out = pack(net.input_layer), pack(net.output_layer, few_out_ok=True)
         self.pc = {id(b): (pack(b.conv1, b.sample == "up"), pack(b.conv2), pack(b.convresidual)) for b in self.blocks}
@@ -282,6 +288,11 @@ class _ADMPlan:
 
     def _conv(self, x, pc, out, up: bool, **kw):
         # nearest x2 upsample is never materialised: FFMA folds it into the gather, tcgen05 runs the sub-pixel form
+        if pc.circular:      # the tcgen05 path reads a halo-padded copy (TMA boxes cannot wrap): one workspace, grown on demand
+            need = ops.conv_pad_ws_bytes(x.shape, x.dtype, pc, up)
+            if need > 0 and (self._pad_ws is None or self._pad_ws.numel() < need):
+                self._pad_ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            kw["pad_ws"] = self._pad_ws
         return ops.conv(x, pc, out=out, up2=up, **kw)
 
     def _attention(self, x, blk, idx):
@@ -327,7 +338,7 @@ class _ADMPlan:
                          out=self.buf("n2", y.shape), film_scale=te1, film_shift=te2,
                          ws=self.buf("ws", (ops.lib.dsk_norm_ws_bytes(B, Ho * Wo, blk.cout),), torch.uint8))
         r = self._conv(xr, pcr, self.buf("r", y.shape), up)                            # conv1x1([pool|up](x))
-        o = ops.conv(h, pc2, out=self.buf(("o", idx), y.shape), residual=r)
+        o = self._conv(h, pc2, self.buf(("o", idx), y.shape), False, residual=r)
         if blk.has_attn:
             o = self._attention(o, blk, idx)
         return o

@@ -146,7 +146,8 @@ class TrainGraph:
             return self._conv1x1_tc(x, cp, residual, up2)
         tc = self.precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize, few_out_ok)
         wdt = torch.bfloat16 if tc else torch.float32
-        circ = bool(getattr(cp, "circular", False))       # CircularConv (commonlayers.py:918-1032): forward, dgrad and wgrad wrap
+        # CircularConv (commonlayers.py:918-1032): forward, dgrad and wgrad wrap; a 1x1 kernel has no halo to wrap
+        circ = bool(getattr(cp, "circular", False)) and cp.ksize > 1
         pc = ops.PackedConv(cp.weight, cp.bias, nd, wdt, subpixel=bool(up2 and tc), circular=circ)
         self._packs.append(pc)
         pws = self.lazy_scratch("pad_ws", max(ops.conv_pad_ws_bytes(x.t.shape, x.t.dtype, pc, up2), 1))

@@ -187,7 +187,7 @@ def adm_block(x, te, sd, p, cfg, sample=None, attn=False, dropout_masks=None):
         return z
 
     y = F.silu(_norm(cfg.first_resblock_norm, x, G, sd[p + "norm1.weight"], sd[p + "norm1.bias"]))
-    y = _conv(resample(y), sd[p + "conv1.weight"], sd[p + "conv1.bias"], dim)
+    y = _pconv(resample(y), sd, p + "conv1", cfg)            # conv_fn: Conv2d | CircularConv2d (adm.py:427-441)
     y = _norm(cfg.second_resblock_norm, y, G, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
     e = F.linear(te, sd[p + "embed_linear.weight"], sd[p + "embed_linear.bias"])
     te1, te2 = torch.chunk(e, 2, dim=-1)
@@ -195,8 +195,8 @@ def adm_block(x, te, sd, p, cfg, sample=None, attn=False, dropout_masks=None):
     y = F.silu(y)
     if dropout_masks is not None:          # ADMBaseBlock.second_block (adm.py:323-329) with an explicit, pre-scaled mask
         y = y * dropout_masks[p[:-1]].to(y)
-    y = _conv(y, sd[p + "conv2.weight"], sd[p + "conv2.bias"], dim)
-    y = y + _conv(resample(x), sd[p + "convresidual.weight"], sd[p + "convresidual.bias"], dim)
+    y = _pconv(y, sd, p + "conv2", cfg)
+    y = y + _pconv(resample(x), sd, p + "convresidual", cfg)
     if attn:
         y = mha_self_attention(y, sd, p + "attn.", cfg.attn_residual)
     return y

@@ -167,13 +167,14 @@ def test_circular_conv_backward(ops, ndim, B, Cin, Cout, sp, k, up2, dtype):
 def build(g, precision="fp32"):
     import diffsci_b200 as d
     from oracle.nets_oracle import synth_state_dict
-    net = d.PUNetG(d.PUNetGConfig(**g["cfg"]), precision=precision)
+    net = (d.ADM(d.ADMConfig(**g["cfg"]), precision=precision) if g.get("kind") == "adm" else
+           d.PUNetG(d.PUNetGConfig(**g["cfg"]), precision=precision))
     assert list(net.state_dict().keys()) == [k for k, _ in g["manifest"]]      # <name>.conv.weight keys, reference order
     net.load_state_dict(synth_state_dict(g["manifest"], g["seed"]))
     return net.to(DEV).eval()
 
 
-@pytest.mark.parametrize("name", ["circ_punetg2d", "circ_punetg3d"])
+@pytest.mark.parametrize("name", ["circ_punetg2d", "circ_punetg3d", "circ_adm2d"])
 def test_circular_network_vs_live_reference(golden, name):
     import diffsci_b200 as d
     from oracle import karras_oracle as K
@@ -293,3 +294,32 @@ def test_norm_apply_padded_and_prepadded_conv(ops, ndim, shape):
         ops.conv(x, pc, residual=res, stats=s1)
         ops.conv(ops.pad_circular(x, ndim), pc, residual=res, stats=s2, prepadded=True)
         assert torch.equal(s1, s2)
+
+
+def test_circular_adm_tensor_core_path():
+    """ADM mc=64 with circular block convolutions in bf16 (tcgen05 through the halo-padded copy, sub-pixel up-convs, the plan's
+    grown-on-demand pad workspace under graph capture) vs the fp64 oracle, next to its zero-padded twin."""
+    import diffsci_b200 as d
+    from oracle import nets_oracle as N
+    from tests.test_oracle_vs_golden import cfg_for
+    kw = dict(input_channels=3, output_channels=3, model_channels=64, channel_expansion=[2], number_resnet_attn_block=2)
+    errs = {}
+    for ct in ("circular", "default"):
+        kwc = dict(kw, convolution_type=ct)
+        net = d.ADM(d.ADMConfig(**kwc), precision="bf16")
+        man = [(k, list(v.shape)) for k, v in net.state_dict().items()]
+        sd = N.synth_state_dict(man, 777)
+        net.load_state_dict(sd)
+        net = net.to(DEV).eval()
+        torch.manual_seed(3)
+        x, t = torch.randn(2, 3, 32, 32), torch.tensor([0.3, -1.0])
+        cfg = cfg_for("adm", kwc)
+        ref = N.adm_forward({k: v.double() for k, v in sd.items()}, cfg, x.double(), t.double())
+        with torch.no_grad():
+            y = net(x.to(DEV), t.to(DEV)).cpu()
+        errs[ct] = rel_l2(y, ref)
+        mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm())
+        s = mod.sample(2, [3, 32, 32], nsteps=3)                       # graph engine: capture + replay
+        assert torch.isfinite(s).all()
+    print(f"ADM bf16 L2 vs fp64: circular {errs['circular']:.3e}, zero-padded {errs['default']:.3e}")
+    assert errs["default"] < 3e-2 and errs["circular"] < max(3 * errs["default"], 3e-2)

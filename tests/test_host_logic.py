@@ -89,7 +89,7 @@ def test_scalar_api_matches_reference(golden):
 
 
 @pytest.mark.parametrize("name", ["punetg2d_mc8", "punetg3d_mc8", "punetg2d_multi", "mlp_silu", "adm2d_mc8", "adm2d_add",
-                                  "nobias_punetg2d", "nobias_punetg3d"])
+                                  "nobias_punetg2d", "nobias_punetg3d", "circ_adm2d"])
 def test_state_dict_layout_is_the_reference_layout(golden, name):
     import diffsci_b200 as d
     g = golden(name)

@@ -188,7 +188,7 @@ def test_conditional_path(golden, name):
 
 
 # ----------------------------------------------------------------------------- circular convolution
-@pytest.mark.parametrize("name", ["circ_punetg2d", "circ_punetg3d"])
+@pytest.mark.parametrize("name", ["circ_punetg2d", "circ_punetg3d", "circ_adm2d"])
 def test_circular_punetg(golden, name):
     g = golden(name)
     net = oracle_net(g)
