@@ -227,38 +227,35 @@ def circular_goldens():
                   convolution_type="circular")
         gk_adm = re.compile(r"^(input_layer|output_layer|encoder\.layers\.0\.input_blocks\.[01]\.|middle_block\.middle_blocks\.2\.|"
                             r"decoder\.layers\.1\.input_blocks\.1\.)")
-        try:
-            net = ADM(ADMConfig(**kw))
-            man = load_synth(net, 123)
-            net.eval()
-            mod = M.KarrasModule(net, M.KarrasModuleConfig.from_edm())
-            mod.eval()
-            torch.manual_seed(1123)
-            shape, nsteps = (2, 3, 16, 16), 3
-            x, t = torch.randn(*shape), torch.randn(2) * 0.7
-            out = dict(kind="adm", cfg=kw, manifest=man, seed=123, x=x, t=t, nsteps=nsteps)
-            with torch.no_grad():
-                out["y"] = net(x, t)
-                out["y64"] = net.double()(x.double(), t.double())
-                net.float()
-                wn = torch.randn(*shape)
-                out["white_noise"] = wn
-                out["heun_hist"] = mod.propagate_white_noise(wn, nsteps=nsteps, record_history=True)
-            sg = torch.exp(torch.randn(2) * 1.2 - 1.2)
-            x0, ln = torch.randn(*shape) * 0.5, torch.randn(*shape)
-            out.update(loss_x=x0, loss_noise=ln, loss_sigma=sg)
-            net.train()
-            net.zero_grad()
-            with _Noise([ln]):
-                L = mod.loss_fn(x0, sg, None, None)
-            L.backward()
-            out["loss_huber"] = L.detach()
-            out["loss_huber_grads"] = {k: p.grad.clone() for k, p in net.named_parameters() if gk_adm.search(k)}
-            torch.save(out, os.path.join(OUT, "circ_adm2d.pt"))
-            print("circ_adm2d fp32-vs-fp64", float((out["y"] - out["y64"]).abs().max() / out["y64"].abs().max()), "loss", float(L.detach()),
-                  len(out["loss_huber_grads"]), "gradient tensors")
-        finally:
-            pass
+        net = ADM(ADMConfig(**kw))
+        man = load_synth(net, 123)
+        net.eval()
+        mod = M.KarrasModule(net, M.KarrasModuleConfig.from_edm())
+        mod.eval()
+        torch.manual_seed(1123)
+        shape, nsteps = (2, 3, 16, 16), 3
+        x, t = torch.randn(*shape), torch.randn(2) * 0.7
+        out = dict(kind="adm", cfg=kw, manifest=man, seed=123, x=x, t=t, nsteps=nsteps)
+        with torch.no_grad():
+            out["y"] = net(x, t)
+            out["y64"] = net.double()(x.double(), t.double())
+            net.float()
+            wn = torch.randn(*shape)
+            out["white_noise"] = wn
+            out["heun_hist"] = mod.propagate_white_noise(wn, nsteps=nsteps, record_history=True)
+        sg = torch.exp(torch.randn(2) * 1.2 - 1.2)
+        x0, ln = torch.randn(*shape) * 0.5, torch.randn(*shape)
+        out.update(loss_x=x0, loss_noise=ln, loss_sigma=sg)
+        net.train()
+        net.zero_grad()
+        with _Noise([ln]):
+            L = mod.loss_fn(x0, sg, None, None)
+        L.backward()
+        out["loss_huber"] = L.detach()
+        out["loss_huber_grads"] = {k: p.grad.clone() for k, p in net.named_parameters() if gk_adm.search(k)}
+        torch.save(out, os.path.join(OUT, "circ_adm2d.pt"))
+        print("circ_adm2d fp32-vs-fp64", float((out["y"] - out["y64"]).abs().max() / out["y64"].abs().max()), "loss", float(L.detach()),
+              len(out["loss_huber_grads"]), "gradient tensors")
         return
     case("circ_punetg2d", dict(dimension=2, model_channels=8, convolution_type="circular"), (2, 1, 16, 24), 121)
     case("circ_punetg3d", dict(dimension=3, model_channels=8, channel_expansion=[2], convolution_type="circular"),

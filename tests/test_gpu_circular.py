@@ -243,7 +243,7 @@ def test_circular_network_tensor_core_path():
     assert e < 6e-2 and e0 < 3e-2 and relmax(y, ref) < 8e-2, (e, e0, relmax(y, ref))
     # training gradients: global L2 against fp64 autograd of the oracle.  fp32 mode pins the logic (wrap in forward, dgrad
     # and wgrad); in bf16 the periodic net is ~2x more rounding-sensitive than its zero-padded twin (fp32: 3.9e-5 vs 1.1e-5,
-    # bf16: 1.2e-1 vs 5.9e-2 measured, tools/diag_circular_grads.py), so the bf16 gate is relative to the twin.
+    # bf16: 1.2e-1 vs 5.9e-2 measured, tests/diag_circular_grads.py), so the bf16 gate is relative to the twin.
     dF = torch.randn(2, 1, 8, 16, 16)
     err = {}
     for ct, s_, c_ in (("circular", sd, cfg), ("default", sd0, cfg0)):
