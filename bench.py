@@ -14,6 +14,7 @@ One rank per GPU; no data-path collective (samples are independent, SURVEY.md 8e
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -44,6 +45,22 @@ NAMES = {"c4": "PUNetG-3D(mc=64,[2,4]) 1x64^3 EDM Heun-64 sampling (BASELINE con
          "c2": "PUNetG-2D(mc=128) 1x28x28 EDM Heun-40 sampling (BASELINE configs[1])",
          "c5": "PUNetG-2D(mc=64) 1x256x256 Euler-Maruyama-256 sampling (BASELINE configs[4])",
          "c1": "MLPUncond(2,[128]*3,SiLU) toy Heun-18 sampling (BASELINE configs[0])"}
+
+
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """stdout carries exactly ONE JSON line.  NCCL writes "NCCL version ..." to the process's stdout (fd 1) when the
+    communicator is created under NCCL_DEBUG=VERSION / INFO (the GPU boxes export VERSION), so fd 1 points at stderr while the
+    process group comes up."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
 
 
 def nfe_per_sample(nsteps, integrator):
@@ -305,7 +322,9 @@ def train_arm(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with stdout_to_stderr():        # eager communicator creation (device_id) + the first collective
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
     precision = args.precision
     if precision == "auto":
         precision = "bf16" if d.TC_CONV_ENABLED else "fp32"
@@ -447,7 +466,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with stdout_to_stderr():        # eager communicator creation (device_id) + the first collective
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
     precision = args.precision
     if precision == "auto":
         precision = "bf16" if d.TC_CONV_ENABLED else "fp32"

@@ -337,3 +337,20 @@ def test_bench_reference_arm_contract():
         assert abs(flops / 1e9 - gf) < 2e-3 * gf, (name, flops / 1e9)
     assert bench.nfe_per_sample(64, "heun") == 127 and bench.nfe_per_sample(256, "euler-maruyama") == 256
     assert bench.nfe_per_sample(256, "karras") == 511
+
+
+def test_bench_stdout_hygiene():
+    """bench.stdout_to_stderr: anything a library writes to fd 1 while the process group comes up (NCCL's "NCCL version ..."
+    under NCCL_DEBUG=VERSION) lands on stderr; stdout keeps the one JSON line."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys; sys.path.insert(0, %r); import bench\n"
+            "with bench.stdout_to_stderr():\n"
+            "    os.write(1, b'NCCL version x\\n'); print('also noise')\n"
+            "print('{\"ok\": 1}')\n") % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == '{"ok": 1}'
+    assert "NCCL version x" in out.stderr and "also noise" in out.stderr
