@@ -354,3 +354,36 @@ def test_bench_stdout_hygiene():
     assert out.returncode == 0, out.stderr
     assert out.stdout.strip() == '{"ok": 1}'
     assert "NCCL version x" in out.stderr and "also noise" in out.stderr
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every ctypes signature in _lib.SIGNATURES has the arity and the scalar / pointer kinds of its declaration in
+    include/diffsci_b200.h -- a wrong binding would otherwise only show up as garbage arguments on the GPU."""
+    import ctypes as C
+    from diffsci_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "diffsci_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    header = re.sub(r"//[^\n]*", " ", header)
+    decls = dict(re.findall(r"\b(dsk_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", header, flags=re.S))
+
+    def kind(param: str) -> str:
+        p = " ".join(param.split())
+        if "*" in p:
+            return "ptr"
+        base = p.rsplit(" ", 1)[0] if " " in p else p
+        return {"int": "i32", "int64_t": "i64", "uint64_t": "u64", "uint32_t": "u32", "float": "f32", "unsigned": "u32",
+                "unsigned int": "u32", "size_t": "u64"}.get(base.replace("const ", ""), base)
+
+    ckind = {C.c_void_p: "ptr", C.c_char_p: "ptr", C.c_int: "i32", C.c_int64: "i64", C.c_uint64: "u64", C.c_uint32: "u32",
+             C.c_float: "f32"}
+    checked = 0
+    for name, sig in _lib.SIGNATURES.items():
+        assert name in decls, name
+        params = [p for p in decls[name].split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(sig), (name, len(params), len(sig))
+        for p, c in zip(params, sig):
+            want = kind(p)
+            got = ckind.get(c, "ptr" if hasattr(c, "contents") or getattr(c, "_type_", None) is not None and not isinstance(getattr(c, "_type_"), str) else None)
+            assert got == want, (name, p.strip(), want, c)
+        checked += 1
+    assert checked == len(_lib.SIGNATURES) >= 60
