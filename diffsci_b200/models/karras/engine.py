@@ -96,6 +96,12 @@ class SamplerEngine:
         self.seed = 0
         self.nfe = 0
 
+    programs = PROGRAMS
+
+    def _program(self, program: str, table: torch.Tensor):
+        """-> (stages of a regular step, stages of the final step)."""
+        return PROGRAMS[program]
+
     # ------------------------------------------------------------------ pieces
     def _net(self):
         self.nfe += 1
@@ -170,14 +176,14 @@ class SamplerEngine:
             noises: Optional[torch.Tensor] = None, seed: int = 0) -> torch.Tensor:
         """white_noise: fp32 [B, *shape] on the device; table: CPU fp32 [nsteps+1, 8] (Scheduler.step_table)."""
         require_cuda(white_noise, "white noise")
-        if program not in PROGRAMS:
+        if program not in self.programs:
             raise ValueError(f"Unknown integrator program: {program}")
         with torch.inference_mode(False), torch.no_grad():
             return self._run(white_noise, table, program, record_history, noises, seed)
 
     def _run(self, white_noise, table, program, record_history, noises, seed):
         nsteps = table.shape[0] - 1
-        regular, final = PROGRAMS[program]
+        regular, final = self._program(program, table)
         N = self.B * self.Cc * self.S
         # static-address inputs of the captured graphs: refill in place, re-capture only on shape change
         if self._tab is None or self._tab.shape != table.shape:
@@ -222,3 +228,42 @@ class SamplerEngine:
         if record_history:
             return self._hist.view((nsteps + 1, self.B) + self.shape).clone()
         return self.x.clone()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+GSTAGE_INIT, GSTAGE_STEP1, GSTAGE_HEUN_MID, GSTAGE_HEUN_FIN = 0, 1, 2, 3      # include/diffsci_b200.h: dsk_gstage
+GENERAL_PROGRAMS = {
+    "euler": ((GSTAGE_STEP1,), (GSTAGE_STEP1,)),
+    "heun": ((GSTAGE_HEUN_MID, GSTAGE_HEUN_FIN), (GSTAGE_STEP1,)),       # final: only when the last step ends at t = 0
+    "euler-maruyama": ((GSTAGE_STEP1,), (GSTAGE_STEP1,)),
+}
+
+
+class GeneralSamplerEngine(SamplerEngine):
+    """The same captured-graph loop for ANY scheduler / preconditioner pair (VP / VE / SR3 / custom): the stages
+    of csrc/sampler_general.cu read rhs = P x + Q F and the network-input scale / c_noise of every evaluation point from
+    Scheduler.general_step_table, so nothing family-specific is left in the kernel.
+
+    EXPERIMENTAL in round 1: the table and the stage program are pinned on the CPU against the oracle
+    (tests/test_host_logic.py: test_general_step_table_program_equals_the_oracle); the kernel has not run on a B200 yet, so
+    KarrasModule only takes this route when DSK_GENERAL_ENGINE=1 -- the default for these configurations stays the
+    Integrator.step seam, which is parity-tested on the GPU."""
+    programs = GENERAL_PROGRAMS
+
+    def __init__(self, model, B, shape, device, use_graphs: bool = True):
+        super().__init__(model, B, shape, device, 0.5, 1.0, 0, use_graphs=use_graphs)
+        if not self.native:
+            raise NotImplementedError("GeneralSamplerEngine drives the native networks")
+
+    def _program(self, program: str, table: torch.Tensor):
+        regular, final = GENERAL_PROGRAMS[program]
+        if program == "heun" and float(table[table.shape[0] - 2, 9]) != 0.0:     # G_HAS2 of the last step
+            final = regular
+        return regular, final
+
+    def _stage(self, stage: int):
+        gstage = GSTAGE_INIT if stage == STAGE_INIT else stage     # _run's initial stage constant is the EDM engine's (== 0)
+        check(lib.dsk_sampler_stage_general(gstage, ptr(self.x), ptr(self.x_aux), ptr(self.r1), ptr(self._F), ptr(self.xin),
+                                            ptr(self.cnoise), ptr(self._tab), ptr(self.row), ptr(self._noise), ptr(self._hist),
+                                            self.B, self.Cc, self.S, self.sigma_max, dt_code(self.act_dtype), self.xin_ld,
+                                            stream()))

@@ -15,6 +15,7 @@ scope and raise NotImplementedError instead of silently doing something else.
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, Optional, Union
 
 import torch
@@ -558,6 +559,10 @@ class KarrasModule(_Base):
         if cond and not hasattr(self.model, "conditioning_vector"):
             fused = False              # foreign / not-yet-conditional networks: the duck-typed seam
         x = x.float().contiguous()
+        if (not fused and os.environ.get("DSK_GENERAL_ENGINE") == "1" and hasattr(self.model, "plan") and not cond and
+                integ.fused_program in sch.GENERAL_PROGRAMS and
+                type(integ) in (integrators.EulerIntegrator, integrators.HeunIntegrator, integrators.EulerMaruyamaIntegrator)):
+            return self._propagate_general(x, sch, integ, nsteps, record_history, _prescaled)
         if not fused:      # foreign preconditioner / scheduler / integrator: the duck-typed seam
             if not _prescaled:
                 x = ops.lincomb(x, float(sch.maximum_scale))
@@ -597,6 +602,30 @@ class KarrasModule(_Base):
         if integ.injected_noise is not None:
             noises = torch.stack([n.to(x) for n in integ.injected_noise[:nsteps]], 0)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if integ.fused_program in ("euler-maruyama", "karras") else 0
+        if getattr(integ, "_fixed_seed", None) is not None:
+            seed = integ._fixed_seed
+        out = eng.run(x, table, integ.fused_program, record_history=record_history, noises=noises, seed=seed)
+        self.last_nfe = eng.nfe
+        return out
+
+    def _propagate_general(self, x: Tensor, sch, integ, nsteps: int, record_history: bool, prescaled: bool) -> Tensor:
+        """EXPERIMENTAL (DSK_GENERAL_ENGINE=1): VP / VE / SR3 / custom configurations on the captured-graph loop through the
+        table-driven stages (engine.GeneralSamplerEngine); the default route for them is the Integrator.step seam."""
+        B, shape = x.shape[0], tuple(x.shape[1:])
+        key = ("general", B, shape, str(x.device), id(self.model), getattr(self.model, "precision", None), self.use_cuda_graphs)
+        eng = self._engines.get(key)
+        if eng is None:
+            if len(self._engines) >= 2:
+                self._engines.clear()
+            with torch.inference_mode(False), torch.no_grad():
+                eng = self._engines[key] = _engine.GeneralSamplerEngine(self.model, B, shape, x.device,
+                                                                        use_graphs=self.use_cuda_graphs)
+        eng.sigma_max = 1.0 if prescaled else float(sch.maximum_scale)
+        table = sch.general_step_table(nsteps, self.config.preconditioner, integ)
+        noises = None
+        if integ.injected_noise is not None:
+            noises = torch.stack([n.to(x) for n in integ.injected_noise[:nsteps]], 0)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if integ.fused_program == "euler-maruyama" else 0
         if getattr(integ, "_fixed_seed", None) is not None:
             seed = integ._fixed_seed
         out = eng.run(x, table, integ.fused_program, record_history=record_history, noises=noises, seed=seed)

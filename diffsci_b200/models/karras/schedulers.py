@@ -91,6 +91,65 @@ class Scheduler(torch.nn.Module):
         tab[:nsteps - 1, TAB_TNEXT] = tab[1:nsteps, TAB_THAT]
         return tab
 
+
+    # ------------------------------------------------------------------ general (table-driven) engine, SURVEY 8f-3
+    GTAB_COLS = 12
+    G_DT, G_P1, G_Q1, G_P2, G_Q2, G_XS1, G_CN1, G_XS2, G_CN2, G_HAS2, G_NZ = range(11)
+    GENERAL_PROGRAMS = ("euler", "heun", "euler-maruyama")
+
+    def rhs_coefficients(self, t, preconditioner, stochastic: bool = False):
+        """(P, Q, c_in / s, c_noise) at time t such that  rhs(x, t) = P x + Q F(c_in/s x, c_noise)  for the backward
+        integration -- Scheduler.rhs (schedulers.py:247-294) with score = (D - z) / sigma^2, D = c_out F + c_skip z,
+        z = x / s, folded into two scalars.  Evaluated with the scheduler's and the preconditioner's own objects."""
+        f = self.scheduler_fns
+        t0 = _f32(t)
+        sigma0, dsigma0 = f.noise_fn(t0), f.noise_fn_deriv(t0)
+        if f.constant_scaling_fn:
+            s, ds = torch.ones_like(t0), torch.zeros_like(t0)
+            mult = f.pf_score_multiplier(t0) if f.has_pf_score_multiplier else sigma0 * dsigma0
+        else:
+            s, ds = f.scaling_fn(t0), f.scaling_fn_deriv(t0)
+            mult = f.pf_score_multiplier(t0) if f.has_pf_score_multiplier else s * (dsigma0 * sigma0)
+        bm = -mult.double()
+        if stochastic:
+            bm = bm - self.langevin_factor(t0).double() / s.double()
+        sg = sigma0.reshape(1).float()
+        c_in, c_out, c_skip, c_noise = (v.reshape(-1)[0].double() for v in (
+            preconditioner.input_scaling(sg), preconditioner.output_scaling(sg), preconditioner.skip_scaling(sg),
+            preconditioner.noise_conditioner(sg)))
+        s, ds, sig2 = s.double(), ds.double(), sigma0.double() ** 2
+        return ds / s + bm * (c_skip - 1.0) / (sig2 * s), bm * c_out / sig2, c_in / s, c_noise
+
+    def general_step_table(self, nsteps: int, preconditioner, integrator: Optional[integrators.Integrator] = None) -> Tensor:
+        """fp32 CPU tensor [nsteps + 1, GTAB_COLS] for dsk_sampler_stage_general (include/diffsci_b200.h: dsk_gtab_col); the
+        last row is zero padding.  Rows follow Scheduler.propagate(backward=True) (schedulers.py:48-89): dt = diff(steps);
+        a Heun step whose end time is 0 has no second evaluation (integrators.py:45-53)."""
+        if nsteps < 2:
+            raise ValueError("nsteps must be >= 2")
+        integ = integrator if integrator is not None else self.integrator
+        prog = integ.fused_program
+        if prog not in self.GENERAL_PROGRAMS:
+            raise NotImplementedError(f"general step table: integrator program {prog!r}")
+        t = self.create_steps(nsteps + 1).float().cpu()
+        dt = torch.diff(t)
+        stoch = bool(integ.stochastic)
+        tab = torch.zeros((nsteps + 1, self.GTAB_COLS), dtype=torch.float64)
+        for i in range(nsteps):
+            P1, Q1, xs1, cn1 = self.rhs_coefficients(t[i], preconditioner, stoch)
+            tab[i, self.G_DT] = dt[i].double()
+            tab[i, self.G_P1], tab[i, self.G_Q1], tab[i, self.G_XS1], tab[i, self.G_CN1] = P1, Q1, xs1, cn1
+            t2 = t[i] + dt[i]                      # fp32 sum, as integrators.py:45 evaluates it
+            if prog == "heun":
+                if float(t2) > 0:
+                    P2, Q2, xs2, cn2 = self.rhs_coefficients(t2, preconditioner, False)
+                    tab[i, self.G_P2], tab[i, self.G_Q2], tab[i, self.G_XS2], tab[i, self.G_CN2] = P2, Q2, xs2, cn2
+                    tab[i, self.G_HAS2] = 1.0
+                elif float(t2) < 0:
+                    raise ValueError("t+dt < 0 in Heun integrator")
+            if prog == "euler-maruyama":
+                tab[i, self.G_NZ] = (self.noise_injection(t[i]).double() * torch.sqrt(torch.abs(dt[i])).double())
+        return tab.float()
+
     # ------------------------------------------------------------------ generic seam
     def propagate(self, x: Tensor, score_fn: ScoreFunction, nsteps: int = 100, record_history: bool = False,
                   backward: bool = True, stochastic: bool = False) -> Tensor:

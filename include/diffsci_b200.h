@@ -100,6 +100,37 @@ int dsk_sampler_stage(int stage, float* x, float* x_aux, float* r1, const void* 
                       void* stream);
 int dsk_sampler_advance(int* row, void* stream);
 
+/* Table-driven stages for ANY scheduler / preconditioner pair (SURVEY 8f-3 on the graph engine; the non-constant-scaling branch
+ * of Scheduler.rhs, karras/schedulers.py:275-293, with any KarrasPreconditioner, karras/preconditioners.py:30-161).  For fixed t
+ * the drift is linear in the state and the network output, rhs = P x + Q F with
+ *   P = s'/s + Bm (c_skip - 1) / (sigma^2 s),  Q = Bm c_out / sigma^2,  network input = (c_in / s) x,
+ * Bm = -(s sigma' sigma | pf_score_multiplier) [- langevin_factor / s on stochastic steps]; the host evaluates these with the
+ * scheduler's and the preconditioner's own objects (diffsci_b200.models.karras.schedulers.Scheduler.general_step_table).
+ * Table: fp32 [nsteps + 1][DSK_GTAB_COLS], last row zero padding.  EXPERIMENTAL in round 1 (not on the default path). */
+#define DSK_GTAB_COLS 12
+enum dsk_gtab_col {
+  DSK_GTAB_DT = 0,   /* dt_i                                                                   */
+  DSK_GTAB_P1 = 1,   /* rhs coefficients of the evaluation at t_i                              */
+  DSK_GTAB_Q1 = 2,
+  DSK_GTAB_P2 = 3,   /* ... at t_i + dt_i (Heun's second evaluation)                           */
+  DSK_GTAB_Q2 = 4,
+  DSK_GTAB_XS1 = 5,  /* network-input scale c_in/s and c_noise of the evaluation at t_i        */
+  DSK_GTAB_CN1 = 6,
+  DSK_GTAB_XS2 = 7,  /* ... at t_i + dt_i                                                      */
+  DSK_GTAB_CN2 = 8,
+  DSK_GTAB_HAS2 = 9, /* 1: the step has a second evaluation (t_i + dt_i > 0, integrators.py:45) */
+  DSK_GTAB_NZ = 10   /* Euler-Maruyama: noise_strength(t_i) * sqrt|dt_i| (integrators.py:66-69) */
+};
+enum dsk_gstage {
+  DSK_GSTAGE_INIT = 0,      /* x *= x_scale ; history[0] ; prepare the evaluation at t_0                          */
+  DSK_GSTAGE_STEP1 = 1,     /* x += dt (P1 x + Q1 F) (+ NZ xi) ; history ; prepare the next step                  */
+  DSK_GSTAGE_HEUN_MID = 2,  /* r1 = P1 x + Q1 F ; x_aux = x + dt r1 ; prepare the evaluation at t + dt            */
+  DSK_GSTAGE_HEUN_FIN = 3   /* r2 = P2 x_aux + Q2 F ; x += 0.5 (r1 + r2) dt ; history ; prepare the next step     */
+};
+int dsk_sampler_stage_general(int stage, float* x, float* x_aux, float* r1, const void* F, void* xin, float* cnoise,
+                              const float* tab, const int* row, const float* noise, float* hist, int B, int C, int64_t S,
+                              float x_scale, int act_dtype, int xin_ld, void* stream);
+
 /* Conditional sampling (KarrasModule.get_denoiser with y / guidance, karrasmodule.py:703-716;
  * PUNetGCond's channel concatenation, nets/punetg.py:716-735).  Same stage, with
  *   xin_ld >= C : the network-input rows hold xin_ld channels, the state x fills channels [0, C); channels [C, xin_ld)

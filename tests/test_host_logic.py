@@ -387,3 +387,73 @@ def test_ctypes_signatures_match_the_header():
             assert got == want, (name, p.strip(), want, c)
         checked += 1
     assert checked == len(_lib.SIGNATURES) >= 60
+
+
+def emulate_general_program(tab, program, net, white_noise, x_scale, noises=None, record_history=False):
+    """The stage program of csrc/sampler_general.cu (general_stage_kernel) in torch, statement for statement: INIT, then per
+    step STEP1 | HEUN_MID + HEUN_FIN, every scalar read from the general step table."""
+    import diffsci_b200 as d
+    S = d.Scheduler
+    dt_ = white_noise.dtype
+    tab = tab.to(dt_)
+    B = white_noise.shape[0]
+    x = white_noise * x_scale                                            # INIT
+    hist = [x]
+    xin, cn = tab[0, S.G_XS1] * x, tab[0, S.G_CN1]
+    nsteps = tab.shape[0] - 1
+    for i in range(nsteps):
+        r, rn = tab[i], tab[i + 1]
+        F = net(xin, cn * torch.ones(B, dtype=dt_))
+        if program == "heun" and r[S.G_HAS2] != 0:
+            r1 = r[S.G_P1] * x + r[S.G_Q1] * F                           # HEUN_MID
+            xa = x + r[S.G_DT] * r1
+            xin, cn = r[S.G_XS2] * xa, r[S.G_CN2]
+            F2 = net(xin, cn * torch.ones(B, dtype=dt_))
+            r2 = r[S.G_P2] * xa + r[S.G_Q2] * F2                         # HEUN_FIN
+            x = x + (0.5 * (r1 + r2)) * r[S.G_DT]
+        else:                                                            # STEP1
+            x = x + r[S.G_DT] * (r[S.G_P1] * x + r[S.G_Q1] * F)
+            if r[S.G_NZ] != 0:
+                x = x + r[S.G_NZ] * noises[i].to(dt_)
+        hist.append(x)
+        xin, cn = rn[S.G_XS1] * x, rn[S.G_CN1]
+    return torch.stack(hist, 0) if record_history else x
+
+
+@pytest.mark.parametrize("name", ["precond_vp_mlp", "precond_ve_mlp", "precond_sr3_mlp", "precond_vp_punetg2d", "sampler_mlp"])
+def test_general_step_table_program_equals_the_oracle(golden, name):
+    """SURVEY 8(f)-3 on the graph engine (experimental, DSK_GENERAL_ENGINE=1): rhs = P x + Q F with the table of
+    Scheduler.general_step_table reproduces Scheduler.propagate for VP / VE / SR3 / EDM x Euler / Heun / Euler-Maruyama --
+    checked in fp64 against the oracle's generic_propagate (which is pinned against the live reference)."""
+    import diffsci_b200 as d
+    from diffsci_b200.models.karras import preconditioners as P, noisesamplers as NS, schedulers as S
+    from oracle import karras_oracle as K
+    from tests.test_oracle_vs_golden import precond_case, oracle_net
+    g = golden(name)
+    if name == "sampler_mlp":
+        net64, tag, kind, cfg = oracle_net(golden("mlp_silu"), torch.float64), "edm", "edm", d.KarrasModuleConfig.from_edm()
+    else:
+        net64, tag, kind = precond_case(g, torch.float64)
+        cfg = (d.KarrasModuleConfig.from_vp() if g["tag"] == "vp" else d.KarrasModuleConfig.from_ve() if g["tag"] == "ve" else
+               d.KarrasModuleConfig(preconditioner=P.SR3Preconditioner(), noisesampler=NS.EDMNoiseSampler(),
+                                    noisescheduler=S.EDMScheduler()))
+    n, wn = g["nsteps"], g["white_noise"].double()
+    sch = cfg.noisescheduler
+    x_scale = float(sch.maximum_scale)
+    rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())  # noqa: E731
+    for key, integ, nz in (("heun_hist", "heun", None), ("euler", "euler", None), ("em", "euler-maruyama", g["noises"])):
+        tab = sch.general_step_table(n, cfg.preconditioner, d.name_to_integrator(integ))
+        assert tab.shape == (n + 1, d.Scheduler.GTAB_COLS) and bool((tab[-1] == 0).all())
+        out = emulate_general_program(tab, integ, net64, wn, x_scale, noises=nz, record_history=True)
+        ref = K.generic_propagate(net64, wn * x_scale, n, tag, kind, integ, record_history=True,
+                                  noises=None if nz is None else [z.double() for z in nz])
+        # the program is exact; the table's scalars are evaluated in fp32 like the reference evaluates its own -- so the
+        # budget is the live reference's fp32-vs-fp64 distance on the same trajectory
+        live = g[key] if key == "heun_hist" else g[key].unsqueeze(0)
+        budget = 2.0 * rel(live, ref if key == "heun_hist" else ref[-1:]) + 2e-5
+        assert rel(out, ref) <= budget, (name, integ, rel(out, ref), budget)
+    if tag == "edm":                                  # t_N = 0: the last Heun step has one evaluation (integrators.py:49-53)
+        tab = sch.general_step_table(n, cfg.preconditioner, d.name_to_integrator("heun"))
+        assert tab[n - 1, d.Scheduler.G_HAS2] == 0 and bool((tab[:n - 1, d.Scheduler.G_HAS2] == 1).all())
+    with pytest.raises(NotImplementedError):
+        sch.general_step_table(n, cfg.preconditioner, d.name_to_integrator("karras"))
