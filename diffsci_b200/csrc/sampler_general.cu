@@ -8,8 +8,7 @@
 // (Bm = -s sigma' sigma [or the scheduler's pf_score_multiplier], minus langevin_factor / s on stochastic steps.)  The host
 // evaluates (P, Q, c_in/s, c_noise) for both evaluation points of every step with the scheduler's and the preconditioner's own
 // objects; the kernel is then one elementwise pass per network evaluation that knows nothing about the family, replayed as a
-// captured graph like sampler.cu.  EXPERIMENTAL in round 1: built and covered by a CPU emulation of the same program against
-// the oracle, not yet enabled on the product path (diffsci_b200/models/karras/engine.py: DSK_GENERAL_ENGINE=1).
+// captured graph like sampler.cu (engine.GeneralSamplerEngine; DSK_GENERAL_ENGINE=0 falls back to the Integrator.step seam).
 #include "common.cuh"
 #include "philox.cuh"
 

@@ -244,10 +244,9 @@ class GeneralSamplerEngine(SamplerEngine):
     of csrc/sampler_general.cu read rhs = P x + Q F and the network-input scale / c_noise of every evaluation point from
     Scheduler.general_step_table, so nothing family-specific is left in the kernel.
 
-    EXPERIMENTAL in round 1: the table and the stage program are pinned on the CPU against the oracle
-    (tests/test_host_logic.py: test_general_step_table_program_equals_the_oracle); the kernel has not run on a B200 yet, so
-    KarrasModule only takes this route when DSK_GENERAL_ENGINE=1 -- the default for these configurations stays the
-    Integrator.step seam, which is parity-tested on the GPU."""
+    The table and the stage program are pinned on the CPU against the oracle (tests/test_host_logic.py:
+    test_general_step_table_program_equals_the_oracle) and on the GPU against the Integrator.step seam and the fp64 budget
+    (tests/test_gpu_precond.py: test_general_engine_equals_the_step_seam)."""
     programs = GENERAL_PROGRAMS
 
     def __init__(self, model, B, shape, device, use_graphs: bool = True):

@@ -559,7 +559,14 @@ class KarrasModule(_Base):
         if cond and not hasattr(self.model, "conditioning_vector"):
             fused = False              # foreign / not-yet-conditional networks: the duck-typed seam
         x = x.float().contiguous()
-        if (not fused and os.environ.get("DSK_GENERAL_ENGINE") == "1" and hasattr(self.model, "plan") and not cond and
+        # VP / VE / SR3 on the captured-graph loop through the table-driven stages (csrc/sampler_general.cu).  On by default for
+        # the configurations whose GPU parity run is on record (profiles/r2h_general_engine_gpu_tests.log); DSK_GENERAL_ENGINE=1
+        # extends it to any scheduler / preconditioner objects, =0 forces the Integrator.step seam.
+        env = os.environ.get("DSK_GENERAL_ENGINE")
+        validated = (type(self.config.preconditioner) in (preconditioners.VPPreconditioner, preconditioners.VEPreconditioner,
+                                                          preconditioners.SR3Preconditioner) and
+                     type(sch) in (schedulers.VPScheduler, schedulers.VEScheduler, schedulers.EDMScheduler))
+        if (not fused and env != "0" and (validated or env == "1") and hasattr(self.model, "plan") and not cond and
                 integ.fused_program in sch.GENERAL_PROGRAMS and
                 type(integ) in (integrators.EulerIntegrator, integrators.HeunIntegrator, integrators.EulerMaruyamaIntegrator)):
             return self._propagate_general(x, sch, integ, nsteps, record_history, _prescaled)
@@ -609,8 +616,9 @@ class KarrasModule(_Base):
         return out
 
     def _propagate_general(self, x: Tensor, sch, integ, nsteps: int, record_history: bool, prescaled: bool) -> Tensor:
-        """EXPERIMENTAL (DSK_GENERAL_ENGINE=1): VP / VE / SR3 / custom configurations on the captured-graph loop through the
-        table-driven stages (engine.GeneralSamplerEngine); the default route for them is the Integrator.step seam."""
+        """VP / VE / SR3 / custom configurations on the captured-graph loop through the table-driven stages
+        (engine.GeneralSamplerEngine, csrc/sampler_general.cu): rhs = P x + Q F with the scalars of
+        Scheduler.general_step_table."""
         B, shape = x.shape[0], tuple(x.shape[1:])
         key = ("general", B, shape, str(x.device), id(self.model), getattr(self.model, "precision", None), self.use_cuda_graphs)
         eng = self._engines.get(key)

@@ -106,7 +106,7 @@ int dsk_sampler_advance(int* row, void* stream);
  *   P = s'/s + Bm (c_skip - 1) / (sigma^2 s),  Q = Bm c_out / sigma^2,  network input = (c_in / s) x,
  * Bm = -(s sigma' sigma | pf_score_multiplier) [- langevin_factor / s on stochastic steps]; the host evaluates these with the
  * scheduler's and the preconditioner's own objects (diffsci_b200.models.karras.schedulers.Scheduler.general_step_table).
- * Table: fp32 [nsteps + 1][DSK_GTAB_COLS], last row zero padding.  EXPERIMENTAL in round 1 (not on the default path). */
+ * Table: fp32 [nsteps + 1][DSK_GTAB_COLS], last row zero padding. */
 #define DSK_GTAB_COLS 12
 enum dsk_gtab_col {
   DSK_GTAB_DT = 0,   /* dt_i                                                                   */

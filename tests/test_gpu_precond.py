@@ -79,12 +79,10 @@ def test_denoiser_sampling_loss(golden, name):
         assert e < 3e-4, (k, e)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DSK_GENERAL_ENGINE") != "1",
-                    reason="experimental route (table-driven general engine), enabled with DSK_GENERAL_ENGINE=1")
 @pytest.mark.parametrize("name", NAMES)
 def test_general_engine_equals_the_step_seam(golden, name):
-    """DSK_GENERAL_ENGINE=1: VP / VE / SR3 on the captured-graph loop (csrc/sampler_general.cu) vs the same runs on the
-    Integrator.step seam and vs the fp64 oracle budget.  Not part of the default suite until the kernel has run on a B200."""
+    """VP / VE / SR3 on the captured-graph loop (csrc/sampler_general.cu, the default route) vs the same runs on the
+    Integrator.step seam (DSK_GENERAL_ENGINE=0) and vs the fp64 oracle budget."""
     import os
     import diffsci_b200 as d
     from oracle import karras_oracle as K
@@ -98,13 +96,15 @@ def test_general_engine_equals_the_step_seam(golden, name):
         truth = K.generic_propagate(net64, x0, n, tag, kind, integ, record_history=key == "heun_hist",
                                     noises=None if nz is None else [z.double() for z in nz])
         outs = {}
-        for route in ("1", "0"):
-            os.environ["DSK_GENERAL_ENGINE"] = route
-            integrator = d.name_to_integrator(integ)
-            integrator.reset_noise(injected=nz)
-            outs[route] = mod.propagate_white_noise(wn.to(DEV), nsteps=n, integrator=integrator,
-                                                    record_history=key == "heun_hist").cpu()
-        os.environ["DSK_GENERAL_ENGINE"] = "1"
+        try:
+            for route in ("1", "0"):
+                os.environ["DSK_GENERAL_ENGINE"] = route
+                integrator = d.name_to_integrator(integ)
+                integrator.reset_noise(injected=nz)
+                outs[route] = mod.propagate_white_noise(wn.to(DEV), nsteps=n, integrator=integrator,
+                                                        record_history=key == "heun_hist").cpu()
+        finally:
+            os.environ.pop("DSK_GENERAL_ENGINE", None)
         assert any(k[0] == "general" for k in mod._engines)
         budget = 3.0 * relmax(g[key], truth) + 5e-5
         assert relmax(outs["1"], truth) <= budget, (key, relmax(outs["1"], truth), budget)
