@@ -457,3 +457,55 @@ def test_general_step_table_program_equals_the_oracle(golden, name):
         assert tab[n - 1, d.Scheduler.G_HAS2] == 0 and bool((tab[:n - 1, d.Scheduler.G_HAS2] == 1).all())
     with pytest.raises(NotImplementedError):
         sch.general_step_table(n, cfg.preconditioner, d.name_to_integrator("karras"))
+
+
+def test_sampling_route_selection(monkeypatch):
+    """Which loop KarrasModule.propagate_toward_sample takes: the EDM graph engine (closed-form stages), the table-driven
+    general engine (VP / VE / SR3 by default, anything with DSK_GENERAL_ENGINE=1) or the Integrator.step seam
+    (DSK_GENERAL_ENGINE=0, foreign networks, integrators without a fused program)."""
+    import diffsci_b200 as d
+    from diffsci_b200.models.karras import karrasmodule as KM, preconditioners as P, noisesamplers as NS, schedulers as S
+    calls = []
+
+    class FakeEngine:
+        def __init__(self, *a, **k):
+            self.kind, self.nfe, self.sigma_max = type(self).__name__, 0, 1.0
+
+        def set_condition(self, *a):
+            pass
+
+        def run(self, x, table, program, **k):
+            calls.append((self.kind, program, tuple(table.shape)))
+            return x
+
+    class FakeGeneral(FakeEngine):
+        pass
+    monkeypatch.setattr(KM, "require_cuda", lambda *a, **k: None)
+    monkeypatch.setattr(KM._engine, "SamplerEngine", FakeEngine)
+    monkeypatch.setattr(KM._engine, "GeneralSamplerEngine", FakeGeneral)
+    monkeypatch.setattr(S.Scheduler, "propagate_backward", lambda self, x, score, n, record_history=False: calls.append(("seam", n)) or x)
+    monkeypatch.setattr(KM.ops, "lincomb", lambda x, a, *r: x * a)
+    net = d.MLPUncond(2, [8], torch.nn.SiLU())
+    x = torch.zeros(4, 2)
+    sr3 = d.KarrasModuleConfig(preconditioner=P.SR3Preconditioner(), noisesampler=NS.EDMNoiseSampler(), noisescheduler=S.EDMScheduler())
+    null = d.KarrasModuleConfig(preconditioner=P.NullPreconditioner(), noisesampler=NS.EDMNoiseSampler(), noisescheduler=S.VPScheduler())
+
+    def route(cfg, integrator=None, model=net, env=None):
+        calls.clear()
+        if env is None:
+            monkeypatch.delenv("DSK_GENERAL_ENGINE", raising=False)
+        else:
+            monkeypatch.setenv("DSK_GENERAL_ENGINE", env)
+        d.KarrasModule(model, cfg).propagate_toward_sample(x, nsteps=4, integrator=integrator)
+        return calls[0][0]
+    assert route(d.KarrasModuleConfig.from_edm()) == "FakeEngine"
+    assert route(d.KarrasModuleConfig.from_edm(), "karras") == "FakeEngine"
+    assert route(d.KarrasModuleConfig.from_edm(), env="1") == "FakeEngine"            # EDM keeps its closed-form stages
+    for cfg in (d.KarrasModuleConfig.from_vp(), d.KarrasModuleConfig.from_ve(), sr3):
+        assert route(cfg) == "FakeGeneral" and calls[0][2] == (5, d.Scheduler.GTAB_COLS)
+        assert route(cfg, "euler-maruyama") == "FakeGeneral"
+        assert route(cfg, env="0") == "seam"
+        assert route(cfg, "karras") == "seam"                                         # no general program for the churn sampler
+    assert route(null) == "seam" and route(null, env="1") == "FakeGeneral"            # unvalidated pairs: opt-in only
+    foreign = torch.nn.Linear(2, 2)
+    assert route(d.KarrasModuleConfig.from_vp(), model=foreign) == "seam"
