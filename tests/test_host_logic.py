@@ -509,3 +509,18 @@ def test_sampling_route_selection(monkeypatch):
     assert route(null) == "seam" and route(null, env="1") == "FakeGeneral"            # unvalidated pairs: opt-in only
     foreign = torch.nn.Linear(2, 2)
     assert route(d.KarrasModuleConfig.from_vp(), model=foreign) == "seam"
+
+
+def test_engine_programs():
+    """Stage programs of the two engines: (regular step, final step); Heun's final step degenerates to one evaluation only when
+    the schedule ends at t = 0 (integrators.py:45-53) -- always for EDM, read from the table's HAS2 column in the general engine."""
+    from diffsci_b200.models.karras import engine as E
+    from diffsci_b200 import _lib
+    assert E.SamplerEngine._program(object(), "heun", None) == ((_lib.STAGE_HEUN_MID, _lib.STAGE_HEUN_FIN), (_lib.STAGE_HEUN_LAST,))
+    assert set(E.SamplerEngine.programs) == {"euler", "heun", "euler-maruyama", "karras"}
+    tab = torch.zeros(5, 12)
+    assert E.GeneralSamplerEngine._program(object(), "heun", tab) == ((E.GSTAGE_HEUN_MID, E.GSTAGE_HEUN_FIN), (E.GSTAGE_STEP1,))
+    tab[3, 9] = 1.0                      # the last step has a second evaluation (VP / VE end at t > 0)
+    assert E.GeneralSamplerEngine._program(object(), "heun", tab) == ((E.GSTAGE_HEUN_MID, E.GSTAGE_HEUN_FIN),) * 2
+    assert set(E.GeneralSamplerEngine.programs) == {"euler", "heun", "euler-maruyama"}
+    assert (E.GSTAGE_INIT, E.GSTAGE_STEP1, E.GSTAGE_HEUN_MID, E.GSTAGE_HEUN_FIN) == (0, 1, 2, 3) and _lib.STAGE_INIT == 0
