@@ -125,6 +125,9 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
 
 
+KARRAS_CONFIG = ["edm"]      # --karras-config (sweeps of the VP / VE route; the headline workloads are EDM)
+
+
 def build_workload(name, device, precision):
     import torch
     import diffsci_b200 as d
@@ -141,7 +144,8 @@ def build_workload(name, device, precision):
         net = d.MLPUncond(kw["dim"], kw["hidden_dims"], torch.nn.SiLU())
         flops = 2 * sum(p.numel() for n, p in net.named_parameters() if n.endswith("weight"))
     net = net.to(device).eval() if device is not None else net.eval()
-    module = d.KarrasModule(net, d.KarrasModuleConfig.from_edm())
+    kcfg = {"edm": d.KarrasModuleConfig.from_edm, "vp": d.KarrasModuleConfig.from_vp, "ve": d.KarrasModuleConfig.from_ve}[KARRAS_CONFIG[0]]
+    module = d.KarrasModule(net, kcfg())
     return module, net, cfg, shape, nsteps, integ, batch, flops
 
 
@@ -422,6 +426,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("DSK_BENCH_WORKLOAD", "c4"), choices=list(WORKLOADS) + list(TRAIN_WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = workload default)")
     ap.add_argument("--nsteps", type=int, default=0, help="integrator steps (0 = workload default)")
+    ap.add_argument("--karras-config", default="edm", choices=["edm", "vp", "ve"],
+                    help="KarrasModuleConfig.from_edm / from_vp / from_ve (vp / ve: the table-driven general engine; "
+                         "DSK_GENERAL_ENGINE=0 times the Integrator.step seam instead)")
     ap.add_argument("--integrator", default="", choices=["", "euler", "heun", "euler-maruyama", "karras"],
                     help="override the workload's integrator (sweeps; e.g. the Karras-churn variant of c5)")
     ap.add_argument("--precision", default=os.environ.get("DSK_BENCH_PRECISION", "auto"))
@@ -435,6 +442,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload in TRAIN_WORKLOADS:
         return train_arm(args, rank, world, local_rank)
+    KARRAS_CONFIG[0] = args.karras_config
     if args.integrator:
         WORKLOADS[args.workload] = WORKLOADS[args.workload][:4] + (args.integrator,) + WORKLOADS[args.workload][5:]
     kind, kw, shape, nsteps, integ, batch = WORKLOADS[args.workload]
@@ -494,7 +502,7 @@ def main():
     if clocks:
         clocks.start()
     n0 = _lib.launch_count()
-    eng_before = next(iter(module._engines.values()))
+    eng_before = next(iter(module._engines.values()), None)      # None: the Integrator.step seam (no engine, no graphs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -508,7 +516,7 @@ def main():
     total_ms = float(ms)
     clk = clocks.summary() if clocks else None
     eager_launches = _lib.launch_count() - n0
-    graph_launches = eng_before.graph_launches_per_run() * args.steps if eng_before.use_graphs else 0
+    graph_launches = eng_before.graph_launches_per_run() * args.steps if (eng_before is not None and eng_before.use_graphs) else 0
     value = world * B * args.steps / (total_ms / 1e3)
 
     # ---------------------------------------------------------------- end-to-end arm (`e2e`)
@@ -545,6 +553,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": NAMES[args.workload], "per_gpu_batch": B, "global_batch": world * B,
                        "integrator": integ, "nsteps": nsteps, "nfe_per_sample": nfe, "precision": precision,
+                       "karras_config": args.karras_config,
                        "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2_policy": "inputs larger than L2: >100 GB of activation traffic per step vs 126 MB L2"},
             "nfe_per_s": value * nfe,
