@@ -550,7 +550,7 @@ def main():
 
     line = {"metric": "EDM Heun samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp16x2": "f16 (activations hi+lo)", "fp32": "f32 (split-f16 x3 on tcgen05)"}.get(precision, "f32"), "data": "synthetic",
             "config": {"workload": NAMES[args.workload], "per_gpu_batch": B, "global_batch": world * B,
                        "integrator": integ, "nsteps": nsteps, "nfe_per_sample": nfe, "precision": precision,
                        "karras_config": args.karras_config,
@@ -570,6 +570,9 @@ def main():
         dist.destroy_process_group()
 
 
+KERNEL_KIND = {}
+
+
 def dominant_conv_roofline(cfg, shape, B, precision, dev, peaks, reps=20):
     """Time the dominant kernel (the full-resolution C->C 3^d convolution: 53% of C4's FLOPs) live with CUDA
     events on the launching stream: `reps` back-to-back launches on buffers larger than L2."""
@@ -578,13 +581,23 @@ def dominant_conv_roofline(cfg, shape, B, precision, dev, peaks, reps=20):
     from diffsci_b200 import ops
     nd, M = cfg.dimension, cfg.model_channels
     sp = (1,) + tuple(shape[1:]) if nd == 2 else tuple(shape[1:])
-    adt = torch.bfloat16 if precision == "bf16" else torch.float32
-    wd = torch.bfloat16 if (precision == "bf16" and d.TC_CONV_ENABLED) else torch.float32
+    KERNEL_KIND.update({torch.float32: "CUDA-core FFMA implicit GEMM", torch.bfloat16: "tcgen05 implicit GEMM, bf16 operands",
+                        torch.float16: "tcgen05 implicit GEMM, fp16 operands" + (", activations split hi+lo: 2 MMAs per k-step"
+                                                                                 if precision == "fp16x2" else ""),
+                        ops.SPLIT: "tcgen05 implicit GEMM, split-fp16 operands: 3 MMAs per k-step, fp32-parity mode; "
+                                   "achieved = algorithmic FLOPs, the tensor pipe executes 3x"})
+    from diffsci_b200.models.nets.punetg import _ACT_DTYPE, _W_DTYPE
+    adt = _ACT_DTYPE[precision]
+    wd = _W_DTYPE.get(precision) if d.TC_CONV_ENABLED else None
+    wd = wd or torch.float32
+    split = precision in ("fp32", "fp16x2") and wd != torch.float32     # split-fp16 activations (hi | lo), fp32 output
     w = torch.randn((M, M) + (cfg.kernel_size,) * nd, device=dev) * 0.02
     pc = ops.PackedConv(w, torch.zeros(M, device=dev), nd, wd)
     nbuf = 4                                      # rotate inputs so consecutive launches do not hit in L2
     xs = [torch.randn((B,) + sp + (M,), device=dev).to(adt) for _ in range(nbuf)]
     out = torch.empty_like(xs[0])
+    if split:
+        xs = [ops.split_f16(x) for x in xs]
     for i in range(3):
         ops.conv(xs[i % nbuf], pc, out=out)
     torch.cuda.synchronize(dev)
@@ -604,7 +617,7 @@ def dominant_conv_roofline(cfg, shape, B, precision, dev, peaks, reps=20):
     # `ncu --set full` capture (profiles/r1q_conv_tc2_64x64_64cube_B8_ncu_full.txt); scaled by batch (the kernel reads its
     # input once and writes its output once: traffic is linear in the number of samples); null for other shapes
     traffic, traffic_src = None, None
-    if nd == 3 and M == 64 and tuple(sp) == (64, 64, 64) and wd == torch.bfloat16:
+    if nd == 3 and M == 64 and tuple(sp) == (64, 64, 64) and wd == torch.bfloat16 and False:
         traffic = 490.4e6 * B / 8.0
         traffic_src = "ncu --set full, profiles/r1q_conv_tc2_64x64_64cube_B8_ncu_full.txt (268.8 MB read + 221.6 MB written at B=8)"
     peak = peaks.get("bf16_tflops")
@@ -612,7 +625,7 @@ def dominant_conv_roofline(cfg, shape, B, precision, dev, peaks, reps=20):
     if peak is None:
         peak, src = 1590.0, "fallback (B200_PROFILING.md)"
     return {"bound": "tensor", "kernel": f"conv{nd}d {M}->{M} k{cfg.kernel_size} @ {'x'.join(map(str, sp[-nd:]))} "
-            f"({'tcgen05 implicit GEMM' if wd == torch.bfloat16 else 'CUDA-core FFMA implicit GEMM, fp32 parity mode'})",
+            f"({KERNEL_KIND.get(wd, 'tcgen05 implicit GEMM')})",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_source": traffic_src, "peak_source": src, "ms_per_launch": ms, "flops_per_launch": flops}
 

@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdiffsci_b200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16, SPLIT_F16 = 0, 1, 2, 3
 TAB_COLS = 8
 TAB_T, TAB_DT, TAB_THAT, TAB_LANG, TAB_NOISE, TAB_SQDT, TAB_TNEXT, TAB_CHURN = range(8)
 (STAGE_INIT, STAGE_EULER, STAGE_HEUN_MID, STAGE_HEUN_FIN, STAGE_HEUN_LAST, STAGE_EM, STAGE_KARRAS_MID,
@@ -62,10 +62,13 @@ SIGNATURES = {
     "dsk_conv_fwd_stats": [C.POINTER(ConvDesc), p, p, p, p, p, p, p, p],
     "dsk_norm_act_prestat": [p, p, p, p, p, p, p, i32, p, i32, i64, i32, i32, i32, i32, i32, i32, p],
     "dsk_upsample2x": [p, p, i32, i32, i32, i32, i32, i32, i32, p],
-    "dsk_pack_upconv_weight": [p, p, i32, i32, i32, p],
+    "dsk_pack_upconv_weight": [p, p, i32, i32, i32, i32, p],
     "dsk_pack_conv_weight": [p, p, i32, i32, i32, i32, p],
     "dsk_gemm_f32": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i32, i32, f32, i32, p],
     "dsk_gemm_bf16_tc": [p, p, p, p, i32, p, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, f32, i32, i32, i32, p],
+    "dsk_gemm_tc": [p, p, p, p, i32, p, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, f32, i32, i32, i32, i32, i32, i32, p],
+    "dsk_attn_softmax_qk_h16": [p, p, p, p, i32, i32, i64, i64, i64, i64, i32, f32, i32, p],
+    "dsk_softmax_rows_h16": [p, p, i64, i32, i32, p],
     "dsk_softmax_bwd_rows_bf16": [p, p, p, i64, i32, p],
     "dsk_attn_softmax_ws_bytes": [i32, i32],
     "dsk_attn_softmax_qk": [p, p, p, p, i32, i32, i64, i64, i64, i64, i32, f32, p],
@@ -78,6 +81,7 @@ SIGNATURES = {
     "dsk_nchw_to_cl": [p, p, i32, i32, i64, i32, p],
     "dsk_cl_to_nchw": [p, p, i32, i32, i64, i32, p],
     "dsk_cast": [p, p, i64, i32, i32, p],
+    "dsk_split_f16": [p, p, i64, i32, p],
     "dsk_concat_channels": [p, p, p, i64, i32, i32, i32, p],
     "dsk_fourier": [p, p, p, i32, i32, p],
     "dsk_grouped_linear": [p, p, p, p, p, p, p, i32, i32, i32, i32, p],
@@ -158,4 +162,6 @@ def dt_code(dtype: torch.dtype) -> int:
         return F32
     if dtype == torch.bfloat16:
         return BF16
+    if dtype == torch.float16:
+        return F16
     raise TypeError(f"diffsci_b200: unsupported dtype {dtype}")

@@ -26,7 +26,20 @@ template <> __device__ __forceinline__ void ld8f<__nv_bfloat16>(const __nv_bfloa
 #pragma unroll
   for (int j = 0; j < 4; ++j) { o[2 * j] = __low2float(h[j]); o[2 * j + 1] = __high2float(h[j]); }
 }
+template <> __device__ __forceinline__ void ld8f<__half>(const __half* p, float* o) {
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { o[2 * j] = __low2float(h[j]); o[2 * j + 1] = __high2float(h[j]); }
+}
 template <typename T> __device__ __forceinline__ void st8f(T* p, const float* v);
+template <> __device__ __forceinline__ void st8f<__half>(__half* p, const float* v) {
+  uint4 o;
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
 template <> __device__ __forceinline__ void st8f<float>(float* p, const float* v) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -230,6 +243,9 @@ int conv_small_dispatch(const dsk_conv_desc* d, const void* in, const void* w, c
   if (ti == DSK_F32 && to == DSK_F32) rc = FN<float, float>(a, st);                                   \
   else if (ti == DSK_BF16 && to == DSK_BF16) rc = FN<__nv_bfloat16, __nv_bfloat16>(a, st);            \
   else if (ti == DSK_BF16 && to == DSK_F32) rc = FN<__nv_bfloat16, float>(a, st);                     \
+  else if (ti == DSK_F16 && to == DSK_F16) rc = FN<__half, __half>(a, st);                            \
+  else if (ti == DSK_F16 && to == DSK_F32) rc = FN<__half, float>(a, st);                             \
+  else if (ti == DSK_F32 && to == DSK_F16) rc = FN<float, __half>(a, st);                             \
   else rc = FN<float, __nv_bfloat16>(a, st);
   if (few_out) { GO(launch_few_out) } else { GO(launch_few_in) }
 #undef GO

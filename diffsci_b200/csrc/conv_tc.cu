@@ -42,8 +42,21 @@ struct TcParams {
   int tiles_w, tiles_h, groups_d, n_tiles, total_tiles;
   const float* bias;      // [Cout] or null
   const float* chan_bias; // [B][Cout] or null
-  const __nv_bfloat16* residual;  // like out, or null
-  __nv_bfloat16* out;     // [B, D, H, W, Cout]
+  const uint16_t* residual;  // like out, or null (16-bit format `f16`, or fp32 when out_f32)
+  uint16_t* out;          // [B, D, H, W, Cout]
+  int f16;                // 16-bit format of the operands and of 16-bit outputs: 0 = bfloat16, 1 = IEEE half
+  int out_f32;            // out / residual are fp32 (split parity mode)
+  // Split operands (DSK_SPLIT_F16: rows of [hi | lo]): every real 64-channel K chunk becomes `vparts` virtual chunks that
+  // accumulate into the same TMEM columns -- vparts = 3: (A hi, W hi), (A hi, W lo), (A lo, W hi); vparts = 2: the weights are
+  // plain fp16, (A hi, W), (A lo, W); vparts = 1: plain 16-bit operands.  a_lo_off / w_lo_off: channel offset of the lo half.
+  int vparts, a_lo_off, w_lo_off;
+  // Accumulator sets (split mode only, nsets = 4; N_TILE = 64): tcgen05 adds into its fp32 accumulators with truncation
+  // (round toward zero; tools/probe_tc_accum.py: -0.7 * 2^-23 relative per chained MMA for same-sign data), so a long chain of
+  // MMAs into ONE accumulator loses what the split operands gained.  The hi*hi products of a tile are therefore dealt
+  // round-robin over three accumulator sets, the hi*lo + lo*hi products -- whose lo operands are stored scaled by 2^11
+  // (DSK_SPLIT_F16), out of fp16's subnormal range -- go to a fourth, and the epilogue adds the four in fp32 (round to
+  // nearest):  acc = (s0 + s1 + s2) + 2^-11 * s3.  The four sets occupy all 512 TMEM columns: no double buffering.
+  int nsets;
   int planes_per_sample;  // D for 3-D; 1 for 2-D  (chan_bias row = plane / planes_per_sample)
   int cout_real;          // N_TILE = 16 path (convout): the first cout_real (<= 16) channels are real, the rest zero padding
   float* out_nchw;        // N_TILE = 16 path: fp32 NC(D)HW output (user layout) instead of channels-last bf16
@@ -56,6 +69,16 @@ struct TcParams {
                           // w-tiles (odd number of w-tiles, e.g. the 7x7 planes of MNIST's bottom level); no fused statistics
 };
 constexpr int TC_STAT_SLOTS = DSK_NUM_SMS;          // one slot per CTA
+constexpr float kLoScale = 1.0f / 2048.0f;          // 2^-11: the lo half of a split operand is stored times 2^11
+// channel coordinate (activation tensor map / weight tensor map) of virtual chunk vc
+__device__ __forceinline__ int vchunk_a(const TcParams& p, int vc) {
+  const int c = vc / p.vparts, part = vc - c * p.vparts;
+  return c * 64 + ((p.vparts > 1 && part == p.vparts - 1) ? p.a_lo_off : 0);
+}
+__device__ __forceinline__ int vchunk_w(const TcParams& p, int vc) {
+  const int c = vc / p.vparts, part = vc - c * p.vparts;
+  return c * 64 + ((p.vparts == 3 && part == 1) ? p.w_lo_off : 0);
+}
 
 struct TileCoord {
   int w0, h0, d0, b, n0;
@@ -90,10 +113,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   __shared__ uint32_t tmem_base_s;
   constexpr uint32_t TMEM_COLS = 2 * P * N_TILE;        // double-buffered accumulators
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
+  // accumulator sets per tile: 1 (plain), 2 (hh | lo; activations-split mode) -- both double-buffered -- or 4 (three hh sets
+  // + lo; fp32-parity mode): 4 * P * 64 = 512 columns, single-buffered.  Host: N_TILE <= 64 when nsets > 1.
+  const int nsets = p.nsets;
+  constexpr uint32_t SET_COLS = P * N_TILE;             // columns of one accumulator set
+  const uint32_t nbuf = nsets == 4 ? 1u : 2u, buf_cols = nsets * SET_COLS, tmem_cols = nbuf * buf_cols;
+  const uint32_t lo_set = nsets - 1, nhh = nsets > 1 ? nsets - 1 : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KD = p.KD, NJ = P + KD - 1;                 // patches per (tile, chunk)
-  const int nchunks = p.Cin / 64;
+  const int nchunks = (p.Cin / 64) * p.vparts;          // virtual K chunks (split operands: 2 or 3 per real chunk)
   const int dpad = KD >> 1;
 
   if (threadIdx.x == 0) {
@@ -103,7 +132,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (warp == 0 && lane == 0) {
@@ -129,7 +158,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             asm volatile(
                 "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
                     smem_u32(sA + (size_t)slot * TC_PATCH_STRIDE)),
-                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(c * 64), "r"(tc.w0 - 1 + p.pad_hw), "r"(tc.h0 - 1 + p.pad_hw), "r"(tc.d0 + j - dpad + p.pad_d), "r"(tc.b),
+                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(vchunk_a(p, c)), "r"(tc.w0 - 1 + p.pad_hw), "r"(tc.h0 - 1 + p.pad_hw), "r"(tc.d0 + j - dpad + p.pad_d), "r"(tc.b),
                 "r"(smem_u32(&full_a[slot]))
                 : "memory");
           }
@@ -151,7 +180,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                     smem_u32(sB + (size_t)slot * B_BYTES)),
-                "l"(reinterpret_cast<uint64_t>(&tmapW)), "r"(c * 64), "r"(tap * p.Cout + tc.n0), "r"(smem_u32(&full_b[slot]))
+                "l"(reinterpret_cast<uint64_t>(&tmapW)), "r"(vchunk_w(p, c)), "r"(tap * p.Cout + tc.n0), "r"(smem_u32(&full_b[slot]))
                 : "memory");
           }
       }
@@ -159,14 +188,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   } else if (warp == 2) {
     // ===================== MMA issuer =====================
     // The whole warp walks the control flow (barrier waits are warp-uniform); one elected lane issues.
-    const uint32_t idesc = umma_idesc_bf16(N_TILE);
+    const uint32_t idesc = umma_idesc_h16(N_TILE, 128, p.f16);
     constexpr uint32_t A_HI = umma_desc_hi(TC_PW * 128), B_HI = umma_desc_hi(1024);
     uint32_t seq_a = 0, seq_b = 0, it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const uint32_t as = nbuf == 1 ? 0u : (it & 1), aph = nbuf == 1 ? (it & 1) : ((it >> 1) & 1);
       mbar_wait(&acc_empty[as], aph ^ 1);               // epilogue has drained this accumulator set
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_acc = tmem_base + as * (P * N_TILE);
+      const uint32_t tmem_acc = tmem_base + as * buf_cols;
+      uint32_t used = 0, hh = 0;                         // accumulator sets written in this tile; round-robin counter
       const TileCoord tc = tile_coord(p, t, N_TILE, P);
       for (int c = 0; c < nchunks; ++c) {
         const uint32_t seq_c = seq_a;                    // first patch of this (tile, chunk)
@@ -187,13 +217,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_BYTES));
               const uint32_t tap_off = (kh * TC_PW + kw) * 8;
-              const uint32_t first = (c | td | thw) == 0 ? 0u : 1u;
+              uint32_t set = 0;                                 // accumulator set of this tap's MMAs
+              if (nsets > 1) { if (c % p.vparts) set = lo_set; else { set = hh; hh = hh + 1 == nhh ? 0 : hh + 1; } }
+              const uint32_t first = (used >> set) & 1u;
+              used |= 1u << set;
+              const uint32_t acc_set = tmem_acc + set * SET_COLS;
               if (elect_one_sync()) {
 #pragma unroll
                 for (int pp = 0; pp < P; ++pp) {
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4)
-                    umma_bf16(tmem_acc + pp * N_TILE, umma_desc64(a_lo[pp] + tap_off + k4 * 2, A_HI),
+                    umma_bf16(acc_set + pp * N_TILE, umma_desc64(a_lo[pp] + tap_off + k4 * 2, A_HI),
                               umma_desc64(b_lo + k4 * 2, B_HI), idesc, k4 == 0 ? first : 1u);
                 }
                 umma_commit(&empty_b[bs]);
@@ -224,13 +258,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_BYTES));
             const uint32_t tap_off = ((khw / 3) * TC_PW + (khw % 3)) * 8;      // (kh*10 + kw) * 128 B >> 4
-            const uint32_t first = (c | kd | khw) == 0 ? 0u : 1u;
+            uint32_t set = 0;                                 // accumulator set of this tap's MMAs
+            if (nsets > 1) { if (c % p.vparts) set = lo_set; else { set = hh; hh = hh + 1 == nhh ? 0 : hh + 1; } }
+            const uint32_t first = (used >> set) & 1u;
+            used |= 1u << set;
+            const uint32_t acc_set = tmem_acc + set * SET_COLS;
             if (elect_one_sync()) {
 #pragma unroll
               for (int pp = 0; pp < P; ++pp) {
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4)
-                  umma_bf16(tmem_acc + pp * N_TILE, umma_desc64(a_lo[pp] + tap_off + k4 * 2, A_HI),
+                  umma_bf16(acc_set + pp * N_TILE, umma_desc64(a_lo[pp] + tap_off + k4 * 2, A_HI),
                             umma_desc64(b_lo + k4 * 2, B_HI), idesc, k4 == 0 ? first : 1u);
               }
               umma_commit(&empty_b[bs]);                 // weight slot free once these MMAs retire
@@ -258,7 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     uint32_t it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const TileCoord tc = tile_coord(p, t, N_TILE, P);
-      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const uint32_t as = nbuf == 1 ? 0u : (it & 1), aph = nbuf == 1 ? (it & 1) : ((it >> 1) & 1);
       mbar_wait(&acc_full[as], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int h = tc.h0 + line, w = tc.w0 + wp;
@@ -275,11 +313,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
           pix = (((int64_t)tc.b * p.D + d) * p.H + h) * p.W + w;
         }
         const int brow = (tc.b * p.D + d) / p.planes_per_sample;
-        const uint32_t taddr = tmem_base + as * (P * N_TILE) + pp * N_TILE + ((uint32_t)(q * 32) << 16);
+        const uint32_t taddr = tmem_base + as * buf_cols + pp * N_TILE + ((uint32_t)(q * 32) << 16);
         if constexpr (N_TILE == 16) {
           // few-output-channel conv (convout, reference punetg.py:209-214): only cout_real columns are stored
           uint32_t v[16];
           DSK_TMEM_LD_X16(v, taddr);
+          if (nsets > 1) {                                  // split mode: (s0 + s1 + s2) + 2^-11 * s3
+            uint32_t u[16];
+#pragma unroll 1
+            for (int sidx = 1; sidx < nsets; ++sidx) {
+              DSK_TMEM_LD_X16(u, taddr + sidx * SET_COLS);
+              const float sc = sidx == (int)lo_set ? kLoScale : 1.0f;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(fmaf(__uint_as_float(u[e]), sc, __uint_as_float(v[e])));
+            }
+          }
           if (valid) {
             const int64_t S = (int64_t)p.planes_per_sample * p.H * p.W;
 #pragma unroll
@@ -288,7 +336,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 float x = __uint_as_float(v[co]);
                 if (p.bias != nullptr) x += __ldg(p.bias + co);
                 if (p.out_nchw != nullptr) p.out_nchw[((int64_t)brow * p.cout_real + co) * S + (pix - (int64_t)brow * S)] = x;
-                else p.out[pix * p.cout_real + co] = __float2bfloat16_rn(x);
+                else if (p.out_f32) reinterpret_cast<float*>(p.out)[pix * p.cout_real + co] = x;
+                else p.out[pix * p.cout_real + co] = pack_h1(x, p.f16);
               }
             }
           }
@@ -305,12 +354,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
               : "r"(taddr + c0));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (nsets > 1) {                                  // split mode: (s0 + s1 + s2) + 2^-11 * s3
+            uint32_t u[32];
+#pragma unroll 1
+            for (int sidx = 1; sidx < nsets; ++sidx) {
+              DSK_TMEM_LD_X32(u, taddr + sidx * SET_COLS + c0);
+              const float sc = sidx == (int)lo_set ? kLoScale : 1.0f;
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(fmaf(__uint_as_float(u[e]), sc, __uint_as_float(v[e])));
+            }
+          }
           if (valid) {
             const int n = tc.n0 + c0;
-            __nv_bfloat16* optr = p.out + pix * p.Cout + n;
-            const __nv_bfloat16* rptr = p.residual != nullptr ? p.residual + pix * p.Cout + n : nullptr;
+            const int64_t off = pix * p.Cout + n;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {                  // 4 x (8 channels = 16 B)
+            for (int g = 0; g < 4; ++g) {                  // 4 x 8 channels
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
@@ -319,17 +377,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 if (p.chan_bias != nullptr) x += __ldg(p.chan_bias + (int64_t)brow * p.Cout + n + g * 8 + e);
                 f[e] = x;
               }
-              if (rptr != nullptr) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(rptr + g * 8);
-                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
+              if (p.out_f32) {                             // warp-uniform
+                float* of = reinterpret_cast<float*>(p.out) + off + g * 8;
+                if (p.residual != nullptr) {
+                  const float4* rf = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off + g * 8);
+                  const float4 r0 = rf[0], r1 = rf[1];
+                  f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w; f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+                }
+                reinterpret_cast<float4*>(of)[0] = make_float4(f[0], f[1], f[2], f[3]);
+                reinterpret_cast<float4*>(of)[1] = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                if (p.residual != nullptr) {
+                  const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + off + g * 8);
+                  const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rr);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { f[2 * e] += __low2float(rh[e]); f[2 * e + 1] += __high2float(rh[e]); }
+                  for (int e = 0; e < 4; ++e) { const float2 t = unpack_h2(rw[e], p.f16); f[2 * e] += t.x; f[2 * e + 1] += t.y; }
+                }
+                uint4 o;
+                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ow[e] = pack_h2(f[2 * e], f[2 * e + 1], p.f16);
+                *reinterpret_cast<uint4*>(p.out + off + g * 8) = o;
               }
-              uint4 o;
-              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-              *reinterpret_cast<uint4*>(optr + g * 8) = o;
             }
           }
         }
@@ -341,7 +410,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
 }
 
 // ====================================================================================================================
@@ -422,6 +491,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   __shared__ uint4 stage_s[8][32 * 4];                  // per epilogue warp: 32 rows x 64 B (coalescing stage of the stores)
   constexpr uint32_t TMEM_COLS = 2 * P * N_TILE;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
+  // accumulator sets per tile: 1 (plain), 2 (hh | lo; activations-split mode) -- both double-buffered -- or 4 (three hh sets
+  // + lo; fp32-parity mode): 4 * P * 64 = 512 columns, single-buffered.  Host: N_TILE <= 64 when nsets > 1.
+  const int nsets = p.nsets;
+  constexpr uint32_t SET_COLS = P * N_TILE;             // columns of one accumulator set
+  const uint32_t nbuf = nsets == 4 ? 1u : 2u, buf_cols = nsets * SET_COLS, tmem_cols = nbuf * buf_cols;
+  const uint32_t lo_set = nsets - 1, nhh = nsets > 1 ? nsets - 1 : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -429,7 +504,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   const int total_pairs = p.total_tiles >> 1;
   const int KD = p.KD, NJ = P + KD - 1;
-  const int nchunks = p.Cin / 64;
+  const int nchunks = (p.Cin / 64) * p.vparts;          // virtual K chunks (split operands: 2 or 3 per real chunk)
   const int dpad = KD >> 1;
 
   if (threadIdx.x == 0) {
@@ -439,7 +514,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   if (warp == 0 && lane == 0) {
@@ -466,7 +541,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             asm volatile(
                 "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
                     smem_u32(sA + (size_t)slot * TC_PATCH_STRIDE)),
-                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(c * 64), "r"(tc.w0 - 1 + p.pad_hw), "r"(tc.h0 - 1 + p.pad_hw), "r"(tc.d0 + j - dpad + p.pad_d), "r"(tc.b),
+                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(vchunk_a(p, c)), "r"(tc.w0 - 1 + p.pad_hw), "r"(tc.h0 - 1 + p.pad_hw), "r"(tc.d0 + j - dpad + p.pad_d), "r"(tc.b),
                 "r"(smem_u32(&full_a[slot]) & kPeerBitMask)
                 : "memory");
           }
@@ -488,7 +563,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             asm volatile(
                 "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                     smem_u32(sB + (size_t)slot * B_HALF)),
-                "l"(reinterpret_cast<uint64_t>(&tmapW)), "r"(c * 64), "r"(tap * p.Cout + tc.n0 + (int)rank * (N_TILE / 2)),
+                "l"(reinterpret_cast<uint64_t>(&tmapW)), "r"(vchunk_w(p, c)), "r"(tap * p.Cout + tc.n0 + (int)rank * (N_TILE / 2)),
                 "r"(smem_u32(&full_b[slot]) & kPeerBitMask)
                 : "memory");
           }
@@ -497,14 +572,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   } else if (warp == 2) {
     if (leader) {
     // ===================== MMA issuer (leader CTA only) =====================
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint32_t idesc = umma_idesc_h16(N_TILE, 256, p.f16);
     constexpr uint32_t A_HI = umma_desc_hi(TC_PW * 128), B_HI = umma_desc_hi(1024);
     uint32_t seq_a = 0, seq_b = 0, it = 0;
     for (int u = cluster_id; u < total_pairs; u += nclusters, ++it) {
-      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const uint32_t as = nbuf == 1 ? 0u : (it & 1), aph = nbuf == 1 ? (it & 1) : ((it >> 1) & 1);
       mbar_wait(&acc_empty[as], aph ^ 1);               // the epilogues of BOTH CTAs have drained this accumulator set
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_acc = tmem_base + as * (P * N_TILE);
+      const uint32_t tmem_acc = tmem_base + as * buf_cols;
+      uint32_t used = 0, hh = 0;                         // accumulator sets written in this tile; round-robin counter
       const TileCoord tc = tile_coord2(p, u, 0, N_TILE, P);
       for (int c = 0; c < nchunks; ++c) {
         const uint32_t seq_c = seq_a;
@@ -524,13 +600,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_HALF));
               const uint32_t tap_off = (kh * TC_PW + kw) * 8;
-              const uint32_t first = (c | td | thw) == 0 ? 0u : 1u;
+              uint32_t set = 0;                                 // accumulator set of this tap's MMAs
+              if (nsets > 1) { if (c % p.vparts) set = lo_set; else { set = hh; hh = hh + 1 == nhh ? 0 : hh + 1; } }
+              const uint32_t first = (used >> set) & 1u;
+              used |= 1u << set;
+              const uint32_t acc_set = tmem_acc + set * SET_COLS;
               if (elect_one_sync()) {
 #pragma unroll
                 for (int pp = 0; pp < P; ++pp) {
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4)
-                    umma_bf16_2cta(tmem_acc + pp * N_TILE, umma_desc64(a_lo[pp] + tap_off + k4 * 2, A_HI),
+                    umma_bf16_2cta(acc_set + pp * N_TILE, umma_desc64(a_lo[pp] + tap_off + k4 * 2, A_HI),
                                    umma_desc64(b_lo + k4 * 2, B_HI), idesc, k4 == 0 ? first : 1u);
                 }
                 umma_commit_2cta(&empty_b[bs]);
@@ -560,13 +640,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_HALF));
             const uint32_t tap_off = ((khw / 3) * TC_PW + (khw % 3)) * 8;
-            const uint32_t first = (c | kd | khw) == 0 ? 0u : 1u;
+            uint32_t set = 0;                                 // accumulator set of this tap's MMAs
+            if (nsets > 1) { if (c % p.vparts) set = lo_set; else { set = hh; hh = hh + 1 == nhh ? 0 : hh + 1; } }
+            const uint32_t first = (used >> set) & 1u;
+            used |= 1u << set;
+            const uint32_t acc_set = tmem_acc + set * SET_COLS;
             if (elect_one_sync()) {
 #pragma unroll
               for (int pp = 0; pp < P; ++pp) {
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4)
-                  umma_bf16_2cta(tmem_acc + pp * N_TILE, umma_desc64(a_lo[pp] + tap_off + k4 * 2, A_HI),
+                  umma_bf16_2cta(acc_set + pp * N_TILE, umma_desc64(a_lo[pp] + tap_off + k4 * 2, A_HI),
                                  umma_desc64(b_lo + k4 * 2, B_HI), idesc, k4 == 0 ? first : 1u);
               }
               umma_commit_2cta(&empty_b[bs]);
@@ -674,7 +758,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       } else {
         st_pix = (((int64_t)tc.b * p.D + d) * p.H + tc.h0 + q * 4) * p.W + w_st;
       }
-      const __nv_bfloat16* rrow = (p.residual != nullptr && valid) ? p.residual + pix * p.Cout + tc.n0 : nullptr;
+      const bool of32 = p.out_f32 != 0;                     // fp32 output + residual (split parity mode); warp-uniform
+      const int64_t roff = pix * p.Cout + tc.n0;
+      const uint16_t* rrow = (p.residual != nullptr && valid && !of32) ? p.residual + roff : nullptr;
+      const float* rrow32 = (p.residual != nullptr && valid && of32) ? reinterpret_cast<const float*>(p.residual) + roff : nullptr;
       // d >= p.D: the second plane of a tile past an odd plane count (e.g. a 2-D batch of 1) -- its row of chan_bias does not exist
       const float* cbrow = (p.chan_bias != nullptr && d < p.D) ? p.chan_bias + (int64_t)brow * p.Cout + tc.n0 : nullptr;
       uint4 rr[DEP][4];
@@ -696,20 +783,30 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           } else {
             pn = (((int64_t)tn.b * p.D + dn) * p.H + hn) * p.W + wn;
           }
-          const __nv_bfloat16* rn = p.residual + pn * p.Cout + tn.n0;
-#pragma unroll
-          for (int c = 0; c < N_TILE / 64; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(rn + c * 64));
+          const int es = of32 ? 4 : 2;
+          const char* rn = reinterpret_cast<const char*>(p.residual) + (pn * p.Cout + tn.n0) * es;
+          for (int c = 0; c < N_TILE * es / 128; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(rn + c * 128));
         }
       }
-      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const uint32_t as = nbuf == 1 ? 0u : (it & 1), aph = nbuf == 1 ? (it & 1) : ((it >> 1) & 1);
       mbar_wait(&acc_full[as], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + as * (P * N_TILE) + pp * N_TILE + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + as * buf_cols + pp * N_TILE + ((uint32_t)(q * 32) << 16);
 #pragma unroll
       for (int gi = 0; gi < NG; ++gi) {
         const int c0 = gi * 32;
         uint32_t v[32];
         DSK_TMEM_LD_X32(v, taddr + c0);
+        if (nsets > 1) {                                    // split mode: (s0 + s1 + s2) + 2^-11 * s3, fp32 round-to-nearest adds
+          uint32_t u[32];
+#pragma unroll 1
+          for (int sidx = 1; sidx < nsets; ++sidx) {
+            DSK_TMEM_LD_X32(u, taddr + sidx * SET_COLS + c0);
+            const float sc = sidx == (int)lo_set ? kLoScale : 1.0f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(fmaf(__uint_as_float(u[e]), sc, __uint_as_float(v[e])));
+          }
+        }
         float f[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
@@ -721,25 +818,57 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         if (rrow != nullptr) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr[gi % DEP][g]);
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rr[gi % DEP][g]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { f[g * 8 + 2 * e] += __low2float(rh[e]); f[g * 8 + 2 * e + 1] += __high2float(rh[e]); }
+            for (int e = 0; e < 4; ++e) { const float2 t = unpack_h2(rw[e], p.f16); f[g * 8 + 2 * e] += t.x; f[g * 8 + 2 * e + 1] += t.y; }
           }
           if (gi + DEP < NG) {                               // refill the slot just consumed
 #pragma unroll
             for (int g = 0; g < 4; ++g) rr[gi % DEP][g] = *reinterpret_cast<const uint4*>(rrow + (gi + DEP) * 32 + g * 8);
           }
         }
-        {
+        if (rrow32 != nullptr) {
+          const float4* rf = reinterpret_cast<const float4*>(rrow32 + c0);
+#pragma unroll
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 r = rf[e4];
+            f[4 * e4] += r.x; f[4 * e4 + 1] += r.y; f[4 * e4 + 2] += r.z; f[4 * e4 + 3] += r.w;
+          }
+        }
+        if (of32) {
+          // fp32 rows are 128 B per 32-channel group: the same 2 KB stage takes them as two 16-channel halves
+          float* outf = reinterpret_cast<float*>(p.out);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              stg[lane * 4 + (g ^ (lane & 3))] =
+                  make_uint4(__float_as_uint(f[hh * 16 + g * 4]), __float_as_uint(f[hh * 16 + g * 4 + 1]),
+                             __float_as_uint(f[hh * 16 + g * 4 + 2]), __float_as_uint(f[hh * 16 + g * 4 + 3]));
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int r = 8 * k + (lane >> 2);
+              const uint4 val = stg[r * 4 + ((lane & 3) ^ (r & 3))];
+              if (st_ok && tc.h0 + q * 4 + k < p.H) {
+                int64_t px;
+                if constexpr (UPS) px = st_pix + (int64_t)k * 2 * (2 * p.W);
+                else px = st_pix + (int64_t)k * p.W;
+                *reinterpret_cast<uint4*>(outf + px * p.Cout + tc.n0 + c0 + hh * 16 + (lane & 3) * 4) = val;
+              }
+            }
+            __syncwarp();
+          }
+        } else {
           // staged, transposed store: a thread holds one pixel ROW, so a direct st.global.v4 touches 32 lines per
           // instruction; through this warp's 2 KB stage (XOR-swizzled 16-byte slots) 4 lanes write 64 contiguous bytes
           // of a row and one instruction covers 8 rows.  Row r = 8k + lane/4 of the warp is pixel (line q*4 + k, w lane/4).
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 o;
-            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+            for (int e = 0; e < 4; ++e) ow[e] = pack_h2(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1], p.f16);
             stg[lane * 4 + (g ^ (lane & 3))] = o;
           }
           __syncwarp();
@@ -788,7 +917,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   cluster_sync_all();                                    // the peer's shared memory / barriers stay alive until both are done
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
 }
 
 template <int N_TILE, int P, int NA, int NB, bool UPS>
@@ -851,8 +980,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const TcParam
 // Sub-pixel weights of conv3(nearest_up2(x)):  out[2i+a] = sum_k w[k] x[i + floor((a+k-1)/2)].  Per axis the three taps
 // collapse onto two input offsets: a = 0: offset -1 <- {k0}, 0 <- {k1,k2};  a = 1: 0 <- {k0,k1}, +1 <- {k2}.
 // Layout: bf16 [phase = (a*2+b)*2+c][tap = (td*2+th)*2+tw][Cout][Cin] (2-D: phase = b*2+c, tap = th*2+tw), summed in fp32.
-__global__ void __launch_bounds__(256) pack_upconv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout,
-                                                                  int Cin, int ndim) {
+__global__ void __launch_bounds__(256) pack_upconv_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ o, int Cout,
+                                                                  int Cin, int ndim, int fmt) {
   const int nax = ndim, nph = 1 << nax, ntap = 1 << nax, k3 = ndim == 3 ? 27 : 9;
   const int64_t total = (int64_t)nph * ntap * Cout * Cin;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -878,7 +1007,7 @@ __global__ void __launch_bounds__(256) pack_upconv_weight_kernel(const float* __
       }
       if (match) acc += wp[k];
     }
-    o[i] = __float2bfloat16_rn(acc);
+    put16(o, i / Cin, Cin, ci, acc, fmt);
   }
 }
 
@@ -886,8 +1015,8 @@ __global__ void __launch_bounds__(256) pack_upconv_weight_kernel(const float* __
 // 2^d x 2^d (phase, tap) sums held in registers, in ascending-k order -- bit-identical to the kernel above, which spends 27
 // predicated iterations per OUTPUT element (121 us per 256x128x27 weight, twice per training iteration).
 template <int NAX>
-__global__ void __launch_bounds__(128) pack_upconv_weight_pair_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout,
-                                                                       int Cin) {
+__global__ void __launch_bounds__(128) pack_upconv_weight_pair_kernel(const float* __restrict__ w, uint16_t* __restrict__ o, int Cout,
+                                                                       int Cin, int fmt) {
   constexpr int NPH = 1 << NAX, K3 = NAX == 3 ? 27 : 9;
   const int64_t pairs = (int64_t)Cout * Cin;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -922,32 +1051,34 @@ __global__ void __launch_bounds__(128) pack_upconv_weight_pair_kernel(const floa
 #pragma unroll
   for (int ph = 0; ph < NPH; ++ph)
 #pragma unroll
-    for (int tap = 0; tap < NPH; ++tap) o[((int64_t)ph * NPH + tap) * pairs + i] = __float2bfloat16_rn(acc[ph][tap]);
+    for (int tap = 0; tap < NPH; ++tap)
+      put16(o, ((int64_t)ph * NPH + tap) * Cout + i / Cin, Cin, (int)(i % Cin), acc[ph][tap], fmt);
 }
 
 }  // namespace dsk
 
 using namespace dsk;
 
-extern "C" int dsk_pack_upconv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int ndim, void* stream) {
+extern "C" int dsk_pack_upconv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int ndim, int dtype, void* stream) {
   DSK_REQUIRE(w_ref && w_packed && Cout > 0 && Cin > 0 && (ndim == 2 || ndim == 3), "dsk_pack_upconv_weight: bad arguments");
+  DSK_REQUIRE(is_h16(dtype) || dtype == DSK_SPLIT_F16, "dsk_pack_upconv_weight: bad dtype %d", dtype);
   static const int old_path = [] { const char* e = getenv("DSK_PACK_UPCONV_OLD"); return e ? atoi(e) : 0; }();   // A/B + bit-exactness tests
   const int64_t pairs = (int64_t)Cout * Cin;
   if (!old_path) {
     const int grid = (int)((pairs + 127) / 128);
-    if (ndim == 3) DSK_LAUNCH(pack_upconv_weight_pair_kernel<3>, grid, 128, 0, as_stream(stream), w_ref, (__nv_bfloat16*)w_packed, Cout, Cin);
-    else DSK_LAUNCH(pack_upconv_weight_pair_kernel<2>, grid, 128, 0, as_stream(stream), w_ref, (__nv_bfloat16*)w_packed, Cout, Cin);
+    if (ndim == 3) DSK_LAUNCH(pack_upconv_weight_pair_kernel<3>, grid, 128, 0, as_stream(stream), w_ref, (uint16_t*)w_packed, Cout, Cin, dtype);
+    else DSK_LAUNCH(pack_upconv_weight_pair_kernel<2>, grid, 128, 0, as_stream(stream), w_ref, (uint16_t*)w_packed, Cout, Cin, dtype);
     return DSK_OK;
   }
   const int64_t total = (int64_t)(1 << ndim) * (1 << ndim) * pairs;
-  DSK_LAUNCH(pack_upconv_weight_kernel, grid_for(total, 256, 8), 256, 0, as_stream(stream), w_ref, (__nv_bfloat16*)w_packed, Cout, Cin,
-             ndim);
+  DSK_LAUNCH(pack_upconv_weight_kernel, grid_for(total, 256, 8), 256, 0, as_stream(stream), w_ref, (uint16_t*)w_packed, Cout, Cin,
+             ndim, dtype);
   return DSK_OK;
 }
 
 extern "C" int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, void* stream) {
   DSK_REQUIRE(x && y && B > 0 && D > 0 && H > 0 && W > 0 && C > 0, "dsk_upsample2x: bad arguments");
-  DSK_REQUIRE(dtype == DSK_BF16 && C % 8 == 0, "dsk_upsample2x: bf16 with C %% 8 == 0 only (got dtype %d, C %d)", dtype, C);
+  DSK_REQUIRE(is_h16(dtype) && C % 8 == 0, "dsk_upsample2x: 16-bit tensors with C %% 8 == 0 only (got dtype %d, C %d)", dtype, C);
   const int64_t total = (int64_t)B * (ndim == 3 ? 2 * D : D) * 2 * H * 2 * W * (C / 8);
   DSK_LAUNCH(upsample2x_kernel, grid_for(total, 256, 16), 256, 0, as_stream(stream), (const uint4*)x, (uint4*)y, B, D, H, W, C / 8, ndim);
   return DSK_OK;
@@ -957,10 +1088,20 @@ namespace dsk {
 int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, void* out, cudaStream_t st, int padded);
 }
 
+// operand / output format combinations the tcgen05 convolutions take:
+//   in bf16, w bf16 | in fp16, w fp16 | in split-fp16, w split-fp16 (3 MMAs per k-step) | in split-fp16, w fp16 (2 MMAs);
+//   out: the 16-bit format of the operands, or fp32 (split parity mode: residual fp32 too)
+static bool tc_formats_ok(const dsk_conv_desc* d) {
+  const bool ops = (d->in_dtype == DSK_BF16 && d->w_dtype == DSK_BF16) || (d->in_dtype == DSK_F16 && d->w_dtype == DSK_F16) ||
+                   (d->in_dtype == DSK_SPLIT_F16 && (d->w_dtype == DSK_SPLIT_F16 || d->w_dtype == DSK_F16));
+  if (!ops) return false;
+  if (d->out_nchw_f32) return true;
+  const int fmt16 = d->in_dtype == DSK_BF16 ? DSK_BF16 : DSK_F16;
+  return d->out_dtype == fmt16 || d->out_dtype == DSK_F32;
+}
 static bool tc_pair_eligible(const dsk_conv_desc* d) {
   static const int force_cg = [] { const char* e = getenv("DSK_CONV_CG"); return e ? atoi(e) : 0; }();
-  if (force_cg == 1 || d->ksize != 3 || d->in_dtype != DSK_BF16 || d->out_dtype != DSK_BF16 || d->out_nchw_f32 || d->w_dtype != DSK_BF16 ||
-      d->Cin % 64 != 0 || d->Cout % 64 != 0)
+  if (force_cg == 1 || d->ksize != 3 || !tc_formats_ok(d) || d->out_nchw_f32 || d->Cin % 64 != 0 || d->Cout % 64 != 0)
     return false;
   const int iW = d->up2 ? d->W / 2 : d->W;
   return (((iW + TC_BW - 1) / TC_BW) % 2) == 0;
@@ -970,8 +1111,8 @@ static bool tc_pair_eligible(const dsk_conv_desc* d) {
 // plane groups per batch entry and no fused statistics (the two CTAs of a pair may work on different samples)
 static bool tc_pair_d_eligible(const dsk_conv_desc* d, bool stats) {
   static const int force_cg = [] { const char* e = getenv("DSK_CONV_CG"); return e ? atoi(e) : 0; }();
-  if (stats || force_cg == 1 || d->ksize != 3 || d->in_dtype != DSK_BF16 || d->out_dtype != DSK_BF16 || d->out_nchw_f32 ||
-      d->w_dtype != DSK_BF16 || d->Cin % 64 != 0 || d->Cout % 64 != 0 || tc_pair_eligible(d))
+  if (stats || force_cg == 1 || d->ksize != 3 || !tc_formats_ok(d) || d->out_nchw_f32 || d->Cin % 64 != 0 || d->Cout % 64 != 0 ||
+      tc_pair_eligible(d))
     return false;
   const int iD = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D;
   const int planes = d->ndim == 3 ? iD : d->B;
@@ -1000,10 +1141,10 @@ extern "C" int dsk_conv_fwd_ffma(const dsk_conv_desc*, const void*, const void*,
 
 // bytes of the halo-padded input copy a circular convolution on the tcgen05 path reads (0: CUDA-core kernel, wraps in place)
 extern "C" int64_t dsk_conv_pad_ws_bytes(const dsk_conv_desc* d) {
-  if (d == nullptr || d->circular != 1 || d->w_dtype != DSK_BF16) return 0;     // circular == 2: the input is already padded
+  if (d == nullptr || d->circular != 1 || d->w_dtype == DSK_F32) return 0;     // circular == 2: the input is already padded
   const int iD = (d->up2 && d->ndim == 3) ? d->D / 2 : d->D, iH = d->up2 ? d->H / 2 : d->H, iW = d->up2 ? d->W / 2 : d->W;
   const int pd = d->ndim == 3 ? 1 : 0;
-  return (int64_t)d->B * (iD + 2 * pd) * (iH + 2) * (iW + 2) * d->Cin * 2;
+  return (int64_t)d->B * (iD + 2 * pd) * (iH + 2) * (iW + 2) * d->Cin * (d->in_dtype == DSK_SPLIT_F16 ? 4 : 2);
 }
 
 extern "C" int dsk_conv_fwd_circ(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, const float* chan_bias,
@@ -1030,13 +1171,15 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
                             const void* residual, void* out, float2* stats, void* pad_ws, void* stream) {
   DSK_REQUIRE(d && in && w && out, "dsk_conv_fwd(tc): null pointer");
   const bool few_out = d->Cout <= 16 && !d->up2 && chan_bias == nullptr && residual == nullptr;
-  if (d->ksize != 3 || (d->out_nchw_f32 && !few_out) || d->in_dtype != DSK_BF16 || (!d->out_nchw_f32 && d->out_dtype != DSK_BF16) ||
-      d->Cin % 64 != 0 || (d->Cout % 64 != 0 && !few_out)) {
-    set_error("dsk_conv_fwd: the tcgen05 path takes k=3, bf16 in/out, Cin %% 64 == 0, Cout %% 64 == 0 "
-              "(got k=%d Cin=%d Cout=%d up2=%d in=%d out=%d nchw=%d)", d->ksize, d->Cin, d->Cout, d->up2, d->in_dtype, d->out_dtype,
-              d->out_nchw_f32);
+  if (d->ksize != 3 || (d->out_nchw_f32 && !few_out) || !tc_formats_ok(d) || d->Cin % 64 != 0 || (d->Cout % 64 != 0 && !few_out)) {
+    set_error("dsk_conv_fwd: the tcgen05 path takes k=3, 16-bit / split-fp16 operands of one format, Cin %% 64 == 0, Cout %% 64 == 0 "
+              "(got k=%d Cin=%d Cout=%d up2=%d in=%d w=%d out=%d nchw=%d)", d->ksize, d->Cin, d->Cout, d->up2, d->in_dtype, d->w_dtype,
+              d->out_dtype, d->out_nchw_f32);
     return DSK_ERR_UNSUPPORTED;
   }
+  const bool a_split = d->in_dtype == DSK_SPLIT_F16, w_split = d->w_dtype == DSK_SPLIT_F16;
+  const int a_ld = d->Cin * (a_split ? 2 : 1), w_ld = d->Cin * (w_split ? 2 : 1);     // channel-row lengths of the two tensor maps
+  const int fmt16 = d->in_dtype == DSK_BF16 ? DSK_BF16 : DSK_F16;
   DSK_REQUIRE((d->ndim == 2 && d->D == 1) || d->ndim == 3, "dsk_conv_fwd(tc): bad ndim/D");
   // circular padding: TMA boxes cannot wrap, so the kernels read a halo-padded copy (one extra pass over the input) and the
   // patch coordinates are shifted into it; nothing else in the kernels changes (no OOB fill is ever hit inside the image).
@@ -1044,7 +1187,7 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   const int pad_hw = d->circular ? 1 : 0, pad_d = (d->circular && d->ndim == 3) ? 1 : 0;
   if (d->circular == 1) {
     DSK_REQUIRE(pad_ws != nullptr, "dsk_conv_fwd(tc): circular padding needs pad_ws");
-    const int rc = pad_circular_launch(in, pad_ws, d->B, d->ndim == 3 ? iD : 1, iH, iW, d->Cin, d->ndim, DSK_BF16, as_stream(stream));
+    const int rc = pad_circular_launch(in, pad_ws, d->B, d->ndim == 3 ? iD : 1, iH, iW, a_ld, d->ndim, DSK_BF16, as_stream(stream));
     if (rc != DSK_OK) return rc;
     in = pad_ws;
   }
@@ -1065,26 +1208,27 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   const int tW = iW + 2 * pad_hw, tH = iH + 2 * pad_hw, tP = planes + 2 * pad_d;
   CUtensorMap ta, tw;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)tW, (cuuint64_t)tH, (cuuint64_t)tP, (cuuint64_t)batch};
-    cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)tW * d->Cin * 2, (cuuint64_t)tH * tW * d->Cin * 2,
-                             (cuuint64_t)tP * tH * tW * d->Cin * 2};
+    cuuint64_t dims[5] = {(cuuint64_t)a_ld, (cuuint64_t)tW, (cuuint64_t)tH, (cuuint64_t)tP, (cuuint64_t)batch};
+    cuuint64_t strides[4] = {(cuuint64_t)a_ld * 2, (cuuint64_t)tW * a_ld * 2, (cuuint64_t)tH * tW * a_ld * 2,
+                             (cuuint64_t)tP * tH * tW * a_ld * 2};
     cuuint32_t box[5] = {64, TC_PW, TC_PH, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, es,
+    CUresult r = encode(&ta, tmap_h16(fmt16), 5, const_cast<void*>(in), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DSK_REQUIRE(r == CUDA_SUCCESS, "dsk_conv_fwd(tc): activation tensor map failed (CUresult %d)", (int)r);
   }
   const int nphase = d->up2 ? (KD == 3 ? 8 : 4) : 1;
   const int ntaps = d->up2 ? nphase * (KD == 3 ? 8 : 4) : KD * 9;     // weight rows: [phase][tap][Cout] or [tap][Cout]
-  const int n_tile = few_out ? 16 : (d->Cout % 128 == 0 ? 128 : 64);
+  // split operands: four accumulator sets of P * 64 columns fill the TMEM -> 64-channel tiles only
+  const int n_tile = few_out ? 16 : ((d->Cout % 128 == 0 && !a_split) ? 128 : 64);
   const int w_rows = few_out ? 16 : d->Cout;                          // few_out weights are zero-padded to 16 output channels
   {
-    cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)ntaps * w_rows};
-    cuuint64_t strides[1] = {(cuuint64_t)d->Cin * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)w_ld, (cuuint64_t)ntaps * w_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)w_ld * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)n_tile};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = encode(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+    CUresult r = encode(&tw, tmap_h16(fmt16), 2, const_cast<void*>(w), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DSK_REQUIRE(r == CUDA_SUCCESS, "dsk_conv_fwd(tc): weight tensor map failed (CUresult %d)", (int)r);
@@ -1101,7 +1245,12 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   p.n_tiles = w_rows / n_tile;
   p.total_tiles = p.tiles_w * p.tiles_h * p.groups_d * batch * p.n_tiles * nphase;
   p.bias = bias; p.chan_bias = chan_bias;
-  p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
+  p.residual = (const uint16_t*)residual; p.out = (uint16_t*)out;
+  p.f16 = fmt16 == DSK_F16 ? 1 : 0;
+  p.out_f32 = (!d->out_nchw_f32 && d->out_dtype == DSK_F32) ? 1 : 0;
+  p.vparts = a_split ? (w_split ? 3 : 2) : 1;
+  p.a_lo_off = d->Cin; p.w_lo_off = d->Cin;
+  p.nsets = a_split ? (w_split ? 4 : 2) : 1;
   p.planes_per_sample = d->ndim == 3 ? iD : 1;
   p.stats = stats; p.samples = d->B;
   p.pad_hw = pad_hw; p.pad_d = pad_d;
@@ -1116,11 +1265,11 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
       DSK_REQUIRE(e == cudaSuccess, "dsk_conv_fwd_stats: memset failed: %s", cudaGetErrorString(e));
     }
     CUtensorMap tw2;
-    cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)ntaps * w_rows};
-    cuuint64_t strides[1] = {(cuuint64_t)d->Cin * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)w_ld, (cuuint64_t)ntaps * w_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)w_ld * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)(n_tile / 2)};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = encode(&tw2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+    CUresult r = encode(&tw2, tmap_h16(fmt16), 2, const_cast<void*>(w), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DSK_REQUIRE(r == CUDA_SUCCESS, "dsk_conv_fwd(tc2): weight tensor map failed (CUresult %d)", (int)r);

@@ -20,10 +20,11 @@ constexpr int CI_STAGES = 6;
 constexpr int CI_A_BYTES = 128 * 128;
 
 struct CiParams {
-  const __nv_bfloat16* x;   // channels-last [B, D, H, W, Cin]
+  const uint16_t* x;        // channels-last [B, D, H, W, Cin], 16-bit format f16 ? half : bfloat16
   const float* w;           // packed fp32 [taps][Cin][Cout]
   const float* bias;
-  __nv_bfloat16* out;       // channels-last [B, D, H, W, Cout]
+  uint16_t* out;            // channels-last [B, D, H, W, Cout]
+  int f16;
   int B, D, H, W, Cin, Cout, ndim;
   int tiles_w, tiles_h, total_tiles;
   int circ;                 // circular padding: the gather wraps instead of zero-filling (CircularConv, commonlayers.py:918-1032)
@@ -55,12 +56,12 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
   // weights -> bf16 K-major SWIZZLE_128B rows: B[co][k = tap*CIN + ci] = w[k][co], zero beyond K
   for (int i = threadIdx.x; i < N * 8; i += CI_THREADS) {
     const int j = i & 7, co = i >> 3;
-    __nv_bfloat162 h[4];
+    uint32_t h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int k0 = j * 8 + 2 * e;
       const float a = k0 < K ? p.w[(int64_t)k0 * N + co] : 0.0f, b = k0 + 1 < K ? p.w[(int64_t)(k0 + 1) * N + co] : 0.0f;
-      h[e] = __floats2bfloat162_rn(a, b);
+      h[e] = pack_h2(a, b, p.f16);
     }
     *reinterpret_cast<uint4*>(sB + co * 128 + ((j ^ (co & 7)) << 4)) = *reinterpret_cast<const uint4*>(h);
   }
@@ -112,10 +113,10 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
         oh[k] = (zh - h) * sH;
         ow[k] = (zw - w) * CIN;
       }
-      const __nv_bfloat16* ctr = p.x + ((((int64_t)b * p.D + d) * p.H + h) * p.W + w) * CIN;
-      __nv_bfloat16 v[64];
+      const uint16_t* ctr = p.x + ((((int64_t)b * p.D + d) * p.H + h) * p.W + w) * CIN;
+      __align__(16) uint16_t v[64];                            // zero bits = 0.0 in both 16-bit formats
 #pragma unroll
-      for (int k = 0; k < 64; ++k) v[k] = __float2bfloat16_rn(0.0f);
+      for (int k = 0; k < 64; ++k) v[k] = 0;
 #pragma unroll
       for (int kd = 0; kd < 3; ++kd) {
         if (kd >= kdn) break;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const bool ok = dv[kd] && hv[kh] && wv[kw];
-            const __nv_bfloat16* src = ctr + od[kd] + oh[kh] + ow[kw];
+            const uint16_t* src = ctr + od[kd] + oh[kh] + ow[kw];
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci)
               if (ok) v[((kd * 3 + kh) * 3 + kw) * CIN + ci] = src[ci];
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
     }
   } else if (warp == CI_BUILD) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_bf16(N);
+    const uint32_t idesc = umma_idesc_h16(N, 128, p.f16);
     constexpr uint32_t HI = umma_desc_hi(1024);
     const uint32_t b_lo = umma_desc_lo(smem_u32(sB));
     uint32_t seq = 0;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int h = h0 + line, w = w0 + wp;
       const bool valid = h < p.H && w < p.W;
-      __nv_bfloat16* orow = p.out + ((((int64_t)b * p.D + d) * p.H + h) * p.W + w) * N;
+      uint16_t* orow = p.out + ((((int64_t)b * p.D + d) * p.H + h) * p.W + w) * N;
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
         DSK_TMEM_LD_X32(v, tmem_base + as * N + c0 + ((uint32_t)(q * 32) << 16));
@@ -186,12 +187,12 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 o;
-            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+            uint32_t* oh = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float f0 = __uint_as_float(v[g * 8 + 2 * e]), f1 = __uint_as_float(v[g * 8 + 2 * e + 1]);
               if (p.bias != nullptr) { f0 += __ldg(p.bias + c0 + g * 8 + 2 * e); f1 += __ldg(p.bias + c0 + g * 8 + 2 * e + 1); }
-              oh[e] = __floats2bfloat162_rn(f0, f1);
+              oh[e] = pack_h2(f0, f1, p.f16);
             }
             *reinterpret_cast<uint4*>(orow + c0 + g * 8) = o;
           }
@@ -221,11 +222,12 @@ static int launch_convin(const CiParams& p, cudaStream_t st) {
 int convin_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, void* out, cudaStream_t st) {
   static const int old_path = [] { const char* e = getenv("DSK_CONVIN_OLD"); return e ? atoi(e) : 0; }();
   const int taps = d->ndim == 3 ? 27 : 9;
-  if (old_path || d->ksize != 3 || d->up2 || d->out_nchw_f32 || d->in_dtype != DSK_BF16 || d->out_dtype != DSK_BF16 || d->w_dtype != DSK_F32 ||
+  if (old_path || d->ksize != 3 || d->up2 || d->out_nchw_f32 || !is_h16(d->in_dtype) || d->out_dtype != d->in_dtype || d->w_dtype != DSK_F32 ||
       d->Cin > 4 || taps * d->Cin > 64 || (d->Cout != 64 && d->Cout != 128 && d->Cout != 256))
     return DSK_ERR_UNSUPPORTED;
   CiParams p;
-  p.x = (const __nv_bfloat16*)in; p.w = (const float*)w; p.bias = bias; p.out = (__nv_bfloat16*)out;
+  p.x = (const uint16_t*)in; p.w = (const float*)w; p.bias = bias; p.out = (uint16_t*)out;
+  p.f16 = d->in_dtype == DSK_F16 ? 1 : 0;
   p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.ndim = d->ndim;
   p.circ = d->circular;
   p.tiles_w = (d->W + CI_BW - 1) / CI_BW; p.tiles_h = (d->H + CI_BH - 1) / CI_BH;

@@ -29,13 +29,23 @@ constexpr int CO_P = 2, CO_NA = 6;
 struct CoParams {
   int B, D, H, W, Cin, Cout, KD;      // as the tensor map sees them (2-D: B = 1, D = batch of planes)
   int tiles_w, tiles_h, groups_d, total_tiles;
-  const __nv_bfloat16* w;             // packed [tap][16][Cin] (PackedConv convout layout, zero rows beyond Cout)
+  const uint16_t* w;                  // packed [tap][16][w_ld] (PackedConv convout layout, zero rows beyond Cout)
   const float* bias;
-  __nv_bfloat16* out;                 // channels-last [.., Cout] bf16, or
+  uint16_t* out;                      // channels-last [.., Cout] in the 16-bit format (fp32 if out_f32), or
   float* out_nchw;                    // fp32 NC(D)HW
   int planes_per_sample;
   int pad_hw, pad_d;                  // circular padding: the tensor map covers the halo-padded copy (see conv_tc.cu)
+  int f16, out_f32;                   // 16-bit format (0 bf16, 1 fp16); channels-last output is fp32
+  int vparts, a_lo_off, w_lo_off, w_ld;   // split operands: virtual K chunks per real chunk (conv_tc.cu), weight row length
 };
+__device__ __forceinline__ int co_vchunk_a(const CoParams& p, int vc) {
+  const int c = vc / p.vparts, part = vc - c * p.vparts;
+  return c * 64 + ((p.vparts > 1 && part == p.vparts - 1) ? p.a_lo_off : 0);
+}
+__device__ __forceinline__ int co_vchunk_w(const CoParams& p, int vc) {
+  const int c = vc / p.vparts, part = vc - c * p.vparts;
+  return c * 64 + ((p.vparts == 3 && part == 1) ? p.w_lo_off : 0);
+}
 
 template <int COUT>
 __global__ void __launch_bounds__(CO_THREADS, 1)
@@ -43,7 +53,7 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
   constexpr int NT = 9 * COUT, N_PAD = NT <= 16 ? 16 : 32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int KD = p.KD, nchunks = p.Cin / 64;
+  const int KD = p.KD, nchunks = (p.Cin / 64) * p.vparts;           // virtual K chunks
   uint8_t* sA = smem;                                               // CO_NA patches
   uint8_t* sW = smem + (size_t)CO_NA * CO_PATCH_STRIDE;             // [kd][chunk][N_PAD rows x 128 B], SWIZZLE_128B
   const int wbytes = KD * nchunks * N_PAD * 128;
@@ -51,7 +61,11 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
   __shared__ uint64_t full_a[CO_NA], empty_a[CO_NA], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   constexpr uint32_t ACC_COLS = CO_P * 2 * N_PAD;                   // [plane][row group] x N_PAD columns
-  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                      // double buffered: 128 (N_PAD 16) / 256 (N_PAD 32)
+  // split operands: a second accumulator set takes the hi*lo + lo*hi products (lo operands are stored times 2^11); the epilogue
+  // combines z = hh + 2^-11 lo.  Chains are short here (taps are the N dimension: KD * 4 MMAs per accumulator and chunk).
+  const uint32_t nsets = p.vparts > 1 ? 2u : 1u;
+  const uint32_t BUF_COLS = nsets * ACC_COLS;
+  const uint32_t TMEM_COLS = 2 * BUF_COLS;                          // double buffered: 128 .. 512 columns
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NJ = CO_P + KD - 1, dpad = KD >> 1;
 
@@ -75,7 +89,7 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
       if (n < NT) {
         const int khw = n / COUT, co = n - khw * COUT;
         const int tap = kd * 9 + khw;
-        v = *reinterpret_cast<const uint4*>(p.w + ((int64_t)tap * 16 + co) * p.Cin + chunk * 64 + j * 8);
+        v = *reinterpret_cast<const uint4*>(p.w + ((int64_t)tap * 16 + co) * p.w_ld + co_vchunk_w(p, chunk) + j * 8);
       }
       *reinterpret_cast<uint4*>(sW + (size_t)tc * N_PAD * 128 + n * 128 + ((j ^ (n & 7)) << 4)) = v;
     }
@@ -109,7 +123,7 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
             asm volatile(
                 "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
                     smem_u32(sA + (size_t)slot * CO_PATCH_STRIDE)),
-                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(c * 64), "r"(w0 - 1 + p.pad_hw), "r"(h0 - 1 + p.pad_hw), "r"(d0 + j - dpad + p.pad_d), "r"(b),
+                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(co_vchunk_a(p, c)), "r"(w0 - 1 + p.pad_hw), "r"(h0 - 1 + p.pad_hw), "r"(d0 + j - dpad + p.pad_d), "r"(b),
                 "r"(smem_u32(&full_a[slot]))
                 : "memory");
           }
@@ -117,14 +131,15 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_bf16(N_PAD);
+    const uint32_t idesc = umma_idesc_h16(N_PAD, 128, p.f16);
     constexpr uint32_t HI = umma_desc_hi(1024);                     // 8 consecutive patch rows = 1024 B (both operands)
     uint32_t seq = 0, it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       mbar_wait(&acc_empty[as], aph ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t acc = tmem_base + as * ACC_COLS;
+      const uint32_t acc = tmem_base + as * BUF_COLS;
+      uint32_t used[2] = {0u, 0u};                                  // per set: output planes already written in this tile
       for (int c = 0; c < nchunks; ++c)
         for (int j = 0; j < NJ; ++j, ++seq) {
           const uint32_t slot = seq % CO_NA;
@@ -138,12 +153,15 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
               const int pp = j - kd;
               if (pp < 0 || pp >= CO_P) continue;
               const uint32_t b_lo = umma_desc_lo(smem_u32(sW + (size_t)(kd * nchunks + c) * N_PAD * 128));
-              const uint32_t first = (c | kd) == 0 ? 0u : 1u;
+              const uint32_t set = (c % p.vparts) ? 1u : 0u;
+              const uint32_t first = (used[set] >> pp) & 1u;         // 0: first MMA into this (set, plane) accumulator
+              used[set] |= 1u << pp;
+              const uint32_t accs = acc + set * ACC_COLS;
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
-                umma_bf16(acc + (pp * 2 + 0) * N_PAD, umma_desc64(a0 + k4 * 2, HI), umma_desc64(b_lo + k4 * 2, HI), idesc,
+                umma_bf16(accs + (pp * 2 + 0) * N_PAD, umma_desc64(a0 + k4 * 2, HI), umma_desc64(b_lo + k4 * 2, HI), idesc,
                           k4 == 0 ? first : 1u);
-                umma_bf16(acc + (pp * 2 + 1) * N_PAD, umma_desc64(a1 + k4 * 2, HI), umma_desc64(b_lo + k4 * 2, HI), idesc,
+                umma_bf16(accs + (pp * 2 + 1) * N_PAD, umma_desc64(a1 + k4 * 2, HI), umma_desc64(b_lo + k4 * 2, HI), idesc,
                           k4 == 0 ? first : 1u);
               }
             }
@@ -172,13 +190,19 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
       for (int pp = 0; pp < CO_P; ++pp)
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          const uint32_t taddr = tmem_base + as * ACC_COLS + (pp * 2 + g) * N_PAD + ((uint32_t)(q * 32) << 16);
+          const uint32_t taddr = tmem_base + as * BUF_COLS + (pp * 2 + g) * N_PAD + ((uint32_t)(q * 32) << 16);
           const int prow = g == 0 ? r0 : r0 + CO_G1;
           const bool mine = g == 0 || prow >= 128;   // rows 52..127 are computed by both groups: group 0 owns them
           float* zrow = sZ + ((size_t)pp * CO_ROWS + prow) * ZS;
           if constexpr (N_PAD == 16) {
             uint32_t v[16];
             DSK_TMEM_LD_X16(v, taddr);
+            if (nsets > 1) {
+              uint32_t u[16];
+              DSK_TMEM_LD_X16(u, taddr + ACC_COLS);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(fmaf(__uint_as_float(u[e]), 1.0f / 2048.0f, __uint_as_float(v[e])));
+            }
             if (mine)
 #pragma unroll
               for (int e = 0; e < 16; ++e)
@@ -186,6 +210,12 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
           } else {
             uint32_t v[32];
             DSK_TMEM_LD_X32(v, taddr);
+            if (nsets > 1) {
+              uint32_t u[32];
+              DSK_TMEM_LD_X32(u, taddr + ACC_COLS);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(fmaf(__uint_as_float(u[e]), 1.0f / 2048.0f, __uint_as_float(v[e])));
+            }
             if (mine)
 #pragma unroll
               for (int e = 0; e < 32; ++e)
@@ -220,7 +250,8 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
               const int64_t sample = ((int64_t)b * p.D + d) / p.planes_per_sample;
               p.out_nchw[(sample * COUT + co) * S + (pix - sample * S)] = x;
             } else {
-              p.out[pix * COUT + co] = __float2bfloat16_rn(x);
+              if (p.out_f32) reinterpret_cast<float*>(p.out)[pix * COUT + co] = x;
+              else p.out[pix * COUT + co] = pack_h1(x, p.f16);
             }
           }
         }
@@ -236,7 +267,7 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
 template <int COUT>
 static int launch_convout(const CUtensorMap& ta, const CoParams& p, cudaStream_t st) {
   constexpr int N_PAD = 9 * COUT <= 16 ? 16 : 32;
-  const int nchunks = p.Cin / 64;
+  const int nchunks = (p.Cin / 64) * p.vparts;
   const size_t wbytes = ((size_t)p.KD * nchunks * N_PAD * 128 + 1023) & ~(size_t)1023;
   const size_t smem = (size_t)CO_NA * CO_PATCH_STRIDE + wbytes + (size_t)CO_P * CO_ROWS * 9 * p.Cout * sizeof(float) + 1024;
   if (smem > 227 * 1024) return DSK_ERR_UNSUPPORTED;
@@ -250,8 +281,10 @@ static int launch_convout(const CUtensorMap& ta, const CoParams& p, cudaStream_t
 // returns DSK_ERR_UNSUPPORTED for shapes it does not take (the caller falls back to the N = 16 tile of conv_tc.cu)
 // padded != 0: `in` is the halo-padded copy [B, D+2 (3-D), H+2, W+2, Cin] of a circular convolution
 int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, void* out, cudaStream_t st, int padded) {
-  if (d->ksize != 3 || d->up2 || d->in_dtype != DSK_BF16 || d->Cin % 64 != 0 || d->Cout > 3) return DSK_ERR_UNSUPPORTED;
-  if (!d->out_nchw_f32 && d->out_dtype != DSK_BF16) return DSK_ERR_UNSUPPORTED;
+  const bool a_split = d->in_dtype == DSK_SPLIT_F16, w_split = d->w_dtype == DSK_SPLIT_F16;
+  if (d->ksize != 3 || d->up2 || !(is_h16(d->in_dtype) || a_split) || d->Cin % 64 != 0 || d->Cout > 3) return DSK_ERR_UNSUPPORTED;
+  if (!d->out_nchw_f32 && !(is_h16(d->out_dtype) || d->out_dtype == DSK_F32)) return DSK_ERR_UNSUPPORTED;
+  const int a_ld = d->Cin * (a_split ? 2 : 1);
   EncodeTiledFn encode = get_encode();
   if (encode == nullptr) return DSK_ERR_UNSUPPORTED;
   const int KD = d->ndim == 3 ? 3 : 1;
@@ -259,12 +292,12 @@ int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, c
   CUtensorMap ta;
   const int pad_hw = padded ? 1 : 0, pad_d = (padded && d->ndim == 3) ? 1 : 0;
   const int tW = d->W + 2 * pad_hw, tH = d->H + 2 * pad_hw, tP = planes + 2 * pad_d;
-  cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)tW, (cuuint64_t)tH, (cuuint64_t)tP, (cuuint64_t)batch};
-  cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)tW * d->Cin * 2, (cuuint64_t)tH * tW * d->Cin * 2,
-                           (cuuint64_t)tP * tH * tW * d->Cin * 2};
+  cuuint64_t dims[5] = {(cuuint64_t)a_ld, (cuuint64_t)tW, (cuuint64_t)tH, (cuuint64_t)tP, (cuuint64_t)batch};
+  cuuint64_t strides[4] = {(cuuint64_t)a_ld * 2, (cuuint64_t)tW * a_ld * 2, (cuuint64_t)tH * tW * a_ld * 2,
+                           (cuuint64_t)tP * tH * tW * a_ld * 2};
   cuuint32_t box[5] = {64, CO_PW, CO_PH, 1, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, es,
+  CUresult r = encode(&ta, tmap_h16(d->in_dtype == DSK_BF16 ? DSK_BF16 : DSK_F16), 5, const_cast<void*>(in), dims, strides, box, es,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("convout_tc: activation tensor map failed (CUresult %d)", (int)r); return DSK_ERR_CUDA; }
@@ -272,8 +305,12 @@ int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, c
   p.B = batch; p.D = planes; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.KD = KD;
   p.tiles_w = (d->W + CO_BW - 1) / CO_BW; p.tiles_h = (d->H + CO_BH - 1) / CO_BH; p.groups_d = (planes + CO_P - 1) / CO_P;
   p.total_tiles = p.tiles_w * p.tiles_h * p.groups_d * batch;
-  p.w = (const __nv_bfloat16*)w; p.bias = bias;
-  p.out = d->out_nchw_f32 ? nullptr : (__nv_bfloat16*)out;
+  p.w = (const uint16_t*)w; p.bias = bias;
+  p.out = d->out_nchw_f32 ? nullptr : (uint16_t*)out;
+  p.f16 = d->in_dtype == DSK_BF16 ? 0 : 1;
+  p.out_f32 = (!d->out_nchw_f32 && d->out_dtype == DSK_F32) ? 1 : 0;
+  p.vparts = a_split ? (w_split ? 3 : 2) : 1;
+  p.a_lo_off = d->Cin; p.w_lo_off = d->Cin; p.w_ld = d->Cin * (w_split ? 2 : 1);
   p.out_nchw = d->out_nchw_f32 ? (float*)out : nullptr;
   p.planes_per_sample = d->ndim == 3 ? d->D : 1;
   p.pad_hw = pad_hw; p.pad_d = pad_d;

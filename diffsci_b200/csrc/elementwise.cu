@@ -34,9 +34,10 @@ __global__ void __launch_bounds__(256) pool2x_kernel(const T* __restrict__ x, T*
 
 // bf16, C % 8 == 0: a thread pools 8 channels (one 16-byte vector) of one output pixel -- 8 (3-D) / 4 (2-D) vector loads,
 // one vector store; max is taken on the bf16 values directly (exact), the mean in fp32.
-template <bool IS_MAX>
+template <typename T, bool IS_MAX>
 __global__ void __launch_bounds__(256) pool2x_vec8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int D, int H, int W,
                                                            int C8, int ndim) {
+  typedef typename H16<T>::T2 T2;
   const int Do = ndim == 3 ? D / 2 : 1, Ho = H / 2, Wo = W / 2;
   const int kd = ndim == 3 ? 2 : 1;
   const int64_t total = (int64_t)B * Do * Ho * Wo * C8;
@@ -58,17 +59,17 @@ __global__ void __launch_bounds__(256) pool2x_vec8_kernel(const uint4* __restric
           if (a < kd) v[(a * 2 + bb) * 2 + cc] = x[base + (((int64_t)a * H + bb) * W + cc) * C8];
     uint4 o;
     if (IS_MAX) {
-      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+      T2* oh = reinterpret_cast<T2*>(&o);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        __nv_bfloat162 m = reinterpret_cast<const __nv_bfloat162*>(&v[0])[e];
+        T2 m = reinterpret_cast<const T2*>(&v[0])[e];
 #pragma unroll
         for (int k = 1; k < 8; ++k)
-          if (k < 4 * kd) m = __hmax2(m, reinterpret_cast<const __nv_bfloat162*>(&v[k])[e]);
+          if (k < 4 * kd) m = __hmax2(m, reinterpret_cast<const T2*>(&v[k])[e]);
         oh[e] = m;
       }
     } else {
-      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+      T2* oh = reinterpret_cast<T2*>(&o);
       const float sc = ndim == 3 ? 0.125f : 0.25f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -76,10 +77,10 @@ __global__ void __launch_bounds__(256) pool2x_vec8_kernel(const uint4* __restric
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           if (k < 4 * kd) {
-            const __nv_bfloat162 t = reinterpret_cast<const __nv_bfloat162*>(&v[k])[e];
+            const T2 t = reinterpret_cast<const T2*>(&v[k])[e];
             lo += __low2float(t); hi += __high2float(t);
           }
-        oh[e] = __floats2bfloat162_rn(lo * sc, hi * sc);
+        oh[e] = H16<T>::pack(lo * sc, hi * sc);
       }
     }
     y[i] = o;
@@ -96,6 +97,27 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = from_f32<TO>(to_f32<TI>(x[i]));
+}
+
+// fp32 [rows, C] -> split-fp16 [rows, 2C] (hi | lo, DSK_SPLIT_F16): the operand format of the split tensor-core kernels, for
+// inputs that no fused producer (norm apply) writes in that form.  One thread = 4 channels of one row.
+__global__ void __launch_bounds__(256) split_f16_kernel(const float4* __restrict__ x, __half* __restrict__ y, int64_t rows, int C4) {
+  const int64_t total = rows * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C4;
+    const int c = (int)(i - r * C4) * 4;
+    const float4 v = x[i];
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn((v.x - f0.x) * 2048.0f, (v.y - f0.y) * 2048.0f);      // lo is stored times 2^11
+    const __half2 l1 = __floats2half2_rn((v.z - f1.x) * 2048.0f, (v.w - f1.y) * 2048.0f);
+    uint2 hi, lo;
+    hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+    __half* row = y + r * (int64_t)(8 * C4);
+    *reinterpret_cast<uint2*>(row + c) = hi;
+    *reinterpret_cast<uint2*>(row + 4 * C4 + c) = lo;
+  }
 }
 
 // y[b, s, c] = x[b, c, s]  (C is small at the module boundary: 1..4 channels)
@@ -419,7 +441,7 @@ __global__ void __launch_bounds__(256) pad_circular_kernel(const VT* __restrict_
 
 int pad_circular_launch(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, cudaStream_t st) {
   const int pd = ndim == 3 ? 1 : 0;
-  const int es = dtype == DSK_BF16 ? 2 : 4;
+  const int es = is_h16(dtype) ? 2 : 4;
   const int64_t row = (int64_t)C * es;                      // bytes of one pixel's channel run
   const int64_t npix = (int64_t)B * (D + 2 * pd) * (H + 2) * (W + 2);
   const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
@@ -476,14 +498,17 @@ extern "C" int dsk_pool2x(const void* x, void* y, int B, int D, int H, int W, in
   const int grid = grid_for(total, 256, 16);
   cudaStream_t st = as_stream(stream);
 #define POOL(T, M) DSK_LAUNCH((pool2x_kernel<T, M>), grid, 256, 0, st, (const T*)x, (T*)y, B, D, H, W, C, ndim)
-  if (dtype == DSK_BF16 && C % 8 == 0) {
+  if (is_h16(dtype) && C % 8 == 0) {
     const int vgrid = grid_for(total / 8, 256, 16);
-    if (is_max) DSK_LAUNCH(pool2x_vec8_kernel<true>, vgrid, 256, 0, st, (const uint4*)x, (uint4*)y, B, D, H, W, C / 8, ndim);
-    else DSK_LAUNCH(pool2x_vec8_kernel<false>, vgrid, 256, 0, st, (const uint4*)x, (uint4*)y, B, D, H, W, C / 8, ndim);
+#define POOLV(T, M) DSK_LAUNCH((pool2x_vec8_kernel<T, M>), vgrid, 256, 0, st, (const uint4*)x, (uint4*)y, B, D, H, W, C / 8, ndim)
+    if (dtype == DSK_F16) { if (is_max) POOLV(__half, true); else POOLV(__half, false); }
+    else { if (is_max) POOLV(__nv_bfloat16, true); else POOLV(__nv_bfloat16, false); }
+#undef POOLV
     return DSK_OK;
   }
   if (dtype == DSK_F32) { if (is_max) POOL(float, true); else POOL(float, false); }
   else if (dtype == DSK_BF16) { if (is_max) POOL(__nv_bfloat16, true); else POOL(__nv_bfloat16, false); }
+  else if (dtype == DSK_F16) { if (is_max) POOL(__half, true); else POOL(__half, false); }
   else DSK_REQUIRE(false, "dsk_pool2x: bad dtype %d", dtype);
 #undef POOL
   return DSK_OK;
@@ -494,6 +519,7 @@ extern "C" int dsk_add(const void* a, const void* b, void* y, int64_t n, int dty
   const int grid = grid_for(n, 256, 16);
   if (dtype == DSK_F32) DSK_LAUNCH(add_kernel<float>, grid, 256, 0, as_stream(stream), (const float*)a, (const float*)b, (float*)y, n);
   else if (dtype == DSK_BF16) DSK_LAUNCH(add_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, n);
+  else if (dtype == DSK_F16) DSK_LAUNCH(add_kernel<__half>, grid, 256, 0, as_stream(stream), (const __half*)a, (const __half*)b, (__half*)y, n);
   else DSK_REQUIRE(false, "dsk_add: bad dtype %d", dtype);
   return DSK_OK;
 }
@@ -505,7 +531,16 @@ extern "C" int dsk_cast(const void* x, void* y, int64_t n, int in_dtype, int out
   if (in_dtype == DSK_F32 && out_dtype == DSK_BF16) DSK_LAUNCH((cast_kernel<float, __nv_bfloat16>), grid, 256, 0, st, (const float*)x, (__nv_bfloat16*)y, n);
   else if (in_dtype == DSK_BF16 && out_dtype == DSK_F32) DSK_LAUNCH((cast_kernel<__nv_bfloat16, float>), grid, 256, 0, st, (const __nv_bfloat16*)x, (float*)y, n);
   else if (in_dtype == DSK_F32 && out_dtype == DSK_F32) DSK_LAUNCH((cast_kernel<float, float>), grid, 256, 0, st, (const float*)x, (float*)y, n);
+  else if (in_dtype == DSK_F32 && out_dtype == DSK_F16) DSK_LAUNCH((cast_kernel<float, __half>), grid, 256, 0, st, (const float*)x, (__half*)y, n);
+  else if (in_dtype == DSK_F16 && out_dtype == DSK_F32) DSK_LAUNCH((cast_kernel<__half, float>), grid, 256, 0, st, (const __half*)x, (float*)y, n);
   else DSK_REQUIRE(false, "dsk_cast: bad dtypes %d -> %d", in_dtype, out_dtype);
+  return DSK_OK;
+}
+
+extern "C" int dsk_split_f16(const float* x, void* y, int64_t rows, int C, void* stream) {
+  DSK_REQUIRE(x && y && rows > 0 && C > 0 && C % 4 == 0, "dsk_split_f16: bad arguments (C %% 4 == 0)");
+  DSK_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, "dsk_split_f16: 16-byte alignment");
+  DSK_LAUNCH(split_f16_kernel, grid_for(rows * (C / 4), 256, 16), 256, 0, as_stream(stream), (const float4*)x, (__half*)y, rows, C / 4);
   return DSK_OK;
 }
 
@@ -514,6 +549,7 @@ extern "C" int dsk_nchw_to_cl(const float* x, void* y, int B, int C, int64_t S, 
   const int grid = grid_for((int64_t)B * C * S, 256, 16);
   if (dtype == DSK_F32) DSK_LAUNCH(nchw_to_cl_kernel<float>, grid, 256, 0, as_stream(stream), x, (float*)y, B, C, S);
   else if (dtype == DSK_BF16) DSK_LAUNCH(nchw_to_cl_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), x, (__nv_bfloat16*)y, B, C, S);
+  else if (dtype == DSK_F16) DSK_LAUNCH(nchw_to_cl_kernel<__half>, grid, 256, 0, as_stream(stream), x, (__half*)y, B, C, S);
   else DSK_REQUIRE(false, "dsk_nchw_to_cl: bad dtype %d", dtype);
   return DSK_OK;
 }
@@ -523,6 +559,7 @@ extern "C" int dsk_cl_to_nchw(const void* x, float* y, int B, int C, int64_t S, 
   const int grid = grid_for((int64_t)B * C * S, 256, 16);
   if (dtype == DSK_F32) DSK_LAUNCH(cl_to_nchw_kernel<float>, grid, 256, 0, as_stream(stream), (const float*)x, y, B, C, S);
   else if (dtype == DSK_BF16) DSK_LAUNCH(cl_to_nchw_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), (const __nv_bfloat16*)x, y, B, C, S);
+  else if (dtype == DSK_F16) DSK_LAUNCH(cl_to_nchw_kernel<__half>, grid, 256, 0, as_stream(stream), (const __half*)x, y, B, C, S);
   else DSK_REQUIRE(false, "dsk_cl_to_nchw: bad dtype %d", dtype);
   return DSK_OK;
 }
@@ -532,7 +569,7 @@ extern "C" int dsk_concat_channels(const void* a, const void* b, void* y, int64_
   DSK_REQUIRE(a && b && y && rows > 0 && Ca > 0 && Cb > 0, "dsk_concat_channels: bad arguments");
   const int grid = grid_for(rows * (Ca + Cb), 256, 16);
   if (dtype == DSK_F32) DSK_LAUNCH(concat_kernel<float>, grid, 256, 0, as_stream(stream), (const float*)a, (const float*)b, (float*)y, rows, Ca, Cb);
-  else if (dtype == DSK_BF16) DSK_LAUNCH(concat_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, rows, Ca, Cb);
+  else if (is_h16(dtype)) DSK_LAUNCH(concat_kernel<uint16_t>, grid, 256, 0, as_stream(stream), (const uint16_t*)a, (const uint16_t*)b, (uint16_t*)y, rows, Ca, Cb);
   else DSK_REQUIRE(false, "dsk_concat_channels: bad dtype %d", dtype);
   return DSK_OK;
 }
@@ -597,6 +634,6 @@ extern "C" int dsk_mask_blend(float* out, const float* x, const float* y, const 
 extern "C" int dsk_pad_circular(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, void* stream) {
   DSK_REQUIRE(x && y && B > 0 && D > 0 && H > 0 && W > 0 && C > 0, "dsk_pad_circular: bad arguments");
   DSK_REQUIRE((ndim == 2 && D == 1) || ndim == 3, "dsk_pad_circular: bad ndim/D");
-  DSK_REQUIRE(dtype == DSK_F32 || dtype == DSK_BF16, "dsk_pad_circular: bad dtype %d", dtype);
+  DSK_REQUIRE(dtype == DSK_F32 || is_h16(dtype), "dsk_pad_circular: bad dtype %d", dtype);
   return pad_circular_launch(x, y, B, D, H, W, C, ndim, dtype, as_stream(stream));
 }

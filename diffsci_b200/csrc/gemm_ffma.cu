@@ -103,6 +103,12 @@ struct ConvProb {
 #pragma unroll
     for (int j = 0; j < 4; ++j) { o[2 * j] = __low2float(h[j]); o[2 * j + 1] = __high2float(h[j]); }
   }
+  static __device__ __forceinline__ void ld8(const __half* p, float* o) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[2 * j] = __low2float(h[j]); o[2 * j + 1] = __high2float(h[j]); }
+  }
   // 4 consecutive n of weight row k
   __device__ __forceinline__ void load_b(int k, int n, float* o) const {
     if (k < K && (Cout & 3) == 0 && n + 3 < N) {
@@ -435,13 +441,14 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // dgrad = 1: the packed weights of the DATA-GRADIENT convolution dX = conv_same(dY, W') with W'[tap'][co -> in][ci -> out],
 // tap' = taps-1-tap (all axes flipped): the same two layouts with the roles of Cin and Cout exchanged.
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, float* __restrict__ o32,
-                                                           __nv_bfloat16* __restrict__ o16, int Cout, int Cin, int taps, int rows,
-                                                           int dgrad) {
+                                                           uint16_t* __restrict__ o16, int Cout, int Cin, int taps, int rows,
+                                                           int dgrad, int fmt) {
   const int64_t total = (int64_t)Cout * Cin * taps;
   if (o16 != nullptr && rows > Cout) {
-    const int64_t padded = (int64_t)taps * rows * Cin;
+    const int64_t padded = (int64_t)taps * rows * Cin * (fmt == DSK_SPLIT_F16 ? 2 : 1);
+    const int rl = Cin * (fmt == DSK_SPLIT_F16 ? 2 : 1);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += (int64_t)gridDim.x * blockDim.x)
-      if ((i / Cin) % rows >= Cout) o16[i] = __float2bfloat16_rn(0.0f);
+      if ((i / rl) % rows >= Cout) o16[i] = 0;
   }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     // reference layout: w[co][ci][tap]
@@ -453,11 +460,11 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
     if (dgrad) {
       const int tf = taps - 1 - tap;
       if (o32 != nullptr) o32[((int64_t)tf * Cout + co) * Cin + ci] = v;                      // [tap'][in = co][out = ci]
-      if (o16 != nullptr) o16[((int64_t)tf * Cin + ci) * Cout + co] = __float2bfloat16_rn(v);   // [tap'][out = ci][in = co]
+      if (o16 != nullptr) put16(o16, (int64_t)tf * Cin + ci, Cout, co, v, fmt);             // [tap'][out = ci][in = co]
       continue;
     }
     if (o32 != nullptr) o32[((int64_t)tap * Cin + ci) * Cout + co] = v;          // [tap][ci][co]
-    if (o16 != nullptr) o16[((int64_t)tap * rows + co) * Cin + ci] = __float2bfloat16_rn(v);  // [tap][co][ci]
+    if (o16 != nullptr) put16(o16, (int64_t)tap * rows + co, Cin, ci, v, fmt);   // [tap][co][ci]
   }
 }
 
@@ -466,8 +473,8 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 // outer operand side x 64 channels of the inner (contiguous-in-output) side x all taps:
 //   dgrad = 0: out[tap][co][ci]  -- block (co, 64 ci): reads 64*taps CONTIGUOUS floats, writes `taps` rows of 128 bytes
 //   dgrad = 1: out[taps-1-tap][ci][co] -- block (ci, 64 co): reads 64 runs of `taps` floats, writes `taps` rows of 128 bytes
-__global__ void __launch_bounds__(256) pack_weight_bf16_tiled_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o16, int Cout,
-                                                                      int Cin, int taps, int dgrad) {
+__global__ void __launch_bounds__(256) pack_weight_bf16_tiled_kernel(const float* __restrict__ w, uint16_t* __restrict__ o16, int Cout,
+                                                                      int Cin, int taps, int dgrad, int fmt) {
   __shared__ float tile[27][65];
   const int inner = dgrad ? Cout : Cin;                    // contiguous dimension of the output rows
   const int chunks = (inner + 63) / 64;
@@ -482,12 +489,12 @@ __global__ void __launch_bounds__(256) pack_weight_bf16_tiled_kernel(const float
   for (int idx = threadIdx.x; idx < n * taps; idx += blockDim.x) {
     const int tap = idx / n, cl = idx - tap * n;
     const int64_t row = dgrad ? (int64_t)(taps - 1 - tap) * Cin + fixed : (int64_t)tap * Cout + fixed;
-    o16[row * inner + c0 + cl] = __float2bfloat16_rn(tile[tap][cl]);
+    put16(o16, row, inner, c0 + cl, tile[tap][cl], fmt);
   }
 }
 
 static bool pack_tiled_ok(int Cout, int Cin, int taps, int rows, int dtype) {
-  return dtype == DSK_BF16 && rows == Cout && taps <= 27 && (int64_t)Cout * Cin * taps >= 16384;
+  return dtype != DSK_F32 && rows == Cout && taps <= 27 && (int64_t)Cout * Cin * taps >= 16384;
 }
 
 template <typename TI, typename TO>
@@ -542,36 +549,39 @@ extern "C" int dsk_conv_fwd_ffma(const dsk_conv_desc* d, const void* in, const v
   if (ti == DSK_BF16 && to == DSK_BF16) return launch_conv<__nv_bfloat16, __nv_bfloat16>(d, in, w, bias, chan_bias, residual, out, st);
   if (ti == DSK_BF16 && to == DSK_F32) return launch_conv<__nv_bfloat16, float>(d, in, w, bias, chan_bias, residual, out, st);
   if (ti == DSK_F32 && to == DSK_BF16) return launch_conv<float, __nv_bfloat16>(d, in, w, bias, chan_bias, residual, out, st);
+  if (ti == DSK_F16 && to == DSK_F16) return launch_conv<__half, __half>(d, in, w, bias, chan_bias, residual, out, st);
+  if (ti == DSK_F16 && to == DSK_F32) return launch_conv<__half, float>(d, in, w, bias, chan_bias, residual, out, st);
+  if (ti == DSK_F32 && to == DSK_F16) return launch_conv<float, __half>(d, in, w, bias, chan_bias, residual, out, st);
   DSK_REQUIRE(false, "dsk_conv_fwd: bad dtypes %d -> %d", ti, to);
   return DSK_OK;
 }
 
 extern "C" int dsk_pack_conv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int taps, int dtype, void* stream) {
   DSK_REQUIRE(w_ref && w_packed && Cout > 0 && Cin > 0 && taps > 0, "dsk_pack_conv_weight: bad arguments");
-  DSK_REQUIRE(dtype == DSK_F32 || dtype == DSK_BF16, "dsk_pack_conv_weight: bad dtype %d", dtype);
-  const int rows = (dtype == DSK_BF16 && Cout <= 16) ? 16 : Cout;
+  DSK_REQUIRE(dtype >= DSK_F32 && dtype <= DSK_SPLIT_F16, "dsk_pack_conv_weight: bad dtype %d", dtype);
+  const int rows = (dtype != DSK_F32 && Cout <= 16) ? 16 : Cout;
   if (pack_tiled_ok(Cout, Cin, taps, rows, dtype)) {
-    DSK_LAUNCH(pack_weight_bf16_tiled_kernel, Cout * ((Cin + 63) / 64), 256, 0, as_stream(stream), w_ref, (__nv_bfloat16*)w_packed, Cout, Cin,
-               taps, 0);
+    DSK_LAUNCH(pack_weight_bf16_tiled_kernel, Cout * ((Cin + 63) / 64), 256, 0, as_stream(stream), w_ref, (uint16_t*)w_packed, Cout, Cin,
+               taps, 0, dtype);
     return DSK_OK;
   }
-  const int grid = grid_for((int64_t)rows * Cin * taps, 256, 8);
+  const int grid = grid_for((int64_t)rows * Cin * taps * (dtype == DSK_SPLIT_F16 ? 2 : 1), 256, 8);
   DSK_LAUNCH(pack_weight_kernel, grid, 256, 0, as_stream(stream), w_ref, dtype == DSK_F32 ? (float*)w_packed : nullptr,
-             dtype == DSK_BF16 ? (__nv_bfloat16*)w_packed : nullptr, Cout, Cin, taps, rows, 0);
+             dtype != DSK_F32 ? (uint16_t*)w_packed : nullptr, Cout, Cin, taps, rows, 0, dtype);
   return DSK_OK;
 }
 
 extern "C" int dsk_pack_conv_weight_dgrad(const float* w_ref, void* w_packed, int Cout, int Cin, int taps, int dtype, void* stream) {
   DSK_REQUIRE(w_ref && w_packed && Cout > 0 && Cin > 0 && taps > 0, "dsk_pack_conv_weight_dgrad: bad arguments");
-  DSK_REQUIRE(dtype == DSK_F32 || dtype == DSK_BF16, "dsk_pack_conv_weight_dgrad: bad dtype %d", dtype);
+  DSK_REQUIRE(dtype == DSK_F32 || is_h16(dtype), "dsk_pack_conv_weight_dgrad: bad dtype %d", dtype);
   if (pack_tiled_ok(Cout, Cin, taps, Cout, dtype)) {
-    DSK_LAUNCH(pack_weight_bf16_tiled_kernel, Cin * ((Cout + 63) / 64), 256, 0, as_stream(stream), w_ref, (__nv_bfloat16*)w_packed, Cout, Cin,
-               taps, 1);
+    DSK_LAUNCH(pack_weight_bf16_tiled_kernel, Cin * ((Cout + 63) / 64), 256, 0, as_stream(stream), w_ref, (uint16_t*)w_packed, Cout, Cin,
+               taps, 1, dtype);
     return DSK_OK;
   }
   const int grid = grid_for((int64_t)Cout * Cin * taps, 256, 8);
   DSK_LAUNCH(pack_weight_kernel, grid, 256, 0, as_stream(stream), w_ref, dtype == DSK_F32 ? (float*)w_packed : nullptr,
-             dtype == DSK_BF16 ? (__nv_bfloat16*)w_packed : nullptr, Cout, Cin, taps, Cout, 1);
+             dtype != DSK_F32 ? (uint16_t*)w_packed : nullptr, Cout, Cin, taps, Cout, 1, dtype);
   return DSK_OK;
 }
 

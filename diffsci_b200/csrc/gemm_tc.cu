@@ -23,9 +23,15 @@ struct GemmTcParams {
   float alpha;
   const float* bias;        // [N] (bias_rows == 0) or [M] (bias_rows == 1), or null
   int bias_rows;
-  const __nv_bfloat16* residual;  // [batch][M][ldc] bf16 or null
-  void* out;                // bf16 or fp32 [batch][M][ldc]
+  const uint16_t* residual; // [batch][M][ldc] in the 16-bit format (fp32 when res_f32) or null
+  void* out;                // 16-bit or fp32 [batch][M][ldc]
   int out_f32;
+  int f16;                  // 16-bit format of operands / 16-bit outputs: 0 bfloat16, 1 IEEE half
+  int res_f32;              // residual is fp32 (split parity mode)
+  // split-fp16 operands (DSK_SPLIT_F16): `vparts` virtual K chunks per real 64-wide chunk accumulate (A hi, B hi), (A hi, B lo),
+  // (A lo, B hi) [vparts = 3] or (A hi, B), (A lo, B) [vparts = 2]; a_lo / b_lo: offset of the lo half along the operand's
+  // CONTIGUOUS coordinate (k for K-major operands, m / n for MN-major ones)
+  int vparts, a_lo, b_lo;
   int64_t ldc, strideC;
   int transA, transB;       // operand stored [K][M] / [K][N] (MN-major)
   int epi;                  // 0: C = alpha A B^T (+bias, +residual);  1: row statistics only;  2: softmax probabilities
@@ -43,9 +49,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   __shared__ uint64_t full[GT_STAGES], empty[GT_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ uint4 stage_s[4][32 * 8];                   // per epilogue warp: 32 rows x 128 B (coalescing stage of the stores)
-  constexpr uint32_t TMEM_COLS = 2 * N_TILE;
+  // split operands: the hi*lo + lo*hi products (lo halves are stored times 2^11) go to a second accumulator set; the epilogue
+  // combines acc = hh + 2^-11 lo (host: N_TILE <= 128 in split mode)
+  const uint32_t nsets = p.vparts > 1 ? 2u : 1u;
+  const uint32_t BUF_COLS = nsets * N_TILE;
+  const uint32_t TMEM_COLS = 2 * BUF_COLS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kchunks = (p.K + 63) / 64;
+  const int kchunks = ((p.K + 63) / 64) * p.vparts;      // virtual K chunks
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -66,7 +76,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       uint32_t seq = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int tn = t % p.tiles_n, tm = (t / p.tiles_n) % p.tiles_m, b = t / (p.tiles_n * p.tiles_m);
-        for (int kc = 0; kc < kchunks; ++kc, ++seq) {
+        for (int vkc = 0; vkc < kchunks; ++vkc, ++seq) {
+          const int kc = vkc / p.vparts, part = vkc - kc * p.vparts;
+          const int ao = (p.vparts > 1 && part == p.vparts - 1) ? p.a_lo : 0, bo = (p.vparts == 3 && part == 1) ? p.b_lo : 0;
           const uint32_t slot = seq % GT_STAGES, ph = (seq / GT_STAGES) & 1;
           mbar_wait(&empty[slot], ph ^ 1);
           mbar_expect_tx(&full[slot], STAGE);
@@ -79,22 +91,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 : "memory");
           };
           if (!p.transA) {
-            tma3(&tmapA, sa, kc * 64, tm * 128, b * p.a_bmul);
+            tma3(&tmapA, sa, kc * 64 + ao, tm * 128, b * p.a_bmul);
           } else {
-            tma3(&tmapA, sa, tm * 128, kc * 64, b * p.a_bmul);
-            tma3(&tmapA, sa + 8192, tm * 128 + 64, kc * 64, b * p.a_bmul);
+            tma3(&tmapA, sa, tm * 128 + ao, kc * 64, b * p.a_bmul);
+            tma3(&tmapA, sa + 8192, tm * 128 + 64 + ao, kc * 64, b * p.a_bmul);
           }
           if (!p.transB) {
-            tma3(&tmapB, sa + A_BYTES, kc * 64, tn * N_TILE, b * p.b_bmul);
+            tma3(&tmapB, sa + A_BYTES, kc * 64 + bo, tn * N_TILE, b * p.b_bmul);
           } else {
 #pragma unroll
-            for (int h = 0; h < N_TILE / 64; ++h) tma3(&tmapB, sa + A_BYTES + h * 8192, tn * N_TILE + h * 64, kc * 64, b * p.b_bmul);
+            for (int h = 0; h < N_TILE / 64; ++h) tma3(&tmapB, sa + A_BYTES + h * 8192, tn * N_TILE + h * 64 + bo, kc * 64, b * p.b_bmul);
           }
         }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_bf16(N_TILE) | (p.transA ? 1u << 15 : 0u) | (p.transB ? 1u << 16 : 0u);
+    const uint32_t idesc = umma_idesc_h16(N_TILE, 128, p.f16) | (p.transA ? 1u << 15 : 0u) | (p.transB ? 1u << 16 : 0u);
     constexpr uint32_t HI = umma_desc_hi(1024);
     // descriptor low word: K-major: LBO field = 1 (unused), k-step of 16 elements = 32 B; MN-major: LBO = 8 KB, k-step of
     // 16 rows = 2 KB
@@ -105,17 +117,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       mbar_wait(&acc_empty[as], aph ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_acc = tmem_base + as * N_TILE;
+      const uint32_t tmem_acc = tmem_base + as * BUF_COLS;
+      uint32_t used = 0;
       for (int kc = 0; kc < kchunks; ++kc, ++seq) {
         const uint32_t slot = seq % GT_STAGES;
         mbar_wait(&full[slot], (seq / GT_STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa16 = smem_u32(smem + (size_t)slot * STAGE) >> 4;
         const uint32_t a_lo = sa16 | a_lbo, b_lo = (sa16 + (A_BYTES >> 4)) | b_lbo;
+        const uint32_t set = (kc % p.vparts) ? 1u : 0u;          // virtual chunk part > 0: a lo operand is involved
+        const uint32_t accum = (used >> set) & 1u;
+        used |= 1u << set;
         if (elect_one_sync()) {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
-            umma_bf16(tmem_acc, umma_desc64(a_lo + k4 * a_step, HI), umma_desc64(b_lo + k4 * b_step, HI), idesc, (kc | k4) != 0);
+            umma_bf16(tmem_acc + set * N_TILE, umma_desc64(a_lo + k4 * a_step, HI), umma_desc64(b_lo + k4 * b_step, HI), idesc,
+                      k4 == 0 ? accum : 1u);
           umma_commit(&empty[slot]);
         }
         __syncwarp();
@@ -136,7 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       const bool mvalid = m < p.M;
       const float rb = (p.bias != nullptr && p.bias_rows && mvalid) ? p.bias[m] : 0.0f;
       const int64_t obase = (int64_t)b * p.strideC + (int64_t)m * p.ldc;
-      const uint32_t taddr = tmem_base + as * N_TILE + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + as * BUF_COLS + ((uint32_t)(q * 32) << 16);
       // The 32-column groups are NOT unrolled and every data-dependent choice (output dtype, residual, bias kind, ragged
       // edge) is a warp-uniform branch around a small straight-line body: the first version unrolled everything into
       // 11.6 K SASS instructions and ran at the speed of the instruction cache (ncu: tensor pipe 4-6 % active).
@@ -185,12 +202,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             DSK_TMEM_LD_X32(v, taddr + c0 + hh * 32);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&pk[hh * 4 + g]);
+              uint32_t* oh = reinterpret_cast<uint32_t*>(&pk[hh * 4 + g]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float f0 = __expf(fmaf(p.alpha, __uint_as_float(v[g * 8 + 2 * e]), -rf.x)) * rf.y;
                 const float f1 = __expf(fmaf(p.alpha, __uint_as_float(v[g * 8 + 2 * e + 1]), -rf.x)) * rf.y;
-                oh[e] = __floats2bfloat162_rn(f0, f1);
+                oh[e] = pack_h2(f0, f1, p.f16);
               }
             }
           }
@@ -221,6 +238,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         uint32_t v[32];
         DSK_TMEM_LD_X32(v, taddr + c0);
+        if (nsets > 1) {
+          uint32_t u[32];
+          DSK_TMEM_LD_X32(u, taddr + N_TILE + c0);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(fmaf(__uint_as_float(u[e]), 1.0f / 2048.0f, __uint_as_float(v[e])));
+        }
         const int n = tn * N_TILE + c0;
         if (n >= p.N) continue;                                 // warp-uniform
         float f[32];
@@ -236,13 +259,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             }
           }
           if (p.residual != nullptr && mvalid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + n);
+            if (p.res_f32) {
+              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + obase + n);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint4 rr = rp[g];
-              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
+              for (int e4 = 0; e4 < 8; ++e4) {
+                const float4 r = rp[e4];
+                f[4 * e4] += r.x; f[4 * e4 + 1] += r.y; f[4 * e4 + 2] += r.z; f[4 * e4 + 3] += r.w;
+              }
+            } else {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + n);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { f[g * 8 + 2 * e] += __low2float(rh[e]); f[g * 8 + 2 * e + 1] += __high2float(rh[e]); }
+              for (int g = 0; g < 4; ++g) {
+                const uint4 rr = rp[g];
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rr);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 t = unpack_h2(rw[e], p.f16); f[g * 8 + 2 * e] += t.x; f[g * 8 + 2 * e + 1] += t.y; }
+              }
             }
           }
           if (p.out_f32) {
@@ -258,9 +290,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 pk;
-              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&pk);
+              uint32_t* oh = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1]);
+              for (int e = 0; e < 4; ++e) oh[e] = pack_h2(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1], p.f16);
               stg[lane * 4 + (g ^ (lane & 3))] = pk;
             }
             __syncwarp();
@@ -281,9 +313,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
           for (int e = 0; e < 32 && n + e < p.N; ++e) {
             float x = f[e];
             if (col_bias) x += __ldg(p.bias + n + e);
-            if (p.residual != nullptr) x += __bfloat162float(p.residual[obase + n + e]);
+            if (p.residual != nullptr)
+              x += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[obase + n + e] : unpack_h1(p.residual[obase + n + e], p.f16);
             if (p.out_f32) reinterpret_cast<float*>(p.out)[obase + n + e] = x;
-            else reinterpret_cast<__nv_bfloat16*>(p.out)[obase + n + e] = __float2bfloat16_rn(x);
+            else reinterpret_cast<uint16_t*>(p.out)[obase + n + e] = pack_h1(x, p.f16);
           }
         }
       }
@@ -299,8 +332,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 }
 
 // fp32 scores -> bf16 probabilities, one block per row (row cached in registers: cols <= 256 * 32)
-__global__ void __launch_bounds__(256) softmax_rows_bf16_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P,
-                                                                 int64_t rows, int cols) {
+// fmt: DSK_BF16 | DSK_F16 (P rows of `cols`), DSK_SPLIT_F16 (P rows of 2 * cols: hi | lo)
+__global__ void __launch_bounds__(256) softmax_rows_bf16_kernel(const float* __restrict__ S, uint16_t* __restrict__ P,
+                                                                 int64_t rows, int cols, int fmt) {
   __shared__ float red[8];
   constexpr int MAXV = 8;   // float4 vectors per thread (cols <= 8192)
   for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
@@ -341,16 +375,24 @@ __global__ void __launch_bounds__(256) softmax_rows_bf16_kernel(const float* __r
     for (int w = 0; w < 8; ++w) sum += red[w];
     __syncthreads();
     const float inv = 1.0f / sum;
-    uint2* dst = reinterpret_cast<uint2*>(P + r * cols);
+    const bool split = fmt == DSK_SPLIT_F16;
+    uint2* dst = reinterpret_cast<uint2*>(P + r * cols * (split ? 2 : 1));
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int idx = threadIdx.x + i * 256;
       if (idx < nv) {
-        __nv_bfloat162 a = __floats2bfloat162_rn(v[i].x * inv, v[i].y * inv), b = __floats2bfloat162_rn(v[i].z * inv, v[i].w * inv);
+        const float p0 = v[i].x * inv, p1 = v[i].y * inv, p2 = v[i].z * inv, p3 = v[i].w * inv;
         uint2 o;
-        o.x = *reinterpret_cast<uint32_t*>(&a);
-        o.y = *reinterpret_cast<uint32_t*>(&b);
+        o.x = pack_h2(p0, p1, fmt != DSK_BF16);
+        o.y = pack_h2(p2, p3, fmt != DSK_BF16);
         dst[idx] = o;
+        if (split) {
+          const float2 h0 = unpack_h2(o.x, 1), h1 = unpack_h2(o.y, 1);
+          uint2 l;
+          l.x = pack_h2((p0 - h0.x) * 2048.0f, (p1 - h0.y) * 2048.0f, 1);      // lo stored times 2^11 (DSK_SPLIT_F16)
+          l.y = pack_h2((p2 - h1.x) * 2048.0f, (p3 - h1.y) * 2048.0f, 1);
+          dst[nv + idx] = l;
+        }
       }
     }
   }
@@ -431,10 +473,16 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
 
 using namespace dsk;
 
+// dtype: DSK_BF16 | DSK_F16: plain 16-bit operands.  DSK_SPLIT_F16: A and B are split-fp16 (hi | lo along their contiguous
+// coordinate, lo halves at element offsets a_lo / b_lo), 3 MMAs per k-step; b_lo < 0: B is plain fp16, 2 MMAs per k-step.
 static int gemm_tc_run(const void* A, const void* Bm, void* C, const float* bias, int bias_rows, const void* residual, int M, int N, int K,
                        int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC, int batch, float alpha,
                        int out_f32, int transA, int transB, int epi, float2* rowstat, const float2* rowfinal, int force_tile,
-                       void* stream) {
+                       void* stream, int dtype = DSK_BF16, int a_lo = 0, int b_lo = 0, int res_f32 = 0) {
+  DSK_REQUIRE(is_h16(dtype) || dtype == DSK_SPLIT_F16, "dsk_gemm_tc: bad dtype %d", dtype);
+  const bool split = dtype == DSK_SPLIT_F16;
+  DSK_REQUIRE(!split || (K % 64 == 0 && a_lo > 0 && a_lo % 8 == 0 && (b_lo < 0 || (b_lo > 0 && b_lo % 8 == 0))),
+              "dsk_gemm_tc: split operands need K %% 64 == 0 and lo offsets that are multiples of 8 elements");
   DSK_REQUIRE(A && Bm && (C || epi == EPI_ROWSTAT), "dsk_gemm_bf16_tc: null pointer");
   DSK_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "dsk_gemm_bf16_tc: bad shape");
   DSK_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && strideA % 8 == 0 && strideB % 8 == 0,
@@ -442,21 +490,22 @@ static int gemm_tc_run(const void* A, const void* Bm, void* C, const float* bias
   DSK_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Bm & 15) == 0 && ((uintptr_t)C & 15) == 0, "dsk_gemm_bf16_tc: 16-byte alignment");
   EncodeTiledFn encode = get_encode();
   DSK_REQUIRE(encode != nullptr, "dsk_gemm_bf16_tc: cuTensorMapEncodeTiled is unavailable");
-  const int n_tile = force_tile ? force_tile : (N > 128 ? 256 : (N > 64 ? 128 : 64));
+  DSK_REQUIRE(!split || epi == EPI_NORMAL, "dsk_gemm_tc: split operands take the plain epilogue only");
+  const int n_tile = force_tile ? force_tile : ((N > 128 && !split) ? 256 : (N > 64 ? 128 : 64));
   CUtensorMap ta, tb;
   // K-major operand [rows][K]: box 64 (k) x box_rows;  MN-major operand [K][rows]: box 64 (rows) x 64 (k)
-  auto make = [&](CUtensorMap* tm, const void* base, int rows, int64_t ld, int64_t stride, int box_rows, int trans) -> bool {
+  auto make = [&](CUtensorMap* tm, const void* base, int rows, int64_t ld, int64_t stride, int box_rows, int trans, int lo_off) -> bool {
     const bool shared = batch == 1 || stride == 0;
-    const int inner = trans ? rows : K, outer = trans ? K : rows;
+    const int inner = (trans ? rows : K) + lo_off, outer = trans ? K : rows;
     cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(shared ? 1 : batch)};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(shared ? (int64_t)outer * ld : stride) * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)(trans ? 64 : box_rows), 1};
     cuuint32_t es[3] = {1, 1, 1};
-    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return encode(tm, tmap_h16(dtype == DSK_BF16 ? DSK_BF16 : DSK_F16), 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
-  DSK_REQUIRE(make(&ta, A, M, lda, strideA, 128, transA), "dsk_gemm_bf16_tc: tensor map for A failed");
-  DSK_REQUIRE(make(&tb, Bm, N, ldb, strideB, n_tile, transB), "dsk_gemm_bf16_tc: tensor map for B failed");
+  DSK_REQUIRE(make(&ta, A, M, lda, strideA, 128, transA, split ? a_lo : 0), "dsk_gemm_bf16_tc: tensor map for A failed");
+  DSK_REQUIRE(make(&tb, Bm, N, ldb, strideB, n_tile, transB, (split && b_lo > 0) ? b_lo : 0), "dsk_gemm_bf16_tc: tensor map for B failed");
   GemmTcParams p;
   p.M = M; p.N = N; p.K = K; p.batch = batch;
   p.a_bmul = (batch > 1 && strideA != 0) ? 1 : 0;
@@ -464,7 +513,9 @@ static int gemm_tc_run(const void* A, const void* Bm, void* C, const float* bias
   p.tiles_m = (M + 127) / 128; p.tiles_n = (N + n_tile - 1) / n_tile;
   p.total_tiles = p.tiles_m * p.tiles_n * batch;
   p.alpha = alpha; p.bias = bias; p.bias_rows = bias_rows;
-  p.residual = (const __nv_bfloat16*)residual; p.out = C; p.out_f32 = out_f32; p.ldc = ldc; p.strideC = strideC;
+  p.residual = (const uint16_t*)residual; p.out = C; p.out_f32 = out_f32; p.ldc = ldc; p.strideC = strideC;
+  p.f16 = dtype == DSK_BF16 ? 0 : 1; p.res_f32 = res_f32;
+  p.vparts = split ? (b_lo > 0 ? 3 : 2) : 1; p.a_lo = a_lo; p.b_lo = b_lo > 0 ? b_lo : 0;
   p.transA = transA ? 1 : 0; p.transB = transB ? 1 : 0;
   p.epi = epi; p.rowstat = rowstat; p.rowfinal = rowfinal;
   cudaStream_t st = as_stream(stream);
@@ -480,6 +531,13 @@ extern "C" int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const fl
                      transB, EPI_NORMAL, nullptr, nullptr, 0, stream);
 }
 
+extern "C" int dsk_gemm_tc(const void* A, const void* Bm, void* C, const float* bias, int bias_rows, const void* residual, int res_f32,
+                           int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC,
+                           int batch, float alpha, int out_f32, int transA, int transB, int dtype, int a_lo, int b_lo, void* stream) {
+  return gemm_tc_run(A, Bm, C, bias, bias_rows, residual, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch, alpha, out_f32, transA,
+                     transB, EPI_NORMAL, nullptr, nullptr, 0, stream, dtype, a_lo, b_lo, res_f32);
+}
+
 extern "C" int64_t dsk_attn_softmax_ws_bytes(int batch, int L) {
   if (batch <= 0 || L <= 0) return 0;
   const int tiles = (L + 255) / 256;
@@ -488,27 +546,38 @@ extern "C" int64_t dsk_attn_softmax_ws_bytes(int batch, int L) {
 
 // P[b] = softmax(alpha Q[b] K[b]^T) as bf16, without the scores ever reaching HBM: pass 1 = QK^T with a row-statistics
 // epilogue (per 256-column tile), a tiny combine, pass 2 = QK^T again with the exp / normalise / bf16 epilogue.
+extern "C" int dsk_attn_softmax_qk_h16(const void* Q, const void* Kmat, void* P, void* ws, int L, int C, int64_t ldq, int64_t ldk,
+                                       int64_t strideQ, int64_t strideK, int batch, float alpha, int dtype, void* stream);
 extern "C" int dsk_attn_softmax_qk(const void* Q, const void* Kmat, void* P, void* ws, int L, int C, int64_t ldq, int64_t ldk,
                                    int64_t strideQ, int64_t strideK, int batch, float alpha, void* stream) {
+  return dsk_attn_softmax_qk_h16(Q, Kmat, P, ws, L, C, ldq, ldk, strideQ, strideK, batch, alpha, DSK_BF16, stream);
+}
+extern "C" int dsk_attn_softmax_qk_h16(const void* Q, const void* Kmat, void* P, void* ws, int L, int C, int64_t ldq, int64_t ldk,
+                                       int64_t strideQ, int64_t strideK, int batch, float alpha, int dtype, void* stream) {
+  DSK_REQUIRE(is_h16(dtype), "dsk_attn_softmax_qk: bad dtype %d", dtype);
   DSK_REQUIRE(Q && Kmat && P && ws && L > 0 && C > 0 && batch > 0 && L % 8 == 0, "dsk_attn_softmax_qk: bad arguments (L %% 8 == 0)");
   const int tiles = (L + 255) / 256;
   float2* part = reinterpret_cast<float2*>(ws);
   float2* fin = part + (int64_t)batch * L * tiles;
   int rc = gemm_tc_run(Q, Kmat, P, nullptr, 0, nullptr, L, L, C, ldq, ldk, L, strideQ, strideK, (int64_t)L * L, batch, alpha, 0, 0, 0,
-                       EPI_ROWSTAT, part, nullptr, 256, stream);
+                       EPI_ROWSTAT, part, nullptr, 256, stream, dtype);
   if (rc != DSK_OK) return rc;
   const int64_t rows = (int64_t)batch * L;
   DSK_LAUNCH(rowstat_combine_kernel, (int)((rows + 255) / 256), 256, 0, as_stream(stream), part, fin, rows, tiles);
   return gemm_tc_run(Q, Kmat, P, nullptr, 0, nullptr, L, L, C, ldq, ldk, L, strideQ, strideK, (int64_t)L * L, batch, alpha, 0, 0, 0,
-                     EPI_SOFTMAX, nullptr, fin, 256, stream);
+                     EPI_SOFTMAX, nullptr, fin, 256, stream, dtype);
 }
 
-extern "C" int dsk_softmax_rows_bf16(const float* S, void* P, int64_t rows, int cols, void* stream) {
-  DSK_REQUIRE(S && P && rows > 0 && cols > 0, "dsk_softmax_rows_bf16: bad arguments");
-  DSK_REQUIRE(cols % 4 == 0 && cols <= 8192, "dsk_softmax_rows_bf16: cols=%d must be a multiple of 4 and <= 8192", cols);
+extern "C" int dsk_softmax_rows_h16(const float* S, void* P, int64_t rows, int cols, int dtype, void* stream) {
+  DSK_REQUIRE(S && P && rows > 0 && cols > 0, "dsk_softmax_rows_h16: bad arguments");
+  DSK_REQUIRE(is_h16(dtype) || dtype == DSK_SPLIT_F16, "dsk_softmax_rows_h16: bad dtype %d", dtype);
+  DSK_REQUIRE(cols % 4 == 0 && cols <= 8192, "dsk_softmax_rows_h16: cols=%d must be a multiple of 4 and <= 8192", cols);
   int64_t grid = rows < (int64_t)DSK_NUM_SMS * 16 ? rows : (int64_t)DSK_NUM_SMS * 16;
-  DSK_LAUNCH(softmax_rows_bf16_kernel, (int)grid, 256, 0, as_stream(stream), S, (__nv_bfloat16*)P, rows, cols);
+  DSK_LAUNCH(softmax_rows_bf16_kernel, (int)grid, 256, 0, as_stream(stream), S, (uint16_t*)P, rows, cols, dtype);
   return DSK_OK;
+}
+extern "C" int dsk_softmax_rows_bf16(const float* S, void* P, int64_t rows, int cols, void* stream) {
+  return dsk_softmax_rows_h16(S, P, rows, cols, DSK_BF16, stream);
 }
 
 extern "C" int dsk_softmax_bwd_rows_bf16(const void* P, const float* dP, void* dS, int64_t rows, int cols, void* stream) {

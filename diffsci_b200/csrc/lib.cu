@@ -46,7 +46,8 @@ extern "C" int dsk_conv_fwd(const dsk_conv_desc* d, const void* in, const void* 
                             const float* chan_bias, const void* residual, void* out, void* stream) {
   DSK_REQUIRE(d != nullptr, "dsk_conv_fwd: null descriptor");
   if (d->w_dtype == DSK_F32) return dsk_conv_fwd_ffma(d, in, w, bias, chan_bias, residual, out, stream);
-  if (d->w_dtype == DSK_BF16) return dsk_conv_fwd_tc(d, in, w, bias, chan_bias, residual, out, stream);
+  if (d->w_dtype == DSK_BF16 || d->w_dtype == DSK_F16 || d->w_dtype == DSK_SPLIT_F16)
+    return dsk_conv_fwd_tc(d, in, w, bias, chan_bias, residual, out, stream);
   set_error("dsk_conv_fwd: bad w_dtype %d", d->w_dtype);
   return DSK_ERR_ARG;
 }

@@ -31,6 +31,15 @@ template <> struct NormVec<__nv_bfloat16> {
     for (int j = 0; j < 4; ++j) { o[2 * j] = __low2float(h[j]); o[2 * j + 1] = __high2float(h[j]); }
   }
 };
+template <> struct NormVec<__half> {
+  static constexpr int V = 8;
+  static __device__ __forceinline__ void ld(const __half* p, float* o) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[2 * j] = __low2float(h[j]); o[2 * j + 1] = __high2float(h[j]); }
+  }
+};
 template <typename T, int V> __device__ __forceinline__ void st_vec(T* p, const float* v);
 template <> __device__ __forceinline__ void st_vec<float, 4>(float* p, const float* v) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -52,6 +61,31 @@ template <> __device__ __forceinline__ void st_vec<__nv_bfloat16, 8>(__nv_bfloat
 #pragma unroll
   for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
   *reinterpret_cast<uint4*>(p) = o;
+}
+
+template <> __device__ __forceinline__ void st_vec<__half, 4>(__half* p, const float* v) {
+  __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  uint2 raw;
+  raw.x = *reinterpret_cast<uint32_t*>(&a);
+  raw.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = raw;
+}
+template <> __device__ __forceinline__ void st_vec<__half, 8>(__half* p, const float* v) {
+  uint4 o;
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+// split-fp16 output (the A operand of the split tensor-core convolutions, conv_tc.cu): hi = fp16(v) at p, lo = fp16(2^11 (v - hi))
+// at p + lo_off; hi + 2^-11 lo carries 22 mantissa bits of v (the scaling keeps lo out of fp16's subnormal range)
+template <int V> __device__ __forceinline__ void st_split(__half* p, int64_t lo_off, const float* v) {
+  float lo[V];
+  float hi[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) { hi[e] = __half2float(__float2half_rn(v[e])); lo[e] = (v[e] - hi[e]) * 2048.0f; }
+  st_vec<__half, V>(p, hi);
+  st_vec<__half, V>(p + lo_off, lo);
 }
 
 static inline int norm_chunks(int B, int64_t S, int C, int V) {
@@ -302,17 +336,20 @@ template <typename TO> __device__ __forceinline__ float silu_out(float v) { retu
 // bf16 output keeps 8 mantissa bits: the approximate exp / divide (rel. error ~1e-6) is invisible after rounding and
 // takes the kernel from instruction-bound back to HBM-bound
 template <> __device__ __forceinline__ float silu_out<__nv_bfloat16>(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+template <> __device__ __forceinline__ float silu_out<__half>(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 // Thread = fixed V-channel vector (scale/shift held in registers), strided over the pixels of one sample.
-template <typename TI, typename TO>
+// SPLIT (TO = __half): y is a split-fp16 tensor [B, S, 2C] -- channels [0, C) the fp16 value, [C, 2C) the fp16 remainder.
+template <typename TI, typename TO, bool SPLIT = false>
 __global__ void __launch_bounds__(NORM_THREADS) norm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ y,
                                                                    const float2* __restrict__ table, int64_t S, int C, int silu) {
   constexpr int V = NormVec<TI>::V;
   const int b = blockIdx.y;
   const int cv = C / V;
   const int pl = max(1, NORM_THREADS / cv);
+  const int CO = SPLIT ? 2 * C : C;                     // output row length
   const TI* xb = x + (int64_t)b * S * C;
-  TO* yb = y + (int64_t)b * S * C;
+  TO* yb = y + (int64_t)b * S * CO;
   for (int v = threadIdx.x; v < pl * cv; v += NORM_THREADS) {
     const int lane = v / cv, c0 = (v - lane * cv) * V;
     float sc[V], sh[V];
@@ -330,11 +367,16 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_apply_kernel(const TI* __re
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         const float t0 = fmaf(e0[k], sc[k], sh[k]), t1 = fmaf(e1[k], sc[k], sh[k]);
-        o0[k] = silu ? silu_out<TO>(t0) : t0;
-        o1[k] = silu ? silu_out<TO>(t1) : t1;
+        o0[k] = silu ? (SPLIT ? silu_f(t0) : silu_out<TO>(t0)) : t0;
+        o1[k] = silu ? (SPLIT ? silu_f(t1) : silu_out<TO>(t1)) : t1;
       }
-      st_vec<TO, V>(yb + s * C + c0, o0);
-      st_vec<TO, V>(yb + (s + step) * C + c0, o1);
+      if constexpr (SPLIT) {
+        st_split<V>(yb + s * CO + c0, C, o0);
+        st_split<V>(yb + (s + step) * CO + c0, C, o1);
+      } else {
+        st_vec<TO, V>(yb + s * C + c0, o0);
+        st_vec<TO, V>(yb + (s + step) * C + c0, o1);
+      }
     }
     for (; s < S; s += step) {
       float e[V], o[V];
@@ -342,9 +384,10 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_apply_kernel(const TI* __re
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         const float t = fmaf(e[k], sc[k], sh[k]);
-        o[k] = silu ? silu_out<TO>(t) : t;
+        o[k] = silu ? (SPLIT ? silu_f(t) : silu_out<TO>(t)) : t;
       }
-      st_vec<TO, V>(yb + s * C + c0, o);
+      if constexpr (SPLIT) st_split<V>(yb + s * CO + c0, C, o);
+      else st_vec<TO, V>(yb + s * C + c0, o);
     }
   }
 }
@@ -407,7 +450,8 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_apply_pad_kernel(const TI* 
 // shared memory.  Replaces the statistics pass + finalize + apply launches (31 us -> ~12 us per norm on MNIST-size tensors,
 // where each of the three is launch-latency bound); writes the same (scale, shift) / (mean, rstd) tables for the backward.
 constexpr int SLAB_THREADS = 256, SLAB_CH = 32;
-__global__ void __launch_bounds__(SLAB_THREADS) norm_slab_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+template <typename T>
+__global__ void __launch_bounds__(SLAB_THREADS) norm_slab_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                                   float2* __restrict__ table, float2* __restrict__ stats,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ fsc, const float* __restrict__ fsh, int S, int C,
@@ -418,7 +462,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) norm_slab_kernel(const __nv_bflo
   __shared__ float2 coef[SLAB_CH];
   const int b = blockIdx.y, c0 = blockIdx.x * SLAB_CH;
   const int j = threadIdx.x & 3, pl = threadIdx.x >> 2;             // piece within the pixel row, pixel lane (64 lanes)
-  const __nv_bfloat16* xb = x + ((int64_t)b * S) * C + c0 + j * 8;
+  const T* xb = x + ((int64_t)b * S) * C + c0 + j * 8;
   float s8[8], q8[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s8[k] = 0.0f; q8[k] = 0.0f; }
@@ -434,7 +478,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) norm_slab_kernel(const __nv_bflo
     for (int u = 0; u < UNR; ++u) {
       const int p = p0 + u * PSTEP;
       if (p < S) slab[p * 4 + j] = raw[u];
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+      const typename H16<T>::T2* h = reinterpret_cast<const typename H16<T>::T2*>(&raw[u]);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {                            // zeros past the end add nothing (same order as a rolled loop)
         const float a = __low2float(h[k]), c = __high2float(h[k]);
@@ -478,19 +522,19 @@ __global__ void __launch_bounds__(SLAB_THREADS) norm_slab_kernel(const __nv_bflo
   float sc[8], sh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { const float2 t = coef[j * 8 + k]; sc[k] = t.x; sh[k] = t.y; }
-  __nv_bfloat16* yb = y + ((int64_t)b * S) * C + c0 + j * 8;
+  T* yb = y + ((int64_t)b * S) * C + c0 + j * 8;
 #pragma unroll 4
   for (int p = pl; p < S; p += SLAB_THREADS / 4) {
     const uint4 raw = slab[p * 4 + j];
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const typename H16<T>::T2* h = reinterpret_cast<const typename H16<T>::T2*>(&raw);
     float o[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float t0 = fmaf(__low2float(h[k]), sc[2 * k], sh[2 * k]), t1 = fmaf(__high2float(h[k]), sc[2 * k + 1], sh[2 * k + 1]);
-      o[2 * k] = silu ? silu_out<__nv_bfloat16>(t0) : t0;
-      o[2 * k + 1] = silu ? silu_out<__nv_bfloat16>(t1) : t1;
+      o[2 * k] = silu ? silu_out<T>(t0) : t0;
+      o[2 * k + 1] = silu ? silu_out<T>(t1) : t1;
     }
-    st_vec<__nv_bfloat16, 8>(yb + (int64_t)p * C, o);
+    st_vec<T, 8>(yb + (int64_t)p * C, o);
   }
 }
 
@@ -498,7 +542,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) norm_slab_kernel(const __nv_bflo
 // enough (sample, channel-group) CTAs to fill the machine
 static bool norm_slab_ok(int B, int64_t S, int C, int G, int in_dtype, int out_dtype) {
   static const int off = [] { const char* e = getenv("DSK_NORM_SLAB_OFF"); return e ? atoi(e) : 0; }();   // A/B measurements
-  return !off && G == C && in_dtype == DSK_BF16 && out_dtype == DSK_BF16 && C % SLAB_CH == 0 && S * 64 <= 96 * 1024 &&
+  return !off && G == C && is_h16(in_dtype) && out_dtype == in_dtype && C % SLAB_CH == 0 && S * 64 <= 96 * 1024 &&
          (int64_t)B * (C / SLAB_CH) >= DSK_NUM_SMS;
 }
 
@@ -506,7 +550,7 @@ static bool norm_slab_ok(int B, int64_t S, int C, int G, int in_dtype, int out_d
 
 using namespace dsk;
 
-static inline int norm_v(int in_dtype) { return in_dtype == DSK_BF16 ? 8 : 4; }
+static inline int norm_v(int in_dtype) { return is_h16(in_dtype) ? 8 : 4; }
 
 extern "C" int64_t dsk_norm_ws_bytes(int B, int64_t S, int C) {
   if (B <= 0 || S <= 0 || C <= 0 || C % 4) return 0;
@@ -532,6 +576,11 @@ static int norm_apply_launch(const void* x, void* y, const float2* table, int B,
   else if (in_dtype == DSK_F32 && out_dtype == DSK_BF16) APPLY(float, __nv_bfloat16);
   else if (in_dtype == DSK_BF16 && out_dtype == DSK_BF16) APPLY(__nv_bfloat16, __nv_bfloat16);
   else if (in_dtype == DSK_BF16 && out_dtype == DSK_F32) APPLY(__nv_bfloat16, float);
+  else if (in_dtype == DSK_F32 && out_dtype == DSK_F16) APPLY(float, __half);
+  else if (in_dtype == DSK_F16 && out_dtype == DSK_F16) APPLY(__half, __half);
+  else if (in_dtype == DSK_F16 && out_dtype == DSK_F32) APPLY(__half, float);
+  else if (in_dtype == DSK_F32 && out_dtype == DSK_SPLIT_F16)
+    DSK_LAUNCH((norm_apply_kernel<float, __half, true>), ag, NORM_THREADS, 0, st, (const float*)x, (__half*)y, table, S, C, silu);
   else DSK_REQUIRE(false, "dsk_norm_act: bad dtype combination %d -> %d", in_dtype, out_dtype);
 #undef APPLY
   return DSK_OK;
@@ -542,7 +591,7 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
                             int in_dtype, int out_dtype, void* stream) {
   DSK_REQUIRE(x && ws, "dsk_norm_act: null pointer");
   DSK_REQUIRE(B > 0 && B <= 65535 && S > 0 && C > 0 && G > 0 && C % G == 0, "dsk_norm_act: bad shape B=%d S=%lld C=%d G=%d", B, (long long)S, C, G);
-  DSK_REQUIRE(in_dtype == DSK_F32 || in_dtype == DSK_BF16, "dsk_norm_act: bad in_dtype %d", in_dtype);
+  DSK_REQUIRE(in_dtype == DSK_F32 || is_h16(in_dtype), "dsk_norm_act: bad in_dtype %d", in_dtype);
   const int V = norm_v(in_dtype);
   DSK_REQUIRE(C % V == 0, "dsk_norm_act: C=%d must be a multiple of %d for this dtype", C, V);
   DSK_REQUIRE(mode == 0 || mode == 1, "dsk_norm_act: bad mode %d", mode);
@@ -553,16 +602,21 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
   float2* table = reinterpret_cast<float2*>(ws);
   float2* stats = table + (int64_t)B * C;
   double2* partial = reinterpret_cast<double2*>(stats + (int64_t)B * C);
-  if (norm_slab_ok(B, S, C, G, in_dtype, y == nullptr ? DSK_BF16 : out_dtype)) {
+  if (norm_slab_ok(B, S, C, G, in_dtype, y == nullptr ? in_dtype : out_dtype)) {
     const size_t smem = (size_t)S * 64;
     static bool configured = false;
     if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(norm_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(norm_slab_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(norm_slab_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
       if (e != cudaSuccess) { set_error("dsk_norm_act: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSK_ERR_CUDA; }
       configured = true;
     }
-    DSK_LAUNCH(norm_slab_kernel, dim3(C / SLAB_CH, B), SLAB_THREADS, smem, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, table, stats, gamma,
-               beta, film_scale, film_shift, (int)S, C, mode, silu, 1e-5f);
+    if (in_dtype == DSK_F16)
+      DSK_LAUNCH(norm_slab_kernel<__half>, dim3(C / SLAB_CH, B), SLAB_THREADS, smem, st, (const __half*)x, (__half*)y, table, stats, gamma,
+                 beta, film_scale, film_shift, (int)S, C, mode, silu, 1e-5f);
+    else
+      DSK_LAUNCH(norm_slab_kernel<__nv_bfloat16>, dim3(C / SLAB_CH, B), SLAB_THREADS, smem, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+                 table, stats, gamma, beta, film_scale, film_shift, (int)S, C, mode, silu, 1e-5f);
     return DSK_OK;
   }
   const int cv = C / V;
@@ -572,6 +626,8 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
   dim3 pg(nchunks, B);
   if (in_dtype == DSK_F32)
     DSK_LAUNCH(norm_partial_kernel<float>, pg, NORM_THREADS, smem, st, (const float*)x, partial, S, C, nchunks);
+  else if (in_dtype == DSK_F16)
+    DSK_LAUNCH(norm_partial_kernel<__half>, pg, NORM_THREADS, smem, st, (const __half*)x, partial, S, C, nchunks);
   else
     DSK_LAUNCH(norm_partial_kernel<__nv_bfloat16>, pg, NORM_THREADS, smem, st, (const __nv_bfloat16*)x, partial, S, C, nchunks);
   if (G == C)
@@ -596,7 +652,7 @@ extern "C" int dsk_norm_act_prestat(const void* x, void* y, const float* gamma, 
                                     int G, int mode, int silu, int in_dtype, int out_dtype, void* stream) {
   DSK_REQUIRE(x && ws && conv_stats, "dsk_norm_act_prestat: null pointer");
   DSK_REQUIRE(B > 0 && B <= 65535 && S > 0 && C > 0 && G == C && nslots > 0, "dsk_norm_act_prestat: needs one channel per group (G == C)");
-  DSK_REQUIRE(in_dtype == DSK_F32 || in_dtype == DSK_BF16, "dsk_norm_act_prestat: bad in_dtype %d", in_dtype);
+  DSK_REQUIRE(in_dtype == DSK_F32 || is_h16(in_dtype), "dsk_norm_act_prestat: bad in_dtype %d", in_dtype);
   DSK_REQUIRE(C % norm_v(in_dtype) == 0 && (mode == 0 || mode == 1), "dsk_norm_act_prestat: bad C / mode");
   DSK_REQUIRE((gamma == nullptr) == (beta == nullptr) && (film_scale == nullptr) == (film_shift == nullptr), "dsk_norm_act_prestat: affine / FiLM mismatch");
   cudaStream_t st = as_stream(stream);
@@ -614,7 +670,7 @@ extern "C" int dsk_norm_apply_padded(const void* x, void* y_padded, const void* 
   DSK_REQUIRE(x && y_padded && ws, "dsk_norm_apply_padded: null pointer");
   DSK_REQUIRE(B > 0 && B <= 65535 && D > 0 && H > 0 && W > 0 && C > 0 && ((ndim == 2 && D == 1) || ndim == 3), "dsk_norm_apply_padded: bad shape");
   DSK_REQUIRE((int64_t)D * H * W < 0x7fffffff, "dsk_norm_apply_padded: sample too large");
-  DSK_REQUIRE(in_dtype == DSK_BF16 && out_dtype == DSK_BF16 && C % 8 == 0, "dsk_norm_apply_padded: bf16 tensors with C %% 8 == 0 only");
+  DSK_REQUIRE(is_h16(in_dtype) && out_dtype == in_dtype && C % 8 == 0, "dsk_norm_apply_padded: 16-bit tensors with C %% 8 == 0 only");
   const float2* table = reinterpret_cast<const float2*>(ws);
   const int64_t S = (int64_t)D * H * W;
   const int cv = C / 8;
@@ -624,7 +680,11 @@ extern "C" int dsk_norm_apply_padded(const void* x, void* y_padded, const void* 
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   dim3 ag((unsigned)gx, B);
-  DSK_LAUNCH((norm_apply_pad_kernel<__nv_bfloat16, __nv_bfloat16>), ag, NORM_THREADS, 0, as_stream(stream), (const __nv_bfloat16*)x,
-             (__nv_bfloat16*)y_padded, table, D, H, W, C, ndim == 3 ? 1 : 0, silu);
+  if (in_dtype == DSK_F16)
+    DSK_LAUNCH((norm_apply_pad_kernel<__half, __half>), ag, NORM_THREADS, 0, as_stream(stream), (const __half*)x, (__half*)y_padded, table, D,
+               H, W, C, ndim == 3 ? 1 : 0, silu);
+  else
+    DSK_LAUNCH((norm_apply_pad_kernel<__nv_bfloat16, __nv_bfloat16>), ag, NORM_THREADS, 0, as_stream(stream), (const __nv_bfloat16*)x,
+               (__nv_bfloat16*)y_padded, table, D, H, W, C, ndim == 3 ? 1 : 0, silu);
   return DSK_OK;
 }

@@ -67,6 +67,8 @@ template <> struct Vec<1> {
   static __device__ __forceinline__ void st(float* p, int64_t i, const float* v) { p[i] = v[0]; }
   static __device__ __forceinline__ void ld(const __nv_bfloat16* p, int64_t i, float* o) { o[0] = __bfloat162float(p[i]); }
   static __device__ __forceinline__ void st(__nv_bfloat16* p, int64_t i, const float* v) { p[i] = __float2bfloat16_rn(v[0]); }
+  static __device__ __forceinline__ void ld(const __half* p, int64_t i, float* o) { o[0] = __half2float(p[i]); }
+  static __device__ __forceinline__ void st(__half* p, int64_t i, const float* v) { p[i] = __float2half_rn(v[0]); }
 };
 template <> struct Vec<4> {
   static __device__ __forceinline__ void ld(const float* p, int64_t i, float* o) {
@@ -83,6 +85,18 @@ template <> struct Vec<4> {
   }
   static __device__ __forceinline__ void st(__nv_bfloat16* p, int64_t i, const float* v) {
     __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 raw;
+    raw.x = *reinterpret_cast<uint32_t*>(&a);
+    raw.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p + i) = raw;
+  }
+  static __device__ __forceinline__ void ld(const __half* p, int64_t i, float* o) {
+    uint2 raw = *reinterpret_cast<const uint2*>(p + i);
+    __half2 a = *reinterpret_cast<__half2*>(&raw.x), b = *reinterpret_cast<__half2*>(&raw.y);
+    o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void st(__half* p, int64_t i, const float* v) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
     uint2 raw;
     raw.x = *reinterpret_cast<uint32_t*>(&a);
     raw.y = *reinterpret_cast<uint32_t*>(&b);
@@ -330,13 +344,14 @@ extern "C" int dsk_sampler_stage_cond(int stage, float* x, float* x_aux, float* 
   const bool needs_aux = stage == DSK_STAGE_HEUN_MID || stage == DSK_STAGE_HEUN_FIN ||
                          stage == DSK_STAGE_KARRAS_MID || stage == DSK_STAGE_KARRAS_FIN;
   DSK_REQUIRE(!needs_aux || (x_aux && r1), "dsk_sampler_stage: x_aux/r1 are null");
-  DSK_REQUIRE(act_dtype == DSK_F32 || act_dtype == DSK_BF16, "dsk_sampler_stage: bad dtype %d", act_dtype);
+  DSK_REQUIRE(act_dtype == DSK_F32 || is_h16(act_dtype), "dsk_sampler_stage: bad dtype %d", act_dtype);
   StageArgs a{x, x_aux, r1, F, xin, cnoise, tab, row, noise, hist, seed, B, C, S, sigma_data, sigma_max, precond_kind,
               xin_ld, cfg ? 1 : 0, guidance};
   const int64_t N = (int64_t)B * C * S;
   const bool vec = (C == 1) && (xin_ld == 1) && (N % 4 == 0);
   cudaStream_t st = as_stream(stream);
   if (act_dtype == DSK_F32) return vec ? launch_stage<float, 4>(stage, a, st) : launch_stage<float, 1>(stage, a, st);
+  if (act_dtype == DSK_F16) return vec ? launch_stage<__half, 4>(stage, a, st) : launch_stage<__half, 1>(stage, a, st);
   return vec ? launch_stage<__nv_bfloat16, 4>(stage, a, st) : launch_stage<__nv_bfloat16, 1>(stage, a, st);
 }
 
@@ -361,6 +376,8 @@ extern "C" int dsk_precond_scale_cond(const float* x, const float* c_in, void* x
   else if (act_dtype == DSK_BF16)
     DSK_LAUNCH(precond_scale_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), x, c_in, (__nv_bfloat16*)xin, B, C, S,
                xin_ld, dup);
+  else if (act_dtype == DSK_F16)
+    DSK_LAUNCH(precond_scale_kernel<__half>, grid, 256, 0, as_stream(stream), x, c_in, (__half*)xin, B, C, S, xin_ld, dup);
   else
     DSK_REQUIRE(false, "dsk_precond_scale: bad dtype %d", act_dtype);
   return DSK_OK;
@@ -374,6 +391,8 @@ extern "C" int dsk_cfg_mix(void* F_uncond, const void* F_cond, float guidance, i
   else if (act_dtype == DSK_BF16)
     DSK_LAUNCH(cfg_mix_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), (__nv_bfloat16*)F_uncond,
                (const __nv_bfloat16*)F_cond, guidance, n);
+  else if (act_dtype == DSK_F16)
+    DSK_LAUNCH(cfg_mix_kernel<__half>, grid, 256, 0, as_stream(stream), (__half*)F_uncond, (const __half*)F_cond, guidance, n);
   else
     DSK_REQUIRE(false, "dsk_cfg_mix: bad dtype %d", act_dtype);
   return DSK_OK;
@@ -390,6 +409,8 @@ extern "C" int dsk_precond_denoise(const void* F, const float* x, const float* c
     DSK_LAUNCH(precond_denoise_kernel<float>, grid, 256, 0, as_stream(stream), (const float*)F, x, c_out, c_skip, sigma, D, score, B, C, S);
   else if (act_dtype == DSK_BF16)
     DSK_LAUNCH(precond_denoise_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), (const __nv_bfloat16*)F, x, c_out, c_skip, sigma, D, score, B, C, S);
+  else if (act_dtype == DSK_F16)
+    DSK_LAUNCH(precond_denoise_kernel<__half>, grid, 256, 0, as_stream(stream), (const __half*)F, x, c_out, c_skip, sigma, D, score, B, C, S);
   else
     DSK_REQUIRE(false, "dsk_precond_denoise: bad dtype %d", act_dtype);
   return DSK_OK;

@@ -128,6 +128,7 @@ extern "C" int dsk_sampler_stage_general(int stage, float* x, float* x_aux, floa
   GenArgs a{x, x_aux, r1, F, xin, cnoise, tab, row, noise, hist, B, C, S, x_scale, xin_ld};
   if (act_dtype == DSK_F32) return launch_general<float>(stage, a, as_stream(stream));
   if (act_dtype == DSK_BF16) return launch_general<__nv_bfloat16>(stage, a, as_stream(stream));
+  if (act_dtype == DSK_F16) return launch_general<__half>(stage, a, as_stream(stream));
   DSK_REQUIRE(false, "dsk_sampler_stage_general: bad act_dtype %d", act_dtype);
   return DSK_ERR_ARG;
 }

@@ -93,6 +93,13 @@ __device__ __forceinline__ uint64_t umma_desc64(uint32_t lo, uint32_t hi) { retu
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+// kind::f16 instruction descriptor for either 16-bit format (a_format bits 7-9, b_format bits 10-12: 0 = F16, 1 = BF16),
+// fp32 accumulate, both operands K-major
+__device__ __forceinline__ uint32_t umma_idesc_h16(int n, int m, int f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+inline CUtensorMapDataType tmap_h16(int dtype) { return dtype == DSK_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -21,7 +21,7 @@ from torch import nn
 from ... import ops
 from ..._lib import require_cuda
 from .layers import AttentionParams, ConvParams, FourierParams, LinearParams, NormParams, _Act, _Holder, make_conv
-from .punetg import _NORM_MODE, _tc_eligible, DEFAULT_PRECISION
+from .punetg import _NORM_MODE, _tc_eligible, DEFAULT_PRECISION, PRECISIONS, _ACT_DTYPE, _W_DTYPE
 
 
 class ADMConfig:
@@ -220,11 +220,13 @@ class ADM(nn.Module):
 
 class _ADMPlan:
     def __init__(self, net: ADM, B: int, spatial: tuple, device, precision: str, sig):
-        if precision not in ("fp32", "bf16"):
-            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}, got {precision!r}")
         c = net.config
         self.net, self.B, self.sig, self.precision = net, B, sig, precision
-        self.act_dtype = adt = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.act_dtype = adt = _ACT_DTYPE[precision]         # modes: see punetg.PRECISIONS
+        wdt = _W_DTYPE.get(precision)
+        self.split = precision in ("fp32", "fp16x2")          # tensor-core convs read split-fp16 inputs (hi | lo)
         self.device = dev = torch.device(device)
         nlev = len(c.channel_expansion)
         H, W = spatial
@@ -238,8 +240,8 @@ class _ADMPlan:
         self.F = torch.empty((B, 1, H, W, c.output_channels), dtype=adt, device=dev)
 
         def pack(cp, subpixel=False, few_out_ok=False):
-            tc = precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize, few_out_ok)
-            return ops.PackedConv(cp.weight, cp.bias, 2, torch.bfloat16 if tc else torch.float32, subpixel and tc,
+            tc = wdt is not None and _tc_eligible(cp.cin, cp.cout, cp.ksize, few_out_ok)
+            return ops.PackedConv(cp.weight, cp.bias, 2, wdt if tc else torch.float32, subpixel and tc,
                                   circular=bool(getattr(cp, "circular", False)) and cp.ksize > 1)
 
         self.pc_in, self.pc_out = pack(net.input_layer), pack(net.output_layer, few_out_ok=True)
@@ -288,6 +290,9 @@ class _ADMPlan:
 
     def _conv(self, x, pc, out, up: bool, **kw):
         # nearest x2 upsample is never materialised: FFMA folds it into the gather, tcgen05 runs the sub-pixel form
+        if self.split and ops.is_tc_dtype(pc.w_dtype) and x.dtype == torch.float32:
+            # split mode: a tensor-core convolution reads the split copy (hi | lo) of its fp32 input
+            x = ops.split_f16(x, out=self.buf("split", x.shape[:-1] + (2 * x.shape[-1],), torch.float16))
         if pc.circular:      # the tcgen05 path reads a halo-padded copy (TMA boxes cannot wrap): one workspace, grown on demand
             need = ops.conv_pad_ws_bytes(x.shape, x.dtype, pc, up)
             if need > 0 and (self._pad_ws is None or self._pad_ws.numel() < need):
@@ -301,15 +306,26 @@ class _ADMPlan:
         m = blk.attn.mhattn
         res = self.net.config.attn_residual
         out = self.buf(("attn_out", idx), x.shape)
-        tc = self.precision == "bf16" and _tc_eligible(C, C) and Lq % 8 == 0 and Lq <= 8192
+        tc = self.act_dtype in ops.H16 and _tc_eligible(C, C) and Lq % 8 == 0 and Lq <= 8192
         f32 = torch.float32
+        if self.precision == "fp32" and _tc_eligible(C, C) and Lq % 64 == 0 and Lq <= 8192:
+            st = self.attn_state.get(idx)
+            if st is None:
+                st = self.attn_state[idx] = (ops.PackedLinear(m.in_proj_weight, ops.SPLIT), ops.PackedLinear(m.out_proj.weight, ops.SPLIT))
+                st[0].packed(), st[1].packed()
+            bufs = self.attn_bufs.get((B, Lq, C))
+            if bufs is None:
+                bufs = self.attn_bufs[(B, Lq, C)] = ops.attention_split_buffers(B, Lq, C, x.device)
+            ops.self_attention_split(x.view(B, Lq, C), st[0], m.in_proj_bias, st[1], m.out_proj.bias, bufs, out.view(B, Lq, C), res)
+            return out
         if tc:
             st = self.attn_state.get(idx)
             if st is None:
-                st = self.attn_state[idx] = (ops.PackedLinear(m.in_proj_weight), ops.PackedLinear(m.out_proj.weight))
+                st = self.attn_state[idx] = (ops.PackedLinear(m.in_proj_weight, self.act_dtype),
+                                             ops.PackedLinear(m.out_proj.weight, self.act_dtype))
             bufs = self.attn_bufs.get((B, Lq, C))
             if bufs is None:
-                bufs = self.attn_bufs[(B, Lq, C)] = ops.attention_tc_buffers(B, Lq, C, x.device)
+                bufs = self.attn_bufs[(B, Lq, C)] = ops.attention_tc_buffers(B, Lq, C, x.device, self.act_dtype)
             ops.self_attention_tc(x.view(B, Lq, C), st[0], m.in_proj_bias, st[1], m.out_proj.bias, bufs, out.view(B, Lq, C), res)
             return out
         bufs = dict(qkv=self.buf("qkv", (B * Lq, 3 * C), f32), scores=self.buf("scores", (B, Lq, Lq), f32),
@@ -376,5 +392,5 @@ class _ADMPlan:
                 x = self._block(x, blk, idx)
                 idx += 1
         if out_nchw is not None:
-            return ops.conv(x, self.pc_out, out=out_nchw, out_nchw=True)
-        return ops.conv(x, self.pc_out, out=self.F)
+            return self._conv(x, self.pc_out, out_nchw, False, out_nchw=True)
+        return self._conv(x, self.pc_out, self.F, False)

@@ -43,8 +43,11 @@ class TrainGraph:
     """Forward/backward launch lists of one network for one (batch, spatial shape, precision)."""
 
     def __init__(self, net: torch.nn.Module, B: int, device, precision: str, ndim: int):
+        if precision == "fp32_ffma":
+            precision = "fp32"       # training in fp32 storage runs the CUDA-core kernels either way
         if precision not in ("fp32", "bf16"):
-            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+            raise ValueError(f"training graphs run in 'fp32' (CUDA-core parity mode) or 'bf16' (tensor cores; gradients need "
+                             f"bf16's exponent range), got {precision!r}; the fp16 modes are inference formats")
         self.net, self.B, self.device, self.precision, self.ndim = net, B, torch.device(device), precision, ndim
         self.act_dtype = torch.float32 if precision == "fp32" else torch.bfloat16
         self.fwd: list[Callable[[], None]] = []

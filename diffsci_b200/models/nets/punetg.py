@@ -29,6 +29,20 @@ from .punetg_config import PUNetGConfig
 _NORM_MODE = {"GroupLN": 0, "GroupRMS": 1}
 DEFAULT_PRECISION = "fp32"
 
+# Precision modes of the inference plans (DESIGN.md section 2 has the measured error of each against the reference's fp32):
+#   "fp32"      fp32 tensors between kernels; every tensor-core-eligible convolution / attention product runs on tcgen05 with
+#               SPLIT fp16 operands (hi + lo, 3 MMAs per k-step, fp32 accumulate): fp32-class results (~4e-6 per network
+#               evaluation) at a third of the 16-bit tensor-core rate.  Layers the tensor-core kernels do not take (first conv,
+#               channel counts that are not multiples of 64) run the CUDA-core FFMA kernels.
+#   "fp32_ffma" the same storage with every contraction on the CUDA-core FFMA kernels (the round-1 parity mode).
+#   "fp16x2"    as "fp32" with plain fp16 weights (activations split only, 2 MMAs per k-step).
+#   "fp16"      fp16 storage and operands, 1 MMA per k-step: the throughput mode (3 more mantissa bits than bf16).
+#   "bf16"      bf16 storage and operands (the training format; fp32's exponent range).
+PRECISIONS = ("fp32", "fp32_ffma", "fp16x2", "fp16", "bf16")
+_ACT_DTYPE = {"fp32": torch.float32, "fp32_ffma": torch.float32, "fp16x2": torch.float32, "fp16": torch.float16,
+              "bf16": torch.bfloat16}
+_W_DTYPE = {"fp32": ops.SPLIT, "fp16x2": torch.float16, "fp16": torch.float16, "bf16": torch.bfloat16}   # tcgen05 weight format
+
 
 def _tc_eligible(cin: int, cout: int, ksize: int = 3, few_out_ok: bool = False) -> bool:
     """Shapes the tcgen05 implicit-GEMM kernel takes (see csrc/conv_tc.cu): Cin % 64 == 0 and Cout % 64 == 0, or -- for a
@@ -213,12 +227,14 @@ class _Plan:
     """Preallocated buffers + packed weights + pointer tables for one (B, shape, precision)."""
 
     def __init__(self, net: PUNetG, B: int, spatial: tuple, device, precision: str, sig):
-        if precision not in ("fp32", "bf16"):
-            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}, got {precision!r}")
         c = net.config
         self.net, self.B, self.sig, self.precision = net, B, sig, precision
         self.ndim = nd = c.dimension
-        self.act_dtype = adt = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.act_dtype = adt = _ACT_DTYPE[precision]
+        wdt = _W_DTYPE.get(precision)                       # None: no tensor-core kernels in this mode
+        self.split = split = precision in ("fp32", "fp16x2")   # conv / GEMM inputs are split-fp16 tensors (hi | lo)
         dev = self.device = torch.device(device)
         if len(spatial) != nd:
             raise ValueError(f"PUNetG(dimension={nd}) got spatial shape {spatial}")
@@ -238,16 +254,20 @@ class _Plan:
             return torch.empty((B,) + sp[l] + (cc,), dtype=dtype, device=dev)
 
         def pack(cp, subpixel=False, few_out_ok=False):
-            tc = precision == "bf16" and _tc_eligible(cp.cin, cp.cout, cp.ksize, few_out_ok)
-            return ops.PackedConv(cp.weight, cp.bias, nd, torch.bfloat16 if tc else torch.float32, subpixel and tc,
-                                  circular=cp.circular)
+            tc = wdt is not None and _tc_eligible(cp.cin, cp.cout, cp.ksize, few_out_ok)
+            return ops.PackedConv(cp.weight, cp.bias, nd, wdt if tc else torch.float32, subpixel and tc, circular=cp.circular)
+
+        def nbuf(l):      # norm + SiLU output == conv input: a split-fp16 tensor where the block convs run on the tensor cores
+            if split and _tc_eligible(ch[l], ch[l], c.kernel_size):
+                return torch.empty((B,) + sp[l] + (2 * ch[l],), dtype=torch.float16, device=dev)
+            return buf(l, ch[l])
 
         self.xin = buf(0, net.convin.cin)
         if net.ones_channel:          # constant last channel; the fused stages / scale kernels only write the state channels
             self.xin[..., -1] = 1.0
         self.X = [buf(l, ch[l]) for l in range(nlev + 1)]          # encoder / bottom state (doubles as skip)
         self.XU = [buf(l, ch[l]) for l in range(nlev)]             # decoder state
-        self.N = [buf(l, ch[l]) for l in range(nlev + 1)]          # norm+SiLU output == conv input
+        self.N = [nbuf(l) for l in range(nlev + 1)]                # norm+SiLU output == conv input
         self.Y = [buf(l, ch[l]) for l in range(nlev + 1)]          # conv1 output
         self.P = [buf(l + 1, ch[l]) for l in range(nlev)]          # pooled
         self.XA = buf(nlev, ch[nlev])
@@ -257,11 +277,12 @@ class _Plan:
         # circular padding: one halo-padded input copy for the tcgen05 convs (TMA boxes cannot wrap), sized for the largest
         self.pad_ws = None
         self.NP = [None] * (nlev + 1)      # norm+SiLU outputs in the halo-padded layout (the norm's apply pass writes the halos)
-        if c.convolution_type == "circular" and precision == "bf16":
+        if c.convolution_type == "circular" and wdt is not None:
             halo = lambda s: (s[0] + (2 if nd == 3 else 0)) * (s[1] + 2) * (s[2] + 2)  # noqa: E731
-            self.pad_ws = torch.empty(max(B * halo(sp[l]) * ch[l] * 2 for l in range(nlev + 1)), dtype=torch.uint8, device=dev)
+            self.pad_ws = torch.empty(max(B * halo(sp[l]) * ch[l] * (4 if split else 2) for l in range(nlev + 1)),
+                                      dtype=torch.uint8, device=dev)
             for l in range(nlev + 1):
-                if _tc_eligible(ch[l], ch[l], c.kernel_size):
+                if _tc_eligible(ch[l], ch[l], c.kernel_size) and not split:   # split mode: a padding pass in front of each conv
                     d_, h_, w_ = sp[l]
                     self.NP[l] = torch.empty((B, d_ + 2 if nd == 3 else d_, h_ + 2, w_ + 2, ch[l]), dtype=adt, device=dev)
         # fused norm statistics (conv epilogue -> following per-channel norm): one buffer per level, consumed by the very
@@ -280,12 +301,27 @@ class _Plan:
         for i in range(nlev):
             self.blocks += [(b, nlev - 1 - i) for b in net.upward_blocks[i]]
         self.pc = {id(b): (pack(b.conv1), pack(b.conv2)) for b, _ in self.blocks}
-        if adt == torch.bfloat16:
-            sup = ops.conv_stats_supported
+        # split mode: the convolutions NOT fed by a norm (down / up samplers, convout) read a split copy of their fp32 input
+        # (dsk_split_f16) held in one scratch buffer
+        self.S16 = None
+        if split:
+            need = [self.P[l].numel() for l in range(nlev) if ops.is_tc_dtype(self.pc_down[l].w_dtype)]
+            need += [self.X[nlev - i].numel() for i in range(nlev) if ops.is_tc_dtype(self.pc_up[i].w_dtype)]
+            if ops.is_tc_dtype(self.pc_out.w_dtype):
+                need.append(self.X[0].numel())
+            if need:
+                self.S16 = torch.empty(2 * max(need), dtype=torch.float16, device=dev)
+        if wdt is not None:
+            def sup(shape, pc, up2=False):
+                if not ops.is_tc_dtype(pc.w_dtype):
+                    return False
+                if split:
+                    shape = tuple(shape[:-1]) + (2 * shape[-1],)
+                return ops.conv_stats_supported(shape, torch.float16 if split else adt, pc, up2=up2, out_dtype=adt)
             lvl_pc = {l: self.pc[id(b)][0] for b, l in self.blocks}
-            self.st_ok = [sup(self.X[l].shape, adt, lvl_pc[l]) for l in range(nlev + 1)]
-            self.st_down = [sup(self.P[l].shape, adt, self.pc_down[l]) for l in range(nlev)]
-            self.st_up = [sup(self.X[nlev - i].shape, adt, self.pc_up[i], up2=True) for i in range(nlev)]
+            self.st_ok = [sup(self.X[l].shape, lvl_pc[l]) for l in range(nlev + 1)]
+            self.st_down = [sup(self.P[l].shape, self.pc_down[l]) for l in range(nlev)]
+            self.st_up = [sup(self.X[nlev - i].shape, self.pc_up[i], up2=True) for i in range(nlev)]
             for l in range(nlev + 1):
                 if self.st_ok[l] or (l > 0 and self.st_down[l - 1]) or (l < nlev and self.st_up[nlev - 1 - l]):
                     self.ST[l] = ops.conv_stats_buffer(B, ch[l], dev)
@@ -309,11 +345,16 @@ class _Plan:
         Lq = sp[nlev][0] * sp[nlev][1] * sp[nlev][2]
         Cb = ch[nlev]
         self.attn = None
-        self.attn_tc = (precision == "bf16" and _tc_eligible(Cb, Cb) and Lq % 8 == 0 and Lq <= 8192)
+        self.attn_tc = (adt in ops.H16 and _tc_eligible(Cb, Cb) and Lq % 8 == 0 and Lq <= 8192)
+        self.attn_split = (precision == "fp32" and _tc_eligible(Cb, Cb) and Lq % 64 == 0 and Lq <= 8192)
         self.attn_hybrid = False
-        if len(net.attn_block) > 0 and self.attn_tc:
-            self.attn = ops.attention_tc_buffers(B, Lq, Cb, dev)
-            self.attn_w = [(ops.PackedLinear(a.mhattn.in_proj_weight), ops.PackedLinear(a.mhattn.out_proj.weight))
+        if len(net.attn_block) > 0 and self.attn_split:
+            self.attn = ops.attention_split_buffers(B, Lq, Cb, dev)
+            self.attn_w = [(ops.PackedLinear(a.mhattn.in_proj_weight, ops.SPLIT), ops.PackedLinear(a.mhattn.out_proj.weight, ops.SPLIT))
+                           for a in net.attn_block]
+        elif len(net.attn_block) > 0 and self.attn_tc:
+            self.attn = ops.attention_tc_buffers(B, Lq, Cb, dev, adt)
+            self.attn_w = [(ops.PackedLinear(a.mhattn.in_proj_weight, adt), ops.PackedLinear(a.mhattn.out_proj.weight, adt))
                            for a in net.attn_block]
         elif len(net.attn_block) > 0:
             self.attn = dict(qkv=torch.empty((B * Lq, 3 * Cb), **f32), scores=torch.empty((B, Lq, Lq), **f32),
@@ -322,8 +363,8 @@ class _Plan:
                 self.attn["tok"] = torch.empty((B, Lq, Cb), **f32)
                 if _tc_eligible(Cb, Cb) and (B * Lq) % 8 == 0:
                     self.attn_hybrid = True
-                    self.attn["ao16"] = torch.empty((B * Lq, Cb), dtype=torch.bfloat16, device=dev)
-                    self.attn_w = [(ops.PackedLinear(a.mhattn.in_proj_weight), ops.PackedLinear(a.mhattn.out_proj.weight))
+                    self.attn["ao16"] = torch.empty((B * Lq, Cb), dtype=adt, device=dev)
+                    self.attn_w = [(ops.PackedLinear(a.mhattn.in_proj_weight, adt), ops.PackedLinear(a.mhattn.out_proj.weight, adt))
                                    for a in net.attn_block]
         self.Lq, self.Cb = Lq, Cb
         self.prepare()
@@ -332,13 +373,17 @@ class _Plan:
         """Materialise packed weights (must happen outside CUDA-graph capture)."""
         for pc in [self.pc_in, self.pc_out, *self.pc_down, *self.pc_up, *[p for pair in self.pc.values() for p in pair]]:
             pc.packed()
-        if (self.attn_tc or self.attn_hybrid) and len(self.net.attn_block) > 0:
+        if (self.attn_tc or self.attn_hybrid or self.attn_split) and len(self.net.attn_block) > 0:
             for wi, wo in self.attn_w:
                 wi.packed()
                 wo.packed()
 
-    def _conv(self, *a, **k):
-        return ops.conv(*a, pad_ws=self.pad_ws, **k)
+    def _conv(self, x, pc, **k):
+        """ops.conv; in split mode a tensor-core convolution whose input is still an fp32 tensor (not the split output of a
+        norm) gets its split copy first."""
+        if self.split and ops.is_tc_dtype(pc.w_dtype) and x.dtype == torch.float32:
+            x = ops.split_f16(x, out=self.S16[:2 * x.numel()].view(x.shape[:-1] + (2 * x.shape[-1],)))
+        return ops.conv(x, pc, pad_ws=self.pad_ws, **k)
 
     # ------------------------------------------------------------------ forward
     def _resblock(self, x, blk, l, out, xs=None):
@@ -367,6 +412,11 @@ class _Plan:
         a = self.attn
         m = attn.mhattn
         B, Lq, Cb = self.B, self.Lq, self.Cb
+        if self.attn_split:
+            wi, wo = self.attn_w[index]
+            ops.self_attention_split(x.view(B, Lq, Cb), wi, m.in_proj_bias, wo, m.out_proj.bias, a, out.view(B, Lq, Cb),
+                                     self.net.config.attn_residual)
+            return out
         if self.attn_tc:
             wi, wo = self.attn_w[index]
             ops.self_attention_tc(x.view(B, Lq, Cb), wi, m.in_proj_bias, wo, m.out_proj.bias, a, out.view(B, Lq, Cb),
@@ -382,7 +432,7 @@ class _Plan:
             ops.gemm_bf16_tc(x.view(M, Cb), wi.packed(), a["qkv"], M=M, N=3 * Cb, K=Cb, lda=Cb, ldb=Cb, ldc=3 * Cb,
                              bias=m.in_proj_bias.detach())
             ops.attention_core_f32(a["qkv"], a["scores"], a["ao"], B, Lq, Cb)
-            ao16 = ops.cast(a["ao"], torch.bfloat16, out=a["ao16"])
+            ao16 = ops.cast(a["ao"], x.dtype, out=a["ao16"])
             ops.gemm_bf16_tc(ao16, wo.packed(), out.view(M, Cb), M=M, N=Cb, K=Cb, lda=Cb, ldb=Cb, ldc=Cb,
                              bias=m.out_proj.bias.detach(), residual=x.view(M, Cb) if self.net.config.attn_residual else None)
             return out

@@ -18,6 +18,27 @@ from ._lib import lib, check, ptr, stream, dt_code, require_cuda
 
 _weight_epoch = [0]
 
+# Weight format marker of the split tensor-core kernels (DSK_SPLIT_F16): packed rows are [hi | lo] fp16, 2 * Cin long.  A split
+# ACTIVATION tensor is a torch.float16 tensor whose last dimension is 2 * C (channels [0, C) = fp16(v), [C, 2C) = fp16(v - hi)).
+SPLIT = "split_f16"
+H16 = (torch.bfloat16, torch.float16)
+
+
+def is_tc_dtype(w_dtype) -> bool:
+    """Weights packed for the tcgen05 kernels (16-bit K-major rows) as opposed to the fp32 FFMA layout."""
+    return w_dtype in H16 or w_dtype == SPLIT
+
+
+def w_code(w_dtype) -> int:
+    return L.SPLIT_F16 if w_dtype == SPLIT else dt_code(w_dtype)
+
+
+def act_code(x: torch.Tensor, channels: int) -> int:
+    """dtype code of a channels-last activation tensor that carries `channels` logical channels (split tensors hold 2x)."""
+    if x.dtype == torch.float16 and x.shape[-1] == 2 * channels:
+        return L.SPLIT_F16
+    return dt_code(x.dtype)
+
 
 def bump_weight_epoch() -> None:
     """Invalidate every packed weight copy: called by code that updates parameters with a library kernel (fused AdamW),
@@ -28,8 +49,9 @@ def bump_weight_epoch() -> None:
 class PackedConv:
     """Device-side packed copy of a reference-layout conv weight [Cout, Cin, k(,k)(,k)].
 
-    fp32 mode  : fp32 [taps][Cin][Cout]  (CUDA-core FFMA implicit GEMM, 1e-5 parity path)
-    bf16 mode  : bf16 [taps][Cout][Cin]  (tcgen05 implicit GEMM, K-major B operand)
+    torch.float32      : fp32 [taps][Cin][Cout]  (CUDA-core FFMA implicit GEMM)
+    bfloat16 / float16 : 16-bit [taps][Cout][Cin]  (tcgen05 implicit GEMM, K-major B operand)
+    SPLIT              : fp16 [taps][Cout][2 Cin] = hi | lo (tcgen05 with split operands: the tensor-core fp32-parity mode)
     Rebuilt whenever the source parameter's version counter changes (optimizer step / load).
     """
 
@@ -37,7 +59,7 @@ class PackedConv:
                  subpixel: bool = False, dgrad: bool = False, circular: bool = False):
         """subpixel=True (bf16 only): pack for the phase-decomposed conv(nearest_up2(x)) of the tcgen05 UpSampler path.
         dgrad=True: the weights of the data-gradient convolution dX = conv_same(dY, flip(W)^T) (Cin and Cout exchanged)."""
-        assert not subpixel or (w_dtype == torch.bfloat16 and int(weight.shape[-1]) == 3)
+        assert not subpixel or (is_tc_dtype(w_dtype) and int(weight.shape[-1]) == 3)
         assert not (dgrad and (subpixel or bias is not None))
         self.subpixel, self.dgrad = subpixel, dgrad
         self.circular = bool(circular)   # circular padding on every spatial axis (CircularConv2d/3d, commonlayers.py:918-1032)
@@ -64,23 +86,27 @@ class PackedConv:
         if True:
             src = w.detach().float().contiguous()
             ntap = (4 ** self.ndim) if self.subpixel else self.taps
-            rows = 16 if (self.w_dtype == torch.bfloat16 and self.cout <= 16 and not self.dgrad) else self.cout   # convout: zero-padded to N = 16
+            tc = is_tc_dtype(self.w_dtype)
+            split = self.w_dtype == SPLIT
+            rows = 16 if (tc and self.cout <= 16 and not self.dgrad) else self.cout   # convout: zero-padded to N = 16
             if self._packed is None or self._packed.device != w.device:
-                self._packed = torch.empty(ntap * self.cin * rows, dtype=self.w_dtype, device=w.device)
+                self._packed = torch.empty(ntap * self.cin * rows * (2 if split else 1),
+                                           dtype=torch.float16 if split else self.w_dtype, device=w.device)
             if self.subpixel:
-                check(lib.dsk_pack_upconv_weight(ptr(src), ptr(self._packed), self.cout, self.cin, self.ndim, stream()))
+                check(lib.dsk_pack_upconv_weight(ptr(src), ptr(self._packed), self.cout, self.cin, self.ndim, w_code(self.w_dtype),
+                                                 stream()))
             elif self.dgrad:   # reference weight is [Cout_w = self.cin, Cin_w = self.cout, taps]
                 check(lib.dsk_pack_conv_weight_dgrad(ptr(src), ptr(self._packed), self.cin, self.cout, self.taps,
-                                                     dt_code(self.w_dtype), stream()))
+                                                     w_code(self.w_dtype), stream()))
             else:
                 check(lib.dsk_pack_conv_weight(ptr(src), ptr(self._packed), self.cout, self.cin, self.taps,
-                                               dt_code(self.w_dtype), stream()))
+                                               w_code(self.w_dtype), stream()))
             self._version = key
         return self._packed
 
 
 def _conv_desc_of(x, pc, out, residual, up2, out_nchw, D, H, W):
-    return L.ConvDesc(x.shape[0], D, H, W, x.shape[-1], pc.cout, pc.ksize, pc.ndim, int(up2), dt_code(pc.w_dtype), dt_code(x.dtype),
+    return L.ConvDesc(x.shape[0], D, H, W, pc.cin, pc.cout, pc.ksize, pc.ndim, int(up2), w_code(pc.w_dtype), act_code(x, pc.cin),
                       dt_code(residual.dtype if (out_nchw and residual is not None) else
                               (torch.float32 if out_nchw else out.dtype)), int(out_nchw), int(pc.circular))
 
@@ -92,7 +118,8 @@ def conv_pad_ws_bytes(x_shape, x_dtype, pc: "PackedConv", up2: bool = False) -> 
     B, D, H, W, Cin = x_shape
     if up2:
         D, H, W = (D * 2 if pc.ndim == 3 else D), H * 2, W * 2
-    d = L.ConvDesc(B, D, H, W, Cin, pc.cout, pc.ksize, pc.ndim, int(up2), dt_code(pc.w_dtype), dt_code(x_dtype), dt_code(x_dtype), 0, 1)
+    code = L.SPLIT_F16 if (x_dtype == torch.float16 and Cin == 2 * pc.cin) else dt_code(x_dtype)
+    d = L.ConvDesc(B, D, H, W, pc.cin, pc.cout, pc.ksize, pc.ndim, int(up2), w_code(pc.w_dtype), code, code, 0, 1)
     return int(lib.dsk_conv_pad_ws_bytes(C.byref(d)))
 
 
@@ -106,12 +133,15 @@ def pad_circular(x: torch.Tensor, ndim: int, out: Optional[torch.Tensor] = None)
     return out
 
 
-def conv_stats_supported(x_shape, x_dtype, pc: "PackedConv", up2: bool = False) -> bool:
-    """Can the convolution of an input of this shape emit fused norm statistics (dsk_conv_stats_supported)?"""
+def conv_stats_supported(x_shape, x_dtype, pc: "PackedConv", up2: bool = False, out_dtype=None) -> bool:
+    """Can the convolution of an input of this shape emit fused norm statistics (dsk_conv_stats_supported)?  A split input is
+    recognised by its doubled channel count (fp16, last dimension 2 * pc.cin); out_dtype defaults to the input dtype."""
     B, D, H, W, Cin = x_shape
     if up2:
         D, H, W = (D * 2 if pc.ndim == 3 else D), H * 2, W * 2
-    d = L.ConvDesc(B, D, H, W, Cin, pc.cout, pc.ksize, pc.ndim, int(up2), dt_code(pc.w_dtype), dt_code(x_dtype), dt_code(x_dtype), 0)
+    code = L.SPLIT_F16 if (x_dtype == torch.float16 and Cin == 2 * pc.cin) else dt_code(x_dtype)
+    d = L.ConvDesc(B, D, H, W, pc.cin, pc.cout, pc.ksize, pc.ndim, int(up2), w_code(pc.w_dtype), code,
+                   dt_code(out_dtype or x_dtype), 0)
     return bool(lib.dsk_conv_stats_supported(C.byref(d)))
 
 
@@ -131,13 +161,15 @@ def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, ch
     require_cuda(x, "conv input")
     B, D, H, W, Cin = x.shape
     if prepadded:
-        assert pc.circular and pc.w_dtype == torch.bfloat16, "a pre-padded input is the layout of circular tcgen05 convolutions"
+        assert pc.circular and pc.w_dtype in H16, "a pre-padded input is the layout of circular tcgen05 convolutions"
         D, H, W = (D - 2 if pc.ndim == 3 else D), H - 2, W - 2
-    assert Cin == pc.cin, (Cin, pc.cin)
-    assert up2 == pc.subpixel or pc.w_dtype == torch.float32, "bf16 weights of an up2 conv must be sub-pixel packed"
+    split_in = x.dtype == torch.float16 and Cin == 2 * pc.cin          # split-fp16 activations (hi | lo)
+    assert Cin == pc.cin or split_in, (Cin, pc.cin)
+    assert not split_in or pc.w_dtype in (SPLIT, torch.float16), "split activations need split or fp16 weights"
+    assert up2 == pc.subpixel or pc.w_dtype == torch.float32, "16-bit weights of an up2 conv must be sub-pixel packed"
     if up2:
         D, H, W = (D * 2 if pc.ndim == 3 else D), H * 2, W * 2
-    out_dtype = out_dtype or x.dtype
+    out_dtype = out_dtype or (torch.float32 if split_in else x.dtype)
     if out is None:
         shape = (B, pc.cout, D, H, W) if out_nchw else (B, D, H, W, pc.cout)
         if out_nchw and pc.ndim == 2:
@@ -215,13 +247,26 @@ def norm_act(x: torch.Tensor, gamma, beta, G: int, mode: int, silu: bool, out: O
         ws = torch.empty(int(lib.dsk_norm_ws_bytes(B, S, Cc)), dtype=torch.uint8, device=x.device)
     g = gamma.detach() if gamma is not None else None
     b = beta.detach() if beta is not None else None
+    ocode = dt_code(x.dtype) if out is None else act_code(out, Cc)     # `out` [.., 2C] fp16: split-fp16 output (fp32 input)
     if conv_stats is not None:
         check(lib.dsk_norm_act_prestat(ptr(x), ptr(out), ptr(g), ptr(b), ptr(film_scale), ptr(film_shift), ptr(conv_stats),
-                                       conv_stats.shape[1], ptr(ws), B, S, Cc, G, mode, int(silu), dt_code(x.dtype),
-                                       dt_code(x.dtype if out is None else out.dtype), stream()))
+                                       conv_stats.shape[1], ptr(ws), B, S, Cc, G, mode, int(silu), dt_code(x.dtype), ocode,
+                                       stream()))
         return out
     check(lib.dsk_norm_act(ptr(x), ptr(out), ptr(g), ptr(b), ptr(film_scale), ptr(film_shift), ptr(ws), B, S, Cc, G,
-                           mode, int(silu), dt_code(x.dtype), dt_code(x.dtype if out is None else out.dtype), stream()))
+                           mode, int(silu), dt_code(x.dtype), ocode, stream()))
+    return out
+
+
+def split_f16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [.., C] -> split-fp16 [.., 2C] (hi | lo): the operand form of the split tensor-core kernels (dsk_split_f16)."""
+    require_cuda(x, "split input")
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    Cc = x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (2 * Cc,), dtype=torch.float16, device=x.device)
+    assert out.dtype == torch.float16 and out.numel() == 2 * x.numel()
+    check(lib.dsk_split_f16(ptr(x), ptr(out), x.numel() // Cc, Cc, stream()))
     return out
 
 
@@ -482,10 +527,12 @@ def dropout(x: torch.Tensor, p: float, seed: int, stream_id: int, out: Optional[
 
 
 class PackedLinear:
-    """bf16 device copy of an fp32 [N, K] weight (K-major B/A operand of dsk_gemm_bf16_tc), version tracked."""
+    """16-bit device copy of an fp32 [N, K] weight (K-major B/A operand of dsk_gemm_tc), version tracked.  dtype: bfloat16 |
+    float16 | SPLIT ([N, 2K] fp16, hi | lo)."""
 
-    def __init__(self, weight: torch.Tensor):
+    def __init__(self, weight: torch.Tensor, dtype=torch.bfloat16):
         self.weight = weight
+        self.dtype = dtype
         self._packed = None
         self._version = None
 
@@ -495,9 +542,14 @@ class PackedLinear:
         if self._packed is None or self._version != key or self._packed.device != w.device:
             require_cuda(w, "linear weight")
             with torch.inference_mode(False), torch.no_grad():
-                if self._packed is None or self._packed.device != w.device:
-                    self._packed = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
-                cast(w.detach().float().contiguous(), torch.bfloat16, out=self._packed)
+                if self.dtype == SPLIT:
+                    if self._packed is None or self._packed.device != w.device:
+                        self._packed = torch.empty((w.shape[0], 2 * w.shape[1]), dtype=torch.float16, device=w.device)
+                    split_f16(w.detach().float().contiguous(), out=self._packed)
+                else:
+                    if self._packed is None or self._packed.device != w.device:
+                        self._packed = torch.empty(w.shape, dtype=self.dtype, device=w.device)
+                    cast(w.detach().float().contiguous(), self.dtype, out=self._packed)
                 self._version = key
         return self._packed
 
@@ -510,20 +562,38 @@ def gemm_bf16_tc(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, *, M: int
     """Batched bf16 tensor-core GEMM C = alpha op(A) op(B)^T + bias (+ residual) on raw buffers (dsk_gemm_bf16_tc).
     transA / transB: the operand is stored [K, M] / [K, N].  Offsets are in elements."""
     require_cuda(A, "gemm A")
-    assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16
+    assert A.dtype in H16 and Bm.dtype == A.dtype
     a = C.c_void_p(A.data_ptr() + a_off * 2)
     b = C.c_void_p(Bm.data_ptr() + b_off * 2)
     c = C.c_void_p(out.data_ptr() + c_off * out.element_size())
-    r = None if residual is None else C.c_void_p(residual.data_ptr() + c_off * 2)
-    check(lib.dsk_gemm_bf16_tc(a, b, c, ptr(bias), int(bias_rows), r, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch,
-                               alpha, int(out.dtype == torch.float32), int(transA), int(transB), stream()))
+    rf32 = residual is not None and residual.dtype == torch.float32
+    r = None if residual is None else C.c_void_p(residual.data_ptr() + c_off * residual.element_size())
+    check(lib.dsk_gemm_tc(a, b, c, ptr(bias), int(bias_rows), r, int(rf32), M, N, K, lda, ldb, ldc, strideA, strideB, strideC,
+                          batch, alpha, int(out.dtype == torch.float32), int(transA), int(transB), dt_code(A.dtype), 0, 0, stream()))
     return out
 
 
-def attention_tc_buffers(B: int, Lq: int, Cc: int, device) -> dict:
-    """Scratch of self_attention_tc: packed Q|K|V, the bf16 probabilities, the attention output and the row-statistics
+def gemm_split_tc(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, lda: int, ldb: int, ldc: int,
+                  a_lo: int, b_lo: int, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                  alpha: float = 1.0, batch: int = 1, strideA: int = 0, strideB: int = 0, strideC: int = 0, a_off: int = 0,
+                  b_off: int = 0, transA: bool = False, transB: bool = False) -> torch.Tensor:
+    """C (fp32) = alpha op(A) op(B)^T + bias (+ fp32 residual) with split-fp16 operands (dsk_gemm_tc, DSK_SPLIT_F16): the lo
+    half of an operand lies a_lo / b_lo elements after its hi half along the operand's contiguous coordinate; lda / ldb are
+    the full row lengths.  Three tcgen05 MMAs per k-step (hi*hi + hi*lo + lo*hi) -- fp32-class products on the tensor cores."""
+    require_cuda(A, "gemm A")
+    assert A.dtype == torch.float16 and Bm.dtype == torch.float16 and out.dtype == torch.float32
+    assert residual is None or residual.dtype == torch.float32
+    a = C.c_void_p(A.data_ptr() + a_off * 2)
+    b = C.c_void_p(Bm.data_ptr() + b_off * 2)
+    check(lib.dsk_gemm_tc(a, b, ptr(out), ptr(bias), 0, ptr(residual), 1, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch,
+                          alpha, 1, int(transA), int(transB), L.SPLIT_F16, a_lo, b_lo, stream()))
+    return out
+
+
+def attention_tc_buffers(B: int, Lq: int, Cc: int, device, dtype=torch.bfloat16) -> dict:
+    """Scratch of self_attention_tc: packed Q|K|V, the 16-bit probabilities, the attention output and the row-statistics
     workspace of dsk_attn_softmax_qk.  (No fp32 score tensor: the scores never leave the SM.)"""
-    bf = dict(dtype=torch.bfloat16, device=device)
+    bf = dict(dtype=dtype, device=device)
     return dict(qkv=torch.empty((B * Lq, 3 * Cc), **bf), probs=torch.empty((B, Lq, Lq), **bf), ao=torch.empty((B * Lq, Cc), **bf),
                 rowstat=torch.empty(int(lib.dsk_attn_softmax_ws_bytes(B, Lq)), dtype=torch.uint8, device=device))
 
@@ -532,8 +602,46 @@ def attn_softmax_qk(qkv: torch.Tensor, probs: torch.Tensor, ws: torch.Tensor, B:
     """probs[b] = softmax(Q[b] K[b]^T / sqrt(C)) (bf16) from packed projections qkv [B*L, 3C] (dsk_attn_softmax_qk)."""
     q = C.c_void_p(qkv.data_ptr())
     k = C.c_void_p(qkv.data_ptr() + Cc * 2)
-    check(lib.dsk_attn_softmax_qk(q, k, ptr(probs), ptr(ws), Lq, Cc, 3 * Cc, 3 * Cc, Lq * 3 * Cc, Lq * 3 * Cc, B, Cc ** -0.5, stream()))
+    check(lib.dsk_attn_softmax_qk_h16(q, k, ptr(probs), ptr(ws), Lq, Cc, 3 * Cc, 3 * Cc, Lq * 3 * Cc, Lq * 3 * Cc, B, Cc ** -0.5,
+                                      dt_code(qkv.dtype), stream()))
     return probs
+
+
+def attention_split_buffers(B: int, Lq: int, Cc: int, device) -> dict:
+    """Scratch of self_attention_split (tensor-core fp32-parity attention): split tokens, fp32 + split packed Q|K|V, fp32
+    scores, split probabilities, fp32 + split attention output."""
+    h = dict(dtype=torch.float16, device=device)
+    f = dict(dtype=torch.float32, device=device)
+    return dict(tok_s=torch.empty((B * Lq, 2 * Cc), **h), qkv=torch.empty((B * Lq, 3 * Cc), **f),
+                qkv_s=torch.empty((B * Lq, 6 * Cc), **h), scores=torch.empty((B, Lq, Lq), **f),
+                probs_s=torch.empty((B, Lq, 2 * Lq), **h), ao=torch.empty((B * Lq, Cc), **f), ao_s=torch.empty((B * Lq, 2 * Cc), **h))
+
+
+def self_attention_split(tok: torch.Tensor, w_in: "PackedLinear", in_b, w_out: "PackedLinear", out_b, bufs: dict,
+                         out: torch.Tensor, residual: bool) -> torch.Tensor:
+    """nn.MultiheadAttention(C, 1 head) on fp32 tokens [B, L, C] (nets/attention.py:54-72) at fp32-class accuracy on the tensor
+    cores: every product is a split-operand tcgen05 GEMM (hi*hi + hi*lo + lo*hi, fp32 accumulate); the scores, the softmax and
+    every stored tensor stay fp32, operands are re-split (dsk_split_f16 / dsk_softmax_rows_h16) in front of each GEMM."""
+    B, Lq, Cc = tok.shape
+    M = B * Lq
+    ts = split_f16(tok.reshape(M, Cc), out=bufs["tok_s"])
+    gemm_split_tc(ts, w_in.packed(), bufs["qkv"], M=M, N=3 * Cc, K=Cc, lda=2 * Cc, ldb=2 * Cc, ldc=3 * Cc, a_lo=Cc, b_lo=Cc,
+                  bias=in_b.detach())
+    qs = split_f16(bufs["qkv"], out=bufs["qkv_s"])                      # rows [q k v | q_lo k_lo v_lo], lo half 3C after hi
+    gemm_split_tc(qs, qs, bufs["scores"], M=Lq, N=Lq, K=Cc, lda=6 * Cc, ldb=6 * Cc, ldc=Lq, a_lo=3 * Cc, b_lo=3 * Cc,
+                  alpha=Cc ** -0.5, batch=B, strideA=Lq * 6 * Cc, strideB=Lq * 6 * Cc, strideC=Lq * Lq, b_off=Cc)
+    check(lib.dsk_softmax_rows_h16(ptr(bufs["scores"]), ptr(bufs["probs_s"]), B * Lq, Lq, L.SPLIT_F16, stream()))
+    # P V in K slices of 1024 keys accumulated through the fp32 residual operand: tcgen05 truncates when it adds into its
+    # accumulators, so a 4096-long chain in one accumulator would cost more than the split operands gain (the [L, C] output is
+    # tiny next to the operands)
+    for k0 in range(0, Lq, 1024):
+        gemm_split_tc(bufs["probs_s"], qs, bufs["ao"], M=Lq, N=Cc, K=min(1024, Lq - k0), lda=2 * Lq, ldb=6 * Cc, ldc=Cc, a_lo=Lq,
+                      b_lo=3 * Cc, batch=B, strideA=Lq * 2 * Lq, strideB=Lq * 6 * Cc, strideC=Lq * Cc, a_off=k0,
+                      b_off=2 * Cc + k0 * 6 * Cc, transB=True, residual=bufs["ao"] if k0 else None)
+    aos = split_f16(bufs["ao"], out=bufs["ao_s"])
+    gemm_split_tc(aos, w_out.packed(), out.view(M, Cc), M=M, N=Cc, K=Cc, lda=2 * Cc, ldb=2 * Cc, ldc=Cc, a_lo=Cc, b_lo=Cc,
+                  bias=out_b.detach(), residual=tok.reshape(M, Cc) if residual else None)
+    return out
 
 
 def self_attention_tc(tok: torch.Tensor, w_in: PackedLinear, in_b: torch.Tensor, w_out: PackedLinear, out_b: torch.Tensor,

@@ -15,7 +15,7 @@
  *  - every launch is asynchronous on the cudaStream_t passed as `stream` (void* here so
  *    that the header needs no CUDA include); functions are CUDA-graph capturable.
  *  - activations inside the networks are CHANNELS-LAST [B, D, H, W, C] (D = 1 for 2-D),
- *    dtype DSK_F32 or DSK_BF16; user-facing tensors x / D(x) / noise are fp32 NC(D)HW as in
+ *    dtype DSK_F32, DSK_BF16 or DSK_F16; user-facing tensors x / D(x) / noise are fp32 NC(D)HW as in
  *    the reference.
  */
 #ifndef DIFFSCI_B200_H
@@ -32,7 +32,20 @@ extern "C" {
 #define DSK_ERR_CUDA -2
 #define DSK_ERR_UNSUPPORTED -3
 
-enum { DSK_F32 = 0, DSK_BF16 = 1 };
+/* Storage / operand formats.  DSK_BF16 and DSK_F16 are the two 16-bit formats of the tensor-core path (same kernels, the
+ * format is a run-time flag: tcgen05 kind::f16 takes either).  fp16 keeps 3 more mantissa bits than bf16 (a forward pass of
+ * the score networks lands at ~2e-3 of the reference's fp32 result instead of ~1.5e-2, oracle/split_budget.py) and is the
+ * inference format; bf16 (fp32's exponent range) is the training format, where gradients need the range. */
+enum { DSK_F32 = 0, DSK_BF16 = 1, DSK_F16 = 2,
+       /* split-fp16: a tensor of fp32-class values v stored as [.., 2C] fp16 -- channels [0, C) hold hi = fp16(v), channels
+        * [C, 2C) hold lo = fp16(2^11 (v - hi)) (the scaling keeps lo a normal fp16 number); hi + 2^-11 lo carries 22 mantissa
+        * bits.  The operand format of the tensor-core fp32-parity mode: a split convolution / GEMM runs 3 tcgen05 MMAs per
+        * k-step -- hi*hi into one group of fp32 TMEM accumulators, hi*lo + lo*hi into another -- and combines them in the
+        * epilogue (products below 2^-22 dropped).  tcgen05 accumulates with truncation (tools/probe_tc_accum.py), so the hi*hi
+        * products of a convolution tile are spread over three accumulator sets added in fp32 afterwards.  Reproduces the
+        * reference's fp32 arithmetic to 1e-5-class over a whole network at a third of the 16-bit tensor-core rate instead of
+        * CUDA-core FFMA rate. */
+       DSK_SPLIT_F16 = 3 };
 
 /* ---- library ---------------------------------------------------------------------- */
 int dsk_version(void);
@@ -169,8 +182,8 @@ int dsk_dropout(const void* x, const void* dres, void* y, int64_t n, float p, ui
  *
  * in  : [B, Di, Hi, Wi, Cin]  (if up2: the conv sees nearest-upsampled x2 input, i.e. F.interpolate
  *        fused into the gather: commonlayers.py:129,145)
- * w   : packed weights. DSK_F32 path: fp32 [taps][Cin][Cout];  DSK_BF16 path: bf16 [taps][Cout][Cin]
- *       (bf16 + up2: the sub-pixel layout of dsk_pack_upconv_weight)
+ * w   : packed weights. DSK_F32 path: fp32 [taps][Cin][Cout];  16-bit paths (DSK_BF16 | DSK_F16): [taps][Cout][Cin];
+ *       DSK_SPLIT_F16: fp16 [taps][Cout][2 Cin] (hi | lo)   (16-bit + up2: the sub-pixel layout of dsk_pack_upconv_weight)
  * out : [B, D, H, W, Cout] ; y = conv(in) + bias[co] + chan_bias[b,co] + residual[b,..,co]
  * ksize in {1,3}; ndim in {2,3} (ndim 2 => D = 1, taps = k*k).
  */
@@ -179,10 +192,13 @@ typedef struct {
   int Cin, Cout;
   int ksize, ndim;
   int up2;             /* 1: nearest x2 upsample fused into the input gather             */
-  int w_dtype;         /* DSK_F32: w is fp32 [taps][Cin][Cout] -> CUDA-core FFMA kernel (fp32 parity mode);
-                          DSK_BF16: w is bf16 [taps][Cout][Cin] -> tcgen05 implicit-GEMM kernel          */
+  int w_dtype;         /* DSK_F32: w is fp32 [taps][Cin][Cout] -> CUDA-core FFMA kernel;
+                          DSK_BF16 | DSK_F16: 16-bit [taps][Cout][Cin] -> tcgen05 implicit-GEMM kernel (in_dtype = the same format);
+                          DSK_SPLIT_F16: [taps][Cout][2 Cin] -> the same kernel with split operands: in_dtype = DSK_SPLIT_F16
+                          ([B,D,H,W,2 Cin]), 3 MMAs per k-step (fp32-parity mode on the tensor cores).  in_dtype = DSK_SPLIT_F16
+                          with w_dtype = DSK_F16: activations split only, 2 MMAs per k-step.                                   */
   int in_dtype;        /* dtype of `in`                                                   */
-  int out_dtype;       /* dtype of `out` and `residual`                                   */
+  int out_dtype;       /* dtype of `out` and `residual`: the 16-bit format of the operands, or DSK_F32 */
   int out_nchw_f32;    /* 1: write fp32 NC(D)HW (user layout) instead of channels-last    */
   int circular;        /* 1: circular ('periodic') padding on every spatial axis instead of zeros:
                           CircularConv2d / CircularConv3d (commonlayers.py:918-1032), PUNetGConfig(convolution_type=
@@ -218,9 +234,10 @@ int dsk_norm_apply_padded(const void* x, void* y_padded, const void* ws, int B, 
 /* nearest x2 upsample of a channels-last tensor (torch.nn.Upsample(scale_factor=2), commonlayers.py:129):
  * only needed in front of the tcgen05 conv; the FFMA conv fuses it into its gather (up2). bf16, C % 8 == 0. */
 int dsk_upsample2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int dtype, void* stream);
-/* Sub-pixel weights for the tcgen05 UpSampler conv (up2 = 1 with bf16 weights): bf16 [2^ndim phases][2^ndim taps][Cout][Cin],
- * the three taps of each axis pre-summed onto the two input offsets an output parity sees (csrc/conv_tc.cu). */
-int dsk_pack_upconv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int ndim, void* stream);
+/* Sub-pixel weights for the tcgen05 UpSampler conv (up2 = 1 with 16-bit weights): [2^ndim phases][2^ndim taps][Cout][Cin] in
+ * `dtype` (DSK_BF16 | DSK_F16 | DSK_SPLIT_F16: rows of [hi | lo], 2 Cin long), the three taps of each axis pre-summed in fp32
+ * onto the two input offsets an output parity sees (csrc/conv_tc.cu). */
+int dsk_pack_upconv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int ndim, int dtype, void* stream);
 /* repack a reference-layout weight [Cout, Cin, k(,k)(,k)] fp32 into the two packed layouts */
 int dsk_pack_conv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int taps, int dtype, void* stream);
 
@@ -246,6 +263,15 @@ int dsk_gemm_f32_ex(const float* A, const float* Bm, float* Cm, const float* bia
 int dsk_gemm_bf16_tc(const void* A, const void* Bm, void* C, const float* bias, int bias_rows, const void* residual, int M,
                      int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
                      int64_t strideC, int batch, float alpha, int out_f32, int transA, int transB, void* stream);
+/* The same kernel for every tensor-core operand format.  dtype DSK_BF16 | DSK_F16: as above in that 16-bit format (residual
+ * and 16-bit C in the same format; res_f32 = 1: the residual is fp32).  dtype DSK_SPLIT_F16: A and B are split-fp16 operands
+ * (hi | lo along their CONTIGUOUS coordinate -- k for K-major, m / n for MN-major operands -- with the lo half a_lo / b_lo
+ * elements after the hi half; lda / ldb are the full row lengths): C accumulates hi*hi + hi*lo + lo*hi, the fp32-parity form
+ * of the projections / QK^T / PV of nn.MultiheadAttention (attention.py:42-44).  b_lo < 0: B is plain fp16 (2 MMAs per
+ * k-step).  Split operands need K % 64 == 0. */
+int dsk_gemm_tc(const void* A, const void* Bm, void* C, const float* bias, int bias_rows, const void* residual, int res_f32, int M,
+                int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC, int batch,
+                float alpha, int out_f32, int transA, int transB, int dtype, int a_lo, int b_lo, void* stream);
 /* softmax backward on rows: dS = P * (dP - rowsum(dP * P)); P bf16, dP fp32, dS bf16 (cols % 4 == 0, cols <= 8192) */
 int dsk_softmax_bwd_rows_bf16(const void* P, const float* dP, void* dS, int64_t rows, int cols, void* stream);
 /* P[b] = softmax(alpha Q[b] K[b]^T) written once as bf16 [batch, L, L] -- the middle of nn.MultiheadAttention
@@ -255,8 +281,13 @@ int dsk_softmax_bwd_rows_bf16(const void* P, const float* dP, void* dS, int64_t 
 int64_t dsk_attn_softmax_ws_bytes(int batch, int L);
 int dsk_attn_softmax_qk(const void* Q, const void* K, void* P, void* ws, int L, int C, int64_t ldq, int64_t ldk,
                         int64_t strideQ, int64_t strideK, int batch, float alpha, void* stream);
+/* ... with Q, K, P in `dtype` (DSK_BF16 | DSK_F16) */
+int dsk_attn_softmax_qk_h16(const void* Q, const void* K, void* P, void* ws, int L, int C, int64_t ldq, int64_t ldk,
+                            int64_t strideQ, int64_t strideK, int batch, float alpha, int dtype, void* stream);
 /* softmax over the last dim: fp32 scores [rows, cols] -> bf16 probabilities (cols % 4 == 0, cols <= 8192) */
 int dsk_softmax_rows_bf16(const float* S, void* P, int64_t rows, int cols, void* stream);
+/* ... -> P in `dtype`: DSK_BF16 | DSK_F16 (rows of cols), DSK_SPLIT_F16 (rows of 2 cols: hi | lo, the A operand of a split PV) */
+int dsk_softmax_rows_h16(const float* S, void* P, int64_t rows, int cols, int dtype, void* stream);
 
 /* ---- K4: per-group norm + affine (+FiLM) + SiLU ---------------------------------------
  * Replaces torch.nn.GroupNorm(G,C) / GroupRMSNorm(G,C) (+ SiLU) in ResnetBlockC
@@ -287,6 +318,10 @@ int dsk_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* s
 int dsk_nchw_to_cl(const float* x, void* y, int B, int C, int64_t S, int dtype, void* stream);
 int dsk_cl_to_nchw(const void* x, float* y, int B, int C, int64_t S, int dtype, void* stream);
 int dsk_cast(const void* x, void* y, int64_t n, int in_dtype, int out_dtype, void* stream);
+/* fp32 [rows, C] -> split-fp16 [rows, 2C] (DSK_SPLIT_F16: hi | lo): the operand form of the split tensor-core kernels for
+ * tensors no fused producer writes in that form (pooled / raw residual-stream inputs of DownSampler, UpSampler and convout,
+ * commonlayers.py:53-58,123-128; punetg.py:209-214; attention tokens, attention.py:42-44).  C % 4 == 0. */
+int dsk_split_f16(const float* x, void* y, int64_t rows, int C, void* stream);
 /* channel concat of two channels-last tensors (ADM 'concat' skips, adm.py:296-297) */
 int dsk_concat_channels(const void* a, const void* b, void* y, int64_t rows, int Ca, int Cb, int dtype,
                         void* stream);
