@@ -140,10 +140,16 @@ _checked_devices: set[int] = set()
 
 
 def require_cuda(t: torch.Tensor, what: str = "tensor") -> None:
-    """The product path is CUDA-only.  Raise (never fall back) for CPU tensors / non-B200 devices."""
+    """The product path is CUDA-only.  Raise (never fall back) for CPU tensors / non-B200 devices.  The library launches on the
+    CURRENT device's current stream (it never calls cudaSetDevice), so a tensor on another GPU is an error too: select the
+    device first (``torch.cuda.set_device`` / ``with torch.cuda.device(...)``), as one-process-per-GPU code does."""
     if not t.is_cuda:
         raise RuntimeError(f"diffsci_b200: {what} is on {t.device}; the hot path is sm_100a CUDA only (no CPU fallback)")
-    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    cur = torch.cuda.current_device()
+    dev = t.device.index if t.device.index is not None else cur
+    if dev != cur:
+        raise RuntimeError(f"diffsci_b200: {what} is on cuda:{dev} but the current device is cuda:{cur}; kernels launch on the "
+                           f"current device's stream -- call torch.cuda.set_device({dev}) (or use `with torch.cuda.device({dev})`)")
     if dev not in _checked_devices:
         check(lib.dsk_check_device(dev))
         _checked_devices.add(dev)

@@ -30,6 +30,21 @@ def _f32(v) -> torch.Tensor:
     return torch.tensor(float(v), dtype=torch.float32)
 
 
+def fresh_noise_seed() -> int:
+    """Philox seed for one sampling run, drawn from torch's global CPU generator -- so ``torch.manual_seed`` governs the
+    stochastic samplers as it governs the reference's ``torch.randn_like`` (integrators.py:68,105) and successive runs get
+    new noise -- and mixed with the process rank: identically seeded ranks of a sharded run (distributed.sample_sharded) index
+    the Philox stream by LOCAL element, so without the mix their Brownian increments would coincide."""
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            seed ^= (dist.get_rank() * 0x9E3779B97F4A7C15) & (2 ** 62 - 1)
+    except Exception:
+        pass
+    return seed
+
+
 class Integrator(torch.nn.Module):
     stochastic = False
     need_fns = False
@@ -40,15 +55,27 @@ class Integrator(torch.nn.Module):
         self.seed = 0xD1FF5C1
         self.injected_noise: Optional[Sequence[Tensor]] = None
         self._draws = 0
+        self._pinned = False         # reset_noise(seed=...) / injected noise: the caller owns the stream
 
     def step(self, x: Tensor, t: Tensor, dt: Tensor, rhs: Callable, noise_strength: Optional[Any] = None):
         raise NotImplementedError
 
     def reset_noise(self, seed: Optional[int] = None, injected: Optional[Sequence[Tensor]] = None):
+        """Pin the noise of the following runs: an explicit Philox seed, or a sequence of injected N(0,1) tensors (parity
+        tests).  Draw numbers then continue across runs until the next reset."""
         if seed is not None:
             self.seed = int(seed)
         self.injected_noise = injected
         self._draws = 0
+        self._pinned = seed is not None or injected is not None
+
+    def begin_run(self):
+        """Called by the scheduler at the start of every integration (Scheduler._run / inpaint): unless the caller pinned the
+        stream, a fresh seed from torch's generator -- a new instance per ``sample(integrator='...')`` call must not replay the
+        same Brownian path (the reference draws torch.randn_like each step)."""
+        if not self._pinned:
+            self.seed = fresh_noise_seed()
+            self._draws = 0
 
     def _randn_like(self, x: Tensor) -> Tensor:
         """Replacement for torch.randn_like (integrators.py:68,105): draw number k of this run."""

@@ -327,7 +327,10 @@ class KarrasModule(_Base):
         S = x.numel() // (B * Cc)
         cond = bool(self.conditional and guidance != 0.0)
         cfg = cond and guidance != 1.0
-        native = hasattr(self.model, "plan") and not (torch.is_grad_enabled() and self.training)
+        # gradients wanted (training, eval-mode fine-tuning, gradient diagnostics): the network's own forward, which takes the
+        # autograd seam; otherwise the allocation-free inference plan
+        wants_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters())
+        native = hasattr(self.model, "plan") and not wants_grad
         if native and cond and not hasattr(self.model, "conditioning_vector"):
             raise NotImplementedError(f"diffsci_b200: {type(self.model).__name__} has no conditional path")
         if native:
@@ -418,7 +421,7 @@ class KarrasModule(_Base):
         if self._injected_loss_noise is not None:
             noise = self._injected_loss_noise.to(x).contiguous()
         else:   # device-side N(0,1) (the reference uses torch.randn_like on the device generator, :591)
-            noise = ops.philox_normal(x.shape, int(torch.randint(0, 2 ** 62, (1,)).item()), 0, x.device)
+            noise = ops.philox_normal(x.shape, integrators.fresh_noise_seed(), 0, x.device)
         x_noised = _rowwise_axpy(sigma.float(), noise, torch.ones_like(sigma, dtype=torch.float32), x)
         pre = self.config.preconditioner
         c_in = pre.input_scaling(sigma).float().contiguous()
@@ -431,8 +434,10 @@ class KarrasModule(_Base):
             F = ops.cl_to_nchw(F.view(B, 1, 1, S, Cc), 3).view(x.shape)
         m = None if mask is None else mask.to(x).expand_as(x).contiguous()
         coeffs = None
-        if self.dynamic_loss_weight is not None or not (type(pre) is preconditioners.EDMPreconditioner and
-                                                        type(self.config.noisesampler) is noisesamplers.EDMNoiseSampler):
+        sd_pre, sd_ns = getattr(pre, "sigma_data", None), getattr(self.config.noisesampler, "sigma_data", None)
+        same_sd = sd_pre is not None and sd_ns is not None and float(sd_pre) == float(sd_ns)
+        if self.dynamic_loss_weight is not None or not same_sd or not (
+                type(pre) is preconditioners.EDMPreconditioner and type(self.config.noisesampler) is noisesamplers.EDMNoiseSampler):
             # VP / VE / SR3 / custom objects: their per-sample scalars, the same fused loss + dL/dF kernel
             coeffs = tuple(v.float().contiguous() for v in (pre.output_scaling(sigma), pre.skip_scaling(sigma),
                                                             self.config.noisesampler.loss_weighting(sigma)))
@@ -608,7 +613,7 @@ class KarrasModule(_Base):
         noises = None
         if integ.injected_noise is not None:
             noises = torch.stack([n.to(x) for n in integ.injected_noise[:nsteps]], 0)
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if integ.fused_program in ("euler-maruyama", "karras") else 0
+        seed = integrators.fresh_noise_seed() if integ.fused_program in ("euler-maruyama", "karras") else 0
         if getattr(integ, "_fixed_seed", None) is not None:
             seed = integ._fixed_seed
         out = eng.run(x, table, integ.fused_program, record_history=record_history, noises=noises, seed=seed)
@@ -633,7 +638,7 @@ class KarrasModule(_Base):
         noises = None
         if integ.injected_noise is not None:
             noises = torch.stack([n.to(x) for n in integ.injected_noise[:nsteps]], 0)
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if integ.fused_program == "euler-maruyama" else 0
+        seed = integrators.fresh_noise_seed() if integ.fused_program == "euler-maruyama" else 0
         if getattr(integ, "_fixed_seed", None) is not None:
             seed = integ._fixed_seed
         out = eng.run(x, table, integ.fused_program, record_history=record_history, noises=noises, seed=seed)
@@ -673,22 +678,29 @@ class KarrasModule(_Base):
 
     def propagate_toward_noise(self, x: Tensor, y=None, nsteps: int = 100, record_history: bool = False,
                                stochastic_integration: bool = False) -> Tensor:
-        """Forward integration data -> noise (karrasmodule.py:1096-1117)."""
+        """Forward integration data -> noise (karrasmodule.py:1096-1117); y is ONE unbatched condition (:1102-1103)."""
         require_cuda(x, "x")
+        if y is not None:
+            y = dict_unsqueeze(y, 0)   # broadcasting takes care of the rest
         with torch.inference_mode():
             return self.config.noisescheduler.propagate_forward(x, self._score_fn(y), nsteps, record_history=record_history,
                                                                 stochastic=stochastic_integration)
 
     def propagate_inpaint_toward_sample(self, x: Tensor, x_inpaint: Tensor, mask: Tensor, y=None,
                                         record_history: bool = False) -> Tensor:
-        """karrasmodule.py:1048-1070: x_inpaint is the forward history [nsteps+1, B, *shape] of the known data."""
+        """karrasmodule.py:1048-1070: x_inpaint is the forward history [nsteps+1, B, *shape] of the known data; y is ONE
+        unbatched condition (:1054-1055)."""
+        if y is not None:
+            y = dict_unsqueeze(y, 0)
         with torch.inference_mode():
             return self.config.noisescheduler.inpaint(x, x_inpaint, mask, self._score_fn(y), x_inpaint.shape[0] - 1,
                                                       record_history=record_history)
 
     def propagate_repaint_toward_sample(self, x: Tensor, x_inpaint: Tensor, mask: Tensor, y=None,
                                         record_history: bool = False) -> Tensor:
-        """karrasmodule.py:1072-1094 (Scheduler.repaint with its default rsteps / nresamples)."""
+        """karrasmodule.py:1072-1094 (Scheduler.repaint with its default rsteps / nresamples); y unbatched (:1078-1079)."""
+        if y is not None:
+            y = dict_unsqueeze(y, 0)
         with torch.inference_mode():
             return self.config.noisescheduler.repaint(x, x_inpaint, mask, self._score_fn(y), x_inpaint.shape[0] - 1,
                                                       record_history=record_history)
@@ -721,6 +733,8 @@ class KarrasModule(_Base):
         require_cuda(x, "images")
         if jitter is not None:
             x = ops.lincomb(x, 1.0, None, 0.0, None, 0.0, self.config.noisescheduler.integrator._randn_like(x), float(jitter))
+        if y is not None:
+            y = dict_unsqueeze(y, 0)   # as the reference (:1130-1131), which unsqueezes here AND in the two calls below
         xn = self.propagate_toward_noise(x, y, nsteps)
         w = torch.linspace(0, 1, ninterp, device=xn.device).view(-1, *([1] * (xn.ndim - 1)))
         xi = (1 - w) * xn[0].unsqueeze(0) + w * xn[1].unsqueeze(0)

@@ -171,6 +171,8 @@ class Scheduler(torch.nn.Module):
         dt = torch.diff(t)
         x = x.float().contiguous()
         rhs = functools.partial(self.rhs, score_fn=score_fn, backward=backward, stochastic=integrator.stochastic)
+        if hasattr(integrator, "begin_run"):
+            integrator.begin_run()
         step = integrator.step
         if integrator.need_fns:
             step = functools.partial(step, scheduler_fns=self.scheduler_fns, nsteps=nsteps)
@@ -196,6 +198,8 @@ class Scheduler(torch.nn.Module):
             history = torch.zeros((nsteps + 1,) + tuple(x.shape), dtype=x.dtype, device=x.device)
             history[0] = x
         rhs = functools.partial(self.rhs, score_fn=score_fn, backward=True)
+        if hasattr(self.integrator, "begin_run"):
+            self.integrator.begin_run()
         x = ops.mask_blend(x, y[-1], mask)
         for i in range(nsteps):
             x = self.integrator.step(x, t[i], dt[i], rhs, self.noise_injection)
@@ -343,6 +347,11 @@ class VPScheduler(Scheduler):
         s = torch.arange(n).to(eps) / (n - 1)
         return 1 + s * (eps - 1)
 
+    def step_from_time(self, t: Tensor, n: int):
+        """Index of the schedule step at time t: the inverse of create_steps (schedulers.py:417-419)."""
+        step = (n - 1) * (t - 1) / (self.epsilon_min - 1)
+        return torch.round(step).int()
+
 
 class VEScheduler(Scheduler):
     def __init__(self, sigma_min: float = 0.02, sigma_max: float = 100, scheduler_fns="VE", *args, **kwargs):
@@ -356,3 +365,9 @@ class VEScheduler(Scheduler):
         smin, smax = self.sigma_min.detach().float().cpu(), self.sigma_max.detach().float().cpu()
         s = torch.arange(n).to(smin) / (n - 1)
         return smax ** 2 * (smin ** 2 / smax ** 2) ** s
+
+    def step_from_time(self, t: Tensor, n: int):
+        """Index of the schedule step at time t: the inverse of create_steps (schedulers.py:446-448)."""
+        step = (n - 1) * (torch.log(t) - torch.log(self.sigma_max ** 2)) / (torch.log(self.sigma_min ** 2) -
+                                                                          torch.log(self.sigma_max ** 2))
+        return torch.round(step).int()

@@ -176,9 +176,9 @@ class ADM(nn.Module):
         require_cuda(x, "ADM input")
         B = x.shape[0]
         ye = self.conditioning_vector(y, B)
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            from .graph import NetFunction
-            graph = self.train_graph(B, tuple(x.shape[2:]), x.device, cond=ye is not None)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .graph import NetFunction        # dropout acts only in training mode, as torch.nn.Dropout does
+            graph = self.train_graph(B, tuple(x.shape[2:]), x.device, cond=ye is not None, dropout=self.training)
             return NetFunction.apply(graph, x, t, None if ye is None else ye.contiguous(), *self.native_parameters())
         if self.training and float(getattr(self.config, "dropout", 0.0)) > 0.0:
             raise NotImplementedError("dropout > 0 acts on the training path (gradients enabled); call .eval() for inference")
@@ -200,17 +200,19 @@ class ADM(nn.Module):
                 plan = self._plans[key] = _ADMPlan(self, B, tuple(spatial), device, precision, sig)
         return plan
 
-    def train_graph(self, B: int, spatial: tuple, device, precision: Optional[str] = None, cond: bool = False):
+    def train_graph(self, B: int, spatial: tuple, device, precision: Optional[str] = None, cond: bool = False,
+                    dropout: bool = True):
         from .graph import build_adm
         precision = precision or self.precision
-        key = ("train", B, tuple(spatial), str(device), precision, bool(cond))
+        dropout = bool(dropout) and float(getattr(self.config, "dropout", 0.0)) > 0.0
+        key = ("train", B, tuple(spatial), str(device), precision, bool(cond), dropout)
         sig = tuple(p.data_ptr() for p in self.native_parameters())
         g = self._plans.get(key)
         if g is None or g.sig != sig:
             for k in [k for k in self._plans if k[0] == "train"]:
                 del self._plans[k]
             with torch.inference_mode(False), torch.no_grad():
-                g = self._plans[key] = build_adm(self, B, tuple(spatial), device, precision, cond=cond)
+                g = self._plans[key] = build_adm(self, B, tuple(spatial), device, precision, cond=cond, dropout=dropout)
         return g
 
     def _apply(self, fn, *a, **k):

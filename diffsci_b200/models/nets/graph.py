@@ -735,6 +735,8 @@ class TrainGraph:
             pc.packed()
 
     def run_forward(self):
+        # the saved activations live in this graph's static buffers: every forward invalidates the previous one's
+        self.generation = getattr(self, "generation", 0) + 1
         self.prepare()
         if self.dropout_sites:
             self.dropout_seed = (int(torch.randint(0, 2 ** 62, (1,)).item()) if self.fixed_dropout_seed is None
@@ -813,7 +815,7 @@ def time_blocks(g: TrainGraph, te: Var, tbs: list) -> list:
     return grouped_linear_layer(g, h, spec(4), False)
 
 
-def build_punetg(net, B: int, spatial: tuple, device, precision: str, cond: bool = False) -> TrainGraph:
+def build_punetg(net, B: int, spatial: tuple, device, precision: str, cond: bool = False, dropout: bool = True) -> TrainGraph:
     """PUNetG.forward (nets/punetg.py:389-416) unrolled into a TrainGraph.  cond: te + ye with ye an input [B, M] whose
     gradient is returned (the conditional embedding that produced it is trained by torch autograd around this graph)."""
     c = net.config
@@ -843,7 +845,7 @@ def build_punetg(net, B: int, spatial: tuple, device, precision: str, cond: bool
         n1 = g.norm(x, blk.gnorm1, C, c.first_resblock_norm, True)
         y = g.conv(n1, blk.conv1, chan_bias=tv, want_stats=True)
         n2 = g.norm(y, blk.gnorm2, C, c.second_resblock_norm, True)
-        if c.dropout > 0.0:                     # conv2(dropout(act(gnorm2(y)))), commonlayers.py:829-831
+        if c.dropout > 0.0 and dropout:         # conv2(dropout(act(gnorm2(y)))), commonlayers.py:829-831; off in eval mode
             n2 = g.dropout(n2, c.dropout, names[id(blk)])
         return g.conv(n2, blk.conv2, residual=x, want_stats=True)
 
@@ -872,7 +874,7 @@ def build_punetg(net, B: int, spatial: tuple, device, precision: str, cond: bool
     return g
 
 
-def build_adm(net, B: int, spatial: tuple, device, precision: str, cond: bool = False) -> TrainGraph:
+def build_adm(net, B: int, spatial: tuple, device, precision: str, cond: bool = False, dropout: bool = True) -> TrainGraph:
     """ADM.forward (nets/adm.py:199-216; block :292-343) unrolled into a TrainGraph.  cond: te = SiLU(mlp(fourier) + ye) with
     ye an input [B, output_embed_dim] whose gradient is returned (adm.py:1047-1053)."""
     c = net.config
@@ -914,7 +916,7 @@ def build_adm(net, B: int, spatial: tuple, device, precision: str, cond: bool = 
             n, xr = g.pool(n, False), g.pool(x, False)
         y = g.conv(n, blk.conv1, up2=up)
         h = g.norm(y, blk.norm2, G, c.second_resblock_norm, True, film=film_of[id(blk)])
-        if pdrop > 0.0:                         # conv2(dropout(SiLU(FiLM(norm2)))), adm.py:305-313
+        if pdrop > 0.0 and dropout:             # conv2(dropout(SiLU(FiLM(norm2)))), adm.py:305-313; off in eval mode
             h = g.dropout(h, pdrop, names[id(blk)])
         r = g.conv(xr, blk.convresidual, up2=up)
         o = g.conv(h, blk.conv2, residual=r)
@@ -968,15 +970,25 @@ class NetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, graph: TrainGraph, x: torch.Tensor, t: torch.Tensor, ye: Optional[torch.Tensor], *params):
         ctx.graph = graph
+        if x.requires_grad:
+            raise NotImplementedError("diffsci_b200: gradients with respect to the network INPUT are not built (the native "
+                                      "backward stops at the parameters and the conditioning vector); detach x")
         if (ye is None) != (graph.ye_in is None):
             raise RuntimeError("NetFunction: conditioning vector does not match the graph (build with cond=True)")
         if ye is not None:
             graph.ye_in.t.copy_(ye.detach().float())
-        return graph.forward_nchw(x, t)
+        out = graph.forward_nchw(x, t)
+        ctx.generation = graph.generation
+        return out
 
     @staticmethod
     def backward(ctx, dF):
         g = ctx.graph
+        if ctx.generation != g.generation:
+            raise RuntimeError(
+                "diffsci_b200: backward of a network call whose saved activations were overwritten by a later forward of the "
+                "same (batch, shape) training graph -- the graph keeps ONE set of activation buffers.  Call backward() before "
+                "the next forward (e.g. sum losses over separate backward passes), or run the extra forward under no_grad.")
         g.backward_nchw(dF)
         dye = None
         if g.ye_in is not None and ctx.needs_input_grad[3]:

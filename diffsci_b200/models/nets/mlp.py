@@ -40,7 +40,7 @@ class MLPUncond(nn.Module):
         require_cuda(x, "MLPUncond input")
         if self.training and self.dropout > 0:
             raise NotImplementedError("diffsci_b200.MLPUncond: training-mode dropout not built")
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .graph import NetFunction        # training: hand-written backward (graph.build_mlp)
             return NetFunction.apply(self.train_graph(x.shape[0], x.device), x, t, None, *self.parameters())
         plan = self.plan(x.shape[0], tuple(x.shape[1:]), x.device)

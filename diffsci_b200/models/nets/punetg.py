@@ -174,11 +174,12 @@ class PUNetG(nn.Module):
         B = x.shape[0]
         if self.ones_channel:
             x = torch.cat([x, torch.ones_like(x[:, :1])], dim=1)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            # training: static forward/backward launch lists with hand-written backward kernels (graph.py)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # gradients wanted (training, or eval-mode fine-tuning / diagnostics): static forward/backward launch lists with
+            # hand-written backward kernels (graph.py); dropout acts only in training mode, as torch.nn.Dropout does
             from .graph import NetFunction
             ye = self.conditioning_vector(y, B)
-            graph = self.train_graph(B, tuple(x.shape[2:]), x.device, cond=ye is not None)
+            graph = self.train_graph(B, tuple(x.shape[2:]), x.device, cond=ye is not None, dropout=self.training)
             return NetFunction.apply(graph, x, t, None if ye is None else ye.contiguous(), *self.native_parameters())
         if self.training and float(getattr(self.config, "dropout", 0.0)) > 0.0:
             raise NotImplementedError("dropout > 0 acts on the training path (gradients enabled); call .eval() for inference")
@@ -203,19 +204,22 @@ class PUNetG(nn.Module):
                 plan = self._plans[key] = _Plan(self, B, tuple(spatial), device, precision, sig)
         return plan
 
-    def train_graph(self, B: int, spatial: tuple, device, precision: Optional[str] = None, cond: bool = False):
+    def train_graph(self, B: int, spatial: tuple, device, precision: Optional[str] = None, cond: bool = False,
+                    dropout: bool = True):
         """The TrainGraph (forward + backward launch lists, saved activations, flat gradient buffer) of this shape.
-        cond: the graph takes a conditioning vector ye [B, M] (te + ye, punetg.py:410) and returns its gradient."""
+        cond: the graph takes a conditioning vector ye [B, M] (te + ye, punetg.py:410) and returns its gradient.
+        dropout=False: the graph of an eval-mode module (config.dropout inactive)."""
         from .graph import build_punetg
         precision = precision or self.precision
-        key = ("train", B, tuple(spatial), str(device), precision, bool(cond))
+        dropout = bool(dropout) and float(getattr(self.config, "dropout", 0.0)) > 0.0
+        key = ("train", B, tuple(spatial), str(device), precision, bool(cond), dropout)
         sig = tuple(p.data_ptr() for p in self.native_parameters())
         g = self._plans.get(key)
         if g is None or g.sig != sig:
             for k in [k for k in self._plans if k[0] == "train"]:
                 del self._plans[k]                                  # one training shape resident at a time
             with torch.inference_mode(False), torch.no_grad():
-                g = self._plans[key] = build_punetg(self, B, tuple(spatial), device, precision, cond=cond)
+                g = self._plans[key] = build_punetg(self, B, tuple(spatial), device, precision, cond=cond, dropout=dropout)
         return g
 
     def _apply(self, fn, *a, **k):

@@ -524,3 +524,38 @@ def test_engine_programs():
     assert E.GeneralSamplerEngine._program(object(), "heun", tab) == ((E.GSTAGE_HEUN_MID, E.GSTAGE_HEUN_FIN),) * 2
     assert set(E.GeneralSamplerEngine.programs) == {"euler", "heun", "euler-maruyama"}
     assert (E.GSTAGE_INIT, E.GSTAGE_STEP1, E.GSTAGE_HEUN_MID, E.GSTAGE_HEUN_FIN) == (0, 1, 2, 3) and _lib.STAGE_INIT == 0
+
+
+def test_step_from_time_inverts_create_steps():
+    """VP / VE / EDM schedulers: step_from_time(create_steps(n)[i], n) == i (reference schedulers.py:387-390, 417-419, 446-448)."""
+    import torch
+    from diffsci_b200.models.karras import schedulers as S
+    n = 17
+    for sch in (S.EDMScheduler(), S.VPScheduler(), S.VEScheduler()):
+        t = sch.create_steps(n)
+        idx = torch.arange(n - 1 if isinstance(sch, S.EDMScheduler) else n)
+        m = n - 1 if isinstance(sch, S.EDMScheduler) else n      # EDM appends t = 0 after its n-1 graded levels
+        got = sch.step_from_time(t[: len(idx)], m)
+        assert torch.equal(got.long(), idx), (type(sch).__name__, got)
+
+
+def test_integrator_noise_is_fresh_per_run_unless_pinned():
+    """a new integrator instance per sample() call must not replay one Brownian path; torch.manual_seed governs
+    the stream; reset_noise(seed=...) pins it."""
+    import torch
+    from diffsci_b200.models.karras import integrators as I
+    torch.manual_seed(5)
+    a = I.EulerMaruyamaIntegrator()
+    a.begin_run()
+    s1 = a.seed
+    b = I.EulerMaruyamaIntegrator()
+    b.begin_run()
+    assert b.seed != s1 and a._draws == 0
+    torch.manual_seed(5)
+    c = I.EulerMaruyamaIntegrator()
+    c.begin_run()
+    assert c.seed == s1                      # reproducible under torch.manual_seed
+    c.reset_noise(seed=123)
+    c._draws = 4
+    c.begin_run()
+    assert c.seed == 123 and c._draws == 4   # pinned: the caller owns the stream
