@@ -149,6 +149,57 @@ def build_workload(name, device, precision):
     return module, net, cfg, shape, nsteps, integ, batch, flops
 
 
+def live_reference_arm(name, steps, warmup, max_seconds=25.0):
+    """The UNMODIFIED reference -- its own PUNetG / MLPUncond modules (default init under torch.manual_seed(0)) inside its own
+    KarrasModule.propagate_white_noise (karras/karrasmodule.py:867-931) -- on the host cores, imported from oracle/_ref (a copy
+    of the reference's package, oracle/build_ref.py) or /root/reference.  Bounded sample: B = 1, two integrator steps,
+    extrapolated linearly in NFE.  Returns None when the reference is not importable (then the oracle port is timed).
+    No diffsci_b200 import, no .so load in this arm."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import refload
+        if refload.reference_root() is None:
+            return None
+        with stdout_to_stderr():
+            refload.load_reference()
+            import diffsci.models as M
+            from diffsci.models.nets.mlp import MLPUncond
+            from diffsci.models.nets.punetg import PUNetG
+            from diffsci.models.nets.punetg_config import PUNetGConfig
+    except Exception as e:                      # a missing optional dependency of the reference on this box
+        print(f"bench.py: live reference unavailable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+        return None
+    kind, kw, shape, nsteps, integ, _ = WORKLOADS[name]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = PUNetG(PUNetGConfig(**kw)) if kind == "punetg" else MLPUncond(kw["dim"], kw["hidden_dims"], nonlinearity=torch.nn.SiLU())
+    mod = M.KarrasModule(net.eval(), M.KarrasModuleConfig.from_edm())
+    mod.eval()
+    B, sub = (1, 2) if kind == "punetg" else (4096, nsteps)
+    if name == "c2":
+        B = 8
+    torch.manual_seed(1234)
+    wn = torch.randn(B, *shape)
+    nfe_sub = nfe_per_sample(sub, integ)
+    vals = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        mod.propagate_white_noise(wn, nsteps=sub, integrator=integ)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            vals.append(dt)
+        if sum(vals) > max_seconds and vals:
+            break
+    per_nfe = (sum(vals) / len(vals)) / (nfe_sub * B)
+    value = 1.0 / (per_nfe * nfe_per_sample(nsteps, integ))
+    sample = (f"the reference itself (diffsci.models.KarrasModule.propagate_white_noise, torch {torch.__version__} CPU fp32, "
+              f"{cores} threads), B={B}, {sub} {integ} steps = {nfe_sub} NFE timed {len(vals)}x, extrapolated linearly to "
+              f"{nfe_per_sample(nsteps, integ)} NFE")
+    return value, cores, sample, sum(vals) / len(vals), "reference", len(vals)
+
+
 def cpu_reference_arm(name, steps, warmup, max_seconds=25.0, ref_device="cpu", ref_mode="fp32", ref_batch=0):
     """The oracle port (torch-CPU restatement of the reference, oracle/*.py) timed on the host cores on a
     BOUNDED sample of the workload: B=1, a few integrator steps, extrapolated linearly in NFE.
@@ -157,6 +208,10 @@ def cpu_reference_arm(name, steps, warmup, max_seconds=25.0, ref_device="cpu", r
     (cuDNN / cuBLAS; ref_mode fp32 = TF32 off, tf32 = TF32 on, bf16 = autocast) -- the "reference on the box's
     PyTorch-CUDA path" SURVEY 8(d) asks for beside the CPU number."""
     import torch
+    if ref_device == "cpu" and not os.environ.get("DSK_BENCH_PORT_ONLY"):
+        live = live_reference_arm(name, steps, warmup, max_seconds)
+        if live is not None:
+            return live
     from oracle import karras_oracle as K, nets_oracle as N
     kind, kw, shape, nsteps, integ, _ = WORKLOADS[name]
     module, net, cfg, *_ = build_workload(name, None, "fp32")
@@ -191,7 +246,7 @@ def cpu_reference_arm(name, steps, warmup, max_seconds=25.0, ref_device="cpu", r
     value = 1.0 / (per_nfe * nfe_per_sample(nsteps, integ))          # samples/s, extrapolated linearly in NFE
     sample = (f"oracle port of the reference (torch {torch.__version__} CPU fp32), B={B}, {sub} {integ} steps = {nfe_sub} NFE "
               f"timed {len(vals)}x, extrapolated linearly to {nfe_per_sample(nsteps, integ)} NFE")
-    return value, cores, sample, sum(vals) / len(vals)
+    return value, cores, sample, sum(vals) / len(vals), "port", len(vals)
 
 
 def cuda_port_arm(name, steps, warmup, sd, cfg, mode, batch, max_seconds):
@@ -233,7 +288,7 @@ def cuda_port_arm(name, steps, warmup, sd, cfg, mode, batch, max_seconds):
     sample = (f"oracle port of the reference on torch {torch.__version__} CUDA ({mode}: cuDNN {torch.backends.cudnn.version()}, "
               f"benchmark=True), B={B}, {sub} {integ} steps = {nfe_sub} NFE timed {len(vals)}x, extrapolated linearly to "
               f"{nfe_per_sample(nsteps, integ)} NFE; {per_nfe * B * 1e3:.2f} ms per batched evaluation")
-    return value, 0, sample, sum(vals) / len(vals)
+    return value, 0, sample, sum(vals) / len(vals), "port-on-torch-cuda", len(vals)
 
 
 def build_train_workload(name, device, precision):
@@ -433,6 +488,9 @@ def main():
                     help="override the workload's integrator (sweeps; e.g. the Karras-churn variant of c5)")
     ap.add_argument("--precision", default=os.environ.get("DSK_BENCH_PRECISION", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the `train` object (c3train it/s in the same run)")
+    ap.add_argument("--no-modes", action="store_true", help="skip `precision_modes` / `parity` (other precision modes + checks)")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip `gpu_library_baseline` (oracle port on torch CUDA)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cuda = the oracle port on torch's cuDNN/cuBLAS path (side measurement)")
     ap.add_argument("--ref-mode", default="fp32", choices=["fp32", "tf32", "bf16"])
@@ -453,14 +511,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        value, cores, sample, secs = cpu_reference_arm(args.workload, max(1, args.steps), min(1, args.warmup),
-                                                       ref_device=args.ref_device, ref_mode=args.ref_mode, ref_batch=args.batch)
+        value, cores, sample, secs, rkind, reps = cpu_reference_arm(args.workload, max(1, args.steps), min(1, args.warmup),
+                                                                    ref_device=args.ref_device, ref_mode=args.ref_mode,
+                                                                    ref_batch=args.batch)
+        # `steps` = the repetitions actually timed (the arm stops after ~25 s of CPU work); ms_per_step = their mean
         line = {"impl": "reference", "metric": "EDM Heun samples/sec", "value": value, "unit": "samples/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3,
+                "n_gpus": args.gpus, "steps": reps, "steps_requested": args.steps, "warmup": min(1, args.warmup),
+                "ms_per_step": secs * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": NAMES[args.workload], "nsteps": nsteps, "nfe_per_sample": nfe},
-                "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores,
-                                 "kind": "port" if args.ref_device == "cpu" else "port-on-torch-cuda", "sample": sample},
+                "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": rkind, "sample": sample},
                 "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "nfe_per_s": value * nfe}
         print(json.dumps(line), flush=True)
@@ -479,24 +539,34 @@ def main():
             dist.barrier()
     precision = args.precision
     if precision == "auto":
-        precision = "bf16" if d.TC_CONV_ENABLED else "fp32"
+        # the fastest mode that meets north_star's 16-bit tolerance (denoiser within 1e-3 of the reference's fp32 result):
+        # fp16 operands with the activations split hi + lo (2 tcgen05 MMAs per k-step).  The other modes are measured in the
+        # same run and reported under `precision_modes`.
+        precision = "fp16x2" if d.TC_CONV_ENABLED else "fp32_ffma"
     module, net, cfg, shape, _, integ, _, flops_per_nfe = build_workload(args.workload, dev, precision)
     table_integrator = d.name_to_integrator(integ)
     N_el = B
     for s in shape:
         N_el *= s
+    from diffsci_b200 import distributed as dsk_dist
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def one_pass(wn):
+        """One step: the local shard through the public API, then the path's ONE collective -- the final all_gather of the
+        samples (distributed.gather_samples) -- so that every rank holds the global batch."""
+        local = module.propagate_white_noise(wn, nsteps=nsteps, integrator=table_integrator)
+        return dsk_dist.gather_samples(local, world * B)
+
     # ---------------------------------------------------------------- resident-input arm (`value`)
     torch.manual_seed(1234 + rank)
     wn_host = torch.randn(B, *shape).pin_memory()
     wn_dev = wn_host.to(dev)
     for _ in range(args.warmup):
-        module.propagate_white_noise(wn_dev, nsteps=nsteps, integrator=table_integrator)
+        one_pass(wn_dev)
     barrier()
     clocks = ClockSampler(local_rank) if rank == 0 else None
     if clocks:
@@ -507,7 +577,7 @@ def main():
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        module.propagate_white_noise(wn_dev, nsteps=nsteps, integrator=table_integrator)
+        one_pass(wn_dev)
     ev1.record()
     barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
@@ -520,18 +590,23 @@ def main():
     value = world * B * args.steps / (total_ms / 1e3)
 
     # ---------------------------------------------------------------- end-to-end arm (`e2e`)
-    out_host = torch.empty(B, *shape).pin_memory()
+    out_host = torch.empty(world * B, *shape).pin_memory()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = module.propagate_white_noise(wn_host, nsteps=nsteps, integrator=table_integrator)   # H2D inside
-        out_host.copy_(res, non_blocking=True)                                                     # D2H inside
+        res = one_pass(wn_host)                                   # H2D of the local white noise inside
+        out_host.copy_(res, non_blocking=True)                    # D2H of the gathered samples inside
         torch.cuda.synchronize(dev)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(e2e_s)
+
+    # ---------------------------------------------------------------- training throughput in the same run (`train`)
+    train = None
+    if args.workload == "c4" and not args.no_train:
+        train = train_measure(dev, rank, world, precision="bf16")
 
     if rank != 0:
         if world > 1:
@@ -550,24 +625,162 @@ def main():
 
     line = {"metric": "EDM Heun samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp16x2": "f16 (activations hi+lo)", "fp32": "f32 (split-f16 x3 on tcgen05)"}.get(precision, "f32"), "data": "synthetic",
+            "vs_baseline": None, "dtype": DTYPE_NAME.get(precision, "f32"), "data": "synthetic",
             "config": {"workload": NAMES[args.workload], "per_gpu_batch": B, "global_batch": world * B,
                        "integrator": integ, "nsteps": nsteps, "nfe_per_sample": nfe, "precision": precision,
                        "karras_config": args.karras_config,
-                       "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "parallelism": f"batch-sharded x{world} (distributed.py: no collective while integrating, ONE final "
+                                      f"all_gather of the samples, inside the timed region)",
                        "l2_policy": "inputs larger than L2: >100 GB of activation traffic per step vs 126 MB L2"},
             "nfe_per_s": value * nfe,
             "model_tflops": value * nfe * flops_per_nfe / 1e12,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": N_el * 4,
-                    "d2h_bytes_per_step": N_el * 4},
+                    "d2h_bytes_per_step": world * N_el * 4},
             "gpu_launches": int(eager_launches + graph_launches),
             "clocks": clk, "roofline": roofline}
+    if train is not None:
+        line["train"] = train
+    if world == 1 and kind == "punetg" and not args.no_modes:
+        try:
+            line["precision_modes"], line["parity"] = precision_modes_and_parity(args, module, net, cfg, shape, B, nsteps, nfe,
+                                                                                 integ, precision, value, dev)
+        except Exception as e:                     # the side measurements must never cost the headline line
+            line["precision_modes_error"] = f"{type(e).__name__}: {e}"
+        if not args.no_library_baseline:
+            try:
+                line["gpu_library_baseline"] = library_baseline(args.workload, net, cfg)
+            except Exception as e:
+                line["gpu_library_baseline_error"] = f"{type(e).__name__}: {e}"
     if not args.no_cpu_baseline and world == 1:
-        v, cores, sample, _ = cpu_reference_arm(args.workload, 1, 1)
-        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+        v, cores, sample, _, rkind, _ = cpu_reference_arm(args.workload, 1, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": rkind, "sample": sample}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+DTYPE_NAME = {"bf16": "bf16", "fp16": "f16", "fp16x2": "f16 (activations hi+lo, 2 MMAs per k-step; fp32 storage)",
+              "fp32": "f32 (split-f16 x3 on tcgen05)", "fp32_ffma": "f32"}
+
+
+def train_measure(dev, rank, world, precision="bf16", workload="c3train", steps=10, warmup=3):
+    """BASELINE.json's "train it/s" in the same run: ADM 3x128x128 EDM training iterations (configs[2]) through
+    EDMTrainer.step on every rank -- noising, forward, fused loss, backward with the bucketed NCCL all-reduce of the flat fp32
+    gradient (N > 1), fused AdamW + EMA -- timed on the device, max over ranks.  Weak scaling: batch 32 per GPU."""
+    import torch
+    import torch.distributed as dist
+    import diffsci_b200 as d
+    kind, kw, shape, metric, batch, _ = TRAIN_WORKLOADS[workload]
+    module, net, cfg, shape, metric, _, flops = build_train_workload(workload, dev, precision)
+    tr = d.EDMTrainer(module, ema=d.ModelEMA(net, ema_type="traditional", decay=0.999))
+    torch.manual_seed(2 + rank)
+    xs = [(torch.randn(batch, *shape) * 0.5).to(dev) for _ in range(4)]
+    for i in range(warmup):
+        tr.step(xs[i % 4])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = tr.step(xs[i % 4])
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    its = steps / (float(ms) / 1e3)
+    out = {"metric": "EDM train it/s", "workload": TRAIN_NAMES[workload], "value": its, "unit": "it/s", "steps": steps,
+           "warmup": warmup, "ms_per_step": float(ms) / steps, "per_gpu_batch": batch, "global_batch": batch * world,
+           "samples_per_s": its * batch * world, "precision": precision, "final_loss": float(loss),
+           "model_tflops": 3.0 * flops * batch * world * its / 1e12,
+           "parallelism": f"data-parallel x{world}, bucketed NCCL all-reduce of the flat fp32 gradient overlapped with backward"}
+    del tr, module, net
+    torch.cuda.empty_cache()
+    return out
+
+
+def precision_modes_and_parity(args, module, net, cfg, shape, B, nsteps, nfe, integ, default_prec, default_value, dev):
+    """(1) samples/s of the same workload in the other precision modes (one warm pass + one timed pass each);
+    (2) `parity`: the denoiser D(x; sigma) of every mode against the CPU oracle's fp32 evaluation (= the reference's
+    arithmetic) on one full-size sample, and the sampled field of the benchmarked mode after the workload's real step count
+    against the tensor-core fp32 mode on the same x_T, per pixel."""
+    import types
+    import torch
+    import diffsci_b200 as d
+    from oracle import karras_oracle as K, nets_oracle as N
+    integrator = d.name_to_integrator(integ)
+    modes = [{"precision": default_prec, "value": default_value, "unit": "samples/s", "timed_passes": args.steps}]
+    torch.manual_seed(4321)
+    wn = torch.randn(B, *shape).to(dev)
+    for prec in ("bf16", "fp16", "fp16x2", "fp32"):
+        if prec == default_prec:
+            continue
+        net.precision = prec
+        module.propagate_white_noise(wn, nsteps=nsteps, integrator=integrator)         # plan + graph capture + warm-up
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        module.propagate_white_noise(wn, nsteps=nsteps, integrator=integrator)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        modes.append({"precision": prec, "value": B / (e0.elapsed_time(e1) / 1e3), "unit": "samples/s", "timed_passes": 1})
+        module._engines.clear()
+        net._plans.clear()
+        torch.cuda.empty_cache()
+    # ---- parity: denoiser
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    ocfg = types.SimpleNamespace(**cfg.export_description())
+    torch.manual_seed(99)
+    sigma = torch.tensor([1.0])
+    x = torch.randn(1, *shape) * 1.5
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = K.denoiser(lambda xx, tt: N.punetg_forward(sd, ocfg, xx, tt), x, sigma)
+    den = {}
+    for m in modes:
+        net.precision = m["precision"]
+        with torch.no_grad():
+            D, _ = module.get_denoiser(x.to(dev), sigma.to(dev))
+        e = (D.cpu().double() - ref.double())
+        m["denoiser_max_rel"] = den[m["precision"]] = float(e.abs().max() / ref.double().abs().max())
+        m["denoiser_rel_l2"] = float(e.norm() / ref.double().norm())
+    # ---- parity: sampled field after the real step count, benchmarked mode vs tensor-core fp32 mode, same x_T, B = 1
+    torch.manual_seed(77)
+    w1 = torch.randn(1, *shape).to(dev)
+    fields = {}
+    for prec in ("fp32", default_prec):
+        net.precision = prec
+        it_ = d.name_to_integrator(integ)
+        it_.reset_noise(seed=12345)
+        fields[prec] = module.propagate_white_noise(w1, nsteps=nsteps, integrator=it_).double().cpu()
+    net.precision = default_prec
+    diff = (fields[default_prec] - fields["fp32"]).abs()
+    frms = float(fields["fp32"].pow(2).mean().sqrt())
+    parity = {"denoiser": {"reference": "CPU oracle (torch CPU fp32 restatement of the reference, pinned against the live "
+                                        "reference by tests/golden), one full-size sample, sigma = 1",
+                           "max_rel": den, "tolerance": {"fp32": 1e-5, "fp16x2": 1e-3},
+                           "benchmarked_mode_within_tolerance": bool(den[default_prec] <= 1e-3)},
+              "sampled_field": {"what": f"{integ}-{nsteps} ({nfe} NFE), B = 1, precision {default_prec} vs the tensor-core fp32 mode "
+                                        f"on the same x_T (that mode vs the LIVE reference at full length: "
+                                        f"tests/test_gpu_fullsteps.py)",
+                                "per_pixel_max_abs": float(diff.max()), "per_pixel_rms": float(diff.pow(2).mean().sqrt()),
+                                "field_rms": frms, "rms_over_field_rms": float(diff.pow(2).mean().sqrt()) / frms}}
+    return modes, parity
+
+
+def library_baseline(workload, net, cfg):
+    """The oracle port of the reference on torch's OWN CUDA path on this GPU (cuDNN convolutions, cuBLAS / SDPA attention;
+    TF32 and autocast-bf16) -- SURVEY 8d's "honest GPU baseline", measured in the same run on a bounded sample."""
+    import types
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    ocfg = types.SimpleNamespace(**cfg.export_description())
+    out = {}
+    for mode in ("tf32", "bf16"):
+        v, _, sample, _, _, _ = cuda_port_arm(workload, 2, 3, sd, ocfg, mode, 8, 10.0)
+        out[mode] = {"value": v, "unit": "samples/s", "sample": sample}
+    return out
 
 
 KERNEL_KIND = {}
@@ -617,9 +830,15 @@ def dominant_conv_roofline(cfg, shape, B, precision, dev, peaks, reps=20):
     # `ncu --set full` capture (profiles/r1q_conv_tc2_64x64_64cube_B8_ncu_full.txt); scaled by batch (the kernel reads its
     # input once and writes its output once: traffic is linear in the number of samples); null for other shapes
     traffic, traffic_src = None, None
-    if nd == 3 and M == 64 and tuple(sp) == (64, 64, 64) and wd == torch.bfloat16 and False:
-        traffic = 490.4e6 * B / 8.0
-        traffic_src = "ncu --set full, profiles/r1q_conv_tc2_64x64_64cube_B8_ncu_full.txt (268.8 MB read + 221.6 MB written at B=8)"
+    try:            # measured, not hard-coded: profiles/conv_traffic.json is written by tools/conv_traffic_from_ncu.py from the
+        #             committed `ncu --set full` captures of THIS kernel at HEAD (per precision mode)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json")))
+        e = tj.get(f"conv{nd}d_{M}x{M}_" + "x".join(map(str, sp[-nd:])), {}).get(precision)
+        if e:
+            traffic = (e["dram_bytes_read"] + e["dram_bytes_write"]) * B / e["batch"]
+            traffic_src = e["source"]
+    except Exception:
+        pass
     peak = peaks.get("bf16_tflops")
     src = "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
     if peak is None:

@@ -113,11 +113,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   __shared__ uint32_t tmem_base_s;
   constexpr uint32_t TMEM_COLS = 2 * P * N_TILE;        // double-buffered accumulators
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
-  // accumulator sets per tile: 1 (plain), 2 (hh | lo; activations-split mode) -- both double-buffered -- or 4 (three hh sets
-  // + lo; fp32-parity mode): 4 * P * 64 = 512 columns, single-buffered.  Host: N_TILE <= 64 when nsets > 1.
+  // accumulator sets per tile: 1 (plain), 2 (hh | lo; activations-split mode) or 4 (three hh sets + lo; fp32-parity mode,
+  // N_TILE = 64 only).  Double-buffered across tiles when two buffers fit the 512 TMEM columns (1 set; 2 sets at N_TILE = 64),
+  // else single-buffered (the epilogue of a tile then runs between its MMAs and the next tile's).
   const int nsets = p.nsets;
   constexpr uint32_t SET_COLS = P * N_TILE;             // columns of one accumulator set
-  const uint32_t nbuf = nsets == 4 ? 1u : 2u, buf_cols = nsets * SET_COLS, tmem_cols = nbuf * buf_cols;
+  const uint32_t buf_cols = nsets * SET_COLS, nbuf = 2 * buf_cols <= 512 ? 2u : 1u, tmem_cols = nbuf * buf_cols;
   const uint32_t lo_set = nsets - 1, nhh = nsets > 1 ? nsets - 1 : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -491,11 +492,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   __shared__ uint4 stage_s[8][32 * 4];                  // per epilogue warp: 32 rows x 64 B (coalescing stage of the stores)
   constexpr uint32_t TMEM_COLS = 2 * P * N_TILE;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
-  // accumulator sets per tile: 1 (plain), 2 (hh | lo; activations-split mode) -- both double-buffered -- or 4 (three hh sets
-  // + lo; fp32-parity mode): 4 * P * 64 = 512 columns, single-buffered.  Host: N_TILE <= 64 when nsets > 1.
+  // accumulator sets per tile: 1 (plain), 2 (hh | lo; activations-split mode) or 4 (three hh sets + lo; fp32-parity mode,
+  // N_TILE = 64 only).  Double-buffered across tiles when two buffers fit the 512 TMEM columns (1 set; 2 sets at N_TILE = 64),
+  // else single-buffered (the epilogue of a tile then runs between its MMAs and the next tile's).
   const int nsets = p.nsets;
   constexpr uint32_t SET_COLS = P * N_TILE;             // columns of one accumulator set
-  const uint32_t nbuf = nsets == 4 ? 1u : 2u, buf_cols = nsets * SET_COLS, tmem_cols = nbuf * buf_cols;
+  const uint32_t buf_cols = nsets * SET_COLS, nbuf = 2 * buf_cols <= 512 ? 2u : 1u, tmem_cols = nbuf * buf_cols;
   const uint32_t lo_set = nsets - 1, nhh = nsets > 1 ? nsets - 1 : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -771,6 +773,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
           for (int g = 0; g < 4; ++g) rr[gg][g] = *reinterpret_cast<const uint4*>(rrow + gg * 32 + g * 8);
       }
+      if constexpr (DEP == 2) {
+        // fp32 residual: the same 32 registers hold ONE 32-channel group (8 float4), requested before the accumulator wait and
+        // refilled with the next group while the current one is stored / reduced
+        if (rrow32 != nullptr) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) rr[k >> 2][k & 3] = *reinterpret_cast<const uint4*>(rrow32 + k * 4);
+        }
+      }
       if (p.residual != nullptr && u + nclusters < total_pairs) {
         // the residual rows of the NEXT tile start their trip from HBM now (one tile time ahead, no registers held)
         const TileCoord tn = tile_coord2(p, u + nclusters, rank, N_TILE, P);
@@ -827,12 +837,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             for (int g = 0; g < 4; ++g) rr[gi % DEP][g] = *reinterpret_cast<const uint4*>(rrow + (gi + DEP) * 32 + g * 8);
           }
         }
-        if (rrow32 != nullptr) {
-          const float4* rf = reinterpret_cast<const float4*>(rrow32 + c0);
+        if constexpr (DEP == 2) {
+          if (rrow32 != nullptr) {
 #pragma unroll
-          for (int e4 = 0; e4 < 8; ++e4) {
-            const float4 r = rf[e4];
-            f[4 * e4] += r.x; f[4 * e4 + 1] += r.y; f[4 * e4 + 2] += r.z; f[4 * e4 + 3] += r.w;
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const uint4 r = rr[e4 >> 2][e4 & 3];
+              f[4 * e4] += __uint_as_float(r.x); f[4 * e4 + 1] += __uint_as_float(r.y);
+              f[4 * e4 + 2] += __uint_as_float(r.z); f[4 * e4 + 3] += __uint_as_float(r.w);
+            }
+            if (gi + 1 < NG) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) rr[k >> 2][k & 3] = *reinterpret_cast<const uint4*>(rrow32 + (gi + 1) * 32 + k * 4);
+            }
           }
         }
         if (of32) {
@@ -1220,8 +1236,8 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   }
   const int nphase = d->up2 ? (KD == 3 ? 8 : 4) : 1;
   const int ntaps = d->up2 ? nphase * (KD == 3 ? 8 : 4) : KD * 9;     // weight rows: [phase][tap][Cout] or [tap][Cout]
-  // split operands: four accumulator sets of P * 64 columns fill the TMEM -> 64-channel tiles only
-  const int n_tile = few_out ? 16 : ((d->Cout % 128 == 0 && !a_split) ? 128 : 64);
+  // fully split operands: four accumulator sets of P * 64 columns fill the TMEM -> 64-channel tiles only
+  const int n_tile = few_out ? 16 : ((d->Cout % 128 == 0 && !(a_split && w_split)) ? 128 : 64);
   const int w_rows = few_out ? 16 : d->Cout;                          // few_out weights are zero-padded to 16 output channels
   {
     cuuint64_t dims[2] = {(cuuint64_t)w_ld, (cuuint64_t)ntaps * w_rows};

@@ -310,7 +310,7 @@ class _ADMPlan:
         out = self.buf(("attn_out", idx), x.shape)
         tc = self.act_dtype in ops.H16 and _tc_eligible(C, C) and Lq % 8 == 0 and Lq <= 8192
         f32 = torch.float32
-        if self.precision == "fp32" and _tc_eligible(C, C) and Lq % 64 == 0 and Lq <= 8192:
+        if self.split and _tc_eligible(C, C) and Lq % 64 == 0 and Lq <= 8192:
             st = self.attn_state.get(idx)
             if st is None:
                 st = self.attn_state[idx] = (ops.PackedLinear(m.in_proj_weight, ops.SPLIT), ops.PackedLinear(m.out_proj.weight, ops.SPLIT))

@@ -350,7 +350,7 @@ class _Plan:
         Cb = ch[nlev]
         self.attn = None
         self.attn_tc = (adt in ops.H16 and _tc_eligible(Cb, Cb) and Lq % 8 == 0 and Lq <= 8192)
-        self.attn_split = (precision == "fp32" and _tc_eligible(Cb, Cb) and Lq % 64 == 0 and Lq <= 8192)
+        self.attn_split = (split and _tc_eligible(Cb, Cb) and Lq % 64 == 0 and Lq <= 8192)
         self.attn_hybrid = False
         if len(net.attn_block) > 0 and self.attn_split:
             self.attn = ops.attention_split_buffers(B, Lq, Cb, dev)

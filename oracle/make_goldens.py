@@ -586,7 +586,73 @@ def nobias_goldens():
               "convin", [s_ for k, s_ in man if k == "convin.weight"])
 
 
+def fullsteps_goldens(which=("c1", "c2", "c5", "c4")):
+    """BASELINE.json's configurations at their REAL step counts through the LIVE reference's own sampling loop
+    (KarrasModule.propagate_white_noise, karrasmodule.py:867-931; Scheduler.propagate, schedulers.py:48-89) on CPU, fp32 and --
+    for the tolerance budget -- fp64:
+      c1  MLPUncond(2, [128, 128, 128], SiLU), Heun 18 steps, B = 64
+      c2  PUNetG 2-D mc = 128, 1 x 28 x 28, Heun 40 steps, B = 2
+      c4  PUNetG 3-D mc = 64, 1 x 64^3, Heun 64 steps, B = 1                 (138 TFLOP per precision: ~15 / 30 min here)
+      c5  PUNetG 2-D mc = 64, 1 x 256 x 256, Euler-Maruyama 256 steps, B = 1, step noise from a seeded CPU generator
+    Weights are synth_state_dict(manifest, seed) (not stored), x_T = randn under torch.manual_seed (not stored either: the test
+    regenerates it with the same CPU generator).   python oracle/make_goldens.py --only fullsteps [c1 c2 c5 c4]"""
+    os.makedirs(OUT, exist_ok=True)
+    refload.load_reference()
+    import diffsci.models as M
+    from diffsci.models.nets.mlp import MLPUncond
+    from diffsci.models.nets.punetg import PUNetG
+    from diffsci.models.nets.punetg_config import PUNetGConfig
+    torch.set_num_threads(os.cpu_count())
+    cases = {
+        "c1": dict(net="mlp", kw=dict(dim=2, hidden_dims=[128, 128, 128]), shape=(64, 2), nsteps=18, integ="heun", wseed=501,
+                   xseed=601),
+        "c2": dict(net="punetg", kw=dict(dimension=2, model_channels=128), shape=(2, 1, 28, 28), nsteps=40, integ="heun",
+                   wseed=502, xseed=602),
+        "c5": dict(net="punetg", kw=dict(dimension=2), shape=(1, 1, 256, 256), nsteps=256, integ="euler-maruyama", wseed=505,
+                   xseed=605, nseed=705),
+        "c4": dict(net="punetg", kw=dict(dimension=3), shape=(1, 1, 64, 64, 64), nsteps=64, integ="heun", wseed=504, xseed=604),
+    }
+    import time
+    for name in which:
+        c = cases[name]
+        if c["net"] == "mlp":
+            net = MLPUncond(c["kw"]["dim"], c["kw"]["hidden_dims"], nonlinearity=torch.nn.SiLU())
+        else:
+            net = PUNetG(PUNetGConfig(**c["kw"]))
+        man = load_synth(net, c["wseed"])
+        net.eval()
+        mod = M.KarrasModule(net, M.KarrasModuleConfig.from_edm())
+        mod.eval()
+        torch.manual_seed(c["xseed"])
+        wn = torch.randn(*c["shape"])
+        noises = None
+        if "nseed" in c:
+            g = torch.Generator().manual_seed(c["nseed"])
+            noises = [torch.randn(c["shape"], generator=g) for _ in range(c["nsteps"])]
+        out = {}
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            m = mod.double() if dt == torch.float64 else mod
+            t0 = time.time()
+            with torch.no_grad():
+                if noises is None:
+                    y = m.propagate_white_noise(wn.to(dt), nsteps=c["nsteps"], integrator=c["integ"])
+                else:
+                    with _Noise(noises):
+                        y = m.propagate_white_noise(wn.to(dt), nsteps=c["nsteps"], integrator=c["integ"])
+            out[tag] = y.detach()
+            print(f"fullsteps {name} {tag}: {time.time() - t0:.1f} s, |y|max {float(y.abs().max()):.4f}", flush=True)
+            torch.save(dict(kw=c["kw"], net=c["net"], manifest=man, wseed=c["wseed"], xseed=c["xseed"], nseed=c.get("nseed"),
+                            shape=c["shape"], nsteps=c["nsteps"], integrator=c["integ"],
+                            out_f32=out.get("f32"), out_f64=out.get("f64")), os.path.join(OUT, f"fullsteps_{name}.pt"))
+        d = (out["f32"].double() - out["f64"]).abs()
+        print(f"fullsteps {name}: reference fp32 vs fp64 max-abs {float(d.max()):.3e} rms {float(d.pow(2).mean().sqrt()):.3e} "
+              f"(field rms {float(out['f64'].pow(2).mean().sqrt()):.3e})", flush=True)
+
+
 def main():
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "fullsteps":
+        rest = [a for a in sys.argv[sys.argv.index("--only") + 2:] if not a.startswith("-")]
+        return fullsteps_goldens(tuple(rest) if rest else ("c1", "c2", "c5", "c4"))
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "nobias":
         return nobias_goldens()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "dropout":

@@ -1,9 +1,9 @@
-"""Import the *live* DiffSci reference from /root/reference (build container only).
+"""Import the *live* DiffSci reference: from /root/reference in the build container, else from the copy under oracle/_ref/
+(oracle/build_ref.py; git-ignored, shipped to the GPU box by gpurun).
 
-TEST INFRASTRUCTURE -- not product code.  Only ``oracle/make_goldens.py`` uses this
-module, and only inside the build container: ``/root/reference`` does not exist on the
-GPU box, so nothing under ``tests/ -m gpu``, ``bench.py`` or ``__graft_entry__`` may
-import it.
+TEST / BENCH INFRASTRUCTURE -- not product code.  Users: ``oracle/make_goldens.py`` (golden vectors, build container) and
+``bench.py``'s reference arm / ``cpu_baseline`` leg (the unmodified reference timed on the host cores).  Nothing under
+``diffsci_b200/`` imports it, and no ``-m gpu`` test or ``smoke()`` reads /root/reference.
 
 The reference eagerly imports ``lightning``, ``diffusers`` and ``matplotlib`` (none of
 which are installed here).  They are irrelevant to the Karras/EDM
@@ -18,6 +18,15 @@ import types
 import torch
 
 REFERENCE_ROOT = "/root/reference"
+REF_COPY_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def reference_root():
+    """Directory that holds the reference's ``diffsci`` package, or None."""
+    for root in (REFERENCE_ROOT, REF_COPY_ROOT):
+        if os.path.isdir(os.path.join(root, "diffsci")):
+            return root
+    return None
 
 
 def _stub_lightning() -> None:
@@ -90,12 +99,14 @@ def _stub_misc() -> None:
 
 def load_reference():
     """Return the imported ``diffsci`` package of the reference (CPU, fp32)."""
-    if not os.path.isdir(REFERENCE_ROOT):
-        raise RuntimeError(f"{REFERENCE_ROOT} is not present (only exists in the build container)")
+    root = reference_root()
+    if root is None:
+        raise RuntimeError(f"neither {REFERENCE_ROOT} nor {REF_COPY_ROOT} holds the reference (run oracle/build_ref.py in the "
+                           "build container)")
     _stub_lightning()
     _stub_misc()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import diffsci.models  # noqa: F401
     import diffsci  # noqa: F401
     return sys.modules["diffsci"]

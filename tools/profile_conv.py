@@ -18,13 +18,18 @@ ap.add_argument("--cout", type=int, default=64)
 ap.add_argument("--reps", type=int, default=6)
 ap.add_argument("--stats", action="store_true")
 ap.add_argument("--residual", action="store_true")
+ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp16x2", "fp32"])
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 w = torch.randn(a.cout, a.cin, 3, 3, 3, device=dev) * 0.02
-pc = ops.PackedConv(w, torch.zeros(a.cout, device=dev), 3, torch.bfloat16)
-xs = [torch.randn(a.batch, a.size, a.size, a.size, a.cin, device=dev).bfloat16() for _ in range(3)]
-out = torch.empty(a.batch, a.size, a.size, a.size, a.cout, device=dev, dtype=torch.bfloat16)
+wdt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp16x2": torch.float16, "fp32": ops.SPLIT}[a.precision]
+adt = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(a.precision, torch.float32)
+pc = ops.PackedConv(w, torch.zeros(a.cout, device=dev), 3, wdt)
+xs = [torch.randn(a.batch, a.size, a.size, a.size, a.cin, device=dev).to(adt) for _ in range(3)]
+if adt == torch.float32:
+    xs = [ops.split_f16(x) for x in xs]          # split-fp16 activations (hi | lo), fp32 output
+out = torch.empty(a.batch, a.size, a.size, a.size, a.cout, device=dev, dtype=adt)
 st = ops.conv_stats_buffer(a.batch, a.cout, dev) if a.stats else None
 res = torch.randn_like(out) if a.residual else None
 for i in range(3):
@@ -38,4 +43,4 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.reps
 fl = 2.0 * a.batch * a.size ** 3 * a.cin * a.cout * 27
-print(f"conv3d {a.cin}->{a.cout} @ {a.size}^3 B={a.batch} stats={a.stats} residual={a.residual}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s")
+print(f"conv3d {a.precision} {a.cin}->{a.cout} @ {a.size}^3 B={a.batch} stats={a.stats} residual={a.residual}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s")
