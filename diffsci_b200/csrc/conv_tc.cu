@@ -57,6 +57,7 @@ struct TcParams {
   // (DSK_SPLIT_F16), out of fp16's subnormal range -- go to a fourth, and the epilogue adds the four in fp32 (round to
   // nearest):  acc = (s0 + s1 + s2) + 2^-11 * s3.  The four sets occupy all 512 TMEM columns: no double buffering.
   int nsets;
+  int dbg;                // DSK_CONV_DBG (measurements only): 1 = epilogue frees the accumulators without reading / storing them
   int planes_per_sample;  // D for 3-D; 1 for 2-D  (chan_bias row = plane / planes_per_sample)
   int cout_real;          // N_TILE = 16 path (convout): the first cout_real (<= 16) channels are real, the rest zero padding
   float* out_nchw;        // N_TILE = 16 path: fp32 NC(D)HW output (user layout) instead of channels-last bf16
@@ -70,15 +71,15 @@ struct TcParams {
 };
 constexpr int TC_STAT_SLOTS = DSK_NUM_SMS;          // one slot per CTA
 constexpr float kLoScale = 1.0f / 2048.0f;          // 2^-11: the lo half of a split operand is stored times 2^11
-// channel coordinate (activation tensor map / weight tensor map) of virtual chunk vc
-__device__ __forceinline__ int vchunk_a(const TcParams& p, int vc) {
-  const int c = vc / p.vparts, part = vc - c * p.vparts;
-  return c * 64 + ((p.vparts > 1 && part == p.vparts - 1) ? p.a_lo_off : 0);
-}
-__device__ __forceinline__ int vchunk_w(const TcParams& p, int vc) {
-  const int c = vc / p.vparts, part = vc - c * p.vparts;
-  return c * 64 + ((p.vparts == 3 && part == 1) ? p.w_lo_off : 0);
-}
+// Virtual K chunks in issue order: (real 64-channel chunk c, part) with part fastest.  A counter pair instead of vc / vparts:
+// an integer division per tap in the MMA issue path costs more than the tap's MMAs take to execute.
+struct VChunk {
+  int c = 0, part = 0;
+  __device__ __forceinline__ void next(const TcParams& p) { if (++part == p.vparts) { part = 0; ++c; } }
+  // channel coordinate in the activation / weight tensor map
+  __device__ __forceinline__ int a(const TcParams& p) const { return c * 64 + ((p.vparts > 1 && part == p.vparts - 1) ? p.a_lo_off : 0); }
+  __device__ __forceinline__ int w(const TcParams& p) const { return c * 64 + ((p.vparts == 3 && part == 1) ? p.w_lo_off : 0); }
+};
 
 struct TileCoord {
   int w0, h0, d0, b, n0;
@@ -151,7 +152,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       uint32_t seq = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = tile_coord(p, t, N_TILE, P);
-        for (int c = 0; c < nchunks; ++c)
+        VChunk vc;
+        for (int c = 0; c < nchunks; ++c, vc.next(p))
           for (int j = 0; j < NJ; ++j, ++seq) {
             const uint32_t slot = seq % NA, ph = (seq / NA) & 1;
             mbar_wait(&empty_a[slot], ph ^ 1);
@@ -159,7 +161,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             asm volatile(
                 "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
                     smem_u32(sA + (size_t)slot * TC_PATCH_STRIDE)),
-                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(vchunk_a(p, c)), "r"(tc.w0 - 1 + p.pad_hw), "r"(tc.h0 - 1 + p.pad_hw), "r"(tc.d0 + j - dpad + p.pad_d), "r"(tc.b),
+                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(vc.a(p)), "r"(tc.w0 - 1 + p.pad_hw), "r"(tc.h0 - 1 + p.pad_hw), "r"(tc.d0 + j - dpad + p.pad_d), "r"(tc.b),
                 "r"(smem_u32(&full_a[slot]))
                 : "memory");
           }
@@ -173,7 +175,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = tile_coord(p, t, N_TILE, P);
         const int tap_base = UPS ? tc.phase * ntaps : 0;
-        for (int c = 0; c < nchunks; ++c)
+        VChunk vc;
+        for (int c = 0; c < nchunks; ++c, vc.next(p))
           for (int tap = tap_base; tap < tap_base + ntaps; ++tap, ++seq) {
             const uint32_t slot = seq % NB, ph = (seq / NB) & 1;
             mbar_wait(&empty_b[slot], ph ^ 1);
@@ -181,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                     smem_u32(sB + (size_t)slot * B_BYTES)),
-                "l"(reinterpret_cast<uint64_t>(&tmapW)), "r"(vchunk_w(p, c)), "r"(tap * p.Cout + tc.n0), "r"(smem_u32(&full_b[slot]))
+                "l"(reinterpret_cast<uint64_t>(&tmapW)), "r"(vc.w(p)), "r"(tap * p.Cout + tc.n0), "r"(smem_u32(&full_b[slot]))
                 : "memory");
           }
       }
@@ -198,6 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_acc = tmem_base + as * buf_cols;
       uint32_t used = 0, hh = 0;                         // accumulator sets written in this tile; round-robin counter
+      int part = 0;                                      // part of the current virtual chunk (0: hi * hi)
       const TileCoord tc = tile_coord(p, t, N_TILE, P);
       for (int c = 0; c < nchunks; ++c) {
         const uint32_t seq_c = seq_a;                    // first patch of this (tile, chunk)
@@ -219,7 +223,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
               const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_BYTES));
               const uint32_t tap_off = (kh * TC_PW + kw) * 8;
               uint32_t set = 0;                                 // accumulator set of this tap's MMAs
-              if (nsets > 1) { if (c % p.vparts) set = lo_set; else { set = hh; hh = hh + 1 == nhh ? 0 : hh + 1; } }
+              if (nsets > 1) { if (part) set = lo_set; else { set = hh; hh = hh + 1 == nhh ? 0 : hh + 1; } }
               const uint32_t first = (used >> set) & 1u;
               used |= 1u << set;
               const uint32_t acc_set = tmem_acc + set * SET_COLS;
@@ -260,7 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_BYTES));
             const uint32_t tap_off = ((khw / 3) * TC_PW + (khw % 3)) * 8;      // (kh*10 + kw) * 128 B >> 4
             uint32_t set = 0;                                 // accumulator set of this tap's MMAs
-            if (nsets > 1) { if (c % p.vparts) set = lo_set; else { set = hh; hh = hh + 1 == nhh ? 0 : hh + 1; } }
+            if (nsets > 1) { if (part) set = lo_set; else { set = hh; hh = hh + 1 == nhh ? 0 : hh + 1; } }
             const uint32_t first = (used >> set) & 1u;
             used |= 1u << set;
             const uint32_t acc_set = tmem_acc + set * SET_COLS;
@@ -285,6 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         }
         }
         seq_a += NJ;
+        if (++part == p.vparts) part = 0;
       }
       if (elect_one_sync()) umma_commit(&acc_full[as]);
       __syncwarp();
@@ -535,7 +540,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       uint32_t seq = 0;
       for (int u = cluster_id; u < total_pairs; u += nclusters) {
         const TileCoord tc = tile_coord2(p, u, rank, N_TILE, P);
-        for (int c = 0; c < nchunks; ++c)
+        VChunk vc;
+        for (int c = 0; c < nchunks; ++c, vc.next(p))
           for (int j = 0; j < NJ; ++j, ++seq) {
             const uint32_t slot = seq % NA, ph = (seq / NA) & 1;
             mbar_wait(&empty_a[slot], ph ^ 1);
@@ -543,7 +549,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             asm volatile(
                 "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
                     smem_u32(sA + (size_t)slot * TC_PATCH_STRIDE)),
-                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(vchunk_a(p, c)), "r"(tc.w0 - 1 + p.pad_hw), "r"(tc.h0 - 1 + p.pad_hw), "r"(tc.d0 + j - dpad + p.pad_d), "r"(tc.b),
+                "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(vc.a(p)), "r"(tc.w0 - 1 + p.pad_hw), "r"(tc.h0 - 1 + p.pad_hw), "r"(tc.d0 + j - dpad + p.pad_d), "r"(tc.b),
                 "r"(smem_u32(&full_a[slot]) & kPeerBitMask)
                 : "memory");
           }
@@ -557,7 +563,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       for (int u = cluster_id; u < total_pairs; u += nclusters) {
         const TileCoord tc = tile_coord2(p, u, rank, N_TILE, P);
         const int tap_base = UPS ? tc.phase * ntaps : 0;
-        for (int c = 0; c < nchunks; ++c)
+        VChunk vc;
+        for (int c = 0; c < nchunks; ++c, vc.next(p))
           for (int tap = tap_base; tap < tap_base + ntaps; ++tap, ++seq) {
             const uint32_t slot = seq % NB, ph = (seq / NB) & 1;
             mbar_wait(&empty_b[slot], ph ^ 1);
@@ -565,7 +572,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             asm volatile(
                 "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                     smem_u32(sB + (size_t)slot * B_HALF)),
-                "l"(reinterpret_cast<uint64_t>(&tmapW)), "r"(vchunk_w(p, c)), "r"(tap * p.Cout + tc.n0 + (int)rank * (N_TILE / 2)),
+                "l"(reinterpret_cast<uint64_t>(&tmapW)), "r"(vc.w(p)), "r"(tap * p.Cout + tc.n0 + (int)rank * (N_TILE / 2)),
                 "r"(smem_u32(&full_b[slot]) & kPeerBitMask)
                 : "memory");
           }
@@ -583,6 +590,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_acc = tmem_base + as * buf_cols;
       uint32_t used = 0, hh = 0;                         // accumulator sets written in this tile; round-robin counter
+      int part = 0;                                      // part of the current virtual chunk (0: hi * hi)
       const TileCoord tc = tile_coord2(p, u, 0, N_TILE, P);
       for (int c = 0; c < nchunks; ++c) {
         const uint32_t seq_c = seq_a;
@@ -603,7 +611,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
               const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_HALF));
               const uint32_t tap_off = (kh * TC_PW + kw) * 8;
               uint32_t set = 0;                                 // accumulator set of this tap's MMAs
-              if (nsets > 1) { if (c % p.vparts) set = lo_set; else { set = hh; hh = hh + 1 == nhh ? 0 : hh + 1; } }
+              if (nsets > 1) { if (part) set = lo_set; else { set = hh; hh = hh + 1 == nhh ? 0 : hh + 1; } }
               const uint32_t first = (used >> set) & 1u;
               used |= 1u << set;
               const uint32_t acc_set = tmem_acc + set * SET_COLS;
@@ -643,7 +651,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_HALF));
             const uint32_t tap_off = ((khw / 3) * TC_PW + (khw % 3)) * 8;
             uint32_t set = 0;                                 // accumulator set of this tap's MMAs
-            if (nsets > 1) { if (c % p.vparts) set = lo_set; else { set = hh; hh = hh + 1 == nhh ? 0 : hh + 1; } }
+            if (nsets > 1) { if (part) set = lo_set; else { set = hh; hh = hh + 1 == nhh ? 0 : hh + 1; } }
             const uint32_t first = (used >> set) & 1u;
             used |= 1u << set;
             const uint32_t acc_set = tmem_acc + set * SET_COLS;
@@ -667,6 +675,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         }
         }
         seq_a += NJ;
+        if (++part == p.vparts) part = 0;
       }
       if (elect_one_sync()) umma_commit_2cta(&acc_full[as]);
       __syncwarp();
@@ -802,6 +811,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       mbar_wait(&acc_full[as], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + as * buf_cols + pp * N_TILE + ((uint32_t)(q * 32) << 16);
+      if (p.dbg & 1) {                                       // measurement: MMA / TMA side alone
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
+        continue;
+      }
 #pragma unroll
       for (int gi = 0; gi < NG; ++gi) {
         const int c0 = gi * 32;
@@ -1267,6 +1282,8 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   p.vparts = a_split ? (w_split ? 3 : 2) : 1;
   p.a_lo_off = d->Cin; p.w_lo_off = d->Cin;
   p.nsets = a_split ? (w_split ? 4 : 2) : 1;
+  static const int dbg = [] { const char* e = getenv("DSK_CONV_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg;
   p.planes_per_sample = d->ndim == 3 ? iD : 1;
   p.stats = stats; p.samples = d->B;
   p.pad_hw = pad_hw; p.pad_d = pad_d;

@@ -140,7 +140,9 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_base + as * BUF_COLS;
       uint32_t used[2] = {0u, 0u};                                  // per set: output planes already written in this tile
-      for (int c = 0; c < nchunks; ++c)
+      int part = -1;
+      for (int c = 0; c < nchunks; ++c) {
+        if (++part == p.vparts) part = 0;                           // part of virtual chunk c (no division in the issue path)
         for (int j = 0; j < NJ; ++j, ++seq) {
           const uint32_t slot = seq % CO_NA;
           mbar_wait(&full_a[slot], (seq / CO_NA) & 1);
@@ -153,7 +155,7 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
               const int pp = j - kd;
               if (pp < 0 || pp >= CO_P) continue;
               const uint32_t b_lo = umma_desc_lo(smem_u32(sW + (size_t)(kd * nchunks + c) * N_PAD * 128));
-              const uint32_t set = (c % p.vparts) ? 1u : 0u;
+              const uint32_t set = part ? 1u : 0u;
               const uint32_t first = (used[set] >> pp) & 1u;         // 0: first MMA into this (set, plane) accumulator
               used[set] |= 1u << pp;
               const uint32_t accs = acc + set * ACC_COLS;
@@ -169,6 +171,7 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
           }
           __syncwarp();
         }
+      }
       if (elect_one_sync()) umma_commit(&acc_full[as]);
       __syncwarp();
     }

@@ -76,8 +76,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       uint32_t seq = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int tn = t % p.tiles_n, tm = (t / p.tiles_n) % p.tiles_m, b = t / (p.tiles_n * p.tiles_m);
+        int kc = 0, part = -1;
         for (int vkc = 0; vkc < kchunks; ++vkc, ++seq) {
-          const int kc = vkc / p.vparts, part = vkc - kc * p.vparts;
+          if (++part == p.vparts) { part = 0; ++kc; }              // (real chunk, part) without a division per chunk
           const int ao = (p.vparts > 1 && part == p.vparts - 1) ? p.a_lo : 0, bo = (p.vparts == 3 && part == 1) ? p.b_lo : 0;
           const uint32_t slot = seq % GT_STAGES, ph = (seq / GT_STAGES) & 1;
           mbar_wait(&empty[slot], ph ^ 1);
@@ -119,13 +120,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_acc = tmem_base + as * BUF_COLS;
       uint32_t used = 0;
+      int part = -1;
       for (int kc = 0; kc < kchunks; ++kc, ++seq) {
+        if (++part == p.vparts) part = 0;
         const uint32_t slot = seq % GT_STAGES;
         mbar_wait(&full[slot], (seq / GT_STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa16 = smem_u32(smem + (size_t)slot * STAGE) >> 4;
         const uint32_t a_lo = sa16 | a_lbo, b_lo = (sa16 + (A_BYTES >> 4)) | b_lbo;
-        const uint32_t set = (kc % p.vparts) ? 1u : 0u;          // virtual chunk part > 0: a lo operand is involved
+        const uint32_t set = part ? 1u : 0u;                      // virtual chunk part > 0: a lo operand is involved
         const uint32_t accum = (used >> set) & 1u;
         used |= 1u << set;
         if (elect_one_sync()) {
