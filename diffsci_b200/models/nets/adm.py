@@ -21,7 +21,7 @@ from torch import nn
 from ... import ops
 from ..._lib import require_cuda
 from .layers import AttentionParams, ConvParams, FourierParams, LinearParams, NormParams, _Act, _Holder, make_conv
-from .punetg import _NORM_MODE, _tc_eligible, DEFAULT_PRECISION, PRECISIONS, _ACT_DTYPE, _W_DTYPE
+from .punetg import _NORM_MODE, _tc_eligible, DEFAULT_PRECISION, PRECISIONS, _ACT_DTYPE, _W_DTYPE, SPLIT_MODES, MIXED_MIN_CIN
 
 
 class ADMConfig:
@@ -228,7 +228,8 @@ class _ADMPlan:
         self.net, self.B, self.sig, self.precision = net, B, sig, precision
         self.act_dtype = adt = _ACT_DTYPE[precision]         # modes: see punetg.PRECISIONS
         wdt = _W_DTYPE.get(precision)
-        self.split = precision in ("fp32", "fp16x2")          # tensor-core convs read split-fp16 inputs (hi | lo)
+        self.split = precision in SPLIT_MODES                 # tensor-core convs read split-fp16 inputs (hi | lo)
+        self.split_min_cin = MIXED_MIN_CIN if precision == "fp16x2m" else 0
         self.device = dev = torch.device(device)
         nlev = len(c.channel_expansion)
         H, W = spatial
@@ -294,7 +295,10 @@ class _ADMPlan:
         # nearest x2 upsample is never materialised: FFMA folds it into the gather, tcgen05 runs the sub-pixel form
         if self.split and ops.is_tc_dtype(pc.w_dtype) and x.dtype == torch.float32:
             # split mode: a tensor-core convolution reads the split copy (hi | lo) of its fp32 input
-            x = ops.split_f16(x, out=self.buf("split", x.shape[:-1] + (2 * x.shape[-1],), torch.float16))
+            if pc.cin < self.split_min_cin:      # mixed mode: plain fp16 operand for the narrow layers
+                x = ops.cast(x, torch.float16, out=self.buf("cast16", x.shape, torch.float16))
+            else:
+                x = ops.split_f16(x, out=self.buf("split", x.shape[:-1] + (2 * x.shape[-1],), torch.float16))
         if pc.circular:      # the tcgen05 path reads a halo-padded copy (TMA boxes cannot wrap): one workspace, grown on demand
             need = ops.conv_pad_ws_bytes(x.shape, x.dtype, pc, up)
             if need > 0 and (self._pad_ws is None or self._pad_ws.numel() < need):

@@ -36,12 +36,18 @@ DEFAULT_PRECISION = "fp32"
 #               channel counts that are not multiples of 64) run the CUDA-core FFMA kernels.
 #   "fp32_ffma" the same storage with every contraction on the CUDA-core FFMA kernels (the round-1 parity mode).
 #   "fp16x2"    as "fp32" with plain fp16 weights (activations split only, 2 MMAs per k-step).
+#   "fp16x2m"   "mixed": as "fp16x2" for the contractions with >= 128 input channels; the 64-channel full-resolution layers
+#               take plain fp16 activations (1 MMA per k-step, fp32 storage).  The many deep layers contribute most of the
+#               operand-rounding error and the few full-resolution ones most of the time (oracle/split_budget.py --mixed).
 #   "fp16"      fp16 storage and operands, 1 MMA per k-step: the throughput mode (3 more mantissa bits than bf16).
 #   "bf16"      bf16 storage and operands (the training format; fp32's exponent range).
-PRECISIONS = ("fp32", "fp32_ffma", "fp16x2", "fp16", "bf16")
-_ACT_DTYPE = {"fp32": torch.float32, "fp32_ffma": torch.float32, "fp16x2": torch.float32, "fp16": torch.float16,
-              "bf16": torch.bfloat16}
-_W_DTYPE = {"fp32": ops.SPLIT, "fp16x2": torch.float16, "fp16": torch.float16, "bf16": torch.bfloat16}   # tcgen05 weight format
+PRECISIONS = ("fp32", "fp32_ffma", "fp16x2", "fp16x2m", "fp16", "bf16")
+_ACT_DTYPE = {"fp32": torch.float32, "fp32_ffma": torch.float32, "fp16x2": torch.float32, "fp16x2m": torch.float32,
+              "fp16": torch.float16, "bf16": torch.bfloat16}
+_W_DTYPE = {"fp32": ops.SPLIT, "fp16x2": torch.float16, "fp16x2m": torch.float16, "fp16": torch.float16,
+            "bf16": torch.bfloat16}   # tcgen05 weight format
+SPLIT_MODES = ("fp32", "fp16x2", "fp16x2m")      # fp32 storage; tensor-core operands are split-fp16 (hi | lo) tensors
+MIXED_MIN_CIN = 128                              # "fp16x2m": contractions with fewer input channels take plain fp16 activations
 
 
 def _tc_eligible(cin: int, cout: int, ksize: int = 3, few_out_ok: bool = False) -> bool:
@@ -238,7 +244,8 @@ class _Plan:
         self.ndim = nd = c.dimension
         self.act_dtype = adt = _ACT_DTYPE[precision]
         wdt = _W_DTYPE.get(precision)                       # None: no tensor-core kernels in this mode
-        self.split = split = precision in ("fp32", "fp16x2")   # conv / GEMM inputs are split-fp16 tensors (hi | lo)
+        self.split = split = precision in SPLIT_MODES      # conv / GEMM inputs are split-fp16 tensors (hi | lo)
+        self.split_min_cin = smin = MIXED_MIN_CIN if precision == "fp16x2m" else 0
         dev = self.device = torch.device(device)
         if len(spatial) != nd:
             raise ValueError(f"PUNetG(dimension={nd}) got spatial shape {spatial}")
@@ -263,6 +270,8 @@ class _Plan:
 
         def nbuf(l):      # norm + SiLU output == conv input: a split-fp16 tensor where the block convs run on the tensor cores
             if split and _tc_eligible(ch[l], ch[l], c.kernel_size):
+                if ch[l] < smin:          # mixed mode: plain fp16 activations for the narrow layers
+                    return buf(l, ch[l], torch.float16)
                 return torch.empty((B,) + sp[l] + (2 * ch[l],), dtype=torch.float16, device=dev)
             return buf(l, ch[l])
 
@@ -319,7 +328,7 @@ class _Plan:
             def sup(shape, pc, up2=False):
                 if not ops.is_tc_dtype(pc.w_dtype):
                     return False
-                if split:
+                if split and pc.cin >= smin:
                     shape = tuple(shape[:-1]) + (2 * shape[-1],)
                 return ops.conv_stats_supported(shape, torch.float16 if split else adt, pc, up2=up2, out_dtype=adt)
             lvl_pc = {l: self.pc[id(b)][0] for b, l in self.blocks}
@@ -386,7 +395,10 @@ class _Plan:
         """ops.conv; in split mode a tensor-core convolution whose input is still an fp32 tensor (not the split output of a
         norm) gets its split copy first."""
         if self.split and ops.is_tc_dtype(pc.w_dtype) and x.dtype == torch.float32:
-            x = ops.split_f16(x, out=self.S16[:2 * x.numel()].view(x.shape[:-1] + (2 * x.shape[-1],)))
+            if pc.cin < self.split_min_cin:      # mixed mode: plain fp16 operand
+                x = ops.cast(x, torch.float16, out=self.S16[:x.numel()].view(x.shape))
+            else:
+                x = ops.split_f16(x, out=self.S16[:2 * x.numel()].view(x.shape[:-1] + (2 * x.shape[-1],)))
         return ops.conv(x, pc, pad_ws=self.pad_ws, **k)
 
     # ------------------------------------------------------------------ forward
