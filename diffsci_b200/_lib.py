@@ -92,6 +92,8 @@ SIGNATURES = {
     "dsk_edm_loss_fwd_bwd": [p, p, p, p, p, p, p, i32, i32, i64, f32, i32, p],
     "dsk_precond_loss_fwd_bwd": [p, p, p, p, p, p, p, p, p, p, i32, i32, i64, i32, p],
     "dsk_precond_loss_rows": [p, p, p, p, p, p, p, p, p, p, i32, i32, i64, i32, p],
+    "dsk_precond_loss_fwd_bwd_huber": [p, p, p, p, p, p, p, p, p, p, i32, i32, i64, i32, f32, p],
+    "dsk_precond_loss_rows_huber": [p, p, p, p, p, p, p, p, p, p, i32, i32, i64, i32, f32, p],
     "dsk_ensemble_noise_add": [p, p, p, p, i32, i32, i64, p],
     "dsk_ensemble_loss_fwd_bwd": [p, p, p, p, p, p, p, p, p, i32, p, p, i32, i32, i32, i64, i32, p],
     "dsk_ema_update": [p, p, p, i32, i64, f32, p],

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256) edm_loss_kernel(const float* __restrict__
                                                         const float* __restrict__ mask, float* __restrict__ loss_out,
                                                         float* __restrict__ dF, int B, int64_t CS, float sd, int kind,
                                                         const float* __restrict__ c_out_v, const float* __restrict__ c_skip_v,
-                                                        const float* __restrict__ lam_v) {
+                                                        const float* __restrict__ lam_v, float delta) {
   const int64_t N = (int64_t)B * CS;
   const float invN = 1.0f / (float)N;
   float local = 0.0f;
@@ -34,10 +34,10 @@ __global__ void __launch_bounds__(256) edm_loss_kernel(const float* __restrict__
     const float D = c_out * F[i] + c_skip * xn;
     const float r = D - xv;
     float l, g;
-    if (kind == 0) {  // Huber, delta = 1 (torch.nn.HuberLoss default, karrasmodule.py:541-542)
+    if (kind == 0) {  // torch.nn.HuberLoss(delta): default 1 (karrasmodule.py:541-542), configurable (:560-562)
       const float a = fabsf(r);
-      l = a <= 1.0f ? 0.5f * r * r : a - 0.5f;
-      g = fminf(fmaxf(r, -1.0f), 1.0f);
+      l = a <= delta ? 0.5f * r * r : delta * (a - 0.5f * delta);
+      g = fminf(fmaxf(r, -delta), delta);
     } else {          // MSE
       l = r * r;
       g = 2.0f * r;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) precond_loss_rows_kernel(const float* __r
                                                                  const float* __restrict__ mask, float* __restrict__ loss_b,
                                                                  float* __restrict__ dF, int B, int64_t CS, int kind,
                                                                  const float* __restrict__ c_out_v, const float* __restrict__ c_skip_v,
-                                                                 const float* __restrict__ lam_v) {
+                                                                 const float* __restrict__ lam_v, float delta) {
   const int b = blockIdx.y;
   const float invN = 1.0f / (float)((int64_t)B * CS);
   const float sg = sigma[b], c_out = c_out_v[b], c_skip = c_skip_v[b], lam = lam_v[b];
@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(256) precond_loss_rows_kernel(const float* __r
     float l, g;
     if (kind == 0) {
       const float a = fabsf(r);
-      l = a <= 1.0f ? 0.5f * r * r : a - 0.5f;
-      g = fminf(fmaxf(r, -1.0f), 1.0f);
+      l = a <= delta ? 0.5f * r * r : delta * (a - 0.5f * delta);
+      g = fminf(fmaxf(r, -delta), delta);
     } else {
       l = r * r;
       g = 2.0f * r;
@@ -328,34 +328,48 @@ extern "C" int dsk_edm_loss_fwd_bwd(const float* F, const float* x, const float*
   DSK_REQUIRE(B > 0 && C > 0 && S > 0 && (loss_kind == 0 || loss_kind == 1), "dsk_edm_loss_fwd_bwd: bad arguments");
   const int grid = grid_for((int64_t)B * C * S, 256, 8);
   DSK_LAUNCH(edm_loss_kernel, grid, 256, 0, as_stream(stream), F, x, noise, sigma, mask, loss_out, dF, B, (int64_t)C * S,
-             sigma_data, loss_kind, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr);
+             sigma_data, loss_kind, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, 1.0f);
   return DSK_OK;
 }
 
+extern "C" int dsk_precond_loss_fwd_bwd_huber(const float* F, const float* x, const float* noise, const float* sigma,
+                                              const float* c_out, const float* c_skip, const float* weight, const float* mask,
+                                              float* loss_out, float* dF, int B, int C, int64_t S, int loss_kind, float delta,
+                                              void* stream) {
+  DSK_REQUIRE(F && x && noise && sigma && c_out && c_skip && weight && loss_out && dF, "dsk_precond_loss_fwd_bwd: null pointer");
+  DSK_REQUIRE(B > 0 && C > 0 && S > 0 && (loss_kind == 0 || loss_kind == 1) && delta > 0.0f, "dsk_precond_loss_fwd_bwd: bad arguments");
+  const int grid = grid_for((int64_t)B * C * S, 256, 8);
+  DSK_LAUNCH(edm_loss_kernel, grid, 256, 0, as_stream(stream), F, x, noise, sigma, mask, loss_out, dF, B, (int64_t)C * S, 0.0f,
+             loss_kind, c_out, c_skip, weight, delta);
+  return DSK_OK;
+}
 extern "C" int dsk_precond_loss_fwd_bwd(const float* F, const float* x, const float* noise, const float* sigma,
                                         const float* c_out, const float* c_skip, const float* weight, const float* mask,
                                         float* loss_out, float* dF, int B, int C, int64_t S, int loss_kind, void* stream) {
-  DSK_REQUIRE(F && x && noise && sigma && c_out && c_skip && weight && loss_out && dF, "dsk_precond_loss_fwd_bwd: null pointer");
-  DSK_REQUIRE(B > 0 && C > 0 && S > 0 && (loss_kind == 0 || loss_kind == 1), "dsk_precond_loss_fwd_bwd: bad arguments");
-  const int grid = grid_for((int64_t)B * C * S, 256, 8);
-  DSK_LAUNCH(edm_loss_kernel, grid, 256, 0, as_stream(stream), F, x, noise, sigma, mask, loss_out, dF, B, (int64_t)C * S, 0.0f,
-             loss_kind, c_out, c_skip, weight);
-  return DSK_OK;
+  return dsk_precond_loss_fwd_bwd_huber(F, x, noise, sigma, c_out, c_skip, weight, mask, loss_out, dF, B, C, S, loss_kind, 1.0f, stream);
 }
 
 
+extern "C" int dsk_precond_loss_rows_huber(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
+                                           const float* c_skip, const float* weight, const float* mask, float* loss_b, float* dF,
+                                           int B, int C, int64_t S, int loss_kind, float delta, void* stream);
 extern "C" int dsk_precond_loss_rows(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
                                      const float* c_skip, const float* weight, const float* mask, float* loss_b, float* dF,
                                      int B, int C, int64_t S, int loss_kind, void* stream) {
+  return dsk_precond_loss_rows_huber(F, x, noise, sigma, c_out, c_skip, weight, mask, loss_b, dF, B, C, S, loss_kind, 1.0f, stream);
+}
+extern "C" int dsk_precond_loss_rows_huber(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
+                                           const float* c_skip, const float* weight, const float* mask, float* loss_b, float* dF,
+                                           int B, int C, int64_t S, int loss_kind, float delta, void* stream) {
   DSK_REQUIRE(F && x && noise && sigma && c_out && c_skip && weight && loss_b && dF, "dsk_precond_loss_rows: null pointer");
-  DSK_REQUIRE(B > 0 && B <= 65535 && C > 0 && S > 0 && (loss_kind == 0 || loss_kind == 1), "dsk_precond_loss_rows: bad arguments");
+  DSK_REQUIRE(B > 0 && B <= 65535 && C > 0 && S > 0 && (loss_kind == 0 || loss_kind == 1) && delta > 0.0f, "dsk_precond_loss_rows: bad arguments");
   const int64_t CS = (int64_t)C * S;
   int per_b = (int)((CS + 255) / 256);
   const int cap = (8 * DSK_NUM_SMS + B - 1) / B;
   if (per_b > cap) per_b = cap;
   if (per_b < 1) per_b = 1;
   DSK_LAUNCH(precond_loss_rows_kernel, dim3(per_b, B), 256, 0, as_stream(stream), F, x, noise, sigma, mask, loss_b, dF, B, CS,
-             loss_kind, c_out, c_skip, weight);
+             loss_kind, c_out, c_skip, weight, delta);
   return DSK_OK;
 }
 

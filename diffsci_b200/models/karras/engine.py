@@ -66,7 +66,7 @@ class SamplerEngine:
         self.r1 = torch.empty(full, **f32)
         self.cnoise = torch.empty((self.Bn,), **f32)
         self.row = torch.zeros((4,), dtype=torch.int32, device=self.device)   # [step, seed_lo, seed_hi, -]
-        self.native = hasattr(model, "plan")
+        self.native = hasattr(model, "plan") and getattr(model, "engine_native", True)
         self.xin_ld = self.Cc + self.cond_channels + int(getattr(model, "ones_channel", 0))   # + the bias=False ones channel
         self.ye = None
         if (self.cond_channels or self.cond_vector or self.cfg) and not self.native:

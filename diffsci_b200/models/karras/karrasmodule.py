@@ -10,7 +10,7 @@ this module drives the fused CUDA stages (csrc/sampler.cu, csrc/train.cu) and, f
 replays one captured CUDA graph per integrator step (engine.SamplerEngine).
 Section 8(f)-4: the latent-diffusion wrapper (``autoencoder=``: a frozen user torch module whose ``encode`` / ``decode``
 bracket the loss and the sampler, karrasmodule.py:1192-1234) and, in ``karrasmodule_new.py``, the ensemble losses.
-Autoregressive, dynamic-loss-weight and multi-space-loss recipes (and ``encode_y`` / ``decode_original_y``) are out of
+Autoregressive, dynamic-loss-weight and multi-space-loss recipes are out of
 scope and raise NotImplementedError instead of silently doing something else.
 """
 from __future__ import annotations
@@ -108,6 +108,17 @@ class KarrasModuleConfig:
                           schedulers.VEScheduler(sigma_min=sigma_min, sigma_max=sigma_max), loss_metric,
                           dict(sigma_min=sigma_min, sigma_max=sigma_max), common)
 
+    @classmethod
+    def conditionalSR3(cls, sigma_min: float = 0.02, sigma_max: float = 100, loss_metric="huber", **common):
+        """karrasmodule.py:291-341, as the reference builds it: EDMScheduler(sigma_min, sigma_max) + SR3Preconditioner +
+        ``EDMNoiseSampler(sigma_min=..., sigma_max=...)``.  The reference's EDMNoiseSampler takes (sigma_data, prior_mean,
+        prior_std) (noisesamplers.py:20-28), so this factory raises TypeError there -- and here, for the same call: the drop-in
+        keeps the reference's error behaviour rather than inventing a sampler the reference never ran."""
+        sch = schedulers.EDMScheduler(sigma_min=sigma_min, sigma_max=sigma_max)
+        return cls._build("conditionalSR3", preconditioners.SR3Preconditioner(),
+                          noisesamplers.EDMNoiseSampler(sigma_min=sigma_min, sigma_max=sigma_max), sch, loss_metric,
+                          dict(sigma_min=sigma_min, sigma_max=sigma_max), common)
+
     def export_description(self) -> dict[str, Any]:
         return dict(tag=self.tag, extra_args=self.extra_args)
 
@@ -116,7 +127,7 @@ class KarrasModuleConfig:
         tag, extra = description["tag"], description["extra_args"]
         if tag == "custom":
             raise ValueError("Cannot load from a custom tag")
-        ctor = {"edm": cls.from_edm, "vp": cls.from_vp, "ve": cls.from_ve}.get(tag)
+        ctor = {"edm": cls.from_edm, "vp": cls.from_vp, "ve": cls.from_ve, "conditionalSR3": cls.conditionalSR3}.get(tag)
         if ctor is None:
             raise ValueError(f"Unknown tag: {tag}")
         return ctor(**extra)
@@ -136,7 +147,7 @@ class _EDMLossFn(torch.autograd.Function):
     the same fused launch (csrc/train.cu: edm_loss_kernel)."""
 
     @staticmethod
-    def forward(ctx, F, x, noise, sigma, mask, sigma_data, kind, coeffs=None):
+    def forward(ctx, F, x, noise, sigma, mask, sigma_data, kind, coeffs=None, delta=1.0):
         """coeffs: None (EDM preconditioner + EDM weighting evaluated in the kernel) or fp32 [B] vectors (c_out, c_skip,
         lambda) from any preconditioner / noise sampler (dsk_precond_loss_fwd_bwd)."""
         B = x.shape[0]
@@ -149,15 +160,15 @@ class _EDMLossFn(torch.autograd.Function):
                                            float(sigma_data), int(kind), stream()))
         else:
             c_out, c_skip, lam = coeffs
-            check(lib.dsk_precond_loss_fwd_bwd(ptr(F), ptr(x), ptr(noise), ptr(sigma), ptr(c_out), ptr(c_skip), ptr(lam),
-                                               ptr(mask), ptr(loss), ptr(dF), B, Cc, S, int(kind), stream()))
+            check(lib.dsk_precond_loss_fwd_bwd_huber(ptr(F), ptr(x), ptr(noise), ptr(sigma), ptr(c_out), ptr(c_skip), ptr(lam),
+                                                     ptr(mask), ptr(loss), ptr(dF), B, Cc, S, int(kind), float(delta), stream()))
         ctx.save_for_backward(dF)
         return loss
 
     @staticmethod
     def backward(ctx, g):
         (dF,) = ctx.saved_tensors
-        return dF * g, None, None, None, None, None, None, None
+        return dF * g, None, None, None, None, None, None, None, None
 
 
 class _RowLossFn(torch.autograd.Function):
@@ -165,22 +176,22 @@ class _RowLossFn(torch.autograd.Function):
     flow to F (m[b] * dF[b], dF from the same launch) and to the per-sample factor m (loss_b)."""
 
     @staticmethod
-    def forward(ctx, F, m, x, noise, sigma, mask, coeffs, kind):
+    def forward(ctx, F, m, x, noise, sigma, mask, coeffs, kind, delta=1.0):
         B = x.shape[0]
         Cc = x.shape[1] if x.ndim > 1 else 1
         S = x.numel() // (B * Cc)
         loss_b = torch.zeros((B,), dtype=torch.float32, device=x.device)
         dF = torch.empty_like(x, dtype=torch.float32)
         c_out, c_skip, lam = coeffs
-        check(lib.dsk_precond_loss_rows(ptr(F), ptr(x), ptr(noise), ptr(sigma), ptr(c_out), ptr(c_skip), ptr(lam), ptr(mask),
-                                        ptr(loss_b), ptr(dF), B, Cc, S, int(kind), stream()))
+        check(lib.dsk_precond_loss_rows_huber(ptr(F), ptr(x), ptr(noise), ptr(sigma), ptr(c_out), ptr(c_skip), ptr(lam), ptr(mask),
+                                              ptr(loss_b), ptr(dF), B, Cc, S, int(kind), float(delta), stream()))
         ctx.save_for_backward(dF, loss_b, m)
         return (m * loss_b).sum()
 
     @staticmethod
     def backward(ctx, g):
         dF, loss_b, m = ctx.saved_tensors
-        return dF * (g * m).view(-1, *([1] * (dF.ndim - 1))), g * loss_b, None, None, None, None, None, None
+        return dF * (g * m).view(-1, *([1] * (dF.ndim - 1))), g * loss_b, None, None, None, None, None, None, None
 
 
 class DynamicLossWeight(torch.nn.Module):
@@ -210,13 +221,14 @@ def _rowwise_axpy(a_vec: Tensor, z: Tensor, b_vec: Tensor, x: Tensor) -> Tensor:
 
 
 class KarrasModule(_Base):
+    huber_delta = 1.0        # torch.nn.HuberLoss(delta) of loss_metric = {"huber": {"delta": d}} (set_loss_metric)
+
     def __init__(self, model: torch.nn.Module, config: KarrasModuleConfig, conditional: bool = False,
                  masked: bool = False, autoencoder: Optional[torch.nn.Module] = None,
                  autoencoder_conditional: bool = False, encode_y: bool = False, decode_original_y: bool = False):
         super().__init__()
-        if encode_y or decode_original_y:
-            raise NotImplementedError("diffsci_b200.KarrasModule: encode_y / decode_original_y (autoencoders that also "
-                                      "re-encode the condition) are not built")
+        if (encode_y or decode_original_y) and not (autoencoder is not None and autoencoder_conditional):
+            raise ValueError("encode_y / decode_original_y need a conditional autoencoder (its encode(x, y) returns (z, y'))")
         if autoencoder_conditional and autoencoder is None:
             raise ValueError("autoencoder_conditional=True needs an autoencoder")
         if config.has_edm_batch_norm:
@@ -228,7 +240,9 @@ class KarrasModule(_Base):
         if self.autoencoder is not None:
             self.freeze_autoencoder()
         self.autoencoder_conditional = bool(autoencoder_conditional)
-        self.encode_y = self.decode_original_y = False
+        # encode_y: the conditional autoencoder also re-encodes the condition, encode(x, y) -> (z, y') (karrasmodule.py:1201-1212);
+        # decode_original_y: sampling decodes with the ORIGINAL y instead of the encoded one (:843-860)
+        self.encode_y, self.decode_original_y = bool(encode_y), bool(decode_original_y)
         self.norm = 1.0
         self.set_optimizer_and_scheduler()
         self.set_loss_metric()
@@ -281,14 +295,15 @@ class KarrasModule(_Base):
         lm = self.config.loss_metric
         if isinstance(lm, dict) and len(lm) == 1 and "losses" not in lm:
             name, params = next(iter(lm.items()))
-            if name == "huber" and (params or {}).get("delta", 1.0) != 1.0:
-                raise NotImplementedError("diffsci_b200: Huber delta != 1 is not fused yet")
+            self.huber_delta = float((params or {}).get("delta", 1.0)) if name == "huber" else 1.0
             lm = name
         if lm not in ("huber", "mse"):
             raise NotImplementedError(f"diffsci_b200.KarrasModule: loss_metric={self.config.loss_metric!r} is out of "
                                       "scope (SURVEY.md section 2 #10); 'huber' (default) and 'mse' are fused")
         self.loss_kind = 0 if lm == "huber" else 1
         self.loss_metric = lm
+        if self.loss_kind != 0 or not (isinstance(self.config.loss_metric, dict) and "huber" in self.config.loss_metric):
+            self.huber_delta = 1.0
 
     # ------------------------------------------------------------------ denoiser
     @property
@@ -301,8 +316,12 @@ class KarrasModule(_Base):
         if record_history:
             return torch.stack([self.encode(xx, y, record_history=False) for xx in x], dim=0)
         if self.latent_model:
-            x = self.autoencoder.encode(x, y) if self.autoencoder_conditional else self.autoencoder.encode(x)
-        return x / self.norm if self.norm != 1.0 else x
+            if self.autoencoder_conditional and self.encode_y:
+                x, y = self.autoencoder.encode(x, y)
+            else:
+                x = self.autoencoder.encode(x, y) if self.autoencoder_conditional else self.autoencoder.encode(x)
+        x = x / self.norm if self.norm != 1.0 else x
+        return (x, y) if self.encode_y else x
 
     def decode(self, x, y=None, record_history=False):
         """karrasmodule.py:1216-1234."""
@@ -330,7 +349,7 @@ class KarrasModule(_Base):
         # gradients wanted (training, eval-mode fine-tuning, gradient diagnostics): the network's own forward, which takes the
         # autograd seam; otherwise the allocation-free inference plan
         wants_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters())
-        native = hasattr(self.model, "plan") and not wants_grad
+        native = hasattr(self.model, "plan") and getattr(self.model, "engine_native", True) and not wants_grad
         if native and cond and not hasattr(self.model, "conditioning_vector"):
             raise NotImplementedError(f"diffsci_b200: {type(self.model).__name__} has no conditional path")
         if native:
@@ -415,7 +434,10 @@ class KarrasModule(_Base):
         require_cuda(x, "x")
         if self.latent_model or self.norm != 1.0:    # the loss lives in the latent space (karrasmodule.py:583-587)
             with torch.no_grad():
-                x = self.encode(x, y)
+                if self.encode_y:
+                    x, y = self.encode(x, y)
+                else:
+                    x = self.encode(x, y)
         x = x.float().contiguous()
         sigma = sigma.to(x).contiguous()
         if self._injected_loss_noise is not None:
@@ -436,7 +458,7 @@ class KarrasModule(_Base):
         coeffs = None
         sd_pre, sd_ns = getattr(pre, "sigma_data", None), getattr(self.config.noisesampler, "sigma_data", None)
         same_sd = sd_pre is not None and sd_ns is not None and float(sd_pre) == float(sd_ns)
-        if self.dynamic_loss_weight is not None or not same_sd or not (
+        if self.dynamic_loss_weight is not None or not same_sd or self.huber_delta != 1.0 or not (
                 type(pre) is preconditioners.EDMPreconditioner and type(self.config.noisesampler) is noisesamplers.EDMNoiseSampler):
             # VP / VE / SR3 / custom objects: their per-sample scalars, the same fused loss + dL/dF kernel
             coeffs = tuple(v.float().contiguous() for v in (pre.output_scaling(sigma), pre.skip_scaling(sigma),
@@ -445,9 +467,9 @@ class KarrasModule(_Base):
             # weight / exp(u), bias + u  (karrasmodule.py:596-602): u on torch autograd, the per-sample losses from one launch
             u = self.dynamic_loss_weight(cond_noise).float()
             return _RowLossFn.apply(F.float().contiguous().view(x.shape), torch.exp(-u), x, noise.contiguous(), sigma, m,
-                                    coeffs, self.loss_kind) + u.mean()
+                                    coeffs, self.loss_kind, self.huber_delta) + u.mean()
         return _EDMLossFn.apply(F.float().contiguous().view(x.shape), x, noise.contiguous(), sigma, m,
-                                self._sigma_data(), self.loss_kind, coeffs)
+                                self._sigma_data(), self.loss_kind, coeffs, self.huber_delta)
 
     _injected_loss_noise: Optional[Tensor] = None
 
@@ -495,8 +517,20 @@ class KarrasModule(_Base):
             if self.latent_model and not is_latent_shape:
                 # `shape` is a data-space shape (karrasmodule.py:842-852): the latent shape is whatever the encoder makes
                 # of it; x_T is then drawn at that shape (here on the CPU generator, like every other x_T).
-                probe = self.encode(torch.zeros(*([nsamples] + list(shape)), device=self.device), y)
+                original_y = None
+                if self.encode_y:      # the encoder also maps the condition (karrasmodule.py:843-848)
+                    if self.decode_original_y:
+                        original_y = y.copy()
+                    probe, y = self.encode(torch.zeros(*([nsamples] + list(shape)), device=self.device), y)
+                    y["y"] = y["y"].squeeze(0)
+                else:
+                    probe = self.encode(torch.zeros(*([nsamples] + list(shape)), device=self.device), y)
                 shape = list(probe.shape[1:])
+                white_noise = torch.randn(*([nsamples] + list(shape))).to(self.device)
+                return self.propagate_white_noise(white_noise, y, guidance, nsteps, record_history, integrator=integrator,
+                                                  original_y=original_y, move_to_cpu=move_to_cpu, latent_shape=is_latent_shape,
+                                                  squeeze_memory_efficiency=squeeze_memory_efficiency,
+                                                  return_in_latent_space=return_in_latent_space)
             white_noise = torch.randn(*([nsamples] + list(shape))).to(self.device)
             return self.propagate_white_noise(white_noise, y, guidance, nsteps, record_history,
                                               integrator=integrator, move_to_cpu=move_to_cpu, latent_shape=is_latent_shape,
@@ -520,7 +554,8 @@ class KarrasModule(_Base):
         samples = self.sample(nsamples, shape, y=y, guidance=guidance, nsteps=nsteps, record_history=record_history,
                               maximum_batch_size=maximum_batch_size, integrator=integrator, move_to_cpu=False)
         with torch.inference_mode():
-            keep = filter_fn(self.encode(samples, y, record_history))
+            enc = self.encode(samples, y, record_history)
+            keep = filter_fn(enc[0] if self.encode_y else enc)
         if return_only_positives:
             samples, keep = samples[keep], keep[keep]
         if move_to_cpu:
@@ -571,7 +606,7 @@ class KarrasModule(_Base):
         validated = (type(self.config.preconditioner) in (preconditioners.VPPreconditioner, preconditioners.VEPreconditioner,
                                                           preconditioners.SR3Preconditioner) and
                      type(sch) in (schedulers.VPScheduler, schedulers.VEScheduler, schedulers.EDMScheduler))
-        if (not fused and env != "0" and (validated or env == "1") and hasattr(self.model, "plan") and not cond and
+        if (not fused and env != "0" and (validated or env == "1") and hasattr(self.model, "plan") and getattr(self.model, "engine_native", True) and not cond and
                 integ.fused_program in sch.GENERAL_PROGRAMS and
                 type(integ) in (integrators.EulerIntegrator, integrators.HeunIntegrator, integrators.EulerMaruyamaIntegrator)):
             return self._propagate_general(x, sch, integ, nsteps, record_history, _prescaled)

@@ -221,7 +221,10 @@ class EnsembleKarrasModule(KarrasModule):
         require_cuda(x, "x")
         if self.latent_model or self.norm != 1.0:
             with torch.no_grad():
-                x = self.encode(x, y)
+                if self.encode_y:
+                    x, y = self.encode(x, y)
+                else:
+                    x = self.encode(x, y)
         x = x.float().contiguous()
         sigma = sigma.to(x).contiguous()
         B = x.shape[0]

@@ -40,13 +40,13 @@ class EDMTrainer:
         if not hasattr(net, "train_graph"):
             raise TypeError("EDMTrainer drives the native networks (PUNetG / ADM); foreign torch modules train through "
                             "KarrasModule.training_step + a torch optimizer")
-        if type(module.config.preconditioner) is not preconditioners.EDMPreconditioner:
-            raise NotImplementedError("EDMTrainer: only the EDM preconditioner is fused")
+        # any KarrasPreconditioner / NoiseSampler pair (EDM, VP, VE, SR3, custom): the EDM pair has its scalars evaluated inside
+        # the loss kernel, the others hand it per-sample (c_out, c_skip, lambda) vectors from their own objects
         if module.conditional or getattr(net, "conditional_embedding", None) is not None or getattr(net, "cond_drop", None) is not None:
             raise NotImplementedError("EDMTrainer: conditional models train through KarrasModule.training_step + a torch "
                                       "optimizer (the native backward returns d loss / d embedding to autograd)")
-        if getattr(module, "dynamic_loss_weight", None) is not None or getattr(module, "latent_model", False):
-            raise NotImplementedError("EDMTrainer: dynamic loss weighting and latent-diffusion wrappers train through "
+        if getattr(module, "dynamic_loss_weight", None) is not None:
+            raise NotImplementedError("EDMTrainer: the learned loss weighting (its own torch parameters) trains through "
                                       "KarrasModule.training_step + a torch optimizer")
         self.module, self.net, self.ema, self.group = module, net, ema, process_group
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
@@ -76,6 +76,9 @@ class EDMTrainer:
         """x: fp32 [B, C, *S] on the device.  Returns the loss as a 0-dim device tensor (no host sync)."""
         require_cuda(x, "training batch")
         mod, net = self.module, self.net
+        if getattr(mod, "latent_model", False):          # latent diffusion: the loss lives on encode(x) (karrasmodule.py:583-587)
+            with torch.no_grad():
+                x = mod.encode(x)
         x = x.float().contiguous()
         B = x.shape[0]
         Cc = x.shape[1]
@@ -103,8 +106,20 @@ class EDMTrainer:
             loss = torch.zeros((), dtype=torch.float32, device=x.device)
             dF = torch.empty_like(x)
             m = None if mask is None else mask.to(x).expand_as(x).contiguous()
-            check(lib.dsk_edm_loss_fwd_bwd(ptr(F), ptr(x), ptr(noise), ptr(sigma), ptr(m), ptr(loss), ptr(dF), B, Cc, S,
-                                           float(mod._sigma_data()), int(mod.loss_kind), stream()))
+            smp = mod.config.noisesampler
+            sd_p, sd_s = getattr(pre, "sigma_data", None), getattr(smp, "sigma_data", None)
+            edm_pair = (type(pre) is preconditioners.EDMPreconditioner and type(smp).__name__ == "EDMNoiseSampler" and
+                        sd_p is not None and sd_s is not None and float(sd_p) == float(sd_s) and
+                        float(getattr(mod, "huber_delta", 1.0)) == 1.0)
+            if edm_pair:
+                check(lib.dsk_edm_loss_fwd_bwd(ptr(F), ptr(x), ptr(noise), ptr(sigma), ptr(m), ptr(loss), ptr(dF), B, Cc, S,
+                                               float(mod._sigma_data()), int(mod.loss_kind), stream()))
+            else:
+                c_out, c_skip, lam = (v.float().contiguous() for v in (pre.output_scaling(sigma), pre.skip_scaling(sigma),
+                                                                       smp.loss_weighting(sigma)))
+                check(lib.dsk_precond_loss_fwd_bwd_huber(ptr(F), ptr(x), ptr(noise), ptr(sigma), ptr(c_out), ptr(c_skip), ptr(lam),
+                                                         ptr(m), ptr(loss), ptr(dF), B, Cc, S, int(mod.loss_kind),
+                                                         float(getattr(mod, "huber_delta", 1.0)), stream()))
             g.backward_nchw(dF, bucketer.hooks())
             gscale = bucketer.finish()
             self.nstep += 1

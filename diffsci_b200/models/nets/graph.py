@@ -954,6 +954,13 @@ def build_mlp(net, B: int, device) -> TrainGraph:
     cat = Var(g.empty((B, net.dim + 1), torch.float32), needs_grad=False)
     xt, tt, ct = g.x_in.t, g.t_in, cat.t
     g.fwd.append(lambda: ops.concat_channels(xt, tt.view(B, 1), out=ct))
+    ydim = int(getattr(net, "ydim", 0))
+    if ydim:                                            # MLPCond: cat[x, t, y] (nets/mlp.py:118-120); y carries no gradient
+        g.y_in = torch.empty((B, ydim), dtype=torch.float32, device=g.device)
+        cat2 = Var(g.empty((B, net.dim + 1 + ydim), torch.float32), needs_grad=False)
+        yt, c2 = g.y_in, cat2.t
+        g.fwd.append(lambda: ops.concat_channels(ct, yt, out=c2))
+        cat = cat2
     layers = [m for m in net.net if isinstance(m, LinearParams)]
     h = cat
     for i, m in enumerate(layers):

@@ -18,6 +18,8 @@ _ACT_CODE = {nn.ReLU: 2, nn.SiLU: 1}
 
 
 class MLPUncond(nn.Module):
+    ydim = 0          # MLPCond: width of the conditioning vector concatenated after [x, t]
+
     def __init__(self, dim: int, hidden_dims=[10], nonlinearity: nn.Module = nn.ReLU(), dropout: float = 0.0):
         super().__init__()
         if type(nonlinearity) not in _ACT_CODE:
@@ -25,7 +27,7 @@ class MLPUncond(nn.Module):
                                       "(ReLU and SiLU are fused into the GEMM epilogue)")
         self.dim, self.act = dim, _ACT_CODE[type(nonlinearity)]
         self.dropout = dropout
-        layers, d = [], dim + 1
+        layers, d = [], dim + 1 + self.ydim
         for h in hidden_dims:
             layers += [LinearParams(d, h), _Act()]
             if dropout > 0:
@@ -36,16 +38,23 @@ class MLPUncond(nn.Module):
         self._plans: dict[Any, "_MLPPlan"] = {}
         self.precision = "fp32"
 
-    def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
-        require_cuda(x, "MLPUncond input")
+    def forward(self, x: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+        require_cuda(x, "MLP input")
+        if (y is None) != (self.ydim == 0):
+            raise TypeError(f"{type(self).__name__}.forward: y must{' not' if self.ydim == 0 else ''} be given")
         if self.training and self.dropout > 0:
-            raise NotImplementedError("diffsci_b200.MLPUncond: training-mode dropout not built")
+            raise NotImplementedError("diffsci_b200 MLP: training-mode dropout not built")
+        if y is not None:
+            y = y.float().expand(x.shape[0], self.ydim).contiguous()        # one condition broadcasts over the batch
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .graph import NetFunction        # training: hand-written backward (graph.build_mlp)
-            return NetFunction.apply(self.train_graph(x.shape[0], x.device), x, t, None, *self.parameters())
+            g = self.train_graph(x.shape[0], x.device)
+            if y is not None:
+                g.y_in.copy_(y.detach())
+            return NetFunction.apply(g, x, t, None, *self.parameters())
         plan = self.plan(x.shape[0], tuple(x.shape[1:]), x.device)
         plan.xin.copy_(x.reshape(plan.xin.shape))
-        return plan.forward(plan.xin, t.float().contiguous()).reshape(x.shape).clone()
+        return plan.forward(plan.xin, t.float().contiguous(), y=y).reshape(x.shape).clone()
 
     def plan(self, B: int, spatial: tuple, device, precision: Optional[str] = None) -> "_MLPPlan":
         key = (B, str(device))
@@ -83,6 +92,7 @@ class _MLPPlan:
         f32 = dict(dtype=torch.float32, device=device)
         self.xin = torch.empty((B, net.dim), **f32)
         self.cat = torch.empty((B, net.dim + 1), **f32)
+        self.cat_y = torch.empty((B, net.dim + 1 + net.ydim), **f32) if net.ydim else None
         self.layers = [m for m in net.net if isinstance(m, LinearParams)]
         self.h = [torch.empty((B, m.weight.shape[0]), **f32) for m in self.layers]
         self.F = self.h[-1]
@@ -90,9 +100,24 @@ class _MLPPlan:
     def prepare(self):
         pass
 
-    def forward(self, xin: torch.Tensor, cnoise: torch.Tensor, **_) -> torch.Tensor:
+    def forward(self, xin: torch.Tensor, cnoise: torch.Tensor, y: Optional[torch.Tensor] = None, **_) -> torch.Tensor:
         h = ops.concat_channels(xin.view(self.B, -1), cnoise.view(self.B, 1), out=self.cat)
+        if self.cat_y is not None:                      # MLPCond: cat[x, t, y] (nets/mlp.py:118-120)
+            h = ops.concat_channels(h, y.view(self.B, -1), out=self.cat_y)
         for i, m in enumerate(self.layers):
             last = i == len(self.layers) - 1
             h = ops.linear(h, m.weight, m.bias, act=0 if last else self.net.act, out=self.h[i])
         return h
+
+
+class MLPCond(MLPUncond):
+    """MLPCond (reference nets/mlp.py:61-121): cat[x, t, y] -> (Linear, act)* -> Linear, y a [B, ydim] conditioning vector.
+    Same state-dict keys as the reference (``net.<i>.weight/bias``).  With ``KarrasModule(model, cfg, conditional=True)`` it is
+    driven through the module's generic denoiser-network call ``model(x_scaled, c_noise, y)`` (no ``plan`` attribute exposed to
+    the graph engine: the conditioning is a per-call argument here, not a time-embedding offset)."""
+
+    engine_native = False     # KarrasModule / the sampler engine call it as a generic denoiser network: model(x, c_noise, y)
+
+    def __init__(self, dim: int, ydim: int, hidden_dims=[10], nonlinearity: nn.Module = nn.ReLU(), dropout: float = 0.0):
+        self.ydim = int(ydim)
+        super().__init__(dim, hidden_dims, nonlinearity, dropout)

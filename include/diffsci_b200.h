@@ -378,6 +378,14 @@ int dsk_edm_loss_fwd_bwd(const float* F, const float* x, const float* noise, con
 int dsk_precond_loss_fwd_bwd(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
                              const float* c_skip, const float* weight, const float* mask, float* loss_out, float* dF,
                              int B, int C, int64_t S, int loss_kind, void* stream);
+/* ... with torch.nn.HuberLoss's delta (loss_metric = {"huber": {"delta": d}}, karrasmodule.py:558-562):
+ * l = r^2 / 2 for |r| <= delta, delta (|r| - delta / 2) otherwise; dl/dr = clamp(r, -delta, delta).  Ignored for MSE. */
+int dsk_precond_loss_fwd_bwd_huber(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
+                                   const float* c_skip, const float* weight, const float* mask, float* loss_out, float* dF,
+                                   int B, int C, int64_t S, int loss_kind, float delta, void* stream);
+int dsk_precond_loss_rows_huber(const float* F, const float* x, const float* noise, const float* sigma, const float* c_out,
+                                const float* c_skip, const float* weight, const float* mask, float* loss_b, float* dF,
+                                int B, int C, int64_t S, int loss_kind, float delta, void* stream);
 /* The same loss reduced PER SAMPLE: loss_b[b] (fp32 [B], zeroed by the caller) = sum over the sample of weight[b] * l * (1-mask)
  * / (B*C*S), so that sum_b loss_b = the scalar above.  For a per-sample factor applied on the host side that needs its own
  * gradient: the learned uncertainty weighting of has_dynamic_loss_weight (karrasmodule.py:594-602, DynamicLossWeight

@@ -183,7 +183,7 @@ def test_latent_wrapper_vs_live_reference(golden):
     out = mod.sample(3, [1, 32, 32], nsteps=3)
     assert out.shape == (3, 1, 32, 32) and torch.isfinite(out).all()
     assert mod.sample(3, [1, 32, 32], nsteps=3, return_in_latent_space=True).shape == (3, 1, 16, 16)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):       # encode_y needs a conditional autoencoder whose encode(x, y) returns (z, y')
         d.KarrasModule(net, d.KarrasModuleConfig.from_edm(), autoencoder=ae, encode_y=True)
 
 
