@@ -47,6 +47,8 @@ SIGNATURES = {
     "dsk_sampler_advance": [p, p],
     "dsk_sampler_stage_general": [i32, p, p, p, p, p, p, p, p, p, p, i32, i32, i64, f32, i32, i32, p],
     "dsk_sampler_stage_cond": [i32, p, p, p, p, p, p, p, p, p, u64, p, i32, i32, i64, f32, f32, i32, i32, i32, i32, f32, p],
+    "dsk_sampler_stage_blend": [i32, p, p, p, p, p, p, p, p, p, u64, p, i32, i32, i64, f32, f32, i32, i32, i32, i32, f32, p, p, i64,
+                                i32, p],
     "dsk_precond_scale_cond": [p, p, p, i32, i32, i64, i32, i32, i32, p],
     "dsk_cfg_mix": [p, p, f32, i64, i32, p],
     "dsk_lincomb": [p, i64, p, f32, p, f32, p, f32, p, f32, p],

@@ -59,6 +59,14 @@ struct StageArgs {
   // 2B batch (rows [0,B) unconditional, [B,2B) conditional) and F = (1-g) F_u + g F_c (karrasmodule.py:705-713).
   int xin_ld, cfg;
   float guidance;
+  // inpainting (Scheduler.inpaint, karras/schedulers.py:91-122): after every completed step -- and at the start of the run --
+  // the known region is re-imposed, x <- x (1 - m) + y[level] m, with y the forward (data -> noise) history [blend_rows, B, C, S]
+  // of the known data, level = blend_rows - 1 - (steps completed).  Null: no blending.  The mask has mask_n elements and is
+  // broadcast over the leading dimensions.
+  const float* blend_y;
+  const float* blend_mask;
+  int64_t mask_n;
+  int blend_rows;
 };
 
 template <int V> struct Vec;
@@ -124,7 +132,8 @@ __global__ void __launch_bounds__(256) sampler_stage_kernel(StageArgs a) {
   bool writes_hist = false, do_prep = true;
   int hist_slot = rowi + 1, noise_row = rowi;
   float ncoef = 0.0f;
-  if (STAGE == DSK_STAGE_INIT) { sig_eval = 1.0f; sig_next = that; writes_hist = true; hist_slot = 0; ncoef = r[DSK_TAB_CHURN]; }
+  // INIT at row r starts a run at step r (r > 0: Scheduler.propagate_partial, schedulers.py:177-217): its history slot is r
+  if (STAGE == DSK_STAGE_INIT) { sig_eval = 1.0f; sig_next = that; writes_hist = true; hist_slot = rowi; ncoef = r[DSK_TAB_CHURN]; }
   else if (STAGE == DSK_STAGE_EULER) { sig_eval = t; sig_next = r[DSK_TAB_TNEXT]; writes_hist = true; }
   else if (STAGE == DSK_STAGE_HEUN_MID) { sig_eval = t; sig_next = t + dt; }
   else if (STAGE == DSK_STAGE_HEUN_FIN) { sig_eval = t + dt; sig_next = r[DSK_TAB_TNEXT]; writes_hist = true; }
@@ -230,11 +239,28 @@ __global__ void __launch_bounds__(256) sampler_stage_kernel(StageArgs a) {
         pv[k] = xo[k];
       }
     }
+    if (a.blend_y != nullptr && STAGE != DSK_STAGE_HEUN_MID && STAGE != DSK_STAGE_KARRAS_MID) {
+      // the state after this stage sits at level rowi (INIT) / rowi + 1 of the schedule: blend with the matching row of the
+      // known data's forward history, then redo what depends on it (churned state / next network input)
+      const int level = a.blend_rows - 1 - (STAGE == DSK_STAGE_INIT ? rowi : rowi + 1);
+      float yv[V];
+      Vec<V>::ld(a.blend_y + (int64_t)level * N, i, yv);
+      if (STAGE == DSK_STAGE_INIT && writes_hist && a.hist != nullptr)     // history[0] is the state BEFORE the first blend
+        Vec<V>::st(a.hist + (int64_t)hist_slot * N, i, xo);                //   (schedulers.py:105-111)
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float m = a.blend_mask[(i + k) % a.mask_n];
+        const float churn = pv[k] - xo[k];                 // Karras churn perturbation added on top of the step result
+        xo[k] = xo[k] * (1.0f - m) + yv[k] * m;
+        pv[k] = xo[k] + churn;
+      }
+    }
     if (STAGE == DSK_STAGE_HEUN_MID || STAGE == DSK_STAGE_KARRAS_MID) {
       Vec<V>::st(a.x_aux, i, auxo);
       Vec<V>::st(a.r1, i, r1o);
     } else {
-      if (writes_hist && a.hist != nullptr) Vec<V>::st(a.hist + (int64_t)hist_slot * N, i, xo);
+      if (writes_hist && a.hist != nullptr && !(STAGE == DSK_STAGE_INIT && a.blend_y != nullptr))
+        Vec<V>::st(a.hist + (int64_t)hist_slot * N, i, xo);
       // the state carried to the next step includes the churn perturbation (x_hat)
       Vec<V>::st(a.x, i, (STAGE == DSK_STAGE_INIT || STAGE == DSK_STAGE_KARRAS_FIN) ? pv : xo);
     }
@@ -334,7 +360,19 @@ extern "C" int dsk_sampler_stage_cond(int stage, float* x, float* x_aux, float* 
                                       float* hist, int B, int C, int64_t S, float sigma_data, float sigma_max,
                                       int precond_kind, int act_dtype, int xin_ld, int cfg, float guidance,
                                       void* stream) {
+  return dsk_sampler_stage_blend(stage, x, x_aux, r1, F, xin, cnoise, tab, row, noise, seed, hist, B, C, S, sigma_data, sigma_max,
+                                 precond_kind, act_dtype, xin_ld, cfg, guidance, nullptr, nullptr, 0, 0, stream);
+}
+
+extern "C" int dsk_sampler_stage_blend(int stage, float* x, float* x_aux, float* r1, const void* F, void* xin,
+                                       float* cnoise, const float* tab, const int* row, const float* noise, uint64_t seed,
+                                       float* hist, int B, int C, int64_t S, float sigma_data, float sigma_max,
+                                       int precond_kind, int act_dtype, int xin_ld, int cfg, float guidance,
+                                       const float* blend_y, const float* blend_mask, int64_t mask_n, int blend_rows,
+                                       void* stream) {
   DSK_REQUIRE(xin_ld >= C, "dsk_sampler_stage_cond: xin_ld=%d < C=%d", xin_ld, C);
+  DSK_REQUIRE(blend_y == nullptr || (blend_mask != nullptr && mask_n > 0 && blend_rows > 1 && ((int64_t)B * C * S) % mask_n == 0),
+              "dsk_sampler_stage_blend: bad blend arguments");
   DSK_REQUIRE(x && tab && row && cnoise, "dsk_sampler_stage: null x/tab/row/cnoise");
   DSK_REQUIRE(B > 0 && C > 0 && S > 0, "dsk_sampler_stage: bad shape B=%d C=%d S=%lld", B, C, (long long)S);
   DSK_REQUIRE(stage == DSK_STAGE_INIT || F != nullptr, "dsk_sampler_stage: F is null");
@@ -346,7 +384,7 @@ extern "C" int dsk_sampler_stage_cond(int stage, float* x, float* x_aux, float* 
   DSK_REQUIRE(!needs_aux || (x_aux && r1), "dsk_sampler_stage: x_aux/r1 are null");
   DSK_REQUIRE(act_dtype == DSK_F32 || is_h16(act_dtype), "dsk_sampler_stage: bad dtype %d", act_dtype);
   StageArgs a{x, x_aux, r1, F, xin, cnoise, tab, row, noise, hist, seed, B, C, S, sigma_data, sigma_max, precond_kind,
-              xin_ld, cfg ? 1 : 0, guidance};
+              xin_ld, cfg ? 1 : 0, guidance, blend_y, blend_mask, mask_n, blend_rows};
   const int64_t N = (int64_t)B * C * S;
   const bool vec = (C == 1) && (xin_ld == 1) && (N % 4 == 0);
   cudaStream_t st = as_stream(stream);

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) general_stage_kernel(GenArgs a) {
   float P = 0.f, Q = 0.f, xs = 0.f, cn = 0.f;      // rhs coefficients of the evaluation that produced F; input scale / c_noise being prepared
   bool prep = true, writes_hist = false;
   int hist_slot = rowi + 1;
-  if (STAGE == DSK_GSTAGE_INIT) { xs = r[DSK_GTAB_XS1]; cn = r[DSK_GTAB_CN1]; writes_hist = true; hist_slot = 0; }
+  if (STAGE == DSK_GSTAGE_INIT) { xs = r[DSK_GTAB_XS1]; cn = r[DSK_GTAB_CN1]; writes_hist = true; hist_slot = rowi; }   // partial runs start at row > 0
   else if (STAGE == DSK_GSTAGE_STEP1) { P = r[DSK_GTAB_P1]; Q = r[DSK_GTAB_Q1]; xs = rn[DSK_GTAB_XS1]; cn = rn[DSK_GTAB_CN1]; writes_hist = true; }
   else if (STAGE == DSK_GSTAGE_HEUN_MID) { P = r[DSK_GTAB_P1]; Q = r[DSK_GTAB_Q1]; xs = r[DSK_GTAB_XS2]; cn = r[DSK_GTAB_CN2]; }
   else { P = r[DSK_GTAB_P2]; Q = r[DSK_GTAB_Q2]; xs = rn[DSK_GTAB_XS1]; cn = rn[DSK_GTAB_CN1]; writes_hist = true; }   // HEUN_FIN

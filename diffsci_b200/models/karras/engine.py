@@ -93,6 +93,9 @@ class SamplerEngine:
         self._noise = None
         self._hist = None
         self._F = None
+        self._blend_y = None      # inpainting: forward history of the known data [nsteps + 1, N] and the mask (static buffers)
+        self._blend_mask = None
+        self._blend_on = False
         self.seed = 0
         self.nfe = 0
 
@@ -120,12 +123,16 @@ class SamplerEngine:
         self._F = F
 
     def _stage(self, stage: int):
-        check(lib.dsk_sampler_stage_cond(stage, ptr(self.x), ptr(self.x_aux), ptr(self.r1), ptr(self._F), ptr(self.xin),
-                                         ptr(self.cnoise), ptr(self._tab), ptr(self.row), ptr(self._noise),
-                                         C.c_uint64(0), ptr(self._hist), self.B, self.Cc,
-                                         self.S, self.sigma_data, self.sigma_max, self.kind, dt_code(self.act_dtype),
-                                         self.xin_ld, 1 if self.cfg else 0,
-                                         float(self.guidance) if self.cfg else 1.0, stream()))
+        by = self._blend_y if self._blend_on else None
+        check(lib.dsk_sampler_stage_blend(stage, ptr(self.x), ptr(self.x_aux), ptr(self.r1), ptr(self._F), ptr(self.xin),
+                                          ptr(self.cnoise), ptr(self._tab), ptr(self.row), ptr(self._noise),
+                                          C.c_uint64(0), ptr(self._hist), self.B, self.Cc,
+                                          self.S, self.sigma_data, self.sigma_max, self.kind, dt_code(self.act_dtype),
+                                          self.xin_ld, 1 if self.cfg else 0,
+                                          float(self.guidance) if self.cfg else 1.0, ptr(by),
+                                          ptr(self._blend_mask) if by is not None else None,
+                                          self._blend_mask.numel() if by is not None else 0,
+                                          self._blend_y.shape[0] if by is not None else 0, stream()))
 
     def set_condition(self, ychan: Optional[torch.Tensor], ye: Optional[torch.Tensor]):
         """Write the run's conditioning into the static buffers the captured graphs read: channel conditioning
@@ -173,16 +180,26 @@ class SamplerEngine:
 
     # ------------------------------------------------------------------ run
     def run(self, white_noise: torch.Tensor, table: torch.Tensor, program: str, record_history: bool = False,
-            noises: Optional[torch.Tensor] = None, seed: int = 0) -> torch.Tensor:
-        """white_noise: fp32 [B, *shape] on the device; table: CPU fp32 [nsteps+1, 8] (Scheduler.step_table)."""
+            noises: Optional[torch.Tensor] = None, seed: int = 0, first: int = 0, last: Optional[int] = None,
+            blend=None) -> torch.Tensor:
+        """white_noise: fp32 [B, *shape] on the device; table: CPU fp32 [nsteps+1, 8] (Scheduler.step_table).
+        first / last: run steps first .. last-1 of the table only, from the state `white_noise` at level t[first] -- scaled by
+        self.sigma_max, so callers of a partial run set it to 1 (Scheduler.propagate_partial, schedulers.py:177-217); the
+        history then has last - first + 1 rows.  blend = (y, mask): Scheduler.inpaint (schedulers.py:91-122) -- y fp32
+        [nsteps + 1, B, *shape] the forward history of the known data, mask broadcastable to the state; the blend is fused
+        into the step-completing stage kernels, so an inpainting run replays the same captured graphs."""
         require_cuda(white_noise, "white noise")
         if program not in self.programs:
             raise ValueError(f"Unknown integrator program: {program}")
         with torch.inference_mode(False), torch.no_grad():
-            return self._run(white_noise, table, program, record_history, noises, seed)
+            return self._run(white_noise, table, program, record_history, noises, seed, first, last, blend)
 
-    def _run(self, white_noise, table, program, record_history, noises, seed):
+    def _run(self, white_noise, table, program, record_history, noises, seed, first=0, last=None, blend=None):
         nsteps = table.shape[0] - 1
+        last = nsteps if last is None else int(last)
+        first = int(first)
+        if not (0 <= first < last <= nsteps):
+            raise ValueError(f"steps [{first}, {last}) outside the schedule of {nsteps} steps")
         regular, final = self._program(program, table)
         N = self.B * self.Cc * self.S
         # static-address inputs of the captured graphs: refill in place, re-capture only on shape change
@@ -200,6 +217,25 @@ class SamplerEngine:
             self._graphs.clear()
         if noises is not None:
             self._noise[:nsteps].copy_(noises.reshape(nsteps, N))
+        if blend is not None:
+            if type(self) is not SamplerEngine:
+                raise NotImplementedError("inpainting on the graph engine: EDM stages only")
+            y, mask = blend
+            if tuple(y.shape) != (nsteps + 1, self.B) + self.shape:
+                raise ValueError(f"inpainting history has shape {tuple(y.shape)}, expected {(nsteps + 1, self.B) + self.shape}")
+            m = mask.to(self.x)
+            if not (m.ndim <= self.x.ndim and tuple(self.x.shape[self.x.ndim - m.ndim:]) == tuple(m.shape)):
+                m = m.expand_as(self.x)              # general broadcasting (size-1 batch / channel dimensions)
+            m = m.contiguous().reshape(-1)
+            if self._blend_y is None or tuple(self._blend_y.shape) != (nsteps + 1, N) or self._blend_mask.numel() != m.numel():
+                self._blend_y = torch.empty((nsteps + 1, N), dtype=torch.float32, device=self.device)
+                self._blend_mask = torch.empty_like(m)
+                self._graphs.clear()
+            self._blend_y.copy_(y.reshape(nsteps + 1, N))
+            self._blend_mask.copy_(m)
+        if self._blend_on != (blend is not None):
+            self._blend_on = blend is not None
+            self._graphs.clear()                     # the blend pointers are baked into the captured stage launches
         self.seed = int(seed)
         if self.native:       # captured graphs read the PACKED weight copies: refresh them (in place, same addresses) when the
             self.plan.prepare()   # parameters changed since the last run (optimizer steps, EMA apply_to, load_state_dict)
@@ -211,22 +247,26 @@ class SamplerEngine:
         self.x.copy_(white_noise.reshape(self.x.shape))
         sd = self.seed & 0xFFFFFFFFFFFFFFFF
         as_i32 = lambda v: v - (1 << 32) if v >= (1 << 31) else v  # noqa: E731
-        self.row.copy_(torch.tensor([0, as_i32(sd & 0xFFFFFFFF), as_i32(sd >> 32), 0], dtype=torch.int32))
+        self.row.copy_(torch.tensor([first, as_i32(sd & 0xFFFFFFFF), as_i32(sd >> 32), 0], dtype=torch.int32))
         self.nfe = 0
         self._stage(STAGE_INIT)
+        n_reg = (last - first - 1) if last == nsteps else (last - first)     # the table's final step has its own stage program
+        n_fin = 1 if last == nsteps else 0
         if self.use_graphs:
-            for _ in range(nsteps - 1):
+            for _ in range(n_reg):
                 g_reg.replay()
-            g_fin.replay()
-            self.nfe = (nsteps - 1) * len(regular) + len(final)
-            self._last_graph_launches = ((nsteps - 1) * self._graph_launches[(program, "regular")] +
-                                         self._graph_launches[(program, "final")])
+            if n_fin:
+                g_fin.replay()
+            self.nfe = n_reg * len(regular) + n_fin * len(final)
+            self._last_graph_launches = (n_reg * self._graph_launches[(program, "regular")] +
+                                         n_fin * self._graph_launches[(program, "final")])
         else:
-            for _ in range(nsteps - 1):
+            for _ in range(n_reg):
                 self._step(regular)
-            self._step(final)
+            if n_fin:
+                self._step(final)
         if record_history:
-            return self._hist.view((nsteps + 1, self.B) + self.shape).clone()
+            return self._hist.view((nsteps + 1, self.B) + self.shape)[first:last + 1].clone()
         return self.x.clone()
 
 

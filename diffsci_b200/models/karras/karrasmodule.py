@@ -621,6 +621,31 @@ class KarrasModule(_Base):
             finally:
                 if integrator is not None:
                     sch.unset_temporary_integrator()
+        eng = self._edm_engine(x, y, guidance, kind, cond)
+        eng.sigma_max = 1.0 if _prescaled else float(sch.maximum_scale)
+        table = sch.step_table(nsteps, integ)
+        noises = None
+        if integ.injected_noise is not None:
+            noises = torch.stack([n.to(x) for n in integ.injected_noise[:nsteps]], 0)
+        seed = integrators.fresh_noise_seed() if integ.fused_program in ("euler-maruyama", "karras") else 0
+        if getattr(integ, "_fixed_seed", None) is not None:
+            seed = integ._fixed_seed
+        out = eng.run(x, table, integ.fused_program, record_history=record_history, noises=noises, seed=seed)
+        self.last_nfe = eng.nfe
+        return out
+
+    def _edm_route(self, integ, y=None, guidance: float = 1.0):
+        """-> (preconditioner kind, conditional?) if the captured-graph EDM engine serves this configuration, else None."""
+        sch = self.config.noisescheduler
+        kind = _engine.precond_kind(self.config.preconditioner)
+        cond = bool(self.conditional and guidance != 0.0)
+        ok = (sch.fused_supported and kind is not None and integ.fused_program in _engine.PROGRAMS and
+              hasattr(self.model, "plan") and getattr(self.model, "engine_native", True) and
+              not (cond and not hasattr(self.model, "conditioning_vector")))
+        return (kind, cond) if ok else None
+
+    def _edm_engine(self, x: Tensor, y, guidance: float, kind: int, cond: bool):
+        """The cached SamplerEngine of this (batch, shape, precision, conditioning) with the run's conditioning written."""
         B, shape = x.shape[0], tuple(x.shape[1:])
         ychan = ye = None
         cfg = cond and guidance != 1.0
@@ -643,15 +668,29 @@ class KarrasModule(_Base):
                                                                  cond_channels=ncond, cond_vector=ye is not None,
                                                                  guidance=float(guidance) if cfg else None)
         eng.set_condition(ychan, ye)
-        eng.sigma_max = 1.0 if _prescaled else float(sch.maximum_scale)
-        table = sch.step_table(nsteps, integ)
+        return eng
+
+    def _engine_partial(self, x: Tensor, y, integ, nsteps: int, first: int, last: int, record_history: bool = False,
+                        blend=None) -> Optional[Tensor]:
+        """Steps first .. last-1 of the nsteps schedule on the captured-graph engine (None: configuration not served there).
+        x is the state at level t[first]; blend = (forward history of the known data, mask): inpainting."""
+        route = self._edm_route(integ, y)
+        if route is None or os.environ.get("DSK_PARTIAL_ENGINE") == "0":
+            return None
+        x = x.float().contiguous()
+        eng = self._edm_engine(x, y, 1.0, *route)
+        eng.sigma_max = 1.0
+        table = self.config.noisescheduler.step_table(nsteps, integ)
         noises = None
-        if integ.injected_noise is not None:
-            noises = torch.stack([n.to(x) for n in integ.injected_noise[:nsteps]], 0)
+        if integ.injected_noise is not None and integ.fused_program in ("euler-maruyama", "karras"):
+            # draw numbers continue across partial runs; the engine indexes its noise rows by schedule step
+            draws = integ.injected_noise[integ._draws:integ._draws + (last - first)]
+            integ._draws += last - first
+            noises = torch.zeros((nsteps,) + tuple(x.shape), dtype=torch.float32, device=x.device)
+            noises[first:last] = torch.stack([n.to(x) for n in draws], 0)
         seed = integrators.fresh_noise_seed() if integ.fused_program in ("euler-maruyama", "karras") else 0
-        if getattr(integ, "_fixed_seed", None) is not None:
-            seed = integ._fixed_seed
-        out = eng.run(x, table, integ.fused_program, record_history=record_history, noises=noises, seed=seed)
+        out = eng.run(x, table, integ.fused_program, record_history=record_history, noises=noises, seed=seed, first=first,
+                      last=last, blend=blend)
         self.last_nfe = eng.nfe
         return out
 
@@ -702,6 +741,13 @@ class KarrasModule(_Base):
             return alpha * s + (1 - alpha) * analytic
         sch = self.config.noisescheduler
         final_step = nsteps if final_step is None else final_step
+        if interp_fn is None and y is None:
+            # the captured-graph engine serves a stretch of the schedule as it serves a whole run (start row + step count)
+            with torch.inference_mode():
+                out = self._engine_partial(x, None, self._resolve_integrator(integrator), nsteps, initial_step, final_step,
+                                           record_history)
+            if out is not None:
+                return out
         with torch.inference_mode():
             if integrator is not None:
                 sch.set_temporary_integrator(integrator)
@@ -728,8 +774,15 @@ class KarrasModule(_Base):
         if y is not None:
             y = dict_unsqueeze(y, 0)
         with torch.inference_mode():
-            return self.config.noisescheduler.inpaint(x, x_inpaint, mask, self._score_fn(y), x_inpaint.shape[0] - 1,
-                                                      record_history=record_history)
+            nsteps = x_inpaint.shape[0] - 1
+            sch = self.config.noisescheduler
+            if y is None and x.is_cuda:
+                # graph engine: the known-region blend is fused into the step-completing stage kernels
+                out = self._engine_partial(x, None, sch.integrator, nsteps, 0, nsteps, record_history,
+                                           blend=(x_inpaint.to(x), mask))
+                if out is not None:
+                    return out
+            return sch.inpaint(x, x_inpaint, mask, self._score_fn(y), nsteps, record_history=record_history)
 
     def propagate_repaint_toward_sample(self, x: Tensor, x_inpaint: Tensor, mask: Tensor, y=None,
                                         record_history: bool = False) -> Tensor:
@@ -737,8 +790,18 @@ class KarrasModule(_Base):
         if y is not None:
             y = dict_unsqueeze(y, 0)
         with torch.inference_mode():
-            return self.config.noisescheduler.repaint(x, x_inpaint, mask, self._score_fn(y), x_inpaint.shape[0] - 1,
-                                                      record_history=record_history)
+            sch = self.config.noisescheduler
+            if y is None and x.is_cuda and self._edm_route(sch.integrator) is not None and \
+                    os.environ.get("DSK_PARTIAL_ENGINE") != "0":
+                # Scheduler.repaint's loop (schedulers.py:124-175) with every integrated stretch on the graph engine
+                module = self
+
+                class _Stretch:
+                    def __call__(self_, xx, score_fn, nsteps, first, last, **_):
+                        return module._engine_partial(xx, None, sch.integrator, nsteps, first, last)
+                return sch.repaint(x, x_inpaint, mask, None, x_inpaint.shape[0] - 1, record_history=record_history,
+                                   _partial=_Stretch())
+            return sch.repaint(x, x_inpaint, mask, self._score_fn(y), x_inpaint.shape[0] - 1, record_history=record_history)
 
     def inpaint(self, x_orig: Tensor, mask: Tensor, y=None, nsteps: int = 100, record_history: bool = False,
                 maximum_batch_size: Optional[int] = None, mode: str = "inpaint") -> Tensor:

@@ -209,30 +209,34 @@ class Scheduler(torch.nn.Module):
         return history if record_history else x
 
     def repaint(self, x: Tensor, y: Tensor, mask: Tensor, score_fn: ScoreFunction, nsteps: int = 100, rsteps: int = 10,
-                nresamples: int = 10, record_history: bool = False) -> Tensor:
+                nresamples: int = 10, record_history: bool = False, _partial=None) -> Tensor:
         """RePaint resampling (schedulers.py:124-175): every `rsteps` steps, `nresamples` times: re-impose the known
         region, jump back in noise level (renoise) and integrate the same stretch again."""
         if not (nsteps % rsteps) == 0:
             raise ValueError("rsteps should divide nsteps")
         t = self.create_steps(nsteps + 1).float().cpu()
         x = x.float().contiguous()
+        # _partial (KarrasModule): integrates a stretch of the schedule on the captured-graph engine instead of the step seam
+        partial = self.propagate_partial if _partial is None else _partial
+        if _partial is not None and hasattr(self.integrator, "begin_run"):
+            self.integrator.begin_run()              # renoise draws from the integrator's stream
         if record_history:
             history = torch.zeros((int(nresamples * (nsteps / rsteps - 1)) + 2,) + tuple(x.shape), dtype=x.dtype,
                                   device=x.device)
             history[0] = x
         x = ops.mask_blend(x, y[-1], mask)
         step, fstep = 0, rsteps
-        x = self.propagate_partial(x, score_fn, nsteps, step, fstep)
+        x = partial(x, score_fn, nsteps, step, fstep)
         step, fstep = fstep, fstep + rsteps
         level = 0
         while fstep <= nsteps:
-            x = self.propagate_partial(x, score_fn, nsteps, step, fstep)
+            x = partial(x, score_fn, nsteps, step, fstep)
             for i in range(nresamples):
                 x = ops.mask_blend(x, y[-fstep - 1], mask)
                 if record_history:
                     history[level + i + 1] = x
                 x = self.renoise(x, t[fstep], t[step])
-                x = self.propagate_partial(x, score_fn, nsteps, step, fstep)
+                x = partial(x, score_fn, nsteps, step, fstep)
             step, fstep = fstep, fstep + rsteps
             level = level + nresamples
         if not step == nsteps:

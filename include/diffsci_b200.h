@@ -155,6 +155,17 @@ int dsk_sampler_stage_cond(int stage, float* x, float* x_aux, float* r1, const v
                            const float* tab, const int* row, const float* noise, uint64_t seed, float* hist,
                            int B, int C, int64_t S, float sigma_data, float sigma_max, int precond_kind, int act_dtype,
                            int xin_ld, int cfg, float guidance, void* stream);
+/* The same stage with the known-region blend of Scheduler.inpaint (karras/schedulers.py:91-122) fused in: after every completed
+ * step (and after DSK_STAGE_INIT) x <- x (1 - mask) + blend_y[level] mask, level = blend_rows - 1 - (steps completed), before the
+ * history write and before the next network input is prepared.  blend_y: fp32 [blend_rows][B, C, S], the forward (data -> noise)
+ * history of the known data (blend_rows = nsteps + 1); blend_mask: fp32, mask_n elements broadcast over the leading dimensions.
+ * blend_y == NULL: dsk_sampler_stage_cond.  DSK_STAGE_INIT at row r > 0 starts a run at step r of the table
+ * (Scheduler.propagate_partial, schedulers.py:177-217) and writes history slot r. */
+int dsk_sampler_stage_blend(int stage, float* x, float* x_aux, float* r1, const void* F, void* xin, float* cnoise,
+                            const float* tab, const int* row, const float* noise, uint64_t seed, float* hist,
+                            int B, int C, int64_t S, float sigma_data, float sigma_max, int precond_kind, int act_dtype,
+                            int xin_ld, int cfg, float guidance, const float* blend_y, const float* blend_mask, int64_t mask_n,
+                            int blend_rows, void* stream);
 /* dsk_precond_scale into rows of xin_ld channels; dup != 0 also fills rows [B, 2B) (the CFG batch). */
 int dsk_precond_scale_cond(const float* x, const float* c_in, void* xin, int B, int C, int64_t S, int act_dtype,
                            int xin_ld, int dup, void* stream);

@@ -80,3 +80,41 @@ def test_trainer_general_preconditioner_and_delta():
     got = float(tr.step(x, sigma=sigma, noise=noise))
     assert abs(got - want) < 1e-4 * abs(want), (got, want)
     assert any(not torch.equal(a, b) for a, b in zip(before, net.parameters()))
+
+
+def test_inpaint_repaint_partial_run_on_the_graph_engine(monkeypatch):
+    """SURVEY 8f-1 on the captured-graph engine: partial stretches start at a schedule row, the inpainting blend
+    is fused into the step-completing stages, repaint chains engine stretches -- each equal to the Integrator.step seam
+    (DSK_PARTIAL_ENGINE=0; the seam itself is pinned against the live reference in test_gpu_nets.py) and replayed from graphs."""
+    import diffsci_b200 as d
+    torch.manual_seed(3)
+    net = d.PUNetG(d.PUNetGConfig(model_channels=8), precision="fp32").to(DEV).eval()
+    mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm())
+    sch = mod.config.noisescheduler
+    n = 8
+    x0 = torch.randn(2, 1, 16, 16, device=DEV)
+    mask = (torch.rand(1, 16, 16, device=DEV) > 0.5).float()
+    sch.stochastic_integrator.reset_noise(seed=11)
+    hist = mod.propagate_toward_noise(x0, nsteps=n, record_history=True, stochastic_integration=True)
+    start = torch.randn(2, 1, 16, 16, device=DEV) * 80
+
+    def both(fn):
+        sch.integrator.reset_noise(seed=7)
+        monkeypatch.setenv("DSK_PARTIAL_ENGINE", "0")
+        seam = fn()
+        sch.integrator.reset_noise(seed=7)
+        monkeypatch.delenv("DSK_PARTIAL_ENGINE")
+        eng = next(iter(mod._engines.values()), None)
+        before = 0 if eng is None else eng.graph_launches_per_run()
+        out = fn()
+        eng = next(iter(mod._engines.values()))
+        assert eng.use_graphs and eng.graph_launches_per_run() > 0, before
+        return seam, out
+
+    for name, fn in [("partial", lambda: mod.propagate_partial_toward_sample(start, 2, 6, nsteps=n, record_history=True)),
+                     ("partial-to-end", lambda: mod.propagate_partial_toward_sample(start, 5, None, nsteps=n)),
+                     ("inpaint", lambda: mod.propagate_inpaint_toward_sample(start, hist, mask, record_history=True)),
+                     ("repaint", lambda: mod.propagate_repaint_toward_sample(start, hist, mask))]:
+        seam, out = both(fn)
+        assert out.shape == seam.shape, name
+        assert relmax(out, seam) < 2e-4, (name, relmax(out, seam))
