@@ -66,6 +66,7 @@ SIGNATURES = {
     "dsk_upsample2x": [p, p, i32, i32, i32, i32, i32, i32, i32, p],
     "dsk_pack_upconv_weight": [p, p, i32, i32, i32, i32, p],
     "dsk_pack_conv_weight": [p, p, i32, i32, i32, i32, p],
+    "dsk_pack_conv_weights_multi": [p, i32, i32, p],
     "dsk_gemm_f32": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i32, i32, f32, i32, p],
     "dsk_gemm_bf16_tc": [p, p, p, p, i32, p, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, f32, i32, i32, i32, p],
     "dsk_gemm_tc": [p, p, p, p, i32, p, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, f32, i32, i32, i32, i32, i32, i32, p],

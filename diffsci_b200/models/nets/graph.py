@@ -731,8 +731,9 @@ class TrainGraph:
 
     def prepare(self):
         """(Re)pack derived weight layouts; called before every forward so optimizer steps are picked up."""
-        for pc in self._packs:
-            pc.packed()
+        if getattr(self, "_packer", None) is None or self._packer_n != len(self._packs):
+            self._packer, self._packer_n = ops.MultiPacker(self._packs), len(self._packs)
+        self._packer.pack()
 
     def run_forward(self):
         # the saved activations live in this graph's static buffers: every forward invalidates the previous one's

@@ -105,6 +105,58 @@ class PackedConv:
         return self._packed
 
 
+class MultiPacker:
+    """Re-packs many PackedConv weights in ONE launch (dsk_pack_conv_weights_multi): the training graphs re-pack every
+    convolution's forward and data-gradient layouts after each optimizer step.  Weights the tiled kernel does not take
+    (sub-pixel up-convolutions, few-channel layers, fp32 layouts) keep their own PackedConv.packed() path."""
+
+    def __init__(self, packs):
+        self.multi, self.rest = [], []
+        for pc in packs:
+            ok = (isinstance(pc, PackedConv) and is_tc_dtype(pc.w_dtype) and not pc.subpixel and pc.taps <= 27 and
+                  (pc.dgrad or pc.cout > 16) and pc.cout * pc.cin * pc.taps >= 16384 and pc.weight.dtype == torch.float32 and
+                  pc.weight.is_contiguous())
+            (self.multi if ok else self.rest).append(pc)
+        self._table = None
+        self._sig = None
+        self._total = 0
+
+    def _build(self):
+        import struct
+        dev = self.multi[0].weight.device
+        raw, block0 = b"", 0
+        for pc in self.multi:
+            split = pc.w_dtype == SPLIT
+            n = pc.taps * pc.cin * pc.cout * (2 if split else 1)
+            if pc._packed is None or pc._packed.device != dev or pc._packed.numel() != n:
+                pc._packed = torch.empty(n, dtype=torch.float16 if split else pc.w_dtype, device=dev)
+            # reference weight [Cout_w, Cin_w, taps]; a dgrad pack swaps the roles (PackedConv stores cout / cin swapped)
+            co, ci = (pc.cin, pc.cout) if pc.dgrad else (pc.cout, pc.cin)
+            raw += struct.pack("2Q6i", pc.weight.data_ptr(), pc._packed.data_ptr(), co, ci, pc.taps, int(pc.dgrad),
+                               w_code(pc.w_dtype), block0)
+            block0 += (ci if pc.dgrad else co) * (((co if pc.dgrad else ci) + 63) // 64)
+        self._table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self._total = block0
+        self._sig = tuple((pc.weight.data_ptr(), pc._packed.data_ptr()) for pc in self.multi)
+
+    def pack(self):
+        for pc in self.rest:
+            pc.packed()
+        if not self.multi:
+            return
+        keys = [(pc.weight._version, pc.weight.data_ptr(), _weight_epoch[0]) for pc in self.multi]
+        if all(pc._packed is not None and pc._version == k for pc, k in zip(self.multi, keys)):
+            return
+        require_cuda(self.multi[0].weight, "conv weight")
+        with torch.inference_mode(False), torch.no_grad():
+            if self._table is None or self._sig != tuple((pc.weight.data_ptr(), 0 if pc._packed is None else pc._packed.data_ptr())
+                                                         for pc in self.multi):
+                self._build()
+            check(lib.dsk_pack_conv_weights_multi(ptr(self._table), len(self.multi), self._total, stream()))
+        for pc, k in zip(self.multi, keys):
+            pc._version = k
+
+
 def _conv_desc_of(x, pc, out, residual, up2, out_nchw, D, H, W):
     return L.ConvDesc(x.shape[0], D, H, W, pc.cin, pc.cout, pc.ksize, pc.ndim, int(up2), w_code(pc.w_dtype), act_code(x, pc.cin),
                       dt_code(residual.dtype if (out_nchw and residual is not None) else

@@ -252,6 +252,13 @@ int dsk_pack_upconv_weight(const float* w_ref, void* w_packed, int Cout, int Cin
 /* repack a reference-layout weight [Cout, Cin, k(,k)(,k)] fp32 into the two packed layouts */
 int dsk_pack_conv_weight(const float* w_ref, void* w_packed, int Cout, int Cin, int taps, int dtype, void* stream);
 
+/* dsk_pack_conv_weight / dsk_pack_conv_weight_dgrad for MANY 16-bit weights in ONE launch (the re-pack after every optimizer
+ * step of a training iteration, karrasmodule.py:1146-1155 + :497-507).  jobs: DEVICE array of
+ *   struct { const float* w_ref; void* w_packed; int Cout, Cin, taps, dgrad, dtype, block0; }
+ * (taps <= 27; dtype DSK_BF16 | DSK_F16 | DSK_SPLIT_F16), block0 = first block of the job = sum over the previous jobs of
+ * (dgrad ? Cin : Cout) * ceil((dgrad ? Cout : Cin) / 64); total_blocks = that sum over all jobs. */
+int dsk_pack_conv_weights_multi(const void* jobs, int njobs, int total_blocks, void* stream);
+
 /* Batched C[b] = act(alpha * A[b] (MxK, row-major, lda) * B[b] + bias[n]) (act: 0 none, 1 SiLU, 2 ReLU);
  * transB = 1: B is [N][K] row-major (C = A*B^T) ; transB = 0: B is [K][N].  fp32 CUDA-core path. */
 int dsk_gemm_f32(const float* A, const float* Bm, float* Cm, const float* bias, int M, int N, int K, int lda,
