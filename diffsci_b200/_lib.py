@@ -72,6 +72,7 @@ SIGNATURES = {
     "dsk_gemm_tc": [p, p, p, p, i32, p, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, f32, i32, i32, i32, i32, i32, i32, p],
     "dsk_attn_softmax_qk_h16": [p, p, p, p, i32, i32, i64, i64, i64, i64, i32, f32, i32, p],
     "dsk_softmax_rows_h16": [p, p, i64, i32, i32, p],
+    "dsk_attn_flash": [p, p, p, p, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i32, f32, i32, i32, p],
     "dsk_softmax_bwd_rows_bf16": [p, p, p, i64, i32, p],
     "dsk_attn_softmax_ws_bytes": [i32, i32],
     "dsk_attn_softmax_qk": [p, p, p, p, i32, i32, i64, i64, i64, i64, i32, f32, p],

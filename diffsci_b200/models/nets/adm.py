@@ -21,7 +21,7 @@ from torch import nn
 from ... import ops
 from ..._lib import require_cuda
 from .layers import AttentionParams, ConvParams, FourierParams, LinearParams, NormParams, _Act, _Holder, make_conv
-from .punetg import _NORM_MODE, _tc_eligible, DEFAULT_PRECISION, PRECISIONS, _ACT_DTYPE, _W_DTYPE, SPLIT_MODES, MIXED_MIN_CIN
+from .punetg import _NORM_MODE, _tc_eligible, DEFAULT_PRECISION, PRECISIONS, _ACT_DTYPE, _W_DTYPE, SPLIT_MODES, MIXED_MIN_CIN, _ATTN_FLASH
 
 
 class ADMConfig:
@@ -314,7 +314,21 @@ class _ADMPlan:
         out = self.buf(("attn_out", idx), x.shape)
         tc = self.act_dtype in ops.H16 and _tc_eligible(C, C) and Lq % 8 == 0 and Lq <= 8192
         f32 = torch.float32
-        if self.split and _tc_eligible(C, C) and Lq % 64 == 0 and Lq <= 8192:
+        split_ok = self.split and _tc_eligible(C, C) and Lq % 64 == 0 and Lq <= 8192
+        if _ATTN_FLASH and ops.attn_flash_supported(Lq, C) and ((split_ok and self.precision != "fp32") or (tc and not self.split)):
+            # flash-style core (dsk_attn_flash) for every 16-bit-operand mode; the fp32 mode keeps the split-operand GEMM chain
+            wfmt = ops.SPLIT if self.split else self.act_dtype
+            st = self.attn_state.get(idx)
+            if st is None:
+                st = self.attn_state[idx] = (ops.PackedLinear(m.in_proj_weight, wfmt), ops.PackedLinear(m.out_proj.weight, wfmt))
+                st[0].packed(), st[1].packed()
+            bufs = self.attn_bufs.get((B, Lq, C))
+            if bufs is None:
+                bufs = self.attn_bufs[(B, Lq, C)] = ops.attention_flash_buffers(B, Lq, C, x.device, self.act_dtype, split=self.split)
+            fn = ops.self_attention_flash_split if self.split else ops.self_attention_flash
+            fn(x.view(B, Lq, C), st[0], m.in_proj_bias, st[1], m.out_proj.bias, bufs, out.view(B, Lq, C), res)
+            return out
+        if split_ok:
             st = self.attn_state.get(idx)
             if st is None:
                 st = self.attn_state[idx] = (ops.PackedLinear(m.in_proj_weight, ops.SPLIT), ops.PackedLinear(m.out_proj.weight, ops.SPLIT))

@@ -16,6 +16,7 @@ Fusions relative to the reference graph:
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Optional
 
 import torch
@@ -47,6 +48,7 @@ _ACT_DTYPE = {"fp32": torch.float32, "fp32_ffma": torch.float32, "fp16x2": torch
 _W_DTYPE = {"fp32": ops.SPLIT, "fp16x2": torch.float16, "fp16x2m": torch.float16, "fp16": torch.float16,
             "bf16": torch.bfloat16}   # tcgen05 weight format
 SPLIT_MODES = ("fp32", "fp16x2", "fp16x2m")      # fp32 storage; tensor-core operands are split-fp16 (hi | lo) tensors
+_ATTN_FLASH = os.environ.get("DSK_ATTN_FLASH", "1") != "0"   # 0: keep the multi-launch GEMM attention (A/B measurements)
 MIXED_MIN_CIN = 128                              # "fp16x2m": contractions with fewer input channels take plain fp16 activations
 
 
@@ -361,7 +363,15 @@ class _Plan:
         self.attn_tc = (adt in ops.H16 and _tc_eligible(Cb, Cb) and Lq % 8 == 0 and Lq <= 8192)
         self.attn_split = (split and _tc_eligible(Cb, Cb) and Lq % 64 == 0 and Lq <= 8192)
         self.attn_hybrid = False
-        if len(net.attn_block) > 0 and self.attn_split:
+        # flash-style core (dsk_attn_flash) for every 16-bit-operand mode; the fp32 mode keeps the split-operand GEMM chain
+        self.attn_flash = (_ATTN_FLASH and ops.attn_flash_supported(Lq, Cb) and
+                           ((self.attn_split and precision != "fp32") or (self.attn_tc and not split)))
+        if len(net.attn_block) > 0 and self.attn_flash:
+            self.attn = ops.attention_flash_buffers(B, Lq, Cb, dev, adt, split=split)
+            wfmt = ops.SPLIT if split else adt
+            self.attn_w = [(ops.PackedLinear(a.mhattn.in_proj_weight, wfmt), ops.PackedLinear(a.mhattn.out_proj.weight, wfmt))
+                           for a in net.attn_block]
+        elif len(net.attn_block) > 0 and self.attn_split:
             self.attn = ops.attention_split_buffers(B, Lq, Cb, dev)
             self.attn_w = [(ops.PackedLinear(a.mhattn.in_proj_weight, ops.SPLIT), ops.PackedLinear(a.mhattn.out_proj.weight, ops.SPLIT))
                            for a in net.attn_block]
@@ -386,7 +396,7 @@ class _Plan:
         """Materialise packed weights (must happen outside CUDA-graph capture)."""
         for pc in [self.pc_in, self.pc_out, *self.pc_down, *self.pc_up, *[p for pair in self.pc.values() for p in pair]]:
             pc.packed()
-        if (self.attn_tc or self.attn_hybrid or self.attn_split) and len(self.net.attn_block) > 0:
+        if (self.attn_tc or self.attn_hybrid or self.attn_split or self.attn_flash) and len(self.net.attn_block) > 0:
             for wi, wo in self.attn_w:
                 wi.packed()
                 wo.packed()
@@ -428,6 +438,11 @@ class _Plan:
         a = self.attn
         m = attn.mhattn
         B, Lq, Cb = self.B, self.Lq, self.Cb
+        if self.attn_flash:
+            wi, wo = self.attn_w[index]
+            fn = ops.self_attention_flash_split if self.split else ops.self_attention_flash
+            fn(x.view(B, Lq, Cb), wi, m.in_proj_bias, wo, m.out_proj.bias, a, out.view(B, Lq, Cb), self.net.config.attn_residual)
+            return out
         if self.attn_split:
             wi, wo = self.attn_w[index]
             ops.self_attention_split(x.view(B, Lq, Cb), wi, m.in_proj_bias, wo, m.out_proj.bias, a, out.view(B, Lq, Cb),

@@ -633,12 +633,12 @@ def gemm_split_tc(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, *, M: in
     half of an operand lies a_lo / b_lo elements after its hi half along the operand's contiguous coordinate; lda / ldb are
     the full row lengths.  Three tcgen05 MMAs per k-step (hi*hi + hi*lo + lo*hi) -- fp32-class products on the tensor cores."""
     require_cuda(A, "gemm A")
-    assert A.dtype == torch.float16 and Bm.dtype == torch.float16 and out.dtype == torch.float32
+    assert A.dtype == torch.float16 and Bm.dtype == torch.float16 and out.dtype in (torch.float32, torch.float16)
     assert residual is None or residual.dtype == torch.float32
     a = C.c_void_p(A.data_ptr() + a_off * 2)
     b = C.c_void_p(Bm.data_ptr() + b_off * 2)
     check(lib.dsk_gemm_tc(a, b, ptr(out), ptr(bias), 0, ptr(residual), 1, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch,
-                          alpha, 1, int(transA), int(transB), L.SPLIT_F16, a_lo, b_lo, stream()))
+                          alpha, int(out.dtype == torch.float32), int(transA), int(transB), L.SPLIT_F16, a_lo, b_lo, stream()))
     return out
 
 
@@ -692,6 +692,74 @@ def self_attention_split(tok: torch.Tensor, w_in: "PackedLinear", in_b, w_out: "
                       b_off=2 * Cc + k0 * 6 * Cc, transB=True, residual=bufs["ao"] if k0 else None)
     aos = split_f16(bufs["ao"], out=bufs["ao_s"])
     gemm_split_tc(aos, w_out.packed(), out.view(M, Cc), M=M, N=Cc, K=Cc, lda=2 * Cc, ldb=2 * Cc, ldc=Cc, a_lo=Cc, b_lo=Cc,
+                  bias=out_b.detach(), residual=tok.reshape(M, Cc) if residual else None)
+    return out
+
+
+def attn_flash_supported(Lq: int, Cc: int) -> bool:
+    """Shapes dsk_attn_flash takes: the output accumulator of a 128-query tile occupies C TMEM columns next to two 128-column
+    score buffers (C = 128 | 256); below 128 tokens a query tile is mostly padding and the GEMM path is kept."""
+    return Cc in (128, 256) and Lq >= 128
+
+
+def attn_flash(qkv: torch.Tensor, out: torch.Tensor, B: int, Lq: int, Cc: int) -> torch.Tensor:
+    """out[b] = softmax(Q[b] K[b]^T / sqrt(C)) V[b] from packed 16-bit projections qkv [B*L, 3C] in one flash-style tcgen05
+    kernel (dsk_attn_flash; nets/attention.py:93-102).  out: [B*L, C] in qkv's dtype or fp32, or a split-fp16 [B*L, 2C] tensor
+    (hi | lo: the A operand of a split output projection)."""
+    require_cuda(qkv, "attention qkv")
+    assert qkv.dtype in H16 and qkv.is_contiguous() and qkv.shape[-1] == 3 * Cc
+    ldo = out.shape[-1]
+    if out.dtype == torch.float32:
+        mode = 1
+    elif out.dtype == torch.float16 and ldo == 2 * Cc:
+        mode = 2
+    else:
+        assert out.dtype == qkv.dtype and ldo == Cc
+        mode = 0
+    base = qkv.data_ptr()
+    check(lib.dsk_attn_flash(C.c_void_p(base), C.c_void_p(base + 2 * Cc), C.c_void_p(base + 4 * Cc), ptr(out), Lq, Cc, 3 * Cc, 3 * Cc,
+                             3 * Cc, ldo, Lq * 3 * Cc, Lq * 3 * Cc, Lq * 3 * Cc, Lq * ldo, B, Cc ** -0.5, dt_code(qkv.dtype), mode,
+                             stream()))
+    return out
+
+
+def attention_flash_buffers(B: int, Lq: int, Cc: int, device, dtype=torch.bfloat16, split: bool = False) -> dict:
+    """Scratch of self_attention_flash (16-bit modes) / self_attention_flash_split (fp32 storage, split projections): packed
+    16-bit Q|K|V and the attention output -- nothing of size L x L."""
+    h = dict(dtype=torch.float16 if split else dtype, device=device)
+    if split:
+        return dict(tok_s=torch.empty((B * Lq, 2 * Cc), **h), qkv=torch.empty((B * Lq, 3 * Cc), **h),
+                    ao_s=torch.empty((B * Lq, 2 * Cc), **h))
+    return dict(qkv=torch.empty((B * Lq, 3 * Cc), **h), ao=torch.empty((B * Lq, Cc), **h))
+
+
+def self_attention_flash(tok: torch.Tensor, w_in: "PackedLinear", in_b: torch.Tensor, w_out: "PackedLinear", out_b: torch.Tensor,
+                         bufs: dict, out: torch.Tensor, residual: bool) -> torch.Tensor:
+    """nn.MultiheadAttention(C, 1 head) on 16-bit tokens [B, L, C] (nets/attention.py:54-72) in three launches: packed Q|K|V
+    projection, dsk_attn_flash, output projection (+ residual).  `bufs`: attention_flash_buffers."""
+    B, Lq, Cc = tok.shape
+    qkv, ao = bufs["qkv"], bufs["ao"]
+    gemm_bf16_tc(tok, w_in.packed(), qkv, M=B * Lq, N=3 * Cc, K=Cc, lda=Cc, ldb=Cc, ldc=3 * Cc, bias=in_b.detach())
+    attn_flash(qkv, ao, B, Lq, Cc)
+    gemm_bf16_tc(ao, w_out.packed(), out, M=B * Lq, N=Cc, K=Cc, lda=Cc, ldb=Cc, ldc=Cc, bias=out_b.detach(),
+                 residual=tok if residual else None)
+    return out
+
+
+def self_attention_flash_split(tok: torch.Tensor, w_in: "PackedLinear", in_b, w_out: "PackedLinear", out_b, bufs: dict,
+                               out: torch.Tensor, residual: bool) -> torch.Tensor:
+    """The attention block of the fp16x2 / fp16x2m modes (fp32 tokens [B, L, C] in and out): both projections are split-operand
+    GEMMs (tokens and weights hi + lo, fp32 accumulate), Q|K|V are rounded ONCE to fp16 by the projection's epilogue and the
+    core is dsk_attn_flash on plain fp16 operands, its output written in split form for the output projection.  Measured
+    against running the core on split operands as well (oracle/split_budget.py emulation, 3-D mc = 64): network max-rel
+    8.3e-4 -> 8.8e-4, L2 4.98e-4 -> 5.08e-4."""
+    B, Lq, Cc = tok.shape
+    M = B * Lq
+    ts = split_f16(tok.reshape(M, Cc), out=bufs["tok_s"])
+    gemm_split_tc(ts, w_in.packed(), bufs["qkv"], M=M, N=3 * Cc, K=Cc, lda=2 * Cc, ldb=2 * Cc, ldc=3 * Cc, a_lo=Cc, b_lo=Cc,
+                  bias=in_b.detach())
+    attn_flash(bufs["qkv"], bufs["ao_s"], B, Lq, Cc)
+    gemm_split_tc(bufs["ao_s"], w_out.packed(), out.view(M, Cc), M=M, N=Cc, K=Cc, lda=2 * Cc, ldb=2 * Cc, ldc=Cc, a_lo=Cc, b_lo=Cc,
                   bias=out_b.detach(), residual=tok.reshape(M, Cc) if residual else None)
     return out
 

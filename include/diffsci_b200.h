@@ -302,6 +302,15 @@ int dsk_attn_softmax_qk(const void* Q, const void* K, void* P, void* ws, int L, 
 /* ... with Q, K, P in `dtype` (DSK_BF16 | DSK_F16) */
 int dsk_attn_softmax_qk_h16(const void* Q, const void* K, void* P, void* ws, int L, int C, int64_t ldq, int64_t ldk,
                             int64_t strideQ, int64_t strideK, int batch, float alpha, int dtype, void* stream);
+/* O[b] = softmax(alpha Q[b] K[b]^T) V[b] as ONE flash-style kernel (replaces the SDPA call inside
+ * torch.nn.MultiheadAttention(C, 1 head), nets/attention.py:42-44, 93-102): scores, probabilities and the output accumulator
+ * live in TMEM (S = Q K^T and O += P V on tcgen05, P as the TMEM A operand), online softmax with a lazily updated row
+ * maximum -- nothing of size L x L reaches shared memory or HBM.  Q, K, V: `dtype` (DSK_BF16 | DSK_F16) [L, C] per batch with
+ * leading dimensions ldq / ldk / ldv (e.g. the three column blocks of a packed projection [L, 3C]); C = 128 | 256; any L.
+ * out_mode 0: O in `dtype` [L, ldo]; 1: fp32; 2 (DSK_F16 only): split fp16 rows [hi (C) | 2^11 lo (C)] for a split GEMM. */
+int dsk_attn_flash(const void* Q, const void* K, const void* V, void* O, int L, int C, int64_t ldq, int64_t ldk, int64_t ldv,
+                   int64_t ldo, int64_t strideQ, int64_t strideK, int64_t strideV, int64_t strideO, int batch, float alpha,
+                   int dtype, int out_mode, void* stream);
 /* softmax over the last dim: fp32 scores [rows, cols] -> bf16 probabilities (cols % 4 == 0, cols <= 8192) */
 int dsk_softmax_rows_bf16(const float* S, void* P, int64_t rows, int cols, void* stream);
 /* ... -> P in `dtype`: DSK_BF16 | DSK_F16 (rows of cols), DSK_SPLIT_F16 (rows of 2 cols: hi | lo, the A operand of a split PV) */

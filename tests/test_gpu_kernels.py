@@ -387,6 +387,89 @@ def test_attn_softmax_qk_fused(ops, B, L, C):
     assert float((P.float().sum(-1) - 1).abs().max()) < 2e-2
 
 
+def _attn_ref(qkv, B, L, C):
+    t = qkv.float().view(B, L, 3 * C)
+    q, k, v = t[..., :C], t[..., C:2 * C], t[..., 2 * C:]
+    return torch.softmax(q @ k.transpose(1, 2) * C ** -0.5, -1) @ v
+
+
+@pytest.mark.parametrize("B,L,C,dtype", [(2, 256, 256, torch.float16), (1, 1024, 256, torch.bfloat16), (3, 200, 128, torch.float16),
+                                         (2, 136, 256, torch.float16), (1, 128, 128, torch.bfloat16), (2, 640, 128, torch.float16),
+                                         (1, 4096, 256, torch.float16)])
+def test_attn_flash(ops, B, L, C, dtype):
+    """dsk_attn_flash (scores / probabilities / output accumulator in TMEM, P as the TMEM A operand) vs softmax(QK^T/sqrt(C)) V in
+    fp32 on the same 16-bit operands: ragged L (key masking in the last tile, partial query tiles), one and many key tiles,
+    both channel counts, 16-bit / fp32 / split outputs.  Tolerance: one 16-bit rounding of the probabilities (and of the
+    stored output for the 16-bit mode) relative to the output range."""
+    torch.manual_seed(31)
+    qkv = (torch.randn(B * L, 3 * C) * 1.5).to(dtype)
+    ref = _attn_ref(qkv, B, L, C)
+    tol = 1.5e-3 if dtype == torch.float16 else 1e-2
+    q = qkv.to(DEV)
+    o32 = torch.full((B * L, C), float("nan"), device=DEV)
+    ops.attn_flash(q, o32, B, L, C)
+    assert relmax(o32.cpu().view(B, L, C), ref) < tol, relmax(o32.cpu().view(B, L, C), ref)
+    o16 = torch.full((B * L, C), float("nan"), dtype=dtype, device=DEV)
+    ops.attn_flash(q, o16, B, L, C)
+    assert relmax(o16.float().cpu().view(B, L, C), ref) < tol + (6e-4 if dtype == torch.float16 else 5e-3)
+    assert torch.equal(o16, o32.to(dtype))                           # the same accumulator, rounded once
+    if dtype == torch.float16:
+        os_ = torch.full((B * L, 2 * C), float("nan"), dtype=dtype, device=DEV)
+        ops.attn_flash(q, os_, B, L, C)
+        assert torch.equal(os_[:, :C], o16)
+        rec = os_[:, :C].float() + os_[:, C:].float() / 2048.0
+        assert float((rec - o32).abs().max()) <= 2.0 ** -21 * float(o32.abs().max())
+
+
+def test_attn_flash_moving_maximum(ops):
+    """Scores that grow along the key axis by far more than the lazy-maximum threshold (2^8): every row's reference maximum
+    has to move, several times, and the accumulated output has to be rescaled in TMEM each time."""
+    torch.manual_seed(32)
+    B, L, C = 2, 1024, 256
+    t = torch.randn(B, L, 3 * C)
+    t[..., :C] *= 2.0
+    t[..., C:2 * C] *= (0.25 + 6.0 * torch.arange(L).view(1, L, 1) / L)          # key norms grow 25-fold along the sequence
+    qkv = t.view(B * L, 3 * C).half()
+    ref = _attn_ref(qkv, B, L, C)
+    s = (qkv.float().view(B, L, 3 * C)[..., :C] @ qkv.float().view(B, L, 3 * C)[..., C:2 * C].transpose(1, 2)) * C ** -0.5
+    first, last = s[..., :128].amax(-1), s.amax(-1)
+    assert float(((last - first) * 1.4427 > 8).float().mean()) > 0.9               # the test does exercise the rescale path
+    out = torch.full((B * L, C), float("nan"), device=DEV)
+    ops.attn_flash(qkv.to(DEV), out, B, L, C)
+    assert relmax(out.cpu().view(B, L, C), ref) < 1.5e-3, relmax(out.cpu().view(B, L, C), ref)
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_self_attention_flash_block(ops, split):
+    """The whole attention block on the flash core (projection GEMMs + dsk_attn_flash) vs the oracle's MultiheadAttention
+    restatement: fp16 tokens (16-bit modes) and fp32 tokens with split projections (fp16x2 / fp16x2m modes)."""
+    from oracle import nets_oracle as N
+    torch.manual_seed(33)
+    B, C, sp = 2, 256, (16, 24)
+    Lq = sp[0] * sp[1]
+    x = torch.randn(B, C, *sp)
+    if not split:
+        x = x.half().float()
+    sd = {"a.mhattn.in_proj_weight": torch.randn(3 * C, C) / math.sqrt(C), "a.mhattn.in_proj_bias": torch.randn(3 * C) * 0.1,
+          "a.mhattn.out_proj.weight": torch.randn(C, C) / math.sqrt(C), "a.mhattn.out_proj.bias": torch.randn(C) * 0.1}
+    if not split:
+        sd = {k: (v.half().float() if k.endswith("weight") else v) for k, v in sd.items()}
+    fmt = ops.SPLIT if split else torch.float16
+    tok = x.reshape(B, C, Lq).permute(0, 2, 1).contiguous().to(DEV)
+    tok = tok if split else tok.half()
+    wi = ops.PackedLinear(sd["a.mhattn.in_proj_weight"].to(DEV), fmt)
+    wo = ops.PackedLinear(sd["a.mhattn.out_proj.weight"].to(DEV), fmt)
+    bufs = ops.attention_flash_buffers(B, Lq, C, DEV, torch.float16, split=split)
+    fn = ops.self_attention_flash_split if split else ops.self_attention_flash
+    for residual in (False, True):
+        ref = N.mha_self_attention(x, sd, "a.", residual)
+        out = torch.empty(B, Lq, C, dtype=tok.dtype, device=DEV)
+        fn(tok, wi, sd["a.mhattn.in_proj_bias"].to(DEV), wo, sd["a.mhattn.out_proj.bias"].to(DEV), bufs, out, residual)
+        got = out.float().cpu().permute(0, 2, 1).reshape(x.shape)
+        # split: Q|K|V and P rounded once to fp16, everything else fp32-class; 16-bit: + fp16 storage of the block's output
+        assert relmax(got, ref) < (1e-3 if split else 3e-3), relmax(got, ref)
+
+
 def test_attention_tcgen05(ops):
     from oracle import nets_oracle as N
     torch.manual_seed(14)
