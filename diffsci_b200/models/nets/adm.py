@@ -21,7 +21,7 @@ from torch import nn
 from ... import ops
 from ..._lib import require_cuda
 from .layers import AttentionParams, ConvParams, FourierParams, LinearParams, NormParams, _Act, _Holder, make_conv
-from .punetg import _NORM_MODE, _tc_eligible, DEFAULT_PRECISION, PRECISIONS, _ACT_DTYPE, _W_DTYPE, SPLIT_MODES, MIXED_MIN_CIN, _ATTN_FLASH
+from .punetg import _NORM_MODE, _tc_eligible, DEFAULT_PRECISION, PRECISIONS, _ACT_DTYPE, _W_DTYPE, SPLIT_MODES, MIXED_MIN_CIN, _ATTN_FLASH, split_min_cin
 
 
 class ADMConfig:
@@ -229,7 +229,7 @@ class _ADMPlan:
         self.act_dtype = adt = _ACT_DTYPE[precision]         # modes: see punetg.PRECISIONS
         wdt = _W_DTYPE.get(precision)
         self.split = precision in SPLIT_MODES                 # tensor-core convs read split-fp16 inputs (hi | lo)
-        self.split_min_cin = MIXED_MIN_CIN if precision == "fp16x2m" else 0
+        self.split_min_cin = split_min_cin(precision)
         self.device = dev = torch.device(device)
         nlev = len(c.channel_expansion)
         H, W = spatial

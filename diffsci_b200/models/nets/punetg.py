@@ -40,16 +40,27 @@ DEFAULT_PRECISION = "fp32"
 #   "fp16x2m"   "mixed": as "fp16x2" for the contractions with >= 128 input channels; the 64-channel full-resolution layers
 #               take plain fp16 activations (1 MMA per k-step, fp32 storage).  The many deep layers contribute most of the
 #               operand-rounding error and the few full-resolution ones most of the time (oracle/split_budget.py --mixed).
+#   "fp16s32"   fp16 operands everywhere (1 MMA per k-step), fp32 STORAGE of every tensor between kernels (residual stream,
+#               skips, conv outputs, norm statistics from the fp32 accumulators); only the attention projections stay split.
+#               Measured on the full-size networks (tools/sweep_mixed_min_cin.py): the fp16 mode's error (2.7e-3 on C4) comes
+#               from rounding the STORED tensors, not the operands -- with fp32 storage plain fp16 operands give 6.2e-4 on C4
+#               (fp16x2m 5.4e-4) and 6.0e-4 on C5 at 0.77x / 0.79x the evaluation time of fp16x2m.
 #   "fp16"      fp16 storage and operands, 1 MMA per k-step: the throughput mode (3 more mantissa bits than bf16).
 #   "bf16"      bf16 storage and operands (the training format; fp32's exponent range).
-PRECISIONS = ("fp32", "fp32_ffma", "fp16x2", "fp16x2m", "fp16", "bf16")
+PRECISIONS = ("fp32", "fp32_ffma", "fp16x2", "fp16x2m", "fp16s32", "fp16", "bf16")
 _ACT_DTYPE = {"fp32": torch.float32, "fp32_ffma": torch.float32, "fp16x2": torch.float32, "fp16x2m": torch.float32,
-              "fp16": torch.float16, "bf16": torch.bfloat16}
-_W_DTYPE = {"fp32": ops.SPLIT, "fp16x2": torch.float16, "fp16x2m": torch.float16, "fp16": torch.float16,
+              "fp16s32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+_W_DTYPE = {"fp32": ops.SPLIT, "fp16x2": torch.float16, "fp16x2m": torch.float16, "fp16s32": torch.float16, "fp16": torch.float16,
             "bf16": torch.bfloat16}   # tcgen05 weight format
-SPLIT_MODES = ("fp32", "fp16x2", "fp16x2m")      # fp32 storage; tensor-core operands are split-fp16 (hi | lo) tensors
+SPLIT_MODES = ("fp32", "fp16x2", "fp16x2m", "fp16s32")   # fp32 storage; tensor-core operands are 16-bit COPIES: split-fp16
+#                                                          (hi | lo) tensors, or plain fp16 below the mode's split_min_cin
 _ATTN_FLASH = os.environ.get("DSK_ATTN_FLASH", "1") != "0"   # 0: keep the multi-launch GEMM attention (A/B measurements)
 MIXED_MIN_CIN = 128                              # "fp16x2m": contractions with fewer input channels take plain fp16 activations
+
+
+def split_min_cin(precision: str) -> int:
+    """Input-channel count from which a contraction of this mode takes split (hi + lo) activations."""
+    return MIXED_MIN_CIN if precision == "fp16x2m" else (1 << 30) if precision == "fp16s32" else 0
 
 
 def _tc_eligible(cin: int, cout: int, ksize: int = 3, few_out_ok: bool = False) -> bool:
@@ -247,7 +258,7 @@ class _Plan:
         self.act_dtype = adt = _ACT_DTYPE[precision]
         wdt = _W_DTYPE.get(precision)                       # None: no tensor-core kernels in this mode
         self.split = split = precision in SPLIT_MODES      # conv / GEMM inputs are split-fp16 tensors (hi | lo)
-        self.split_min_cin = smin = MIXED_MIN_CIN if precision == "fp16x2m" else 0
+        self.split_min_cin = smin = split_min_cin(precision)
         dev = self.device = torch.device(device)
         if len(spatial) != nd:
             raise ValueError(f"PUNetG(dimension={nd}) got spatial shape {spatial}")
@@ -283,7 +294,11 @@ class _Plan:
         self.X = [buf(l, ch[l]) for l in range(nlev + 1)]          # encoder / bottom state (doubles as skip)
         self.XU = [buf(l, ch[l]) for l in range(nlev)]             # decoder state
         self.N = [nbuf(l) for l in range(nlev + 1)]                # norm+SiLU output == conv input
-        self.Y = [buf(l, ch[l]) for l in range(nlev + 1)]          # conv1 output
+        # conv1 output.  DSK_Y16=1 (experiment, fp16s32 only): stored as fp16 where the block convs run on the tensor cores -- it is
+        # read once, by the second norm, whose statistics come from the fp32 accumulators either way
+        y16 = precision == "fp16s32" and os.environ.get("DSK_Y16", "0") == "1"
+        self.Y = [buf(l, ch[l], torch.float16 if (y16 and _tc_eligible(ch[l], ch[l], c.kernel_size)) else adt)
+                  for l in range(nlev + 1)]
         self.P = [buf(l + 1, ch[l]) for l in range(nlev)]          # pooled
         self.XA = buf(nlev, ch[nlev])
         self.XA2 = buf(nlev, ch[nlev])

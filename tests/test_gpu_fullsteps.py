@@ -15,7 +15,7 @@ STATED TOLERANCES
     evaluations of a random-weight network); two fp32 implementations that sum in different orders differ by a few d0 (the
     CUDA-core FFMA mode and the tensor-core split mode land at the same distance: c5 5.4 x d0 and 5.6 x d0); ours must stay
     within 8 x d0 + 2e-5 x field RMS of the fp64 field, per pixel (max) and in RMS.
-  * 16-bit modes vs the reference's fp32 field, RMS relative to the field RMS: fp16x2 <= 3e-3, fp16x2m <= 4e-3, fp16 <= 2e-2, bf16 <= 1.5e-1
+  * 16-bit modes vs the reference's fp32 field, RMS relative to the field RMS: fp16x2 <= 3e-3, fp16x2m / fp16s32 <= 4e-3, fp16 <= 2e-2, bf16 <= 1.5e-1
     for c2; the long runs of the random-weight default-width networks (c4: 127 chained evaluations, c5: 256 SDE steps) amplify
     rounding chaotically for EVERY arithmetic (c5: fp32 vs fp64 of the reference itself differ by 1.3e-3 of the field RMS; c4:
     the two fp32 modes differ from the reference's fp32 by 7e-5 and 2e-4): 16-bit modes <= 1.5e-1 there (measured 1e-2 ... 9e-2)
@@ -30,7 +30,7 @@ import torch
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-RMS_TOL = {"fp16x2": 3e-3, "fp16x2m": 4e-3, "fp16": 2e-2, "bf16": 1.5e-1}
+RMS_TOL = {"fp16x2": 3e-3, "fp16x2m": 4e-3, "fp16s32": 4e-3, "fp16": 2e-2, "bf16": 1.5e-1}
 
 
 def _errs(a, b):
@@ -83,7 +83,7 @@ def run_case(name, modes):
 
 @pytest.mark.parametrize("name", ["c1", "c2", "c4", "c5"])
 def test_full_length_sampling_vs_live_reference(name):
-    modes = ["fp32"] if name == "c1" else ["fp32", "fp32_ffma", "fp16x2", "fp16x2m", "fp16", "bf16"]
+    modes = ["fp32"] if name == "c1" else ["fp32", "fp32_ffma", "fp16x2", "fp16x2m", "fp16s32", "fp16", "bf16"]
     out, d0, field_rms = run_case(name, modes)
     (_, _), (m64, r64) = out["fp32"]
     assert m64 <= 8 * d0[0] + 2e-5 * field_rms, (m64, d0)

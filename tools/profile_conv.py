@@ -18,7 +18,7 @@ ap.add_argument("--cout", type=int, default=64)
 ap.add_argument("--reps", type=int, default=6)
 ap.add_argument("--stats", action="store_true")
 ap.add_argument("--residual", action="store_true")
-ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp16x2", "fp32"])
+ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp16s32", "fp16x2", "fp32"])
 ap.add_argument("--quantize", default="", choices=["", "bf16", "zero"],
                 help="input values exactly representable in bf16 (few mantissa bits toggle; split lo halves are zero) or all zero: "
                      "separates data-dependent power throttling from pipeline effects")
@@ -27,7 +27,7 @@ a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 w = torch.randn(a.cout, a.cin, 3, 3, 3, device=dev) * 0.02
-wdt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp16x2": torch.float16, "fp32": ops.SPLIT}[a.precision]
+wdt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp16s32": torch.float16, "fp16x2": torch.float16, "fp32": ops.SPLIT}[a.precision]
 adt = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(a.precision, torch.float32)
 pc = ops.PackedConv(w, torch.zeros(a.cout, device=dev), 3, wdt)
 xs = [torch.randn(a.batch, a.size, a.size, a.size, a.cin, device=dev) for _ in range(3)]
@@ -38,7 +38,9 @@ if a.quantize == "bf16":
 elif a.quantize == "zero":
     xs = [torch.zeros_like(x) for x in xs]
 xs = [x.to(adt) for x in xs]
-if adt == torch.float32:
+if a.precision == "fp16s32":
+    xs = [x.half() for x in xs]                   # plain fp16 activations, fp32 output
+elif adt == torch.float32:
     xs = [ops.split_f16(x) for x in xs]          # split-fp16 activations (hi | lo), fp32 output
 out = torch.empty(a.batch, a.size, a.size, a.size, a.cout, device=dev, dtype=adt)
 st = ops.conv_stats_buffer(a.batch, a.cout, dev) if a.stats else None
