@@ -32,7 +32,7 @@ p, i32, i64, u64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("B", "D", "H", "W", "Cin", "Cout", "ksize", "ndim", "up2", "w_dtype", "in_dtype",
-                                   "out_dtype", "out_nchw_f32", "circular")]
+                                   "out_dtype", "out_nchw_f32", "circular", "res_dtype", "operand16")]
 
 
 # name -> argtypes (every function returns int unless listed in _RESTYPE)
@@ -81,6 +81,7 @@ SIGNATURES = {
     "dsk_norm_act": [p, p, p, p, p, p, p, i32, i64, i32, i32, i32, i32, i32, i32, p],
     "dsk_norm_apply_padded": [p, p, p, i32, i32, i32, i32, i32, i32, i32, i32, i32, p],
     "dsk_pool2x": [p, p, i32, i32, i32, i32, i32, i32, i32, i32, p],
+    "dsk_pool2x_f32": [p, p, i32, i32, i32, i32, i32, i32, i32, i32, p],
     "dsk_add": [p, p, p, i64, i32, p],
     "dsk_nchw_to_cl": [p, p, i32, i32, i64, i32, p],
     "dsk_cl_to_nchw": [p, p, i32, i32, i64, i32, p],

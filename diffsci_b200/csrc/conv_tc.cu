@@ -68,7 +68,22 @@ struct TcParams {
                           // these offsets move the patch coordinates into it (0: zero 'same' padding through TMA OOB fill)
   int pair_d;             // cta_group::2 kernel: the two CTAs of a pair take neighbouring plane groups instead of neighbouring
                           // w-tiles (odd number of w-tiles, e.g. the 7x7 planes of MNIST's bottom level); no fused statistics
+  int res_f32;            // residual is fp32 (== out_f32 unless the output is a 16-bit operand copy of an fp32-storage mode)
+  // tile index -> coordinates without integer division (cta_group::2 kernel): divisors nphase, pairs along the fastest tile
+  // axis (w-pairs, or tiles_w when pairing along d), tiles_h, plane groups (or pairs of them), B
+  uint32_t dv_m[5], dv_s[5];
 };
+// n / d for n < 2^31, d < 2^31 as a multiply + shift (Granlund-Montgomery, N = 31): m = ceil(2^(31+l) / d), l = ceil(log2 d)
+struct FastDivHost {
+  uint32_t m, s;
+  explicit FastDivHost(uint32_t d) {
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    s = 31 + l;
+    m = (uint32_t)(((1ull << s) + d - 1) / d);      // d == 1: 2^31; d > 2^(l-1) keeps m < 2^32
+  }
+};
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t m, uint32_t s) { return (uint32_t)(((uint64_t)n * m) >> s); }
 constexpr int TC_STAT_SLOTS = DSK_NUM_SMS;          // one slot per CTA
 constexpr float kLoScale = 1.0f / 2048.0f;          // 2^-11: the lo half of a split operand is stored times 2^11
 // Virtual K chunks in issue order: (real 64-channel chunk c, part) with part fastest.  A counter pair instead of vc / vparts:
@@ -383,22 +398,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 if (p.chan_bias != nullptr) x += __ldg(p.chan_bias + (int64_t)brow * p.Cout + n + g * 8 + e);
                 f[e] = x;
               }
-              if (p.out_f32) {                             // warp-uniform
-                float* of = reinterpret_cast<float*>(p.out) + off + g * 8;
-                if (p.residual != nullptr) {
+              if (p.residual != nullptr) {                 // warp-uniform; the residual's format is independent of the output's
+                if (p.res_f32) {
                   const float4* rf = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off + g * 8);
                   const float4 r0 = rf[0], r1 = rf[1];
                   f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w; f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-                }
-                reinterpret_cast<float4*>(of)[0] = make_float4(f[0], f[1], f[2], f[3]);
-                reinterpret_cast<float4*>(of)[1] = make_float4(f[4], f[5], f[6], f[7]);
-              } else {
-                if (p.residual != nullptr) {
+                } else {
                   const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + off + g * 8);
                   const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rr);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) { const float2 t = unpack_h2(rw[e], p.f16); f[2 * e] += t.x; f[2 * e + 1] += t.y; }
                 }
+              }
+              if (p.out_f32) {                             // warp-uniform
+                float* of = reinterpret_cast<float*>(p.out) + off + g * 8;
+                reinterpret_cast<float4*>(of)[0] = make_float4(f[0], f[1], f[2], f[3]);
+                reinterpret_cast<float4*>(of)[1] = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
                 uint4 o;
                 uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
@@ -463,23 +479,26 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;    // shared::cluster address of the even (leader) CTA of a pair
 
-__device__ __forceinline__ TileCoord tile_coord2(const TcParams& p, int u, int rank, int n_tile_size, int P) {
+__device__ __forceinline__ TileCoord tile_coord2(const TcParams& p, int u_, int rank, int n_tile_size, int P) {
   TileCoord c;
-  c.phase = u % p.nphase; u /= p.nphase;
+  uint32_t u = (uint32_t)u_, q;
+  // u -> (phase, w, h, d, b, n-tile), fastest first; quotients by multiply + shift (dv_m / dv_s, host-computed): the five
+  // integer divisions of the plain form were ~10 % of the epilogue warps' samples
+  q = fast_div(u, p.dv_m[0], p.dv_s[0]); c.phase = (int)(u - q * (uint32_t)p.nphase); u = q;
   c.pc = c.phase & 1; c.pb = (c.phase >> 1) & 1; c.pa = (c.phase >> 2) & 1;
   if (p.pair_d) {
-    c.w0 = (u % p.tiles_w) * TC_BW; u /= p.tiles_w;
-    c.h0 = (u % p.tiles_h) * TC_BH; u /= p.tiles_h;
-    const int pairs_d = p.groups_d >> 1;
-    c.d0 = ((u % pairs_d) * 2 + rank) * P; u /= pairs_d;
+    q = fast_div(u, p.dv_m[1], p.dv_s[1]); c.w0 = (int)(u - q * (uint32_t)p.tiles_w) * TC_BW; u = q;
+    q = fast_div(u, p.dv_m[2], p.dv_s[2]); c.h0 = (int)(u - q * (uint32_t)p.tiles_h) * TC_BH; u = q;
+    const uint32_t pairs_d = (uint32_t)p.groups_d >> 1;
+    q = fast_div(u, p.dv_m[3], p.dv_s[3]); c.d0 = (int)((u - q * pairs_d) * 2 + rank) * P; u = q;
   } else {
-    const int pairs_w = p.tiles_w >> 1;
-    c.w0 = ((u % pairs_w) * 2 + rank) * TC_BW; u /= pairs_w;
-    c.h0 = (u % p.tiles_h) * TC_BH; u /= p.tiles_h;
-    c.d0 = (u % p.groups_d) * P;    u /= p.groups_d;
+    const uint32_t pairs_w = (uint32_t)p.tiles_w >> 1;
+    q = fast_div(u, p.dv_m[1], p.dv_s[1]); c.w0 = (int)((u - q * pairs_w) * 2 + rank) * TC_BW; u = q;
+    q = fast_div(u, p.dv_m[2], p.dv_s[2]); c.h0 = (int)(u - q * (uint32_t)p.tiles_h) * TC_BH; u = q;
+    q = fast_div(u, p.dv_m[3], p.dv_s[3]); c.d0 = (int)(u - q * (uint32_t)p.groups_d) * P; u = q;
   }
-  c.b = u % p.B;                  u /= p.B;
-  c.n0 = u * n_tile_size;
+  q = fast_div(u, p.dv_m[4], p.dv_s[4]); c.b = (int)(u - q * (uint32_t)p.B); u = q;
+  c.n0 = (int)u * n_tile_size;
   return c;
 }
 
@@ -495,6 +514,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   __shared__ uint64_t full_a[NA], empty_a[NA], full_b[NB], empty_b[NB], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ uint4 stage_s[8][32 * 4];                  // per epilogue warp: 32 rows x 64 B (coalescing stage of the stores)
+  __shared__ __align__(16) float bias_s[8][N_TILE];     // per epilogue warp: bias + chan_bias row of its current (sample, n-tile)
   constexpr uint32_t TMEM_COLS = 2 * P * N_TILE;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
   // accumulator sets per tile: 1 (plain), 2 (hh | lo; activations-split mode) or 4 (three hh sets + lo; fp32-parity mode,
@@ -709,6 +729,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     const int nranges = total_pairs / per_range;             // n_tiles * srange
     int cur_range = -1;
     uint4* stg = stage_s[warp - 4];
+    // bias[n0 + c] + chan_bias[sample][n0 + c] of the warp's current (sample row, n-tile): the tile order keeps both fixed for
+    // many tiles, so the 2 x N_TILE scalar loads per row (13 % of the epilogue's samples when issued per tile behind the
+    // accumulator wait) happen once per change and the tiles read the sum as shared-memory broadcasts
+    float* bsm = bias_s[warp - 4];
+    int bias_key = -1;
+    const bool any_bias = p.bias != nullptr || p.chan_bias != nullptr;
     // flush: the 8 epilogue warps of the CTA reach a range change together (same tile sequence); their partials meet in
     // shared memory (the store stage is idle between tiles) and ONE slot per CTA goes to global memory, summed in a fixed
     // order.  3-D: all 8 warps belong to one sample; 2-D: the warps of plane pp belong to sample d0 + pp.
@@ -769,12 +795,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       } else {
         st_pix = (((int64_t)tc.b * p.D + d) * p.H + tc.h0 + q * 4) * p.W + w_st;
       }
-      const bool of32 = p.out_f32 != 0;                     // fp32 output + residual (split parity mode); warp-uniform
+      const bool of32 = p.out_f32 != 0;                     // fp32 output (fp32-storage modes); warp-uniform
+      const bool rf32 = p.res_f32 != 0;                     // fp32 residual (independent of the output format); warp-uniform
       const int64_t roff = pix * p.Cout + tc.n0;
-      const uint16_t* rrow = (p.residual != nullptr && valid && !of32) ? p.residual + roff : nullptr;
-      const float* rrow32 = (p.residual != nullptr && valid && of32) ? reinterpret_cast<const float*>(p.residual) + roff : nullptr;
-      // d >= p.D: the second plane of a tile past an odd plane count (e.g. a 2-D batch of 1) -- its row of chan_bias does not exist
-      const float* cbrow = (p.chan_bias != nullptr && d < p.D) ? p.chan_bias + (int64_t)brow * p.Cout + tc.n0 : nullptr;
+      const uint16_t* rrow = (p.residual != nullptr && valid && !rf32) ? p.residual + roff : nullptr;
+      const float* rrow32 = (p.residual != nullptr && valid && rf32) ? reinterpret_cast<const float*>(p.residual) + roff : nullptr;
+      if (any_bias) {
+        // d >= p.D: the second plane of a tile past an odd plane count (e.g. a 2-D batch of 1) -- its chan_bias row does not exist
+        const int key = (d < p.D ? brow : p.B * p.D) * p.n_tiles + tc.n0 / N_TILE;
+        if (key != bias_key) {                              // warp-uniform
+          bias_key = key;
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            float bv = p.bias != nullptr ? __ldg(p.bias + tc.n0 + g * 32 + lane) : 0.0f;
+            if (p.chan_bias != nullptr && d < p.D) bv += __ldg(p.chan_bias + (int64_t)brow * p.Cout + tc.n0 + g * 32 + lane);
+            bsm[g * 32 + lane] = bv;
+          }
+          __syncwarp();
+        }
+      }
       uint4 rr[DEP][4];
       if (rrow != nullptr) {
 #pragma unroll
@@ -802,7 +842,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           } else {
             pn = (((int64_t)tn.b * p.D + dn) * p.H + hn) * p.W + wn;
           }
-          const int es = of32 ? 4 : 2;
+          const int es = rf32 ? 4 : 2;
           const char* rn = reinterpret_cast<const char*>(p.residual) + (pn * p.Cout + tn.n0) * es;
           for (int c = 0; c < N_TILE * es / 128; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(rn + c * 128));
         }
@@ -833,12 +873,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           }
         }
         float f[32];
+        if (any_bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(bsm + c0);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float x = __uint_as_float(v[e]);
-          if (p.bias != nullptr) x += __ldg(p.bias + tc.n0 + c0 + e);
-          if (cbrow != nullptr) x += __ldg(cbrow + c0 + e);
-          f[e] = x;
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 bb = b4[e4];
+            f[4 * e4] = __uint_as_float(v[4 * e4]) + bb.x; f[4 * e4 + 1] = __uint_as_float(v[4 * e4 + 1]) + bb.y;
+            f[4 * e4 + 2] = __uint_as_float(v[4 * e4 + 2]) + bb.z; f[4 * e4 + 3] = __uint_as_float(v[4 * e4 + 3]) + bb.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
         }
         if (rrow != nullptr) {
 #pragma unroll
@@ -1128,6 +1173,7 @@ static bool tc_formats_ok(const dsk_conv_desc* d) {
   if (!ops) return false;
   if (d->out_nchw_f32) return true;
   const int fmt16 = d->in_dtype == DSK_BF16 ? DSK_BF16 : DSK_F16;
+  if (d->res_dtype != DSK_RES_SAME && d->res_dtype != DSK_RES_F32) return false;
   return d->out_dtype == fmt16 || d->out_dtype == DSK_F32;
 }
 static bool tc_pair_eligible(const dsk_conv_desc* d) {
@@ -1279,6 +1325,7 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   p.residual = (const uint16_t*)residual; p.out = (uint16_t*)out;
   p.f16 = fmt16 == DSK_F16 ? 1 : 0;
   p.out_f32 = (!d->out_nchw_f32 && d->out_dtype == DSK_F32) ? 1 : 0;
+  p.res_f32 = d->res_dtype == DSK_RES_F32 ? 1 : (d->res_dtype == DSK_RES_SAME ? p.out_f32 : 0);
   p.vparts = a_split ? (w_split ? 3 : 2) : 1;
   p.a_lo_off = d->Cin; p.w_lo_off = d->Cin;
   p.nsets = a_split ? (w_split ? 4 : 2) : 1;
@@ -1288,6 +1335,11 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   p.stats = stats; p.samples = d->B;
   p.pad_hw = pad_hw; p.pad_d = pad_d;
   p.pair_d = (!few_out && tc_pair_d_eligible(d, stats != nullptr)) ? 1 : 0;
+  {
+    const uint32_t dv[5] = {(uint32_t)nphase, (uint32_t)(p.pair_d ? p.tiles_w : (p.tiles_w >> 1 ? p.tiles_w >> 1 : 1)), (uint32_t)p.tiles_h,
+                            (uint32_t)(p.pair_d ? (p.groups_d >> 1 ? p.groups_d >> 1 : 1) : p.groups_d), (uint32_t)batch};
+    for (int i = 0; i < 5; ++i) { const FastDivHost f(dv[i]); p.dv_m[i] = f.m; p.dv_s[i] = f.s; }
+  }
   cudaStream_t st = as_stream(stream);
   // cta_group::2 (CTA pairs): needs an even number of w-tiles (the pair sits side by side in w).  DSK_CONV_CG=1 forces
   // the single-CTA kernel (A/B measurements).

@@ -4,8 +4,10 @@
 // With Cin = 1..3 the whole receptive field of an output pixel is K = taps * Cin <= 64 numbers: the im2col row of a pixel
 // is ONE 128-byte shared-memory row.  Four builder warps gather those rows (the input tensor is tiny and L1/L2 resident)
 // straight into the K-major SWIZZLE_128B layout, one tcgen05 MMA group (M = 128 pixels, N = Cout, K = 64) turns a tile
-// into accumulators, and four epilogue warps stream the C-channel result out -- the kernel is bound by the write of the
-// output tensor (the CUDA-core version was bound by shared-memory weight reads at 1/10 of that).
+// into accumulators, and two sets of four epilogue warps (one per accumulator buffer, alternating tiles) stream the
+// C-channel result out through a shared-memory stage so that every store instruction writes whole 128-byte lines -- the kernel
+// is bound by the write of the output tensor (the CUDA-core version was bound by shared-memory weight reads at 1/10 of that).
+// Input fp32 or 16-bit (rounded to the operand format while gathering), output 16-bit or fp32 (the fp32-storage modes).
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -15,12 +17,15 @@ namespace dsk {
 constexpr int CI_BW = 8, CI_BH = 16;               // 128 output pixels per tile
 constexpr int CI_NG = 3;                           // builder groups of 4 warps: CI_NG tiles are gathered concurrently
 constexpr int CI_BUILD = CI_NG * 4;                // warps 0..CI_BUILD-1: im2col builders
-constexpr int CI_THREADS = (CI_BUILD + 1 + 4) * 32;  // + warp CI_BUILD: MMA / TMEM owner, + 4 epilogue warps
+constexpr int CI_EPI = 8;                          // epilogue warps: set (w >> 2) drains accumulator buffer (tile seq & 1)
+constexpr int CI_THREADS = (CI_BUILD + 1 + CI_EPI) * 32;  // + warp CI_BUILD: MMA / TMEM owner
+constexpr int CI_STG_BYTES = 32 * 128;             // per epilogue warp: 32 rows x 128 B (one 32-channel fp32 group)
 constexpr int CI_STAGES = 6;
 constexpr int CI_A_BYTES = 128 * 128;
 
 struct CiParams {
-  const uint16_t* x;        // channels-last [B, D, H, W, Cin], 16-bit format f16 ? half : bfloat16
+  const uint16_t* x;        // channels-last [B, D, H, W, Cin], 16-bit format f16 ? half : bfloat16 (fp32 when in_f32)
+  int in_f32, out_f32;      // fp32 input (rounded to the 16-bit operand format in the gather) / fp32 output
   const float* w;           // packed fp32 [taps][Cin][Cout]
   const float* bias;
   uint16_t* out;            // channels-last [B, D, H, W, Cout]
@@ -36,6 +41,8 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                        // CI_STAGES x [128 rows x 128 B]
   uint8_t* sB = smem + (size_t)CI_STAGES * CI_A_BYTES;       // [Cout rows x 128 B]
+  uint8_t* sStg = sB + (size_t)p.Cout * 128;                 // CI_EPI x [32 rows x 128 B] store stages
+  float* sBias = reinterpret_cast<float*>(sStg + (size_t)CI_EPI * CI_STG_BYTES);   // [Cout]
   __shared__ uint64_t full_a[CI_STAGES], empty_a[CI_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -65,6 +72,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
     }
     *reinterpret_cast<uint4*>(sB + co * 128 + ((j ^ (co & 7)) << 4)) = *reinterpret_cast<const uint4*>(h);
   }
+  for (int i = threadIdx.x; i < N; i += CI_THREADS) sBias[i] = p.bias != nullptr ? p.bias[i] : 0.0f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -113,7 +121,9 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
         oh[k] = (zh - h) * sH;
         ow[k] = (zw - w) * CIN;
       }
-      const uint16_t* ctr = p.x + ((((int64_t)b * p.D + d) * p.H + h) * p.W + w) * CIN;
+      const int64_t ctr_off = ((((int64_t)b * p.D + d) * p.H + h) * p.W + w) * CIN;
+      const uint16_t* ctr = p.x + ctr_off;
+      const float* ctr32 = reinterpret_cast<const float*>(p.x) + ctr_off;
       __align__(16) uint16_t v[64];                            // zero bits = 0.0 in both 16-bit formats
 #pragma unroll
       for (int k = 0; k < 64; ++k) v[k] = 0;
@@ -125,10 +135,10 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const bool ok = dv[kd] && hv[kh] && wv[kw];
-            const uint16_t* src = ctr + od[kd] + oh[kh] + ow[kw];
+            const int so = od[kd] + oh[kh] + ow[kw];
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci)
-              if (ok) v[((kd * 3 + kh) * 3 + kw) * CIN + ci] = src[ci];
+              if (ok) v[((kd * 3 + kh) * 3 + kw) * CIN + ci] = p.in_f32 ? pack_h1(ctr32[so + ci], p.f16) : ctr[so + ci];
           }
       }
       mbar_wait(&empty_a[slot], ph ^ 1);
@@ -168,35 +178,65 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
     }
   } else {
     // ===================== epilogue =====================
-    const int q = warp & 3;
-    const int r = q * 32 + lane, line = r >> 3, wp = r & 7;
-    uint32_t seq = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++seq) {
+    // warp e = warp - CI_BUILD - 1: TMEM lane quadrant q = warp & 3 (hardware rule), set es = e >> 2 takes the tiles whose
+    // sequence number has parity es (= accumulator buffer es).  A thread holds one pixel ROW of the tile; the 32 x 32 block of a
+    // channel group goes through the warp's stage (XOR-swizzled 16-byte slots) and leaves as whole lines: fp32: 8 lanes per
+    // row, 4 rows per instruction; 16-bit: 4 lanes per row, 8 rows per instruction.
+    const int e = warp - CI_BUILD - 1, q = warp & 3, es = e >> 2;
+    uint4* stg = reinterpret_cast<uint4*>(sStg + (size_t)e * CI_STG_BYTES);
+    for (int t = blockIdx.x + es * gridDim.x, seq = es; t < p.total_tiles; t += 2 * gridDim.x, seq += 2) {
       int w0, h0, d, b;
       coord(t, w0, h0, d, b);
-      const uint32_t as = seq & 1, aph = (seq >> 1) & 1;
+      const uint32_t as = es, aph = (seq >> 1) & 1;
       mbar_wait(&acc_full[as], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int h = h0 + line, w = w0 + wp;
-      const bool valid = h < p.H && w < p.W;
-      uint16_t* orow = p.out + ((((int64_t)b * p.D + d) * p.H + h) * p.W + w) * N;
+      const int64_t plane = ((int64_t)b * p.D + d) * p.H;
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
         DSK_TMEM_LD_X32(v, tmem_base + as * N + c0 + ((uint32_t)(q * 32) << 16));
-        if (valid) {
+        float f[32];
+        const float4* b4 = reinterpret_cast<const float4*>(sBias + c0);
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 bb = b4[e4];
+          f[4 * e4] = __uint_as_float(v[4 * e4]) + bb.x; f[4 * e4 + 1] = __uint_as_float(v[4 * e4 + 1]) + bb.y;
+          f[4 * e4 + 2] = __uint_as_float(v[4 * e4 + 2]) + bb.z; f[4 * e4 + 3] = __uint_as_float(v[4 * e4 + 3]) + bb.w;
+        }
+        if (p.out_f32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            stg[lane * 8 + (g ^ (lane & 7))] = make_uint4(__float_as_uint(f[4 * g]), __float_as_uint(f[4 * g + 1]),
+                                                          __float_as_uint(f[4 * g + 2]), __float_as_uint(f[4 * g + 3]));
+          __syncwarp();
+          float* outf = reinterpret_cast<float*>(p.out);
+          const int j = lane & 7;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = 4 * k + (lane >> 3), R = q * 32 + r;
+            const int h = h0 + (R >> 3), w = w0 + (R & 7);
+            const uint4 val = stg[r * 8 + (j ^ (r & 7))];
+            if (h < p.H && w < p.W) *reinterpret_cast<uint4*>(outf + ((plane + h) * p.W + w) * N + c0 + j * 4) = val;
+          }
+        } else {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 o;
             uint32_t* oh = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float f0 = __uint_as_float(v[g * 8 + 2 * e]), f1 = __uint_as_float(v[g * 8 + 2 * e + 1]);
-              if (p.bias != nullptr) { f0 += __ldg(p.bias + c0 + g * 8 + 2 * e); f1 += __ldg(p.bias + c0 + g * 8 + 2 * e + 1); }
-              oh[e] = pack_h2(f0, f1, p.f16);
-            }
-            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = o;
+            for (int k = 0; k < 4; ++k) oh[k] = pack_h2(f[g * 8 + 2 * k], f[g * 8 + 2 * k + 1], p.f16);
+            stg[lane * 4 + (g ^ (lane & 3))] = o;
+          }
+          __syncwarp();
+          const int j = lane & 3;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = 8 * k + (lane >> 2), R = q * 32 + r;
+            const int h = h0 + (R >> 3), w = w0 + (R & 7);
+            const uint4 val = stg[r * 4 + (j ^ (r & 3))];
+            if (h < p.H && w < p.W) *reinterpret_cast<uint4*>(p.out + ((plane + h) * p.W + w) * N + c0 + j * 8) = val;
           }
         }
+        __syncwarp();
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -210,7 +250,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
 
 template <int CIN>
 static int launch_convin(const CiParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)CI_STAGES * CI_A_BYTES + (size_t)p.Cout * 128 + 1024;
+  const size_t smem = (size_t)CI_STAGES * CI_A_BYTES + (size_t)p.Cout * 128 + (size_t)CI_EPI * CI_STG_BYTES + (size_t)p.Cout * 4 + 1024;
   cudaError_t e = cudaFuncSetAttribute(convin_tc_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("convin_tc: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e)); return DSK_ERR_CUDA; }
   const int grid = p.total_tiles < DSK_NUM_SMS ? p.total_tiles : DSK_NUM_SMS;
@@ -222,12 +262,17 @@ static int launch_convin(const CiParams& p, cudaStream_t st) {
 int convin_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, const float* bias, void* out, cudaStream_t st) {
   static const int old_path = [] { const char* e = getenv("DSK_CONVIN_OLD"); return e ? atoi(e) : 0; }();
   const int taps = d->ndim == 3 ? 27 : 9;
-  if (old_path || d->ksize != 3 || d->up2 || d->out_nchw_f32 || !is_h16(d->in_dtype) || d->out_dtype != d->in_dtype || d->w_dtype != DSK_F32 ||
+  // formats: 16-bit in -> the same 16-bit out (the 16-bit modes), or -- descriptor field `operand16` = DSK_BF16 | DSK_F16 naming
+  // the tensor-core operand format -- fp32 in -> fp32 out (the fp32-storage modes with 16-bit operands)
+  const bool h16 = is_h16(d->in_dtype) && d->out_dtype == d->in_dtype;
+  const bool f32 = d->in_dtype == DSK_F32 && d->out_dtype == DSK_F32 && is_h16(d->operand16);
+  if (old_path || d->ksize != 3 || d->up2 || d->out_nchw_f32 || !(h16 || f32) || d->w_dtype != DSK_F32 ||
       d->Cin > 4 || taps * d->Cin > 64 || (d->Cout != 64 && d->Cout != 128 && d->Cout != 256))
     return DSK_ERR_UNSUPPORTED;
   CiParams p;
   p.x = (const uint16_t*)in; p.w = (const float*)w; p.bias = bias; p.out = (uint16_t*)out;
-  p.f16 = d->in_dtype == DSK_F16 ? 1 : 0;
+  p.f16 = (f32 ? d->operand16 : d->in_dtype) == DSK_F16 ? 1 : 0;
+  p.in_f32 = f32 ? 1 : 0; p.out_f32 = f32 ? 1 : 0;
   p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.ndim = d->ndim;
   p.circ = d->circular;
   p.tiles_w = (d->W + CI_BW - 1) / CI_BW; p.tiles_h = (d->H + CI_BH - 1) / CI_BH;

@@ -489,6 +489,61 @@ extern "C" int dsk_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t 
   return DSK_OK;
 }
 
+// fp32 input, C % 4 == 0: a thread pools 4 channels (one float4) of one output pixel; the result is stored as fp32 or rounded
+// once to a 16-bit format (OUT16: 1 bf16, 2 fp16) -- the fp32-storage modes pool straight into the operand copy of the
+// DownSampler convolution instead of writing fp32 and casting it in a second pass.
+template <int OUT16, bool IS_MAX>
+__global__ void __launch_bounds__(256) pool2x_f32v4_kernel(const float4* __restrict__ x, void* __restrict__ y, int B, int D, int H, int W,
+                                                            int C4, int ndim) {
+  const int Do = ndim == 3 ? D / 2 : 1, Ho = H / 2, Wo = W / 2;
+  const int kd = ndim == 3 ? 2 : 1;
+  const int64_t total = (int64_t)B * Do * Ho * Wo * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    int64_t p = i / C4;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho); p /= Ho;
+    const int dz = (int)(p % Do);
+    const int b = (int)(p / Do);
+    const int64_t base = ((((int64_t)b * D + dz * kd) * H + ho * 2) * W + wo * 2) * C4 + c;
+    float4 v[8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+          if (a < kd) v[(a * 2 + bb) * 2 + cc] = x[base + (((int64_t)a * H + bb) * W + cc) * C4];
+    float4 o = v[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+      if (k < 4 * kd) {
+        if (IS_MAX) { o.x = fmaxf(o.x, v[k].x); o.y = fmaxf(o.y, v[k].y); o.z = fmaxf(o.z, v[k].z); o.w = fmaxf(o.w, v[k].w); }
+        else { o.x += v[k].x; o.y += v[k].y; o.z += v[k].z; o.w += v[k].w; }
+      }
+    if (!IS_MAX) { const float sc = ndim == 3 ? 0.125f : 0.25f; o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc; }
+    if (OUT16 == 0) reinterpret_cast<float4*>(y)[i] = o;
+    else reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_h2(o.x, o.y, OUT16 == 2), pack_h2(o.z, o.w, OUT16 == 2));
+  }
+}
+
+extern "C" int dsk_pool2x_f32(const float* x, void* y, int B, int D, int H, int W, int C, int ndim, int is_max, int out_dtype,
+                              void* stream) {
+  DSK_REQUIRE(x && y, "dsk_pool2x_f32: null pointer");
+  DSK_REQUIRE(B > 0 && D > 0 && H > 1 && W > 1 && C > 0 && C % 4 == 0 && (ndim == 2 || ndim == 3), "dsk_pool2x_f32: bad shape (C %% 4 == 0)");
+  DSK_REQUIRE(ndim == 2 ? D == 1 : D > 1, "dsk_pool2x_f32: D=%d inconsistent with ndim=%d", D, ndim);
+  DSK_REQUIRE(out_dtype == DSK_F32 || is_h16(out_dtype), "dsk_pool2x_f32: bad out_dtype %d", out_dtype);
+  const int64_t total = (int64_t)B * (ndim == 3 ? D / 2 : 1) * (H / 2) * (W / 2) * (C / 4);
+  const int grid = grid_for(total, 256, 16);
+  cudaStream_t st = as_stream(stream);
+#define POOLF(O, M) DSK_LAUNCH((pool2x_f32v4_kernel<O, M>), grid, 256, 0, st, (const float4*)x, y, B, D, H, W, C / 4, ndim)
+  if (out_dtype == DSK_F32) { if (is_max) POOLF(0, true); else POOLF(0, false); }
+  else if (out_dtype == DSK_BF16) { if (is_max) POOLF(1, true); else POOLF(1, false); }
+  else { if (is_max) POOLF(2, true); else POOLF(2, false); }
+#undef POOLF
+  return DSK_OK;
+}
+
 extern "C" int dsk_pool2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int is_max, int dtype,
                           void* stream) {
   DSK_REQUIRE(x && y, "dsk_pool2x: null pointer");

@@ -570,6 +570,8 @@ extern "C" int dsk_conv_fwd_ffma(const dsk_conv_desc* d, const void* in, const v
                                  const float* chan_bias, const void* residual, void* out, void* stream) {
   DSK_REQUIRE(d && in && w && out, "dsk_conv_fwd: null pointer");
   DSK_REQUIRE(d->circular != 2, "dsk_conv_fwd: a pre-padded input (circular = 2) is a tcgen05-path layout");
+  DSK_REQUIRE(residual == nullptr || d->res_dtype == DSK_RES_SAME || (d->res_dtype == DSK_RES_F32 && d->out_dtype == DSK_F32 && !d->out_nchw_f32),
+              "dsk_conv_fwd: an fp32 residual with a 16-bit output (res_dtype) is a tcgen05-path combination");
   DSK_REQUIRE(d->B > 0 && d->D > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "dsk_conv_fwd: bad shape");
   DSK_REQUIRE((d->ksize == 1 || d->ksize == 3) && (d->ndim == 2 || d->ndim == 3), "dsk_conv_fwd: ksize=%d ndim=%d unsupported", d->ksize, d->ndim);
   DSK_REQUIRE(d->ndim == 3 || d->D == 1, "dsk_conv_fwd: ndim=2 needs D=1");

@@ -299,7 +299,7 @@ class _Plan:
         y16 = precision == "fp16s32" and os.environ.get("DSK_Y16", "0") == "1"
         self.Y = [buf(l, ch[l], torch.float16 if (y16 and _tc_eligible(ch[l], ch[l], c.kernel_size)) else adt)
                   for l in range(nlev + 1)]
-        self.P = [buf(l + 1, ch[l]) for l in range(nlev)]          # pooled
+        self.P = [buf(l + 1, ch[l]) for l in range(nlev)]          # pooled (re-typed below where only a 16-bit operand is needed)
         self.XA = buf(nlev, ch[nlev])
         self.XA2 = buf(nlev, ch[nlev])
         self.F = buf(0, c.output_channels)
@@ -331,6 +331,21 @@ class _Plan:
         for i in range(nlev):
             self.blocks += [(b, nlev - 1 - i) for b in net.upward_blocks[i]]
         self.pc = {id(b): (pack(b.conv1), pack(b.conv2)) for b, _ in self.blocks}
+        # fp32-storage modes: a tensor whose ONLY reader is a tensor-core convolution taking plain fp16 activations is produced
+        # directly as that fp16 operand (the value is rounded exactly as the cast pass would round it; an fp32 copy plus a cast
+        # launch per such tensor otherwise):  the pooled tensor (reader: the DownSampler conv) and the output of the last ResNet
+        # block in front of an UpSampler conv / convout (conv2 adds the fp32 residual and writes fp16: DSK_RES_F32).
+        def plain16(pc):
+            return split and ops.is_tc_dtype(pc.w_dtype) and pc.cin < smin and os.environ.get("DSK_OPERAND16", "1") != "0"
+        for l in range(nlev):
+            if plain16(self.pc_down[l]):
+                self.P[l] = buf(l + 1, ch[l], torch.float16)
+        self.X16 = [None] * (nlev + 1)      # per level: fp16 output of the last block before pc_up / pc_out
+        for l in range(nlev + 1):
+            reader = self.pc_out if l == 0 else self.pc_up[nlev - l]
+            last = (net.upward_blocks[nlev - 1 - l] if l < nlev else net.after_block)
+            if plain16(reader) and len(last) > 0 and ops.is_tc_dtype(self.pc[id(last[-1])][1].w_dtype):
+                self.X16[l] = buf(l, ch[l], torch.float16)
         # split mode: the convolutions NOT fed by a norm (down / up samplers, convout) read a split copy of their fp32 input
         # (dsk_split_f16) held in one scratch buffer
         self.S16 = None
@@ -428,11 +443,14 @@ class _Plan:
 
     # ------------------------------------------------------------------ forward
     def _resblock(self, x, blk, l, out, xs=None):
-        """-> (block output, its fused norm statistics or None).  `xs`: statistics of x left by the conv that produced it."""
+        """-> (block output, its fused norm statistics or None).  `xs`: statistics of x left by the conv that produced it.
+        A 16-bit `out` in an fp32-storage mode (self.X16): the block's output is only the operand of the next convolution --
+        no statistics, fp32 residual added in the epilogue."""
         c = self.net.config
         C = blk.channels
         pc1, pc2 = self.pc[id(blk)]
         st = self.ST[l] if self.st_ok[l] else None
+        st2 = None if (out.dtype != x.dtype) else st
         if self.NP[l] is not None:      # periodic net on the tcgen05 path: the norm's apply pass writes the padded conv input
             ops.norm_act(x, blk.gnorm1.weight, blk.gnorm1.bias, C, _NORM_MODE[c.first_resblock_norm], True, ws=self.WS[l],
                          conv_stats=xs, table_only=True)
@@ -441,13 +459,13 @@ class _Plan:
             ops.norm_act(y, blk.gnorm2.weight, blk.gnorm2.bias, C, _NORM_MODE[c.second_resblock_norm], True, ws=self.WS[l],
                          conv_stats=st, table_only=True)
             n = ops.norm_apply_padded(y, self.WS[l], self.NP[l], self.ndim)
-            return self._conv(n, pc2, out=out, residual=x, stats=st, prepadded=True), st
+            return self._conv(n, pc2, out=out, residual=x, stats=st2, prepadded=True), st2
         n = ops.norm_act(x, blk.gnorm1.weight, blk.gnorm1.bias, C, _NORM_MODE[c.first_resblock_norm], True,
                          out=self.N[l], ws=self.WS[l], conv_stats=xs)
         y = self._conv(n, pc1, out=self.Y[l], chan_bias=self.tvec[id(blk)], stats=st)
         n = ops.norm_act(y, blk.gnorm2.weight, blk.gnorm2.bias, C, _NORM_MODE[c.second_resblock_norm], True,
                          out=self.N[l], ws=self.WS[l], conv_stats=st)
-        return self._conv(n, pc2, out=out, residual=x, stats=st), st
+        return self._conv(n, pc2, out=out, residual=x, stats=st2), st2
 
     def _attention(self, x, attn, out, index=0):
         a = self.attn
@@ -503,7 +521,13 @@ class _Plan:
             ops.add_ex(self.te, ye, self.te)
         for g in self.tmlp:
             g.run()
-        x, xs = self._conv(xin, self.pc_in, out=self.X[0]), None
+        # first layer of the modes whose narrow contractions take plain fp16 operands: im2col on the tensor cores (convin_tc)
+        # (DSK_CONVIN_TC16=1 only: measured on C4 the fp16 rounding of the network INPUT and of the 27 first-layer weights alone
+        # moves the denoiser error of fp16s32 from 6.2e-4 to 7.0e-4 -- every later layer sees it -- so the default keeps the first
+        # layer exact in fp32 on the CUDA cores, 2 % of an evaluation)
+        op16 = torch.float16 if (self.split and self.split_min_cin > net.convin.cin and
+                                 os.environ.get("DSK_CONVIN_TC16", "0") == "1") else None
+        x, xs = self._conv(xin, self.pc_in, out=self.X[0], operand16=op16), None
         for l in range(nlev):
             for blk in net.downward_blocks[l]:
                 x, xs = self._resblock(x, blk, l, x, xs)
@@ -519,15 +543,17 @@ class _Plan:
                 xa, xas = self._attention(xa, net.attn_block[r], self.XA2, r), None
                 # next block reads XA2 and writes XA (its residual input is XA2)
         x, xs = ops.add(x, xa, out=x), None
-        for blk in net.after_block:
-            x, xs = self._resblock(x, blk, nlev, x, xs)
+        for r, blk in enumerate(net.after_block):
+            o16 = self.X16[nlev] if r == len(net.after_block) - 1 else None
+            x, xs = self._resblock(x, blk, nlev, x if o16 is None else o16, xs)
         for i in range(nlev):
             l = nlev - 1 - i
             # conv(F.interpolate(x, 2)) + skip, fused (commonlayers.py:145; punetg.py:372-373)
             xs = self.ST[l] if self.st_up[i] else None
             x = self._conv(x, self.pc_up[i], out=self.XU[l], residual=self.X[l], up2=True, stats=xs)
-            for blk in net.upward_blocks[i]:
-                x, xs = self._resblock(x, blk, l, x, xs)
+            for r, blk in enumerate(net.upward_blocks[i]):
+                o16 = self.X16[l] if r == len(net.upward_blocks[i]) - 1 else None
+                x, xs = self._resblock(x, blk, l, x if o16 is None else o16, xs)
         if out_nchw is not None:
             return self._conv(x, self.pc_out, out=out_nchw, out_nchw=True)
         return self._conv(x, self.pc_out, out=self.F)

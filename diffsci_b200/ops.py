@@ -158,9 +158,12 @@ class MultiPacker:
 
 
 def _conv_desc_of(x, pc, out, residual, up2, out_nchw, D, H, W):
+    # res_dtype = 1 (DSK_RES_F32): an fp32 residual added into a 16-bit output (the operand copy an fp32-storage mode writes
+    # when the block's output is read by one convolution only)
+    res_f32 = residual is not None and not out_nchw and residual.dtype == torch.float32 and out.dtype != torch.float32
     return L.ConvDesc(x.shape[0], D, H, W, pc.cin, pc.cout, pc.ksize, pc.ndim, int(up2), w_code(pc.w_dtype), act_code(x, pc.cin),
                       dt_code(residual.dtype if (out_nchw and residual is not None) else
-                              (torch.float32 if out_nchw else out.dtype)), int(out_nchw), int(pc.circular))
+                              (torch.float32 if out_nchw else out.dtype)), int(out_nchw), int(pc.circular), int(res_f32))
 
 
 def conv_pad_ws_bytes(x_shape, x_dtype, pc: "PackedConv", up2: bool = False) -> int:
@@ -204,12 +207,15 @@ def conv_stats_buffer(B: int, cout: int, device) -> torch.Tensor:
 
 def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, chan_bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, up2: bool = False, out_dtype: Optional[torch.dtype] = None,
-         out_nchw: bool = False, stats: Optional[torch.Tensor] = None, pad_ws=None, prepadded: bool = False) -> torch.Tensor:
+         out_nchw: bool = False, stats: Optional[torch.Tensor] = None, pad_ws=None, prepadded: bool = False,
+         operand16: Optional[torch.dtype] = None) -> torch.Tensor:
     """y = conv_same(x) + bias + chan_bias[b, :] + residual  (dsk_conv_fwd).  `stats` (conv_stats_buffer): also leave the
     per-(sample, channel) statistics of y for norm_act(..., conv_stats=stats) (dsk_conv_fwd_stats).
     pc.circular: circular instead of zero padding (dsk_conv_fwd_circ); `pad_ws` (tensor, or callable returning one) is the
     preallocated workspace of the padded copy the tcgen05 path reads -- allocated here if missing (not graph-safe).
-    prepadded: x IS the halo-padded tensor [B, D+2 (3-D), H+2, W+2, Cin] (norm_apply_padded): no padding pass."""
+    prepadded: x IS the halo-padded tensor [B, D+2 (3-D), H+2, W+2, Cin] (norm_apply_padded): no padding pass.
+    operand16 (fp32 x, fp32 weights, fp32 out, Cin <= 4: the first layer of an fp32-storage mode): run on the tensor cores with
+    operands rounded to this 16-bit format (dsk_conv_desc.operand16) where the im2col kernel takes the shape."""
     require_cuda(x, "conv input")
     B, D, H, W, Cin = x.shape
     if prepadded:
@@ -228,6 +234,8 @@ def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, ch
             shape = (B, pc.cout, H, W)
         out = torch.empty(shape, dtype=torch.float32 if out_nchw else out_dtype, device=x.device)
     d = _conv_desc_of(x, pc, out, residual, up2, out_nchw, D, H, W)
+    if operand16 is not None and x.dtype == torch.float32 and pc.w_dtype == torch.float32 and out.dtype == torch.float32:
+        d.operand16 = dt_code(operand16)
     bias = pc.bias.detach() if pc.bias is not None else None
     if prepadded:
         d.circular = 2
@@ -342,6 +350,10 @@ def pool2x(x: torch.Tensor, ndim: int, is_max: bool, out: Optional[torch.Tensor]
     B, D, H, W, Cc = x.shape
     if out is None:
         out = torch.empty((B, D // 2 if ndim == 3 else 1, H // 2, W // 2, Cc), dtype=x.dtype, device=x.device)
+    if x.dtype == torch.float32 and Cc % 4 == 0:      # float4 kernel; `out` may be a 16-bit operand copy (fp32-storage modes)
+        check(lib.dsk_pool2x_f32(ptr(x), ptr(out), B, D, H, W, Cc, ndim, int(is_max), dt_code(out.dtype), stream()))
+        return out
+    assert out.dtype == x.dtype
     check(lib.dsk_pool2x(ptr(x), ptr(out), B, D, H, W, Cc, ndim, int(is_max), dt_code(x.dtype), stream()))
     return out
 

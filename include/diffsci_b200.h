@@ -215,7 +215,15 @@ typedef struct {
                           CircularConv2d / CircularConv3d (commonlayers.py:918-1032), PUNetGConfig(convolution_type=
                           "circular").  CUDA-core kernels wrap their gather; tcgen05 kernels read a halo-padded copy
                           (dsk_conv_fwd_circ / the workspace of dsk_conv_wgrad).                                       */
+  int res_dtype;       /* DSK_RES_SAME (0): `residual` has out_dtype;  DSK_RES_F32: `residual` is fp32 whatever out_dtype is --
+                          tcgen05 kernels only: a block of an fp32-storage mode whose output is read by ONE convolution writes
+                          the 16-bit operand copy directly (fp32 residual stream in, fp16 out) instead of fp32 + a cast pass */
+  int operand16;       /* 0, or DSK_BF16 | DSK_F16 with in_dtype = out_dtype = w_dtype = DSK_F32 on a few-input-channel convolution
+                          (convin, Cin <= 4): run it on the tensor cores with operands rounded to this format (the first layer of
+                          the fp32-storage 16-bit-operand modes) instead of the CUDA-core fp32 kernel                          */
 } dsk_conv_desc;
+#define DSK_RES_SAME 0
+#define DSK_RES_F32 1
 int dsk_conv_fwd(const dsk_conv_desc* d, const void* in, const void* w, const float* bias,
                  const float* chan_bias, const void* residual, void* out, void* stream);
 /* The same convolution with the statistics of the FOLLOWING per-channel norm fused into its epilogue (the reference
@@ -339,6 +347,9 @@ int dsk_norm_act_prestat(const void* x, void* y, const float* gamma, const float
  * x: [B, D, H, W, C] -> y: [B, D/2 (or 1), H/2, W/2, C] (floor, like torch). */
 int dsk_pool2x(const void* x, void* y, int B, int D, int H, int W, int C, int ndim, int is_max, int dtype,
                void* stream);
+/* ... fp32 input (C % 4 == 0, float4 per thread), output fp32 or rounded once to out_dtype = DSK_BF16 | DSK_F16: the fp32-storage
+ * precision modes pool straight into the 16-bit operand copy of the DownSampler convolution (commonlayers.py:53-63) */
+int dsk_pool2x_f32(const float* x, void* y, int B, int D, int H, int W, int C, int ndim, int is_max, int out_dtype, void* stream);
 /* y = a + b (elementwise, same dtype); used for the additive U-Net skips (punetg.py:373,384) */
 int dsk_add(const void* a, const void* b, void* y, int64_t n, int dtype, void* stream);
 /* NCHW fp32 <-> channels-last conversions at the module boundary */

@@ -580,3 +580,69 @@ def test_convin_tcgen05(ops, ndim, B, Cin, Cout, sp):
     pc = ops.PackedConv(w.to(DEV), b.to(DEV), ndim, torch.float32)        # the few-channel path keeps fp32 packed weights
     y = ops.conv(to_cl(x).bfloat16(), pc)
     assert y.dtype == torch.bfloat16 and relmax(from_cl(y, ndim), ref) < 6e-3
+
+
+@pytest.mark.parametrize("ndim,B,Cin,Cout,sp", [(3, 2, 1, 64, (5, 16, 8)), (3, 1, 2, 64, (4, 9, 11)), (2, 3, 3, 128, (20, 12)),
+                                                (2, 2, 1, 64, (28, 28)), (2, 2, 4, 256, (7, 9))])
+def test_convin_fp32_storage_paths(ops, ndim, B, Cin, Cout, sp):
+    """The first layer of the fp32-storage modes: (1) fp32 in / fp32 out on the CUDA cores (pixel-major few-input-channel kernel)
+    vs ATen fp32; (2) the same tensors with operand16 = fp16: im2col on the tensor cores with operands rounded to fp16 while
+    gathering (convin_tc.cu, fp32 output through the staged epilogue) vs ATen on fp16-rounded operands."""
+    torch.manual_seed(24)
+    x = torch.randn(B, Cin, *sp)
+    w = torch.randn(Cout, Cin, *([3] * ndim)) / math.sqrt(Cin * 3 ** ndim)
+    b = torch.randn(Cout) * 0.1
+    conv = F.conv2d if ndim == 2 else F.conv3d
+    pc = ops.PackedConv(w.to(DEV), b.to(DEV), ndim, torch.float32)
+    y = ops.conv(to_cl(x), pc)
+    assert y.dtype == torch.float32 and relmax(from_cl(y, ndim), conv(x, w, b, padding=1)) < 2e-5
+    y16 = ops.conv(to_cl(x), pc, operand16=torch.float16)
+    ref16 = conv(x.half().float(), w.half().float(), b, padding=1)
+    assert y16.dtype == torch.float32 and relmax(from_cl(y16, ndim), ref16) < 2e-5
+    # 16-bit in / out through the same kernel (two epilogue warp sets, staged stores)
+    yh = ops.conv(to_cl(x).half(), pc)
+    assert yh.dtype == torch.float16 and relmax(from_cl(yh, ndim), ref16) < 1e-3
+
+
+@pytest.mark.parametrize("ndim,B,Cin,Cout,sp,up2", [(3, 2, 64, 64, (4, 16, 16), False), (3, 1, 128, 128, (4, 16, 16), False),
+                                                    (2, 3, 64, 128, (16, 16), False), (3, 1, 128, 64, (2, 8, 8), True),
+                                                    (2, 2, 64, 64, (7, 9), False)])
+def test_conv_tc_fp32_residual_16bit_out(ops, ndim, B, Cin, Cout, sp, up2):
+    """dsk_conv_desc.res_dtype = DSK_RES_F32: fp16 operands, fp32 residual added in the epilogue, fp16 OUTPUT (the operand copy a
+    block of an fp32-storage mode writes for the single convolution that reads it) -- CTA-pair kernel and the single-CTA
+    kernel (odd tile counts), with the per-warp staged bias + chan_bias."""
+    torch.manual_seed(25)
+    x = torch.randn(B, Cin, *sp).half().float()
+    w = (torch.randn(Cout, Cin, *([3] * ndim)) / math.sqrt(Cin * 3 ** ndim)).half().float()
+    b = torch.randn(Cout) * 0.1
+    cb = torch.randn(B, Cout) * 0.3
+    conv = F.conv2d if ndim == 2 else F.conv3d
+    xr = F.interpolate(x, scale_factor=2, mode="nearest") if up2 else x
+    ref = conv(xr, w, b, padding=1) + cb.view(B, Cout, *([1] * ndim))
+    res = torch.randn_like(ref)                                            # fp32 residual, not representable in fp16
+    pc = ops.PackedConv(w.to(DEV), b.to(DEV), ndim, torch.float16, subpixel=up2)
+    out = torch.empty(to_cl(ref).shape, dtype=torch.float16, device=DEV)
+    y = ops.conv(to_cl(x).half(), pc, out=out, chan_bias=cb.to(DEV), residual=to_cl(res), up2=up2)
+    tol = 1.2e-3 if not up2 else 3e-3                                      # one fp16 rounding of the output (sub-pixel: + summed taps)
+    assert y.dtype == torch.float16 and relmax(from_cl(y, ndim), ref + res) < tol
+    y32 = ops.conv(to_cl(x).half(), pc, out=torch.empty_like(out, dtype=torch.float32), chan_bias=cb.to(DEV), residual=to_cl(res),
+                   up2=up2)
+    assert relmax(from_cl(y32, ndim), ref + res) < (2e-5 if not up2 else 2e-3)
+    assert torch.equal(y, y32.half())                                      # the same accumulator + residual, rounded once
+
+
+@pytest.mark.parametrize("ndim,sp", [(3, (4, 6, 8)), (2, (10, 12))])
+@pytest.mark.parametrize("is_max", [True, False])
+def test_pool2x_fp32_to_operand_copy(ops, ndim, sp, is_max):
+    """dsk_pool2x_f32: float4 pooling of an fp32 tensor into fp32, or rounded once into the fp16 / bf16 operand copy."""
+    torch.manual_seed(26)
+    x = torch.randn(2, 64, *sp)
+    pool = (F.max_pool3d if ndim == 3 else F.max_pool2d) if is_max else (F.avg_pool3d if ndim == 3 else F.avg_pool2d)
+    ref = pool(x, 2)
+    xc = to_cl(x)
+    y = ops.pool2x(xc, ndim, is_max)
+    assert y.dtype == torch.float32 and relmax(from_cl(y, ndim), ref) < 1e-6
+    for dt in (torch.float16, torch.bfloat16):
+        o = torch.empty(y.shape, dtype=dt, device=DEV)
+        ops.pool2x(xc, ndim, is_max, out=o)
+        assert torch.equal(o, y.to(dt))
