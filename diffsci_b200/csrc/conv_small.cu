@@ -193,7 +193,10 @@ __global__ void __launch_bounds__(256) conv_few_in_kernel(SmallConvArgs a) {
 // k = 3, CIN * taps <= 54 (Cin = 1, or 2 in 2-D): thread = one pixel, ALL output channels.  The receptive field (27 or 9 taps
 // per input channel) is gathered once into registers -- zero for taps outside the image, so the inner loops carry no bounds
 // logic -- and reused for every 32-channel chunk of the output; 32-bit index arithmetic (the pixel-times-chunk form above
-// spends as many instructions on its 64-bit divisions as on its FMAs).  Weights: shared-memory float4 broadcasts.
+// spends as many instructions on its 64-bit divisions as on its FMAs).  Weights: shared-memory float4 broadcasts, which is what
+// bounds it (8 LDS.128 per 32 FMAs: 387 us for C4's first layer, 537 MB of fp32 output).  Tried and dropped: the thread's weights
+// in registers (4 channels x 2 pixels per thread, 174 registers): one resident block per SM, latency-bound, 697 us.  The
+// 16-bit-operand modes take the tensor-core im2col kernel instead (convin_tc.cu, exact split rows).
 template <typename TI, typename TO, int CIN, bool D3>
 __global__ void __launch_bounds__(256) conv_few_in_px_kernel(SmallConvArgs a) {
   extern __shared__ float wsm[];                      // [taps][CIN][Cout]
@@ -249,67 +252,6 @@ __global__ void __launch_bounds__(256) conv_few_in_px_kernel(SmallConvArgs a) {
   }
 }
 
-// k = 3, K = CIN * taps <= 27 (Cin = 1 in 3-D; Cin <= 3 in 2-D): thread = (4 output channels, 2 neighbouring pixels along w).
-// The thread's 4 x K weights live in REGISTERS for the whole kernel (the pixel-major form above reads them from shared memory:
-// 8 LDS.128 per 32 FMAs, which is what bounds it -- 387 us for the 537 MB fp32 output of C4's first layer); the Cout / 4
-// threads of a pixel pair are adjacent lanes, so their tap loads are warp broadcasts and their stores cover whole rows.
-template <typename TI, typename TO, int CIN, bool D3>
-__global__ void __launch_bounds__(256) conv_few_in_cg_kernel(SmallConvArgs a) {
-  constexpr int TAPS = D3 ? 27 : 9, KD = D3 ? 3 : 1, K = TAPS * CIN;
-  const int ngroups = a.Cout >> 2;                                   // host: 256 % ngroups == 0
-  const int cg = threadIdx.x % ngroups, pl = threadIdx.x / ngroups, ppb = 256 / ngroups;
-  float4 wr[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(a.w + (int64_t)k * a.Cout) + cg);
-  const float4 b4 = a.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(a.bias) + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
-  const TI* in = reinterpret_cast<const TI*>(a.in);
-  TO* out = reinterpret_cast<TO*>(a.out);
-  const uint32_t W2 = (uint32_t)(a.W + 1) >> 1;
-  const uint32_t npair = (uint32_t)a.B * a.D * a.H * W2;             // host: pixel count < 2^31
-  for (uint32_t pp = blockIdx.x * ppb + pl; pp < npair; pp += gridDim.x * ppb) {
-    uint32_t t = pp;
-    const int w0 = (int)(t % W2) * 2; t /= W2;
-    const int h0 = (int)(t % (uint32_t)a.H); t /= (uint32_t)a.H;
-    const int d0 = D3 ? (int)(t % (uint32_t)a.D) : 0;
-    const int b = D3 ? (int)(t / (uint32_t)a.D) : (int)t;
-    const int64_t pix = (((int64_t)b * a.D + d0) * a.H + h0) * a.W + w0;
-    float4 acc0 = b4, acc1 = b4;
-#pragma unroll
-    for (int kd = 0; kd < KD; ++kd)
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int zd = D3 ? d0 + kd - 1 : 0, zh = h0 + kh - 1;
-        const bool okr = (unsigned)zd < (unsigned)a.D && (unsigned)zh < (unsigned)a.H;
-        const int64_t rowoff = (pix + ((D3 ? kd - 1 : 0) * a.H + (kh - 1)) * (int64_t)a.W) * CIN;
-        float xr[4][CIN];                                             // input columns w0 - 1 .. w0 + 2 of this row
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const bool ok = okr && (unsigned)(w0 + c - 1) < (unsigned)a.W;
-#pragma unroll
-          for (int ci = 0; ci < CIN; ++ci) xr[c][ci] = ok ? to_f32<TI>(in[rowoff + (c - 1) * CIN + ci]) : 0.0f;
-        }
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-          for (int ci = 0; ci < CIN; ++ci) {
-            const float4 w4 = wr[((kd * 3 + kh) * 3 + kw) * CIN + ci];
-            const float x0 = xr[kw][ci], x1 = xr[kw + 1][ci];
-            acc0.x = fmaf(x0, w4.x, acc0.x); acc0.y = fmaf(x0, w4.y, acc0.y); acc0.z = fmaf(x0, w4.z, acc0.z); acc0.w = fmaf(x0, w4.w, acc0.w);
-            acc1.x = fmaf(x1, w4.x, acc1.x); acc1.y = fmaf(x1, w4.y, acc1.y); acc1.z = fmaf(x1, w4.z, acc1.z); acc1.w = fmaf(x1, w4.w, acc1.w);
-          }
-      }
-    TO* o0 = out + pix * a.Cout + cg * 4;
-    if (sizeof(TO) == 4) {
-      *reinterpret_cast<float4*>(o0) = acc0;
-      if (w0 + 1 < a.W) *reinterpret_cast<float4*>(o0 + a.Cout) = acc1;
-    } else {
-      const bool f16 = sizeof(TO) == 2 && !std::is_same<TO, __nv_bfloat16>::value;
-      *reinterpret_cast<uint2*>(o0) = make_uint2(pack_h2(acc0.x, acc0.y, f16), pack_h2(acc0.z, acc0.w, f16));
-      if (w0 + 1 < a.W) *reinterpret_cast<uint2*>(o0 + a.Cout) = make_uint2(pack_h2(acc1.x, acc1.y, f16), pack_h2(acc1.z, acc1.w, f16));
-    }
-  }
-}
-
 template <typename TI, typename TO>
 static int launch_few_out(const SmallConvArgs& a, cudaStream_t st) {
   const int taps = a.ndim == 3 ? a.ks * a.ks * a.ks : a.ks * a.ks;
@@ -330,16 +272,6 @@ static int launch_few_in(const SmallConvArgs& a, cudaStream_t st) {
   const int taps = a.ndim == 3 ? a.ks * a.ks * a.ks : a.ks * a.ks;
   const size_t smem = (size_t)taps * a.Cin * a.Cout * sizeof(float);
   const int64_t npix = (int64_t)a.B * a.D * a.H * a.W;
-  const int ngroups = a.Cout / 4;
-  if (a.ks == 3 && taps * a.Cin <= 27 && npix < (1ll << 31) && ngroups <= 256 && 256 % ngroups == 0) {   // weights in registers
-    const int64_t npair = (int64_t)a.B * a.D * a.H * ((a.W + 1) / 2);
-    const int cgrid = grid_for(npair * ngroups, 256, 8);
-    if (a.ndim == 3) DSK_LAUNCH((conv_few_in_cg_kernel<TI, TO, 1, true>), cgrid, 256, 0, st, a);
-    else if (a.Cin == 1) DSK_LAUNCH((conv_few_in_cg_kernel<TI, TO, 1, false>), cgrid, 256, 0, st, a);
-    else if (a.Cin == 2) DSK_LAUNCH((conv_few_in_cg_kernel<TI, TO, 2, false>), cgrid, 256, 0, st, a);
-    else DSK_LAUNCH((conv_few_in_cg_kernel<TI, TO, 3, false>), cgrid, 256, 0, st, a);
-    return DSK_OK;
-  }
   if (a.ks == 3 && taps * a.Cin <= 54 && npix < (1ll << 31) && npix * a.Cin < (1ll << 31)) {   // pixel-major kernel (see above)
     const int pgrid = grid_for(npix, 256, 16);
     if (a.ndim == 3 && a.Cin == 1) DSK_LAUNCH((conv_few_in_px_kernel<TI, TO, 1, true>), pgrid, 256, smem, st, a);

@@ -15,7 +15,7 @@
 namespace dsk {
 
 constexpr int CI_BW = 8, CI_BH = 16;               // 128 output pixels per tile
-constexpr int CI_NG = 3;                           // builder groups of 4 warps: CI_NG tiles are gathered concurrently
+constexpr int CI_NG = 2;                           // builder groups of 4 warps: CI_NG tiles are gathered concurrently
 constexpr int CI_BUILD = CI_NG * 4;                // warps 0..CI_BUILD-1: im2col builders
 constexpr int CI_EPI = 8;                          // epilogue warps: set (w >> 2) drains accumulator buffer (tile seq & 1)
 constexpr int CI_THREADS = (CI_BUILD + 1 + CI_EPI) * 32;  // + warp CI_BUILD: MMA / TMEM owner
@@ -26,6 +26,10 @@ constexpr int CI_A_BYTES = 128 * 128;
 struct CiParams {
   const uint16_t* x;        // channels-last [B, D, H, W, Cin], 16-bit format f16 ? half : bfloat16 (fp32 when in_f32)
   int in_f32, out_f32;      // fp32 input (rounded to the 16-bit operand format in the gather) / fp32 output
+  int split;                // fp32 input only: EXACT fp32-class product on fp16 operands -- the im2col row becomes
+                            // [x_hi (K) | x_lo (K) | x_hi (K)] and the weight row [w_hi | w_hi | w_lo] (3K <= 128: two 128-byte
+                            // K chunks), i.e. x_hi w_hi + x_lo w_hi + x_hi w_lo in one accumulator chain of <= 8 MMAs
+  int nstages;              // A ring depth (6; 4 in split mode: stages are twice as large)
   const float* w;           // packed fp32 [taps][Cin][Cout]
   const float* bias;
   uint16_t* out;            // channels-last [B, D, H, W, Cout]
@@ -35,24 +39,27 @@ struct CiParams {
   int circ;                 // circular padding: the gather wraps instead of zero-filling (CircularConv, commonlayers.py:918-1032)
 };
 
-template <int CIN>
+template <int CIN, bool D3>
 __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                                        // CI_STAGES x [128 rows x 128 B]
-  uint8_t* sB = smem + (size_t)CI_STAGES * CI_A_BYTES;       // [Cout rows x 128 B]
-  uint8_t* sStg = sB + (size_t)p.Cout * 128;                 // CI_EPI x [32 rows x 128 B] store stages
+  const int nch = p.split ? 2 : 1;                           // 128-byte K chunks per im2col row
+  const int NST = p.nstages;
+  const size_t a_stage = (size_t)nch * CI_A_BYTES;
+  uint8_t* sA = smem;                                        // NST x nch x [128 rows x 128 B]
+  uint8_t* sB = smem + (size_t)NST * a_stage;                // nch x [Cout rows x 128 B]
+  uint8_t* sStg = sB + (size_t)nch * p.Cout * 128;           // CI_EPI x [32 rows x 128 B] store stages
   float* sBias = reinterpret_cast<float*>(sStg + (size_t)CI_EPI * CI_STG_BYTES);   // [Cout]
   __shared__ uint64_t full_a[CI_STAGES], empty_a[CI_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.Cout;
   const uint32_t tmem_cols = N <= 64 ? 128u : (N <= 128 ? 256u : 512u);   // 2 x N, power of two
-  const int taps = p.ndim == 3 ? 27 : 9;
-  const int K = taps * CIN;                                  // <= 64 (host-checked)
+  constexpr int TAPS = D3 ? 27 : 9;
+  constexpr int K = TAPS * CIN;                              // <= 64 (host-checked)
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < CI_STAGES; ++i) { mbar_init(&full_a[i], 4); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < CI_STAGES; ++i) { mbar_init(&full_a[i], 4); mbar_init(&empty_a[i], 1); }   // the first p.nstages are used
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -61,16 +68,28 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // weights -> bf16 K-major SWIZZLE_128B rows: B[co][k = tap*CIN + ci] = w[k][co], zero beyond K
-  for (int i = threadIdx.x; i < N * 8; i += CI_THREADS) {
-    const int j = i & 7, co = i >> 3;
+  for (int i = threadIdx.x; i < N * 8 * nch; i += CI_THREADS) {
+    const int j = i & 7, co = (i >> 3) % N, c = (i >> 3) / N;
     uint32_t h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int k0 = j * 8 + 2 * e;
-      const float a = k0 < K ? p.w[(int64_t)k0 * N + co] : 0.0f, b = k0 + 1 < K ? p.w[(int64_t)(k0 + 1) * N + co] : 0.0f;
-      h[e] = pack_h2(a, b, p.f16);
+      float ab[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kk = c * 64 + j * 8 + 2 * e + u;           // position in the (virtual) K axis
+        float val = 0.0f;
+        if (!p.split) {
+          if (kk < K) val = p.w[(int64_t)kk * N + co];
+        } else if (kk < 3 * K) {
+          const int k0 = kk < K ? kk : (kk < 2 * K ? kk - K : kk - 2 * K);
+          const float wv = p.w[(int64_t)k0 * N + co];
+          val = kk < 2 * K ? wv : wv - __half2float(__float2half_rn(wv));   // [w_hi | w_hi | w_lo] (pack rounds w_hi below)
+        }
+        ab[u] = val;
+      }
+      h[e] = pack_h2(ab[0], ab[1], p.f16);
     }
-    *reinterpret_cast<uint4*>(sB + co * 128 + ((j ^ (co & 7)) << 4)) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(sB + (size_t)c * N * 128 + co * 128 + ((j ^ (co & 7)) << 4)) = *reinterpret_cast<const uint4*>(h);
   }
   for (int i = threadIdx.x; i < N; i += CI_THREADS) sBias[i] = p.bias != nullptr ? p.bias[i] : 0.0f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -90,13 +109,13 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
     // ===================== im2col builders: group g gathers tiles seq = g, g + CI_NG, ...; thread = one pixel row ===========
     const int grp = warp >> 2;
     const int r = threadIdx.x & 127, line = r >> 3, wp = r & 7;
-    const int kdn = p.ndim == 3 ? 3 : 1;
+    constexpr int kdn = D3 ? 3 : 1;
     uint32_t seq = grp;
     for (int t = blockIdx.x + grp * gridDim.x; t < p.total_tiles; t += CI_NG * gridDim.x, seq += CI_NG) {
       int w0, h0, d, b;
       coord(t, w0, h0, d, b);
       const int h = h0 + line, w = w0 + wp;
-      const uint32_t slot = seq % CI_STAGES, ph = (seq / CI_STAGES) & 1;
+      const uint32_t slot = seq % NST, ph = (seq / NST) & 1;
       // gather the receptive field first (loads in flight while waiting for the slot); validity factorises per axis
       bool dv[3], hv[3], wv[3];
       const int sH = p.W * CIN, sD = p.H * sH;
@@ -124,9 +143,12 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
       const int64_t ctr_off = ((((int64_t)b * p.D + d) * p.H + h) * p.W + w) * CIN;
       const uint16_t* ctr = p.x + ctr_off;
       const float* ctr32 = reinterpret_cast<const float*>(p.x) + ctr_off;
-      __align__(16) uint16_t v[64];                            // zero bits = 0.0 in both 16-bit formats
+      // one 32-bit register per tap holding its 16-bit operand(s): hi in the low half; split mode: lo = x - fp16(x) in the high
+      // half.  Every index below is a compile-time constant after unrolling, and the 16-byte pieces are assembled from these
+      // registers with shifts / PRMT -- a uint16 array reinterpreted as uint4 goes through local memory (the first version did).
+      uint32_t tv[K];
 #pragma unroll
-      for (int k = 0; k < 64; ++k) v[k] = 0;
+      for (int k = 0; k < K; ++k) tv[k] = 0;                   // zero bits = 0.0 in both 16-bit formats
 #pragma unroll
       for (int kd = 0; kd < 3; ++kd) {
         if (kd >= kdn) break;
@@ -138,17 +160,48 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
             const int so = od[kd] + oh[kh] + ow[kw];
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci)
-              if (ok) v[((kd * 3 + kh) * 3 + kw) * CIN + ci] = p.in_f32 ? pack_h1(ctr32[so + ci], p.f16) : ctr[so + ci];
+              if (ok) {
+                const int k = ((kd * 3 + kh) * 3 + kw) * CIN + ci;
+                if (p.in_f32) {
+                  const float xf = ctr32[so + ci];
+                  const uint32_t hi = pack_h1(xf, p.f16);
+                  tv[k] = hi | ((uint32_t)pack_h1(xf - unpack_h1((uint16_t)hi, p.f16), p.f16) << 16);
+                } else {
+                  tv[k] = ctr[so + ci];
+                }
+              }
           }
       }
       mbar_wait(&empty_a[slot], ph ^ 1);
-      uint8_t* row = sA + (size_t)slot * CI_A_BYTES + r * 128;
-      constexpr int PIECES = (27 * CIN + 7) / 8;               // 16-byte pieces that can be non-zero
+      uint8_t* row = sA + (size_t)slot * a_stage + r * 128;
+      // element at virtual K position i of the row: plain: x_hi[i]; split: [x_hi (K) | x_lo (K) | x_hi (K)]; zero beyond
+      auto elem = [&](int i, bool split) -> uint32_t {
+        if (!split) return i < K ? (tv[i < K ? i : 0] & 0xffffu) : 0u;
+        if (i < K) return tv[i < K ? i : 0] & 0xffffu;
+        if (i < 2 * K) return tv[(i - K) < K ? (i - K) : 0] >> 16;
+        if (i < 3 * K) return tv[(i - 2 * K) < K ? (i - 2 * K) : 0] & 0xffffu;
+        return 0u;
+      };
+      if (!p.split) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint4 piece = make_uint4(0, 0, 0, 0);
-        if (j < PIECES) piece = *reinterpret_cast<const uint4*>(&v[j * 8]);
-        *reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4)) = piece;
+        for (int j = 0; j < 8; ++j) {
+          uint4 piece;
+          piece.x = elem(j * 8, false) | (elem(j * 8 + 1, false) << 16);
+          piece.y = elem(j * 8 + 2, false) | (elem(j * 8 + 3, false) << 16);
+          piece.z = elem(j * 8 + 4, false) | (elem(j * 8 + 5, false) << 16);
+          piece.w = elem(j * 8 + 6, false) | (elem(j * 8 + 7, false) << 16);
+          *reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4)) = piece;
+        }
+      } else if (3 * K <= 128) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          uint4 piece;
+          piece.x = elem(j * 8, true) | (elem(j * 8 + 1, true) << 16);
+          piece.y = elem(j * 8 + 2, true) | (elem(j * 8 + 3, true) << 16);
+          piece.z = elem(j * 8 + 4, true) | (elem(j * 8 + 5, true) << 16);
+          piece.w = elem(j * 8 + 6, true) | (elem(j * 8 + 7, true) << 16);
+          *reinterpret_cast<uint4*>(row + (j >> 3) * CI_A_BYTES + (((j & 7) ^ (r & 7)) << 4)) = piece;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       __syncwarp();
@@ -162,15 +215,20 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
     uint32_t seq = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++seq) {
       const uint32_t as = seq & 1, aph = (seq >> 1) & 1;
-      const uint32_t slot = seq % CI_STAGES;
+      const uint32_t slot = seq % NST;
       mbar_wait(&acc_empty[as], aph ^ 1);
-      mbar_wait(&full_a[slot], (seq / CI_STAGES) & 1);
+      mbar_wait(&full_a[slot], (seq / NST) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_lo = umma_desc_lo(smem_u32(sA + (size_t)slot * CI_A_BYTES));
+      const uint32_t a_lo = umma_desc_lo(smem_u32(sA + (size_t)slot * a_stage));
+      const int Kv = p.split ? 3 * K : K;                     // virtual K
       if (elect_one_sync()) {
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          if (k4 * 16 < K) umma_bf16(tmem_base + as * N, umma_desc64(a_lo + k4 * 2, HI), umma_desc64(b_lo + k4 * 2, HI), idesc, k4 != 0);
+        for (int k8 = 0; k8 < 8; ++k8) {
+          const uint32_t c = k8 >> 2, k4 = k8 & 3;
+          if (k8 * 16 < Kv)
+            umma_bf16(tmem_base + as * N, umma_desc64(a_lo + c * (CI_A_BYTES >> 4) + k4 * 2, HI),
+                      umma_desc64(b_lo + c * (uint32_t)((N * 128) >> 4) + k4 * 2, HI), idesc, k8 != 0);
+        }
         umma_commit(&empty_a[slot]);
         umma_commit(&acc_full[as]);
       }
@@ -208,14 +266,18 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
             stg[lane * 8 + (g ^ (lane & 7))] = make_uint4(__float_as_uint(f[4 * g]), __float_as_uint(f[4 * g + 1]),
                                                           __float_as_uint(f[4 * g + 2]), __float_as_uint(f[4 * g + 3]));
           __syncwarp();
-          float* outf = reinterpret_cast<float*>(p.out);
-          const int j = lane & 7;
+          // row r = 4k + lane / 8 of the warp = pixel (line q*4 + k/2, column 4 (k & 1) + lane / 8) of the tile: ONE 64-bit base per
+          // tile and 32-bit row offsets with compile-time structure (eight hoisted 64-bit addresses spilled to local memory)
+          const int j = lane & 7, l3 = lane >> 3;
+          float* ob = reinterpret_cast<float*>(p.out) + ((plane + h0 + q * 4) * p.W + w0 + l3) * N + c0 + j * 4;
+          int wn = p.W * N, n4 = 4 * N;
+          asm volatile("" : "+r"(wn), "+r"(n4));                // opaque per pass: keeps the row offsets out of the loop-invariant set
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const int r = 4 * k + (lane >> 3), R = q * 32 + r;
-            const int h = h0 + (R >> 3), w = w0 + (R & 7);
+            const int r = 4 * k + l3;
             const uint4 val = stg[r * 8 + (j ^ (r & 7))];
-            if (h < p.H && w < p.W) *reinterpret_cast<uint4*>(outf + ((plane + h) * p.W + w) * N + c0 + j * 4) = val;
+            if (h0 + q * 4 + (k >> 1) < p.H && w0 + 4 * (k & 1) + l3 < p.W)
+              *reinterpret_cast<uint4*>(ob + (k >> 1) * wn + (k & 1) * n4) = val;
           }
         } else {
 #pragma unroll
@@ -227,13 +289,15 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
             stg[lane * 4 + (g ^ (lane & 3))] = o;
           }
           __syncwarp();
-          const int j = lane & 3;
+          const int j = lane & 3, l2 = lane >> 2;               // row r = 8k + lane / 4 = pixel (line q*4 + k, column lane / 4)
+          uint16_t* ob = p.out + ((plane + h0 + q * 4) * p.W + w0 + l2) * N + c0 + j * 8;
+          int wn = p.W * N;
+          asm volatile("" : "+r"(wn));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int r = 8 * k + (lane >> 2), R = q * 32 + r;
-            const int h = h0 + (R >> 3), w = w0 + (R & 7);
+            const int r = 8 * k + l2;
             const uint4 val = stg[r * 4 + (j ^ (r & 3))];
-            if (h < p.H && w < p.W) *reinterpret_cast<uint4*>(p.out + ((plane + h) * p.W + w) * N + c0 + j * 8) = val;
+            if (h0 + q * 4 + k < p.H && w0 + l2 < p.W) *reinterpret_cast<uint4*>(ob + k * wn) = val;
           }
         }
         __syncwarp();
@@ -248,13 +312,15 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
   if (warp == CI_BUILD) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
 }
 
-template <int CIN>
+template <int CIN, bool D3>
 static int launch_convin(const CiParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)CI_STAGES * CI_A_BYTES + (size_t)p.Cout * 128 + (size_t)CI_EPI * CI_STG_BYTES + (size_t)p.Cout * 4 + 1024;
-  cudaError_t e = cudaFuncSetAttribute(convin_tc_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int nch = p.split ? 2 : 1;
+  const size_t smem = (size_t)p.nstages * nch * CI_A_BYTES + (size_t)nch * p.Cout * 128 + (size_t)CI_EPI * CI_STG_BYTES +
+                      (size_t)p.Cout * 4 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(convin_tc_kernel<CIN, D3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("convin_tc: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e)); return DSK_ERR_CUDA; }
   const int grid = p.total_tiles < DSK_NUM_SMS ? p.total_tiles : DSK_NUM_SMS;
-  DSK_LAUNCH((convin_tc_kernel<CIN>), grid, CI_THREADS, smem, st, p);
+  DSK_LAUNCH((convin_tc_kernel<CIN, D3>), grid, CI_THREADS, smem, st, p);
   return DSK_OK;
 }
 
@@ -265,23 +331,27 @@ int convin_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, co
   // formats: 16-bit in -> the same 16-bit out (the 16-bit modes), or -- descriptor field `operand16` = DSK_BF16 | DSK_F16 naming
   // the tensor-core operand format -- fp32 in -> fp32 out (the fp32-storage modes with 16-bit operands)
   const bool h16 = is_h16(d->in_dtype) && d->out_dtype == d->in_dtype;
-  const bool f32 = d->in_dtype == DSK_F32 && d->out_dtype == DSK_F32 && is_h16(d->operand16);
+  const bool split = d->operand16 == DSK_SPLIT_F16 && 3 * taps * d->Cin <= 128;      // exact: [x_hi | x_lo | x_hi] . [w_hi | w_hi | w_lo]
+  const bool f32 = d->in_dtype == DSK_F32 && d->out_dtype == DSK_F32 && (is_h16(d->operand16) || split);
   if (old_path || d->ksize != 3 || d->up2 || d->out_nchw_f32 || !(h16 || f32) || d->w_dtype != DSK_F32 ||
       d->Cin > 4 || taps * d->Cin > 64 || (d->Cout != 64 && d->Cout != 128 && d->Cout != 256))
     return DSK_ERR_UNSUPPORTED;
   CiParams p;
   p.x = (const uint16_t*)in; p.w = (const float*)w; p.bias = bias; p.out = (uint16_t*)out;
-  p.f16 = (f32 ? d->operand16 : d->in_dtype) == DSK_F16 ? 1 : 0;
+  p.f16 = split ? 1 : ((f32 ? d->operand16 : d->in_dtype) == DSK_F16 ? 1 : 0);
   p.in_f32 = f32 ? 1 : 0; p.out_f32 = f32 ? 1 : 0;
+  p.split = (f32 && split) ? 1 : 0;
+  p.nstages = p.split ? 4 : CI_STAGES;
   p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.ndim = d->ndim;
   p.circ = d->circular;
   p.tiles_w = (d->W + CI_BW - 1) / CI_BW; p.tiles_h = (d->H + CI_BH - 1) / CI_BH;
   p.total_tiles = p.tiles_w * p.tiles_h * d->D * d->B;
+  if (d->ndim == 3) return d->Cin == 1 ? launch_convin<1, true>(p, st) : launch_convin<2, true>(p, st);   // 27 * Cin <= 64
   switch (d->Cin) {
-    case 1: return launch_convin<1>(p, st);
-    case 2: return launch_convin<2>(p, st);
-    case 3: return launch_convin<3>(p, st);
-    default: return launch_convin<4>(p, st);
+    case 1: return launch_convin<1, false>(p, st);
+    case 2: return launch_convin<2, false>(p, st);
+    case 3: return launch_convin<3, false>(p, st);
+    default: return launch_convin<4, false>(p, st);
   }
 }
 

@@ -521,12 +521,13 @@ class _Plan:
             ops.add_ex(self.te, ye, self.te)
         for g in self.tmlp:
             g.run()
-        # first layer of the modes whose narrow contractions take plain fp16 operands: im2col on the tensor cores (convin_tc)
-        # (DSK_CONVIN_TC16=1 only: measured on C4 the fp16 rounding of the network INPUT and of the 27 first-layer weights alone
-        # moves the denoiser error of fp16s32 from 6.2e-4 to 7.0e-4 -- every later layer sees it -- so the default keeps the first
-        # layer exact in fp32 on the CUDA cores, 2 % of an evaluation)
-        op16 = torch.float16 if (self.split and self.split_min_cin > net.convin.cin and
-                                 os.environ.get("DSK_CONVIN_TC16", "0") == "1") else None
+        # first layer of the 16-bit-operand fp32-storage modes: im2col on the tensor cores (convin_tc) with the input AND the
+        # weights split hi + lo inside the im2col row -- an fp32-class product.  (Plain fp16 operands here, DSK_CONVIN_TC16=1,
+        # measured on C4: the rounding of the network input and of the 27 first-layer weights alone moves the denoiser error of
+        # fp16s32 from 6.2e-4 to 7.0e-4 -- every later layer sees it.)  The fp32 mode keeps the CUDA-core kernel.
+        op16 = None
+        if self.split and self.precision != "fp32" and os.environ.get("DSK_CONVIN_TC", "1") != "0":
+            op16 = torch.float16 if os.environ.get("DSK_CONVIN_TC16", "0") == "1" else ops.SPLIT
         x, xs = self._conv(xin, self.pc_in, out=self.X[0], operand16=op16), None
         for l in range(nlev):
             for blk in net.downward_blocks[l]:

@@ -214,8 +214,9 @@ def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, ch
     pc.circular: circular instead of zero padding (dsk_conv_fwd_circ); `pad_ws` (tensor, or callable returning one) is the
     preallocated workspace of the padded copy the tcgen05 path reads -- allocated here if missing (not graph-safe).
     prepadded: x IS the halo-padded tensor [B, D+2 (3-D), H+2, W+2, Cin] (norm_apply_padded): no padding pass.
-    operand16 (fp32 x, fp32 weights, fp32 out, Cin <= 4: the first layer of an fp32-storage mode): run on the tensor cores with
-    operands rounded to this 16-bit format (dsk_conv_desc.operand16) where the im2col kernel takes the shape."""
+    operand16 (fp32 x, fp32 weights, fp32 out, Cin <= 4: the first layer of an fp32-storage mode): run on the tensor cores
+    (dsk_conv_desc.operand16) where the im2col kernel takes the shape -- a 16-bit dtype: operands rounded to it; SPLIT: fp16
+    operands split hi + lo inside the im2col row, an fp32-class result."""
     require_cuda(x, "conv input")
     B, D, H, W, Cin = x.shape
     if prepadded:
@@ -235,7 +236,7 @@ def conv(x: torch.Tensor, pc: PackedConv, out: Optional[torch.Tensor] = None, ch
         out = torch.empty(shape, dtype=torch.float32 if out_nchw else out_dtype, device=x.device)
     d = _conv_desc_of(x, pc, out, residual, up2, out_nchw, D, H, W)
     if operand16 is not None and x.dtype == torch.float32 and pc.w_dtype == torch.float32 and out.dtype == torch.float32:
-        d.operand16 = dt_code(operand16)
+        d.operand16 = w_code(operand16)          # torch.float16 / torch.bfloat16: rounded operands; SPLIT: exact (hi + lo rows)
     bias = pc.bias.detach() if pc.bias is not None else None
     if prepadded:
         d.circular = 2

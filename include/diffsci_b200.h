@@ -218,9 +218,10 @@ typedef struct {
   int res_dtype;       /* DSK_RES_SAME (0): `residual` has out_dtype;  DSK_RES_F32: `residual` is fp32 whatever out_dtype is --
                           tcgen05 kernels only: a block of an fp32-storage mode whose output is read by ONE convolution writes
                           the 16-bit operand copy directly (fp32 residual stream in, fp16 out) instead of fp32 + a cast pass */
-  int operand16;       /* 0, or DSK_BF16 | DSK_F16 with in_dtype = out_dtype = w_dtype = DSK_F32 on a few-input-channel convolution
-                          (convin, Cin <= 4): run it on the tensor cores with operands rounded to this format (the first layer of
-                          the fp32-storage 16-bit-operand modes) instead of the CUDA-core fp32 kernel                          */
+  int operand16;       /* 0, or -- with in_dtype = out_dtype = w_dtype = DSK_F32 on a few-input-channel convolution (convin, Cin <= 4:
+                          the first layer of the fp32-storage modes) -- run it on the tensor cores instead of the CUDA-core fp32
+                          kernel: DSK_BF16 | DSK_F16: operands rounded to this format; DSK_SPLIT_F16 (taps * Cin <= 32): fp16
+                          operands split hi + lo inside one im2col row, x_hi w_hi + x_lo w_hi + x_hi w_lo: fp32-class result */
 } dsk_conv_desc;
 #define DSK_RES_SAME 0
 #define DSK_RES_F32 1

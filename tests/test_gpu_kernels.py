@@ -599,6 +599,10 @@ def test_convin_fp32_storage_paths(ops, ndim, B, Cin, Cout, sp):
     y16 = ops.conv(to_cl(x), pc, operand16=torch.float16)
     ref16 = conv(x.half().float(), w.half().float(), b, padding=1)
     assert y16.dtype == torch.float32 and relmax(from_cl(y16, ndim), ref16) < 2e-5
+    # (3) operand16 = SPLIT: [x_hi | x_lo | x_hi] . [w_hi | w_hi | w_lo] in one im2col row where 3 * taps * Cin <= 128 (else the
+    # CUDA-core kernel answers): fp32-class against the fp32 reference
+    ys = ops.conv(to_cl(x), pc, operand16=ops.SPLIT)
+    assert ys.dtype == torch.float32 and relmax(from_cl(ys, ndim), conv(x, w, b, padding=1)) < 2e-5
     # 16-bit in / out through the same kernel (two epilogue warp sets, staged stores)
     yh = ops.conv(to_cl(x).half(), pc)
     assert yh.dtype == torch.float16 and relmax(from_cl(yh, ndim), ref16) < 1e-3
