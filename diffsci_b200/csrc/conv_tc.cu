@@ -912,7 +912,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           }
         }
         if (of32) {
-          // fp32 rows are 128 B per 32-channel group: the same 2 KB stage takes them as two 16-channel halves
+          // fp32 rows are 128 B per 32-channel group: the same 2 KB stage takes them as two 16-channel halves.  (Measured: storing
+          // the thread's full 128-byte line straight from registers instead -- no shared-memory traffic next to the operand
+          // fetches -- is SLOWER: 64->64 @ 64^3, B = 8: 403 -> 424 us plain, 539 -> 585 us with residual + statistics.)
           float* outf = reinterpret_cast<float*>(p.out);
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
