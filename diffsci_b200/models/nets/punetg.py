@@ -392,7 +392,7 @@ class _Plan:
         self.attn = None
         self.attn_tc = (adt in ops.H16 and _tc_eligible(Cb, Cb) and Lq % 8 == 0 and Lq <= 8192)
         self.attn_split = (split and _tc_eligible(Cb, Cb) and Lq % 64 == 0 and Lq <= 8192)
-        self.attn_hybrid = False
+        self.attn_hybrid = self.attn_hybrid_split = False
         # flash-style core (dsk_attn_flash) for every 16-bit-operand mode; the fp32 mode keeps the split-operand GEMM chain
         self.attn_flash = (_ATTN_FLASH and ops.attn_flash_supported(Lq, Cb) and
                            ((self.attn_split and precision != "fp32") or (self.attn_tc and not split)))
@@ -412,6 +412,15 @@ class _Plan:
         elif len(net.attn_block) > 0:
             self.attn = dict(qkv=torch.empty((B * Lq, 3 * Cb), **f32), scores=torch.empty((B, Lq, Lq), **f32),
                              ao=torch.empty((B * Lq, Cb), **f32), out=torch.empty((B, Lq, Cb), **f32))
+            if split and _tc_eligible(Cb, Cb) and (B * Lq) % 8 == 0:
+                # fp32-storage modes at token counts the tensor-core score paths do not take (the 7 x 7 bottom level of MNIST): the
+                # two projections -- 99 % of the block's FLOPs at small L -- as split-operand tcgen05 GEMMs, the L x L core in fp32
+                # (the all-FFMA block was 18 % of a C2 evaluation in fp16s32)
+                self.attn_hybrid_split = True
+                self.attn["tok_s"] = torch.empty((B * Lq, 2 * Cb), dtype=torch.float16, device=dev)
+                self.attn["ao_s"] = torch.empty((B * Lq, 2 * Cb), dtype=torch.float16, device=dev)
+                self.attn_w = [(ops.PackedLinear(a.mhattn.in_proj_weight, ops.SPLIT), ops.PackedLinear(a.mhattn.out_proj.weight, ops.SPLIT))
+                               for a in net.attn_block]
             if adt != torch.float32:
                 self.attn["tok"] = torch.empty((B, Lq, Cb), **f32)
                 if _tc_eligible(Cb, Cb) and (B * Lq) % 8 == 0:
@@ -426,7 +435,7 @@ class _Plan:
         """Materialise packed weights (must happen outside CUDA-graph capture)."""
         for pc in [self.pc_in, self.pc_out, *self.pc_down, *self.pc_up, *[p for pair in self.pc.values() for p in pair]]:
             pc.packed()
-        if (self.attn_tc or self.attn_hybrid or self.attn_split or self.attn_flash) and len(self.net.attn_block) > 0:
+        if (self.attn_tc or self.attn_hybrid or self.attn_hybrid_split or self.attn_split or self.attn_flash) and len(self.net.attn_block) > 0:
             for wi, wo in self.attn_w:
                 wi.packed()
                 wo.packed()
@@ -485,6 +494,17 @@ class _Plan:
             wi, wo = self.attn_w[index]
             ops.self_attention_tc(x.view(B, Lq, Cb), wi, m.in_proj_bias, wo, m.out_proj.bias, a, out.view(B, Lq, Cb),
                                   self.net.config.attn_residual)
+            return out
+        if self.attn_hybrid_split:
+            wi, wo = self.attn_w[index]
+            M = B * Lq
+            ts = ops.split_f16(x.view(M, Cb), out=a["tok_s"])
+            ops.gemm_split_tc(ts, wi.packed(), a["qkv"], M=M, N=3 * Cb, K=Cb, lda=2 * Cb, ldb=2 * Cb, ldc=3 * Cb, a_lo=Cb, b_lo=Cb,
+                              bias=m.in_proj_bias.detach())
+            ops.attention_core_f32(a["qkv"], a["scores"], a["ao"], B, Lq, Cb)
+            aos = ops.split_f16(a["ao"], out=a["ao_s"])
+            ops.gemm_split_tc(aos, wo.packed(), out.view(M, Cb), M=M, N=Cb, K=Cb, lda=2 * Cb, ldb=2 * Cb, ldc=Cb, a_lo=Cb, b_lo=Cb,
+                              bias=m.out_proj.bias.detach(), residual=x.view(M, Cb) if self.net.config.attn_residual else None)
             return out
         if x.dtype == torch.float32:
             tok = x.view(B, Lq, Cb)
