@@ -120,14 +120,51 @@ SIGNATURES = {
     "dsk_relu_bwd": [p, p, p, i64, p],
     "dsk_add_ex": [p, i32, p, i32, p, i32, i64, p],
     "dsk_split_channels": [p, p, p, p, p, i64, i32, i32, i32, p],
+    "dsk_edm_coeffs": [p, f32, p, p, p, p, i32, p],
+    "dsk_plan_create_from_tape": [p, i64, p],
+    "dsk_plan_load": [C.c_char_p, p],
+    "dsk_plan_info": [p, i32],
+    "dsk_plan_bind": [p, p, p],
+    "dsk_denoiser_fwd": [p, p, p, p, p],
+    "dsk_plan_destroy": [p],
 }
 _RESTYPE = {"dsk_conv_pad_ws_bytes": i64, "dsk_last_error": C.c_char_p, "dsk_launch_count": u64, "dsk_norm_ws_bytes": i64,
-            "dsk_conv_wgrad_ws_bytes": i64, "dsk_bwd_ws_bytes": i64, "dsk_attn_softmax_ws_bytes": i64}
+            "dsk_conv_wgrad_ws_bytes": i64, "dsk_bwd_ws_bytes": i64, "dsk_attn_softmax_ws_bytes": i64, "dsk_plan_info": i64}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)          # AttributeError here == header/library mismatch: fail loudly
     _fn.argtypes = _args
     _fn.restype = _RESTYPE.get(_name, i32)
+
+
+class _Lib:
+    """The library object every module imports.  Entry points are the ctypes functions themselves, except while a tape is being
+    recorded (diffsci_b200/tape.py): then every call of an `int dsk_*` entry point is also appended -- name + raw arguments -- to
+    the active recorder, which is how the launch list the Python plan assembles becomes replayable from C (dsk_denoiser_fwd)."""
+    _NOT_LAUNCHES = ("dsk_plan_", "dsk_denoiser_fwd", "dsk_check_device", "dsk_version")
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self.recorder = None
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        if name not in SIGNATURES or _RESTYPE.get(name, i32) is not i32 or name.startswith(self._NOT_LAUNCHES):
+            setattr(self, name, fn)
+            return fn
+
+        def call(*args, _fn=fn, _name=name):
+            rc = _fn(*args)
+            if self.recorder is not None:
+                self.recorder.append((_name, args))
+            return rc
+        call.__name__ = name
+        call.argtypes, call.restype = fn.argtypes, fn.restype
+        setattr(self, name, call)
+        return call
+
+
+lib = _Lib(lib)
 
 
 def last_error() -> str:

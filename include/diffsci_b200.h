@@ -509,6 +509,30 @@ int dsk_add_ex(const void* a, int a_dtype, const void* b, int b_dtype, void* y, 
 int dsk_split_channels(const void* dy, const void* ra, const void* rb, void* da, void* db, int64_t rows, int Ca, int Cb,
                        int dtype, void* stream);
 
+/* ---- Whole-network evaluation from a non-Python host (dsk_plan_* / dsk_denoiser_fwd) ------------------------------
+ * The launch list of a network evaluation is assembled by the Python plan (models/nets/punetg.py, adm.py).  A TAPE is that list
+ * recorded once for a (network, batch, shape, precision): every entry point of this header that was called, with its arguments
+ * -- pointers as (buffer, offset), descriptors by value --, the sizes of all device buffers, and the contents of the constant
+ * ones (packed weights, parameters, pointer tables with their relocations).  diffsci_b200.tape.export_denoiser(module, B, shape,
+ * path) writes it; this API replays it from C with no Python in the process:
+ *     D(x; sigma) = c_skip x + c_out F(c_in x, c_noise)     KarrasModule.get_denoiser (karrasmodule.py:673-719) with the
+ *     EDMPreconditioner scalars (preconditioners.py:30-53) computed on the device by dsk_edm_coeffs.
+ * No hidden allocations: the caller provides ONE device workspace of dsk_plan_info(plan, DSK_PLAN_WORKSPACE_BYTES) bytes;
+ * dsk_plan_bind uploads the constants into it (asynchronously on `stream`); dsk_denoiser_fwd enqueues the launches.
+ * x, out: fp32 [B, C, *S] (the reference's NC(D)HW), sigma: fp32 [B], all device memory.  One host thread per plan. */
+typedef struct dsk_plan dsk_plan;
+enum { DSK_PLAN_WORKSPACE_BYTES = 0, DSK_PLAN_BATCH = 1, DSK_PLAN_CHANNELS = 2, DSK_PLAN_SAMPLE_ELEMS = 3, DSK_PLAN_LAUNCHES = 4 };
+int dsk_plan_create_from_tape(const void* tape, int64_t nbytes, dsk_plan** plan);
+int dsk_plan_load(const char* path, dsk_plan** plan);
+int64_t dsk_plan_info(const dsk_plan* plan, int what);
+int dsk_plan_bind(dsk_plan* plan, void* workspace, void* stream);
+int dsk_denoiser_fwd(dsk_plan* plan, const float* x, const float* sigma, float* out, void* stream);
+int dsk_plan_destroy(dsk_plan* plan);
+/* EDM preconditioner scalars of a batch of noise levels (preconditioners.py:30-53): c_in = 1 / sqrt(s^2 + sd^2),
+ * c_out = s sd / sqrt(s^2 + sd^2), c_skip = sd^2 / (s^2 + sd^2), c_noise = log(s) / 2, in the reference's fp32 operation order. */
+int dsk_edm_coeffs(const float* sigma, float sigma_data, float* c_in, float* c_out, float* c_skip, float* c_noise, int B,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif
