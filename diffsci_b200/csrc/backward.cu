@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(128) norm_bwd_finalize_kernel(const double2* _
   for (int i = threadIdx.x; i < cg; i += blockDim.x) {
     const int c = g * cg + i;
     double s1 = 0, sx = 0;
+#pragma unroll 8
     for (int ch = 0; ch < nchunks; ++ch) {
       const double2 v = partial[((int64_t)b * nchunks + ch) * C + c];
       s1 += v.x;
@@ -310,21 +311,24 @@ __global__ void __launch_bounds__(BW_THREADS) norm_bwd_apply_kernel(const T* __r
 }
 
 // channel sums: out[b][c] (per_sample) or out[c] = sum over chunk partials (and samples)
-__global__ void __launch_bounds__(256) chansum_finalize_kernel(const double2* __restrict__ partial, float* __restrict__ out, int B,
+__global__ void __launch_bounds__(1024) chansum_finalize_kernel(const double2* __restrict__ partial, float* __restrict__ out, int B,
                                                                 int C, int nchunks, int per_sample) {
-  // block = 32 channels x 8 row lanes over the (sample, chunk) partial rows
+  // block = 32 channels x 32 row lanes over the (sample, chunk) partial rows (8 row lanes: 9 us per launch, 45 launches per
+  // ADM iteration)
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
   const int64_t r0 = per_sample ? (int64_t)blockIdx.y * nchunks : 0;
   const int64_t rows = per_sample ? nchunks : (int64_t)B * nchunks;
   double s = 0;
-  if (c < C)
-    for (int64_t r = rl; r < rows; r += 8) s += partial[(r0 + r) * C + c].x;
-  __shared__ double red[8][33];
+  if (c < C) {
+#pragma unroll 4
+    for (int64_t r = rl; r < rows; r += 32) s += partial[(r0 + r) * C + c].x;
+  }
+  __shared__ double red[32][33];
   red[rl][threadIdx.x & 31] = s;
   __syncthreads();
   if (rl == 0 && c < C) {
     double t = 0;
-    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+    for (int k = 0; k < 32; ++k) t += red[k][threadIdx.x & 31];
     out[per_sample ? (int64_t)blockIdx.y * C + c : c] = (float)t;
   }
 }
@@ -336,13 +340,16 @@ __global__ void __launch_bounds__(256) chansum_small_kernel(const T* __restrict_
                                                              int per_sample, double* __restrict__ part) {
   // one block per (b or all, c[, slice of the pixels]): with `part` the pixel range is cut into gridDim.z slices whose sums
   // chansum_small_finalize_kernel adds in a fixed order (a single block per channel took 267 us on a 2 x 64^3 volume)
-  const int c = blockIdx.x, b0 = per_sample ? blockIdx.y : 0, b1 = per_sample ? blockIdx.y + 1 : B;
-  const int64_t per = (S + gridDim.z - 1) / gridDim.z;
-  const int64_t sa = (int64_t)blockIdx.z * per, sb = min(S, sa + per);
+  // the slices cut the pixel axis of ONE sample (per_sample) or the flattened (sample, pixel) axis (sum over the batch too: many
+  // small samples, e.g. 32 x 128^2, are then spread over all slices instead of 3 blocks walking the whole tensor: 289 -> ~10 us)
+  const int c = blockIdx.x;
+  const int64_t base = per_sample ? (int64_t)blockIdx.y * S : 0, n = per_sample ? S : (int64_t)B * S;
+  const int64_t per = (n + gridDim.z - 1) / gridDim.z;
+  const int64_t sa = (int64_t)blockIdx.z * per, sb = min(n, sa + per);
   double acc = 0;
-  for (int b = b0; b < b1; ++b) {
+  for (int64_t s0 = sa; s0 < sb; s0 += 16 * 256) {          // fp32 within a run of 16 elements per thread, fp64 across runs
     float local = 0.0f;
-    for (int64_t s = sa + threadIdx.x; s < sb; s += blockDim.x) local += to_f32<T>(dy[((int64_t)b * S + s) * C + c]);
+    for (int64_t s = s0 + threadIdx.x; s < min(sb, s0 + 16 * 256); s += 256) local += to_f32<T>(dy[(base + s) * C + c]);
     acc += (double)local;
   }
   __shared__ double red[256];
@@ -713,7 +720,7 @@ extern "C" int dsk_channel_sum(const void* dy, float* out, void* ws, int B, int6
   if (C % V != 0) {
     DSK_REQUIRE(C <= 65535, "dsk_channel_sum: C too large for the scalar path");
     const int rows = per_sample ? B : 1;
-    const bool split = ws != nullptr && S >= 65536 && (int64_t)rows * C <= 4096;
+    const bool split = ws != nullptr && (per_sample ? S : (int64_t)B * S) >= 65536 && (int64_t)rows * C <= 4096;
     double* part = split ? reinterpret_cast<double*>(reinterpret_cast<float2*>(ws) + 2 * (int64_t)B * C) : nullptr;
     dim3 g(C, rows, split ? CS_SPLITS : 1);
     if (dtype == DSK_F32) DSK_LAUNCH(chansum_small_kernel<float>, g, 256, 0, st, (const float*)dy, out, B, S, C, per_sample, part);
@@ -735,7 +742,7 @@ extern "C" int dsk_channel_sum(const void* dy, float* out, void* ws, int B, int6
     DSK_LAUNCH((bwd_partial_kernel<__nv_bfloat16, false>), pg, BW_THREADS, smem, st, nullptr, (const __nv_bfloat16*)dy, nullptr, partial, S, C,
                nchunks, 0);
   dim3 fg((C + 31) / 32, per_sample ? B : 1);
-  DSK_LAUNCH(chansum_finalize_kernel, fg, 256, 0, st, partial, out, B, C, nchunks, per_sample);
+  DSK_LAUNCH(chansum_finalize_kernel, fg, 1024, 0, st, partial, out, B, C, nchunks, per_sample);
   return DSK_OK;
 }
 
