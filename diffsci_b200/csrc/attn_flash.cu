@@ -332,14 +332,14 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmapQ, const __grid_consta
               }
               oh[e] = pack2<F16>(v0, v1);
             }
-            stg[lane * 4 + (g ^ (lane & 3))] = pk;
+            stg[lane * 4 + (g ^ ((lane >> 1) & 3))] = pk;
           }
           __syncwarp();
           const int jj = lane & 3;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int r = 8 * k + (lane >> 2);
-            const uint4 val = stg[r * 4 + (jj ^ (r & 3))];
+            const uint4 val = stg[r * 4 + (jj ^ ((r >> 1) & 3))];
             if (m_warp + r < p.L)
               *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (int64_t)b * p.strideO + (int64_t)(m_warp + r) * p.ldo +
                                         part * C + c0 + jj * 8) = val;

@@ -920,14 +920,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-              stg[lane * 4 + (g ^ (lane & 3))] =
+              stg[lane * 4 + (g ^ ((lane >> 1) & 3))] =
                   make_uint4(__float_as_uint(f[hh * 16 + g * 4]), __float_as_uint(f[hh * 16 + g * 4 + 1]),
                              __float_as_uint(f[hh * 16 + g * 4 + 2]), __float_as_uint(f[hh * 16 + g * 4 + 3]));
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int r = 8 * k + (lane >> 2);
-              const uint4 val = stg[r * 4 + ((lane & 3) ^ (r & 3))];
+              const uint4 val = stg[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))];
               if (st_ok && tc.h0 + q * 4 + k < p.H) {
                 int64_t px;
                 if constexpr (UPS) px = st_pix + (int64_t)k * 2 * (2 * p.W);
@@ -938,6 +938,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             __syncwarp();
           }
         } else {
+          // (slot swizzle g ^ ((row >> 1) & 3): rows are 64 B apart, so rows r and r + 2 start in the same bank and the 8 lanes of a
+          // 128-bit store phase need 4 distinct slot permutations; the first version used g ^ (row & 3) and paid a 2-way bank
+          // conflict on every stage write -- 28 % of the epilogue's shared-memory wavefronts in a kernel bound by that port)
           // staged, transposed store: a thread holds one pixel ROW, so a direct st.global.v4 touches 32 lines per
           // instruction; through this warp's 2 KB stage (XOR-swizzled 16-byte slots) 4 lanes write 64 contiguous bytes
           // of a row and one instruction covers 8 rows.  Row r = 8k + lane/4 of the warp is pixel (line q*4 + k, w lane/4).
@@ -947,13 +950,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
             for (int e = 0; e < 4; ++e) ow[e] = pack_h2(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1], p.f16);
-            stg[lane * 4 + (g ^ (lane & 3))] = o;
+            stg[lane * 4 + (g ^ ((lane >> 1) & 3))] = o;
           }
           __syncwarp();
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int r = 8 * k + (lane >> 2);
-            const uint4 val = stg[r * 4 + ((lane & 3) ^ (r & 3))];
+            const uint4 val = stg[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))];
             if (st_ok && tc.h0 + q * 4 + k < p.H) {
               int64_t px;
               if constexpr (UPS) px = st_pix + (int64_t)k * 2 * (2 * p.W);

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
             uint32_t* oh = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
             for (int k = 0; k < 4; ++k) oh[k] = pack_h2(f[g * 8 + 2 * k], f[g * 8 + 2 * k + 1], p.f16);
-            stg[lane * 4 + (g ^ (lane & 3))] = o;
+            stg[lane * 4 + (g ^ ((lane >> 1) & 3))] = o;
           }
           __syncwarp();
           const int j = lane & 3, l2 = lane >> 2;               // row r = 8k + lane / 4 = pixel (line q*4 + k, column lane / 4)
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int r = 8 * k + l2;
-            const uint4 val = stg[r * 4 + (j ^ (r & 3))];
+            const uint4 val = stg[r * 4 + (j ^ ((r >> 1) & 3))];
             if (h0 + q * 4 + k < p.H && w0 + l2 < p.W) *reinterpret_cast<uint4*>(ob + k * wn) = val;
           }
         }

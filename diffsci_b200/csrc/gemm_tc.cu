@@ -296,14 +296,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
               uint32_t* oh = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
               for (int e = 0; e < 4; ++e) oh[e] = pack_h2(f[g * 8 + 2 * e], f[g * 8 + 2 * e + 1], p.f16);
-              stg[lane * 4 + (g ^ (lane & 3))] = pk;
+              stg[lane * 4 + (g ^ ((lane >> 1) & 3))] = pk;
             }
             __syncwarp();
             const int j = lane & 3;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int r = 8 * k + (lane >> 2);
-              const uint4 val = stg[r * 4 + (j ^ (r & 3))];
+              const uint4 val = stg[r * 4 + (j ^ ((r >> 1) & 3))];
               if (m_warp + r < p.M)
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)b * p.strideC + (int64_t)(m_warp + r) * p.ldc + n +
                                           j * 8) = val;
