@@ -741,9 +741,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     auto flush = [&](int range, bool zero) {
       const int nt = range / srange, sr = range - nt * srange;  // range -> (n-tile, sample range)
       float2* mine = reinterpret_cast<float2*>(stage_s[warp - 4]);      // each warp parks its partials in its OWN stage
+      // channel of the 32-channel group this lane's running sums belong to: l (accumulator-mapping butterfly, 16-bit outputs) or
+      // 16 b4 + 4 (l & 3) + 2 b3 + b2 (store-mapping reduce-scatter, fp32 outputs)
+      const int own = p.out_f32 ? (((lane >> 4) & 1) * 16 + (lane & 3) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)) : lane;
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
-        mine[g * 32 + lane] = zero ? make_float2(0.0f, 0.0f) : make_float2(st_s[g], st_q[g]);
+        mine[g * 32 + own] = zero ? make_float2(0.0f, 0.0f) : make_float2(st_s[g], st_q[g]);
         st_s[g] = 0.0f; st_q[g] = 0.0f;
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -822,10 +825,33 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
           for (int g = 0; g < 4; ++g) rr[gg][g] = *reinterpret_cast<const uint4*>(rrow + gg * 32 + g * 8);
       }
+      // fp32 OUTPUT: residual add and statistics happen in the STORE mapping (after the stage has transposed the tile: lane =
+      // (row 8k + lane/4, 16-byte chunk lane&3)), so the residual is read exactly like the output is written -- 4 lanes per
+      // 64 contiguous bytes, 8 wavefronts per load instruction.  Reading it in the accumulator mapping (a thread per pixel row,
+      // 32 lines per instruction) cost 256 L1 wavefronts per warp and 32-channel group in a kernel that is bound by the
+      // shared-memory / L1 data path: 4x the stage traffic it avoided.
+      const bool res_st = of32 && p.residual != nullptr;
+      const float* res32 = reinterpret_cast<const float*>(p.residual);
+      auto st_row = [&](int k) -> int64_t {                 // pixel index of stage row 8k + lane/4
+        if constexpr (UPS) return st_pix + (int64_t)k * 2 * (2 * p.W);
+        else return st_pix + (int64_t)k * p.W;
+      };
+      auto load_res_st = [&](int c0) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            rr[hh][k] = make_uint4(0, 0, 0, 0);
+            if (st_ok && tc.h0 + q * 4 + k < p.H)
+              rr[hh][k] = *reinterpret_cast<const uint4*>(res32 + st_row(k) * p.Cout + tc.n0 + c0 + hh * 16 + (lane & 3) * 4);
+          }
+      };
       if constexpr (DEP == 2) {
-        // fp32 residual: the same 32 registers hold ONE 32-channel group (8 float4), requested before the accumulator wait and
-        // refilled with the next group while the current one is stored / reduced
-        if (rrow32 != nullptr) {
+        if (res_st) {
+          load_res_st(0);
+        } else if (rrow32 != nullptr) {
+          // fp32 residual into a 16-bit output (operand copy): accumulator mapping, ONE 32-channel group (8 float4) in the same
+          // 32 registers, requested before the accumulator wait and refilled with the next group while the current one is stored
 #pragma unroll
           for (int k = 0; k < 8; ++k) rr[k >> 2][k & 3] = *reinterpret_cast<const uint4*>(rrow32 + k * 4);
         }
@@ -898,7 +924,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           }
         }
         if constexpr (DEP == 2) {
-          if (rrow32 != nullptr) {
+          if (rrow32 != nullptr && !res_st) {
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
               const uint4 r = rr[e4 >> 2][e4 & 3];
@@ -916,6 +942,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           // the thread's full 128-byte line straight from registers instead -- no shared-memory traffic next to the operand
           // fetches -- is SLOWER: 64->64 @ 64^3, B = 8: 403 -> 424 us plain, 539 -> 585 us with residual + statistics.)
           float* outf = reinterpret_cast<float*>(p.out);
+          float ps[8], pq[8];                                // this lane's (half, channel-of-chunk) partial sums over its 4 rows
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { ps[e] = 0.0f; pq[e] = 0.0f; }
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
@@ -927,15 +956,41 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int r = 8 * k + (lane >> 2);
-              const uint4 val = stg[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))];
+              const uint4 sv = stg[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))];
+              float4 val = make_float4(__uint_as_float(sv.x), __uint_as_float(sv.y), __uint_as_float(sv.z), __uint_as_float(sv.w));
+              if (res_st) {
+                val.x += __uint_as_float(rr[hh][k].x); val.y += __uint_as_float(rr[hh][k].y);
+                val.z += __uint_as_float(rr[hh][k].z); val.w += __uint_as_float(rr[hh][k].w);
+              }
               if (st_ok && tc.h0 + q * 4 + k < p.H) {
-                int64_t px;
-                if constexpr (UPS) px = st_pix + (int64_t)k * 2 * (2 * p.W);
-                else px = st_pix + (int64_t)k * p.W;
-                *reinterpret_cast<uint4*>(outf + px * p.Cout + tc.n0 + c0 + hh * 16 + (lane & 3) * 4) = val;
+                *reinterpret_cast<float4*>(outf + st_row(k) * p.Cout + tc.n0 + c0 + hh * 16 + (lane & 3) * 4) = val;
+                if (do_stats) {
+                  ps[hh * 4] += val.x; ps[hh * 4 + 1] += val.y; ps[hh * 4 + 2] += val.z; ps[hh * 4 + 3] += val.w;
+                  pq[hh * 4] = fmaf(val.x, val.x, pq[hh * 4]); pq[hh * 4 + 1] = fmaf(val.y, val.y, pq[hh * 4 + 1]);
+                  pq[hh * 4 + 2] = fmaf(val.z, val.z, pq[hh * 4 + 2]); pq[hh * 4 + 3] = fmaf(val.w, val.w, pq[hh * 4 + 3]);
+                }
               }
             }
             __syncwarp();
+          }
+          if (res_st && gi + 1 < NG) load_res_st((gi + 1) * 32);   // next group's residual while this one's statistics reduce
+          if (do_stats) {
+            // reduce-scatter over the 8 lanes that share a chunk (lane bits 4, 3, 2): 8 values -> 1 per lane in 3 halving steps
+            // (7 + 7 shuffles; the accumulator-mapping butterfly of the 16-bit path needs 31 + 31).  Lane keeps index
+            // 4 b4 + 2 b3 + b2 = (half b4, channel 2 b3 + b2 of its chunk): channel 16 b4 + 4 (lane & 3) + 2 b3 + b2 of the group.
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1) {
+              const bool up = (lane & (o << 2)) != 0;
+#pragma unroll
+              for (int i = 0; i < o; ++i) {
+                const float ks = up ? ps[i + o] : ps[i], gs = up ? ps[i] : ps[i + o];
+                const float kq = up ? pq[i + o] : pq[i], gq = up ? pq[i] : pq[i + o];
+                ps[i] = ks + __shfl_xor_sync(0xffffffffu, gs, o << 2);
+                pq[i] = kq + __shfl_xor_sync(0xffffffffu, gq, o << 2);
+              }
+            }
+            st_s[gi] += ps[0];
+            st_q[gi] += pq[0];
           }
         } else {
           // (slot swizzle g ^ ((row >> 1) & 3): rows are 64 B apart, so rows r and r + 2 start in the same bank and the 8 lanes of a
@@ -966,7 +1021,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           }
           __syncwarp();
         }
-        if (do_stats) {
+        if (do_stats && !of32) {
           // butterfly transpose-reduce over the 32 lanes (= 32 pixels): lane l keeps channel c0 + l
           float sq[32];
 #pragma unroll
