@@ -393,10 +393,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                float x = __uint_as_float(v[g * 8 + e]);
-                if (p.bias != nullptr) x += __ldg(p.bias + n + g * 8 + e);
-                if (p.chan_bias != nullptr) x += __ldg(p.chan_bias + (int64_t)brow * p.Cout + n + g * 8 + e);
-                f[e] = x;
+                // acc + (bias + chan_bias): the order of the pair kernel's staged bias sum -- which of the two kernels runs depends
+                // on the batch (parity of the plane-group count), and sharded sampling must reproduce the single-GPU run bit for bit
+                float bsum = p.bias != nullptr ? __ldg(p.bias + n + g * 8 + e) : 0.0f;
+                if (p.chan_bias != nullptr) bsum += __ldg(p.chan_bias + (int64_t)brow * p.Cout + n + g * 8 + e);
+                f[e] = __uint_as_float(v[g * 8 + e]) + bsum;
               }
               if (p.residual != nullptr) {                 // warp-uniform; the residual's format is independent of the output's
                 if (p.res_f32) {

@@ -413,3 +413,19 @@ def test_bias_false_punetg(golden, name):
     grads = dict(net.named_parameters())
     for k, ref in g["loss_huber_grads"].items():
         assert relmax(grads[k].grad.cpu(), ref) < 3e-4, (k, relmax(grads[k].grad.cpu(), ref))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16s32"])
+def test_sampling_is_bit_identical_across_batch_splits_2d(precision):
+    """What sharded sampling relies on (distributed.sample_sharded): samples do not interact, so 6 samples in one batch and
+    the same 6 as two batches of 3 give the same bits -- although the batch decides which convolution kernel a layer takes (CTA pairs
+    along w, pairs along the plane axis when the plane-group count is even, or the single-CTA kernel), all of them must sum in the
+    same order.  The two-GPU form of this test (tests/test_gpu_multi.py) only runs on multi-GPU boxes."""
+    import diffsci_b200 as d
+    torch.manual_seed(3)
+    net = d.PUNetG(d.PUNetGConfig(dimension=2, model_channels=64), precision=precision).to(DEV).eval()
+    mod = d.KarrasModule(net, d.KarrasModuleConfig.from_edm())
+    wn = torch.randn(6, 1, 32, 32, generator=torch.Generator().manual_seed(99)).to(DEV)
+    whole = mod.propagate_white_noise(wn, nsteps=6)
+    halves = torch.cat([mod.propagate_white_noise(wn[:3], nsteps=6), mod.propagate_white_noise(wn[3:], nsteps=6)])
+    assert torch.equal(whole, halves)
