@@ -20,6 +20,9 @@ constexpr int CI_BUILD = CI_NG * 4;                // warps 0..CI_BUILD-1: im2co
 constexpr int CI_EPI = 8;                          // epilogue warps: set (w >> 2) drains accumulator buffer (tile seq & 1)
 constexpr int CI_THREADS = (CI_BUILD + 1 + CI_EPI) * 32;  // + warp CI_BUILD: MMA / TMEM owner
 constexpr int CI_STG_BYTES = 32 * 128;             // per epilogue warp: 32 rows x 128 B (one 32-channel fp32 group)
+constexpr int CI_PW = 12;                          // patch row pitch in values (10 used)
+constexpr int CI_PATCH_WORDS = 3 * 18 * CI_PW;     // 648 32-bit containers (fp32 bits, or a zero-extended 16-bit value)
+constexpr int CI_PATCH_LD = (CI_PATCH_WORDS + 127) / 128;   // loads per thread of a 128-thread builder group
 constexpr int CI_STAGES = 6;
 constexpr int CI_A_BYTES = 128 * 128;
 
@@ -30,6 +33,10 @@ struct CiParams {
                             // [x_hi (K) | x_lo (K) | x_hi (K)] and the weight row [w_hi | w_hi | w_lo] (3K <= 128: two 128-byte
                             // K chunks), i.e. x_hi w_hi + x_lo w_hi + x_hi w_lo in one accumulator chain of <= 8 MMAs
   int nstages;              // A ring depth (6; 4 in split mode: stages are twice as large)
+  int staged;               // CIN == 1: the builder group loads the tile's halo'd input patch (3 planes x 18 x 12 values) cooperatively
+                            // -- ~5 coalesced loads per thread, requested ONE TILE AHEAD -- into shared memory and every thread reads
+                            // its 27 taps from there.  (27 predicated global loads per thread and tile, issued when the tile starts,
+                            // left the two builder groups waiting on memory latency: 305 us for a 100 us write.)
   const float* w;           // packed fp32 [taps][Cin][Cout]
   const float* bias;
   uint16_t* out;            // channels-last [B, D, H, W, Cout]
@@ -50,6 +57,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
   uint8_t* sB = smem + (size_t)NST * a_stage;                // nch x [Cout rows x 128 B]
   uint8_t* sStg = sB + (size_t)nch * p.Cout * 128;           // CI_EPI x [32 rows x 128 B] store stages
   float* sBias = reinterpret_cast<float*>(sStg + (size_t)CI_EPI * CI_STG_BYTES);   // [Cout]
+  __shared__ uint32_t patch_s[CI_NG][2][CI_PATCH_WORDS];     // per builder group: double-buffered input patch (staged mode)
   __shared__ uint64_t full_a[CI_STAGES], empty_a[CI_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -111,11 +119,113 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convin_tc_kernel(const CiParams
     const int r = threadIdx.x & 127, line = r >> 3, wp = r & 7;
     constexpr int kdn = D3 ? 3 : 1;
     uint32_t seq = grp;
-    for (int t = blockIdx.x + grp * gridDim.x; t < p.total_tiles; t += CI_NG * gridDim.x, seq += CI_NG) {
+    // ---- staged mode (CIN == 1) ----
+    uint32_t pre[CI_PATCH_LD];                                 // this thread's share of the NEXT tile's patch, in flight
+    auto patch_request = [&](int t_) {                         // issue the loads of tile t_'s patch (zero / wrapped outside the image)
+      int w0_, h0_, d_, b_;
+      coord(t_, w0_, h0_, d_, b_);
+#pragma unroll
+      for (int i = 0; i < CI_PATCH_LD; ++i) {
+        const int idx = r + i * 128;
+        pre[i] = 0;
+        if (idx < kdn * 18 * CI_PW) {
+          const int pcol = idx % CI_PW, prow = idx / CI_PW, kd = prow / 18, hh = prow - kd * 18;
+          int z = D3 ? d_ + kd - 1 : 0, y = h0_ + hh - 1, x = w0_ + pcol - 1;
+          bool ok = pcol < 10;
+          if (p.circ) {
+            z = z < 0 ? z + p.D : (z >= p.D ? z - p.D : z);
+            y = y < 0 ? y + p.H : (y >= p.H ? y - p.H : y);
+            x = x < 0 ? x + p.W : (x >= p.W ? x - p.W : x);
+            ok = ok && (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W;      // rows / columns of ragged tiles far outside
+          } else {
+            ok = ok && (unsigned)z < (unsigned)p.D && (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W;
+          }
+          if (ok) {
+            const int64_t off = (((int64_t)b_ * p.D + z) * p.H + y) * p.W + x;
+            pre[i] = p.in_f32 ? __float_as_uint(reinterpret_cast<const float*>(p.x)[off]) : (uint32_t)p.x[off];
+          }
+        }
+      }
+    };
+    auto patch_commit = [&](uint32_t buf) {                    // registers -> shared memory, then the group meets
+#pragma unroll
+      for (int i = 0; i < CI_PATCH_LD; ++i) {
+        const int idx = r + i * 128;
+        if (idx < kdn * 18 * CI_PW) patch_s[grp][buf][idx] = pre[i];
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+    };
+    uint32_t pn = 0;
+    if (p.staged) {
+      const int t0 = blockIdx.x + grp * gridDim.x;
+      if (t0 < p.total_tiles) { patch_request(t0); patch_commit(0); }
+    }
+    for (int t = blockIdx.x + grp * gridDim.x; t < p.total_tiles; t += CI_NG * gridDim.x, seq += CI_NG, ++pn) {
       int w0, h0, d, b;
       coord(t, w0, h0, d, b);
       const int h = h0 + line, w = w0 + wp;
       const uint32_t slot = seq % NST, ph = (seq / NST) & 1;
+      if (p.staged) {
+        if constexpr (CIN == 1) {
+          const int tn = t + CI_NG * gridDim.x;
+          const bool more = tn < p.total_tiles;                // group-uniform
+          if (more) patch_request(tn);                         // next tile's loads fly while this tile is packed
+          const uint32_t* pat = patch_s[grp][pn & 1];
+          uint32_t tv[K];
+#pragma unroll
+          for (int kd = 0; kd < kdn; ++kd)
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint32_t raw = pat[(kd * 18 + line + kh) * CI_PW + wp + kw];
+                const int k = (kd * 3 + kh) * 3 + kw;
+                if (p.in_f32) {
+                  const float xf = __uint_as_float(raw);
+                  const uint32_t hi = pack_h1(xf, p.f16);
+                  tv[k] = hi | ((uint32_t)pack_h1(xf - unpack_h1((uint16_t)hi, p.f16), p.f16) << 16);
+                } else {
+                  tv[k] = raw;
+                }
+              }
+          mbar_wait(&empty_a[slot], ph ^ 1);
+          uint8_t* row = sA + (size_t)slot * a_stage + r * 128;
+          auto elem = [&](int i, bool split) -> uint32_t {
+            if (!split) return i < K ? (tv[i < K ? i : 0] & 0xffffu) : 0u;
+            if (i < K) return tv[i < K ? i : 0] & 0xffffu;
+            if (i < 2 * K) return tv[(i - K) < K ? (i - K) : 0] >> 16;
+            if (i < 3 * K) return tv[(i - 2 * K) < K ? (i - 2 * K) : 0] & 0xffffu;
+            return 0u;
+          };
+          if (!p.split) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 piece;
+              piece.x = elem(j * 8, false) | (elem(j * 8 + 1, false) << 16);
+              piece.y = elem(j * 8 + 2, false) | (elem(j * 8 + 3, false) << 16);
+              piece.z = elem(j * 8 + 4, false) | (elem(j * 8 + 5, false) << 16);
+              piece.w = elem(j * 8 + 6, false) | (elem(j * 8 + 7, false) << 16);
+              *reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4)) = piece;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              uint4 piece;
+              piece.x = elem(j * 8, true) | (elem(j * 8 + 1, true) << 16);
+              piece.y = elem(j * 8 + 2, true) | (elem(j * 8 + 3, true) << 16);
+              piece.z = elem(j * 8 + 4, true) | (elem(j * 8 + 5, true) << 16);
+              piece.w = elem(j * 8 + 6, true) | (elem(j * 8 + 7, true) << 16);
+              *reinterpret_cast<uint4*>(row + (j >> 3) * CI_A_BYTES + (((j & 7) ^ (r & 7)) << 4)) = piece;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_a[slot]);
+          // the other buffer was last read one tile ago, and every thread of the group has passed the barrier since
+          if (more) patch_commit((pn + 1) & 1);
+          continue;
+        }
+      }
       // gather the receptive field first (loads in flight while waiting for the slot); validity factorises per axis
       bool dv[3], hv[3], wv[3];
       const int sH = p.W * CIN, sD = p.H * sH;
@@ -342,6 +452,8 @@ int convin_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, co
   p.in_f32 = f32 ? 1 : 0; p.out_f32 = f32 ? 1 : 0;
   p.split = (f32 && split) ? 1 : 0;
   p.nstages = p.split ? 4 : CI_STAGES;
+  static const int gather = [] { const char* e = getenv("DSK_CONVIN_GATHER"); return e ? atoi(e) : 0; }();
+  p.staged = (d->Cin == 1 && !gather) ? 1 : 0;
   p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.ndim = d->ndim;
   p.circ = d->circular;
   p.tiles_w = (d->W + CI_BW - 1) / CI_BW; p.tiles_h = (d->H + CI_BH - 1) / CI_BH;
