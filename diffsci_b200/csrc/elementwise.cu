@@ -257,13 +257,16 @@ __global__ void __launch_bounds__(256) grouped_linear_wgrad_kernel(const float* 
 // (b) dX[b,k] = sum_n dZ[b,n] W[n,k]; `shared`: every group consumed the same X, so ONE dX = sum over groups too
 //     (ADM's per-block FiLM projections of the shared embedding).  Block = 128 k-columns x GLB_ROWS batch rows.
 constexpr int GLB_ROWS = 8;
-__global__ void __launch_bounds__(128) grouped_linear_dgrad_kernel(const float* const* __restrict__ dZ, const float* const* __restrict__ Wt,
-                                                                    float* const* __restrict__ dX, const int* __restrict__ in_dim,
-                                                                    const int* __restrict__ out_dim, int ngroups, int B, int shared,
-                                                                    int accumulate) {
+constexpr int GLB_NL = 8;        // lanes over the reduction (n) axis: a `shared` dX over 28 groups x 256 outputs was ONE block of 128
+                                 // threads walking 7 168 terms (100 us per launch in C4 training); 8 lanes + a fixed-order combine
+__global__ void __launch_bounds__(128 * GLB_NL) grouped_linear_dgrad_kernel(const float* const* __restrict__ dZ, const float* const* __restrict__ Wt,
+                                                                             float* const* __restrict__ dX, const int* __restrict__ in_dim,
+                                                                             const int* __restrict__ out_dim, int ngroups, int B, int shared,
+                                                                             int accumulate) {
   const int g0 = shared ? 0 : blockIdx.z, g1 = shared ? ngroups : blockIdx.z + 1;
   const int K = in_dim[g0];
-  const int k = blockIdx.x * 128 + threadIdx.x;
+  const int kx = threadIdx.x & 127, nl = threadIdx.x >> 7;
+  const int k = blockIdx.x * 128 + kx;
   const int b0 = blockIdx.y * GLB_ROWS;
   if (dX[g0] == nullptr) return;
   float acc[GLB_ROWS];
@@ -274,20 +277,27 @@ __global__ void __launch_bounds__(128) grouped_linear_dgrad_kernel(const float* 
     const float* w = Wt[g];
     const float* dz = dZ[g];
     if (k < K)
-      for (int n = 0; n < N; ++n) {
+      for (int n = nl; n < N; n += GLB_NL) {
         const float wv = w[(int64_t)n * K + k];
 #pragma unroll
         for (int r = 0; r < GLB_ROWS; ++r)
           if (b0 + r < B) acc[r] = fmaf(dz[(int64_t)(b0 + r) * N + n], wv, acc[r]);
       }
   }
-  if (k < K) {
+  __shared__ float red[GLB_NL][GLB_ROWS][128];
+#pragma unroll
+  for (int r = 0; r < GLB_ROWS; ++r) red[nl][r][kx] = acc[r];
+  __syncthreads();
+  if (nl == 0 && k < K) {
     float* o = dX[g0];
 #pragma unroll
     for (int r = 0; r < GLB_ROWS; ++r)
       if (b0 + r < B) {
+        float t = 0.0f;
+#pragma unroll
+        for (int l = 0; l < GLB_NL; ++l) t += red[l][r][kx];
         const int64_t i = (int64_t)(b0 + r) * K + k;
-        o[i] = accumulate ? o[i] + acc[r] : acc[r];
+        o[i] = accumulate ? o[i] + t : t;
       }
   }
 }
@@ -658,7 +668,7 @@ extern "C" int dsk_grouped_linear_bwd(const float* const* dY, const float* const
   if (dX != nullptr) {
     DSK_REQUIRE((B + GLB_ROWS - 1) / GLB_ROWS <= 65535, "dsk_grouped_linear_bwd: B too large");
     dim3 dg((max_in + 127) / 128, (B + GLB_ROWS - 1) / GLB_ROWS, shared_dx ? 1 : ngroups);
-    DSK_LAUNCH(grouped_linear_dgrad_kernel, dg, 128, 0, st, (const float* const*)dZ, W, dX, in_dim, out_dim, ngroups, B, shared_dx,
+    DSK_LAUNCH(grouped_linear_dgrad_kernel, dg, 128 * GLB_NL, 0, st, (const float* const*)dZ, W, dX, in_dim, out_dim, ngroups, B, shared_dx,
                accumulate_dx);
   }
   return DSK_OK;
