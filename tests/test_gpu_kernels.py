@@ -566,6 +566,23 @@ def test_conv_fused_norm_statistics(ops, B, Cin, Cout, sp, up2):
         ref = ops.norm_act(y, g, b_, Cout, mode, True)
         got = ops.norm_act(y, g, b_, Cout, mode, True, conv_stats=st)
         assert relmax(got.float(), ref.float()) < 1e-2
+    # fp32-storage modes: fp16 operands, fp32 output and fp32 residual -- residual add and statistics happen in the STORE mapping
+    # of the epilogue (coalesced residual reads, reduce-scatter over the lanes of a chunk); the sums are of the stored fp32 values
+    xh = x.half()
+    pch = ops.PackedConv(w, pc.bias, nd, torch.float16, subpixel=up2)
+    res32 = torch.randn(B, *osp, Cout, device=DEV)
+    out32 = torch.empty(B, *osp, Cout, device=DEV)
+    st.fill_(float("nan"))
+    y32 = ops.conv(xh, pch, out=out32, chan_bias=None if up2 else cb, residual=res32, up2=up2, stats=st)
+    y32_0 = ops.conv(xh, pch, out=torch.empty_like(out32), chan_bias=None if up2 else cb, residual=res32, up2=up2)
+    assert torch.equal(y32, y32_0)
+    tot = st.double().sum(1)
+    yf = y32.double().flatten(1, 3)
+    assert relmax(tot[..., 0], yf.sum(1)) < 1e-5
+    assert relmax(tot[..., 1], (yf * yf).sum(1)) < 1e-5
+    ref32 = ops.norm_act(y32, g, b_, Cout, 0, True, out=torch.empty(y32.shape, dtype=torch.float16, device=DEV))
+    got32 = ops.norm_act(y32, g, b_, Cout, 0, True, out=torch.empty(y32.shape, dtype=torch.float16, device=DEV), conv_stats=st)
+    assert relmax(got32.float(), ref32.float()) < 2e-3
 
 
 @pytest.mark.parametrize("ndim,B,Cin,Cout,sp", [(3, 2, 1, 64, (5, 16, 8)), (3, 1, 2, 64, (4, 9, 11)), (2, 3, 3, 128, (20, 12)),
