@@ -1260,9 +1260,18 @@ static bool tc_pair_d_eligible(const dsk_conv_desc* d, bool stats) {
 // 1 if dsk_conv_fwd_stats should emit fused norm statistics for this convolution: the cta_group::2 kernel, 3-D only.
 // (The epilogue can do it for 2-D too -- tests exercise it with DSK_CONV_STATS_2D=1 -- but a 2-D tile has 3x fewer MMAs to
 // hide the reduction behind and one slot set per sample of a large batch: measured on C5 / C2 it does not pay.)
+// 2-D, fp32 OUTPUT (the fp32-storage modes): since the statistics of that epilogue became a 14-shuffle reduce-scatter in the store
+// mapping they pay in 2-D as well -- where a sample spans enough tile pairs that the per-range flush is rare (>= 32: planes of
+// 128^2 and up; C5 evaluation at B = 32 10.27 -> 10.0 ms; the 28^2 planes of MNIST flush every 4 tiles and lose).  16-bit outputs
+// keep the butterfly and stay off in 2-D (C5 bf16 8.14 -> 8.89 ms when forced).  DSK_CONV_STATS_2D = 1 forces all on, -1 all off.
 extern "C" int dsk_conv_stats_supported(const dsk_conv_desc* d) {
   static const int allow2d = [] { const char* e = getenv("DSK_CONV_STATS_2D"); return e ? atoi(e) : 0; }();
-  return d != nullptr && (d->ndim == 3 || allow2d) && tc_pair_eligible(d) ? 1 : 0;
+  if (d == nullptr || !tc_pair_eligible(d)) return 0;
+  if (d->ndim == 3 || allow2d > 0) return 1;
+  if (allow2d < 0 || d->out_dtype != DSK_F32 || d->out_nchw_f32) return 0;
+  const int iH = d->up2 ? d->H / 2 : d->H, iW = d->up2 ? d->W / 2 : d->W;
+  const int pairs = (((iW + TC_BW - 1) / TC_BW) / 2) * ((iH + TC_BH - 1) / TC_BH) * (d->up2 ? 4 : 1);
+  return pairs >= 32 ? 1 : 0;
 }
 extern "C" int dsk_conv_stats_slots(void) { return TC_STAT_SLOTS; }
 
