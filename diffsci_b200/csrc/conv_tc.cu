@@ -72,6 +72,7 @@ struct TcParams {
   // tile index -> coordinates without integer division (cta_group::2 kernel): divisors nphase, pairs along the fastest tile
   // axis (w-pairs, or tiles_w when pairing along d), tiles_h, plane groups (or pairs of them), B
   uint32_t dv_m[5], dv_s[5];
+  int bh;                 // cta_group::2 kernel: output rows per CTA tile = 16 * T (T = 2: two 16-row sub-tiles share every weight load)
 };
 // n / d for n < 2^31, d < 2^31 as a multiply + shift (Granlund-Montgomery, N = 31): m = ceil(2^(31+l) / d), l = ceil(log2 d)
 struct FastDivHost {
@@ -489,13 +490,13 @@ __device__ __forceinline__ TileCoord tile_coord2(const TcParams& p, int u_, int 
   c.pc = c.phase & 1; c.pb = (c.phase >> 1) & 1; c.pa = (c.phase >> 2) & 1;
   if (p.pair_d) {
     q = fast_div(u, p.dv_m[1], p.dv_s[1]); c.w0 = (int)(u - q * (uint32_t)p.tiles_w) * TC_BW; u = q;
-    q = fast_div(u, p.dv_m[2], p.dv_s[2]); c.h0 = (int)(u - q * (uint32_t)p.tiles_h) * TC_BH; u = q;
+    q = fast_div(u, p.dv_m[2], p.dv_s[2]); c.h0 = (int)(u - q * (uint32_t)p.tiles_h) * p.bh; u = q;
     const uint32_t pairs_d = (uint32_t)p.groups_d >> 1;
     q = fast_div(u, p.dv_m[3], p.dv_s[3]); c.d0 = (int)((u - q * pairs_d) * 2 + rank) * P; u = q;
   } else {
     const uint32_t pairs_w = (uint32_t)p.tiles_w >> 1;
     q = fast_div(u, p.dv_m[1], p.dv_s[1]); c.w0 = (int)((u - q * pairs_w) * 2 + rank) * TC_BW; u = q;
-    q = fast_div(u, p.dv_m[2], p.dv_s[2]); c.h0 = (int)(u - q * (uint32_t)p.tiles_h) * TC_BH; u = q;
+    q = fast_div(u, p.dv_m[2], p.dv_s[2]); c.h0 = (int)(u - q * (uint32_t)p.tiles_h) * p.bh; u = q;
     q = fast_div(u, p.dv_m[3], p.dv_s[3]); c.d0 = (int)(u - q * (uint32_t)p.groups_d) * P; u = q;
   }
   q = fast_div(u, p.dv_m[4], p.dv_s[4]); c.b = (int)(u - q * (uint32_t)p.B); u = q;
@@ -504,25 +505,43 @@ __device__ __forceinline__ TileCoord tile_coord2(const TcParams& p, int u_, int 
 }
 
 constexpr int TC2_THREADS = 384;   // warp 0/1: TMA producers, warp 2: MMA issuer, warp 3: idle, warps 4-11: epilogue
-template <int N_TILE, int P, int NA, int NB, bool UPS>
+// T = 2 ("merged depth taps", 3-D, N_TILE = 64, plain 16-bit operands): an input plane j of the tile feeds up to two output planes
+// (plane 0 through depth tap kd, plane 1 through kd - 1), and the two accumulators sit side by side in TMEM -- so ONE MMA of
+// N = 128 whose B operand is [W(kd, khw) ; W(kd - 1, khw)] does both.  The activation rows (4 KB per MMA and SM) are then read
+// once for two tap-GEMMs: 6 KB of shared-memory operands per 64 tensor clocks instead of 2 x 5 KB, which takes the 64-channel
+// layers off the operand-port ceiling (0.80 of the tensor peak with N = 64 pairs).  The two CTAs of a pair each supply one of
+// the two stacked taps (the hardware takes B rows 0..63 from rank 0 and 64..127 from rank 1), so a CTA loads whole taps (8 KB)
+// where the N = 64 form loads half taps: to keep the L2 -> SM weight stream where it was, a CTA tile is T = 2 sub-tiles of
+// 16 x 8 pixels stacked in h (one 34 x 10 patch per input plane) that share every weight slot; accumulators [t][plane][64],
+// 256 columns, double-buffered = all 512.  Input planes are walked in the order 1, 2, 0, 3 (relative to d0 - 1) so that the
+// first MMA into a buffer is a merged one that initialises both planes.
+__device__ __forceinline__ int t2_plane(int jj) { return jj == 0 ? 1 : (jj == 1 ? 2 : (jj == 2 ? 0 : 3)); }
+template <int T> struct Tc2Geom {
+  static constexpr int PATCH_ROWS = TC_PW * (TC_BH * T + 2);
+  static constexpr int PATCH_BYTES = PATCH_ROWS * 128;                       // T = 2: 43520
+  static constexpr int PATCH_STRIDE = (PATCH_BYTES + 1023) / 1024 * 1024;    // T = 1: 23552, T = 2: 44032
+};
+template <int N_TILE, int P, int NA, int NB, bool UPS, int T = 1>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW, const TcParams p) {
+  static_assert(T == 1 || (T == 2 && N_TILE == 64 && P == 2 && !UPS), "merged depth taps: N_TILE = 64, P = 2, no sub-pixel phases");
+  constexpr int PATCH_BYTES = Tc2Geom<T>::PATCH_BYTES, PATCH_STRIDE = Tc2Geom<T>::PATCH_STRIDE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)NA * TC_PATCH_STRIDE;
-  constexpr int B_HALF = (N_TILE / 2) * 128;            // this CTA's half of a weight tap tile
+  uint8_t* sB = smem + (size_t)NA * PATCH_STRIDE;
+  constexpr int B_HALF = T == 2 ? N_TILE * 128 : (N_TILE / 2) * 128;   // weight ring slot: this CTA's half of a tap tile (T = 2: a whole tap)
   __shared__ uint64_t full_a[NA], empty_a[NA], full_b[NB], empty_b[NB], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ uint4 stage_s[8][32 * 4];                  // per epilogue warp: 32 rows x 64 B (coalescing stage of the stores)
   __shared__ __align__(16) float bias_s[8][N_TILE];     // per epilogue warp: bias + chan_bias row of its current (sample, n-tile)
-  constexpr uint32_t TMEM_COLS = 2 * P * N_TILE;
+  constexpr uint32_t TMEM_COLS = 2 * T * P * N_TILE;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
   // accumulator sets per tile: 1 (plain), 2 (hh | lo; activations-split mode) or 4 (three hh sets + lo; fp32-parity mode,
   // N_TILE = 64 only).  Double-buffered across tiles when two buffers fit the 512 TMEM columns (1 set; 2 sets at N_TILE = 64),
   // else single-buffered (the epilogue of a tile then runs between its MMAs and the next tile's).
   const int nsets = p.nsets;
-  constexpr uint32_t SET_COLS = P * N_TILE;             // columns of one accumulator set
+  constexpr uint32_t SET_COLS = T * P * N_TILE;         // columns of one accumulator set ([t][plane][N_TILE])
   const uint32_t buf_cols = nsets * SET_COLS, nbuf = 2 * buf_cols <= 512 ? 2u : 1u, tmem_cols = nbuf * buf_cols;
   const uint32_t lo_set = nsets - 1, nhh = nsets > 1 ? nsets - 1 : 1;
 
@@ -563,13 +582,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         const TileCoord tc = tile_coord2(p, u, rank, N_TILE, P);
         VChunk vc;
         for (int c = 0; c < nchunks; ++c, vc.next(p))
-          for (int j = 0; j < NJ; ++j, ++seq) {
+          for (int jj = 0; jj < NJ; ++jj, ++seq) {
+            const int j = T == 2 ? t2_plane(jj) : jj;       // T = 2: planes in the order 1, 2, 0, 3
             const uint32_t slot = seq % NA, ph = (seq / NA) & 1;
             mbar_wait(&empty_a[slot], ph ^ 1);
-            if (leader) mbar_expect_tx(&full_a[slot], 2 * TC_PATCH_BYTES);
+            if (leader) mbar_expect_tx(&full_a[slot], 2 * PATCH_BYTES);
             asm volatile(
                 "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
-                    smem_u32(sA + (size_t)slot * TC_PATCH_STRIDE)),
+                    smem_u32(sA + (size_t)slot * PATCH_STRIDE)),
                 "l"(reinterpret_cast<uint64_t>(&tmapA)), "r"(vc.a(p)), "r"(tc.w0 - 1 + p.pad_hw), "r"(tc.h0 - 1 + p.pad_hw), "r"(tc.d0 + j - dpad + p.pad_d), "r"(tc.b),
                 "r"(smem_u32(&full_a[slot]) & kPeerBitMask)
                 : "memory");
@@ -585,6 +605,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         const TileCoord tc = tile_coord2(p, u, rank, N_TILE, P);
         const int tap_base = UPS ? tc.phase * ntaps : 0;
         VChunk vc;
+        if constexpr (T == 2) {
+          // slot (jj, khw): merged planes (jj < 2) take ONE WHOLE tap per CTA -- rank 0 the tap of output plane 0 (kd = j),
+          // rank 1 the tap of output plane 1 (kd = j - 1) -- as two 32-row boxes; the outer planes take this CTA's half of
+          // the single tap (kd = 0 for plane 0 of the tile, kd = 2 for plane 3)
+          for (int c = 0; c < nchunks; ++c, vc.next(p))
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = t2_plane(jj);
+              const bool wide = jj < 2;
+              const int kd = wide ? j - (int)rank : (j == 0 ? 0 : 2);
+              for (int khw = 0; khw < 9; ++khw, ++seq) {
+                const uint32_t slot = seq % NB, ph = (seq / NB) & 1;
+                mbar_wait(&empty_b[slot], ph ^ 1);
+                if (leader) mbar_expect_tx(&full_b[slot], wide ? 2 * B_HALF : B_HALF);
+                const int row = (kd * 9 + khw) * p.Cout + tc.n0 + (wide ? 0 : (int)rank * 32);
+                for (int hb = 0; hb < (wide ? 2 : 1); ++hb)
+                  asm volatile(
+                      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                          smem_u32(sB + (size_t)slot * B_HALF + hb * 4096)),
+                      "l"(reinterpret_cast<uint64_t>(&tmapW)), "r"(vc.w(p)), "r"(row + hb * 32),
+                      "r"(smem_u32(&full_b[slot]) & kPeerBitMask)
+                      : "memory");
+              }
+            }
+          continue;
+        }
         for (int c = 0; c < nchunks; ++c, vc.next(p))
           for (int tap = tap_base; tap < tap_base + ntaps; ++tap, ++seq) {
             const uint32_t slot = seq % NB, ph = (seq / NB) & 1;
@@ -615,7 +660,39 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       const TileCoord tc = tile_coord2(p, u, 0, N_TILE, P);
       for (int c = 0; c < nchunks; ++c) {
         const uint32_t seq_c = seq_a;
-        if constexpr (UPS) {
+        if constexpr (T == 2) {
+          const uint32_t idesc_w = umma_idesc_h16(2 * N_TILE, 256, p.f16);
+          for (int jj = 0; jj < 4; ++jj) {
+            const uint32_t s = seq_c + jj;
+            mbar_wait(&full_a[s % NA], (s / NA) & 1);
+            const uint32_t a_lo = umma_desc_lo(smem_u32(sA + (size_t)(s % NA) * PATCH_STRIDE));
+            const bool wide = jj < 2;
+            const uint32_t dcol = jj == 3 ? N_TILE : 0;      // plane 3 feeds output plane 1 only
+            const uint32_t id = wide ? idesc_w : idesc;
+#pragma unroll
+            for (int khw = 0; khw < 9; ++khw, ++seq_b) {
+              const uint32_t bs = seq_b % NB;
+              mbar_wait(&full_b[bs], (seq_b / NB) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t b_lo = umma_desc_lo(smem_u32(sB + (size_t)bs * B_HALF));
+              const uint32_t tap_off = ((khw / 3) * TC_PW + (khw % 3)) * 8;
+              const uint32_t first = (c == 0 && jj == 0 && khw == 0) ? 0u : 1u;
+              if (elect_one_sync()) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    umma_bf16_2cta(tmem_acc + t * (P * N_TILE) + dcol, umma_desc64(a_lo + tap_off + t * (TC_BH * TC_PW * 8) + k4 * 2, A_HI),
+                                   umma_desc64(b_lo + k4 * 2, B_HI), id, k4 == 0 ? first : 1u);
+                }
+                umma_commit_2cta(&empty_b[bs]);
+              }
+              __syncwarp();
+            }
+            if (elect_one_sync()) umma_commit_2cta(&empty_a[s % NA]);
+            __syncwarp();
+          }
+        } else if constexpr (UPS) {
           for (int j = 0; j < NJ; ++j) mbar_wait(&full_a[(seq_c + j) % NA], ((seq_c + j) / NA) & 1);
           const int ntd = KD == 3 ? 2 : 1;
           for (int td = 0; td < ntd; ++td) {
@@ -769,7 +846,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     };
     uint32_t it = 0;
     for (int u = cluster_id; u < total_pairs; u += nclusters, ++it) {
-      const TileCoord tc = tile_coord2(p, u, rank, N_TILE, P);
+      const TileCoord tc0 = tile_coord2(p, u, rank, N_TILE, P);
       if (do_stats) {
         const int r = u / per_range;
         if (r != cur_range) {
@@ -778,6 +855,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           cur_range = r;
         }
       }
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {                           // T = 2: the two 16-row sub-tiles of the CTA tile, one accumulator buffer
+      TileCoord tc = tc0;
+      tc.h0 += t * TC_BH;
       const int h = tc.h0 + line, w = tc.w0 + wp;
       const int d = tc.d0 + pp;
       const bool valid = h < p.H && w < p.W && d < p.D;
@@ -860,7 +941,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       if (p.residual != nullptr && u + nclusters < total_pairs) {
         // the residual rows of the NEXT tile start their trip from HBM now (one tile time ahead, no registers held)
         const TileCoord tn = tile_coord2(p, u + nclusters, rank, N_TILE, P);
-        const int hn = tn.h0 + line, wn = tn.w0 + wp, dn = tn.d0 + pp;
+        const int hn = tn.h0 + t * TC_BH + line, wn = tn.w0 + wp, dn = tn.d0 + pp;
         if (hn < p.H && wn < p.W && dn < p.D) {
           int64_t pn;
           if constexpr (UPS) {
@@ -875,13 +956,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         }
       }
       const uint32_t as = nbuf == 1 ? 0u : (it & 1), aph = nbuf == 1 ? (it & 1) : ((it >> 1) & 1);
-      mbar_wait(&acc_full[as], aph);
+      if (t == 0) mbar_wait(&acc_full[as], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + as * buf_cols + pp * N_TILE + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + as * buf_cols + (t * P + pp) * N_TILE + ((uint32_t)(q * 32) << 16);
       if (p.dbg & 1) {                                       // measurement: MMA / TMA side alone
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
+        if (t == T - 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
+        }
         continue;
       }
 #pragma unroll
@@ -1042,9 +1125,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           st_q[gi] += sq[0];
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);   // 2 CTAs x 8 epilogue warps -> count 16 on the leader
+      if (t == T - 1) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);   // 2 CTAs x 8 epilogue warps -> count 16 on the leader
+      }
+      }
     }
     if (do_stats) {
       if (cur_range >= 0) flush(cur_range, false);
@@ -1057,12 +1143,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
 }
 
-template <int N_TILE, int P, int NA, int NB, bool UPS>
+template <int N_TILE, int P, int NA, int NB, bool UPS, int T = 1>
 static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const TcParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)NA * TC_PATCH_STRIDE + (size_t)NB * (N_TILE / 2) * 128 + 1024;
+  const size_t smem = (size_t)NA * Tc2Geom<T>::PATCH_STRIDE + (size_t)NB * (T == 2 ? N_TILE : N_TILE / 2) * 128 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<N_TILE, P, NA, NB, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<N_TILE, P, NA, NB, UPS, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv_tc2: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e)); return DSK_ERR_CUDA; }
     configured = true;
   }
@@ -1077,7 +1163,7 @@ static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const TcPara
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<N_TILE, P, NA, NB, UPS>, ta, tw, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<N_TILE, P, NA, NB, UPS, T>, ta, tw, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) { set_error("conv_tc2_kernel launch failed: %s", cudaGetErrorString(e)); return DSK_ERR_CUDA; }
   return DSK_OK;
@@ -1353,12 +1439,17 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   const int planes = d->ndim == 3 ? iD : d->B;
   const int batch = d->ndim == 3 ? d->B : 1;
   const int tW = iW + 2 * pad_hw, tH = iH + 2 * pad_hw, tP = planes + 2 * pad_d;
+  // merged depth taps (conv_tc2_kernel<.., T = 2>): 3-D, 64-channel output tiles, plain 16-bit operands, CTA pairs side by side in w,
+  // rows in whole 32-row tiles.  DSK_CONV_T2=0 keeps the N = 64 pair kernel (A/B measurements).
+  static const int allow_t2 = [] { const char* e = getenv("DSK_CONV_T2"); return e ? atoi(e) : 1; }();
+  const bool t2 = allow_t2 && !few_out && !d->up2 && KD == 3 && !a_split && !w_split && d->Cout % 128 != 0 && tc_pair_eligible(d) &&
+                  iH % (2 * TC_BH) == 0;
   CUtensorMap ta, tw;
   {
     cuuint64_t dims[5] = {(cuuint64_t)a_ld, (cuuint64_t)tW, (cuuint64_t)tH, (cuuint64_t)tP, (cuuint64_t)batch};
     cuuint64_t strides[4] = {(cuuint64_t)a_ld * 2, (cuuint64_t)tW * a_ld * 2, (cuuint64_t)tH * tW * a_ld * 2,
                              (cuuint64_t)tP * tH * tW * a_ld * 2};
-    cuuint32_t box[5] = {64, TC_PW, TC_PH, 1, 1};
+    cuuint32_t box[5] = {64, TC_PW, (cuuint32_t)(t2 ? 2 * TC_BH + 2 : TC_PH), 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&ta, tmap_h16(fmt16), 5, const_cast<void*>(in), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1387,7 +1478,8 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
   constexpr int P = 2;
   p.nphase = nphase;
   p.tiles_w = (iW + TC_BW - 1) / TC_BW;
-  p.tiles_h = (iH + TC_BH - 1) / TC_BH;
+  p.bh = t2 ? 2 * TC_BH : TC_BH;
+  p.tiles_h = (iH + p.bh - 1) / p.bh;
   p.groups_d = (planes + P - 1) / P;
   p.n_tiles = w_rows / n_tile;
   p.total_tiles = p.tiles_w * p.tiles_h * p.groups_d * batch * p.n_tiles * nphase;
@@ -1433,6 +1525,7 @@ static int conv_fwd_tc_impl(const dsk_conv_desc* d, const void* in, const void* 
       if (n_tile == 64) return launch_tc2<64, P, 7, 8, true>(ta, tw2, p, st);
       return launch_tc2<128, P, 6, 8, true>(ta, tw2, p, st);
     }
+    if (t2) return launch_tc2<64, P, 3, 8, false, 2>(ta, tw2, p, st);   // 3 patches of 43 KB + 8 whole taps of 8 KB = 196 KB
     if (n_tile == 64) return launch_tc2<64, P, 7, 8, false>(ta, tw2, p, st);
     return launch_tc2<128, P, 6, 8, false>(ta, tw2, p, st);
   }
