@@ -925,7 +925,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           for (int k = 0; k < 4; ++k) {
             rr[hh][k] = make_uint4(0, 0, 0, 0);
             if (st_ok && tc.h0 + q * 4 + k < p.H)
-              rr[hh][k] = *reinterpret_cast<const uint4*>(res32 + st_row(k) * p.Cout + tc.n0 + c0 + hh * 16 + (lane & 3) * 4);
+              rr[hh][k] = __ldcs(reinterpret_cast<const uint4*>(res32 + st_row(k) * p.Cout + tc.n0 + c0 + hh * 16 + (lane & 3) * 4));
           }
       };
       if constexpr (DEP == 2) {
@@ -1047,7 +1047,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
                 val.z += __uint_as_float(rr[hh][k].z); val.w += __uint_as_float(rr[hh][k].w);
               }
               if (st_ok && tc.h0 + q * 4 + k < p.H) {
-                *reinterpret_cast<float4*>(outf + st_row(k) * p.Cout + tc.n0 + c0 + hh * 16 + (lane & 3) * 4) = val;
+                __stcs(reinterpret_cast<float4*>(outf + st_row(k) * p.Cout + tc.n0 + c0 + hh * 16 + (lane & 3) * 4), val);
                 if (do_stats) {
                   ps[hh * 4] += val.x; ps[hh * 4 + 1] += val.y; ps[hh * 4 + 2] += val.z; ps[hh * 4 + 3] += val.w;
                   pq[hh * 4] = fmaf(val.x, val.x, pq[hh * 4]); pq[hh * 4 + 1] = fmaf(val.y, val.y, pq[hh * 4 + 1]);
