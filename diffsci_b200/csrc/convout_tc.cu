@@ -14,6 +14,8 @@
 // row-shifted view of the same TMA patch), so an activation patch is read from shared memory 2 x (number of output planes
 // it feeds) times instead of 27 x.  N = 9 * Cout padded to 16 / 32.  The kernel is then bound by the L2 -> SM patch
 // stream (halo factor ~2.8), not by the tensor core's operand port.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace dsk {
@@ -24,7 +26,7 @@ constexpr int CO_PATCH_BYTES = CO_ROWS * 128;        // 23040
 constexpr int CO_PATCH_STRIDE = 23552;
 constexpr int CO_G1 = CO_ROWS - 128;                 // 52: first row of the second M = 128 row group
 constexpr int CO_THREADS = 192;                      // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: epilogue
-constexpr int CO_P = 2, CO_NA = 6;
+constexpr int CO_NA = 6;   // CO_P (template): output planes per tile -- 3-D depth halo (P + 2) / P of the L2 -> SM patch stream
 
 struct CoParams {
   int B, D, H, W, Cin, Cout, KD;      // as the tensor map sees them (2-D: B = 1, D = batch of planes)
@@ -47,7 +49,7 @@ __device__ __forceinline__ int co_vchunk_w(const CoParams& p, int vc) {
   return c * 64 + ((p.vparts == 3 && part == 1) ? p.w_lo_off : 0);
 }
 
-template <int COUT>
+template <int COUT, int CO_P = 2>
 __global__ void __launch_bounds__(CO_THREADS, 1)
 convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
   constexpr int NT = 9 * COUT, N_PAD = NT <= 16 ? 16 : 32;
@@ -267,17 +269,17 @@ convout_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const CoParams p) {
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
 }
 
-template <int COUT>
+template <int COUT, int CO_P = 2>
 static int launch_convout(const CUtensorMap& ta, const CoParams& p, cudaStream_t st) {
   constexpr int N_PAD = 9 * COUT <= 16 ? 16 : 32;
   const int nchunks = (p.Cin / 64) * p.vparts;
   const size_t wbytes = ((size_t)p.KD * nchunks * N_PAD * 128 + 1023) & ~(size_t)1023;
   const size_t smem = (size_t)CO_NA * CO_PATCH_STRIDE + wbytes + (size_t)CO_P * CO_ROWS * 9 * p.Cout * sizeof(float) + 1024;
   if (smem > 227 * 1024) return DSK_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(convout_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(convout_tc_kernel<COUT, CO_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("convout_tc: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e)); return DSK_ERR_CUDA; }
   const int grid = p.total_tiles < DSK_NUM_SMS ? p.total_tiles : DSK_NUM_SMS;
-  DSK_LAUNCH((convout_tc_kernel<COUT>), grid, CO_THREADS, smem, st, ta, p);
+  DSK_LAUNCH((convout_tc_kernel<COUT, CO_P>), grid, CO_THREADS, smem, st, ta, p);
   return DSK_OK;
 }
 
@@ -306,7 +308,17 @@ int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, c
   if (r != CUDA_SUCCESS) { set_error("convout_tc: activation tensor map failed (CUresult %d)", (int)r); return DSK_ERR_CUDA; }
   CoParams p;
   p.B = batch; p.D = planes; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.KD = KD;
-  p.tiles_w = (d->W + CO_BW - 1) / CO_BW; p.tiles_h = (d->H + CO_BH - 1) / CO_BH; p.groups_d = (planes + CO_P - 1) / CO_P;
+  // planes per tile: 3-D single-channel outputs with plain operands take 8 or 4 planes per tile (depth halo 1.25 / 1.5 instead of
+  // 2.0: the kernel is bound by the L2 -> SM patch stream) as long as the grid keeps >= 6 rounds of tiles; DSK_CONVOUT_P forces.
+  static const int force_p = [] { const char* e = getenv("DSK_CONVOUT_P"); return e ? atoi(e) : 0; }();
+  p.tiles_w = (d->W + CO_BW - 1) / CO_BW; p.tiles_h = (d->H + CO_BH - 1) / CO_BH;
+  int P = 2;
+  if (KD == 3 && d->Cout == 1 && !a_split) {
+    for (int cand = 8; cand >= 4; cand >>= 1)
+      if (planes % cand == 0 && (int64_t)p.tiles_w * p.tiles_h * (planes / cand) * batch >= 6 * DSK_NUM_SMS) { P = cand; break; }
+    if (force_p == 2 || ((force_p == 4 || force_p == 8) && planes % force_p == 0)) P = force_p;
+  }
+  p.groups_d = (planes + P - 1) / P;
   p.total_tiles = p.tiles_w * p.tiles_h * p.groups_d * batch;
   p.w = (const uint16_t*)w; p.bias = bias;
   p.out = d->out_nchw_f32 ? nullptr : (uint16_t*)out;
@@ -317,6 +329,8 @@ int convout_tc_dispatch(const dsk_conv_desc* d, const void* in, const void* w, c
   p.out_nchw = d->out_nchw_f32 ? (float*)out : nullptr;
   p.planes_per_sample = d->ndim == 3 ? d->D : 1;
   p.pad_hw = pad_hw; p.pad_d = pad_d;
+  if (d->Cout == 1 && P == 8) return launch_convout<1, 8>(ta, p, st);
+  if (d->Cout == 1 && P == 4) return launch_convout<1, 4>(ta, p, st);
   if (d->Cout == 1) return launch_convout<1>(ta, p, st);
   if (d->Cout == 2) return launch_convout<2>(ta, p, st);
   return launch_convout<3>(ta, p, st);
