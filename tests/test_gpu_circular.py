@@ -69,6 +69,7 @@ CASES = [
     (3, 1, 64, 64, (4, 16, 8), 3, False),    # tcgen05, one tile pair
     (3, 2, 64, 64, (5, 20, 12), 3, False),   # tcgen05, ragged tiles + wrap
     (3, 1, 128, 64, (4, 16, 16), 3, False),  # two K chunks
+    (3, 1, 64, 64, (3, 32, 16), 3, False),   # merged depth taps (conv_tc2 T = 2: 34-row patches) on the padded copy
     (3, 1, 64, 128, (2, 16, 8), 3, False),   # N_TILE = 128
     (2, 3, 64, 64, (16, 8), 3, False),       # 2-D: planes are samples (no depth halo)
     (2, 5, 128, 128, (7, 7), 3, False),      # single-CTA kernel (odd number of w-tiles)

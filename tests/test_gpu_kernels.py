@@ -282,6 +282,9 @@ TC_CASES = [
     (2, 4, 128, 128, (7, 7)),            # odd number of w-tiles, even number of plane groups: CTA pairs along the plane axis
     (2, 8, 64, 64, (14, 7)),
     (3, 2, 64, 128, (4, 16, 24)),        # 3-D, 3 w-tiles: pairs along depth
+    (3, 1, 128, 64, (5, 32, 16)),        # merged depth taps (T = 2: rows in whole 32-row tiles, 64-channel output tiles): odd plane
+                                         # count, two K chunks
+    (3, 2, 64, 192, (3, 64, 16)),        # merged depth taps: three N tiles of 64, two 32-row tiles per plane
 ]
 
 
@@ -534,6 +537,7 @@ def test_convout_tcgen05(ops, ndim, B, Cin, Cout, sp):
 @pytest.mark.parametrize("B,Cin,Cout,sp,up2", [(2, 64, 64, (4, 16, 16), False), (1, 128, 128, (6, 32, 16), False),
                                                (3, 64, 128, (2, 16, 32), False), (2, 128, 64, (4, 8, 16), True),
                                                (1, 64, 64, (64, 64, 64), False), (5, 64, 64, (32, 48), False),
+                                               (3, 64, 64, (5, 32, 16), False), (2, 128, 64, (6, 32, 32), False),   # merged depth taps
                                                (2, 128, 256, (16, 16), False), (3, 128, 64, (8, 16), True)])
 def test_conv_fused_norm_statistics(ops, B, Cin, Cout, sp, up2):
     """dsk_conv_fwd_stats: the per-(sample, channel) sum / sum of squares left by the cta_group::2 conv epilogue equal the
