@@ -53,6 +53,12 @@ template <> __device__ __forceinline__ float dsilu_t<__nv_bfloat16>(float z) {
   return s * (1.0f + z * (1.0f - s));
 }
 
+// block size of norm_bwd_finalize_kernel: (channels of a group) x (chunk lanes), a power of two in 128 .. 1024
+static inline int bwd_finalize_threads(int cg, int nchunks) {
+  int t = 128;
+  while (t < 1024 && t < (int64_t)cg * nchunks) t <<= 1;
+  return t;
+}
 static inline int bw_chunks(int B, int64_t S, int C, int V) {
   int cv = C / V;
   int pl = BW_THREADS / cv;
@@ -128,44 +134,63 @@ __global__ void __launch_bounds__(BW_THREADS) bwd_partial_kernel(const T* __rest
 // One block per (sample, group): combine chunk partials; per-(b,c) sums S1 = sum dz, S2 = sum dz*xhat; group means of
 // dxhat and dxhat*xhat (dxhat = dz*gamma*film); the apply-pass coefficients dx = dz*a + x*cb + cc with
 //   cb = -rstd^2*m2,  cc = -rstd*m1 + mean*rstd^2*m2   (m1 = 0 for RMS);  FiLM gradients written directly.
-__global__ void __launch_bounds__(128) norm_bwd_finalize_kernel(const double2* __restrict__ partial, const float2* __restrict__ stats,
-                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                 const float* __restrict__ fsc, float2* __restrict__ coef,
-                                                                 float2* __restrict__ sums, float* __restrict__ dfsc,
-                                                                 float* __restrict__ dfsh, int64_t S, int C, int G, int nchunks,
-                                                                 int mode) {
+__global__ void __launch_bounds__(1024) norm_bwd_finalize_kernel(const double2* __restrict__ partial, const float2* __restrict__ stats,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ fsc, float2* __restrict__ coef,
+                                                                  float2* __restrict__ sums, float* __restrict__ dfsc,
+                                                                  float* __restrict__ dfsh, int64_t S, int C, int G, int nchunks,
+                                                                  int mode) {
+  // block = cgp channel lanes (all channels of the group when they fit) x blockDim / cgp chunk lanes: the chunk partials of a
+  // channel are summed by several lanes with every load of the block in flight at once (one thread per channel walking all chunks
+  // was latency-bound: 8 - 15 us per launch with ADM's single group), combined through shared memory in a fixed order
   const int b = blockIdx.x / G, g = blockIdx.x % G;
   const int cg = C / G;
   const float2 mr = stats[blockIdx.x];
   const double mean = mr.x, rstd = mr.y;
-  __shared__ double r1[128], r2[128];
+  __shared__ double r1[1024], r2[1024];
+  const int cgp = cg < (int)blockDim.x ? cg : (int)blockDim.x;   // channel lanes
+  const int nrl = blockDim.x / cgp;                               // chunk lanes (>= 1)
+  const int cl = threadIdx.x % cgp, rl = threadIdx.x / cgp;
   double a1 = 0, a2 = 0;
-  for (int i = threadIdx.x; i < cg; i += blockDim.x) {
-    const int c = g * cg + i;
+  for (int i0 = 0; i0 < cg; i0 += cgp) {
+    const int i = i0 + cl;
     double s1 = 0, sx = 0;
-#pragma unroll 8
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const double2 v = partial[((int64_t)b * nchunks + ch) * C + c];
-      s1 += v.x;
-      sx += v.y;
+    if (i < cg && rl < nrl) {
+      const int c = g * cg + i;
+#pragma unroll 4
+      for (int ch = rl; ch < nchunks; ch += nrl) {
+        const double2 v = partial[((int64_t)b * nchunks + ch) * C + c];
+        s1 += v.x;
+        sx += v.y;
+      }
     }
-    const double s2 = rstd * (sx - mean * s1);
-    sums[(int64_t)b * C + c] = make_float2((float)s1, (float)s2);
-    const double gm = gamma != nullptr ? (double)gamma[c] : 1.0;
-    const double f = fsc != nullptr ? (double)fsc[(int64_t)b * C + c] : 1.0;
-    a1 += gm * f * s1;
-    a2 += gm * f * s2;
-    if (dfsc != nullptr) {
-      const double bt = beta != nullptr ? (double)beta[c] : 0.0;
-      dfsc[(int64_t)b * C + c] = (float)(gm * s2 + bt * s1);     // d/dfilm_scale of (xhat*gamma + beta)*fsc + fsh
-      dfsh[(int64_t)b * C + c] = (float)s1;
+    __syncthreads();                                    // r1 / r2 free again (previous channel block consumed)
+    r1[threadIdx.x] = s1;
+    r2[threadIdx.x] = sx;
+    __syncthreads();
+    if (rl == 0 && i < cg) {
+      const int c = g * cg + i;
+      s1 = 0; sx = 0;
+      for (int k = 0; k < nrl; ++k) { s1 += r1[k * cgp + cl]; sx += r2[k * cgp + cl]; }
+      const double s2 = rstd * (sx - mean * s1);
+      sums[(int64_t)b * C + c] = make_float2((float)s1, (float)s2);
+      const double gm = gamma != nullptr ? (double)gamma[c] : 1.0;
+      const double f = fsc != nullptr ? (double)fsc[(int64_t)b * C + c] : 1.0;
+      a1 += gm * f * s1;
+      a2 += gm * f * s2;
+      if (dfsc != nullptr) {
+        const double bt = beta != nullptr ? (double)beta[c] : 0.0;
+        dfsc[(int64_t)b * C + c] = (float)(gm * s2 + bt * s1);     // d/dfilm_scale of (xhat*gamma + beta)*fsc + fsh
+        dfsh[(int64_t)b * C + c] = (float)s1;
+      }
     }
   }
-  r1[threadIdx.x] = a1;
+  __syncthreads();
+  r1[threadIdx.x] = a1;                                 // non-zero in the first cgp threads only
   r2[threadIdx.x] = a2;
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; }
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; }
     __syncthreads();
   }
   const double n = (double)S * cg;
@@ -313,22 +338,30 @@ __global__ void __launch_bounds__(BW_THREADS) norm_bwd_apply_kernel(const T* __r
 // channel sums: out[b][c] (per_sample) or out[c] = sum over chunk partials (and samples)
 __global__ void __launch_bounds__(1024) chansum_finalize_kernel(const double2* __restrict__ partial, float* __restrict__ out, int B,
                                                                 int C, int nchunks, int per_sample) {
-  // block = 32 channels x 32 row lanes over the (sample, chunk) partial rows (8 row lanes: 9 us per launch, 45 launches per
-  // ADM iteration)
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  // block = 8 channels x 128 row lanes over the (sample, chunk) partial rows: the kernel is a chain of dependent L2 loads on a
+  // handful of blocks (32 channels x 32 row lanes: 9 us per launch, 45 launches per ADM iteration), so rows are spread over as
+  // many lanes and blocks as the shape has; fixed-order combine through shared memory
+  const int c = blockIdx.x * 8 + (threadIdx.x & 7), rl = threadIdx.x >> 3;
   const int64_t r0 = per_sample ? (int64_t)blockIdx.y * nchunks : 0;
   const int64_t rows = per_sample ? nchunks : (int64_t)B * nchunks;
   double s = 0;
   if (c < C) {
 #pragma unroll 4
-    for (int64_t r = rl; r < rows; r += 32) s += partial[(r0 + r) * C + c].x;
+    for (int64_t r = rl; r < rows; r += 128) s += partial[(r0 + r) * C + c].x;
   }
-  __shared__ double red[32][33];
-  red[rl][threadIdx.x & 31] = s;
+  __shared__ double red[128][9];
+  red[rl][threadIdx.x & 7] = s;
+  __syncthreads();
+  const int ch = threadIdx.x & 7;
+  double t = 0;
+  if (rl < 8)                                            // 8 lanes per channel add 16 rows each ...
+    for (int k = 0; k < 16; ++k) t += red[rl * 16 + k][ch];
+  __syncthreads();
+  if (rl < 8) red[rl][ch] = t;                           // ... and lane 0 adds the 8 partial sums
   __syncthreads();
   if (rl == 0 && c < C) {
-    double t = 0;
-    for (int k = 0; k < 32; ++k) t += red[k][threadIdx.x & 31];
+    t = 0;
+    for (int k = 0; k < 8; ++k) t += red[k][ch];
     out[per_sample ? (int64_t)blockIdx.y * C + c : c] = (float)t;
   }
 }
@@ -695,7 +728,7 @@ extern "C" int dsk_norm_act_bwd(const void* x, const void* dy, const void* dres,
                  dfilm_scale, dfilm_shift, S, B, C, nchunks, mode);
   }
   else
-    DSK_LAUNCH(norm_bwd_finalize_kernel, B * G, 128, 0, st, partial, stats, gamma, beta, film_scale, coef, sums, dfilm_scale, dfilm_shift, S,
+    DSK_LAUNCH(norm_bwd_finalize_kernel, B * G, bwd_finalize_threads(C / G, nchunks), 0, st, partial, stats, gamma, beta, film_scale, coef, sums, dfilm_scale, dfilm_shift, S,
                C, G, nchunks, mode);
   if (dgamma != nullptr) DSK_LAUNCH(norm_bwd_param_kernel, (C + 31) / 32, 256, 0, st, sums, film_scale, dgamma, dbeta, B, C);
   int64_t gx = (S + (int64_t)pl * 4 - 1) / ((int64_t)pl * 4);
@@ -741,7 +774,7 @@ extern "C" int dsk_channel_sum(const void* dy, float* out, void* ws, int B, int6
   else
     DSK_LAUNCH((bwd_partial_kernel<__nv_bfloat16, false>), pg, BW_THREADS, smem, st, nullptr, (const __nv_bfloat16*)dy, nullptr, partial, S, C,
                nchunks, 0);
-  dim3 fg((C + 31) / 32, per_sample ? B : 1);
+  dim3 fg((C + 7) / 8, per_sample ? B : 1);
   DSK_LAUNCH(chansum_finalize_kernel, fg, 1024, 0, st, partial, out, B, C, nchunks, per_sample);
   return DSK_OK;
 }

@@ -88,6 +88,12 @@ template <int V> __device__ __forceinline__ void st_split(__half* p, int64_t lo_
   st_vec<__half, V>(p + lo_off, lo);
 }
 
+// block size of the per-(sample, group) finalize kernels: the power of two covering `items` partials, 128 .. 1024
+static inline int finalize_threads(int64_t items) {
+  int t = 128;
+  while (t < 1024 && t < items) t <<= 1;
+  return t;
+}
 static inline int norm_chunks(int B, int64_t S, int C, int V) {
   int cv = C / V;
   int pl = NORM_THREADS / cv;
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_partial_kernel(const T* __r
 
 // One block per (sample, group): combine the chunk partials, then fold mean / rstd / gamma / beta / FiLM into a
 // per-(b, c) scale-shift pair:  y = act(x * a + s).
-__global__ void __launch_bounds__(128) norm_finalize_kernel(const double2* __restrict__ partial, float2* __restrict__ table,
+__global__ void __launch_bounds__(1024) norm_finalize_kernel(const double2* __restrict__ partial, float2* __restrict__ table,
                                                              float2* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              const float* __restrict__ fsc, const float* __restrict__ fsh,
                                                              int64_t S, int C, int G, int nchunks, int mode, float eps) {
@@ -177,12 +183,12 @@ __global__ void __launch_bounds__(128) norm_finalize_kernel(const double2* __res
     a += v.x;
     q += v.y;
   }
-  __shared__ double sa[128], sq[128];
+  __shared__ double sa[1024], sq[1024];                // block = 128 .. 1024 threads (a power of two; norm_finalize_threads)
   __shared__ float2 mr;
   sa[threadIdx.x] = a;
   sq[threadIdx.x] = q;
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
     if (threadIdx.x < o) {
       sa[threadIdx.x] += sa[threadIdx.x + o];
       sq[threadIdx.x] += sq[threadIdx.x + o];
@@ -644,7 +650,8 @@ extern "C" int dsk_norm_act(const void* x, void* y, const float* gamma, const fl
                  S, B, C, nchunks, mode, 1e-5f);
   }
   else
-    DSK_LAUNCH(norm_finalize_kernel, B * G, 128, 0, st, partial, table, stats, gamma, beta, film_scale, film_shift, S, C, G, nchunks, mode,
+    // few groups (ADM: G = 1): a block reduces nchunks * C / G partials -- one load per thread instead of a latency-bound loop
+    DSK_LAUNCH(norm_finalize_kernel, B * G, finalize_threads((int64_t)nchunks * (C / G)), 0, st, partial, table, stats, gamma, beta, film_scale, film_shift, S, C, G, nchunks, mode,
                1e-5f);
   if (y == nullptr) return DSK_OK;      // statistics + folded table only (dsk_norm_apply_padded follows)
   return norm_apply_launch(x, y, table, B, S, C, silu, in_dtype, out_dtype, st);
