@@ -674,7 +674,7 @@ def main():
 AUTO_MODES = ("fp16s32", "fp16x2m", "fp16x2")      # --precision auto: the first whose denoiser max-rel is <= AUTO_MAX_REL, else the last
 AUTO_MAX_REL = 8e-4
 DTYPE_NAME = {"bf16": "bf16", "fp16": "f16", "fp16x2": "f16 (activations hi+lo, 2 MMAs per k-step; fp32 storage)",
-              "fp16s32": "f16 (fp16 tensor-core operands, 1 MMA per k-step; fp32 accumulation and fp32 storage of every tensor between kernels)",
+              "fp16s32": "f16 (fp16 tensor-core operands, 1 MMA per k-step; fp32 accumulation and fp32 storage of the tensors between kernels -- except, in 3-D, the conv1 outputs of the full-resolution blocks, read once by the next norm, stored as fp16)",
               "fp16x2m": "f16 (activations hi+lo in the >=128-channel layers: 2 MMAs per k-step there, 1 elsewhere; fp32 storage)",
               "fp32": "f32 (split-f16 x3 on tcgen05)", "fp32_ffma": "f32"}
 

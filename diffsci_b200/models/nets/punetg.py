@@ -45,6 +45,12 @@ DEFAULT_PRECISION = "fp32"
 #               Measured on the full-size networks (tools/sweep_mixed_min_cin.py): the fp16 mode's error (2.7e-3 on C4) comes
 #               from rounding the STORED tensors, not the operands -- with fp32 storage plain fp16 operands give 6.2e-4 on C4
 #               (fp16x2m 5.4e-4) and 6.0e-4 on C5 at 0.77x / 0.79x the evaluation time of fp16x2m.
+#               One exception (3-D networks): conv1's output of the FULL-RESOLUTION ResNet blocks is stored as fp16 -- it is read
+#               exactly once, by the second norm, whose statistics come from the fp32 accumulators either way.  Measured on C4
+#               (tools/check_mode.py, B = 8): denoiser max-rel 7.1e-4 -> 6.8e-4, rel-L2 5.6e-4 -> 5.9e-4, one evaluation
+#               8.74 -> 8.29 ms (the level holds 8x the bytes of the next one and its convolutions are bound by the L2 -> SM
+#               stream; at every level: 6.8e-4 / 6.0e-4 for 8.54 ms -- the 16-bit epilogue's statistics butterfly costs more
+#               than the bytes save on the small levels).  DSK_Y16 = 0: fp32 everywhere, 1: fp16 at every level.
 #   "fp16"      fp16 storage and operands, 1 MMA per k-step: the throughput mode (3 more mantissa bits than bf16).
 #   "bf16"      bf16 storage and operands (the training format; fp32's exponent range).
 PRECISIONS = ("fp32", "fp32_ffma", "fp16x2", "fp16x2m", "fp16s32", "fp16", "bf16")
@@ -294,10 +300,11 @@ class _Plan:
         self.X = [buf(l, ch[l]) for l in range(nlev + 1)]          # encoder / bottom state (doubles as skip)
         self.XU = [buf(l, ch[l]) for l in range(nlev)]             # decoder state
         self.N = [nbuf(l) for l in range(nlev + 1)]                # norm+SiLU output == conv input
-        # conv1 output.  DSK_Y16=1 (experiment, fp16s32 only): stored as fp16 where the block convs run on the tensor cores -- it is
-        # read once, by the second norm, whose statistics come from the fp32 accumulators either way
-        y16 = precision == "fp16s32" and os.environ.get("DSK_Y16", "0") == "1"
-        self.Y = [buf(l, ch[l], torch.float16 if (y16 and _tc_eligible(ch[l], ch[l], c.kernel_size)) else adt)
+        # conv1 output: read once, by the second norm, whose statistics come from the fp32 accumulators either way
+        # fp16s32, 3-D: fp16 at the full-resolution level (default, "l0"; see the mode table above); DSK_Y16 = 0 / 1: nowhere / everywhere
+        y16e = os.environ.get("DSK_Y16", "l0" if nd == 3 else "0") if precision == "fp16s32" else "0"
+        y16 = [y16e == "1" or (y16e == "l0" and l == 0) for l in range(nlev + 1)]
+        self.Y = [buf(l, ch[l], torch.float16 if (y16[l] and _tc_eligible(ch[l], ch[l], c.kernel_size)) else adt)
                   for l in range(nlev + 1)]
         self.P = [buf(l + 1, ch[l]) for l in range(nlev)]          # pooled (re-typed below where only a 16-bit operand is needed)
         self.XA = buf(nlev, ch[nlev])
