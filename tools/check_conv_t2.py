@@ -67,6 +67,9 @@ if not quick:
     case(2, 64, 64, 64, "bf16", False, False)
     case(8, 64, 64, 64, "bf16", False, False)
     case(8, 64, 64, 64, "bf16", True, True)
+    case(8, 64, 64, 64, "fp16", False, False)
+    case(8, 64, 64, 64, "fp16", False, True)         # conv1 of a full-resolution block in the fp16s32 mode: fp16 out + statistics
+    case(8, 64, 64, 64, "fp16s32", False, True)
     case(8, 64, 64, 64, "fp16s32", False, False)
     case(8, 64, 64, 64, "fp16s32", True, True)
 print("ok")
