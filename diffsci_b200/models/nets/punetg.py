@@ -48,9 +48,9 @@ DEFAULT_PRECISION = "fp32"
 #               One exception (3-D networks): conv1's output of the FULL-RESOLUTION ResNet blocks is stored as fp16 -- it is read
 #               exactly once, by the second norm, whose statistics come from the fp32 accumulators either way.  Measured on C4
 #               (tools/check_mode.py, B = 8): denoiser max-rel 7.1e-4 -> 6.8e-4, rel-L2 5.6e-4 -> 5.9e-4, one evaluation
-#               8.74 -> 8.29 ms (the level holds 8x the bytes of the next one and its convolutions are bound by the L2 -> SM
-#               stream; at every level: 6.8e-4 / 6.0e-4 for 8.54 ms -- the 16-bit epilogue's statistics butterfly costs more
-#               than the bytes save on the small levels).  DSK_Y16 = 0: fp32 everywhere, 1: fp16 at every level.
+#               8.74 -> 8.29 ms (the level holds 8x the bytes of the next one; at every level: 6.8e-4 / 6.0e-4 for 8.54 ms --
+#               the 16-bit epilogue costs more than the bytes save on the small levels).  DSK_Y16 = 0: fp32 everywhere,
+#               1: fp16 at every level.
 #   "fp16"      fp16 storage and operands, 1 MMA per k-step: the throughput mode (3 more mantissa bits than bf16).
 #   "bf16"      bf16 storage and operands (the training format; fp32's exponent range).
 PRECISIONS = ("fp32", "fp32_ffma", "fp16x2", "fp16x2m", "fp16s32", "fp16", "bf16")
